@@ -1,0 +1,92 @@
+/* orgpu.h -- C ABI of liborgpu.so: the B200-native explicit element cycle for the OpenRadioss
+ * Engine (8-node bricks SFORC3, 4-node shells CFORC3/CZFORC3, LAW2/LAW36, dt argmin, /PARITH/ON
+ * assembly ASSPAR4, ACCELE/VELOCITY/DEPLA).  Plain pointers and sizes only; every entry returns
+ * 0 on success or a negative status, and orgpu_last_error() gives the text (the reference's own
+ * GPU ABI aborts with exit(EXIT_FAILURE), shell_gpu_driver.cu:47-55; a Fortran shim may do the
+ * same on a non-zero status).
+ *
+ * What each entry replaces in the reference (paths under /root/reference):
+ *   engine/source/elements/shell/coque/shell_gpu_driver.h:44-206  -- the shipped "-gpu" C ABI
+ *   engine/source/elements/shell/coque/shell_gpu_mod.F90:284-715   -- its ISO_C_BINDING side
+ *   engine/source/elements/shell/coque/shell_internal_forces.F90   -- FORINTC_PREPARE_GPU (:370),
+ *        gpu_shell_launch_async (:62), gpu_shell_sync_scatter (:177), called from
+ *        engine/source/engine/resol.F:2657, 3670, 4295
+ * This ABI is a superset: bricks, QEPH and LAW36 are eligible, nodal arrays stay resident on the
+ * device, assembly is the deterministic FSKY/ADSKY gather of ASSPAR4 (asspar4.F:164-181) and the
+ * nodal update (accele.F, velocity.F, displacement.F) also runs on the device.
+ *
+ * Array conventions follow the Fortran caller: X(3,NUMNOD) column-major => X[3*n+c]; IXS(11,*),
+ * IXC(7,*), IADS(8,*), IADC(4,*), ADSKY(NUMNOD+1) are passed as the Engine holds them (1-based
+ * node numbers and 1-based FSKY slot addresses).  Host arrays stay owned by the caller; all
+ * device memory is owned by the library.  Calls on one handle must come from one thread at a
+ * time (the reference calls its GPU ABI from the master thread only, resol.F:3665-3671).
+ */
+#ifndef ORGPU_H
+#define ORGPU_H
+#include "orgpu_model.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orgpu_engine orgpu_engine;
+
+/* -- life cycle: shell_gpu_global_create / shell_gpu_data_create (+ cudaSetDevice from the local rank) */
+int  orgpu_create(orgpu_engine** out, int device, int numnod, const orgpu_control* ctl);
+int  orgpu_destroy(orgpu_engine* e);
+const char* orgpu_last_error(void);
+
+/* -- model upload (once): shell_gpu_global_upload_nodes / shell_gpu_upload_constant /
+ *    shell_gpu_upload_ip_state / shell_gpu_set_mat_params, generalised.  NULL = keep current. */
+int  orgpu_upload_nodes(orgpu_engine* e, const double* X, const double* V, const double* VR,
+                        const double* D, const double* MS, const double* IN);
+int  orgpu_set_loads(orgpu_engine* e, const double* FEXT, const double* MEXT); /* constant nodal loads (3,N) */
+int  orgpu_set_bcs(orgpu_engine* e, const int* icodt, const int* icodr);       /* BCS10 codes 4:x 2:y 1:z  */
+int  orgpu_set_solids(orgpu_engine* e, int numels, const int* ixs, const int* iads);
+int  orgpu_set_shells(orgpu_engine* e, int numelc, const int* ixc, const int* iadc);
+int  orgpu_set_pon(orgpu_engine* e, const int* adsky, int lsky);              /* parith_on_mod.F90:39-74 */
+int  orgpu_set_functions(orgpu_engine* e, int nfunc, const int* npf, const double* tf);
+/* one element group (<= NVSIZ elements, one material / property): elements [nft, nft+nel) */
+int  orgpu_add_solid_group(orgpu_engine* e, int nel, int nft, const orgpu_law2* mat,
+                           const orgpu_prop_solid* prop, const double* vol0);
+int  orgpu_add_shell_group(orgpu_engine* e, int nel, int nft, int law, const void* mat,
+                           const orgpu_prop_shell* prop);
+/* FORINTC_PREPARE_GPU analogue: fuse consecutive compatible groups into super-groups, re-lay
+ * ELBUF out as device SoA, upload tables.  Must be called once before stepping. */
+int  orgpu_finalize(orgpu_engine* e);
+
+/* -- one cycle in the three phases RESOL sees (host supplies the time steps) */
+int  orgpu_forces_phase(orgpu_engine* e, double dt1);  /* FORINTC+FORINT: corner rows into FSKY, DT2T argmin */
+int  orgpu_assemble(orgpu_engine* e);                  /* ASSPAR4: A, AR, STIFN, STIFR                       */
+int  orgpu_advance(orgpu_engine* e, double dt12, double dt2); /* ACCELE, BCS, VELOCITY, DEPLA               */
+/* -- device-resident time loop: ncycles passes with the RESOL dt bookkeeping on the device
+ *    (resol.F:2721, 6124-6128, 6352, 6494-6497); no host synchronisation inside. */
+int  orgpu_run_cycles(orgpu_engine* e, int ncycles);
+int  orgpu_synchronize(orgpu_engine* e);
+
+/* -- read-back (output / restart cycles): shell_gpu_global_download_forces / shell_gpu_download_state */
+int  orgpu_get_time(orgpu_engine* e, double out[5] /*tt,dt1,dt2,dt12,dt2t*/, int iout[3] /*neltst,ityptst,ncycle*/);
+int  orgpu_download_nodes(orgpu_engine* e, double* X, double* V, double* VR, double* D,
+                          double* A, double* AR, double* STIFN, double* STIFR);
+int  orgpu_download_fsky(orgpu_engine* e, double* fsky /*(8,LSKY)*/);
+/* fields: 0 sig(6) 1 eint 2 rho 3 qvis 4 pla 5 epsd 6 vol 7 off 8 temp 9 smstr(21); out[k*numels+e] */
+int  orgpu_download_solid_state(orgpu_engine* e, int field, double* out);
+int  orgpu_download_shell_state(orgpu_engine* e, int field, double* out);
+
+/* -- host-buffer convenience used for end-to-end timing: upload X,V(,VR), run, download X,V,A */
+int  orgpu_step_host(orgpu_engine* e, const double* X, const double* V, const double* VR,
+                     int ncycles, double* Xout, double* Vout);
+
+/* -- instrumentation: number of kernels launched by this handle so far; device ms of the last
+ *    orgpu_run_cycles measured with CUDA events on the library's stream */
+long long orgpu_launch_count(orgpu_engine* e);
+double    orgpu_last_run_ms(orgpu_engine* e);
+/* per-kernel-class accumulated device time (ms) and launches of the last profiled run:
+ *   cls 0 = brick forces, 1 = shell forces, 2 = node gather+update; enable with profile=1 */
+int  orgpu_set_profile(orgpu_engine* e, int profile);
+int  orgpu_get_profile(orgpu_engine* e, int cls, double* ms, long long* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

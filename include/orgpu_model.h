@@ -1,0 +1,112 @@
+/* orgpu_model.h -- plain-C model description shared by the C-ABI library (include/orgpu.h)
+ * and the CPU oracle (oracle/).  INTERFACE ONLY: no algorithm lives here.
+ *
+ * These structs carry what the reference Engine keeps in PM(NPROPM,mat), GEO(NPROPG,pid),
+ * MAT_PARAM(mat)%UPARAM/IPARAM, IPARG(NPARG,ng) and a few /COMMON/ scalars, restricted to
+ * the slots the hot path reads:
+ *   - LAW2 solid  : engine/source/materials/mat/mat002/m2law.F:135-169
+ *   - LAW2 shell  : engine/source/materials/mat/mat002/sigeps02c.F:91-123
+ *   - LAW36 shell : engine/source/materials/mat/mat036/sigeps36c.F:197-260
+ *   - solid prop  : engine/source/materials/mat_share/mqviscb.F:201-207, solid/solide/shvis3.F:164-168
+ *   - shell prop  : engine/source/elements/sh3n/coquedk/cncoef3.F, shell/coque/ccoef3.F:124-168
+ *   - groups      : engine/source/elements/forintc.F:254-300 (IPARG slots)
+ * All reals are fp64 (my_real = DOUBLE PRECISION, engine/share/r8/my_real.inc).
+ */
+#ifndef ORGPU_MODEL_H
+#define ORGPU_MODEL_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORGPU_MAXFUNC36 10   /* max yield curves (NRATE) carried for LAW36 */
+
+/* element family (IPARG(5)=ITY and IPARG(23)=JHBE) */
+enum { ORGPU_FAM_BRICK = 1,      /* ITY=1, SFORC3            */
+       ORGPU_FAM_SHELL_BT = 3,   /* ITY=3, JHBE<11,  CFORC3   */
+       ORGPU_FAM_SHELL_QEPH = 24 /* ITY=3, JHBE=21..29, CZFORC3 */ };
+
+/* /MAT/LAW2 (PLAS_JOHNS / PLAS_ZERIL).  uparam(1:11), iparam(1:4), therm. */
+typedef struct orgpu_law2 {
+  double rho0;      /* mat_param%rho  = PM(1)  (reference density) */
+  double young;     /* mat_param%young = PM(20) */
+  double nu;        /* PM(21) */
+  double shear;     /* mat_param%shear = PM(22) */
+  double bulk;      /* mat_param%bulk  = PM(32) */
+  double ca, cb, cn;        /* uparam(1:3)  A, B, n            */
+  double epmx;              /* uparam(4)    eps_p max          */
+  double sigmx;             /* uparam(5)    sigma max          */
+  double cc;                /* uparam(6)    C (strain rate)    */
+  double epdr;              /* uparam(7)    eps_dot_0          */
+  double fisokin;           /* uparam(8)    0=isotropic 1=kinematic */
+  double asrate;            /* uparam(9)    2*pi*Fcut          */
+  double z3;                /* uparam(10)   m (JC) / C3 (ZA)   */
+  double z4;                /* uparam(11)   C4 (ZA)            */
+  double tref, tmelt, rhocp;/* mat_param%therm                 */
+  double tini;              /* initial element temperature     */
+  double pshift;            /* PM(88) pressure shift           */
+  double a11, a12, ssp;     /* shells: PM(24), PM(25), PM(27)  */
+  int iform, icc, vp, israte; /* iparam(1:4) */
+  int has_temp;             /* ELBUF L_TEMP>0 (adiabatic heating tracked) */
+} orgpu_law2;
+
+/* /MAT/LAW36 (PLAS_TAB), old-style UPARAM0 view used by SIGEPS36C/SIGEPS36. */
+typedef struct orgpu_law36 {
+  double rho0, young, nu, shear, bulk;
+  double a11, a12, ssp;     /* shells: PM(24), PM(25), PM(27)  */
+  int    nrate;             /* uparam(1): number of yield curves */
+  double epsmax;            /* uparam(2*nrate+7) */
+  double epsr1, epsr2;      /* tension failure strains (uparam(2*nrate+8/9)) */
+  double fisokin;           /* uparam(2*nrate+14) */
+  double rate[ORGPU_MAXFUNC36];   /* uparam(6+j)        strain rates        */
+  double yfac[ORGPU_MAXFUNC36];   /* uparam(6+nrate+j)  curve scale factors */
+  int    ifunc[ORGPU_MAXFUNC36];  /* 0-based curve ids into the function table */
+  int    israte;            /* strain-rate filtering flag (Fsmooth) */
+  double asrate;            /* 2*pi*Fcut */
+  int    vp;                /* 0: total strain rate (only mode built) */
+  double pfac_unused;       /* pressure-dependence not built: must be 0 */
+} orgpu_law36;
+
+/* Function table TF/NPF for LAW36 curves: curve c occupies points
+ * [npf[c], npf[c+1]) of (x,y) pairs: x = tf[2*p], y = tf[2*p+1]. */
+
+/* /PROP/SOLID (IGTYP 14) slots read on the path */
+typedef struct orgpu_prop_solid {
+  double qa, qb;        /* GEO(14), GEO(15) bulk viscosity            */
+  double cns1, cns2;    /* GEO(16), GEO(17) Navier-Stokes viscosity   */
+  double hcoef;         /* GEO(13) hourglass coefficient h            */
+  double dtmin;         /* GEO(172)                                    */
+  int    jhbe;          /* Isolid -> IPARG(23): 0,1,2                  */
+  int    ismstr;        /* IPARG(9): 1,2,4                             */
+} orgpu_prop_solid;
+
+/* /PROP/SHELL (IGTYP 1) slots read on the path */
+typedef struct orgpu_prop_shell {
+  double thick;         /* GEO(1)                                     */
+  double h1, h2, h3;    /* GEO(13:15) BT hourglass hm, hf, hr         */
+  double srh1, srh2, srh3; /* GEO(18:20)                              */
+  double shf;           /* GEO(38) shear factor (5/6 default)         */
+  double fac1_qeph;     /* GEO(17): QEPH hourglass plasticity factor  */
+  int    npt;           /* IPARG(6)                                   */
+  int    ismstr;        /* IPARG(9)                                   */
+  int    ithk;          /* IPARG(28)                                  */
+  int    ipla;          /* IPARG(29)                                  */
+  int    ihbe;          /* Ishell: 1..4 BT, 24 QEPH                   */
+} orgpu_prop_shell;
+
+/* Engine-wide scalars (COMMON blocks / engine deck) the path reads */
+typedef struct orgpu_control {
+  double dtfac_brick;   /* DTFAC1(1)  /DT/BRICK scale                 */
+  double dtfac_shell;   /* DTFAC1(3)  /DT/SHELL scale                 */
+  double dtmx;          /* DTMX (EP20 when unset)                     */
+  double dt_init;       /* DT2 carried in from the restart (becomes DT1 of cycle 0) */
+  double dt2old_init;   /* DT2OLD carried in from the restart         */
+  double tt_init;       /* TT                                          */
+  int    iroddl;        /* rotational dofs present (shells)           */
+  int    nodadt;        /* /DT/NODA (0 only)                          */
+} orgpu_control;
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,145 @@
+"""ctypes plumbing shared by the product binding (engine.py -> liborgpu.so) and the test-only
+oracle binding (oracle/orc.py -> liborc.so).  Both libraries export the same call surface
+(prefix ``orgpu_`` / ``orc_``), so one driver loads a :class:`Model` into either."""
+from __future__ import annotations
+import ctypes as C
+import numpy as np
+from .model import Model, Law2, Law36, PropSolid, PropShell, Control
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def _opt(a, dtype):
+    """numpy array -> pointer (or NULL)."""
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Binding:
+    """Thin object wrapper over one handle of either library."""
+    SOLID_FIELDS = dict(sig=(0, 6), eint=(1, 1), rho=(2, 1), qvis=(3, 1), pla=(4, 1), epsd=(5, 1),
+                        vol=(6, 1), off=(7, 1), temp=(8, 1), smstr=(9, 21))
+    SHELL_FIELDS = dict(forc=(0, 5), mom=(1, 3), eint=(2, 2), thk=(3, 1), off=(4, 1), stra=(5, 8),
+                        epsd=(6, 1), hourg=(7, 12), smstr=(8, 6), sig=(9, 5), pla=(10, 1),
+                        epsd_ip=(11, 1), sigb=(12, 5))
+
+    def __init__(self, lib: C.CDLL, prefix: str, returns_status: bool):
+        self.lib, self.p, self.status = lib, prefix, returns_status
+        self.h = C.c_void_p()
+        self.model = None
+        self._keep = []
+
+    # -- call helper: raise on a negative status for the product library
+    def _f(self, name):
+        return getattr(self.lib, self.p + name)
+
+    def _call(self, name, *args):
+        fn = self._f(name)
+        fn.restype = C.c_int if self.status else None
+        r = fn(*args)
+        if self.status and r is not None and r < 0:
+            err = self._f("last_error"); err.restype = C.c_char_p
+            raise RuntimeError(f"{self.p}{name} failed ({r}): {err().decode()}")
+        return r
+
+    # -- model load --------------------------------------------------------------------
+    def load(self, m: Model, device: int = 0):
+        self.model = m
+        ctl = m.control
+        if self.status:
+            self._call("create", C.byref(self.h), C.c_int(device), C.c_int(m.numnod), C.byref(ctl))
+        else:
+            fn = self._f("create"); fn.restype = C.c_void_p
+            self.h = C.c_void_p(fn(C.c_int(m.numnod), C.byref(ctl)))
+        self.upload_nodes(X=m.X, V=m.V, VR=m.VR, MS=m.MS, IN=m.IN)
+        if m.fext is not None or m.mext is not None:
+            self._call("set_loads", self.h, _opt(m.fext, np.float64), _opt(m.mext, np.float64))
+        if m.icodt is not None:
+            self._call("set_bcs", self.h, _opt(m.icodt, np.int32), _opt(m.icodr, np.int32))
+        if m.numels:
+            self._call("set_solids", self.h, C.c_int(m.numels), _opt(m.ixs, np.int32), _opt(m.iads, np.int32))
+        if m.numelc:
+            self._call("set_shells", self.h, C.c_int(m.numelc), _opt(m.ixc, np.int32), _opt(m.iadc, np.int32))
+        self._call("set_pon", self.h, _opt(m.adsky, np.int32), C.c_int(m.lsky))
+        if m.npf is not None:
+            self._call("set_functions", self.h, C.c_int(len(m.npf) - 1), _opt(m.npf, np.int32), _opt(m.tf, np.float64))
+        for g in m.shell_groups:
+            r = self._call_group("add_shell_group", self.h, C.c_int(g.nel), C.c_int(g.nft), C.c_int(g.law),
+                                 C.byref(g.mat), C.byref(g.prop))
+        for g in m.solid_groups:
+            v0 = np.ascontiguousarray(m.vol0[g.nft:g.nft + g.nel])
+            self._call_group("add_solid_group", self.h, C.c_int(g.nel), C.c_int(g.nft), C.byref(g.mat),
+                             C.byref(g.prop), v0.ctypes.data_as(C.c_void_p))
+        self._call("finalize", self.h)
+        return self
+
+    def _call_group(self, name, *args):
+        fn = self._f(name); fn.restype = C.c_int
+        r = fn(*args)
+        if r < 0:
+            msg = ""
+            if self.status:
+                err = self._f("last_error"); err.restype = C.c_char_p; msg = err().decode()
+            raise RuntimeError(f"{self.p}{name} failed ({r}) {msg}")
+        return r
+
+    def close(self):
+        if self.h:
+            self._call("destroy", self.h); self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- nodal arrays ------------------------------------------------------------------
+    def upload_nodes(self, X=None, V=None, VR=None, D=None, MS=None, IN=None):
+        self._call("upload_nodes", self.h, *[_opt(a, np.float64) for a in (X, V, VR, D, MS, IN)])
+
+    def download_nodes(self, names=("X", "V", "D", "A")):
+        n = self.model.numnod
+        order = ("X", "V", "VR", "D", "A", "AR", "STIFN", "STIFR")
+        out = {k: (np.zeros((n, 3)) if k not in ("STIFN", "STIFR") else np.zeros(n)) for k in names}
+        args = [out[k].ctypes.data_as(C.c_void_p) if k in out else None for k in order]
+        self._call("download_nodes", self.h, *args)
+        return out
+
+    def download_fsky(self):
+        f = np.zeros((self.model.lsky, 8))
+        self._call("download_fsky", self.h, f.ctypes.data_as(C.c_void_p))
+        return f
+
+    def solid_state(self, name):
+        fid, nc = self.SOLID_FIELDS[name]
+        out = np.zeros((nc, self.model.numels))
+        self._call("download_solid_state", self.h, C.c_int(fid), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def shell_state(self, name):
+        fid, nc = self.SHELL_FIELDS[name]
+        npt = 1
+        if name in ("sig", "pla", "epsd_ip", "sigb"):
+            npt = max(g.prop.npt for g in self.model.shell_groups)
+        out = np.zeros((nc * npt, self.model.numelc))
+        self._call("download_shell_state", self.h, C.c_int(fid), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    # -- stepping ----------------------------------------------------------------------
+    def forces_phase(self, dt1): self._call("forces_phase", self.h, C.c_double(dt1))
+    def assemble(self): self._call("assemble", self.h)
+    def advance(self, dt12, dt2): self._call("advance", self.h, C.c_double(dt12), C.c_double(dt2))
+    def run_cycles(self, n): self._call("run_cycles", self.h, C.c_int(n))
+
+    def synchronize(self):
+        if self.status:
+            self._call("synchronize", self.h)
+
+    def time(self):
+        out = (C.c_double * 5)(); iout = (C.c_int * 3)()
+        self._call("get_time", self.h, out, iout)
+        return dict(tt=out[0], dt1=out[1], dt2=out[2], dt12=out[3], dt2t=out[4],
+                    neltst=iout[0], ityptst=iout[1], ncycle=iout[2])

@@ -1,0 +1,512 @@
+// brick_kernel.cuh -- fused internal-force kernel for 8-node bricks, one element per thread.
+//
+// One launch does, for every element of a super-group, what the reference does in SFORC3
+// (engine/source/elements/solid/solide/sforc3.F:131, Lagrangian JCVT=0 path) for one group:
+//   SCOOR3 (scoor3.F:107-386) gather            -> 16 x 32-byte nodal records (pos, vel)
+//   SDERI3 (sderi3.F:105-336) + SCHKJABT3       -> Jacobian, volume, PXi..PZi, hourglass PXiHj
+//   SDLEN3 (sdlen3.F:89-168, slen.F:68-88)      -> characteristic length
+//   SDEFO3 (sdefo3.F:115-271)                   -> strain rates, spin
+//   SRHO3 (srho3.F:110-239), SROTA3 (srota3.F:72-94), SMALLA3, S8SAV3
+//   MMAIN -> M2LAW (m2law.F:133-561) + MQVISCB (mqviscb.F:141-631): stress, dt, nodal stiffness
+//   SMALLB3, SHVIS3 (shvis3.F:164-412), SFINT3 (sfint3.F:257-323)
+//   SCUMU3P (scumu3p.F:104-309): corner rows into the FSKY slots of IADS
+// followed by the CTA-level (dt, user id) arg-min.  State is read and written exactly once,
+// coalesced (SoA over the super-group); nothing intermediate touches HBM.
+#pragma once
+#include "common.cuh"
+
+struct BrickParams {            // scalar copies so the kernel reads them from the constant bank
+  BrickSG sg; DevNodes nd; double* fsky; int roww; CycleState* cs; DtBlocks db; FinalizeArgs fa;
+};
+
+// SLEN (slen.F:68-88)
+__device__ __forceinline__ double slen_face(const double* x, const double* y, const double* z,
+                                            int a, int b, int c, int d)
+{
+  double X13 = x[c] - x[a], X24 = x[d] - x[b];
+  double Y13 = y[c] - y[a], Y24 = y[d] - y[b];
+  double Z13 = z[c] - z[a], Z24 = z[d] - z[b];
+  double FS1 = X13 - X24, FT1 = X13 + X24;
+  double FS2 = Y13 - Y24, FT2 = Y13 + Y24;
+  double FS3 = Z13 - Z24, FT3 = Z13 + Z24;
+  double E = FS1 * FS1 + FS2 * FS2 + FS3 * FS3;
+  double F = FS1 * FT1 + FS2 * FT2 + FS3 * FT3;
+  double G = FT1 * FT1 + FT2 * FT2 + FT3 * FT3;
+  return E * G - F * F;
+}
+
+struct Jac { double J1, J2, J3, J4, J5, J6, J7, J8, J9, c5968, c6749, c4857, vol; };
+__device__ __forceinline__ Jac brick_jac(const double* x, const double* y, const double* z)
+{
+  Jac r;
+  double X17 = x[6] - x[0], X28 = x[7] - x[1], X35 = x[4] - x[2], X46 = x[5] - x[3];
+  double Y17 = y[6] - y[0], Y28 = y[7] - y[1], Y35 = y[4] - y[2], Y46 = y[5] - y[3];
+  double Z17 = z[6] - z[0], Z28 = z[7] - z[1], Z35 = z[4] - z[2], Z46 = z[5] - z[3];
+  r.J1 = X17 + X28 - X35 - X46;
+  r.J2 = Y17 + Y28 - Y35 - Y46;
+  r.J3 = Z17 + Z28 - Z35 - Z46;
+  double xa = X17 + X46, xb = X28 + X35, ya = Y17 + Y46, yb = Y28 + Y35, za = Z17 + Z46, zb = Z28 + Z35;
+  r.J4 = xa + xb; r.J5 = ya + yb; r.J6 = za + zb;
+  r.J7 = xa - xb; r.J8 = ya - yb; r.J9 = za - zb;
+  r.c5968 = r.J5 * r.J9 - r.J6 * r.J8;
+  r.c6749 = r.J6 * r.J7 - r.J4 * r.J9;
+  r.c4857 = r.J4 * r.J8 - r.J5 * r.J7;
+  r.vol = K_ONE_OVER_64 * (r.J1 * r.c5968 + r.J2 * r.c6749 + r.J3 * r.c4857);
+  return r;
+}
+
+template <int JHBE, int ISMSTR>
+__global__ void __launch_bounds__(ORGPU_BLOCK)
+brick_forces_kernel(const __grid_constant__ BrickParams P)
+{
+  const BrickSG& g = P.sg;
+  const int e = blockIdx.x * ORGPU_BLOCK + threadIdx.x;
+  const int np = g.ne_pad;
+  double dt_cand = K_EP30; int ngl = 0; int order = -1;
+  if (e < g.ne) {
+    const double DT1 = P.cs->dt2;                         // DT1 = DT2 of the previous cycle (resol.F:2721)
+    const double TT = P.cs->tt;
+    const orgpu_law2& m = g.mat;
+    int nc[8];
+    #pragma unroll
+    for (int k = 0; k < 8; k++) nc[k] = g.conn[k * np + e];
+    double OFFG = g.off[e];
+    ngl = g.ngl[e]; order = g.order0 + e;
+    // ---- SCOOR3
+    double x[8], y[8], z[8];
+    #pragma unroll
+    for (int k = 0; k < 8; k++) { double4 p = P.nd.pos[nc[k]]; x[k] = p.x; y[k] = p.y; z[k] = p.z; }
+    double OFF;
+    if (ISMSTR <= 4 && fabs(OFFG) > K_ONE) {
+      #pragma unroll
+      for (int k = 0; k < 7; k++) { x[k] = g.smstr[(3 * k) * np + e]; y[k] = g.smstr[(3 * k + 1) * np + e]; z[k] = g.smstr[(3 * k + 2) * np + e]; }
+      x[7] = K_ZERO; y[7] = K_ZERO; z[7] = K_ZERO;
+      OFF = fabs(OFFG) - K_ONE;
+    } else OFF = fabs(OFFG);
+    // SDLEN3 works on the X1..Z8 copies taken here (before a possible negative-volume switch)
+    double areamax = K_EM20;
+    areamax = fmax(slen_face(x, y, z, 0, 1, 2, 3), areamax);
+    areamax = fmax(slen_face(x, y, z, 4, 5, 6, 7), areamax);
+    areamax = fmax(slen_face(x, y, z, 0, 1, 5, 4), areamax);
+    areamax = fmax(slen_face(x, y, z, 1, 2, 6, 5), areamax);
+    areamax = fmax(slen_face(x, y, z, 2, 3, 7, 6), areamax);
+    areamax = fmax(slen_face(x, y, z, 3, 0, 4, 7), areamax);
+    // ---- SDERI3 + SCHKJABT3
+    Jac J = brick_jac(x, y, z);
+    double VOLN = J.vol;
+    if (OFF == K_ZERO) VOLN = K_ONE;
+    else if (OFFG > K_ONE) {}
+    else if (VOLN <= K_ZERO) {
+      if (OFFG <= K_ONE && OFFG != K_ZERO) {             // switch to small strain: geometry from SAV
+        #pragma unroll
+        for (int k = 0; k < 7; k++) { x[k] = g.smstr[(3 * k) * np + e]; y[k] = g.smstr[(3 * k + 1) * np + e]; z[k] = g.smstr[(3 * k + 2) * np + e]; }
+        x[7] = K_ZERO; y[7] = K_ZERO; z[7] = K_ZERO;
+        J = brick_jac(x, y, z); VOLN = J.vol; OFFG = K_TWO;
+      }
+    }
+    double PX[4], PY[4], PZ[4];
+    {
+      double DETT = K_ONE_OVER_64 / VOLN;
+      double JI1 = DETT * J.c5968, JI4 = DETT * J.c6749, JI7 = DETT * J.c4857;
+      double JI2 = DETT * (J.J3 * J.J8 - J.J2 * J.J9);
+      double JI5 = DETT * (J.J1 * J.J9 - J.J3 * J.J7);
+      double JI8 = DETT * (J.J2 * J.J7 - J.J1 * J.J8);
+      double JI3 = DETT * (J.J2 * J.J6 - J.J3 * J.J5);
+      double JI6 = DETT * (J.J3 * J.J4 - J.J1 * J.J6);
+      double JI9 = DETT * (J.J1 * J.J5 - J.J2 * J.J4);
+      double J12 = JI1 + JI2, J45 = JI4 + JI5, J78 = JI7 + JI8;
+      PX[0] = -J12 - JI3; PY[0] = -J45 - JI6; PZ[0] = -J78 - JI9;
+      PX[1] = -J12 + JI3; PY[1] = -J45 + JI6; PZ[1] = -J78 + JI9;
+      J12 = JI1 - JI2; J45 = JI4 - JI5; J78 = JI7 - JI8;
+      PX[2] = J12 + JI3; PY[2] = J45 + JI6; PZ[2] = J78 + JI9;
+      PX[3] = J12 - JI3; PY[3] = J45 - JI6; PZ[3] = J78 - JI9;
+    }
+    double PH[3][4];                                      // PXkHm -> PH[m][k]
+    if (JHBE != 0) {
+      double HX, HY, HZ;
+      HX = (x[0] - x[1] + x[2] - x[3] + x[4] - x[5] + x[6] - x[7]);
+      HY = (y[0] - y[1] + y[2] - y[3] + y[4] - y[5] + y[6] - y[7]);
+      HZ = (z[0] - z[1] + z[2] - z[3] + z[4] - z[5] + z[6] - z[7]);
+      #pragma unroll
+      for (int k = 0; k < 4; k++) PH[0][k] = PX[k] * HX + PY[k] * HY + PZ[k] * HZ;
+      HX = (x[0] + x[1] - x[2] - x[3] - x[4] - x[5] + x[6] + x[7]);
+      HY = (y[0] + y[1] - y[2] - y[3] - y[4] - y[5] + y[6] + y[7]);
+      HZ = (z[0] + z[1] - z[2] - z[3] - z[4] - z[5] + z[6] + z[7]);
+      #pragma unroll
+      for (int k = 0; k < 4; k++) PH[1][k] = PX[k] * HX + PY[k] * HY + PZ[k] * HZ;
+      HX = (x[0] - x[1] - x[2] + x[3] - x[4] + x[5] + x[6] - x[7]);
+      HY = (y[0] - y[1] - y[2] + y[3] - y[4] + y[5] + y[6] - y[7]);
+      HZ = (z[0] - z[1] - z[2] + z[3] - z[4] + z[5] + z[6] - z[7]);
+      #pragma unroll
+      for (int k = 0; k < 4; k++) PH[2][k] = PX[k] * HX + PY[k] * HY + PZ[k] * HZ;
+    }
+    const double DELTAX = K_FOUR * VOLN * K_ONE / sqrt(areamax);
+    // ---- S8SAV3 (reference configuration refresh; done here while the coordinates are live)
+    const bool sav_refresh = (ISMSTR <= 4) && (fabs(OFFG) <= K_ONE);
+    // ---- velocities (SCOOR3) and SDEFO3
+    double vx[8], vy[8], vz[8];
+    #pragma unroll
+    for (int k = 0; k < 8; k++) { double4 p = P.nd.vel[nc[k]]; vx[k] = p.x; vy[k] = p.y; vz[k] = p.z; }
+    if (OFFG < K_ZERO) {
+      #pragma unroll
+      for (int k = 0; k < 8; k++) { vx[k] = K_ZERO; vy[k] = K_ZERO; vz[k] = K_ZERO; }
+    }
+    double DXX, DYY, DZZ, DXY, DXZ, DYX, DYZ, DZX, DZY, D4, D5, D6, WXX, WYY, WZZ;
+    {
+      double VX17 = vx[0] - vx[6], VX28 = vx[1] - vx[7], VX35 = vx[2] - vx[4], VX46 = vx[3] - vx[5];
+      double VY17 = vy[0] - vy[6], VY28 = vy[1] - vy[7], VY35 = vy[2] - vy[4], VY46 = vy[3] - vy[5];
+      double VZ17 = vz[0] - vz[6], VZ28 = vz[1] - vz[7], VZ35 = vz[2] - vz[4], VZ46 = vz[3] - vz[5];
+      DXX = PX[0] * VX17 + PX[1] * VX28 + PX[2] * VX35 + PX[3] * VX46;
+      DYY = PY[0] * VY17 + PY[1] * VY28 + PY[2] * VY35 + PY[3] * VY46;
+      DZZ = PZ[0] * VZ17 + PZ[1] * VZ28 + PZ[2] * VZ35 + PZ[3] * VZ46;
+      DXY = PY[0] * VX17 + PY[1] * VX28 + PY[2] * VX35 + PY[3] * VX46;
+      DXZ = PZ[0] * VX17 + PZ[1] * VX28 + PZ[2] * VX35 + PZ[3] * VX46;
+      DYX = PX[0] * VY17 + PX[1] * VY28 + PX[2] * VY35 + PX[3] * VY46;
+      DYZ = PZ[0] * VY17 + PZ[1] * VY28 + PZ[2] * VY35 + PZ[3] * VY46;
+      DZX = PX[0] * VZ17 + PX[1] * VZ28 + PX[2] * VZ35 + PX[3] * VZ46;
+      DZY = PY[0] * VZ17 + PY[1] * VZ28 + PY[2] * VZ35 + PY[3] * VZ46;
+    }
+    const double DT1D2 = K_HALF * DT1;
+    if (JHBE >= 2) {
+      double EXX = DXX, EYY = DYY, EZZ = DZZ, EXY = DXY, EYX = DYX, EXZ = DXZ, EZX = DZX, EYZ = DYZ, EZY = DZY;
+      DXX = DXX - DT1D2 * (EXX * EXX + EYX * EYX + EZX * EZX);
+      DYY = DYY - DT1D2 * (EYY * EYY + EZY * EZY + EXY * EXY);
+      DZZ = DZZ - DT1D2 * (EZZ * EZZ + EXZ * EXZ + EYZ * EYZ);
+      double AAA = DT1D2 * (EXX * EXY + EYX * EYY + EZX * EZY);
+      DXY = DXY - AAA; DYX = DYX - AAA; D4 = DXY + DYX;
+      AAA = DT1D2 * (EYY * EYZ + EZY * EZZ + EXY * EXZ);
+      DYZ = DYZ - AAA; DZY = DZY - AAA; D5 = DYZ + DZY;
+      AAA = DT1D2 * (EZZ * EZX + EXZ * EXX + EYZ * EYX);
+      DXZ = DXZ - AAA; DZX = DZX - AAA; D6 = DXZ + DZX;
+      double PXX2 = PX[0] * PX[0] + PX[1] * PX[1] + PX[2] * PX[2] + PX[3] * PX[3];
+      double PYY2 = PY[0] * PY[0] + PY[1] * PY[1] + PY[2] * PY[2] + PY[3] * PY[3];
+      double PZZ2 = PZ[0] * PZ[0] + PZ[1] * PZ[1] + PZ[2] * PZ[2] + PZ[3] * PZ[3];
+      WZZ = DT1 * (PYY2 * DYX - PXX2 * DXY) / (PXX2 + PYY2);
+      WXX = DT1 * (PZZ2 * DZY - PYY2 * DYZ) / (PYY2 + PZZ2);
+      WYY = DT1 * (PXX2 * DXZ - PZZ2 * DZX) / (PZZ2 + PXX2);
+    } else {
+      D4 = DXY + DYX; D5 = DYZ + DZY; D6 = DXZ + DZX;
+      WZZ = DT1D2 * (DYX - DXY);
+      WYY = DT1D2 * (DXZ - DZX);
+      WXX = DT1D2 * (DZY - DYZ);
+    }
+    const double DIVDE = DT1 * (DXX + DYY + DZZ);        // sforc3.F:790
+    // ---- SRHO3
+    double VOLO = g.vol[e];
+    double RHON = g.rho[e];
+    double EINT = g.eint[e];
+    double DVOL;
+    {
+      const double RHON_OLD = RHON, RHO0 = m.rho0;
+      if (ISMSTR == 1 && TT == K_ZERO && OFFG > K_ONE) VOLO = VOLN;     // srho3.F:128-136 (VOLO is const otherwise)
+      if (OFFG == K_ZERO && VOLN == K_ONE) VOLN = VOLO;
+      DVOL = VOLN - (RHO0 / RHON) * VOLO;
+      RHON = RHO0 * (VOLO / VOLN);
+      EINT = EINT * VOLO;
+      if (ISMSTR <= 4 && OFFG > K_ONE) {
+        double RHOREF = RHON;
+        RHON = RHON_OLD - RHOREF * DIVDE;
+        RHON = fmax(RHON, K_EM30);
+        DVOL = VOLN * DIVDE;
+      }
+    }
+    // ---- SROTA3
+    double S1 = g.sig[e], S2 = g.sig[np + e], S3 = g.sig[2 * np + e], S4 = g.sig[3 * np + e], S5 = g.sig[4 * np + e], S6 = g.sig[5 * np + e];
+    double SG1, SG2, SG3, SG4, SG5, SG6;
+    {
+      double Q1 = K_TWO * S4 * WZZ, Q2 = K_TWO * S6 * WYY, Q3 = K_TWO * S5 * WXX;
+      SG1 = S1 - Q1 + Q2;
+      SG2 = S2 + Q1 - Q3;
+      SG3 = S3 - Q2 + Q3;
+      SG4 = S4 + WZZ * (S1 - S2) + WYY * S5 - WXX * S6;
+      SG5 = S5 + WXX * (S2 - S3) + WZZ * S6 - WYY * S4;
+      SG6 = S6 + WYY * (S3 - S1) + WXX * S4 - WZZ * S5;
+    }
+    // ---- SMALLA3 (rotate the frozen reference) then S8SAV3 (refresh it)
+    if (ISMSTR <= 4 && OFFG > K_ONE) {
+      #pragma unroll
+      for (int k = 0; k < 7; k++) {
+        double X = g.smstr[(3 * k) * np + e], Y = g.smstr[(3 * k + 1) * np + e], Z = g.smstr[(3 * k + 2) * np + e];
+        g.smstr[(3 * k) * np + e] = X - Y * WZZ + Z * WYY;
+        g.smstr[(3 * k + 1) * np + e] = Y - Z * WXX + X * WZZ;
+        g.smstr[(3 * k + 2) * np + e] = Z - X * WYY + Y * WXX;
+      }
+    }
+    if (sav_refresh) {
+      #pragma unroll
+      for (int k = 0; k < 7; k++) {
+        g.smstr[(3 * k) * np + e] = x[k] - x[7];
+        g.smstr[(3 * k + 1) * np + e] = y[k] - y[7];
+        g.smstr[(3 * k + 2) * np + e] = z[k] - z[7];
+      }
+    }
+    // ---- MMAIN pre-law (mmain.F90:597-800)
+    const double QOLD = g.qvis[e];
+    const double VOL_AVG = VOLN - K_HALF * DVOL;
+    const double AMU = RHON / m.rho0 - K_ONE;
+    double RHOREF;
+    if (ISMSTR == 1) RHOREF = m.rho0;
+    else if (ISMSTR == 2) RHOREF = (fabs(OFFG) <= K_ONE) ? RHON : m.rho0 * VOLO / fmax(K_EM20, VOLN);
+    else RHOREF = RHON;
+    double TEMP = K_ZERO, TSTAR = K_ZERO;
+    if (m.has_temp) { TEMP = g.temp[e]; TSTAR = fmax(K_ZERO, (TEMP - m.tref) / fmax((m.tmelt - m.tref), K_EM20)); }
+    // ---- M2LAW
+    double EPXE = g.pla[e], EPSD = g.epsd[e];
+    double SSP, QNEW, STI, SSP_EQ;
+    {
+      const double asrate = fmin(K_ONE, m.asrate * DT1);
+      const double rhocpi = (m.rhocp > K_ZERO) ? K_ONE / m.rhocp : K_ZERO;
+      const double G = m.shear * OFF;
+      double CA = m.ca, SIGMX = m.sigmx;
+      double Pm = -K_THIRD * (SG1 + SG2 + SG3);
+      double DAV = -K_THIRD * (DXX + DYY + DZZ);
+      double G1 = DT1 * G, G2 = K_TWO * G1;
+      SSP = sqrt((K_ONEP333 * G + m.bulk) / m.rho0);
+      SG1 = SG1 + Pm + G2 * (DXX + DAV);
+      SG2 = SG2 + Pm + G2 * (DYY + DAV);
+      SG3 = SG3 + Pm + G2 * (DZZ + DAV);
+      SG4 = SG4 + G1 * D4;
+      SG5 = SG5 + G1 * D5;
+      SG6 = SG6 + G1 * D6;
+      double AJ2 = K_HALF * (SG1 * SG1 + SG2 * SG2 + SG3 * SG3) + SG4 * SG4 + SG5 * SG5 + SG6 * SG6;
+      AJ2 = sqrt(K_THREE * AJ2);
+      // MSTRAIN_RATE (mstrain_rate.F:60-91)
+      if (m.israte >= 0) {
+        double epsdot;
+        if (m.vp - 2 == 0) {
+          double E4 = K_HALF * D4, E5 = K_HALF * D5, E6 = K_HALF * D6;
+          double epsp = DXX * DXX + DYY * DYY + DZZ * DZZ + K_TWO * (E4 * E4 + E5 * E5 + E6 * E6);
+          epsdot = sqrt(epsp);
+        } else {
+          double dav = (DXX + DYY + DZZ) * K_THIRD;
+          double E1 = DXX - dav, E2 = DYY - dav, E3 = DZZ - dav, E4 = K_HALF * D4, E5 = K_HALF * D5, E6 = K_HALF * D6;
+          double epsp = K_HALF * (E1 * E1 + E2 * E2 + E3 * E3) + E4 * E4 + E5 * E5 + E6 * E6;
+          epsdot = sqrt(K_THREE * epsp) / K_THREE_HALF;
+        }
+        if (m.israte == 0) EPSD = epsdot; else EPSD = asrate * epsdot + (K_ONE - asrate) * EPSD;
+      }
+      double EPD = K_ONE;
+      if (m.cc != K_ZERO) {
+        if (m.vp == 1) { EPD = fmax(EPSD, m.epdr); EPD = log(EPD / m.epdr); }
+        else           { EPD = fmax(EPSD, K_EM15); EPD = log(EPD / m.epdr); }
+        if (m.iform == 0) {
+          double MT = fmax(K_EM15, m.z3);
+          EPD = fmax(K_ZERO, EPD);
+          EPD = (K_ONE + m.cc * EPD) * (K_ONE - pow(TSTAR, MT));
+          if (m.icc == 1) SIGMX = m.sigmx * EPD;
+        } else if (m.iform == 1) {
+          EPD = m.cc * exp((-m.z3 + m.z4 * EPD) * TEMP);
+          if (m.icc == 1) SIGMX = m.sigmx + EPD;
+          CA = m.ca + EPD;
+          EPD = K_ONE;
+        }
+      } else if (m.iform == 0) {
+        double MT = fmax(K_EM15, m.z3);
+        EPD = K_ONE - pow(TSTAR, MT);
+        if (m.icc == 1) SIGMX = m.sigmx * EPD;
+      }
+      double AK, QH;
+      if (m.cn == K_ONE) { AK = CA + m.cb * EPXE; QH = m.cb * EPD; }
+      else if (EPXE > K_ZERO) {
+        AK = CA + m.cb * pow(EPXE, m.cn);
+        if (m.cn > K_ONE) QH = (m.cb * m.cn * pow(EPXE, (m.cn - K_ONE))) * EPD;
+        else              QH = (m.cb * m.cn / pow(EPXE, (K_ONE - m.cn))) * EPD;
+      } else { AK = CA; QH = K_ZERO; }
+      AK = AK * EPD;
+      if (SIGMX < AK) { AK = SIGMX; QH = K_ZERO; }
+      double SIGY = AK;
+      if (EPXE > m.epmx) { AK = K_ZERO; QH = K_ZERO; }
+      double SCALE = fmin(K_ONE, AK / fmax(AJ2, K_EM15));
+      const double DPLA = (K_ONE - SCALE) * AJ2 / fmax(K_THREE * G + QH, K_EM15);
+      AK = AK + (K_ONE - m.fisokin) * DPLA * QH;
+      SCALE = fmin(K_ONE, AK / fmax(AJ2, K_EM15));
+      SG1 = SCALE * SG1; SG2 = SCALE * SG2; SG3 = SCALE * SG3; SG4 = SCALE * SG4; SG5 = SCALE * SG5; SG6 = SCALE * SG6;
+      EPXE = EPXE + DPLA;
+      // ---- MQVISCB (IMPL=0, N2D=0, NPG=1, JTHE=0, IDTMINS/=2, NODADT=0)
+      {
+        const double DD = -DXX - DYY - DZZ;
+        double AD = K_ZERO, AL = K_ZERO;
+        const double CX = SSP + sqrt(K_ZERO);              // VD2 = 0 (Lagrangian)
+        if (OFF == K_ONE) {
+          AL = (VOLN > K_ZERO) ? pow(VOLN, 1.0 / 3.0) : K_ZERO;
+          AD = fmax(K_ZERO, DD);
+        }
+        const double NRHO = sqrt(RHOREF * m.rho0);
+        const double QA = K_ONE * g.prop.qa, QB = K_ONE * g.prop.qb;
+        const double CNS1_0 = 1.0 * g.prop.cns1, CNS2_0 = 1.0 * g.prop.cns2;
+        const double QAA_0 = QA * QA;
+        double CNS1 = CNS1_0 * AL * NRHO * SSP * OFF;
+        double CNS2 = CNS2_0 * AL * NRHO * SSP * OFF;
+        double QAA = QAA_0 * AD;
+        double QX = QB * SSP + AL * QAA
+                  + K_ONE * K_TWO * K_ZERO / fmax(K_EM20, RHON * DELTAX)
+                  + (CNS1 + K_ONE * CNS2) / fmax(K_EM20, RHOREF * DELTAX);
+        QNEW = RHON * AD * AL * (QAA * AL + QB * SSP);
+        SSP_EQ = fmax(K_EM20, QX + sqrt(QX * QX + CX * CX));
+        double DTX = DELTAX / SSP_EQ;
+        STI = K_ZERO;
+        if (!(OFF == K_ZERO || OFFG < K_ZERO)) {
+          double TIDT = K_ONE / DTX, TRHO, TVOL;
+          if (ISMSTR == 1 && OFFG > K_ONE) { TRHO = m.rho0 * TIDT; TVOL = VOLO * TIDT; }
+          else                             { TRHO = RHON * TIDT;   TVOL = VOLN * TIDT; }
+          STI = TRHO * TVOL;
+        }
+        DTX = g.dtfac * DTX;
+        if (VOLN > K_ZERO && OFF > K_ZERO && OFFG > K_ZERO) dt_cand = DTX;
+      }
+      // ---- pressure + internal energy (m2law.F:433-453)
+      const double DTA = K_HALF * DT1;
+      const double PNEW = m.bulk * AMU;
+      SG1 = (SG1 - PNEW) * OFF; SG2 = (SG2 - PNEW) * OFF; SG3 = (SG3 - PNEW) * OFF;
+      SG4 = SG4 * OFF; SG5 = SG5 * OFF; SG6 = SG6 * OFF;
+      double E1 = DXX * (S1 + SG1), E2 = DYY * (S2 + SG2), E3 = DZZ * (S3 + SG3);
+      double E4 = D4 * (S4 + SG4), E5 = D5 * (S5 + SG5), E6 = D6 * (S6 + SG6);
+      double EINC = VOL_AVG * (E1 + E2 + E3 + E4 + E5 + E6) * DTA - K_HALF * DVOL * (QOLD + QNEW);
+      EINT = (EINT + EINC * OFF) / fmax(K_EM15, VOLO);
+      if (m.vp == 1) { double PLAP = DPLA / fmax(K_EM20, DT1); EPSD = asrate * PLAP + (K_ONE - asrate) * EPSD; }
+      if (m.rhocp > K_ZERO) { SIGY = fmax(SIGY, AK); TEMP = TEMP + SIGY * DPLA * rhocpi; }
+    }
+    // mmain.F90 tail: entropy heating of the artificial viscosity when the buffer tracks temperature
+    if (m.has_temp) {
+      double cv = m.rhocp / m.rho0;
+      if (cv > K_ZERO && OFF == K_ONE) {
+        double mcv = RHON * VOLN * cv;
+        double qheat = -K_HALF * (QOLD + QNEW) * DVOL;
+        TEMP = TEMP + qheat / mcv;
+        TEMP = fmax(K_ZERO, TEMP);
+      }
+      g.temp[e] = TEMP;
+    }
+    // ---- state write-back
+    g.sig[e] = SG1; g.sig[np + e] = SG2; g.sig[2 * np + e] = SG3; g.sig[3 * np + e] = SG4; g.sig[4 * np + e] = SG5; g.sig[5 * np + e] = SG6;
+    g.eint[e] = EINT; g.rho[e] = RHON; g.qvis[e] = QNEW; g.pla[e] = EPXE; g.epsd[e] = EPSD;
+    // ---- SMALLB3
+    if (ISMSTR == 1 || ISMSTR == 3) { if (OFFG > K_ZERO) OFFG = K_TWO; }
+    if (OFF < K_ONE) {
+      if (OFF == K_ZERO) OFFG = K_ZERO;
+      else if (OFFG > K_ONE) OFFG = K_ONE + OFF;
+      else OFFG = OFF;
+    }
+    g.off[e] = OFFG;
+    // ---- SHVIS3
+    double F1[8], F2[8], F3[8];
+    {
+      const double CAQ = K_FOURTH * OFF * g.prop.hcoef;
+      double FCL, FCQ;
+      if (ISMSTR == 1) FCL = CAQ * m.rho0 * pow(VOLN, K_TWO_THIRD);
+      else if (ISMSTR == 2 && OFFG > K_ONE) { double AA = m.rho0 * VOLO / fmax(K_EM20, VOLN); FCL = CAQ * AA * pow(VOLN, K_TWO_THIRD); }
+      else FCL = CAQ * RHON * pow(VOLN, K_TWO_THIRD);
+      FCQ = FCL * CAQ * K_HUNDRED;
+      FCL = FCL * SSP;
+      double HGX[4], HGY[4], HGZ[4];
+      double G_[3][8];
+      if (JHBE == 0) {
+        #define HG0(V, H) { double V3478 = V[2] - V[3] - V[6] + V[7], V2358 = V[1] - V[2] - V[4] + V[7], \
+                                   V1467 = V[0] - V[3] - V[5] + V[6], V1256 = V[0] - V[1] - V[4] + V[5]; \
+                            H[0] = V1467 - V2358; H[1] = V1467 + V2358; H[2] = V1256 - V3478; H[3] = V1256 + V3478; }
+        HG0(vx, HGX) HG0(vy, HGY) HG0(vz, HGZ)
+        #undef HG0
+      } else {
+        G_[0][0] =  K_ONE - PH[0][0]; G_[0][1] = -K_ONE - PH[0][1]; G_[0][2] =  K_ONE - PH[0][2]; G_[0][3] = -K_ONE - PH[0][3];
+        G_[0][4] =  K_ONE + PH[0][2]; G_[0][5] = -K_ONE + PH[0][3]; G_[0][6] =  K_ONE + PH[0][0]; G_[0][7] = -K_ONE + PH[0][1];
+        G_[1][0] =  K_ONE - PH[1][0]; G_[1][1] =  K_ONE - PH[1][1]; G_[1][2] = -K_ONE - PH[1][2]; G_[1][3] = -K_ONE - PH[1][3];
+        G_[1][4] = -K_ONE + PH[1][2]; G_[1][5] = -K_ONE + PH[1][3]; G_[1][6] =  K_ONE + PH[1][0]; G_[1][7] =  K_ONE + PH[1][1];
+        G_[2][0] =  K_ONE - PH[2][0]; G_[2][1] = -K_ONE - PH[2][1]; G_[2][2] = -K_ONE - PH[2][2]; G_[2][3] =  K_ONE - PH[2][3];
+        G_[2][4] = -K_ONE + PH[2][2]; G_[2][5] =  K_ONE + PH[2][3]; G_[2][6] =  K_ONE + PH[2][0]; G_[2][7] = -K_ONE + PH[2][1];
+        #pragma unroll
+        for (int mm = 0; mm < 3; mm++) {
+          HGX[mm] = G_[mm][0] * vx[0] + G_[mm][1] * vx[1] + G_[mm][2] * vx[2] + G_[mm][3] * vx[3] + G_[mm][4] * vx[4] + G_[mm][5] * vx[5] + G_[mm][6] * vx[6] + G_[mm][7] * vx[7];
+          HGY[mm] = G_[mm][0] * vy[0] + G_[mm][1] * vy[1] + G_[mm][2] * vy[2] + G_[mm][3] * vy[3] + G_[mm][4] * vy[4] + G_[mm][5] * vy[5] + G_[mm][6] * vy[6] + G_[mm][7] * vy[7];
+          HGZ[mm] = G_[mm][0] * vz[0] + G_[mm][1] * vz[1] + G_[mm][2] * vz[2] + G_[mm][3] * vz[3] + G_[mm][4] * vz[4] + G_[mm][5] * vz[5] + G_[mm][6] * vz[6] + G_[mm][7] * vz[7];
+        }
+        HGX[3] = vx[0] - vx[1] + vx[2] - vx[3] - vx[4] + vx[5] - vx[6] + vx[7];
+        HGY[3] = vy[0] - vy[1] + vy[2] - vy[3] - vy[4] + vy[5] - vy[6] + vy[7];
+        HGZ[3] = vz[0] - vz[1] + vz[2] - vz[3] - vz[4] + vz[5] - vz[6] + vz[7];
+      }
+      double HX[4], HY[4], HZ[4];
+      #pragma unroll
+      for (int mm = 0; mm < 4; mm++) {
+        HX[mm] = HGX[mm] * (FCL + fabs(HGX[mm]) * FCQ);
+        HY[mm] = HGY[mm] * (FCL + fabs(HGY[mm]) * FCQ);
+        HZ[mm] = HGZ[mm] * (FCL + fabs(HGZ[mm]) * FCQ);
+      }
+      if (JHBE == 0) {
+        #define FILL0(F, H) F[0] = -H[0] - H[1] - H[2] - H[3]; F[1] =  H[0] - H[1] + H[2] + H[3]; \
+                            F[2] = -H[0] + H[1] + H[2] - H[3]; F[3] =  H[0] + H[1] - H[2] + H[3]; \
+                            F[4] = -H[0] + H[1] + H[2] + H[3]; F[5] =  H[0] + H[1] - H[2] - H[3]; \
+                            F[6] = -H[0] - H[1] - H[2] + H[3]; F[7] =  H[0] - H[1] + H[2] - H[3];
+        FILL0(F1, HX) FILL0(F2, HY) FILL0(F3, HZ)
+        #undef FILL0
+      } else {
+        #define FILL1(F, H) F[0] = -G_[0][0] * H[0] - G_[1][0] * H[1] - G_[2][0] * H[2] - H[3]; \
+                            F[1] = -G_[0][1] * H[0] - G_[1][1] * H[1] - G_[2][1] * H[2] + H[3]; \
+                            F[2] = -G_[0][2] * H[0] - G_[1][2] * H[1] - G_[2][2] * H[2] - H[3]; \
+                            F[3] = -G_[0][3] * H[0] - G_[1][3] * H[1] - G_[2][3] * H[2] + H[3]; \
+                            F[4] = -G_[0][4] * H[0] - G_[1][4] * H[1] - G_[2][4] * H[2] + H[3]; \
+                            F[5] = -G_[0][5] * H[0] - G_[1][5] * H[1] - G_[2][5] * H[2] - H[3]; \
+                            F[6] = -G_[0][6] * H[0] - G_[1][6] * H[1] - G_[2][6] * H[2] + H[3]; \
+                            F[7] = -G_[0][7] * H[0] - G_[1][7] * H[1] - G_[2][7] * H[2] - H[3];
+        FILL1(F1, HX) FILL1(F2, HY) FILL1(F3, HZ)
+        #undef FILL1
+      }
+    }
+    // ---- SFINT3 (pairs 1-7, 2-8, 3-5, 4-6)
+    {
+      const double s1 = (SG1 + K_ZERO - QNEW) * VOLN, s2 = (SG2 + K_ZERO - QNEW) * VOLN, s3 = (SG3 + K_ZERO - QNEW) * VOLN;
+      const double s4 = (SG4 + K_ZERO) * VOLN, s5 = (SG5 + K_ZERO) * VOLN, s6 = (SG6 + K_ZERO) * VOLN;
+      const int a[4] = {0, 1, 2, 3}, b[4] = {6, 7, 4, 5};
+      #pragma unroll
+      for (int k = 0; k < 4; k++) {
+        double FINT = s1 * PX[k] + s4 * PY[k] + s6 * PZ[k];
+        F1[a[k]] = F1[a[k]] - FINT; F1[b[k]] = F1[b[k]] + FINT;
+        FINT = s2 * PY[k] + s4 * PX[k] + s5 * PZ[k];
+        F2[a[k]] = F2[a[k]] - FINT; F2[b[k]] = F2[b[k]] + FINT;
+        FINT = s3 * PZ[k] + s6 * PX[k] + s5 * PY[k];
+        F3[a[k]] = F3[a[k]] - FINT; F3[b[k]] = F3[b[k]] + FINT;
+      }
+    }
+    // ---- SCUMU3P
+    if (OFFG < K_ZERO) {
+      #pragma unroll
+      for (int k = 0; k < 8; k++) { F1[k] = K_ZERO; F2[k] = K_ZERO; F3[k] = K_ZERO; }
+    }
+    STI = K_FOURTH * STI;
+    if (P.roww == 4) {
+      #pragma unroll
+      for (int k = 0; k < 8; k++) {
+        double4* row = reinterpret_cast<double4*>(P.fsky + (size_t)4 * g.slot[k * np + e]);
+        *row = make_double4(F1[k], F2[k], F3[k], STI);
+      }
+    } else {
+      #pragma unroll
+      for (int k = 0; k < 8; k++) {
+        double* row = P.fsky + (size_t)8 * g.slot[k * np + e];
+        row[0] = F1[k]; row[1] = F2[k]; row[2] = F3[k]; row[6] = STI;
+      }
+    }
+  }
+  block_dt_reduce<true>(dt_cand, ngl, order, P.db, g.blk0 + blockIdx.x);
+  element_phase_finalize(P.cs, P.db, P.fa);
+}
+
+template <int JHBE>
+static void launch_brick_ismstr(const BrickParams& P, int ismstr, int nblk, cudaStream_t st)
+{
+  switch (ismstr) {
+    case 1: brick_forces_kernel<JHBE, 1><<<nblk, ORGPU_BLOCK, 0, st>>>(P); break;
+    case 2: brick_forces_kernel<JHBE, 2><<<nblk, ORGPU_BLOCK, 0, st>>>(P); break;
+    default: brick_forces_kernel<JHBE, 4><<<nblk, ORGPU_BLOCK, 0, st>>>(P); break;
+  }
+}
+
+void launch_brick_forces(const BrickSG& sg, const DevNodes& nd, double* fsky, int roww,
+                         CycleState* cs, const DtBlocks& db, const FinalizeArgs& fa, cudaStream_t st)
+{
+  BrickParams P{sg, nd, fsky, roww, cs, db, fa};
+  const int nblk = (sg.ne + ORGPU_BLOCK - 1) / ORGPU_BLOCK;
+  switch (sg.prop.jhbe) {
+    case 0: launch_brick_ismstr<0>(P, sg.prop.ismstr, nblk, st); break;
+    case 2: launch_brick_ismstr<2>(P, sg.prop.ismstr, nblk, st); break;
+    default: launch_brick_ismstr<1>(P, sg.prop.ismstr, nblk, st); break;
+  }
+}

@@ -1,0 +1,477 @@
+// engine.cu -- host side of liborgpu.so: the C ABI of include/orgpu.h.
+//
+// Mirrors what the reference's Fortran glue does around its own GPU path
+// (engine/source/elements/shell/coque/shell_internal_forces.F90: FORINTC_PREPARE_GPU :370 builds
+// "super-groups" of consecutive compatible groups :547-558 and flattens ELBUF into SoA :829-886;
+// shell_gpu_driver.cu:94-263 owns the device memory), generalised to bricks / QEPH / LAW36 and
+// with the nodal arrays, the /PARITH/ON gather and the nodal update resident on the device.
+// Single translation unit (kernels are included) so no relocatable device code is needed.
+#include <cstdio>
+#include <cstdlib>
+#include <cstdarg>
+#include <cstring>
+#include <vector>
+#include <string>
+#include "../../include/orgpu.h"
+#include "common.cuh"
+#include "brick_kernel.cuh"
+#include "shell_kernel.cuh"
+#include "node_kernel.cuh"
+
+static thread_local char g_err[1024] = "";
+void orgpu_set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); }
+extern "C" const char* orgpu_last_error(void) { return g_err; }
+
+#define FAIL(code, ...) do { orgpu_set_error(__VA_ARGS__); return (code); } while (0)
+#define NEED(cond, code, ...) do { if (!(cond)) FAIL(code, __VA_ARGS__); } while (0)
+
+template <class T> static int dev_alloc(T** p, size_t n) {
+  *p = nullptr; if (n == 0) return 0;
+  CUDA_OK(cudaMalloc((void**)p, n * sizeof(T)));
+  CUDA_OK(cudaMemset(*p, 0, n * sizeof(T)));
+  return 0;
+}
+
+struct HostSolidGroup { int nel, nft; orgpu_law2 mat; orgpu_prop_solid prop; std::vector<double> vol0; };
+
+struct BrickSGHost { BrickSG d; int first_elem; std::vector<void*> owned; };
+
+struct orgpu_engine {
+  int device = 0, numnod = 0;
+  orgpu_control ctl{};
+  cudaStream_t st = nullptr;
+  DevNodes nd{};                      // device pointers
+  double *d_stage3a = nullptr, *d_stage3b = nullptr;   // (3,N) staging for pack/unpack
+  double *d_fext = nullptr, *d_mext = nullptr; int *d_icodt = nullptr, *d_icodr = nullptr, *d_adsky = nullptr;
+  // connectivity as given by the caller
+  std::vector<int> ixs, iads, ixc, iadc, adsky; int numels = 0, numelc = 0, lsky = 0;
+  std::vector<int> npf; std::vector<double> tf;
+  std::vector<HostSolidGroup> sgroups;
+  std::vector<HostShellGroup> cgroups;
+  // device model
+  std::vector<BrickSGHost> bsg;
+  std::vector<ShellSGHost> csg;
+  double* d_fsky = nullptr; int roww = 4;
+  CycleState* d_cs = nullptr;
+  DtBlocks db{}; FinalizeArgs fa{};
+  bool finalized = false;
+  // graph of one fused cycle
+  cudaGraphExec_t gexec = nullptr;
+  // instrumentation
+  long long launches = 0; double last_run_ms = 0; int profile = 0;
+  double prof_ms[3] = {0, 0, 0}; long long prof_n[3] = {0, 0, 0};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> evpool;
+};
+
+// ---- small layout kernels ---------------------------------------------------------------
+__global__ void pack3to4_kernel(const double* __restrict__ a3, double4* __restrict__ a4, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  a4[i] = make_double4(a3[3 * i], a3[3 * i + 1], a3[3 * i + 2], 0.0);
+}
+__global__ void unpack4to3_kernel(const double4* __restrict__ a4, double* __restrict__ a3, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  double4 v = a4[i]; a3[3 * i] = v.x; a3[3 * i + 1] = v.y; a3[3 * i + 2] = v.z;
+}
+
+static int upload3to4(orgpu_engine* e, const double* h, double4* d4) {
+  const int n = e->numnod;
+  CUDA_OK(cudaMemcpyAsync(e->d_stage3a, h, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, e->st));
+  pack3to4_kernel<<<(n + 255) / 256, 256, 0, e->st>>>(e->d_stage3a, d4, n); e->launches++;
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+static int download4to3(orgpu_engine* e, const double4* d4, double* h) {
+  const int n = e->numnod;
+  unpack4to3_kernel<<<(n + 255) / 256, 256, 0, e->st>>>(d4, e->d_stage3a, n); e->launches++;
+  CUDA_OK(cudaMemcpyAsync(h, e->d_stage3a, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, e->st));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+template <class T> static int push_dev(std::vector<void*>& owned, T** p, size_t n) { int r = dev_alloc(p, n); if (!r && *p) owned.push_back(*p); return r; }
+template <class T> static int upload_vec(std::vector<void*>& owned, T** p, const std::vector<T>& h) {
+  if (push_dev(owned, p, h.size())) return -100;
+  if (h.size()) CUDA_OK(cudaMemcpy(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" {
+
+int orgpu_create(orgpu_engine** out, int device, int numnod, const orgpu_control* ctl)
+{
+  NEED(out && ctl && numnod > 0, -1, "orgpu_create: bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) FAIL(-2, "orgpu_create: no CUDA device (this library has no CPU path)");
+  NEED(device >= 0 && device < ndev, -3, "orgpu_create: device %d out of range (%d devices)", device, ndev);
+  CUDA_OK(cudaSetDevice(device));
+  orgpu_engine* e = new orgpu_engine();
+  e->device = device; e->numnod = numnod; e->ctl = *ctl;
+  CUDA_OK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+  const size_t n = numnod;
+  e->nd.n = numnod;
+  if (dev_alloc(&e->nd.pos, n) || dev_alloc(&e->nd.vel, n) || dev_alloc(&e->nd.D, 3 * n) || dev_alloc(&e->nd.A, 3 * n) ||
+      dev_alloc(&e->nd.AR, 3 * n) || dev_alloc(&e->nd.STIFN, n) || dev_alloc(&e->nd.STIFR, n) || dev_alloc(&e->nd.MS, n) ||
+      dev_alloc(&e->nd.IN, n) || dev_alloc(&e->d_stage3a, 3 * n) || dev_alloc(&e->d_stage3b, 3 * n)) return -100;
+  if (ctl->iroddl) { if (dev_alloc(&e->nd.rot, n)) return -100; }
+  if (dev_alloc(&e->d_cs, 1)) return -100;
+  CycleState cs{}; cs.tt = ctl->tt_init; cs.dt2 = ctl->dt_init; cs.dt2old = ctl->dt2old_init; cs.dtmx = ctl->dtmx;
+  CUDA_OK(cudaMemcpy(e->d_cs, &cs, sizeof cs, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaEventCreate(&e->ev0)); CUDA_OK(cudaEventCreate(&e->ev1));
+  *out = e;
+  return 0;
+}
+
+int orgpu_destroy(orgpu_engine* e)
+{
+  if (!e) return 0;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->st);
+  if (e->gexec) cudaGraphExecDestroy(e->gexec);
+  for (auto& s : e->bsg) for (void* p : s.owned) cudaFree(p);
+  for (auto& s : e->csg) for (void* p : s.owned) cudaFree(p);
+  void* ptrs[] = {e->nd.pos, e->nd.vel, e->nd.rot, e->nd.D, e->nd.A, e->nd.AR, e->nd.STIFN, e->nd.STIFR, e->nd.MS, e->nd.IN,
+                  e->d_stage3a, e->d_stage3b, e->d_fext, e->d_mext, e->d_icodt, e->d_icodr, e->d_adsky, e->d_fsky, e->d_cs,
+                  e->db.dt, e->db.ngl, e->db.order};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto ev : e->evpool) cudaEventDestroy(ev);
+  if (e->ev0) cudaEventDestroy(e->ev0); if (e->ev1) cudaEventDestroy(e->ev1);
+  cudaStreamDestroy(e->st);
+  delete e;
+  return 0;
+}
+
+int orgpu_upload_nodes(orgpu_engine* e, const double* X, const double* V, const double* VR,
+                       const double* D, const double* MS, const double* IN)
+{
+  NEED(e, -1, "null handle"); CUDA_OK(cudaSetDevice(e->device));
+  const size_t n = e->numnod;
+  if (X) { if (upload3to4(e, X, e->nd.pos)) return -100; }
+  if (V) { if (upload3to4(e, V, e->nd.vel)) return -100; }
+  if (VR && e->nd.rot) { if (upload3to4(e, VR, e->nd.rot)) return -100; }
+  if (D) CUDA_OK(cudaMemcpy(e->nd.D, D, 24 * n, cudaMemcpyHostToDevice));
+  if (MS) CUDA_OK(cudaMemcpy(e->nd.MS, MS, 8 * n, cudaMemcpyHostToDevice));
+  if (IN) CUDA_OK(cudaMemcpy(e->nd.IN, IN, 8 * n, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int orgpu_set_loads(orgpu_engine* e, const double* FEXT, const double* MEXT)
+{
+  NEED(e, -1, "null handle"); CUDA_OK(cudaSetDevice(e->device));
+  const size_t n = e->numnod;
+  if (FEXT) { if (!e->d_fext && dev_alloc(&e->d_fext, 3 * n)) return -100; CUDA_OK(cudaMemcpy(e->d_fext, FEXT, 24 * n, cudaMemcpyHostToDevice)); e->nd.FEXT = e->d_fext; }
+  else e->nd.FEXT = nullptr;
+  if (MEXT) { if (!e->d_mext && dev_alloc(&e->d_mext, 3 * n)) return -100; CUDA_OK(cudaMemcpy(e->d_mext, MEXT, 24 * n, cudaMemcpyHostToDevice)); e->nd.MEXT = e->d_mext; }
+  else e->nd.MEXT = nullptr;
+  if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
+  return 0;
+}
+
+int orgpu_set_bcs(orgpu_engine* e, const int* icodt, const int* icodr)
+{
+  NEED(e && icodt, -1, "orgpu_set_bcs: bad arguments"); CUDA_OK(cudaSetDevice(e->device));
+  const size_t n = e->numnod;
+  if (!e->d_icodt && dev_alloc(&e->d_icodt, n)) return -100;
+  if (!e->d_icodr && dev_alloc(&e->d_icodr, n)) return -100;
+  CUDA_OK(cudaMemcpy(e->d_icodt, icodt, 4 * n, cudaMemcpyHostToDevice));
+  if (icodr) CUDA_OK(cudaMemcpy(e->d_icodr, icodr, 4 * n, cudaMemcpyHostToDevice));
+  e->nd.icodt = e->d_icodt; e->nd.icodr = e->d_icodr;
+  if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
+  return 0;
+}
+
+int orgpu_set_solids(orgpu_engine* e, int numels, const int* ixs, const int* iads)
+{
+  NEED(e && numels >= 0 && !e->finalized, -1, "orgpu_set_solids: bad arguments / already finalized");
+  e->numels = numels; e->ixs.assign(ixs, ixs + (size_t)11 * numels); e->iads.assign(iads, iads + (size_t)8 * numels);
+  return 0;
+}
+int orgpu_set_shells(orgpu_engine* e, int numelc, const int* ixc, const int* iadc)
+{
+  NEED(e && numelc >= 0 && !e->finalized, -1, "orgpu_set_shells: bad arguments / already finalized");
+  e->numelc = numelc; e->ixc.assign(ixc, ixc + (size_t)7 * numelc); e->iadc.assign(iadc, iadc + (size_t)4 * numelc);
+  return 0;
+}
+int orgpu_set_pon(orgpu_engine* e, const int* adsky, int lsky)
+{
+  NEED(e && adsky && lsky >= 0 && !e->finalized, -1, "orgpu_set_pon: bad arguments / already finalized");
+  e->adsky.assign(adsky, adsky + e->numnod + 1); e->lsky = lsky;
+  NEED(e->adsky[0] == 1 && e->adsky[e->numnod] == lsky + 1, -4, "orgpu_set_pon: ADSKY does not span 1..LSKY+1");
+  return 0;
+}
+int orgpu_set_functions(orgpu_engine* e, int nfunc, const int* npf, const double* tf)
+{
+  NEED(e && nfunc >= 0 && !e->finalized, -1, "orgpu_set_functions: bad arguments / already finalized");
+  e->npf.assign(npf, npf + nfunc + 1); e->tf.assign(tf, tf + (size_t)2 * npf[nfunc]);
+  return 0;
+}
+
+int orgpu_add_solid_group(orgpu_engine* e, int nel, int nft, const orgpu_law2* mat,
+                          const orgpu_prop_solid* prop, const double* vol0)
+{
+  NEED(e && mat && prop && vol0 && nel > 0 && !e->finalized, -1, "orgpu_add_solid_group: bad arguments / already finalized");
+  NEED(nft >= 0 && nft + nel <= e->numels, -4, "orgpu_add_solid_group: elements [%d,%d) outside IXS (%d)", nft, nft + nel, e->numels);
+  NEED(mat->fisokin == 0.0, -5, "LAW2 kinematic hardening (FISOKIN>0) is outside the built path");
+  NEED(prop->jhbe == 0 || prop->jhbe == 1 || prop->jhbe == 2, -5, "Isolid=%d is outside the built path (0,1,2)", prop->jhbe);
+  NEED(prop->ismstr == 1 || prop->ismstr == 2 || prop->ismstr == 4, -5, "Ismstr=%d is outside the built path (1,2,4)", prop->ismstr);
+  HostSolidGroup g; g.nel = nel; g.nft = nft; g.mat = *mat; g.prop = *prop; g.vol0.assign(vol0, vol0 + nel);
+  e->sgroups.push_back(std::move(g));
+  return (int)e->sgroups.size() - 1;
+}
+
+int orgpu_add_shell_group(orgpu_engine* e, int nel, int nft, int law, const void* mat, const orgpu_prop_shell* prop)
+{
+  NEED(e && mat && prop && nel > 0 && !e->finalized, -1, "orgpu_add_shell_group: bad arguments / already finalized");
+  NEED(nft >= 0 && nft + nel <= e->numelc, -4, "orgpu_add_shell_group: elements [%d,%d) outside IXC (%d)", nft, nft + nel, e->numelc);
+  return shell_add_group(e->cgroups, nel, nft, law, mat, prop);
+}
+
+// ---- FORINTC_PREPARE_GPU analogue -----------------------------------------------------------
+
+int orgpu_finalize(orgpu_engine* e)
+{
+  NEED(e && !e->finalized, -1, "orgpu_finalize: bad handle / already finalized");
+  NEED(!e->adsky.empty(), -4, "orgpu_finalize: /PARITH/ON tables missing (orgpu_set_pon)");
+  CUDA_OK(cudaSetDevice(e->device));
+  const bool has_shell = !e->cgroups.empty();
+  e->roww = (has_shell || e->ctl.iroddl) ? 8 : 4;
+  if (dev_alloc(&e->d_fsky, (size_t)e->roww * (e->lsky > 0 ? e->lsky : 1))) return -100;
+  { std::vector<int> a0(e->adsky.size()); for (size_t i = 0; i < a0.size(); i++) a0[i] = e->adsky[i] - 1;
+    if (dev_alloc(&e->d_adsky, a0.size())) return -100;
+    CUDA_OK(cudaMemcpy(e->d_adsky, a0.data(), 4 * a0.size(), cudaMemcpyHostToDevice)); e->nd.adsky = e->d_adsky; }
+  int order = 0, blk = 0; e->fa.nsg = 0;
+  // shells are processed first (FORINTC resol.F:4138), solids after (FORINT resol.F:4225)
+  { int rc = shell_build_supergroups(e->cgroups, e->csg, e->ixc, e->iadc, e->npf, e->tf, e->ctl, order, blk, e->fa); if (rc) return rc; }
+  // consecutive solid groups with identical material / property fuse into one super-group
+  size_t gi = 0;
+  while (gi < e->sgroups.size()) {
+    size_t gj = gi + 1;
+    while (gj < e->sgroups.size() && e->sgroups[gj].nft == e->sgroups[gj - 1].nft + e->sgroups[gj - 1].nel &&
+           !memcmp(&e->sgroups[gj].mat, &e->sgroups[gi].mat, sizeof(orgpu_law2)) &&
+           !memcmp(&e->sgroups[gj].prop, &e->sgroups[gi].prop, sizeof(orgpu_prop_solid))) gj++;
+    int ne = 0; for (size_t k = gi; k < gj; k++) ne += e->sgroups[k].nel;
+    const int nft = e->sgroups[gi].nft;
+    const int np = ((ne + ORGPU_BLOCK - 1) / ORGPU_BLOCK) * ORGPU_BLOCK;
+    e->bsg.emplace_back(); BrickSGHost& S = e->bsg.back(); S.first_elem = nft;
+    BrickSG& d = S.d; d.ne = ne; d.ne_pad = np; d.order0 = order; d.blk0 = blk;
+    d.mat = e->sgroups[gi].mat; d.prop = e->sgroups[gi].prop; d.dtfac = e->ctl.dtfac_brick;
+    std::vector<int> conn((size_t)8 * np, 0), slot((size_t)8 * np, 0), ngl(np, 0);
+    std::vector<double> vol(np, 1.0), rho(np, d.mat.rho0), off(np, 0.0), temp(np, d.mat.tini);
+    for (int i = 0; i < ne; i++) {
+      const int* ix = &e->ixs[(size_t)11 * (nft + i)];
+      for (int k = 0; k < 8; k++) {
+        int node = ix[1 + k]; NEED(node >= 1 && node <= e->numnod, -4, "IXS node %d out of range (element %d)", node, nft + i + 1);
+        int sl = e->iads[(size_t)8 * (nft + i) + k]; NEED(sl >= 1 && sl <= e->lsky, -4, "IADS slot %d out of range (element %d)", sl, nft + i + 1);
+        conn[(size_t)k * np + i] = node - 1; slot[(size_t)k * np + i] = sl - 1;
+      }
+      ngl[i] = ix[10]; off[i] = 1.0;
+    }
+    { int i = 0; for (size_t k = gi; k < gj; k++) for (int j = 0; j < e->sgroups[k].nel; j++) vol[i++] = e->sgroups[k].vol0[j]; }
+    int *dconn, *dslot, *dngl; double *dvol, *drho, *doff, *dtemp;
+    if (upload_vec(S.owned, &dconn, conn) || upload_vec(S.owned, &dslot, slot) || upload_vec(S.owned, &dngl, ngl) ||
+        upload_vec(S.owned, &dvol, vol) || upload_vec(S.owned, &drho, rho) || upload_vec(S.owned, &doff, off) ||
+        upload_vec(S.owned, &dtemp, temp)) return -100;
+    d.conn = dconn; d.slot = dslot; d.ngl = dngl; d.vol = dvol; d.rho = drho; d.off = doff; d.temp = dtemp;
+    if (push_dev(S.owned, &d.sig, (size_t)6 * np) || push_dev(S.owned, &d.eint, np) || push_dev(S.owned, &d.qvis, np) ||
+        push_dev(S.owned, &d.pla, np) || push_dev(S.owned, &d.epsd, np) || push_dev(S.owned, &d.smstr, (size_t)21 * np)) return -100;
+    const int nblk = np / ORGPU_BLOCK;
+    NEED(e->fa.nsg < ORGPU_MAX_SG, -6, "too many super-groups (%d)", ORGPU_MAX_SG);
+    e->fa.sg[e->fa.nsg++] = SGRange{blk, nblk, ORGPU_FAM_BRICK};
+    order += ne; blk += nblk; gi = gj;
+  }
+  NEED(blk > 0, -4, "orgpu_finalize: no element groups");
+  e->db.nblocks_total = blk;
+  if (dev_alloc(&e->db.dt, blk) || dev_alloc(&e->db.ngl, blk) || dev_alloc(&e->db.order, blk)) return -100;
+  e->finalized = true;
+  return 0;
+}
+
+// ---- stepping ---------------------------------------------------------------------------------
+static cudaEvent_t get_event(orgpu_engine* e, size_t i) {
+  while (e->evpool.size() <= i) { cudaEvent_t ev; cudaEventCreate(&ev); e->evpool.push_back(ev); }
+  return e->evpool[i];
+}
+
+static void launch_element_phase(orgpu_engine* e, int fused, size_t* evi)
+{
+  e->fa.fused = fused;
+  for (auto& S : e->csg) {
+    if (evi) cudaEventRecord(get_event(e, (*evi)++), e->st);
+    launch_shell_forces(S, e->nd, e->d_fsky, e->roww, e->d_cs, e->db, e->fa, e->st); e->launches++;
+    if (evi) cudaEventRecord(get_event(e, (*evi)++), e->st);
+  }
+  for (auto& S : e->bsg) {
+    if (evi) cudaEventRecord(get_event(e, (*evi)++), e->st);
+    launch_brick_forces(S.d, e->nd, e->d_fsky, e->roww, e->d_cs, e->db, e->fa, e->st); e->launches++;
+    if (evi) cudaEventRecord(get_event(e, (*evi)++), e->st);
+  }
+}
+
+int orgpu_forces_phase(orgpu_engine* e, double dt1)
+{
+  NEED(e && e->finalized, -1, "orgpu_forces_phase: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
+  launch_set_dt(e->d_cs, dt1, 0, 0, 0, e->st); e->launches++;
+  launch_element_phase(e, 0, nullptr);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int orgpu_assemble(orgpu_engine* e)
+{
+  NEED(e && e->finalized, -1, "orgpu_assemble: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
+  launch_node_assemble(e->nd, e->d_fsky, e->roww, e->ctl.iroddl, e->st); e->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int orgpu_advance(orgpu_engine* e, double dt12, double dt2)
+{
+  NEED(e && e->finalized, -1, "orgpu_advance: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
+  launch_set_dt(e->d_cs, 0, dt12, dt2, 1, e->st); e->launches++;
+  launch_node_advance(e->nd, e->d_cs, e->ctl.iroddl, e->st); e->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int orgpu_run_cycles(orgpu_engine* e, int ncycles)
+{
+  NEED(e && e->finalized && ncycles >= 0, -1, "orgpu_run_cycles: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
+  const int per_cycle = (int)(e->csg.size() + e->bsg.size()) + 1;
+  if (e->profile) {
+    // un-graphed, one event pair around every launch: per-class device time on the launching stream
+    for (int k = 0; k < 3; k++) { e->prof_ms[k] = 0; e->prof_n[k] = 0; }
+    const int chunk = 64;
+    CUDA_OK(cudaEventRecord(e->ev0, e->st));
+    for (int c0 = 0; c0 < ncycles; c0 += chunk) {
+      const int nc = (ncycles - c0 < chunk) ? ncycles - c0 : chunk;
+      size_t evi = 0;
+      for (int c = 0; c < nc; c++) {
+        launch_element_phase(e, 1, &evi);
+        cudaEventRecord(get_event(e, evi++), e->st);
+        launch_node_fused(e->nd, e->d_fsky, e->roww, e->d_cs, e->ctl.iroddl, e->st); e->launches++;
+        cudaEventRecord(get_event(e, evi++), e->st);
+      }
+      CUDA_OK(cudaStreamSynchronize(e->st));
+      size_t k = 0;
+      for (int c = 0; c < nc; c++) {
+        for (size_t s = 0; s < e->csg.size(); s++, k += 2) { float ms; cudaEventElapsedTime(&ms, e->evpool[k], e->evpool[k + 1]); e->prof_ms[1] += ms; e->prof_n[1]++; }
+        for (size_t s = 0; s < e->bsg.size(); s++, k += 2) { float ms; cudaEventElapsedTime(&ms, e->evpool[k], e->evpool[k + 1]); e->prof_ms[0] += ms; e->prof_n[0]++; }
+        { float ms; cudaEventElapsedTime(&ms, e->evpool[k], e->evpool[k + 1]); e->prof_ms[2] += ms; e->prof_n[2]++; k += 2; }
+      }
+    }
+    CUDA_OK(cudaEventRecord(e->ev1, e->st));
+    CUDA_OK(cudaStreamSynchronize(e->st));
+    float ms; CUDA_OK(cudaEventElapsedTime(&ms, e->ev0, e->ev1)); e->last_run_ms = ms;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  if (!e->gexec) {                         // capture one fused cycle once, replay it ncycles times
+    cudaGraph_t g;
+    CUDA_OK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeThreadLocal));
+    launch_element_phase(e, 1, nullptr);
+    launch_node_fused(e->nd, e->d_fsky, e->roww, e->d_cs, e->ctl.iroddl, e->st);
+    CUDA_OK(cudaStreamEndCapture(e->st, &g));
+    CUDA_OK(cudaGraphInstantiate(&e->gexec, g, 0));
+    CUDA_OK(cudaGraphDestroy(g));
+    e->launches -= per_cycle - 1;          // the capture pass did not execute
+  }
+  CUDA_OK(cudaEventRecord(e->ev0, e->st));
+  for (int c = 0; c < ncycles; c++) CUDA_OK(cudaGraphLaunch(e->gexec, e->st));
+  CUDA_OK(cudaEventRecord(e->ev1, e->st));
+  e->launches += (long long)per_cycle * ncycles;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int orgpu_synchronize(orgpu_engine* e)
+{
+  NEED(e, -1, "null handle"); CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  if (!e->profile) { float ms = 0; if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_run_ms = ms; else cudaGetLastError(); }
+  return 0;
+}
+
+int orgpu_get_time(orgpu_engine* e, double out[5], int iout[3])
+{
+  NEED(e, -1, "null handle"); CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  CycleState cs; CUDA_OK(cudaMemcpy(&cs, e->d_cs, sizeof cs, cudaMemcpyDeviceToHost));
+  out[0] = cs.tt; out[1] = cs.dt1; out[2] = cs.dt2; out[3] = cs.dt12; out[4] = cs.dt2t;
+  iout[0] = cs.neltst; iout[1] = cs.ityptst; iout[2] = (int)cs.ncycle;
+  return 0;
+}
+
+int orgpu_download_nodes(orgpu_engine* e, double* X, double* V, double* VR, double* D,
+                         double* A, double* AR, double* STIFN, double* STIFR)
+{
+  NEED(e, -1, "null handle"); CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  const size_t n = e->numnod;
+  if (X) { if (download4to3(e, e->nd.pos, X)) return -100; }
+  if (V) { if (download4to3(e, e->nd.vel, V)) return -100; }
+  if (VR) { if (e->nd.rot) { if (download4to3(e, e->nd.rot, VR)) return -100; } else memset(VR, 0, 24 * n); }
+  if (D) CUDA_OK(cudaMemcpy(D, e->nd.D, 24 * n, cudaMemcpyDeviceToHost));
+  if (A) CUDA_OK(cudaMemcpy(A, e->nd.A, 24 * n, cudaMemcpyDeviceToHost));
+  if (AR) CUDA_OK(cudaMemcpy(AR, e->nd.AR, 24 * n, cudaMemcpyDeviceToHost));
+  if (STIFN) CUDA_OK(cudaMemcpy(STIFN, e->nd.STIFN, 8 * n, cudaMemcpyDeviceToHost));
+  if (STIFR) CUDA_OK(cudaMemcpy(STIFR, e->nd.STIFR, 8 * n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int orgpu_download_fsky(orgpu_engine* e, double* fsky)
+{
+  NEED(e && e->finalized, -1, "engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  const size_t L = e->lsky;
+  if (e->roww == 8) { CUDA_OK(cudaMemcpy(fsky, e->d_fsky, 64 * L, cudaMemcpyDeviceToHost)); return 0; }
+  std::vector<double> h(4 * L);
+  CUDA_OK(cudaMemcpy(h.data(), e->d_fsky, 32 * L, cudaMemcpyDeviceToHost));
+  for (size_t k = 0; k < L; k++) { double* f = fsky + 8 * k; f[0] = h[4 * k]; f[1] = h[4 * k + 1]; f[2] = h[4 * k + 2]; f[3] = f[4] = f[5] = 0; f[6] = h[4 * k + 3]; f[7] = 0; }
+  return 0;
+}
+
+int orgpu_download_solid_state(orgpu_engine* e, int field, double* out)
+{
+  NEED(e && e->finalized && out, -1, "engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  const size_t NE = e->numels;
+  for (auto& S : e->bsg) {
+    const BrickSG& d = S.d; const double* src = nullptr; int nc = 1;
+    switch (field) { case 0: src = d.sig; nc = 6; break; case 1: src = d.eint; break; case 2: src = d.rho; break; case 3: src = d.qvis; break;
+                     case 4: src = d.pla; break; case 5: src = d.epsd; break; case 6: src = d.vol; break; case 7: src = d.off; break;
+                     case 8: src = d.temp; break; case 9: src = d.smstr; nc = 21; break; default: FAIL(-1, "unknown solid field %d", field); }
+    for (int k = 0; k < nc; k++)
+      CUDA_OK(cudaMemcpy(out + k * NE + S.first_elem, src + (size_t)k * d.ne_pad, 8 * (size_t)d.ne, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+int orgpu_download_shell_state(orgpu_engine* e, int field, double* out)
+{
+  NEED(e && e->finalized && out, -1, "engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  return shell_download_state(e->csg, e->numelc, field, out);
+}
+
+int orgpu_step_host(orgpu_engine* e, const double* X, const double* V, const double* VR,
+                    int ncycles, double* Xout, double* Vout)
+{
+  NEED(e && e->finalized, -1, "engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
+  const int n = e->numnod; const int nb = (n + 255) / 256;
+  if (X) { CUDA_OK(cudaMemcpyAsync(e->d_stage3a, X, 24 * (size_t)n, cudaMemcpyHostToDevice, e->st)); pack3to4_kernel<<<nb, 256, 0, e->st>>>(e->d_stage3a, e->nd.pos, n); e->launches++; }
+  if (V) { CUDA_OK(cudaMemcpyAsync(e->d_stage3b, V, 24 * (size_t)n, cudaMemcpyHostToDevice, e->st)); pack3to4_kernel<<<nb, 256, 0, e->st>>>(e->d_stage3b, e->nd.vel, n); e->launches++; }
+  if (VR && e->nd.rot) { CUDA_OK(cudaStreamSynchronize(e->st)); CUDA_OK(cudaMemcpyAsync(e->d_stage3a, VR, 24 * (size_t)n, cudaMemcpyHostToDevice, e->st)); pack3to4_kernel<<<nb, 256, 0, e->st>>>(e->d_stage3a, e->nd.rot, n); e->launches++; }
+  { int rc = orgpu_run_cycles(e, ncycles); if (rc) return rc; }
+  if (Xout) { unpack4to3_kernel<<<nb, 256, 0, e->st>>>(e->nd.pos, e->d_stage3a, n); e->launches++; CUDA_OK(cudaMemcpyAsync(Xout, e->d_stage3a, 24 * (size_t)n, cudaMemcpyDeviceToHost, e->st)); }
+  if (Vout) { unpack4to3_kernel<<<nb, 256, 0, e->st>>>(e->nd.vel, e->d_stage3b, n); e->launches++; CUDA_OK(cudaMemcpyAsync(Vout, e->d_stage3b, 24 * (size_t)n, cudaMemcpyDeviceToHost, e->st)); }
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+long long orgpu_launch_count(orgpu_engine* e) { return e ? e->launches : 0; }
+double orgpu_last_run_ms(orgpu_engine* e) { return e ? e->last_run_ms : 0; }
+int orgpu_set_profile(orgpu_engine* e, int profile) { NEED(e, -1, "null handle"); e->profile = profile; return 0; }
+int orgpu_get_profile(orgpu_engine* e, int cls, double* ms, long long* launches)
+{
+  NEED(e && cls >= 0 && cls < 3, -1, "bad class"); *ms = e->prof_ms[cls]; *launches = e->prof_n[cls]; return 0;
+}
+
+} // extern "C"

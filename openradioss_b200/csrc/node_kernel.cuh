@@ -1,0 +1,142 @@
+// node_kernel.cuh -- per-node kernels: deterministic /PARITH/ON gather and central-difference update.
+//
+//   ASSPAR4  (engine/source/assembly/asspar4.F:164-181): A(:,N) etc. += FSKY(:,K), K = ADSKY(N)..ADSKY(N+1)-1,
+//            a LEFT FOLD in ascending K that starts from the value already in A (the external loads).
+//   ACCELE   (accele.F:65-131)   A *= 1/MS (0 when MS<=0), AR *= 1/IN
+//   BCS10    fixed-dof masks (constraints/general/bcs/bcs10.F, global-frame codes)
+//   VELOCITY (velocity.F:57-89)  V += DT12*A ; A = 0
+//   DEPLA    (displacement.F:91-103) D += DT2*V ; X += DT2*V
+// One thread owns one node; the slot rows of a node are contiguous, so a warp reads a contiguous
+// span of FSKY.  No atomics: the summation order is the Starter's slot order on any GPU count.
+#pragma once
+#include "common.cuh"
+
+struct NodeAcc { double a[3], ar[3], stifn, stifr; };
+
+template <int ROWW>
+__device__ __forceinline__ NodeAcc node_gather(const DevNodes& nd, const double* __restrict__ fsky, int n, int iroddl)
+{
+  NodeAcc r;
+  if (nd.FEXT) { r.a[0] = nd.FEXT[3 * n]; r.a[1] = nd.FEXT[3 * n + 1]; r.a[2] = nd.FEXT[3 * n + 2]; }
+  else { r.a[0] = K_ZERO; r.a[1] = K_ZERO; r.a[2] = K_ZERO; }
+  if (nd.MEXT) { r.ar[0] = nd.MEXT[3 * n]; r.ar[1] = nd.MEXT[3 * n + 1]; r.ar[2] = nd.MEXT[3 * n + 2]; }
+  else { r.ar[0] = K_ZERO; r.ar[1] = K_ZERO; r.ar[2] = K_ZERO; }
+  r.stifn = K_ZERO; r.stifr = K_ZERO;
+  const int k0 = nd.adsky[n], k1 = nd.adsky[n + 1];
+  for (int k = k0; k < k1; k++) {
+    if (ROWW == 4) {
+      const double2* p = reinterpret_cast<const double2*>(fsky) + 2 * (size_t)k;
+      const double2 f = __ldcs(p), h = __ldcs(p + 1);
+      r.a[0] = r.a[0] + f.x; r.a[1] = r.a[1] + f.y; r.a[2] = r.a[2] + h.x; r.stifn = r.stifn + h.y;
+    } else {
+      const double2* p = reinterpret_cast<const double2*>(fsky) + 4 * (size_t)k;
+      const double2 f0 = __ldcs(p), f1 = __ldcs(p + 1), f2 = __ldcs(p + 2), f3 = __ldcs(p + 3);
+      r.a[0] = r.a[0] + f0.x; r.a[1] = r.a[1] + f0.y; r.a[2] = r.a[2] + f1.x;
+      r.ar[0] = r.ar[0] + f1.y; r.ar[1] = r.ar[1] + f2.x; r.ar[2] = r.ar[2] + f2.y;
+      r.stifn = r.stifn + f3.x; r.stifr = r.stifr + f3.y;
+    }
+  }
+  (void)iroddl;
+  return r;
+}
+
+__device__ __forceinline__ void node_update(const DevNodes& nd, int n, NodeAcc& r, double dt12, double dt2, int iroddl)
+{
+  // ACCELE
+  const double ms = nd.MS[n];
+  if (ms > K_ZERO) { const double rt = K_ONE / ms; r.a[0] = r.a[0] * rt; r.a[1] = r.a[1] * rt; r.a[2] = r.a[2] * rt; }
+  else { r.a[0] = K_ZERO; r.a[1] = K_ZERO; r.a[2] = K_ZERO; }
+  if (iroddl) {
+    const double in = nd.IN[n];
+    if (in > K_ZERO) { const double rt = K_ONE / in; r.ar[0] = r.ar[0] * rt; r.ar[1] = r.ar[1] * rt; r.ar[2] = r.ar[2] * rt; }
+    else { r.ar[0] = K_ZERO; r.ar[1] = K_ZERO; r.ar[2] = K_ZERO; }
+  }
+  // BCS
+  if (nd.icodt) {
+    const int c = nd.icodt[n];
+    if (c & 4) r.a[0] = K_ZERO; if (c & 2) r.a[1] = K_ZERO; if (c & 1) r.a[2] = K_ZERO;
+    if (iroddl) { const int q = nd.icodr[n]; if (q & 4) r.ar[0] = K_ZERO; if (q & 2) r.ar[1] = K_ZERO; if (q & 1) r.ar[2] = K_ZERO; }
+  }
+  // VELOCITY
+  double4 v = nd.vel[n];
+  v.x = v.x + dt12 * r.a[0]; v.y = v.y + dt12 * r.a[1]; v.z = v.z + dt12 * r.a[2];
+  nd.vel[n] = v;
+  if (iroddl) {
+    double4 w = nd.rot[n];
+    w.x = w.x + dt12 * r.ar[0]; w.y = w.y + dt12 * r.ar[1]; w.z = w.z + dt12 * r.ar[2];
+    nd.rot[n] = w;
+  }
+  // DEPLA
+  double4 p = nd.pos[n];
+  double vdt = dt2 * v.x; nd.D[3 * n] = nd.D[3 * n] + vdt; p.x = p.x + vdt;
+  vdt = dt2 * v.y; nd.D[3 * n + 1] = nd.D[3 * n + 1] + vdt; p.y = p.y + vdt;
+  vdt = dt2 * v.z; nd.D[3 * n + 2] = nd.D[3 * n + 2] + vdt; p.z = p.z + vdt;
+  nd.pos[n] = p;
+}
+
+// phased mode, step 2: ASSPAR4 only (A, AR, STIFN, STIFR stored for the caller)
+template <int ROWW>
+__global__ void __launch_bounds__(ORGPU_NODE_BLOCK)
+node_assemble_kernel(const __grid_constant__ DevNodes nd, const double* __restrict__ fsky, int iroddl)
+{
+  const int n = blockIdx.x * ORGPU_NODE_BLOCK + threadIdx.x;
+  if (n >= nd.n) return;
+  NodeAcc r = node_gather<ROWW>(nd, fsky, n, iroddl);
+  nd.A[3 * n] = r.a[0]; nd.A[3 * n + 1] = r.a[1]; nd.A[3 * n + 2] = r.a[2];
+  nd.AR[3 * n] = r.ar[0]; nd.AR[3 * n + 1] = r.ar[1]; nd.AR[3 * n + 2] = r.ar[2];
+  nd.STIFN[n] = r.stifn; nd.STIFR[n] = r.stifr;
+}
+
+// phased mode, step 3: ACCELE + BCS + VELOCITY + DEPLA from the stored A / AR
+__global__ void __launch_bounds__(ORGPU_NODE_BLOCK)
+node_advance_kernel(const __grid_constant__ DevNodes nd, const CycleState* __restrict__ cs, int iroddl)
+{
+  const int n = blockIdx.x * ORGPU_NODE_BLOCK + threadIdx.x;
+  if (n >= nd.n) return;
+  NodeAcc r;
+  r.a[0] = nd.A[3 * n]; r.a[1] = nd.A[3 * n + 1]; r.a[2] = nd.A[3 * n + 2];
+  r.ar[0] = nd.AR[3 * n]; r.ar[1] = nd.AR[3 * n + 1]; r.ar[2] = nd.AR[3 * n + 2];
+  node_update(nd, n, r, cs->dt12, cs->dt2, iroddl);
+  nd.A[3 * n] = K_ZERO; nd.A[3 * n + 1] = K_ZERO; nd.A[3 * n + 2] = K_ZERO;        // velocity.F:62-64
+  nd.AR[3 * n] = K_ZERO; nd.AR[3 * n + 1] = K_ZERO; nd.AR[3 * n + 2] = K_ZERO;
+}
+
+// device-resident loop: gather + update in one pass, A never leaves registers
+template <int ROWW>
+__global__ void __launch_bounds__(ORGPU_NODE_BLOCK)
+node_fused_kernel(const __grid_constant__ DevNodes nd, const double* __restrict__ fsky,
+                  const CycleState* __restrict__ cs, int iroddl)
+{
+  const int n = blockIdx.x * ORGPU_NODE_BLOCK + threadIdx.x;
+  if (n >= nd.n) return;
+  NodeAcc r = node_gather<ROWW>(nd, fsky, n, iroddl);
+  node_update(nd, n, r, cs->dt12, cs->dt2, iroddl);
+}
+
+__global__ void set_dt_kernel(CycleState* cs, double dt1, double dt12, double dt2, int which)
+{
+  if (which == 0) { cs->dt2 = dt1; }                       // forces phase: element kernels read DT1 from dt2
+  else { cs->dt1 = cs->dt2; cs->dt12 = dt12; cs->dt2 = dt2; cs->tt = cs->tt + dt2; cs->ncycle += 1; cs->dt2old = dt2; }
+}
+
+void launch_node_assemble(const DevNodes& nd, const double* fsky, int roww, int iroddl, cudaStream_t st)
+{
+  const int nb = (nd.n + ORGPU_NODE_BLOCK - 1) / ORGPU_NODE_BLOCK;
+  if (roww == 4) node_assemble_kernel<4><<<nb, ORGPU_NODE_BLOCK, 0, st>>>(nd, fsky, iroddl);
+  else           node_assemble_kernel<8><<<nb, ORGPU_NODE_BLOCK, 0, st>>>(nd, fsky, iroddl);
+}
+void launch_node_advance(const DevNodes& nd, const CycleState* cs, int iroddl, cudaStream_t st)
+{
+  const int nb = (nd.n + ORGPU_NODE_BLOCK - 1) / ORGPU_NODE_BLOCK;
+  node_advance_kernel<<<nb, ORGPU_NODE_BLOCK, 0, st>>>(nd, cs, iroddl);
+}
+void launch_node_fused(const DevNodes& nd, const double* fsky, int roww, const CycleState* cs, int iroddl, cudaStream_t st)
+{
+  const int nb = (nd.n + ORGPU_NODE_BLOCK - 1) / ORGPU_NODE_BLOCK;
+  if (roww == 4) node_fused_kernel<4><<<nb, ORGPU_NODE_BLOCK, 0, st>>>(nd, fsky, cs, iroddl);
+  else           node_fused_kernel<8><<<nb, ORGPU_NODE_BLOCK, 0, st>>>(nd, fsky, cs, iroddl);
+}
+void launch_set_dt(CycleState* cs, double dt1, double dt12, double dt2, int which, cudaStream_t st)
+{
+  set_dt_kernel<<<1, 1, 0, st>>>(cs, dt1, dt12, dt2, which);
+}

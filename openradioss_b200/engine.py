@@ -1,0 +1,59 @@
+"""Product binding: the CUDA library ``csrc/liborgpu.so`` behind the C ABI of include/orgpu.h.
+
+There is deliberately no fallback: if the library is not built (``__graft_entry__.build()`` or
+``make -C openradioss_b200/csrc``) or no GPU is visible, creating an engine raises.
+"""
+from __future__ import annotations
+import ctypes as C
+import os
+import numpy as np
+from ._binding import Binding, _opt
+from .model import Model
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "liborgpu.so")
+_lib = None
+
+EXPORTS = """create destroy last_error upload_nodes set_loads set_bcs set_solids set_shells set_pon
+set_functions add_solid_group add_shell_group finalize forces_phase assemble advance run_cycles
+synchronize get_time download_nodes download_fsky download_solid_state download_shell_state
+step_host launch_count last_run_ms set_profile get_profile""".split()
+
+
+def load_library() -> C.CDLL:
+    """dlopen liborgpu.so (no compute call, works without a GPU).  Raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError(f"{_LIB_PATH} is not built: run __graft_entry__.build() "
+                               "(nvcc, sm_100a).  There is no CPU fallback for this path.")
+        _lib = C.CDLL(_LIB_PATH)
+    return _lib
+
+
+class Engine(Binding):
+    """One device-resident model (one domain / one GPU)."""
+
+    def __init__(self, model: Model = None, device: int = 0):
+        super().__init__(load_library(), "orgpu_", True)
+        if model is not None:
+            self.load(model, device)
+
+    def step_host(self, X, V, VR, ncycles, Xout, Vout):
+        """End-to-end entry: host nodal arrays in, ncycles on the device, host arrays out."""
+        self._call("step_host", self.h, _opt(X, np.float64), _opt(V, np.float64), _opt(VR, np.float64),
+                   C.c_int(ncycles), Xout.ctypes.data_as(C.c_void_p), Vout.ctypes.data_as(C.c_void_p))
+
+    def launch_count(self) -> int:
+        fn = self.lib.orgpu_launch_count; fn.restype = C.c_longlong
+        return int(fn(self.h))
+
+    def last_run_ms(self) -> float:
+        fn = self.lib.orgpu_last_run_ms; fn.restype = C.c_double
+        return float(fn(self.h))
+
+    def set_profile(self, on: bool): self._call("set_profile", self.h, C.c_int(1 if on else 0))
+
+    def profile(self, cls: int):
+        ms = C.c_double(); n = C.c_longlong()
+        self._call("get_profile", self.h, C.c_int(cls), C.byref(ms), C.byref(n))
+        return ms.value, n.value

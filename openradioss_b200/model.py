@@ -1,0 +1,106 @@
+"""Model description: ctypes mirrors of include/orgpu_model.h plus the in-memory "restart"
+(what the Starter hands the Engine: nodes, connectivity, groups, /PARITH/ON tables).
+
+Reference data model: common_source/modules/nodal_arrays.F90:125-176 (nodal arrays),
+common_source/modules/parith_on_mod.F90:39-74 (ADSKY/IADS/IADC/FSKY),
+engine/source/elements/forintc.F:254-300 (group descriptors).
+"""
+from __future__ import annotations
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+import numpy as np
+
+MAXFUNC36 = 10
+NVSIZ = 128          # group size (engine/share/spe_inc/mvsiz_p.inc:51-55)
+
+d, i = C.c_double, C.c_int
+
+
+class Law2(C.Structure):
+    _fields_ = [(n, d) for n in ("rho0 young nu shear bulk ca cb cn epmx sigmx cc epdr fisokin asrate "
+                                 "z3 z4 tref tmelt rhocp tini pshift a11 a12 ssp").split()] + \
+               [(n, i) for n in "iform icc vp israte has_temp".split()]
+
+
+class Law36(C.Structure):
+    _fields_ = [(n, d) for n in "rho0 young nu shear bulk a11 a12 ssp".split()] + \
+               [("nrate", i), ("epsmax", d), ("epsr1", d), ("epsr2", d), ("fisokin", d),
+                ("rate", d * MAXFUNC36), ("yfac", d * MAXFUNC36), ("ifunc", i * MAXFUNC36),
+                ("israte", i), ("asrate", d), ("vp", i), ("pfac_unused", d)]
+
+
+class PropSolid(C.Structure):
+    _fields_ = [(n, d) for n in "qa qb cns1 cns2 hcoef dtmin".split()] + [("jhbe", i), ("ismstr", i)]
+
+
+class PropShell(C.Structure):
+    _fields_ = [(n, d) for n in "thick h1 h2 h3 srh1 srh2 srh3 shf fac1_qeph".split()] + \
+               [(n, i) for n in "npt ismstr ithk ipla ihbe".split()]
+
+
+class Control(C.Structure):
+    _fields_ = [(n, d) for n in "dtfac_brick dtfac_shell dtmx dt_init dt2old_init tt_init".split()] + \
+               [("iroddl", i), ("nodadt", i)]
+
+
+def elastic_constants(young: float, nu: float):
+    """PM(22)=G, PM(32)=K, PM(24)=A11, PM(25)=A12 as the Starter derives them."""
+    g = young / (2.0 * (1.0 + nu))
+    k = young / (3.0 * (1.0 - 2.0 * nu))
+    a11 = young / (1.0 - nu * nu)
+    a12 = nu * a11
+    return g, k, a11, a12
+
+
+@dataclass
+class SolidGroup:
+    nft: int
+    nel: int
+    mat: Law2
+    prop: PropSolid
+
+
+@dataclass
+class ShellGroup:
+    nft: int
+    nel: int
+    law: int                 # 2 or 36
+    mat: object              # Law2 | Law36
+    prop: PropShell
+
+
+@dataclass
+class Model:
+    """Everything a domain's restart file gives the Engine for this path."""
+    X: np.ndarray                       # (numnod,3) float64  == Fortran X(3,NUMNOD)
+    V: np.ndarray
+    VR: np.ndarray
+    MS: np.ndarray
+    IN: np.ndarray
+    control: Control
+    ixs: np.ndarray = field(default_factory=lambda: np.zeros((0, 11), np.int32))   # IXS(11,NUMELS)^T
+    ixc: np.ndarray = field(default_factory=lambda: np.zeros((0, 7), np.int32))    # IXC(7,NUMELC)^T
+    vol0: np.ndarray = field(default_factory=lambda: np.zeros(0))                  # brick initial volumes
+    solid_groups: List[SolidGroup] = field(default_factory=list)
+    shell_groups: List[ShellGroup] = field(default_factory=list)
+    icodt: Optional[np.ndarray] = None  # BCS translation codes (4:x 2:y 1:z)
+    icodr: Optional[np.ndarray] = None
+    fext: Optional[np.ndarray] = None   # constant nodal loads (numnod,3)
+    mext: Optional[np.ndarray] = None
+    itab: Optional[np.ndarray] = None   # user node ids
+    # /PARITH/ON tables (1-based), filled by pon.build_pon
+    adsky: Optional[np.ndarray] = None
+    iads: Optional[np.ndarray] = None
+    iadc: Optional[np.ndarray] = None
+    lsky: int = 0
+    # LAW36 function table
+    npf: Optional[np.ndarray] = None
+    tf: Optional[np.ndarray] = None
+
+    @property
+    def numnod(self): return int(self.X.shape[0])
+    @property
+    def numels(self): return int(self.ixs.shape[0])
+    @property
+    def numelc(self): return int(self.ixc.shape[0])

@@ -1,0 +1,131 @@
+/* oracle/api.cpp -- TEST INFRASTRUCTURE ONLY (see oracle.h).  C entry points used through
+ * ctypes by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs.  The call
+ * surface mirrors include/orgpu.h one-to-one (orc_* vs orgpu_*) so the parity tests drive
+ * both sides with the same arrays. */
+#include "oracle.h"
+#include <cstring>
+#include <cstdio>
+#include <omp.h>
+
+struct OrcShellGroup;
+void orc_shell_group_free(OrcShellGroup*);
+void orc_forces(Oracle& o);
+
+extern "C" {
+
+void* orc_create(int numnod, const orgpu_control* ctl)
+{
+  Oracle* o=new Oracle();
+  o->numnod=numnod; o->ctl=*ctl;
+  size_t n=numnod;
+  o->X.assign(3*n,0); o->V.assign(3*n,0); o->VR.assign(3*n,0); o->D.assign(3*n,0); o->DR.assign(3*n,0);
+  o->A.assign(3*n,0); o->AR.assign(3*n,0); o->MS.assign(n,0); o->IN.assign(n,0);
+  o->STIFN.assign(n,0); o->STIFR.assign(n,0);
+  o->TT=ctl->tt_init; o->DT2=ctl->dt_init; o->DT2OLD=ctl->dt2old_init; o->DT1=0; o->DT12=0;
+  return o;
+}
+void orc_destroy(void* h){
+  Oracle* o=(Oracle*)h;
+  for(auto* g:o->cgroups) orc_shell_group_free(g);
+  delete o;
+}
+void orc_set_threads(void* h,int nt){ ((Oracle*)h)->nthreads = nt>0? nt : omp_get_max_threads(); }
+
+/* nodal arrays, Fortran (3,NUMNOD); any pointer may be NULL (left unchanged) */
+void orc_upload_nodes(void* h,const double* X,const double* V,const double* VR,const double* D,
+                      const double* MS,const double* IN)
+{
+  Oracle* o=(Oracle*)h; size_t n=o->numnod;
+  if(X)  memcpy(o->X.data(),X,24*n);
+  if(V)  memcpy(o->V.data(),V,24*n);
+  if(VR) memcpy(o->VR.data(),VR,24*n);
+  if(D)  memcpy(o->D.data(),D,24*n);
+  if(MS) memcpy(o->MS.data(),MS,8*n);
+  if(IN) memcpy(o->IN.data(),IN,8*n);
+}
+void orc_set_loads(void* h,const double* FEXT,const double* MEXT){
+  Oracle* o=(Oracle*)h; size_t n=o->numnod;
+  if(FEXT) o->FEXT.assign(FEXT,FEXT+3*n); else o->FEXT.clear();
+  if(MEXT) o->MEXT.assign(MEXT,MEXT+3*n); else o->MEXT.clear();
+}
+void orc_set_bcs(void* h,const int* icodt,const int* icodr){
+  Oracle* o=(Oracle*)h; size_t n=o->numnod;
+  o->ICODT.assign(icodt,icodt+n);
+  if(icodr) o->ICODR.assign(icodr,icodr+n); else o->ICODR.assign(n,0);
+}
+/* connectivity + /PARITH/ON tables (all 1-based, Fortran layout) */
+void orc_set_solids(void* h,int numels,const int* ixs /*(11,numels)*/,const int* iads /*(8,numels)*/){
+  Oracle* o=(Oracle*)h; o->numels=numels;
+  o->IXS.assign(ixs,ixs+(size_t)11*numels); o->IADS.assign(iads,iads+(size_t)8*numels);
+}
+void orc_set_shells(void* h,int numelc,const int* ixc /*(7,numelc)*/,const int* iadc /*(4,numelc)*/){
+  Oracle* o=(Oracle*)h; o->numelc=numelc;
+  o->IXC.assign(ixc,ixc+(size_t)7*numelc); o->IADC.assign(iadc,iadc+(size_t)4*numelc);
+}
+void orc_set_pon(void* h,const int* adsky /*numnod+1*/,int lsky){
+  Oracle* o=(Oracle*)h; o->ADSKY.assign(adsky,adsky+o->numnod+1); o->lsky=lsky;
+  o->FSKY.assign((size_t)8*lsky,0.0);
+}
+void orc_set_functions(void* h,int nfunc,const int* npf /*nfunc+1*/,const double* tf){
+  Oracle* o=(Oracle*)h; o->NPF.assign(npf,npf+nfunc+1); o->TF.assign(tf,tf+(size_t)2*npf[nfunc]);
+}
+
+/* one solid group: elements [nft, nft+nel) of IXS; vol0 = initial volumes (Starter output) */
+int orc_add_solid_group(void* h,int nel,int nft,const orgpu_law2* mat,const orgpu_prop_solid* prop,
+                        const double* vol0)
+{
+  Oracle* o=(Oracle*)h;
+  if(nel>MVSIZ-1) return -1;
+  if(mat->fisokin!=0.0) return -2;
+  OrcSolidGroup g; g.nel=nel; g.nft=nft; g.mat=*mat; g.prop=*prop;
+  g.sig.assign(6*nel,0); g.eint.assign(nel,0); g.rho.assign(nel,mat->rho0); g.qvis.assign(nel,0);
+  g.pla.assign(nel,0); g.epsd.assign(nel,0); g.vol.assign(vol0,vol0+nel); g.off.assign(nel,1.0);
+  g.temp.assign(nel,mat->tini); g.dmg.assign(nel,0); g.smstr.assign(21*nel,0);
+  o->sgroups.push_back(std::move(g));
+  return (int)o->sgroups.size()-1;
+}
+
+void orc_finalize(void*){}
+
+/* phases (same split as the device library) */
+void orc_forces_phase(void* h,double dt1){
+  Oracle* o=(Oracle*)h; o->DT1=dt1; o->DT2=K_EP06; orc_forces(*o);
+}
+void orc_assemble(void* h){ orc_asspar4(*(Oracle*)h); }
+void orc_advance(void* h,double dt12,double dt2){
+  Oracle* o=(Oracle*)h; o->DT12=dt12; o->DT2=dt2;
+  orc_accele(*o); orc_bcs(*o); orc_velocity(*o); orc_depla(*o); o->TT+=dt2; o->NCYCLE++;
+}
+void orc_run_cycles(void* h,int ncycles){ Oracle* o=(Oracle*)h; for(int c=0;c<ncycles;c++) orc_cycle(*o); }
+
+/* read-back */
+void orc_get_time(void* h,double* out /*tt,dt1,dt2,dt12,dt2t*/,int* iout /*neltst,ityptst,ncycle*/){
+  Oracle* o=(Oracle*)h;
+  out[0]=o->TT; out[1]=o->DT1; out[2]=o->DT2; out[3]=o->DT12; out[4]=o->DT2T;
+  iout[0]=o->NELTST; iout[1]=o->ITYPTST; iout[2]=(int)o->NCYCLE;
+}
+void orc_download_nodes(void* h,double* X,double* V,double* VR,double* D,double* A,double* AR,
+                        double* STIFN,double* STIFR){
+  Oracle* o=(Oracle*)h; size_t n=o->numnod;
+  if(X) memcpy(X,o->X.data(),24*n); if(V) memcpy(V,o->V.data(),24*n); if(VR) memcpy(VR,o->VR.data(),24*n);
+  if(D) memcpy(D,o->D.data(),24*n); if(A) memcpy(A,o->A.data(),24*n); if(AR) memcpy(AR,o->AR.data(),24*n);
+  if(STIFN) memcpy(STIFN,o->STIFN.data(),8*n); if(STIFR) memcpy(STIFR,o->STIFR.data(),8*n);
+}
+void orc_download_fsky(void* h,double* fsky){ Oracle* o=(Oracle*)h; memcpy(fsky,o->FSKY.data(),64*(size_t)o->lsky); }
+
+/* solid state of all groups concatenated in element order, component-major over NUMELS:
+ * sig[k*numels+e] ; fields: 0 sig(6) 1 eint 2 rho 3 qvis 4 pla 5 epsd 6 vol 7 off 8 temp 9 smstr(21) */
+void orc_download_solid_state(void* h,int field,double* out){
+  Oracle* o=(Oracle*)h; size_t ne=o->numels;
+  for(auto& g:o->sgroups){
+    auto cp=[&](const std::vector<double>& v,int nc){ for(int k=0;k<nc;k++) for(int i=0;i<g.nel;i++) out[k*ne+g.nft+i]=v[(size_t)k*g.nel+i]; };
+    switch(field){
+      case 0: cp(g.sig,6); break; case 1: cp(g.eint,1); break; case 2: cp(g.rho,1); break;
+      case 3: cp(g.qvis,1); break; case 4: cp(g.pla,1); break; case 5: cp(g.epsd,1); break;
+      case 6: cp(g.vol,1); break; case 7: cp(g.off,1); break; case 8: cp(g.temp,1); break;
+      case 9: cp(g.smstr,21); break;
+    }
+  }
+}
+
+} // extern "C"

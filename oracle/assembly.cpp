@@ -1,0 +1,144 @@
+/* oracle/assembly.cpp -- TEST INFRASTRUCTURE ONLY (see oracle.h).
+ * Restates: ASSPAR4 (engine/source/assembly/asspar4.F:164-181), ACCELE (accele.F:65-131),
+ * BCS10-style fixed dof masks (constraints/general/bcs/bcs10.F), VELOCITY (velocity.F:57-89),
+ * DEPLA (displacement.F:91-113) and the RESOL time-step bookkeeping
+ * (engine/source/engine/resol.F:2721-2722, 4165-4171, 6124-6128, 6352, 6494-6497, 8599-8608).
+ */
+#include "oracle.h"
+#include <omp.h>
+
+struct OrcShellGroup;
+void orc_shell_dispatch(Oracle& o, OrcShellGroup& g, double& dt2t, int& neltst, int& ityptst);
+
+/* ASSPAR4: left fold of slots ADSKY(N)..ADSKY(N+1)-1 into the EXISTING A/AR/STIFN/STIFR */
+void orc_asspar4(Oracle& o)
+{
+  const int n=o.numnod;
+  #pragma omp parallel for schedule(static) num_threads(o.nthreads)
+  for(int N=0;N<n;N++){
+    int nct=o.ADSKY[N]-1; int nc=o.ADSKY[N+1]-o.ADSKY[N];
+    for(int k=nct;k<nct+nc;k++){
+      const double* f=&o.FSKY[8*(size_t)k];
+      o.A[3*N]  =o.A[3*N]  +f[0];
+      o.A[3*N+1]=o.A[3*N+1]+f[1];
+      o.A[3*N+2]=o.A[3*N+2]+f[2];
+      o.AR[3*N]  =o.AR[3*N]  +f[3];
+      o.AR[3*N+1]=o.AR[3*N+1]+f[4];
+      o.AR[3*N+2]=o.AR[3*N+2]+f[5];
+      o.STIFN[N]=o.STIFN[N]+f[6];
+      o.STIFR[N]=o.STIFR[N]+f[7];
+    }
+  }
+}
+
+/* ACCELE accele.F:65-131 (N2D=0, NMULT=0) */
+void orc_accele(Oracle& o)
+{
+  const int n=o.numnod;
+  #pragma omp parallel for schedule(static) num_threads(o.nthreads)
+  for(int N=0;N<n;N++){
+    if(o.MS[N]>K_ZERO){
+      double rtmp=K_ONE/o.MS[N];
+      o.A[3*N]*=rtmp; o.A[3*N+1]*=rtmp; o.A[3*N+2]*=rtmp;
+    } else { o.A[3*N]=K_ZERO; o.A[3*N+1]=K_ZERO; o.A[3*N+2]=K_ZERO; }
+    if(o.ctl.iroddl!=0){
+      if(o.IN[N]>K_ZERO){
+        double rtmp=K_ONE/o.IN[N];
+        o.AR[3*N]*=rtmp; o.AR[3*N+1]*=rtmp; o.AR[3*N+2]*=rtmp;
+      } else { o.AR[3*N]=K_ZERO; o.AR[3*N+1]=K_ZERO; o.AR[3*N+2]=K_ZERO; }
+    }
+  }
+}
+
+/* BCS10 (global-frame codes only): zero the acceleration of fixed dofs.
+ * code bits as in ICODT/ICODR: 4 -> x, 2 -> y, 1 -> z   (bcs10.F, skew 0 branch) */
+void orc_bcs(Oracle& o)
+{
+  const int n=o.numnod;
+  if(o.ICODT.empty()) return;
+  #pragma omp parallel for schedule(static) num_threads(o.nthreads)
+  for(int N=0;N<n;N++){
+    int c=o.ICODT[N];
+    if(c&4) o.A[3*N]=K_ZERO; if(c&2) o.A[3*N+1]=K_ZERO; if(c&1) o.A[3*N+2]=K_ZERO;
+    if(o.ctl.iroddl!=0){
+      int r=o.ICODR[N];
+      if(r&4) o.AR[3*N]=K_ZERO; if(r&2) o.AR[3*N+1]=K_ZERO; if(r&1) o.AR[3*N+2]=K_ZERO;
+    }
+  }
+}
+
+/* VELOCITY velocity.F:57-89 */
+void orc_velocity(Oracle& o)
+{
+  const int n=o.numnod; const double DT12=o.DT12;
+  #pragma omp parallel for schedule(static) num_threads(o.nthreads)
+  for(int N=0;N<n;N++){
+    for(int c=0;c<3;c++){ o.V[3*N+c]=o.V[3*N+c]+DT12*o.A[3*N+c]; o.A[3*N+c]=K_ZERO; }
+    if(o.ctl.iroddl!=0) for(int c=0;c<3;c++){ o.VR[3*N+c]=o.VR[3*N+c]+DT12*o.AR[3*N+c]; o.AR[3*N+c]=K_ZERO; }
+  }
+}
+
+/* DEPLA displacement.F:91-103 (IRESP=0; DR not advanced: ISECUT=IISROT=IMPOSE_DR=IDROT=0) */
+void orc_depla(Oracle& o)
+{
+  const int n=o.numnod; const double DT2=o.DT2;
+  #pragma omp parallel for schedule(static) num_threads(o.nthreads)
+  for(int N=0;N<n;N++){
+    for(int c=0;c<3;c++){
+      double VDT=DT2*o.V[3*N+c];
+      o.D[3*N+c]=o.D[3*N+c]+VDT;
+      o.X[3*N+c]=o.X[3*N+c]+VDT;
+    }
+  }
+}
+
+/* element force phase: external loads pre-loaded into A/AR, then all groups write FSKY */
+void orc_forces(Oracle& o)
+{
+  const int n=o.numnod;
+  /* resol.F: A/AR hold external nodal loads when the element loop starts (FORCE, resol.F:2929);
+   * STIFN/STIFR restart from zero each cycle */
+  for(int i=0;i<3*n;i++){ o.A[i]= o.FEXT.empty()? K_ZERO : o.FEXT[i]; o.AR[i]= o.MEXT.empty()? K_ZERO : o.MEXT[i]; }
+  for(int i=0;i<n;i++){ o.STIFN[i]=K_ZERO; o.STIFR[i]=K_ZERO; }
+  double DT2T=o.DT2; int NELTST=0, ITYPTST=0;   /* thread mins are merged with strict "<" (resol.F:4165-4171) */
+  /* shells first (FORINTC resol.F:4138), then solids (FORINT resol.F:4225) */
+  const int ncg=(int)o.cgroups.size(), nsg=(int)o.sgroups.size();
+  if(o.nthreads<=1){
+    for(int g=0;g<ncg;g++) orc_shell_dispatch(o,*o.cgroups[g],DT2T,NELTST,ITYPTST);
+    for(int g=0;g<nsg;g++) orc_sforc3(o,o.sgroups[g],DT2T,NELTST,ITYPTST);
+  } else {
+    /* OpenMP over groups as forintc.F:238 (!$OMP DO SCHEDULE(DYNAMIC,1)); thread-private DT2TT */
+    #pragma omp parallel num_threads(o.nthreads)
+    {
+      double dt2tt=o.DT2; int nelt=0, ityp=0;
+      #pragma omp for schedule(dynamic,1) nowait
+      for(int g=0;g<ncg;g++) orc_shell_dispatch(o,*o.cgroups[g],dt2tt,nelt,ityp);
+      #pragma omp for schedule(dynamic,1)
+      for(int g=0;g<nsg;g++) orc_sforc3(o,o.sgroups[g],dt2tt,nelt,ityp);
+      #pragma omp critical
+      { if(dt2tt<DT2T){ DT2T=dt2tt; NELTST=nelt; ITYPTST=ityp; } }
+    }
+  }
+  o.DT2T=DT2T; o.NELTST=NELTST; o.ITYPTST=ITYPTST;
+}
+
+/* one pass of RESOL restricted to the hot path */
+void orc_cycle(Oracle& o)
+{
+  o.DT1=o.DT2;                    /* resol.F:2721 */
+  o.DT2=K_EP06;                   /* resol.F:2722 */
+  orc_forces(o);
+  orc_asspar4(o);
+  if(o.DT2T<o.DT2) o.DT2=o.DT2T;  /* resol.F:6124-6128 */
+  {                               /* resol.F:6352: DT2=MIN(DT2,1.1*DT2OLD,DTMX) -- 1.1 is a REAL*4 literal */
+    double c11=(double)1.1f;
+    o.DT2=std::min(o.DT2,std::min(c11*o.DT2OLD,o.ctl.dtmx));
+  }
+  o.DT2OLD=o.DT2;                 /* resol.F:6494 */
+  o.DT12=K_HALF*(o.DT1+o.DT2);    /* resol.F:6496 */
+  orc_accele(o);
+  orc_bcs(o);
+  orc_velocity(o);
+  orc_depla(o);
+  o.TT=o.TT+o.DT2; o.NCYCLE++;    /* resol.F:8599-8608 */
+}

@@ -1,0 +1,83 @@
+/* oracle/oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (C++17, scalar, libm, compiled with -ffp-contract=off like the reference's
+ * -ffp-contract=off / -no-fma builds) of the OpenRadioss Engine routines on the explicit
+ * element cycle hot path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference leg may link or call anything under oracle/.  The product path
+ * (openradioss_b200/csrc) never includes this directory.
+ *
+ * PARITY PINNING: the reference Engine is Fortran and cannot be compiled in this image (no
+ * Fortran compiler), and its own QA suite holds no routine-level vectors for this path
+ * (SURVEY.md 8c).  The restatement is therefore pinned by (1) line-by-line correspondence to
+ * the cited Fortran, (2) analytic patch tests (tests/test_oracle_*.py), and (3) coarse anchors.
+ * Per-cycle force parity of the CUDA path is "parity vs the restatement" -- see DESIGN.md.
+ *
+ * The oracle keeps the reference's data model: Fortran-ordered nodal arrays X(3,NUMNOD),
+ * element groups of NEL<=MVSIZ elements with ELBUF-style component-major state
+ * (sig[(k)*nel+i]), IXS(11,*) / IXC(7,*) connectivity, FSKY(8,LSKY) + ADSKY + IADS/IADC.
+ */
+#ifndef ORACLE_H
+#define ORACLE_H
+#include <vector>
+#include <cmath>
+#include <cstdint>
+#include <algorithm>
+#include "../include/orgpu_model.h"
+#include "../include/or_constants.h"
+
+#define MVSIZ 129   /* engine/share/spe_inc/mvsiz_p.inc:54-55 */
+
+struct OrcSolidGroup {          /* one element group, ITY=1 (forint.F -> SFORC3) */
+  int nel = 0, nft = 0;         /* nft: offset of first element in IXS/IADS (0-based) */
+  orgpu_law2 mat;               /* MLW=2 */
+  orgpu_prop_solid prop;
+  /* ELBUF (gbuf == lbuf for 1-IP solids), component-major (k*nel+i) */
+  std::vector<double> sig;      /* 6*nel */
+  std::vector<double> eint, rho, qvis, pla, epsd, vol, off, temp, dmg;
+  std::vector<double> smstr;    /* SAV(nel,21) */
+};
+
+struct OrcShellGroup;           /* defined in shell files */
+
+struct Oracle {
+  int numnod = 0;
+  orgpu_control ctl{};
+  /* nodal arrays, Fortran (3,NUMNOD) column-major -> [3*n+c]  (nodal_arrays.F90:125-176) */
+  std::vector<double> X, V, VR, D, DR, A, AR, MS, IN, STIFN, STIFR;
+  std::vector<double> FEXT, MEXT;     /* constant external nodal loads (3,N) pre-loaded into A/AR */
+  std::vector<int>    ICODT, ICODR;   /* BCS codes (bit 4=x,2=y,1=z fixed), bcs10.F */
+  /* connectivity */
+  std::vector<int> IXS;   /* (11,NUMELS) 1-based nodes in 2..9, user id in 11 */
+  std::vector<int> IXC;   /* (7,NUMELC)  1-based nodes in 2..5, user id in 7  */
+  int numels = 0, numelc = 0;
+  /* /PARITH/ON tables (parith_on_mod.F90:39-74) */
+  std::vector<int> ADSKY;  /* numnod+1, 1-based slot addresses */
+  std::vector<int> IADS;   /* (8,NUMELS) 1-based slot of each brick corner */
+  std::vector<int> IADC;   /* (4,NUMELC) */
+  std::vector<double> FSKY;/* (8,LSKY) */
+  int lsky = 0;
+  std::vector<OrcSolidGroup> sgroups;
+  std::vector<OrcShellGroup*> cgroups;
+  /* LAW36 function table */
+  std::vector<double> TF; std::vector<int> NPF;
+  /* time-step bookkeeping (resol.F:2721, 6124-6128, 6352, 6494-6497) */
+  double TT = 0, DT1 = 0, DT2 = 0, DT12 = 0, DT2OLD = 0;
+  double DT2T = 0; int NELTST = 0, ITYPTST = 0;
+  long NCYCLE = 0;
+  int nthreads = 1;
+};
+
+/* solid.cpp */
+void orc_sforc3(Oracle& o, OrcSolidGroup& g, double& dt2t, int& neltst, int& ityptst);
+/* shell_qeph.cpp / shell_bt.cpp */
+void orc_czforc3(Oracle& o, OrcShellGroup& g, double& dt2t, int& neltst, int& ityptst);
+void orc_cforc3(Oracle& o, OrcShellGroup& g, double& dt2t, int& neltst, int& ityptst);
+/* assembly.cpp */
+void orc_asspar4(Oracle& o);
+void orc_accele(Oracle& o);
+void orc_bcs(Oracle& o);
+void orc_velocity(Oracle& o);
+void orc_depla(Oracle& o);
+void orc_cycle(Oracle& o);
+
+#endif
