@@ -1,0 +1,238 @@
+#!/usr/bin/env python3
+"""bench.py -- element-cycles/s of the explicit element cycle on N B200s (BASELINE.json metric).
+
+A "step" is one explicit cycle (internal forces -> dt argmin -> /PARITH/ON assembly -> nodal
+update) over the whole synthetic mesh.  `value` is measured with the model resident in HBM
+(orgpu_run_cycles, CUDA events on the library's stream, max over ranks); `e2e` drives the same
+cycles through the host-buffer C-ABI call orgpu_step_host (pinned host X/V in, X/V out, every
+step) -- the usage pattern of the reference's own -gpu path, which re-uploads the nodal arrays
+each cycle (shell_internal_forces.F90:106).  `--impl reference` times the CPU oracle restatement
+(the reference Engine itself is Fortran and cannot be built in this image) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# algorithmic HBM bytes per element-cycle (SURVEY.md 8d / BASELINE.md 3), split per kernel:
+#   brick forces : IXS 32 + X,V gather 48 + state r/w 208 + SMSTR write 168 + corner rows write 256
+#   node kernel  : corner rows read 256 + nodal update 152     (1 node / element)
+B_ALG = {
+    "brick": dict(total=1120, forces=712, node=408),
+    "shell": dict(total=1872, forces=1408, node=464),   # forces: 16+72+48+416+560+40+256 ; node: 256+208
+}
+
+
+def workload(name, rank=0):
+    from openradioss_b200 import meshgen
+    if name == "c5_brick_slab_2m":          # per-GPU share of C5: 200 x 200 x 50 bricks, LAW2
+        return meshgen.hex_block(200, 200, 50, 200.0, 200.0, 50.0, vrand=1.0, vseed=12345 + rank), "brick"
+    if name == "c1_taylor_bar":
+        return meshgen.taylor_bar(1), "brick"
+    if name == "brick_small":
+        return meshgen.hex_block(40, 40, 40, 40.0, 40.0, 40.0, vrand=1.0), "brick"
+    if name == "c2_plate_qeph_1m":
+        return meshgen.plate_qeph(1000, 1000), "shell"
+    if name == "plate_small":
+        return meshgen.plate_qeph(200, 200), "shell"
+    raise SystemExit(f"unknown workload {name}")
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, dev):
+        self.dev, self.rows, self.stop = dev, [], False
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.dev), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self): self.t.start(); return self
+
+    def __exit__(self, *a): self.stop = True; self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args, rank):
+    """CPU arm: the oracle restatement on all host cores, same workload / metric."""
+    if rank != 0:
+        return
+    from oracle.orc import Oracle
+    m, fam = workload(args.workload)
+    ne = m.numels + m.numelc
+    cores = os.cpu_count() or 1
+    o = Oracle(m, threads=cores)
+    o.run_cycles(max(1, args.warmup))
+    t0 = time.perf_counter(); o.run_cycles(args.steps); dt = time.perf_counter() - t0
+    val = ne * args.steps / dt
+    line = {"impl": "reference", "metric": "element-cycles/sec", "value": val, "unit": "element-cycles/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "elements": ne, "nodes": m.numnod, "family": fam},
+            "cpu_baseline": {"value": val, "unit": "element-cycles/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.workload}: {ne} elements x {args.steps} cycles, OpenMP over groups of 128"},
+            "e2e": {"value": val, "unit": "element-cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="orgpu", choices=["orgpu", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("ORGPU_WORKLOAD", "c5_brick_slab_2m"))
+    ap.add_argument("--cpu-cycles", type=int, default=20, help="cycles of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if args.steps > 40:
+            args.steps = 40          # bounded: one CPU step of 2 M bricks is ~0.4 s on 8 cores
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from openradioss_b200.engine import Engine
+    m, fam = workload(args.workload, rank)
+    ne = m.numels + m.numelc
+    g = Engine(m, device=local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        g.synchronize(); torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    g.run_cycles(args.warmup); barrier()
+    l0 = g.launch_count()
+    with ClockSampler(local) as cs:
+        barrier()
+        g.run_cycles(args.steps)
+        barrier()
+    ms = g.last_run_ms()
+    launches = g.launch_count() - l0
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = ne * world * args.steps / (ms * 1e-3)
+    clocks = cs.summary()
+
+    # ---- per-kernel durations (CUDA events around every launch on the library's stream)
+    g.set_profile(True)
+    g.run_cycles(min(args.steps, 64)); g.synchronize()
+    prof = {k: g.profile(i) for i, k in enumerate(("brick_forces", "shell_forces", "node"))}
+    g.set_profile(False)
+    peak, peak_src = peaks()
+    dom = "shell_forces" if fam == "shell" else "brick_forces"
+    dms, dn = prof[dom]
+    b = B_ALG[fam]
+    ach = (b["forces"] * ne) / (dms / dn * 1e-3) / 1e9 if dn else 0.0
+    nms, nn = prof["node"]
+    roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": None, "peak_source": peak_src, "bytes_per_element": b["forces"],
+            "avg_launch_ms": dms / dn if dn else None,
+            "node_kernel": {"achieved": (b["node"] * m.numnod) / (nms / nn * 1e-3) / 1e9 if nn else None,
+                            "avg_launch_ms": nms / nn if nn else None, "bytes_per_node": b["node"]},
+            "whole_cycle": {"achieved": b["total"] * ne * world / (ms * 1e-3 / args.steps) / 1e9 / world,
+                            "frac": b["total"] * ne / (ms * 1e-3 / args.steps) / 1e9 / peak, "bytes_per_element": b["total"]}}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roof["traffic"] = json.load(open(tr)).get(dom)
+        except Exception:
+            pass
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host arrays, copies inside the timed region)
+    n = m.numnod
+    hX = torch.empty((n, 3), dtype=torch.float64).pin_memory(); hV = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    oX = torch.empty((n, 3), dtype=torch.float64).pin_memory(); oV = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    nd = g.download_nodes(("X", "V"))
+    hX.numpy()[:] = nd["X"]; hV.numpy()[:] = nd["V"]
+    e2e_steps = max(3, min(args.steps, 50))
+    for _ in range(3):
+        g.step_host(hX.numpy(), hV.numpy(), None, 1, oX.numpy(), oV.numpy()); hX.copy_(oX); hV.copy_(oV)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        g.step_host(hX.numpy(), hV.numpy(), None, 1, oX.numpy(), oV.numpy())
+        hX, oX = oX, hX; hV, oV = oV, hV
+    barrier()
+    e2e_dt = time.perf_counter() - t0
+    t = torch.tensor([e2e_dt], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = ne * world * e2e_steps / float(t.item())
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.orc import Oracle
+        cores = os.cpu_count() or 1
+        o = Oracle(m, threads=cores)
+        o.run_cycles(2)
+        t0 = time.perf_counter(); o.run_cycles(args.cpu_cycles); dt = time.perf_counter() - t0
+        cpu = {"value": ne * args.cpu_cycles / dt, "unit": "element-cycles/s", "cores": cores, "kind": "port",
+               "sample": f"{args.workload}: {ne} elements x {args.cpu_cycles} cycles (oracle restatement, OpenMP over groups of 128)"}
+        o.close()
+
+    if rank == 0:
+        line = {"metric": "element-cycles/sec", "value": value, "unit": "element-cycles/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "family": fam, "elements_per_gpu": ne, "nodes_per_gpu": n,
+                           "l2": "inputs larger than L2 (element state >> 126 MB)" if ne >= 500000 else "working set may fit L2",
+                           "parallelism": f"domains={world}"},
+                "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": "element-cycles/s", "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 48 * n,
+                        "steps": e2e_steps, "call": "orgpu_step_host (X,V pinned host -> 1 cycle -> X,V host)"},
+                "gpu_launches": launches,
+                "kernel_ms": {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
