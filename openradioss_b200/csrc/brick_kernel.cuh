@@ -35,6 +35,14 @@ __device__ __forceinline__ double slen_face(const double* x, const double* y, co
   return E * G - F * F;
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+__device__ __forceinline__ double4 ldg4(const double4* p) {     // read-only 32-byte nodal record
+  const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
 struct Jac { double J1, J2, J3, J4, J5, J6, J7, J8, J9, c5968, c6749, c4857, vol; };
 __device__ __forceinline__ Jac brick_jac(const double* x, const double* y, const double* z)
 {
@@ -55,8 +63,20 @@ __device__ __forceinline__ Jac brick_jac(const double* x, const double* y, const
   return r;
 }
 
+// hourglass shape vectors gamma = h - (h.x) B  (shvis3.F:320-355), from PXkHm
+#define BRICK_GAMMA(G_, PH) \
+        G_[0][0] =  K_ONE - PH[0][0]; G_[0][1] = -K_ONE - PH[0][1]; G_[0][2] =  K_ONE - PH[0][2]; G_[0][3] = -K_ONE - PH[0][3]; \
+        G_[0][4] =  K_ONE + PH[0][2]; G_[0][5] = -K_ONE + PH[0][3]; G_[0][6] =  K_ONE + PH[0][0]; G_[0][7] = -K_ONE + PH[0][1]; \
+        G_[1][0] =  K_ONE - PH[1][0]; G_[1][1] =  K_ONE - PH[1][1]; G_[1][2] = -K_ONE - PH[1][2]; G_[1][3] = -K_ONE - PH[1][3]; \
+        G_[1][4] = -K_ONE + PH[1][2]; G_[1][5] = -K_ONE + PH[1][3]; G_[1][6] =  K_ONE + PH[1][0]; G_[1][7] =  K_ONE + PH[1][1]; \
+        G_[2][0] =  K_ONE - PH[2][0]; G_[2][1] = -K_ONE - PH[2][1]; G_[2][2] = -K_ONE - PH[2][2]; G_[2][3] =  K_ONE - PH[2][3]; \
+        G_[2][4] = -K_ONE + PH[2][2]; G_[2][5] =  K_ONE + PH[2][3]; G_[2][6] =  K_ONE + PH[2][0]; G_[2][7] = -K_ONE + PH[2][1];
+
 template <int JHBE, int ISMSTR>
-__global__ void __launch_bounds__(ORGPU_BLOCK)
+#ifndef ORGPU_BRICK_MINB
+#define ORGPU_BRICK_MINB 3
+#endif
+__global__ void __launch_bounds__(ORGPU_BLOCK, ORGPU_BRICK_MINB)
 brick_forces_kernel(const __grid_constant__ BrickParams P)
 {
   const BrickSG& g = P.sg;
@@ -69,13 +89,27 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     const orgpu_law2& m = g.mat;
     int nc[8];
     #pragma unroll
-    for (int k = 0; k < 8; k++) nc[k] = g.conn[k * np + e];
+    for (int k = 0; k < 8; k++) nc[k] = __ldg(g.conn + k * np + e);
+    if ((threadIdx.x & 7) == 0) {           // slot indices are consumed last: start them toward L2 now
+      #pragma unroll
+      for (int k = 0; k < 8; k++) prefetch_l2(g.slot + k * np + e);
+    }
     double OFFG = g.off[e];
-    ngl = g.ngl[e]; order = g.order0 + e;
+    ngl = __ldg(g.ngl + e); order = g.order0 + e;
+    // start the element-state and slot-index lines moving toward L1/L2 now: they are consumed
+    // after the geometry phase, and one element per thread leaves few warps to hide HBM latency
+    if ((threadIdx.x & 3) == 0) {           // 4 consecutive doubles share a 32-byte sector
+      #pragma unroll
+      for (int k = 0; k < 6; k++) prefetch_l2(g.sig + k * np + e);
+      prefetch_l2(g.eint + e); prefetch_l2(g.rho + e); prefetch_l2(g.qvis + e); prefetch_l2(g.pla + e);
+      prefetch_l2(g.epsd + e); prefetch_l2(g.vol + e); if (m.has_temp) prefetch_l2(g.temp + e);
+    }
     // ---- SCOOR3
     double x[8], y[8], z[8];
     #pragma unroll
-    for (int k = 0; k < 8; k++) { double4 p = P.nd.pos[nc[k]]; x[k] = p.x; y[k] = p.y; z[k] = p.z; }
+    for (int k = 0; k < 8; k++) { double4 p = ldg4(P.nd.pos + nc[k]); x[k] = p.x; y[k] = p.y; z[k] = p.z; }
+    #pragma unroll
+    for (int k = 0; k < 8; k++) prefetch_l1(P.nd.vel + nc[k]);
     double OFF;
     if (ISMSTR <= 4 && fabs(OFFG) > K_ONE) {
       #pragma unroll
@@ -143,10 +177,18 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     const double DELTAX = K_FOUR * VOLN * K_ONE / sqrt(areamax);
     // ---- S8SAV3 (reference configuration refresh; done here while the coordinates are live)
     const bool sav_refresh = (ISMSTR <= 4) && (fabs(OFFG) <= K_ONE);
+    if (sav_refresh) {                       // exclusive with SMALLA3 (OFFG > 1), so the order is free
+      #pragma unroll
+      for (int k = 0; k < 7; k++) {
+        __stcs(&g.smstr[(3 * k) * np + e], x[k] - x[7]);
+        __stcs(&g.smstr[(3 * k + 1) * np + e], y[k] - y[7]);
+        __stcs(&g.smstr[(3 * k + 2) * np + e], z[k] - z[7]);
+      }
+    }
     // ---- velocities (SCOOR3) and SDEFO3
     double vx[8], vy[8], vz[8];
     #pragma unroll
-    for (int k = 0; k < 8; k++) { double4 p = P.nd.vel[nc[k]]; vx[k] = p.x; vy[k] = p.y; vz[k] = p.z; }
+    for (int k = 0; k < 8; k++) { double4 p = ldg4(P.nd.vel + nc[k]); vx[k] = p.x; vy[k] = p.y; vz[k] = p.z; }
     if (OFFG < K_ZERO) {
       #pragma unroll
       for (int k = 0; k < 8; k++) { vx[k] = K_ZERO; vy[k] = K_ZERO; vz[k] = K_ZERO; }
@@ -165,6 +207,29 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       DYZ = PZ[0] * VY17 + PZ[1] * VY28 + PZ[2] * VY35 + PZ[3] * VY46;
       DZX = PX[0] * VZ17 + PX[1] * VZ28 + PX[2] * VZ35 + PX[3] * VZ46;
       DZY = PY[0] * VZ17 + PY[1] * VZ28 + PY[2] * VZ35 + PY[3] * VZ46;
+    }
+    // hourglass mode velocities (SHVIS3 first half) while the nodal velocities are live
+    double HGX[4], HGY[4], HGZ[4];
+    {
+      double G_[3][8];
+      if (JHBE == 0) {
+        #define HG0(V, H) { double V3478 = V[2] - V[3] - V[6] + V[7], V2358 = V[1] - V[2] - V[4] + V[7], \
+                                   V1467 = V[0] - V[3] - V[5] + V[6], V1256 = V[0] - V[1] - V[4] + V[5]; \
+                            H[0] = V1467 - V2358; H[1] = V1467 + V2358; H[2] = V1256 - V3478; H[3] = V1256 + V3478; }
+        HG0(vx, HGX) HG0(vy, HGY) HG0(vz, HGZ)
+        #undef HG0
+      } else {
+        BRICK_GAMMA(G_, PH)
+        #pragma unroll
+        for (int mm = 0; mm < 3; mm++) {
+          HGX[mm] = G_[mm][0] * vx[0] + G_[mm][1] * vx[1] + G_[mm][2] * vx[2] + G_[mm][3] * vx[3] + G_[mm][4] * vx[4] + G_[mm][5] * vx[5] + G_[mm][6] * vx[6] + G_[mm][7] * vx[7];
+          HGY[mm] = G_[mm][0] * vy[0] + G_[mm][1] * vy[1] + G_[mm][2] * vy[2] + G_[mm][3] * vy[3] + G_[mm][4] * vy[4] + G_[mm][5] * vy[5] + G_[mm][6] * vy[6] + G_[mm][7] * vy[7];
+          HGZ[mm] = G_[mm][0] * vz[0] + G_[mm][1] * vz[1] + G_[mm][2] * vz[2] + G_[mm][3] * vz[3] + G_[mm][4] * vz[4] + G_[mm][5] * vz[5] + G_[mm][6] * vz[6] + G_[mm][7] * vz[7];
+        }
+        HGX[3] = vx[0] - vx[1] + vx[2] - vx[3] - vx[4] + vx[5] - vx[6] + vx[7];
+        HGY[3] = vy[0] - vy[1] + vy[2] - vy[3] - vy[4] + vy[5] - vy[6] + vy[7];
+        HGZ[3] = vz[0] - vz[1] + vz[2] - vz[3] - vz[4] + vz[5] - vz[6] + vz[7];
+      }
     }
     const double DT1D2 = K_HALF * DT1;
     if (JHBE >= 2) {
@@ -192,7 +257,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     }
     const double DIVDE = DT1 * (DXX + DYY + DZZ);        // sforc3.F:790
     // ---- SRHO3
-    double VOLO = g.vol[e];
+    double VOLO = __ldg(g.vol + e);
     double RHON = g.rho[e];
     double EINT = g.eint[e];
     double DVOL;
@@ -230,14 +295,6 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
         g.smstr[(3 * k) * np + e] = X - Y * WZZ + Z * WYY;
         g.smstr[(3 * k + 1) * np + e] = Y - Z * WXX + X * WZZ;
         g.smstr[(3 * k + 2) * np + e] = Z - X * WYY + Y * WXX;
-      }
-    }
-    if (sav_refresh) {
-      #pragma unroll
-      for (int k = 0; k < 7; k++) {
-        g.smstr[(3 * k) * np + e] = x[k] - x[7];
-        g.smstr[(3 * k + 1) * np + e] = y[k] - y[7];
-        g.smstr[(3 * k + 2) * np + e] = z[k] - z[7];
       }
     }
     // ---- MMAIN pre-law (mmain.F90:597-800)
@@ -398,30 +455,9 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       else FCL = CAQ * RHON * pow(VOLN, K_TWO_THIRD);
       FCQ = FCL * CAQ * K_HUNDRED;
       FCL = FCL * SSP;
-      double HGX[4], HGY[4], HGZ[4];
       double G_[3][8];
-      if (JHBE == 0) {
-        #define HG0(V, H) { double V3478 = V[2] - V[3] - V[6] + V[7], V2358 = V[1] - V[2] - V[4] + V[7], \
-                                   V1467 = V[0] - V[3] - V[5] + V[6], V1256 = V[0] - V[1] - V[4] + V[5]; \
-                            H[0] = V1467 - V2358; H[1] = V1467 + V2358; H[2] = V1256 - V3478; H[3] = V1256 + V3478; }
-        HG0(vx, HGX) HG0(vy, HGY) HG0(vz, HGZ)
-        #undef HG0
-      } else {
-        G_[0][0] =  K_ONE - PH[0][0]; G_[0][1] = -K_ONE - PH[0][1]; G_[0][2] =  K_ONE - PH[0][2]; G_[0][3] = -K_ONE - PH[0][3];
-        G_[0][4] =  K_ONE + PH[0][2]; G_[0][5] = -K_ONE + PH[0][3]; G_[0][6] =  K_ONE + PH[0][0]; G_[0][7] = -K_ONE + PH[0][1];
-        G_[1][0] =  K_ONE - PH[1][0]; G_[1][1] =  K_ONE - PH[1][1]; G_[1][2] = -K_ONE - PH[1][2]; G_[1][3] = -K_ONE - PH[1][3];
-        G_[1][4] = -K_ONE + PH[1][2]; G_[1][5] = -K_ONE + PH[1][3]; G_[1][6] =  K_ONE + PH[1][0]; G_[1][7] =  K_ONE + PH[1][1];
-        G_[2][0] =  K_ONE - PH[2][0]; G_[2][1] = -K_ONE - PH[2][1]; G_[2][2] = -K_ONE - PH[2][2]; G_[2][3] =  K_ONE - PH[2][3];
-        G_[2][4] = -K_ONE + PH[2][2]; G_[2][5] =  K_ONE + PH[2][3]; G_[2][6] =  K_ONE + PH[2][0]; G_[2][7] = -K_ONE + PH[2][1];
-        #pragma unroll
-        for (int mm = 0; mm < 3; mm++) {
-          HGX[mm] = G_[mm][0] * vx[0] + G_[mm][1] * vx[1] + G_[mm][2] * vx[2] + G_[mm][3] * vx[3] + G_[mm][4] * vx[4] + G_[mm][5] * vx[5] + G_[mm][6] * vx[6] + G_[mm][7] * vx[7];
-          HGY[mm] = G_[mm][0] * vy[0] + G_[mm][1] * vy[1] + G_[mm][2] * vy[2] + G_[mm][3] * vy[3] + G_[mm][4] * vy[4] + G_[mm][5] * vy[5] + G_[mm][6] * vy[6] + G_[mm][7] * vy[7];
-          HGZ[mm] = G_[mm][0] * vz[0] + G_[mm][1] * vz[1] + G_[mm][2] * vz[2] + G_[mm][3] * vz[3] + G_[mm][4] * vz[4] + G_[mm][5] * vz[5] + G_[mm][6] * vz[6] + G_[mm][7] * vz[7];
-        }
-        HGX[3] = vx[0] - vx[1] + vx[2] - vx[3] - vx[4] + vx[5] - vx[6] + vx[7];
-        HGY[3] = vy[0] - vy[1] + vy[2] - vy[3] - vy[4] + vy[5] - vy[6] + vy[7];
-        HGZ[3] = vz[0] - vz[1] + vz[2] - vz[3] - vz[4] + vz[5] - vz[6] + vz[7];
+      if (JHBE != 0) {
+        BRICK_GAMMA(G_, PH)
       }
       double HX[4], HY[4], HZ[4];
       #pragma unroll
@@ -471,16 +507,21 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       for (int k = 0; k < 8; k++) { F1[k] = K_ZERO; F2[k] = K_ZERO; F3[k] = K_ZERO; }
     }
     STI = K_FOURTH * STI;
+    // all eight FSKY slots in one batch of read-only loads ahead of the row stores: a load placed
+    // between the stores would serialise behind them (it may alias them as far as the compiler knows)
+    int sl[8];
+    #pragma unroll
+    for (int k = 0; k < 8; k++) sl[k] = __ldg(g.slot + k * np + e);
     if (P.roww == 4) {
       #pragma unroll
       for (int k = 0; k < 8; k++) {
-        double4* row = reinterpret_cast<double4*>(P.fsky + (size_t)4 * g.slot[k * np + e]);
-        *row = make_double4(F1[k], F2[k], F3[k], STI);
+        double2* row = reinterpret_cast<double2*>(P.fsky + (size_t)4 * sl[k]);
+        row[0] = make_double2(F1[k], F2[k]); row[1] = make_double2(F3[k], STI);
       }
     } else {
       #pragma unroll
       for (int k = 0; k < 8; k++) {
-        double* row = P.fsky + (size_t)8 * g.slot[k * np + e];
+        double* row = P.fsky + (size_t)8 * sl[k];
         row[0] = F1[k]; row[1] = F2[k]; row[2] = F3[k]; row[6] = STI;
       }
     }

@@ -10,7 +10,7 @@ import numpy as np
 from ._binding import Binding, _opt
 from .model import Model
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "liborgpu.so")
+_LIB_PATH = os.environ.get("ORGPU_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "liborgpu.so")
 _lib = None
 
 EXPORTS = """create destroy last_error upload_nodes set_loads set_bcs set_solids set_shells set_pon
