@@ -50,21 +50,25 @@ typedef struct orgpu_law2 {
   int has_temp;             /* ELBUF L_TEMP>0 (adiabatic heating tracked) */
 } orgpu_law2;
 
-/* /MAT/LAW36 (PLAS_TAB), old-style UPARAM0 view used by SIGEPS36C/SIGEPS36. */
+/* /MAT/LAW36 (PLAS_TAB).  Values are the Starter-computed UPARAM entries SIGEPS36C reads
+ * (starter/source/materials/mat/mat036/hm_read_mat36.F:268-320, engine sigeps36c.F:166-200);
+ * built path: VP=0, FISOKIN=0, no failure (IFAIL=0), no E(epsp) / pressure scaling. */
 typedef struct orgpu_law36 {
   double rho0, young, nu, shear, bulk;
-  double a11, a12, ssp;     /* shells: PM(24), PM(25), PM(27)  */
-  int    nrate;             /* uparam(1): number of yield curves */
-  double epsmax;            /* uparam(2*nrate+7) */
-  double epsr1, epsr2;      /* tension failure strains (uparam(2*nrate+8/9)) */
-  double fisokin;           /* uparam(2*nrate+14) */
-  double rate[ORGPU_MAXFUNC36];   /* uparam(6+j)        strain rates        */
-  double yfac[ORGPU_MAXFUNC36];   /* uparam(6+nrate+j)  curve scale factors */
-  int    ifunc[ORGPU_MAXFUNC36];  /* 0-based curve ids into the function table */
-  int    israte;            /* strain-rate filtering flag (Fsmooth) */
-  double asrate;            /* 2*pi*Fcut */
-  int    vp;                /* 0: total strain rate (only mode built) */
-  double pfac_unused;       /* pressure-dependence not built: must be 0 */
+  double a11, a12, ssp;     /* PM(24), PM(25), PM(27) as CNCOEF3B reads them          */
+  double a1u, a2u;          /* UPARAM(3) = E/(1-nu^2), UPARAM(4) = nu*UPARAM(3)        */
+  double g3;                /* UPARAM(2*nrate+11) = 3G                                 */
+  double soundsp;           /* UPARAM(2*nrate+18) shell sound speed                    */
+  double nu_mnu, t_pnu, u_mnu; /* UPARAM(2*nrate+19..21): nu/(1-nu), 3/(1+nu), 1/(1-nu) */
+  double epsmax;            /* UPARAM(2*nrate+7)  (INFINITY when unset)                */
+  double fisokin;           /* UPARAM(2*nrate+14) must be 0                            */
+  double asrate;            /* PM(9) = 2*pi*Fcut                                       */
+  double rate[ORGPU_MAXFUNC36];   /* UPARAM(6+j)        strain rates                   */
+  double yfac[ORGPU_MAXFUNC36];   /* UPARAM(6+nrate+j)  curve scale factors            */
+  int    ifunc[ORGPU_MAXFUNC36];  /* 0-based curve ids into the function table         */
+  int    nrate;             /* UPARAM(1)                                               */
+  int    israte;            /* IPM(3)                                                  */
+  int    vp, ifail, yldcheck, ismooth; /* UPARAM(2*nrate+26..29)                       */
 } orgpu_law36;
 
 /* Function table TF/NPF for LAW36 curves: curve c occupies points
@@ -80,18 +84,20 @@ typedef struct orgpu_prop_solid {
   int    ismstr;        /* IPARG(9): 1,2,4                             */
 } orgpu_prop_solid;
 
-/* /PROP/SHELL (IGTYP 1) slots read on the path */
+/* /PROP/SHELL (IGTYP 1) slots read on the path (starter hm_read_prop01.F:156-262) */
 typedef struct orgpu_prop_shell {
-  double thick;         /* GEO(1)                                     */
-  double h1, h2, h3;    /* GEO(13:15) BT hourglass hm, hf, hr         */
-  double srh1, srh2, srh3; /* GEO(18:20)                              */
-  double shf;           /* GEO(38) shear factor (5/6 default)         */
-  double fac1_qeph;     /* GEO(17): QEPH hourglass plasticity factor  */
-  int    npt;           /* IPARG(6)                                   */
-  int    ismstr;        /* IPARG(9)                                   */
-  int    ithk;          /* IPARG(28)                                  */
-  int    ipla;          /* IPARG(29)                                  */
-  int    ihbe;          /* Ishell: 1..4 BT, 24 QEPH                   */
+  double thick;         /* GEO(1)  THKE                                           */
+  double h1, h2, h3;    /* BT: GEO(13:15) hm, hf, hr ; QEPH: h1 = GEO(13) = Dn    */
+  double srh1, srh2, srh3; /* GEO(18:20)                                          */
+  double shf;           /* GEO(38) shear factor (5/6; 0 when NPT=1)               */
+  double cvis;          /* QEPH: GEO(17) = hourglass factor FAC1 (default 1)      */
+  double dm;            /* GROUP_PARAM%VISC_DM membrane damping                   */
+  int    npt;           /* IPARG(6)                                               */
+  int    ismstr;        /* IPARG(9)                                               */
+  int    ithk;          /* IPARG(28)                                              */
+  int    ipla;          /* IPARG(29)                                              */
+  int    ihbe;          /* Ishell: 1..4 BT (JHBE<11), 24 QEPH                     */
+  int    istrain;       /* IPARG(44): accumulate GBUF%STRA                        */
 } orgpu_prop_shell;
 
 /* Engine-wide scalars (COMMON blocks / engine deck) the path reads */

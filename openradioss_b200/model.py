@@ -24,10 +24,10 @@ class Law2(C.Structure):
 
 
 class Law36(C.Structure):
-    _fields_ = [(n, d) for n in "rho0 young nu shear bulk a11 a12 ssp".split()] + \
-               [("nrate", i), ("epsmax", d), ("epsr1", d), ("epsr2", d), ("fisokin", d),
-                ("rate", d * MAXFUNC36), ("yfac", d * MAXFUNC36), ("ifunc", i * MAXFUNC36),
-                ("israte", i), ("asrate", d), ("vp", i), ("pfac_unused", d)]
+    _fields_ = [(n, d) for n in ("rho0 young nu shear bulk a11 a12 ssp a1u a2u g3 soundsp nu_mnu t_pnu u_mnu "
+                                 "epsmax fisokin asrate").split()] + \
+               [("rate", d * MAXFUNC36), ("yfac", d * MAXFUNC36), ("ifunc", i * MAXFUNC36)] + \
+               [(n, i) for n in "nrate israte vp ifail yldcheck ismooth".split()]
 
 
 class PropSolid(C.Structure):
@@ -35,8 +35,8 @@ class PropSolid(C.Structure):
 
 
 class PropShell(C.Structure):
-    _fields_ = [(n, d) for n in "thick h1 h2 h3 srh1 srh2 srh3 shf fac1_qeph".split()] + \
-               [(n, i) for n in "npt ismstr ithk ipla ihbe".split()]
+    _fields_ = [(n, d) for n in "thick h1 h2 h3 srh1 srh2 srh3 shf cvis dm".split()] + \
+               [(n, i) for n in "npt ismstr ithk ipla ihbe istrain".split()]
 
 
 class Control(C.Structure):
