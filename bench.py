@@ -39,10 +39,10 @@ def workload(name, rank=0):
         return meshgen.taylor_bar(1), "brick"
     if name == "brick_small":
         return meshgen.hex_block(40, 40, 40, 40.0, 40.0, 40.0, vrand=1.0), "brick"
-    if name == "c2_plate_qeph_1m":
-        return meshgen.plate_qeph(1000, 1000), "shell"
+    if name == "c2_plate_qeph_1m":          # C2: 1000 x 1000 QEPH shells, LAW36, NPT=5, clamped, pressure
+        return meshgen.plate_c2(1), "shell"
     if name == "plate_small":
-        return meshgen.plate_qeph(200, 200), "shell"
+        return meshgen.plate_c2(5), "shell"
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -113,7 +113,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="orgpu", choices=["orgpu", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("ORGPU_WORKLOAD", "c5_brick_slab_2m"))
+    ap.add_argument("--workload", default=os.environ.get("ORGPU_WORKLOAD", "c2_plate_qeph_1m"))
     ap.add_argument("--cpu-cycles", type=int, default=20, help="cycles of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -46,6 +46,8 @@ typedef struct orgpu_law2 {
   double tini;              /* initial element temperature     */
   double pshift;            /* PM(88) pressure shift           */
   double a11, a12, ssp;     /* shells: PM(24), PM(25), PM(27)  */
+  double gsr, a11sr, a12sr, nusr; /* QEPH: PM(12), PM(13), PM(14), PM(190) = sqrt(G, A11, A12, nu)
+                                     (starter/source/materials/mat/hm_read_mat.F90:1638-1641) */
   int iform, icc, vp, israte; /* iparam(1:4) */
   int has_temp;             /* ELBUF L_TEMP>0 (adiabatic heating tracked) */
 } orgpu_law2;
@@ -56,6 +58,8 @@ typedef struct orgpu_law2 {
 typedef struct orgpu_law36 {
   double rho0, young, nu, shear, bulk;
   double a11, a12, ssp;     /* PM(24), PM(25), PM(27) as CNCOEF3B reads them          */
+  double gsr, a11sr, a12sr, nusr; /* PM(12), PM(13), PM(14), PM(190): sqrt(G, A11, A12, nu)
+                                     (starter/source/materials/mat/hm_read_mat.F90:1638-1641) */
   double a1u, a2u;          /* UPARAM(3) = E/(1-nu^2), UPARAM(4) = nu*UPARAM(3)        */
   double g3;                /* UPARAM(2*nrate+11) = 3G                                 */
   double soundsp;           /* UPARAM(2*nrate+18) shell sound speed                    */
@@ -90,6 +94,7 @@ typedef struct orgpu_prop_shell {
   double h1, h2, h3;    /* BT: GEO(13:15) hm, hf, hr ; QEPH: h1 = GEO(13) = Dn    */
   double srh1, srh2, srh3; /* GEO(18:20)                                          */
   double shf;           /* GEO(38) shear factor (5/6; 0 when NPT=1)               */
+  double shfsr;         /* GEO(100) = sqrt(GEO(38)) (starter hm_read_properties.F:796) */
   double cvis;          /* QEPH: GEO(17) = hourglass factor FAC1 (default 1)      */
   double dm;            /* GROUP_PARAM%VISC_DM membrane damping                   */
   int    npt;           /* IPARG(6)                                               */

@@ -241,7 +241,7 @@ int orgpu_finalize(orgpu_engine* e)
     CUDA_OK(cudaMemcpy(e->d_adsky, a0.data(), 4 * a0.size(), cudaMemcpyHostToDevice)); e->nd.adsky = e->d_adsky; }
   int order = 0, blk = 0; e->fa.nsg = 0;
   // shells are processed first (FORINTC resol.F:4138), solids after (FORINT resol.F:4225)
-  { int rc = shell_build_supergroups(e->cgroups, e->csg, e->ixc, e->iadc, e->npf, e->tf, e->ctl, order, blk, e->fa); if (rc) return rc; }
+  { int rc = shell_build_supergroups(e->cgroups, e->csg, e->ixc, e->iadc, e->npf, e->tf, e->ctl, e->numnod, e->lsky, order, blk, e->fa); if (rc) return rc; }
   // consecutive solid groups with identical material / property fuse into one super-group
   size_t gi = 0;
   while (gi < e->sgroups.size()) {

@@ -1,0 +1,448 @@
+// shell_common.cuh -- 4-node shell super-groups: device layout and the through-thickness material
+// loop shared by the QEPH (CZFORC3) and Belytschko-Tsay (CFORC3) kernels.
+//
+// Device layout of ELBUF for one super-group (consecutive groups with identical family, law,
+// property): every field is SoA over ne_pad elements, component-major like the reference's
+// G_BUFEL_/L_BUFEL_ (elbufdef_mod.F90:739-1013, 1184-1300) so a warp reads contiguous doubles.
+// Per-integration-point fields are IP-major: sig[(ipt*5+k)*ne_pad + e] (the reference GPU path
+// flattens the same way, shell_internal_forces.F90:829-886).
+//
+// The material loop restates, one element per thread, all in registers:
+//   CMAIN3 -> LAYINI (layini.F:246-254) -> MULAWC (mulawc.F90:542-604, 718-1114, 2630-2662,
+//   2818-2845, 2934-3091) with SIGEPS36C (sigeps36c.F:171-661, VP=0) + VINTER (vinter.F:100-130)
+//   or SIGEPS02C (sigeps02c.F:91-230) + M2CPLR (m2cplr.F:108-507).
+#pragma once
+#include "common.cuh"
+#include "../../include/or_quadrature.h"
+
+struct ShellSG {
+  int ne, ne_pad, order0, blk0;
+  int law, npt, nvartmp, nhourg;
+  const int* conn;            // [4][ne_pad] 0-based node
+  const int* slot;            // [4][ne_pad] 0-based FSKY slot
+  const int* ngl;             // user ids
+  double *forc, *mom, *eint;  // [5],[3],[2]
+  double *thk, *off, *stra, *epsd, *hourg, *smstr;   // [1],[1],[8],[1],[nhourg],[6]
+  const double* thke;         // initial thickness (read only when ITHK=0)
+  double *sig, *pla, *epsd_ip, *temp;  // [npt*5], [npt], [npt], [npt]
+  int* vartmp;                // [npt*nvartmp]
+  const double* tf; const int* npf;    // LAW36 function table (pairs), 0-based curve starts
+  orgpu_law2 m2; orgpu_law36 m36; orgpu_prop_shell prop;
+  double dtfac;               // DTFAC1(3)
+};
+
+struct ShellParams {
+  ShellSG sg; DevNodes nd; double* fsky; CycleState* cs; DtBlocks db; FinalizeArgs fa;
+};
+
+__constant__ double c_Z0[121];
+__constant__ double c_WF[121];
+__constant__ double c_WM[121];
+
+// strains handed to the material loop and what comes back (the MULAWC argument list, reduced)
+struct MatIO {
+  double exx, eyy, exy, exz, eyz, kxx, kyy, kxy;   // in : increments
+  double area, thk0, gs, rho, epsd_pg;             // in
+  double off;                                      // in/out
+  double ssp, viscmx, sigy, zcfac1, zcfac2, vol0;  // out (ssp in: PM(27))
+  double fo[5], mo[3];                             // out: new GBUF%FOR / GBUF%MOM
+};
+
+// VINTER for one element: forward-only cursor walk + linear interpolation (vinter.F:100-130)
+__device__ __forceinline__ void vinter1(const double* __restrict__ tf, int iad, int npts, int& ipos,
+                                        double x, double& dydx, double& y)
+{
+  const int ilen = npts - 1 - ipos;
+  for (int j = 1; j <= ilen - 1; j++) {
+    if (x > __ldg(tf + 2 * (iad + ipos + 1))) ipos++; else break;
+  }
+  const double2 p1 = __ldg(reinterpret_cast<const double2*>(tf) + iad + ipos);
+  const double2 p2 = __ldg(reinterpret_cast<const double2*>(tf) + iad + ipos + 1);
+  dydx = (p2.y - p1.y) / (p2.x - p1.x);
+  y = p1.y + dydx * (x - p1.x);
+}
+
+struct IpState { double sxx, syy, sxy, syz, szx; };
+
+// ---- SIGEPS36C, VP = 0 -------------------------------------------------------------------
+__device__ __forceinline__ void law36_ip(const ShellSG& g, int e, int ipt, int ipla, double asrate,
+                                         double dexx, double deyy, double dexy, double deyz, double dezx, double dtinv,
+                                         double thklyl, double gs, double epsd_pg, double off,
+                                         IpState& s, double& thk, double& ssp, double& etse, double& yld_out)
+{
+  const orgpu_law36& m = g.m36;
+  const int np = g.ne_pad;
+  const double E = m.young, A1 = m.a1u, A2 = m.a2u, G = m.shear, G3 = m.g3;
+  ssp = m.soundsp; etse = K_ONE;
+  double pla = g.pla[(size_t)ipt * np + e];
+  // elastic predictor
+  const double sox = s.sxx, soy = s.syy, soxy = s.sxy;
+  s.sxx = sox + A1 * dexx + A2 * deyy;
+  s.syy = soy + A2 * dexx + A1 * deyy;
+  s.sxy = soxy + G * dexy;
+  s.syz = s.syz + gs * deyz;
+  s.szx = s.szx + gs * dezx;
+  // strain rate
+  double epsd;
+  if (m.israte == 0) {
+    const double exx = dexx * dtinv, eyy = deyy * dtinv, exy = dexy * dtinv;
+    epsd = K_HALF * (fabs(exx + eyy) + sqrt((exx - eyy) * (exx - eyy) + exy * exy));
+  } else {
+    epsd = asrate * epsd_pg + (K_ONE - asrate) * g.epsd_ip[(size_t)ipt * np + e];
+  }
+  g.epsd_ip[(size_t)ipt * np + e] = epsd;
+  // yield stress and hardening modulus from the tabulated curves
+  double YLD, H;
+  int* vt = g.vartmp + (size_t)ipt * g.nvartmp * np + e;
+  if (m.nrate == 1) {
+    int ipos = vt[2 * np];
+    const int f = m.ifunc[0];
+    const int i0 = __ldg(g.npf + f), i1 = __ldg(g.npf + f + 1);
+    double dydx, y1;
+    vinter1(g.tf, i0, i1 - i0, ipos, pla, dydx, y1);
+    vt[2 * np] = ipos;
+    const double FACT = K_ONE * K_ONE * (m.yfac[0] * K_ONE);
+    H = dydx * FACT;
+    YLD = y1 * FACT;
+  } else {
+    int JJ = 1;
+    for (int J = 2; J <= m.nrate - 1; J++) if (epsd >= m.rate[J - 1]) JJ = J;
+    double RFAC;
+    if (m.ismooth == 2) {
+      const double EPSP1 = fmax(m.rate[JJ - 1], K_EM20), EPSP2 = m.rate[JJ];
+      RFAC = log(fmax(epsd, K_EM20) / EPSP1) / log(EPSP2 / EPSP1);
+    } else {
+      const double EPSP1 = m.rate[JJ - 1], EPSP2 = m.rate[JJ];
+      RFAC = (epsd - EPSP1) / (EPSP2 - EPSP1);
+    }
+    const double YFAC1 = m.yfac[JJ - 1] * K_ONE, YFAC2 = m.yfac[JJ] * K_ONE;
+    const int f1 = m.ifunc[JJ - 1], f2 = m.ifunc[JJ];
+    int ipos1 = vt[(size_t)(1 + JJ) * np], ipos2 = vt[(size_t)(2 + JJ) * np];
+    double dydx1, y1, dydx2, y2;
+    { const int i0 = __ldg(g.npf + f1), i1 = __ldg(g.npf + f1 + 1); vinter1(g.tf, i0, i1 - i0, ipos1, pla, dydx1, y1); }
+    { const int i0 = __ldg(g.npf + f2), i1 = __ldg(g.npf + f2 + 1); vinter1(g.tf, i0, i1 - i0, ipos2, pla, dydx2, y2); }
+    y1 = y1 * YFAC1; y2 = y2 * YFAC2;
+    YLD = K_ONE * (y1 + RFAC * (y2 - y1));
+    YLD = fmax(YLD, K_EM20);
+    dydx1 = dydx1 * YFAC1; dydx2 = dydx2 * YFAC2;
+    H = K_ONE * (dydx1 + RFAC * (dydx2 - dydx1));
+    YLD = YLD * fmax(K_ZERO, K_ONE);
+    H = H * fmax(K_ZERO, K_ONE);
+    vt[(size_t)(1 + JJ) * np] = ipos1; vt[(size_t)(2 + JJ) * np] = ipos2;
+  }
+  if (m.yldcheck == 1) YLD = fmax(YLD, K_EM20);
+  // projection on the yield surface
+  if (ipla == 0) {
+    const double NU3 = K_ONE - m.nu_mnu;
+    const double SVM2 = s.sxx * s.sxx + s.syy * s.syy - s.sxx * s.syy + K_THREE * s.sxy * s.sxy;
+    if (SVM2 > YLD * YLD) {
+      const double SVM = sqrt(SVM2);
+      const double R = YLD / SVM;
+      s.sxx = s.sxx * R; s.syy = s.syy * R; s.sxy = s.sxy * R;
+      const double DPLA = off * SVM * (K_ONE - R) / (G3 + H);
+      pla = pla + DPLA;
+      double DEZZ = (YLD != 0) ? DPLA * K_HALF * (s.sxx + s.syy) / YLD : K_ZERO;
+      DEZZ = -(dexx + deyy) * m.nu_mnu - NU3 * DEZZ;
+      thk = thk + DEZZ * thklyl * off;
+      etse = H / (H + E);
+    }
+  } else if (ipla == 1) {
+    H = fmax(K_ZERO, H);
+    double S1 = s.sxx + s.syy, S2 = s.sxx - s.syy; const double S3 = s.sxy;
+    const double AA = K_FOURTH * S1 * S1;
+    const double BB = K_THREE_OVER_4 * S2 * S2 + K_THREE * S3 * S3;
+    const double SVM2 = AA + BB;
+    { const double DEZZ = -(dexx + deyy) * m.nu_mnu; thk = thk + DEZZ * thklyl * off; }
+    if (SVM2 > YLD * YLD && off == K_ONE) {
+      const double SVM = sqrt(SVM2);
+      double DPLA_J = (SVM - YLD) / (G3 + H);
+      etse = H / (H + E);
+      const double HI = H * (K_ONE - m.fisokin);
+      const double HK = K_TWO_THIRD * H * m.fisokin;
+      const double NU3 = K_ONE - m.nu_mnu;
+      const double AAA = K_THREE * HK / E;
+      const double NU11 = m.u_mnu + AAA, NU21 = m.t_pnu + AAA;
+      double DPLA_I = K_ZERO, DR = K_ZERO, PP = K_ONE, QQ = K_ONE;
+      #pragma unroll
+      for (int N = 0; N < 3; N++) {                       // NITER = 3 (sigeps36c.F:167)
+        DPLA_I = DPLA_J;
+        const double YLD_I = YLD + HI * DPLA_I;
+        DR = K_HALF * E * DPLA_I / YLD_I;
+        PP = K_ONE / (K_ONE + DR * NU11);
+        QQ = K_ONE / (K_ONE + DR * NU21);
+        const double P2 = PP * PP, Q2 = QQ * QQ;
+        const double F = AA * P2 + BB * Q2 - YLD_I * YLD_I;
+        double DF = -(AA * NU11 * P2 * PP + BB * NU21 * Q2 * QQ) * (E - K_TWO * DR * HI) / YLD_I - K_TWO * HI * YLD_I;
+        DF = copysign(fmax(fabs(DF), K_EM20), DF);
+        DPLA_J = (DPLA_I > K_ZERO) ? fmax(K_ZERO, DPLA_I - F / DF) : K_ZERO;
+      }
+      pla = pla + DPLA_I;
+      S1 = (s.sxx + s.syy) * PP;
+      S2 = (s.sxx - s.syy) * QQ;
+      s.sxx = K_HALF * (S1 + S2);
+      s.syy = K_HALF * (S1 - S2);
+      s.sxy = s.sxy * QQ;
+      { const double DEZZ = -NU3 * DR * S1 / E; thk = thk + DEZZ * thklyl * off; }
+      YLD = YLD + HI * DPLA_I;
+    }
+  } else {
+    H = fmax(K_ZERO, H);
+    const double SVM2 = s.sxx * s.sxx + s.syy * s.syy - s.sxx * s.syy + K_THREE * s.sxy * s.sxy;
+    { const double DEZZ = -(dexx + deyy) * m.nu_mnu; thk = thk + DEZZ * thklyl * off; }
+    const double YLD2 = YLD * YLD;
+    if (SVM2 > YLD2 && off == K_ONE) {
+      const double NU3 = K_ONE - m.nu_mnu;
+      const double A = (SVM2 - YLD2) / (K_FIVE * SVM2 + K_THREE * (-s.sxx * s.syy + s.sxy * s.sxy));
+      const double S1 = (K_ONE - K_TWO * A) * s.sxx + A * s.syy;
+      const double S2 = A * s.sxx + (K_ONE - K_TWO * A) * s.syy;
+      const double S3 = (K_ONE - K_THREE * A) * s.sxy;
+      s.sxx = S1; s.syy = S2; s.sxy = S3;
+      double SVM = sqrt(SVM2);
+      const double DPLA = off * (SVM - YLD) / (G3 + H);
+      YLD = YLD + H * (K_ONE - m.fisokin) * DPLA;
+      SVM = sqrt(s.sxx * s.sxx + s.syy * s.syy - s.sxx * s.syy + K_THREE * s.sxy * s.sxy);
+      const double R = fmin(K_ONE, YLD / fmax(K_EM20, SVM));
+      s.sxx = s.sxx * R; s.syy = s.syy * R; s.sxy = s.sxy * R;
+      pla = pla + DPLA;
+      double DEZZ = DPLA * K_HALF * (s.sxx + s.syy) / YLD;
+      DEZZ = -NU3 * DEZZ;
+      thk = thk + DEZZ * thklyl * off;
+      etse = H / (H + E);
+    }
+  }
+  g.pla[(size_t)ipt * np + e] = pla;
+  yld_out = YLD;
+}
+
+// ---- SIGEPS02C + M2CPLR (FISOKIN = 0) --------------------------------------------------------
+__device__ __forceinline__ void law2_ip(const ShellSG& g, int e, int ipt, int ipla, int npttot, double dt1, double asrate,
+                                        double dexx, double deyy, double dexy, double deyz, double dezx, double dtinv,
+                                        double thklyl, double gs, double epsd_pg, double& off, double off_old, int& ioff_duct,
+                                        double& epchk, IpState& s, double& thk, double& etse, double& sigy)
+{
+  const orgpu_law2& m = g.m2;
+  const int np = g.ne_pad;
+  const double SMALL = K_EM7;
+  const double young = m.young, gg = m.shear, nu = m.nu;
+  const double a11 = young / (K_ONE - nu * nu);
+  const double a12 = a11 * nu;
+  const double cn = m.cn;
+  const double epdr = fmax(m.epdr * dt1, K_EM20);
+  double pla = g.pla[(size_t)ipt * np + e];
+  double epsd = g.epsd_ip[(size_t)ipt * np + e];
+  const bool has_temp = m.has_temp != 0;
+  const double tempel = has_temp ? g.temp[(size_t)ipt * np + e] : K_ZERO;
+  double z3, z4, m_exp, tstar = K_ZERO;
+  if (m.iform == 1) { z3 = m.z3; z4 = m.z4; m_exp = K_ONE; if (has_temp) tstar = fmax(K_ZERO, (tempel - m.tref) / fmax(m.tmelt - m.tref, K_EM20)); }
+  else { z3 = K_ZERO; z4 = K_ZERO; m_exp = m.z3; tstar = fmax(K_ZERO, (tempel - m.tref) / (m.tmelt - m.tref)); }
+  double EZZ = K_ZERO, epsdot = K_ZERO;
+  if (m.vp == 1) epsdot = epsd * dt1;
+  else if (m.vp == 2) { epsd = asrate * epsd_pg + (K_ONE - asrate) * epsd; epsdot = epsd * dt1; }
+  else if (m.vp == 3) {
+    const double exx = dexx * dtinv, eyy = deyy * dtinv, exy = dexy * dtinv;
+    const double DAV = (exx + eyy) * K_THIRD;
+    const double D1 = exx - DAV, D2 = eyy - DAV, D3 = -DAV, D4 = K_HALF * exy;
+    epsdot = K_HALF * (D1 * D1 + D2 * D2 + D3 * D3) + D4 * D4;
+    epsdot = sqrt(K_THREE * epsdot) / K_THREE_HALF;
+    if (m.israte > 0) epsdot = asrate * epsdot + (K_ONE - asrate) * epsd;
+    epsd = epsdot; epsdot = epsdot * dt1;
+  }
+  // M2CPLR
+  double CA = m.ca, CB = m.cb, YMAX = m.sigmx, H = K_ZERO, DPLA = K_ZERO, YLD;
+  etse = K_ONE;
+  s.sxx = s.sxx + a11 * dexx + a12 * deyy;
+  { const double t = s.syy + a12 * dexx + a11 * deyy; s.syy = t; }
+  s.sxy = s.sxy + gg * dexy;
+  s.syz = s.syz + gs * deyz;
+  s.szx = s.szx + gs * dezx;
+  double EPSP = epsdot, Q;
+  if (m.cc != K_ZERO) {
+    if (m.iform == 0) {
+      if (m.israte == 0 && m.vp == 2) EPSP = fmax(fmax(fabs(dexx), fabs(deyy)), K_HALF * fabs(dexy));
+      EPSP = fmax(EPSP, epdr);
+      const double LOGEP = log(EPSP / epdr);
+      if (tstar == K_ZERO) Q = (K_ONE + m.cc * LOGEP);
+      else Q = (K_ONE + m.cc * LOGEP) * (K_ONE - exp(m_exp * log(tstar)));
+      Q = fmax(Q, K_EM20);
+      CA = CA * Q; CB = CB * Q;
+      if (m.icc == 1) YMAX = YMAX * Q;
+    } else if (m.iform == 1) {
+      if (m.israte == 0 && m.vp == 2) EPSP = fmax(fmax(fabs(dexx), fabs(deyy)), K_HALF * fabs(dexy));
+      EPSP = fmax(EPSP, K_EM20);
+      Q = log(EPSP / epdr);
+      Q = m.cc * exp((-z3 + z4 * Q) * tempel);
+      if (m.icc == 1) YMAX = YMAX + Q;
+      CA = CA + Q;
+    }
+  } else if (m.iform == 0) {
+    if (tstar != K_ZERO) { Q = K_ONE - exp(m_exp * log(tstar)); Q = fmax(Q, K_EM20); CA = CA * Q; CB = CB * Q; }
+  }
+  if (pla == K_ZERO) YLD = CA;
+  else { const double BETA = CB * (K_ONE - m.fisokin); YLD = CA + BETA * exp(cn * log(pla)); }
+  YLD = fmin(YLD, YMAX);
+  if (ipla == 0) {
+    const double SVM = sqrt(s.sxx * s.sxx + s.syy * s.syy - s.sxx * s.syy + K_THREE * s.sxy * s.sxy);
+    const double R = fmin(K_ONE, YLD / (SVM + K_EM15));
+    if (R < K_ONE) {
+      s.sxx = s.sxx * R; s.syy = s.syy * R; s.sxy = s.sxy * R;
+      DPLA = off_old * fmax(K_ZERO, (SVM - YLD) / young);
+      const double S1 = K_HALF * (s.sxx + s.syy);
+      EZZ = DPLA * S1 / YLD;
+      pla = pla + DPLA;
+      epchk = fmax(pla, epchk);
+      H = (YLD >= YMAX) ? K_ZERO : cn * CB * exp((cn - K_ONE) * log(pla + SMALL));
+      etse = H / (H + young);
+    }
+  } else if (ipla == 1) {
+    double S1 = s.sxx + s.syy, S2 = s.sxx - s.syy; const double S3 = s.sxy;
+    const double A = K_FOURTH * S1 * S1;
+    const double B = K_THREE_OVER_4 * S2 * S2 + K_THREE * S3 * S3;
+    const double SVM = sqrt(A + B);
+    if (SVM > YLD && off_old == K_ONE) {
+      const double NU1 = K_ONE / (K_ONE - nu), NU2 = K_ONE / (K_ONE + nu);
+      H = (YLD >= YMAX) ? K_ZERO : cn * CB * exp((cn - K_ONE) * log(pla + SMALL));
+      double DPLA_J = (SVM - YLD) / (K_THREE * gg + H);
+      etse = H / (H + young);
+      const double ANU1 = A * NU1, BNU2 = K_THREE * B * NU2, H2 = K_TWO * H;
+      double DPLA_I = K_ZERO, DR = K_ZERO, P = K_ONE, Qq = K_ONE;
+      #pragma unroll 1
+      for (int N = 0; N < 3; N++) {                       // NMAX = 3 (m2cplr.F:104)
+        DPLA_I = DPLA_J;
+        const double PLA_I = pla + DPLA_I;
+        DPLA = DPLA_J;
+        double YLD_I;
+        if (PLA_I == K_ZERO) YLD_I = fmin(YMAX, CA);
+        else YLD_I = fmin(YMAX, CA + CB * exp(cn * log(PLA_I)));
+        DR = K_HALF * young * DPLA_I / YLD_I;
+        P = K_ONE / (K_ONE + DR * NU1);
+        Qq = K_ONE / (K_ONE + K_THREE * DR * NU2);
+        const double P2 = P * P, Q2 = Qq * Qq;
+        const double F = A * P2 + B * Q2 - YLD_I * YLD_I;
+        const double DF = -(ANU1 * P2 * P + BNU2 * Q2 * Qq) * (young - DR * H2) / YLD_I - H2 * YLD_I;
+        DPLA_J = (DPLA_I > K_ZERO) ? fmax(K_ZERO, DPLA_I - F / DF) : K_ZERO;
+      }
+      pla = pla + DPLA_I;
+      epchk = fmax(pla, epchk);
+      S1 = (s.sxx + s.syy) * P;
+      S2 = (s.sxx - s.syy) * Qq;
+      s.sxx = K_HALF * (S1 + S2);
+      s.syy = K_HALF * (S1 - S2);
+      s.sxy = s.sxy * Qq;
+      EZZ = DR * S1 / young;
+    }
+  } else {
+    const double SVM2 = s.sxx * s.sxx + s.syy * s.syy - s.sxx * s.syy + K_THREE * s.sxy * s.sxy;
+    double SVM = sqrt(SVM2);
+    const double YLD2 = YLD * YLD;
+    if (SVM2 > YLD2 && off_old == K_ONE) {
+      H = (YLD >= YMAX) ? K_ZERO : cn * CB * exp((cn - K_ONE) * log(pla + SMALL));
+      etse = H / (H + young);
+      const double AA = (SVM2 - YLD2) / (K_FIVE * SVM2 + K_THREE * (-s.sxx * s.syy + s.sxy * s.sxy));
+      const double S1 = (K_ONE - K_TWO * AA) * s.sxx + AA * s.syy;
+      const double S2 = AA * s.sxx + (K_ONE - K_TWO * AA) * s.syy;
+      const double S3 = (K_ONE - K_THREE * AA) * s.sxy;
+      s.sxx = S1; s.syy = S2; s.sxy = S3;
+      DPLA = off_old * (SVM - YLD) / (K_THREE * gg + H);
+      pla = pla + DPLA;
+      YLD = YLD + H * DPLA;
+      SVM = sqrt(s.sxx * s.sxx + s.syy * s.syy - s.sxx * s.syy + K_THREE * s.sxy * s.sxy);
+      const double R = fmin(K_ONE, YLD / fmax(K_EM20, SVM));
+      s.sxx = s.sxx * R; s.syy = s.syy * R; s.sxy = s.sxy * R;
+      EZZ = DPLA * K_HALF * (s.sxx + s.syy) / YLD;
+    }
+  }
+  if (m.vp == 1) { epsdot = DPLA / fmax(K_EM20, dt1); epsd = asrate * epsdot + (K_ONE - asrate) * epsd; }
+  sigy = sigy + YLD / npttot;
+  if (off == off_old && off > K_ZERO) {
+    if (off == K_ONE && epchk >= m.epmx) { off = K_FOUR_OVER_5; ioff_duct = 1; }
+    else if (off < K_ONE) off = off * K_FOUR_OVER_5;
+  }
+  EZZ = -(dexx + deyy) * nu - (K_ONE - K_TWO * nu) * EZZ;
+  EZZ = EZZ / (K_ONE - nu);
+  thk = thk + EZZ * thklyl * off;
+  if (m.rhocp > K_ZERO && has_temp) g.temp[(size_t)ipt * np + e] = tempel + sigy * DPLA / m.rhocp;
+  g.pla[(size_t)ipt * np + e] = pla;
+  g.epsd_ip[(size_t)ipt * np + e] = epsd;
+}
+
+// ---- CMAIN3 / MULAWC for one element --------------------------------------------------------
+// FLAG_ZCFAC: QEPH (JHBE 21..29) keeps SIGY / ZCFAC for the hourglass plasticity (mulawc.F90:521-522).
+template <int LAW, bool FLAG_ZCFAC>
+__device__ __forceinline__ void shell_material_loop(const ShellSG& g, int e, double dt1, MatIO& io)
+{
+  const int np = g.ne_pad, npt = g.prop.npt;
+  const double DM = g.prop.dm;
+  double* fo = io.fo; double* mo = io.mo;
+  #pragma unroll
+  for (int k = 0; k < 5; k++) fo[k] = g.forc[(size_t)k * np + e];
+  #pragma unroll
+  for (int k = 0; k < 3; k++) mo[k] = g.mom[(size_t)k * np + e];
+  double degmb = fo[0] * io.exx + fo[1] * io.eyy + fo[2] * io.exy + fo[3] * io.eyz + fo[4] * io.exz;
+  double degfx = mo[0] * io.kxx + mo[1] * io.kyy + mo[2] * io.kxy;
+  const double vol0 = io.area * io.thk0;
+  double thkn = g.thk[e];
+  #pragma unroll
+  for (int k = 0; k < 5; k++) fo[k] = K_ZERO;
+  #pragma unroll
+  for (int k = 0; k < 3; k++) mo[k] = K_ZERO;
+  double sigy = io.sigy;
+  if (LAW == 2 || !FLAG_ZCFAC) sigy = K_ZERO;
+  double zcfac1 = K_ZERO, zcfac2 = FLAG_ZCFAC ? K_ONE : K_ZERO, etse = K_ONE;
+  double off = io.off; const double off_old = off;
+  int ioff_duct = 0;
+  double epchk = K_ZERO, viscmx = K_ZERO, ssp = io.ssp;
+  const double dtinv = dt1 / fmax(dt1 * dt1, K_EM20);
+  const int israte = (LAW == 36) ? g.m36.israte : g.m2.israte;
+  const double pm9 = (LAW == 36) ? g.m36.asrate : g.m2.asrate;
+  const double asrate = (israte > 0) ? fmin(K_ONE, pm9 * dt1) : K_ONE;
+  const int qrow = (npt - 1) * 11;
+  for (int ipt = 0; ipt < npt; ipt++) {
+    const double thkly = c_WF[qrow + ipt];
+    const double posly = c_Z0[qrow + ipt] + K_ZERO;
+    const double wmc = c_WM[qrow + ipt];
+    const double thklyl = thkly * io.thk0;
+    const double zt = posly * io.thk0;
+    const double dexx = io.exx + zt * io.kxx;
+    const double deyy = io.eyy + zt * io.kyy;
+    const double dexy = io.exy + zt * io.kxy;
+    double* sg = g.sig + (size_t)ipt * 5 * np + e;
+    IpState s{sg[0], sg[np], sg[2 * (size_t)np], sg[3 * (size_t)np], sg[4 * (size_t)np]};
+    if (LAW == 36) {
+      law36_ip(g, e, ipt, g.prop.ipla, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, thklyl, io.gs, io.epsd_pg, off,
+               s, thkn, ssp, etse, sigy);
+    } else {
+      law2_ip(g, e, ipt, g.prop.ipla, npt, dt1, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, thklyl, io.gs, io.epsd_pg,
+              off, off_old, ioff_duct, epchk, s, thkn, etse, sigy);
+    }
+    viscmx = fmax(DM, viscmx);
+    sg[0] = s.sxx; sg[np] = s.syy; sg[2 * (size_t)np] = s.sxy; sg[3 * (size_t)np] = s.syz; sg[4 * (size_t)np] = s.szx;
+    fo[0] = fo[0] + thkly * s.sxx; fo[1] = fo[1] + thkly * s.syy; fo[2] = fo[2] + thkly * s.sxy;
+    fo[3] = fo[3] + thkly * s.syz; fo[4] = fo[4] + thkly * s.szx;
+    mo[0] = mo[0] + wmc * s.sxx; mo[1] = mo[1] + wmc * s.syy; mo[2] = mo[2] + wmc * s.sxy;
+    if (FLAG_ZCFAC) {
+      if (LAW != 2) zcfac1 = zcfac1 + etse * thkly; else zcfac1 = zcfac1 + etse / npt;
+      zcfac2 = fmin(etse, zcfac2);
+    }
+  }
+  if ((off == K_FOUR_OVER_5 && ioff_duct == 0) || (off > K_ZERO && off_old < K_EM01)) off = K_ZERO;
+  g.thk[e] = fmax(thkn, K_EM30);
+  const double fact = K_ONEP414 * DM;
+  const double visc = fact * ssp * sqrt(io.area) * dtinv * io.rho;
+  fo[0] = fo[0] + visc * (io.exx + K_HALF * io.eyy);
+  fo[1] = fo[1] + visc * (io.eyy + K_HALF * io.exx);
+  fo[2] = fo[2] + visc * io.exy * K_THIRD;
+  #pragma unroll
+  for (int k = 0; k < 5; k++) fo[k] = fo[k] * off;
+  #pragma unroll
+  for (int k = 0; k < 3; k++) mo[k] = mo[k] * off;
+  degmb = degmb + fo[0] * io.exx + fo[1] * io.eyy + fo[2] * io.exy + fo[3] * io.eyz + fo[4] * io.exz;
+  degfx = degfx + mo[0] * io.kxx + mo[1] * io.kyy + mo[2] * io.kxy;
+  const double vol2 = K_HALF * vol0;
+  g.eint[e] = g.eint[e] + degmb * vol2;
+  g.eint[np + e] = g.eint[np + e] + degfx * io.thk0 * vol2;
+  #pragma unroll
+  for (int k = 0; k < 5; k++) g.forc[(size_t)k * np + e] = fo[k];
+  #pragma unroll
+  for (int k = 0; k < 3; k++) g.mom[(size_t)k * np + e] = mo[k];
+  io.off = off; io.ssp = ssp; io.viscmx = viscmx; io.sigy = sigy; io.zcfac1 = zcfac1; io.zcfac2 = zcfac2; io.vol0 = vol0;
+}

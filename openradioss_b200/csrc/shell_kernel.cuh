@@ -1,13 +1,161 @@
-// shell_kernel.cuh -- 4-node shell super-groups (placeholder: the QEPH/BT kernels land next).
+// shell_kernel.cuh -- host side of the 4-node shell path: group registration, the
+// FORINTC_PREPARE_GPU-style fusion of consecutive compatible groups into super-groups
+// (shell_internal_forces.F90:547-558, 829-886), ELBUF -> device SoA, kernel dispatch
+// (forintc.F:383-385 QEPH -> CZFORC3, :452 BT -> CFORC3) and state read-back
+// (shell_gpu_download_state, shell_gpu_driver.cu:743).
 #pragma once
 #include <vector>
+#include <cstring>
 #include "common.cuh"
+#include "shell_common.cuh"
+#include "qeph_kernel.cuh"
+#include "bt_kernel.cuh"
+
 struct HostShellGroup { int nel, nft, law; orgpu_prop_shell prop; orgpu_law2 m2; orgpu_law36 m36; };
-struct ShellSGHost { int first_elem = 0; std::vector<void*> owned; };
-static int shell_add_group(std::vector<HostShellGroup>&, int, int, int, const void*, const orgpu_prop_shell*)
-{ orgpu_set_error("shell groups are not built yet"); return -5; }
-static int shell_build_supergroups(std::vector<HostShellGroup>&, std::vector<ShellSGHost>&, const std::vector<int>&,
-                                   const std::vector<int>&, const std::vector<int>&, const std::vector<double>&,
-                                   const orgpu_control&, int&, int&, FinalizeArgs&) { return 0; }
-static void launch_shell_forces(ShellSGHost&, const DevNodes&, double*, int, CycleState*, const DtBlocks&, const FinalizeArgs&, cudaStream_t) {}
-static int shell_download_state(std::vector<ShellSGHost>&, int, int, double*) { orgpu_set_error("no shell groups"); return -5; }
+struct ShellSGHost { ShellSG d; int first_elem = 0; std::vector<void*> owned; };
+
+static inline bool shell_is_qeph(const orgpu_prop_shell& p) { return p.ihbe >= 21 && p.ihbe <= 29; }
+
+static int shell_add_group(std::vector<HostShellGroup>& groups, int nel, int nft, int law, const void* mat,
+                           const orgpu_prop_shell* prop)
+{
+  if (law != 2 && law != 36) { orgpu_set_error("shell law %d is outside the built path (2, 36)", law); return -5; }
+  if (prop->npt < 1 || prop->npt > 10) { orgpu_set_error("NPT=%d is outside the built path (1..10)", prop->npt); return -5; }
+  if (prop->ipla < 0 || prop->ipla > 2) { orgpu_set_error("Iplas=%d is outside the built path (0,1,2)", prop->ipla); return -5; }
+  if (!(prop->ismstr == 1 || prop->ismstr == 2 || prop->ismstr == 4)) { orgpu_set_error("shell Ismstr=%d is outside the built path (1,2,4)", prop->ismstr); return -5; }
+  const bool qeph = shell_is_qeph(*prop);
+  if (!qeph && !(prop->ihbe >= 0 && prop->ihbe <= 4)) { orgpu_set_error("Ishell=%d is outside the built path (BT 1..4, QEPH 24)", prop->ihbe); return -5; }
+  if (!qeph) { orgpu_set_error("Belytschko-Tsay groups: kernel not built yet"); return -5; }
+  HostShellGroup g; memset(&g, 0, sizeof g);
+  g.nel = nel; g.nft = nft; g.law = law; g.prop = *prop;
+  if (law == 36) {
+    g.m36 = *(const orgpu_law36*)mat;
+    if (g.m36.fisokin != 0.0 || g.m36.vp != 0 || g.m36.ifail != 0) { orgpu_set_error("LAW36 kinematic hardening / VP=1 / failure are outside the built path"); return -5; }
+    if (g.m36.nrate < 1 || g.m36.nrate > ORGPU_MAXFUNC36) { orgpu_set_error("LAW36 NRATE=%d out of range", g.m36.nrate); return -5; }
+  } else {
+    g.m2 = *(const orgpu_law2*)mat;
+    if (g.m2.fisokin != 0.0) { orgpu_set_error("LAW2 kinematic hardening (FISOKIN>0) is outside the built path"); return -5; }
+  }
+  groups.push_back(g);
+  return (int)groups.size() - 1;
+}
+
+template <class T> static int sh_alloc(std::vector<void*>& owned, T** p, size_t n) {
+  *p = nullptr; if (n == 0) return 0;
+  if (cudaMalloc((void**)p, n * sizeof(T)) != cudaSuccess) { orgpu_set_error("cudaMalloc of %zu bytes failed", n * sizeof(T)); return -100; }
+  cudaMemset(*p, 0, n * sizeof(T)); owned.push_back(*p); return 0;
+}
+template <class T> static int sh_upload(std::vector<void*>& owned, T** p, const std::vector<T>& h) {
+  if (sh_alloc(owned, p, h.size())) return -100;
+  if (h.size() && cudaMemcpy(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) { orgpu_set_error("upload failed"); return -100; }
+  return 0;
+}
+
+static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vector<ShellSGHost>& out,
+                                   const std::vector<int>& ixc, const std::vector<int>& iadc,
+                                   const std::vector<int>& npf, const std::vector<double>& tf,
+                                   const orgpu_control& ctl, int numnod, int lsky, int& order, int& blk, FinalizeArgs& fa)
+{
+  if (groups.empty()) return 0;
+  if (!ctl.iroddl) { orgpu_set_error("shell groups need rotational dofs (control.iroddl=1)"); return -4; }
+  cudaMemcpyToSymbol(c_Z0, OR_Z0, sizeof OR_Z0); cudaMemcpyToSymbol(c_WF, OR_WF, sizeof OR_WF); cudaMemcpyToSymbol(c_WM, OR_WM, sizeof OR_WM);
+  // one device copy of the function table, shared by every LAW36 super-group
+  const double* d_tf = nullptr; const int* d_npf = nullptr;
+  size_t gi = 0;
+  while (gi < groups.size()) {
+    size_t gj = gi + 1;
+    while (gj < groups.size() && groups[gj].nft == groups[gj - 1].nft + groups[gj - 1].nel && groups[gj].law == groups[gi].law &&
+           !memcmp(&groups[gj].prop, &groups[gi].prop, sizeof(orgpu_prop_shell)) &&
+           !memcmp(&groups[gj].m2, &groups[gi].m2, sizeof(orgpu_law2)) && !memcmp(&groups[gj].m36, &groups[gi].m36, sizeof(orgpu_law36))) gj++;
+    int ne = 0; for (size_t k = gi; k < gj; k++) ne += groups[k].nel;
+    const HostShellGroup& G = groups[gi];
+    const int nft = G.nft;
+    const int np = ((ne + ORGPU_BLOCK - 1) / ORGPU_BLOCK) * ORGPU_BLOCK;
+    out.emplace_back(); ShellSGHost& S = out.back(); S.first_elem = nft;
+    ShellSG& d = S.d; memset(&d, 0, sizeof d);
+    d.ne = ne; d.ne_pad = np; d.order0 = order; d.blk0 = blk; d.law = G.law; d.npt = G.prop.npt;
+    d.nvartmp = (G.law == 36) ? 2 + G.m36.nrate : 0;
+    d.nhourg = shell_is_qeph(G.prop) ? 12 : 5;
+    d.m2 = G.m2; d.m36 = G.m36; d.prop = G.prop; d.dtfac = ctl.dtfac_shell;
+    if (G.law == 36) {
+      if (npf.empty()) { orgpu_set_error("LAW36 group without a function table (orgpu_set_functions)"); return -4; }
+      for (int j = 0; j < G.m36.nrate; j++) {
+        const int f = G.m36.ifunc[j];
+        if (f < 0 || f + 1 >= (int)npf.size() || npf[f + 1] - npf[f] < 2) { orgpu_set_error("LAW36 curve %d missing or shorter than 2 points", f); return -4; }
+      }
+      if (!d_tf) {
+        double* t; int* n; std::vector<void*>& own = S.owned;
+        if (sh_upload(own, &t, tf) || sh_upload(own, &n, npf)) return -100;
+        d_tf = t; d_npf = n;
+      }
+      d.tf = d_tf; d.npf = d_npf;
+    }
+    std::vector<int> conn((size_t)4 * np, 0), slot((size_t)4 * np, 0), ngl(np, 0);
+    std::vector<double> thk(np, G.prop.thick), off(np, 0.0);
+    for (int i = 0; i < ne; i++) {
+      const int* ix = &ixc[(size_t)7 * (nft + i)];
+      for (int k = 0; k < 4; k++) {
+        const int node = ix[1 + k];
+        if (node < 1 || node > numnod) { orgpu_set_error("IXC node %d out of range (element %d)", node, nft + i + 1); return -4; }
+        const int sl = iadc[(size_t)4 * (nft + i) + k];
+        if (sl < 1 || sl > lsky) { orgpu_set_error("IADC slot %d out of range (element %d)", sl, nft + i + 1); return -4; }
+        conn[(size_t)k * np + i] = node - 1; slot[(size_t)k * np + i] = sl - 1;
+      }
+      ngl[i] = ix[6]; off[i] = 1.0;
+    }
+    int *dconn, *dslot, *dngl; double *dthke;
+    if (sh_upload(S.owned, &dconn, conn) || sh_upload(S.owned, &dslot, slot) || sh_upload(S.owned, &dngl, ngl) ||
+        sh_upload(S.owned, &d.thk, thk) || sh_upload(S.owned, &dthke, thk) || sh_upload(S.owned, &d.off, off)) return -100;
+    d.conn = dconn; d.slot = dslot; d.ngl = dngl; d.thke = dthke;
+    const size_t n = np, npt = d.npt;
+    if (sh_alloc(S.owned, &d.forc, 5 * n) || sh_alloc(S.owned, &d.mom, 3 * n) || sh_alloc(S.owned, &d.eint, 2 * n) ||
+        sh_alloc(S.owned, &d.stra, 8 * n) || sh_alloc(S.owned, &d.epsd, n) || sh_alloc(S.owned, &d.hourg, (size_t)d.nhourg * n) ||
+        sh_alloc(S.owned, &d.smstr, 6 * n) || sh_alloc(S.owned, &d.sig, npt * 5 * n) || sh_alloc(S.owned, &d.pla, npt * n) ||
+        sh_alloc(S.owned, &d.epsd_ip, npt * n) || sh_alloc(S.owned, &d.vartmp, npt * (size_t)(d.nvartmp > 0 ? d.nvartmp : 1) * n)) return -100;
+    if (G.law == 2) {
+      std::vector<double> temp(npt * n, G.m2.tini);
+      if (sh_upload(S.owned, &d.temp, temp)) return -100;
+    }
+    const int nblk = np / ORGPU_BLOCK;
+    if (fa.nsg >= ORGPU_MAX_SG) { orgpu_set_error("too many super-groups (%d)", ORGPU_MAX_SG); return -6; }
+    fa.sg[fa.nsg++] = SGRange{blk, nblk, shell_is_qeph(G.prop) ? ORGPU_FAM_SHELL_QEPH : ORGPU_FAM_SHELL_BT};
+    order += ne; blk += nblk; gi = gj;
+  }
+  return 0;
+}
+
+static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky, int roww, CycleState* cs,
+                                const DtBlocks& db, const FinalizeArgs& fa, cudaStream_t st)
+{
+  (void)roww;                                  // shell models always use 8-wide rows
+  ShellParams P{S.d, nd, fsky, cs, db, fa};
+  const int nblk = S.d.ne_pad / ORGPU_BLOCK;
+  if (shell_is_qeph(S.d.prop)) {
+    if (S.d.law == 36) qeph_forces_kernel<36><<<nblk, ORGPU_BLOCK, 0, st>>>(P);
+    else               qeph_forces_kernel<2><<<nblk, ORGPU_BLOCK, 0, st>>>(P);
+  } else {
+    launch_bt_forces(P, nblk, st);
+  }
+}
+
+// fields: 0 for(5) 1 mom(3) 2 eint(2) 3 thk 4 off 5 stra(8) 6 epsd 7 hourg(nhourg) 8 smstr(6)
+//         9 sig(5*npt) 10 pla(npt) 11 epsd_ip(npt) 12 temp(npt) ; out[k*numelc + e]
+static int shell_download_state(std::vector<ShellSGHost>& sgs, int numelc, int field, double* out)
+{
+  const size_t NE = numelc;
+  for (auto& S : sgs) {
+    const ShellSG& d = S.d; const double* src = nullptr; int nc = 1;
+    switch (field) {
+      case 0: src = d.forc; nc = 5; break; case 1: src = d.mom; nc = 3; break; case 2: src = d.eint; nc = 2; break;
+      case 3: src = d.thk; break; case 4: src = d.off; break; case 5: src = d.stra; nc = 8; break; case 6: src = d.epsd; break;
+      case 7: src = d.hourg; nc = d.nhourg; break; case 8: src = d.smstr; nc = 6; break;
+      case 9: src = d.sig; nc = 5 * d.npt; break; case 10: src = d.pla; nc = d.npt; break; case 11: src = d.epsd_ip; nc = d.npt; break;
+      case 12: src = d.temp; nc = d.npt; if (!src) continue; break;
+      default: orgpu_set_error("unknown shell field %d", field); return -1;
+    }
+    for (int k = 0; k < nc; k++)
+      if (cudaMemcpy(out + k * NE + S.first_elem, src + (size_t)k * d.ne_pad, 8 * (size_t)d.ne, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        orgpu_set_error("shell state download failed"); return -100; }
+  }
+  return 0;
+}

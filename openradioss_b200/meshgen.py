@@ -9,6 +9,7 @@ import numpy as np
 from .model import (Model, Control, Law2, Law36, PropSolid, PropShell, SolidGroup, ShellGroup,
                     elastic_constants, NVSIZ, MAXFUNC36)
 from .pon import build_pon
+from .constants import K
 
 EP20 = 1e20
 
@@ -45,7 +46,86 @@ def copper_law2(tini: float = 300.0) -> Law2:
     m.pshift = 0.0; m.a11 = a11; m.a12 = a12
     m.ssp = np.sqrt(a11 / m.rho0)
     m.iform = 0; m.icc = 1; m.vp = 2; m.israte = 0; m.has_temp = 1
+    _sqrt_constants(m)
     return m
+
+
+def _sqrt_constants(m):
+    """PM(12), PM(13), PM(14), PM(190) (starter/source/materials/mat/hm_read_mat.F90:1638-1641)."""
+    m.gsr = np.sqrt(max(0.0, m.shear)); m.a11sr = np.sqrt(max(0.0, m.a11))
+    m.a12sr = np.sqrt(max(0.0, m.a12)); m.nusr = np.sqrt(max(0.0, m.nu))
+
+
+def steel_law2_shell() -> Law2:
+    """Mild steel Johnson-Cook set for shells (mm, ms, g): used by the BT / LAW2 decks."""
+    young, nu = 210.0e3, 0.3
+    g, k, a11, a12 = elastic_constants(young, nu)
+    m = Law2()
+    m.rho0 = 7.85e-3; m.young = young; m.nu = nu; m.shear = g; m.bulk = k
+    m.ca, m.cb, m.cn = 250.0, 400.0, 0.4
+    m.epmx = 1e30; m.sigmx = 1e30
+    m.cc = 0.02; m.epdr = 1.0e-3
+    m.fisokin = 0.0; m.asrate = 0.0
+    m.z3 = 1.0; m.z4 = 0.0
+    m.tref = 300.0; m.tmelt = 1.0e30; m.rhocp = 0.0; m.tini = 300.0
+    m.pshift = 0.0; m.a11 = a11; m.a12 = a12
+    m.ssp = np.sqrt(a11 / m.rho0)
+    m.iform = 0; m.icc = 1; m.vp = 2; m.israte = 0; m.has_temp = 0
+    _sqrt_constants(m)
+    return m
+
+
+def steel_law36(curves=None, rates=None):
+    """/MAT/LAW36 steel of SURVEY.md 8d, filled as the Starter does
+    (starter/source/materials/mat/mat036/hm_read_mat36.F:268-320; generic PM slots
+    hm_read_mat.F90:1466-1479).  Returns (Law36, npf, tf): one static curve of 8 points,
+    sigma_y 250 -> 450 MPa over eps_p 0 -> 0.3, unless `curves` (list of (x,y) arrays) and `rates`
+    are given."""
+    young, nu, rho0 = 210.0e3, 0.3, 7.85e-3
+    m = Law36()
+    m.rho0 = rho0; m.young = young; m.nu = nu
+    m.shear = 0.5 * young / (1.0 + nu)
+    m.bulk = young / 3.0 / (1.0 - 2.0 * nu)
+    m.a1u = young / (1.0 - nu * nu); m.a2u = nu * m.a1u
+    m.g3 = 3.0 * m.shear
+    m.soundsp = np.sqrt(young / (1.0 - nu * nu) / rho0)
+    m.nu_mnu = nu / (1.0 - nu); m.t_pnu = 3.0 / (1.0 + nu); m.u_mnu = 1.0 / (1.0 - nu)
+    m.epsmax = K["INFINITY"]; m.fisokin = 0.0; m.asrate = 0.0
+    m.a11 = young / (1.0 - nu ** 2); m.a12 = 0.0          # PM(25) is not set for user-type laws
+    m.ssp = np.sqrt(young / rho0)                          # PM(27) (hm_read_mat36.F:325)
+    _sqrt_constants(m)
+    if curves is None:
+        x = np.array([0.0, 0.01, 0.02, 0.05, 0.10, 0.15, 0.20, 0.30])
+        y = np.array([250.0, 290.0, 315.0, 355.0, 395.0, 420.0, 435.0, 450.0])
+        curves, rates = [(x, y)], [0.0]
+    m.nrate = len(curves)
+    npf = [0]; tf = []
+    for c, (x, y) in enumerate(curves):
+        m.rate[c] = rates[c]; m.yfac[c] = 1.0; m.ifunc[c] = c
+        tf.append(np.stack([x, y], 1).reshape(-1)); npf.append(npf[-1] + len(x))
+    m.israte = 0 if m.nrate == 1 else 1
+    if m.nrate > 1:
+        m.asrate = 2.0 * np.pi * 10000.0                   # FCUT default (hm_read_mat36.F:216-218)
+    m.vp = 0; m.ifail = 0; m.yldcheck = 0; m.ismooth = 0 if m.nrate == 1 else 1
+    return m, np.asarray(npf, np.int32), np.concatenate(tf)
+
+
+def default_prop_shell(thick=2.0, ihbe=24, npt=5, ismstr=2, ithk=1, ipla=1) -> PropShell:
+    """/PROP/SHELL defaults as the Starter fills GEO (hm_read_prop01.F:196-262)."""
+    p = PropShell()
+    p.thick = thick
+    if 11 < ihbe < 29:                       # QEPH: GEO(13) <- Dn (default 0.015), GEO(17) <- CVIS = 1
+        p.h1 = K["ZEP015"]; p.h2 = K["EM02"]; p.h3 = K["EM02"]; p.cvis = 1.0
+    elif ihbe == 3:
+        p.h1 = K["EM01"]; p.h2 = K["EM01"]; p.h3 = K["EM02"]; p.cvis = 0.0
+    else:
+        p.h1 = K["EM02"]; p.h2 = K["EM02"]; p.h3 = K["EM02"]; p.cvis = 0.0
+    p.srh1 = np.sqrt(p.h1); p.srh2 = np.sqrt(p.h2); p.srh3 = np.sqrt(p.h3)
+    p.shf = 0.0 if npt == 1 else K["FIVE_OVER_6"]
+    p.shfsr = np.sqrt(p.shf)
+    p.dm = 0.0
+    p.npt = npt; p.ismstr = ismstr; p.ithk = ithk; p.ipla = ipla; p.ihbe = ihbe; p.istrain = 1
+    return p
 
 
 def default_prop_solid(jhbe=1, ismstr=4) -> PropSolid:
@@ -125,3 +205,81 @@ def taylor_bar(scale: int = 1) -> Model:
     """C1: 32x32x98 = 100 352 bricks, 6.4 x 6.4 x 32.4 mm copper bar, V0z = -227 m/s, anvil z-BC."""
     nx = ny = max(2, 32 // scale); nz = max(2, 98 // scale)
     return hex_block(nx, ny, nz, 6.4, 6.4, 32.4, v0=(0.0, 0.0, -227.0), fix_bottom_z=True)
+
+
+def shell_areas(X: np.ndarray, ixc: np.ndarray) -> np.ndarray:
+    """Quad areas as the Starter measures them: half the norm of the diagonal cross product."""
+    c = X[ixc[:, 1:5] - 1]
+    d1 = c[:, 2] - c[:, 0]; d2 = c[:, 3] - c[:, 1]
+    return 0.5 * np.linalg.norm(np.cross(d1, d2), axis=1)
+
+
+def shell_plate(nx: int, ny: int, lx: float = 1000.0, ly: float = 1000.0, *, thick: float = 2.0, law: int = 36,
+                mat=None, prop: PropShell = None, jitter: float = 0.05, zjitter: float = 0.05, seed: int = 2024,
+                pressure: float = 1.0, clamp: bool = True, vrand: float = 0.0, vseed: int = 12345,
+                user_id_perm: bool = False, curves=None, rates=None) -> Model:
+    """Square plate of nx*ny 4-node shells in the xy plane (C2: 1000 x 1000 QEPH / LAW36, clamped
+    edges, uniform pressure as constant nodal forces)."""
+    prop = prop or default_prop_shell(thick=thick)
+    npf = tf = None
+    if mat is None:
+        if law == 36:
+            mat, npf, tf = steel_law36(curves, rates)
+        else:
+            mat = steel_law2_shell()
+    nnx, nny = nx + 1, ny + 1
+    gx, gy = np.meshgrid(np.arange(nnx), np.arange(nny), indexing="ij")
+    nid = lambda i, j: i + nnx * j
+    numnod = nnx * nny
+    X = np.zeros((numnod, 3))
+    idx = nid(gx, gy).reshape(-1)
+    X[idx, 0] = (gx * (lx / nx)).reshape(-1); X[idx, 1] = (gy * (ly / ny)).reshape(-1)
+    h = min(lx / nx, ly / ny)
+    rng = np.random.default_rng(seed)
+    if jitter:
+        X[:, :2] += rng.uniform(-jitter, jitter, (numnod, 2)) * h
+    if zjitter:
+        X[:, 2] += rng.uniform(-zjitter, zjitter, numnod) * h
+    ex, ey = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    ex, ey = ex.T.reshape(-1), ey.T.reshape(-1)
+    ne = nx * ny
+    ixc = np.zeros((ne, 7), np.int32)
+    ixc[:, 0] = 1; ixc[:, 5] = 1
+    for c, (a, b) in enumerate([(0, 0), (1, 0), (1, 1), (0, 1)]):
+        ixc[:, 1 + c] = nid(ex + a, ey + b) + 1
+    uid = np.arange(1, ne + 1, dtype=np.int32)
+    if user_id_perm:
+        uid = np.random.default_rng(seed + 1).permutation(ne).astype(np.int32) + 1
+    ixc[:, 6] = uid
+    area = shell_areas(X, ixc)
+    ems = mat.rho0 * prop.thick * area * 0.25                       # cinmas.F:851
+    fac = 12.0 if prop.ihbe >= 11 else 9.0                          # cinmas.F:921-927
+    xi = ems * (area / fac + prop.thick * prop.thick * (1.0 / 12.0))  # cinmas.F:1383
+    MS = np.zeros(numnod); IN = np.zeros(numnod)
+    np.add.at(MS, (ixc[:, 1:5] - 1).reshape(-1), np.repeat(ems, 4))
+    np.add.at(IN, (ixc[:, 1:5] - 1).reshape(-1), np.repeat(xi, 4))
+    V = np.zeros((numnod, 3)); VR = np.zeros((numnod, 3))
+    if vrand:
+        g = np.random.Generator(np.random.PCG64(vseed))
+        V += g.uniform(-vrand, vrand, V.shape); VR += g.uniform(-vrand, vrand, VR.shape) / h
+    fext = None
+    if pressure:
+        fext = np.zeros((numnod, 3))
+        np.add.at(fext[:, 2], (ixc[:, 1:5] - 1).reshape(-1), np.repeat(pressure * area * 0.25, 4))
+    icodt = icodr = None
+    if clamp:
+        icodt = np.zeros(numnod, np.int32); icodr = np.zeros(numnod, np.int32)
+        edge = (gx == 0) | (gx == nx) | (gy == 0) | (gy == ny)
+        icodt[nid(gx, gy)[edge]] = 7; icodr[nid(gx, gy)[edge]] = 7
+        V[icodt == 7] = 0.0; VR[icodr == 7] = 0.0
+    m = Model(X=X, V=V, VR=VR, MS=MS, IN=IN, control=default_control(1), ixc=ixc, icodt=icodt, icodr=icodr,
+              fext=fext, itab=np.arange(1, numnod + 1, dtype=np.int32), npf=npf, tf=tf)
+    m.shell_groups = [ShellGroup(nft=s, nel=n, law=law, mat=mat, prop=prop) for s, n in _groups(ne)]
+    m.adsky, m.iads, m.iadc, m.lsky = build_pon(numnod, m.ixs, m.ixc)
+    return m
+
+
+def plate_c2(scale: int = 1) -> Model:
+    """C2: 1000 x 1000 QEPH shells, LAW36, NPT=5, clamped, pressure pulse (1 MPa step)."""
+    n = max(4, 1000 // scale)
+    return shell_plate(n, n)

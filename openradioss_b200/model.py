@@ -19,12 +19,12 @@ d, i = C.c_double, C.c_int
 
 class Law2(C.Structure):
     _fields_ = [(n, d) for n in ("rho0 young nu shear bulk ca cb cn epmx sigmx cc epdr fisokin asrate "
-                                 "z3 z4 tref tmelt rhocp tini pshift a11 a12 ssp").split()] + \
+                                 "z3 z4 tref tmelt rhocp tini pshift a11 a12 ssp gsr a11sr a12sr nusr").split()] + \
                [(n, i) for n in "iform icc vp israte has_temp".split()]
 
 
 class Law36(C.Structure):
-    _fields_ = [(n, d) for n in ("rho0 young nu shear bulk a11 a12 ssp a1u a2u g3 soundsp nu_mnu t_pnu u_mnu "
+    _fields_ = [(n, d) for n in ("rho0 young nu shear bulk a11 a12 ssp gsr a11sr a12sr nusr a1u a2u g3 soundsp nu_mnu t_pnu u_mnu "
                                  "epsmax fisokin asrate").split()] + \
                [("rate", d * MAXFUNC36), ("yfac", d * MAXFUNC36), ("ifunc", i * MAXFUNC36)] + \
                [(n, i) for n in "nrate israte vp ifail yldcheck ismooth".split()]
@@ -35,7 +35,7 @@ class PropSolid(C.Structure):
 
 
 class PropShell(C.Structure):
-    _fields_ = [(n, d) for n in "thick h1 h2 h3 srh1 srh2 srh3 shf cvis dm".split()] + \
+    _fields_ = [(n, d) for n in "thick h1 h2 h3 srh1 srh2 srh3 shf shfsr cvis dm".split()] + \
                [(n, i) for n in "npt ismstr ithk ipla ihbe istrain".split()]
 
 

@@ -9,6 +9,8 @@
 
 struct OrcShellGroup;
 void orc_shell_group_free(OrcShellGroup*);
+OrcShellGroup* orc_shell_group_new(int nel,int nft,int law,const void* mat,const orgpu_prop_shell* prop);
+void orc_shell_group_state(const OrcShellGroup& g,int field,size_t ne,double* out);
 void orc_forces(Oracle& o);
 
 extern "C" {
@@ -85,6 +87,17 @@ int orc_add_solid_group(void* h,int nel,int nft,const orgpu_law2* mat,const orgp
   return (int)o->sgroups.size()-1;
 }
 
+/* one shell group: elements [nft, nft+nel) of IXC; law = 2 (orgpu_law2) or 36 (orgpu_law36) */
+int orc_add_shell_group(void* h,int nel,int nft,int law,const void* mat,const orgpu_prop_shell* prop)
+{
+  Oracle* o=(Oracle*)h;
+  if(nel>MVSIZ-1) return -1;
+  if(law!=2 && law!=36) return -2;
+  if(prop->npt<1 || prop->npt>10) return -3;
+  o->cgroups.push_back(orc_shell_group_new(nel,nft,law,mat,prop));
+  return (int)o->cgroups.size()-1;
+}
+
 void orc_finalize(void*){}
 
 /* phases (same split as the device library) */
@@ -126,6 +139,11 @@ void orc_download_solid_state(void* h,int field,double* out){
       case 9: cp(g.smstr,21); break;
     }
   }
+}
+
+void orc_download_shell_state(void* h,int field,double* out){
+  Oracle* o=(Oracle*)h;
+  for(auto* g:o->cgroups) orc_shell_group_state(*g,field,(size_t)o->numelc,out);
 }
 
 } // extern "C"

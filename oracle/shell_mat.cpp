@@ -1,0 +1,425 @@
+/* oracle/shell_mat.cpp -- TEST INFRASTRUCTURE ONLY (see oracle.h).
+ * Through-thickness material loop of 4-node shells, restated per element from:
+ *   CMAIN3    engine/source/materials/mat_share/cmain3.F:204-352      (NPT>0 Radioss-law branch)
+ *   LAYINI    engine/source/elements/shell/coque/layini.F:246-254     (IGTYP 1: THKLY=WF, POSLY=Z0)
+ *   MULAWC    engine/source/materials/mat_share/mulawc.F90:542-604 (pre), 718-1114 (IP frame),
+ *             2630-2662 (stress store, FOR/MOM), 2818-2845 (ZCFAC, SSP_EQ), 2934-3091 (tail)
+ *   SIGEPS36C engine/source/materials/mat/mat036/sigeps36c.F:171-661  (VP=0; IPLAS 0/1/2)
+ *   VINTER    engine/source/tools/curve/vinter.F:100-130
+ *   SIGEPS02C engine/source/materials/mat/mat002/sigeps02c.F:91-230
+ *   M2CPLR    engine/source/materials/mat/mat002/m2cplr.F:108-507     (FISOKIN=0)
+ * Built path: IGTYP=1 (/PROP/SHELL), no failure model, no thermal coupling (JTHE=0), no
+ * non-local, NPG=1.  Expressions keep the Fortran evaluation order (left to right).
+ */
+#include "shell.h"
+
+/* VINTER: monotone forward walk of the persistent cursor, then linear interpolation.
+ * Curve points are (x,y) pairs TF[2*p], TF[2*p+1], p in [iad, iad+npts). */
+void orc_vinter(const std::vector<double>& TF, int iad, int npts, int& ipos, double x, double& dydx, double& y)
+{
+  /* ILEN = NPF(f+1)/2 - IAD - IPOS = npts-1-ipos ; at most ILEN-1 advances (vinter.F:104-113) */
+  const int ilen=npts-1-ipos;
+  for(int j=1;j<=ilen-1;j++){
+    int j1=ipos+iad+1;
+    if(x>TF[2*(size_t)j1]) ipos=ipos+1; else break;
+  }
+  const int j1=ipos+iad, j2=j1+1;
+  dydx=(TF[2*(size_t)j2+1]-TF[2*(size_t)j1+1])/(TF[2*(size_t)j2]-TF[2*(size_t)j1]);
+  y=TF[2*(size_t)j1+1]+dydx*(x-TF[2*(size_t)j1]);
+}
+
+namespace {
+
+struct IpIO {             /* one integration point, one element */
+  double depsxx,depsyy,depsxy,depsyz,depszx, epspxx,epspyy,epspxy;
+  double sigoxx,sigoyy,sigoxy,sigoyz,sigozx;
+  double signxx,signyy,signxy,signyz,signzx;
+  double thklyl;
+};
+
+/* ---- SIGEPS36C, VP=0 branch, one element ------------------------------------------------ */
+void sigeps36c(const Oracle& o, const orgpu_law36& m, int ipla, double asrate, const ShellMatIn& in, IpIO& s,
+               double& pla, double& epsd, int* vartmp, double off, double& thk, double& ssp, double& viscmax,
+               double& etse, double& yld_out)
+{
+  const int NITER=3;
+  const int nrate=m.nrate;
+  const double E=m.young, A1=m.a1u, A2=m.a2u, G=m.shear, G3=m.g3;
+  const double NU_MNU=m.nu_mnu, T_PNU=m.t_pnu, U_MNU=m.u_mnu, FISOKIN=m.fisokin;
+  const double GS=in.gs;
+  viscmax=K_ZERO; etse=K_ONE; ssp=m.soundsp;
+  const double FAIL=K_ONE, PFAC=K_ONE, FACYLDI=K_ONE;
+  /* elastic predictor (sigeps36c.F:272-284); back stress is zero (FISOKIN=0) */
+  s.sigoxx=s.sigoxx-K_ZERO; s.sigoyy=s.sigoyy-K_ZERO; s.sigoxy=s.sigoxy-K_ZERO;
+  s.signxx=s.sigoxx+A1*s.depsxx+A2*s.depsyy;
+  s.signyy=s.sigoyy+A2*s.depsxx+A1*s.depsyy;
+  s.signxy=s.sigoxy+G*s.depsxy;
+  s.signyz=s.sigoyz+GS*s.depsyz;
+  s.signzx=s.sigozx+GS*s.depszx;
+  /* strain rate (:288-296) */
+  if(m.israte==0){
+    epsd=K_HALF*( std::fabs(s.epspxx+s.epspyy)
+         + std::sqrt( (s.epspxx-s.epspyy)*(s.epspxx-s.epspyy) + s.epspxy*s.epspxy ) );
+  } else {
+    epsd=asrate*in.epsd_pg+(K_ONE-asrate)*epsd;
+  }
+  /* yield (:317-462) */
+  double YLD,H;
+  if(nrate==1){
+    int ipos=vartmp[2];
+    const int f=m.ifunc[0];
+    double dydx1,y1;
+    orc_vinter(o.TF,o.NPF[f],o.NPF[f+1]-o.NPF[f],ipos,pla,dydx1,y1);
+    const double YFAC1=m.yfac[0]*FACYLDI;
+    vartmp[2]=ipos;
+    const double FACT=FAIL*PFAC*YFAC1;
+    H=dydx1*FACT;
+    YLD=y1*FACT;
+  } else {
+    int JJ=1;
+    for(int J=2;J<=nrate-1;J++) if(epsd>=m.rate[J-1]) JJ=J;
+    double RFAC,YFAC1,YFAC2;
+    if(m.ismooth==2){
+      double EPSP1=std::max(m.rate[JJ-1],K_EM20), EPSP2=m.rate[JJ];
+      RFAC=std::log(std::max(epsd,K_EM20)/EPSP1)/std::log(EPSP2/EPSP1);
+    } else {
+      double EPSP1=m.rate[JJ-1], EPSP2=m.rate[JJ];
+      RFAC=(epsd-EPSP1)/(EPSP2-EPSP1);
+    }
+    YFAC1=m.yfac[JJ-1]*FACYLDI; YFAC2=m.yfac[JJ]*FACYLDI;
+    const int J1=JJ,J2=JJ+1;
+    const int f1=m.ifunc[J1-1], f2=m.ifunc[J2-1];
+    int ipos1=vartmp[1+J1], ipos2=vartmp[1+J2];
+    double dydx1,y1,dydx2,y2;
+    orc_vinter(o.TF,o.NPF[f1],o.NPF[f1+1]-o.NPF[f1],ipos1,pla,dydx1,y1);
+    orc_vinter(o.TF,o.NPF[f2],o.NPF[f2+1]-o.NPF[f2],ipos2,pla,dydx2,y2);
+    y1=y1*YFAC1; y2=y2*YFAC2;
+    const double FAC=RFAC;
+    YLD=FAIL*(y1+FAC*(y2-y1));
+    YLD=std::max(YLD,K_EM20);
+    dydx1=dydx1*YFAC1; dydx2=dydx2*YFAC2;
+    H=FAIL*(dydx1+FAC*(dydx2-dydx1));
+    YLD=YLD*std::max(K_ZERO,PFAC);
+    H=H*std::max(K_ZERO,PFAC);
+    vartmp[1+J1]=ipos1; vartmp[1+J2]=ipos2;
+  }
+  if(m.yldcheck==1) YLD=std::max(YLD,K_EM20);
+  /* projection (:472-661) */
+  if(ipla==0){
+    const double NU3=K_ONE-NU_MNU;
+    double SVM2=s.signxx*s.signxx+s.signyy*s.signyy-s.signxx*s.signyy+K_THREE*s.signxy*s.signxy;
+    if(SVM2>YLD*YLD){
+      double SVM=std::sqrt(SVM2);
+      double R=YLD/SVM;
+      s.signxx=s.signxx*R; s.signyy=s.signyy*R; s.signxy=s.signxy*R;
+      double DPLA=off*SVM*(K_ONE-R)/(G3+H);
+      pla=pla+DPLA;
+      double DEZZ;
+      if(YLD!=0) DEZZ=DPLA*K_HALF*(s.signxx+s.signyy)/YLD; else DEZZ=K_ZERO;
+      DEZZ=-(s.depsxx+s.depsyy)*NU_MNU-NU3*DEZZ;
+      thk=thk+DEZZ*s.thklyl*off;
+      etse=H/(H+E);
+    }
+  } else if(ipla==1){
+    H=std::max(K_ZERO,H);
+    double S1=s.signxx+s.signyy, S2=s.signxx-s.signyy, S3=s.signxy;
+    const double AA=K_FOURTH*S1*S1;
+    const double BB=K_THREE_OVER_4*S2*S2+K_THREE*S3*S3;
+    const double SVM2=AA+BB;
+    { double DEZZ=-(s.depsxx+s.depsyy)*NU_MNU; thk=thk+DEZZ*s.thklyl*off; }
+    if(SVM2>YLD*YLD && off==K_ONE){
+      double SVM=std::sqrt(SVM2);
+      double DPLA_J=(SVM-YLD)/(G3+H);
+      etse=H/(H+E);
+      const double HI=H*(K_ONE-FISOKIN);
+      const double HK=K_TWO_THIRD*H*FISOKIN;
+      const double NU3=K_ONE-NU_MNU;
+      double DPLA_I=K_ZERO,DR=K_ZERO,PP=K_ONE,QQ=K_ONE;
+      for(int N=1;N<=NITER;N++){
+        DPLA_I=DPLA_J;
+        double YLD_I=YLD+HI*DPLA_I;
+        DR=K_HALF*E*DPLA_I/YLD_I;
+        double AAA=K_THREE*HK/E;
+        double NU11=U_MNU+AAA, NU21=T_PNU+AAA;
+        PP=K_ONE/(K_ONE+DR*NU11);
+        QQ=K_ONE/(K_ONE+DR*NU21);
+        double P2=PP*PP, Q2=QQ*QQ;
+        double F=AA*P2+BB*Q2-YLD_I*YLD_I;
+        double DF=-(AA*NU11*P2*PP+BB*NU21*Q2*QQ)*(E-K_TWO*DR*HI)/YLD_I-K_TWO*HI*YLD_I;
+        DF=std::copysign(std::max(std::fabs(DF),K_EM20),DF);
+        if(DPLA_I>K_ZERO) DPLA_J=std::max(K_ZERO,DPLA_I-F/DF); else DPLA_J=K_ZERO;
+      }
+      pla=pla+DPLA_I;
+      S1=(s.signxx+s.signyy)*PP;
+      S2=(s.signxx-s.signyy)*QQ;
+      s.signxx=K_HALF*(S1+S2);
+      s.signyy=K_HALF*(S1-S2);
+      s.signxy=s.signxy*QQ;
+      { double DEZZ=-NU3*DR*S1/E; thk=thk+DEZZ*s.thklyl*off; }
+      YLD=YLD+HI*DPLA_I;
+    }
+  } else {            /* IPLAS == 2 */
+    H=std::max(K_ZERO,H);
+    double SVM2=s.signxx*s.signxx+s.signyy*s.signyy-s.signxx*s.signyy+K_THREE*s.signxy*s.signxy;
+    { double DEZZ=-(s.depsxx+s.depsyy)*NU_MNU; thk=thk+DEZZ*s.thklyl*off; }
+    const double YLD2=YLD*YLD;
+    if(SVM2>YLD2 && off==K_ONE){
+      const double NU3=K_ONE-NU_MNU;
+      double A=(SVM2-YLD2)/(K_FIVE*SVM2+K_THREE*(-s.signxx*s.signyy+s.signxy*s.signxy));
+      double S1=(K_ONE-K_TWO*A)*s.signxx+A*s.signyy;
+      double S2=A*s.signxx+(K_ONE-K_TWO*A)*s.signyy;
+      double S3=(K_ONE-K_THREE*A)*s.signxy;
+      s.signxx=S1; s.signyy=S2; s.signxy=S3;
+      double SVM=std::sqrt(SVM2);
+      double DPLA=off*(SVM-YLD)/(G3+H);
+      double HK=H*(K_ONE-FISOKIN);
+      YLD=YLD+HK*DPLA;
+      SVM=std::sqrt(s.signxx*s.signxx+s.signyy*s.signyy-s.signxx*s.signyy+K_THREE*s.signxy*s.signxy);
+      double R=std::min(K_ONE,YLD/std::max(K_EM20,SVM));
+      s.signxx=s.signxx*R; s.signyy=s.signyy*R; s.signxy=s.signxy*R;
+      pla=pla+DPLA;
+      double DEZZ=DPLA*K_HALF*(s.signxx+s.signyy)/YLD;
+      DEZZ=-NU3*DEZZ;
+      thk=thk+DEZZ*s.thklyl*off;
+      etse=H/(H+E);
+    }
+  }
+  yld_out=YLD;
+}
+
+/* ---- SIGEPS02C + M2CPLR, one element (FISOKIN=0) ------------------------------------------ */
+void sigeps02c(const orgpu_law2& m, int ipla, int npttot, double dt1, double asrate, const ShellMatIn& in, IpIO& s,
+               double& pla, double& epsd, double& temp, bool has_temp, double& off, double off_old, int& ioff_duct,
+               double& epchk, double& thk, double& etse, double& sigy)
+{
+  const int NMAX=3;
+  const double SMALL=K_EM7;
+  const int iform=m.iform, icc=m.icc, vp=m.vp, israte=m.israte;
+  const double young=m.young, g=m.shear, nu=m.nu;
+  const double a11=young/(K_ONE-nu*nu);
+  const double a12=a11*nu;
+  double ca=m.ca, cb=m.cb; const double cn=m.cn, epmx=m.epmx; double ymax=m.sigmx; const double cc=m.cc;
+  double epdr=m.epdr; epdr=std::max(epdr*dt1,K_EM20);
+  const double tref=m.tref, tmelt=m.tmelt, rhocp=m.rhocp;
+  double z3,z4,m_exp,tstar=K_ZERO;
+  double tempel= has_temp? temp : K_ZERO;
+  if(iform==1){ z3=m.z3; z4=m.z4; m_exp=K_ONE;
+    if(has_temp) tstar=std::max(K_ZERO,(tempel-tref)/std::max(tmelt-tref,K_EM20));   /* mulawc.F90:1104-1110 */
+  } else { z3=K_ZERO; z4=K_ZERO; m_exp=m.z3; tstar=std::max(K_ZERO,(tempel-tref)/(tmelt-tref)); }
+  double EZZ=K_ZERO, epsdot=K_ZERO;
+  if(vp==1){ epsdot=epsd*dt1; }
+  else if(vp==2){ epsd=asrate*in.epsd_pg+(K_ONE-asrate)*epsd; epsdot=epsd*dt1; }
+  else if(vp==3){
+    double DAV=(s.epspxx+s.epspyy)*K_THIRD;
+    double DEVE1=s.epspxx-DAV, DEVE2=s.epspyy-DAV, DEVE3=-DAV, DEVE4=K_HALF*s.epspxy;
+    epsdot=K_HALF*(DEVE1*DEVE1+DEVE2*DEVE2+DEVE3*DEVE3)+DEVE4*DEVE4;
+    epsdot=std::sqrt(K_THREE*epsdot)/K_THREE_HALF;
+    if(israte>0) epsdot=asrate*epsdot+(K_ONE-asrate)*epsd;
+    epsd=epsdot; epsdot=epsdot*dt1;
+  }
+  /* ---- M2CPLR */
+  double CA=ca, CB=cb, YMAX=ymax, H=K_ZERO, DPLA=K_ZERO, YLD;
+  etse=K_ONE;
+  s.signxx=s.sigoxx; s.signyy=s.sigoyy; s.signxy=s.sigoxy; s.signyz=s.sigoyz; s.signzx=s.sigozx;
+  s.signxx=s.signxx+a11*s.depsxx+a12*s.depsyy;
+  s.signyy=s.signyy+a12*s.depsxx+a11*s.depsyy;
+  s.signxy=s.signxy+g*s.depsxy;
+  s.signyz=s.signyz+in.gs*s.depsyz;
+  s.signzx=s.signzx+in.gs*s.depszx;
+  double EPSP=epsdot, LOGEP=K_ZERO, Q;
+  if(cc!=K_ZERO){
+    if(iform==0){
+      if(israte==0&&vp==2) EPSP=std::max(std::max(std::fabs(s.depsxx),std::fabs(s.depsyy)),K_HALF*std::fabs(s.depsxy));
+      EPSP=std::max(EPSP,epdr);
+      LOGEP=std::log(EPSP/epdr);
+      if(tstar==K_ZERO) Q=(K_ONE+cc*LOGEP);
+      else Q=(K_ONE+cc*LOGEP)*(K_ONE-std::exp(m_exp*std::log(tstar)));
+      Q=std::max(Q,K_EM20);
+      CA=CA*Q; CB=CB*Q;
+      if(icc==1) YMAX=YMAX*Q;
+    } else if(iform==1){
+      if(israte==0&&vp==2) EPSP=std::max(std::max(std::fabs(s.depsxx),std::fabs(s.depsyy)),K_HALF*std::fabs(s.depsxy));
+      EPSP=std::max(EPSP,K_EM20);
+      LOGEP=std::log(EPSP/epdr);
+      Q=LOGEP;
+      Q=cc*std::exp((-z3+z4*Q)*tempel);
+      if(icc==1) YMAX=YMAX+Q;
+      CA=CA+Q;
+    }
+  } else if(iform==0){
+    if(tstar!=K_ZERO){
+      Q=K_ONE-std::exp(m_exp*std::log(tstar));
+      Q=std::max(Q,K_EM20);
+      CA=CA*Q; CB=CB*Q;
+    }
+  }
+  if(pla==K_ZERO) YLD=CA;
+  else { double BETA=CB*(K_ONE-m.fisokin); YLD=CA+BETA*std::exp(cn*std::log(pla)); }
+  YLD=std::min(YLD,YMAX);
+  const double offp=off_old;                 /* M2CPLR receives OFF_OLD as OFF (sigeps02c.F:161) */
+  if(ipla==0){
+    double SVM=std::sqrt(s.signxx*s.signxx+s.signyy*s.signyy-s.signxx*s.signyy+K_THREE*s.signxy*s.signxy);
+    double R=std::min(K_ONE,YLD/(SVM+K_EM15));
+    if(R<K_ONE){
+      s.signxx=s.signxx*R; s.signyy=s.signyy*R; s.signxy=s.signxy*R;
+      DPLA=offp*std::max(K_ZERO,(SVM-YLD)/young);
+      double S1=K_HALF*(s.signxx+s.signyy);
+      EZZ=DPLA*S1/YLD;
+      pla=pla+DPLA;
+      epchk=std::max(pla,epchk);
+      if(YLD>=YMAX) H=K_ZERO; else H=cn*CB*std::exp((cn-K_ONE)*std::log(pla+SMALL));
+      etse=H/(H+young);
+    }
+  } else if(ipla==1){
+    double S1=s.signxx+s.signyy, S2=s.signxx-s.signyy, S3=s.signxy;
+    const double A=K_FOURTH*S1*S1;
+    const double B=K_THREE_OVER_4*S2*S2+K_THREE*S3*S3;
+    const double SVM=std::sqrt(A+B);
+    if(SVM>YLD && offp==K_ONE){
+      const double NU1=K_ONE/(K_ONE-nu), NU2=K_ONE/(K_ONE+nu);
+      if(YLD>=YMAX) H=K_ZERO; else H=cn*CB*std::exp((cn-K_ONE)*std::log(pla+SMALL));
+      double DPLA_J=(SVM-YLD)/(K_THREE*g+H);
+      etse=H/(H+young);
+      const double ANU1=A*NU1, BNU2=K_THREE*B*NU2, H2=K_TWO*H;
+      double DPLA_I=K_ZERO,DR=K_ZERO,P=K_ONE,Qq=K_ONE;
+      for(int N=1;N<=NMAX;N++){
+        DPLA_I=DPLA_J;
+        double PLA_I=pla+DPLA_I;
+        DPLA=DPLA_J;
+        double YLD_I;
+        if(PLA_I==K_ZERO) YLD_I=std::min(YMAX,CA);
+        else YLD_I=std::min(YMAX,CA+CB*std::exp(cn*std::log(PLA_I)));
+        DR=K_HALF*young*DPLA_I/YLD_I;
+        P=K_ONE/(K_ONE+DR*NU1);
+        Qq=K_ONE/(K_ONE+K_THREE*DR*NU2);
+        double P2=P*P, Q2=Qq*Qq;
+        double F=A*P2+B*Q2-YLD_I*YLD_I;
+        double DF=-(ANU1*P2*P+BNU2*Q2*Qq)*(young-DR*H2)/YLD_I-H2*YLD_I;
+        if(DPLA_I>K_ZERO) DPLA_J=std::max(K_ZERO,DPLA_I-F/DF); else DPLA_J=K_ZERO;
+      }
+      pla=pla+DPLA_I;
+      epchk=std::max(pla,epchk);
+      S1=(s.signxx+s.signyy)*P;
+      S2=(s.signxx-s.signyy)*Qq;
+      s.signxx=K_HALF*(S1+S2);
+      s.signyy=K_HALF*(S1-S2);
+      s.signxy=s.signxy*Qq;
+      EZZ=DR*S1/young;
+    }
+  } else {
+    double SVM2=s.signxx*s.signxx+s.signyy*s.signyy-s.signxx*s.signyy+K_THREE*s.signxy*s.signxy;
+    double SVM=std::sqrt(SVM2);
+    const double YLD2=YLD*YLD;
+    if(SVM2>YLD2 && offp==K_ONE){
+      if(YLD>=YMAX) H=K_ZERO; else H=cn*CB*std::exp((cn-K_ONE)*std::log(pla+SMALL));
+      etse=H/(H+young);
+      double AA=(SVM2-YLD2)/(K_FIVE*SVM2+K_THREE*(-s.signxx*s.signyy+s.signxy*s.signxy));
+      double S1=(K_ONE-K_TWO*AA)*s.signxx+AA*s.signyy;
+      double S2=AA*s.signxx+(K_ONE-K_TWO*AA)*s.signyy;
+      double S3=(K_ONE-K_THREE*AA)*s.signxy;
+      s.signxx=S1; s.signyy=S2; s.signxy=S3;
+      DPLA=offp*(SVM-YLD)/(K_THREE*g+H);
+      pla=pla+DPLA;
+      YLD=YLD+H*DPLA;
+      SVM=std::sqrt(s.signxx*s.signxx+s.signyy*s.signyy-s.signxx*s.signyy+K_THREE*s.signxy*s.signxy);
+      double R=std::min(K_ONE,YLD/std::max(K_EM20,SVM));
+      s.signxx=s.signxx*R; s.signyy=s.signyy*R; s.signxy=s.signxy*R;
+      EZZ=DPLA*K_HALF*(s.signxx+s.signyy)/YLD;
+    }
+  }
+  /* ---- back in SIGEPS02C (:172-230) */
+  if(vp==1){ epsdot=DPLA/std::max(K_EM20,dt1); epsd=asrate*epsdot+(K_ONE-asrate)*epsd; }
+  sigy=sigy+YLD/npttot;
+  if(off==off_old && off>K_ZERO){
+    if(off==K_ONE && epchk>=epmx){ off=K_FOUR_OVER_5; ioff_duct=1; }
+    else if(off<K_ONE) off=off*K_FOUR_OVER_5;
+  }
+  EZZ=-(s.depsxx+s.depsyy)*nu-(K_ONE-K_TWO*nu)*EZZ;
+  EZZ=EZZ/(K_ONE-nu);
+  thk=thk+EZZ*s.thklyl*off;
+  if(rhocp>K_ZERO && has_temp) temp=tempel+sigy*DPLA/rhocp;
+}
+
+} // namespace
+
+/* ---- CMAIN3 -> LAYINI -> MULAWC for one element ------------------------------------------- */
+void orc_cmain3(const Oracle& o, OrcShellGroup& g, int i, bool flag_zcfac, ShellMatIn& in, ShellMatOut& out)
+{
+  const int nel=g.nel, npt=g.prop.npt;
+  const double dt1=o.DT1;
+  const double DM=g.prop.dm;
+  double* FOR=g.FOR.data(); double* MOM=g.MOM.data();
+#define F_(k) FOR[(size_t)(k-1)*nel+i]
+#define M_(k) MOM[(size_t)(k-1)*nel+i]
+  /* mulawc.F90:542-546 */
+  double degmb=F_(1)*in.exx+F_(2)*in.eyy+F_(3)*in.exy+F_(4)*in.eyz+F_(5)*in.exz;
+  double degfx=M_(1)*in.kxx+M_(2)*in.kyy+M_(3)*in.kxy;
+  const double vol0=in.area*in.thk0;
+  double thkn=g.THK[i];
+  for(int k=1;k<=5;k++) F_(k)=K_ZERO;
+  for(int k=1;k<=3;k++) M_(k)=K_ZERO;
+  double sigy=out.sigy;
+  if(g.law==2 || !flag_zcfac) sigy=K_ZERO;
+  double zcfac1=K_ZERO, zcfac2= flag_zcfac? K_ONE : K_ZERO;
+  double etse=K_ONE;
+  double off=in.off; const double off_old=off;
+  int ioff_duct=0;
+  double epchk=K_ZERO, viscmx=K_ZERO, ssp=in.ssp, ssp_eq=K_ZERO;
+  const double dtinv=dt1/std::max(dt1*dt1,K_EM20);
+  /* strain-rate filter of the layer material (mulawc.F90:695-700) */
+  const int israte= (g.law==36)? g.m36.israte : g.m2.israte;
+  const double pm9= (g.law==36)? g.m36.asrate : g.m2.asrate;
+  double asrate; if(israte>0) asrate=std::min(K_ONE,pm9*dt1); else asrate=K_ONE;
+  for(int ipt=1;ipt<=npt;ipt++){
+    OrcShellGroup::Lbuf& lb=g.ip[ipt-1];
+    const double thkly=OR_WF[(npt-1)*11+(ipt-1)];          /* layini.F:250 */
+    const double posly=OR_Z0[(npt-1)*11+(ipt-1)]+K_ZERO;   /* layini.F:251 (ZSHIFT=0) */
+    const double wmc=OR_WM[(npt-1)*11+(ipt-1)];            /* mulawc.F90:771-773 */
+    IpIO s;
+    s.thklyl=thkly*in.thk0;
+    const double zt=posly*in.thk0;
+    s.depsxx=in.exx+zt*in.kxx;
+    s.depsyy=in.eyy+zt*in.kyy;
+    s.depsxy=in.exy+zt*in.kxy;
+    s.depsyz=in.eyz; s.depszx=in.exz;
+    s.epspxx=s.depsxx*dtinv; s.epspyy=s.depsyy*dtinv; s.epspxy=s.depsxy*dtinv;
+    s.sigoxx=lb.sig[i]; s.sigoyy=lb.sig[nel+i]; s.sigoxy=lb.sig[2*nel+i]; s.sigoyz=lb.sig[3*nel+i]; s.sigozx=lb.sig[4*nel+i];
+    if(g.law==36){
+      sigeps36c(o,g.m36,g.prop.ipla,asrate,in,s,lb.pla[i],lb.epsd[i],&lb.vartmp[(size_t)g.nvartmp*i],off,thkn,ssp,viscmx,etse,sigy);
+    } else {
+      sigeps02c(g.m2,g.prop.ipla,npt,dt1,asrate,in,s,lb.pla[i],lb.epsd[i],lb.temp[i],g.m2.has_temp!=0,off,off_old,ioff_duct,
+                epchk,thkn,etse,sigy);
+    }
+    viscmx=std::max(DM,viscmx);
+    lb.sig[i]=s.signxx*K_ONE; lb.sig[nel+i]=s.signyy*K_ONE; lb.sig[2*nel+i]=s.signxy*K_ONE;
+    lb.sig[3*nel+i]=s.signyz*K_ONE; lb.sig[4*nel+i]=s.signzx*K_ONE;
+    F_(1)=F_(1)+thkly*s.signxx; F_(2)=F_(2)+thkly*s.signyy; F_(3)=F_(3)+thkly*s.signxy;
+    F_(4)=F_(4)+thkly*s.signyz; F_(5)=F_(5)+thkly*s.signzx;
+    M_(1)=M_(1)+wmc*s.signxx; M_(2)=M_(2)+wmc*s.signyy; M_(3)=M_(3)+wmc*s.signxy;
+    if(g.law!=2){
+      if(flag_zcfac){ zcfac1=zcfac1+etse*thkly; zcfac2=std::min(etse,zcfac2); }
+    } else {
+      if(flag_zcfac){ zcfac1=zcfac1+etse/npt; zcfac2=std::min(etse,zcfac2); }
+    }
+    ssp_eq=ssp_eq+ssp*thkly;
+  }
+  /* tail (mulawc.F90:2934-3091) */
+  if((off==K_FOUR_OVER_5 && ioff_duct==0) || (off>K_ZERO && off_old<K_EM01)) off=K_ZERO;
+  g.THK[i]=std::max(thkn,K_EM30);
+  const double fact=K_ONEP414*DM;
+  const double visc=fact*ssp*std::sqrt(in.area)*dtinv*in.rho;
+  F_(1)=F_(1)+visc*(in.exx+K_HALF*in.eyy);
+  F_(2)=F_(2)+visc*(in.eyy+K_HALF*in.exx);
+  F_(3)=F_(3)+visc*in.exy*K_THIRD;
+  for(int k=1;k<=5;k++) F_(k)=F_(k)*off*K_ONE;
+  for(int k=1;k<=3;k++) M_(k)=M_(k)*off*K_ONE;
+  degmb=degmb+F_(1)*in.exx+F_(2)*in.eyy+F_(3)*in.exy+F_(4)*in.eyz+F_(5)*in.exz;
+  degfx=degfx+M_(1)*in.kxx+M_(2)*in.kyy+M_(3)*in.kxy;
+  const double vol2=K_HALF*vol0;
+  g.EINT[i]=g.EINT[i]+degmb*vol2;
+  g.EINT[nel+i]=g.EINT[nel+i]+degfx*in.thk0*vol2;
+#undef F_
+#undef M_
+  in.off=off;
+  out.ssp=ssp; out.viscmx=viscmx; out.sigy=sigy; out.zcfac1=zcfac1; out.zcfac2=zcfac2; out.ssp_eq=ssp_eq; out.vol0=vol0;
+}
