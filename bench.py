@@ -31,18 +31,20 @@ B_ALG = {
 }
 
 
-def workload(name, rank=0):
+def workload(name, world=1):
+    """Global model of the run: per-GPU work is fixed (weak scaling), the mesh grows along the
+    decomposition axis with the GPU count and is cut into `world` strips / slabs."""
     from openradioss_b200 import meshgen
-    if name == "c5_brick_slab_2m":          # per-GPU share of C5: 200 x 200 x 50 bricks, LAW2
-        return meshgen.hex_block(200, 200, 50, 200.0, 200.0, 50.0, vrand=1.0, vseed=12345 + rank), "brick"
+    if name == "c5_brick_slab_2m":          # C5: 200 x 200 x 50 bricks (2 M) per GPU, z slabs, LAW2
+        return meshgen.hex_block(200, 200, 50 * world, 200.0, 200.0, 50.0 * world, vrand=1.0, vseed=12345), "brick", 2
     if name == "c1_taylor_bar":
-        return meshgen.taylor_bar(1), "brick"
+        return meshgen.taylor_bar(1), "brick", 2
     if name == "brick_small":
-        return meshgen.hex_block(40, 40, 40, 40.0, 40.0, 40.0, vrand=1.0), "brick"
-    if name == "c2_plate_qeph_1m":          # C2: 1000 x 1000 QEPH shells, LAW36, NPT=5, clamped, pressure
-        return meshgen.plate_c2(1), "shell"
+        return meshgen.hex_block(40, 40, 40 * world, 40.0, 40.0, 40.0 * world, vrand=1.0), "brick", 2
+    if name == "c2_plate_qeph_1m":          # C2 / C3: 1000 x 1000 QEPH shells per GPU (x strips), LAW36, NPT=5
+        return meshgen.shell_plate(1000 * world, 1000, 1000.0 * world, 1000.0), "shell", 0
     if name == "plate_small":
-        return meshgen.plate_c2(5), "shell"
+        return meshgen.shell_plate(200 * world, 200, 1000.0 * world, 1000.0), "shell", 0
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -90,7 +92,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     from oracle.orc import Oracle
-    m, fam = workload(args.workload)
+    m, fam, _ = workload(args.workload)
     ne = m.numels + m.numelc
     cores = os.cpu_count() or 1
     o = Oracle(m, threads=cores)
@@ -134,9 +136,22 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from openradioss_b200.engine import Engine
-    m, fam = workload(args.workload, rank)
+    gm, fam, axis = workload(args.workload, world)
+    if world > 1:                                   # this rank's domain of the global model
+        from openradioss_b200 import domdec
+        dom = domdec.decompose_strips(gm, world, rank, axis=axis)
+        m = dom.model
+        del gm
+    else:
+        m = gm
     ne = m.numels + m.numelc
     g = Engine(m, device=local)
+    if world > 1:
+        g.comm_init(dist, dom)
+    net = torch.tensor([ne], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(net)
+    ne_total = int(net.item())
 
     def barrier():
         if world > 1:
@@ -156,7 +171,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    value = ne * world * args.steps / (ms * 1e-3)
+    value = ne_total * args.steps / (ms * 1e-3)
     clocks = cs.summary()
 
     # ---- per-kernel durations (CUDA events around every launch on the library's stream)
@@ -203,7 +218,7 @@ def main():
     t = torch.tensor([e2e_dt], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = ne * world * e2e_steps / float(t.item())
+    e2e_val = ne_total * e2e_steps / float(t.item())
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
@@ -223,7 +238,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": args.workload, "family": fam, "elements_per_gpu": ne, "nodes_per_gpu": n,
                            "l2": "inputs larger than L2 (element state >> 126 MB)" if ne >= 500000 else "working set may fit L2",
-                           "parallelism": f"domains={world}"},
+                           "parallelism": f"domains={world}" + ("" if world == 1 else " (strips, NCCL corner-row exchange + dt fold per cycle)")},
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "element-cycles/s", "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 48 * n,
                         "steps": e2e_steps, "call": "orgpu_step_host (X,V pinned host -> 1 cycle -> X,V host)"},

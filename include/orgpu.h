@@ -73,6 +73,26 @@ int  orgpu_download_fsky(orgpu_engine* e, double* fsky /*(8,LSKY)*/);
 int  orgpu_download_solid_state(orgpu_engine* e, int field, double* out);
 int  orgpu_download_shell_state(orgpu_engine* e, int field, double* out);
 
+/* -- domain decomposition (one process / MPI rank per GPU).
+ *    Host-staged: corner rows of the given 0-based local FSKY slots out of / into the device
+ *    skyline as (8,n) rows -- exactly what SPMD_EXCH2_A_PON packs from FSKY(:,ISENDP(j))
+ *    (engine/source/mpi/forces/spmd_exch2_a_pon.F:545-557) and unpacks into FSKY(:,IRECVP(j))
+ *    (:1190-1201), so the Engine can keep its MPI exchange (resol.F:4801) between
+ *    orgpu_forces_phase and orgpu_assemble. */
+int  orgpu_pack_rows(orgpu_engine* e, int n, const int* slots, double* rows /*(8,n)*/);
+int  orgpu_unpack_rows(orgpu_engine* e, int n, const int* slots, const double* rows /*(8,n)*/);
+/*    Device-resident: NCCL over NVLink replaces SPMD_EXCH2_A_PON and SPMD_GLOB_MIN5
+ *    (engine/source/mpi/generic/spmd_glob_min5.F:34-128) inside orgpu_run_cycles.  Rank 0 creates the
+ *    128-byte id, the host broadcasts it (MPI_BCAST / torch.distributed), every rank calls
+ *    orgpu_comm_init, then orgpu_set_exchange with its neighbour lists: neighbour k sends rows of
+ *    send_slots[send_ptr[k]..send_ptr[k+1]) and fills recv_slots[recv_ptr[k]..recv_ptr[k+1]); both sides
+ *    list a pair's rows in ascending global slot order (IADSDP / IADRCP equivalents). */
+int  orgpu_comm_unique_id(unsigned char id[128]);
+int  orgpu_comm_init(orgpu_engine* e, int nranks, int rank, const unsigned char id[128]);
+int  orgpu_set_exchange(orgpu_engine* e, int nneigh, const int* ranks, const int* send_ptr, const int* send_slots,
+                        const int* recv_ptr, const int* recv_slots);
+int  orgpu_exchange(orgpu_engine* e);   /* phased mode: pack -> NCCL -> unpack on the library stream */
+
 /* -- host-buffer convenience used for end-to-end timing: upload X,V(,VR), run, download X,V,A */
 int  orgpu_step_host(orgpu_engine* e, const double* X, const double* V, const double* VR,
                      int ncycles, double* Xout, double* Vout);

@@ -130,6 +130,19 @@ class Binding:
         self._call("download_shell_state", self.h, C.c_int(fid), out.ctypes.data_as(C.c_void_p))
         return out
 
+    # -- corner rows of the skyline (domain exchange) ------------------------------------
+    def pack_rows(self, slots):
+        slots = np.ascontiguousarray(slots, np.int32)
+        buf = np.zeros((len(slots), 8))
+        if len(slots):
+            self._call("pack_rows", self.h, C.c_int(len(slots)), slots.ctypes.data_as(C.c_void_p), buf.ctypes.data_as(C.c_void_p))
+        return buf
+
+    def unpack_rows(self, slots, buf):
+        slots = np.ascontiguousarray(slots, np.int32); buf = np.ascontiguousarray(buf, np.float64)
+        if len(slots):
+            self._call("unpack_rows", self.h, C.c_int(len(slots)), slots.ctypes.data_as(C.c_void_p), buf.ctypes.data_as(C.c_void_p))
+
     # -- stepping ----------------------------------------------------------------------
     def forces_phase(self, dt1): self._call("forces_phase", self.h, C.c_double(dt1))
     def assemble(self): self._call("assemble", self.h)

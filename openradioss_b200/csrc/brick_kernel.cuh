@@ -35,8 +35,6 @@ __device__ __forceinline__ double slen_face(const double* x, const double* y, co
   return E * G - F * F;
 }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 __device__ __forceinline__ double4 ldg4(const double4* p) {     // read-only 32-byte nodal record
   const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);

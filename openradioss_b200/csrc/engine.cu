@@ -17,6 +17,7 @@
 #include "brick_kernel.cuh"
 #include "shell_kernel.cuh"
 #include "node_kernel.cuh"
+#include "exchange.cuh"
 
 static thread_local char g_err[1024] = "";
 void orgpu_set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); }
@@ -62,6 +63,7 @@ struct orgpu_engine {
   double prof_ms[3] = {0, 0, 0}; long long prof_n[3] = {0, 0, 0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> evpool;
+  Exchange xc;                        // domain exchange (one process per GPU)
 };
 
 // ---- small layout kernels ---------------------------------------------------------------
@@ -134,6 +136,10 @@ int orgpu_destroy(orgpu_engine* e)
                   e->d_stage3a, e->d_stage3b, e->d_fext, e->d_mext, e->d_icodt, e->d_icodr, e->d_adsky, e->d_fsky, e->d_cs,
                   e->db.dt, e->db.ngl, e->db.order};
   for (void* p : ptrs) if (p) cudaFree(p);
+  { Exchange& x = e->xc;
+    void* xp[] = {x.d_send_slots, x.d_recv_slots, x.d_sendbuf, x.d_recvbuf, x.d_cand_send, x.d_cand_recv, x.d_slots_tmp, x.d_rows_tmp};
+    for (void* p : xp) if (p) cudaFree(p);
+    if (x.comm && nccl_api()) nccl_api()->CommDestroy(x.comm); }
   for (auto ev : e->evpool) cudaEventDestroy(ev);
   if (e->ev0) cudaEventDestroy(e->ev0); if (e->ev1) cudaEventDestroy(e->ev1);
   cudaStreamDestroy(e->st);
@@ -331,10 +337,77 @@ int orgpu_advance(orgpu_engine* e, double dt12, double dt2)
   return 0;
 }
 
+#define NCCL_OK(call) do { ncclResult_t _r = (call); if (_r != ncclSuccess) { \
+  orgpu_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, nccl_api()->GetErrorString(_r)); return -101; } } while (0)
+
+// pack -> one NCCL group (neighbour rows + every rank's dt candidate) -> unpack (+ dt fold when with_dt)
+static int exchange_on_stream(orgpu_engine* e, bool with_dt)
+{
+  Exchange& x = e->xc; NcclApi* N = nccl_api();
+  NEED(N && x.comm, -7, "orgpu: exchange requested without orgpu_comm_init");
+  const int V = e->roww / 2;
+  { const int nthr = x.nsend * V > 1 ? x.nsend * V : 1; const int nb = (nthr + 255) / 256;
+    if (e->roww == 8) rows_pack_kernel<8><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_send_slots, x.nsend, x.d_sendbuf, e->d_cs, with_dt ? x.d_cand_send : nullptr);
+    else              rows_pack_kernel<4><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_send_slots, x.nsend, x.d_sendbuf, e->d_cs, with_dt ? x.d_cand_send : nullptr);
+    e->launches++; }
+  NCCL_OK(N->GroupStart());
+  for (size_t k = 0; k < x.nb_rank.size(); k++) {
+    const size_t ns = x.send_ptr[k + 1] - x.send_ptr[k], nr = x.recv_ptr[k + 1] - x.recv_ptr[k];
+    if (ns) NCCL_OK(N->Send(x.d_sendbuf + (size_t)e->roww * x.send_ptr[k], ns * e->roww, ncclDouble, x.nb_rank[k], x.comm, e->st));
+    if (nr) NCCL_OK(N->Recv(x.d_recvbuf + (size_t)e->roww * x.recv_ptr[k], nr * e->roww, ncclDouble, x.nb_rank[k], x.comm, e->st));
+  }
+  if (with_dt) {
+    for (int q = 0; q < x.nranks; q++) {
+      if (q == x.rank) continue;
+      NCCL_OK(N->Send(x.d_cand_send, 4, ncclDouble, q, x.comm, e->st));
+      NCCL_OK(N->Recv(x.d_cand_recv + 4 * q, 4, ncclDouble, q, x.comm, e->st));
+    }
+  }
+  NCCL_OK(N->GroupEnd());
+  if (with_dt) CUDA_OK(cudaMemcpyAsync(x.d_cand_recv + 4 * x.rank, x.d_cand_send, 32, cudaMemcpyDeviceToDevice, e->st));
+  { const int nthr = x.nrecv * V > 1 ? x.nrecv * V : 1; const int nb = (nthr + 255) / 256;
+    if (e->roww == 8) rows_unpack_kernel<8><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_recv_slots, x.nrecv, x.d_recvbuf, e->d_cs, with_dt ? x.d_cand_recv : nullptr, x.nranks);
+    else              rows_unpack_kernel<4><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_recv_slots, x.nrecv, x.d_recvbuf, e->d_cs, with_dt ? x.d_cand_recv : nullptr, x.nranks);
+    e->launches++; }
+  return 0;
+}
+
 int orgpu_run_cycles(orgpu_engine* e, int ncycles)
 {
   NEED(e && e->finalized && ncycles >= 0, -1, "orgpu_run_cycles: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
   const int per_cycle = (int)(e->csg.size() + e->bsg.size()) + 1;
+  if (e->xc.nranks > 1) {
+    // one process per GPU: element phase writes the local dt candidate only; the exchange folds all
+    // ranks' candidates and advances the clock; then the ordered gather + nodal update
+    const bool prof = e->profile != 0;
+    if (prof) for (int k = 0; k < 3; k++) { e->prof_ms[k] = 0; e->prof_n[k] = 0; }
+    CUDA_OK(cudaEventRecord(e->ev0, e->st));
+    const int chunk = 64;
+    for (int c0 = 0; c0 < ncycles; c0 += chunk) {
+      const int nc = (ncycles - c0 < chunk) ? ncycles - c0 : chunk;
+      size_t evi = 0;
+      for (int c = 0; c < nc; c++) {
+        launch_element_phase(e, 0, prof ? &evi : nullptr);
+        { int rc = exchange_on_stream(e, true); if (rc) return rc; }
+        if (prof) cudaEventRecord(get_event(e, evi++), e->st);
+        launch_node_fused(e->nd, e->d_fsky, e->roww, e->d_cs, e->ctl.iroddl, e->st); e->launches++;
+        if (prof) cudaEventRecord(get_event(e, evi++), e->st);
+      }
+      if (prof) {
+        CUDA_OK(cudaStreamSynchronize(e->st));
+        size_t k = 0;
+        for (int c = 0; c < nc; c++) {
+          for (size_t s = 0; s < e->csg.size(); s++, k += 2) { float ms; cudaEventElapsedTime(&ms, e->evpool[k], e->evpool[k + 1]); e->prof_ms[1] += ms; e->prof_n[1]++; }
+          for (size_t s = 0; s < e->bsg.size(); s++, k += 2) { float ms; cudaEventElapsedTime(&ms, e->evpool[k], e->evpool[k + 1]); e->prof_ms[0] += ms; e->prof_n[0]++; }
+          { float ms; cudaEventElapsedTime(&ms, e->evpool[k], e->evpool[k + 1]); e->prof_ms[2] += ms; e->prof_n[2]++; k += 2; }
+        }
+      }
+    }
+    CUDA_OK(cudaEventRecord(e->ev1, e->st));
+    if (prof) { CUDA_OK(cudaStreamSynchronize(e->st)); float ms; CUDA_OK(cudaEventElapsedTime(&ms, e->ev0, e->ev1)); e->last_run_ms = ms; }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   if (e->profile) {
     // un-graphed, one event pair around every launch: per-class device time on the launching stream
     for (int k = 0; k < 3; k++) { e->prof_ms[k] = 0; e->prof_n[k] = 0; }
@@ -464,6 +537,86 @@ int orgpu_step_host(orgpu_engine* e, const double* X, const double* V, const dou
   if (Vout) { unpack4to3_kernel<<<nb, 256, 0, e->st>>>(e->nd.vel, e->d_stage3b, n); e->launches++; CUDA_OK(cudaMemcpyAsync(Vout, e->d_stage3b, 24 * (size_t)n, cudaMemcpyDeviceToHost, e->st)); }
   CUDA_OK(cudaStreamSynchronize(e->st));
   return 0;
+}
+
+// ---- domain exchange ------------------------------------------------------------------------------
+
+static int rows_tmp(orgpu_engine* e, size_t n)
+{
+  Exchange& x = e->xc;
+  if (n <= x.tmp_cap) return 0;
+  if (x.d_slots_tmp) cudaFree(x.d_slots_tmp); if (x.d_rows_tmp) cudaFree(x.d_rows_tmp);
+  x.tmp_cap = n + n / 2 + 64;
+  CUDA_OK(cudaMalloc((void**)&x.d_slots_tmp, 4 * x.tmp_cap)); CUDA_OK(cudaMalloc((void**)&x.d_rows_tmp, 64 * x.tmp_cap));
+  return 0;
+}
+
+int orgpu_pack_rows(orgpu_engine* e, int n, const int* slots, double* buf)
+{
+  NEED(e && e->finalized && n >= 0 && (n == 0 || (slots && buf)), -1, "orgpu_pack_rows: bad arguments"); CUDA_OK(cudaSetDevice(e->device));
+  if (n == 0) return 0;
+  for (int j = 0; j < n; j++) NEED(slots[j] >= 0 && slots[j] < e->lsky, -4, "orgpu_pack_rows: slot %d out of range", slots[j]);
+  if (rows_tmp(e, n)) return -100;
+  CUDA_OK(cudaMemcpyAsync(e->xc.d_slots_tmp, slots, 4 * (size_t)n, cudaMemcpyHostToDevice, e->st));
+  rows_gather8_kernel<<<(n + 255) / 256, 256, 0, e->st>>>(e->d_fsky, e->roww, e->xc.d_slots_tmp, n, e->xc.d_rows_tmp); e->launches++;
+  CUDA_OK(cudaMemcpyAsync(buf, e->xc.d_rows_tmp, 64 * (size_t)n, cudaMemcpyDeviceToHost, e->st));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+int orgpu_unpack_rows(orgpu_engine* e, int n, const int* slots, const double* buf)
+{
+  NEED(e && e->finalized && n >= 0 && (n == 0 || (slots && buf)), -1, "orgpu_unpack_rows: bad arguments"); CUDA_OK(cudaSetDevice(e->device));
+  if (n == 0) return 0;
+  for (int j = 0; j < n; j++) NEED(slots[j] >= 0 && slots[j] < e->lsky, -4, "orgpu_unpack_rows: slot %d out of range", slots[j]);
+  if (rows_tmp(e, n)) return -100;
+  CUDA_OK(cudaMemcpyAsync(e->xc.d_slots_tmp, slots, 4 * (size_t)n, cudaMemcpyHostToDevice, e->st));
+  CUDA_OK(cudaMemcpyAsync(e->xc.d_rows_tmp, buf, 64 * (size_t)n, cudaMemcpyHostToDevice, e->st));
+  rows_scatter8_kernel<<<(n + 255) / 256, 256, 0, e->st>>>(e->d_fsky, e->roww, e->xc.d_slots_tmp, n, e->xc.d_rows_tmp); e->launches++;
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+int orgpu_comm_unique_id(unsigned char id[128])
+{
+  NcclApi* N = nccl_api(); if (!N) return -7;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId u; NCCL_OK(N->GetUniqueId(&u)); memcpy(id, &u, 128);
+  return 0;
+}
+
+int orgpu_comm_init(orgpu_engine* e, int nranks, int rank, const unsigned char id[128])
+{
+  NEED(e && nranks >= 1 && rank >= 0 && rank < nranks && id, -1, "orgpu_comm_init: bad arguments"); CUDA_OK(cudaSetDevice(e->device));
+  NcclApi* N = nccl_api(); if (!N) return -7;
+  ncclUniqueId u; memcpy(&u, id, 128);
+  NCCL_OK(N->CommInitRank(&e->xc.comm, nranks, u, rank));
+  e->xc.nranks = nranks; e->xc.rank = rank;
+  if (dev_alloc(&e->xc.d_cand_send, 4) || dev_alloc(&e->xc.d_cand_recv, 4 * (size_t)nranks)) return -100;
+  return 0;
+}
+
+int orgpu_set_exchange(orgpu_engine* e, int nneigh, const int* ranks, const int* send_ptr, const int* send_slots,
+                       const int* recv_ptr, const int* recv_slots)
+{
+  NEED(e && e->finalized && nneigh >= 0, -1, "orgpu_set_exchange: engine not finalized / bad arguments"); CUDA_OK(cudaSetDevice(e->device));
+  Exchange& x = e->xc;
+  x.nb_rank.assign(ranks, ranks + nneigh); x.send_ptr.assign(send_ptr, send_ptr + nneigh + 1); x.recv_ptr.assign(recv_ptr, recv_ptr + nneigh + 1);
+  x.nsend = nneigh ? send_ptr[nneigh] : 0; x.nrecv = nneigh ? recv_ptr[nneigh] : 0;
+  for (int j = 0; j < x.nsend; j++) NEED(send_slots[j] >= 0 && send_slots[j] < e->lsky, -4, "orgpu_set_exchange: send slot out of range");
+  for (int j = 0; j < x.nrecv; j++) NEED(recv_slots[j] >= 0 && recv_slots[j] < e->lsky, -4, "orgpu_set_exchange: recv slot out of range");
+  for (int k = 0; k < nneigh; k++) NEED(ranks[k] >= 0 && ranks[k] < x.nranks && ranks[k] != x.rank, -4, "orgpu_set_exchange: neighbour rank %d invalid", ranks[k]);
+  if (dev_alloc(&x.d_send_slots, (size_t)x.nsend + 1) || dev_alloc(&x.d_recv_slots, (size_t)x.nrecv + 1) ||
+      dev_alloc(&x.d_sendbuf, (size_t)e->roww * (x.nsend + 1)) || dev_alloc(&x.d_recvbuf, (size_t)e->roww * (x.nrecv + 1))) return -100;
+  if (x.nsend) CUDA_OK(cudaMemcpy(x.d_send_slots, send_slots, 4 * (size_t)x.nsend, cudaMemcpyHostToDevice));
+  if (x.nrecv) CUDA_OK(cudaMemcpy(x.d_recv_slots, recv_slots, 4 * (size_t)x.nrecv, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int orgpu_exchange(orgpu_engine* e)
+{
+  NEED(e && e->finalized, -1, "orgpu_exchange: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
+  return exchange_on_stream(e, false);
 }
 
 long long orgpu_launch_count(orgpu_engine* e) { return e ? e->launches : 0; }

@@ -1,0 +1,119 @@
+// exchange.cuh -- domain exchange of the /PARITH/ON skyline and the global time-step arg-min.
+//
+// Reference: SPMD_EXCH2_A_PON (engine/source/mpi/forces/spmd_exch2_a_pon.F:545-557 pack
+// FSKY(:,ISENDP(j)), :1156 MPI_ISEND, :1165 MPI_WAITANY, :1190-1201 unpack into FSKY(:,IRECVP(j)))
+// and SPMD_GLOB_MIN5 (engine/source/mpi/generic/spmd_glob_min5.F:34-128, custom op GLOB_MIN :122).
+// Here: one process per GPU; rows are packed by a kernel straight from the device skyline, all
+// neighbour sends/receives plus the 32-byte (dt, type, id) candidates of every rank travel in ONE
+// NCCL group (one fused NCCL kernel over NVLink), and one kernel scatters the received rows into
+// their reserved slots and folds the candidates in rank order + advances the RESOL time-step
+// bookkeeping.  NCCL is loaded with dlopen so single-GPU users (and the CPU symbol test) do not
+// need it at all.
+#pragma once
+#include <dlfcn.h>
+#include <nccl.h>
+#include <vector>
+#include "common.cuh"
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi* nccl_api()
+{
+  static NcclApi api; static bool tried = false;
+  if (tried) return api.lib ? &api : nullptr;
+  tried = true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) { api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+  if (!api.lib) { orgpu_set_error("NCCL not found (dlopen libnccl.so.2): %s", dlerror()); return nullptr; }
+#define LOAD(f) api.f = (decltype(api.f))dlsym(api.lib, "nccl" #f); if (!api.f) { orgpu_set_error("NCCL symbol nccl" #f " missing"); api.lib = nullptr; return nullptr; }
+  LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(Send) LOAD(Recv) LOAD(GroupStart) LOAD(GroupEnd) LOAD(GetErrorString)
+#undef LOAD
+  return &api;
+}
+
+struct Exchange {
+  int nranks = 1, rank = 0;
+  ncclComm_t comm = nullptr;
+  // neighbour lists (device): rows sendbuf[j] <- fsky[send_slots[j]], fsky[recv_slots[j]] <- recvbuf[j]
+  std::vector<int> nb_rank, send_ptr, recv_ptr;       // host copies: [nneigh], [nneigh+1]
+  int* d_send_slots = nullptr; int* d_recv_slots = nullptr;
+  double* d_sendbuf = nullptr; double* d_recvbuf = nullptr;
+  int nsend = 0, nrecv = 0;
+  double* d_cand_send = nullptr;                       // (dt2t, ityptst, neltst, 0)
+  double* d_cand_recv = nullptr;                       // 4 doubles per rank
+  // scratch for the host-staged entry points
+  int* d_slots_tmp = nullptr; double* d_rows_tmp = nullptr; size_t tmp_cap = 0;
+};
+
+// rows out of the skyline into a contiguous buffer; ROWW doubles per row on both sides
+template <int ROWW>
+__global__ void rows_pack_kernel(const double* __restrict__ fsky, const int* __restrict__ slots, int n,
+                                 double* __restrict__ buf, const CycleState* cs, double* cand)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;           // one thread per double2 of a row
+  constexpr int V = ROWW / 2;
+  if (i < n * V) {
+    const int j = i / V, c = i - j * V;
+    reinterpret_cast<double2*>(buf)[(size_t)j * V + c] = reinterpret_cast<const double2*>(fsky)[(size_t)slots[j] * V + c];
+  }
+  if (cand && i == 0) { cand[0] = cs->dt2t; cand[1] = (double)cs->ityptst; cand[2] = (double)cs->neltst; cand[3] = 0.0; }
+}
+
+// received rows into their reserved slots; thread 0 of block 0 folds the dt candidates of all ranks in
+// rank order (strict "<": the lowest rank keeps a tie) and advances the time-step bookkeeping
+// (resol.F:2721-2722, 6124-6128, 6327, 6352, 6494-6497, 8599-8608)
+template <int ROWW>
+__global__ void rows_unpack_kernel(double* __restrict__ fsky, const int* __restrict__ slots, int n,
+                                   const double* __restrict__ buf, CycleState* cs, const double* __restrict__ cand, int nranks)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int V = ROWW / 2;
+  if (i < n * V) {
+    const int j = i / V, c = i - j * V;
+    reinterpret_cast<double2*>(fsky)[(size_t)slots[j] * V + c] = reinterpret_cast<const double2*>(buf)[(size_t)j * V + c];
+  }
+  if (cand && i == 0) {
+    double cur = K_EP06; int typ = 0, ngl = 0;
+    for (int r = 0; r < nranks; r++) {
+      const double d = cand[4 * r];
+      if (d < cur) { cur = d; typ = (int)cand[4 * r + 1]; ngl = (int)cand[4 * r + 2]; }
+    }
+    cs->dt2t = cur; cs->ityptst = typ; cs->neltst = ngl;
+    const double dt1 = cs->dt2;
+    double dt2 = K_EP06;
+    if (cur < dt2) dt2 = cur;
+    const double c11 = (double)1.1f;
+    dt2 = fmin(dt2, fmin(c11 * cs->dt2old, cs->dtmx));
+    cs->dt2old = dt2;
+    cs->dt12 = K_HALF * (dt1 + dt2);
+    cs->dt1 = dt1; cs->dt2 = dt2;
+    cs->tt = cs->tt + dt2; cs->ncycle += 1;
+  }
+}
+
+// host-staged variants always speak 8-double rows (the reference FSKY(8,LSKY)); ROWW=4 device rows
+// hold (Fx,Fy,Fz,STI) -> components 1,2,3,7
+__global__ void rows_gather8_kernel(const double* __restrict__ fsky, int roww, const int* __restrict__ slots, int n, double* __restrict__ out)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x; if (j >= n) return;
+  const double* r = fsky + (size_t)roww * slots[j]; double* o = out + 8 * (size_t)j;
+  if (roww == 8) { for (int c = 0; c < 8; c++) o[c] = r[c]; }
+  else { o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = o[4] = o[5] = 0.0; o[6] = r[3]; o[7] = 0.0; }
+}
+__global__ void rows_scatter8_kernel(double* __restrict__ fsky, int roww, const int* __restrict__ slots, int n, const double* __restrict__ in)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x; if (j >= n) return;
+  double* r = fsky + (size_t)roww * slots[j]; const double* o = in + 8 * (size_t)j;
+  if (roww == 8) { for (int c = 0; c < 8; c++) r[c] = o[c]; }
+  else { r[0] = o[0]; r[1] = o[1]; r[2] = o[2]; r[3] = o[6]; }
+}

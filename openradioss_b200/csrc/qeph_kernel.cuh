@@ -33,6 +33,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     #pragma unroll
     for (int k = 0; k < 4; k++) nc[k] = __ldg(g.conn + k * np + e);
     ngl = __ldg(g.ngl + e); order = g.order0 + e;
+    if ((threadIdx.x & 3) == 0) shell_prefetch_state(g, e);   // state is consumed after the geometry phase
     double OFFG = g.off[e];
     double px[4], py[4], pz[4];
     #pragma unroll

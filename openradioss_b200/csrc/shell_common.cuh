@@ -62,7 +62,49 @@ __device__ __forceinline__ void vinter1(const double* __restrict__ tf, int iad, 
   y = p1.y + dydx * (x - p1.x);
 }
 
-struct IpState { double sxx, syy, sxy, syz, szx; };
+struct IpState { double sxx, syy, sxy, syz, szx, pla, epsd, temp; int ipos; };
+
+// streaming access for element state: read once / written once per cycle, keep L2 for the nodal records
+template <int LAW>
+__device__ __forceinline__ IpState ip_load(const ShellSG& g, int e, int ipt)
+{
+  const size_t np = g.ne_pad;
+  const double* sg = g.sig + (size_t)ipt * 5 * np + e;
+  IpState s;
+  s.sxx = __ldcs(sg); s.syy = __ldcs(sg + np); s.sxy = __ldcs(sg + 2 * np); s.syz = __ldcs(sg + 3 * np); s.szx = __ldcs(sg + 4 * np);
+  s.pla = __ldcs(g.pla + (size_t)ipt * np + e);
+  s.epsd = __ldcs(g.epsd_ip + (size_t)ipt * np + e);
+  s.temp = K_ZERO; s.ipos = 0;
+  if (LAW == 2) { if (g.m2.has_temp) s.temp = __ldcs(g.temp + (size_t)ipt * np + e); }
+  else if (g.m36.nrate == 1) s.ipos = __ldcs(g.vartmp + ((size_t)ipt * g.nvartmp + 2) * np + e);
+  return s;
+}
+template <int LAW>
+__device__ __forceinline__ void ip_store(const ShellSG& g, int e, int ipt, const IpState& s, int ipos_old, double temp_old)
+{
+  const size_t np = g.ne_pad;
+  double* sg = g.sig + (size_t)ipt * 5 * np + e;
+  __stcs(sg, s.sxx); __stcs(sg + np, s.syy); __stcs(sg + 2 * np, s.sxy); __stcs(sg + 3 * np, s.syz); __stcs(sg + 4 * np, s.szx);
+  __stcs(g.pla + (size_t)ipt * np + e, s.pla);
+  __stcs(g.epsd_ip + (size_t)ipt * np + e, s.epsd);
+  if (LAW == 2) { if (g.m2.has_temp && s.temp != temp_old) __stcs(g.temp + (size_t)ipt * np + e, s.temp); }
+  else if (g.m36.nrate == 1 && s.ipos != ipos_old) __stcs(g.vartmp + ((size_t)ipt * g.nvartmp + 2) * np + e, s.ipos);
+}
+
+// start every element-state line of this thread's 4-element sector toward L2 (called by one lane in 4)
+__device__ __forceinline__ void shell_prefetch_state(const ShellSG& g, int e)
+{
+  const size_t np = g.ne_pad;
+  for (int k = 0; k < 5; k++) prefetch_l2(g.forc + k * np + e);
+  for (int k = 0; k < 3; k++) prefetch_l2(g.mom + k * np + e);
+  prefetch_l2(g.eint + e); prefetch_l2(g.eint + np + e); prefetch_l2(g.thk + e); prefetch_l2(g.epsd + e);
+  for (int k = 0; k < 8; k++) prefetch_l2(g.stra + k * np + e);
+  for (int k = 0; k < g.nhourg; k++) prefetch_l2(g.hourg + k * np + e);
+  for (int k = 0; k < g.npt * 5; k++) prefetch_l2(g.sig + k * np + e);
+  for (int k = 0; k < g.npt; k++) { prefetch_l2(g.pla + k * np + e); prefetch_l2(g.epsd_ip + k * np + e); }
+  if (g.temp) for (int k = 0; k < g.npt; k++) prefetch_l2(g.temp + k * np + e);
+  if (g.law == 36 && (e & 7) == 0) for (int k = 0; k < g.npt; k++) prefetch_l2(g.vartmp + ((size_t)k * g.nvartmp + 2) * np + e);
+}
 
 // ---- SIGEPS36C, VP = 0 -------------------------------------------------------------------
 __device__ __forceinline__ void law36_ip(const ShellSG& g, int e, int ipt, int ipla, double asrate,
@@ -74,7 +116,7 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, int e, int ipt, int i
   const int np = g.ne_pad;
   const double E = m.young, A1 = m.a1u, A2 = m.a2u, G = m.shear, G3 = m.g3;
   ssp = m.soundsp; etse = K_ONE;
-  double pla = g.pla[(size_t)ipt * np + e];
+  double pla = s.pla;
   // elastic predictor
   const double sox = s.sxx, soy = s.syy, soxy = s.sxy;
   s.sxx = sox + A1 * dexx + A2 * deyy;
@@ -88,19 +130,19 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, int e, int ipt, int i
     const double exx = dexx * dtinv, eyy = deyy * dtinv, exy = dexy * dtinv;
     epsd = K_HALF * (fabs(exx + eyy) + sqrt((exx - eyy) * (exx - eyy) + exy * exy));
   } else {
-    epsd = asrate * epsd_pg + (K_ONE - asrate) * g.epsd_ip[(size_t)ipt * np + e];
+    epsd = asrate * epsd_pg + (K_ONE - asrate) * s.epsd;
   }
-  g.epsd_ip[(size_t)ipt * np + e] = epsd;
+  s.epsd = epsd;
   // yield stress and hardening modulus from the tabulated curves
   double YLD, H;
   int* vt = g.vartmp + (size_t)ipt * g.nvartmp * np + e;
   if (m.nrate == 1) {
-    int ipos = vt[2 * np];
+    int ipos = s.ipos;
     const int f = m.ifunc[0];
     const int i0 = __ldg(g.npf + f), i1 = __ldg(g.npf + f + 1);
     double dydx, y1;
     vinter1(g.tf, i0, i1 - i0, ipos, pla, dydx, y1);
-    vt[2 * np] = ipos;
+    s.ipos = ipos;
     const double FACT = K_ONE * K_ONE * (m.yfac[0] * K_ONE);
     H = dydx * FACT;
     YLD = y1 * FACT;
@@ -210,7 +252,7 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, int e, int ipt, int i
       etse = H / (H + E);
     }
   }
-  g.pla[(size_t)ipt * np + e] = pla;
+  s.pla = pla;
   yld_out = YLD;
 }
 
@@ -228,10 +270,10 @@ __device__ __forceinline__ void law2_ip(const ShellSG& g, int e, int ipt, int ip
   const double a12 = a11 * nu;
   const double cn = m.cn;
   const double epdr = fmax(m.epdr * dt1, K_EM20);
-  double pla = g.pla[(size_t)ipt * np + e];
-  double epsd = g.epsd_ip[(size_t)ipt * np + e];
+  double pla = s.pla;
+  double epsd = s.epsd;
   const bool has_temp = m.has_temp != 0;
-  const double tempel = has_temp ? g.temp[(size_t)ipt * np + e] : K_ZERO;
+  const double tempel = has_temp ? s.temp : K_ZERO;
   double z3, z4, m_exp, tstar = K_ZERO;
   if (m.iform == 1) { z3 = m.z3; z4 = m.z4; m_exp = K_ONE; if (has_temp) tstar = fmax(K_ZERO, (tempel - m.tref) / fmax(m.tmelt - m.tref, K_EM20)); }
   else { z3 = K_ZERO; z4 = K_ZERO; m_exp = m.z3; tstar = fmax(K_ZERO, (tempel - m.tref) / (m.tmelt - m.tref)); }
@@ -360,9 +402,9 @@ __device__ __forceinline__ void law2_ip(const ShellSG& g, int e, int ipt, int ip
   EZZ = -(dexx + deyy) * nu - (K_ONE - K_TWO * nu) * EZZ;
   EZZ = EZZ / (K_ONE - nu);
   thk = thk + EZZ * thklyl * off;
-  if (m.rhocp > K_ZERO && has_temp) g.temp[(size_t)ipt * np + e] = tempel + sigy * DPLA / m.rhocp;
-  g.pla[(size_t)ipt * np + e] = pla;
-  g.epsd_ip[(size_t)ipt * np + e] = epsd;
+  if (m.rhocp > K_ZERO && has_temp) s.temp = tempel + sigy * DPLA / m.rhocp;
+  s.pla = pla;
+  s.epsd = epsd;
 }
 
 // ---- CMAIN3 / MULAWC for one element --------------------------------------------------------
@@ -396,7 +438,11 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, int e, dou
   const double pm9 = (LAW == 36) ? g.m36.asrate : g.m2.asrate;
   const double asrate = (israte > 0) ? fmin(K_ONE, pm9 * dt1) : K_ONE;
   const int qrow = (npt - 1) * 11;
+  IpState nxt = ip_load<LAW>(g, e, 0);
   for (int ipt = 0; ipt < npt; ipt++) {
+    IpState s = nxt;
+    if (ipt + 1 < npt) nxt = ip_load<LAW>(g, e, ipt + 1);        // software pipeline: next point's state in flight
+    const int ipos_old = s.ipos; const double temp_old = s.temp;
     const double thkly = c_WF[qrow + ipt];
     const double posly = c_Z0[qrow + ipt] + K_ZERO;
     const double wmc = c_WM[qrow + ipt];
@@ -405,8 +451,6 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, int e, dou
     const double dexx = io.exx + zt * io.kxx;
     const double deyy = io.eyy + zt * io.kyy;
     const double dexy = io.exy + zt * io.kxy;
-    double* sg = g.sig + (size_t)ipt * 5 * np + e;
-    IpState s{sg[0], sg[np], sg[2 * (size_t)np], sg[3 * (size_t)np], sg[4 * (size_t)np]};
     if (LAW == 36) {
       law36_ip(g, e, ipt, g.prop.ipla, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, thklyl, io.gs, io.epsd_pg, off,
                s, thkn, ssp, etse, sigy);
@@ -415,7 +459,7 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, int e, dou
               off, off_old, ioff_duct, epchk, s, thkn, etse, sigy);
     }
     viscmx = fmax(DM, viscmx);
-    sg[0] = s.sxx; sg[np] = s.syy; sg[2 * (size_t)np] = s.sxy; sg[3 * (size_t)np] = s.syz; sg[4 * (size_t)np] = s.szx;
+    ip_store<LAW>(g, e, ipt, s, ipos_old, temp_old);
     fo[0] = fo[0] + thkly * s.sxx; fo[1] = fo[1] + thkly * s.syy; fo[2] = fo[2] + thkly * s.sxy;
     fo[3] = fo[3] + thkly * s.syz; fo[4] = fo[4] + thkly * s.szx;
     mo[0] = mo[0] + wmc * s.sxx; mo[1] = mo[1] + wmc * s.syy; mo[2] = mo[2] + wmc * s.sxy;

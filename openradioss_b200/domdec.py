@@ -1,0 +1,147 @@
+"""Domain decomposition of a model for one-process-per-GPU runs, the way the Starter does it.
+
+Reference behaviour: elements are owned by exactly one domain
+(starter/source/spmd/domdec2.F); frontier nodes are duplicated on every domain that touches
+them **with identical full slot lists** (the local ADDCNE is copied from the global one,
+starter/source/restart/ddsplit/w_pon.F:617-631) and PROCNE records the owner of each slot.  At run
+time SPMD_EXCH2_A_PON (engine/source/mpi/forces/spmd_exch2_a_pon.F:545-557 pack from
+FSKY(:,ISENDP), :1190-1201 unpack into FSKY(:,IRECVP)) ships the corner rows of remote elements
+into their reserved slots, then the same ordered ASSPAR4 gather runs on every replica, so nodal
+sums are bitwise identical on any domain count.
+
+`decompose` builds, for one rank, the local Model (local node / element / slot numbering) plus the
+per-neighbour send and receive slot lists (ISENDP / IRECVP equivalents, 0-based local slots, both
+sides ordered by ascending global slot so the message layouts agree without negotiation).
+"""
+from __future__ import annotations
+from dataclasses import dataclass, field
+from typing import List, Optional
+import numpy as np
+from .model import Model, SolidGroup, ShellGroup, NVSIZ
+
+
+@dataclass
+class Neighbor:
+    rank: int
+    send: np.ndarray          # local 0-based FSKY slots whose rows go to `rank`   (ISENDP)
+    recv: np.ndarray          # local 0-based FSKY slots filled by rows from `rank` (IRECVP)
+
+
+@dataclass
+class Domain:
+    rank: int
+    nproc: int
+    model: Model
+    node_gid: np.ndarray      # local node -> global node (0-based)
+    shell_gid: np.ndarray     # local shell -> global shell (0-based)
+    solid_gid: np.ndarray
+    owner: np.ndarray         # bool per local node: this rank is the lowest rank holding it (WEIGHT)
+    neighbors: List[Neighbor] = field(default_factory=list)
+
+
+def strips(centroids: np.ndarray, nproc: int, axis: int = 0) -> np.ndarray:
+    """Balanced contiguous strips along one axis (C3: x strips, C4/C5: z slabs): element -> domain."""
+    order = np.argsort(centroids[:, axis], kind="stable")
+    dom = np.empty(len(order), np.int32)
+    dom[order] = (np.arange(len(order), dtype=np.int64) * nproc // max(1, len(order))).astype(np.int32)
+    return dom
+
+
+def element_centroids(m: Model):
+    cs = m.X[m.ixs[:, 1:9] - 1].mean(axis=1) if m.numels else np.zeros((0, 3))
+    cc = m.X[m.ixc[:, 1:5] - 1].mean(axis=1) if m.numelc else np.zeros((0, 3))
+    return cs, cc
+
+
+def _regroup(groups, gid_of_local, cls):
+    """local element groups: runs of consecutive local elements that came from one global group."""
+    out = []
+    if len(gid_of_local) == 0:
+        return out
+    start = 0
+    for i in range(1, len(gid_of_local) + 1):
+        if i == len(gid_of_local) or gid_of_local[i] != gid_of_local[start] or i - start == NVSIZ:
+            g = groups[gid_of_local[start]]
+            if cls is SolidGroup:
+                out.append(SolidGroup(nft=start, nel=i - start, mat=g.mat, prop=g.prop))
+            else:
+                out.append(ShellGroup(nft=start, nel=i - start, law=g.law, mat=g.mat, prop=g.prop))
+            start = i
+    return out
+
+
+def decompose(m: Model, dom_s: Optional[np.ndarray], dom_c: Optional[np.ndarray], nproc: int, rank: int) -> Domain:
+    numnod = m.numnod
+    dom_s = np.zeros(0, np.int32) if dom_s is None else np.asarray(dom_s, np.int32)
+    dom_c = np.zeros(0, np.int32) if dom_c is None else np.asarray(dom_c, np.int32)
+    adsky0 = m.adsky.astype(np.int64) - 1                       # 0-based global slot offsets per node
+    # owner domain of every global slot (PROCNE)
+    slot_dom = np.full(m.lsky, -1, np.int32)
+    if m.numels:
+        slot_dom[m.iads.reshape(-1).astype(np.int64) - 1] = np.repeat(dom_s, 8)
+    if m.numelc:
+        slot_dom[m.iadc.reshape(-1).astype(np.int64) - 1] = np.repeat(dom_c, 4)
+    assert (slot_dom >= 0).all(), "every FSKY slot must belong to an element corner"
+    slot_node = np.repeat(np.arange(numnod, dtype=np.int64), np.diff(adsky0))
+    # node sets per domain
+    masks = np.zeros((nproc, numnod), bool)
+    for q in range(nproc):
+        if m.numels:
+            masks[q, (m.ixs[dom_s == q, 1:9] - 1).reshape(-1)] = True
+        if m.numelc:
+            masks[q, (m.ixc[dom_c == q, 1:5] - 1).reshape(-1)] = True
+    mine = masks[rank]
+    node_gid = np.nonzero(mine)[0]
+    g2l = np.full(numnod, -1, np.int64); g2l[node_gid] = np.arange(len(node_gid))
+    counts = (adsky0[1:] - adsky0[:-1])[node_gid]
+    ladsky0 = np.zeros(len(node_gid) + 1, np.int64); ladsky0[1:] = np.cumsum(counts)
+    lsky = int(ladsky0[-1])
+    # global slot -> local slot for slots of local nodes
+    gslots = np.nonzero(mine[slot_node])[0]                    # ascending global slot == local slot order
+    gs2l = np.full(m.lsky, -1, np.int64); gs2l[gslots] = np.arange(lsky)
+    solid_gid = np.nonzero(dom_s == rank)[0]; shell_gid = np.nonzero(dom_c == rank)[0]
+    ixs = m.ixs[solid_gid].copy(); ixc = m.ixc[shell_gid].copy()
+    if len(solid_gid):
+        ixs[:, 1:9] = (g2l[ixs[:, 1:9] - 1] + 1).astype(np.int32)
+    if len(shell_gid):
+        ixc[:, 1:5] = (g2l[ixc[:, 1:5] - 1] + 1).astype(np.int32)
+    iads = (gs2l[m.iads[solid_gid].astype(np.int64) - 1] + 1).astype(np.int32) if len(solid_gid) else np.zeros((0, 8), np.int32)
+    iadc = (gs2l[m.iadc[shell_gid].astype(np.int64) - 1] + 1).astype(np.int32) if len(shell_gid) else np.zeros((0, 4), np.int32)
+    sub = lambda a: None if a is None else np.ascontiguousarray(a[node_gid])
+    lm = Model(X=sub(m.X), V=sub(m.V), VR=sub(m.VR), MS=sub(m.MS), IN=sub(m.IN), control=m.control, ixs=ixs, ixc=ixc,
+               vol0=m.vol0[solid_gid] if len(m.vol0) else m.vol0, icodt=sub(m.icodt), icodr=sub(m.icodr),
+               fext=sub(m.fext), mext=sub(m.mext), itab=sub(m.itab), npf=m.npf, tf=m.tf)
+    lm.adsky = (ladsky0 + 1).astype(np.int32); lm.iads = iads; lm.iadc = iadc; lm.lsky = lsky
+    # groups
+    if m.solid_groups:
+        gid = np.zeros(m.numels, np.int64)
+        for k, g in enumerate(m.solid_groups):
+            gid[g.nft:g.nft + g.nel] = k
+        lm.solid_groups = _regroup(m.solid_groups, gid[solid_gid], SolidGroup)
+    if m.shell_groups:
+        gid = np.zeros(m.numelc, np.int64)
+        for k, g in enumerate(m.shell_groups):
+            gid[g.nft:g.nft + g.nel] = k
+        lm.shell_groups = _regroup(m.shell_groups, gid[shell_gid], ShellGroup)
+    # ownership (lowest rank holding the node) for global reductions
+    first = np.argmax(masks, axis=0)
+    owner = first[node_gid] == rank
+    d = Domain(rank=rank, nproc=nproc, model=lm, node_gid=node_gid, shell_gid=shell_gid, solid_gid=solid_gid, owner=owner)
+    # exchange lists
+    ldom = slot_dom[gslots]                                     # owner of each local slot
+    for q in range(nproc):
+        if q == rank:
+            continue
+        recv = np.nonzero(ldom == q)[0]                         # rows rank q computes for my nodes
+        theirs = np.nonzero((slot_dom == rank) & masks[q][slot_node])[0]   # my rows at nodes q also holds
+        send = gs2l[theirs]
+        if len(recv) or len(send):
+            d.neighbors.append(Neighbor(rank=q, send=send.astype(np.int32), recv=recv.astype(np.int32)))
+    return d
+
+
+def decompose_strips(m: Model, nproc: int, rank: int, axis: int = 0) -> Domain:
+    cs, cc = element_centroids(m)
+    both = np.concatenate([cs, cc])
+    dom = strips(both, nproc, axis)
+    return decompose(m, dom[:len(cs)], dom[len(cs):], nproc, rank)

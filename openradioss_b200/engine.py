@@ -16,7 +16,8 @@ _lib = None
 EXPORTS = """create destroy last_error upload_nodes set_loads set_bcs set_solids set_shells set_pon
 set_functions add_solid_group add_shell_group finalize forces_phase assemble advance run_cycles
 synchronize get_time download_nodes download_fsky download_solid_state download_shell_state
-step_host launch_count last_run_ms set_profile get_profile""".split()
+step_host launch_count last_run_ms set_profile get_profile pack_rows unpack_rows comm_unique_id comm_init
+set_exchange exchange""".split()
 
 
 def load_library() -> C.CDLL:
@@ -42,6 +43,32 @@ class Engine(Binding):
         """End-to-end entry: host nodal arrays in, ncycles on the device, host arrays out."""
         self._call("step_host", self.h, _opt(X, np.float64), _opt(V, np.float64), _opt(VR, np.float64),
                    C.c_int(ncycles), Xout.ctypes.data_as(C.c_void_p), Vout.ctypes.data_as(C.c_void_p))
+
+    # -- one process per GPU: NCCL exchange inside run_cycles ------------------------------------
+    def comm_init(self, dist, domain):
+        """Create the NCCL communicator (id from rank 0, broadcast through torch.distributed) and
+        register the neighbour send / receive slot lists of this rank's Domain."""
+        import torch
+        rank, world = dist.get_rank(), dist.get_world_size()
+        uid = (C.c_ubyte * 128)()
+        if rank == 0:
+            self._call("comm_unique_id", uid)
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(uid), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, 0)
+        uid = (C.c_ubyte * 128)(*t.cpu().tolist())
+        self._call("comm_init", self.h, C.c_int(world), C.c_int(rank), uid)
+        nbs = domain.neighbors
+        ranks = np.array([nb.rank for nb in nbs], np.int32)
+        sp = np.zeros(len(nbs) + 1, np.int32); rp = np.zeros(len(nbs) + 1, np.int32)
+        for k, nb in enumerate(nbs):
+            sp[k + 1] = sp[k] + len(nb.send); rp[k + 1] = rp[k] + len(nb.recv)
+        ss = np.concatenate([nb.send for nb in nbs]).astype(np.int32) if nbs else np.zeros(0, np.int32)
+        rs = np.concatenate([nb.recv for nb in nbs]).astype(np.int32) if nbs else np.zeros(0, np.int32)
+        self._call("set_exchange", self.h, C.c_int(len(nbs)), _opt(ranks, np.int32), _opt(sp, np.int32), _opt(ss, np.int32),
+                   _opt(rp, np.int32), _opt(rs, np.int32))
+
+    def exchange(self): self._call("exchange", self.h)
 
     def launch_count(self) -> int:
         fn = self.lib.orgpu_launch_count; fn.restype = C.c_longlong

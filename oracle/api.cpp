@@ -141,6 +141,17 @@ void orc_download_solid_state(void* h,int field,double* out){
   }
 }
 
+/* corner rows of n FSKY slots (0-based) out of / into the skyline: what SPMD_EXCH2_A_PON packs
+ * (spmd_exch2_a_pon.F:545-557) and unpacks (:1190-1201); rows are 8 doubles */
+void orc_pack_rows(void* h,int n,const int* slots,double* buf){
+  Oracle* o=(Oracle*)h;
+  for(int j=0;j<n;j++) memcpy(buf+8*(size_t)j,&o->FSKY[8*(size_t)slots[j]],64);
+}
+void orc_unpack_rows(void* h,int n,const int* slots,const double* buf){
+  Oracle* o=(Oracle*)h;
+  for(int j=0;j<n;j++) memcpy(&o->FSKY[8*(size_t)slots[j]],buf+8*(size_t)j,64);
+}
+
 void orc_download_shell_state(void* h,int field,double* out){
   Oracle* o=(Oracle*)h;
   for(auto* g:o->cgroups) orc_shell_group_state(*g,field,(size_t)o->numelc,out);

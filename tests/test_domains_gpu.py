@@ -1,0 +1,87 @@
+"""Domain decomposition on the GPU path.
+
+1 GPU: two Engine handles play two domains, rows travel through the host-staged C-ABI entry points
+(orgpu_pack_rows / orgpu_unpack_rows) -- nodal sums must be bitwise those of the single-domain run.
+>= 2 GPUs: one process per GPU, NCCL exchange + dt fold inside orgpu_run_cycles (skipped on 1 GPU)."""
+import os
+import numpy as np
+import pytest
+import torch
+from openradioss_b200 import meshgen, domdec, spmd
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from openradioss_b200.engine import Engine
+
+
+def models():
+    yield "shell", meshgen.shell_plate(12, 9, 120.0, 90.0, pressure=20.0, vrand=5.0, user_id_perm=True)
+    yield "brick", meshgen.hex_block(6, 5, 7, 1.2, 1.0, 1.4, v0=(0, 0, -100.0), vrand=5.0, fix_bottom_z=True, user_id_perm=True)
+
+
+@pytest.mark.parametrize("nproc", [2, 3])
+def test_host_staged_domains_bitwise(nproc):
+    for name, m in models():
+        ref = Engine(m)
+        doms = [domdec.decompose_strips(m, nproc, r) for r in range(nproc)]
+        backs = [Engine(d.model) for d in doms]
+        ncyc = 20
+        st = spmd.initial_state(m.control)
+        ref_acc = []
+        for c in range(ncyc):
+            dt1 = st["dt2"]
+            ref.forces_phase(dt1); ref.assemble()
+            ref_acc.append(ref.download_nodes(("A", "AR", "STIFN")))
+            dt2 = min(spmd.EP06, ref.time()["dt2t"], float(np.float32(1.1)) * st["dt2old"], st["dtmx"])
+            ref.advance(0.5 * (dt1 + dt2), dt2); st["dt2"] = dt2; st["dt2old"] = dt2
+
+        def check(c):
+            for b, d in zip(backs, doms):
+                a = b.download_nodes(("A", "AR", "STIFN"))
+                for k in ("A", "AR", "STIFN"):
+                    assert np.array_equal(a[k], ref_acc[c][k][d.node_gid]), (name, c, k, d.rank)
+        spmd.run_local(backs, doms, ncyc, on_cycle=check)
+        xr = ref.download_nodes(("X", "V"))
+        for b, d in zip(backs, doms):
+            x = b.download_nodes(("X", "V"))
+            assert np.array_equal(x["X"], xr["X"][d.node_gid]) and np.array_equal(x["V"], xr["V"][d.node_gid])
+
+
+def _nccl_worker(rank, world, port, q, kind):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    m = dict(models())[kind]
+    d = domdec.decompose_strips(m, world, rank)
+    g = Engine(d.model, device=rank)
+    g.comm_init(dist, d)
+    g.run_cycles(40); g.synchronize()
+    out = g.download_nodes(("X", "V"))
+    q.put((rank, d.node_gid, out["X"], out["V"], g.time()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("kind", ["shell", "brick"])
+def test_nccl_domains_match_single_gpu_bitwise(kind):
+    import torch.multiprocessing as mp
+    world = min(4, torch.cuda.device_count())
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q, kind)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    m = dict(models())[kind]
+    ref = Engine(m); ref.run_cycles(40); ref.synchronize()
+    xr = ref.download_nodes(("X", "V")); tr = ref.time()
+    for rank, gid, x, v, t in res:
+        assert np.array_equal(x, xr["X"][gid]) and np.array_equal(v, xr["V"][gid]), (kind, rank)
+        assert t["tt"] == tr["tt"] and t["ncycle"] == tr["ncycle"] and t["dt2"] == tr["dt2"]
