@@ -24,8 +24,8 @@ static int shell_add_group(std::vector<HostShellGroup>& groups, int nel, int nft
   if (prop->ipla < 0 || prop->ipla > 2) { orgpu_set_error("Iplas=%d is outside the built path (0,1,2)", prop->ipla); return -5; }
   if (!(prop->ismstr == 1 || prop->ismstr == 2 || prop->ismstr == 4)) { orgpu_set_error("shell Ismstr=%d is outside the built path (1,2,4)", prop->ismstr); return -5; }
   const bool qeph = shell_is_qeph(*prop);
-  if (!qeph && !(prop->ihbe >= 0 && prop->ihbe <= 4)) { orgpu_set_error("Ishell=%d is outside the built path (BT 1..4, QEPH 24)", prop->ihbe); return -5; }
-  if (!qeph) { orgpu_set_error("Belytschko-Tsay groups: kernel not built yet"); return -5; }
+  if (!qeph && !(prop->ihbe == 1 || prop->ihbe == 3 || prop->ihbe == 4)) { orgpu_set_error("Ishell=%d is outside the built path (BT 1, 3, 4; QEPH 24)", prop->ihbe); return -5; }
+  if (!qeph && prop->npt == 1) { orgpu_set_error("Belytschko-Tsay with NPT=1 (MHVIS3 hourglass) is outside the built path"); return -5; }
   HostShellGroup g; memset(&g, 0, sizeof g);
   g.nel = nel; g.nft = nft; g.law = law; g.prop = *prop;
   if (law == 36) {

@@ -108,6 +108,50 @@ def test_qeph_ithk0_uses_initial_thickness():
     cycle_check(m, ncheck=3)
 
 
+@pytest.mark.parametrize("ihbe", [1, 3, 4])
+@pytest.mark.parametrize("law", [36, 2])
+def test_bt_phases_match_oracle(ihbe, law):
+    prop = meshgen.default_prop_shell(ihbe=ihbe, npt=5)
+    m = meshgen.shell_plate(9, 7, 90.0, 70.0, prop=prop, law=law, pressure=30.0, vrand=30.0, user_id_perm=True)
+    g, o = cycle_check(m, ncheck=4, state_tol=1e-10 if law == 2 else 1e-11)
+    assert o.shell_state("pla").max() > 0.0
+
+
+@pytest.mark.parametrize("ismstr", [1, 2, 4])
+@pytest.mark.parametrize("ipla,npt", [(0, 3), (2, 5), (1, 2)])
+def test_bt_ismstr_iplas_npt(ismstr, ipla, npt):
+    prop = meshgen.default_prop_shell(ihbe=1, npt=npt, ismstr=ismstr, ipla=ipla)
+    m = meshgen.shell_plate(6, 6, 60.0, 60.0, prop=prop, pressure=30.0, vrand=30.0)
+    cycle_check(m, ncheck=4)
+
+
+def test_bt_plate_1000_cycles():
+    prop = meshgen.default_prop_shell(ihbe=1, npt=5)
+    m = meshgen.shell_plate(20, 20, 200.0, 200.0, prop=prop, pressure=2.0)
+    g, o = pair(m)
+    g.run_cycles(1000); o.run_cycles(1000)
+    ng, no = g.download_nodes(("D", "X", "V")), o.download_nodes(("D", "X", "V"))
+    assert rel_err(ng["D"], no["D"]) <= DISP_TOL
+    (keg, ieg), (keo, ieo) = energies(g, m), energies(o, m)
+    assert abs(ieg - ieo) <= ENERGY_TOL * abs(ieo) and abs(keg - keo) <= ENERGY_TOL * max(abs(keo), abs(ieo))
+    assert o.shell_state("pla").max() > 0.0
+
+
+def test_mixed_qeph_and_bt_groups_one_model():
+    """two properties in one model: shells of both families share nodes and the skyline"""
+    m = meshgen.shell_plate(10, 8, 100.0, 80.0, pressure=30.0, vrand=20.0)
+    bt = meshgen.default_prop_shell(ihbe=1, npt=3)
+    for k, gr in enumerate(m.shell_groups):
+        pass
+    # second half of the elements becomes BT / NPT=3 (groups are rebuilt so that each stays homogeneous)
+    from openradioss_b200.model import ShellGroup
+    ne = m.numelc; half = ne // 2
+    qe = m.shell_groups[0]
+    m.shell_groups = [ShellGroup(nft=0, nel=half, law=36, mat=qe.mat, prop=qe.prop),
+                      ShellGroup(nft=half, nel=ne - half, law=36, mat=qe.mat, prop=bt)]
+    cycle_check(m, ncheck=4, fields=("forc", "mom", "eint", "thk", "off", "stra", "epsd", "smstr"))
+
+
 def energies(b, m):
     d = b.download_nodes(("V", "VR"))
     ke = 0.5 * (m.MS[:, None] * d["V"] ** 2).sum() + 0.5 * (m.IN[:, None] * d["VR"] ** 2).sum()
