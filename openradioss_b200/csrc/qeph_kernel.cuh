@@ -15,7 +15,7 @@
 #include "shell_common.cuh"
 
 #ifndef ORGPU_SHELL_MINB
-#define ORGPU_SHELL_MINB 2
+#define ORGPU_SHELL_MINB 3
 #endif
 
 template <int LAW>
