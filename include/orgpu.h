@@ -73,6 +73,11 @@ int  orgpu_download_fsky(orgpu_engine* e, double* fsky /*(8,LSKY)*/);
 int  orgpu_download_solid_state(orgpu_engine* e, int field, double* out);
 int  orgpu_download_shell_state(orgpu_engine* e, int field, double* out);
 
+/* -- print-cycle energy balances (SBILAN sbilan.F:138-157, CBILAN cbilan.F:183-275 -> PARTSAV(1,.)
+ *    -> ECRIT output/ecrit.F:259-373): out = internal energy of solids, of shells, nodal kinetic
+ *    energy of translations, of rotations.  Deterministic (fixed-order) reduction. */
+int  orgpu_get_energies(orgpu_engine* e, double out[4]);
+
 /* -- domain decomposition (one process / MPI rank per GPU).
  *    Host-staged: corner rows of the given 0-based local FSKY slots out of / into the device
  *    skyline as (8,n) rows -- exactly what SPMD_EXCH2_A_PON packs from FSKY(:,ISENDP(j))

@@ -619,6 +619,32 @@ int orgpu_exchange(orgpu_engine* e)
   return exchange_on_stream(e, false);
 }
 
+static int energy_sum(orgpu_engine* e, const double* a, const double* b, const double* off, int n, int mode, double* out)
+{
+  if (n <= 0) return 0;
+  const int nb = (n + 255) / 256;
+  double* d_part = nullptr; CUDA_OK(cudaMalloc((void**)&d_part, 8 * (size_t)nb));
+  energy_partial_kernel<<<nb, 256, 0, e->st>>>(a, b, off, n, mode, d_part); e->launches++;
+  std::vector<double> h(nb);
+  CUDA_OK(cudaMemcpyAsync(h.data(), d_part, 8 * (size_t)nb, cudaMemcpyDeviceToHost, e->st));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  cudaFree(d_part);
+  double s = 0.0; for (int k = 0; k < nb; k++) s += h[k];
+  *out += s;
+  return 0;
+}
+
+int orgpu_get_energies(orgpu_engine* e, double out[4])
+{
+  NEED(e && e->finalized && out, -1, "orgpu_get_energies: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
+  out[0] = out[1] = out[2] = out[3] = 0.0;        // internal solids, internal shells, kinetic translation, kinetic rotation
+  for (auto& S : e->bsg) if (energy_sum(e, S.d.eint, S.d.vol, nullptr, S.d.ne, 0, &out[0])) return -100;
+  for (auto& S : e->csg) if (energy_sum(e, S.d.eint, S.d.eint + S.d.ne_pad, S.d.off, S.d.ne, 1, &out[1])) return -100;
+  if (energy_sum(e, e->nd.MS, (const double*)e->nd.vel, nullptr, e->numnod, 2, &out[2])) return -100;
+  if (e->nd.rot && energy_sum(e, e->nd.IN, (const double*)e->nd.rot, nullptr, e->numnod, 2, &out[3])) return -100;
+  return 0;
+}
+
 long long orgpu_launch_count(orgpu_engine* e) { return e ? e->launches : 0; }
 double orgpu_last_run_ms(orgpu_engine* e) { return e ? e->last_run_ms : 0; }
 int orgpu_set_profile(orgpu_engine* e, int profile) { NEED(e, -1, "null handle"); e->profile = profile; return 0; }

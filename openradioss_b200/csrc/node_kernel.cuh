@@ -140,3 +140,26 @@ void launch_set_dt(CycleState* cs, double dt1, double dt12, double dt2, int whic
 {
   set_dt_kernel<<<1, 1, 0, st>>>(cs, dt1, dt12, dt2, which);
 }
+
+// ---- print-cycle energy balances ----------------------------------------------------------------
+// Internal energy as SBILAN / CBILAN book it into PARTSAV(1,part) (sbilan.F:138-157: EI = EINT*VOL for
+// solids; cbilan.F:183: EI = EINT(1)+EINT(2) for shells, deleted elements excluded :261) and the nodal
+// kinetic energies.  Deterministic: fixed 256-wide CTA partial sums in a fixed tree, final sum on the host
+// in block order.
+__global__ void __launch_bounds__(256)
+energy_partial_kernel(const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ off, int n, int mode,
+                      double* __restrict__ partial)
+{
+  // mode 0: sum a[i]*b[i] (off ignored) ; 1: sum (a[i] + b[i]) where off[i] != 0 ; 2: sum 0.5*a[i]*|v_i|^2 with b = double4 records
+  __shared__ double s[256];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  double v = 0.0;
+  if (i < n) {
+    if (mode == 0) v = a[i] * b[i];
+    else if (mode == 1) v = (off[i] != 0.0) ? a[i] + b[i] : 0.0;
+    else { const double4 w = reinterpret_cast<const double4*>(b)[i]; v = 0.5 * a[i] * (w.x * w.x + w.y * w.y + w.z * w.z); }
+  }
+  s[threadIdx.x] = v; __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) s[threadIdx.x] = s[threadIdx.x] + s[threadIdx.x + k]; __syncthreads(); }
+  if (threadIdx.x == 0) partial[blockIdx.x] = s[0];
+}

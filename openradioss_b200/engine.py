@@ -17,7 +17,7 @@ EXPORTS = """create destroy last_error upload_nodes set_loads set_bcs set_solids
 set_functions add_solid_group add_shell_group finalize forces_phase assemble advance run_cycles
 synchronize get_time download_nodes download_fsky download_solid_state download_shell_state
 step_host launch_count last_run_ms set_profile get_profile pack_rows unpack_rows comm_unique_id comm_init
-set_exchange exchange""".split()
+set_exchange exchange get_energies""".split()
 
 
 def load_library() -> C.CDLL:
@@ -69,6 +69,12 @@ class Engine(Binding):
                    _opt(rp, np.int32), _opt(rs, np.int32))
 
     def exchange(self): self._call("exchange", self.h)
+
+    def energies(self):
+        """(internal solids, internal shells, kinetic translation, kinetic rotation), summed on the device."""
+        out = (C.c_double * 4)()
+        self._call("get_energies", self.h, out)
+        return tuple(out)
 
     def launch_count(self) -> int:
         fn = self.lib.orgpu_launch_count; fn.restype = C.c_longlong

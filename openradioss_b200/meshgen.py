@@ -283,3 +283,39 @@ def plate_c2(scale: int = 1) -> Model:
     """C2: 1000 x 1000 QEPH shells, LAW36, NPT=5, clamped, pressure pulse (1 MPa step)."""
     n = max(4, 1000 // scale)
     return shell_plate(n, n)
+
+
+def shell_on_block(nx: int, ny: int, nz: int, h: float = 5.0, *, thick: float = 1.0, ihbe: int = 24, vrand: float = 5.0,
+                   seed: int = 2024) -> Model:
+    """Mixed model (C4 in miniature): an nx*ny*nz brick block (LAW2) with an nx*ny shell skin (LAW36)
+    glued on its top face -- shells and bricks share nodes, one skyline, solids' slots first
+    (FILLCNE type order, starter/source/spmd/domdec2.F:2138-2240)."""
+    b = hex_block(nx, ny, nz, h * nx, h * ny, h * nz, jitter=0.05, seed=seed, vrand=vrand, fix_bottom_z=True)
+    nnx, nny = nx + 1, ny + 1
+    nid = lambda i, j, k: i + nnx * (j + nny * k)
+    ex, ey = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    ex, ey = ex.T.reshape(-1), ey.T.reshape(-1)
+    ne = nx * ny
+    ixc = np.zeros((ne, 7), np.int32); ixc[:, 0] = 2; ixc[:, 5] = 2
+    for c, (a, bb) in enumerate([(0, 0), (1, 0), (1, 1), (0, 1)]):
+        ixc[:, 1 + c] = nid(ex + a, ey + bb, nz) + 1
+    ixc[:, 6] = np.arange(1, ne + 1) + 10_000_000            # user ids of another part
+    prop = default_prop_shell(thick=thick, ihbe=ihbe)
+    mat, npf, tf = steel_law36()
+    area = shell_areas(b.X, ixc)
+    ems = mat.rho0 * thick * area * 0.25
+    xi = ems * (area / (12.0 if ihbe >= 11 else 9.0) + thick * thick / 12.0)
+    MS = b.MS.copy(); IN = np.zeros(b.numnod)
+    np.add.at(MS, (ixc[:, 1:5] - 1).reshape(-1), np.repeat(ems, 4))
+    np.add.at(IN, (ixc[:, 1:5] - 1).reshape(-1), np.repeat(xi, 4))
+    rng = np.random.default_rng(seed + 7)
+    VR = np.zeros_like(b.X)
+    top = np.unique(ixc[:, 1:5] - 1)
+    VR[top] = rng.uniform(-vrand, vrand, (len(top), 3)) / h
+    ctl = default_control(1)
+    m = Model(X=b.X, V=b.V, VR=VR, MS=MS, IN=IN, control=ctl, ixs=b.ixs, ixc=ixc, vol0=b.vol0, icodt=b.icodt,
+              icodr=np.zeros(b.numnod, np.int32), itab=b.itab, npf=npf, tf=tf)
+    m.solid_groups = b.solid_groups
+    m.shell_groups = [ShellGroup(nft=s, nel=n, law=36, mat=mat, prop=prop) for s, n in _groups(ne)]
+    m.adsky, m.iads, m.iadc, m.lsky = build_pon(m.numnod, m.ixs, m.ixc)
+    return m

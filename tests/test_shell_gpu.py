@@ -150,6 +150,44 @@ def test_mixed_qeph_and_bt_groups_one_model():
     cycle_check(m, ncheck=4, fields=("forc", "mom", "eint", "thk", "off", "stra", "epsd", "smstr"))
 
 
+@pytest.mark.parametrize("ihbe", [24, 1])
+def test_mixed_shells_and_bricks_share_nodes(ihbe):
+    """C4 in miniature: LAW36 shell skin on a LAW2 brick block, one skyline (solid slots first)."""
+    m = meshgen.shell_on_block(6, 5, 3, ihbe=ihbe)
+    g, o = pair(m)
+    dt1 = 0.0
+    for c in range(4):
+        for b in (g, o):
+            b.forces_phase(dt1)
+        fg, fo = g.download_fsky(), o.download_fsky()
+        assert rel_err(fg[:, :3], fo[:, :3]) <= FORCE_TOL and rel_err(fg[:, 3:6], fo[:, 3:6]) <= FORCE_TOL
+        assert rel_err(fg[:, 6:], fo[:, 6:]) <= FORCE_TOL
+        tg, to = g.time(), o.time()
+        assert tg["dt2t"] == pytest.approx(to["dt2t"], rel=1e-13) and tg["neltst"] == to["neltst"] and tg["ityptst"] == to["ityptst"]
+        for b in (g, o):
+            b.assemble()
+        ng, no = g.download_nodes(("A", "AR", "STIFN")), o.download_nodes(("A", "AR", "STIFN"))
+        for k in ("A", "AR", "STIFN"):
+            assert rel_err(ng[k], no[k]) <= FORCE_TOL, (k, c)
+        dt2 = to["dt2t"]
+        for b in (g, o):
+            b.advance(0.5 * (dt1 + dt2), dt2)
+        dt1 = dt2
+    for f in ("sig", "eint", "pla"):
+        assert rel_err(g.solid_state(f), o.solid_state(f)) <= 1e-11
+    check_state(g, o)
+    g2, o2 = pair(m)
+    g2.run_cycles(200); o2.run_cycles(200)
+    assert rel_err(g2.download_nodes(("D",))["D"], o2.download_nodes(("D",))["D"]) <= DISP_TOL
+    # device energy balances (SBILAN / CBILAN formulas) against the same sums on the oracle's state
+    es, ec, kt, kr = g2.energies()
+    d = o2.download_nodes(("V", "VR"))
+    assert es == pytest.approx((o2.solid_state("eint")[0] * o2.solid_state("vol")[0]).sum(), rel=ENERGY_TOL)
+    assert ec == pytest.approx(o2.shell_state("eint").sum(), rel=ENERGY_TOL)
+    assert kt == pytest.approx(0.5 * (m.MS[:, None] * d["V"] ** 2).sum(), rel=ENERGY_TOL)
+    assert kr == pytest.approx(0.5 * (m.IN[:, None] * d["VR"] ** 2).sum(), rel=ENERGY_TOL)
+
+
 def energies(b, m):
     d = b.download_nodes(("V", "VR"))
     ke = 0.5 * (m.MS[:, None] * d["V"] ** 2).sum() + 0.5 * (m.IN[:, None] * d["VR"] ** 2).sum()
