@@ -12,11 +12,11 @@
 #include "shell_common.cuh"
 
 template <int LAW>
-__global__ void __launch_bounds__(ORGPU_BLOCK, 3)
+__global__ void __launch_bounds__(ORGPU_SHELL_CTA, 3 * (ORGPU_BLOCK / ORGPU_SHELL_CTA))
 bt_forces_kernel(const __grid_constant__ ShellParams P)
 {
   const ShellSG& g = P.sg;
-  const int e = blockIdx.x * ORGPU_BLOCK + threadIdx.x;
+  const int e = blockIdx.x * ORGPU_SHELL_CTA + threadIdx.x;
   const int np = g.ne_pad;
   double dt_cand = K_EP30; int ngl = 0; int order = 0x7fffffff;
   if (e < g.ne) {
@@ -326,6 +326,6 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
 
 static void launch_bt_forces(const ShellParams& P, int nblk, cudaStream_t st)
 {
-  if (P.sg.law == 36) bt_forces_kernel<36><<<nblk, ORGPU_BLOCK, 0, st>>>(P);
-  else                bt_forces_kernel<2><<<nblk, ORGPU_BLOCK, 0, st>>>(P);
+  if (P.sg.law == 36) bt_forces_kernel<36><<<nblk, ORGPU_SHELL_CTA, 0, st>>>(P);
+  else                bt_forces_kernel<2><<<nblk, ORGPU_SHELL_CTA, 0, st>>>(P);
 }

@@ -19,11 +19,11 @@
 #endif
 
 template <int LAW>
-__global__ void __launch_bounds__(ORGPU_BLOCK, ORGPU_SHELL_MINB)
+__global__ void __launch_bounds__(ORGPU_SHELL_CTA, ORGPU_SHELL_MINB * (ORGPU_BLOCK / ORGPU_SHELL_CTA))
 qeph_forces_kernel(const __grid_constant__ ShellParams P)
 {
   const ShellSG& g = P.sg;
-  const int e = blockIdx.x * ORGPU_BLOCK + threadIdx.x;
+  const int e = blockIdx.x * ORGPU_SHELL_CTA + threadIdx.x;
   const int np = g.ne_pad;
   double dt_cand = K_EP30; int ngl = 0; int order = 0x7fffffff;
   if (e < g.ne) {
@@ -336,6 +336,9 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     }
     // ---- CMAIN3
     io.area = AREA; io.thk0 = THK0; io.gs = G * SHF; io.rho = RHO; io.off = OFF; io.sigy = K_EP30;
+#ifdef ORGPU_UNROLL_NPT5
+    if (NPT == 5) shell_material_loop<LAW, true, 5>(g, e, DT1, io); else
+#endif
     shell_material_loop<LAW, true>(g, e, DT1, io);
     OFF = io.off;
     // ---- CNDT3

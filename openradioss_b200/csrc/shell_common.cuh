@@ -91,6 +91,12 @@ __device__ __forceinline__ void ip_store(const ShellSG& g, int e, int ipt, const
   else if (g.m36.nrate == 1 && s.ipos != ipos_old) __stcs(g.vartmp + ((size_t)ipt * g.nvartmp + 2) * np + e, s.ipos);
 }
 
+#ifndef ORGPU_SHELL_CTA
+#define ORGPU_SHELL_CTA 128      // threads per CTA of the shell kernels (ne_pad is a multiple of ORGPU_BLOCK = 128)
+#endif
+#ifdef ORGPU_PREFETCH_L1
+#define prefetch_l2 prefetch_l1
+#endif
 // start every element-state line of this thread's 4-element sector toward L2 (called by one lane in 4)
 __device__ __forceinline__ void shell_prefetch_state(const ShellSG& g, int e)
 {
@@ -105,6 +111,9 @@ __device__ __forceinline__ void shell_prefetch_state(const ShellSG& g, int e)
   if (g.temp) for (int k = 0; k < g.npt; k++) prefetch_l2(g.temp + k * np + e);
   if (g.law == 36 && (e & 7) == 0) for (int k = 0; k < g.npt; k++) prefetch_l2(g.vartmp + ((size_t)k * g.nvartmp + 2) * np + e);
 }
+#ifdef ORGPU_PREFETCH_L1
+#undef prefetch_l2
+#endif
 
 // ---- SIGEPS36C, VP = 0 -------------------------------------------------------------------
 __device__ __forceinline__ void law36_ip(const ShellSG& g, int e, int ipt, int ipla, double asrate,
@@ -409,10 +418,12 @@ __device__ __forceinline__ void law2_ip(const ShellSG& g, int e, int ipt, int ip
 
 // ---- CMAIN3 / MULAWC for one element --------------------------------------------------------
 // FLAG_ZCFAC: QEPH (JHBE 21..29) keeps SIGY / ZCFAC for the hourglass plasticity (mulawc.F90:521-522).
-template <int LAW, bool FLAG_ZCFAC>
+// NPTC > 0: compile-time point count (loop fully unrolled so independent points overlap in the
+// fp64 pipe); NPTC = 0: run-time count.
+template <int LAW, bool FLAG_ZCFAC, int NPTC = 0>
 __device__ __forceinline__ void shell_material_loop(const ShellSG& g, int e, double dt1, MatIO& io)
 {
-  const int np = g.ne_pad, npt = g.prop.npt;
+  const int np = g.ne_pad, npt = NPTC > 0 ? NPTC : g.prop.npt;
   const double DM = g.prop.dm;
   double* fo = io.fo; double* mo = io.mo;
   #pragma unroll
@@ -439,6 +450,7 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, int e, dou
   const double asrate = (israte > 0) ? fmin(K_ONE, pm9 * dt1) : K_ONE;
   const int qrow = (npt - 1) * 11;
   IpState nxt = ip_load<LAW>(g, e, 0);
+  #pragma unroll
   for (int ipt = 0; ipt < npt; ipt++) {
     IpState s = nxt;
     if (ipt + 1 < npt) nxt = ip_load<LAW>(g, e, ipt + 1);        // software pipeline: next point's state in flight

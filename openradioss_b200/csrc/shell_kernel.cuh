@@ -116,7 +116,7 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
       std::vector<double> temp(npt * n, G.m2.tini);
       if (sh_upload(S.owned, &d.temp, temp)) return -100;
     }
-    const int nblk = np / ORGPU_BLOCK;
+    const int nblk = np / ORGPU_SHELL_CTA;
     if (fa.nsg >= ORGPU_MAX_SG) { orgpu_set_error("too many super-groups (%d)", ORGPU_MAX_SG); return -6; }
     fa.sg[fa.nsg++] = SGRange{blk, nblk, shell_is_qeph(G.prop) ? ORGPU_FAM_SHELL_QEPH : ORGPU_FAM_SHELL_BT};
     order += ne; blk += nblk; gi = gj;
@@ -129,10 +129,10 @@ static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky
 {
   (void)roww;                                  // shell models always use 8-wide rows
   ShellParams P{S.d, nd, fsky, cs, db, fa};
-  const int nblk = S.d.ne_pad / ORGPU_BLOCK;
+  const int nblk = S.d.ne_pad / ORGPU_SHELL_CTA;
   if (shell_is_qeph(S.d.prop)) {
-    if (S.d.law == 36) qeph_forces_kernel<36><<<nblk, ORGPU_BLOCK, 0, st>>>(P);
-    else               qeph_forces_kernel<2><<<nblk, ORGPU_BLOCK, 0, st>>>(P);
+    if (S.d.law == 36) qeph_forces_kernel<36><<<nblk, ORGPU_SHELL_CTA, 0, st>>>(P);
+    else               qeph_forces_kernel<2><<<nblk, ORGPU_SHELL_CTA, 0, st>>>(P);
   } else {
     launch_bt_forces(P, nblk, st);
   }
