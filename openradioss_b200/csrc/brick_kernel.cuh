@@ -16,7 +16,7 @@
 #include "common.cuh"
 
 struct BrickParams {            // scalar copies so the kernel reads them from the constant bank
-  BrickSG sg; DevNodes nd; double* fsky; int roww; CycleState* cs; DtBlocks db; FinalizeArgs fa;
+  BrickSG sg; DevNodes nd; double* fsky; int roww; CycleState* cs; DtBlocks db;
 };
 
 // SLEN (slen.F:68-88)
@@ -525,7 +525,6 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     }
   }
   block_dt_reduce<true>(dt_cand, ngl, order, P.db, g.blk0 + blockIdx.x);
-  element_phase_finalize(P.cs, P.db, P.fa);
 }
 
 template <int JHBE>
@@ -541,7 +540,7 @@ static void launch_brick_ismstr(const BrickParams& P, int ismstr, int nblk, cuda
 void launch_brick_forces(const BrickSG& sg, const DevNodes& nd, double* fsky, int roww,
                          CycleState* cs, const DtBlocks& db, const FinalizeArgs& fa, cudaStream_t st)
 {
-  BrickParams P{sg, nd, fsky, roww, cs, db, fa};
+  BrickParams P{sg, nd, fsky, roww, cs, db};
   const int nblk = (sg.ne + ORGPU_BLOCK - 1) / ORGPU_BLOCK;
   switch (sg.prop.jhbe) {
     case 0: launch_brick_ismstr<0>(P, sg.prop.ismstr, nblk, st); break;

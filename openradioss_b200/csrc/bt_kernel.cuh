@@ -321,7 +321,6 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
     }
   }
   block_dt_reduce<false>(dt_cand, ngl, order, P.db, g.blk0 + blockIdx.x);
-  element_phase_finalize(P.cs, P.db, P.fa);
 }
 
 static void launch_bt_forces(const ShellParams& P, int nblk, cudaStream_t st)

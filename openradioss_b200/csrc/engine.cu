@@ -311,6 +311,7 @@ static void launch_element_phase(orgpu_engine* e, int fused, size_t* evi)
     launch_brick_forces(S.d, e->nd, e->d_fsky, e->roww, e->d_cs, e->db, e->fa, e->st); e->launches++;
     if (evi) cudaEventRecord(get_event(e, (*evi)++), e->st);
   }
+  element_finalize_kernel<<<1, ORGPU_FINALIZE_BLOCK, 0, e->st>>>(e->d_cs, e->db, e->fa); e->launches++;
 }
 
 int orgpu_forces_phase(orgpu_engine* e, double dt1)
@@ -375,7 +376,7 @@ static int exchange_on_stream(orgpu_engine* e, bool with_dt)
 int orgpu_run_cycles(orgpu_engine* e, int ncycles)
 {
   NEED(e && e->finalized && ncycles >= 0, -1, "orgpu_run_cycles: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
-  const int per_cycle = (int)(e->csg.size() + e->bsg.size()) + 1;
+  const int per_cycle = (int)(e->csg.size() + e->bsg.size()) + 2;   // force kernels + dt finalize + node kernel
   if (e->xc.nranks > 1) {
     // one process per GPU: element phase writes the local dt candidate only; the exchange folds all
     // ranks' candidates and advances the clock; then the ordered gather + nodal update

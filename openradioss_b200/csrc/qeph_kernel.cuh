@@ -323,8 +323,11 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     io.kxx = VDEF[5] * DT1; io.kyy = VDEF[6] * DT1; io.kxy = VDEF[7] * DT1;
     if (g.prop.istrain != 0) {
       const double de[8] = {io.exx, io.eyy, io.exy, io.eyz, io.exz, io.kxx, io.kyy, io.kxy};
+      double st[8];                          // all eight loads in flight before the first store (which could alias them)
       #pragma unroll
-      for (int k = 0; k < 8; k++) { double* p = g.stra + (size_t)k * np + e; *p = *p + de[k]; }
+      for (int k = 0; k < 8; k++) st[k] = __ldcs(g.stra + (size_t)k * np + e);
+      #pragma unroll
+      for (int k = 0; k < 8; k++) __stcs(g.stra + (size_t)k * np + e, st[k] + de[k]);
     }
     {
       const double dtinv = DT1 / fmax(DT1 * DT1, K_EM20);
@@ -573,5 +576,4 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     }
   }
   block_dt_reduce<false>(dt_cand, ngl, order, P.db, g.blk0 + blockIdx.x);
-  element_phase_finalize(P.cs, P.db, P.fa);
 }

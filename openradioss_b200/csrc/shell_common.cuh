@@ -32,7 +32,7 @@ struct ShellSG {
 };
 
 struct ShellParams {
-  ShellSG sg; DevNodes nd; double* fsky; CycleState* cs; DtBlocks db; FinalizeArgs fa;
+  ShellSG sg; DevNodes nd; double* fsky; CycleState* cs; DtBlocks db;
 };
 
 __constant__ double c_Z0[121];

@@ -128,7 +128,7 @@ static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky
                                 const DtBlocks& db, const FinalizeArgs& fa, cudaStream_t st)
 {
   (void)roww;                                  // shell models always use 8-wide rows
-  ShellParams P{S.d, nd, fsky, cs, db, fa};
+  ShellParams P{S.d, nd, fsky, cs, db};
   const int nblk = S.d.ne_pad / ORGPU_SHELL_CTA;
   if (shell_is_qeph(S.d.prop)) {
     if (S.d.law == 36) qeph_forces_kernel<36><<<nblk, ORGPU_SHELL_CTA, 0, st>>>(P);
