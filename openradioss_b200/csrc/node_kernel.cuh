@@ -13,64 +13,103 @@
 
 struct NodeAcc { double a[3], ar[3], stifn, stifr; };
 
+// Rows of one node are folded strictly in slot order, but their LOADS are independent: a batch of
+// NB rows (all of a regular node's rows: 8 brick corners / 4 shell corners) is issued before the first
+// add, so one thread keeps 256 bytes in flight instead of one row (the kernel is a pure stream and
+// needs ~45 KB in flight per SM to cover HBM latency).
 template <int ROWW>
 __device__ __forceinline__ NodeAcc node_gather(const DevNodes& nd, const double* __restrict__ fsky, int n, int iroddl)
 {
   NodeAcc r;
+  const int k0 = nd.adsky[n], k1 = nd.adsky[n + 1];
+  constexpr int NB = (ROWW == 4) ? 8 : 4;
+  constexpr int NV = ROWW / 2;
+  const double2* base = reinterpret_cast<const double2*>(fsky);
+  double2 buf[NB][NV];
+  #pragma unroll
+  for (int j = 0; j < NB; j++) {
+    if (k0 + j < k1) {
+      #pragma unroll
+      for (int c = 0; c < NV; c++) buf[j][c] = __ldcs(base + (size_t)NV * (k0 + j) + c);
+    }
+  }
   if (nd.FEXT) { r.a[0] = nd.FEXT[3 * n]; r.a[1] = nd.FEXT[3 * n + 1]; r.a[2] = nd.FEXT[3 * n + 2]; }
   else { r.a[0] = K_ZERO; r.a[1] = K_ZERO; r.a[2] = K_ZERO; }
   if (nd.MEXT) { r.ar[0] = nd.MEXT[3 * n]; r.ar[1] = nd.MEXT[3 * n + 1]; r.ar[2] = nd.MEXT[3 * n + 2]; }
   else { r.ar[0] = K_ZERO; r.ar[1] = K_ZERO; r.ar[2] = K_ZERO; }
   r.stifn = K_ZERO; r.stifr = K_ZERO;
-  const int k0 = nd.adsky[n], k1 = nd.adsky[n + 1];
-  for (int k = k0; k < k1; k++) {
-    if (ROWW == 4) {
-      const double2* p = reinterpret_cast<const double2*>(fsky) + 2 * (size_t)k;
-      const double2 f = __ldcs(p), h = __ldcs(p + 1);
-      r.a[0] = r.a[0] + f.x; r.a[1] = r.a[1] + f.y; r.a[2] = r.a[2] + h.x; r.stifn = r.stifn + h.y;
-    } else {
-      const double2* p = reinterpret_cast<const double2*>(fsky) + 4 * (size_t)k;
-      const double2 f0 = __ldcs(p), f1 = __ldcs(p + 1), f2 = __ldcs(p + 2), f3 = __ldcs(p + 3);
-      r.a[0] = r.a[0] + f0.x; r.a[1] = r.a[1] + f0.y; r.a[2] = r.a[2] + f1.x;
-      r.ar[0] = r.ar[0] + f1.y; r.ar[1] = r.ar[1] + f2.x; r.ar[2] = r.ar[2] + f2.y;
-      r.stifn = r.stifn + f3.x; r.stifr = r.stifr + f3.y;
+  for (int kb = k0; kb < k1; kb += NB) {
+    if (kb != k0) {                                  // irregular node with more than NB corners
+      #pragma unroll
+      for (int j = 0; j < NB; j++) {
+        if (kb + j < k1) {
+          #pragma unroll
+          for (int c = 0; c < NV; c++) buf[j][c] = __ldcs(base + (size_t)NV * (kb + j) + c);
+        }
+      }
+    }
+    #pragma unroll
+    for (int j = 0; j < NB; j++) {
+      if (kb + j < k1) {
+        if (ROWW == 4) {
+          r.a[0] = r.a[0] + buf[j][0].x; r.a[1] = r.a[1] + buf[j][0].y; r.a[2] = r.a[2] + buf[j][1].x; r.stifn = r.stifn + buf[j][1].y;
+        } else {
+          r.a[0] = r.a[0] + buf[j][0].x; r.a[1] = r.a[1] + buf[j][0].y; r.a[2] = r.a[2] + buf[j][1].x;
+          r.ar[0] = r.ar[0] + buf[j][1].y; r.ar[1] = r.ar[1] + buf[j][NV - 2].x; r.ar[2] = r.ar[2] + buf[j][NV - 2].y;
+          r.stifn = r.stifn + buf[j][NV - 1].x; r.stifr = r.stifr + buf[j][NV - 1].y;
+        }
+      }
     }
   }
   (void)iroddl;
   return r;
 }
 
-__device__ __forceinline__ void node_update(const DevNodes& nd, int n, NodeAcc& r, double dt12, double dt2, int iroddl)
+// nodal fields of one node, loaded ahead of the row fold so every load of the thread is in flight at once
+struct NodeIn { double ms, in; int ct, cr; double4 v, w, p; double d[3]; };
+
+__device__ __forceinline__ NodeIn node_load(const DevNodes& nd, int n, int iroddl)
+{
+  NodeIn q;
+  q.ms = nd.MS[n]; q.in = iroddl ? nd.IN[n] : K_ZERO;
+  q.ct = nd.icodt ? nd.icodt[n] : 0; q.cr = (nd.icodt && iroddl) ? nd.icodr[n] : 0;
+  q.v = nd.vel[n]; q.p = nd.pos[n];
+  if (iroddl) q.w = nd.rot[n];
+  q.d[0] = nd.D[3 * n]; q.d[1] = nd.D[3 * n + 1]; q.d[2] = nd.D[3 * n + 2];
+  return q;
+}
+
+__device__ __forceinline__ void node_update(const DevNodes& nd, int n, const NodeIn& q, NodeAcc& r, double dt12, double dt2, int iroddl)
 {
   // ACCELE
-  const double ms = nd.MS[n];
+  const double ms = q.ms;
   if (ms > K_ZERO) { const double rt = K_ONE / ms; r.a[0] = r.a[0] * rt; r.a[1] = r.a[1] * rt; r.a[2] = r.a[2] * rt; }
   else { r.a[0] = K_ZERO; r.a[1] = K_ZERO; r.a[2] = K_ZERO; }
   if (iroddl) {
-    const double in = nd.IN[n];
+    const double in = q.in;
     if (in > K_ZERO) { const double rt = K_ONE / in; r.ar[0] = r.ar[0] * rt; r.ar[1] = r.ar[1] * rt; r.ar[2] = r.ar[2] * rt; }
     else { r.ar[0] = K_ZERO; r.ar[1] = K_ZERO; r.ar[2] = K_ZERO; }
   }
   // BCS
   if (nd.icodt) {
-    const int c = nd.icodt[n];
+    const int c = q.ct;
     if (c & 4) r.a[0] = K_ZERO; if (c & 2) r.a[1] = K_ZERO; if (c & 1) r.a[2] = K_ZERO;
-    if (iroddl) { const int q = nd.icodr[n]; if (q & 4) r.ar[0] = K_ZERO; if (q & 2) r.ar[1] = K_ZERO; if (q & 1) r.ar[2] = K_ZERO; }
+    if (iroddl) { const int qq = q.cr; if (qq & 4) r.ar[0] = K_ZERO; if (qq & 2) r.ar[1] = K_ZERO; if (qq & 1) r.ar[2] = K_ZERO; }
   }
   // VELOCITY
-  double4 v = nd.vel[n];
+  double4 v = q.v;
   v.x = v.x + dt12 * r.a[0]; v.y = v.y + dt12 * r.a[1]; v.z = v.z + dt12 * r.a[2];
   nd.vel[n] = v;
   if (iroddl) {
-    double4 w = nd.rot[n];
+    double4 w = q.w;
     w.x = w.x + dt12 * r.ar[0]; w.y = w.y + dt12 * r.ar[1]; w.z = w.z + dt12 * r.ar[2];
     nd.rot[n] = w;
   }
   // DEPLA
-  double4 p = nd.pos[n];
-  double vdt = dt2 * v.x; nd.D[3 * n] = nd.D[3 * n] + vdt; p.x = p.x + vdt;
-  vdt = dt2 * v.y; nd.D[3 * n + 1] = nd.D[3 * n + 1] + vdt; p.y = p.y + vdt;
-  vdt = dt2 * v.z; nd.D[3 * n + 2] = nd.D[3 * n + 2] + vdt; p.z = p.z + vdt;
+  double4 p = q.p;
+  double vdt = dt2 * v.x; nd.D[3 * n] = q.d[0] + vdt; p.x = p.x + vdt;
+  vdt = dt2 * v.y; nd.D[3 * n + 1] = q.d[1] + vdt; p.y = p.y + vdt;
+  vdt = dt2 * v.z; nd.D[3 * n + 2] = q.d[2] + vdt; p.z = p.z + vdt;
   nd.pos[n] = p;
 }
 
@@ -96,7 +135,8 @@ node_advance_kernel(const __grid_constant__ DevNodes nd, const CycleState* __res
   NodeAcc r;
   r.a[0] = nd.A[3 * n]; r.a[1] = nd.A[3 * n + 1]; r.a[2] = nd.A[3 * n + 2];
   r.ar[0] = nd.AR[3 * n]; r.ar[1] = nd.AR[3 * n + 1]; r.ar[2] = nd.AR[3 * n + 2];
-  node_update(nd, n, r, cs->dt12, cs->dt2, iroddl);
+  const NodeIn q = node_load(nd, n, iroddl);
+  node_update(nd, n, q, r, cs->dt12, cs->dt2, iroddl);
   nd.A[3 * n] = K_ZERO; nd.A[3 * n + 1] = K_ZERO; nd.A[3 * n + 2] = K_ZERO;        // velocity.F:62-64
   nd.AR[3 * n] = K_ZERO; nd.AR[3 * n + 1] = K_ZERO; nd.AR[3 * n + 2] = K_ZERO;
 }
@@ -109,8 +149,9 @@ node_fused_kernel(const __grid_constant__ DevNodes nd, const double* __restrict_
 {
   const int n = blockIdx.x * ORGPU_NODE_BLOCK + threadIdx.x;
   if (n >= nd.n) return;
+  const NodeIn q = node_load(nd, n, iroddl);
   NodeAcc r = node_gather<ROWW>(nd, fsky, n, iroddl);
-  node_update(nd, n, r, cs->dt12, cs->dt2, iroddl);
+  node_update(nd, n, q, r, cs->dt12, cs->dt2, iroddl);
 }
 
 __global__ void set_dt_kernel(CycleState* cs, double dt1, double dt12, double dt2, int which)
