@@ -10,8 +10,9 @@
 //   MMAIN -> M2LAW (m2law.F:133-561) + MQVISCB (mqviscb.F:141-631): stress, dt, nodal stiffness
 //   SMALLB3, SHVIS3 (shvis3.F:164-412), SFINT3 (sfint3.F:257-323)
 //   SCUMU3P (scumu3p.F:104-309): corner rows into the FSKY slots of IADS
-// followed by the CTA-level (dt, user id) arg-min.  State is read and written exactly once,
-// coalesced (SoA over the super-group); nothing intermediate touches HBM.
+// followed by the CTA-level (dt, user id) arg-min.  The CTA's state tile (common.cuh) is read by one
+// TMA bulk copy into shared memory and written back by one bulk store: every state word crosses HBM
+// exactly once each way, and no thread ever waits on a state load.
 #pragma once
 #include "common.cuh"
 
@@ -70,48 +71,43 @@ __device__ __forceinline__ Jac brick_jac(const double* x, const double* y, const
         G_[2][0] =  K_ONE - PH[2][0]; G_[2][1] = -K_ONE - PH[2][1]; G_[2][2] = -K_ONE - PH[2][2]; G_[2][3] =  K_ONE - PH[2][3]; \
         G_[2][4] = -K_ONE + PH[2][2]; G_[2][5] =  K_ONE + PH[2][3]; G_[2][6] =  K_ONE + PH[2][0]; G_[2][7] = -K_ONE + PH[2][1];
 
-template <int JHBE, int ISMSTR>
 #ifndef ORGPU_BRICK_MINB
 #define ORGPU_BRICK_MINB 3
 #endif
+
+template <int JHBE, int ISMSTR, bool STAGED>
 __global__ void __launch_bounds__(ORGPU_BLOCK, ORGPU_BRICK_MINB)
 brick_forces_kernel(const __grid_constant__ BrickParams P)
 {
   const BrickSG& g = P.sg;
-  const int e = blockIdx.x * ORGPU_BLOCK + threadIdx.x;
-  const int np = g.ne_pad;
-  double dt_cand = K_EP30; int ngl = 0; int order = -1;
+  const int e = blockIdx.x * ORGPU_TILE + threadIdx.x;
+  __shared__ __align__(8) unsigned long long s_bar;
+  double* const g_tile = g.slab + (size_t)blockIdx.x * g.nw * ORGPU_TILE;
+  if (STAGED) tile_load_begin(s_tile_dyn, &s_bar, g_tile, (unsigned)g.nw * ORGPU_TILE * 8u);
+  const TileAcc<STAGED> T{(STAGED ? s_tile_dyn : g_tile) + threadIdx.x};
+  double* const sm = g.smstr + (size_t)blockIdx.x * 21 * ORGPU_TILE + threadIdx.x;     // SMSTR word k at sm[k*128]
+  double dt_cand = K_EP30; int order = -1;
   if (e < g.ne) {
     const double DT1 = P.cs->dt2;                         // DT1 = DT2 of the previous cycle (resol.F:2721)
     const double TT = P.cs->tt;
     const orgpu_law2& m = g.mat;
     int nc[8];
-    #pragma unroll
-    for (int k = 0; k < 8; k++) nc[k] = __ldg(g.conn + k * np + e);
-    if ((threadIdx.x & 7) == 0) {           // slot indices are consumed last: start them toward L2 now
+    { const int* cn = g.conn + (size_t)blockIdx.x * 8 * ORGPU_TILE + threadIdx.x;
       #pragma unroll
-      for (int k = 0; k < 8; k++) prefetch_l2(g.slot + k * np + e);
-    }
-    double OFFG = g.off[e];
-    ngl = __ldg(g.ngl + e); order = g.order0 + e;
-    // start the element-state and slot-index lines moving toward L1/L2 now: they are consumed
-    // after the geometry phase, and one element per thread leaves few warps to hide HBM latency
-    if ((threadIdx.x & 3) == 0) {           // 4 consecutive doubles share a 32-byte sector
-      #pragma unroll
-      for (int k = 0; k < 6; k++) prefetch_l2(g.sig + k * np + e);
-      prefetch_l2(g.eint + e); prefetch_l2(g.rho + e); prefetch_l2(g.qvis + e); prefetch_l2(g.pla + e);
-      prefetch_l2(g.epsd + e); prefetch_l2(g.vol + e); if (m.has_temp) prefetch_l2(g.temp + e);
-    }
+      for (int k = 0; k < 8; k++) nc[k] = __ldg(cn + k * ORGPU_TILE); }
+    order = g.order0 + e;
     // ---- SCOOR3
     double x[8], y[8], z[8];
     #pragma unroll
     for (int k = 0; k < 8; k++) { double4 p = ldg4(P.nd.pos + nc[k]); x[k] = p.x; y[k] = p.y; z[k] = p.z; }
     #pragma unroll
     for (int k = 0; k < 8; k++) prefetch_l1(P.nd.vel + nc[k]);
+    if (STAGED) mbar_wait(&s_bar, 0);                     // the state tile has landed (issued before the gather)
+    double OFFG = T.ld(BW_OFF);
     double OFF;
     if (ISMSTR <= 4 && fabs(OFFG) > K_ONE) {
       #pragma unroll
-      for (int k = 0; k < 7; k++) { x[k] = g.smstr[(3 * k) * np + e]; y[k] = g.smstr[(3 * k + 1) * np + e]; z[k] = g.smstr[(3 * k + 2) * np + e]; }
+      for (int k = 0; k < 7; k++) { x[k] = sm[(3 * k) * ORGPU_TILE]; y[k] = sm[(3 * k + 1) * ORGPU_TILE]; z[k] = sm[(3 * k + 2) * ORGPU_TILE]; }
       x[7] = K_ZERO; y[7] = K_ZERO; z[7] = K_ZERO;
       OFF = fabs(OFFG) - K_ONE;
     } else OFF = fabs(OFFG);
@@ -131,7 +127,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     else if (VOLN <= K_ZERO) {
       if (OFFG <= K_ONE && OFFG != K_ZERO) {             // switch to small strain: geometry from SAV
         #pragma unroll
-        for (int k = 0; k < 7; k++) { x[k] = g.smstr[(3 * k) * np + e]; y[k] = g.smstr[(3 * k + 1) * np + e]; z[k] = g.smstr[(3 * k + 2) * np + e]; }
+        for (int k = 0; k < 7; k++) { x[k] = sm[(3 * k) * ORGPU_TILE]; y[k] = sm[(3 * k + 1) * ORGPU_TILE]; z[k] = sm[(3 * k + 2) * ORGPU_TILE]; }
         x[7] = K_ZERO; y[7] = K_ZERO; z[7] = K_ZERO;
         J = brick_jac(x, y, z); VOLN = J.vol; OFFG = K_TWO;
       }
@@ -178,9 +174,9 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     if (sav_refresh) {                       // exclusive with SMALLA3 (OFFG > 1), so the order is free
       #pragma unroll
       for (int k = 0; k < 7; k++) {
-        __stcs(&g.smstr[(3 * k) * np + e], x[k] - x[7]);
-        __stcs(&g.smstr[(3 * k + 1) * np + e], y[k] - y[7]);
-        __stcs(&g.smstr[(3 * k + 2) * np + e], z[k] - z[7]);
+        __stcs(&sm[(3 * k) * ORGPU_TILE], x[k] - x[7]);
+        __stcs(&sm[(3 * k + 1) * ORGPU_TILE], y[k] - y[7]);
+        __stcs(&sm[(3 * k + 2) * ORGPU_TILE], z[k] - z[7]);
       }
     }
     // ---- velocities (SCOOR3) and SDEFO3
@@ -255,9 +251,9 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     }
     const double DIVDE = DT1 * (DXX + DYY + DZZ);        // sforc3.F:790
     // ---- SRHO3
-    double VOLO = __ldg(g.vol + e);
-    double RHON = g.rho[e];
-    double EINT = g.eint[e];
+    double VOLO = T.ld(g.w_vol);
+    double RHON = T.ld(BW_RHO);
+    double EINT = T.ld(BW_EINT);
     double DVOL;
     {
       const double RHON_OLD = RHON, RHO0 = m.rho0;
@@ -274,7 +270,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       }
     }
     // ---- SROTA3
-    double S1 = g.sig[e], S2 = g.sig[np + e], S3 = g.sig[2 * np + e], S4 = g.sig[3 * np + e], S5 = g.sig[4 * np + e], S6 = g.sig[5 * np + e];
+    double S1 = T.ld(BW_SIG), S2 = T.ld(BW_SIG + 1), S3 = T.ld(BW_SIG + 2), S4 = T.ld(BW_SIG + 3), S5 = T.ld(BW_SIG + 4), S6 = T.ld(BW_SIG + 5);
     double SG1, SG2, SG3, SG4, SG5, SG6;
     {
       double Q1 = K_TWO * S4 * WZZ, Q2 = K_TWO * S6 * WYY, Q3 = K_TWO * S5 * WXX;
@@ -289,14 +285,14 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     if (ISMSTR <= 4 && OFFG > K_ONE) {
       #pragma unroll
       for (int k = 0; k < 7; k++) {
-        double X = g.smstr[(3 * k) * np + e], Y = g.smstr[(3 * k + 1) * np + e], Z = g.smstr[(3 * k + 2) * np + e];
-        g.smstr[(3 * k) * np + e] = X - Y * WZZ + Z * WYY;
-        g.smstr[(3 * k + 1) * np + e] = Y - Z * WXX + X * WZZ;
-        g.smstr[(3 * k + 2) * np + e] = Z - X * WYY + Y * WXX;
+        double X = sm[(3 * k) * ORGPU_TILE], Y = sm[(3 * k + 1) * ORGPU_TILE], Z = sm[(3 * k + 2) * ORGPU_TILE];
+        sm[(3 * k) * ORGPU_TILE] = X - Y * WZZ + Z * WYY;
+        sm[(3 * k + 1) * ORGPU_TILE] = Y - Z * WXX + X * WZZ;
+        sm[(3 * k + 2) * ORGPU_TILE] = Z - X * WYY + Y * WXX;
       }
     }
     // ---- MMAIN pre-law (mmain.F90:597-800)
-    const double QOLD = g.qvis[e];
+    const double QOLD = T.ld(BW_QVIS);
     const double VOL_AVG = VOLN - K_HALF * DVOL;
     const double AMU = RHON / m.rho0 - K_ONE;
     double RHOREF;
@@ -304,9 +300,9 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     else if (ISMSTR == 2) RHOREF = (fabs(OFFG) <= K_ONE) ? RHON : m.rho0 * VOLO / fmax(K_EM20, VOLN);
     else RHOREF = RHON;
     double TEMP = K_ZERO, TSTAR = K_ZERO;
-    if (m.has_temp) { TEMP = g.temp[e]; TSTAR = fmax(K_ZERO, (TEMP - m.tref) / fmax((m.tmelt - m.tref), K_EM20)); }
+    if (m.has_temp) { TEMP = T.ld(g.w_temp); TSTAR = fmax(K_ZERO, (TEMP - m.tref) / fmax((m.tmelt - m.tref), K_EM20)); }
     // ---- M2LAW
-    double EPXE = g.pla[e], EPSD = g.epsd[e];
+    double EPXE = T.ld(BW_PLA), EPSD = T.ld(BW_EPSD);
     double SSP, QNEW, STI, SSP_EQ;
     {
       const double asrate = fmin(K_ONE, m.asrate * DT1);
@@ -430,11 +426,11 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
         TEMP = TEMP + qheat / mcv;
         TEMP = fmax(K_ZERO, TEMP);
       }
-      g.temp[e] = TEMP;
+      T.st(g.w_temp, TEMP);
     }
     // ---- state write-back
-    g.sig[e] = SG1; g.sig[np + e] = SG2; g.sig[2 * np + e] = SG3; g.sig[3 * np + e] = SG4; g.sig[4 * np + e] = SG5; g.sig[5 * np + e] = SG6;
-    g.eint[e] = EINT; g.rho[e] = RHON; g.qvis[e] = QNEW; g.pla[e] = EPXE; g.epsd[e] = EPSD;
+    T.st(BW_SIG, SG1); T.st(BW_SIG + 1, SG2); T.st(BW_SIG + 2, SG3); T.st(BW_SIG + 3, SG4); T.st(BW_SIG + 4, SG5); T.st(BW_SIG + 5, SG6);
+    T.st(BW_EINT, EINT); T.st(BW_RHO, RHON); T.st(BW_QVIS, QNEW); T.st(BW_PLA, EPXE); T.st(BW_EPSD, EPSD);
     // ---- SMALLB3
     if (ISMSTR == 1 || ISMSTR == 3) { if (OFFG > K_ZERO) OFFG = K_TWO; }
     if (OFF < K_ONE) {
@@ -442,7 +438,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       else if (OFFG > K_ONE) OFFG = K_ONE + OFF;
       else OFFG = OFF;
     }
-    g.off[e] = OFFG;
+    T.st(BW_OFF, OFFG);
     // ---- SHVIS3
     double F1[8], F2[8], F3[8];
     {
@@ -509,7 +505,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     // between the stores would serialise behind them (it may alias them as far as the compiler knows)
     int sl[8];
     #pragma unroll
-    for (int k = 0; k < 8; k++) sl[k] = __ldg(g.slot + k * np + e);
+    for (int k = 0; k < 8; k++) sl[k] = T.ldi(g.w_slot, k);
     if (P.roww == 4) {
       #pragma unroll
       for (int k = 0; k < 8; k++) {
@@ -524,16 +520,31 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       }
     }
   }
-  block_dt_reduce<true>(dt_cand, ngl, order, P.db, g.blk0 + blockIdx.x);
+  if (STAGED) tile_store(g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
+  block_dt_reduce<true>(dt_cand, order, g.ngl, g.order0, P.db, g.blk0 + blockIdx.x);
+}
+
+template <int JHBE, int ISMSTR>
+static void launch_brick_staged(const BrickParams& P, int nblk, cudaStream_t st)
+{
+  const size_t bytes = (size_t)P.sg.nw * ORGPU_TILE * 8;
+#ifndef ORGPU_NO_STAGING
+  if (bytes <= ORGPU_STAGE_MAX_BYTES) {
+    stage_attr((const void*)brick_forces_kernel<JHBE, ISMSTR, true>, bytes, ORGPU_BRICK_MINB);
+    brick_forces_kernel<JHBE, ISMSTR, true><<<nblk, ORGPU_BLOCK, bytes, st>>>(P);
+    return;
+  }
+#endif
+  brick_forces_kernel<JHBE, ISMSTR, false><<<nblk, ORGPU_BLOCK, 0, st>>>(P);
 }
 
 template <int JHBE>
 static void launch_brick_ismstr(const BrickParams& P, int ismstr, int nblk, cudaStream_t st)
 {
   switch (ismstr) {
-    case 1: brick_forces_kernel<JHBE, 1><<<nblk, ORGPU_BLOCK, 0, st>>>(P); break;
-    case 2: brick_forces_kernel<JHBE, 2><<<nblk, ORGPU_BLOCK, 0, st>>>(P); break;
-    default: brick_forces_kernel<JHBE, 4><<<nblk, ORGPU_BLOCK, 0, st>>>(P); break;
+    case 1: launch_brick_staged<JHBE, 1>(P, nblk, st); break;
+    case 2: launch_brick_staged<JHBE, 2>(P, nblk, st); break;
+    default: launch_brick_staged<JHBE, 4>(P, nblk, st); break;
   }
 }
 
@@ -541,7 +552,7 @@ void launch_brick_forces(const BrickSG& sg, const DevNodes& nd, double* fsky, in
                          CycleState* cs, const DtBlocks& db, const FinalizeArgs& fa, cudaStream_t st)
 {
   BrickParams P{sg, nd, fsky, roww, cs, db};
-  const int nblk = (sg.ne + ORGPU_BLOCK - 1) / ORGPU_BLOCK;
+  const int nblk = sg.ne_pad / ORGPU_TILE;
   switch (sg.prop.jhbe) {
     case 0: launch_brick_ismstr<0>(P, sg.prop.ismstr, nblk, st); break;
     case 2: launch_brick_ismstr<2>(P, sg.prop.ismstr, nblk, st); break;

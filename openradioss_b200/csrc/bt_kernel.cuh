@@ -11,32 +11,39 @@
 #pragma once
 #include "shell_common.cuh"
 
-template <int LAW>
-__global__ void __launch_bounds__(ORGPU_SHELL_CTA, 3 * (ORGPU_BLOCK / ORGPU_SHELL_CTA))
+template <int LAW, bool STAGED>
+__global__ void __launch_bounds__(ORGPU_SHELL_CTA, 3)
 bt_forces_kernel(const __grid_constant__ ShellParams P)
 {
   const ShellSG& g = P.sg;
-  const int e = blockIdx.x * ORGPU_SHELL_CTA + threadIdx.x;
-  const int np = g.ne_pad;
-  double dt_cand = K_EP30; int ngl = 0; int order = 0x7fffffff;
+  const int e = blockIdx.x * ORGPU_TILE + threadIdx.x;
+  __shared__ __align__(8) unsigned long long s_bar;
+  double* const g_tile = g.slab + (size_t)blockIdx.x * g.nw * ORGPU_TILE;
+  if (STAGED) tile_load_begin(s_tile_dyn, &s_bar, g_tile, (unsigned)g.nw * ORGPU_TILE * 8u);
+  const TileAcc<STAGED> T{(STAGED ? s_tile_dyn : g_tile) + threadIdx.x};
+  double* const sm = g.smstr + (size_t)blockIdx.x * 6 * ORGPU_TILE + threadIdx.x;      // SMSTR word k at sm[k*128]
+  double dt_cand = K_EP30; int order = 0x7fffffff;
   if (e < g.ne) {
     const double DT1 = P.cs->dt2;
     const int ISMSTR = g.prop.ismstr, NPT = g.prop.npt, IHBE = g.prop.ihbe;
     int nc[4];
+    { const int* cn = g.conn + (size_t)blockIdx.x * 4 * ORGPU_TILE + threadIdx.x;
+      #pragma unroll
+      for (int k = 0; k < 4; k++) nc[k] = __ldg(cn + k * ORGPU_TILE); }
+    order = g.order0 + e;
+    double xg[4], yg[4], zg[4];
     #pragma unroll
-    for (int k = 0; k < 4; k++) nc[k] = __ldg(g.conn + k * np + e);
-    ngl = __ldg(g.ngl + e); order = g.order0 + e;
-    if ((threadIdx.x & 3) == 0) shell_prefetch_state(g, e);
-    double OFFG = g.off[e];
+    for (int k = 0; k < 4; k++) { const double4 p = P.nd.pos[nc[k]]; xg[k] = p.x; yg[k] = p.y; zg[k] = p.z; }
+    #pragma unroll
+    for (int k = 0; k < 4; k++) { prefetch_l1(P.nd.rot + nc[k]); prefetch_l1(P.nd.vel + nc[k]); }
+    if (STAGED) mbar_wait(&s_bar, 0);                     // the state tile has landed (issued before the gather)
+    double OFFG = T.ld(SW_OFF);
     const bool dead_in = OFFG < K_ZERO;
     double OFF = fmin(K_ONE, fabs(OFFG));
     // ---- frame (CNVEC3) from the four corner positions
     double e1[3], e2[3], e3[3];
     double X2, Y2, X3, Y3, X4, Y4, Z2;
     {
-      double xg[4], yg[4], zg[4];
-      #pragma unroll
-      for (int k = 0; k < 4; k++) { const double4 p = P.nd.pos[nc[k]]; xg[k] = p.x; yg[k] = p.y; zg[k] = p.z; }
       const double X21 = xg[1] - xg[0], X32 = xg[2] - xg[1], X34 = xg[2] - xg[3], X41 = xg[3] - xg[0];
       const double Y21 = yg[1] - yg[0], Y32 = yg[2] - yg[1], Y34 = yg[2] - yg[3], Y41 = yg[3] - yg[0];
       const double Z21 = zg[1] - zg[0], Z32 = zg[2] - zg[1], Z34 = zg[2] - zg[3], Z41 = zg[3] - zg[0];
@@ -64,11 +71,11 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
     }
     if (ISMSTR == 1 || ISMSTR == 2) {
       if (fabs(OFFG) == K_TWO) {
-        X2 = g.smstr[e]; Y2 = g.smstr[np + e]; X3 = g.smstr[2 * (size_t)np + e];
-        Y3 = g.smstr[3 * (size_t)np + e]; X4 = g.smstr[4 * (size_t)np + e]; Y4 = g.smstr[5 * (size_t)np + e]; Z2 = K_ZERO;
+        X2 = sm[0]; Y2 = sm[ORGPU_TILE]; X3 = sm[2 * ORGPU_TILE];
+        Y3 = sm[3 * ORGPU_TILE]; X4 = sm[4 * ORGPU_TILE]; Y4 = sm[5 * ORGPU_TILE]; Z2 = K_ZERO;
       } else {
-        __stcs(&g.smstr[e], X2); __stcs(&g.smstr[np + e], Y2); __stcs(&g.smstr[2 * (size_t)np + e], X3);
-        __stcs(&g.smstr[3 * (size_t)np + e], Y3); __stcs(&g.smstr[4 * (size_t)np + e], X4); __stcs(&g.smstr[5 * (size_t)np + e], Y4);
+        __stcs(&sm[0], X2); __stcs(&sm[ORGPU_TILE], Y2); __stcs(&sm[2 * ORGPU_TILE], X3);
+        __stcs(&sm[3 * ORGPU_TILE], Y3); __stcs(&sm[4 * ORGPU_TILE], X4); __stcs(&sm[5 * ORGPU_TILE], Y4);
       }
       if (ISMSTR == 1 && OFFG == K_ONE) OFFG = K_TWO;
     }
@@ -76,8 +83,7 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
     const double AREA = fmax(K_TWO * (PY2 * PX1 - PY1 * PX2), K_EM20);
     const double VHX = (-X2 + X3 - X4) / AREA, VHY = (-Y2 + Y3 - Y4) / AREA;
     // ---- CCOEF3
-    double THK0 = __ldg(g.thke + e);
-    if (g.prop.ithk > 0) THK0 = g.thk[e];
+    const double THK0 = (g.prop.ithk > 0) ? T.ld(SW_THK) : T.ld(g.w_thke);
     const double THK02 = THK0 * THK0;
     double RHO, YM, NU, G;
     MatIO io;
@@ -196,18 +202,18 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
       if (g.prop.istrain != 0) {
         const double de[8] = {io.exx, io.eyy, io.exy, io.eyz, io.exz, io.kxx, io.kyy, io.kxy};
         #pragma unroll
-        for (int k = 0; k < 8; k++) { double* p = g.stra + (size_t)k * np + e; __stcs(p, __ldcs(p) + de[k]); }
+        for (int k = 0; k < 8; k++) T.st(SW_STRA + k, T.ld(SW_STRA + k) + de[k]);
       }
       const double dtinv = DT1 / fmax(DT1 * DT1, K_EM20);
-      const double thk = g.thk[e];
+      const double thk = T.ld(SW_THK);
       const double eps_k2 = (io.kxx * io.kxx + io.kyy * io.kyy + io.kxx * io.kyy + K_FOURTH * (io.kxy * io.kxy)) * K_ONE_OVER_9 * (thk * thk);
       const double eps_m2 = K_FOUR_OVER_3 * (io.exx * io.exx + io.eyy * io.eyy + io.exx * io.eyy + K_FOURTH * (io.exy * io.exy));
       io.epsd_pg = sqrt(eps_k2 + eps_m2) * dtinv;
-      g.epsd[e] = K_ONE * io.epsd_pg + (K_ONE - K_ONE) * g.epsd[e];
+      T.st(SW_EPSD, K_ONE * io.epsd_pg + (K_ONE - K_ONE) * T.ld(SW_EPSD));
     }
     // ---- CMAIN3
     io.area = AREA; io.thk0 = THK0; io.gs = G * SHF; io.rho = RHO; io.off = OFF; io.sigy = K_EP30;
-    shell_material_loop<LAW, false>(g, e, DT1, io);
+    shell_material_loop<LAW, false, STAGED>(g, T, DT1, io);
     OFF = io.off;
     const double SSP = io.ssp;
     const double VISCMX = sqrt(K_ONE + io.viscmx * io.viscmx) - io.viscmx;
@@ -247,7 +253,7 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
       double HG1, HG2;
       if (plain) { HG1 = (VX[0] - VX[1] + VX[2] - VX[3]) * OFF; HG2 = (VY[0] - VY[1] + VY[2] - VY[3]) * OFF; }
       else { HG1 = VX[0] * GAMA1 + VX[1] * GAMA2 + VX[2] * GAMA3 + VX[3] * GAMA4; HG2 = VY[0] * GAMA1 + VY[1] * GAMA2 + VY[2] * GAMA3 + VY[3] * GAMA4; }
-      double hr1 = __ldcs(g.hourg + e), hr2 = __ldcs(g.hourg + np + e), hr3 = __ldcs(g.hourg + 2 * (size_t)np + e);
+      double hr1 = T.ld(SW_HOURG), hr2 = T.ld(SW_HOURG + 1), hr3 = T.ld(SW_HOURG + 2);
       hr1 = hr1 + HG1 * HH1;
       hr2 = hr2 + HG2 * HH1;
       const double HOUR1A = hr1 + HG1 * (H1L + H1Q * fabs(HG1));
@@ -263,8 +269,8 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
       HG2 = RY[0] - RY[1] + RY[2] - RY[3];
       const double hr4 = HG1 * (H3L + H3Q * fabs(HG1));
       const double hr5 = HG2 * (H3L + H3Q * fabs(HG2));
-      __stcs(g.hourg + e, hr1); __stcs(g.hourg + np + e, hr2); __stcs(g.hourg + 2 * (size_t)np + e, hr3);
-      __stcs(g.hourg + 3 * (size_t)np + e, hr4); __stcs(g.hourg + 4 * (size_t)np + e, hr5);
+      T.st(SW_HOURG, hr1); T.st(SW_HOURG + 1, hr2); T.st(SW_HOURG + 2, hr3);
+      T.st(SW_HOURG + 3, hr4); T.st(SW_HOURG + 4, hr5);
       B1r = hr4 * OFF; B2r = hr5 * OFF;               // B11 = B13 = B1r, B12 = B14 = -B1r ; same for B2x
     }
     // ---- CDT3
@@ -296,12 +302,12 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
     }
     // ---- CUPDT3P
     if (OFF < K_ONE) OFFG = OFF;
-    g.off[e] = OFFG;
+    T.st(SW_OFF, OFFG);
     const bool dead = OFFG < K_ZERO;
     if (dead) STI = K_ZERO;
     int sl[4];
     #pragma unroll
-    for (int k = 0; k < 4; k++) sl[k] = __ldg(g.slot + k * np + e);
+    for (int k = 0; k < 4; k++) sl[k] = T.ldi(g.w_slot, k);
     double f4[3] = {K_ZERO, K_ZERO, K_ZERO};
     #pragma unroll
     for (int J = 0; J < 4; J++) {
@@ -320,11 +326,6 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
       row[2] = make_double2(-mm[1], -mm[2]); row[3] = make_double2(STI, K_ZERO);
     }
   }
-  block_dt_reduce<false>(dt_cand, ngl, order, P.db, g.blk0 + blockIdx.x);
-}
-
-static void launch_bt_forces(const ShellParams& P, int nblk, cudaStream_t st)
-{
-  if (P.sg.law == 36) bt_forces_kernel<36><<<nblk, ORGPU_SHELL_CTA, 0, st>>>(P);
-  else                bt_forces_kernel<2><<<nblk, ORGPU_SHELL_CTA, 0, st>>>(P);
+  if (STAGED) tile_store(g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
+  block_dt_reduce<false>(dt_cand, order, g.ngl, g.order0, P.db, g.blk0 + blockIdx.x);
 }

@@ -261,25 +261,28 @@ int orgpu_finalize(orgpu_engine* e)
     e->bsg.emplace_back(); BrickSGHost& S = e->bsg.back(); S.first_elem = nft;
     BrickSG& d = S.d; d.ne = ne; d.ne_pad = np; d.order0 = order; d.blk0 = blk;
     d.mat = e->sgroups[gi].mat; d.prop = e->sgroups[gi].prop; d.dtfac = e->ctl.dtfac_brick;
-    std::vector<int> conn((size_t)8 * np, 0), slot((size_t)8 * np, 0), ngl(np, 0);
-    std::vector<double> vol(np, 1.0), rho(np, d.mat.rho0), off(np, 0.0), temp(np, d.mat.tini);
+    std::vector<int> conn((size_t)8 * np, 0), ngl(np, 0), conn_t;
+    // state slab: read/write words first (SIG 6, EINT, RHO, QVIS, PLA, EPSD, OFF[, TEMP]), then VOL and the slot rows
+    d.w_temp = d.mat.has_temp ? BW_NFIX : -1;
+    d.nw_rw = BW_NFIX + (d.mat.has_temp ? 1 : 0);
+    d.w_vol = d.nw_rw; d.w_slot = d.nw_rw + 1; d.nw = d.nw_rw + 1 + 4;
+    HostSlab H; H.init(d.nw, np);
+    for (int i = 0; i < np; i++) { H.at(d.w_vol, i) = 1.0; H.at(BW_RHO, i) = d.mat.rho0; if (d.w_temp >= 0) H.at(d.w_temp, i) = d.mat.tini; }
     for (int i = 0; i < ne; i++) {
       const int* ix = &e->ixs[(size_t)11 * (nft + i)];
       for (int k = 0; k < 8; k++) {
         int node = ix[1 + k]; NEED(node >= 1 && node <= e->numnod, -4, "IXS node %d out of range (element %d)", node, nft + i + 1);
         int sl = e->iads[(size_t)8 * (nft + i) + k]; NEED(sl >= 1 && sl <= e->lsky, -4, "IADS slot %d out of range (element %d)", sl, nft + i + 1);
-        conn[(size_t)k * np + i] = node - 1; slot[(size_t)k * np + i] = sl - 1;
+        conn[(size_t)k * np + i] = node - 1; H.iat(d.w_slot, k, i) = sl - 1;
       }
-      ngl[i] = ix[10]; off[i] = 1.0;
+      ngl[i] = ix[10]; H.at(BW_OFF, i) = 1.0;
     }
-    { int i = 0; for (size_t k = gi; k < gj; k++) for (int j = 0; j < e->sgroups[k].nel; j++) vol[i++] = e->sgroups[k].vol0[j]; }
-    int *dconn, *dslot, *dngl; double *dvol, *drho, *doff, *dtemp;
-    if (upload_vec(S.owned, &dconn, conn) || upload_vec(S.owned, &dslot, slot) || upload_vec(S.owned, &dngl, ngl) ||
-        upload_vec(S.owned, &dvol, vol) || upload_vec(S.owned, &drho, rho) || upload_vec(S.owned, &doff, off) ||
-        upload_vec(S.owned, &dtemp, temp)) return -100;
-    d.conn = dconn; d.slot = dslot; d.ngl = dngl; d.vol = dvol; d.rho = drho; d.off = doff; d.temp = dtemp;
-    if (push_dev(S.owned, &d.sig, (size_t)6 * np) || push_dev(S.owned, &d.eint, np) || push_dev(S.owned, &d.qvis, np) ||
-        push_dev(S.owned, &d.pla, np) || push_dev(S.owned, &d.epsd, np) || push_dev(S.owned, &d.smstr, (size_t)21 * np)) return -100;
+    { int i = 0; for (size_t k = gi; k < gj; k++) for (int j = 0; j < e->sgroups[k].nel; j++) H.at(d.w_vol, i++) = e->sgroups[k].vol0[j]; }
+    tile_major_ints(conn_t, conn, 8, np);
+    int *dconn, *dngl;
+    if (upload_vec(S.owned, &dconn, conn_t) || upload_vec(S.owned, &dngl, ngl) || upload_vec(S.owned, &d.slab, H.h)) return -100;
+    d.conn = dconn; d.ngl = dngl;
+    if (push_dev(S.owned, &d.smstr, (size_t)21 * np)) return -100;
     const int nblk = np / ORGPU_BLOCK;
     NEED(e->fa.nsg < ORGPU_MAX_SG, -6, "too many super-groups (%d)", ORGPU_MAX_SG);
     e->fa.sg[e->fa.nsg++] = SGRange{blk, nblk, ORGPU_FAM_BRICK};
@@ -508,12 +511,13 @@ int orgpu_download_solid_state(orgpu_engine* e, int field, double* out)
   CUDA_OK(cudaStreamSynchronize(e->st));
   const size_t NE = e->numels;
   for (auto& S : e->bsg) {
-    const BrickSG& d = S.d; const double* src = nullptr; int nc = 1;
-    switch (field) { case 0: src = d.sig; nc = 6; break; case 1: src = d.eint; break; case 2: src = d.rho; break; case 3: src = d.qvis; break;
-                     case 4: src = d.pla; break; case 5: src = d.epsd; break; case 6: src = d.vol; break; case 7: src = d.off; break;
-                     case 8: src = d.temp; break; case 9: src = d.smstr; nc = 21; break; default: FAIL(-1, "unknown solid field %d", field); }
+    const BrickSG& d = S.d; int w0 = 0, nc = 1; const double* base = d.slab; int nw = d.nw;
+    switch (field) { case 0: w0 = BW_SIG; nc = 6; break; case 1: w0 = BW_EINT; break; case 2: w0 = BW_RHO; break; case 3: w0 = BW_QVIS; break;
+                     case 4: w0 = BW_PLA; break; case 5: w0 = BW_EPSD; break; case 6: w0 = d.w_vol; break; case 7: w0 = BW_OFF; break;
+                     case 8: w0 = d.w_temp; break; case 9: base = d.smstr; nw = 21; w0 = 0; nc = 21; break; default: FAIL(-1, "unknown solid field %d", field); }
+    if (w0 < 0) { for (int i = 0; i < d.ne; i++) out[S.first_elem + i] = d.mat.tini; continue; }   // no temperature buffer
     for (int k = 0; k < nc; k++)
-      CUDA_OK(cudaMemcpy(out + k * NE + S.first_elem, src + (size_t)k * d.ne_pad, 8 * (size_t)d.ne, cudaMemcpyDeviceToHost));
+      CUDA_OK(slab_download_word(base, nw, w0 + k, d.ne, out + k * NE + S.first_elem));
   }
   return 0;
 }
@@ -620,12 +624,13 @@ int orgpu_exchange(orgpu_engine* e)
   return exchange_on_stream(e, false);
 }
 
-static int energy_sum(orgpu_engine* e, const double* a, const double* b, const double* off, int n, int mode, double* out)
+// a, b, off: word rows of a tile-major slab (nw words per tile) when nw > 0, plain arrays when nw == 0
+static int energy_sum(orgpu_engine* e, const double* a, const double* b, const double* off, int nw, int n, int mode, double* out)
 {
   if (n <= 0) return 0;
   const int nb = (n + 255) / 256;
   double* d_part = nullptr; CUDA_OK(cudaMalloc((void**)&d_part, 8 * (size_t)nb));
-  energy_partial_kernel<<<nb, 256, 0, e->st>>>(a, b, off, n, mode, d_part); e->launches++;
+  energy_partial_kernel<<<nb, 256, 0, e->st>>>(a, b, off, nw, n, mode, d_part); e->launches++;
   std::vector<double> h(nb);
   CUDA_OK(cudaMemcpyAsync(h.data(), d_part, 8 * (size_t)nb, cudaMemcpyDeviceToHost, e->st));
   CUDA_OK(cudaStreamSynchronize(e->st));
@@ -639,10 +644,10 @@ int orgpu_get_energies(orgpu_engine* e, double out[4])
 {
   NEED(e && e->finalized && out, -1, "orgpu_get_energies: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
   out[0] = out[1] = out[2] = out[3] = 0.0;        // internal solids, internal shells, kinetic translation, kinetic rotation
-  for (auto& S : e->bsg) if (energy_sum(e, S.d.eint, S.d.vol, nullptr, S.d.ne, 0, &out[0])) return -100;
-  for (auto& S : e->csg) if (energy_sum(e, S.d.eint, S.d.eint + S.d.ne_pad, S.d.off, S.d.ne, 1, &out[1])) return -100;
-  if (energy_sum(e, e->nd.MS, (const double*)e->nd.vel, nullptr, e->numnod, 2, &out[2])) return -100;
-  if (e->nd.rot && energy_sum(e, e->nd.IN, (const double*)e->nd.rot, nullptr, e->numnod, 2, &out[3])) return -100;
+  for (auto& S : e->bsg) if (energy_sum(e, S.d.slab + BW_EINT * ORGPU_TILE, S.d.slab + S.d.w_vol * ORGPU_TILE, nullptr, S.d.nw, S.d.ne, 0, &out[0])) return -100;
+  for (auto& S : e->csg) if (energy_sum(e, S.d.slab + SW_EINT * ORGPU_TILE, S.d.slab + (SW_EINT + 1) * ORGPU_TILE, S.d.slab + SW_OFF * ORGPU_TILE, S.d.nw, S.d.ne, 1, &out[1])) return -100;
+  if (energy_sum(e, e->nd.MS, (const double*)e->nd.vel, nullptr, 0, e->numnod, 2, &out[2])) return -100;
+  if (e->nd.rot && energy_sum(e, e->nd.IN, (const double*)e->nd.rot, nullptr, 0, e->numnod, 2, &out[3])) return -100;
   return 0;
 }
 

@@ -188,16 +188,18 @@ void launch_set_dt(CycleState* cs, double dt1, double dt12, double dt2, int whic
 // kinetic energies.  Deterministic: fixed 256-wide CTA partial sums in a fixed tree, final sum on the host
 // in block order.
 __global__ void __launch_bounds__(256)
-energy_partial_kernel(const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ off, int n, int mode,
+energy_partial_kernel(const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ off, int nw, int n, int mode,
                       double* __restrict__ partial)
 {
+  // nw > 0: a, b, off are word rows of a tile-major slab -> element i sits at ((i>>7)*nw)*128 + (i&127)
   // mode 0: sum a[i]*b[i] (off ignored) ; 1: sum (a[i] + b[i]) where off[i] != 0 ; 2: sum 0.5*a[i]*|v_i|^2 with b = double4 records
   __shared__ double s[256];
   const int i = blockIdx.x * 256 + threadIdx.x;
   double v = 0.0;
   if (i < n) {
-    if (mode == 0) v = a[i] * b[i];
-    else if (mode == 1) v = (off[i] != 0.0) ? a[i] + b[i] : 0.0;
+    const size_t j = nw > 0 ? ((size_t)(i >> 7) * nw) * ORGPU_TILE + (i & 127) : (size_t)i;
+    if (mode == 0) v = a[j] * b[j];
+    else if (mode == 1) v = (off[j] != 0.0) ? a[j] + b[j] : 0.0;
     else { const double4 w = reinterpret_cast<const double4*>(b)[i]; v = 0.5 * a[i] * (w.x * w.x + w.y * w.y + w.z * w.z); }
   }
   s[threadIdx.x] = v; __syncthreads();

@@ -14,30 +14,118 @@
 #pragma once
 #include "shell_common.cuh"
 
+// The element working set (local frame, centred coordinates, warped-element projection matrices ...) is
+// larger than a thread's register budget at three CTAs per SM, and everything the compiler parks in
+// local memory competes with the staged state tile for the SM's L1/shared storage.  So only a minimal
+// set crosses the through-thickness loop (local corner coordinates, Z1, area, frame, hourglass rates);
+// the derived quantities are RE-DERIVED after the loop by the same expressions -- bit-identical, ~350
+// fp64 instructions -- behind an optimisation barrier that stops the compiler from keeping them alive.
+#define ORGPU_OPAQUE(x) asm volatile("" : "+d"(x))
+
+struct QephGeo {                 // centred corner coordinates and B-matrix ingredients (czcorc.F:336-375)
+  double CX[4], CY[4], X13, X24, Y13, Y24, MX13, MX23, MX34, MY13, MY23, MY34, L13, L24;
+};
+__device__ __forceinline__ void qeph_geo(double XL2, double YL2, double XL3, double YL3, double XL4, double YL4, QephGeo& q)
+{
+  const double LX = K_FOURTH * (XL2 + XL3 + XL4), LY = K_FOURTH * (YL2 + YL3 + YL4);
+  q.CX[0] = -LX; q.CX[1] = XL2 - LX; q.CX[2] = XL3 - LX; q.CX[3] = XL4 - LX;
+  q.CY[0] = -LY; q.CY[1] = YL2 - LY; q.CY[2] = YL3 - LY; q.CY[3] = YL4 - LY;
+  q.X13 = (q.CX[0] - q.CX[2]) * K_HALF; q.X24 = (q.CX[1] - q.CX[3]) * K_HALF;
+  q.Y13 = (q.CY[0] - q.CY[2]) * K_HALF; q.Y24 = (q.CY[1] - q.CY[3]) * K_HALF;
+  q.MX13 = (q.CX[0] + q.CX[2]) * K_HALF; q.MX23 = (q.CX[1] + q.CX[2]) * K_HALF; q.MX34 = (q.CX[2] + q.CX[3]) * K_HALF;
+  q.MY13 = (q.CY[0] + q.CY[2]) * K_HALF; q.MY23 = (q.CY[1] + q.CY[2]) * K_HALF; q.MY34 = (q.CY[2] + q.CY[3]) * K_HALF;
+  q.L13 = q.X13 * q.X13 + q.Y13 * q.Y13; q.L24 = q.X24 * q.X24 + q.Y24 * q.Y24;
+}
+
+// CZCORP5 (czcorp5.F:83-250), geometry-only part for a warped element: nodal normals VQN, the inverse DI of
+// the rigid-mode Gram matrix and DB = DI * VQN
+__device__ __forceinline__ void qeph_warp_proj(const QephGeo& q, double Z1, double AREA, double VQN[3][4], double DI[6], double DB[3][4])
+{
+  const double Z2 = Z1 * Z1;
+  const double A_4 = AREA * K_FOURTH;
+  double SZ1 = q.MX13 * q.Y24 - q.MY13 * q.X24;
+  double SZ2 = A_4 + SZ1;
+  double SZ = Z2 * q.L24;
+  double SL = K_ONE / sqrt(SZ + SZ2 * SZ2);
+  VQN[0][0] = -Z1 * q.Y24; VQN[1][0] = Z1 * q.X24; VQN[2][0] = SZ2 * SL;
+  VQN[0][2] = -VQN[0][0]; VQN[1][2] = -VQN[1][0];
+  VQN[0][0] = VQN[0][0] * SL; VQN[1][0] = VQN[1][0] * SL;
+  SZ2 = A_4 - SZ1;
+  SL = K_ONE / sqrt(SZ + SZ2 * SZ2);
+  VQN[0][2] = VQN[0][2] * SL; VQN[1][2] = VQN[1][2] * SL; VQN[2][2] = SZ2 * SL;
+  SZ1 = q.MX13 * q.Y13 - q.MY13 * q.X13;
+  SZ2 = A_4 + SZ1;
+  SZ = Z2 * q.L13;
+  SL = K_ONE / sqrt(SZ + SZ2 * SZ2);
+  VQN[0][1] = -Z1 * q.Y13; VQN[1][1] = Z1 * q.X13; VQN[2][1] = SZ2 * SL;
+  VQN[0][3] = -VQN[0][1]; VQN[1][3] = -VQN[1][1];
+  VQN[0][1] = VQN[0][1] * SL; VQN[1][1] = VQN[1][1] * SL;
+  SZ2 = A_4 - SZ1;
+  SL = K_ONE / sqrt(SZ + SZ2 * SZ2);
+  VQN[0][3] = VQN[0][3] * SL; VQN[1][3] = VQN[1][3] * SL; VQN[2][3] = SZ2 * SL;
+  const double* CX = q.CX; const double* CY = q.CY;
+  const double XX = CX[0] * CX[0] + CX[1] * CX[1] + CX[2] * CX[2] + CX[3] * CX[3];
+  const double YY = CY[0] * CY[0] + CY[1] * CY[1] + CY[2] * CY[2] + CY[3] * CY[3];
+  const double XY = CX[0] * CY[0] + CX[1] * CY[1] + CX[2] * CY[2] + CX[3] * CY[3];
+  const double XZ = (CX[0] - CX[1] + CX[2] - CX[3]) * Z1;
+  const double YZ = (CY[0] - CY[1] + CY[2] - CY[3]) * Z1;
+  const double ZZ = K_FOUR * Z2;
+  double D[6];
+  D[0] = YY + ZZ + K_FOUR - (VQN[0][0] * VQN[0][0] + VQN[0][1] * VQN[0][1] + VQN[0][2] * VQN[0][2] + VQN[0][3] * VQN[0][3]);
+  D[1] = XX + ZZ + K_FOUR - (VQN[1][0] * VQN[1][0] + VQN[1][1] * VQN[1][1] + VQN[1][2] * VQN[1][2] + VQN[1][3] * VQN[1][3]);
+  D[2] = XX + YY + K_FOUR - (VQN[2][0] * VQN[2][0] + VQN[2][1] * VQN[2][1] + VQN[2][2] * VQN[2][2] + VQN[2][3] * VQN[2][3]);
+  D[3] = -XY - (VQN[0][0] * VQN[1][0] + VQN[0][1] * VQN[1][1] + VQN[0][2] * VQN[1][2] + VQN[0][3] * VQN[1][3]);
+  D[4] = -XZ - (VQN[0][0] * VQN[2][0] + VQN[0][1] * VQN[2][1] + VQN[0][2] * VQN[2][2] + VQN[0][3] * VQN[2][3]);
+  D[5] = -YZ - (VQN[1][0] * VQN[2][0] + VQN[1][1] * VQN[2][1] + VQN[1][2] * VQN[2][2] + VQN[1][3] * VQN[2][3]);
+  const double ABC = D[0] * D[1] * D[2];
+  const double XXYZ2 = D[0] * D[5] * D[5], YYXZ2 = D[1] * D[4] * D[4], ZZXY2 = D[2] * D[3] * D[3];
+  double DETA = fabs(ABC + K_TWO * D[3] * D[4] * D[5] - XXYZ2 - YYXZ2 - ZZXY2);
+  DETA = K_ONE / fmax(DETA, K_EM20);
+  DI[0] = (ABC - XXYZ2) * DETA / fmax(D[0], K_EM20);
+  DI[1] = (ABC - YYXZ2) * DETA / fmax(D[1], K_EM20);
+  DI[2] = (ABC - ZZXY2) * DETA / fmax(D[2], K_EM20);
+  DI[3] = (D[4] * D[5] - D[3] * D[2]) * DETA;
+  DI[4] = (D[5] * D[3] - D[4] * D[1]) * DETA;
+  DI[5] = (D[3] * D[4] - D[5] * D[0]) * DETA;
+  #pragma unroll
+  for (int J = 0; J < 4; J++) {
+    DB[0][J] = DI[0] * VQN[0][J] + DI[3] * VQN[1][J] + DI[4] * VQN[2][J];
+    DB[1][J] = DI[3] * VQN[0][J] + DI[1] * VQN[1][J] + DI[5] * VQN[2][J];
+    DB[2][J] = DI[4] * VQN[0][J] + DI[5] * VQN[1][J] + DI[2] * VQN[2][J];
+  }
+}
+
 #ifndef ORGPU_SHELL_MINB
 #define ORGPU_SHELL_MINB 3
 #endif
 
-template <int LAW>
-__global__ void __launch_bounds__(ORGPU_SHELL_CTA, ORGPU_SHELL_MINB * (ORGPU_BLOCK / ORGPU_SHELL_CTA))
+template <int LAW, bool STAGED>
+__global__ void __launch_bounds__(ORGPU_SHELL_CTA, ORGPU_SHELL_MINB)
 qeph_forces_kernel(const __grid_constant__ ShellParams P)
 {
   const ShellSG& g = P.sg;
-  const int e = blockIdx.x * ORGPU_SHELL_CTA + threadIdx.x;
-  const int np = g.ne_pad;
-  double dt_cand = K_EP30; int ngl = 0; int order = 0x7fffffff;
+  const int e = blockIdx.x * ORGPU_TILE + threadIdx.x;
+  __shared__ __align__(8) unsigned long long s_bar;
+  double* const g_tile = g.slab + (size_t)blockIdx.x * g.nw * ORGPU_TILE;
+  if (STAGED) tile_load_begin(s_tile_dyn, &s_bar, g_tile, (unsigned)g.nw * ORGPU_TILE * 8u);
+  const TileAcc<STAGED> T{(STAGED ? s_tile_dyn : g_tile) + threadIdx.x};
+  double* const sm = g.smstr + (size_t)blockIdx.x * 6 * ORGPU_TILE + threadIdx.x;      // SMSTR word k at sm[k*128]
+  double dt_cand = K_EP30; int order = 0x7fffffff;
   if (e < g.ne) {
     const double DT1 = P.cs->dt2;
     const int ISMSTR = g.prop.ismstr, NPT = g.prop.npt;
     int nc[4];
-    #pragma unroll
-    for (int k = 0; k < 4; k++) nc[k] = __ldg(g.conn + k * np + e);
-    ngl = __ldg(g.ngl + e); order = g.order0 + e;
-    if ((threadIdx.x & 3) == 0) shell_prefetch_state(g, e);   // state is consumed after the geometry phase
-    double OFFG = g.off[e];
+    { const int* cn = g.conn + (size_t)blockIdx.x * 4 * ORGPU_TILE + threadIdx.x;
+      #pragma unroll
+      for (int k = 0; k < 4; k++) nc[k] = __ldg(cn + k * ORGPU_TILE); }
+    order = g.order0 + e;
     double px[4], py[4], pz[4];
     #pragma unroll
     for (int k = 0; k < 4; k++) { const double4 p = P.nd.pos[nc[k]]; px[k] = p.x; py[k] = p.y; pz[k] = p.z; }
+    #pragma unroll
+    for (int k = 0; k < 4; k++) { prefetch_l1(P.nd.rot + nc[k]); prefetch_l1(P.nd.vel + nc[k]); }
+    if (STAGED) mbar_wait(&s_bar, 0);                     // the state tile has landed (issued before the gather)
+    double OFFG = T.ld(SW_OFF);
     // ---- local frame (CLSKEW3, IREP=0)
     double VQ[3][3];                                   // VQ[a][b] = R_ab : columns are e1, e2, e3
     double AREA, AREA_I;
@@ -86,31 +174,29 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     // ---- small-strain reference (czcorc.F:297-324)
     if (ISMSTR == 1 || ISMSTR == 2) {
       if (fabs(OFFG) == K_TWO) {
-        XL2 = g.smstr[e]; YL2 = g.smstr[np + e]; XL3 = g.smstr[2 * (size_t)np + e];
-        YL3 = g.smstr[3 * (size_t)np + e]; XL4 = g.smstr[4 * (size_t)np + e]; YL4 = g.smstr[5 * (size_t)np + e];
+        XL2 = sm[0]; YL2 = sm[ORGPU_TILE]; XL3 = sm[2 * ORGPU_TILE];
+        YL3 = sm[3 * ORGPU_TILE]; XL4 = sm[4 * ORGPU_TILE]; YL4 = sm[5 * ORGPU_TILE];
         Z1 = K_ZERO;
         AREA = K_HALF * ((XL2 - XL4) * YL3 - XL3 * (YL2 - YL4));
         AREA_I = K_ONE / fmax(K_EM20, AREA);
       } else {
-        __stcs(&g.smstr[e], XL2); __stcs(&g.smstr[np + e], YL2); __stcs(&g.smstr[2 * (size_t)np + e], XL3);
-        __stcs(&g.smstr[3 * (size_t)np + e], YL3); __stcs(&g.smstr[4 * (size_t)np + e], XL4); __stcs(&g.smstr[5 * (size_t)np + e], YL4);
+        __stcs(&sm[0], XL2); __stcs(&sm[ORGPU_TILE], YL2); __stcs(&sm[2 * ORGPU_TILE], XL3);
+        __stcs(&sm[3 * ORGPU_TILE], YL3); __stcs(&sm[4 * ORGPU_TILE], XL4); __stcs(&sm[5 * ORGPU_TILE], YL4);
       }
     }
     if (ISMSTR == 1 && OFFG == K_ONE) OFFG = K_TWO;
     // ---- centred corner coordinates and the B-matrix ingredients (czcorc.F:336-375)
-    double CX[4], CY[4];
-    {
-      const double LX = K_FOURTH * (XL2 + XL3 + XL4), LY = K_FOURTH * (YL2 + YL3 + YL4);
-      CX[0] = -LX; CX[1] = XL2 - LX; CX[2] = XL3 - LX; CX[3] = XL4 - LX;
-      CY[0] = -LY; CY[1] = YL2 - LY; CY[2] = YL3 - LY; CY[3] = YL4 - LY;
-    }
-    const double X13 = (CX[0] - CX[2]) * K_HALF, X24 = (CX[1] - CX[3]) * K_HALF;
-    const double Y13 = (CY[0] - CY[2]) * K_HALF, Y24 = (CY[1] - CY[3]) * K_HALF;
-    const double MX13 = (CX[0] + CX[2]) * K_HALF, MX23 = (CX[1] + CX[2]) * K_HALF, MX34 = (CX[2] + CX[3]) * K_HALF;
-    const double MY13 = (CY[0] + CY[2]) * K_HALF, MY23 = (CY[1] + CY[2]) * K_HALF, MY34 = (CY[2] + CY[3]) * K_HALF;
-    const double L13 = X13 * X13 + Y13 * Y13, L24 = X24 * X24 + Y24 * Y24;
+    MatIO io;
+    double VHG[6], OFF, THK0, LL, FACN1, FACN2;
+    bool PLAT;
+    {   // ======== everything in this scope is re-derived after the through-thickness loop ========
+    QephGeo q0; qeph_geo(XL2, YL2, XL3, YL3, XL4, YL4, q0);
+    const double* CX = q0.CX; const double* CY = q0.CY;
+    const double X13 = q0.X13, X24 = q0.X24, Y13 = q0.Y13, Y24 = q0.Y24;
+    const double MX13 = q0.MX13, MX23 = q0.MX23, MX34 = q0.MX34, MY13 = q0.MY13, MY23 = q0.MY23, MY34 = q0.MY34;
+    const double L13 = q0.L13, L24 = q0.L24;
     // ---- characteristic length (czcorc.F:380-404)
-    double LL, LM, FACN1, FACN2;
+    double LM;
     {
       const double c1 = CX[1] * CY[3] - CY[1] * CX[3];
       const double c2 = CX[0] * CY[2] - CY[0] * CX[2];
@@ -171,34 +257,13 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       VHI[1] = VHI[1] - DDRX * VHI[2] - DDRZ2 * VHIX;
     }
     // ---- CZCORP5: flat test, nodal normals and full projection for warped elements
-    bool PLAT;
-    double VQN[3][4], DI[6], DB[3][4];
     {
       const double Z2 = Z1 * Z1;
       if (Z2 < LM * K_EM8 || NPT == 1) { Z1 = K_ZERO; PLAT = true; }
       else {
         PLAT = false;
-        const double A_4 = AREA * K_FOURTH;
-        double SZ1 = MX13 * Y24 - MY13 * X24;
-        double SZ2 = A_4 + SZ1;
-        double SZ = Z2 * L24;
-        double SL = K_ONE / sqrt(SZ + SZ2 * SZ2);
-        VQN[0][0] = -Z1 * Y24; VQN[1][0] = Z1 * X24; VQN[2][0] = SZ2 * SL;
-        VQN[0][2] = -VQN[0][0]; VQN[1][2] = -VQN[1][0];
-        VQN[0][0] = VQN[0][0] * SL; VQN[1][0] = VQN[1][0] * SL;
-        SZ2 = A_4 - SZ1;
-        SL = K_ONE / sqrt(SZ + SZ2 * SZ2);
-        VQN[0][2] = VQN[0][2] * SL; VQN[1][2] = VQN[1][2] * SL; VQN[2][2] = SZ2 * SL;
-        SZ1 = MX13 * Y13 - MY13 * X13;
-        SZ2 = A_4 + SZ1;
-        SZ = Z2 * L13;
-        SL = K_ONE / sqrt(SZ + SZ2 * SZ2);
-        VQN[0][1] = -Z1 * Y13; VQN[1][1] = Z1 * X13; VQN[2][1] = SZ2 * SL;
-        VQN[0][3] = -VQN[0][1]; VQN[1][3] = -VQN[1][1];
-        VQN[0][1] = VQN[0][1] * SL; VQN[1][1] = VQN[1][1] * SL;
-        SZ2 = A_4 - SZ1;
-        SL = K_ONE / sqrt(SZ + SZ2 * SZ2);
-        VQN[0][3] = VQN[0][3] * SL; VQN[1][3] = VQN[1][3] * SL; VQN[2][3] = SZ2 * SL;
+        double VQN[3][4], DI[6], DB[3][4];
+        qeph_warp_proj(q0, Z1, AREA, VQN, DI, DB);
         double AR[3], AD[4];
         AR[0] = -Z1 * VHI[1] + Y13 * V13[2] + Y24 * V24[2] + MY13 * VHI[2] + RL[0][0] + RL[0][1] + RL[0][2] + RL[0][3];
         AR[1] = Z1 * VHI[0] - X13 * V13[2] - X24 * V24[2] - MX13 * VHI[2] + RL[1][0] + RL[1][1] + RL[1][2] + RL[1][3];
@@ -206,35 +271,6 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
               + RL[2][0] + RL[2][1] + RL[2][2] + RL[2][3];
         #pragma unroll
         for (int k = 0; k < 4; k++) AD[k] = VQN[0][k] * RL[0][k] + VQN[1][k] * RL[1][k] + VQN[2][k] * RL[2][k];
-        const double XX = CX[0] * CX[0] + CX[1] * CX[1] + CX[2] * CX[2] + CX[3] * CX[3];
-        const double YY = CY[0] * CY[0] + CY[1] * CY[1] + CY[2] * CY[2] + CY[3] * CY[3];
-        const double XY = CX[0] * CY[0] + CX[1] * CY[1] + CX[2] * CY[2] + CX[3] * CY[3];
-        const double XZ = (CX[0] - CX[1] + CX[2] - CX[3]) * Z1;
-        const double YZ = (CY[0] - CY[1] + CY[2] - CY[3]) * Z1;
-        const double ZZ = K_FOUR * Z2;
-        double D[6];
-        D[0] = YY + ZZ + K_FOUR - (VQN[0][0] * VQN[0][0] + VQN[0][1] * VQN[0][1] + VQN[0][2] * VQN[0][2] + VQN[0][3] * VQN[0][3]);
-        D[1] = XX + ZZ + K_FOUR - (VQN[1][0] * VQN[1][0] + VQN[1][1] * VQN[1][1] + VQN[1][2] * VQN[1][2] + VQN[1][3] * VQN[1][3]);
-        D[2] = XX + YY + K_FOUR - (VQN[2][0] * VQN[2][0] + VQN[2][1] * VQN[2][1] + VQN[2][2] * VQN[2][2] + VQN[2][3] * VQN[2][3]);
-        D[3] = -XY - (VQN[0][0] * VQN[1][0] + VQN[0][1] * VQN[1][1] + VQN[0][2] * VQN[1][2] + VQN[0][3] * VQN[1][3]);
-        D[4] = -XZ - (VQN[0][0] * VQN[2][0] + VQN[0][1] * VQN[2][1] + VQN[0][2] * VQN[2][2] + VQN[0][3] * VQN[2][3]);
-        D[5] = -YZ - (VQN[1][0] * VQN[2][0] + VQN[1][1] * VQN[2][1] + VQN[1][2] * VQN[2][2] + VQN[1][3] * VQN[2][3]);
-        const double ABC = D[0] * D[1] * D[2];
-        const double XXYZ2 = D[0] * D[5] * D[5], YYXZ2 = D[1] * D[4] * D[4], ZZXY2 = D[2] * D[3] * D[3];
-        double DETA = fabs(ABC + K_TWO * D[3] * D[4] * D[5] - XXYZ2 - YYXZ2 - ZZXY2);
-        DETA = K_ONE / fmax(DETA, K_EM20);
-        DI[0] = (ABC - XXYZ2) * DETA / fmax(D[0], K_EM20);
-        DI[1] = (ABC - YYXZ2) * DETA / fmax(D[1], K_EM20);
-        DI[2] = (ABC - ZZXY2) * DETA / fmax(D[2], K_EM20);
-        DI[3] = (D[4] * D[5] - D[3] * D[2]) * DETA;
-        DI[4] = (D[5] * D[3] - D[4] * D[1]) * DETA;
-        DI[5] = (D[3] * D[4] - D[5] * D[0]) * DETA;
-        #pragma unroll
-        for (int J = 0; J < 4; J++) {
-          DB[0][J] = DI[0] * VQN[0][J] + DI[3] * VQN[1][J] + DI[4] * VQN[2][J];
-          DB[1][J] = DI[3] * VQN[0][J] + DI[1] * VQN[1][J] + DI[5] * VQN[2][J];
-          DB[2][J] = DI[4] * VQN[0][J] + DI[5] * VQN[1][J] + DI[2] * VQN[2][J];
-        }
         double DBAD[3], ALR[3];
         #pragma unroll
         for (int c = 0; c < 3; c++) DBAD[c] = DB[c][0] * AD[0] + DB[c][1] * AD[1] + DB[c][2] * AD[2] + DB[c][3] * AD[3];
@@ -261,18 +297,13 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     #pragma unroll
     for (int c = 0; c < 3; c++) { V13[c] = V13[c] * AREA_I; V24[c] = V24[c] * AREA_I; VHI[c] = VHI[c] * K_FOURTH; }
     // ---- CNCOEF3B
-    const double THK0 = (g.prop.ithk > 0) ? fmax(K_EM20, g.thk[e]) : __ldg(g.thke + e);
-    const double THK02 = THK0 * THK0;
-    double RHO, G, A11, A12, GSR, A11SR, A12SR;
-    MatIO io;
-    if (LAW == 36) { const orgpu_law36& m = g.m36; RHO = m.rho0; G = m.shear; A11 = m.a11; io.ssp = m.ssp;
-                     GSR = m.gsr; A11SR = m.a11sr; A12 = m.nu * A11; A12SR = m.nusr * A11SR; }
-    else           { const orgpu_law2& m = g.m2; RHO = m.rho0; G = m.shear; A11 = m.a11; A12 = m.a12; io.ssp = m.ssp;
-                     GSR = m.gsr; A11SR = m.a11sr; A12SR = m.a12sr; }
-    const double SHF = (NPT == 1) ? K_ZERO : g.prop.shf, SHFSR = (NPT == 1) ? K_ZERO : g.prop.shfsr;
-    const double AMU = (g.prop.h1 == K_ZERO) ? K_ZEP01 + K_FIVEEM3 : g.prop.h1;
+    THK0 = (g.prop.ithk > 0) ? fmax(K_EM20, T.ld(SW_THK)) : T.ld(g.w_thke);
+    double RHO, G;
+    if (LAW == 36) { const orgpu_law36& m = g.m36; RHO = m.rho0; G = m.shear; io.ssp = m.ssp; }
+    else           { const orgpu_law2& m = g.m2; RHO = m.rho0; G = m.shear; io.ssp = m.ssp; }
+    const double SHF = (NPT == 1) ? K_ZERO : g.prop.shf;
     // ---- CZDEF
-    double VDEF[8], VHG[6], OFF;
+    double VDEF[8];
     {
       double R13v[2], R24v[2], RSOM[2], RHI[2];
       #pragma unroll
@@ -325,25 +356,41 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       const double de[8] = {io.exx, io.eyy, io.exy, io.eyz, io.exz, io.kxx, io.kyy, io.kxy};
       double st[8];                          // all eight loads in flight before the first store (which could alias them)
       #pragma unroll
-      for (int k = 0; k < 8; k++) st[k] = __ldcs(g.stra + (size_t)k * np + e);
+      for (int k = 0; k < 8; k++) st[k] = T.ld(SW_STRA + k);
       #pragma unroll
-      for (int k = 0; k < 8; k++) __stcs(g.stra + (size_t)k * np + e, st[k] + de[k]);
+      for (int k = 0; k < 8; k++) T.st(SW_STRA + k, st[k] + de[k]);
     }
     {
       const double dtinv = DT1 / fmax(DT1 * DT1, K_EM20);
-      const double thk = g.thk[e];
+      const double thk = T.ld(SW_THK);
       const double eps_k2 = (io.kxx * io.kxx + io.kyy * io.kyy + io.kxx * io.kyy + K_FOURTH * (io.kxy * io.kxy)) * K_ONE_OVER_9 * (thk * thk);
       const double eps_m2 = K_FOUR_OVER_3 * (io.exx * io.exx + io.eyy * io.eyy + io.exx * io.eyy + K_FOURTH * (io.exy * io.exy));
       io.epsd_pg = sqrt(eps_k2 + eps_m2) * dtinv;
-      g.epsd[e] = K_ONE * io.epsd_pg + (K_ONE - K_ONE) * g.epsd[e];
+      T.st(SW_EPSD, K_ONE * io.epsd_pg + (K_ONE - K_ONE) * T.ld(SW_EPSD));
     }
-    // ---- CMAIN3
     io.area = AREA; io.thk0 = THK0; io.gs = G * SHF; io.rho = RHO; io.off = OFF; io.sigy = K_EP30;
+    }   // ======== end of the pre-loop scope ========
+    ORGPU_OPAQUE(XL2); ORGPU_OPAQUE(YL2); ORGPU_OPAQUE(XL3); ORGPU_OPAQUE(YL3); ORGPU_OPAQUE(XL4); ORGPU_OPAQUE(YL4);
+    ORGPU_OPAQUE(Z1); ORGPU_OPAQUE(AREA);
+    // ---- CMAIN3
 #ifdef ORGPU_UNROLL_NPT5
-    if (NPT == 5) shell_material_loop<LAW, true, 5>(g, e, DT1, io); else
+    if (NPT == 5) shell_material_loop<LAW, true, STAGED, 5>(g, T, DT1, io); else
 #endif
-    shell_material_loop<LAW, true>(g, e, DT1, io);
+    shell_material_loop<LAW, true, STAGED>(g, T, DT1, io);
     OFF = io.off;
+    // ---- re-derive the geometry needed by the force assembly (same expressions as before the loop)
+    QephGeo q1; qeph_geo(XL2, YL2, XL3, YL3, XL4, YL4, q1);
+    const double* CX = q1.CX; const double* CY = q1.CY;
+    const double X13 = q1.X13, X24 = q1.X24, Y13 = q1.Y13, Y24 = q1.Y24;
+    const double MX13 = q1.MX13, MX23 = q1.MX23, MX34 = q1.MX34, MY13 = q1.MY13, MY23 = q1.MY23, MY34 = q1.MY34;
+    const double THK02 = THK0 * THK0;
+    double A11, A12, GSR, A11SR, A12SR;
+    const double RHO = io.rho;
+    double G;
+    if (LAW == 36) { const orgpu_law36& m = g.m36; G = m.shear; A11 = m.a11; GSR = m.gsr; A11SR = m.a11sr; A12 = m.nu * A11; A12SR = m.nusr * A11SR; }
+    else           { const orgpu_law2& m = g.m2; G = m.shear; A11 = m.a11; A12 = m.a12; GSR = m.gsr; A11SR = m.a11sr; A12SR = m.a12sr; }
+    const double SHF = (NPT == 1) ? K_ZERO : g.prop.shf, SHFSR = (NPT == 1) ? K_ZERO : g.prop.shfsr;
+    const double AMU = (g.prop.h1 == K_ZERO) ? K_ZEP01 + K_FIVEEM3 : g.prop.h1;
     // ---- CNDT3
     double STI;
     {
@@ -390,7 +437,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       const double COEF1 = (NPT == 0) ? K_SIXTEEN : K_TWENTY5;
       double VG[12], DG[12], DHG[6];
       #pragma unroll
-      for (int k = 0; k < 12; k++) VG[k] = g.hourg[(size_t)k * np + e];
+      for (int k = 0; k < 12; k++) VG[k] = T.ld(SW_HOURG + k);
       #pragma unroll
       for (int k = 0; k < 6; k++) DHG[k] = VHG[k] * DT1;
       const double C3 = K_FOUR * AREA_I;
@@ -416,7 +463,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       double SC6 = MY23 * VG[10] + MX23 * VG[11];
       const double C5 = K_HALF * OFF * THK0 * C7;
       const double ESX = SS1 * DHG[0] + SS2 * DHG[1];
-      double ein1 = g.eint[e], ein2 = g.eint[np + e];
+      double ein1 = T.ld(SW_EINT), ein2 = T.ld(SW_EINT + 1);
       ein1 = ein1 + C5 * (ESX + K_FOURTH * (SC5 * DHG[4] + SC6 * DHG[5]));
       const double EMX = (SF1 * DHG[2] - SF2 * DHG[3]) * C6;
       ein2 = ein2 + C5 * EMX;
@@ -451,7 +498,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
         }
       }
       #pragma unroll
-      for (int k = 0; k < 12; k++) g.hourg[(size_t)k * np + e] = VG[k];
+      for (int k = 0; k < 12; k++) T.st(SW_HOURG + k, VG[k]);
       const double C8 = C7 * OFF;
       SS1 = (MY34 * VG[0] + MY23 * VG[6]) * C8;
       SS2 = (MX23 * VG[7] + MX34 * VG[1]) * C8;
@@ -507,11 +554,11 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       ein1 = ein1 + K_HALF * ESY;
       const double EMY = (SF1 - SF1_V) * DHG[2] - (SF2 - SF2_V) * DHG[3];
       ein2 = ein2 + K_HALF * C6 * EMY * THK0;
-      g.eint[e] = ein1; g.eint[np + e] = ein2;
+      T.st(SW_EINT, ein1); T.st(SW_EINT + 1, ein2);
     }
     // ---- CZPROJN (IFINI=0) + CUPDTN3P
     if (OFF < K_ONE) OFFG = OFF;
-    g.off[e] = OFFG;
+    T.st(SW_OFF, OFFG);
     const bool dead = OFFG < K_ZERO;
     if (dead) STI = K_ZERO;
     double FL[3][4], MM[3][4];
@@ -526,6 +573,8 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       MM[c][2] = -VM[c][0] + VM[c][2]; MM[c][3] = -VM[c][1] + VM[c][3];
     }
     if (!PLAT) {
+      double VQN[3][4], DI[6], DB[3][4];
+      qeph_warp_proj(q1, Z1, AREA, VQN, DI, DB);
       double AR[3], AD[4], DBAD[3], ALR[3];
       AR[0] = -Z1 * (FL[1][0] - FL[1][1] + FL[1][2] - FL[1][3])
             + CY[0] * FL[2][0] + MM[0][0] + CY[1] * FL[2][1] + MM[0][1] + CY[2] * FL[2][2] + MM[0][2] + CY[3] * FL[2][3] + MM[0][3];
@@ -558,7 +607,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     }
     int sl[4];
     #pragma unroll
-    for (int k = 0; k < 4; k++) sl[k] = __ldg(g.slot + k * np + e);
+    for (int k = 0; k < 4; k++) sl[k] = T.ldi(g.w_slot, k);
     #pragma unroll
     for (int J = 0; J < 4; J++) {
       double f[3], mm[3];
@@ -575,5 +624,6 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       row[2] = make_double2(-mm[1], -mm[2]); row[3] = make_double2(STI * fac, K_ZERO * fac);
     }
   }
-  block_dt_reduce<false>(dt_cand, ngl, order, P.db, g.blk0 + blockIdx.x);
+  if (STAGED) tile_store(g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
+  block_dt_reduce<false>(dt_cand, order, g.ngl, g.order0, P.db, g.blk0 + blockIdx.x);
 }

@@ -2,10 +2,13 @@
 // loop shared by the QEPH (CZFORC3) and Belytschko-Tsay (CFORC3) kernels.
 //
 // Device layout of ELBUF for one super-group (consecutive groups with identical family, law,
-// property): every field is SoA over ne_pad elements, component-major like the reference's
-// G_BUFEL_/L_BUFEL_ (elbufdef_mod.F90:739-1013, 1184-1300) so a warp reads contiguous doubles.
-// Per-integration-point fields are IP-major: sig[(ipt*5+k)*ne_pad + e] (the reference GPU path
-// flattens the same way, shell_internal_forces.F90:829-886).
+// property): one tile-major slab [tile][word][128] (common.cuh).  Words of one element, in order:
+//   G_BUFEL_ (elbufdef_mod.F90:739-1013): FOR 0-4, MOM 5-7, EINT 8-9, THK 10, OFF 11, STRA 12-19,
+//   EPSD 20, HOURG 21..21+nhourg-1;
+//   then per integration point (L_BUFEL_, :1184-1300; IP-major like shell_internal_forces.F90:829-886)
+//   SIG 0-4, PLA 5, EPSD 6 (, TEMP 7 for LAW2 with a temperature buffer);
+//   then the LAW36 VARTMP table cursors as int half-rows; then read-only words: the initial thickness
+//   (only when ITHK=0 keeps using it) and the four FSKY slot indices (int half-rows).
 //
 // The material loop restates, one element per thread, all in registers:
 //   CMAIN3 -> LAYINI (layini.F:246-254) -> MULAWC (mulawc.F90:542-604, 718-1114, 2630-2662,
@@ -18,18 +21,21 @@
 struct ShellSG {
   int ne, ne_pad, order0, blk0;
   int law, npt, nvartmp, nhourg;
-  const int* conn;            // [4][ne_pad] 0-based node
-  const int* slot;            // [4][ne_pad] 0-based FSKY slot
-  const int* ngl;             // user ids
-  double *forc, *mom, *eint;  // [5],[3],[2]
-  double *thk, *off, *stra, *epsd, *hourg, *smstr;   // [1],[1],[8],[1],[nhourg],[6]
-  const double* thke;         // initial thickness (read only when ITHK=0)
-  double *sig, *pla, *epsd_ip, *temp;  // [npt*5], [npt], [npt], [npt]
-  int* vartmp;                // [npt*nvartmp]
+  const int* conn;            // tile-major [tile][4][128], 0-based node
+  const int* ngl;             // user ids [ne_pad]
+  double* slab;               // [tile][nw][128]
+  int nw, nw_rw;              // words per tile / written back
+  int w_ip0, nwip;            // first word of integration point 0, words per point
+  int w_vt, nvt;              // first word of the VARTMP int rows, int rows per point (1 when NRATE=1: only cursor 3 is live)
+  int w_thke, w_slot;         // initial-thickness word (-1 when ITHK>0), first word of the 4 slot int rows
+  double* smstr;              // tile-major [tile][6][128]
   const double* tf; const int* npf;    // LAW36 function table (pairs), 0-based curve starts
   orgpu_law2 m2; orgpu_law36 m36; orgpu_prop_shell prop;
   double dtfac;               // DTFAC1(3)
 };
+
+enum { SW_FOR = 0, SW_MOM = 5, SW_EINT = 8, SW_THK = 10, SW_OFF = 11, SW_STRA = 12, SW_EPSD = 20, SW_HOURG = 21 };
+enum { IW_SIG = 0, IW_PLA = 5, IW_EPSD = 6, IW_TEMP = 7 };
 
 struct ShellParams {
   ShellSG sg; DevNodes nd; double* fsky; CycleState* cs; DtBlocks db;
@@ -64,65 +70,41 @@ __device__ __forceinline__ void vinter1(const double* __restrict__ tf, int iad, 
 
 struct IpState { double sxx, syy, sxy, syz, szx, pla, epsd, temp; int ipos; };
 
-// streaming access for element state: read once / written once per cycle, keep L2 for the nodal records
-template <int LAW>
-__device__ __forceinline__ IpState ip_load(const ShellSG& g, int e, int ipt)
+// state of one integration point out of / into the CTA's tile
+template <int LAW, bool STAGED>
+__device__ __forceinline__ IpState ip_load(const ShellSG& g, const TileAcc<STAGED>& T, int ipt)
 {
-  const size_t np = g.ne_pad;
-  const double* sg = g.sig + (size_t)ipt * 5 * np + e;
+  const int w = g.w_ip0 + ipt * g.nwip;
   IpState s;
-  s.sxx = __ldcs(sg); s.syy = __ldcs(sg + np); s.sxy = __ldcs(sg + 2 * np); s.syz = __ldcs(sg + 3 * np); s.szx = __ldcs(sg + 4 * np);
-  s.pla = __ldcs(g.pla + (size_t)ipt * np + e);
-  s.epsd = __ldcs(g.epsd_ip + (size_t)ipt * np + e);
+  s.sxx = T.ld(w + IW_SIG); s.syy = T.ld(w + IW_SIG + 1); s.sxy = T.ld(w + IW_SIG + 2); s.syz = T.ld(w + IW_SIG + 3); s.szx = T.ld(w + IW_SIG + 4);
+  s.pla = T.ld(w + IW_PLA);
+  s.epsd = T.ld(w + IW_EPSD);
   s.temp = K_ZERO; s.ipos = 0;
-  if (LAW == 2) { if (g.m2.has_temp) s.temp = __ldcs(g.temp + (size_t)ipt * np + e); }
-  else if (g.m36.nrate == 1) s.ipos = __ldcs(g.vartmp + ((size_t)ipt * g.nvartmp + 2) * np + e);
+  if (LAW == 2) { if (g.m2.has_temp) s.temp = T.ld(w + IW_TEMP); }
+  else if (g.m36.nrate == 1) s.ipos = T.ldi(g.w_vt, ipt);
   return s;
 }
-template <int LAW>
-__device__ __forceinline__ void ip_store(const ShellSG& g, int e, int ipt, const IpState& s, int ipos_old, double temp_old)
+template <int LAW, bool STAGED>
+__device__ __forceinline__ void ip_store(const ShellSG& g, const TileAcc<STAGED>& T, int ipt, const IpState& s, int ipos_old, double temp_old)
 {
-  const size_t np = g.ne_pad;
-  double* sg = g.sig + (size_t)ipt * 5 * np + e;
-  __stcs(sg, s.sxx); __stcs(sg + np, s.syy); __stcs(sg + 2 * np, s.sxy); __stcs(sg + 3 * np, s.syz); __stcs(sg + 4 * np, s.szx);
-  __stcs(g.pla + (size_t)ipt * np + e, s.pla);
-  __stcs(g.epsd_ip + (size_t)ipt * np + e, s.epsd);
-  if (LAW == 2) { if (g.m2.has_temp && s.temp != temp_old) __stcs(g.temp + (size_t)ipt * np + e, s.temp); }
-  else if (g.m36.nrate == 1 && s.ipos != ipos_old) __stcs(g.vartmp + ((size_t)ipt * g.nvartmp + 2) * np + e, s.ipos);
+  const int w = g.w_ip0 + ipt * g.nwip;
+  T.st(w + IW_SIG, s.sxx); T.st(w + IW_SIG + 1, s.syy); T.st(w + IW_SIG + 2, s.sxy); T.st(w + IW_SIG + 3, s.syz); T.st(w + IW_SIG + 4, s.szx);
+  T.st(w + IW_PLA, s.pla);
+  T.st(w + IW_EPSD, s.epsd);
+  if (LAW == 2) { if (g.m2.has_temp && s.temp != temp_old) T.st(w + IW_TEMP, s.temp); }
+  else if (g.m36.nrate == 1 && s.ipos != ipos_old) T.sti(g.w_vt, ipt, s.ipos);
 }
 
-#ifndef ORGPU_SHELL_CTA
-#define ORGPU_SHELL_CTA 128      // threads per CTA of the shell kernels (ne_pad is a multiple of ORGPU_BLOCK = 128)
-#endif
-#ifdef ORGPU_PREFETCH_L1
-#define prefetch_l2 prefetch_l1
-#endif
-// start every element-state line of this thread's 4-element sector toward L2 (called by one lane in 4)
-__device__ __forceinline__ void shell_prefetch_state(const ShellSG& g, int e)
-{
-  const size_t np = g.ne_pad;
-  for (int k = 0; k < 5; k++) prefetch_l2(g.forc + k * np + e);
-  for (int k = 0; k < 3; k++) prefetch_l2(g.mom + k * np + e);
-  prefetch_l2(g.eint + e); prefetch_l2(g.eint + np + e); prefetch_l2(g.thk + e); prefetch_l2(g.epsd + e);
-  for (int k = 0; k < 8; k++) prefetch_l2(g.stra + k * np + e);
-  for (int k = 0; k < g.nhourg; k++) prefetch_l2(g.hourg + k * np + e);
-  for (int k = 0; k < g.npt * 5; k++) prefetch_l2(g.sig + k * np + e);
-  for (int k = 0; k < g.npt; k++) { prefetch_l2(g.pla + k * np + e); prefetch_l2(g.epsd_ip + k * np + e); }
-  if (g.temp) for (int k = 0; k < g.npt; k++) prefetch_l2(g.temp + k * np + e);
-  if (g.law == 36 && (e & 7) == 0) for (int k = 0; k < g.npt; k++) prefetch_l2(g.vartmp + ((size_t)k * g.nvartmp + 2) * np + e);
-}
-#ifdef ORGPU_PREFETCH_L1
-#undef prefetch_l2
-#endif
+#define ORGPU_SHELL_CTA ORGPU_TILE   // one CTA = one state tile
 
 // ---- SIGEPS36C, VP = 0 -------------------------------------------------------------------
-__device__ __forceinline__ void law36_ip(const ShellSG& g, int e, int ipt, int ipla, double asrate,
+template <bool STAGED>
+__device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>& T, int ipt, int ipla, double asrate,
                                          double dexx, double deyy, double dexy, double deyz, double dezx, double dtinv,
                                          double thklyl, double gs, double epsd_pg, double off,
                                          IpState& s, double& thk, double& ssp, double& etse, double& yld_out)
 {
   const orgpu_law36& m = g.m36;
-  const int np = g.ne_pad;
   const double E = m.young, A1 = m.a1u, A2 = m.a2u, G = m.shear, G3 = m.g3;
   ssp = m.soundsp; etse = K_ONE;
   double pla = s.pla;
@@ -144,7 +126,6 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, int e, int ipt, int i
   s.epsd = epsd;
   // yield stress and hardening modulus from the tabulated curves
   double YLD, H;
-  int* vt = g.vartmp + (size_t)ipt * g.nvartmp * np + e;
   if (m.nrate == 1) {
     int ipos = s.ipos;
     const int f = m.ifunc[0];
@@ -168,7 +149,7 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, int e, int ipt, int i
     }
     const double YFAC1 = m.yfac[JJ - 1] * K_ONE, YFAC2 = m.yfac[JJ] * K_ONE;
     const int f1 = m.ifunc[JJ - 1], f2 = m.ifunc[JJ];
-    int ipos1 = vt[(size_t)(1 + JJ) * np], ipos2 = vt[(size_t)(2 + JJ) * np];
+    int ipos1 = T.ldi(g.w_vt, ipt * g.nvt + 1 + JJ), ipos2 = T.ldi(g.w_vt, ipt * g.nvt + 2 + JJ);
     double dydx1, y1, dydx2, y2;
     { const int i0 = __ldg(g.npf + f1), i1 = __ldg(g.npf + f1 + 1); vinter1(g.tf, i0, i1 - i0, ipos1, pla, dydx1, y1); }
     { const int i0 = __ldg(g.npf + f2), i1 = __ldg(g.npf + f2 + 1); vinter1(g.tf, i0, i1 - i0, ipos2, pla, dydx2, y2); }
@@ -179,7 +160,7 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, int e, int ipt, int i
     H = K_ONE * (dydx1 + RFAC * (dydx2 - dydx1));
     YLD = YLD * fmax(K_ZERO, K_ONE);
     H = H * fmax(K_ZERO, K_ONE);
-    vt[(size_t)(1 + JJ) * np] = ipos1; vt[(size_t)(2 + JJ) * np] = ipos2;
+    T.sti(g.w_vt, ipt * g.nvt + 1 + JJ, ipos1); T.sti(g.w_vt, ipt * g.nvt + 2 + JJ, ipos2);
   }
   if (m.yldcheck == 1) YLD = fmax(YLD, K_EM20);
   // projection on the yield surface
@@ -266,13 +247,12 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, int e, int ipt, int i
 }
 
 // ---- SIGEPS02C + M2CPLR (FISOKIN = 0) --------------------------------------------------------
-__device__ __forceinline__ void law2_ip(const ShellSG& g, int e, int ipt, int ipla, int npttot, double dt1, double asrate,
+__device__ __forceinline__ void law2_ip(const ShellSG& g, int ipla, int npttot, double dt1, double asrate,
                                         double dexx, double deyy, double dexy, double deyz, double dezx, double dtinv,
                                         double thklyl, double gs, double epsd_pg, double& off, double off_old, int& ioff_duct,
                                         double& epchk, IpState& s, double& thk, double& etse, double& sigy)
 {
   const orgpu_law2& m = g.m2;
-  const int np = g.ne_pad;
   const double SMALL = K_EM7;
   const double young = m.young, gg = m.shear, nu = m.nu;
   const double a11 = young / (K_ONE - nu * nu);
@@ -420,20 +400,20 @@ __device__ __forceinline__ void law2_ip(const ShellSG& g, int e, int ipt, int ip
 // FLAG_ZCFAC: QEPH (JHBE 21..29) keeps SIGY / ZCFAC for the hourglass plasticity (mulawc.F90:521-522).
 // NPTC > 0: compile-time point count (loop fully unrolled so independent points overlap in the
 // fp64 pipe); NPTC = 0: run-time count.
-template <int LAW, bool FLAG_ZCFAC, int NPTC = 0>
-__device__ __forceinline__ void shell_material_loop(const ShellSG& g, int e, double dt1, MatIO& io)
+template <int LAW, bool FLAG_ZCFAC, bool STAGED, int NPTC = 0>
+__device__ __forceinline__ void shell_material_loop(const ShellSG& g, const TileAcc<STAGED>& T, double dt1, MatIO& io)
 {
-  const int np = g.ne_pad, npt = NPTC > 0 ? NPTC : g.prop.npt;
+  const int npt = NPTC > 0 ? NPTC : g.prop.npt;
   const double DM = g.prop.dm;
   double* fo = io.fo; double* mo = io.mo;
   #pragma unroll
-  for (int k = 0; k < 5; k++) fo[k] = g.forc[(size_t)k * np + e];
+  for (int k = 0; k < 5; k++) fo[k] = T.ld(SW_FOR + k);
   #pragma unroll
-  for (int k = 0; k < 3; k++) mo[k] = g.mom[(size_t)k * np + e];
+  for (int k = 0; k < 3; k++) mo[k] = T.ld(SW_MOM + k);
   double degmb = fo[0] * io.exx + fo[1] * io.eyy + fo[2] * io.exy + fo[3] * io.eyz + fo[4] * io.exz;
   double degfx = mo[0] * io.kxx + mo[1] * io.kyy + mo[2] * io.kxy;
   const double vol0 = io.area * io.thk0;
-  double thkn = g.thk[e];
+  double thkn = T.ld(SW_THK);
   #pragma unroll
   for (int k = 0; k < 5; k++) fo[k] = K_ZERO;
   #pragma unroll
@@ -449,11 +429,13 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, int e, dou
   const double pm9 = (LAW == 36) ? g.m36.asrate : g.m2.asrate;
   const double asrate = (israte > 0) ? fmin(K_ONE, pm9 * dt1) : K_ONE;
   const int qrow = (npt - 1) * 11;
-  IpState nxt = ip_load<LAW>(g, e, 0);
+  IpState nxt;
+  if (!STAGED) nxt = ip_load<LAW>(g, T, 0);
   #pragma unroll
   for (int ipt = 0; ipt < npt; ipt++) {
-    IpState s = nxt;
-    if (ipt + 1 < npt) nxt = ip_load<LAW>(g, e, ipt + 1);        // software pipeline: next point's state in flight
+    IpState s;
+    if (STAGED) s = ip_load<LAW>(g, T, ipt);                     // shared memory: no latency to hide
+    else { s = nxt; if (ipt + 1 < npt) nxt = ip_load<LAW>(g, T, ipt + 1); }   // software pipeline: next point's state in flight
     const int ipos_old = s.ipos; const double temp_old = s.temp;
     const double thkly = c_WF[qrow + ipt];
     const double posly = c_Z0[qrow + ipt] + K_ZERO;
@@ -464,14 +446,14 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, int e, dou
     const double deyy = io.eyy + zt * io.kyy;
     const double dexy = io.exy + zt * io.kxy;
     if (LAW == 36) {
-      law36_ip(g, e, ipt, g.prop.ipla, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, thklyl, io.gs, io.epsd_pg, off,
+      law36_ip(g, T, ipt, g.prop.ipla, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, thklyl, io.gs, io.epsd_pg, off,
                s, thkn, ssp, etse, sigy);
     } else {
-      law2_ip(g, e, ipt, g.prop.ipla, npt, dt1, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, thklyl, io.gs, io.epsd_pg,
+      law2_ip(g, g.prop.ipla, npt, dt1, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, thklyl, io.gs, io.epsd_pg,
               off, off_old, ioff_duct, epchk, s, thkn, etse, sigy);
     }
     viscmx = fmax(DM, viscmx);
-    ip_store<LAW>(g, e, ipt, s, ipos_old, temp_old);
+    ip_store<LAW>(g, T, ipt, s, ipos_old, temp_old);
     fo[0] = fo[0] + thkly * s.sxx; fo[1] = fo[1] + thkly * s.syy; fo[2] = fo[2] + thkly * s.sxy;
     fo[3] = fo[3] + thkly * s.syz; fo[4] = fo[4] + thkly * s.szx;
     mo[0] = mo[0] + wmc * s.sxx; mo[1] = mo[1] + wmc * s.syy; mo[2] = mo[2] + wmc * s.sxy;
@@ -481,7 +463,7 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, int e, dou
     }
   }
   if ((off == K_FOUR_OVER_5 && ioff_duct == 0) || (off > K_ZERO && off_old < K_EM01)) off = K_ZERO;
-  g.thk[e] = fmax(thkn, K_EM30);
+  T.st(SW_THK, fmax(thkn, K_EM30));
   const double fact = K_ONEP414 * DM;
   const double visc = fact * ssp * sqrt(io.area) * dtinv * io.rho;
   fo[0] = fo[0] + visc * (io.exx + K_HALF * io.eyy);
@@ -494,11 +476,11 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, int e, dou
   degmb = degmb + fo[0] * io.exx + fo[1] * io.eyy + fo[2] * io.exy + fo[3] * io.eyz + fo[4] * io.exz;
   degfx = degfx + mo[0] * io.kxx + mo[1] * io.kyy + mo[2] * io.kxy;
   const double vol2 = K_HALF * vol0;
-  g.eint[e] = g.eint[e] + degmb * vol2;
-  g.eint[np + e] = g.eint[np + e] + degfx * io.thk0 * vol2;
+  T.st(SW_EINT, T.ld(SW_EINT) + degmb * vol2);
+  T.st(SW_EINT + 1, T.ld(SW_EINT + 1) + degfx * io.thk0 * vol2);
   #pragma unroll
-  for (int k = 0; k < 5; k++) g.forc[(size_t)k * np + e] = fo[k];
+  for (int k = 0; k < 5; k++) T.st(SW_FOR + k, fo[k]);
   #pragma unroll
-  for (int k = 0; k < 3; k++) g.mom[(size_t)k * np + e] = mo[k];
+  for (int k = 0; k < 3; k++) T.st(SW_MOM + k, mo[k]);
   io.off = off; io.ssp = ssp; io.viscmx = viscmx; io.sigy = sigy; io.zcfac1 = zcfac1; io.zcfac2 = zcfac2; io.vol0 = vol0;
 }

@@ -90,8 +90,22 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
       }
       d.tf = d_tf; d.npf = d_npf;
     }
-    std::vector<int> conn((size_t)4 * np, 0), slot((size_t)4 * np, 0), ngl(np, 0);
-    std::vector<double> thk(np, G.prop.thick), off(np, 0.0);
+    // ---- slab word map (shell_common.cuh)
+    const bool has_temp = (G.law == 2) && G.m2.has_temp;
+    d.w_ip0 = SW_HOURG + d.nhourg; d.nwip = has_temp ? 8 : 7;
+    d.w_vt = d.w_ip0 + d.npt * d.nwip;
+    d.nvt = (G.law == 36) ? (G.m36.nrate == 1 ? 1 : d.nvartmp) : 0;
+    d.nw_rw = d.w_vt + (d.npt * d.nvt + 1) / 2;
+    int w = d.nw_rw;
+    d.w_thke = (G.prop.ithk > 0) ? -1 : w; if (d.w_thke >= 0) w++;
+    d.w_slot = w; w += 2;
+    d.nw = w;
+    HostSlab H; H.init(d.nw, np);
+    std::vector<int> conn((size_t)4 * np, 0), ngl(np, 0), conn_t;
+    for (int i = 0; i < np; i++) {
+      H.at(SW_THK, i) = G.prop.thick; if (d.w_thke >= 0) H.at(d.w_thke, i) = G.prop.thick;
+      if (has_temp) for (int ip = 0; ip < d.npt; ip++) H.at(d.w_ip0 + ip * d.nwip + IW_TEMP, i) = G.m2.tini;
+    }
     for (int i = 0; i < ne; i++) {
       const int* ix = &ixc[(size_t)7 * (nft + i)];
       for (int k = 0; k < 4; k++) {
@@ -99,23 +113,15 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
         if (node < 1 || node > numnod) { orgpu_set_error("IXC node %d out of range (element %d)", node, nft + i + 1); return -4; }
         const int sl = iadc[(size_t)4 * (nft + i) + k];
         if (sl < 1 || sl > lsky) { orgpu_set_error("IADC slot %d out of range (element %d)", sl, nft + i + 1); return -4; }
-        conn[(size_t)k * np + i] = node - 1; slot[(size_t)k * np + i] = sl - 1;
+        conn[(size_t)k * np + i] = node - 1; H.iat(d.w_slot, k, i) = sl - 1;
       }
-      ngl[i] = ix[6]; off[i] = 1.0;
+      ngl[i] = ix[6]; H.at(SW_OFF, i) = 1.0;
     }
-    int *dconn, *dslot, *dngl; double *dthke;
-    if (sh_upload(S.owned, &dconn, conn) || sh_upload(S.owned, &dslot, slot) || sh_upload(S.owned, &dngl, ngl) ||
-        sh_upload(S.owned, &d.thk, thk) || sh_upload(S.owned, &dthke, thk) || sh_upload(S.owned, &d.off, off)) return -100;
-    d.conn = dconn; d.slot = dslot; d.ngl = dngl; d.thke = dthke;
-    const size_t n = np, npt = d.npt;
-    if (sh_alloc(S.owned, &d.forc, 5 * n) || sh_alloc(S.owned, &d.mom, 3 * n) || sh_alloc(S.owned, &d.eint, 2 * n) ||
-        sh_alloc(S.owned, &d.stra, 8 * n) || sh_alloc(S.owned, &d.epsd, n) || sh_alloc(S.owned, &d.hourg, (size_t)d.nhourg * n) ||
-        sh_alloc(S.owned, &d.smstr, 6 * n) || sh_alloc(S.owned, &d.sig, npt * 5 * n) || sh_alloc(S.owned, &d.pla, npt * n) ||
-        sh_alloc(S.owned, &d.epsd_ip, npt * n) || sh_alloc(S.owned, &d.vartmp, npt * (size_t)(d.nvartmp > 0 ? d.nvartmp : 1) * n)) return -100;
-    if (G.law == 2) {
-      std::vector<double> temp(npt * n, G.m2.tini);
-      if (sh_upload(S.owned, &d.temp, temp)) return -100;
-    }
+    tile_major_ints(conn_t, conn, 4, np);
+    int *dconn, *dngl;
+    if (sh_upload(S.owned, &dconn, conn_t) || sh_upload(S.owned, &dngl, ngl) || sh_upload(S.owned, &d.slab, H.h)) return -100;
+    d.conn = dconn; d.ngl = dngl;
+    if (sh_alloc(S.owned, &d.smstr, (size_t)6 * np)) return -100;
     const int nblk = np / ORGPU_SHELL_CTA;
     if (fa.nsg >= ORGPU_MAX_SG) { orgpu_set_error("too many super-groups (%d)", ORGPU_MAX_SG); return -6; }
     fa.sg[fa.nsg++] = SGRange{blk, nblk, shell_is_qeph(G.prop) ? ORGPU_FAM_SHELL_QEPH : ORGPU_FAM_SHELL_BT};
@@ -124,17 +130,32 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
   return 0;
 }
 
+template <class K>
+static void shell_launch_one(K kern_staged, K kern_direct, const ShellParams& P, int nblk, cudaStream_t st)
+{
+  const size_t bytes = (size_t)P.sg.nw * ORGPU_TILE * 8;
+#ifndef ORGPU_NO_STAGING
+  if (bytes <= ORGPU_STAGE_MAX_BYTES) {
+    stage_attr((const void*)kern_staged, bytes, 3);
+    kern_staged<<<nblk, ORGPU_SHELL_CTA, bytes, st>>>(P);
+    return;
+  }
+#endif
+  kern_direct<<<nblk, ORGPU_SHELL_CTA, 0, st>>>(P);
+}
+
 static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky, int roww, CycleState* cs,
                                 const DtBlocks& db, const FinalizeArgs& fa, cudaStream_t st)
 {
-  (void)roww;                                  // shell models always use 8-wide rows
+  (void)roww; (void)fa;                        // shell models always use 8-wide rows
   ShellParams P{S.d, nd, fsky, cs, db};
-  const int nblk = S.d.ne_pad / ORGPU_SHELL_CTA;
+  const int nblk = S.d.ne_pad / ORGPU_TILE;
   if (shell_is_qeph(S.d.prop)) {
-    if (S.d.law == 36) qeph_forces_kernel<36><<<nblk, ORGPU_SHELL_CTA, 0, st>>>(P);
-    else               qeph_forces_kernel<2><<<nblk, ORGPU_SHELL_CTA, 0, st>>>(P);
+    if (S.d.law == 36) shell_launch_one(qeph_forces_kernel<36, true>, qeph_forces_kernel<36, false>, P, nblk, st);
+    else               shell_launch_one(qeph_forces_kernel<2, true>, qeph_forces_kernel<2, false>, P, nblk, st);
   } else {
-    launch_bt_forces(P, nblk, st);
+    if (S.d.law == 36) shell_launch_one(bt_forces_kernel<36, true>, bt_forces_kernel<36, false>, P, nblk, st);
+    else               shell_launch_one(bt_forces_kernel<2, true>, bt_forces_kernel<2, false>, P, nblk, st);
   }
 }
 
@@ -144,18 +165,21 @@ static int shell_download_state(std::vector<ShellSGHost>& sgs, int numelc, int f
 {
   const size_t NE = numelc;
   for (auto& S : sgs) {
-    const ShellSG& d = S.d; const double* src = nullptr; int nc = 1;
+    const ShellSG& d = S.d; const double* base = d.slab; int nw = d.nw, nc = 1, w0 = 0, ipw = -1;
     switch (field) {
-      case 0: src = d.forc; nc = 5; break; case 1: src = d.mom; nc = 3; break; case 2: src = d.eint; nc = 2; break;
-      case 3: src = d.thk; break; case 4: src = d.off; break; case 5: src = d.stra; nc = 8; break; case 6: src = d.epsd; break;
-      case 7: src = d.hourg; nc = d.nhourg; break; case 8: src = d.smstr; nc = 6; break;
-      case 9: src = d.sig; nc = 5 * d.npt; break; case 10: src = d.pla; nc = d.npt; break; case 11: src = d.epsd_ip; nc = d.npt; break;
-      case 12: src = d.temp; nc = d.npt; if (!src) continue; break;
+      case 0: w0 = SW_FOR; nc = 5; break; case 1: w0 = SW_MOM; nc = 3; break; case 2: w0 = SW_EINT; nc = 2; break;
+      case 3: w0 = SW_THK; break; case 4: w0 = SW_OFF; break; case 5: w0 = SW_STRA; nc = 8; break; case 6: w0 = SW_EPSD; break;
+      case 7: w0 = SW_HOURG; nc = d.nhourg; break; case 8: base = d.smstr; nw = 6; w0 = 0; nc = 6; break;
+      case 9: ipw = IW_SIG; nc = 5 * d.npt; break; case 10: ipw = IW_PLA; nc = d.npt; break; case 11: ipw = IW_EPSD; nc = d.npt; break;
+      case 12: if (d.nwip <= IW_TEMP) continue; ipw = IW_TEMP; nc = d.npt; break;
       default: orgpu_set_error("unknown shell field %d", field); return -1;
     }
-    for (int k = 0; k < nc; k++)
-      if (cudaMemcpy(out + k * NE + S.first_elem, src + (size_t)k * d.ne_pad, 8 * (size_t)d.ne, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    for (int k = 0; k < nc; k++) {
+      int w = w0 + k;
+      if (ipw >= 0) w = (field == 9) ? d.w_ip0 + (k / 5) * d.nwip + IW_SIG + (k % 5) : d.w_ip0 + k * d.nwip + ipw;
+      if (slab_download_word(base, nw, w, d.ne, out + k * NE + S.first_elem) != cudaSuccess) {
         orgpu_set_error("shell state download failed"); return -100; }
+    }
   }
   return 0;
 }
