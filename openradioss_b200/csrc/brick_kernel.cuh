@@ -134,7 +134,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     }
     double PX[4], PY[4], PZ[4];
     {
-      double DETT = K_ONE_OVER_64 / VOLN;
+      double DETT = or_div(K_ONE_OVER_64, VOLN);
       double JI1 = DETT * J.c5968, JI4 = DETT * J.c6749, JI7 = DETT * J.c4857;
       double JI2 = DETT * (J.J3 * J.J8 - J.J2 * J.J9);
       double JI5 = DETT * (J.J1 * J.J9 - J.J3 * J.J7);
@@ -168,7 +168,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       #pragma unroll
       for (int k = 0; k < 4; k++) PH[2][k] = PX[k] * HX + PY[k] * HY + PZ[k] * HZ;
     }
-    const double DELTAX = K_FOUR * VOLN * K_ONE / sqrt(areamax);
+    const double DELTAX = or_div(K_FOUR * VOLN * K_ONE, or_sqrt(areamax));
     // ---- S8SAV3 (reference configuration refresh; done here while the coordinates are live)
     const bool sav_refresh = (ISMSTR <= 4) && (fabs(OFFG) <= K_ONE);
     if (sav_refresh) {                       // exclusive with SMALLA3 (OFFG > 1), so the order is free
@@ -240,9 +240,9 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       double PXX2 = PX[0] * PX[0] + PX[1] * PX[1] + PX[2] * PX[2] + PX[3] * PX[3];
       double PYY2 = PY[0] * PY[0] + PY[1] * PY[1] + PY[2] * PY[2] + PY[3] * PY[3];
       double PZZ2 = PZ[0] * PZ[0] + PZ[1] * PZ[1] + PZ[2] * PZ[2] + PZ[3] * PZ[3];
-      WZZ = DT1 * (PYY2 * DYX - PXX2 * DXY) / (PXX2 + PYY2);
-      WXX = DT1 * (PZZ2 * DZY - PYY2 * DYZ) / (PYY2 + PZZ2);
-      WYY = DT1 * (PXX2 * DXZ - PZZ2 * DZX) / (PZZ2 + PXX2);
+      WZZ = or_div(DT1 * (PYY2 * DYX - PXX2 * DXY), (PXX2 + PYY2));
+      WXX = or_div(DT1 * (PZZ2 * DZY - PYY2 * DYZ), (PYY2 + PZZ2));
+      WYY = or_div(DT1 * (PXX2 * DXZ - PZZ2 * DZX), (PZZ2 + PXX2));
     } else {
       D4 = DXY + DYX; D5 = DYZ + DZY; D6 = DXZ + DZX;
       WZZ = DT1D2 * (DYX - DXY);
@@ -259,8 +259,8 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       const double RHON_OLD = RHON, RHO0 = m.rho0;
       if (ISMSTR == 1 && TT == K_ZERO && OFFG > K_ONE) VOLO = VOLN;     // srho3.F:128-136 (VOLO is const otherwise)
       if (OFFG == K_ZERO && VOLN == K_ONE) VOLN = VOLO;
-      DVOL = VOLN - (RHO0 / RHON) * VOLO;
-      RHON = RHO0 * (VOLO / VOLN);
+      DVOL = VOLN - (or_div(RHO0, RHON)) * VOLO;
+      RHON = RHO0 * (or_div(VOLO, VOLN));
       EINT = EINT * VOLO;
       if (ISMSTR <= 4 && OFFG > K_ONE) {
         double RHOREF = RHON;
@@ -294,25 +294,25 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     // ---- MMAIN pre-law (mmain.F90:597-800)
     const double QOLD = T.ld(BW_QVIS);
     const double VOL_AVG = VOLN - K_HALF * DVOL;
-    const double AMU = RHON / m.rho0 - K_ONE;
+    const double AMU = or_div(RHON, m.rho0) - K_ONE;
     double RHOREF;
     if (ISMSTR == 1) RHOREF = m.rho0;
-    else if (ISMSTR == 2) RHOREF = (fabs(OFFG) <= K_ONE) ? RHON : m.rho0 * VOLO / fmax(K_EM20, VOLN);
+    else if (ISMSTR == 2) RHOREF = (fabs(OFFG) <= K_ONE) ? RHON : or_div(m.rho0 * VOLO, fmax(K_EM20, VOLN));
     else RHOREF = RHON;
     double TEMP = K_ZERO, TSTAR = K_ZERO;
-    if (m.has_temp) { TEMP = T.ld(g.w_temp); TSTAR = fmax(K_ZERO, (TEMP - m.tref) / fmax((m.tmelt - m.tref), K_EM20)); }
+    if (m.has_temp) { TEMP = T.ld(g.w_temp); TSTAR = fmax(K_ZERO, or_div((TEMP - m.tref), fmax((m.tmelt - m.tref), K_EM20))); }
     // ---- M2LAW
     double EPXE = T.ld(BW_PLA), EPSD = T.ld(BW_EPSD);
     double SSP, QNEW, STI, SSP_EQ;
     {
       const double asrate = fmin(K_ONE, m.asrate * DT1);
-      const double rhocpi = (m.rhocp > K_ZERO) ? K_ONE / m.rhocp : K_ZERO;
+      const double rhocpi = (m.rhocp > K_ZERO) ? or_div(K_ONE, m.rhocp) : K_ZERO;
       const double G = m.shear * OFF;
       double CA = m.ca, SIGMX = m.sigmx;
       double Pm = -K_THIRD * (SG1 + SG2 + SG3);
       double DAV = -K_THIRD * (DXX + DYY + DZZ);
       double G1 = DT1 * G, G2 = K_TWO * G1;
-      SSP = sqrt((K_ONEP333 * G + m.bulk) / m.rho0);
+      SSP = or_sqrt(or_div((K_ONEP333 * G + m.bulk), m.rho0));
       SG1 = SG1 + Pm + G2 * (DXX + DAV);
       SG2 = SG2 + Pm + G2 * (DYY + DAV);
       SG3 = SG3 + Pm + G2 * (DZZ + DAV);
@@ -320,26 +320,26 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       SG5 = SG5 + G1 * D5;
       SG6 = SG6 + G1 * D6;
       double AJ2 = K_HALF * (SG1 * SG1 + SG2 * SG2 + SG3 * SG3) + SG4 * SG4 + SG5 * SG5 + SG6 * SG6;
-      AJ2 = sqrt(K_THREE * AJ2);
+      AJ2 = or_sqrt(K_THREE * AJ2);
       // MSTRAIN_RATE (mstrain_rate.F:60-91)
       if (m.israte >= 0) {
         double epsdot;
         if (m.vp - 2 == 0) {
           double E4 = K_HALF * D4, E5 = K_HALF * D5, E6 = K_HALF * D6;
           double epsp = DXX * DXX + DYY * DYY + DZZ * DZZ + K_TWO * (E4 * E4 + E5 * E5 + E6 * E6);
-          epsdot = sqrt(epsp);
+          epsdot = or_sqrt(epsp);
         } else {
           double dav = (DXX + DYY + DZZ) * K_THIRD;
           double E1 = DXX - dav, E2 = DYY - dav, E3 = DZZ - dav, E4 = K_HALF * D4, E5 = K_HALF * D5, E6 = K_HALF * D6;
           double epsp = K_HALF * (E1 * E1 + E2 * E2 + E3 * E3) + E4 * E4 + E5 * E5 + E6 * E6;
-          epsdot = sqrt(K_THREE * epsp) / K_THREE_HALF;
+          epsdot = or_div(or_sqrt(K_THREE * epsp), K_THREE_HALF);
         }
         if (m.israte == 0) EPSD = epsdot; else EPSD = asrate * epsdot + (K_ONE - asrate) * EPSD;
       }
       double EPD = K_ONE;
       if (m.cc != K_ZERO) {
-        if (m.vp == 1) { EPD = fmax(EPSD, m.epdr); EPD = log(EPD / m.epdr); }
-        else           { EPD = fmax(EPSD, K_EM15); EPD = log(EPD / m.epdr); }
+        if (m.vp == 1) { EPD = fmax(EPSD, m.epdr); EPD = log(or_div(EPD, m.epdr)); }
+        else           { EPD = fmax(EPSD, K_EM15); EPD = log(or_div(EPD, m.epdr)); }
         if (m.iform == 0) {
           double MT = fmax(K_EM15, m.z3);
           EPD = fmax(K_ZERO, EPD);
@@ -361,28 +361,28 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       else if (EPXE > K_ZERO) {
         AK = CA + m.cb * pow(EPXE, m.cn);
         if (m.cn > K_ONE) QH = (m.cb * m.cn * pow(EPXE, (m.cn - K_ONE))) * EPD;
-        else              QH = (m.cb * m.cn / pow(EPXE, (K_ONE - m.cn))) * EPD;
+        else              QH = (or_div(m.cb * m.cn, pow(EPXE, (K_ONE - m.cn)))) * EPD;
       } else { AK = CA; QH = K_ZERO; }
       AK = AK * EPD;
       if (SIGMX < AK) { AK = SIGMX; QH = K_ZERO; }
       double SIGY = AK;
       if (EPXE > m.epmx) { AK = K_ZERO; QH = K_ZERO; }
-      double SCALE = fmin(K_ONE, AK / fmax(AJ2, K_EM15));
-      const double DPLA = (K_ONE - SCALE) * AJ2 / fmax(K_THREE * G + QH, K_EM15);
+      double SCALE = fmin(K_ONE, or_div(AK, fmax(AJ2, K_EM15)));
+      const double DPLA = or_div((K_ONE - SCALE) * AJ2, fmax(K_THREE * G + QH, K_EM15));
       AK = AK + (K_ONE - m.fisokin) * DPLA * QH;
-      SCALE = fmin(K_ONE, AK / fmax(AJ2, K_EM15));
+      SCALE = fmin(K_ONE, or_div(AK, fmax(AJ2, K_EM15)));
       SG1 = SCALE * SG1; SG2 = SCALE * SG2; SG3 = SCALE * SG3; SG4 = SCALE * SG4; SG5 = SCALE * SG5; SG6 = SCALE * SG6;
       EPXE = EPXE + DPLA;
       // ---- MQVISCB (IMPL=0, N2D=0, NPG=1, JTHE=0, IDTMINS/=2, NODADT=0)
       {
         const double DD = -DXX - DYY - DZZ;
         double AD = K_ZERO, AL = K_ZERO;
-        const double CX = SSP + sqrt(K_ZERO);              // VD2 = 0 (Lagrangian)
+        const double CX = SSP + K_ZERO;              // VD2 = 0 (Lagrangian)
         if (OFF == K_ONE) {
           AL = (VOLN > K_ZERO) ? pow(VOLN, 1.0 / 3.0) : K_ZERO;
           AD = fmax(K_ZERO, DD);
         }
-        const double NRHO = sqrt(RHOREF * m.rho0);
+        const double NRHO = or_sqrt(RHOREF * m.rho0);
         const double QA = K_ONE * g.prop.qa, QB = K_ONE * g.prop.qb;
         const double CNS1_0 = 1.0 * g.prop.cns1, CNS2_0 = 1.0 * g.prop.cns2;
         const double QAA_0 = QA * QA;
@@ -390,14 +390,14 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
         double CNS2 = CNS2_0 * AL * NRHO * SSP * OFF;
         double QAA = QAA_0 * AD;
         double QX = QB * SSP + AL * QAA
-                  + K_ONE * K_TWO * K_ZERO / fmax(K_EM20, RHON * DELTAX)
-                  + (CNS1 + K_ONE * CNS2) / fmax(K_EM20, RHOREF * DELTAX);
+                  + K_ZERO /* K_ONE*K_TWO*K_ZERO / max(EM20, RHON*DELTAX): the thermal term of mqviscb.F, exactly +0 */
+                  + or_div((CNS1 + K_ONE * CNS2), fmax(K_EM20, RHOREF * DELTAX));
         QNEW = RHON * AD * AL * (QAA * AL + QB * SSP);
-        SSP_EQ = fmax(K_EM20, QX + sqrt(QX * QX + CX * CX));
-        double DTX = DELTAX / SSP_EQ;
+        SSP_EQ = fmax(K_EM20, QX + or_sqrt(QX * QX + CX * CX));
+        double DTX = or_div(DELTAX, SSP_EQ);
         STI = K_ZERO;
         if (!(OFF == K_ZERO || OFFG < K_ZERO)) {
-          double TIDT = K_ONE / DTX, TRHO, TVOL;
+          double TIDT = or_div(K_ONE, DTX), TRHO, TVOL;
           if (ISMSTR == 1 && OFFG > K_ONE) { TRHO = m.rho0 * TIDT; TVOL = VOLO * TIDT; }
           else                             { TRHO = RHON * TIDT;   TVOL = VOLN * TIDT; }
           STI = TRHO * TVOL;
@@ -413,17 +413,17 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       double E1 = DXX * (S1 + SG1), E2 = DYY * (S2 + SG2), E3 = DZZ * (S3 + SG3);
       double E4 = D4 * (S4 + SG4), E5 = D5 * (S5 + SG5), E6 = D6 * (S6 + SG6);
       double EINC = VOL_AVG * (E1 + E2 + E3 + E4 + E5 + E6) * DTA - K_HALF * DVOL * (QOLD + QNEW);
-      EINT = (EINT + EINC * OFF) / fmax(K_EM15, VOLO);
-      if (m.vp == 1) { double PLAP = DPLA / fmax(K_EM20, DT1); EPSD = asrate * PLAP + (K_ONE - asrate) * EPSD; }
+      EINT = or_div((EINT + EINC * OFF), fmax(K_EM15, VOLO));
+      if (m.vp == 1) { double PLAP = or_div(DPLA, fmax(K_EM20, DT1)); EPSD = asrate * PLAP + (K_ONE - asrate) * EPSD; }
       if (m.rhocp > K_ZERO) { SIGY = fmax(SIGY, AK); TEMP = TEMP + SIGY * DPLA * rhocpi; }
     }
     // mmain.F90 tail: entropy heating of the artificial viscosity when the buffer tracks temperature
     if (m.has_temp) {
-      double cv = m.rhocp / m.rho0;
+      double cv = or_div(m.rhocp, m.rho0);
       if (cv > K_ZERO && OFF == K_ONE) {
         double mcv = RHON * VOLN * cv;
         double qheat = -K_HALF * (QOLD + QNEW) * DVOL;
-        TEMP = TEMP + qheat / mcv;
+        TEMP = TEMP + or_div(qheat, mcv);
         TEMP = fmax(K_ZERO, TEMP);
       }
       T.st(g.w_temp, TEMP);
@@ -445,7 +445,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       const double CAQ = K_FOURTH * OFF * g.prop.hcoef;
       double FCL, FCQ;
       if (ISMSTR == 1) FCL = CAQ * m.rho0 * pow(VOLN, K_TWO_THIRD);
-      else if (ISMSTR == 2 && OFFG > K_ONE) { double AA = m.rho0 * VOLO / fmax(K_EM20, VOLN); FCL = CAQ * AA * pow(VOLN, K_TWO_THIRD); }
+      else if (ISMSTR == 2 && OFFG > K_ONE) { double AA = or_div(m.rho0 * VOLO, fmax(K_EM20, VOLN)); FCL = CAQ * AA * pow(VOLN, K_TWO_THIRD); }
       else FCL = CAQ * RHON * pow(VOLN, K_TWO_THIRD);
       FCQ = FCL * CAQ * K_HUNDRED;
       FCL = FCL * SSP;

@@ -51,15 +51,15 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
       e2[0] = (X32 + X41); e2[1] = (Y32 + Y41); e2[2] = (Z32 + Z41);
       e3[0] = e1[1] * e2[2] - e1[2] * e2[1]; e3[1] = e1[2] * e2[0] - e1[0] * e2[2]; e3[2] = e1[0] * e2[1] - e1[1] * e2[0];
       double S = e3[0] * e3[0] + e3[1] * e3[1] + e3[2] * e3[2];
-      S = K_ONE / fmax(sqrt(S), K_EM20);
+      S = or_div(K_ONE, fmax(or_sqrt(S), K_EM20));
       e3[0] = e3[0] * S; e3[1] = e3[1] * S; e3[2] = e3[2] * S;
       const double S1 = e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2], S2 = e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2];
-      S = sqrt(S1 / S2);
+      S = or_sqrt(or_div(S1, S2));
       e1[0] = e1[0] + (e2[1] * e3[2] - e2[2] * e3[1]) * S;
       e1[1] = e1[1] + (e2[2] * e3[0] - e2[0] * e3[2]) * S;
       e1[2] = e1[2] + (e2[0] * e3[1] - e2[1] * e3[0]) * S;
       S = e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2];
-      S = K_ONE / fmax(sqrt(S), K_EM20);
+      S = or_div(K_ONE, fmax(or_sqrt(S), K_EM20));
       e1[0] = e1[0] * S; e1[1] = e1[1] * S; e1[2] = e1[2] * S;
       e2[0] = e3[1] * e1[2] - e3[2] * e1[1]; e2[1] = e3[2] * e1[0] - e3[0] * e1[2]; e2[2] = e3[0] * e1[1] - e3[1] * e1[0];
       // CDERI3: local coordinates relative to node 1
@@ -81,7 +81,7 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
     }
     const double PX1 = K_HALF * (Y2 - Y4), PY1 = K_HALF * (X4 - X2), PX2 = K_HALF * Y3, PY2 = -K_HALF * X3;
     const double AREA = fmax(K_TWO * (PY2 * PX1 - PY1 * PX2), K_EM20);
-    const double VHX = (-X2 + X3 - X4) / AREA, VHY = (-Y2 + Y3 - Y4) / AREA;
+    const double VHX = or_div((-X2 + X3 - X4), AREA), VHY = or_div((-Y2 + Y3 - Y4), AREA);
     // ---- CCOEF3
     const double THK0 = (g.prop.ithk > 0) ? T.ld(SW_THK) : T.ld(g.w_thke);
     const double THK02 = THK0 * THK0;
@@ -92,7 +92,7 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
     const double H1 = g.prop.h1, H2 = g.prop.h2, H3 = g.prop.h3;
     double SHF = K_ZERO;
     if (NPT != 1) { const double FAC1TMP = 2. * (1. + NU) * THK02; const int ISH = 0; const double FSH = g.prop.shf;
-                    SHF = FSH * (1. - ISH + ISH * FAC1TMP / (FSH * AREA + FAC1TMP)); }
+                    SHF = FSH * (1. - ISH + or_div(ISH * FAC1TMP, (FSH * AREA + FAC1TMP))); }
     // ---- CDLEN3
     double ALDT;
     {
@@ -105,11 +105,11 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
       double ALMIN = fmin(fmin(AL1, AL2), AL4);
       const double ALQUAD = fmin(fmin(AL3, AL5), AL6);
       if (AL3 != K_ZERO) ALMIN = fmin(ALMIN, ALQUAD);
-      const double DTDYN = AREA * AREA / fmax(fmax(AL5, AL6), K_EM20);
+      const double DTDYN = or_div(AREA * AREA, fmax(fmax(AL5, AL6), K_EM20));
       ALDT = fmax(DTDYN, ALMIN);
-      const double DTHOUR = K_HALF * (ALMIN + ALDT) / fmax(H1, H2);
+      const double DTHOUR = or_div(K_HALF * (ALMIN + ALDT), fmax(H1, H2));
       if (IHBE != 0) { if (DTHOUR < ALDT) ALDT = DTHOUR; } else ALDT = fmin(ALDT, DTHOUR);
-      ALDT = sqrt(ALDT);
+      ALDT = or_sqrt(ALDT);
     }
     // ---- CDEFO3: nodal velocities in the local frame, membrane + transverse shear rates
     double VX[4], VY[4], VZ[4], EXX, EYY, EXY, EXZ, EYZ;
@@ -131,22 +131,22 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
         const double DT1V4 = K_FOURTH * DT1;
         const double TMP2A = PY2 + PY1;
         const double TMP3A = copysign(fmax(fabs(TMP2A), K_EM20), TMP2A);
-        const double TMP1A = DT1V4 * (VZ13 - VZ24) * (VZ13 - VZ24) / TMP3A;
+        const double TMP1A = or_div(DT1V4 * (VZ13 - VZ24) * (VZ13 - VZ24), TMP3A);
         VX13 = VX[0] - VX[2]; VX24 = VX[1] - VX[3];
         VX13 = VX13 - TMP1A; VX24 = VX24 + TMP1A;
         const double TMP1B = PX2 - PX1;
         const double TMP3B = copysign(fmax(fabs(TMP1B), K_EM20), TMP1B);
-        const double TMP2B = DT1V4 * (VZ13 + VZ24) * (VZ13 + VZ24) / TMP3B;
+        const double TMP2B = or_div(DT1V4 * (VZ13 + VZ24) * (VZ13 + VZ24), TMP3B);
         VY13 = VY[0] - VY[2]; VY24 = VY[1] - VY[3];
         VY13 = VY13 + TMP2B; VY24 = VY24 + TMP2B;
       } else if (IHBE == 2 || IHBE == 3) {
         const double DT1V4 = K_HALF * DT1;
-        const double GZX = EXZ / AREA, EXZZ2 = GZX * Z2, EXZ2 = GZX * GZX * DT1V4;
+        const double GZX = or_div(EXZ, AREA), EXZZ2 = GZX * Z2, EXZ2 = GZX * GZX * DT1V4;
         VX[2] = VX[2] - EXZ2 * X3 - VX[0];
         VX[1] = VX[1] + EXZZ2 - EXZ2 * X2 - VX[0];
         VX[3] = VX[3] + EXZZ2 - EXZ2 * X4 - VX[0];
         VX[0] = K_ZERO;
-        const double GZY = EYZ / AREA, EYZZ2 = GZY * Z2, EYZ2 = GZY * GZY * DT1V4;
+        const double GZY = or_div(EYZ, AREA), EYZZ2 = GZY * Z2, EYZ2 = GZY * GZY * DT1V4;
         VY[2] = VY[2] - EYZ2 * Y3 - VY[0];
         VY[1] = VY[1] + EYZZ2 - EYZ2 * Y2 - VY[0];
         VY[3] = VY[3] + EYZZ2 - EYZ2 * Y4 - VY[0];
@@ -161,10 +161,10 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
       } else {
         const double DT1V4 = K_HALF * DT1;
         const double ZZ2 = K_HALF * Z2;
-        const double GZX = EXZ / AREA, EXZZ2 = GZX * ZZ2, EXZ2 = GZX * GZX * DT1V4, EXZ2PY2 = EXZ2 * PY2, EXZ2PY1 = EXZ2 * PY1;
+        const double GZX = or_div(EXZ, AREA), EXZZ2 = GZX * ZZ2, EXZ2 = GZX * GZX * DT1V4, EXZ2PY2 = EXZ2 * PY2, EXZ2PY1 = EXZ2 * PY1;
         VX[0] = VX[0] - EXZZ2 - EXZ2PY2; VX[2] = VX[2] - EXZZ2 + EXZ2PY2;
         VX[1] = VX[1] + EXZZ2 + EXZ2PY1; VX[3] = VX[3] + EXZZ2 - EXZ2PY1;
-        const double GZY = EYZ / AREA, EYZZ2 = GZY * ZZ2, EYZ2 = GZY * GZY * DT1V4, EYZ2PX2 = EYZ2 * PX2, EYZ2PX1 = EYZ2 * PX1;
+        const double GZY = or_div(EYZ, AREA), EYZZ2 = GZY * ZZ2, EYZ2 = GZY * GZY * DT1V4, EYZ2PX2 = EYZ2 * PX2, EYZ2PX1 = EYZ2 * PX1;
         VY[0] = VY[0] - EYZZ2 + EYZ2PX2; VY[2] = VY[2] - EYZZ2 - EYZ2PX2;
         VY[1] = VY[1] + EYZZ2 - EYZ2PX1; VY[3] = VY[3] + EYZZ2 + EYZ2PX1;
         VX13 = VX[0] - VX[2]; VX24 = VX[1] - VX[3];
@@ -196,7 +196,7 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
     }
     // ---- CSTRA3 + element strain rate
     {
-      const double FAC1 = DT1 / AREA;
+      const double FAC1 = or_div(DT1, AREA);
       io.exx = EXX * FAC1; io.eyy = EYY * FAC1; io.exy = EXY * FAC1; io.eyz = EYZ * FAC1; io.exz = EXZ * FAC1;
       io.kxx = KXX * FAC1; io.kyy = KYY * FAC1; io.kxy = KXY * FAC1;
       if (g.prop.istrain != 0) {
@@ -204,11 +204,11 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
         #pragma unroll
         for (int k = 0; k < 8; k++) T.st(SW_STRA + k, T.ld(SW_STRA + k) + de[k]);
       }
-      const double dtinv = DT1 / fmax(DT1 * DT1, K_EM20);
+      const double dtinv = or_div(DT1, fmax(DT1 * DT1, K_EM20));
       const double thk = T.ld(SW_THK);
       const double eps_k2 = (io.kxx * io.kxx + io.kyy * io.kyy + io.kxx * io.kyy + K_FOURTH * (io.kxy * io.kxy)) * K_ONE_OVER_9 * (thk * thk);
       const double eps_m2 = K_FOUR_OVER_3 * (io.exx * io.exx + io.eyy * io.eyy + io.exx * io.eyy + K_FOURTH * (io.exy * io.exy));
-      io.epsd_pg = sqrt(eps_k2 + eps_m2) * dtinv;
+      io.epsd_pg = or_sqrt(eps_k2 + eps_m2) * dtinv;
       T.st(SW_EPSD, K_ONE * io.epsd_pg + (K_ONE - K_ONE) * T.ld(SW_EPSD));
     }
     // ---- CMAIN3
@@ -216,12 +216,12 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
     shell_material_loop<LAW, false, STAGED>(g, T, DT1, io);
     OFF = io.off;
     const double SSP = io.ssp;
-    const double VISCMX = sqrt(K_ONE + io.viscmx * io.viscmx) - io.viscmx;
+    const double VISCMX = or_sqrt(K_ONE + io.viscmx * io.viscmx) - io.viscmx;
     // ---- CHVIS3
     double H11, H12, H13, H21, H22, H23, H31, H32, H33, B1r, B2r;
     {
       const double HELAS = K_HALF, HVISC = K_HALF, HVLIN = K_ZERO;     // radioss2.F:641-643
-      const double SR2D2 = sqrt(K_TWO) * K_HALF;
+      const double SR2D2 = or_sqrt(K_TWO) * K_HALF;
       double GAMA1, GAMA2, GAMA3, GAMA4;
       const bool plain = (ISMSTR == 1 || ISMSTR == 11 || IHBE < 1);
       if (!plain) {
@@ -229,12 +229,12 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
         GAMA1 = OFF * (K_ONE - PX1V - PY1V); GAMA3 = OFF * (K_ONE + PX1V + PY1V);
         GAMA2 = OFF * (-K_ONE - PX2V - PY2V); GAMA4 = OFF * (-K_ONE + PX2V + PY2V);
       } else { GAMA1 = OFF; GAMA3 = OFF; GAMA2 = -OFF; GAMA4 = -OFF; }
-      const double SHFPR3 = SHF / (K_THREE * (K_ONE + NU));
+      const double SHFPR3 = or_div(SHF, (K_THREE * (K_ONE + NU)));
       const double HVISH1 = HVISC * H1, HVISH2 = HVISC * H2;
       double R0 = K_FOURTH * RHO; const double R1 = R0 * K_HUNDRED; R0 = R0 * HVLIN;
       const double A1 = R1 * HVISH1;
       const double A2 = R0 * SR2D2 * g.prop.srh1;
-      const double SRSHFPR3 = sqrt(SHFPR3);
+      const double SRSHFPR3 = or_sqrt(SHFPR3);
       const double A3 = R1 * HVISH2 * SRSHFPR3;
       const double A4 = R0 * SR2D2 * g.prop.srh2 * SRSHFPR3;
       double HH3 = HELAS * H3;
@@ -243,12 +243,12 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
       const double A6 = HH3 * R0 * K_ZEP072169;
       R0 = K_FOURTH * YM * HELAS;
       const double A7 = H1 * R0, A8 = H2 * R0 * SHFPR3;
-      const double T2A = THK02 * AREA, TSA = sqrt(T2A);
+      const double T2A = THK02 * AREA, TSA = or_sqrt(T2A);
       double H1Q = A1 * TSA, H1L = A2 * SSP * TSA, H2Q = A3 * THK02, H2L = A4 * SSP * THK02, H3Q = A5 * T2A, H3L = A6 * SSP * T2A;
       const double TD = THK0 * DT1;
       double HH1 = A7 * TD;
       const double B1 = PX1 * PX1 + PY1 * PY1, B2 = PX2 * PX2 + PY2 * PY2;
-      double HH2 = A8 * THK02 * TD / (B1 + B2);
+      double HH2 = or_div(A8 * THK02 * TD, (B1 + B2));
       if (nc[2] == nc[3]) { H1Q = H1L = H2Q = H2L = H3Q = H3L = HH1 = HH2 = K_ZERO; }
       double HG1, HG2;
       if (plain) { HG1 = (VX[0] - VX[1] + VX[2] - VX[3]) * OFF; HG2 = (VY[0] - VY[1] + VY[2] - VY[3]) * OFF; }
@@ -276,11 +276,11 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
     // ---- CDT3
     double STI;
     {
-      ALDT = ALDT * VISCMX / sqrt(K_ONE);
-      const double DT = g.dtfac * ALDT / SSP;
+      ALDT = ALDT * VISCMX;                // / sqrt(ALPE), ALPE = 1: exact
+      const double DT = or_div(g.dtfac * ALDT, SSP);
       if (OFFG > K_ZERO && OFF != K_ZERO) dt_cand = DT;
       const double DIVM = fmax(ALDT * ALDT, K_EM20);
-      STI = K_HALF * io.vol0 * YM / DIVM;
+      STI = or_div(K_HALF * io.vol0 * YM, DIVM);
       STI = K_ZEP81 * STI * OFF;
     }
     // ---- CFINT3

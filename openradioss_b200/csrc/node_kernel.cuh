@@ -83,11 +83,11 @@ __device__ __forceinline__ void node_update(const DevNodes& nd, int n, const Nod
 {
   // ACCELE
   const double ms = q.ms;
-  if (ms > K_ZERO) { const double rt = K_ONE / ms; r.a[0] = r.a[0] * rt; r.a[1] = r.a[1] * rt; r.a[2] = r.a[2] * rt; }
+  if (ms > K_ZERO) { const double rt = or_div(K_ONE, ms); r.a[0] = r.a[0] * rt; r.a[1] = r.a[1] * rt; r.a[2] = r.a[2] * rt; }
   else { r.a[0] = K_ZERO; r.a[1] = K_ZERO; r.a[2] = K_ZERO; }
   if (iroddl) {
     const double in = q.in;
-    if (in > K_ZERO) { const double rt = K_ONE / in; r.ar[0] = r.ar[0] * rt; r.ar[1] = r.ar[1] * rt; r.ar[2] = r.ar[2] * rt; }
+    if (in > K_ZERO) { const double rt = or_div(K_ONE, in); r.ar[0] = r.ar[0] * rt; r.ar[1] = r.ar[1] * rt; r.ar[2] = r.ar[2] * rt; }
     else { r.ar[0] = K_ZERO; r.ar[1] = K_ZERO; r.ar[2] = K_ZERO; }
   }
   // BCS

@@ -46,22 +46,22 @@ __device__ __forceinline__ void qeph_warp_proj(const QephGeo& q, double Z1, doub
   double SZ1 = q.MX13 * q.Y24 - q.MY13 * q.X24;
   double SZ2 = A_4 + SZ1;
   double SZ = Z2 * q.L24;
-  double SL = K_ONE / sqrt(SZ + SZ2 * SZ2);
+  double SL = or_div(K_ONE, or_sqrt(SZ + SZ2 * SZ2));
   VQN[0][0] = -Z1 * q.Y24; VQN[1][0] = Z1 * q.X24; VQN[2][0] = SZ2 * SL;
   VQN[0][2] = -VQN[0][0]; VQN[1][2] = -VQN[1][0];
   VQN[0][0] = VQN[0][0] * SL; VQN[1][0] = VQN[1][0] * SL;
   SZ2 = A_4 - SZ1;
-  SL = K_ONE / sqrt(SZ + SZ2 * SZ2);
+  SL = or_div(K_ONE, or_sqrt(SZ + SZ2 * SZ2));
   VQN[0][2] = VQN[0][2] * SL; VQN[1][2] = VQN[1][2] * SL; VQN[2][2] = SZ2 * SL;
   SZ1 = q.MX13 * q.Y13 - q.MY13 * q.X13;
   SZ2 = A_4 + SZ1;
   SZ = Z2 * q.L13;
-  SL = K_ONE / sqrt(SZ + SZ2 * SZ2);
+  SL = or_div(K_ONE, or_sqrt(SZ + SZ2 * SZ2));
   VQN[0][1] = -Z1 * q.Y13; VQN[1][1] = Z1 * q.X13; VQN[2][1] = SZ2 * SL;
   VQN[0][3] = -VQN[0][1]; VQN[1][3] = -VQN[1][1];
   VQN[0][1] = VQN[0][1] * SL; VQN[1][1] = VQN[1][1] * SL;
   SZ2 = A_4 - SZ1;
-  SL = K_ONE / sqrt(SZ + SZ2 * SZ2);
+  SL = or_div(K_ONE, or_sqrt(SZ + SZ2 * SZ2));
   VQN[0][3] = VQN[0][3] * SL; VQN[1][3] = VQN[1][3] * SL; VQN[2][3] = SZ2 * SL;
   const double* CX = q.CX; const double* CY = q.CY;
   const double XX = CX[0] * CX[0] + CX[1] * CX[1] + CX[2] * CX[2] + CX[3] * CX[3];
@@ -80,10 +80,10 @@ __device__ __forceinline__ void qeph_warp_proj(const QephGeo& q, double Z1, doub
   const double ABC = D[0] * D[1] * D[2];
   const double XXYZ2 = D[0] * D[5] * D[5], YYXZ2 = D[1] * D[4] * D[4], ZZXY2 = D[2] * D[3] * D[3];
   double DETA = fabs(ABC + K_TWO * D[3] * D[4] * D[5] - XXYZ2 - YYXZ2 - ZZXY2);
-  DETA = K_ONE / fmax(DETA, K_EM20);
-  DI[0] = (ABC - XXYZ2) * DETA / fmax(D[0], K_EM20);
-  DI[1] = (ABC - YYXZ2) * DETA / fmax(D[1], K_EM20);
-  DI[2] = (ABC - ZZXY2) * DETA / fmax(D[2], K_EM20);
+  DETA = or_div(K_ONE, fmax(DETA, K_EM20));
+  DI[0] = or_div((ABC - XXYZ2) * DETA, fmax(D[0], K_EM20));
+  DI[1] = or_div((ABC - YYXZ2) * DETA, fmax(D[1], K_EM20));
+  DI[2] = or_div((ABC - ZZXY2) * DETA, fmax(D[2], K_EM20));
   DI[3] = (D[4] * D[5] - D[3] * D[2]) * DETA;
   DI[4] = (D[5] * D[3] - D[4] * D[1]) * DETA;
   DI[5] = (D[3] * D[4] - D[5] * D[0]) * DETA;
@@ -134,27 +134,27 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       const double RY = py[1] + py[2] - py[0] - py[3], SY = py[2] + py[3] - py[0] - py[1];
       const double RZ = pz[1] + pz[2] - pz[0] - pz[3], SZ = pz[2] + pz[3] - pz[0] - pz[1];
       double E3X = RY * SZ - RZ * SY, E3Y = RZ * SX - RX * SZ, E3Z = RX * SY - RY * SX;
-      double DET = sqrt(E3X * E3X + E3Y * E3Y + E3Z * E3Z);
+      double DET = or_sqrt(E3X * E3X + E3Y * E3Y + E3Z * E3Z);
       if (DET < K_EM20 && OFFG != K_ZERO) OFFG = K_ZERO;
       const double OFF_LOC = (fabs(OFFG) != K_ZERO) ? K_ONE : K_ZERO;
       DET = fmax(K_EM20, DET);
-      const double CC = fmax(OFF_LOC / DET, K_EM20);
+      const double CC = fmax(or_div(OFF_LOC, DET), K_EM20);
       E3X = E3X * CC; E3Y = E3Y * CC; E3Z = E3Z * CC;
       const double C1C1 = RX * RX + RY * RY + RZ * RZ, C2C2 = SX * SX + SY * SY + SZ * SZ;
       double C2_1 = K_ZERO, C1_1 = K_ZERO;
-      if (C1C1 != K_ZERO) { C2_1 = sqrt(C2C2 / fmax(K_EM20, C1C1)); C1_1 = K_ONE; }
-      else if (C2C2 != K_ZERO) { C2_1 = K_ONE; C1_1 = sqrt(C1C1 / fmax(K_EM20, C2C2)); }
+      if (C1C1 != K_ZERO) { C2_1 = or_sqrt(or_div(C2C2, fmax(K_EM20, C1C1))); C1_1 = K_ONE; }
+      else if (C2C2 != K_ZERO) { C2_1 = K_ONE; C1_1 = or_sqrt(or_div(C1C1, fmax(K_EM20, C2C2))); }
       double E1X = RX * C2_1 + (SY * E3Z - SZ * E3Y) * C1_1;
       double E1Y = RY * C2_1 + (SZ * E3X - SX * E3Z) * C1_1;
       double E1Z = RZ * C2_1 + (SX * E3Y - SY * E3X) * C1_1;
-      double C1 = sqrt(E1X * E1X + E1Y * E1Y + E1Z * E1Z);
-      if (C1 != K_ZERO) C1 = K_ONE / fmax(K_EM20, C1);
+      double C1 = or_sqrt(E1X * E1X + E1Y * E1Y + E1Z * E1Z);
+      if (C1 != K_ZERO) C1 = or_div(K_ONE, fmax(K_EM20, C1));
       E1X = E1X * C1; E1Y = E1Y * C1; E1Z = E1Z * C1;
       VQ[0][0] = E1X; VQ[1][0] = E1Y; VQ[2][0] = E1Z;
       VQ[0][1] = E3Y * E1Z - E3Z * E1Y; VQ[1][1] = E3Z * E1X - E3X * E1Z; VQ[2][1] = E3X * E1Y - E3Y * E1X;
       VQ[0][2] = E3X; VQ[1][2] = E3Y; VQ[2][2] = E3Z;
       AREA = K_FOURTH * DET;
-      AREA_I = fmax(OFF_LOC / AREA, K_EM20);
+      AREA_I = fmax(or_div(OFF_LOC, AREA), K_EM20);
     }
     // ---- local coordinates relative to node 1 (czcorc.F:195-229)
     double XL2, YL2, XL3, YL3, XL4, YL4, Z1;
@@ -178,7 +178,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
         YL3 = sm[3 * ORGPU_TILE]; XL4 = sm[4 * ORGPU_TILE]; YL4 = sm[5 * ORGPU_TILE];
         Z1 = K_ZERO;
         AREA = K_HALF * ((XL2 - XL4) * YL3 - XL3 * (YL2 - YL4));
-        AREA_I = K_ONE / fmax(K_EM20, AREA);
+        AREA_I = or_div(K_ONE, fmax(K_EM20, AREA));
       } else {
         __stcs(&sm[0], XL2); __stcs(&sm[ORGPU_TILE], YL2); __stcs(&sm[2 * ORGPU_TILE], XL3);
         __stcs(&sm[3 * ORGPU_TILE], YL3); __stcs(&sm[4 * ORGPU_TILE], XL4); __stcs(&sm[5 * ORGPU_TILE], YL4);
@@ -202,19 +202,19 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       const double c2 = CX[0] * CY[2] - CY[0] * CX[2];
       const double HS = fmax(fabs(c1), fabs(c2)) * AREA_I;
       const double rx = XL2 + XL3 - XL4, ry = YL2 + YL3 - YL4, sx = -XL2 + XL3 + XL4, sy = -YL2 + YL3 + YL4;
-      const double C1 = sqrt(rx * rx + ry * ry), C2 = sqrt(sx * sx + sy * sy);
-      double S1 = K_FOURTH * (fmax(C1, C2) / fmin(C1, C2) - K_ONE);
+      const double C1 = or_sqrt(rx * rx + ry * ry), C2 = or_sqrt(sx * sx + sy * sy);
+      double S1 = K_FOURTH * (or_div(fmax(C1, C2), fmin(C1, C2)) - K_ONE);
       const double f1 = fmin(K_HALF, S1) + K_ONE;
-      double f2 = K_FOUR * AREA / (C1 * C2);
+      double f2 = or_div(K_FOUR * AREA, (C1 * C2));
       f2 = (double)3.413f * fmax(K_ZERO, f2 - (double)0.7071f);
       f2 = (double)0.78f + (double)0.22f * f2 * f2 * f2;
       const double FACI = K_TWO * f1 * f2;
       LL = fmax(L13, L24);
       LM = K_HALF * (L13 + L24);
-      FACN1 = sqrt(L24 / LL); FACN2 = sqrt(L13 / LL);
-      S1 = sqrt(FACI * (K_FIVE_OVER_4 + HS) * LL);
+      FACN1 = or_sqrt(or_div(L24, LL)); FACN2 = or_sqrt(or_div(L13, LL));
+      S1 = or_sqrt(FACI * (K_FIVE_OVER_4 + HS) * LL);
       S1 = fmax(S1, K_EM10);
-      LL = AREA / S1;
+      LL = or_div(AREA, S1);
     }
     // ---- nodal velocities: translations to V13/V24/VHI, rotations to the local frame
     double RL[3][4];                                     // RL[2][k] = e3 component (used only when warped)
@@ -247,11 +247,11 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       const double EYZ = -X24 * V13[2] + X13 * V24[2];
       const double DDRY = DT05 * EXZ * AREA_I, DDRX = DT05 * EYZ * AREA_I;
       const double V13X = V13[0], V24X = V24[0], VHIX = VHI[0];
-      const double DDRZ1 = (fabs(X13 - X24) < K_EM10) ? K_ZERO : DT025 * (V13[1] - V24[1]) / (X13 - X24);
+      const double DDRZ1 = (fabs(X13 - X24) < K_EM10) ? K_ZERO : or_div(DT025 * (V13[1] - V24[1]), (X13 - X24));
       V13[0] = V13[0] - DDRY * V13[2] - DDRZ1 * V13[1];
       V24[0] = V24[0] - DDRY * V24[2] - DDRZ1 * V24[1];
       VHI[0] = VHI[0] - DDRY * VHI[2] - DDRZ1 * VHI[1];
-      const double DDRZ2 = (fabs(Y13 + Y24) < K_EM10) ? K_ZERO : DT025 * (V13X + V24X) / (Y13 + Y24);
+      const double DDRZ2 = (fabs(Y13 + Y24) < K_EM10) ? K_ZERO : or_div(DT025 * (V13X + V24X), (Y13 + Y24));
       V13[1] = V13[1] - DDRX * V13[2] - DDRZ2 * V13X;
       V24[1] = V24[1] - DDRX * V24[2] - DDRZ2 * V24X;
       VHI[1] = VHI[1] - DDRX * VHI[2] - DDRZ2 * VHIX;
@@ -361,11 +361,11 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       for (int k = 0; k < 8; k++) T.st(SW_STRA + k, st[k] + de[k]);
     }
     {
-      const double dtinv = DT1 / fmax(DT1 * DT1, K_EM20);
+      const double dtinv = or_div(DT1, fmax(DT1 * DT1, K_EM20));
       const double thk = T.ld(SW_THK);
       const double eps_k2 = (io.kxx * io.kxx + io.kyy * io.kyy + io.kxx * io.kyy + K_FOURTH * (io.kxy * io.kxy)) * K_ONE_OVER_9 * (thk * thk);
       const double eps_m2 = K_FOUR_OVER_3 * (io.exx * io.exx + io.eyy * io.eyy + io.exx * io.eyy + K_FOURTH * (io.exy * io.exy));
-      io.epsd_pg = sqrt(eps_k2 + eps_m2) * dtinv;
+      io.epsd_pg = or_sqrt(eps_k2 + eps_m2) * dtinv;
       T.st(SW_EPSD, K_ONE * io.epsd_pg + (K_ONE - K_ONE) * T.ld(SW_EPSD));
     }
     io.area = AREA; io.thk0 = THK0; io.gs = G * SHF; io.rho = RHO; io.off = OFF; io.sigy = K_EP30;
@@ -395,14 +395,14 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     double STI;
     {
       double VISCMX = fmax(io.viscmx, AMU);
-      VISCMX = sqrt(K_ONE + VISCMX * VISCMX) - VISCMX;
-      const double ALDT = LL * VISCMX / sqrt(K_ONE);
-      const double F_OSET = K_ONE + K_HALF * fabs(K_ZERO * THK0) / THK0;
-      const double F_DTE = K_ONE / sqrt(F_OSET);
-      const double DT = g.dtfac * F_DTE * ALDT / io.ssp;
+      VISCMX = or_sqrt(K_ONE + VISCMX * VISCMX) - VISCMX;
+      const double ALDT = LL * VISCMX;      // / sqrt(ALPE), ALPE = 1: exact
+      const double F_OSET = K_ONE + K_ZERO;   // HALF*|Z_OFFSET*THK0|/THK0 with zero offset: exactly +0
+      const double F_DTE = or_div(K_ONE, or_sqrt(F_OSET));
+      const double DT = or_div(g.dtfac * F_DTE * ALDT, io.ssp);
       if (OFFG > K_ZERO && OFF != K_ZERO) dt_cand = DT;
       const double DIVM = fmax(ALDT * ALDT, K_EM20);
-      STI = K_HALF * F_OSET * io.vol0 * A11 * OFF / DIVM;
+      STI = or_div(K_HALF * F_OSET * io.vol0 * A11 * OFF, DIVM);
     }
     // ---- CZFINTCE : constant part of the generalised internal forces
     const double* FO = io.fo; const double* MO = io.mo;
@@ -488,7 +488,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
           SVM = SXY0 + COEF1 * MXY0;
         }
         if (UFAC >= K_EM18 || SVM > SIGY2) {
-          double EH1 = fmin(SXY0 / fmax(SIGY2, K_EM18), K_ONE);
+          double EH1 = fmin(or_div(SXY0, fmax(SIGY2, K_EM18)), K_ONE);
           EH1 = fmax(K_ZEP999 * EH1, (K_ONE - io.zcfac1));
           double EH2 = fmax(K_ZEP999, (K_ONE - io.zcfac2));
           if (ESX < K_ZERO) EH1 = K_ZERO;
@@ -509,12 +509,12 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       SC5 = (MY34 * VG[4] + MX34 * VG[5]) * C2;
       SC6 = (MY23 * VG[10] + MX23 * VG[11]) * C2;
       double SS3 = SC5 + SC6;
-      const double HVL = AMU * sqrt(RHO * AREA * FAC1) * OFF;
+      const double HVL = AMU * or_sqrt(RHO * AREA * FAC1) * OFF;
       const double SSV0 = MY23 * MY23, SSV1 = MY34 * MY34, SSV2 = MX23 * MX23, SSV3 = MX34 * MX34;
       const double HXX_V = K_FIVEP333 * (SSV1 + SSV0);
       const double HXY_V = -K_FIVEP333 * (MY34 * MX34 + MY23 * MX23);
       const double HYY_V = K_FIVEP333 * (SSV2 + SSV3);
-      C2 = HVL * GSR * SHFSR * sqrt(K_ONE_OVER_12);
+      C2 = HVL * GSR * SHFSR * or_sqrt(K_ONE_OVER_12);
       const double CXZ_V = (SSV1 + SSV3) * C2, CYZ_V = (SSV2 + SSV0) * C2;
       const double AUX = AREA_I * HVL;
       const double C1Mv = A11SR * AUX, C2Mv = A12SR * AUX;

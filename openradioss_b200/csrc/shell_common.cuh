@@ -64,7 +64,7 @@ __device__ __forceinline__ void vinter1(const double* __restrict__ tf, int iad, 
   }
   const double2 p1 = __ldg(reinterpret_cast<const double2*>(tf) + iad + ipos);
   const double2 p2 = __ldg(reinterpret_cast<const double2*>(tf) + iad + ipos + 1);
-  dydx = (p2.y - p1.y) / (p2.x - p1.x);
+  dydx = or_div((p2.y - p1.y), (p2.x - p1.x));
   y = p1.y + dydx * (x - p1.x);
 }
 
@@ -119,7 +119,7 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
   double epsd;
   if (m.israte == 0) {
     const double exx = dexx * dtinv, eyy = deyy * dtinv, exy = dexy * dtinv;
-    epsd = K_HALF * (fabs(exx + eyy) + sqrt((exx - eyy) * (exx - eyy) + exy * exy));
+    epsd = K_HALF * (fabs(exx + eyy) + or_sqrt((exx - eyy) * (exx - eyy) + exy * exy));
   } else {
     epsd = asrate * epsd_pg + (K_ONE - asrate) * s.epsd;
   }
@@ -142,10 +142,10 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
     double RFAC;
     if (m.ismooth == 2) {
       const double EPSP1 = fmax(m.rate[JJ - 1], K_EM20), EPSP2 = m.rate[JJ];
-      RFAC = log(fmax(epsd, K_EM20) / EPSP1) / log(EPSP2 / EPSP1);
+      RFAC = or_div(log(or_div(fmax(epsd, K_EM20), EPSP1)), log(or_div(EPSP2, EPSP1)));
     } else {
       const double EPSP1 = m.rate[JJ - 1], EPSP2 = m.rate[JJ];
-      RFAC = (epsd - EPSP1) / (EPSP2 - EPSP1);
+      RFAC = or_div((epsd - EPSP1), (EPSP2 - EPSP1));
     }
     const double YFAC1 = m.yfac[JJ - 1] * K_ONE, YFAC2 = m.yfac[JJ] * K_ONE;
     const int f1 = m.ifunc[JJ - 1], f2 = m.ifunc[JJ];
@@ -168,15 +168,15 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
     const double NU3 = K_ONE - m.nu_mnu;
     const double SVM2 = s.sxx * s.sxx + s.syy * s.syy - s.sxx * s.syy + K_THREE * s.sxy * s.sxy;
     if (SVM2 > YLD * YLD) {
-      const double SVM = sqrt(SVM2);
-      const double R = YLD / SVM;
+      const double SVM = or_sqrt(SVM2);
+      const double R = or_div(YLD, SVM);
       s.sxx = s.sxx * R; s.syy = s.syy * R; s.sxy = s.sxy * R;
-      const double DPLA = off * SVM * (K_ONE - R) / (G3 + H);
+      const double DPLA = or_div(off * SVM * (K_ONE - R), (G3 + H));
       pla = pla + DPLA;
-      double DEZZ = (YLD != 0) ? DPLA * K_HALF * (s.sxx + s.syy) / YLD : K_ZERO;
+      double DEZZ = (YLD != 0) ? or_div(DPLA * K_HALF * (s.sxx + s.syy), YLD) : K_ZERO;
       DEZZ = -(dexx + deyy) * m.nu_mnu - NU3 * DEZZ;
       thk = thk + DEZZ * thklyl * off;
-      etse = H / (H + E);
+      etse = or_div(H, (H + E));
     }
   } else if (ipla == 1) {
     H = fmax(K_ZERO, H);
@@ -186,27 +186,27 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
     const double SVM2 = AA + BB;
     { const double DEZZ = -(dexx + deyy) * m.nu_mnu; thk = thk + DEZZ * thklyl * off; }
     if (SVM2 > YLD * YLD && off == K_ONE) {
-      const double SVM = sqrt(SVM2);
-      double DPLA_J = (SVM - YLD) / (G3 + H);
-      etse = H / (H + E);
+      const double SVM = or_sqrt(SVM2);
+      double DPLA_J = or_div((SVM - YLD), (G3 + H));
+      etse = or_div(H, (H + E));
       const double HI = H * (K_ONE - m.fisokin);
       const double HK = K_TWO_THIRD * H * m.fisokin;
       const double NU3 = K_ONE - m.nu_mnu;
-      const double AAA = K_THREE * HK / E;
+      const double AAA = or_div(K_THREE * HK, E);
       const double NU11 = m.u_mnu + AAA, NU21 = m.t_pnu + AAA;
       double DPLA_I = K_ZERO, DR = K_ZERO, PP = K_ONE, QQ = K_ONE;
       #pragma unroll
       for (int N = 0; N < 3; N++) {                       // NITER = 3 (sigeps36c.F:167)
         DPLA_I = DPLA_J;
         const double YLD_I = YLD + HI * DPLA_I;
-        DR = K_HALF * E * DPLA_I / YLD_I;
-        PP = K_ONE / (K_ONE + DR * NU11);
-        QQ = K_ONE / (K_ONE + DR * NU21);
+        DR = or_div(K_HALF * E * DPLA_I, YLD_I);
+        PP = or_div(K_ONE, (K_ONE + DR * NU11));
+        QQ = or_div(K_ONE, (K_ONE + DR * NU21));
         const double P2 = PP * PP, Q2 = QQ * QQ;
         const double F = AA * P2 + BB * Q2 - YLD_I * YLD_I;
-        double DF = -(AA * NU11 * P2 * PP + BB * NU21 * Q2 * QQ) * (E - K_TWO * DR * HI) / YLD_I - K_TWO * HI * YLD_I;
+        double DF = -or_div((AA * NU11 * P2 * PP + BB * NU21 * Q2 * QQ) * (E - K_TWO * DR * HI), YLD_I) - K_TWO * HI * YLD_I;
         DF = copysign(fmax(fabs(DF), K_EM20), DF);
-        DPLA_J = (DPLA_I > K_ZERO) ? fmax(K_ZERO, DPLA_I - F / DF) : K_ZERO;
+        DPLA_J = (DPLA_I > K_ZERO) ? fmax(K_ZERO, DPLA_I - or_div(F, DF)) : K_ZERO;
       }
       pla = pla + DPLA_I;
       S1 = (s.sxx + s.syy) * PP;
@@ -214,7 +214,7 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
       s.sxx = K_HALF * (S1 + S2);
       s.syy = K_HALF * (S1 - S2);
       s.sxy = s.sxy * QQ;
-      { const double DEZZ = -NU3 * DR * S1 / E; thk = thk + DEZZ * thklyl * off; }
+      { const double DEZZ = -or_div(NU3 * DR * S1, E); thk = thk + DEZZ * thklyl * off; }
       YLD = YLD + HI * DPLA_I;
     }
   } else {
@@ -224,22 +224,22 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
     const double YLD2 = YLD * YLD;
     if (SVM2 > YLD2 && off == K_ONE) {
       const double NU3 = K_ONE - m.nu_mnu;
-      const double A = (SVM2 - YLD2) / (K_FIVE * SVM2 + K_THREE * (-s.sxx * s.syy + s.sxy * s.sxy));
+      const double A = or_div((SVM2 - YLD2), (K_FIVE * SVM2 + K_THREE * (-s.sxx * s.syy + s.sxy * s.sxy)));
       const double S1 = (K_ONE - K_TWO * A) * s.sxx + A * s.syy;
       const double S2 = A * s.sxx + (K_ONE - K_TWO * A) * s.syy;
       const double S3 = (K_ONE - K_THREE * A) * s.sxy;
       s.sxx = S1; s.syy = S2; s.sxy = S3;
-      double SVM = sqrt(SVM2);
-      const double DPLA = off * (SVM - YLD) / (G3 + H);
+      double SVM = or_sqrt(SVM2);
+      const double DPLA = or_div(off * (SVM - YLD), (G3 + H));
       YLD = YLD + H * (K_ONE - m.fisokin) * DPLA;
-      SVM = sqrt(s.sxx * s.sxx + s.syy * s.syy - s.sxx * s.syy + K_THREE * s.sxy * s.sxy);
-      const double R = fmin(K_ONE, YLD / fmax(K_EM20, SVM));
+      SVM = or_sqrt(s.sxx * s.sxx + s.syy * s.syy - s.sxx * s.syy + K_THREE * s.sxy * s.sxy);
+      const double R = fmin(K_ONE, or_div(YLD, fmax(K_EM20, SVM)));
       s.sxx = s.sxx * R; s.syy = s.syy * R; s.sxy = s.sxy * R;
       pla = pla + DPLA;
-      double DEZZ = DPLA * K_HALF * (s.sxx + s.syy) / YLD;
+      double DEZZ = or_div(DPLA * K_HALF * (s.sxx + s.syy), YLD);
       DEZZ = -NU3 * DEZZ;
       thk = thk + DEZZ * thklyl * off;
-      etse = H / (H + E);
+      etse = or_div(H, (H + E));
     }
   }
   s.pla = pla;
@@ -255,7 +255,7 @@ __device__ __forceinline__ void law2_ip(const ShellSG& g, int ipla, int npttot, 
   const orgpu_law2& m = g.m2;
   const double SMALL = K_EM7;
   const double young = m.young, gg = m.shear, nu = m.nu;
-  const double a11 = young / (K_ONE - nu * nu);
+  const double a11 = or_div(young, (K_ONE - nu * nu));
   const double a12 = a11 * nu;
   const double cn = m.cn;
   const double epdr = fmax(m.epdr * dt1, K_EM20);
@@ -264,8 +264,8 @@ __device__ __forceinline__ void law2_ip(const ShellSG& g, int ipla, int npttot, 
   const bool has_temp = m.has_temp != 0;
   const double tempel = has_temp ? s.temp : K_ZERO;
   double z3, z4, m_exp, tstar = K_ZERO;
-  if (m.iform == 1) { z3 = m.z3; z4 = m.z4; m_exp = K_ONE; if (has_temp) tstar = fmax(K_ZERO, (tempel - m.tref) / fmax(m.tmelt - m.tref, K_EM20)); }
-  else { z3 = K_ZERO; z4 = K_ZERO; m_exp = m.z3; tstar = fmax(K_ZERO, (tempel - m.tref) / (m.tmelt - m.tref)); }
+  if (m.iform == 1) { z3 = m.z3; z4 = m.z4; m_exp = K_ONE; if (has_temp) tstar = fmax(K_ZERO, or_div((tempel - m.tref), fmax(m.tmelt - m.tref, K_EM20))); }
+  else { z3 = K_ZERO; z4 = K_ZERO; m_exp = m.z3; tstar = fmax(K_ZERO, or_div((tempel - m.tref), (m.tmelt - m.tref))); }
   double EZZ = K_ZERO, epsdot = K_ZERO;
   if (m.vp == 1) epsdot = epsd * dt1;
   else if (m.vp == 2) { epsd = asrate * epsd_pg + (K_ONE - asrate) * epsd; epsdot = epsd * dt1; }
@@ -274,7 +274,7 @@ __device__ __forceinline__ void law2_ip(const ShellSG& g, int ipla, int npttot, 
     const double DAV = (exx + eyy) * K_THIRD;
     const double D1 = exx - DAV, D2 = eyy - DAV, D3 = -DAV, D4 = K_HALF * exy;
     epsdot = K_HALF * (D1 * D1 + D2 * D2 + D3 * D3) + D4 * D4;
-    epsdot = sqrt(K_THREE * epsdot) / K_THREE_HALF;
+    epsdot = or_div(or_sqrt(K_THREE * epsdot), K_THREE_HALF);
     if (m.israte > 0) epsdot = asrate * epsdot + (K_ONE - asrate) * epsd;
     epsd = epsdot; epsdot = epsdot * dt1;
   }
@@ -291,7 +291,7 @@ __device__ __forceinline__ void law2_ip(const ShellSG& g, int ipla, int npttot, 
     if (m.iform == 0) {
       if (m.israte == 0 && m.vp == 2) EPSP = fmax(fmax(fabs(dexx), fabs(deyy)), K_HALF * fabs(dexy));
       EPSP = fmax(EPSP, epdr);
-      const double LOGEP = log(EPSP / epdr);
+      const double LOGEP = log(or_div(EPSP, epdr));
       if (tstar == K_ZERO) Q = (K_ONE + m.cc * LOGEP);
       else Q = (K_ONE + m.cc * LOGEP) * (K_ONE - exp(m_exp * log(tstar)));
       Q = fmax(Q, K_EM20);
@@ -300,7 +300,7 @@ __device__ __forceinline__ void law2_ip(const ShellSG& g, int ipla, int npttot, 
     } else if (m.iform == 1) {
       if (m.israte == 0 && m.vp == 2) EPSP = fmax(fmax(fabs(dexx), fabs(deyy)), K_HALF * fabs(dexy));
       EPSP = fmax(EPSP, K_EM20);
-      Q = log(EPSP / epdr);
+      Q = log(or_div(EPSP, epdr));
       Q = m.cc * exp((-z3 + z4 * Q) * tempel);
       if (m.icc == 1) YMAX = YMAX + Q;
       CA = CA + Q;
@@ -312,28 +312,28 @@ __device__ __forceinline__ void law2_ip(const ShellSG& g, int ipla, int npttot, 
   else { const double BETA = CB * (K_ONE - m.fisokin); YLD = CA + BETA * exp(cn * log(pla)); }
   YLD = fmin(YLD, YMAX);
   if (ipla == 0) {
-    const double SVM = sqrt(s.sxx * s.sxx + s.syy * s.syy - s.sxx * s.syy + K_THREE * s.sxy * s.sxy);
-    const double R = fmin(K_ONE, YLD / (SVM + K_EM15));
+    const double SVM = or_sqrt(s.sxx * s.sxx + s.syy * s.syy - s.sxx * s.syy + K_THREE * s.sxy * s.sxy);
+    const double R = fmin(K_ONE, or_div(YLD, (SVM + K_EM15)));
     if (R < K_ONE) {
       s.sxx = s.sxx * R; s.syy = s.syy * R; s.sxy = s.sxy * R;
-      DPLA = off_old * fmax(K_ZERO, (SVM - YLD) / young);
+      DPLA = off_old * fmax(K_ZERO, or_div((SVM - YLD), young));
       const double S1 = K_HALF * (s.sxx + s.syy);
-      EZZ = DPLA * S1 / YLD;
+      EZZ = or_div(DPLA * S1, YLD);
       pla = pla + DPLA;
       epchk = fmax(pla, epchk);
       H = (YLD >= YMAX) ? K_ZERO : cn * CB * exp((cn - K_ONE) * log(pla + SMALL));
-      etse = H / (H + young);
+      etse = or_div(H, (H + young));
     }
   } else if (ipla == 1) {
     double S1 = s.sxx + s.syy, S2 = s.sxx - s.syy; const double S3 = s.sxy;
     const double A = K_FOURTH * S1 * S1;
     const double B = K_THREE_OVER_4 * S2 * S2 + K_THREE * S3 * S3;
-    const double SVM = sqrt(A + B);
+    const double SVM = or_sqrt(A + B);
     if (SVM > YLD && off_old == K_ONE) {
-      const double NU1 = K_ONE / (K_ONE - nu), NU2 = K_ONE / (K_ONE + nu);
+      const double NU1 = or_div(K_ONE, (K_ONE - nu)), NU2 = or_div(K_ONE, (K_ONE + nu));
       H = (YLD >= YMAX) ? K_ZERO : cn * CB * exp((cn - K_ONE) * log(pla + SMALL));
-      double DPLA_J = (SVM - YLD) / (K_THREE * gg + H);
-      etse = H / (H + young);
+      double DPLA_J = or_div((SVM - YLD), (K_THREE * gg + H));
+      etse = or_div(H, (H + young));
       const double ANU1 = A * NU1, BNU2 = K_THREE * B * NU2, H2 = K_TWO * H;
       double DPLA_I = K_ZERO, DR = K_ZERO, P = K_ONE, Qq = K_ONE;
       #pragma unroll 1
@@ -344,13 +344,13 @@ __device__ __forceinline__ void law2_ip(const ShellSG& g, int ipla, int npttot, 
         double YLD_I;
         if (PLA_I == K_ZERO) YLD_I = fmin(YMAX, CA);
         else YLD_I = fmin(YMAX, CA + CB * exp(cn * log(PLA_I)));
-        DR = K_HALF * young * DPLA_I / YLD_I;
-        P = K_ONE / (K_ONE + DR * NU1);
-        Qq = K_ONE / (K_ONE + K_THREE * DR * NU2);
+        DR = or_div(K_HALF * young * DPLA_I, YLD_I);
+        P = or_div(K_ONE, (K_ONE + DR * NU1));
+        Qq = or_div(K_ONE, (K_ONE + K_THREE * DR * NU2));
         const double P2 = P * P, Q2 = Qq * Qq;
         const double F = A * P2 + B * Q2 - YLD_I * YLD_I;
-        const double DF = -(ANU1 * P2 * P + BNU2 * Q2 * Qq) * (young - DR * H2) / YLD_I - H2 * YLD_I;
-        DPLA_J = (DPLA_I > K_ZERO) ? fmax(K_ZERO, DPLA_I - F / DF) : K_ZERO;
+        const double DF = -or_div((ANU1 * P2 * P + BNU2 * Q2 * Qq) * (young - DR * H2), YLD_I) - H2 * YLD_I;
+        DPLA_J = (DPLA_I > K_ZERO) ? fmax(K_ZERO, DPLA_I - or_div(F, DF)) : K_ZERO;
       }
       pla = pla + DPLA_I;
       epchk = fmax(pla, epchk);
@@ -359,39 +359,39 @@ __device__ __forceinline__ void law2_ip(const ShellSG& g, int ipla, int npttot, 
       s.sxx = K_HALF * (S1 + S2);
       s.syy = K_HALF * (S1 - S2);
       s.sxy = s.sxy * Qq;
-      EZZ = DR * S1 / young;
+      EZZ = or_div(DR * S1, young);
     }
   } else {
     const double SVM2 = s.sxx * s.sxx + s.syy * s.syy - s.sxx * s.syy + K_THREE * s.sxy * s.sxy;
-    double SVM = sqrt(SVM2);
+    double SVM = or_sqrt(SVM2);
     const double YLD2 = YLD * YLD;
     if (SVM2 > YLD2 && off_old == K_ONE) {
       H = (YLD >= YMAX) ? K_ZERO : cn * CB * exp((cn - K_ONE) * log(pla + SMALL));
-      etse = H / (H + young);
-      const double AA = (SVM2 - YLD2) / (K_FIVE * SVM2 + K_THREE * (-s.sxx * s.syy + s.sxy * s.sxy));
+      etse = or_div(H, (H + young));
+      const double AA = or_div((SVM2 - YLD2), (K_FIVE * SVM2 + K_THREE * (-s.sxx * s.syy + s.sxy * s.sxy)));
       const double S1 = (K_ONE - K_TWO * AA) * s.sxx + AA * s.syy;
       const double S2 = AA * s.sxx + (K_ONE - K_TWO * AA) * s.syy;
       const double S3 = (K_ONE - K_THREE * AA) * s.sxy;
       s.sxx = S1; s.syy = S2; s.sxy = S3;
-      DPLA = off_old * (SVM - YLD) / (K_THREE * gg + H);
+      DPLA = or_div(off_old * (SVM - YLD), (K_THREE * gg + H));
       pla = pla + DPLA;
       YLD = YLD + H * DPLA;
-      SVM = sqrt(s.sxx * s.sxx + s.syy * s.syy - s.sxx * s.syy + K_THREE * s.sxy * s.sxy);
-      const double R = fmin(K_ONE, YLD / fmax(K_EM20, SVM));
+      SVM = or_sqrt(s.sxx * s.sxx + s.syy * s.syy - s.sxx * s.syy + K_THREE * s.sxy * s.sxy);
+      const double R = fmin(K_ONE, or_div(YLD, fmax(K_EM20, SVM)));
       s.sxx = s.sxx * R; s.syy = s.syy * R; s.sxy = s.sxy * R;
-      EZZ = DPLA * K_HALF * (s.sxx + s.syy) / YLD;
+      EZZ = or_div(DPLA * K_HALF * (s.sxx + s.syy), YLD);
     }
   }
-  if (m.vp == 1) { epsdot = DPLA / fmax(K_EM20, dt1); epsd = asrate * epsdot + (K_ONE - asrate) * epsd; }
-  sigy = sigy + YLD / npttot;
+  if (m.vp == 1) { epsdot = or_div(DPLA, fmax(K_EM20, dt1)); epsd = asrate * epsdot + (K_ONE - asrate) * epsd; }
+  sigy = sigy + or_div(YLD, npttot);
   if (off == off_old && off > K_ZERO) {
     if (off == K_ONE && epchk >= m.epmx) { off = K_FOUR_OVER_5; ioff_duct = 1; }
     else if (off < K_ONE) off = off * K_FOUR_OVER_5;
   }
   EZZ = -(dexx + deyy) * nu - (K_ONE - K_TWO * nu) * EZZ;
-  EZZ = EZZ / (K_ONE - nu);
+  EZZ = or_div(EZZ, (K_ONE - nu));
   thk = thk + EZZ * thklyl * off;
-  if (m.rhocp > K_ZERO && has_temp) s.temp = tempel + sigy * DPLA / m.rhocp;
+  if (m.rhocp > K_ZERO && has_temp) s.temp = tempel + or_div(sigy * DPLA, m.rhocp);
   s.pla = pla;
   s.epsd = epsd;
 }
@@ -424,7 +424,7 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const Tile
   double off = io.off; const double off_old = off;
   int ioff_duct = 0;
   double epchk = K_ZERO, viscmx = K_ZERO, ssp = io.ssp;
-  const double dtinv = dt1 / fmax(dt1 * dt1, K_EM20);
+  const double dtinv = or_div(dt1, fmax(dt1 * dt1, K_EM20));
   const int israte = (LAW == 36) ? g.m36.israte : g.m2.israte;
   const double pm9 = (LAW == 36) ? g.m36.asrate : g.m2.asrate;
   const double asrate = (israte > 0) ? fmin(K_ONE, pm9 * dt1) : K_ONE;
@@ -458,14 +458,14 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const Tile
     fo[3] = fo[3] + thkly * s.syz; fo[4] = fo[4] + thkly * s.szx;
     mo[0] = mo[0] + wmc * s.sxx; mo[1] = mo[1] + wmc * s.syy; mo[2] = mo[2] + wmc * s.sxy;
     if (FLAG_ZCFAC) {
-      if (LAW != 2) zcfac1 = zcfac1 + etse * thkly; else zcfac1 = zcfac1 + etse / npt;
+      if (LAW != 2) zcfac1 = zcfac1 + etse * thkly; else zcfac1 = zcfac1 + or_div(etse, npt);
       zcfac2 = fmin(etse, zcfac2);
     }
   }
   if ((off == K_FOUR_OVER_5 && ioff_duct == 0) || (off > K_ZERO && off_old < K_EM01)) off = K_ZERO;
   T.st(SW_THK, fmax(thkn, K_EM30));
   const double fact = K_ONEP414 * DM;
-  const double visc = fact * ssp * sqrt(io.area) * dtinv * io.rho;
+  const double visc = fact * ssp * or_sqrt(io.area) * dtinv * io.rho;
   fo[0] = fo[0] + visc * (io.exx + K_HALF * io.eyy);
   fo[1] = fo[1] + visc * (io.eyy + K_HALF * io.exx);
   fo[2] = fo[2] + visc * io.exy * K_THIRD;
