@@ -38,8 +38,7 @@ __device__ __forceinline__ double slen_face(const double* x, const double* y, co
 
 
 __device__ __forceinline__ double4 ldg4(const double4* p) {     // read-only 32-byte nodal record
-  const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
-  return make_double4(a.x, a.y, b.x, b.y);
+  return ld256_nc(p);
 }
 
 struct Jac { double J1, J2, J3, J4, J5, J6, J7, J8, J9, c5968, c6749, c4857, vol; };
@@ -76,7 +75,7 @@ __device__ __forceinline__ Jac brick_jac(const double* x, const double* y, const
 #endif
 
 template <int JHBE, int ISMSTR, bool STAGED>
-__global__ void __launch_bounds__(ORGPU_BLOCK, ORGPU_BRICK_MINB)
+__global__ void __launch_bounds__(ORGPU_BLOCK, ORGPU_BRICK_MINB * ORGPU_PER128)
 brick_forces_kernel(const __grid_constant__ BrickParams P)
 {
   const BrickSG& g = P.sg;
@@ -509,8 +508,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     if (P.roww == 4) {
       #pragma unroll
       for (int k = 0; k < 8; k++) {
-        double2* row = reinterpret_cast<double2*>(P.fsky + (size_t)4 * sl[k]);
-        row[0] = make_double2(F1[k], F2[k]); row[1] = make_double2(F3[k], STI);
+        st256(reinterpret_cast<double4*>(P.fsky + (size_t)4 * sl[k]), make_double4(F1[k], F2[k], F3[k], STI));
       }
     } else {
       #pragma unroll
@@ -521,7 +519,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     }
   }
   if (STAGED) tile_store(g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
-  block_dt_reduce<true>(dt_cand, order, g.ngl, g.order0, P.db, g.blk0 + blockIdx.x);
+  warp_dt_reduce<true>(dt_cand, order, g.ngl, g.order0, P.db, g.blk0 + blockIdx.x * (ORGPU_TILE / 32) + (threadIdx.x >> 5));
 }
 
 template <int JHBE, int ISMSTR>

@@ -12,7 +12,7 @@
 #include "shell_common.cuh"
 
 template <int LAW, bool STAGED>
-__global__ void __launch_bounds__(ORGPU_SHELL_CTA, 3)
+__global__ void __launch_bounds__(ORGPU_SHELL_CTA, 3 * ORGPU_PER128)
 bt_forces_kernel(const __grid_constant__ ShellParams P)
 {
   const ShellSG& g = P.sg;
@@ -33,7 +33,7 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
     order = g.order0 + e;
     double xg[4], yg[4], zg[4];
     #pragma unroll
-    for (int k = 0; k < 4; k++) { const double4 p = P.nd.pos[nc[k]]; xg[k] = p.x; yg[k] = p.y; zg[k] = p.z; }
+    for (int k = 0; k < 4; k++) { const double4 p = ld256_nc(P.nd.pos + nc[k]); xg[k] = p.x; yg[k] = p.y; zg[k] = p.z; }
     #pragma unroll
     for (int k = 0; k < 4; k++) { prefetch_l1(P.nd.rot + nc[k]); prefetch_l1(P.nd.vel + nc[k]); }
     if (STAGED) mbar_wait(&s_bar, 0);                     // the state tile has landed (issued before the gather)
@@ -116,7 +116,7 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
     {
       #pragma unroll
       for (int k = 0; k < 4; k++) {
-        double4 v = P.nd.vel[nc[k]];
+        double4 v = ld256_nc(P.nd.vel + nc[k]);
         if (dead_in) { v.x = K_ZERO; v.y = K_ZERO; v.z = K_ZERO; }
         VX[k] = e1[0] * v.x + e1[1] * v.y + e1[2] * v.z;
         VY[k] = e2[0] * v.x + e2[1] * v.y + e2[2] * v.z;
@@ -180,7 +180,7 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
     {
       #pragma unroll
       for (int k = 0; k < 4; k++) {
-        double4 w = P.nd.rot[nc[k]];
+        double4 w = ld256_nc(P.nd.rot + nc[k]);
         if (dead_in) { w.x = K_ZERO; w.y = K_ZERO; w.z = K_ZERO; }
         RX[k] = e1[0] * w.x + e1[1] * w.y + e1[2] * w.z;
         RY[k] = e2[0] * w.x + e2[1] * w.y + e2[2] * w.z;
@@ -321,11 +321,11 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
       else if (J < 3) { f4[0] = f4[0] - f[0]; f4[1] = f4[1] - f[1]; f4[2] = f4[2] - f[2]; }
       else { f[0] = f4[0]; f[1] = f4[1]; f[2] = f4[2]; }
       if (dead) { f[0] = f[1] = f[2] = K_ZERO; mm[0] = mm[1] = mm[2] = K_ZERO; }
-      double2* row = reinterpret_cast<double2*>(P.fsky + (size_t)8 * sl[J]);
-      row[0] = make_double2(-f[0], -f[1]); row[1] = make_double2(-f[2], -mm[0]);
-      row[2] = make_double2(-mm[1], -mm[2]); row[3] = make_double2(STI, K_ZERO);
+      double4* row = reinterpret_cast<double4*>(P.fsky + (size_t)8 * sl[J]);
+      st256(row, make_double4(-f[0], -f[1], -f[2], -mm[0]));
+      st256(row + 1, make_double4(-mm[1], -mm[2], STI, K_ZERO));
     }
   }
   if (STAGED) tile_store(g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
-  block_dt_reduce<false>(dt_cand, order, g.ngl, g.order0, P.db, g.blk0 + blockIdx.x);
+  warp_dt_reduce<false>(dt_cand, order, g.ngl, g.order0, P.db, g.blk0 + blockIdx.x * (ORGPU_TILE / 32) + (threadIdx.x >> 5));
 }

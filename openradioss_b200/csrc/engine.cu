@@ -283,7 +283,7 @@ int orgpu_finalize(orgpu_engine* e)
     if (upload_vec(S.owned, &dconn, conn_t) || upload_vec(S.owned, &dngl, ngl) || upload_vec(S.owned, &d.slab, H.h)) return -100;
     d.conn = dconn; d.ngl = dngl;
     if (push_dev(S.owned, &d.smstr, (size_t)21 * np)) return -100;
-    const int nblk = np / ORGPU_BLOCK;
+    const int nblk = np / 32;                            // dt candidate slots: one per warp
     NEED(e->fa.nsg < ORGPU_MAX_SG, -6, "too many super-groups (%d)", ORGPU_MAX_SG);
     e->fa.sg[e->fa.nsg++] = SGRange{blk, nblk, ORGPU_FAM_BRICK};
     order += ne; blk += nblk; gi = gj;

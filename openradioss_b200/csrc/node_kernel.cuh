@@ -23,14 +23,14 @@ __device__ __forceinline__ NodeAcc node_gather(const DevNodes& nd, const double*
   NodeAcc r;
   const int k0 = nd.adsky[n], k1 = nd.adsky[n + 1];
   constexpr int NB = (ROWW == 4) ? 8 : 4;
-  constexpr int NV = ROWW / 2;
-  const double2* base = reinterpret_cast<const double2*>(fsky);
-  double2 buf[NB][NV];
+  constexpr int NV = ROWW / 4;                       // 32-byte vectors per row
+  const double4* base = reinterpret_cast<const double4*>(fsky);
+  double4 buf[NB][NV];
   #pragma unroll
   for (int j = 0; j < NB; j++) {
     if (k0 + j < k1) {
       #pragma unroll
-      for (int c = 0; c < NV; c++) buf[j][c] = __ldcs(base + (size_t)NV * (k0 + j) + c);
+      for (int c = 0; c < NV; c++) buf[j][c] = ld256_cs(base + (size_t)NV * (k0 + j) + c);
     }
   }
   if (nd.FEXT) { r.a[0] = nd.FEXT[3 * n]; r.a[1] = nd.FEXT[3 * n + 1]; r.a[2] = nd.FEXT[3 * n + 2]; }
@@ -44,19 +44,18 @@ __device__ __forceinline__ NodeAcc node_gather(const DevNodes& nd, const double*
       for (int j = 0; j < NB; j++) {
         if (kb + j < k1) {
           #pragma unroll
-          for (int c = 0; c < NV; c++) buf[j][c] = __ldcs(base + (size_t)NV * (kb + j) + c);
+          for (int c = 0; c < NV; c++) buf[j][c] = ld256_cs(base + (size_t)NV * (kb + j) + c);
         }
       }
     }
     #pragma unroll
     for (int j = 0; j < NB; j++) {
       if (kb + j < k1) {
-        if (ROWW == 4) {
-          r.a[0] = r.a[0] + buf[j][0].x; r.a[1] = r.a[1] + buf[j][0].y; r.a[2] = r.a[2] + buf[j][1].x; r.stifn = r.stifn + buf[j][1].y;
-        } else {
-          r.a[0] = r.a[0] + buf[j][0].x; r.a[1] = r.a[1] + buf[j][0].y; r.a[2] = r.a[2] + buf[j][1].x;
-          r.ar[0] = r.ar[0] + buf[j][1].y; r.ar[1] = r.ar[1] + buf[j][NV - 2].x; r.ar[2] = r.ar[2] + buf[j][NV - 2].y;
-          r.stifn = r.stifn + buf[j][NV - 1].x; r.stifr = r.stifr + buf[j][NV - 1].y;
+        r.a[0] = r.a[0] + buf[j][0].x; r.a[1] = r.a[1] + buf[j][0].y; r.a[2] = r.a[2] + buf[j][0].z;
+        if (ROWW == 4) { r.stifn = r.stifn + buf[j][0].w; }
+        else {
+          r.ar[0] = r.ar[0] + buf[j][0].w; r.ar[1] = r.ar[1] + buf[j][NV - 1].x; r.ar[2] = r.ar[2] + buf[j][NV - 1].y;
+          r.stifn = r.stifn + buf[j][NV - 1].z; r.stifr = r.stifr + buf[j][NV - 1].w;
         }
       }
     }
@@ -73,8 +72,8 @@ __device__ __forceinline__ NodeIn node_load(const DevNodes& nd, int n, int irodd
   NodeIn q;
   q.ms = nd.MS[n]; q.in = iroddl ? nd.IN[n] : K_ZERO;
   q.ct = nd.icodt ? nd.icodt[n] : 0; q.cr = (nd.icodt && iroddl) ? nd.icodr[n] : 0;
-  q.v = nd.vel[n]; q.p = nd.pos[n];
-  if (iroddl) q.w = nd.rot[n];
+  q.v = ld256(nd.vel + n); q.p = ld256(nd.pos + n);
+  if (iroddl) q.w = ld256(nd.rot + n);
   q.d[0] = nd.D[3 * n]; q.d[1] = nd.D[3 * n + 1]; q.d[2] = nd.D[3 * n + 2];
   return q;
 }
@@ -99,18 +98,18 @@ __device__ __forceinline__ void node_update(const DevNodes& nd, int n, const Nod
   // VELOCITY
   double4 v = q.v;
   v.x = v.x + dt12 * r.a[0]; v.y = v.y + dt12 * r.a[1]; v.z = v.z + dt12 * r.a[2];
-  nd.vel[n] = v;
+  st256(nd.vel + n, v);
   if (iroddl) {
     double4 w = q.w;
     w.x = w.x + dt12 * r.ar[0]; w.y = w.y + dt12 * r.ar[1]; w.z = w.z + dt12 * r.ar[2];
-    nd.rot[n] = w;
+    st256(nd.rot + n, w);
   }
   // DEPLA
   double4 p = q.p;
   double vdt = dt2 * v.x; nd.D[3 * n] = q.d[0] + vdt; p.x = p.x + vdt;
   vdt = dt2 * v.y; nd.D[3 * n + 1] = q.d[1] + vdt; p.y = p.y + vdt;
   vdt = dt2 * v.z; nd.D[3 * n + 2] = q.d[2] + vdt; p.z = p.z + vdt;
-  nd.pos[n] = p;
+  st256(nd.pos + n, p);
 }
 
 // phased mode, step 2: ASSPAR4 only (A, AR, STIFN, STIFR stored for the caller)
@@ -197,7 +196,7 @@ energy_partial_kernel(const double* __restrict__ a, const double* __restrict__ b
   const int i = blockIdx.x * 256 + threadIdx.x;
   double v = 0.0;
   if (i < n) {
-    const size_t j = nw > 0 ? ((size_t)(i >> 7) * nw) * ORGPU_TILE + (i & 127) : (size_t)i;
+    const size_t j = nw > 0 ? ((size_t)(i >> ORGPU_TILE_SHIFT) * nw) * ORGPU_TILE + (i & (ORGPU_TILE - 1)) : (size_t)i;
     if (mode == 0) v = a[j] * b[j];
     else if (mode == 1) v = (off[j] != 0.0) ? a[j] + b[j] : 0.0;
     else { const double4 w = reinterpret_cast<const double4*>(b)[i]; v = 0.5 * a[i] * (w.x * w.x + w.y * w.y + w.z * w.z); }

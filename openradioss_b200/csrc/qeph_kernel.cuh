@@ -100,7 +100,7 @@ __device__ __forceinline__ void qeph_warp_proj(const QephGeo& q, double Z1, doub
 #endif
 
 template <int LAW, bool STAGED>
-__global__ void __launch_bounds__(ORGPU_SHELL_CTA, ORGPU_SHELL_MINB)
+__global__ void __launch_bounds__(ORGPU_SHELL_CTA, ORGPU_SHELL_MINB * ORGPU_PER128)
 qeph_forces_kernel(const __grid_constant__ ShellParams P)
 {
   const ShellSG& g = P.sg;
@@ -121,7 +121,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     order = g.order0 + e;
     double px[4], py[4], pz[4];
     #pragma unroll
-    for (int k = 0; k < 4; k++) { const double4 p = P.nd.pos[nc[k]]; px[k] = p.x; py[k] = p.y; pz[k] = p.z; }
+    for (int k = 0; k < 4; k++) { const double4 p = ld256_nc(P.nd.pos + nc[k]); px[k] = p.x; py[k] = p.y; pz[k] = p.z; }
     #pragma unroll
     for (int k = 0; k < 4; k++) { prefetch_l1(P.nd.rot + nc[k]); prefetch_l1(P.nd.vel + nc[k]); }
     if (STAGED) mbar_wait(&s_bar, 0);                     // the state tile has landed (issued before the gather)
@@ -220,7 +220,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     double RL[3][4];                                     // RL[2][k] = e3 component (used only when warped)
     #pragma unroll
     for (int k = 0; k < 4; k++) {
-      const double4 w = P.nd.rot[nc[k]];
+      const double4 w = ld256_nc(P.nd.rot + nc[k]);
       RL[0][k] = VQ[0][0] * w.x + VQ[1][0] * w.y + VQ[2][0] * w.z;
       RL[1][k] = VQ[0][1] * w.x + VQ[1][1] * w.y + VQ[2][1] * w.z;
       RL[2][k] = VQ[0][2] * w.x + VQ[1][2] * w.y + VQ[2][2] * w.z;
@@ -229,7 +229,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     {
       double vx[4], vy[4], vz[4];
       #pragma unroll
-      for (int k = 0; k < 4; k++) { const double4 v = P.nd.vel[nc[k]]; vx[k] = v.x; vy[k] = v.y; vz[k] = v.z; }
+      for (int k = 0; k < 4; k++) { const double4 v = ld256_nc(P.nd.vel + nc[k]); vx[k] = v.x; vy[k] = v.y; vz[k] = v.z; }
       const double G13x = vx[0] - vx[2], G24x = vx[1] - vx[3], GHx = vx[0] - vx[1] + vx[2] - vx[3];
       const double G13y = vy[0] - vy[2], G24y = vy[1] - vy[3], GHy = vy[0] - vy[1] + vy[2] - vy[3];
       const double G13z = vz[0] - vz[2], G24z = vz[1] - vz[3], GHz = vz[0] - vz[1] + vz[2] - vz[3];
@@ -619,11 +619,11 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
         if (dead) { f[I] = K_ZERO; mm[I] = K_ZERO; }
       }
       const double fac = (J & 1) ? FACN2 : FACN1;
-      double2* row = reinterpret_cast<double2*>(P.fsky + (size_t)8 * sl[J]);
-      row[0] = make_double2(-f[0], -f[1]); row[1] = make_double2(-f[2], -mm[0]);
-      row[2] = make_double2(-mm[1], -mm[2]); row[3] = make_double2(STI * fac, K_ZERO * fac);
+      double4* row = reinterpret_cast<double4*>(P.fsky + (size_t)8 * sl[J]);
+      st256(row, make_double4(-f[0], -f[1], -f[2], -mm[0]));
+      st256(row + 1, make_double4(-mm[1], -mm[2], STI * fac, K_ZERO * fac));
     }
   }
   if (STAGED) tile_store(g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
-  block_dt_reduce<false>(dt_cand, order, g.ngl, g.order0, P.db, g.blk0 + blockIdx.x);
+  warp_dt_reduce<false>(dt_cand, order, g.ngl, g.order0, P.db, g.blk0 + blockIdx.x * (ORGPU_TILE / 32) + (threadIdx.x >> 5));
 }

@@ -122,7 +122,7 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
     if (sh_upload(S.owned, &dconn, conn_t) || sh_upload(S.owned, &dngl, ngl) || sh_upload(S.owned, &d.slab, H.h)) return -100;
     d.conn = dconn; d.ngl = dngl;
     if (sh_alloc(S.owned, &d.smstr, (size_t)6 * np)) return -100;
-    const int nblk = np / ORGPU_SHELL_CTA;
+    const int nblk = np / 32;                            // dt candidate slots: one per warp
     if (fa.nsg >= ORGPU_MAX_SG) { orgpu_set_error("too many super-groups (%d)", ORGPU_MAX_SG); return -6; }
     fa.sg[fa.nsg++] = SGRange{blk, nblk, shell_is_qeph(G.prop) ? ORGPU_FAM_SHELL_QEPH : ORGPU_FAM_SHELL_BT};
     order += ne; blk += nblk; gi = gj;
@@ -136,7 +136,7 @@ static void shell_launch_one(K kern_staged, K kern_direct, const ShellParams& P,
   const size_t bytes = (size_t)P.sg.nw * ORGPU_TILE * 8;
 #ifndef ORGPU_NO_STAGING
   if (bytes <= ORGPU_STAGE_MAX_BYTES) {
-    stage_attr((const void*)kern_staged, bytes, 3);
+    stage_attr((const void*)kern_staged, bytes, ORGPU_SHELL_MINB);
     kern_staged<<<nblk, ORGPU_SHELL_CTA, bytes, st>>>(P);
     return;
   }
