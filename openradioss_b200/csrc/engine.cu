@@ -285,7 +285,7 @@ int orgpu_finalize(orgpu_engine* e)
     if (push_dev(S.owned, &d.smstr, (size_t)21 * np)) return -100;
     const int nblk = np / 32;                            // dt candidate slots: one per warp
     NEED(e->fa.nsg < ORGPU_MAX_SG, -6, "too many super-groups (%d)", ORGPU_MAX_SG);
-    e->fa.sg[e->fa.nsg++] = SGRange{blk, nblk, ORGPU_FAM_BRICK};
+    e->fa.sg[e->fa.nsg++] = SGRange{blk, nblk, ORGPU_FAM_BRICK, d.order0, d.ngl};
     order += ne; blk += nblk; gi = gj;
   }
   NEED(blk > 0, -4, "orgpu_finalize: no element groups");

@@ -142,7 +142,7 @@ node_advance_kernel(const __grid_constant__ DevNodes nd, const CycleState* __res
 
 // device-resident loop: gather + update in one pass, A never leaves registers
 template <int ROWW>
-__global__ void __launch_bounds__(ORGPU_NODE_BLOCK)
+__global__ void __launch_bounds__(ORGPU_NODE_BLOCK, ORGPU_NODE_MINB)
 node_fused_kernel(const __grid_constant__ DevNodes nd, const double* __restrict__ fsky,
                   const CycleState* __restrict__ cs, int iroddl)
 {

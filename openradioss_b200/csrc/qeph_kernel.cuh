@@ -625,5 +625,5 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     }
   }
   if (STAGED) tile_store(g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
-  warp_dt_reduce<false>(dt_cand, order, g.ngl, g.order0, P.db, g.blk0 + blockIdx.x * (ORGPU_TILE / 32) + (threadIdx.x >> 5));
+  warp_dt_reduce<false>(dt_cand, order, P.db, g.blk0 + blockIdx.x * (ORGPU_TILE / 32) + (threadIdx.x >> 5));
 }
