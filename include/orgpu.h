@@ -97,6 +97,13 @@ int  orgpu_comm_init(orgpu_engine* e, int nranks, int rank, const unsigned char 
 int  orgpu_set_exchange(orgpu_engine* e, int nneigh, const int* ranks, const int* send_ptr, const int* send_slots,
                         const int* recv_ptr, const int* recv_slots);
 int  orgpu_exchange(orgpu_engine* e);   /* phased mode: pack -> NCCL -> unpack on the library stream */
+/*    Peer-memory exchange (ranks of one NVLink / NVSwitch node): after orgpu_set_exchange every rank exports
+ *    the CUDA IPC handle of its receive window, the host gathers the nranks handles (MPI_ALLGATHER /
+ *    torch.distributed) and every rank connects.  From then on orgpu_run_cycles pushes the corner rows and
+ *    the dt candidate straight into the neighbours' HBM with its own kernels (no NCCL call in the cycle,
+ *    one CUDA graph per cycle); SPMD_EXCH2_A_PON / SPMD_GLOB_MIN5 semantics are unchanged. */
+int  orgpu_p2p_export(orgpu_engine* e, unsigned char handle[64]);
+int  orgpu_p2p_connect(orgpu_engine* e, const unsigned char* handles /*[nranks][64] in rank order*/);
 
 /* -- host-buffer convenience used for end-to-end timing: upload X,V(,VR), run, download X,V,A */
 int  orgpu_step_host(orgpu_engine* e, const double* X, const double* V, const double* VR,

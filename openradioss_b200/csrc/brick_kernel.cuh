@@ -520,8 +520,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       }
     }
   }
-  if (STAGED) tile_store(g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
-  warp_dt_reduce<true>(dt_cand, order, P.db, g.blk0 + blockIdx.x * (ORGPU_TILE / 32) + (threadIdx.x >> 5));
+  cta_epilogue<true, STAGED>(dt_cand, order, P.db, g.blk0 + blockIdx.x, g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
 }
 
 template <int JHBE, int ISMSTR>

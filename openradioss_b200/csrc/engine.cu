@@ -139,6 +139,9 @@ int orgpu_destroy(orgpu_engine* e)
   { Exchange& x = e->xc;
     void* xp[] = {x.d_send_slots, x.d_recv_slots, x.d_sendbuf, x.d_recvbuf, x.d_cand_send, x.d_cand_recv, x.d_slots_tmp, x.d_rows_tmp};
     for (void* p : xp) if (p) cudaFree(p);
+    for (size_t q = 0; q < x.peer.size(); q++) if (x.peer[q] && (int)q != x.rank) cudaIpcCloseMemHandle(x.peer[q]);
+    void* pp[] = {x.win, x.d_send_nb, x.d_nb_sendptr, x.d_nb_rows, x.d_peer_cand, x.d_peer_flag, x.d_xcycle, x.d_done, x.d_err};
+    for (void* p : pp) if (p) cudaFree(p);
     if (x.comm && nccl_api()) nccl_api()->CommDestroy(x.comm); }
   for (auto ev : e->evpool) cudaEventDestroy(ev);
   if (e->ev0) cudaEventDestroy(e->ev0); if (e->ev1) cudaEventDestroy(e->ev1);
@@ -283,7 +286,7 @@ int orgpu_finalize(orgpu_engine* e)
     if (upload_vec(S.owned, &dconn, conn_t) || upload_vec(S.owned, &dngl, ngl) || upload_vec(S.owned, &d.slab, H.h)) return -100;
     d.conn = dconn; d.ngl = dngl;
     if (push_dev(S.owned, &d.smstr, (size_t)21 * np)) return -100;
-    const int nblk = np / 32;                            // dt candidate slots: one per warp
+    const int nblk = np / ORGPU_TILE;                    // dt candidate slots: one per CTA
     NEED(e->fa.nsg < ORGPU_MAX_SG, -6, "too many super-groups (%d)", ORGPU_MAX_SG);
     e->fa.sg[e->fa.nsg++] = SGRange{blk, nblk, ORGPU_FAM_BRICK, d.order0, d.ngl};
     order += ne; blk += nblk; gi = gj;
@@ -376,10 +379,49 @@ static int exchange_on_stream(orgpu_engine* e, bool with_dt)
   return 0;
 }
 
+// peer-memory exchange on the stream: push rows + dt candidate into the neighbours' windows, then wait for
+// theirs, scatter them and advance the clock (exchange.cuh).  Pure kernels: capturable in a CUDA graph.
+static void p2p_exchange_on_stream(orgpu_engine* e)
+{
+  Exchange& x = e->xc;
+  const int V = e->roww / 4;
+  { const int nthr = x.nsend * V > 1 ? x.nsend * V : 1; const int nb = (nthr + 255) / 256;
+    if (e->roww == 8) p2p_push_kernel<8><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_send_slots, x.d_send_nb, x.d_nb_sendptr, x.d_nb_rows, x.nsend, e->d_cs, x.d_peer_cand, x.d_peer_flag, x.nranks, x.rank, x.d_xcycle, x.d_done);
+    else              p2p_push_kernel<4><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_send_slots, x.d_send_nb, x.d_nb_sendptr, x.d_nb_rows, x.nsend, e->d_cs, x.d_peer_cand, x.d_peer_flag, x.nranks, x.rank, x.d_xcycle, x.d_done);
+    e->launches++; }
+  { const int nthr = x.nrecv * V > 1 ? x.nrecv * V : 1; const int nb = (nthr + 255) / 256;
+    if (e->roww == 8) p2p_wait_unpack_kernel<8><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_recv_slots, x.nrecv, x.win, e->d_cs, x.nranks, x.d_xcycle, x.d_err);
+    else              p2p_wait_unpack_kernel<4><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_recv_slots, x.nrecv, x.win, e->d_cs, x.nranks, x.d_xcycle, x.d_err);
+    e->launches++; }
+}
+
 int orgpu_run_cycles(orgpu_engine* e, int ncycles)
 {
   NEED(e && e->finalized && ncycles >= 0, -1, "orgpu_run_cycles: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
   const int per_cycle = (int)(e->csg.size() + e->bsg.size()) + 2;   // force kernels + dt finalize + node kernel
+  if (e->xc.nranks > 1 && e->xc.p2p && !e->profile) {
+    // one process per GPU, peer-memory exchange: the whole cycle (forces, dt fold, push, wait+unpack, gather+update)
+    // is one CUDA graph, replayed ncycles times with no host involvement and no library call
+    const int per = (int)(e->csg.size() + e->bsg.size()) + 4;
+    if (!e->gexec) {
+      cudaGraph_t g;
+      CUDA_OK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeThreadLocal));
+      const long long l0 = e->launches;
+      launch_element_phase(e, 0, nullptr);
+      p2p_exchange_on_stream(e);
+      launch_node_fused(e->nd, e->d_fsky, e->roww, e->d_cs, e->ctl.iroddl, e->st);
+      e->launches = l0;                      // the capture pass did not execute
+      CUDA_OK(cudaStreamEndCapture(e->st, &g));
+      CUDA_OK(cudaGraphInstantiate(&e->gexec, g, 0));
+      CUDA_OK(cudaGraphDestroy(g));
+    }
+    CUDA_OK(cudaEventRecord(e->ev0, e->st));
+    for (int c = 0; c < ncycles; c++) CUDA_OK(cudaGraphLaunch(e->gexec, e->st));
+    CUDA_OK(cudaEventRecord(e->ev1, e->st));
+    e->launches += (long long)per * ncycles;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   if (e->xc.nranks > 1) {
     // one process per GPU: element phase writes the local dt candidate only; the exchange folds all
     // ranks' candidates and advances the clock; then the ordered gather + nodal update
@@ -392,7 +434,8 @@ int orgpu_run_cycles(orgpu_engine* e, int ncycles)
       size_t evi = 0;
       for (int c = 0; c < nc; c++) {
         launch_element_phase(e, 0, prof ? &evi : nullptr);
-        { int rc = exchange_on_stream(e, true); if (rc) return rc; }
+        if (e->xc.p2p) p2p_exchange_on_stream(e);
+        else { int rc = exchange_on_stream(e, true); if (rc) return rc; }
         if (prof) cudaEventRecord(get_event(e, evi++), e->st);
         launch_node_fused(e->nd, e->d_fsky, e->roww, e->d_cs, e->ctl.iroddl, e->st); e->launches++;
         if (prof) cudaEventRecord(get_event(e, evi++), e->st);
@@ -462,6 +505,8 @@ int orgpu_synchronize(orgpu_engine* e)
 {
   NEED(e, -1, "null handle"); CUDA_OK(cudaSetDevice(e->device));
   CUDA_OK(cudaStreamSynchronize(e->st));
+  if (e->xc.p2p) { int err = 0; CUDA_OK(cudaMemcpy(&err, e->xc.d_err, 4, cudaMemcpyDeviceToHost));
+                   NEED(err == 0, -8, "orgpu: peer-memory exchange timed out waiting for a neighbour's rows (a rank stopped stepping)"); }
   if (!e->profile) { float ms = 0; if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_run_ms = ms; else cudaGetLastError(); }
   return 0;
 }
@@ -615,6 +660,69 @@ int orgpu_set_exchange(orgpu_engine* e, int nneigh, const int* ranks, const int*
       dev_alloc(&x.d_sendbuf, (size_t)e->roww * (x.nsend + 1)) || dev_alloc(&x.d_recvbuf, (size_t)e->roww * (x.nrecv + 1))) return -100;
   if (x.nsend) CUDA_OK(cudaMemcpy(x.d_send_slots, send_slots, 4 * (size_t)x.nsend, cudaMemcpyHostToDevice));
   if (x.nrecv) CUDA_OK(cudaMemcpy(x.d_recv_slots, recv_slots, 4 * (size_t)x.nrecv, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int orgpu_p2p_export(orgpu_engine* e, unsigned char handle[64])
+{
+  NEED(e && e->finalized && handle, -1, "orgpu_p2p_export: engine not finalized / bad arguments"); CUDA_OK(cudaSetDevice(e->device));
+  Exchange& x = e->xc;
+  NEED(x.nranks > 1 && !x.nb_rank.empty(), -7, "orgpu_p2p_export: call orgpu_comm_init and orgpu_set_exchange first");
+  NEED(x.nranks <= 32, -7, "orgpu_p2p_export: more than 32 ranks on one node");
+  NEED(!x.win, -7, "orgpu_p2p_export: window already exported");
+  x.win_bytes = win_rows_off(x.nranks) + (size_t)2 * (x.nrecv + 1) * e->roww * 8;
+  CUDA_OK(cudaMalloc((void**)&x.win, x.win_bytes));
+  CUDA_OK(cudaMemset(x.win, 0, x.win_bytes));
+  std::vector<int> hdr(256, -1); hdr[0] = x.nranks; hdr[1] = x.nrecv;
+  for (size_t k = 0; k < x.nb_rank.size(); k++) hdr[2 + x.nb_rank[k]] = x.recv_ptr[k];
+  CUDA_OK(cudaMemcpy(x.win, hdr.data(), 1024, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h; CUDA_OK(cudaIpcGetMemHandle(&h, x.win));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle, &h, 64);
+  return 0;
+}
+
+int orgpu_p2p_connect(orgpu_engine* e, const unsigned char* handles /*[nranks][64], rank order*/)
+{
+  NEED(e && e->finalized && handles, -1, "orgpu_p2p_connect: bad arguments"); CUDA_OK(cudaSetDevice(e->device));
+  Exchange& x = e->xc;
+  NEED(x.win, -7, "orgpu_p2p_connect: call orgpu_p2p_export first");
+  const int R = x.nranks, nn = (int)x.nb_rank.size();
+  x.peer.assign(R, nullptr); x.peer[x.rank] = x.win;
+  for (int q = 0; q < R; q++) {
+    if (q == x.rank) continue;
+    cudaIpcMemHandle_t h; memcpy(&h, handles + (size_t)64 * q, 64);
+    void* p = nullptr; CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    x.peer[q] = (unsigned char*)p;
+  }
+  // where do my rows land in each neighbour's window, and how long is its row area (for the parity offset)
+  std::vector<double*> nb_rows(2 * (nn > 0 ? nn : 1), nullptr);
+  for (int k = 0; k < nn; k++) {
+    const int q = x.nb_rank[k]; int hdr[64];
+    CUDA_OK(cudaMemcpy(hdr, x.peer[q], sizeof hdr, cudaMemcpyDefault));
+    NEED(hdr[0] == R && 2 + x.rank < 64 && hdr[2 + x.rank] >= 0, -7, "orgpu_p2p_connect: rank %d does not list rank %d as a neighbour", q, x.rank);
+    const int off = hdr[2 + x.rank], nrecv_q = hdr[1];
+    double* rows = reinterpret_cast<double*>(x.peer[q] + win_rows_off(R));
+    nb_rows[2 * k] = rows + (size_t)off * e->roww;
+    nb_rows[2 * k + 1] = rows + ((size_t)nrecv_q + off) * e->roww;
+  }
+  std::vector<int> send_nb(x.nsend > 0 ? x.nsend : 1, 0), sendptr(nn > 0 ? nn : 1, 0);
+  for (int k = 0; k < nn; k++) { sendptr[k] = x.send_ptr[k]; for (int j = x.send_ptr[k]; j < x.send_ptr[k + 1]; j++) send_nb[j] = k; }
+  std::vector<double*> pcand(R); std::vector<unsigned long long*> pflag(R);
+  for (int q = 0; q < R; q++) { pcand[q] = reinterpret_cast<double*>(x.peer[q] + ORGPU_WIN_CAND);
+                                pflag[q] = reinterpret_cast<unsigned long long*>(x.peer[q] + ORGPU_WIN_FLAGS) + x.rank; }
+  if (dev_alloc(&x.d_send_nb, send_nb.size()) || dev_alloc(&x.d_nb_sendptr, sendptr.size()) || dev_alloc(&x.d_nb_rows, nb_rows.size()) ||
+      dev_alloc(&x.d_peer_cand, (size_t)R) || dev_alloc(&x.d_peer_flag, (size_t)R) || dev_alloc(&x.d_xcycle, 1) || dev_alloc(&x.d_done, 1) ||
+      dev_alloc(&x.d_err, 1)) return -100;
+  CUDA_OK(cudaMemcpy(x.d_send_nb, send_nb.data(), 4 * send_nb.size(), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(x.d_nb_sendptr, sendptr.data(), 4 * sendptr.size(), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(x.d_nb_rows, nb_rows.data(), 8 * nb_rows.size(), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(x.d_peer_cand, pcand.data(), 8 * (size_t)R, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(x.d_peer_flag, pflag.data(), 8 * (size_t)R, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaDeviceSynchronize());
+  if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
+  x.p2p = true;
   return 0;
 }
 

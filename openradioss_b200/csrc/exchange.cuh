@@ -53,7 +53,121 @@ struct Exchange {
   double* d_cand_recv = nullptr;                       // 4 doubles per rank
   // scratch for the host-staged entry points
   int* d_slots_tmp = nullptr; double* d_rows_tmp = nullptr; size_t tmp_cap = 0;
+  // ---- peer-memory exchange (one-sided pushes over NVLink into the neighbours' windows; see below)
+  unsigned char* win = nullptr; size_t win_bytes = 0;   // this rank's receive window (cudaMalloc, exported by CUDA IPC)
+  std::vector<unsigned char*> peer;                     // every rank's window mapped here (peer[rank] = win)
+  bool p2p = false;
+  int* d_send_nb = nullptr; int* d_nb_sendptr = nullptr;
+  double** d_nb_rows = nullptr;                          // [nneigh][2] destination of neighbour k's rows, per parity
+  double** d_peer_cand = nullptr;                        // [nranks] candidate area of every window
+  unsigned long long** d_peer_flag = nullptr;            // [nranks] &flags[rank] inside every window
+  unsigned long long* d_xcycle = nullptr; unsigned int* d_done = nullptr; int* d_err = nullptr;
 };
+
+// ---- peer-memory exchange --------------------------------------------------------------------------
+// Replaces pack -> NCCL send/recv -> unpack by two kernels of ours and no library call, so the multi-GPU
+// cycle is one CUDA graph like the single-GPU one.  Every rank owns a receive WINDOW in its HBM:
+//   int   hdr[256]            [0]=nranks [1]=nrecv [2+q]=first row of the rows rank q sends here (-1: not a neighbour)
+//   u64   flags[nranks]       flags[q] = last exchange cycle rank q has completely pushed into this window
+//   f64   cand[2][nranks][4]  (dt2t, ityptst, neltst, -) of rank q for cycle parity p
+//   f64   rows[2][nrecv][roww] received corner rows for cycle parity p
+// p2p_push_kernel copies this rank's send rows straight from its skyline into the neighbours' windows with
+// 256-bit stores over NVLink (peer pointers from cudaIpcOpenMemHandle), and its last CTA then publishes the dt
+// candidate to every rank and releases flags[rank] = cycle with system scope.  p2p_wait_unpack_kernel
+// acquires all flags >= cycle, scatters the received rows into their reserved FSKY slots and folds the
+// candidates in rank order (GLOB_MIN).  Two parities: a neighbour may run one exchange ahead, never two
+// (its next push comes after its own wait on OUR flag of the cycle in between).
+__device__ __forceinline__ size_t win_rows_off_dev(int nranks) { return 2048 + (((size_t)2 * nranks * 32 + 255) / 256) * 256; }
+__device__ __forceinline__ double4 ld256_cg(const double4* p) {      // L2 only: written by a peer GPU during this kernel
+  double4 v; asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p) : "memory"); return v; }
+#define ORGPU_WIN_FLAGS 1024
+#define ORGPU_WIN_CAND 2048
+static inline size_t win_rows_off(int nranks) { return ORGPU_WIN_CAND + (((size_t)2 * nranks * 32 + 255) / 256) * 256; }
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+
+template <int ROWW>
+__global__ void __launch_bounds__(256)
+p2p_push_kernel(const double* __restrict__ fsky, const int* __restrict__ send_slots, const int* __restrict__ send_nb,
+                const int* __restrict__ nb_sendptr, double* const* __restrict__ nb_rows, int nsend,
+                const CycleState* cs, double* const* __restrict__ peer_cand, unsigned long long* const* __restrict__ peer_flag,
+                int nranks, int rank, unsigned long long* xcycle, unsigned int* done)
+{
+  const unsigned long long c = *reinterpret_cast<volatile unsigned long long*>(xcycle) + 1ull;   // the exchange being pushed
+  const int par = (int)(c & 1ull);
+  constexpr int V = ROWW / 4;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nsend * V) {
+    const int j = i / V, cc = i - j * V, nb = send_nb[j];
+    double* dst = nb_rows[2 * nb + par] + (size_t)(j - nb_sendptr[nb]) * ROWW + 4 * cc;
+    st256(reinterpret_cast<double4*>(dst), ld256(reinterpret_cast<const double4*>(fsky + (size_t)send_slots[j] * ROWW + 4 * cc)));
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {                      // last CTA: every row of this rank is on its way
+      *done = 0u;
+      const double d0 = cs->dt2t, d1 = (double)cs->ityptst, d2 = (double)cs->neltst;
+      for (int q = 0; q < nranks; q++) {
+        double* cd = peer_cand[q] + ((size_t)par * nranks + rank) * 4;
+        cd[0] = d0; cd[1] = d1; cd[2] = d2; cd[3] = 0.0;
+      }
+      __threadfence_system();
+      for (int q = 0; q < nranks; q++) st_release_sys(peer_flag[q], c);
+      *reinterpret_cast<volatile unsigned long long*>(xcycle) = c;
+    }
+  }
+}
+
+template <int ROWW>
+__global__ void __launch_bounds__(256)
+p2p_wait_unpack_kernel(double* __restrict__ fsky, const int* __restrict__ recv_slots, int nrecv, const unsigned char* win,
+                       CycleState* cs, int nranks, const unsigned long long* xcycle, int* err)
+{
+  const unsigned long long c = *reinterpret_cast<const volatile unsigned long long*>(xcycle);
+  const int par = (int)(c & 1ull);
+  if (threadIdx.x == 0) {
+    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(win + ORGPU_WIN_FLAGS);
+    const long long t0 = clock64();
+    for (int q = 0; q < nranks; q++) {
+      while (ld_acquire_sys(flags + q) < c) {
+        if (clock64() - t0 > 8000000000ll) { *err = 1; break; }      // ~4 s: a peer died; never hang the GPU
+        __nanosleep(100);
+      }
+    }
+  }
+  __syncthreads();
+  constexpr int V = ROWW / 4;
+  const double* rows = reinterpret_cast<const double*>(win + win_rows_off_dev(nranks)) + (size_t)par * nrecv * ROWW;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nrecv * V) {
+    const int j = i / V, cc = i - j * V;
+    const double4 v = ld256_cg(reinterpret_cast<const double4*>(rows + (size_t)j * ROWW + 4 * cc));
+    st256(reinterpret_cast<double4*>(fsky + (size_t)recv_slots[j] * ROWW + 4 * cc), v);
+  }
+  if (i == 0) {                                       // GLOB_MIN over the ranks + RESOL bookkeeping (as rows_unpack_kernel)
+    const double* cand = reinterpret_cast<const double*>(win + ORGPU_WIN_CAND) + (size_t)par * nranks * 4;
+    double cur = K_EP06; int typ = 0, ngl = 0;
+    for (int r = 0; r < nranks; r++) {
+      const double d = __ldcg(cand + 4 * r);
+      if (d < cur) { cur = d; typ = (int)__ldcg(cand + 4 * r + 1); ngl = (int)__ldcg(cand + 4 * r + 2); }
+    }
+    cs->dt2t = cur; cs->ityptst = typ; cs->neltst = ngl;
+    const double dt1 = cs->dt2;
+    double dt2 = K_EP06;
+    if (cur < dt2) dt2 = cur;
+    const double c11 = (double)1.1f;
+    dt2 = fmin(dt2, fmin(c11 * cs->dt2old, cs->dtmx));
+    cs->dt2old = dt2;
+    cs->dt12 = K_HALF * (dt1 + dt2);
+    cs->dt1 = dt1; cs->dt2 = dt2;
+    cs->tt = cs->tt + dt2; cs->ncycle += 1;
+  }
+}
 
 // rows out of the skyline into a contiguous buffer; ROWW doubles per row on both sides
 template <int ROWW>

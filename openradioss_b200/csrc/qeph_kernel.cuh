@@ -624,6 +624,5 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       st256(row + 1, make_double4(-mm[1], -mm[2], STI * fac, K_ZERO * fac));
     }
   }
-  if (STAGED) tile_store(g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
-  warp_dt_reduce<false>(dt_cand, order, P.db, g.blk0 + blockIdx.x * (ORGPU_TILE / 32) + (threadIdx.x >> 5));
+  cta_epilogue<false, STAGED>(dt_cand, order, P.db, g.blk0 + blockIdx.x, g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
 }

@@ -122,7 +122,7 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
     if (sh_upload(S.owned, &dconn, conn_t) || sh_upload(S.owned, &dngl, ngl) || sh_upload(S.owned, &d.slab, H.h)) return -100;
     d.conn = dconn; d.ngl = dngl;
     if (sh_alloc(S.owned, &d.smstr, (size_t)6 * np)) return -100;
-    const int nblk = np / 32;                            // dt candidate slots: one per warp
+    const int nblk = np / ORGPU_TILE;                    // dt candidate slots: one per CTA
     if (fa.nsg >= ORGPU_MAX_SG) { orgpu_set_error("too many super-groups (%d)", ORGPU_MAX_SG); return -6; }
     fa.sg[fa.nsg++] = SGRange{blk, nblk, shell_is_qeph(G.prop) ? ORGPU_FAM_SHELL_QEPH : ORGPU_FAM_SHELL_BT, d.order0, d.ngl};
     order += ne; blk += nblk; gi = gj;

@@ -17,7 +17,7 @@ EXPORTS = """create destroy last_error upload_nodes set_loads set_bcs set_solids
 set_functions add_solid_group add_shell_group finalize forces_phase assemble advance run_cycles
 synchronize get_time download_nodes download_fsky download_solid_state download_shell_state
 step_host launch_count last_run_ms set_profile get_profile pack_rows unpack_rows comm_unique_id comm_init
-set_exchange exchange get_energies""".split()
+set_exchange exchange get_energies p2p_export p2p_connect""".split()
 
 
 def load_library() -> C.CDLL:
@@ -45,9 +45,11 @@ class Engine(Binding):
                    C.c_int(ncycles), Xout.ctypes.data_as(C.c_void_p), Vout.ctypes.data_as(C.c_void_p))
 
     # -- one process per GPU: NCCL exchange inside run_cycles ------------------------------------
-    def comm_init(self, dist, domain):
+    def comm_init(self, dist, domain, p2p=True):
         """Create the NCCL communicator (id from rank 0, broadcast through torch.distributed) and
-        register the neighbour send / receive slot lists of this rank's Domain."""
+        register the neighbour send / receive slot lists of this rank's Domain.  With p2p (default, ranks of
+        one NVLink node) the receive windows are then exchanged through CUDA IPC and run_cycles uses the
+        library's own peer-memory exchange kernels instead of NCCL."""
         import torch
         rank, world = dist.get_rank(), dist.get_world_size()
         uid = (C.c_ubyte * 128)()
@@ -67,6 +69,15 @@ class Engine(Binding):
         rs = np.concatenate([nb.recv for nb in nbs]).astype(np.int32) if nbs else np.zeros(0, np.int32)
         self._call("set_exchange", self.h, C.c_int(len(nbs)), _opt(ranks, np.int32), _opt(sp, np.int32), _opt(ss, np.int32),
                    _opt(rp, np.int32), _opt(rs, np.int32))
+        if p2p and os.environ.get("ORGPU_NO_P2P", "0") != "1":
+            h = (C.c_ubyte * 64)()
+            self._call("p2p_export", self.h, h)
+            mine = torch.tensor(list(h), dtype=torch.uint8, device=dev)
+            allh = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine)                       # also orders "window initialised" before "peers read it"
+            flat = np.concatenate([t_.cpu().numpy() for t_ in allh]).astype(np.uint8)
+            self._call("p2p_connect", self.h, flat.ctypes.data_as(C.c_void_p))
+            dist.barrier()
 
     def exchange(self): self._call("exchange", self.h)
 

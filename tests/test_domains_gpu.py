@@ -2,7 +2,8 @@
 
 1 GPU: two Engine handles play two domains, rows travel through the host-staged C-ABI entry points
 (orgpu_pack_rows / orgpu_unpack_rows) -- nodal sums must be bitwise those of the single-domain run.
->= 2 GPUs: one process per GPU, NCCL exchange + dt fold inside orgpu_run_cycles (skipped on 1 GPU)."""
+>= 2 GPUs: one process per GPU, exchange + dt fold inside orgpu_run_cycles, once through the library's own
+peer-memory kernels (CUDA IPC windows over NVLink, one CUDA graph per cycle) and once through NCCL (skipped on 1 GPU)."""
 import os
 import numpy as np
 import pytest
@@ -48,7 +49,7 @@ def test_host_staged_domains_bitwise(nproc):
             assert np.array_equal(x["X"], xr["X"][d.node_gid]) and np.array_equal(x["V"], xr["V"][d.node_gid])
 
 
-def _nccl_worker(rank, world, port, q, kind):
+def _nccl_worker(rank, world, port, q, kind, p2p=True):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -56,8 +57,9 @@ def _nccl_worker(rank, world, port, q, kind):
     m = dict(models())[kind]
     d = domdec.decompose_strips(m, world, rank)
     g = Engine(d.model, device=rank)
-    g.comm_init(dist, d)
-    g.run_cycles(40); g.synchronize()
+    g.comm_init(dist, d, p2p=p2p)
+    g.run_cycles(25); g.synchronize()
+    g.run_cycles(15); g.synchronize()          # a second call replays the captured graph / re-enters the exchange
     out = g.download_nodes(("X", "V"))
     q.put((rank, d.node_gid, out["X"], out["V"], g.time()))
     dist.barrier()
@@ -65,14 +67,15 @@ def _nccl_worker(rank, world, port, q, kind):
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("p2p", [True, False], ids=["peer_memory", "nccl"])
 @pytest.mark.parametrize("kind", ["shell", "brick"])
-def test_nccl_domains_match_single_gpu_bitwise(kind):
+def test_multi_gpu_domains_match_single_gpu_bitwise(kind, p2p):
     import torch.multiprocessing as mp
     world = min(4, torch.cuda.device_count())
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q, kind)) for r in range(world)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q, kind, p2p)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
