@@ -31,10 +31,20 @@ B_ALG = {
 }
 
 
+STRONG = ("c3_plate_qeph_4m", "c4_tube", "c4_tube_small", "c1_taylor_bar")    # total model fixed, cut into `world` domains
+
+
 def workload(name, world=1):
-    """Global model of the run: per-GPU work is fixed (weak scaling), the mesh grows along the
-    decomposition axis with the GPU count and is cut into `world` strips / slabs."""
+    """Global model of the run.  Weak-scaling workloads (c2, c5): per-GPU work is fixed, the mesh grows along
+    the decomposition axis with the GPU count.  Strong-scaling ones (c1, c3, c4): the BASELINE model, cut into
+    `world` strips / slabs.  Returns (model, family of the dominant kernel, decomposition axis)."""
     from openradioss_b200 import meshgen
+    if name == "c3_plate_qeph_4m":          # C3: 2000 x 2000 QEPH shells, LAW36, x strips
+        return meshgen.shell_plate(2000, 2000, 2000.0, 2000.0, pulse_tau=0.05), "shell", 0
+    if name == "c4_tube":                   # C4: 2.0 M QEPH shells (LAW36) + 501 k bricks (LAW2), imposed-velocity crush, z slabs
+        return meshgen.crush_tube(708, 706, 1), "mixed", 2
+    if name == "c4_tube_small":
+        return meshgen.crush_tube(100, 100, 1), "mixed", 2
     if name == "c5_brick_slab_2m":          # C5: 200 x 200 x 50 bricks (2 M) per GPU, z slabs, LAW2
         return meshgen.hex_block(200, 200, 50 * world, 200.0, 200.0, 50.0 * world, vrand=1.0, vseed=12345), "brick", 2
     if name == "c1_taylor_bar":
@@ -42,7 +52,7 @@ def workload(name, world=1):
     if name == "brick_small":
         return meshgen.hex_block(40, 40, 40 * world, 40.0, 40.0, 40.0 * world, vrand=1.0), "brick", 2
     if name == "c2_plate_qeph_1m":          # C2 / C3: 1000 x 1000 QEPH shells per GPU (x strips), LAW36, NPT=5
-        return meshgen.shell_plate(1000 * world, 1000, 1000.0 * world, 1000.0), "shell", 0
+        return meshgen.shell_plate(1000 * world, 1000, 1000.0 * world, 1000.0, pulse_tau=0.05), "shell", 0
     if name == "plate_small":
         return meshgen.shell_plate(200 * world, 200, 1000.0 * world, 1000.0), "shell", 0
     raise SystemExit(f"unknown workload {name}")
@@ -180,10 +190,13 @@ def main():
     prof = {k: g.profile(i) for i, k in enumerate(("brick_forces", "shell_forces", "node"))}
     g.set_profile(False)
     peak, peak_src = peaks()
-    dom = "shell_forces" if fam == "shell" else "brick_forces"
+    dom = "brick_forces" if fam == "brick" else "shell_forces"
     dms, dn = prof[dom]
-    b = B_ALG[fam]
-    ach = (b["forces"] * ne) / (dms / dn * 1e-3) / 1e9 if dn else 0.0
+    b = B_ALG["brick" if fam == "brick" else "shell"]
+    ne_dom = m.numels if fam == "brick" else m.numelc       # elements the dominant kernel processes per launch
+    if fam == "mixed":                                      # whole-cycle bytes: weighted sum of both families
+        b = dict(b, total=(B_ALG["shell"]["total"] * m.numelc + B_ALG["brick"]["total"] * m.numels) / max(ne, 1))
+    ach = (b["forces"] * ne_dom) / (dms / dn * 1e-3) / 1e9 if dn else 0.0
     nms, nn = prof["node"]
     roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "traffic": None, "peak_source": peak_src, "bytes_per_element": b["forces"],
@@ -235,7 +248,7 @@ def main():
     if rank == 0:
         line = {"metric": "element-cycles/sec", "value": value, "unit": "element-cycles/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "strong" if args.workload in STRONG else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": args.workload, "family": fam, "elements_per_gpu": ne, "nodes_per_gpu": n,
                            "l2": "inputs larger than L2 (element state >> 126 MB)" if ne >= 500000 else "working set may fit L2",
                            "parallelism": f"domains={world}" + ("" if world == 1 else " (strips, NCCL corner-row exchange + dt fold per cycle)")},

@@ -42,6 +42,14 @@ int  orgpu_upload_nodes(orgpu_engine* e, const double* X, const double* V, const
                         const double* D, const double* MS, const double* IN);
 int  orgpu_set_loads(orgpu_engine* e, const double* FEXT, const double* MEXT); /* constant nodal loads (3,N) */
 int  orgpu_set_bcs(orgpu_engine* e, const int* icodt, const int* icodr);       /* BCS10 codes 4:x 2:y 1:z  */
+/* time variation of the nodal loads above: A += FEXT * FINTER(ifunc, TT*fcx) as the concentrated loads of
+ * FORCE (engine/source/loads/general/force.F90:195-196, 235, 301-312; resol.F:2929) sharing one function;
+ * ifunc = 0-based curve of orgpu_set_functions, -1 = constant loads.  Before orgpu_finalize. */
+int  orgpu_set_load_function(orgpu_engine* e, int ifunc, double fcx);
+/* imposed velocities (FIXVEL, engine/source/constraints/general/impvel/fixvel.F:141-147, 334-378; resol.F:7610):
+ * record k = IBFV(1,k) node (1-based), IBFV(2,k) direction 1..3 in the global frame, IBFV(3,k) curve (0-based),
+ * VEL(1,k) FAC, VEL(2,k) start time, VEL(3,k) stop time, VEL(5,k) FACX.  Before orgpu_finalize. */
+int  orgpu_set_fixvel(orgpu_engine* e, int nfxvel, const int* ibfv /*(3,n)*/, const double* vel /*(4,n)*/);
 int  orgpu_set_solids(orgpu_engine* e, int numels, const int* ixs, const int* iads);
 int  orgpu_set_shells(orgpu_engine* e, int numelc, const int* ixc, const int* iadc);
 int  orgpu_set_pon(orgpu_engine* e, const int* adsky, int lsky);              /* parith_on_mod.F90:39-74 */

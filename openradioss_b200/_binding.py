@@ -66,6 +66,10 @@ class Binding:
         self._call("set_pon", self.h, _opt(m.adsky, np.int32), C.c_int(m.lsky))
         if m.npf is not None:
             self._call("set_functions", self.h, C.c_int(len(m.npf) - 1), _opt(m.npf, np.int32), _opt(m.tf, np.float64))
+        if m.load_func is not None:
+            self._call("set_load_function", self.h, C.c_int(int(m.load_func[0])), C.c_double(float(m.load_func[1])))
+        if m.ibfv is not None and len(m.ibfv):
+            self._call("set_fixvel", self.h, C.c_int(len(m.ibfv)), _opt(m.ibfv, np.int32), _opt(m.vel, np.float64))
         for g in m.shell_groups:
             r = self._call_group("add_shell_group", self.h, C.c_int(g.nel), C.c_int(g.nft), C.c_int(g.law),
                                  C.byref(g.mat), C.byref(g.prop))

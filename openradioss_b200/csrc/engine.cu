@@ -47,6 +47,9 @@ struct orgpu_engine {
   // connectivity as given by the caller
   std::vector<int> ixs, iads, ixc, iadc, adsky; int numels = 0, numelc = 0, lsky = 0;
   std::vector<int> npf; std::vector<double> tf;
+  int lf_func = -1; double lf_fcx = 1.0;            // time function of the nodal loads
+  std::vector<int> fv_idx; std::vector<FixVelNode> fv;   // imposed velocities, per node
+  double* d_ftf = nullptr; int* d_fnpf = nullptr; int* d_fv_idx = nullptr; FixVelNode* d_fv = nullptr;
   std::vector<HostSolidGroup> sgroups;
   std::vector<HostShellGroup> cgroups;
   // device model
@@ -118,6 +121,7 @@ int orgpu_create(orgpu_engine** out, int device, int numnod, const orgpu_control
   if (ctl->iroddl) { if (dev_alloc(&e->nd.rot, n)) return -100; }
   if (dev_alloc(&e->d_cs, 1)) return -100;
   CycleState cs{}; cs.tt = ctl->tt_init; cs.dt2 = ctl->dt_init; cs.dt2old = ctl->dt2old_init; cs.dtmx = ctl->dtmx;
+  cs.tt0 = ctl->tt_init; cs.fscale = 1.0;
   CUDA_OK(cudaMemcpy(e->d_cs, &cs, sizeof cs, cudaMemcpyHostToDevice));
   CUDA_OK(cudaEventCreate(&e->ev0)); CUDA_OK(cudaEventCreate(&e->ev1));
   *out = e;
@@ -134,7 +138,7 @@ int orgpu_destroy(orgpu_engine* e)
   for (auto& s : e->csg) for (void* p : s.owned) cudaFree(p);
   void* ptrs[] = {e->nd.pos, e->nd.vel, e->nd.rot, e->nd.D, e->nd.A, e->nd.AR, e->nd.STIFN, e->nd.STIFR, e->nd.MS, e->nd.IN,
                   e->d_stage3a, e->d_stage3b, e->d_fext, e->d_mext, e->d_icodt, e->d_icodr, e->d_adsky, e->d_fsky, e->d_cs,
-                  e->db.dt, e->db.ngl, e->db.order};
+                  e->db.dt, e->db.ngl, e->db.order, e->d_ftf, e->d_fnpf, e->d_fv_idx, e->d_fv};
   for (void* p : ptrs) if (p) cudaFree(p);
   { Exchange& x = e->xc;
     void* xp[] = {x.d_send_slots, x.d_recv_slots, x.d_sendbuf, x.d_recvbuf, x.d_cand_send, x.d_cand_recv, x.d_slots_tmp, x.d_rows_tmp};
@@ -215,6 +219,33 @@ int orgpu_set_functions(orgpu_engine* e, int nfunc, const int* npf, const double
   return 0;
 }
 
+int orgpu_set_load_function(orgpu_engine* e, int ifunc, double fcx)
+{
+  NEED(e && !e->finalized, -1, "orgpu_set_load_function: bad handle / already finalized");
+  NEED(ifunc >= -1, -1, "orgpu_set_load_function: bad function index %d", ifunc);
+  e->lf_func = ifunc; e->lf_fcx = fcx;
+  return 0;
+}
+
+int orgpu_set_fixvel(orgpu_engine* e, int nfxvel, const int* ibfv /*(3,n): node, direction 1..3, function*/,
+                     const double* vel /*(4,n): FAC, STARTT, STOPT, FACX*/)
+{
+  NEED(e && !e->finalized && nfxvel >= 0 && (nfxvel == 0 || (ibfv && vel)), -1, "orgpu_set_fixvel: bad arguments / already finalized");
+  e->fv_idx.assign(e->numnod, -1); e->fv.clear();
+  for (int k = 0; k < nfxvel; k++) {
+    const int node = ibfv[3 * k], j = ibfv[3 * k + 1], f = ibfv[3 * k + 2];
+    NEED(node >= 1 && node <= e->numnod, -4, "orgpu_set_fixvel: node %d out of range", node);
+    NEED(j >= 1 && j <= 3, -5, "imposed velocity on direction %d (rotations, skew / moving frames) is outside the built path", j);
+    NEED(f >= 0, -4, "orgpu_set_fixvel: bad function index %d", f);
+    int& idx = e->fv_idx[node - 1];
+    if (idx < 0) { idx = (int)e->fv.size(); FixVelNode r; memset(&r, 0, sizeof r); r.func[0] = r.func[1] = r.func[2] = -1; e->fv.push_back(r); }
+    FixVelNode& r = e->fv[idx];
+    NEED(r.func[j - 1] < 0, -4, "orgpu_set_fixvel: node %d direction %d imposed twice", node, j);
+    r.func[j - 1] = f; r.fac[j - 1] = vel[4 * k]; r.tstart[j - 1] = vel[4 * k + 1]; r.tstop[j - 1] = vel[4 * k + 2]; r.facx[j - 1] = vel[4 * k + 3];
+  }
+  return 0;
+}
+
 int orgpu_add_solid_group(orgpu_engine* e, int nel, int nft, const orgpu_law2* mat,
                           const orgpu_prop_solid* prop, const double* vol0)
 {
@@ -292,6 +323,26 @@ int orgpu_finalize(orgpu_engine* e)
     order += ne; blk += nblk; gi = gj;
   }
   NEED(blk > 0, -4, "orgpu_finalize: no element groups");
+  // time functions used at node level (loads, imposed velocities)
+  e->fa.lf_func = -1; e->fa.lf_fcx = 1.0; e->fa.ft = FuncTable{nullptr, nullptr};
+  if (e->lf_func >= 0 || !e->fv.empty()) {
+    NEED(!e->npf.empty(), -4, "a load / imposed-velocity time function needs orgpu_set_functions");
+    const int nf = (int)e->npf.size() - 1;
+    auto check = [&](int f, int maxpts) { return f >= 0 && f < nf && e->npf[f + 1] - e->npf[f] >= 1 && e->npf[f + 1] - e->npf[f] <= maxpts; };
+    if (e->lf_func >= 0) NEED(check(e->lf_func, 20), -5, "load function %d missing or longer than 20 points (FINTER dichotomy branch is outside the built path)", e->lf_func);
+    for (auto& r : e->fv) for (int j = 0; j < 3; j++) if (r.func[j] >= 0) NEED(check(r.func[j], 1 << 30) && e->npf[r.func[j] + 1] - e->npf[r.func[j]] >= 2, -4, "imposed-velocity function %d missing or shorter than 2 points", r.func[j]);
+    if (dev_alloc(&e->d_ftf, e->tf.size()) || dev_alloc(&e->d_fnpf, e->npf.size())) return -100;
+    CUDA_OK(cudaMemcpy(e->d_ftf, e->tf.data(), 8 * e->tf.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(e->d_fnpf, e->npf.data(), 4 * e->npf.size(), cudaMemcpyHostToDevice));
+    e->fa.ft = FuncTable{e->d_ftf, e->d_fnpf}; e->nd.ft = e->fa.ft;
+    e->fa.lf_func = e->lf_func; e->fa.lf_fcx = e->lf_fcx;
+    if (!e->fv.empty()) {
+      if (dev_alloc(&e->d_fv_idx, e->fv_idx.size()) || dev_alloc(&e->d_fv, e->fv.size())) return -100;
+      CUDA_OK(cudaMemcpy(e->d_fv_idx, e->fv_idx.data(), 4 * e->fv_idx.size(), cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(e->d_fv, e->fv.data(), sizeof(FixVelNode) * e->fv.size(), cudaMemcpyHostToDevice));
+      e->nd.fv_idx = e->d_fv_idx; e->nd.fv = e->d_fv;
+    }
+  }
   e->db.nblocks_total = blk;
   if (dev_alloc(&e->db.dt, blk) || dev_alloc(&e->db.ngl, blk) || dev_alloc(&e->db.order, blk)) return -100;
   e->finalized = true;
@@ -331,7 +382,7 @@ int orgpu_forces_phase(orgpu_engine* e, double dt1)
 int orgpu_assemble(orgpu_engine* e)
 {
   NEED(e && e->finalized, -1, "orgpu_assemble: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
-  launch_node_assemble(e->nd, e->d_fsky, e->roww, e->ctl.iroddl, e->st); e->launches++;
+  launch_node_assemble(e->nd, e->d_fsky, e->roww, e->d_cs, e->ctl.iroddl, e->st); e->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -18,7 +18,7 @@ struct NodeAcc { double a[3], ar[3], stifn, stifr; };
 // add, so one thread keeps 256 bytes in flight instead of one row (the kernel is a pure stream and
 // needs ~45 KB in flight per SM to cover HBM latency).
 template <int ROWW>
-__device__ __forceinline__ NodeAcc node_gather(const DevNodes& nd, const double* __restrict__ fsky, int n, int iroddl)
+__device__ __forceinline__ NodeAcc node_gather(const DevNodes& nd, const double* __restrict__ fsky, int n, int iroddl, double fscale)
 {
   NodeAcc r;
   const int k0 = nd.adsky[n], k1 = nd.adsky[n + 1];
@@ -33,9 +33,10 @@ __device__ __forceinline__ NodeAcc node_gather(const DevNodes& nd, const double*
       for (int c = 0; c < NV; c++) buf[j][c] = ld256_cs(base + (size_t)NV * (k0 + j) + c);
     }
   }
-  if (nd.FEXT) { r.a[0] = nd.FEXT[3 * n]; r.a[1] = nd.FEXT[3 * n + 1]; r.a[2] = nd.FEXT[3 * n + 2]; }
+  // A starts from the external nodal loads (FORCE, force.F90:301-312: A += FCY * FINTER(IFUN, TT*FCX))
+  if (nd.FEXT) { r.a[0] = nd.FEXT[3 * n] * fscale; r.a[1] = nd.FEXT[3 * n + 1] * fscale; r.a[2] = nd.FEXT[3 * n + 2] * fscale; }
   else { r.a[0] = K_ZERO; r.a[1] = K_ZERO; r.a[2] = K_ZERO; }
-  if (nd.MEXT) { r.ar[0] = nd.MEXT[3 * n]; r.ar[1] = nd.MEXT[3 * n + 1]; r.ar[2] = nd.MEXT[3 * n + 2]; }
+  if (nd.MEXT) { r.ar[0] = nd.MEXT[3 * n] * fscale; r.ar[1] = nd.MEXT[3 * n + 1] * fscale; r.ar[2] = nd.MEXT[3 * n + 2] * fscale; }
   else { r.ar[0] = K_ZERO; r.ar[1] = K_ZERO; r.ar[2] = K_ZERO; }
   r.stifn = K_ZERO; r.stifr = K_ZERO;
   for (int kb = k0; kb < k1; kb += NB) {
@@ -78,7 +79,7 @@ __device__ __forceinline__ NodeIn node_load(const DevNodes& nd, int n, int irodd
   return q;
 }
 
-__device__ __forceinline__ void node_update(const DevNodes& nd, int n, const NodeIn& q, NodeAcc& r, double dt12, double dt2, int iroddl)
+__device__ __forceinline__ void node_update(const DevNodes& nd, int n, const NodeIn& q, NodeAcc& r, double dt12, double dt2, double tt0, int iroddl)
 {
   // ACCELE
   const double ms = q.ms;
@@ -94,6 +95,25 @@ __device__ __forceinline__ void node_update(const DevNodes& nd, int n, const Nod
     const int c = q.ct;
     if (c & 4) r.a[0] = K_ZERO; if (c & 2) r.a[1] = K_ZERO; if (c & 1) r.a[2] = K_ZERO;
     if (iroddl) { const int qq = q.cr; if (qq & 4) r.ar[0] = K_ZERO; if (qq & 2) r.ar[1] = K_ZERO; if (qq & 1) r.ar[2] = K_ZERO; }
+  }
+  // FIXVEL (constraints/general/impvel/fixvel.F:141-147, 362-378; imposed velocity IBFV(7)=1, global frame, no sensor):
+  // the acceleration that makes VELOCITY land on FAC * f((TT + DT2/2) * FACX)
+  if (nd.fv_idx) {
+    const int k = nd.fv_idx[n];
+    if (k >= 0) {
+      const FixVelNode& f = nd.fv[k];
+      const double vj[3] = {q.v.x, q.v.y, q.v.z};
+      #pragma unroll
+      for (int j = 0; j < 3; j++) {
+        if (f.func[j] >= 0 && !(tt0 < f.tstart[j]) && !(tt0 > f.tstop[j])) {
+          const double tsc = (tt0 + K_HALF * dt2) * f.facx[j];
+          const int i0 = nd.ft.npf[f.func[j]];
+          double yc = or_vinterdp(nd.ft.tf, i0, nd.ft.npf[f.func[j] + 1] - i0, tsc);
+          yc = yc * f.fac[j];
+          r.a[j] = or_div(yc - vj[j], dt12);
+        }
+      }
+    }
   }
   // VELOCITY
   double4 v = q.v;
@@ -115,11 +135,11 @@ __device__ __forceinline__ void node_update(const DevNodes& nd, int n, const Nod
 // phased mode, step 2: ASSPAR4 only (A, AR, STIFN, STIFR stored for the caller)
 template <int ROWW>
 __global__ void __launch_bounds__(ORGPU_NODE_BLOCK)
-node_assemble_kernel(const __grid_constant__ DevNodes nd, const double* __restrict__ fsky, int iroddl)
+node_assemble_kernel(const __grid_constant__ DevNodes nd, const double* __restrict__ fsky, const CycleState* __restrict__ cs, int iroddl)
 {
   const int n = blockIdx.x * ORGPU_NODE_BLOCK + threadIdx.x;
   if (n >= nd.n) return;
-  NodeAcc r = node_gather<ROWW>(nd, fsky, n, iroddl);
+  NodeAcc r = node_gather<ROWW>(nd, fsky, n, iroddl, cs->fscale);
   nd.A[3 * n] = r.a[0]; nd.A[3 * n + 1] = r.a[1]; nd.A[3 * n + 2] = r.a[2];
   nd.AR[3 * n] = r.ar[0]; nd.AR[3 * n + 1] = r.ar[1]; nd.AR[3 * n + 2] = r.ar[2];
   nd.STIFN[n] = r.stifn; nd.STIFR[n] = r.stifr;
@@ -135,7 +155,7 @@ node_advance_kernel(const __grid_constant__ DevNodes nd, const CycleState* __res
   r.a[0] = nd.A[3 * n]; r.a[1] = nd.A[3 * n + 1]; r.a[2] = nd.A[3 * n + 2];
   r.ar[0] = nd.AR[3 * n]; r.ar[1] = nd.AR[3 * n + 1]; r.ar[2] = nd.AR[3 * n + 2];
   const NodeIn q = node_load(nd, n, iroddl);
-  node_update(nd, n, q, r, cs->dt12, cs->dt2, iroddl);
+  node_update(nd, n, q, r, cs->dt12, cs->dt2, cs->tt0, iroddl);
   nd.A[3 * n] = K_ZERO; nd.A[3 * n + 1] = K_ZERO; nd.A[3 * n + 2] = K_ZERO;        // velocity.F:62-64
   nd.AR[3 * n] = K_ZERO; nd.AR[3 * n + 1] = K_ZERO; nd.AR[3 * n + 2] = K_ZERO;
 }
@@ -149,8 +169,8 @@ node_fused_kernel(const __grid_constant__ DevNodes nd, const double* __restrict_
   const int n = blockIdx.x * ORGPU_NODE_BLOCK + threadIdx.x;
   if (n >= nd.n) return;
   const NodeIn q = node_load(nd, n, iroddl);
-  NodeAcc r = node_gather<ROWW>(nd, fsky, n, iroddl);
-  node_update(nd, n, q, r, cs->dt12, cs->dt2, iroddl);
+  NodeAcc r = node_gather<ROWW>(nd, fsky, n, iroddl, cs->fscale);
+  node_update(nd, n, q, r, cs->dt12, cs->dt2, cs->tt0, iroddl);
 }
 
 __global__ void set_dt_kernel(CycleState* cs, double dt1, double dt12, double dt2, int which)
@@ -159,11 +179,11 @@ __global__ void set_dt_kernel(CycleState* cs, double dt1, double dt12, double dt
   else { cs->dt1 = cs->dt2; cs->dt12 = dt12; cs->dt2 = dt2; cs->tt = cs->tt + dt2; cs->ncycle += 1; cs->dt2old = dt2; }
 }
 
-void launch_node_assemble(const DevNodes& nd, const double* fsky, int roww, int iroddl, cudaStream_t st)
+void launch_node_assemble(const DevNodes& nd, const double* fsky, int roww, const CycleState* cs, int iroddl, cudaStream_t st)
 {
   const int nb = (nd.n + ORGPU_NODE_BLOCK - 1) / ORGPU_NODE_BLOCK;
-  if (roww == 4) node_assemble_kernel<4><<<nb, ORGPU_NODE_BLOCK, 0, st>>>(nd, fsky, iroddl);
-  else           node_assemble_kernel<8><<<nb, ORGPU_NODE_BLOCK, 0, st>>>(nd, fsky, iroddl);
+  if (roww == 4) node_assemble_kernel<4><<<nb, ORGPU_NODE_BLOCK, 0, st>>>(nd, fsky, cs, iroddl);
+  else           node_assemble_kernel<8><<<nb, ORGPU_NODE_BLOCK, 0, st>>>(nd, fsky, cs, iroddl);
 }
 void launch_node_advance(const DevNodes& nd, const CycleState* cs, int iroddl, cudaStream_t st)
 {

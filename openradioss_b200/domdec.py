@@ -110,7 +110,11 @@ def decompose(m: Model, dom_s: Optional[np.ndarray], dom_c: Optional[np.ndarray]
     sub = lambda a: None if a is None else np.ascontiguousarray(a[node_gid])
     lm = Model(X=sub(m.X), V=sub(m.V), VR=sub(m.VR), MS=sub(m.MS), IN=sub(m.IN), control=m.control, ixs=ixs, ixc=ixc,
                vol0=m.vol0[solid_gid] if len(m.vol0) else m.vol0, icodt=sub(m.icodt), icodr=sub(m.icodr),
-               fext=sub(m.fext), mext=sub(m.mext), itab=sub(m.itab), npf=m.npf, tf=m.tf)
+               fext=sub(m.fext), mext=sub(m.mext), itab=sub(m.itab), npf=m.npf, tf=m.tf, load_func=m.load_func)
+    if m.ibfv is not None and len(m.ibfv):
+        keep = mine[m.ibfv[:, 0] - 1]
+        lm.ibfv = m.ibfv[keep].copy(); lm.vel = m.vel[keep].copy()
+        lm.ibfv[:, 0] = (g2l[lm.ibfv[:, 0] - 1] + 1).astype(np.int32)
     lm.adsky = (ladsky0 + 1).astype(np.int32); lm.iads = iads; lm.iadc = iadc; lm.lsky = lsky
     # groups
     if m.solid_groups:

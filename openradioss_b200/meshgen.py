@@ -217,9 +217,10 @@ def shell_areas(X: np.ndarray, ixc: np.ndarray) -> np.ndarray:
 def shell_plate(nx: int, ny: int, lx: float = 1000.0, ly: float = 1000.0, *, thick: float = 2.0, law: int = 36,
                 mat=None, prop: PropShell = None, jitter: float = 0.05, zjitter: float = 0.05, seed: int = 2024,
                 pressure: float = 1.0, clamp: bool = True, vrand: float = 0.0, vseed: int = 12345,
-                user_id_perm: bool = False, curves=None, rates=None) -> Model:
+                user_id_perm: bool = False, curves=None, rates=None, pulse_tau: float = 0.0) -> Model:
     """Square plate of nx*ny 4-node shells in the xy plane (C2: 1000 x 1000 QEPH / LAW36, clamped
-    edges, uniform pressure as constant nodal forces)."""
+    edges, uniform pressure as nodal forces; pulse_tau > 0 ramps them as p0*min(t/tau, 1) through a time
+    function, the /CLOAD path of force.F90)."""
     prop = prop or default_prop_shell(thick=thick)
     npf = tf = None
     if mat is None:
@@ -276,7 +277,19 @@ def shell_plate(nx: int, ny: int, lx: float = 1000.0, ly: float = 1000.0, *, thi
               fext=fext, itab=np.arange(1, numnod + 1, dtype=np.int32), npf=npf, tf=tf)
     m.shell_groups = [ShellGroup(nft=s, nel=n, law=law, mat=mat, prop=prop) for s, n in _groups(ne)]
     m.adsky, m.iads, m.iadc, m.lsky = build_pon(numnod, m.ixs, m.ixc)
+    if pulse_tau > 0.0 and fext is not None:
+        m.load_func = (add_function(m, [0.0, pulse_tau, 1.0e30], [0.0, 1.0, 1.0]), 1.0)
     return m
+
+
+def add_function(m: Model, x, y) -> int:
+    """Append one (x, y) curve to the model's NPC / TF table; returns its 0-based index."""
+    x = np.asarray(x, float); y = np.asarray(y, float)
+    npf = np.zeros(1, np.int32) if m.npf is None else np.asarray(m.npf, np.int32)
+    tf = np.zeros(0) if m.tf is None else np.asarray(m.tf, float)
+    m.tf = np.concatenate([tf, np.stack([x, y], 1).reshape(-1)])
+    m.npf = np.concatenate([npf, [npf[-1] + len(x)]]).astype(np.int32)
+    return len(m.npf) - 2
 
 
 def plate_c2(scale: int = 1) -> Model:
@@ -318,4 +331,57 @@ def shell_on_block(nx: int, ny: int, nz: int, h: float = 5.0, *, thick: float = 
     m.solid_groups = b.solid_groups
     m.shell_groups = [ShellGroup(nft=s, nel=n, law=36, mat=mat, prop=prop) for s, n in _groups(ne)]
     m.adsky, m.iads, m.iadc, m.lsky = build_pon(m.numnod, m.ixs, m.ixc)
+    return m
+
+
+def crush_tube(nw: int, nz: int, nbz: int = 1, h: float = 2.5, *, thick: float = 1.5, v_imp: float = -10.0,
+               ramp: float = 0.05, jitter: float = 0.05, seed: int = 2024) -> Model:
+    """C4: thin-walled square tube (4 walls x nw x nz QEPH shells, LAW36) standing on an nw x nw x nbz brick
+    end block (LAW2) whose top-face perimeter nodes are the tube's bottom ring; the block's bottom face is
+    z-fixed (BCS), the top ring is driven at v_imp (mm/ms = m/s) along z through FIXVEL with a ramp of
+    `ramp` ms.  BASELINE size: crush_tube(708, 706) = 2.0 M shells + 501 k bricks."""
+    b = hex_block(nw, nw, nbz, h * nw, h * nw, h * nbz, jitter=jitter, seed=seed, fix_bottom_z=True)
+    b.X[:, 2] -= h * nbz                                   # block top face at z = 0
+    nn1 = nw + 1
+    nid = lambda i, j, k: i + nn1 * (j + nn1 * k)
+    P = 4 * nw
+    p = np.arange(P)
+    side, q = p // nw, p % nw
+    ri = np.select([side == 0, side == 1, side == 2, side == 3], [q, nw, nw - q, 0])
+    rj = np.select([side == 0, side == 1, side == 2, side == 3], [0, q, nw, nw - q])
+    ring0 = nid(ri, rj, nbz)                               # tube ring 0 = perimeter of the block's top face
+    nb_nodes = b.numnod
+    numnod = nb_nodes + nz * P
+    X = np.zeros((numnod, 3)); X[:nb_nodes] = b.X
+    rng = np.random.default_rng(seed + 11)
+    for k in range(1, nz + 1):
+        sl = slice(nb_nodes + (k - 1) * P, nb_nodes + k * P)
+        X[sl, 0] = ri * h; X[sl, 1] = rj * h; X[sl, 2] = k * h
+        X[sl] += rng.uniform(-jitter, jitter, (P, 3)) * h
+    ring = lambda pp, k: np.where(k == 0, ring0[pp % P], nb_nodes + (k - 1) * P + (pp % P))
+    ek, ep = np.meshgrid(np.arange(nz), p, indexing="ij")
+    ek, ep = ek.reshape(-1), ep.reshape(-1)
+    ne = nz * P
+    ixc = np.zeros((ne, 7), np.int32); ixc[:, 0] = 2; ixc[:, 5] = 2
+    ixc[:, 1] = ring(ep, ek) + 1; ixc[:, 2] = ring(ep + 1, ek) + 1
+    ixc[:, 3] = ring(ep + 1, ek + 1) + 1; ixc[:, 4] = ring(ep, ek + 1) + 1
+    ixc[:, 6] = np.arange(1, ne + 1) + 10_000_000
+    prop = default_prop_shell(thick=thick)
+    mat, npf, tf = steel_law36()
+    area = shell_areas(X, ixc)
+    ems = mat.rho0 * thick * area * 0.25
+    xi = ems * (area / 12.0 + thick * thick / 12.0)
+    MS = np.zeros(numnod); MS[:nb_nodes] = b.MS; IN = np.zeros(numnod)
+    np.add.at(MS, (ixc[:, 1:5] - 1).reshape(-1), np.repeat(ems, 4))
+    np.add.at(IN, (ixc[:, 1:5] - 1).reshape(-1), np.repeat(xi, 4))
+    icodt = np.zeros(numnod, np.int32); icodt[:nb_nodes] = b.icodt
+    m = Model(X=X, V=np.zeros((numnod, 3)), VR=np.zeros((numnod, 3)), MS=MS, IN=IN, control=default_control(1), ixs=b.ixs, ixc=ixc,
+              vol0=b.vol0, icodt=icodt, icodr=np.zeros(numnod, np.int32), itab=np.arange(1, numnod + 1, dtype=np.int32), npf=npf, tf=tf)
+    m.solid_groups = b.solid_groups
+    m.shell_groups = [ShellGroup(nft=s, nel=n, law=36, mat=mat, prop=prop) for s, n in _groups(ne)]
+    m.adsky, m.iads, m.iadc, m.lsky = build_pon(numnod, m.ixs, m.ixc)
+    f = add_function(m, [0.0, ramp, 1.0e30], [0.0, 1.0, 1.0])
+    top = nb_nodes + (nz - 1) * P + p if nz >= 1 else ring0
+    m.ibfv = np.stack([top + 1, np.full(P, 3), np.full(P, f)], 1).astype(np.int32)
+    m.vel = np.tile(np.array([v_imp, 0.0, 1.0e30, 1.0]), (P, 1))
     return m

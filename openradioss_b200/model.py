@@ -97,6 +97,9 @@ class Model:
     # LAW36 function table
     npf: Optional[np.ndarray] = None
     tf: Optional[np.ndarray] = None
+    load_func: Optional[tuple] = None   # (curve index, FCX): time function shared by the nodal loads fext / mext
+    ibfv: Optional[np.ndarray] = None   # imposed velocities (n,3) int32: node (1-based), direction 1..3, curve index
+    vel: Optional[np.ndarray] = None    # (n,4): FAC, STARTT, STOPT, FACX
 
     @property
     def numnod(self): return int(self.X.shape[0])

@@ -55,6 +55,10 @@ void orc_set_bcs(void* h,const int* icodt,const int* icodr){
   o->ICODT.assign(icodt,icodt+n);
   if(icodr) o->ICODR.assign(icodr,icodr+n); else o->ICODR.assign(n,0);
 }
+void orc_set_load_function(void* h,int ifunc,double fcx){ Oracle* o=(Oracle*)h; o->LF_FUNC=ifunc; o->LF_FCX=fcx; }
+void orc_set_fixvel(void* h,int nfxvel,const int* ibfv /*(3,n)*/,const double* vel /*(4,n)*/){
+  Oracle* o=(Oracle*)h; o->IBFV.assign(ibfv,ibfv+(size_t)3*nfxvel); o->VEL.assign(vel,vel+(size_t)4*nfxvel);
+}
 /* connectivity + /PARITH/ON tables (all 1-based, Fortran layout) */
 void orc_set_solids(void* h,int numels,const int* ixs /*(11,numels)*/,const int* iads /*(8,numels)*/){
   Oracle* o=(Oracle*)h; o->numels=numels;
@@ -107,7 +111,7 @@ void orc_forces_phase(void* h,double dt1){
 void orc_assemble(void* h){ orc_asspar4(*(Oracle*)h); }
 void orc_advance(void* h,double dt12,double dt2){
   Oracle* o=(Oracle*)h; o->DT12=dt12; o->DT2=dt2;
-  orc_accele(*o); orc_bcs(*o); orc_velocity(*o); orc_depla(*o); o->TT+=dt2; o->NCYCLE++;
+  orc_accele(*o); orc_bcs(*o); orc_fixvel(*o); orc_velocity(*o); orc_depla(*o); o->TT+=dt2; o->NCYCLE++;
 }
 void orc_run_cycles(void* h,int ncycles){ Oracle* o=(Oracle*)h; for(int c=0;c<ncycles;c++) orc_cycle(*o); }
 

@@ -67,6 +67,56 @@ void orc_bcs(Oracle& o)
   }
 }
 
+/* FINTER, classical branch (engine/source/tools/curve/finter.F:165-246; fewer than 20 segments).
+ * TF holds (x,y) pairs; curve f = points NPF[f] .. NPF[f+1]-1 (0-based) */
+static double orc_finter(const Oracle& o,int f,double XX)
+{
+  const int i0=o.NPF[f], n=o.NPF[f+1]-o.NPF[f];
+  const double* TF=o.TF.data();
+  if(n==1) return TF[2*i0+1];
+  double DX2=TF[2*i0]-XX;
+  for(int I=1;I<n;I++){
+    double DX1=-DX2;
+    DX2=TF[2*(i0+I)]-XX;
+    if(DX2>=K_ZERO || I==n-1){
+      double DIV0=TF[2*(i0+I)]-TF[2*(i0+I-1)];
+      double DIV=std::max(std::fabs(DIV0),K_EM16);
+      DIV=std::copysign(DIV,DIV0);
+      double DERI=(TF[2*(i0+I)+1]-TF[2*(i0+I-1)+1])/DIV;
+      if(DX1<=DX2) return TF[2*(i0+I-1)+1]+DX1*DERI;
+      return TF[2*(i0+I)+1]-DX2*DERI;
+    }
+  }
+  return K_ZERO;
+}
+double orc_load_scale(const Oracle& o){ return o.LF_FUNC>=0 ? orc_finter(o,o.LF_FUNC,o.TT*o.LF_FCX) : K_ONE; }
+
+/* FIXVEL (engine/source/constraints/general/impvel/fixvel.F), restricted to imposed velocities
+ * (IBFV(7,N)=1) in the global frame without sensor: TSC=(TT+HALF*DT2)*FACX (:146), YC from VINTERDP
+ * (vinterdp.F:35-70, cursor from 0), YC=YC*FAC (:344), A(J,I)=(YC-V(J,I))/DT12 (:375-377).  Called after
+ * BCS (resol.F:7322) and before VELOCITY (resol.F:8947), with TT = time at the start of the cycle. */
+void orc_fixvel(Oracle& o)
+{
+  const int nfx=(int)(o.IBFV.size()/3);
+  for(int N=0;N<nfx;N++){
+    const double FAC=o.VEL[4*N], STARTT=o.VEL[4*N+1], STOPT=o.VEL[4*N+2], FACX=o.VEL[4*N+3];
+    if(o.TT<STARTT) continue;
+    if(o.TT>STOPT) continue;
+    const int I=o.IBFV[3*N]-1, J=o.IBFV[3*N+1]-1, L=o.IBFV[3*N+2];
+    const double TSC=(o.TT+K_HALF*o.DT2)*FACX;
+    const int IAD=o.NPF[L], NP=o.NPF[L+1]-o.NPF[L];
+    const double* TF=o.TF.data();
+    int IPOS=0;
+    for(int JJ=1;JJ<=NP-2;JJ++){ if(TSC>TF[2*(IAD+IPOS+1)]) IPOS++; else break; }
+    const double TF1J1=TF[2*(IAD+IPOS)], TF2J1=TF[2*(IAD+IPOS)+1], TF1J2=TF[2*(IAD+IPOS+1)], TF2J2=TF[2*(IAD+IPOS+1)+1];
+    const double DYDX=(TF2J2-TF2J1)/(TF1J2-TF1J1);
+    double YC=TF2J1+DYDX*(TSC-TF1J1);
+    YC=YC*FAC;
+    YC=(YC-o.V[3*I+J])/o.DT12;
+    o.A[3*I+J]=YC;
+  }
+}
+
 /* VELOCITY velocity.F:57-89 */
 void orc_velocity(Oracle& o)
 {
@@ -98,7 +148,8 @@ void orc_forces(Oracle& o)
   const int n=o.numnod;
   /* resol.F: A/AR hold external nodal loads when the element loop starts (FORCE, resol.F:2929);
    * STIFN/STIFR restart from zero each cycle */
-  for(int i=0;i<3*n;i++){ o.A[i]= o.FEXT.empty()? K_ZERO : o.FEXT[i]; o.AR[i]= o.MEXT.empty()? K_ZERO : o.MEXT[i]; }
+  const double fs=orc_load_scale(o);   /* force.F90:235, 301-312: AA = FCY*FINTER(IFUN,TT*FCX) */
+  for(int i=0;i<3*n;i++){ o.A[i]= o.FEXT.empty()? K_ZERO : o.FEXT[i]*fs; o.AR[i]= o.MEXT.empty()? K_ZERO : o.MEXT[i]*fs; }
   for(int i=0;i<n;i++){ o.STIFN[i]=K_ZERO; o.STIFR[i]=K_ZERO; }
   double DT2T=o.DT2; int NELTST=0, ITYPTST=0;   /* thread mins are merged with strict "<" (resol.F:4165-4171) */
   /* shells first (FORINTC resol.F:4138), then solids (FORINT resol.F:4225) */
@@ -138,6 +189,7 @@ void orc_cycle(Oracle& o)
   o.DT12=K_HALF*(o.DT1+o.DT2);    /* resol.F:6496 */
   orc_accele(o);
   orc_bcs(o);
+  orc_fixvel(o);
   orc_velocity(o);
   orc_depla(o);
   o.TT=o.TT+o.DT2; o.NCYCLE++;    /* resol.F:8599-8608 */

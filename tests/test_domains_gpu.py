@@ -19,6 +19,7 @@ if torch.cuda.is_available():
 def models():
     yield "shell", meshgen.shell_plate(12, 9, 120.0, 90.0, pressure=20.0, vrand=5.0, user_id_perm=True)
     yield "brick", meshgen.hex_block(6, 5, 7, 1.2, 1.0, 1.4, v0=(0, 0, -100.0), vrand=5.0, fix_bottom_z=True, user_id_perm=True)
+    yield "tube", meshgen.crush_tube(5, 8, 1, ramp=0.002)      # shells + bricks, imposed velocity, load records follow their nodes
 
 
 @pytest.mark.parametrize("nproc", [2, 3])
@@ -68,7 +69,7 @@ def _nccl_worker(rank, world, port, q, kind, p2p=True):
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 @pytest.mark.parametrize("p2p", [True, False], ids=["peer_memory", "nccl"])
-@pytest.mark.parametrize("kind", ["shell", "brick"])
+@pytest.mark.parametrize("kind", ["shell", "brick", "tube"])
 def test_multi_gpu_domains_match_single_gpu_bitwise(kind, p2p):
     import torch.multiprocessing as mp
     world = min(4, torch.cuda.device_count())
