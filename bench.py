@@ -251,7 +251,7 @@ def main():
                 "scaling": "strong" if args.workload in STRONG else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": args.workload, "family": fam, "elements_per_gpu": ne, "nodes_per_gpu": n,
                            "l2": "inputs larger than L2 (element state >> 126 MB)" if ne >= 500000 else "working set may fit L2",
-                           "parallelism": f"domains={world}" + ("" if world == 1 else " (strips, NCCL corner-row exchange + dt fold per cycle)")},
+                           "parallelism": f"domains={world}" + ("" if world == 1 else " (strips / slabs; peer-memory corner-row exchange + dt fold per cycle, one CUDA graph)")},
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "element-cycles/s", "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 48 * n,
                         "steps": e2e_steps, "call": "orgpu_step_host (X,V pinned host -> 1 cycle -> X,V host)"},

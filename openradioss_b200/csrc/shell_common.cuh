@@ -431,7 +431,11 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const Tile
   const int qrow = (npt - 1) * 11;
   IpState nxt;
   if (!STAGED) nxt = ip_load<LAW>(g, T, 0);
+#ifdef ORGPU_IP_UNROLL1
+  #pragma unroll 1
+#else
   #pragma unroll
+#endif
   for (int ipt = 0; ipt < npt; ipt++) {
     IpState s;
     if (STAGED) s = ip_load<LAW>(g, T, ipt);                     // shared memory: no latency to hide

@@ -102,6 +102,24 @@ def test_qeph_law2_johnson_cook():
     assert o.shell_state("pla").max() > 0.0
 
 
+@pytest.mark.parametrize("ihbe,npt", [(24, 7), (24, 10), (1, 8)])
+def test_in_place_state_path_for_tiles_too_large_to_stage(ihbe, npt):
+    """NPT > 5: the state tile does not fit three CTAs per SM, the kernels read / write the same tile-major
+    slab in place (TileAcc<false>) -- same results."""
+    prop = meshgen.default_prop_shell(thick=1.5, npt=npt, ihbe=ihbe)
+    m = meshgen.shell_plate(9, 7, 90.0, 70.0, prop=prop, pressure=40.0, vrand=30.0)
+    g, o = cycle_check(m, ncheck=4)
+    assert o.shell_state("pla").max() > 0.0
+
+
+def test_law2_shell_with_temperature_buffer():
+    """LAW2 with a temperature word per integration point (8 words per point instead of 7)."""
+    mat = meshgen.steel_law2_shell(); mat.has_temp = 1; mat.rhocp = 3.6; mat.tini = 300.0
+    m = meshgen.shell_plate(7, 7, 70.0, 70.0, law=2, mat=mat, pressure=30.0, vrand=30.0)
+    g, o = cycle_check(m, ncheck=4, state_tol=1e-10)
+    assert o.shell_state("pla").max() > 0.0
+
+
 def test_qeph_ithk0_uses_initial_thickness():
     prop = meshgen.default_prop_shell(ithk=0)
     m = meshgen.shell_plate(5, 5, 50.0, 50.0, prop=prop, pressure=30.0, vrand=20.0)
