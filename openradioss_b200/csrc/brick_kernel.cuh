@@ -87,6 +87,11 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
   // SMSTR (21 words, rewritten every cycle by S8SAV3 / SMALLA3) goes straight to HBM with streaming stores:
   // collecting it in shared memory for a bulk store was measured slower (0.472 vs 0.450 ms on C5)
   double* const sm = g.smstr + (size_t)blockIdx.x * 21 * ORGPU_TILE + threadIdx.x;     // SMSTR word k at sm[k*TILE]
+#if ORGPU_PREFETCH_NEXT > 0
+  // a CTA about one wave ahead: start its connectivity toward L2 (its first load is then an L2 hit: -3 % kernel time)
+  { const unsigned nb = blockIdx.x + ORGPU_PREFETCH_NEXT;
+    if (nb < gridDim.x && threadIdx.x < (8 * ORGPU_TILE * 4) / 128) prefetch_l2(reinterpret_cast<const char*>(g.conn + (size_t)nb * 8 * ORGPU_TILE) + 128 * threadIdx.x); }
+#endif
   double dt_cand = K_EP30; int order = -1;
   if (e < g.ne) {
     const double DT1 = P.cs->dt2;                         // DT1 = DT2 of the previous cycle (resol.F:2721)
@@ -520,6 +525,17 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       }
     }
   }
+#ifdef ORGPU_PREFETCH_NODES
+  { const unsigned nb = blockIdx.x + ORGPU_PREFETCH_NODES;
+    if (nb < gridDim.x) {
+      const int* cn = g.conn + (size_t)nb * 8 * ORGPU_TILE + threadIdx.x;
+      int nn[8];
+      #pragma unroll
+      for (int k = 0; k < 8; k++) nn[k] = __ldg(cn + k * ORGPU_TILE);
+      #pragma unroll
+      for (int k = 0; k < 8; k++) { prefetch_l2(P.nd.pos + nn[k]); prefetch_l2(P.nd.vel + nn[k]); }
+    } }
+#endif
   cta_epilogue<true, STAGED>(dt_cand, order, P.db, g.blk0 + blockIdx.x, g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
 }
 

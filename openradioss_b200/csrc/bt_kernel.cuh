@@ -22,6 +22,11 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
   if (STAGED) tile_load_begin(s_tile_dyn, &s_bar, g_tile, (unsigned)g.nw * ORGPU_TILE * 8u);
   const TileAcc<STAGED> T{(STAGED ? s_tile_dyn : g_tile) + threadIdx.x};
   double* const sm = g.smstr + (size_t)blockIdx.x * 6 * ORGPU_TILE + threadIdx.x;      // SMSTR word k at sm[k*128]
+#if ORGPU_PREFETCH_NEXT > 0
+  // a CTA about one wave ahead: start its connectivity toward L2 (its first load is then an L2 hit: -3 % kernel time)
+  { const unsigned nb = blockIdx.x + ORGPU_PREFETCH_NEXT;
+    if (nb < gridDim.x && threadIdx.x < (4 * ORGPU_TILE * 4) / 128) prefetch_l2(reinterpret_cast<const char*>(g.conn + (size_t)nb * 4 * ORGPU_TILE) + 128 * threadIdx.x); }
+#endif
   double dt_cand = K_EP30; int order = 0x7fffffff;
   if (e < g.ne) {
     const double DT1 = P.cs->dt2;

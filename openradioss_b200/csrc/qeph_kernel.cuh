@@ -110,6 +110,11 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
   if (STAGED) tile_load_begin(s_tile_dyn, &s_bar, g_tile, (unsigned)g.nw * ORGPU_TILE * 8u);
   const TileAcc<STAGED> T{(STAGED ? s_tile_dyn : g_tile) + threadIdx.x};
   double* const sm = g.smstr + (size_t)blockIdx.x * 6 * ORGPU_TILE + threadIdx.x;      // SMSTR word k at sm[k*128]
+#if ORGPU_PREFETCH_NEXT > 0
+  // a CTA about one wave ahead: start its connectivity toward L2 (its first load is then an L2 hit: -3 % kernel time)
+  { const unsigned nb = blockIdx.x + ORGPU_PREFETCH_NEXT;
+    if (nb < gridDim.x && threadIdx.x < (4 * ORGPU_TILE * 4) / 128) prefetch_l2(reinterpret_cast<const char*>(g.conn + (size_t)nb * 4 * ORGPU_TILE) + 128 * threadIdx.x); }
+#endif
   double dt_cand = K_EP30; int order = 0x7fffffff;
   if (e < g.ne) {
     const double DT1 = P.cs->dt2;
@@ -624,5 +629,16 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       st256(row + 1, make_double4(-mm[1], -mm[2], STI * fac, K_ZERO * fac));
     }
   }
+#ifdef ORGPU_PREFETCH_NODES
+  { const unsigned nb = blockIdx.x + ORGPU_PREFETCH_NODES;       // that CTA's connectivity is in L2 by now (prefetched one wave ago)
+    if (nb < gridDim.x) {
+      const int* cn = g.conn + (size_t)nb * 4 * ORGPU_TILE + threadIdx.x;
+      int nn[4];
+      #pragma unroll
+      for (int k = 0; k < 4; k++) nn[k] = __ldg(cn + k * ORGPU_TILE);
+      #pragma unroll
+      for (int k = 0; k < 4; k++) { prefetch_l2(P.nd.pos + nn[k]); prefetch_l2(P.nd.vel + nn[k]); prefetch_l2(P.nd.rot + nn[k]); }
+    } }
+#endif
   cta_epilogue<false, STAGED>(dt_cand, order, P.db, g.blk0 + blockIdx.x, g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
 }
