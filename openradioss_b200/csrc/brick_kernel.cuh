@@ -525,17 +525,6 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       }
     }
   }
-#ifdef ORGPU_PREFETCH_NODES
-  { const unsigned nb = blockIdx.x + ORGPU_PREFETCH_NODES;
-    if (nb < gridDim.x) {
-      const int* cn = g.conn + (size_t)nb * 8 * ORGPU_TILE + threadIdx.x;
-      int nn[8];
-      #pragma unroll
-      for (int k = 0; k < 8; k++) nn[k] = __ldg(cn + k * ORGPU_TILE);
-      #pragma unroll
-      for (int k = 0; k < 8; k++) { prefetch_l2(P.nd.pos + nn[k]); prefetch_l2(P.nd.vel + nn[k]); }
-    } }
-#endif
   cta_epilogue<true, STAGED>(dt_cand, order, P.db, g.blk0 + blockIdx.x, g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
 }
 

@@ -629,16 +629,5 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       st256(row + 1, make_double4(-mm[1], -mm[2], STI * fac, K_ZERO * fac));
     }
   }
-#ifdef ORGPU_PREFETCH_NODES
-  { const unsigned nb = blockIdx.x + ORGPU_PREFETCH_NODES;       // that CTA's connectivity is in L2 by now (prefetched one wave ago)
-    if (nb < gridDim.x) {
-      const int* cn = g.conn + (size_t)nb * 4 * ORGPU_TILE + threadIdx.x;
-      int nn[4];
-      #pragma unroll
-      for (int k = 0; k < 4; k++) nn[k] = __ldg(cn + k * ORGPU_TILE);
-      #pragma unroll
-      for (int k = 0; k < 4; k++) { prefetch_l2(P.nd.pos + nn[k]); prefetch_l2(P.nd.vel + nn[k]); prefetch_l2(P.nd.rot + nn[k]); }
-    } }
-#endif
   cta_epilogue<false, STAGED>(dt_cand, order, P.db, g.blk0 + blockIdx.x, g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
 }
