@@ -80,6 +80,12 @@ int  orgpu_download_fsky(orgpu_engine* e, double* fsky /*(8,LSKY)*/);
 /* fields: 0 sig(6) 1 eint 2 rho 3 qvis 4 pla 5 epsd 6 vol 7 off 8 temp 9 smstr(21); out[k*numels+e] */
 int  orgpu_download_solid_state(orgpu_engine* e, int field, double* out);
 int  orgpu_download_shell_state(orgpu_engine* e, int field, double* out);
+/* -- state hand-over in the other direction (restart / a run that starts from an initial state: the role of
+ *    shell_gpu_upload_ip_state, shell_gpu_driver.h, and of RDRESB reading ELBUF from the restart file): same
+ *    fields and layout as the downloads; orgpu_set_time restores TT, DT2, DT2OLD, NCYCLE (resol.F restart values). */
+int  orgpu_upload_solid_state(orgpu_engine* e, int field, const double* in);
+int  orgpu_upload_shell_state(orgpu_engine* e, int field, const double* in);
+int  orgpu_set_time(orgpu_engine* e, double tt, double dt2, double dt2old, long long ncycle);
 
 /* -- print-cycle energy balances (SBILAN sbilan.F:138-157, CBILAN cbilan.F:183-275 -> PARTSAV(1,.)
  *    -> ECRIT output/ecrit.F:259-373): out = internal energy of solids, of shells, nodal kinetic

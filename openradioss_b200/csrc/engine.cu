@@ -601,28 +601,47 @@ int orgpu_download_fsky(orgpu_engine* e, double* fsky)
   return 0;
 }
 
-int orgpu_download_solid_state(orgpu_engine* e, int field, double* out)
+static int solid_state_xfer(orgpu_engine* e, int field, double* buf, bool up)
 {
-  NEED(e && e->finalized && out, -1, "engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
+  NEED(e && e->finalized && buf, -1, "engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
   CUDA_OK(cudaStreamSynchronize(e->st));
   const size_t NE = e->numels;
   for (auto& S : e->bsg) {
-    const BrickSG& d = S.d; int w0 = 0, nc = 1; const double* base = d.slab; int nw = d.nw;
+    const BrickSG& d = S.d; int w0 = 0, nc = 1; double* base = d.slab; int nw = d.nw;
     switch (field) { case 0: w0 = BW_SIG; nc = 6; break; case 1: w0 = BW_EINT; break; case 2: w0 = BW_RHO; break; case 3: w0 = BW_QVIS; break;
                      case 4: w0 = BW_PLA; break; case 5: w0 = BW_EPSD; break; case 6: w0 = d.w_vol; break; case 7: w0 = BW_OFF; break;
                      case 8: w0 = d.w_temp; break; case 9: base = d.smstr; nw = 21; w0 = 0; nc = 21; break; default: FAIL(-1, "unknown solid field %d", field); }
-    if (w0 < 0) { for (int i = 0; i < d.ne; i++) out[S.first_elem + i] = d.mat.tini; continue; }   // no temperature buffer
+    if (w0 < 0) { if (!up) for (int i = 0; i < d.ne; i++) buf[S.first_elem + i] = d.mat.tini; continue; }   // no temperature buffer
     for (int k = 0; k < nc; k++)
-      CUDA_OK(slab_download_word(base, nw, w0 + k, d.ne, out + k * NE + S.first_elem));
+      CUDA_OK(up ? slab_upload_word(base, nw, w0 + k, d.ne, buf + k * NE + S.first_elem)
+                 : slab_download_word(base, nw, w0 + k, d.ne, buf + k * NE + S.first_elem));
   }
   return 0;
 }
+int orgpu_download_solid_state(orgpu_engine* e, int field, double* out) { return solid_state_xfer(e, field, out, false); }
+int orgpu_upload_solid_state(orgpu_engine* e, int field, const double* in) { return solid_state_xfer(e, field, const_cast<double*>(in), true); }
 
 int orgpu_download_shell_state(orgpu_engine* e, int field, double* out)
 {
   NEED(e && e->finalized && out, -1, "engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
   CUDA_OK(cudaStreamSynchronize(e->st));
-  return shell_download_state(e->csg, e->numelc, field, out);
+  return shell_state_xfer(e->csg, e->numelc, field, out, false);
+}
+int orgpu_upload_shell_state(orgpu_engine* e, int field, const double* in)
+{
+  NEED(e && e->finalized && in, -1, "engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  return shell_state_xfer(e->csg, e->numelc, field, const_cast<double*>(in), true);
+}
+/* LAW36 table cursors (VARTMP) are integer state: per integration point the live cursor(s) */
+int orgpu_set_time(orgpu_engine* e, double tt, double dt2, double dt2old, long long ncycle)
+{
+  NEED(e, -1, "null handle"); CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  CycleState cs; CUDA_OK(cudaMemcpy(&cs, e->d_cs, sizeof cs, cudaMemcpyDeviceToHost));
+  cs.tt = tt; cs.tt0 = tt; cs.dt2 = dt2; cs.dt2old = dt2old; cs.ncycle = ncycle;
+  CUDA_OK(cudaMemcpy(e->d_cs, &cs, sizeof cs, cudaMemcpyHostToDevice));
+  return 0;
 }
 
 int orgpu_step_host(orgpu_engine* e, const double* X, const double* V, const double* VR,

@@ -161,11 +161,11 @@ static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky
 
 // fields: 0 for(5) 1 mom(3) 2 eint(2) 3 thk 4 off 5 stra(8) 6 epsd 7 hourg(nhourg) 8 smstr(6)
 //         9 sig(5*npt) 10 pla(npt) 11 epsd_ip(npt) 12 temp(npt) ; out[k*numelc + e]
-static int shell_download_state(std::vector<ShellSGHost>& sgs, int numelc, int field, double* out)
+static int shell_state_xfer(std::vector<ShellSGHost>& sgs, int numelc, int field, double* out, bool up)
 {
   const size_t NE = numelc;
   for (auto& S : sgs) {
-    const ShellSG& d = S.d; const double* base = d.slab; int nw = d.nw, nc = 1, w0 = 0, ipw = -1;
+    const ShellSG& d = S.d; double* base = d.slab; int nw = d.nw, nc = 1, w0 = 0, ipw = -1;
     switch (field) {
       case 0: w0 = SW_FOR; nc = 5; break; case 1: w0 = SW_MOM; nc = 3; break; case 2: w0 = SW_EINT; nc = 2; break;
       case 3: w0 = SW_THK; break; case 4: w0 = SW_OFF; break; case 5: w0 = SW_STRA; nc = 8; break; case 6: w0 = SW_EPSD; break;
@@ -177,8 +177,9 @@ static int shell_download_state(std::vector<ShellSGHost>& sgs, int numelc, int f
     for (int k = 0; k < nc; k++) {
       int w = w0 + k;
       if (ipw >= 0) w = (field == 9) ? d.w_ip0 + (k / 5) * d.nwip + IW_SIG + (k % 5) : d.w_ip0 + k * d.nwip + ipw;
-      if (slab_download_word(base, nw, w, d.ne, out + k * NE + S.first_elem) != cudaSuccess) {
-        orgpu_set_error("shell state download failed"); return -100; }
+      if ((up ? slab_upload_word(base, nw, w, d.ne, out + k * NE + S.first_elem)
+              : slab_download_word(base, nw, w, d.ne, out + k * NE + S.first_elem)) != cudaSuccess) {
+        orgpu_set_error("shell state transfer failed"); return -100; }
     }
   }
   return 0;

@@ -17,7 +17,7 @@ EXPORTS = """create destroy last_error upload_nodes set_loads set_bcs set_solids
 set_functions add_solid_group add_shell_group finalize forces_phase assemble advance run_cycles
 synchronize get_time download_nodes download_fsky download_solid_state download_shell_state
 step_host launch_count last_run_ms set_profile get_profile pack_rows unpack_rows comm_unique_id comm_init
-set_exchange exchange get_energies p2p_export p2p_connect set_load_function set_fixvel""".split()
+set_exchange exchange get_energies p2p_export p2p_connect set_load_function set_fixvel upload_solid_state upload_shell_state set_time""".split()
 
 
 def load_library() -> C.CDLL:
@@ -80,6 +80,42 @@ class Engine(Binding):
             dist.barrier()
 
     def exchange(self): self._call("exchange", self.h)
+
+    # -- restart / state hand-over ------------------------------------------------------------------
+    def upload_solid_state(self, name, arr):
+        fid, nc = self.SOLID_FIELDS[name]
+        a = np.ascontiguousarray(arr, np.float64); assert a.shape == (nc, self.model.numels)
+        self._call("upload_solid_state", self.h, C.c_int(fid), a.ctypes.data_as(C.c_void_p))
+
+    def upload_shell_state(self, name, arr):
+        fid, _ = self.SHELL_FIELDS[name]
+        a = np.ascontiguousarray(arr, np.float64); assert a.shape[1] == self.model.numelc
+        self._call("upload_shell_state", self.h, C.c_int(fid), a.ctypes.data_as(C.c_void_p))
+
+    def set_time(self, tt, dt2, dt2old, ncycle):
+        self._call("set_time", self.h, C.c_double(tt), C.c_double(dt2), C.c_double(dt2old), C.c_longlong(ncycle))
+
+    def checkpoint(self):
+        """Everything a restart needs: nodal arrays, clock, element state of both families."""
+        self.synchronize()
+        ck = dict(nodes=self.download_nodes(("X", "V", "VR", "D")), time=self.time())
+        if self.model.numels:
+            ck["solid"] = {f: self.solid_state(f) for f in ("sig", "eint", "rho", "qvis", "pla", "epsd", "off", "temp", "smstr")}
+        if self.model.numelc:
+            ck["shell"] = {f: self.shell_state(f) for f in ("forc", "mom", "eint", "thk", "off", "stra", "epsd", "hourg", "smstr", "sig", "pla", "epsd_ip")}
+        return ck
+
+    def restore(self, ck):
+        n = ck["nodes"]
+        self.upload_nodes(X=n["X"], V=n["V"], VR=n["VR"], D=n["D"])
+        t = ck["time"]
+        self.set_time(t["tt"], t["dt2"], t["dt2"], t["ncycle"])       # DT2OLD = DT2 after a completed cycle (resol.F:6494)
+        for f, a in ck.get("solid", {}).items():
+            if f == "temp" and not any(g.mat.has_temp for g in self.model.solid_groups):
+                continue
+            self.upload_solid_state(f, a)
+        for f, a in ck.get("shell", {}).items():
+            self.upload_shell_state(f, a)
 
     def energies(self):
         """(internal solids, internal shells, kinetic translation, kinetic rotation), summed on the device."""
