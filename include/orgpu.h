@@ -46,6 +46,9 @@ int  orgpu_set_bcs(orgpu_engine* e, const int* icodt, const int* icodr);       /
  * FORCE (engine/source/loads/general/force.F90:195-196, 235, 301-312; resol.F:2929) sharing one function;
  * ifunc = 0-based curve of orgpu_set_functions, -1 = constant loads.  Before orgpu_finalize. */
 int  orgpu_set_load_function(orgpu_engine* e, int ifunc, double fcx);
+/* user node ids ITAB(NUMNOD): NELTST of a nodal time step (control.nodadt = 1: DTNODA, engine/source/time_step/
+ * dtnoda.F:221-260, 324-338, 445-462; resol.F:6066).  Before orgpu_finalize. */
+int  orgpu_set_itab(orgpu_engine* e, const int* itab);
 /* imposed velocities (FIXVEL, engine/source/constraints/general/impvel/fixvel.F:141-147, 334-378; resol.F:7610):
  * record k = IBFV(1,k) node (1-based), IBFV(2,k) direction 1..3 in the global frame, IBFV(3,k) curve (0-based),
  * VEL(1,k) FAC, VEL(2,k) start time, VEL(3,k) stop time, VEL(5,k) FACX.  Before orgpu_finalize. */

@@ -114,7 +114,8 @@ typedef struct orgpu_control {
   double dt2old_init;   /* DT2OLD carried in from the restart         */
   double tt_init;       /* TT                                          */
   int    iroddl;        /* rotational dofs present (shells)           */
-  int    nodadt;        /* /DT/NODA (0 only)                          */
+  int    nodadt;        /* NODADT: 1 = /DT/NODA nodal time step (bricks and QEPH shells; no /DT/NODA/CST) */
+  double dtfac_node;    /* DTFAC1(11) /DT/NODA scale                  */
 } orgpu_control;
 
 #ifdef __cplusplus

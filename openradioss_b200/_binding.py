@@ -66,6 +66,8 @@ class Binding:
         self._call("set_pon", self.h, _opt(m.adsky, np.int32), C.c_int(m.lsky))
         if m.npf is not None:
             self._call("set_functions", self.h, C.c_int(len(m.npf) - 1), _opt(m.npf, np.int32), _opt(m.tf, np.float64))
+        if m.itab is not None:
+            self._call("set_itab", self.h, _opt(m.itab, np.int32))
         if m.load_func is not None:
             self._call("set_load_function", self.h, C.c_int(int(m.load_func[0])), C.c_double(float(m.load_func[1])))
         if m.ibfv is not None and len(m.ibfv):

@@ -409,7 +409,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
           STI = TRHO * TVOL;
         }
         DTX = g.dtfac * DTX;
-        if (VOLN > K_ZERO && OFF > K_ZERO && OFFG > K_ZERO) dt_cand = DTX;
+        if (VOLN > K_ZERO && OFF > K_ZERO && OFFG > K_ZERO && g.nodadt == 0) dt_cand = DTX;
       }
       // ---- pressure + internal energy (m2law.F:433-453)
       const double DTA = K_HALF * DT1;

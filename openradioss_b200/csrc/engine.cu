@@ -50,6 +50,7 @@ struct orgpu_engine {
   int lf_func = -1; double lf_fcx = 1.0;            // time function of the nodal loads
   std::vector<int> fv_idx; std::vector<FixVelNode> fv;   // imposed velocities, per node
   double* d_ftf = nullptr; int* d_fnpf = nullptr; int* d_fv_idx = nullptr; FixVelNode* d_fv = nullptr;
+  std::vector<int> itab; int* d_itab = nullptr; double* d_nd_dt = nullptr; int* d_nd_node = nullptr;   // /DT/NODA
   std::vector<HostSolidGroup> sgroups;
   std::vector<HostShellGroup> cgroups;
   // device model
@@ -138,7 +139,7 @@ int orgpu_destroy(orgpu_engine* e)
   for (auto& s : e->csg) for (void* p : s.owned) cudaFree(p);
   void* ptrs[] = {e->nd.pos, e->nd.vel, e->nd.rot, e->nd.D, e->nd.A, e->nd.AR, e->nd.STIFN, e->nd.STIFR, e->nd.MS, e->nd.IN,
                   e->d_stage3a, e->d_stage3b, e->d_fext, e->d_mext, e->d_icodt, e->d_icodr, e->d_adsky, e->d_fsky, e->d_cs,
-                  e->db.dt, e->db.ngl, e->db.order, e->d_ftf, e->d_fnpf, e->d_fv_idx, e->d_fv};
+                  e->db.dt, e->db.ngl, e->db.order, e->d_ftf, e->d_fnpf, e->d_fv_idx, e->d_fv, e->d_itab, e->d_nd_dt, e->d_nd_node};
   for (void* p : ptrs) if (p) cudaFree(p);
   { Exchange& x = e->xc;
     void* xp[] = {x.d_send_slots, x.d_recv_slots, x.d_sendbuf, x.d_recvbuf, x.d_cand_send, x.d_cand_recv, x.d_slots_tmp, x.d_rows_tmp};
@@ -219,6 +220,13 @@ int orgpu_set_functions(orgpu_engine* e, int nfunc, const int* npf, const double
   return 0;
 }
 
+int orgpu_set_itab(orgpu_engine* e, const int* itab)
+{
+  NEED(e && itab && !e->finalized, -1, "orgpu_set_itab: bad arguments / already finalized");
+  e->itab.assign(itab, itab + e->numnod);
+  return 0;
+}
+
 int orgpu_set_load_function(orgpu_engine* e, int ifunc, double fcx)
 {
   NEED(e && !e->finalized, -1, "orgpu_set_load_function: bad handle / already finalized");
@@ -294,7 +302,7 @@ int orgpu_finalize(orgpu_engine* e)
     const int np = ((ne + ORGPU_BLOCK - 1) / ORGPU_BLOCK) * ORGPU_BLOCK;
     e->bsg.emplace_back(); BrickSGHost& S = e->bsg.back(); S.first_elem = nft;
     BrickSG& d = S.d; d.ne = ne; d.ne_pad = np; d.order0 = order; d.blk0 = blk;
-    d.mat = e->sgroups[gi].mat; d.prop = e->sgroups[gi].prop; d.dtfac = e->ctl.dtfac_brick;
+    d.mat = e->sgroups[gi].mat; d.prop = e->sgroups[gi].prop; d.dtfac = e->ctl.dtfac_brick; d.nodadt = e->ctl.nodadt;
     std::vector<int> conn((size_t)8 * np, 0), ngl(np, 0), conn_t;
     // state slab: read/write words first (SIG 6, EINT, RHO, QVIS, PLA, EPSD, OFF[, TEMP]), then VOL and the slot rows
     d.w_temp = d.mat.has_temp ? BW_NFIX : -1;
@@ -323,6 +331,17 @@ int orgpu_finalize(orgpu_engine* e)
     order += ne; blk += nblk; gi = gj;
   }
   NEED(blk > 0, -4, "orgpu_finalize: no element groups");
+  // /DT/NODA
+  NEED(e->ctl.nodadt == 0 || e->ctl.nodadt == 1, -5, "NODADT=%d is outside the built path (0, 1)", e->ctl.nodadt);
+  e->nd.nodadt = e->ctl.nodadt; e->nd.dtfac_node = e->ctl.dtfac_node;
+  if (e->ctl.nodadt) {
+    for (auto& S : e->csg) NEED(shell_is_qeph(S.d.prop), -5, "/DT/NODA with Belytschko-Tsay shells (CHVIS3 nodal stiffnesses) is outside the built path");
+    const size_t ncta = (e->numnod + ORGPU_NODE_BLOCK - 1) / ORGPU_NODE_BLOCK;
+    if (dev_alloc(&e->d_nd_dt, 2 * ncta) || dev_alloc(&e->d_nd_node, 2 * ncta)) return -100;
+    e->nd.nd_dt = e->d_nd_dt; e->nd.nd_node = e->d_nd_node;
+    if (!e->itab.empty()) { if (dev_alloc(&e->d_itab, e->itab.size())) return -100;
+      CUDA_OK(cudaMemcpy(e->d_itab, e->itab.data(), 4 * e->itab.size(), cudaMemcpyHostToDevice)); e->nd.itab = e->d_itab; }
+  }
   // time functions used at node level (loads, imposed velocities)
   e->fa.lf_func = -1; e->fa.lf_fcx = 1.0; e->fa.ft = FuncTable{nullptr, nullptr};
   if (e->lf_func >= 0 || !e->fv.empty()) {
@@ -371,6 +390,17 @@ static void launch_element_phase(orgpu_engine* e, int fused, size_t* evi)
   element_finalize_kernel<<<1, ORGPU_FINALIZE_BLOCK, 0, e->st>>>(e->d_cs, e->db, e->fa); e->launches++;
 }
 
+// gather + update: one fused kernel, or with /DT/NODA assemble (+ nodal dt candidates) -> fold + clock -> advance
+static void launch_node_phase(orgpu_engine* e)
+{
+  if (e->ctl.nodadt) {
+    launch_node_assemble(e->nd, e->d_fsky, e->roww, e->d_cs, e->ctl.iroddl, e->st);
+    launch_dtnoda_finalize(e->nd, e->d_cs, 1, e->st);
+    launch_node_advance(e->nd, e->d_cs, e->ctl.iroddl, e->st);
+    e->launches += 3;
+  } else { launch_node_fused(e->nd, e->d_fsky, e->roww, e->d_cs, e->ctl.iroddl, e->st); e->launches++; }
+}
+
 int orgpu_forces_phase(orgpu_engine* e, double dt1)
 {
   NEED(e && e->finalized, -1, "orgpu_forces_phase: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
@@ -383,6 +413,7 @@ int orgpu_assemble(orgpu_engine* e)
 {
   NEED(e && e->finalized, -1, "orgpu_assemble: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
   launch_node_assemble(e->nd, e->d_fsky, e->roww, e->d_cs, e->ctl.iroddl, e->st); e->launches++;
+  if (e->ctl.nodadt) { launch_dtnoda_finalize(e->nd, e->d_cs, 0, e->st); e->launches++; }   // DTNODA: DT2T / NELTST / ITYPTST for the caller
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -449,7 +480,8 @@ static void p2p_exchange_on_stream(orgpu_engine* e)
 int orgpu_run_cycles(orgpu_engine* e, int ncycles)
 {
   NEED(e && e->finalized && ncycles >= 0, -1, "orgpu_run_cycles: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
-  const int per_cycle = (int)(e->csg.size() + e->bsg.size()) + 2;   // force kernels + dt finalize + node kernel
+  const int per_cycle = (int)(e->csg.size() + e->bsg.size()) + (e->ctl.nodadt ? 4 : 2);   // force kernels + dt finalize + node kernel(s)
+  NEED(!(e->ctl.nodadt && e->xc.nranks > 1), -5, "/DT/NODA across domains (nodal dt exchange) is outside the built path");
   if (e->xc.nranks > 1 && e->xc.p2p && !e->profile) {
     // one process per GPU, peer-memory exchange: the whole cycle (forces, dt fold, push, wait+unpack, gather+update)
     // is one CUDA graph, replayed ncycles times with no host involvement and no library call
@@ -515,9 +547,9 @@ int orgpu_run_cycles(orgpu_engine* e, int ncycles)
       const int nc = (ncycles - c0 < chunk) ? ncycles - c0 : chunk;
       size_t evi = 0;
       for (int c = 0; c < nc; c++) {
-        launch_element_phase(e, 1, &evi);
+        launch_element_phase(e, e->ctl.nodadt ? 0 : 1, &evi);
         cudaEventRecord(get_event(e, evi++), e->st);
-        launch_node_fused(e->nd, e->d_fsky, e->roww, e->d_cs, e->ctl.iroddl, e->st); e->launches++;
+        launch_node_phase(e);
         cudaEventRecord(get_event(e, evi++), e->st);
       }
       CUDA_OK(cudaStreamSynchronize(e->st));
@@ -537,12 +569,13 @@ int orgpu_run_cycles(orgpu_engine* e, int ncycles)
   if (!e->gexec) {                         // capture one fused cycle once, replay it ncycles times
     cudaGraph_t g;
     CUDA_OK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeThreadLocal));
-    launch_element_phase(e, 1, nullptr);
-    launch_node_fused(e->nd, e->d_fsky, e->roww, e->d_cs, e->ctl.iroddl, e->st);
+    const long long l0 = e->launches;
+    launch_element_phase(e, e->ctl.nodadt ? 0 : 1, nullptr);
+    launch_node_phase(e);
+    e->launches = l0;                      // the capture pass did not execute
     CUDA_OK(cudaStreamEndCapture(e->st, &g));
     CUDA_OK(cudaGraphInstantiate(&e->gexec, g, 0));
     CUDA_OK(cudaGraphDestroy(g));
-    e->launches -= per_cycle - 1;          // the capture pass did not execute
   }
   CUDA_OK(cudaEventRecord(e->ev0, e->st));
   for (int c = 0; c < ncycles; c++) CUDA_OK(cudaGraphLaunch(e->gexec, e->st));

@@ -38,7 +38,7 @@ __device__ __forceinline__ NodeAcc node_gather(const DevNodes& nd, const double*
   else { r.a[0] = K_ZERO; r.a[1] = K_ZERO; r.a[2] = K_ZERO; }
   if (nd.MEXT) { r.ar[0] = nd.MEXT[3 * n] * fscale; r.ar[1] = nd.MEXT[3 * n + 1] * fscale; r.ar[2] = nd.MEXT[3 * n + 2] * fscale; }
   else { r.ar[0] = K_ZERO; r.ar[1] = K_ZERO; r.ar[2] = K_ZERO; }
-  r.stifn = K_ZERO; r.stifr = K_ZERO;
+  r.stifn = nd.nodadt ? K_EM20 : K_ZERO; r.stifr = r.stifn;
   for (int kb = k0; kb < k1; kb += NB) {
     if (kb != k0) {                                  // irregular node with more than NB corners
       #pragma unroll
@@ -138,11 +138,70 @@ __global__ void __launch_bounds__(ORGPU_NODE_BLOCK)
 node_assemble_kernel(const __grid_constant__ DevNodes nd, const double* __restrict__ fsky, const CycleState* __restrict__ cs, int iroddl)
 {
   const int n = blockIdx.x * ORGPU_NODE_BLOCK + threadIdx.x;
-  if (n >= nd.n) return;
-  NodeAcc r = node_gather<ROWW>(nd, fsky, n, iroddl, cs->fscale);
-  nd.A[3 * n] = r.a[0]; nd.A[3 * n + 1] = r.a[1]; nd.A[3 * n + 2] = r.a[2];
-  nd.AR[3 * n] = r.ar[0]; nd.AR[3 * n + 1] = r.ar[1]; nd.AR[3 * n + 2] = r.ar[2];
-  nd.STIFN[n] = r.stifn; nd.STIFR[n] = r.stifr;
+  double dtt = K_EP30, dtr = K_EP30;
+  if (n < nd.n) {
+    NodeAcc r = node_gather<ROWW>(nd, fsky, n, iroddl, cs->fscale);
+    nd.A[3 * n] = r.a[0]; nd.A[3 * n + 1] = r.a[1]; nd.A[3 * n + 2] = r.a[2];
+    nd.AR[3 * n] = r.ar[0]; nd.AR[3 * n + 1] = r.ar[1]; nd.AR[3 * n + 2] = r.ar[2];
+    nd.STIFN[n] = r.stifn; nd.STIFR[n] = r.stifr;
+    if (nd.nodadt) {                                        // DTNODA: dtnoda.F:221-260 (translations), :445-462 (rotations)
+      const double ms = nd.MS[n];
+      if (r.stifn > K_ZERO && ms > K_ZERO) dtt = nd.dtfac_node * or_sqrt(or_div(K_TWO * ms, r.stifn));
+      if (iroddl) { const double in = nd.IN[n]; if (r.stifr > K_ZERO && in > K_ZERO) dtr = nd.dtfac_node * or_sqrt(or_div(K_TWO * in, r.stifr)); }
+    }
+  }
+  if (nd.nodadt) {                                          // one candidate per CTA and family; first node in node order keeps a tie
+    __shared__ double s_d[2][ORGPU_NODE_BLOCK / 32]; __shared__ int s_n[2][ORGPU_NODE_BLOCK / 32];
+    double d[2] = {dtt, dtr}; int id[2] = {n, n};
+    #pragma unroll
+    for (int f = 0; f < 2; f++) {
+      #pragma unroll
+      for (int s = 16; s > 0; s >>= 1) {
+        const double d2 = __shfl_down_sync(0xffffffffu, d[f], s); const int n2 = __shfl_down_sync(0xffffffffu, id[f], s);
+        if (dt_better<false>(d2, n2, d[f], id[f])) { d[f] = d2; id[f] = n2; }
+      }
+      if ((threadIdx.x & 31) == 0) { s_d[f][threadIdx.x >> 5] = d[f]; s_n[f][threadIdx.x >> 5] = id[f]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      const int f = threadIdx.x; double bd = s_d[f][0]; int bn = s_n[f][0];
+      for (int w = 1; w < ORGPU_NODE_BLOCK / 32; w++) if (dt_better<false>(s_d[f][w], s_n[f][w], bd, bn)) { bd = s_d[f][w]; bn = s_n[f][w]; }
+      nd.nd_dt[f * gridDim.x + blockIdx.x] = bd; nd.nd_node[f * gridDim.x + blockIdx.x] = bn;
+    }
+  }
+}
+
+// /DT/NODA: fold the per-CTA nodal candidates into DT2T (strict "<": translations in node order, then rotations,
+// against what the elements left -- nothing, they do not lower DT2T in this mode), NELTST = ITAB(N), ITYPTST = 11;
+// fused = 1 also runs the RESOL bookkeeping that element_finalize_kernel skipped
+__global__ void __launch_bounds__(1024)
+dtnoda_finalize_kernel(CycleState* cs, const __grid_constant__ DevNodes nd, int ncta, int fused)
+{
+  __shared__ double s_dt[32]; __shared__ int s_ngl[32]; __shared__ int s_ord[32];
+  double cur = cs->dt2t; int curn = -1;
+  for (int f = 0; f < 2; f++) {
+    double dt = K_EP30; int ngl = 0, ord = 0x7fffffff;
+    for (int b = threadIdx.x; b < ncta; b += 1024) {
+      const double d2 = __ldcg(nd.nd_dt + f * ncta + b); const int o2 = __ldcg(nd.nd_node + f * ncta + b);
+      if (dt_better<false>(d2, o2, dt, ord)) { dt = d2; ord = o2; }
+    }
+    finalize_fold<false>(dt, ngl, ord, s_dt, s_ngl, s_ord);
+    if (threadIdx.x == 0 && dt < cur) { cur = dt; curn = ord; }
+  }
+  if (threadIdx.x == 0) {
+    if (curn >= 0) { cs->dt2t = cur; cs->neltst = nd.itab ? nd.itab[curn] : curn + 1; cs->ityptst = 11; }
+    if (fused) {
+      const double dt1 = cs->dt2;
+      double dt2 = K_EP06;
+      if (cs->dt2t < dt2) dt2 = cs->dt2t;
+      const double c11 = (double)1.1f;
+      dt2 = fmin(dt2, fmin(c11 * cs->dt2old, cs->dtmx));
+      cs->dt2old = dt2;
+      cs->dt12 = K_HALF * (dt1 + dt2);
+      cs->dt1 = dt1; cs->dt2 = dt2;
+      cs->tt = cs->tt + dt2; cs->ncycle += 1;
+    }
+  }
 }
 
 // phased mode, step 3: ACCELE + BCS + VELOCITY + DEPLA from the stored A / AR
@@ -184,6 +243,11 @@ void launch_node_assemble(const DevNodes& nd, const double* fsky, int roww, cons
   const int nb = (nd.n + ORGPU_NODE_BLOCK - 1) / ORGPU_NODE_BLOCK;
   if (roww == 4) node_assemble_kernel<4><<<nb, ORGPU_NODE_BLOCK, 0, st>>>(nd, fsky, cs, iroddl);
   else           node_assemble_kernel<8><<<nb, ORGPU_NODE_BLOCK, 0, st>>>(nd, fsky, cs, iroddl);
+}
+void launch_dtnoda_finalize(const DevNodes& nd, CycleState* cs, int fused, cudaStream_t st)
+{
+  const int nb = (nd.n + ORGPU_NODE_BLOCK - 1) / ORGPU_NODE_BLOCK;
+  dtnoda_finalize_kernel<<<1, 1024, 0, st>>>(cs, nd, nb, fused);
 }
 void launch_node_advance(const DevNodes& nd, const CycleState* cs, int iroddl, cudaStream_t st)
 {

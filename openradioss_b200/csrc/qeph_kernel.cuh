@@ -397,7 +397,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     const double SHF = (NPT == 1) ? K_ZERO : g.prop.shf, SHFSR = (NPT == 1) ? K_ZERO : g.prop.shfsr;
     const double AMU = (g.prop.h1 == K_ZERO) ? K_ZEP01 + K_FIVEEM3 : g.prop.h1;
     // ---- CNDT3
-    double STI;
+    double STI, STIR = K_ZERO;
     {
       double VISCMX = fmax(io.viscmx, AMU);
       VISCMX = or_sqrt(K_ONE + VISCMX * VISCMX) - VISCMX;
@@ -405,9 +405,15 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       const double F_OSET = K_ONE + K_ZERO;   // HALF*|Z_OFFSET*THK0|/THK0 with zero offset: exactly +0
       const double F_DTE = or_div(K_ONE, or_sqrt(F_OSET));
       const double DT = or_div(g.dtfac * F_DTE * ALDT, io.ssp);
+      if (g.nodadt != 0) {                                  // cndt3.F:194-221 (IGTYP=1), no element time step (:231, :294)
+        if (OFF == K_ZERO) { STI = K_ZERO; STIR = K_ZERO; }
+        else { STI = or_div(K_HALF * F_OSET * io.vol0 * A11, ALDT * ALDT);
+               STIR = STI * (THK0 * THK0 + AREA) * K_ONE_OVER_12 + STI * (K_ZERO * THK0) * (K_ZERO * THK0); }
+      } else {
       if (OFFG > K_ZERO && OFF != K_ZERO) dt_cand = DT;
       const double DIVM = fmax(ALDT * ALDT, K_EM20);
       STI = or_div(K_HALF * F_OSET * io.vol0 * A11 * OFF, DIVM);
+      }
     }
     // ---- CZFINTCE : constant part of the generalised internal forces
     const double* FO = io.fo; const double* MO = io.mo;
@@ -565,7 +571,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     if (OFF < K_ONE) OFFG = OFF;
     T.st(SW_OFF, OFFG);
     const bool dead = OFFG < K_ZERO;
-    if (dead) STI = K_ZERO;
+    if (dead) { STI = K_ZERO; STIR = K_ZERO; }
     double FL[3][4], MM[3][4];
     #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -626,7 +632,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       const double fac = (J & 1) ? FACN2 : FACN1;
       double4* row = reinterpret_cast<double4*>(P.fsky + (size_t)8 * sl[J]);
       st256(row, make_double4(-f[0], -f[1], -f[2], -mm[0]));
-      st256(row + 1, make_double4(-mm[1], -mm[2], STI * fac, K_ZERO * fac));
+      st256(row + 1, make_double4(-mm[1], -mm[2], STI * fac, STIR * fac));
     }
   }
   cta_epilogue<false, STAGED>(dt_cand, order, P.db, g.blk0 + blockIdx.x, g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);

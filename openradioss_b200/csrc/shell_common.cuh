@@ -32,6 +32,7 @@ struct ShellSG {
   const double* tf; const int* npf;    // LAW36 function table (pairs), 0-based curve starts
   orgpu_law2 m2; orgpu_law36 m36; orgpu_prop_shell prop;
   double dtfac;               // DTFAC1(3)
+  int nodadt;                 // /DT/NODA: nodal stiffnesses of cndt3.F:194-221, no element time step
 };
 
 enum { SW_FOR = 0, SW_MOM = 5, SW_EINT = 8, SW_THK = 10, SW_OFF = 11, SW_STRA = 12, SW_EPSD = 20, SW_HOURG = 21 };

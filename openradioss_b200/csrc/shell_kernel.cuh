@@ -76,7 +76,7 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
     d.ne = ne; d.ne_pad = np; d.order0 = order; d.blk0 = blk; d.law = G.law; d.npt = G.prop.npt;
     d.nvartmp = (G.law == 36) ? 2 + G.m36.nrate : 0;
     d.nhourg = shell_is_qeph(G.prop) ? 12 : 5;
-    d.m2 = G.m2; d.m36 = G.m36; d.prop = G.prop; d.dtfac = ctl.dtfac_shell;
+    d.m2 = G.m2; d.m36 = G.m36; d.prop = G.prop; d.dtfac = ctl.dtfac_shell; d.nodadt = ctl.nodadt;
     if (G.law == 36) {
       if (npf.empty()) { orgpu_set_error("LAW36 group without a function table (orgpu_set_functions)"); return -4; }
       for (int j = 0; j < G.m36.nrate; j++) {

@@ -145,7 +145,7 @@ def default_control(iroddl=0) -> Control:
     c.dt_init = 0.0            # DT1 of cycle 0
     c.dt2old_init = EP20
     c.tt_init = 0.0
-    c.iroddl = iroddl; c.nodadt = 0
+    c.iroddl = iroddl; c.nodadt = 0; c.dtfac_node = 0.9
     return c
 
 

@@ -41,7 +41,7 @@ class PropShell(C.Structure):
 
 class Control(C.Structure):
     _fields_ = [(n, d) for n in "dtfac_brick dtfac_shell dtmx dt_init dt2old_init tt_init".split()] + \
-               [("iroddl", i), ("nodadt", i)]
+               [("iroddl", i), ("nodadt", i), ("dtfac_node", d)]
 
 
 def elastic_constants(young: float, nu: float):

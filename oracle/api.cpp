@@ -108,7 +108,8 @@ void orc_finalize(void*){}
 void orc_forces_phase(void* h,double dt1){
   Oracle* o=(Oracle*)h; o->DT1=dt1; o->DT2=K_EP06; orc_forces(*o);
 }
-void orc_assemble(void* h){ orc_asspar4(*(Oracle*)h); }
+void orc_assemble(void* h){ Oracle* o=(Oracle*)h; orc_asspar4(*o); if(o->ctl.nodadt!=0) orc_dtnoda(*o); }
+void orc_set_itab(void* h,const int* itab){ Oracle* o=(Oracle*)h; o->ITAB.assign(itab,itab+o->numnod); }
 void orc_advance(void* h,double dt12,double dt2){
   Oracle* o=(Oracle*)h; o->DT12=dt12; o->DT2=dt2;
   orc_accele(*o); orc_bcs(*o); orc_fixvel(*o); orc_velocity(*o); orc_depla(*o); o->TT+=dt2; o->NCYCLE++;

@@ -150,7 +150,9 @@ void orc_forces(Oracle& o)
    * STIFN/STIFR restart from zero each cycle */
   const double fs=orc_load_scale(o);   /* force.F90:235, 301-312: AA = FCY*FINTER(IFUN,TT*FCX) */
   for(int i=0;i<3*n;i++){ o.A[i]= o.FEXT.empty()? K_ZERO : o.FEXT[i]*fs; o.AR[i]= o.MEXT.empty()? K_ZERO : o.MEXT[i]*fs; }
-  for(int i=0;i<n;i++){ o.STIFN[i]=K_ZERO; o.STIFR[i]=K_ZERO; }
+  /* with /DT/NODA the nodal stiffnesses restart from EM20 (dtnoda.F:336-338, rotational part alike) */
+  const double st0 = o.ctl.nodadt!=0 ? K_EM20 : K_ZERO;
+  for(int i=0;i<n;i++){ o.STIFN[i]=st0; o.STIFR[i]=st0; }
   double DT2T=o.DT2; int NELTST=0, ITYPTST=0;   /* thread mins are merged with strict "<" (resol.F:4165-4171) */
   /* shells first (FORINTC resol.F:4138), then solids (FORINT resol.F:4225) */
   const int ncg=(int)o.cgroups.size(), nsg=(int)o.sgroups.size();
@@ -173,6 +175,28 @@ void orc_forces(Oracle& o)
   o.DT2T=DT2T; o.NELTST=NELTST; o.ITYPTST=ITYPTST;
 }
 
+/* DTNODA (engine/source/time_step/dtnoda.F:221-260, 324-334 translations; :445-462 + fold rotations), NODADT>0,
+ * IDTMIN(11)=0, Lagrangian: DTN = DTFAC1(11)*SQRT(TWO*MS/STIFN) over nodes with MS>0 (STIFN>0), strict "<" in node
+ * order, NELTST=ITAB(N), ITYPTST=11; then the same with IN / STIFR when IRODDL/=0.  Called after ASSPAR4 (resol.F:6066). */
+void orc_dtnoda(Oracle& o)
+{
+  const int n=o.numnod; const double fac=o.ctl.dtfac_node;
+  for(int N=0;N<n;N++){
+    if(o.STIFN[N]<=K_ZERO) continue;
+    if(!(o.MS[N]>K_ZERO)) continue;
+    const double DTN=fac*std::sqrt(K_TWO*o.MS[N]/o.STIFN[N]);
+    if(DTN<o.DT2T){ o.DT2T=DTN; o.NELTST=o.ITAB.empty()? N+1 : o.ITAB[N]; o.ITYPTST=11; }
+  }
+  if(o.ctl.iroddl!=0){
+    for(int N=0;N<n;N++){
+      if(o.STIFR[N]<=K_ZERO) continue;
+      if(!(o.IN[N]>K_ZERO)) continue;
+      const double DTN=fac*std::sqrt(K_TWO*o.IN[N]/o.STIFR[N]);
+      if(DTN<o.DT2T){ o.DT2T=DTN; o.NELTST=o.ITAB.empty()? N+1 : o.ITAB[N]; o.ITYPTST=11; }
+    }
+  }
+}
+
 /* one pass of RESOL restricted to the hot path */
 void orc_cycle(Oracle& o)
 {
@@ -180,6 +204,7 @@ void orc_cycle(Oracle& o)
   o.DT2=K_EP06;                   /* resol.F:2722 */
   orc_forces(o);
   orc_asspar4(o);
+  if(o.ctl.nodadt!=0) orc_dtnoda(o);
   if(o.DT2T<o.DT2) o.DT2=o.DT2T;  /* resol.F:6124-6128 */
   {                               /* resol.F:6352: DT2=MIN(DT2,1.1*DT2OLD,DTMX) -- 1.1 is a REAL*4 literal */
     double c11=(double)1.1f;

@@ -46,6 +46,7 @@ struct Oracle {
   std::vector<double> X, V, VR, D, DR, A, AR, MS, IN, STIFN, STIFR;
   std::vector<double> FEXT, MEXT;     /* constant external nodal loads (3,N) pre-loaded into A/AR */
   std::vector<int>    ICODT, ICODR;   /* BCS codes (bit 4=x,2=y,1=z fixed), bcs10.F */
+  std::vector<int> ITAB;              /* user node ids (NELTST of a nodal time step) */
   int LF_FUNC=-1; double LF_FCX=1.0;  /* time function of the concentrated loads (force.F90:195-196, 235) */
   std::vector<int> IBFV;              /* imposed velocities (3,n): node, direction, curve (fixvel.F) */
   std::vector<double> VEL;            /* (4,n): FAC, STARTT, STOPT, FACX */
@@ -80,6 +81,7 @@ void orc_asspar4(Oracle& o);
 void orc_accele(Oracle& o);
 void orc_bcs(Oracle& o);
 void orc_fixvel(Oracle& o);
+void orc_dtnoda(Oracle& o);
 void orc_velocity(Oracle& o);
 void orc_depla(Oracle& o);
 void orc_cycle(Oracle& o);

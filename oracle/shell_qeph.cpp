@@ -356,10 +356,19 @@ void orc_czforc3(Oracle& o, OrcShellGroup& g, double& DT2T, int& NELTST, int& IT
       double F_OSET=K_ONE+K_HALF*std::fabs(ZOFFSET)/THK0;
       double F_DTE=K_ONE/std::sqrt(F_OSET);
       double DT=o.ctl.dtfac_shell*F_DTE*ALDT/SSP;
+      if(o.ctl.nodadt!=0){
+        /* cndt3.F:96-101 F_OSET (IGTYP=1), :194-221 nodal stiffnesses; :231 and :294 return before the element dt */
+        if(OFF==K_ZERO){ STI=K_ZERO; STIR=K_ZERO; }
+        else {
+          STI=K_HALF*F_OSET*VOL0*A11/(ALDT*ALDT);
+          STIR=STI*(THK0*THK0+AREA)*K_ONE_OVER_12+STI*ZOFFSET*ZOFFSET;
+        }
+      } else {
       if(OFFG>K_ZERO && OFF!=K_ZERO && DT<DT2T){ DT2T=DT; NELTST=NGL; ITYPTST=3; }
       double DIVM=std::max(ALDT*ALDT,K_EM20);
       STI=K_HALF*F_OSET*VOL0*A11*OFF/DIVM;
       STIR=K_ZERO;
+      }
     }
     /* ---- CZFINTCE */
     double VF[3][4]={{0}},VM[2][4]={{0}};

@@ -137,7 +137,8 @@ static void mqviscb(const Oracle& o,const OrcSolidGroup& g,int nel,const int* ng
     sti[i]=trho*tvol;
   }
   for(int i=0;i<nel;i++) dtx[i]=o.ctl.dtfac_brick*dtx[i];
-  /* NODADT==0 : :351-355 / :411-415 */
+  /* NODADT==0 : :351-355 / :411-415 ; with /DT/NODA the element does not lower DT2T (:351, :411, :621) */
+  if(o.ctl.nodadt!=0) return;
   for(int i=0;i<nel;i++)
     if(vol[i]>K_ZERO && (off[i]!=K_ZERO && offg[i]>=K_ZERO)) dt2t=std::min(dtx[i],dt2t);
   /* :621-631 argmin bookkeeping (note: ">" so the LAST element at the minimum wins) */
