@@ -224,6 +224,8 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
     const double VISCMX = or_sqrt(K_ONE + io.viscmx * io.viscmx) - io.viscmx;
     // ---- CHVIS3
     double H11, H12, H13, H21, H22, H23, H31, H32, H33, B1r, B2r;
+    double STI = K_ZERO, STIR = K_ZERO;
+    const double A11N = (LAW == 36) ? g.m36.a11 : g.m2.a11;     // PM(24)
     {
       const double HELAS = K_HALF, HVISC = K_HALF, HVLIN = K_ZERO;     // radioss2.F:641-643
       const double SR2D2 = or_sqrt(K_TWO) * K_HALF;
@@ -277,10 +279,20 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
       T.st(SW_HOURG, hr1); T.st(SW_HOURG + 1, hr2); T.st(SW_HOURG + 2, hr3);
       T.st(SW_HOURG + 3, hr4); T.st(SW_HOURG + 4, hr5);
       B1r = hr4 * OFF; B2r = hr5 * OFF;               // B11 = B13 = B1r, B12 = B14 = -B1r ; same for B2x
+      if (g.nodadt != 0) {                            // nodal stiffnesses of chvis3.F:196-207, 242-253 (STI enters as ZERO, cderi3.F:91)
+        const double SCALE = or_div(fmax(fmax(GAMA1 * GAMA1, GAMA2 * GAMA2), fmax(GAMA3 * GAMA3, GAMA4 * GAMA4))
+                                    * DT1 * fmax(fmax(HH1 + H1L, HH2 + H2L), H3L), fmax(DT1 * DT1, K_EM20));
+        STI = K_ZERO + SCALE;
+        if (OFF == K_ZERO) { STI = K_ZERO; STIR = K_ZERO; }
+        else {
+          const double VV = VISCMX * VISCMX * K_ONE;
+          STI = STI + or_div(fmax(B1, B2) * THK0 * A11N, AREA * VV);
+          STIR = STI * (THK02 * K_ONE_OVER_12 + AREA * K_ONE_OVER_9);
+        }
+      }
     }
-    // ---- CDT3
-    double STI;
-    {
+    // ---- CDT3 (not called with /DT/NODA, cforc3.F:668)
+    if (g.nodadt == 0) {
       ALDT = ALDT * VISCMX;                // / sqrt(ALPE), ALPE = 1: exact
       const double DT = or_div(g.dtfac * ALDT, SSP);
       if (OFFG > K_ZERO && OFF != K_ZERO) dt_cand = DT;
@@ -309,7 +321,7 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
     if (OFF < K_ONE) OFFG = OFF;
     T.st(SW_OFF, OFFG);
     const bool dead = OFFG < K_ZERO;
-    if (dead) STI = K_ZERO;
+    if (dead) { STI = K_ZERO; STIR = K_ZERO; }
     int sl[4];
     #pragma unroll
     for (int k = 0; k < 4; k++) sl[k] = T.ldi(g.w_slot, k);
@@ -328,7 +340,7 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
       if (dead) { f[0] = f[1] = f[2] = K_ZERO; mm[0] = mm[1] = mm[2] = K_ZERO; }
       double4* row = reinterpret_cast<double4*>(P.fsky + (size_t)8 * sl[J]);
       st256(row, make_double4(-f[0], -f[1], -f[2], -mm[0]));
-      st256(row + 1, make_double4(-mm[1], -mm[2], STI, K_ZERO));
+      st256(row + 1, make_double4(-mm[1], -mm[2], STI, STIR));
     }
   }
   cta_epilogue<false, STAGED>(dt_cand, order, P.db, g.blk0 + blockIdx.x, g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);

@@ -335,7 +335,6 @@ int orgpu_finalize(orgpu_engine* e)
   NEED(e->ctl.nodadt == 0 || e->ctl.nodadt == 1, -5, "NODADT=%d is outside the built path (0, 1)", e->ctl.nodadt);
   e->nd.nodadt = e->ctl.nodadt; e->nd.dtfac_node = e->ctl.dtfac_node;
   if (e->ctl.nodadt) {
-    for (auto& S : e->csg) NEED(shell_is_qeph(S.d.prop), -5, "/DT/NODA with Belytschko-Tsay shells (CHVIS3 nodal stiffnesses) is outside the built path");
     const size_t ncta = (e->numnod + ORGPU_NODE_BLOCK - 1) / ORGPU_NODE_BLOCK;
     if (dev_alloc(&e->d_nd_dt, 2 * ncta) || dev_alloc(&e->d_nd_node, 2 * ncta)) return -100;
     e->nd.nd_dt = e->d_nd_dt; e->nd.nd_node = e->d_nd_node;

@@ -285,9 +285,21 @@ void orc_cforc3(Oracle& o, OrcShellGroup& g, double& DT2T, int& NELTST, int& ITY
       B11=HR(4)*OFF; B12=-HR(4)*OFF; B13=HR(4)*OFF; B14=-HR(4)*OFF;
       B21=HR(5)*OFF; B22=-HR(5)*OFF; B23=HR(5)*OFF; B24=-HR(5)*OFF;
 #undef HR
+      /* STIFFNESS - DT (chvis3.F:196-207, 242-253; NODADT/=0, IGTYP=1, NADMESH=0); STI enters as ZERO (cderi3.F:91) */
+      if(o.ctl.nodadt!=0){
+        double SCALE=std::max(std::max(GAMA1*GAMA1,GAMA2*GAMA2),std::max(GAMA3*GAMA3,GAMA4*GAMA4))
+                    *DT1C*std::max(std::max(HH1+H1L,HH2+H2L),H3L)/std::max(DT1C*DT1C,K_EM20);
+        STI=K_ZERO+SCALE;
+        if(OFF==K_ZERO){ STI=K_ZERO; STIR=K_ZERO; }
+        else {
+          double VV=VISCMX*VISCMX*ALPE;
+          STI=STI+std::max(B1,B2)*THK0*A11/(AREA*VV);
+          STIR=STI*(THK02*K_ONE_OVER_12+AREA*K_ONE_OVER_9);
+        }
+      }
     }
-    /* ---- CDT3 (NODADT=0, IDTMIN(3)=2 with DTMIN1(3)=0: no deletion) */
-    {
+    /* ---- CDT3 (NODADT=0, IDTMIN(3)=2 with DTMIN1(3)=0: no deletion); not called with /DT/NODA (cforc3.F:668) */
+    if(o.ctl.nodadt==0){
       ALDT=ALDT*VISCMX/std::sqrt(ALPE);
       double DT=o.ctl.dtfac_shell*ALDT/SSP;
       if(OFFG>K_ZERO&&OFF!=K_ZERO&&DT<DT2T){ DT2T=DT; NELTST=NGL; ITYPTST=3; }

@@ -36,6 +36,10 @@ def test_nodal_time_step_qeph_shells():
     _check(meshgen.shell_plate(7, 6, 70.0, 60.0, pressure=20.0, vrand=5.0))
 
 
+def test_nodal_time_step_bt_shells():
+    _check(meshgen.shell_plate(7, 6, 70.0, 60.0, prop=meshgen.default_prop_shell(ihbe=1, npt=3), pressure=20.0, vrand=5.0))
+
+
 def test_nodal_and_element_time_steps_are_of_the_same_order():
     for mk in (lambda: meshgen.hex_block(5, 5, 5, 5.0, 5.0, 5.0, vrand=1.0), lambda: meshgen.shell_plate(8, 8, 80.0, 80.0, vrand=5.0)):
         dts = []
