@@ -206,9 +206,10 @@ def main():
             "whole_cycle": {"achieved": b["total"] * ne * world / (ms * 1e-3 / args.steps) / 1e9 / world,
                             "frac": b["total"] * ne / (ms * 1e-3 / args.steps) / 1e9 / peak, "bytes_per_element": b["total"]}}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr):
+    if os.path.exists(tr):                     # DRAM bytes per launch from the committed ncu capture (per element x elements of this launch)
         try:
-            roof["traffic"] = json.load(open(tr)).get(dom)
+            per = json.load(open(tr)).get(dom + "_per_element")
+            roof["traffic"] = per * ne_dom if per else None
         except Exception:
             pass
 
