@@ -145,7 +145,7 @@ int orgpu_destroy(orgpu_engine* e)
     void* xp[] = {x.d_send_slots, x.d_recv_slots, x.d_sendbuf, x.d_recvbuf, x.d_cand_send, x.d_cand_recv, x.d_slots_tmp, x.d_rows_tmp};
     for (void* p : xp) if (p) cudaFree(p);
     for (size_t q = 0; q < x.peer.size(); q++) if (x.peer[q] && (int)q != x.rank) cudaIpcCloseMemHandle(x.peer[q]);
-    void* pp[] = {x.win, x.d_send_nb, x.d_nb_sendptr, x.d_nb_rows, x.d_peer_cand, x.d_peer_flag, x.d_xcycle, x.d_done, x.d_err};
+    void* pp[] = {x.win, x.d_send_nb, x.d_nb_sendptr, x.d_nb_rows, x.d_peer_cand, x.d_peer_flag, x.d_xcycle, x.d_done, x.d_err, x.d_peer_win};
     for (void* p : pp) if (p) cudaFree(p);
     if (x.comm && nccl_api()) nccl_api()->CommDestroy(x.comm); }
   for (auto ev : e->evpool) cudaEventDestroy(ev);
@@ -471,27 +471,40 @@ static void p2p_exchange_on_stream(orgpu_engine* e)
     else              p2p_push_kernel<4><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_send_slots, x.d_send_nb, x.d_nb_sendptr, x.d_nb_rows, x.nsend, e->d_cs, x.d_peer_cand, x.d_peer_flag, x.nranks, x.rank, x.d_xcycle, x.d_done);
     e->launches++; }
   { const int nthr = x.nrecv * V > 1 ? x.nrecv * V : 1; const int nb = (nthr + 255) / 256;
-    if (e->roww == 8) p2p_wait_unpack_kernel<8><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_recv_slots, x.nrecv, x.win, e->d_cs, x.nranks, x.d_xcycle, x.d_err);
-    else              p2p_wait_unpack_kernel<4><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_recv_slots, x.nrecv, x.win, e->d_cs, x.nranks, x.d_xcycle, x.d_err);
+    const int adv = e->ctl.nodadt ? 0 : 1;                 // /DT/NODA: the clock advances after the nodal dt exchange
+    if (e->roww == 8) p2p_wait_unpack_kernel<8><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_recv_slots, x.nrecv, x.win, e->d_cs, x.nranks, x.d_xcycle, x.d_err, adv);
+    else              p2p_wait_unpack_kernel<4><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_recv_slots, x.nrecv, x.win, e->d_cs, x.nranks, x.d_xcycle, x.d_err, adv);
     e->launches++; }
+}
+// node phase of a multi-domain cycle over peer memory
+static void p2p_node_phase(orgpu_engine* e)
+{
+  Exchange& x = e->xc;
+  if (!e->ctl.nodadt) { launch_node_fused(e->nd, e->d_fsky, e->roww, e->d_cs, e->ctl.iroddl, e->st); e->launches++; return; }
+  launch_node_assemble(e->nd, e->d_fsky, e->roww, e->d_cs, e->ctl.iroddl, e->st);
+  launch_dtnoda_finalize(e->nd, e->d_cs, 0, e->st);                       // local nodal DT2T
+  p2p_dt_push_kernel<<<1, 32, 0, e->st>>>(e->d_cs, x.d_peer_win, x.nranks, x.rank, x.d_xcycle);
+  p2p_dt_wait_kernel<<<1, 32, 0, e->st>>>(e->d_cs, x.win, x.nranks, x.d_xcycle, x.d_err);
+  launch_node_advance(e->nd, e->d_cs, e->ctl.iroddl, e->st);
+  e->launches += 5;
 }
 
 int orgpu_run_cycles(orgpu_engine* e, int ncycles)
 {
   NEED(e && e->finalized && ncycles >= 0, -1, "orgpu_run_cycles: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
   const int per_cycle = (int)(e->csg.size() + e->bsg.size()) + (e->ctl.nodadt ? 4 : 2);   // force kernels + dt finalize + node kernel(s)
-  NEED(!(e->ctl.nodadt && e->xc.nranks > 1), -5, "/DT/NODA across domains (nodal dt exchange) is outside the built path");
+  NEED(!(e->ctl.nodadt && e->xc.nranks > 1 && (!e->xc.p2p || e->profile)), -5, "/DT/NODA across domains needs the peer-memory exchange (orgpu_p2p_connect), unprofiled");
   if (e->xc.nranks > 1 && e->xc.p2p && !e->profile) {
     // one process per GPU, peer-memory exchange: the whole cycle (forces, dt fold, push, wait+unpack, gather+update)
     // is one CUDA graph, replayed ncycles times with no host involvement and no library call
-    const int per = (int)(e->csg.size() + e->bsg.size()) + 4;
+    const int per = (int)(e->csg.size() + e->bsg.size()) + (e->ctl.nodadt ? 8 : 4);
     if (!e->gexec) {
       cudaGraph_t g;
       CUDA_OK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeThreadLocal));
       const long long l0 = e->launches;
       launch_element_phase(e, 0, nullptr);
       p2p_exchange_on_stream(e);
-      launch_node_fused(e->nd, e->d_fsky, e->roww, e->d_cs, e->ctl.iroddl, e->st);
+      p2p_node_phase(e);
       e->launches = l0;                      // the capture pass did not execute
       CUDA_OK(cudaStreamEndCapture(e->st, &g));
       CUDA_OK(cudaGraphInstantiate(&e->gexec, g, 0));
@@ -822,6 +835,8 @@ int orgpu_p2p_connect(orgpu_engine* e, const unsigned char* handles /*[nranks][6
   CUDA_OK(cudaMemcpy(x.d_nb_rows, nb_rows.data(), 8 * nb_rows.size(), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(x.d_peer_cand, pcand.data(), 8 * (size_t)R, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(x.d_peer_flag, pflag.data(), 8 * (size_t)R, cudaMemcpyHostToDevice));
+  if (dev_alloc(&x.d_peer_win, (size_t)R)) return -100;
+  CUDA_OK(cudaMemcpy(x.d_peer_win, x.peer.data(), 8 * (size_t)R, cudaMemcpyHostToDevice));
   CUDA_OK(cudaDeviceSynchronize());
   if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
   x.p2p = true;

@@ -62,6 +62,7 @@ struct Exchange {
   double** d_peer_cand = nullptr;                        // [nranks] candidate area of every window
   unsigned long long** d_peer_flag = nullptr;            // [nranks] &flags[rank] inside every window
   unsigned long long* d_xcycle = nullptr; unsigned int* d_done = nullptr; int* d_err = nullptr;
+  unsigned char** d_peer_win = nullptr;                  // [nranks] window bases (for the /DT/NODA candidate exchange)
 };
 
 // ---- peer-memory exchange --------------------------------------------------------------------------
@@ -69,7 +70,8 @@ struct Exchange {
 // cycle is one CUDA graph like the single-GPU one.  Every rank owns a receive WINDOW in its HBM:
 //   int   hdr[256]            [0]=nranks [1]=nrecv [2+q]=first row of the rows rank q sends here (-1: not a neighbour)
 //   u64   flags[nranks]       flags[q] = last exchange cycle rank q has completely pushed into this window
-//   f64   cand[2][nranks][4]  (dt2t, ityptst, neltst, -) of rank q for cycle parity p
+//   u64   flags2[nranks]      second flag set (at +512 B): nodal time-step candidates of /DT/NODA, published after the assembly
+//   f64   cand[2][nranks][4]  (dt2t, ityptst, neltst, -) of rank q for cycle parity p ; then cand2[2][nranks][4] likewise
 //   f64   rows[2][nrecv][roww] received corner rows for cycle parity p
 // p2p_push_kernel copies this rank's send rows straight from its skyline into the neighbours' windows with
 // 256-bit stores over NVLink (peer pointers from cudaIpcOpenMemHandle), and its last CTA then publishes the dt
@@ -77,12 +79,14 @@ struct Exchange {
 // acquires all flags >= cycle, scatters the received rows into their reserved FSKY slots and folds the
 // candidates in rank order (GLOB_MIN).  Two parities: a neighbour may run one exchange ahead, never two
 // (its next push comes after its own wait on OUR flag of the cycle in between).
-__device__ __forceinline__ size_t win_rows_off_dev(int nranks) { return 2048 + (((size_t)2 * nranks * 32 + 255) / 256) * 256; }
+__device__ __forceinline__ size_t win_rows_off_dev(int nranks) { return 2048 + (((size_t)4 * nranks * 32 + 255) / 256) * 256; }
 __device__ __forceinline__ double4 ld256_cg(const double4* p) {      // L2 only: written by a peer GPU during this kernel
   double4 v; asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p) : "memory"); return v; }
 #define ORGPU_WIN_FLAGS 1024
 #define ORGPU_WIN_CAND 2048
-static inline size_t win_rows_off(int nranks) { return ORGPU_WIN_CAND + (((size_t)2 * nranks * 32 + 255) / 256) * 256; }
+#define ORGPU_WIN_FLAGS2 (ORGPU_WIN_FLAGS + 512)
+static inline size_t win_cand2_off(int nranks) { return ORGPU_WIN_CAND + (size_t)2 * nranks * 32; }
+static inline size_t win_rows_off(int nranks) { return ORGPU_WIN_CAND + (((size_t)4 * nranks * 32 + 255) / 256) * 256; }
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
@@ -126,7 +130,7 @@ p2p_push_kernel(const double* __restrict__ fsky, const int* __restrict__ send_sl
 template <int ROWW>
 __global__ void __launch_bounds__(256)
 p2p_wait_unpack_kernel(double* __restrict__ fsky, const int* __restrict__ recv_slots, int nrecv, const unsigned char* win,
-                       CycleState* cs, int nranks, const unsigned long long* xcycle, int* err)
+                       CycleState* cs, int nranks, const unsigned long long* xcycle, int* err, int advance)
 {
   const unsigned long long c = *reinterpret_cast<const volatile unsigned long long*>(xcycle);
   const int par = (int)(c & 1ull);
@@ -149,7 +153,7 @@ p2p_wait_unpack_kernel(double* __restrict__ fsky, const int* __restrict__ recv_s
     const double4 v = ld256_cg(reinterpret_cast<const double4*>(rows + (size_t)j * ROWW + 4 * cc));
     st256(reinterpret_cast<double4*>(fsky + (size_t)recv_slots[j] * ROWW + 4 * cc), v);
   }
-  if (i == 0) {                                       // GLOB_MIN over the ranks + RESOL bookkeeping (as rows_unpack_kernel)
+  if (i == 0 && advance) {                            // GLOB_MIN over the ranks + RESOL bookkeeping (as rows_unpack_kernel)
     const double* cand = reinterpret_cast<const double*>(win + ORGPU_WIN_CAND) + (size_t)par * nranks * 4;
     double cur = K_EP06; int typ = 0, ngl = 0;
     for (int r = 0; r < nranks; r++) {
@@ -230,4 +234,48 @@ __global__ void rows_scatter8_kernel(double* __restrict__ fsky, int roww, const 
   double* r = fsky + (size_t)roww * slots[j]; const double* o = in + 8 * (size_t)j;
   if (roww == 8) { for (int c = 0; c < 8; c++) r[c] = o[c]; }
   else { r[0] = o[0]; r[1] = o[1]; r[2] = o[2]; r[3] = o[6]; }
+}
+
+// /DT/NODA across domains: the nodal time step is known only after the assembly, so it travels in a second, tiny
+// exchange: one thread publishes this rank's (DT2T, ITYPTST, NELTST) to every window and releases flags2[rank];
+// one thread waits for all ranks, folds them in rank order (strict "<") and runs the RESOL bookkeeping.
+__global__ void p2p_dt_push_kernel(const CycleState* cs, unsigned char* const* __restrict__ peer_win, int nranks, int rank,
+                                   const unsigned long long* xcycle)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const unsigned long long c = *reinterpret_cast<const volatile unsigned long long*>(xcycle);
+  const int par = (int)(c & 1ull);
+  const double d0 = cs->dt2t, d1 = (double)cs->ityptst, d2 = (double)cs->neltst;
+  for (int q = 0; q < nranks; q++) {
+    double* cd = reinterpret_cast<double*>(peer_win[q] + ORGPU_WIN_CAND + (size_t)2 * nranks * 32) + ((size_t)par * nranks + rank) * 4;
+    cd[0] = d0; cd[1] = d1; cd[2] = d2; cd[3] = 0.0;
+  }
+  __threadfence_system();
+  for (int q = 0; q < nranks; q++) st_release_sys(reinterpret_cast<unsigned long long*>(peer_win[q] + ORGPU_WIN_FLAGS2) + rank, c);
+}
+__global__ void p2p_dt_wait_kernel(CycleState* cs, const unsigned char* win, int nranks, const unsigned long long* xcycle, int* err)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const unsigned long long c = *reinterpret_cast<const volatile unsigned long long*>(xcycle);
+  const int par = (int)(c & 1ull);
+  const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(win + ORGPU_WIN_FLAGS2);
+  const long long t0 = clock64();
+  for (int q = 0; q < nranks; q++)
+    while (ld_acquire_sys(flags + q) < c) { if (clock64() - t0 > 8000000000ll) { *err = 1; break; } __nanosleep(100); }
+  const double* cand = reinterpret_cast<const double*>(win + ORGPU_WIN_CAND + (size_t)2 * nranks * 32) + (size_t)par * nranks * 4;
+  double cur = K_EP06; int typ = 0, ngl = 0;
+  for (int r = 0; r < nranks; r++) {
+    const double d = __ldcg(cand + 4 * r);
+    if (d < cur) { cur = d; typ = (int)__ldcg(cand + 4 * r + 1); ngl = (int)__ldcg(cand + 4 * r + 2); }
+  }
+  cs->dt2t = cur; cs->ityptst = typ; cs->neltst = ngl;
+  const double dt1 = cs->dt2;
+  double dt2 = K_EP06;
+  if (cur < dt2) dt2 = cur;
+  const double c11 = (double)1.1f;
+  dt2 = fmin(dt2, fmin(c11 * cs->dt2old, cs->dtmx));
+  cs->dt2old = dt2;
+  cs->dt12 = K_HALF * (dt1 + dt2);
+  cs->dt1 = dt1; cs->dt2 = dt2;
+  cs->tt = cs->tt + dt2; cs->ncycle += 1;
 }
