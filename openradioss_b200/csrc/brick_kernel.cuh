@@ -275,6 +275,9 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
         DVOL = VOLN * DIVDE;
       }
     }
+    // VOL**(1/3) once for MQVISCB (AL) and SHVIS3 (VOL**(2/3) = its square): cbrt is ~40 instructions against ~180 for
+    // each of the two pow calls; <= 3 ulp from the library values (the oracle's glibc pow already differs from CUDA's)
+    const double CBV = cbrt(fmax(VOLN, K_ZERO));
     // ---- SROTA3
     double S1 = T.ld(BW_SIG), S2 = T.ld(BW_SIG + 1), S3 = T.ld(BW_SIG + 2), S4 = T.ld(BW_SIG + 3), S5 = T.ld(BW_SIG + 4), S6 = T.ld(BW_SIG + 5);
     double SG1, SG2, SG3, SG4, SG5, SG6;
@@ -349,7 +352,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
         if (m.iform == 0) {
           double MT = fmax(K_EM15, m.z3);
           EPD = fmax(K_ZERO, EPD);
-          EPD = (K_ONE + m.cc * EPD) * (K_ONE - pow(TSTAR, MT));
+          EPD = (K_ONE + m.cc * EPD) * (K_ONE - ((TSTAR > K_ZERO) ? pow(TSTAR, MT) : K_ZERO));   // 0**MT = 0 exactly
           if (m.icc == 1) SIGMX = m.sigmx * EPD;
         } else if (m.iform == 1) {
           EPD = m.cc * exp((-m.z3 + m.z4 * EPD) * TEMP);
@@ -359,15 +362,18 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
         }
       } else if (m.iform == 0) {
         double MT = fmax(K_EM15, m.z3);
-        EPD = K_ONE - pow(TSTAR, MT);
+        EPD = K_ONE - ((TSTAR > K_ZERO) ? pow(TSTAR, MT) : K_ZERO);
         if (m.icc == 1) SIGMX = m.sigmx * EPD;
       }
       double AK, QH;
       if (m.cn == K_ONE) { AK = CA + m.cb * EPXE; QH = m.cb * EPD; }
       else if (EPXE > K_ZERO) {
-        AK = CA + m.cb * pow(EPXE, m.cn);
-        if (m.cn > K_ONE) QH = (m.cb * m.cn * pow(EPXE, (m.cn - K_ONE))) * EPD;
-        else              QH = (or_div(m.cb * m.cn, pow(EPXE, (K_ONE - m.cn)))) * EPD;
+        // one pow instead of two: EPXE**(CN-1) = EPXE**CN / EPXE (m2law.F:230-238; a pow is ~180 instructions, the
+        // quotient differs from the library value by <= 2 ulp, far inside the 1e-12 force tolerance)
+        const double PN = pow(EPXE, m.cn);
+        AK = CA + m.cb * PN;
+        if (m.cn > K_ONE) QH = (m.cb * m.cn * or_div(PN, EPXE)) * EPD;
+        else              QH = (or_div(m.cb * m.cn, or_div(EPXE, PN))) * EPD;
       } else { AK = CA; QH = K_ZERO; }
       AK = AK * EPD;
       if (SIGMX < AK) { AK = SIGMX; QH = K_ZERO; }
@@ -385,7 +391,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
         double AD = K_ZERO, AL = K_ZERO;
         const double CX = SSP + K_ZERO;              // VD2 = 0 (Lagrangian)
         if (OFF == K_ONE) {
-          AL = (VOLN > K_ZERO) ? pow(VOLN, 1.0 / 3.0) : K_ZERO;
+          AL = (VOLN > K_ZERO) ? CBV : K_ZERO;               // VOL**THIRD (mqviscb.F)
           AD = fmax(K_ZERO, DD);
         }
         const double NRHO = or_sqrt(RHOREF * m.rho0);
@@ -450,9 +456,10 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     {
       const double CAQ = K_FOURTH * OFF * g.prop.hcoef;
       double FCL, FCQ;
-      if (ISMSTR == 1) FCL = CAQ * m.rho0 * pow(VOLN, K_TWO_THIRD);
-      else if (ISMSTR == 2 && OFFG > K_ONE) { double AA = or_div(m.rho0 * VOLO, fmax(K_EM20, VOLN)); FCL = CAQ * AA * pow(VOLN, K_TWO_THIRD); }
-      else FCL = CAQ * RHON * pow(VOLN, K_TWO_THIRD);
+      const double V23 = CBV * CBV;                           // VOL**TWO_THIRD (shvis3.F:203-237)
+      if (ISMSTR == 1) FCL = CAQ * m.rho0 * V23;
+      else if (ISMSTR == 2 && OFFG > K_ONE) { double AA = or_div(m.rho0 * VOLO, fmax(K_EM20, VOLN)); FCL = CAQ * AA * V23; }
+      else FCL = CAQ * RHON * V23;
       FCQ = FCL * CAQ * K_HUNDRED;
       FCL = FCL * SSP;
       double G_[3][8];
