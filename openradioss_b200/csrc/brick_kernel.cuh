@@ -527,8 +527,11 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     } else {
       #pragma unroll
       for (int k = 0; k < 8; k++) {
-        double* row = P.fsky + (size_t)8 * sl[k];
-        row[0] = F1[k]; row[1] = F2[k]; row[2] = F3[k]; row[6] = STI;
+        // mixed models (8-wide rows): write the whole row -- two full 32-byte sectors instead of four partial stores that
+        // the L2 would have to merge; the moment / rotational-stiffness words of a brick corner are zero anyway
+        double4* row = reinterpret_cast<double4*>(P.fsky + (size_t)8 * sl[k]);
+        st256(row, make_double4(F1[k], F2[k], F3[k], K_ZERO));
+        st256(row + 1, make_double4(K_ZERO, K_ZERO, STI, K_ZERO));
       }
     }
   }
