@@ -139,7 +139,7 @@ int orgpu_destroy(orgpu_engine* e)
   for (auto& s : e->csg) for (void* p : s.owned) cudaFree(p);
   void* ptrs[] = {e->nd.pos, e->nd.vel, e->nd.rot, e->nd.D, e->nd.A, e->nd.AR, e->nd.STIFN, e->nd.STIFR, e->nd.MS, e->nd.IN,
                   e->d_stage3a, e->d_stage3b, e->d_fext, e->d_mext, e->d_icodt, e->d_icodr, e->d_adsky, e->d_fsky, e->d_cs,
-                  e->db.dt, e->db.ngl, e->db.order, e->d_ftf, e->d_fnpf, e->d_fv_idx, e->d_fv, e->d_itab, e->d_nd_dt, e->d_nd_node};
+                  e->db.dt, e->db.order, e->d_ftf, e->d_fnpf, e->d_fv_idx, e->d_fv, e->d_itab, e->d_nd_dt, e->d_nd_node};
   for (void* p : ptrs) if (p) cudaFree(p);
   { Exchange& x = e->xc;
     void* xp[] = {x.d_send_slots, x.d_recv_slots, x.d_sendbuf, x.d_recvbuf, x.d_cand_send, x.d_cand_recv, x.d_slots_tmp, x.d_rows_tmp};
@@ -362,7 +362,7 @@ int orgpu_finalize(orgpu_engine* e)
     }
   }
   e->db.nblocks_total = blk;
-  if (dev_alloc(&e->db.dt, blk) || dev_alloc(&e->db.ngl, blk) || dev_alloc(&e->db.order, blk)) return -100;
+  if (dev_alloc(&e->db.dt, blk) || dev_alloc(&e->db.order, blk)) return -100;
   e->finalized = true;
   return 0;
 }

@@ -177,15 +177,15 @@ node_assemble_kernel(const __grid_constant__ DevNodes nd, const double* __restri
 __global__ void __launch_bounds__(1024)
 dtnoda_finalize_kernel(CycleState* cs, const __grid_constant__ DevNodes nd, int ncta, int fused)
 {
-  __shared__ double s_dt[32]; __shared__ int s_ngl[32]; __shared__ int s_ord[32];
+  __shared__ double s_dt[32]; __shared__ int s_ord[32];
   double cur = cs->dt2t; int curn = -1;
   for (int f = 0; f < 2; f++) {
-    double dt = K_EP30; int ngl = 0, ord = 0x7fffffff;
+    double dt = K_EP30; int ord = 0x7fffffff;
     for (int b = threadIdx.x; b < ncta; b += 1024) {
       const double d2 = __ldcg(nd.nd_dt + f * ncta + b); const int o2 = __ldcg(nd.nd_node + f * ncta + b);
       if (dt_better<false>(d2, o2, dt, ord)) { dt = d2; ord = o2; }
     }
-    finalize_fold<false>(dt, ngl, ord, s_dt, s_ngl, s_ord);
+    finalize_fold<false>(dt, ord, s_dt, s_ord);
     if (threadIdx.x == 0 && dt < cur) { cur = dt; curn = ord; }
   }
   if (threadIdx.x == 0) {
