@@ -8,9 +8,12 @@
  *
  * PARITY PINNING: the reference Engine is Fortran and cannot be compiled in this image (no
  * Fortran compiler), and its own QA suite holds no routine-level vectors for this path
- * (SURVEY.md 8c).  The restatement is therefore pinned by (1) line-by-line correspondence to
- * the cited Fortran, (2) analytic patch tests (tests/test_oracle_*.py), and (3) coarse anchors.
- * Per-cycle force parity of the CUDA path is "parity vs the restatement" -- see DESIGN.md.
+ * (SURVEY.md 8c).  PINNED by executing reference code: Belytschko-Tsay + LAW2 membrane /
+ * transverse-shear response against the reference's own CUDA shell path built unmodified into
+ * oracle/_ref (tests/test_ref_gpu_pin.py, golden vectors in tests/golden/refgpu_bt_law2_*.npz replayed
+ * by tests/test_golden_refgpu.py: forces, moments, time step to 1e-12).  PARITY UNPINNED for the rest
+ * (bending, QEPH, LAW36, bricks, assembly, update): there the restatement stands on line-by-line
+ * correspondence to the cited Fortran and analytic patch tests (tests/test_oracle_*.py) -- see DESIGN.md.
  *
  * The oracle keeps the reference's data model: Fortran-ordered nodal arrays X(3,NUMNOD),
  * element groups of NEL<=MVSIZ elements with ELBUF-style component-major state
