@@ -70,6 +70,12 @@ class RefShellGPU:
         L.shell_gpu_synchronize(self.g)
         return self.out.reshape(8, self.n).T.copy()
 
+    def pin(self, X, V, VR):
+        """shell_gpu_global_pin_host: page-lock the caller's nodal arrays and the force buffer (what FORINTC_PREPARE_GPU does)"""
+        self._pinned = [np.ascontiguousarray(a, np.float64) for a in (X, V, VR)]
+        self.lib.shell_gpu_global_pin_host(_p(self._pinned[0]), _p(self._pinned[1]), _p(self._pinned[2]), _p(self.out), C.c_int(self.n))
+        return self._pinned
+
     def run_kernels_only(self, dt1):
         self.lib.shell_gpu_run_kernels(self.g, R(float(dt1)))
 
