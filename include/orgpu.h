@@ -60,6 +60,10 @@ int  orgpu_set_functions(orgpu_engine* e, int nfunc, const int* npf, const doubl
 /* one element group (<= NVSIZ elements, one material / property): elements [nft, nft+nel) */
 int  orgpu_add_solid_group(orgpu_engine* e, int nel, int nft, const orgpu_law2* mat,
                            const orgpu_prop_solid* prop, const double* vol0);
+/* same for any built solid law: law = 2 (orgpu_law2, M2LAW) or 36 (orgpu_law36: MMAIN -> MULAW -> SIGEPS36,
+ * engine/source/materials/mat_share/mulaw.F90:1133-1166, mat/mat036/sigeps36.F:35); needs orgpu_set_functions */
+int  orgpu_add_solid_group_law(orgpu_engine* e, int nel, int nft, int law, const void* mat,
+                               const orgpu_prop_solid* prop, const double* vol0);
 int  orgpu_add_shell_group(orgpu_engine* e, int nel, int nft, int law, const void* mat,
                            const orgpu_prop_shell* prop);
 /* FORINTC_PREPARE_GPU analogue: fuse consecutive compatible groups into super-groups, re-lay
@@ -80,7 +84,7 @@ int  orgpu_get_time(orgpu_engine* e, double out[5] /*tt,dt1,dt2,dt12,dt2t*/, int
 int  orgpu_download_nodes(orgpu_engine* e, double* X, double* V, double* VR, double* D,
                           double* A, double* AR, double* STIFN, double* STIFR);
 int  orgpu_download_fsky(orgpu_engine* e, double* fsky /*(8,LSKY)*/);
-/* fields: 0 sig(6) 1 eint 2 rho 3 qvis 4 pla 5 epsd 6 vol 7 off 8 temp 9 smstr(21); out[k*numels+e] */
+/* fields: 0 sig(6) 1 eint 2 rho 3 qvis 4 pla 5 epsd 6 vol 7 off 8 temp 9 smstr(21) 10 stra(6) 11 wpla (LAW36); out[k*numels+e] */
 int  orgpu_download_solid_state(orgpu_engine* e, int field, double* out);
 int  orgpu_download_shell_state(orgpu_engine* e, int field, double* out);
 /* -- state hand-over in the other direction (restart / a run that starts from an initial state: the role of

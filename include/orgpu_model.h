@@ -7,6 +7,7 @@
  *   - LAW2 solid  : engine/source/materials/mat/mat002/m2law.F:135-169
  *   - LAW2 shell  : engine/source/materials/mat/mat002/sigeps02c.F:91-123
  *   - LAW36 shell : engine/source/materials/mat/mat036/sigeps36c.F:197-260
+ *   - LAW36 solid : engine/source/materials/mat/mat036/sigeps36.F:170-207
  *   - solid prop  : engine/source/materials/mat_share/mqviscb.F:201-207, solid/solide/shvis3.F:164-168
  *   - shell prop  : engine/source/elements/sh3n/coquedk/cncoef3.F, shell/coque/ccoef3.F:124-168
  *   - groups      : engine/source/elements/forintc.F:254-300 (IPARG slots)
@@ -62,6 +63,8 @@ typedef struct orgpu_law36 {
                                      (starter/source/materials/mat/hm_read_mat.F90:1638-1641) */
   double a1u, a2u;          /* UPARAM(3) = E/(1-nu^2), UPARAM(4) = nu*UPARAM(3)        */
   double g3;                /* UPARAM(2*nrate+11) = 3G                                 */
+  double g2;                /* UPARAM(2*nrate+10) = 2G                  (solids, sigeps36.F:181) */
+  double ssp3d;             /* UPARAM(2*nrate+13) = sqrt((K+4G/3)/rho0) (solids, sigeps36.F:184) */
   double soundsp;           /* UPARAM(2*nrate+18) shell sound speed                    */
   double nu_mnu, t_pnu, u_mnu; /* UPARAM(2*nrate+19..21): nu/(1-nu), 3/(1+nu), 1/(1-nu) */
   double epsmax;            /* UPARAM(2*nrate+7)  (INFINITY when unset)                */
@@ -86,6 +89,8 @@ typedef struct orgpu_prop_solid {
   double dtmin;         /* GEO(172)                                    */
   int    jhbe;          /* Isolid -> IPARG(23): 0,1,2                  */
   int    ismstr;        /* IPARG(9): 1,2,4                             */
+  int    ipla;          /* IPARG(29) = IPLAST (default 1, starter sgrtails.F:510): radial-return variant of SIGEPS36 */
+  int    istrain;       /* IPARG(44): MULAW accumulates LBUF%STRA (mulaw.F90:886-892)   */
 } orgpu_prop_solid;
 
 /* /PROP/SHELL (IGTYP 1) slots read on the path (starter hm_read_prop01.F:156-262) */

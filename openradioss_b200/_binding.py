@@ -21,7 +21,7 @@ def _opt(a, dtype):
 class Binding:
     """Thin object wrapper over one handle of either library."""
     SOLID_FIELDS = dict(sig=(0, 6), eint=(1, 1), rho=(2, 1), qvis=(3, 1), pla=(4, 1), epsd=(5, 1),
-                        vol=(6, 1), off=(7, 1), temp=(8, 1), smstr=(9, 21))
+                        vol=(6, 1), off=(7, 1), temp=(8, 1), smstr=(9, 21), stra=(10, 6), wpla=(11, 1))
     SHELL_FIELDS = dict(forc=(0, 5), mom=(1, 3), eint=(2, 2), thk=(3, 1), off=(4, 1), stra=(5, 8),
                         epsd=(6, 1), hourg=(7, 12), smstr=(8, 6), sig=(9, 5), pla=(10, 1),
                         epsd_ip=(11, 1), temp=(12, 1))
@@ -77,8 +77,12 @@ class Binding:
                                  C.byref(g.mat), C.byref(g.prop))
         for g in m.solid_groups:
             v0 = np.ascontiguousarray(m.vol0[g.nft:g.nft + g.nel])
-            self._call_group("add_solid_group", self.h, C.c_int(g.nel), C.c_int(g.nft), C.byref(g.mat),
-                             C.byref(g.prop), v0.ctypes.data_as(C.c_void_p))
+            if getattr(g, "law", 2) == 2:
+                self._call_group("add_solid_group", self.h, C.c_int(g.nel), C.c_int(g.nft), C.byref(g.mat),
+                                 C.byref(g.prop), v0.ctypes.data_as(C.c_void_p))
+            else:
+                self._call_group("add_solid_group_law", self.h, C.c_int(g.nel), C.c_int(g.nft), C.c_int(g.law),
+                                 C.byref(g.mat), C.byref(g.prop), v0.ctypes.data_as(C.c_void_p))
         self._call("finalize", self.h)
         return self
 

@@ -8,6 +8,7 @@
 //   SDEFO3 (sdefo3.F:115-271)                   -> strain rates, spin
 //   SRHO3 (srho3.F:110-239), SROTA3 (srota3.F:72-94), SMALLA3, S8SAV3
 //   MMAIN -> M2LAW (m2law.F:133-561) + MQVISCB (mqviscb.F:141-631): stress, dt, nodal stiffness
+//         or MULAW (mulaw.F90) -> SIGEPS36 (sigeps36.F) for LAW36 (template parameter LAW)
 //   SMALLB3, SHVIS3 (shvis3.F:164-412), SFINT3 (sfint3.F:257-323)
 //   SCUMU3P (scumu3p.F:104-309): corner rows into the FSKY slots of IADS
 // followed by the CTA-level (dt, user id) arg-min.  The CTA's state tile (common.cuh) is read by one
@@ -70,11 +71,51 @@ __device__ __forceinline__ Jac brick_jac(const double* x, const double* y, const
         G_[2][0] =  K_ONE - PH[2][0]; G_[2][1] = -K_ONE - PH[2][1]; G_[2][2] = -K_ONE - PH[2][2]; G_[2][3] =  K_ONE - PH[2][3]; \
         G_[2][4] = -K_ONE + PH[2][2]; G_[2][5] =  K_ONE + PH[2][3]; G_[2][6] =  K_ONE + PH[2][0]; G_[2][7] = -K_ONE + PH[2][1];
 
+
+// MQVISCB (mqviscb.F:141-631; IMPL=0, N2D=0, NPG=1, JTHE=0, IDTMINS/=2): bulk viscosity, equivalent sound speed,
+// nodal stiffness and the element's time-step candidate.  Shared by the M2LAW and MULAW branches.
+template <int ISMSTR>
+__device__ __forceinline__ void brick_mqviscb(const BrickSG& g, double DXX, double DYY, double DZZ, double SSP, double OFF, double OFFG,
+                                              double VOLN, double VOLO, double RHON, double RHOREF, double CBV, double DELTAX,
+                                              double& QNEW, double& SSP_EQ, double& STI, double& dt_cand)
+{
+  const orgpu_law2& m = g.mat;
+  const double DD = -DXX - DYY - DZZ;
+  double AD = K_ZERO, AL = K_ZERO;
+  const double CX = SSP + K_ZERO;              // VD2 = 0 (Lagrangian)
+  if (OFF == K_ONE) {
+    AL = (VOLN > K_ZERO) ? CBV : K_ZERO;               // VOL**THIRD (mqviscb.F)
+    AD = fmax(K_ZERO, DD);
+  }
+  const double NRHO = or_sqrt(RHOREF * m.rho0);
+  const double QA = K_ONE * g.prop.qa, QB = K_ONE * g.prop.qb;
+  const double CNS1_0 = 1.0 * g.prop.cns1, CNS2_0 = 1.0 * g.prop.cns2;
+  const double QAA_0 = QA * QA;
+  double CNS1 = CNS1_0 * AL * NRHO * SSP * OFF;
+  double CNS2 = CNS2_0 * AL * NRHO * SSP * OFF;
+  double QAA = QAA_0 * AD;
+  double QX = QB * SSP + AL * QAA
+            + K_ZERO /* K_ONE*K_TWO*K_ZERO / max(EM20, RHON*DELTAX): the thermal term of mqviscb.F, exactly +0 */
+            + or_div((CNS1 + K_ONE * CNS2), fmax(K_EM20, RHOREF * DELTAX));
+  QNEW = RHON * AD * AL * (QAA * AL + QB * SSP);
+  SSP_EQ = fmax(K_EM20, QX + or_sqrt(QX * QX + CX * CX));
+  double DTX = or_div(DELTAX, SSP_EQ);
+  STI = K_ZERO;
+  if (!(OFF == K_ZERO || OFFG < K_ZERO)) {
+    double TIDT = or_div(K_ONE, DTX), TRHO, TVOL;
+    if (ISMSTR == 1 && OFFG > K_ONE) { TRHO = m.rho0 * TIDT; TVOL = VOLO * TIDT; }
+    else                             { TRHO = RHON * TIDT;   TVOL = VOLN * TIDT; }
+    STI = TRHO * TVOL;
+  }
+  DTX = g.dtfac * DTX;
+  if (VOLN > K_ZERO && OFF > K_ZERO && OFFG > K_ZERO && g.nodadt == 0) dt_cand = DTX;
+}
+
 #ifndef ORGPU_BRICK_MINB
 #define ORGPU_BRICK_MINB 3
 #endif
 
-template <int JHBE, int ISMSTR, bool STAGED>
+template <int JHBE, int ISMSTR, int LAW, bool STAGED>
 __global__ void __launch_bounds__(ORGPU_BLOCK, ORGPU_BRICK_MINB * ORGPU_PER128)
 brick_forces_kernel(const __grid_constant__ BrickParams P)
 {
@@ -313,7 +354,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     // ---- M2LAW
     double EPXE = T.ld(BW_PLA), EPSD = T.ld(BW_EPSD);
     double SSP, QNEW, STI, SSP_EQ;
-    {
+    if (LAW == 2) {
       const double asrate = fmin(K_ONE, m.asrate * DT1);
       const double rhocpi = (m.rhocp > K_ZERO) ? or_div(K_ONE, m.rhocp) : K_ZERO;
       const double G = m.shear * OFF;
@@ -386,37 +427,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       SG1 = SCALE * SG1; SG2 = SCALE * SG2; SG3 = SCALE * SG3; SG4 = SCALE * SG4; SG5 = SCALE * SG5; SG6 = SCALE * SG6;
       EPXE = EPXE + DPLA;
       // ---- MQVISCB (IMPL=0, N2D=0, NPG=1, JTHE=0, IDTMINS/=2, NODADT=0)
-      {
-        const double DD = -DXX - DYY - DZZ;
-        double AD = K_ZERO, AL = K_ZERO;
-        const double CX = SSP + K_ZERO;              // VD2 = 0 (Lagrangian)
-        if (OFF == K_ONE) {
-          AL = (VOLN > K_ZERO) ? CBV : K_ZERO;               // VOL**THIRD (mqviscb.F)
-          AD = fmax(K_ZERO, DD);
-        }
-        const double NRHO = or_sqrt(RHOREF * m.rho0);
-        const double QA = K_ONE * g.prop.qa, QB = K_ONE * g.prop.qb;
-        const double CNS1_0 = 1.0 * g.prop.cns1, CNS2_0 = 1.0 * g.prop.cns2;
-        const double QAA_0 = QA * QA;
-        double CNS1 = CNS1_0 * AL * NRHO * SSP * OFF;
-        double CNS2 = CNS2_0 * AL * NRHO * SSP * OFF;
-        double QAA = QAA_0 * AD;
-        double QX = QB * SSP + AL * QAA
-                  + K_ZERO /* K_ONE*K_TWO*K_ZERO / max(EM20, RHON*DELTAX): the thermal term of mqviscb.F, exactly +0 */
-                  + or_div((CNS1 + K_ONE * CNS2), fmax(K_EM20, RHOREF * DELTAX));
-        QNEW = RHON * AD * AL * (QAA * AL + QB * SSP);
-        SSP_EQ = fmax(K_EM20, QX + or_sqrt(QX * QX + CX * CX));
-        double DTX = or_div(DELTAX, SSP_EQ);
-        STI = K_ZERO;
-        if (!(OFF == K_ZERO || OFFG < K_ZERO)) {
-          double TIDT = or_div(K_ONE, DTX), TRHO, TVOL;
-          if (ISMSTR == 1 && OFFG > K_ONE) { TRHO = m.rho0 * TIDT; TVOL = VOLO * TIDT; }
-          else                             { TRHO = RHON * TIDT;   TVOL = VOLN * TIDT; }
-          STI = TRHO * TVOL;
-        }
-        DTX = g.dtfac * DTX;
-        if (VOLN > K_ZERO && OFF > K_ZERO && OFFG > K_ZERO && g.nodadt == 0) dt_cand = DTX;
-      }
+      brick_mqviscb<ISMSTR>(g, DXX, DYY, DZZ, SSP, OFF, OFFG, VOLN, VOLO, RHON, RHOREF, CBV, DELTAX, QNEW, SSP_EQ, STI, dt_cand);
       // ---- pressure + internal energy (m2law.F:433-453)
       const double DTA = K_HALF * DT1;
       const double PNEW = m.bulk * AMU;
@@ -428,6 +439,125 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       EINT = or_div((EINT + EINC * OFF), fmax(K_EM15, VOLO));
       if (m.vp == 1) { double PLAP = or_div(DPLA, fmax(K_EM20, DT1)); EPSD = asrate * PLAP + (K_ONE - asrate) * EPSD; }
       if (m.rhocp > K_ZERO) { SIGY = fmax(SIGY, AK); TEMP = TEMP + SIGY * DPLA * rhocpi; }
+    } else {
+      // ---- MULAW (mulaw.F90:668-700, 846-905, 1049-1052, 1133-1166, 2187-2219, 2876-2915, 3000-3016) -> SIGEPS36
+      //      (sigeps36.F:170-207, 266-295, 398-603, 1453-1460, 1507-1510): VP=0, FISOKIN=0, IFAIL=0, isotropic global frame
+      const orgpu_law36& m6 = g.m36;
+      const double DEFP0 = EPXE;
+      const double EP1 = DXX * OFF, EP2 = DYY * OFF, EP3 = DZZ * OFF, EP4 = D4 * OFF, EP5 = D5 * OFF, EP6 = D6 * OFF;
+      const double DE1 = EP1 * DT1, DE2 = EP2 * DT1, DE3 = EP3 * DT1, DE4 = EP4 * DT1, DE5 = EP5 * DT1, DE6 = EP6 * DT1;
+      const double SO1 = SG1, SO2 = SG2, SO3 = SG3, SO4 = SG4, SO5 = SG5, SO6 = SG6;
+      if (g.w_stra >= 0) {                                 // LBUF%STRA: rotated, then incremented (ISTRAIN>0)
+        const double WXXF = WXX * OFF, WYYF = WYY * OFF, WZZF = WZZ * OFF;
+        const double T1 = T.ld(g.w_stra), T2 = T.ld(g.w_stra + 1), T3 = T.ld(g.w_stra + 2), T4 = T.ld(g.w_stra + 3), T5 = T.ld(g.w_stra + 4), T6 = T.ld(g.w_stra + 5);
+        const double Q1 = T4 * WZZF, Q2 = T6 * WYYF, Q3 = T5 * WXXF;
+        const double SS1 = T1 - Q1 + Q2, SS2 = T2 + Q1 - Q3, SS3 = T3 - Q2 + Q3;
+        const double SS4 = T4 + 2. * WZZF * (T1 - T2) + WYYF * T5 - WXXF * T6;
+        const double SS5 = T5 + 2. * WXXF * (T2 - T3) + WZZF * T6 - WYYF * T4;
+        const double SS6 = T6 + 2. * WYYF * (T3 - T1) + WXXF * T4 - WZZF * T5;
+        T.st(g.w_stra, SS1 + DE1); T.st(g.w_stra + 1, SS2 + DE2); T.st(g.w_stra + 2, SS3 + DE3);
+        T.st(g.w_stra + 3, SS4 + DE4); T.st(g.w_stra + 4, SS5 + DE5); T.st(g.w_stra + 5, SS6 + DE6);
+      }
+      // MSTRAIN_RATE, IDEV = 1 (mstrain_rate.F:60-91)
+      if (m6.israte >= 0) {
+        const double dav = (EP1 + EP2 + EP3) * K_THIRD;
+        const double E1 = EP1 - dav, E2 = EP2 - dav, E3 = EP3 - dav, E4 = K_HALF * EP4, E5 = K_HALF * EP5, E6 = K_HALF * EP6;
+        const double epsp = K_HALF * (E1 * E1 + E2 * E2 + E3 * E3) + E4 * E4 + E5 * E5 + E6 * E6;
+        const double epsdot = or_div(or_sqrt(K_THREE * epsp), K_THREE_HALF);
+        if (m6.israte == 0) EPSD = epsdot;
+        else { const double asrate = fmin(K_ONE, m6.asrate * DT1); EPSD = asrate * epsdot + (K_ONE - asrate) * EPSD; }
+      }
+      // SIGEPS36: deviatoric elastic predictor
+      SSP = m6.ssp3d;
+      {
+        const double DAV = (DE1 + DE2 + DE3) * K_THIRD;
+        const double P0 = -(SO1 + SO2 + SO3) * K_THIRD;
+        SG1 = SO1 + P0 + m6.g2 * (DE1 - DAV);
+        SG2 = SO2 + P0 + m6.g2 * (DE2 - DAV);
+        SG3 = SO3 + P0 + m6.g2 * (DE3 - DAV);
+        SG4 = SO4 + m6.shear * DE4;
+        SG5 = SO5 + m6.shear * DE5;
+        SG6 = SO6 + m6.shear * DE6;
+      }
+      // yield stress and hardening modulus from the tabulated curves (VINTER, forward-only cursors in VARTMP)
+      double YLD, H;
+      if (m6.nrate == 1) {
+        int ipos = T.ldi(g.w_vt, 0); const int ipos_old = ipos;
+        const int f = m6.ifunc[0];
+        const int i0 = __ldg(g.npf + f), i1 = __ldg(g.npf + f + 1);
+        double dydx, y1;
+        vinter1(g.tf, i0, i1 - i0, ipos, EPXE, dydx, y1);
+        if (ipos != ipos_old) T.sti(g.w_vt, 0, ipos);
+        const double FACT = K_ONE * K_ONE * (m6.yfac[0] * K_ONE);
+        H = dydx * FACT;
+        YLD = y1 * FACT;
+      } else {
+        int JJ = 1;
+        for (int J = 2; J <= m6.nrate - 1; J++) if (EPSD >= m6.rate[J - 1]) JJ = J;
+        double RFAC;
+        if (m6.ismooth == 2) {
+          const double EPSP1 = fmax(m6.rate[JJ - 1], K_EM20), EPSP2 = m6.rate[JJ];
+          RFAC = or_div(log(or_div(fmax(EPSD, K_EM20), EPSP1)), log(or_div(EPSP2, EPSP1)));
+        } else {
+          const double EPSP1 = m6.rate[JJ - 1], EPSP2 = m6.rate[JJ];
+          RFAC = or_div((EPSD - EPSP1), (EPSP2 - EPSP1));
+        }
+        const double YFAC1 = m6.yfac[JJ - 1] * K_ONE, YFAC2 = m6.yfac[JJ] * K_ONE;
+        const int f1 = m6.ifunc[JJ - 1], f2 = m6.ifunc[JJ];
+        int ipos1 = T.ldi(g.w_vt, 1 + JJ), ipos2 = T.ldi(g.w_vt, 2 + JJ);
+        double dydx1, y1, dydx2, y2;
+        { const int i0 = __ldg(g.npf + f1), i1 = __ldg(g.npf + f1 + 1); vinter1(g.tf, i0, i1 - i0, ipos1, EPXE, dydx1, y1); }
+        { const int i0 = __ldg(g.npf + f2), i1 = __ldg(g.npf + f2 + 1); vinter1(g.tf, i0, i1 - i0, ipos2, EPXE, dydx2, y2); }
+        T.sti(g.w_vt, 1 + JJ, ipos1); T.sti(g.w_vt, 2 + JJ, ipos2);
+        y1 = y1 * YFAC1; y2 = y2 * YFAC2;
+        YLD = (y1 + RFAC * (y2 - y1)) * (K_ONE * K_ONE);
+        dydx1 = dydx1 * YFAC1; dydx2 = dydx2 * YFAC2;
+        H = (dydx1 + RFAC * (dydx2 - dydx1)) * (K_ONE * K_ONE);
+      }
+      if (m6.yldcheck == 1) YLD = fmax(YLD, K_EM20);
+      // projection on the yield surface (radial return), IPLA = 0 / 2 / 1
+      {
+        double VM = K_THREE * (K_HALF * (SG1 * SG1 + SG2 * SG2 + SG3 * SG3) + SG4 * SG4 + SG5 * SG5 + SG6 * SG6);
+        if (VM > YLD * YLD) {
+          VM = or_sqrt(VM);
+          double R = or_div(YLD, fmax(VM, K_EM20));
+          if (g.prop.ipla == 0) {
+            EPXE = EPXE + or_div((K_ONE - R) * VM, fmax(m6.g3 + H, K_EM20));
+          } else if (g.prop.ipla == 2) {
+            EPXE = EPXE + or_div((K_ONE - R) * VM, fmax(m6.g3, K_EM20));
+          } else {
+            const double DPLA = or_div((K_ONE - R) * VM, fmax(m6.g3 + H, K_EM20));
+            YLD = fmax(YLD + (K_ONE - m6.fisokin) * DPLA * H, K_ZERO);
+            R = fmin(K_ONE, or_div(YLD, fmax(VM, K_EM20)));
+            EPXE = EPXE + DPLA;
+          }
+          SG1 = SG1 * R; SG2 = SG2 * R; SG3 = SG3 * R; SG4 = SG4 * R; SG5 = SG5 * R; SG6 = SG6 * R;
+        }
+      }
+      { const double Pn = m6.bulk * AMU; SG1 = SG1 - Pn; SG2 = SG2 - Pn; SG3 = SG3 - Pn; }   // IEOS = 0
+      if (OFF < K_EM01) OFF = K_ZERO;
+      if (OFF < K_ONE) OFF = OFF * K_FOUR_OVER_5;
+      // MULAW: plastic work (L_PLA>0, von Mises of the old and new stresses)
+      {
+        const double DPLA = EPXE - DEFP0;
+        const double VM0 = or_sqrt(K_HALF * ((SO1 - SO2) * (SO1 - SO2) + (SO2 - SO3) * (SO2 - SO3) + (SO3 - SO1) * (SO3 - SO1))
+                                   + K_THREE * (SO4 * SO4 + SO5 * SO5 + SO6 * SO6));
+        const double VMN = or_sqrt(K_HALF * ((SG1 - SG2) * (SG1 - SG2) + (SG2 - SG3) * (SG2 - SG3) + (SG3 - SG1) * (SG3 - SG1))
+                                   + K_THREE * (SG4 * SG4 + SG5 * SG5 + SG6 * SG6));
+        T.st(g.w_wpla, T.ld(g.w_wpla) + K_HALF * (VM0 + VMN) * DPLA * VOLN);
+      }
+      SG1 = SG1 * OFF; SG2 = SG2 * OFF; SG3 = SG3 * OFF; SG4 = SG4 * OFF; SG5 = SG5 * OFF; SG6 = SG6 * OFF;
+      if (SSP == K_ZERO) SSP = or_sqrt(or_div(m6.bulk, m6.rho0));
+      brick_mqviscb<ISMSTR>(g, DXX, DYY, DZZ, SSP, OFF, OFFG, VOLN, VOLO, RHON, RHOREF, CBV, DELTAX, QNEW, SSP_EQ, STI, dt_cand);
+      // internal energy (mulaw.F90:3000-3013), then energy -> energy density (mmain.F90:1996-2004)
+      {
+        const double P2 = -(S1 + SG1 + S2 + SG2 + S3 + SG3) * K_THIRD;
+        const double E1 = DXX * (S1 + SG1 + P2 + K_TWO * K_ZERO), E2 = DYY * (S2 + SG2 + P2 + K_TWO * K_ZERO), E3 = DZZ * (S3 + SG3 + P2 + K_TWO * K_ZERO);
+        const double E4 = D4 * (S4 + SG4 + K_TWO * K_ZERO), E5 = D5 * (S5 + SG5 + K_TWO * K_ZERO), E6 = D6 * (S6 + SG6 + K_TWO * K_ZERO);
+        const double EINC = OFF * (VOL_AVG * DT1 * (E1 + E2 + E3 + E4 + E5 + E6 + K_ZERO) - DVOL * (QNEW + QOLD + P2)) * K_HALF;
+        EINT = EINT + EINC;
+        EINT = (VOLO > K_ZERO) ? or_div(EINT, fmax(VOLO, K_EM20)) : K_ZERO;
+      }
     }
     // mmain.F90 tail: entropy heating of the artificial viscosity when the buffer tracks temperature
     if (m.has_temp) {
@@ -538,27 +668,37 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
   cta_epilogue<true, STAGED>(dt_cand, order, P.db, g.blk0 + blockIdx.x, g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
 }
 
-template <int JHBE, int ISMSTR>
+template <int JHBE, int ISMSTR, int LAW>
 static void launch_brick_staged(const BrickParams& P, int nblk, cudaStream_t st)
 {
   const size_t bytes = (size_t)P.sg.nw * ORGPU_TILE * 8;
 #ifndef ORGPU_NO_STAGING
   if (bytes <= ORGPU_STAGE_MAX_BYTES) {
-    stage_attr((const void*)brick_forces_kernel<JHBE, ISMSTR, true>, bytes, ORGPU_BRICK_MINB);
-    brick_forces_kernel<JHBE, ISMSTR, true><<<nblk, ORGPU_BLOCK, bytes, st>>>(P);
+    stage_attr((const void*)brick_forces_kernel<JHBE, ISMSTR, LAW, true>, bytes, ORGPU_BRICK_MINB);
+    brick_forces_kernel<JHBE, ISMSTR, LAW, true><<<nblk, ORGPU_BLOCK, bytes, st>>>(P);
     return;
   }
 #endif
-  brick_forces_kernel<JHBE, ISMSTR, false><<<nblk, ORGPU_BLOCK, 0, st>>>(P);
+  brick_forces_kernel<JHBE, ISMSTR, LAW, false><<<nblk, ORGPU_BLOCK, 0, st>>>(P);
 }
 
-template <int JHBE>
+template <int JHBE, int LAW>
 static void launch_brick_ismstr(const BrickParams& P, int ismstr, int nblk, cudaStream_t st)
 {
   switch (ismstr) {
-    case 1: launch_brick_staged<JHBE, 1>(P, nblk, st); break;
-    case 2: launch_brick_staged<JHBE, 2>(P, nblk, st); break;
-    default: launch_brick_staged<JHBE, 4>(P, nblk, st); break;
+    case 1: launch_brick_staged<JHBE, 1, LAW>(P, nblk, st); break;
+    case 2: launch_brick_staged<JHBE, 2, LAW>(P, nblk, st); break;
+    default: launch_brick_staged<JHBE, 4, LAW>(P, nblk, st); break;
+  }
+}
+
+template <int LAW>
+static void launch_brick_jhbe(const BrickParams& P, int nblk, cudaStream_t st)
+{
+  switch (P.sg.prop.jhbe) {
+    case 0: launch_brick_ismstr<0, LAW>(P, P.sg.prop.ismstr, nblk, st); break;
+    case 2: launch_brick_ismstr<2, LAW>(P, P.sg.prop.ismstr, nblk, st); break;
+    default: launch_brick_ismstr<1, LAW>(P, P.sg.prop.ismstr, nblk, st); break;
   }
 }
 
@@ -567,9 +707,6 @@ void launch_brick_forces(const BrickSG& sg, const DevNodes& nd, double* fsky, in
 {
   BrickParams P{sg, nd, fsky, roww, cs, db};
   const int nblk = sg.ne_pad / ORGPU_TILE;
-  switch (sg.prop.jhbe) {
-    case 0: launch_brick_ismstr<0>(P, sg.prop.ismstr, nblk, st); break;
-    case 2: launch_brick_ismstr<2>(P, sg.prop.ismstr, nblk, st); break;
-    default: launch_brick_ismstr<1>(P, sg.prop.ismstr, nblk, st); break;
-  }
+  if (sg.law == 36) launch_brick_jhbe<36>(P, nblk, st);
+  else              launch_brick_jhbe<2>(P, nblk, st);
 }

@@ -33,7 +33,7 @@ template <class T> static int dev_alloc(T** p, size_t n) {
   return 0;
 }
 
-struct HostSolidGroup { int nel, nft; orgpu_law2 mat; orgpu_prop_solid prop; std::vector<double> vol0; };
+struct HostSolidGroup { int nel, nft, law; orgpu_law2 mat; orgpu_law36 m36; orgpu_prop_solid prop; std::vector<double> vol0; };
 
 struct BrickSGHost { BrickSG d; int first_elem; std::vector<void*> owned; };
 
@@ -49,6 +49,7 @@ struct orgpu_engine {
   std::vector<int> npf; std::vector<double> tf;
   int lf_func = -1; double lf_fcx = 1.0;            // time function of the nodal loads
   std::vector<int> fv_idx; std::vector<FixVelNode> fv;   // imposed velocities, per node
+  double* d_btf = nullptr; int* d_bnpf = nullptr;   // LAW36 function table of the brick super-groups
   double* d_ftf = nullptr; int* d_fnpf = nullptr; int* d_fv_idx = nullptr; FixVelNode* d_fv = nullptr;
   std::vector<int> itab; int* d_itab = nullptr; double* d_nd_dt = nullptr; int* d_nd_node = nullptr;   // /DT/NODA
   std::vector<HostSolidGroup> sgroups;
@@ -139,7 +140,7 @@ int orgpu_destroy(orgpu_engine* e)
   for (auto& s : e->csg) for (void* p : s.owned) cudaFree(p);
   void* ptrs[] = {e->nd.pos, e->nd.vel, e->nd.rot, e->nd.D, e->nd.A, e->nd.AR, e->nd.STIFN, e->nd.STIFR, e->nd.MS, e->nd.IN,
                   e->d_stage3a, e->d_stage3b, e->d_fext, e->d_mext, e->d_icodt, e->d_icodr, e->d_adsky, e->d_fsky, e->d_cs,
-                  e->db.dt, e->db.order, e->d_ftf, e->d_fnpf, e->d_fv_idx, e->d_fv, e->d_itab, e->d_nd_dt, e->d_nd_node};
+                  e->db.dt, e->db.order, e->d_btf, e->d_bnpf, e->d_ftf, e->d_fnpf, e->d_fv_idx, e->d_fv, e->d_itab, e->d_nd_dt, e->d_nd_node};
   for (void* p : ptrs) if (p) cudaFree(p);
   { Exchange& x = e->xc;
     void* xp[] = {x.d_send_slots, x.d_recv_slots, x.d_sendbuf, x.d_recvbuf, x.d_cand_send, x.d_cand_recv, x.d_slots_tmp, x.d_rows_tmp};
@@ -262,7 +263,26 @@ int orgpu_add_solid_group(orgpu_engine* e, int nel, int nft, const orgpu_law2* m
   NEED(mat->fisokin == 0.0, -5, "LAW2 kinematic hardening (FISOKIN>0) is outside the built path");
   NEED(prop->jhbe == 0 || prop->jhbe == 1 || prop->jhbe == 2, -5, "Isolid=%d is outside the built path (0,1,2)", prop->jhbe);
   NEED(prop->ismstr == 1 || prop->ismstr == 2 || prop->ismstr == 4, -5, "Ismstr=%d is outside the built path (1,2,4)", prop->ismstr);
-  HostSolidGroup g; g.nel = nel; g.nft = nft; g.mat = *mat; g.prop = *prop; g.vol0.assign(vol0, vol0 + nel);
+  HostSolidGroup g; g.nel = nel; g.nft = nft; g.law = 2; g.mat = *mat; memset(&g.m36, 0, sizeof g.m36); g.prop = *prop; g.vol0.assign(vol0, vol0 + nel);
+  e->sgroups.push_back(std::move(g));
+  return (int)e->sgroups.size() - 1;
+}
+
+int orgpu_add_solid_group_law(orgpu_engine* e, int nel, int nft, int law, const void* mat,
+                              const orgpu_prop_solid* prop, const double* vol0)
+{
+  if (law == 2) return orgpu_add_solid_group(e, nel, nft, (const orgpu_law2*)mat, prop, vol0);
+  NEED(law == 36, -5, "solid law %d is outside the built path (2, 36)", law);
+  NEED(e && mat && prop && vol0 && nel > 0 && !e->finalized, -1, "orgpu_add_solid_group_law: bad arguments / already finalized");
+  NEED(nft >= 0 && nft + nel <= e->numels, -4, "orgpu_add_solid_group_law: elements [%d,%d) outside IXS (%d)", nft, nft + nel, e->numels);
+  const orgpu_law36* m = (const orgpu_law36*)mat;
+  NEED(m->fisokin == 0.0 && m->vp == 0 && m->ifail == 0, -5, "LAW36 kinematic hardening / VP=1 / failure are outside the built path");
+  NEED(m->nrate >= 1 && m->nrate <= ORGPU_MAXFUNC36, -5, "LAW36 NRATE=%d out of range", m->nrate);
+  NEED(prop->jhbe == 0 || prop->jhbe == 1 || prop->jhbe == 2, -5, "Isolid=%d is outside the built path (0,1,2)", prop->jhbe);
+  NEED(prop->ismstr == 1 || prop->ismstr == 2 || prop->ismstr == 4, -5, "Ismstr=%d is outside the built path (1,2,4)", prop->ismstr);
+  NEED(prop->ipla >= 0 && prop->ipla <= 2, -5, "solid Iplas=%d is outside the built path (0,1,2)", prop->ipla);
+  HostSolidGroup g; g.nel = nel; g.nft = nft; g.law = 36; memset(&g.mat, 0, sizeof g.mat); g.mat.rho0 = m->rho0;
+  g.m36 = *m; g.prop = *prop; g.vol0.assign(vol0, vol0 + nel);
   e->sgroups.push_back(std::move(g));
   return (int)e->sgroups.size() - 1;
 }
@@ -295,7 +315,8 @@ int orgpu_finalize(orgpu_engine* e)
   while (gi < e->sgroups.size()) {
     size_t gj = gi + 1;
     while (gj < e->sgroups.size() && e->sgroups[gj].nft == e->sgroups[gj - 1].nft + e->sgroups[gj - 1].nel &&
-           !memcmp(&e->sgroups[gj].mat, &e->sgroups[gi].mat, sizeof(orgpu_law2)) &&
+           e->sgroups[gj].law == e->sgroups[gi].law &&
+           !memcmp(&e->sgroups[gj].mat, &e->sgroups[gi].mat, sizeof(orgpu_law2)) && !memcmp(&e->sgroups[gj].m36, &e->sgroups[gi].m36, sizeof(orgpu_law36)) &&
            !memcmp(&e->sgroups[gj].prop, &e->sgroups[gi].prop, sizeof(orgpu_prop_solid))) gj++;
     int ne = 0; for (size_t k = gi; k < gj; k++) ne += e->sgroups[k].nel;
     const int nft = e->sgroups[gi].nft;
@@ -305,8 +326,27 @@ int orgpu_finalize(orgpu_engine* e)
     d.mat = e->sgroups[gi].mat; d.prop = e->sgroups[gi].prop; d.dtfac = e->ctl.dtfac_brick; d.nodadt = e->ctl.nodadt;
     std::vector<int> conn((size_t)8 * np, 0), ngl(np, 0), conn_t;
     // state slab: read/write words first (SIG 6, EINT, RHO, QVIS, PLA, EPSD, OFF[, TEMP]), then VOL and the slot rows
+    d.law = e->sgroups[gi].law; d.m36 = e->sgroups[gi].m36;
     d.w_temp = d.mat.has_temp ? BW_NFIX : -1;
     d.nw_rw = BW_NFIX + (d.mat.has_temp ? 1 : 0);
+    d.w_stra = d.w_wpla = d.w_vt = -1; d.nvt = 0; d.tf = nullptr; d.npf = nullptr;
+    if (d.law == 36) {                                   // LBUF%WPLA, LBUF%STRA (ISTRAIN>0), VARTMP cursors
+      d.w_wpla = d.nw_rw++;
+      if (d.prop.istrain > 0) { d.w_stra = d.nw_rw; d.nw_rw += 6; }
+      d.nvt = (d.m36.nrate == 1) ? 1 : 2 + d.m36.nrate;
+      d.w_vt = d.nw_rw; d.nw_rw += (d.nvt + 1) / 2;
+      NEED(!e->npf.empty(), -4, "LAW36 group without a function table (orgpu_set_functions)");
+      for (int j = 0; j < d.m36.nrate; j++) {
+        const int f = d.m36.ifunc[j];
+        NEED(f >= 0 && f + 1 < (int)e->npf.size() && e->npf[f + 1] - e->npf[f] >= 2, -4, "LAW36 curve %d missing or shorter than 2 points", f);
+      }
+      if (!e->d_btf) {
+        if (dev_alloc(&e->d_btf, e->tf.size()) || dev_alloc(&e->d_bnpf, e->npf.size())) return -100;
+        CUDA_OK(cudaMemcpy(e->d_btf, e->tf.data(), 8 * e->tf.size(), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(e->d_bnpf, e->npf.data(), 4 * e->npf.size(), cudaMemcpyHostToDevice));
+      }
+      d.tf = e->d_btf; d.npf = e->d_bnpf;
+    }
     d.w_vol = d.nw_rw; d.w_slot = d.nw_rw + 1; d.nw = d.nw_rw + 1 + 4;
     HostSlab H; H.init(d.nw, np);
     for (int i = 0; i < np; i++) { H.at(d.w_vol, i) = 1.0; H.at(BW_RHO, i) = d.mat.rho0; if (d.w_temp >= 0) H.at(d.w_temp, i) = d.mat.tini; }
@@ -655,7 +695,8 @@ static int solid_state_xfer(orgpu_engine* e, int field, double* buf, bool up)
     const BrickSG& d = S.d; int w0 = 0, nc = 1; double* base = d.slab; int nw = d.nw;
     switch (field) { case 0: w0 = BW_SIG; nc = 6; break; case 1: w0 = BW_EINT; break; case 2: w0 = BW_RHO; break; case 3: w0 = BW_QVIS; break;
                      case 4: w0 = BW_PLA; break; case 5: w0 = BW_EPSD; break; case 6: w0 = d.w_vol; break; case 7: w0 = BW_OFF; break;
-                     case 8: w0 = d.w_temp; break; case 9: base = d.smstr; nw = 21; w0 = 0; nc = 21; break; default: FAIL(-1, "unknown solid field %d", field); }
+                     case 8: w0 = d.w_temp; break; case 9: base = d.smstr; nw = 21; w0 = 0; nc = 21; break;
+                     case 10: w0 = d.w_stra; nc = 6; if (w0 < 0) continue; break; case 11: w0 = d.w_wpla; if (w0 < 0) continue; break; default: FAIL(-1, "unknown solid field %d", field); }
     if (w0 < 0) { if (!up) for (int i = 0; i < d.ne; i++) buf[S.first_elem + i] = d.mat.tini; continue; }   // no temperature buffer
     for (int k = 0; k < nc; k++)
       CUDA_OK(up ? slab_upload_word(base, nw, w0 + k, d.ne, buf + k * NE + S.first_elem)

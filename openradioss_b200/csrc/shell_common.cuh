@@ -55,20 +55,6 @@ struct MatIO {
   double fo[5], mo[3];                             // out: new GBUF%FOR / GBUF%MOM
 };
 
-// VINTER for one element: forward-only cursor walk + linear interpolation (vinter.F:100-130)
-__device__ __forceinline__ void vinter1(const double* __restrict__ tf, int iad, int npts, int& ipos,
-                                        double x, double& dydx, double& y)
-{
-  const int ilen = npts - 1 - ipos;
-  for (int j = 1; j <= ilen - 1; j++) {
-    if (x > __ldg(tf + 2 * (iad + ipos + 1))) ipos++; else break;
-  }
-  const double2 p1 = __ldg(reinterpret_cast<const double2*>(tf) + iad + ipos);
-  const double2 p2 = __ldg(reinterpret_cast<const double2*>(tf) + iad + ipos + 1);
-  dydx = or_div((p2.y - p1.y), (p2.x - p1.x));
-  y = p1.y + dydx * (x - p1.x);
-}
-
 struct IpState { double sxx, syy, sxy, syz, szx, pla, epsd, temp; int ipos; };
 
 // state of one integration point out of / into the CTA's tile

@@ -88,6 +88,8 @@ def steel_law36(curves=None, rates=None):
     m.bulk = young / 3.0 / (1.0 - 2.0 * nu)
     m.a1u = young / (1.0 - nu * nu); m.a2u = nu * m.a1u
     m.g3 = 3.0 * m.shear
+    m.g2 = 2.0 * m.shear
+    m.ssp3d = np.sqrt((m.bulk + K["FOUR_OVER_3"] * m.shear) / rho0)   # solids (hm_read_mat36.F:271)
     m.soundsp = np.sqrt(young / (1.0 - nu * nu) / rho0)
     m.nu_mnu = nu / (1.0 - nu); m.t_pnu = 3.0 / (1.0 + nu); m.u_mnu = 1.0 / (1.0 - nu)
     m.epsmax = K["INFINITY"]; m.fisokin = 0.0; m.asrate = 0.0
@@ -128,13 +130,14 @@ def default_prop_shell(thick=2.0, ihbe=24, npt=5, ismstr=2, ithk=1, ipla=1) -> P
     return p
 
 
-def default_prop_solid(jhbe=1, ismstr=4) -> PropSolid:
+def default_prop_solid(jhbe=1, ismstr=4, ipla=1, istrain=0) -> PropSolid:
     p = PropSolid()
     p.qa, p.qb = 1.1, 0.05
     p.cns1 = p.cns2 = 0.0
     p.hcoef = 0.1
     p.dtmin = 0.0
     p.jhbe = jhbe; p.ismstr = ismstr
+    p.ipla = ipla; p.istrain = istrain
     return p
 
 
@@ -156,8 +159,12 @@ def _groups(ne: int):
 def hex_block(nx: int, ny: int, nz: int, lx: float, ly: float, lz: float, *, mat: Law2 = None,
               prop: PropSolid = None, jitter: float = 0.05, seed: int = 2024, v0=(0.0, 0.0, 0.0),
               vrand: float = 0.0, vseed: int = 12345, fix_bottom_z: bool = False,
-              user_id_perm: bool = False) -> Model:
-    """Structured block of nx*ny*nz 8-node bricks (Taylor bar C1 / weak-scaling block C5)."""
+              user_id_perm: bool = False, law: int = 2, curves=None, rates=None) -> Model:
+    """Structured block of nx*ny*nz 8-node bricks (Taylor bar C1 / weak-scaling block C5).
+    law=36: the steel of steel_law36 through MMAIN -> MULAW -> SIGEPS36."""
+    npf = tf = None
+    if law == 36 and mat is None:
+        mat, npf, tf = steel_law36(curves, rates)
     mat = mat or copper_law2(); prop = prop or default_prop_solid()
     nnx, nny, nnz = nx + 1, ny + 1, nz + 1
     gx, gy, gz = np.meshgrid(np.arange(nnx), np.arange(nny), np.arange(nnz), indexing="ij")
@@ -196,7 +203,9 @@ def hex_block(nx: int, ny: int, nz: int, lx: float, ly: float, lz: float, *, mat
         V[icodt == 1, 2] = 0.0
     m = Model(X=X, V=V, VR=np.zeros_like(X), MS=MS, IN=np.zeros(numnod), control=default_control(0),
               ixs=ixs, vol0=vol0, icodt=icodt, itab=np.arange(1, numnod + 1, dtype=np.int32))
-    m.solid_groups = [SolidGroup(nft=s, nel=n, mat=mat, prop=prop) for s, n in _groups(ne)]
+    m.solid_groups = [SolidGroup(nft=s, nel=n, mat=mat, prop=prop, law=law) for s, n in _groups(ne)]
+    if npf is not None:
+        m.npf, m.tf = npf, tf
     m.adsky, m.iads, m.iadc, m.lsky = build_pon(numnod, m.ixs, m.ixc)
     return m
 

@@ -24,14 +24,14 @@ class Law2(C.Structure):
 
 
 class Law36(C.Structure):
-    _fields_ = [(n, d) for n in ("rho0 young nu shear bulk a11 a12 ssp gsr a11sr a12sr nusr a1u a2u g3 soundsp nu_mnu t_pnu u_mnu "
+    _fields_ = [(n, d) for n in ("rho0 young nu shear bulk a11 a12 ssp gsr a11sr a12sr nusr a1u a2u g3 g2 ssp3d soundsp nu_mnu t_pnu u_mnu "
                                  "epsmax fisokin asrate").split()] + \
                [("rate", d * MAXFUNC36), ("yfac", d * MAXFUNC36), ("ifunc", i * MAXFUNC36)] + \
                [(n, i) for n in "nrate israte vp ifail yldcheck ismooth".split()]
 
 
 class PropSolid(C.Structure):
-    _fields_ = [(n, d) for n in "qa qb cns1 cns2 hcoef dtmin".split()] + [("jhbe", i), ("ismstr", i)]
+    _fields_ = [(n, d) for n in "qa qb cns1 cns2 hcoef dtmin".split()] + [("jhbe", i), ("ismstr", i), ("ipla", i), ("istrain", i)]
 
 
 class PropShell(C.Structure):
@@ -57,8 +57,9 @@ def elastic_constants(young: float, nu: float):
 class SolidGroup:
     nft: int
     nel: int
-    mat: Law2
+    mat: object              # Law2 | Law36
     prop: PropSolid
+    law: int = 2             # 2 (M2LAW) or 36 (MULAW -> SIGEPS36)
 
 
 @dataclass

@@ -91,6 +91,26 @@ int orc_add_solid_group(void* h,int nel,int nft,const orgpu_law2* mat,const orgp
   return (int)o->sgroups.size()-1;
 }
 
+/* same, any built law: law = 2 (orgpu_law2) or 36 (orgpu_law36: MMAIN -> MULAW -> SIGEPS36) */
+int orc_add_solid_group_law(void* h,int nel,int nft,int law,const void* mat,const orgpu_prop_solid* prop,
+                            const double* vol0)
+{
+  if(law==2) return orc_add_solid_group(h,nel,nft,(const orgpu_law2*)mat,prop,vol0);
+  if(law!=36) return -3;
+  Oracle* o=(Oracle*)h;
+  if(nel>MVSIZ-1) return -1;
+  const orgpu_law36* m=(const orgpu_law36*)mat;
+  if(m->fisokin!=0.0 || m->vp!=0 || m->ifail!=0) return -2;
+  OrcSolidGroup g; g.nel=nel; g.nft=nft; g.law=36; g.m36=*m; g.prop=*prop;
+  g.mat=orgpu_law2{}; g.mat.rho0=m->rho0;
+  g.sig.assign(6*nel,0); g.eint.assign(nel,0); g.rho.assign(nel,m->rho0); g.qvis.assign(nel,0);
+  g.pla.assign(nel,0); g.epsd.assign(nel,0); g.vol.assign(vol0,vol0+nel); g.off.assign(nel,1.0);
+  g.temp.assign(nel,0); g.dmg.assign(nel,0); g.smstr.assign(21*nel,0);
+  g.stra.assign(6*nel,0); g.wpla.assign(nel,0); g.vartmp.assign((size_t)(2+m->nrate)*nel,0);
+  o->sgroups.push_back(std::move(g));
+  return (int)o->sgroups.size()-1;
+}
+
 /* one shell group: elements [nft, nft+nel) of IXC; law = 2 (orgpu_law2) or 36 (orgpu_law36) */
 int orc_add_shell_group(void* h,int nel,int nft,int law,const void* mat,const orgpu_prop_shell* prop)
 {
@@ -132,7 +152,7 @@ void orc_download_nodes(void* h,double* X,double* V,double* VR,double* D,double*
 void orc_download_fsky(void* h,double* fsky){ Oracle* o=(Oracle*)h; memcpy(fsky,o->FSKY.data(),64*(size_t)o->lsky); }
 
 /* solid state of all groups concatenated in element order, component-major over NUMELS:
- * sig[k*numels+e] ; fields: 0 sig(6) 1 eint 2 rho 3 qvis 4 pla 5 epsd 6 vol 7 off 8 temp 9 smstr(21) */
+ * sig[k*numels+e] ; fields: 0 sig(6) 1 eint 2 rho 3 qvis 4 pla 5 epsd 6 vol 7 off 8 temp 9 smstr(21) 10 stra(6) 11 wpla */
 void orc_download_solid_state(void* h,int field,double* out){
   Oracle* o=(Oracle*)h; size_t ne=o->numels;
   for(auto& g:o->sgroups){
@@ -142,6 +162,7 @@ void orc_download_solid_state(void* h,int field,double* out){
       case 3: cp(g.qvis,1); break; case 4: cp(g.pla,1); break; case 5: cp(g.epsd,1); break;
       case 6: cp(g.vol,1); break; case 7: cp(g.off,1); break; case 8: cp(g.temp,1); break;
       case 9: cp(g.smstr,21); break;
+      case 10: if(!g.stra.empty()) cp(g.stra,6); break; case 11: if(!g.wpla.empty()) cp(g.wpla,1); break;
     }
   }
 }

@@ -32,12 +32,16 @@
 
 struct OrcSolidGroup {          /* one element group, ITY=1 (forint.F -> SFORC3) */
   int nel = 0, nft = 0;         /* nft: offset of first element in IXS/IADS (0-based) */
-  orgpu_law2 mat;               /* MLW=2 */
+  int law = 2;                  /* MLW: 2 (M2LAW) or 36 (MULAW -> SIGEPS36) */
+  orgpu_law2 mat;               /* MLW=2 (for MLW=36 only rho0 = PM(1) is mirrored here) */
+  orgpu_law36 m36;              /* MLW=36 */
   orgpu_prop_solid prop;
   /* ELBUF (gbuf == lbuf for 1-IP solids), component-major (k*nel+i) */
   std::vector<double> sig;      /* 6*nel */
   std::vector<double> eint, rho, qvis, pla, epsd, vol, off, temp, dmg;
   std::vector<double> smstr;    /* SAV(nel,21) */
+  std::vector<double> stra, wpla; /* MLW=36: LBUF%STRA(6*nel) when ISTRAIN>0, LBUF%WPLA */
+  std::vector<int> vartmp;      /* MLW=36: VARTMP(nel,2+NRATE) table cursors */
 };
 
 struct OrcShellGroup;           /* defined in shell files */

@@ -7,6 +7,7 @@
  * shapes are kept so that, compiled with -ffp-contract=off, the arithmetic is the reference's.
  */
 #include "oracle.h"
+#include "shell.h"   /* orc_vinter */
 
 namespace {
 
@@ -285,6 +286,185 @@ static void m2law(const Oracle& o,OrcSolidGroup& g,int nel,const int* ngl,
   }
 }
 
+/* SIGEPS36  materials/mat/mat036/sigeps36.F:35 -- the solid (3-D) LAW36, explicit (IMPL_S=0), built
+ * envelope as for shells: VP=0, FISOKIN=0, IFAIL=0, OPTE=0, CE1=0, PFUN=0, IEOS=0.
+ * uparam slots: :170-196 ; predictor :266-290 ; yield from the tables :398-525 ; projection :530-603 ;
+ * pressure :1453-1460 ; OFF relaxation :1507-1510. */
+static void sigeps36(const Oracle& o,const orgpu_law36& m,int nel,int ipla,
+                     const double* de1,const double* de2,const double* de3,const double* de4,const double* de5,const double* de6,
+                     const double* so1,const double* so2,const double* so3,const double* so4,const double* so5,const double* so6,
+                     double* s1,double* s2,double* s3,double* s4,double* s5,double* s6,
+                     double* soundsp,double* viscmax,double* off,const double* epsp,double* yld,double* pla,double* dpla1,
+                     const double* amu,int* vartmp /*(nel,nvartmp) column-major: VARTMP(I,k) -> vartmp[(k-1)*nel+i]*/)
+{
+  const int nrate=m.nrate;
+  const double G=m.shear, G2=m.g2, G3=m.g3, BULK=m.bulk, SSP=m.ssp3d, FISOKIN=m.fisokin;
+  double P0[MVSIZ],H[MVSIZ],R[MVSIZ];
+  for(int i=0;i<nel;i++) soundsp[i]=SSP;                                   /* :199-207 */
+  for(int i=0;i<nel;i++){                                                  /* :266-281 */
+    double DAV=(de1[i]+de2[i]+de3[i])*K_THIRD;
+    P0[i]=-(so1[i]+so2[i]+so3[i])*K_THIRD;
+    s1[i]=so1[i]+P0[i]+G2*(de1[i]-DAV);
+    s2[i]=so2[i]+P0[i]+G2*(de2[i]-DAV);
+    s3[i]=so3[i]+P0[i]+G2*(de3[i]-DAV);
+  }
+  for(int i=0;i<nel;i++){ s4[i]=so4[i]+G*de4[i]; s5[i]=so5[i]+G*de5[i]; s6[i]=so6[i]+G*de6[i]; }   /* :283-285 */
+  for(int i=0;i<nel;i++){ viscmax[i]=K_ZERO; dpla1[i]=K_ZERO; }            /* :292-295 (FAIL=1, PFAC=1) */
+  auto VT=[&](int i,int k)->int&{ return vartmp[(size_t)(k-1)*nel+i]; };
+  if(nrate==1){                                                            /* :398-414 */
+    const int f=m.ifunc[0];
+    for(int i=0;i<nel;i++){
+      double dydx,y1; int ipos=VT(i,3);
+      orc_vinter(o.TF,o.NPF[f],o.NPF[f+1]-o.NPF[f],ipos,pla[i],dydx,y1);
+      VT(i,3)=ipos;
+      double YFAC=m.yfac[0]*K_ONE;                  /* FACYLDI = 1 (no L_FAC_YLD) */
+      double FACT=K_ONE*K_ONE*YFAC;
+      H[i]=dydx*FACT;
+      yld[i]=y1*FACT;                               /* FISOKIN == 0 */
+    }
+  } else {                                                                 /* :420-482 */
+    for(int i=0;i<nel;i++){
+      int JJ=1;
+      for(int J=2;J<=nrate-1;J++) if(epsp[i]>=m.rate[J-1]) JJ=J;
+      double RFAC;
+      if(m.ismooth==2){
+        double EPSP1=std::max(m.rate[JJ-1],K_EM20), EPSP2=m.rate[JJ];
+        RFAC=std::log(std::max(epsp[i],K_EM20)/EPSP1)/std::log(EPSP2/EPSP1);
+      } else {
+        double EPSP1=m.rate[JJ-1], EPSP2=m.rate[JJ];
+        RFAC=(epsp[i]-EPSP1)/(EPSP2-EPSP1);
+      }
+      const int J1=JJ,J2=JJ+1;
+      int ipos1=VT(i,J1+2), ipos2=VT(i,J2+2);
+      double YFAC1=m.yfac[J1-1]*K_ONE, YFAC2=m.yfac[J2-1]*K_ONE;
+      const int f1=m.ifunc[J1-1], f2=m.ifunc[J2-1];
+      double dydx1,y1,dydx2,y2;
+      orc_vinter(o.TF,o.NPF[f1],o.NPF[f1+1]-o.NPF[f1],ipos1,pla[i],dydx1,y1);
+      orc_vinter(o.TF,o.NPF[f2],o.NPF[f2+1]-o.NPF[f2],ipos2,pla[i],dydx2,y2);
+      VT(i,J1+2)=ipos1; VT(i,J2+2)=ipos2;
+      y1=y1*YFAC1; y2=y2*YFAC2;
+      double FAC=RFAC, CC=K_ONE*K_ONE;
+      yld[i]=(y1+FAC*(y2-y1))*CC;
+      dydx1=dydx1*YFAC1; dydx2=dydx2*YFAC2;
+      H[i]=(dydx1+FAC*(dydx2-dydx1))*CC;
+    }
+  }
+  if(m.yldcheck==1) for(int i=0;i<nel;i++) yld[i]=std::max(yld[i],K_EM20);   /* :519-523 */
+  /* projection :527-603 */
+  for(int i=0;i<nel;i++){
+    double VM=K_THREE*(K_HALF*(s1[i]*s1[i]+s2[i]*s2[i]+s3[i]*s3[i])+s4[i]*s4[i]+s5[i]*s5[i]+s6[i]*s6[i]);
+    if(!(VM>yld[i]*yld[i])) continue;
+    VM=std::sqrt(VM);
+    R[i]=yld[i]/std::max(VM,K_EM20);
+    if(ipla==0){
+      s1[i]*=R[i]; s2[i]*=R[i]; s3[i]*=R[i]; s4[i]*=R[i]; s5[i]*=R[i]; s6[i]*=R[i];
+      pla[i]=pla[i]+(K_ONE-R[i])*VM/std::max(G3+H[i],K_EM20);
+      dpla1[i]=(K_ONE-R[i])*VM/std::max(G3+H[i],K_EM20);
+    } else if(ipla==2){
+      s1[i]*=R[i]; s2[i]*=R[i]; s3[i]*=R[i]; s4[i]*=R[i]; s5[i]*=R[i]; s6[i]*=R[i];
+      pla[i]=pla[i]+(K_ONE-R[i])*VM/std::max(G3,K_EM20);
+      dpla1[i]=(K_ONE-R[i])*VM/std::max(G3,K_EM20);
+    } else {
+      double DPLA=(K_ONE-R[i])*VM/std::max(G3+H[i],K_EM20);
+      yld[i]=std::max(yld[i]+(K_ONE-FISOKIN)*DPLA*H[i],K_ZERO);
+      R[i]=std::min(K_ONE,yld[i]/std::max(VM,K_EM20));
+      s1[i]*=R[i]; s2[i]*=R[i]; s3[i]*=R[i]; s4[i]*=R[i]; s5[i]*=R[i]; s6[i]*=R[i];
+      pla[i]=pla[i]+DPLA;
+      dpla1[i]=DPLA;
+    }
+  }
+  for(int i=0;i<nel;i++){ double P=BULK*amu[i]; s1[i]-=P; s2[i]-=P; s3[i]-=P; }   /* :1453-1460 (IEOS=0) */
+  for(int i=0;i<nel;i++){                                                    /* :1507-1510 */
+    if(off[i]<K_EM01) off[i]=K_ZERO;
+    if(off[i]<K_ONE) off[i]=off[i]*K_FOUR_OVER_5;
+  }
+}
+
+/* MULAW  materials/mat_share/mulaw.F90 -- "user type" law driver for solids, MTN=36, isotropic global frame
+ * (JCVT=0, ISORTH=0), no /VISC, no /FAIL, no non-local, ISVIS=0, JSPH=0.
+ * :668-700 (old values, EP=D*OFF) ; :846-884 (DE, SO, strain rotation) ; :886-905 (ISTRAIN) ; :1049-1052
+ * (rate filter) ; :1133-1166 (MSTRAIN_RATE IDEV=1, SIGEPS36) ; :2187-2219 (plastic work) ; :2876-2890
+ * (SIG=S*OFF) ; :2895-2915 (SSP, MQVISCB) ; :3000-3016 (internal energy, QOLD). */
+static void mulaw36(const Oracle& o,OrcSolidGroup& g,int nel,const int* ngl,
+                    double* off,double* sig,double* eint,const double* rho,double* qold,double* defp,double* epsd,
+                    const double* vol,double* stifn,double& dt2t,int& neltst,int& ityptst,const double* offg,
+                    const double* amu,const double* vol_avg,double* ssp,const double* dvol,
+                    const double* voln,const double* vd2,const double* deltax,double* vis,
+                    const double* d1,const double* d2,const double* d3,const double* d4,const double* d5,const double* d6,
+                    double* q,double* ssp_eq,
+                    const double* sold1,const double* sold2,const double* sold3,
+                    const double* sold4,const double* sold5,const double* sold6,
+                    const double* wxx,const double* wyy,const double* wzz,const double* rhoref)
+{
+  const orgpu_law36& m=g.m36;
+  const double DT1=o.DT1, facq0=K_ONE;
+  double defp0[MVSIZ],ep1[MVSIZ],ep2[MVSIZ],ep3[MVSIZ],ep4[MVSIZ],ep5[MVSIZ],ep6[MVSIZ];
+  double de1[MVSIZ],de2[MVSIZ],de3[MVSIZ],de4[MVSIZ],de5[MVSIZ],de6[MVSIZ];
+  double so1[MVSIZ],so2[MVSIZ],so3[MVSIZ],so4[MVSIZ],so5[MVSIZ],so6[MVSIZ];
+  double s1[MVSIZ],s2[MVSIZ],s3[MVSIZ],s4[MVSIZ],s5[MVSIZ],s6[MVSIZ];
+  double dpla[MVSIZ],sigy[MVSIZ],viscmax[MVSIZ];
+  auto S=[&](int i,int k)->double&{ return sig[k*nel+i]; };
+  for(int i=0;i<nel;i++) defp0[i]=defp[i];
+  for(int i=0;i<nel;i++){
+    vis[i]=K_ZERO;
+    ep1[i]=d1[i]*off[i]; ep2[i]=d2[i]*off[i]; ep3[i]=d3[i]*off[i];
+    ep4[i]=d4[i]*off[i]; ep5[i]=d5[i]*off[i]; ep6[i]=d6[i]*off[i];
+  }
+  for(int i=0;i<nel;i++){
+    de1[i]=ep1[i]*DT1; de2[i]=ep2[i]*DT1; de3[i]=ep3[i]*DT1; de4[i]=ep4[i]*DT1; de5[i]=ep5[i]*DT1; de6[i]=ep6[i]*DT1;
+    so1[i]=S(i,0); so2[i]=S(i,1); so3[i]=S(i,2); so4[i]=S(i,3); so5[i]=S(i,4); so6[i]=S(i,5);
+  }
+  if(g.prop.istrain>0){                                   /* L_STRA>0: LBUF%STRA rotated (:860-884) then incremented (:886-892) */
+    auto E=[&](int i,int k)->double&{ return g.stra[(size_t)(k-1)*nel+i]; };
+    for(int i=0;i<nel;i++){
+      double wxxf=wxx[i]*off[i], wyyf=wyy[i]*off[i], wzzf=wzz[i]*off[i];
+      double q1=E(i,4)*wzzf, q2=E(i,6)*wyyf, q3=E(i,5)*wxxf;
+      double ss1=E(i,1)-q1+q2, ss2=E(i,2)+q1-q3, ss3=E(i,3)-q2+q3;
+      double ss4=E(i,4)+2.*wzzf*(E(i,1)-E(i,2))+wyyf*E(i,5)-wxxf*E(i,6);
+      double ss5=E(i,5)+2.*wxxf*(E(i,2)-E(i,3))+wzzf*E(i,6)-wyyf*E(i,4);
+      double ss6=E(i,6)+2.*wyyf*(E(i,3)-E(i,1))+wxxf*E(i,4)-wzzf*E(i,5);
+      E(i,1)=ss1; E(i,2)=ss2; E(i,3)=ss3; E(i,4)=ss4; E(i,5)=ss5; E(i,6)=ss6;
+    }
+    for(int i=0;i<nel;i++){
+      E(i,1)=E(i,1)+de1[i]; E(i,2)=E(i,2)+de2[i]; E(i,3)=E(i,3)+de3[i];
+      E(i,4)=E(i,4)+de4[i]; E(i,5)=E(i,5)+de5[i]; E(i,6)=E(i,6)+de6[i];
+    }
+  }
+  const int israte=m.israte; double asrate=K_ZERO;
+  if(israte>0) asrate=std::min(K_ONE,m.asrate*DT1);
+  mstrain_rate(nel,israte,asrate,epsd,1,ep1,ep2,ep3,ep4,ep5,ep6);
+  sigeps36(o,m,nel,g.prop.ipla,de1,de2,de3,de4,de5,de6,so1,so2,so3,so4,so5,so6,s1,s2,s3,s4,s5,s6,
+           ssp,viscmax,off,epsd,sigy,defp,dpla,amu,g.vartmp.data());
+  /* plastic work (L_PLA>0, no L_SEQ) */
+  for(int i=0;i<nel;i++){
+    dpla[i]=defp[i]-defp0[i];
+    double vm0=std::sqrt(K_HALF*((so1[i]-so2[i])*(so1[i]-so2[i])+(so2[i]-so3[i])*(so2[i]-so3[i])+(so3[i]-so1[i])*(so3[i]-so1[i]))
+                         +K_THREE*(so4[i]*so4[i]+so5[i]*so5[i]+so6[i]*so6[i]));
+    double vm =std::sqrt(K_HALF*((s1[i]-s2[i])*(s1[i]-s2[i])+(s2[i]-s3[i])*(s2[i]-s3[i])+(s3[i]-s1[i])*(s3[i]-s1[i]))
+                         +K_THREE*(s4[i]*s4[i]+s5[i]*s5[i]+s6[i]*s6[i]));
+    g.wpla[i]=g.wpla[i]+K_HALF*(vm0+vm)*dpla[i]*voln[i];
+  }
+  for(int i=0;i<nel;i++){
+    S(i,0)=s1[i]*off[i]; S(i,1)=s2[i]*off[i]; S(i,2)=s3[i]*off[i];
+    S(i,3)=s4[i]*off[i]; S(i,4)=s5[i]*off[i]; S(i,5)=s6[i]*off[i];
+  }
+  for(int i=0;i<nel;i++) if(ssp[i]==K_ZERO) ssp[i]=std::sqrt(m.bulk/m.rho0);
+  mqviscb(o,g,nel,ngl,off,rho,ssp,stifn,dt2t,neltst,ityptst,offg,voln,vd2,deltax,vis,d1,d2,d3,
+          q,ssp_eq,vol,rhoref,facq0);
+  for(int i=0;i<nel;i++){
+    double p2=-(sold1[i]+S(i,0)+sold2[i]+S(i,1)+sold3[i]+S(i,2))*K_THIRD;
+    double e1=d1[i]*(sold1[i]+S(i,0)+p2+K_TWO*K_ZERO);
+    double e2=d2[i]*(sold2[i]+S(i,1)+p2+K_TWO*K_ZERO);
+    double e3=d3[i]*(sold3[i]+S(i,2)+p2+K_TWO*K_ZERO);
+    double e4=d4[i]*(sold4[i]+S(i,3)+K_TWO*K_ZERO);
+    double e5=d5[i]*(sold5[i]+S(i,4)+K_TWO*K_ZERO);
+    double e6=d6[i]*(sold6[i]+S(i,5)+K_TWO*K_ZERO);
+    double einc=off[i]*(vol_avg[i]*DT1*(e1+e2+e3+e4+e5+e6+K_ZERO)-dvol[i]*(q[i]+qold[i]+p2))*K_HALF;
+    eint[i]=eint[i]+einc;
+  }
+  for(int i=0;i<nel;i++) qold[i]=q[i];
+}
+
 /* SFORC3 */
 void orc_sforc3(Oracle& o, OrcSolidGroup& g, double& dt2t, int& neltst, int& ityptst)
 {
@@ -549,6 +729,16 @@ void orc_sforc3(Oracle& o, OrcSolidGroup& g, double& dt2t, int& neltst, int& ity
     } else { for(int i=0;i<nel;i++) TSTAR[i]=K_ZERO; }
     double vecnul[MVSIZ]; for(int i=0;i<nel;i++) vecnul[i]=K_ZERO;
     double* el_temp = g.mat.has_temp ? g.temp.data() : vecnul;
+    if(g.law==36){
+      /* mmain.F90:1899-1960 MULAW, then :1996-2004 energy -> energy density */
+      mulaw36(o,g,nel,NGL,OFF,SIG,EINT,RHON,g.qvis.data(),g.pla.data(),g.epsd.data(),g.vol.data(),STI,
+              dt2t,neltst,ityptst,OFFG,AMU,VOL_AVG,CXX,DVOL,VOLN,VD2,DELTAX,VIS,
+              DXX,DYY,DZZ,D4,D5,D6,QVIS,SSP_EQ,S1,S2,S3,S4,S5,S6,WXX,WYY,WZZ,RHOREF);
+      for(int i=0;i<nel;i++){
+        if(g.vol[i]>K_ZERO) EINT[i]=EINT[i]/std::max(g.vol[i],K_EM20);
+        else EINT[i]=K_ZERO;
+      }
+    } else
     m2law(o,g,nel,NGL,OFF,SIG,EINT,RHON,g.qvis.data(),g.pla.data(),g.epsd.data(),g.vol.data(),STI,
           dt2t,neltst,ityptst,OFFG,AMU,VOL_AVG,CXX,DVOL,VOLN,VD2,DELTAX,VIS,
           DXX,DYY,DZZ,D4,D5,D6,QVIS,SSP_EQ,S1,S2,S3,S4,S5,S6,TSTAR,el_temp,g.dmg.data(),RHOREF);

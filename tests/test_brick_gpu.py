@@ -168,6 +168,112 @@ def test_full_size_taylor_bar_properties():
     assert np.array_equal(ref, A)
 
 
+# ---- LAW36 solids: MMAIN -> MULAW -> SIGEPS36 -------------------------------------------
+
+LAW36_FIELDS = ("sig", "eint", "rho", "qvis", "pla", "epsd", "off", "smstr", "wpla")
+
+
+def check_state36(g, o, tol=1e-11, fields=LAW36_FIELDS):
+    for f in fields:
+        a, b = g.solid_state(f), o.solid_state(f)
+        assert rel_err(a, b) <= tol, (f, rel_err(a, b))
+
+
+@pytest.mark.parametrize("ipla", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(5, 5, 5), (16, 8, 3), (1, 1, 1)])
+def test_law36_phases_match_oracle(shape, ipla):
+    nx, ny, nz = shape
+    m = meshgen.hex_block(nx, ny, nz, 2.0 * nx, 2.0 * ny, 3.3 * nz, law=36, v0=(0, 0, -60.0), fix_bottom_z=True,
+                          vrand=25.0, user_id_perm=True, prop=meshgen.default_prop_solid(ipla=ipla, istrain=1))
+    g, o = pair(m)
+    dt1 = 0.0
+    for cyc in range(5):                                  # phased cycles, host-side dt as RESOL computes it
+        for b in (g, o):
+            b.forces_phase(dt1)
+        assert rel_err(g.download_fsky(), o.download_fsky()) <= FORCE_TOL, cyc
+        tg, to = g.time(), o.time()
+        assert tg["dt2t"] == pytest.approx(to["dt2t"], rel=1e-14) and tg["neltst"] == to["neltst"] and tg["ityptst"] == 1
+        for b in (g, o):
+            b.assemble()
+        ng, no = g.download_nodes(("A", "STIFN")), o.download_nodes(("A", "STIFN"))
+        assert rel_err(ng["A"], no["A"]) <= FORCE_TOL and rel_err(ng["STIFN"], no["STIFN"]) <= FORCE_TOL
+        dt2 = to["dt2t"]
+        for b in (g, o):
+            b.advance(0.5 * (dt1 + dt2), dt2)
+        dt1 = dt2
+    check_state36(g, o, fields=LAW36_FIELDS + ("stra",))
+    assert o.solid_state("pla").max() > 1e-4              # yielded
+
+
+def test_law36_elastic_and_return_are_bit_exact():
+    """No libm call on the LAW36 path except VOL**(1/3) (MQVISCB, SHVIS3): stresses, plastic strain, strain rate,
+    density and the small-strain reference must agree bit for bit."""
+    m = meshgen.hex_block(6, 5, 4, 12.0, 10.0, 8.0, law=36, vrand=30.0)
+    g, o = pair(m)
+    for b in (g, o):
+        b.forces_phase(0.0)
+    for b in (g, o):
+        b.forces_phase(1e-3)
+    assert o.solid_state("pla").max() > 0
+    for f in ("sig", "pla", "epsd", "rho", "off", "smstr", "wpla"):
+        assert np.array_equal(g.solid_state(f), o.solid_state(f)), f
+    assert rel_err(g.solid_state("eint"), o.solid_state("eint")) <= 1e-14
+
+
+@pytest.mark.parametrize("jhbe,ismstr", [(1, 4), (2, 4), (0, 4), (1, 1), (1, 2), (2, 2)])
+def test_law36_formulation_variants_match_oracle(jhbe, ismstr):
+    m = meshgen.hex_block(6, 6, 10, 12.0, 12.0, 33.0, law=36, v0=(0, 0, -40.0), fix_bottom_z=True, vrand=10.0,
+                          prop=meshgen.default_prop_solid(jhbe=jhbe, ismstr=ismstr))
+    g, o = pair(m)
+    g.run_cycles(60); o.run_cycles(60)
+    ng, no = g.download_nodes(("X", "V", "D")), o.download_nodes(("X", "V", "D"))
+    assert rel_err(ng["D"], no["D"]) <= DISP_TOL and rel_err(ng["V"], no["V"]) <= DISP_TOL
+    assert g.time()["dt2"] == pytest.approx(o.time()["dt2"], rel=1e-10)
+    check_state36(g, o, tol=1e-8)
+
+
+def test_law36_rate_dependent_curves_match_oracle():
+    x = np.array([0.0, 0.01, 0.05, 0.3]); y = np.array([250.0, 300.0, 360.0, 450.0])
+    curves = [(x, y), (x, 1.2 * y), (x, 1.5 * y)]; rates = [0.0, 1.0, 50.0]
+    m = meshgen.hex_block(5, 5, 8, 10.0, 10.0, 26.0, law=36, curves=curves, rates=rates, v0=(0, 0, -60.0),
+                          fix_bottom_z=True, vrand=20.0)
+    g, o = pair(m)
+    g.run_cycles(80); o.run_cycles(80)
+    ng, no = g.download_nodes(("X", "V", "D")), o.download_nodes(("X", "V", "D"))
+    assert rel_err(ng["D"], no["D"]) <= DISP_TOL and rel_err(ng["V"], no["V"]) <= DISP_TOL
+    check_state36(g, o, tol=1e-8)
+    assert o.solid_state("pla").max() > 1e-3
+
+
+def test_law36_bar_1000_cycles_matches_oracle():
+    """A steel LAW36 bar on the anvil, 1000 cycles of the device loop: displacements and energies to 1e-8."""
+    m = meshgen.hex_block(8, 8, 24, 6.4, 6.4, 32.4, law=36, v0=(0, 0, -150.0), fix_bottom_z=True)
+    g, o = pair(m)
+    g.run_cycles(1000); o.run_cycles(1000)
+    ng, no = g.download_nodes(("X", "V", "D")), o.download_nodes(("X", "V", "D"))
+    assert rel_err(ng["D"], no["D"]) <= DISP_TOL
+    keg, ieg = energies(g, m); keo, ieo = energies(o, m)
+    assert abs(keg - keo) <= ENERGY_TOL * abs(keo) and abs(ieg - ieo) <= ENERGY_TOL * abs(ieo)
+    assert abs((keg + ieg) - (keo + ieo)) <= ENERGY_TOL * abs(keo + ieo)
+    assert g.time()["tt"] == pytest.approx(o.time()["tt"], rel=1e-10)
+    assert o.solid_state("pla").max() > 0.05
+
+
+def test_law36_and_law2_groups_in_one_model():
+    """Two brick super-groups with different laws in one model (material change breaks the fusion)."""
+    m = meshgen.hex_block(6, 6, 8, 12.0, 12.0, 16.0, v0=(0, 0, -80.0), fix_bottom_z=True, vrand=10.0)
+    m36, npf, tf = meshgen.steel_law36()
+    m.npf, m.tf = npf, tf
+    half = len(m.solid_groups) // 2
+    for sg in m.solid_groups[half:]:
+        sg.law = 36; sg.mat = m36
+    g, o = pair(m)
+    g.run_cycles(50); o.run_cycles(50)
+    ng, no = g.download_nodes(("X", "V", "D")), o.download_nodes(("X", "V", "D"))
+    assert rel_err(ng["D"], no["D"]) <= DISP_TOL and rel_err(ng["V"], no["V"]) <= DISP_TOL
+    check_state36(g, o, tol=1e-8, fields=("sig", "eint", "rho", "qvis", "pla", "epsd", "off"))
+
+
 def test_bad_inputs_are_rejected():
     m = meshgen.hex_block(2, 2, 2, 1.0, 1.0, 1.0)
     m.ixs = m.ixs.copy(); m.ixs[0, 3] = m.numnod + 5
@@ -177,3 +283,11 @@ def test_bad_inputs_are_rejected():
     m2.solid_groups[0].mat.fisokin = 0.5
     with pytest.raises(RuntimeError, match="outside the built path"):
         Engine(m2)
+    m3 = meshgen.hex_block(2, 2, 2, 1.0, 1.0, 1.0, law=36)
+    m3.solid_groups[0].mat.vp = 1
+    with pytest.raises(RuntimeError, match="outside the built path"):
+        Engine(m3)
+    m4 = meshgen.hex_block(2, 2, 2, 1.0, 1.0, 1.0, law=36)
+    m4.npf = None
+    with pytest.raises(RuntimeError, match="function table"):
+        Engine(m4)

@@ -127,3 +127,103 @@ def test_openmp_groups_give_identical_results():
     a.run_cycles(20); b.run_cycles(20)
     assert np.array_equal(a.download_nodes(("X",))["X"], b.download_nodes(("X",))["X"])
     assert a.time()["dt2"] == b.time()["dt2"]
+
+
+# ---- LAW36 solids: MMAIN -> MULAW -> SIGEPS36 -------------------------------------------
+
+def _law36_block(n=3, **kw):
+    return meshgen.hex_block(n, n, n, 1.0 * n, 1.0 * n, 1.0 * n, jitter=kw.pop("jitter", 0.05), law=36, **kw)
+
+
+def test_law36_elastic_step_matches_hooke():
+    """Below yield SIGEPS36 is the deviatoric predictor 2G(de - dav) plus the pressure K*mu."""
+    m = _law36_block(3)
+    L = 1e-6 * np.array([[1.0, 0.3, -0.2], [0.1, -0.5, 0.4], [0.25, -0.15, 0.7]])
+    m.V = m.X @ L.T
+    o = Oracle(m)
+    dt1 = 1e-3
+    o.forces_phase(dt1)
+    sig = o.solid_state("sig")
+    D = 0.5 * (L + L.T); tr = np.trace(D)
+    G = m.solid_groups[0].mat.shear
+    exp = np.array([2 * G * dt1 * (D[0, 0] - tr / 3), 2 * G * dt1 * (D[1, 1] - tr / 3), 2 * G * dt1 * (D[2, 2] - tr / 3),
+                    G * dt1 * 2 * D[0, 1], G * dt1 * 2 * D[1, 2], G * dt1 * 2 * D[0, 2]])
+    assert np.allclose(sig, exp[:, None], rtol=1e-9, atol=1e-16)      # rho == rho0 on the first cycle: no pressure yet
+    assert np.all(o.solid_state("pla") == 0.0) and np.all(o.solid_state("wpla") == 0.0)
+
+
+@pytest.mark.parametrize("ipla", [0, 1, 2])
+def test_law36_radial_return_lands_on_the_tabulated_yield_curve(ipla):
+    """One large pure-shear increment: the von Mises stress after the return equals the tabulated yield
+    stress -- at the old plastic strain for Iplas 0 / 2, updated by H*dpla for Iplas 1 -- and the plastic
+    strain increment is the closed-form radial-return value."""
+    m = _law36_block(2, jitter=0.0, prop=meshgen.default_prop_solid(ipla=ipla))
+    gam = 40.0                                              # shear rate: trial stress G*gam*dt1 ~ 3200 MPa >> 250
+    m.V = np.zeros_like(m.X); m.V[:, 0] = gam * m.X[:, 1]
+    o = Oracle(m)
+    dt1 = 1e-3
+    o.forces_phase(dt1)
+    mat = m.solid_groups[0].mat
+    sig, pla = o.solid_state("sig"), o.solid_state("pla")[0]
+    vm = np.sqrt(0.5 * ((sig[0] - sig[1]) ** 2 + (sig[1] - sig[2]) ** 2 + (sig[2] - sig[0]) ** 2) + 3 * (sig[3] ** 2 + sig[4] ** 2 + sig[5] ** 2))
+    x, y = m.tf[0::2], m.tf[1::2]
+    y0, h0 = y[0], (y[1] - y[0]) / (x[1] - x[0])            # static curve at pla = 0
+    trial = np.sqrt(3.0) * mat.shear * gam * dt1
+    if ipla == 2:
+        dp = (trial - y0) / mat.g3; target = y0
+    else:
+        dp = (trial - y0) / (mat.g3 + h0); target = y0 if ipla == 0 else y0 + h0 * dp
+    assert np.allclose(pla, dp, rtol=1e-12)
+    assert np.allclose(vm, target, rtol=1e-12)
+    # plastic work = 0.5 (vm_old + vm_new) dpla V  (mulaw.F90:2187-2219)
+    assert np.allclose(o.solid_state("wpla")[0], 0.5 * (0.0 + vm) * dp * m.vol0, rtol=1e-12)
+
+
+def test_law36_rate_dependent_curves_interpolate_in_strain_rate():
+    """NRATE = 2: yield = y1 + (epsd - r1)/(r2 - r1) (y2 - y1), with the filtered equivalent deviatoric strain rate."""
+    x = np.array([0.0, 0.1, 0.5]); y = np.array([250.0, 350.0, 450.0])
+    curves = [(x, y), (x, 1.5 * y)]; rates = [0.0, 100.0]
+    m = _law36_block(2, jitter=0.0, curves=curves, rates=rates, prop=meshgen.default_prop_solid(ipla=0))
+    gam = 40.0
+    m.V = np.zeros_like(m.X); m.V[:, 0] = gam * m.X[:, 1]
+    o = Oracle(m)
+    dt1 = 1e-3
+    o.forces_phase(dt1)
+    mat = m.solid_groups[0].mat
+    epsdot = gam / np.sqrt(3.0)                             # sqrt(3 * (gam/2)^2) / 1.5
+    asrate = min(1.0, mat.asrate * dt1)
+    epsd = asrate * epsdot
+    assert np.allclose(o.solid_state("epsd")[0], epsd, rtol=1e-13)
+    yld = 250.0 + epsd / 100.0 * (375.0 - 250.0)
+    sig = o.solid_state("sig")
+    vm = np.sqrt(3.0) * np.abs(sig[3])
+    assert np.allclose(vm, yld, rtol=1e-12)
+
+
+def test_law36_energy_is_conserved_for_an_elastic_free_block():
+    """No hourglass / bulk viscosity, below yield: leap-frog energy oscillates around KE0 (MULAW energy integration)."""
+    m = _law36_block(4, jitter=0.0)
+    p = m.solid_groups[0].prop; p.hcoef = 0.0; p.qa = 0.0; p.qb = 0.0
+    m.V = (m.X - m.X.mean(0)) * np.array([1e-1, -5e-2, 2e-2])
+    o = Oracle(m)
+    ke0 = 0.5 * (m.MS[:, None] * m.V ** 2).sum()
+    tot = []
+    for _ in range(40):
+        o.run_cycles(13)
+        V = o.download_nodes(("V",))["V"]
+        ke = 0.5 * (m.MS[:, None] * V ** 2).sum()
+        ie = (o.solid_state("eint")[0] * o.solid_state("vol")[0]).sum()
+        tot.append((ke + ie) / ke0)
+    assert o.solid_state("pla").max() == 0.0
+    assert 0.85 < np.mean(tot) < 1.25 and min(tot) > 0.5 and max(tot) < 1.6
+
+
+def test_law36_istrain_accumulates_total_strain():
+    m = _law36_block(2, jitter=0.0, prop=meshgen.default_prop_solid(istrain=1))
+    L = 1e-4 * np.array([[1.0, 0.0, 0.0], [0.0, -0.5, 0.0], [0.0, 0.0, 0.25]])
+    m.V = m.X @ L.T
+    o = Oracle(m)
+    o.forces_phase(1e-3)
+    st = o.solid_state("stra")
+    assert np.allclose(st[0], 1e-7, rtol=1e-9) and np.allclose(st[1], -0.5e-7, rtol=1e-9) and np.allclose(st[2], 0.25e-7, rtol=1e-9)
+    assert np.abs(st[3:]).max() < 1e-20
