@@ -484,9 +484,9 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       if (m6.nrate == 1) {
         int ipos = T.ldi(g.w_vt, 0); const int ipos_old = ipos;
         const int f = m6.ifunc[0];
-        const int i0 = __ldg(g.npf + f), i1 = __ldg(g.npf + f + 1);
         double dydx, y1;
-        vinter1(g.tf, i0, i1 - i0, ipos, EPXE, dydx, y1);
+        if (g.ct.n > 0) vinter1c(g.ct, 0, ipos, EPXE, dydx, y1);
+        else { const int i0 = __ldg(g.npf + f), i1 = __ldg(g.npf + f + 1); vinter1(g.tf, i0, i1 - i0, ipos, EPXE, dydx, y1); }
         if (ipos != ipos_old) T.sti(g.w_vt, 0, ipos);
         const double FACT = K_ONE * K_ONE * (m6.yfac[0] * K_ONE);
         H = dydx * FACT;
@@ -506,8 +506,11 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
         const int f1 = m6.ifunc[JJ - 1], f2 = m6.ifunc[JJ];
         int ipos1 = T.ldi(g.w_vt, 1 + JJ), ipos2 = T.ldi(g.w_vt, 2 + JJ);
         double dydx1, y1, dydx2, y2;
-        { const int i0 = __ldg(g.npf + f1), i1 = __ldg(g.npf + f1 + 1); vinter1(g.tf, i0, i1 - i0, ipos1, EPXE, dydx1, y1); }
-        { const int i0 = __ldg(g.npf + f2), i1 = __ldg(g.npf + f2 + 1); vinter1(g.tf, i0, i1 - i0, ipos2, EPXE, dydx2, y2); }
+        if (g.ct.n > 0) { vinter1c(g.ct, JJ - 1, ipos1, EPXE, dydx1, y1); vinter1c(g.ct, JJ, ipos2, EPXE, dydx2, y2); }
+        else {
+          { const int i0 = __ldg(g.npf + f1), i1 = __ldg(g.npf + f1 + 1); vinter1(g.tf, i0, i1 - i0, ipos1, EPXE, dydx1, y1); }
+          { const int i0 = __ldg(g.npf + f2), i1 = __ldg(g.npf + f2 + 1); vinter1(g.tf, i0, i1 - i0, ipos2, EPXE, dydx2, y2); }
+        }
         T.sti(g.w_vt, 1 + JJ, ipos1); T.sti(g.w_vt, 2 + JJ, ipos2);
         y1 = y1 * YFAC1; y2 = y2 * YFAC2;
         YLD = (y1 + RFAC * (y2 - y1)) * (K_ONE * K_ONE);

@@ -329,7 +329,7 @@ int orgpu_finalize(orgpu_engine* e)
     d.law = e->sgroups[gi].law; d.m36 = e->sgroups[gi].m36;
     d.w_temp = d.mat.has_temp ? BW_NFIX : -1;
     d.nw_rw = BW_NFIX + (d.mat.has_temp ? 1 : 0);
-    d.w_stra = d.w_wpla = d.w_vt = -1; d.nvt = 0; d.tf = nullptr; d.npf = nullptr;
+    d.w_stra = d.w_wpla = d.w_vt = -1; d.nvt = 0; d.tf = nullptr; d.npf = nullptr; memset(&d.ct, 0, sizeof d.ct);
     if (d.law == 36) {                                   // LBUF%WPLA, LBUF%STRA (ISTRAIN>0), VARTMP cursors
       d.w_wpla = d.nw_rw++;
       if (d.prop.istrain > 0) { d.w_stra = d.nw_rw; d.nw_rw += 6; }
@@ -346,6 +346,7 @@ int orgpu_finalize(orgpu_engine* e)
         CUDA_OK(cudaMemcpy(e->d_bnpf, e->npf.data(), 4 * e->npf.size(), cudaMemcpyHostToDevice));
       }
       d.tf = e->d_btf; d.npf = e->d_bnpf;
+      curve_tab_fill(d.ct, d.m36, e->npf, e->tf);
     }
     d.w_vol = d.nw_rw; d.w_slot = d.nw_rw + 1; d.nw = d.nw_rw + 1 + 4;
     HostSlab H; H.init(d.nw, np);

@@ -30,6 +30,7 @@ struct ShellSG {
   int w_thke, w_slot;         // initial-thickness word (-1 when ITHK>0), first word of the 4 slot int rows
   double* smstr;              // tile-major [tile][6][128]
   const double* tf; const int* npf;    // LAW36 function table (pairs), 0-based curve starts
+  CurveTab ct;                // ... and its parameter-space copy when small (ct.n > 0)
   orgpu_law2 m2; orgpu_law36 m36; orgpu_prop_shell prop;
   double dtfac;               // DTFAC1(3)
   int nodadt;                 // /DT/NODA: nodal stiffnesses of cndt3.F:194-221, no element time step
@@ -116,9 +117,9 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
   if (m.nrate == 1) {
     int ipos = s.ipos;
     const int f = m.ifunc[0];
-    const int i0 = __ldg(g.npf + f), i1 = __ldg(g.npf + f + 1);
     double dydx, y1;
-    vinter1(g.tf, i0, i1 - i0, ipos, pla, dydx, y1);
+    if (g.ct.n > 0) vinter1c(g.ct, 0, ipos, pla, dydx, y1);
+    else { const int i0 = __ldg(g.npf + f), i1 = __ldg(g.npf + f + 1); vinter1(g.tf, i0, i1 - i0, ipos, pla, dydx, y1); }
     s.ipos = ipos;
     const double FACT = K_ONE * K_ONE * (m.yfac[0] * K_ONE);
     H = dydx * FACT;
@@ -138,8 +139,11 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
     const int f1 = m.ifunc[JJ - 1], f2 = m.ifunc[JJ];
     int ipos1 = T.ldi(g.w_vt, ipt * g.nvt + 1 + JJ), ipos2 = T.ldi(g.w_vt, ipt * g.nvt + 2 + JJ);
     double dydx1, y1, dydx2, y2;
-    { const int i0 = __ldg(g.npf + f1), i1 = __ldg(g.npf + f1 + 1); vinter1(g.tf, i0, i1 - i0, ipos1, pla, dydx1, y1); }
-    { const int i0 = __ldg(g.npf + f2), i1 = __ldg(g.npf + f2 + 1); vinter1(g.tf, i0, i1 - i0, ipos2, pla, dydx2, y2); }
+    if (g.ct.n > 0) { vinter1c(g.ct, JJ - 1, ipos1, pla, dydx1, y1); vinter1c(g.ct, JJ, ipos2, pla, dydx2, y2); }
+    else {
+      { const int i0 = __ldg(g.npf + f1), i1 = __ldg(g.npf + f1 + 1); vinter1(g.tf, i0, i1 - i0, ipos1, pla, dydx1, y1); }
+      { const int i0 = __ldg(g.npf + f2), i1 = __ldg(g.npf + f2 + 1); vinter1(g.tf, i0, i1 - i0, ipos2, pla, dydx2, y2); }
+    }
     y1 = y1 * YFAC1; y2 = y2 * YFAC2;
     YLD = K_ONE * (y1 + RFAC * (y2 - y1));
     YLD = fmax(YLD, K_EM20);

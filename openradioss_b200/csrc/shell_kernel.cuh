@@ -89,6 +89,7 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
         d_tf = t; d_npf = n;
       }
       d.tf = d_tf; d.npf = d_npf;
+      curve_tab_fill(d.ct, G.m36, npf, tf);
     }
     // ---- slab word map (shell_common.cuh)
     const bool has_temp = (G.law == 2) && G.m2.has_temp;
