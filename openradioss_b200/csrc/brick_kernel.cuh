@@ -125,6 +125,10 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
   double* const g_tile = g.slab + (size_t)blockIdx.x * g.nw * ORGPU_TILE;
   if (STAGED) tile_load_begin(s_tile_dyn, &s_bar, g_tile, (unsigned)g.nw * ORGPU_TILE * 8u);
   const TileAcc<STAGED> T{(STAGED ? s_tile_dyn : g_tile) + threadIdx.x};
+#if ORGPU_PREFETCH_TILE > 0
+  if (!STAGED && threadIdx.x == 0 && blockIdx.x + ORGPU_PREFETCH_TILE < gridDim.x)      // in-place tiles: same wave-ahead L2 prefetch
+    bulk_prefetch_l2(g_tile + (size_t)ORGPU_PREFETCH_TILE * g.nw * ORGPU_TILE, (unsigned)g.nw * ORGPU_TILE * 8u);
+#endif
   // SMSTR (21 words, rewritten every cycle by S8SAV3 / SMALLA3) goes straight to HBM with streaming stores:
   // collecting it in shared memory for a bulk store was measured slower (0.472 vs 0.450 ms on C5)
   double* const sm = g.smstr + (size_t)blockIdx.x * 21 * ORGPU_TILE + threadIdx.x;     // SMSTR word k at sm[k*TILE]

@@ -21,6 +21,10 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
   double* const g_tile = g.slab + (size_t)blockIdx.x * g.nw * ORGPU_TILE;
   if (STAGED) tile_load_begin(s_tile_dyn, &s_bar, g_tile, (unsigned)g.nw * ORGPU_TILE * 8u);
   const TileAcc<STAGED> T{(STAGED ? s_tile_dyn : g_tile) + threadIdx.x};
+#if ORGPU_PREFETCH_TILE > 0
+  if (!STAGED && threadIdx.x == 0 && blockIdx.x + ORGPU_PREFETCH_TILE < gridDim.x)      // in-place tiles: same wave-ahead L2 prefetch
+    bulk_prefetch_l2(g_tile + (size_t)ORGPU_PREFETCH_TILE * g.nw * ORGPU_TILE, (unsigned)g.nw * ORGPU_TILE * 8u);
+#endif
   double* const sm = g.smstr + (size_t)blockIdx.x * 6 * ORGPU_TILE + threadIdx.x;      // SMSTR word k at sm[k*128]
 #if ORGPU_PREFETCH_NEXT > 0
   // a CTA about one wave ahead: start its connectivity toward L2 (its first load is then an L2 hit: -3 % kernel time)
