@@ -55,6 +55,9 @@ int  orgpu_set_itab(orgpu_engine* e, const int* itab);
 int  orgpu_set_fixvel(orgpu_engine* e, int nfxvel, const int* ibfv /*(3,n)*/, const double* vel /*(4,n)*/);
 int  orgpu_set_solids(orgpu_engine* e, int numels, const int* ixs, const int* iads);
 int  orgpu_set_shells(orgpu_engine* e, int numelc, const int* ixc, const int* iadc);
+/* 3-node shells (ITY=7, C3FORC3: engine/source/elements/sh3n/coque3n/c3forc3.F:35, called forintc.F:628): IXTG(6,NUMELTG)
+ * and their FSKY slots IADTG(3,NUMELTG) (parith_on_mod.F90), 1-based as the Engine holds them */
+int  orgpu_set_sh3n(orgpu_engine* e, int numeltg, const int* ixtg, const int* iadtg);
 int  orgpu_set_pon(orgpu_engine* e, const int* adsky, int lsky);              /* parith_on_mod.F90:39-74 */
 int  orgpu_set_functions(orgpu_engine* e, int nfunc, const int* npf, const double* tf);
 /* one element group (<= NVSIZ elements, one material / property): elements [nft, nft+nel) */
@@ -66,6 +69,9 @@ int  orgpu_add_solid_group_law(orgpu_engine* e, int nel, int nft, int law, const
                                const orgpu_prop_solid* prop, const double* vol0);
 int  orgpu_add_shell_group(orgpu_engine* e, int nel, int nft, int law, const void* mat,
                            const orgpu_prop_shell* prop);
+/* one 3-node shell group: elements [nft, nft+nel) of IXTG; prop->ihbe carries Ish3n = IPARG(23) (1 or 2) */
+int  orgpu_add_sh3n_group(orgpu_engine* e, int nel, int nft, int law, const void* mat,
+                          const orgpu_prop_shell* prop);
 /* FORINTC_PREPARE_GPU analogue: fuse consecutive compatible groups into super-groups, re-lay
  * ELBUF out as device SoA, upload tables.  Must be called once before stepping. */
 int  orgpu_finalize(orgpu_engine* e);
@@ -87,11 +93,13 @@ int  orgpu_download_fsky(orgpu_engine* e, double* fsky /*(8,LSKY)*/);
 /* fields: 0 sig(6) 1 eint 2 rho 3 qvis 4 pla 5 epsd 6 vol 7 off 8 temp 9 smstr(21) 10 stra(6) 11 wpla (LAW36); out[k*numels+e] */
 int  orgpu_download_solid_state(orgpu_engine* e, int field, double* out);
 int  orgpu_download_shell_state(orgpu_engine* e, int field, double* out);
+int  orgpu_download_sh3n_state(orgpu_engine* e, int field, double* out);   /* shell fields; smstr has 3 words, no hourg */
 /* -- state hand-over in the other direction (restart / a run that starts from an initial state: the role of
  *    shell_gpu_upload_ip_state, shell_gpu_driver.h, and of RDRESB reading ELBUF from the restart file): same
  *    fields and layout as the downloads; orgpu_set_time restores TT, DT2, DT2OLD, NCYCLE (resol.F restart values). */
 int  orgpu_upload_solid_state(orgpu_engine* e, int field, const double* in);
 int  orgpu_upload_shell_state(orgpu_engine* e, int field, const double* in);
+int  orgpu_upload_sh3n_state(orgpu_engine* e, int field, const double* in);
 int  orgpu_set_time(orgpu_engine* e, double tt, double dt2, double dt2old, long long ncycle);
 
 /* -- print-cycle energy balances (SBILAN sbilan.F:138-157, CBILAN cbilan.F:183-275 -> PARTSAV(1,.)

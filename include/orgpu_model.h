@@ -25,7 +25,8 @@ extern "C" {
 /* element family (IPARG(5)=ITY and IPARG(23)=JHBE) */
 enum { ORGPU_FAM_BRICK = 1,      /* ITY=1, SFORC3            */
        ORGPU_FAM_SHELL_BT = 3,   /* ITY=3, JHBE<11,  CFORC3   */
-       ORGPU_FAM_SHELL_QEPH = 24 /* ITY=3, JHBE=21..29, CZFORC3 */ };
+       ORGPU_FAM_SHELL_QEPH = 24,/* ITY=3, JHBE=21..29, CZFORC3 */
+       ORGPU_FAM_SH3N = 7        /* ITY=7, Ish3n 1/2, C3FORC3   */ };
 
 /* /MAT/LAW2 (PLAS_JOHNS / PLAS_ZERIL).  uparam(1:11), iparam(1:4), therm. */
 typedef struct orgpu_law2 {
@@ -121,6 +122,7 @@ typedef struct orgpu_control {
   int    iroddl;        /* rotational dofs present (shells)           */
   int    nodadt;        /* NODADT: 1 = /DT/NODA nodal time step (bricks and QEPH shells; no /DT/NODA/CST) */
   double dtfac_node;    /* DTFAC1(11) /DT/NODA scale                  */
+  double dtfac_sh3n;    /* DTFAC1(7)  /DT/SH_3N scale                 */
 } orgpu_control;
 
 #ifdef __cplusplus

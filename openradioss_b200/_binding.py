@@ -63,6 +63,8 @@ class Binding:
             self._call("set_solids", self.h, C.c_int(m.numels), _opt(m.ixs, np.int32), _opt(m.iads, np.int32))
         if m.numelc:
             self._call("set_shells", self.h, C.c_int(m.numelc), _opt(m.ixc, np.int32), _opt(m.iadc, np.int32))
+        if m.numeltg:
+            self._call("set_sh3n", self.h, C.c_int(m.numeltg), _opt(m.ixtg, np.int32), _opt(m.iadtg, np.int32))
         self._call("set_pon", self.h, _opt(m.adsky, np.int32), C.c_int(m.lsky))
         if m.npf is not None:
             self._call("set_functions", self.h, C.c_int(len(m.npf) - 1), _opt(m.npf, np.int32), _opt(m.tf, np.float64))
@@ -75,6 +77,9 @@ class Binding:
         for g in m.shell_groups:
             r = self._call_group("add_shell_group", self.h, C.c_int(g.nel), C.c_int(g.nft), C.c_int(g.law),
                                  C.byref(g.mat), C.byref(g.prop))
+        for g in m.sh3n_groups:
+            self._call_group("add_sh3n_group", self.h, C.c_int(g.nel), C.c_int(g.nft), C.c_int(g.law),
+                             C.byref(g.mat), C.byref(g.prop))
         for g in m.solid_groups:
             v0 = np.ascontiguousarray(m.vol0[g.nft:g.nft + g.nel])
             if getattr(g, "law", 2) == 2:
@@ -138,6 +143,18 @@ class Binding:
             nc = 12 if any(21 <= g.prop.ihbe <= 29 for g in self.model.shell_groups) else 5
         out = np.zeros((nc * npt, self.model.numelc))
         self._call("download_shell_state", self.h, C.c_int(fid), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def sh3n_state(self, name):
+        """State of the 3-node shells, same field names as shell_state (no hourglass words; smstr has 3 components)."""
+        fid, nc = self.SHELL_FIELDS[name]
+        npt = 1
+        if name in ("sig", "pla", "epsd_ip", "temp"):
+            npt = max(g.prop.npt for g in self.model.sh3n_groups)
+        if name == "smstr":
+            nc = 3
+        out = np.zeros((nc * npt, self.model.numeltg))
+        self._call("download_sh3n_state", self.h, C.c_int(fid), out.ctypes.data_as(C.c_void_p))
         return out
 
     # -- corner rows of the skyline (domain exchange) ------------------------------------

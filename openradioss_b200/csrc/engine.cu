@@ -46,6 +46,8 @@ struct orgpu_engine {
   double *d_fext = nullptr, *d_mext = nullptr; int *d_icodt = nullptr, *d_icodr = nullptr, *d_adsky = nullptr;
   // connectivity as given by the caller
   std::vector<int> ixs, iads, ixc, iadc, adsky; int numels = 0, numelc = 0, lsky = 0;
+  std::vector<int> ixtg, iadtg; int numeltg = 0;            // 3-node shells: IXTG(6,*), IADTG(3,*)
+  std::vector<HostShellGroup> tgroups;
   std::vector<int> npf; std::vector<double> tf;
   int lf_func = -1; double lf_fcx = 1.0;            // time function of the nodal loads
   std::vector<int> fv_idx; std::vector<FixVelNode> fv;   // imposed velocities, per node
@@ -207,6 +209,12 @@ int orgpu_set_shells(orgpu_engine* e, int numelc, const int* ixc, const int* iad
   e->numelc = numelc; e->ixc.assign(ixc, ixc + (size_t)7 * numelc); e->iadc.assign(iadc, iadc + (size_t)4 * numelc);
   return 0;
 }
+int orgpu_set_sh3n(orgpu_engine* e, int numeltg, const int* ixtg, const int* iadtg)
+{
+  NEED(e && numeltg >= 0 && !e->finalized, -1, "orgpu_set_sh3n: bad arguments / already finalized");
+  e->numeltg = numeltg; e->ixtg.assign(ixtg, ixtg + (size_t)6 * numeltg); e->iadtg.assign(iadtg, iadtg + (size_t)3 * numeltg);
+  return 0;
+}
 int orgpu_set_pon(orgpu_engine* e, const int* adsky, int lsky)
 {
   NEED(e && adsky && lsky >= 0 && !e->finalized, -1, "orgpu_set_pon: bad arguments / already finalized");
@@ -294,6 +302,13 @@ int orgpu_add_shell_group(orgpu_engine* e, int nel, int nft, int law, const void
   return shell_add_group(e->cgroups, nel, nft, law, mat, prop);
 }
 
+int orgpu_add_sh3n_group(orgpu_engine* e, int nel, int nft, int law, const void* mat, const orgpu_prop_shell* prop)
+{
+  NEED(e && mat && prop && nel > 0 && !e->finalized, -1, "orgpu_add_sh3n_group: bad arguments / already finalized");
+  NEED(nft >= 0 && nft + nel <= e->numeltg, -4, "orgpu_add_sh3n_group: elements [%d,%d) outside IXTG (%d)", nft, nft + nel, e->numeltg);
+  return shell_add_group(e->tgroups, nel, nft, law, mat, prop, true);
+}
+
 // ---- FORINTC_PREPARE_GPU analogue -----------------------------------------------------------
 
 int orgpu_finalize(orgpu_engine* e)
@@ -301,7 +316,7 @@ int orgpu_finalize(orgpu_engine* e)
   NEED(e && !e->finalized, -1, "orgpu_finalize: bad handle / already finalized");
   NEED(!e->adsky.empty(), -4, "orgpu_finalize: /PARITH/ON tables missing (orgpu_set_pon)");
   CUDA_OK(cudaSetDevice(e->device));
-  const bool has_shell = !e->cgroups.empty();
+  const bool has_shell = !e->cgroups.empty() || !e->tgroups.empty();
   e->roww = (has_shell || e->ctl.iroddl) ? 8 : 4;
   if (dev_alloc(&e->d_fsky, (size_t)e->roww * (e->lsky > 0 ? e->lsky : 1))) return -100;
   { std::vector<int> a0(e->adsky.size()); for (size_t i = 0; i < a0.size(); i++) a0[i] = e->adsky[i] - 1;
@@ -309,7 +324,9 @@ int orgpu_finalize(orgpu_engine* e)
     CUDA_OK(cudaMemcpy(e->d_adsky, a0.data(), 4 * a0.size(), cudaMemcpyHostToDevice)); e->nd.adsky = e->d_adsky; }
   int order = 0, blk = 0; e->fa.nsg = 0;
   // shells are processed first (FORINTC resol.F:4138), solids after (FORINT resol.F:4225)
-  { int rc = shell_build_supergroups(e->cgroups, e->csg, e->ixc, e->iadc, e->npf, e->tf, e->ctl, e->numnod, e->lsky, order, blk, e->fa); if (rc) return rc; }
+  { int rc = shell_build_supergroups(e->cgroups, e->csg, e->ixc, e->iadc, 4, e->npf, e->tf, e->ctl, e->numnod, e->lsky, order, blk, e->fa); if (rc) return rc; }
+  // 3-node shell groups (ITY=7) follow the 4-node ones in the Engine's group list, inside the same FORINTC pass
+  { int rc = shell_build_supergroups(e->tgroups, e->csg, e->ixtg, e->iadtg, 3, e->npf, e->tf, e->ctl, e->numnod, e->lsky, order, blk, e->fa); if (rc) return rc; }
   // consecutive solid groups with identical material / property fuse into one super-group
   size_t gi = 0;
   while (gi < e->sgroups.size()) {
@@ -719,6 +736,18 @@ int orgpu_upload_shell_state(orgpu_engine* e, int field, const double* in)
   NEED(e && e->finalized && in, -1, "engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
   CUDA_OK(cudaStreamSynchronize(e->st));
   return shell_state_xfer(e->csg, e->numelc, field, const_cast<double*>(in), true);
+}
+int orgpu_download_sh3n_state(orgpu_engine* e, int field, double* out)
+{
+  NEED(e && e->finalized && out, -1, "engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  return shell_state_xfer(e->csg, e->numeltg, field, out, false, true);
+}
+int orgpu_upload_sh3n_state(orgpu_engine* e, int field, const double* in)
+{
+  NEED(e && e->finalized && in, -1, "engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  return shell_state_xfer(e->csg, e->numeltg, field, const_cast<double*>(in), true, true);
 }
 /* LAW36 table cursors (VARTMP) are integer state: per integration point the live cursor(s) */
 int orgpu_set_time(orgpu_engine* e, double tt, double dt2, double dt2old, long long ncycle)

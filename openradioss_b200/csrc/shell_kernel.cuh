@@ -10,24 +10,29 @@
 #include "shell_common.cuh"
 #include "qeph_kernel.cuh"
 #include "bt_kernel.cuh"
+#include "c3_kernel.cuh"
 
-struct HostShellGroup { int nel, nft, law; orgpu_prop_shell prop; orgpu_law2 m2; orgpu_law36 m36; };
-struct ShellSGHost { ShellSG d; int first_elem = 0; std::vector<void*> owned; };
+struct HostShellGroup { int nel, nft, law, sh3n; orgpu_prop_shell prop; orgpu_law2 m2; orgpu_law36 m36; };
+struct ShellSGHost { ShellSG d; int first_elem = 0; bool sh3n = false; std::vector<void*> owned; };
 
 static inline bool shell_is_qeph(const orgpu_prop_shell& p) { return p.ihbe >= 21 && p.ihbe <= 29; }
 
 static int shell_add_group(std::vector<HostShellGroup>& groups, int nel, int nft, int law, const void* mat,
-                           const orgpu_prop_shell* prop)
+                           const orgpu_prop_shell* prop, bool sh3n = false)
 {
   if (law != 2 && law != 36) { orgpu_set_error("shell law %d is outside the built path (2, 36)", law); return -5; }
   if (prop->npt < 1 || prop->npt > 10) { orgpu_set_error("NPT=%d is outside the built path (1..10)", prop->npt); return -5; }
   if (prop->ipla < 0 || prop->ipla > 2) { orgpu_set_error("Iplas=%d is outside the built path (0,1,2)", prop->ipla); return -5; }
   if (!(prop->ismstr == 1 || prop->ismstr == 2 || prop->ismstr == 4)) { orgpu_set_error("shell Ismstr=%d is outside the built path (1,2,4)", prop->ismstr); return -5; }
-  const bool qeph = shell_is_qeph(*prop);
-  if (!qeph && !(prop->ihbe == 1 || prop->ihbe == 3 || prop->ihbe == 4)) { orgpu_set_error("Ishell=%d is outside the built path (BT 1, 3, 4; QEPH 24)", prop->ihbe); return -5; }
-  if (!qeph && prop->npt == 1) { orgpu_set_error("Belytschko-Tsay with NPT=1 (MHVIS3 hourglass) is outside the built path"); return -5; }
+  const bool qeph = !sh3n && shell_is_qeph(*prop);
+  if (sh3n) {
+    if (!(prop->ihbe == 1 || prop->ihbe == 2)) { orgpu_set_error("Ish3n=%d is outside the built path (1, 2: C3FORC3)", prop->ihbe); return -5; }
+  } else {
+    if (!qeph && !(prop->ihbe == 1 || prop->ihbe == 3 || prop->ihbe == 4)) { orgpu_set_error("Ishell=%d is outside the built path (BT 1, 3, 4; QEPH 24)", prop->ihbe); return -5; }
+    if (!qeph && prop->npt == 1) { orgpu_set_error("Belytschko-Tsay with NPT=1 (MHVIS3 hourglass) is outside the built path"); return -5; }
+  }
   HostShellGroup g; memset(&g, 0, sizeof g);
-  g.nel = nel; g.nft = nft; g.law = law; g.prop = *prop;
+  g.nel = nel; g.nft = nft; g.law = law; g.sh3n = sh3n ? 1 : 0; g.prop = *prop;
   if (law == 36) {
     g.m36 = *(const orgpu_law36*)mat;
     if (g.m36.fisokin != 0.0 || g.m36.vp != 0 || g.m36.ifail != 0) { orgpu_set_error("LAW36 kinematic hardening / VP=1 / failure are outside the built path"); return -5; }
@@ -51,8 +56,9 @@ template <class T> static int sh_upload(std::vector<void*>& owned, T** p, const 
   return 0;
 }
 
+// nnode = 4: IXC(7,*) / IADC(4,*); nnode = 3: IXTG(6,*) / IADTG(3,*) (3-node shells, C3FORC3)
 static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vector<ShellSGHost>& out,
-                                   const std::vector<int>& ixc, const std::vector<int>& iadc,
+                                   const std::vector<int>& ixc, const std::vector<int>& iadc, const int nnode,
                                    const std::vector<int>& npf, const std::vector<double>& tf,
                                    const orgpu_control& ctl, int numnod, int lsky, int& order, int& blk, FinalizeArgs& fa)
 {
@@ -71,12 +77,12 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
     const HostShellGroup& G = groups[gi];
     const int nft = G.nft;
     const int np = ((ne + ORGPU_BLOCK - 1) / ORGPU_BLOCK) * ORGPU_BLOCK;
-    out.emplace_back(); ShellSGHost& S = out.back(); S.first_elem = nft;
+    out.emplace_back(); ShellSGHost& S = out.back(); S.first_elem = nft; S.sh3n = (nnode == 3);
     ShellSG& d = S.d; memset(&d, 0, sizeof d);
     d.ne = ne; d.ne_pad = np; d.order0 = order; d.blk0 = blk; d.law = G.law; d.npt = G.prop.npt;
     d.nvartmp = (G.law == 36) ? 2 + G.m36.nrate : 0;
-    d.nhourg = shell_is_qeph(G.prop) ? 12 : 5;
-    d.m2 = G.m2; d.m36 = G.m36; d.prop = G.prop; d.dtfac = ctl.dtfac_shell; d.nodadt = ctl.nodadt;
+    d.nhourg = (nnode == 3) ? 0 : shell_is_qeph(G.prop) ? 12 : 5;
+    d.m2 = G.m2; d.m36 = G.m36; d.prop = G.prop; d.dtfac = (nnode == 3) ? ctl.dtfac_sh3n : ctl.dtfac_shell; d.nodadt = ctl.nodadt;
     if (G.law == 36) {
       if (npf.empty()) { orgpu_set_error("LAW36 group without a function table (orgpu_set_functions)"); return -4; }
       for (int j = 0; j < G.m36.nrate; j++) {
@@ -102,30 +108,31 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
     d.w_slot = w; w += 2;
     d.nw = w;
     HostSlab H; H.init(d.nw, np);
-    std::vector<int> conn((size_t)4 * np, 0), ngl(np, 0), conn_t;
+    const int ixs_ = (nnode == 3) ? 6 : 7, iuid = (nnode == 3) ? 5 : 6;      // row length of IXTG / IXC, column of the user id
+    std::vector<int> conn((size_t)nnode * np, 0), ngl(np, 0), conn_t;
     for (int i = 0; i < np; i++) {
       H.at(SW_THK, i) = G.prop.thick; if (d.w_thke >= 0) H.at(d.w_thke, i) = G.prop.thick;
       if (has_temp) for (int ip = 0; ip < d.npt; ip++) H.at(d.w_ip0 + ip * d.nwip + IW_TEMP, i) = G.m2.tini;
     }
     for (int i = 0; i < ne; i++) {
-      const int* ix = &ixc[(size_t)7 * (nft + i)];
-      for (int k = 0; k < 4; k++) {
+      const int* ix = &ixc[(size_t)ixs_ * (nft + i)];
+      for (int k = 0; k < nnode; k++) {
         const int node = ix[1 + k];
-        if (node < 1 || node > numnod) { orgpu_set_error("IXC node %d out of range (element %d)", node, nft + i + 1); return -4; }
-        const int sl = iadc[(size_t)4 * (nft + i) + k];
-        if (sl < 1 || sl > lsky) { orgpu_set_error("IADC slot %d out of range (element %d)", sl, nft + i + 1); return -4; }
+        if (node < 1 || node > numnod) { orgpu_set_error("IXC / IXTG node %d out of range (element %d)", node, nft + i + 1); return -4; }
+        const int sl = iadc[(size_t)nnode * (nft + i) + k];
+        if (sl < 1 || sl > lsky) { orgpu_set_error("IADC / IADTG slot %d out of range (element %d)", sl, nft + i + 1); return -4; }
         conn[(size_t)k * np + i] = node - 1; H.iat(d.w_slot, k, i) = sl - 1;
       }
-      ngl[i] = ix[6]; H.at(SW_OFF, i) = 1.0;
+      ngl[i] = ix[iuid]; H.at(SW_OFF, i) = 1.0;
     }
-    tile_major_ints(conn_t, conn, 4, np);
+    tile_major_ints(conn_t, conn, nnode, np);
     int *dconn, *dngl;
     if (sh_upload(S.owned, &dconn, conn_t) || sh_upload(S.owned, &dngl, ngl) || sh_upload(S.owned, &d.slab, H.h)) return -100;
     d.conn = dconn; d.ngl = dngl;
-    if (sh_alloc(S.owned, &d.smstr, (size_t)6 * np)) return -100;
+    if (sh_alloc(S.owned, &d.smstr, (size_t)(nnode == 3 ? 3 : 6) * np)) return -100;
     const int nblk = np / ORGPU_TILE;                    // dt candidate slots: one per CTA
     if (fa.nsg >= ORGPU_MAX_SG) { orgpu_set_error("too many super-groups (%d)", ORGPU_MAX_SG); return -6; }
-    fa.sg[fa.nsg++] = SGRange{blk, nblk, shell_is_qeph(G.prop) ? ORGPU_FAM_SHELL_QEPH : ORGPU_FAM_SHELL_BT, d.order0, d.ngl};
+    fa.sg[fa.nsg++] = SGRange{blk, nblk, (nnode == 3) ? ORGPU_FAM_SH3N : shell_is_qeph(G.prop) ? ORGPU_FAM_SHELL_QEPH : ORGPU_FAM_SHELL_BT, d.order0, d.ngl};
     order += ne; blk += nblk; gi = gj;
   }
   return 0;
@@ -151,7 +158,10 @@ static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky
   (void)roww; (void)fa;                        // shell models always use 8-wide rows
   ShellParams P{S.d, nd, fsky, cs, db};
   const int nblk = S.d.ne_pad / ORGPU_TILE;
-  if (shell_is_qeph(S.d.prop)) {
+  if (S.sh3n) {
+    if (S.d.law == 36) shell_launch_one(c3_forces_kernel<36, true>, c3_forces_kernel<36, false>, P, nblk, st);
+    else               shell_launch_one(c3_forces_kernel<2, true>, c3_forces_kernel<2, false>, P, nblk, st);
+  } else if (shell_is_qeph(S.d.prop)) {
     if (S.d.law == 36) shell_launch_one(qeph_forces_kernel<36, true>, qeph_forces_kernel<36, false>, P, nblk, st);
     else               shell_launch_one(qeph_forces_kernel<2, true>, qeph_forces_kernel<2, false>, P, nblk, st);
   } else {
@@ -162,15 +172,16 @@ static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky
 
 // fields: 0 for(5) 1 mom(3) 2 eint(2) 3 thk 4 off 5 stra(8) 6 epsd 7 hourg(nhourg) 8 smstr(6)
 //         9 sig(5*npt) 10 pla(npt) 11 epsd_ip(npt) 12 temp(npt) ; out[k*numelc + e]
-static int shell_state_xfer(std::vector<ShellSGHost>& sgs, int numelc, int field, double* out, bool up)
+static int shell_state_xfer(std::vector<ShellSGHost>& sgs, int numelc, int field, double* out, bool up, bool sh3n = false)
 {
   const size_t NE = numelc;
   for (auto& S : sgs) {
+    if (S.sh3n != sh3n) continue;
     const ShellSG& d = S.d; double* base = d.slab; int nw = d.nw, nc = 1, w0 = 0, ipw = -1;
     switch (field) {
       case 0: w0 = SW_FOR; nc = 5; break; case 1: w0 = SW_MOM; nc = 3; break; case 2: w0 = SW_EINT; nc = 2; break;
       case 3: w0 = SW_THK; break; case 4: w0 = SW_OFF; break; case 5: w0 = SW_STRA; nc = 8; break; case 6: w0 = SW_EPSD; break;
-      case 7: w0 = SW_HOURG; nc = d.nhourg; break; case 8: base = d.smstr; nw = 6; w0 = 0; nc = 6; break;
+      case 7: w0 = SW_HOURG; nc = d.nhourg; if (nc == 0) continue; break; case 8: base = d.smstr; nw = S.sh3n ? 3 : 6; w0 = 0; nc = nw; break;
       case 9: ipw = IW_SIG; nc = 5 * d.npt; break; case 10: ipw = IW_PLA; nc = d.npt; break; case 11: ipw = IW_EPSD; nc = d.npt; break;
       case 12: if (d.nwip <= IW_TEMP) continue; ipw = IW_TEMP; nc = d.npt; break;
       default: orgpu_set_error("unknown shell field %d", field); return -1;

@@ -14,7 +14,7 @@ _LIB_PATH = os.environ.get("ORGPU_LIB") or os.path.join(os.path.dirname(os.path.
 _lib = None
 
 EXPORTS = """create destroy last_error upload_nodes set_loads set_bcs set_solids set_shells set_pon
-set_functions add_solid_group add_solid_group_law add_shell_group finalize forces_phase assemble advance run_cycles
+set_functions add_solid_group add_solid_group_law add_shell_group set_sh3n add_sh3n_group download_sh3n_state upload_sh3n_state finalize forces_phase assemble advance run_cycles
 synchronize get_time download_nodes download_fsky download_solid_state download_shell_state
 step_host launch_count last_run_ms set_profile get_profile pack_rows unpack_rows comm_unique_id comm_init
 set_exchange exchange get_energies p2p_export p2p_connect set_load_function set_fixvel upload_solid_state upload_shell_state set_time set_itab""".split()
@@ -92,6 +92,11 @@ class Engine(Binding):
         a = np.ascontiguousarray(arr, np.float64); assert a.shape[1] == self.model.numelc
         self._call("upload_shell_state", self.h, C.c_int(fid), a.ctypes.data_as(C.c_void_p))
 
+    def upload_sh3n_state(self, name, arr):
+        fid, _ = self.SHELL_FIELDS[name]
+        a = np.ascontiguousarray(arr, np.float64); assert a.shape[1] == self.model.numeltg
+        self._call("upload_sh3n_state", self.h, C.c_int(fid), a.ctypes.data_as(C.c_void_p))
+
     def set_time(self, tt, dt2, dt2old, ncycle):
         self._call("set_time", self.h, C.c_double(tt), C.c_double(dt2), C.c_double(dt2old), C.c_longlong(ncycle))
 
@@ -103,6 +108,10 @@ class Engine(Binding):
             ck["solid"] = {f: self.solid_state(f) for f in ("sig", "eint", "rho", "qvis", "pla", "epsd", "off", "temp", "smstr")}
         if self.model.numelc:
             ck["shell"] = {f: self.shell_state(f) for f in ("forc", "mom", "eint", "thk", "off", "stra", "epsd", "hourg", "smstr", "sig", "pla", "epsd_ip")}
+        if self.model.numeltg:
+            ck["sh3n"] = {f: self.sh3n_state(f) for f in ("forc", "mom", "eint", "thk", "off", "stra", "epsd", "smstr", "sig", "pla", "epsd_ip")}
+        if self.model.numels and any(getattr(g, "law", 2) == 36 for g in self.model.solid_groups):
+            ck["solid"].update({f: self.solid_state(f) for f in ("wpla", "stra")})
         return ck
 
     def restore(self, ck):
@@ -111,11 +120,13 @@ class Engine(Binding):
         t = ck["time"]
         self.set_time(t["tt"], t["dt2"], t["dt2"], t["ncycle"])       # DT2OLD = DT2 after a completed cycle (resol.F:6494)
         for f, a in ck.get("solid", {}).items():
-            if f == "temp" and not any(g.mat.has_temp for g in self.model.solid_groups):
+            if f == "temp" and not any(getattr(g.mat, "has_temp", 0) for g in self.model.solid_groups):
                 continue
             self.upload_solid_state(f, a)
         for f, a in ck.get("shell", {}).items():
             self.upload_shell_state(f, a)
+        for f, a in ck.get("sh3n", {}).items():
+            self.upload_sh3n_state(f, a)
 
     def energies(self):
         """(internal solids, internal shells, kinetic translation, kinetic rotation), summed on the device."""

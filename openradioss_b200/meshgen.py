@@ -143,7 +143,7 @@ def default_prop_solid(jhbe=1, ismstr=4, ipla=1, istrain=0) -> PropSolid:
 
 def default_control(iroddl=0) -> Control:
     c = Control()
-    c.dtfac_brick = 0.9; c.dtfac_shell = 0.9
+    c.dtfac_brick = 0.9; c.dtfac_shell = 0.9; c.dtfac_sh3n = 0.9
     c.dtmx = EP20
     c.dt_init = 0.0            # DT1 of cycle 0
     c.dt2old_init = EP20
@@ -288,6 +288,93 @@ def shell_plate(nx: int, ny: int, lx: float = 1000.0, ly: float = 1000.0, *, thi
     m.adsky, m.iads, m.iadc, m.lsky = build_pon(numnod, m.ixs, m.ixc)
     if pulse_tau > 0.0 and fext is not None:
         m.load_func = (add_function(m, [0.0, pulse_tau, 1.0e30], [0.0, 1.0, 1.0]), 1.0)
+    return m
+
+
+def tri_plate(nx: int, ny: int, lx: float = 1000.0, ly: float = 1000.0, *, thick: float = 2.0, law: int = 36, mat=None,
+              prop: PropShell = None, quads: str = "none", jitter: float = 0.05, zjitter: float = 0.05, seed: int = 2024,
+              pressure: float = 1.0, clamp: bool = True, vrand: float = 0.0, vseed: int = 12345, user_id_perm: bool = False,
+              curves=None, rates=None, quad_prop: PropShell = None) -> Model:
+    """Plate of 3-node shells (C3FORC3, Ish3n = prop.ihbe in {1, 2}): every cell of an nx*ny grid split into two triangles;
+    quads="checker" keeps every other cell as a 4-node shell (quad_prop, default QEPH) so that both families share nodes.
+    Nodal masses / inertias of the triangles as the Starter distributes them (c3inmas.F:598, 1113, 1126-1140: by the
+    corner angles)."""
+    prop = prop or default_prop_shell(thick=thick, ihbe=2)
+    quad_prop = quad_prop or default_prop_shell(thick=thick)
+    npf = tf = None
+    if mat is None:
+        if law == 36:
+            mat, npf, tf = steel_law36(curves, rates)
+        else:
+            mat = steel_law2_shell()
+    nnx, nny = nx + 1, ny + 1
+    gx, gy = np.meshgrid(np.arange(nnx), np.arange(nny), indexing="ij")
+    nid = lambda i, j: i + nnx * j
+    numnod = nnx * nny
+    X = np.zeros((numnod, 3))
+    idx = nid(gx, gy).reshape(-1)
+    X[idx, 0] = (gx * (lx / nx)).reshape(-1); X[idx, 1] = (gy * (ly / ny)).reshape(-1)
+    h = min(lx / nx, ly / ny)
+    rng = np.random.default_rng(seed)
+    if jitter:
+        X[:, :2] += rng.uniform(-jitter, jitter, (numnod, 2)) * h
+    if zjitter:
+        X[:, 2] += rng.uniform(-zjitter, zjitter, numnod) * h
+    ex, ey = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    ex, ey = ex.T.reshape(-1), ey.T.reshape(-1)
+    isq = ((ex + ey) % 2 == 0) if quads == "checker" else np.zeros(ex.size, bool)
+    c00, c10, c11, c01 = nid(ex, ey) + 1, nid(ex + 1, ey) + 1, nid(ex + 1, ey + 1) + 1, nid(ex, ey + 1) + 1
+    tq = ~isq
+    tri = np.concatenate([np.stack([c00[tq], c10[tq], c11[tq]], 1), np.stack([c00[tq], c11[tq], c01[tq]], 1)]).astype(np.int32)
+    order = np.argsort(np.concatenate([np.flatnonzero(tq) * 2, np.flatnonzero(tq) * 2 + 1]), kind="stable")
+    tri = tri[order]
+    ntg, nq = tri.shape[0], int(isq.sum())
+    ixtg = np.zeros((ntg, 6), np.int32); ixtg[:, 0] = 1; ixtg[:, 1:4] = tri; ixtg[:, 4] = 2
+    ixc = np.zeros((nq, 7), np.int32); ixc[:, 0] = 1; ixc[:, 5] = 1
+    ixc[:, 1] = c00[isq]; ixc[:, 2] = c10[isq]; ixc[:, 3] = c11[isq]; ixc[:, 4] = c01[isq]
+    uidq = np.arange(1, nq + 1, dtype=np.int32); uidt = np.arange(1, ntg + 1, dtype=np.int32) + 10 * (nq + 1)
+    if user_id_perm:
+        r = np.random.default_rng(seed + 1)
+        uidq = r.permutation(nq).astype(np.int32) + 1; uidt = r.permutation(ntg).astype(np.int32) + 1 + 10 * (nq + 1)
+    ixc[:, 6] = uidq; ixtg[:, 5] = uidt
+    MS = np.zeros(numnod); IN = np.zeros(numnod)
+    fext = np.zeros((numnod, 3)) if pressure else None
+    # triangles
+    P = X[tri - 1]
+    a = np.linalg.norm(P[:, 1] - P[:, 0], axis=1); b = np.linalg.norm(P[:, 2] - P[:, 1], axis=1); c = np.linalg.norm(P[:, 2] - P[:, 0], axis=1)
+    area_t = 0.5 * np.linalg.norm(np.cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0]), axis=1)
+    ang = np.stack([np.arccos((a * a + c * c - b * b) / (2 * a * c)), np.arccos((a * a + b * b - c * c) / (2 * a * b)),
+                    np.arccos((b * b + c * c - a * a) / (2 * b * c))], 1) / np.pi
+    em = mat.rho0 * prop.thick * area_t
+    xi = em * (area_t / 4.5 + prop.thick * prop.thick / 12.0)
+    np.add.at(MS, (tri - 1).reshape(-1), (em[:, None] * ang).reshape(-1))
+    np.add.at(IN, (tri - 1).reshape(-1), (xi[:, None] * ang).reshape(-1))
+    if pressure:
+        np.add.at(fext[:, 2], (tri - 1).reshape(-1), np.repeat(pressure * area_t / 3.0, 3))
+    if nq:
+        area = shell_areas(X, ixc)
+        ems = mat.rho0 * quad_prop.thick * area * 0.25
+        fac = 12.0 if quad_prop.ihbe >= 11 else 9.0
+        xq = ems * (area / fac + quad_prop.thick * quad_prop.thick * (1.0 / 12.0))
+        np.add.at(MS, (ixc[:, 1:5] - 1).reshape(-1), np.repeat(ems, 4))
+        np.add.at(IN, (ixc[:, 1:5] - 1).reshape(-1), np.repeat(xq, 4))
+        if pressure:
+            np.add.at(fext[:, 2], (ixc[:, 1:5] - 1).reshape(-1), np.repeat(pressure * area * 0.25, 4))
+    V = np.zeros((numnod, 3)); VR = np.zeros((numnod, 3))
+    if vrand:
+        g = np.random.Generator(np.random.PCG64(vseed))
+        V += g.uniform(-vrand, vrand, V.shape); VR += g.uniform(-vrand, vrand, VR.shape) / h
+    icodt = icodr = None
+    if clamp:
+        icodt = np.zeros(numnod, np.int32); icodr = np.zeros(numnod, np.int32)
+        edge = (gx == 0) | (gx == nx) | (gy == 0) | (gy == ny)
+        icodt[nid(gx, gy)[edge]] = 7; icodr[nid(gx, gy)[edge]] = 7
+        V[icodt == 7] = 0.0; VR[icodr == 7] = 0.0
+    m = Model(X=X, V=V, VR=VR, MS=MS, IN=IN, control=default_control(1), ixc=ixc, ixtg=ixtg, icodt=icodt, icodr=icodr,
+              fext=fext, itab=np.arange(1, numnod + 1, dtype=np.int32), npf=npf, tf=tf)
+    m.shell_groups = [ShellGroup(nft=s, nel=n, law=law, mat=mat, prop=quad_prop) for s, n in _groups(nq)] if nq else []
+    m.sh3n_groups = [ShellGroup(nft=s, nel=n, law=law, mat=mat, prop=prop) for s, n in _groups(ntg)]
+    m.adsky, m.iads, m.iadc, m.lsky, m.iadtg = build_pon(numnod, m.ixs, m.ixc, m.ixtg)
     return m
 
 

@@ -41,7 +41,7 @@ class PropShell(C.Structure):
 
 class Control(C.Structure):
     _fields_ = [(n, d) for n in "dtfac_brick dtfac_shell dtmx dt_init dt2old_init tt_init".split()] + \
-               [("iroddl", i), ("nodadt", i), ("dtfac_node", d)]
+               [("iroddl", i), ("nodadt", i), ("dtfac_node", d), ("dtfac_sh3n", d)]
 
 
 def elastic_constants(young: float, nu: float):
@@ -82,9 +82,11 @@ class Model:
     control: Control
     ixs: np.ndarray = field(default_factory=lambda: np.zeros((0, 11), np.int32))   # IXS(11,NUMELS)^T
     ixc: np.ndarray = field(default_factory=lambda: np.zeros((0, 7), np.int32))    # IXC(7,NUMELC)^T
+    ixtg: np.ndarray = field(default_factory=lambda: np.zeros((0, 6), np.int32))   # IXTG(6,NUMELTG)^T: mat, n1..n3, pid, user id
     vol0: np.ndarray = field(default_factory=lambda: np.zeros(0))                  # brick initial volumes
     solid_groups: List[SolidGroup] = field(default_factory=list)
     shell_groups: List[ShellGroup] = field(default_factory=list)
+    sh3n_groups: List[ShellGroup] = field(default_factory=list)                    # 3-node shells (ITY=7); prop.ihbe = Ish3n
     icodt: Optional[np.ndarray] = None  # BCS translation codes (4:x 2:y 1:z)
     icodr: Optional[np.ndarray] = None
     fext: Optional[np.ndarray] = None   # constant nodal loads (numnod,3)
@@ -94,6 +96,7 @@ class Model:
     adsky: Optional[np.ndarray] = None
     iads: Optional[np.ndarray] = None
     iadc: Optional[np.ndarray] = None
+    iadtg: Optional[np.ndarray] = None
     lsky: int = 0
     # LAW36 function table
     npf: Optional[np.ndarray] = None
@@ -108,3 +111,5 @@ class Model:
     def numels(self): return int(self.ixs.shape[0])
     @property
     def numelc(self): return int(self.ixc.shape[0])
+    @property
+    def numeltg(self): return int(self.ixtg.shape[0])

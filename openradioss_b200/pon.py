@@ -9,9 +9,12 @@ IADC(K,I) hold the 1-based FSKY slot of each corner (starter/source/restart/ddsp
 import numpy as np
 
 
-def build_pon(numnod: int, ixs: np.ndarray, ixc: np.ndarray):
-    """Return (adsky[numnod+1], iads[numels,8], iadc[numelc,4], lsky), all 1-based int32."""
+def build_pon(numnod: int, ixs: np.ndarray, ixc: np.ndarray, ixtg: np.ndarray = None):
+    """Return (adsky[numnod+1], iads[numels,8], iadc[numelc,4], lsky), all 1-based int32; with `ixtg` (3-node shells,
+    which FILLCNE places after the 4-node shells, sorted by IXTG(6,.): domdec2.F:2295-2310) also iadtg[numeltg,3]
+    as a fifth value."""
     numels, numelc = ixs.shape[0], ixc.shape[0]
+    numeltg = 0 if ixtg is None else ixtg.shape[0]
     nodes, owner = [], []
     if numels:
         order = np.argsort(ixs[:, 10], kind="stable")
@@ -21,6 +24,10 @@ def build_pon(numnod: int, ixs: np.ndarray, ixc: np.ndarray):
         order = np.argsort(ixc[:, 6], kind="stable")
         nodes.append(ixc[order, 1:5].reshape(-1))
         owner.append((8 * numels + order[:, None] * 4 + np.arange(4)[None, :]).reshape(-1))
+    if numeltg:
+        order = np.argsort(ixtg[:, 5], kind="stable")
+        nodes.append(ixtg[order, 1:4].reshape(-1))
+        owner.append((8 * numels + 4 * numelc + order[:, None] * 3 + np.arange(3)[None, :]).reshape(-1))
     nodes = np.concatenate(nodes).astype(np.int64)
     owner = np.concatenate(owner).astype(np.int64)
     lsky = nodes.size
@@ -31,5 +38,8 @@ def build_pon(numnod: int, ixs: np.ndarray, ixc: np.ndarray):
     adsky = np.ones(numnod + 1, np.int64)
     adsky[1:] = 1 + np.cumsum(counts)
     iads = slot_of_corner[:8 * numels].reshape(numels, 8).astype(np.int32)
-    iadc = slot_of_corner[8 * numels:].reshape(numelc, 4).astype(np.int32)
+    iadc = slot_of_corner[8 * numels:8 * numels + 4 * numelc].reshape(numelc, 4).astype(np.int32)
+    if ixtg is not None:
+        iadtg = slot_of_corner[8 * numels + 4 * numelc:].reshape(numeltg, 3).astype(np.int32)
+        return adsky.astype(np.int32), iads, iadc, int(lsky), iadtg
     return adsky.astype(np.int32), iads, iadc, int(lsky)

@@ -2,12 +2,11 @@
  * ctypes by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs.  The call
  * surface mirrors include/orgpu.h one-to-one (orc_* vs orgpu_*) so the parity tests drive
  * both sides with the same arrays. */
-#include "oracle.h"
+#include "shell.h"
 #include <cstring>
 #include <cstdio>
 #include <omp.h>
 
-struct OrcShellGroup;
 void orc_shell_group_free(OrcShellGroup*);
 OrcShellGroup* orc_shell_group_new(int nel,int nft,int law,const void* mat,const orgpu_prop_shell* prop);
 void orc_shell_group_state(const OrcShellGroup& g,int field,size_t ne,double* out);
@@ -29,6 +28,7 @@ void* orc_create(int numnod, const orgpu_control* ctl)
 void orc_destroy(void* h){
   Oracle* o=(Oracle*)h;
   for(auto* g:o->cgroups) orc_shell_group_free(g);
+  for(auto* g:o->tgroups) orc_shell_group_free(g);
   delete o;
 }
 void orc_set_threads(void* h,int nt){ ((Oracle*)h)->nthreads = nt>0? nt : omp_get_max_threads(); }
@@ -67,6 +67,10 @@ void orc_set_solids(void* h,int numels,const int* ixs /*(11,numels)*/,const int*
 void orc_set_shells(void* h,int numelc,const int* ixc /*(7,numelc)*/,const int* iadc /*(4,numelc)*/){
   Oracle* o=(Oracle*)h; o->numelc=numelc;
   o->IXC.assign(ixc,ixc+(size_t)7*numelc); o->IADC.assign(iadc,iadc+(size_t)4*numelc);
+}
+void orc_set_sh3n(void* h,int numeltg,const int* ixtg /*(6,numeltg)*/,const int* iadtg /*(3,numeltg)*/){
+  Oracle* o=(Oracle*)h; o->numeltg=numeltg;
+  o->IXTG.assign(ixtg,ixtg+(size_t)6*numeltg); o->IADTG.assign(iadtg,iadtg+(size_t)3*numeltg);
 }
 void orc_set_pon(void* h,const int* adsky /*numnod+1*/,int lsky){
   Oracle* o=(Oracle*)h; o->ADSKY.assign(adsky,adsky+o->numnod+1); o->lsky=lsky;
@@ -120,6 +124,20 @@ int orc_add_shell_group(void* h,int nel,int nft,int law,const void* mat,const or
   if(prop->npt<1 || prop->npt>10) return -3;
   o->cgroups.push_back(orc_shell_group_new(nel,nft,law,mat,prop));
   return (int)o->cgroups.size()-1;
+}
+
+/* one 3-node shell group (ITY=7): elements [nft, nft+nel) of IXTG; prop->ihbe carries Ish3n (1, 2) */
+int orc_add_sh3n_group(void* h,int nel,int nft,int law,const void* mat,const orgpu_prop_shell* prop)
+{
+  Oracle* o=(Oracle*)h;
+  if(nel>MVSIZ-1) return -1;
+  if(law!=2 && law!=36) return -2;
+  if(prop->npt<1 || prop->npt>10) return -3;
+  if(prop->ihbe!=1 && prop->ihbe!=2) return -4;
+  OrcShellGroup* g=orc_shell_group_new(nel,nft,law,mat,prop);
+  g->nhourg=0; g->HOURG.clear(); g->SMSTR.assign(3*nel,0);
+  o->tgroups.push_back(g);
+  return (int)o->tgroups.size()-1;
 }
 
 void orc_finalize(void*){}
@@ -181,6 +199,16 @@ void orc_unpack_rows(void* h,int n,const int* slots,const double* buf){
 void orc_download_shell_state(void* h,int field,double* out){
   Oracle* o=(Oracle*)h;
   for(auto* g:o->cgroups) orc_shell_group_state(*g,field,(size_t)o->numelc,out);
+}
+
+/* 3-node shells: same fields as the 4-node shells (7 hourg: none, 8 smstr(3)); out[k*numeltg+e] */
+void orc_download_sh3n_state(void* h,int field,double* out){
+  Oracle* o=(Oracle*)h;
+  for(auto* g:o->tgroups){
+    if(field==7) continue;
+    if(field==8){ for(int k=0;k<3;k++) for(int i=0;i<g->nel;i++) out[(size_t)k*o->numeltg+g->nft+i]=g->SMSTR[(size_t)k*g->nel+i]; continue; }
+    orc_shell_group_state(*g,field,(size_t)o->numeltg,out);
+  }
 }
 
 } // extern "C"

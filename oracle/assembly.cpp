@@ -155,9 +155,10 @@ void orc_forces(Oracle& o)
   for(int i=0;i<n;i++){ o.STIFN[i]=st0; o.STIFR[i]=st0; }
   double DT2T=o.DT2; int NELTST=0, ITYPTST=0;   /* thread mins are merged with strict "<" (resol.F:4165-4171) */
   /* shells first (FORINTC resol.F:4138), then solids (FORINT resol.F:4225) */
-  const int ncg=(int)o.cgroups.size(), nsg=(int)o.sgroups.size();
+  const int ncg=(int)o.cgroups.size(), nsg=(int)o.sgroups.size(), ntg=(int)o.tgroups.size();
   if(o.nthreads<=1){
     for(int g=0;g<ncg;g++) orc_shell_dispatch(o,*o.cgroups[g],DT2T,NELTST,ITYPTST);
+    for(int g=0;g<ntg;g++) orc_c3forc3(o,*o.tgroups[g],DT2T,NELTST,ITYPTST);      /* ITY=7 groups follow ITY=3 in the group list */
     for(int g=0;g<nsg;g++) orc_sforc3(o,o.sgroups[g],DT2T,NELTST,ITYPTST);
   } else {
     /* OpenMP over groups as forintc.F:238 (!$OMP DO SCHEDULE(DYNAMIC,1)); thread-private DT2TT */
@@ -166,6 +167,8 @@ void orc_forces(Oracle& o)
       double dt2tt=o.DT2; int nelt=0, ityp=0;
       #pragma omp for schedule(dynamic,1) nowait
       for(int g=0;g<ncg;g++) orc_shell_dispatch(o,*o.cgroups[g],dt2tt,nelt,ityp);
+      #pragma omp for schedule(dynamic,1) nowait
+      for(int g=0;g<ntg;g++) orc_c3forc3(o,*o.tgroups[g],dt2tt,nelt,ityp);
       #pragma omp for schedule(dynamic,1)
       for(int g=0;g<nsg;g++) orc_sforc3(o,o.sgroups[g],dt2tt,nelt,ityp);
       #pragma omp critical

@@ -60,15 +60,18 @@ struct Oracle {
   /* connectivity */
   std::vector<int> IXS;   /* (11,NUMELS) 1-based nodes in 2..9, user id in 11 */
   std::vector<int> IXC;   /* (7,NUMELC)  1-based nodes in 2..5, user id in 7  */
-  int numels = 0, numelc = 0;
+  std::vector<int> IXTG;  /* (6,NUMELTG) mat, 1-based nodes in 2..4, pid, user id in 6 */
+  int numels = 0, numelc = 0, numeltg = 0;
   /* /PARITH/ON tables (parith_on_mod.F90:39-74) */
   std::vector<int> ADSKY;  /* numnod+1, 1-based slot addresses */
   std::vector<int> IADS;   /* (8,NUMELS) 1-based slot of each brick corner */
   std::vector<int> IADC;   /* (4,NUMELC) */
+  std::vector<int> IADTG;  /* (3,NUMELTG) */
   std::vector<double> FSKY;/* (8,LSKY) */
   int lsky = 0;
   std::vector<OrcSolidGroup> sgroups;
   std::vector<OrcShellGroup*> cgroups;
+  std::vector<OrcShellGroup*> tgroups;   /* 3-node shell groups (ITY=7), processed after the 4-node shells */
   /* LAW36 function table */
   std::vector<double> TF; std::vector<int> NPF;
   /* time-step bookkeeping (resol.F:2721, 6124-6128, 6352, 6494-6497) */
@@ -83,6 +86,8 @@ void orc_sforc3(Oracle& o, OrcSolidGroup& g, double& dt2t, int& neltst, int& ity
 /* shell_qeph.cpp / shell_bt.cpp */
 void orc_czforc3(Oracle& o, OrcShellGroup& g, double& dt2t, int& neltst, int& ityptst);
 void orc_cforc3(Oracle& o, OrcShellGroup& g, double& dt2t, int& neltst, int& ityptst);
+/* shell_c3.cpp */
+void orc_c3forc3(Oracle& o, OrcShellGroup& g, double& dt2t, int& neltst, int& ityptst);
 /* assembly.cpp */
 void orc_asspar4(Oracle& o);
 void orc_accele(Oracle& o);
