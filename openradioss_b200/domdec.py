@@ -35,7 +35,8 @@ class Domain:
     node_gid: np.ndarray      # local node -> global node (0-based)
     shell_gid: np.ndarray     # local shell -> global shell (0-based)
     solid_gid: np.ndarray
-    owner: np.ndarray         # bool per local node: this rank is the lowest rank holding it (WEIGHT)
+    sh3n_gid: np.ndarray = None   # local 3-node shell -> global (0-based)
+    owner: np.ndarray = None        # bool per local node: this rank is the lowest rank holding it (WEIGHT)
     neighbors: List[Neighbor] = field(default_factory=list)
 
 
@@ -53,6 +54,10 @@ def element_centroids(m: Model):
     return cs, cc
 
 
+def sh3n_centroids(m: Model):
+    return m.X[m.ixtg[:, 1:4] - 1].mean(axis=1) if m.numeltg else np.zeros((0, 3))
+
+
 def _regroup(groups, gid_of_local, cls):
     """local element groups: runs of consecutive local elements that came from one global group."""
     out = []
@@ -63,17 +68,21 @@ def _regroup(groups, gid_of_local, cls):
         if i == len(gid_of_local) or gid_of_local[i] != gid_of_local[start] or i - start == NVSIZ:
             g = groups[gid_of_local[start]]
             if cls is SolidGroup:
-                out.append(SolidGroup(nft=start, nel=i - start, mat=g.mat, prop=g.prop))
+                out.append(SolidGroup(nft=start, nel=i - start, mat=g.mat, prop=g.prop, law=getattr(g, "law", 2)))
             else:
                 out.append(ShellGroup(nft=start, nel=i - start, law=g.law, mat=g.mat, prop=g.prop))
             start = i
     return out
 
 
-def decompose(m: Model, dom_s: Optional[np.ndarray], dom_c: Optional[np.ndarray], nproc: int, rank: int) -> Domain:
+def decompose(m: Model, dom_s: Optional[np.ndarray], dom_c: Optional[np.ndarray], nproc: int, rank: int,
+              dom_t: Optional[np.ndarray] = None) -> Domain:
+    """dom_s / dom_c / dom_t: domain of every brick / 4-node shell / 3-node shell."""
     numnod = m.numnod
     dom_s = np.zeros(0, np.int32) if dom_s is None else np.asarray(dom_s, np.int32)
     dom_c = np.zeros(0, np.int32) if dom_c is None else np.asarray(dom_c, np.int32)
+    dom_t = np.zeros(0, np.int32) if dom_t is None else np.asarray(dom_t, np.int32)
+    assert len(dom_t) == m.numeltg, "dom_t must give the domain of every 3-node shell"
     adsky0 = m.adsky.astype(np.int64) - 1                       # 0-based global slot offsets per node
     # owner domain of every global slot (PROCNE)
     slot_dom = np.full(m.lsky, -1, np.int32)
@@ -81,6 +90,8 @@ def decompose(m: Model, dom_s: Optional[np.ndarray], dom_c: Optional[np.ndarray]
         slot_dom[m.iads.reshape(-1).astype(np.int64) - 1] = np.repeat(dom_s, 8)
     if m.numelc:
         slot_dom[m.iadc.reshape(-1).astype(np.int64) - 1] = np.repeat(dom_c, 4)
+    if m.numeltg:
+        slot_dom[m.iadtg.reshape(-1).astype(np.int64) - 1] = np.repeat(dom_t, 3)
     assert (slot_dom >= 0).all(), "every FSKY slot must belong to an element corner"
     slot_node = np.repeat(np.arange(numnod, dtype=np.int64), np.diff(adsky0))
     # node sets per domain
@@ -90,6 +101,8 @@ def decompose(m: Model, dom_s: Optional[np.ndarray], dom_c: Optional[np.ndarray]
             masks[q, (m.ixs[dom_s == q, 1:9] - 1).reshape(-1)] = True
         if m.numelc:
             masks[q, (m.ixc[dom_c == q, 1:5] - 1).reshape(-1)] = True
+        if m.numeltg:
+            masks[q, (m.ixtg[dom_t == q, 1:4] - 1).reshape(-1)] = True
     mine = masks[rank]
     node_gid = np.nonzero(mine)[0]
     g2l = np.full(numnod, -1, np.int64); g2l[node_gid] = np.arange(len(node_gid))
@@ -107,15 +120,20 @@ def decompose(m: Model, dom_s: Optional[np.ndarray], dom_c: Optional[np.ndarray]
         ixc[:, 1:5] = (g2l[ixc[:, 1:5] - 1] + 1).astype(np.int32)
     iads = (gs2l[m.iads[solid_gid].astype(np.int64) - 1] + 1).astype(np.int32) if len(solid_gid) else np.zeros((0, 8), np.int32)
     iadc = (gs2l[m.iadc[shell_gid].astype(np.int64) - 1] + 1).astype(np.int32) if len(shell_gid) else np.zeros((0, 4), np.int32)
+    sh3n_gid = np.nonzero(dom_t == rank)[0]
+    ixtg = m.ixtg[sh3n_gid].copy()
+    if len(sh3n_gid):
+        ixtg[:, 1:4] = (g2l[ixtg[:, 1:4] - 1] + 1).astype(np.int32)
+    iadtg = (gs2l[m.iadtg[sh3n_gid].astype(np.int64) - 1] + 1).astype(np.int32) if len(sh3n_gid) else np.zeros((0, 3), np.int32)
     sub = lambda a: None if a is None else np.ascontiguousarray(a[node_gid])
-    lm = Model(X=sub(m.X), V=sub(m.V), VR=sub(m.VR), MS=sub(m.MS), IN=sub(m.IN), control=m.control, ixs=ixs, ixc=ixc,
+    lm = Model(X=sub(m.X), V=sub(m.V), VR=sub(m.VR), MS=sub(m.MS), IN=sub(m.IN), control=m.control, ixs=ixs, ixc=ixc, ixtg=ixtg,
                vol0=m.vol0[solid_gid] if len(m.vol0) else m.vol0, icodt=sub(m.icodt), icodr=sub(m.icodr),
                fext=sub(m.fext), mext=sub(m.mext), itab=sub(m.itab), npf=m.npf, tf=m.tf, load_func=m.load_func)
     if m.ibfv is not None and len(m.ibfv):
         keep = mine[m.ibfv[:, 0] - 1]
         lm.ibfv = m.ibfv[keep].copy(); lm.vel = m.vel[keep].copy()
         lm.ibfv[:, 0] = (g2l[lm.ibfv[:, 0] - 1] + 1).astype(np.int32)
-    lm.adsky = (ladsky0 + 1).astype(np.int32); lm.iads = iads; lm.iadc = iadc; lm.lsky = lsky
+    lm.adsky = (ladsky0 + 1).astype(np.int32); lm.iads = iads; lm.iadc = iadc; lm.iadtg = iadtg; lm.lsky = lsky
     # groups
     if m.solid_groups:
         gid = np.zeros(m.numels, np.int64)
@@ -127,10 +145,15 @@ def decompose(m: Model, dom_s: Optional[np.ndarray], dom_c: Optional[np.ndarray]
         for k, g in enumerate(m.shell_groups):
             gid[g.nft:g.nft + g.nel] = k
         lm.shell_groups = _regroup(m.shell_groups, gid[shell_gid], ShellGroup)
+    if m.sh3n_groups:
+        gid = np.zeros(m.numeltg, np.int64)
+        for k, g in enumerate(m.sh3n_groups):
+            gid[g.nft:g.nft + g.nel] = k
+        lm.sh3n_groups = _regroup(m.sh3n_groups, gid[sh3n_gid], ShellGroup)
     # ownership (lowest rank holding the node) for global reductions
     first = np.argmax(masks, axis=0)
     owner = first[node_gid] == rank
-    d = Domain(rank=rank, nproc=nproc, model=lm, node_gid=node_gid, shell_gid=shell_gid, solid_gid=solid_gid, owner=owner)
+    d = Domain(rank=rank, nproc=nproc, model=lm, node_gid=node_gid, shell_gid=shell_gid, solid_gid=solid_gid, sh3n_gid=sh3n_gid, owner=owner)
     # exchange lists
     ldom = slot_dom[gslots]                                     # owner of each local slot
     for q in range(nproc):
@@ -146,6 +169,7 @@ def decompose(m: Model, dom_s: Optional[np.ndarray], dom_c: Optional[np.ndarray]
 
 def decompose_strips(m: Model, nproc: int, rank: int, axis: int = 0) -> Domain:
     cs, cc = element_centroids(m)
-    both = np.concatenate([cs, cc])
+    ct = sh3n_centroids(m)
+    both = np.concatenate([cs, cc, ct])
     dom = strips(both, nproc, axis)
-    return decompose(m, dom[:len(cs)], dom[len(cs):], nproc, rank)
+    return decompose(m, dom[:len(cs)], dom[len(cs):len(cs) + len(cc)], nproc, rank, dom_t=dom[len(cs) + len(cc):])

@@ -12,13 +12,15 @@ from oracle.orc import Oracle
 def models():
     yield "shell", meshgen.shell_plate(9, 7, 90.0, 70.0, pressure=20.0, vrand=5.0, user_id_perm=True)
     yield "brick", meshgen.hex_block(5, 4, 6, 1.0, 0.8, 1.2, v0=(0, 0, -100.0), vrand=5.0, fix_bottom_z=True, user_id_perm=True)
+    yield "sh3n_mixed", meshgen.tri_plate(9, 7, 90.0, 70.0, quads="checker", pressure=20.0, vrand=5.0, user_id_perm=True)
+    yield "brick_law36", meshgen.hex_block(5, 4, 6, 10.0, 8.0, 12.0, law=36, v0=(0, 0, -60.0), vrand=20.0, fix_bottom_z=True)
 
 
 @pytest.mark.parametrize("nproc", [2, 3, 4])
 def test_decomposition_invariants(nproc):
     for name, m in models():
         doms = [domdec.decompose_strips(m, nproc, r) for r in range(nproc)]
-        assert sum(d.model.numelc + d.model.numels for d in doms) == m.numelc + m.numels
+        assert sum(d.model.numelc + d.model.numels + d.model.numeltg for d in doms) == m.numelc + m.numels + m.numeltg
         owned = np.zeros(m.numnod, int)
         for d in doms:
             owned[d.node_gid[d.owner]] += 1
@@ -29,8 +31,8 @@ def test_decomposition_invariants(nproc):
                 assert len(nb.send) == len(other.recv) and len(nb.recv) == len(other.send)
             # every local slot is either filled by a local corner or received exactly once
             filled = np.zeros(d.model.lsky, int)
-            for a in (d.model.iads, d.model.iadc):
-                if a.size:
+            for a in (d.model.iads, d.model.iadc, d.model.iadtg):
+                if a is not None and a.size:
                     filled[a.reshape(-1) - 1] += 1
             for nb in d.neighbors:
                 filled[nb.recv] += 1

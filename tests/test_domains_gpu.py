@@ -21,6 +21,8 @@ def models():
     yield "brick", meshgen.hex_block(6, 5, 7, 1.2, 1.0, 1.4, v0=(0, 0, -100.0), vrand=5.0, fix_bottom_z=True, user_id_perm=True)
     yield "tube", meshgen.crush_tube(5, 8, 1, ramp=0.002)      # shells + bricks, imposed velocity, load records follow their nodes
     t = meshgen.crush_tube(5, 8, 1, ramp=0.002); t.control.nodadt = 1
+    yield "sh3n_mixed", meshgen.tri_plate(12, 9, 120.0, 90.0, quads="checker", pressure=20.0, vrand=5.0, user_id_perm=True)
+    yield "brick_law36", meshgen.hex_block(6, 5, 7, 12.0, 10.0, 14.0, law=36, v0=(0, 0, -60.0), vrand=20.0, fix_bottom_z=True, user_id_perm=True)
     yield "tube_dtnoda", t                                     # /DT/NODA: the nodal dt crosses the domains after the assembly
 
 
@@ -73,7 +75,7 @@ def _nccl_worker(rank, world, port, q, kind, p2p=True):
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 @pytest.mark.parametrize("kind,p2p", [("shell", True), ("shell", False), ("brick", True), ("brick", False), ("tube", True), ("tube", False),
-                                      ("tube_dtnoda", True)])
+                                      ("tube_dtnoda", True), ("sh3n_mixed", True), ("brick_law36", True)])
 def test_multi_gpu_domains_match_single_gpu_bitwise(kind, p2p):
     import torch.multiprocessing as mp
     world = min(4, torch.cuda.device_count())
