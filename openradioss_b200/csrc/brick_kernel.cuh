@@ -544,6 +544,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       { const double Pn = m6.bulk * AMU; SG1 = SG1 - Pn; SG2 = SG2 - Pn; SG3 = SG3 - Pn; }   // IEOS = 0
       if (OFF < K_EM01) OFF = K_ZERO;
       if (OFF < K_ONE) OFF = OFF * K_FOUR_OVER_5;
+      if (m6.ifail == 1) { if (EPXE > m6.epsmax && OFF == K_ONE) OFF = K_FOUR_OVER_5; }    // sigeps36.F:1546-1555
       // MULAW: plastic work (L_PLA>0, von Mises of the old and new stresses)
       {
         const double DPLA = EPXE - DEFP0;

@@ -89,7 +89,7 @@ __device__ __forceinline__ void ip_store(const ShellSG& g, const TileAcc<STAGED>
 template <bool STAGED>
 __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>& T, int ipt, int ipla, double asrate,
                                          double dexx, double deyy, double dexy, double deyz, double dezx, double dtinv,
-                                         double thklyl, double gs, double epsd_pg, double off,
+                                         double thklyl, double gs, double epsd_pg, double& off,
                                          IpState& s, double& thk, double& ssp, double& etse, double& yld_out)
 {
   const orgpu_law36& m = g.m36;
@@ -233,6 +233,8 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
       etse = or_div(H, (H + E));
     }
   }
+  // IFAIL = 1: failure on the maximum plastic strain (sigeps36c.F:928-938); MULAWC completes the deletion in the same cycle
+  if (m.ifail == 1) { if (off == K_ONE && pla > m.epsmax) off = K_FOUR_OVER_5; }
   s.pla = pla;
   yld_out = YLD;
 }

@@ -35,7 +35,7 @@ static int shell_add_group(std::vector<HostShellGroup>& groups, int nel, int nft
   g.nel = nel; g.nft = nft; g.law = law; g.sh3n = sh3n ? 1 : 0; g.prop = *prop;
   if (law == 36) {
     g.m36 = *(const orgpu_law36*)mat;
-    if (g.m36.fisokin != 0.0 || g.m36.vp != 0 || g.m36.ifail != 0) { orgpu_set_error("LAW36 kinematic hardening / VP=1 / failure are outside the built path"); return -5; }
+    if (g.m36.fisokin != 0.0 || g.m36.vp != 0 || g.m36.ifail < 0 || g.m36.ifail > 1) { orgpu_set_error("LAW36 kinematic hardening / VP=1 / tensile-strain failure (IFAIL=2) are outside the built path"); return -5; }
     if (g.m36.nrate < 1 || g.m36.nrate > ORGPU_MAXFUNC36) { orgpu_set_error("LAW36 NRATE=%d out of range", g.m36.nrate); return -5; }
   } else {
     g.m2 = *(const orgpu_law2*)mat;

@@ -75,7 +75,7 @@ def steel_law2_shell() -> Law2:
     return m
 
 
-def steel_law36(curves=None, rates=None):
+def steel_law36(curves=None, rates=None, epsmax=None):
     """/MAT/LAW36 steel of SURVEY.md 8d, filled as the Starter does
     (starter/source/materials/mat/mat036/hm_read_mat36.F:268-320; generic PM slots
     hm_read_mat.F90:1466-1479).  Returns (Law36, npf, tf): one static curve of 8 points,
@@ -109,6 +109,8 @@ def steel_law36(curves=None, rates=None):
     if m.nrate > 1:
         m.asrate = 2.0 * np.pi * 10000.0                   # FCUT default (hm_read_mat36.F:216-218)
     m.vp = 0; m.ifail = 0; m.yldcheck = 0; m.ismooth = 0 if m.nrate == 1 else 1
+    if epsmax is not None:                                 # failure plastic strain: IFAIL = 1 (hm_read_mat36.F:228-233)
+        m.epsmax = epsmax; m.ifail = 1
     return m, np.asarray(npf, np.int32), np.concatenate(tf)
 
 

@@ -39,7 +39,7 @@ struct IpIO {             /* one integration point, one element */
 
 /* ---- SIGEPS36C, VP=0 branch, one element ------------------------------------------------ */
 void sigeps36c(const Oracle& o, const orgpu_law36& m, int ipla, double asrate, const ShellMatIn& in, IpIO& s,
-               double& pla, double& epsd, int* vartmp, double off, double& thk, double& ssp, double& viscmax,
+               double& pla, double& epsd, int* vartmp, double& off, double& thk, double& ssp, double& viscmax,
                double& etse, double& yld_out)
 {
   const int NITER=3;
@@ -184,6 +184,9 @@ void sigeps36c(const Oracle& o, const orgpu_law36& m, int ipla, double asrate, c
       etse=H/(H+E);
     }
   }
+  /* IFAIL = 1: failure on the maximum plastic strain (sigeps36c.F:928-938, no non-local): the element starts its
+   * deletion; MULAWC completes it in the same cycle (mulawc.F90:2937-2941) */
+  if(m.ifail==1){ if(off==K_ONE && pla>m.epsmax) off=K_FOUR_OVER_5; }
   yld_out=YLD;
 }
 

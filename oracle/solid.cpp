@@ -378,6 +378,9 @@ static void sigeps36(const Oracle& o,const orgpu_law36& m,int nel,int ipla,
     if(off[i]<K_EM01) off[i]=K_ZERO;
     if(off[i]<K_ONE) off[i]=off[i]*K_FOUR_OVER_5;
   }
+  if(m.ifail==1){                                                            /* :1546-1555 (IFAIL=1, no non-local) */
+    for(int i=0;i<nel;i++) if(pla[i]>m.epsmax && off[i]==K_ONE) off[i]=K_FOUR_OVER_5;
+  }
 }
 
 /* MULAW  materials/mat_share/mulaw.F90 -- "user type" law driver for solids, MTN=36, isotropic global frame

@@ -259,6 +259,26 @@ def test_law36_bar_1000_cycles_matches_oracle():
     assert o.solid_state("pla").max() > 0.05
 
 
+def test_law36_epsmax_failure_erodes_the_same_bricks():
+    """LAW36 IFAIL = 1 on solids: PLA > EPSMAX starts the deletion (OFF = 0.8, then x 0.8 per cycle down to zero:
+    sigeps36.F:1507-1510, 1546-1555); SMALLB3 carries OFF into OFFG."""
+    mat, npf, tf = meshgen.steel_law36(epsmax=4.0e-3)
+    m = meshgen.hex_block(6, 6, 8, 12.0, 12.0, 16.0, law=36, mat=mat, v0=(0, 0, -40.0), fix_bottom_z=True, vrand=10.0)
+    m.npf, m.tf = npf, tf
+    g, o = pair(m)
+    dead = []
+    for c in range(6):
+        g.run_cycles(15); o.run_cycles(15)
+        og, oo = g.solid_state("off"), o.solid_state("off")
+        assert np.array_equal(og, oo), c
+        dead.append(int((oo == 0).sum()))
+        ng, no = g.download_nodes(("X", "V")), o.download_nodes(("X", "V"))
+        assert rel_err(ng["X"], no["X"]) <= 1e-9 and rel_err(ng["V"], no["V"]) <= 1e-8, c
+    assert 0 < dead[-1] < m.numels and dead[-1] > dead[0]
+    assert ((oo > 0) & (oo < 1)).sum() >= 0
+    assert np.isfinite(g.download_fsky()).all()
+
+
 def test_law36_and_law2_groups_in_one_model():
     """Two brick super-groups with different laws in one model (material change breaks the fusion)."""
     m = meshgen.hex_block(6, 6, 8, 12.0, 12.0, 16.0, v0=(0, 0, -80.0), fix_bottom_z=True, vrand=10.0)

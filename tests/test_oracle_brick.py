@@ -227,3 +227,22 @@ def test_law36_istrain_accumulates_total_strain():
     st = o.solid_state("stra")
     assert np.allclose(st[0], 1e-7, rtol=1e-9) and np.allclose(st[1], -0.5e-7, rtol=1e-9) and np.allclose(st[2], 0.25e-7, rtol=1e-9)
     assert np.abs(st[3:]).max() < 1e-20
+
+
+def test_law36_epsmax_failure_relaxes_the_brick_off():
+    """IFAIL = 1 on solids: once PLA > EPSMAX the element's OFF goes 1 -> 0.8 and then x 0.8 per cycle until it falls
+    below 0.1 and becomes 0 (sigeps36.F:1507-1510, 1546-1555); stresses are scaled by OFF and SMALLB3 copies OFF to OFFG."""
+    mat, npf, tf = meshgen.steel_law36(epsmax=1.0e-3)
+    m = meshgen.hex_block(1, 1, 1, 10.0, 10.0, 10.0, law=36, mat=mat, jitter=0.0)
+    m.npf, m.tf = npf, tf
+    m.V = np.zeros_like(m.X); m.V[:, 0] = 50.0 * m.X[:, 1]            # simple shear, well beyond yield
+    o = Oracle(m)
+    seq = []
+    for _ in range(16):
+        o.forces_phase(1e-3)
+        seq.append(float(o.solid_state("off")[0, 0]))
+    k = next(i for i, v in enumerate(seq) if v < 1.0)
+    assert seq[k] == pytest.approx(0.8)
+    assert np.allclose(seq[k:k + 10], 0.8 * 0.8 ** np.arange(10), rtol=1e-14)   # 0.8^11 = 0.0859 < 0.1 -> zero next
+    assert seq[k + 11] == 0.0 and seq[-1] == 0.0
+    assert np.abs(o.solid_state("sig")).max() == 0.0

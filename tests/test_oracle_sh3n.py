@@ -97,3 +97,22 @@ def test_openmp_groups_give_identical_results():
     for k in ("X", "V", "VR"):
         assert np.array_equal(a.download_nodes((k,))[k], b.download_nodes((k,))[k])
     assert a.time()["neltst"] == b.time()["neltst"]
+
+
+def test_law36_epsmax_failure_deletes_the_triangle_in_one_cycle():
+    """IFAIL = 1 on shells: the first integration point beyond EPSMAX sets OFF = 0.8 and MULAWC finishes the deletion in
+    the same cycle (sigeps36c.F:928-938, mulawc.F90:2937-2941): forces vanish, OFFG = 0 from then on."""
+    mat, npf, tf = meshgen.steel_law36(epsmax=1.0e-3)
+    m = meshgen.tri_plate(1, 1, 10.0, 10.0, mat=mat, jitter=0.0, zjitter=0.0, pressure=0.0, clamp=False)
+    m.npf, m.tf = npf, tf
+    m.V = np.zeros_like(m.X); m.V[:, 0] = 0.5 * m.X[:, 0]             # uniaxial stretching at 0.5 / ms
+    o = Oracle(m)
+    offs, plas = [], []
+    for _ in range(12):
+        o.forces_phase(1e-3)
+        offs.append(o.sh3n_state("off")[0].copy()); plas.append(o.sh3n_state("pla").max())
+    offs = np.array(offs)
+    k = int(np.argmax(offs[:, 0] == 0.0))
+    assert k > 0 and np.all(offs[:k] == 1.0) and np.all(offs[k:] == 0.0)
+    assert plas[k - 1] <= 1.0e-3 < plas[k]
+    assert np.all(o.download_fsky() == 0.0)

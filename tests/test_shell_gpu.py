@@ -206,6 +206,29 @@ def test_mixed_shells_and_bricks_share_nodes(ihbe):
     assert kr == pytest.approx(0.5 * (m.IN[:, None] * d["VR"] ** 2).sum(), rel=ENERGY_TOL)
 
 
+@pytest.mark.parametrize("ihbe", [24, 1])
+def test_law36_epsmax_failure_deletes_the_same_shells(ihbe):
+    """LAW36 IFAIL = 1: an integration point beyond EPSMAX deletes its element (sigeps36c.F:928-938, mulawc.F90:2937):
+    the same elements die in the same cycles on both sides, and the run goes on without them."""
+    mat, npf, tf = meshgen.steel_law36(epsmax=2.0e-3)
+    m = meshgen.shell_plate(10, 9, 100.0, 90.0, mat=mat, prop=meshgen.default_prop_shell(ihbe=ihbe, npt=5), pressure=60.0, vrand=8.0)
+    m.npf, m.tf = npf, tf
+    g, o = pair(m)
+    dead = []
+    for c in range(6):
+        g.run_cycles(10); o.run_cycles(10)
+        og, oo = g.shell_state("off"), o.shell_state("off")
+        assert np.array_equal(og, oo), c
+        dead.append(int((oo == 0).sum()))
+        ng, no = g.download_nodes(("X", "V", "VR")), o.download_nodes(("X", "V", "VR"))
+        for k in ("X", "V", "VR"):
+            assert rel_err(ng[k], no[k]) <= 1e-9, (k, c)
+    assert 0 < dead[-1] < m.numelc and dead[-1] > dead[0]        # some, not all; more as the run goes on
+    assert np.isfinite(g.download_fsky()).all()
+    f = g.download_fsky()[m.iadc - 1]
+    assert np.all(f[g.shell_state("off")[0] == 0][:, :, :6] == 0.0)   # deleted elements leave zero rows
+
+
 def energies(b, m):
     d = b.download_nodes(("V", "VR"))
     ke = 0.5 * (m.MS[:, None] * d["V"] ** 2).sum() + 0.5 * (m.IN[:, None] * d["VR"] ** 2).sum()
