@@ -28,6 +28,10 @@ import numpy as np  # noqa: E402
 B_ALG = {
     "brick": dict(total=1120, forces=712, node=408),
     "shell": dict(total=1872, forces=1408, node=464),   # forces: 16+72+48+416+560+40+256 ; node: 256+208
+    # 3-node shell (C3FORC3, NPT=5, LAW36; not a BASELINE config, same counting rules as SURVEY 8d with half a node per
+    # element): IXTG 12 + X,V,VR 36 + SMSTR 24 + element r/w 21 x 16 = 336 + IP 560 + VARTMP 40 + rows 3 x 64 = 192;
+    # node side per node: rows 6 x 64 read + update 208
+    "sh3n": dict(total=1200 + 192 + 296, forces=1200, node=592),
 }
 
 
@@ -53,6 +57,8 @@ def workload(name, world=1):
         return meshgen.hex_block(40, 40, 40 * world, 40.0, 40.0, 40.0 * world, vrand=1.0), "brick", 2
     if name == "c2_plate_qeph_1m":          # C2 / C3: 1000 x 1000 QEPH shells per GPU (x strips), LAW36, NPT=5
         return meshgen.shell_plate(1000 * world, 1000, 1000.0 * world, 1000.0, pulse_tau=0.05), "shell", 0
+    if name == "tri_plate_1m":              # extra: 707 x 707 cells x 2 = 999 698 3-node shells per GPU, LAW36, NPT=5
+        return meshgen.tri_plate(707 * world, 707, 1000.0 * world, 1000.0), "sh3n", 0
     if name == "plate_small":
         return meshgen.shell_plate(200 * world, 200, 1000.0 * world, 1000.0), "shell", 0
     raise SystemExit(f"unknown workload {name}")
@@ -103,7 +109,7 @@ def run_reference(args, rank):
         return
     from oracle.orc import Oracle
     m, fam, _ = workload(args.workload)
-    ne = m.numels + m.numelc
+    ne = m.numels + m.numelc + m.numeltg
     cores = os.cpu_count() or 1
     o = Oracle(m, threads=cores)
     o.run_cycles(max(1, args.warmup))
@@ -154,7 +160,7 @@ def main():
         del gm
     else:
         m = gm
-    ne = m.numels + m.numelc
+    ne = m.numels + m.numelc + m.numeltg
     g = Engine(m, device=local)
     if world > 1:
         g.comm_init(dist, dom)
@@ -192,8 +198,8 @@ def main():
     peak, peak_src = peaks()
     dom = "brick_forces" if fam == "brick" else "shell_forces"
     dms, dn = prof[dom]
-    b = B_ALG["brick" if fam == "brick" else "shell"]
-    ne_dom = m.numels if fam == "brick" else m.numelc       # elements the dominant kernel processes per launch
+    b = B_ALG["brick" if fam == "brick" else "sh3n" if fam == "sh3n" else "shell"]
+    ne_dom = m.numels if fam == "brick" else m.numeltg if fam == "sh3n" else m.numelc   # elements the dominant kernel processes per launch
     if fam == "mixed":                                      # whole-cycle bytes: weighted sum of both families
         b = dict(b, total=(B_ALG["shell"]["total"] * m.numelc + B_ALG["brick"]["total"] * m.numels) / max(ne, 1))
     ach = (b["forces"] * ne_dom) / (dms / dn * 1e-3) / 1e9 if dn else 0.0
@@ -206,7 +212,7 @@ def main():
             "whole_cycle": {"achieved": b["total"] * ne * world / (ms * 1e-3 / args.steps) / 1e9 / world,
                             "frac": b["total"] * ne / (ms * 1e-3 / args.steps) / 1e9 / peak, "bytes_per_element": b["total"]}}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr):                     # DRAM bytes per launch from the committed ncu capture (per element x elements of this launch)
+    if os.path.exists(tr) and fam != "sh3n":                     # DRAM bytes per launch from the committed ncu capture (per element x elements of this launch)
         try:
             per = json.load(open(tr)).get(dom + "_per_element")
             roof["traffic"] = per * ne_dom if per else None
