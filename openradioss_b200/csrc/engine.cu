@@ -61,7 +61,7 @@ struct orgpu_engine {
   std::vector<ShellSGHost> csg;
   double* d_fsky = nullptr; int roww = 4;
   CycleState* d_cs = nullptr;
-  DtBlocks db{}; FinalizeArgs fa{};
+  DtBlocks db{}; FinalizeArgs fa{}; std::vector<SGRange> sgr; SGRange* d_sgr = nullptr;
   bool finalized = false;
   // graph of one fused cycle
   cudaGraphExec_t gexec = nullptr;
@@ -142,7 +142,7 @@ int orgpu_destroy(orgpu_engine* e)
   for (auto& s : e->csg) for (void* p : s.owned) cudaFree(p);
   void* ptrs[] = {e->nd.pos, e->nd.vel, e->nd.rot, e->nd.D, e->nd.A, e->nd.AR, e->nd.STIFN, e->nd.STIFR, e->nd.MS, e->nd.IN,
                   e->d_stage3a, e->d_stage3b, e->d_fext, e->d_mext, e->d_icodt, e->d_icodr, e->d_adsky, e->d_fsky, e->d_cs,
-                  e->db.dt, e->db.order, e->d_btf, e->d_bnpf, e->d_ftf, e->d_fnpf, e->d_fv_idx, e->d_fv, e->d_itab, e->d_nd_dt, e->d_nd_node};
+                  e->db.dt, e->db.order, e->d_sgr, e->d_btf, e->d_bnpf, e->d_ftf, e->d_fnpf, e->d_fv_idx, e->d_fv, e->d_itab, e->d_nd_dt, e->d_nd_node};
   for (void* p : ptrs) if (p) cudaFree(p);
   { Exchange& x = e->xc;
     void* xp[] = {x.d_send_slots, x.d_recv_slots, x.d_sendbuf, x.d_recvbuf, x.d_cand_send, x.d_cand_recv, x.d_slots_tmp, x.d_rows_tmp};
@@ -322,11 +322,11 @@ int orgpu_finalize(orgpu_engine* e)
   { std::vector<int> a0(e->adsky.size()); for (size_t i = 0; i < a0.size(); i++) a0[i] = e->adsky[i] - 1;
     if (dev_alloc(&e->d_adsky, a0.size())) return -100;
     CUDA_OK(cudaMemcpy(e->d_adsky, a0.data(), 4 * a0.size(), cudaMemcpyHostToDevice)); e->nd.adsky = e->d_adsky; }
-  int order = 0, blk = 0; e->fa.nsg = 0;
+  int order = 0, blk = 0; e->fa.nsg = 0; e->sgr.clear();
   // shells are processed first (FORINTC resol.F:4138), solids after (FORINT resol.F:4225)
-  { int rc = shell_build_supergroups(e->cgroups, e->csg, e->ixc, e->iadc, 4, e->npf, e->tf, e->ctl, e->numnod, e->lsky, order, blk, e->fa); if (rc) return rc; }
+  { int rc = shell_build_supergroups(e->cgroups, e->csg, e->ixc, e->iadc, 4, e->npf, e->tf, e->ctl, e->numnod, e->lsky, order, blk, e->sgr); if (rc) return rc; }
   // 3-node shell groups (ITY=7) follow the 4-node ones in the Engine's group list, inside the same FORINTC pass
-  { int rc = shell_build_supergroups(e->tgroups, e->csg, e->ixtg, e->iadtg, 3, e->npf, e->tf, e->ctl, e->numnod, e->lsky, order, blk, e->fa); if (rc) return rc; }
+  { int rc = shell_build_supergroups(e->tgroups, e->csg, e->ixtg, e->iadtg, 3, e->npf, e->tf, e->ctl, e->numnod, e->lsky, order, blk, e->sgr); if (rc) return rc; }
   // consecutive solid groups with identical material / property fuse into one super-group
   size_t gi = 0;
   while (gi < e->sgroups.size()) {
@@ -384,11 +384,14 @@ int orgpu_finalize(orgpu_engine* e)
     d.conn = dconn; d.ngl = dngl;
     if (push_dev(S.owned, &d.smstr, (size_t)21 * np)) return -100;
     const int nblk = np / ORGPU_TILE;                    // dt candidate slots: one per CTA
-    NEED(e->fa.nsg < ORGPU_MAX_SG, -6, "too many super-groups (%d)", ORGPU_MAX_SG);
-    e->fa.sg[e->fa.nsg++] = SGRange{blk, nblk, ORGPU_FAM_BRICK, d.order0, d.ngl};
+    NEED((int)e->sgr.size() < ORGPU_MAX_SG, -6, "too many super-groups (%d)", ORGPU_MAX_SG);
+    e->sgr.push_back(SGRange{blk, nblk, ORGPU_FAM_BRICK, d.order0, d.ngl});
     order += ne; blk += nblk; gi = gj;
   }
   NEED(blk > 0, -4, "orgpu_finalize: no element groups");
+  if (dev_alloc(&e->d_sgr, e->sgr.size())) return -100;
+  CUDA_OK(cudaMemcpy(e->d_sgr, e->sgr.data(), sizeof(SGRange) * e->sgr.size(), cudaMemcpyHostToDevice));
+  e->fa.nsg = (int)e->sgr.size(); e->fa.sg = e->d_sgr;
   // /DT/NODA
   NEED(e->ctl.nodadt == 0 || e->ctl.nodadt == 1, -5, "NODADT=%d is outside the built path (0, 1)", e->ctl.nodadt);
   e->nd.nodadt = e->ctl.nodadt; e->nd.dtfac_node = e->ctl.dtfac_node;

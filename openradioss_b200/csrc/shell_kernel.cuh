@@ -60,7 +60,7 @@ template <class T> static int sh_upload(std::vector<void*>& owned, T** p, const 
 static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vector<ShellSGHost>& out,
                                    const std::vector<int>& ixc, const std::vector<int>& iadc, const int nnode,
                                    const std::vector<int>& npf, const std::vector<double>& tf,
-                                   const orgpu_control& ctl, int numnod, int lsky, int& order, int& blk, FinalizeArgs& fa)
+                                   const orgpu_control& ctl, int numnod, int lsky, int& order, int& blk, std::vector<SGRange>& sgr)
 {
   if (groups.empty()) return 0;
   if (!ctl.iroddl) { orgpu_set_error("shell groups need rotational dofs (control.iroddl=1)"); return -4; }
@@ -131,8 +131,8 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
     d.conn = dconn; d.ngl = dngl;
     if (sh_alloc(S.owned, &d.smstr, (size_t)(nnode == 3 ? 3 : 6) * np)) return -100;
     const int nblk = np / ORGPU_TILE;                    // dt candidate slots: one per CTA
-    if (fa.nsg >= ORGPU_MAX_SG) { orgpu_set_error("too many super-groups (%d)", ORGPU_MAX_SG); return -6; }
-    fa.sg[fa.nsg++] = SGRange{blk, nblk, (nnode == 3) ? ORGPU_FAM_SH3N : shell_is_qeph(G.prop) ? ORGPU_FAM_SHELL_QEPH : ORGPU_FAM_SHELL_BT, d.order0, d.ngl};
+    if ((int)sgr.size() >= ORGPU_MAX_SG) { orgpu_set_error("too many super-groups (%d)", ORGPU_MAX_SG); return -6; }
+    sgr.push_back(SGRange{blk, nblk, (nnode == 3) ? ORGPU_FAM_SH3N : shell_is_qeph(G.prop) ? ORGPU_FAM_SHELL_QEPH : ORGPU_FAM_SHELL_BT, d.order0, d.ngl});
     order += ne; blk += nblk; gi = gj;
   }
   return 0;

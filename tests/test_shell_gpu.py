@@ -229,6 +229,24 @@ def test_law36_epsmax_failure_deletes_the_same_shells(ihbe):
     assert np.all(f[g.shell_state("off")[0] == 0][:, :, :6] == 0.0)   # deleted elements leave zero rows
 
 
+def test_many_super_groups_one_model():
+    """a model whose consecutive groups never fuse (alternating properties): 100 super-groups, one launch each; the
+    table of super-groups lives in device memory (limit ORGPU_MAX_SG = 4096)"""
+    m = meshgen.shell_plate(128, 100, 1280.0, 1000.0, pressure=20.0, vrand=5.0)
+    pa, pb = meshgen.default_prop_shell(thick=2.0), meshgen.default_prop_shell(thick=2.0)
+    pb.h1 = pa.h1 * 1.25
+    for k, sg in enumerate(m.shell_groups):
+        sg.prop = pa if k % 2 == 0 else pb
+    assert len(m.shell_groups) == 100
+    g, o = pair(m)
+    g.run_cycles(20); o.run_cycles(20)
+    ng, no = g.download_nodes(("X", "V", "VR")), o.download_nodes(("X", "V", "VR"))
+    for k in ("X", "V", "VR"):
+        assert rel_err(ng[k], no[k]) <= 1e-10, k
+    tg, to = g.time(), o.time()
+    assert tg["neltst"] == to["neltst"] and tg["dt2"] == pytest.approx(to["dt2"], rel=1e-12)
+
+
 def energies(b, m):
     d = b.download_nodes(("V", "VR"))
     ke = 0.5 * (m.MS[:, None] * d["V"] ** 2).sum() + 0.5 * (m.IN[:, None] * d["VR"] ** 2).sum()
