@@ -41,6 +41,9 @@ struct orgpu_engine {
   int device = 0, numnod = 0;
   orgpu_control ctl{};
   cudaStream_t st = nullptr;
+#define ORGPU_NSIDE 15
+  cudaStream_t side[ORGPU_NSIDE] = {};     // side streams: super-groups are independent, their kernels may overlap
+  cudaEvent_t ev_fork = nullptr, ev_join[ORGPU_NSIDE] = {};
   DevNodes nd{};                      // device pointers
   double *d_stage3a = nullptr, *d_stage3b = nullptr;   // (3,N) staging for pack/unpack
   double *d_fext = nullptr, *d_mext = nullptr; int *d_icodt = nullptr, *d_icodr = nullptr, *d_adsky = nullptr;
@@ -117,6 +120,8 @@ int orgpu_create(orgpu_engine** out, int device, int numnod, const orgpu_control
   orgpu_engine* e = new orgpu_engine();
   e->device = device; e->numnod = numnod; e->ctl = *ctl;
   CUDA_OK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+  for (int k = 0; k < ORGPU_NSIDE; k++) { CUDA_OK(cudaStreamCreateWithFlags(&e->side[k], cudaStreamNonBlocking)); CUDA_OK(cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming)); }
+  CUDA_OK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
   const size_t n = numnod;
   e->nd.n = numnod;
   if (dev_alloc(&e->nd.pos, n) || dev_alloc(&e->nd.vel, n) || dev_alloc(&e->nd.D, 3 * n) || dev_alloc(&e->nd.A, 3 * n) ||
@@ -153,6 +158,8 @@ int orgpu_destroy(orgpu_engine* e)
     if (x.comm && nccl_api()) nccl_api()->CommDestroy(x.comm); }
   for (auto ev : e->evpool) cudaEventDestroy(ev);
   if (e->ev0) cudaEventDestroy(e->ev0); if (e->ev1) cudaEventDestroy(e->ev1);
+  for (int k = 0; k < ORGPU_NSIDE; k++) { if (e->side[k]) cudaStreamDestroy(e->side[k]); if (e->ev_join[k]) cudaEventDestroy(e->ev_join[k]); }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   cudaStreamDestroy(e->st);
   delete e;
   return 0;
@@ -327,6 +334,7 @@ int orgpu_finalize(orgpu_engine* e)
   { int rc = shell_build_supergroups(e->cgroups, e->csg, e->ixc, e->iadc, 4, e->npf, e->tf, e->ctl, e->numnod, e->lsky, order, blk, e->sgr); if (rc) return rc; }
   // 3-node shell groups (ITY=7) follow the 4-node ones in the Engine's group list, inside the same FORINTC pass
   { int rc = shell_build_supergroups(e->tgroups, e->csg, e->ixtg, e->iadtg, 3, e->npf, e->tf, e->ctl, e->numnod, e->lsky, order, blk, e->sgr); if (rc) return rc; }
+  e->fa.brick_blk0 = blk;          // dt slots from here on belong to solids
   // consecutive solid groups with identical material / property fuse into one super-group
   size_t gi = 0;
   while (gi < e->sgroups.size()) {
@@ -437,16 +445,29 @@ static cudaEvent_t get_event(orgpu_engine* e, size_t i) {
 static void launch_element_phase(orgpu_engine* e, int fused, size_t* evi)
 {
   e->fa.fused = fused;
+  // Super-groups write disjoint FSKY rows, state tiles and dt slots: with more than one of them (models with many parts)
+  // their kernels are spread over the main stream and up to 15 side streams (fork / join by events, also inside the graph
+  // capture of run_cycles) so that small launches overlap; the profiled run keeps them in sequence to time each one.
+  const size_t nsg = e->csg.size() + e->bsg.size();
+  const bool fork = (evi == nullptr) && nsg > 1;
+  const int nside = fork ? (int)((nsg - 1 < (size_t)ORGPU_NSIDE) ? nsg - 1 : ORGPU_NSIDE) : 0;
+  size_t k = 0;
+  auto pick = [&]() -> cudaStream_t {
+    const size_t j = k++ % (size_t)(nside + 1);
+    return (j == 0) ? e->st : e->side[j - 1];
+  };
+  if (fork) { cudaEventRecord(e->ev_fork, e->st); for (int j = 0; j < nside; j++) cudaStreamWaitEvent(e->side[j], e->ev_fork, 0); }
   for (auto& S : e->csg) {
     if (evi) cudaEventRecord(get_event(e, (*evi)++), e->st);
-    launch_shell_forces(S, e->nd, e->d_fsky, e->roww, e->d_cs, e->db, e->fa, e->st); e->launches++;
+    launch_shell_forces(S, e->nd, e->d_fsky, e->roww, e->d_cs, e->db, e->fa, pick()); e->launches++;
     if (evi) cudaEventRecord(get_event(e, (*evi)++), e->st);
   }
   for (auto& S : e->bsg) {
     if (evi) cudaEventRecord(get_event(e, (*evi)++), e->st);
-    launch_brick_forces(S.d, e->nd, e->d_fsky, e->roww, e->d_cs, e->db, e->fa, e->st); e->launches++;
+    launch_brick_forces(S.d, e->nd, e->d_fsky, e->roww, e->d_cs, e->db, e->fa, pick()); e->launches++;
     if (evi) cudaEventRecord(get_event(e, (*evi)++), e->st);
   }
+  for (int j = 0; j < nside; j++) { cudaEventRecord(e->ev_join[j], e->side[j]); cudaStreamWaitEvent(e->st, e->ev_join[j], 0); }
   element_finalize_kernel<<<1, ORGPU_FINALIZE_BLOCK, 0, e->st>>>(e->d_cs, e->db, e->fa); e->launches++;
 }
 
