@@ -56,7 +56,7 @@ typedef struct orgpu_law2 {
 
 /* /MAT/LAW36 (PLAS_TAB).  Values are the Starter-computed UPARAM entries SIGEPS36C reads
  * (starter/source/materials/mat/mat036/hm_read_mat36.F:268-320, engine sigeps36c.F:166-200);
- * built path: VP=0, FISOKIN=0, no failure (IFAIL=0), no E(epsp) / pressure scaling. */
+ * built path: VP=0, FISOKIN=0, IFAIL 0 / 1 / 2, no E(epsp) / pressure scaling. */
 typedef struct orgpu_law36 {
   double rho0, young, nu, shear, bulk;
   double a11, a12, ssp;     /* PM(24), PM(25), PM(27) as CNCOEF3B reads them          */
@@ -69,6 +69,8 @@ typedef struct orgpu_law36 {
   double soundsp;           /* UPARAM(2*nrate+18) shell sound speed                    */
   double nu_mnu, t_pnu, u_mnu; /* UPARAM(2*nrate+19..21): nu/(1-nu), 3/(1+nu), 1/(1-nu) */
   double epsmax;            /* UPARAM(2*nrate+7)  (INFINITY when unset)                */
+  double epsr1, epsr2, epsf;/* UPARAM(2*nrate+8), (2*nrate+9), (2*nrate+15): tensile failure strains (IFAIL = 2;
+                               INFINITY, 2*INFINITY, 3*INFINITY when unset, hm_read_mat36.F:246-248) */
   double fisokin;           /* UPARAM(2*nrate+14) must be 0                            */
   double asrate;            /* PM(9) = 2*pi*Fcut                                       */
   double rate[ORGPU_MAXFUNC36];   /* UPARAM(6+j)        strain rates                   */

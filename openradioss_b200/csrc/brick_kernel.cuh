@@ -483,6 +483,40 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
         SG5 = SO5 + m6.shear * DE5;
         SG6 = SO6 + m6.shear * DE6;
       }
+      // IFAIL = 2: largest principal total strain by 4 Newton steps on the deviatoric cubic, damage factor on the
+      // yield stress (sigeps36.F:331-395)
+      double FAIL = K_ONE, EPSTT = K_ZERO;
+      if (LAW == 37) {                                     // its own kernel variant: the common LAW36 kernels carry none of it
+        const double EXX = T.ld(g.w_stra), EYY = T.ld(g.w_stra + 1), EZZ = T.ld(g.w_stra + 2);
+        const double EXY = T.ld(g.w_stra + 3), EYZ = T.ld(g.w_stra + 4), EZX = T.ld(g.w_stra + 5);
+        const double DAV = (EXX + EYY + EZZ) * K_THIRD;
+        const double E1 = EXX - DAV, E2 = EYY - DAV, E3 = EZZ - DAV, E4 = K_HALF * EXY, E5 = K_HALF * EYZ, E6 = K_HALF * EZX;
+        const double E42 = E4 * E4, E52 = E5 * E5, E62 = E6 * E6;
+        const double C = -K_HALF * (E1 * E1 + E2 * E2 + E3 * E3) - E42 - E52 - E62;
+        double EPST = or_sqrt(-C * K_THIRD);
+        const double EPSR1DAV = fmin(m6.epsr1, m6.epsf) - DAV;
+        bool done = !(EPST + EPST < EPSR1DAV);
+        if (done) {
+          const double D = -E1 * E2 * E3 + E1 * E52 + E2 * E62 + E3 * E42 - K_TWO * E4 * E5 * E6;
+          double EPST2 = EPST * EPST;
+          double Y = (EPST2 + C) * EPST + D;
+          if (fabs(Y) > K_EM8) {
+            EPST = K_ONEP75 * EPST;
+            #pragma unroll 1
+            for (int it = 0; it < 4; it++) {
+              EPST2 = EPST * EPST; Y = (EPST2 + C) * EPST + D;
+              const double YP = K_THREE * EPST2 + C;
+              EPST = EPST - or_div(Y, YP);
+              if (it < 3 && EPST < EPSR1DAV) { done = false; break; }
+            }
+          }
+          if (done) {
+            EPST = EPST + DAV;
+            EPSTT = EPST;
+            FAIL = fmax(K_EM20, fmin(K_ONE, or_div(m6.epsr2 - EPST, m6.epsr2 - m6.epsr1)));
+          }
+        }
+      }
       // yield stress and hardening modulus from the tabulated curves (VINTER, forward-only cursors in VARTMP)
       double YLD, H;
       if (m6.nrate == 1) {
@@ -492,7 +526,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
         if (g.ct.n > 0) vinter1c(g.ct, 0, ipos, EPXE, dydx, y1);
         else { const int i0 = __ldg(g.npf + f), i1 = __ldg(g.npf + f + 1); vinter1(g.tf, i0, i1 - i0, ipos, EPXE, dydx, y1); }
         if (ipos != ipos_old) T.sti(g.w_vt, 0, ipos);
-        const double FACT = K_ONE * K_ONE * (m6.yfac[0] * K_ONE);
+        const double FACT = FAIL * K_ONE * (m6.yfac[0] * K_ONE);
         H = dydx * FACT;
         YLD = y1 * FACT;
       } else {
@@ -517,9 +551,9 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
         }
         T.sti(g.w_vt, 1 + JJ, ipos1); T.sti(g.w_vt, 2 + JJ, ipos2);
         y1 = y1 * YFAC1; y2 = y2 * YFAC2;
-        YLD = (y1 + RFAC * (y2 - y1)) * (K_ONE * K_ONE);
+        YLD = (y1 + RFAC * (y2 - y1)) * (FAIL * K_ONE);
         dydx1 = dydx1 * YFAC1; dydx2 = dydx2 * YFAC2;
-        H = (dydx1 + RFAC * (dydx2 - dydx1)) * (K_ONE * K_ONE);
+        H = (dydx1 + RFAC * (dydx2 - dydx1)) * (FAIL * K_ONE);
       }
       if (m6.yldcheck == 1) YLD = fmax(YLD, K_EM20);
       // projection on the yield surface (radial return), IPLA = 0 / 2 / 1
@@ -544,7 +578,8 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       { const double Pn = m6.bulk * AMU; SG1 = SG1 - Pn; SG2 = SG2 - Pn; SG3 = SG3 - Pn; }   // IEOS = 0
       if (OFF < K_EM01) OFF = K_ZERO;
       if (OFF < K_ONE) OFF = OFF * K_FOUR_OVER_5;
-      if (m6.ifail == 1) { if (EPXE > m6.epsmax && OFF == K_ONE) OFF = K_FOUR_OVER_5; }    // sigeps36.F:1546-1555
+      if (LAW != 37 && m6.ifail == 1) { if (EPXE > m6.epsmax && OFF == K_ONE) OFF = K_FOUR_OVER_5; }    // sigeps36.F:1546-1555
+      else if (LAW == 37) { if ((EPXE > m6.epsmax || EPSTT > m6.epsf) && OFF == K_ONE) OFF = K_FOUR_OVER_5; }   // :1524-1533
       // MULAW: plastic work (L_PLA>0, von Mises of the old and new stresses)
       {
         const double DPLA = EPXE - DEFP0;
@@ -715,6 +750,7 @@ void launch_brick_forces(const BrickSG& sg, const DevNodes& nd, double* fsky, in
 {
   BrickParams P{sg, nd, fsky, roww, cs, db};
   const int nblk = sg.ne_pad / ORGPU_TILE;
-  if (sg.law == 36) launch_brick_jhbe<36>(P, nblk, st);
+  if (sg.law == 36 && sg.m36.ifail == 2) launch_brick_jhbe<37>(P, nblk, st);
+  else if (sg.law == 36) launch_brick_jhbe<36>(P, nblk, st);
   else              launch_brick_jhbe<2>(P, nblk, st);
 }

@@ -96,7 +96,7 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
     const double THK02 = THK0 * THK0;
     double RHO, YM, NU, G;
     MatIO io;
-    if (LAW == 36) { const orgpu_law36& m = g.m36; RHO = m.rho0; YM = m.young; NU = m.nu; G = m.shear; io.ssp = m.ssp; }
+    if (LAW != 2) { const orgpu_law36& m = g.m36; RHO = m.rho0; YM = m.young; NU = m.nu; G = m.shear; io.ssp = m.ssp; }
     else           { const orgpu_law2& m = g.m2;   RHO = m.rho0; YM = m.young; NU = m.nu; G = m.shear; io.ssp = m.ssp; }
     const double H1 = g.prop.h1, H2 = g.prop.h2, H3 = g.prop.h3;
     double SHF = K_ZERO;
@@ -229,7 +229,7 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
     // ---- CHVIS3
     double H11, H12, H13, H21, H22, H23, H31, H32, H33, B1r, B2r;
     double STI = K_ZERO, STIR = K_ZERO;
-    const double A11N = (LAW == 36) ? g.m36.a11 : g.m2.a11;     // PM(24)
+    const double A11N = (LAW != 2) ? g.m36.a11 : g.m2.a11;     // PM(24)
     {
       const double HELAS = K_HALF, HVISC = K_HALF, HVLIN = K_ZERO;     // radioss2.F:641-643
       const double SR2D2 = or_sqrt(K_TWO) * K_HALF;

@@ -87,7 +87,7 @@ c3_forces_kernel(const __grid_constant__ ShellParams P)
     const double THK02 = THK0 * THK0;
     double RHO, NU, G, A11;
     MatIO io;
-    if (LAW == 36) { const orgpu_law36& m = g.m36; RHO = m.rho0; NU = m.nu; G = m.shear; A11 = m.a11; io.ssp = m.ssp; }
+    if (LAW != 2) { const orgpu_law36& m = g.m36; RHO = m.rho0; NU = m.nu; G = m.shear; A11 = m.a11; io.ssp = m.ssp; }
     else           { const orgpu_law2& m = g.m2;   RHO = m.rho0; NU = m.nu; G = m.shear; A11 = m.a11; io.ssp = m.ssp; }
     double SHF = K_ZERO;
     if (NPT != 1) { const double FAC1 = K_TWO * (K_ONE + NU) * THK02; const int ISH = 0; const double FSH = g.prop.shf;

@@ -291,7 +291,8 @@ int orgpu_add_solid_group_law(orgpu_engine* e, int nel, int nft, int law, const 
   NEED(e && mat && prop && vol0 && nel > 0 && !e->finalized, -1, "orgpu_add_solid_group_law: bad arguments / already finalized");
   NEED(nft >= 0 && nft + nel <= e->numels, -4, "orgpu_add_solid_group_law: elements [%d,%d) outside IXS (%d)", nft, nft + nel, e->numels);
   const orgpu_law36* m = (const orgpu_law36*)mat;
-  NEED(m->fisokin == 0.0 && m->vp == 0 && m->ifail >= 0 && m->ifail <= 1, -5, "LAW36 kinematic hardening / VP=1 / tensile-strain failure (IFAIL=2) are outside the built path");
+  NEED(m->fisokin == 0.0 && m->vp == 0 && m->ifail >= 0 && m->ifail <= 2, -5, "LAW36 kinematic hardening / VP=1 are outside the built path");
+  NEED(m->ifail != 2 || prop->istrain > 0, -5, "LAW36 tensile-strain failure (IFAIL=2) needs the total strains (Istrain=1)");
   NEED(m->nrate >= 1 && m->nrate <= ORGPU_MAXFUNC36, -5, "LAW36 NRATE=%d out of range", m->nrate);
   NEED(prop->jhbe == 0 || prop->jhbe == 1 || prop->jhbe == 2, -5, "Isolid=%d is outside the built path (0,1,2)", prop->jhbe);
   NEED(prop->ismstr == 1 || prop->ismstr == 2 || prop->ismstr == 4, -5, "Ismstr=%d is outside the built path (1,2,4)", prop->ismstr);

@@ -308,7 +308,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     // ---- CNCOEF3B
     THK0 = (g.prop.ithk > 0) ? fmax(K_EM20, T.ld(SW_THK)) : T.ld(g.w_thke);
     double RHO, G;
-    if (LAW == 36) { const orgpu_law36& m = g.m36; RHO = m.rho0; G = m.shear; io.ssp = m.ssp; }
+    if (LAW != 2) { const orgpu_law36& m = g.m36; RHO = m.rho0; G = m.shear; io.ssp = m.ssp; }
     else           { const orgpu_law2& m = g.m2; RHO = m.rho0; G = m.shear; io.ssp = m.ssp; }
     const double SHF = (NPT == 1) ? K_ZERO : g.prop.shf;
     // ---- CZDEF
@@ -396,7 +396,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     double A11, A12, GSR, A11SR, A12SR;
     const double RHO = io.rho;
     double G;
-    if (LAW == 36) { const orgpu_law36& m = g.m36; G = m.shear; A11 = m.a11; GSR = m.gsr; A11SR = m.a11sr; A12 = m.nu * A11; A12SR = m.nusr * A11SR; }
+    if (LAW != 2) { const orgpu_law36& m = g.m36; G = m.shear; A11 = m.a11; GSR = m.gsr; A11SR = m.a11sr; A12 = m.nu * A11; A12SR = m.nusr * A11SR; }
     else           { const orgpu_law2& m = g.m2; G = m.shear; A11 = m.a11; A12 = m.a12; GSR = m.gsr; A11SR = m.a11sr; A12SR = m.a12sr; }
     const double SHF = (NPT == 1) ? K_ZERO : g.prop.shf, SHFSR = (NPT == 1) ? K_ZERO : g.prop.shfsr;
     const double AMU = (g.prop.h1 == K_ZERO) ? K_ZEP01 + K_FIVEEM3 : g.prop.h1;

@@ -86,13 +86,25 @@ __device__ __forceinline__ void ip_store(const ShellSG& g, const TileAcc<STAGED>
 #define ORGPU_SHELL_CTA ORGPU_TILE   // one CTA = one state tile
 
 // ---- SIGEPS36C, VP = 0 -------------------------------------------------------------------
-template <bool STAGED>
+// FAIL2: IFAIL = 2 (tensile-strain damage / failure), compiled as its own kernel variant (template LAW = 37) so that
+// the common LAW36 kernels carry none of it
+template <bool STAGED, bool FAIL2>
 __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>& T, int ipt, int ipla, double asrate,
                                          double dexx, double deyy, double dexy, double deyz, double dezx, double dtinv,
-                                         double thklyl, double gs, double epsd_pg, double& off,
+                                         double thklyl, double gs, double epsd_pg, double zt, double& off,
                                          IpState& s, double& thk, double& ssp, double& etse, double& yld_out)
 {
   const orgpu_law36& m = g.m36;
+  // IFAIL = 2: damage factor on the largest in-plane principal total strain at the point (mulawc.F90:856-862,
+  // sigeps36c.F:256-264); GBUF%STRA was accumulated by the strain routine earlier in this cycle
+  double FAIL = K_ONE, EPST = K_ZERO;
+  if (FAIL2) {
+    const double epsxx = T.ld(SW_STRA) + zt * T.ld(SW_STRA + 5);
+    const double epsyy = T.ld(SW_STRA + 1) + zt * T.ld(SW_STRA + 6);
+    const double epsxy = T.ld(SW_STRA + 2) + zt * T.ld(SW_STRA + 7);
+    EPST = K_HALF * (epsxx + epsyy + or_sqrt((epsxx - epsyy) * (epsxx - epsyy) + epsxy * epsxy));
+    FAIL = fmax(K_EM20, fmin(K_ONE, or_div(m.epsr2 - EPST, m.epsr2 - m.epsr1)));
+  }
   const double E = m.young, A1 = m.a1u, A2 = m.a2u, G = m.shear, G3 = m.g3;
   ssp = m.soundsp; etse = K_ONE;
   double pla = s.pla;
@@ -121,7 +133,7 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
     if (g.ct.n > 0) vinter1c(g.ct, 0, ipos, pla, dydx, y1);
     else { const int i0 = __ldg(g.npf + f), i1 = __ldg(g.npf + f + 1); vinter1(g.tf, i0, i1 - i0, ipos, pla, dydx, y1); }
     s.ipos = ipos;
-    const double FACT = K_ONE * K_ONE * (m.yfac[0] * K_ONE);
+    const double FACT = FAIL * K_ONE * (m.yfac[0] * K_ONE);
     H = dydx * FACT;
     YLD = y1 * FACT;
   } else {
@@ -145,10 +157,10 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
       { const int i0 = __ldg(g.npf + f2), i1 = __ldg(g.npf + f2 + 1); vinter1(g.tf, i0, i1 - i0, ipos2, pla, dydx2, y2); }
     }
     y1 = y1 * YFAC1; y2 = y2 * YFAC2;
-    YLD = K_ONE * (y1 + RFAC * (y2 - y1));
+    YLD = FAIL * (y1 + RFAC * (y2 - y1));
     YLD = fmax(YLD, K_EM20);
     dydx1 = dydx1 * YFAC1; dydx2 = dydx2 * YFAC2;
-    H = K_ONE * (dydx1 + RFAC * (dydx2 - dydx1));
+    H = FAIL * (dydx1 + RFAC * (dydx2 - dydx1));
     YLD = YLD * fmax(K_ZERO, K_ONE);
     H = H * fmax(K_ZERO, K_ONE);
     T.sti(g.w_vt, ipt * g.nvt + 1 + JJ, ipos1); T.sti(g.w_vt, ipt * g.nvt + 2 + JJ, ipos2);
@@ -234,7 +246,8 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
     }
   }
   // IFAIL = 1: failure on the maximum plastic strain (sigeps36c.F:928-938); MULAWC completes the deletion in the same cycle
-  if (m.ifail == 1) { if (off == K_ONE && pla > m.epsmax) off = K_FOUR_OVER_5; }
+  if (!FAIL2 && m.ifail == 1) { if (off == K_ONE && pla > m.epsmax) off = K_FOUR_OVER_5; }
+  else if (FAIL2) { if (off == K_ONE && (pla > m.epsmax || EPST > m.epsf)) off = K_FOUR_OVER_5; }   // :940-950
   s.pla = pla;
   yld_out = YLD;
 }
@@ -418,8 +431,8 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const Tile
   int ioff_duct = 0;
   double epchk = K_ZERO, viscmx = K_ZERO, ssp = io.ssp;
   const double dtinv = or_div(dt1, fmax(dt1 * dt1, K_EM20));
-  const int israte = (LAW == 36) ? g.m36.israte : g.m2.israte;
-  const double pm9 = (LAW == 36) ? g.m36.asrate : g.m2.asrate;
+  const int israte = (LAW != 2) ? g.m36.israte : g.m2.israte;
+  const double pm9 = (LAW != 2) ? g.m36.asrate : g.m2.asrate;
   const double asrate = (israte > 0) ? fmin(K_ONE, pm9 * dt1) : K_ONE;
   const int qrow = (npt - 1) * 11;
   IpState nxt;
@@ -442,8 +455,8 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const Tile
     const double dexx = io.exx + zt * io.kxx;
     const double deyy = io.eyy + zt * io.kyy;
     const double dexy = io.exy + zt * io.kxy;
-    if (LAW == 36) {
-      law36_ip(g, T, ipt, g.prop.ipla, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, thklyl, io.gs, io.epsd_pg, off,
+    if (LAW != 2) {
+      law36_ip<STAGED, LAW == 37>(g, T, ipt, g.prop.ipla, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, thklyl, io.gs, io.epsd_pg, zt, off,
                s, thkn, ssp, etse, sigy);
     } else {
       law2_ip(g, g.prop.ipla, npt, dt1, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, thklyl, io.gs, io.epsd_pg,

@@ -35,7 +35,8 @@ static int shell_add_group(std::vector<HostShellGroup>& groups, int nel, int nft
   g.nel = nel; g.nft = nft; g.law = law; g.sh3n = sh3n ? 1 : 0; g.prop = *prop;
   if (law == 36) {
     g.m36 = *(const orgpu_law36*)mat;
-    if (g.m36.fisokin != 0.0 || g.m36.vp != 0 || g.m36.ifail < 0 || g.m36.ifail > 1) { orgpu_set_error("LAW36 kinematic hardening / VP=1 / tensile-strain failure (IFAIL=2) are outside the built path"); return -5; }
+    if (g.m36.fisokin != 0.0 || g.m36.vp != 0 || g.m36.ifail < 0 || g.m36.ifail > 2) { orgpu_set_error("LAW36 kinematic hardening / VP=1 are outside the built path"); return -5; }
+    if (g.m36.ifail == 2 && prop->istrain == 0) { orgpu_set_error("LAW36 tensile-strain failure (IFAIL=2) needs the total strains (Istrain=1)"); return -5; }
     if (g.m36.nrate < 1 || g.m36.nrate > ORGPU_MAXFUNC36) { orgpu_set_error("LAW36 NRATE=%d out of range", g.m36.nrate); return -5; }
   } else {
     g.m2 = *(const orgpu_law2*)mat;
@@ -159,13 +160,16 @@ static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky
   ShellParams P{S.d, nd, fsky, cs, db};
   const int nblk = S.d.ne_pad / ORGPU_TILE;
   if (S.sh3n) {
-    if (S.d.law == 36) shell_launch_one(c3_forces_kernel<36, true>, c3_forces_kernel<36, false>, P, nblk, st);
+    if (S.d.law == 36 && S.d.m36.ifail == 2) shell_launch_one(c3_forces_kernel<37, true>, c3_forces_kernel<37, false>, P, nblk, st);
+    else if (S.d.law == 36) shell_launch_one(c3_forces_kernel<36, true>, c3_forces_kernel<36, false>, P, nblk, st);
     else               shell_launch_one(c3_forces_kernel<2, true>, c3_forces_kernel<2, false>, P, nblk, st);
   } else if (shell_is_qeph(S.d.prop)) {
-    if (S.d.law == 36) shell_launch_one(qeph_forces_kernel<36, true>, qeph_forces_kernel<36, false>, P, nblk, st);
+    if (S.d.law == 36 && S.d.m36.ifail == 2) shell_launch_one(qeph_forces_kernel<37, true>, qeph_forces_kernel<37, false>, P, nblk, st);
+    else if (S.d.law == 36) shell_launch_one(qeph_forces_kernel<36, true>, qeph_forces_kernel<36, false>, P, nblk, st);
     else               shell_launch_one(qeph_forces_kernel<2, true>, qeph_forces_kernel<2, false>, P, nblk, st);
   } else {
-    if (S.d.law == 36) shell_launch_one(bt_forces_kernel<36, true>, bt_forces_kernel<36, false>, P, nblk, st);
+    if (S.d.law == 36 && S.d.m36.ifail == 2) shell_launch_one(bt_forces_kernel<37, true>, bt_forces_kernel<37, false>, P, nblk, st);
+    else if (S.d.law == 36) shell_launch_one(bt_forces_kernel<36, true>, bt_forces_kernel<36, false>, P, nblk, st);
     else               shell_launch_one(bt_forces_kernel<2, true>, bt_forces_kernel<2, false>, P, nblk, st);
   }
 }

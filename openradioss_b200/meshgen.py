@@ -75,7 +75,7 @@ def steel_law2_shell() -> Law2:
     return m
 
 
-def steel_law36(curves=None, rates=None, epsmax=None):
+def steel_law36(curves=None, rates=None, epsmax=None, eps_t=None):
     """/MAT/LAW36 steel of SURVEY.md 8d, filled as the Starter does
     (starter/source/materials/mat/mat036/hm_read_mat36.F:268-320; generic PM slots
     hm_read_mat.F90:1466-1479).  Returns (Law36, npf, tf): one static curve of 8 points,
@@ -93,6 +93,7 @@ def steel_law36(curves=None, rates=None, epsmax=None):
     m.soundsp = np.sqrt(young / (1.0 - nu * nu) / rho0)
     m.nu_mnu = nu / (1.0 - nu); m.t_pnu = 3.0 / (1.0 + nu); m.u_mnu = 1.0 / (1.0 - nu)
     m.epsmax = K["INFINITY"]; m.fisokin = 0.0; m.asrate = 0.0
+    m.epsr1 = K["INFINITY"]; m.epsr2 = 2.0 * K["INFINITY"]; m.epsf = 3.0 * K["INFINITY"]
     m.a11 = young / (1.0 - nu ** 2); m.a12 = 0.0          # PM(25) is not set for user-type laws
     m.ssp = np.sqrt(young / rho0)                          # PM(27) (hm_read_mat36.F:325)
     _sqrt_constants(m)
@@ -111,6 +112,8 @@ def steel_law36(curves=None, rates=None, epsmax=None):
     m.vp = 0; m.ifail = 0; m.yldcheck = 0; m.ismooth = 0 if m.nrate == 1 else 1
     if epsmax is not None:                                 # failure plastic strain: IFAIL = 1 (hm_read_mat36.F:228-233)
         m.epsmax = epsmax; m.ifail = 1
+    if eps_t is not None:                                  # (EPSR1, EPSR2, EPSF) tensile failure: IFAIL = 2 (hm_read_mat36.F:234-236)
+        m.epsr1, m.epsr2, m.epsf = eps_t; m.ifail = 2
     return m, np.asarray(npf, np.int32), np.concatenate(tf)
 
 

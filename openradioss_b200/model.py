@@ -25,7 +25,7 @@ class Law2(C.Structure):
 
 class Law36(C.Structure):
     _fields_ = [(n, d) for n in ("rho0 young nu shear bulk a11 a12 ssp gsr a11sr a12sr nusr a1u a2u g3 g2 ssp3d soundsp nu_mnu t_pnu u_mnu "
-                                 "epsmax fisokin asrate").split()] + \
+                                 "epsmax epsr1 epsr2 epsf fisokin asrate").split()] + \
                [("rate", d * MAXFUNC36), ("yfac", d * MAXFUNC36), ("ifunc", i * MAXFUNC36)] + \
                [(n, i) for n in "nrate israte vp ifail yldcheck ismooth".split()]
 

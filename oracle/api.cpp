@@ -104,7 +104,8 @@ int orc_add_solid_group_law(void* h,int nel,int nft,int law,const void* mat,cons
   Oracle* o=(Oracle*)h;
   if(nel>MVSIZ-1) return -1;
   const orgpu_law36* m=(const orgpu_law36*)mat;
-  if(m->fisokin!=0.0 || m->vp!=0 || m->ifail<0 || m->ifail>1) return -2;
+  if(m->fisokin!=0.0 || m->vp!=0 || m->ifail<0 || m->ifail>2) return -2;
+  if(m->ifail==2 && prop->istrain==0) return -4;
   OrcSolidGroup g; g.nel=nel; g.nft=nft; g.law=36; g.m36=*m; g.prop=*prop;
   g.mat=orgpu_law2{}; g.mat.rho0=m->rho0;
   g.sig.assign(6*nel,0); g.eint.assign(nel,0); g.rho.assign(nel,m->rho0); g.qvis.assign(nel,0);

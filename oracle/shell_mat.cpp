@@ -35,6 +35,7 @@ struct IpIO {             /* one integration point, one element */
   double sigoxx,sigoyy,sigoxy,sigoyz,sigozx;
   double signxx,signyy,signxy,signyz,signzx;
   double thklyl;
+  double epsxx,epsyy,epsxy;   /* total strains at the point (mulawc.F90:856-862), IFAIL = 2 */
 };
 
 /* ---- SIGEPS36C, VP=0 branch, one element ------------------------------------------------ */
@@ -48,7 +49,13 @@ void sigeps36c(const Oracle& o, const orgpu_law36& m, int ipla, double asrate, c
   const double NU_MNU=m.nu_mnu, T_PNU=m.t_pnu, U_MNU=m.u_mnu, FISOKIN=m.fisokin;
   const double GS=in.gs;
   viscmax=K_ZERO; etse=K_ONE; ssp=m.soundsp;
-  const double FAIL=K_ONE, PFAC=K_ONE, FACYLDI=K_ONE;
+  const double PFAC=K_ONE, FACYLDI=K_ONE;
+  /* damage factor on the largest in-plane principal strain (sigeps36c.F:256-264) */
+  double FAIL=K_ONE, EPST=K_ZERO;
+  if(m.ifail==2){
+    EPST=K_HALF*(s.epsxx+s.epsyy+std::sqrt((s.epsxx-s.epsyy)*(s.epsxx-s.epsyy)+s.epsxy*s.epsxy));
+    FAIL=std::max(K_EM20,std::min(K_ONE,(m.epsr2-EPST)/(m.epsr2-m.epsr1)));
+  }
   /* elastic predictor (sigeps36c.F:272-284); back stress is zero (FISOKIN=0) */
   s.sigoxx=s.sigoxx-K_ZERO; s.sigoyy=s.sigoyy-K_ZERO; s.sigoxy=s.sigoxy-K_ZERO;
   s.signxx=s.sigoxx+A1*s.depsxx+A2*s.depsyy;
@@ -187,6 +194,7 @@ void sigeps36c(const Oracle& o, const orgpu_law36& m, int ipla, double asrate, c
   /* IFAIL = 1: failure on the maximum plastic strain (sigeps36c.F:928-938, no non-local): the element starts its
    * deletion; MULAWC completes it in the same cycle (mulawc.F90:2937-2941) */
   if(m.ifail==1){ if(off==K_ONE && pla>m.epsmax) off=K_FOUR_OVER_5; }
+  else if(m.ifail==2){ if(off==K_ONE && (pla>m.epsmax || EPST>m.epsf)) off=K_FOUR_OVER_5; }   /* :940-950 */
   yld_out=YLD;
 }
 
@@ -386,6 +394,7 @@ void orc_cmain3(const Oracle& o, OrcShellGroup& g, int i, bool flag_zcfac, Shell
     s.depsxy=in.exy+zt*in.kxy;
     s.depsyz=in.eyz; s.depszx=in.exz;
     s.epspxx=s.depsxx*dtinv; s.epspyy=s.depsyy*dtinv; s.epspxy=s.depsxy*dtinv;
+    { const double* GS_=g.STRA.data(); s.epsxx=GS_[i]+zt*GS_[5*nel+i]; s.epsyy=GS_[nel+i]+zt*GS_[6*nel+i]; s.epsxy=GS_[2*nel+i]+zt*GS_[7*nel+i]; }
     s.sigoxx=lb.sig[i]; s.sigoyy=lb.sig[nel+i]; s.sigoxy=lb.sig[2*nel+i]; s.sigoyz=lb.sig[3*nel+i]; s.sigozx=lb.sig[4*nel+i];
     if(g.law==36){
       sigeps36c(o,g.m36,g.prop.ipla,asrate,in,s,lb.pla[i],lb.epsd[i],&lb.vartmp[(size_t)g.nvartmp*i],off,thkn,ssp,viscmx,etse,sigy);

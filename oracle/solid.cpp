@@ -295,7 +295,8 @@ static void sigeps36(const Oracle& o,const orgpu_law36& m,int nel,int ipla,
                      const double* so1,const double* so2,const double* so3,const double* so4,const double* so5,const double* so6,
                      double* s1,double* s2,double* s3,double* s4,double* s5,double* s6,
                      double* soundsp,double* viscmax,double* off,const double* epsp,double* yld,double* pla,double* dpla1,
-                     const double* amu,int* vartmp /*(nel,nvartmp) column-major: VARTMP(I,k) -> vartmp[(k-1)*nel+i]*/)
+                     const double* amu,int* vartmp /*(nel,nvartmp) column-major: VARTMP(I,k) -> vartmp[(k-1)*nel+i]*/,
+                     const double* es /*total strains (6,nel) comp-major, IFAIL = 2*/)
 {
   const int nrate=m.nrate;
   const double G=m.shear, G2=m.g2, G3=m.g3, BULK=m.bulk, SSP=m.ssp3d, FISOKIN=m.fisokin;
@@ -309,7 +310,39 @@ static void sigeps36(const Oracle& o,const orgpu_law36& m,int nel,int ipla,
     s3[i]=so3[i]+P0[i]+G2*(de3[i]-DAV);
   }
   for(int i=0;i<nel;i++){ s4[i]=so4[i]+G*de4[i]; s5[i]=so5[i]+G*de5[i]; s6[i]=so6[i]+G*de6[i]; }   /* :283-285 */
-  for(int i=0;i<nel;i++){ viscmax[i]=K_ZERO; dpla1[i]=K_ZERO; }            /* :292-295 (FAIL=1, PFAC=1) */
+  for(int i=0;i<nel;i++){ viscmax[i]=K_ZERO; dpla1[i]=K_ZERO; }            /* :292-295 (PFAC=1) */
+  double FAIL[MVSIZ],EPSTT[MVSIZ];
+  for(int i=0;i<nel;i++){ FAIL[i]=K_ONE; EPSTT[i]=K_ZERO; }
+  if(m.ifail>1){                                                           /* :299-360 largest principal strain, 4 Newton steps */
+    const double EPSR1F=std::min(m.epsr1,m.epsf);
+    for(int i=0;i<nel;i++){
+      const double EXX=es[i],EYY=es[nel+i],EZZ=es[2*nel+i],EXY=es[3*nel+i],EYZ=es[4*nel+i],EZX=es[5*nel+i];
+      double DAV=(EXX+EYY+EZZ)*K_THIRD;
+      double E1=EXX-DAV,E2=EYY-DAV,E3=EZZ-DAV,E4=K_HALF*EXY,E5=K_HALF*EYZ,E6=K_HALF*EZX;
+      double E42=E4*E4,E52=E5*E5,E62=E6*E6;
+      double C=-K_HALF*(E1*E1+E2*E2+E3*E3)-E42-E52-E62;
+      double EPST=std::sqrt(-C*K_THIRD);
+      double EPSR1DAV=EPSR1F-DAV;
+      if(EPST+EPST<EPSR1DAV) continue;
+      double D=-E1*E2*E3+E1*E52+E2*E62+E3*E42-K_TWO*E4*E5*E6;
+      double EPST2=EPST*EPST;
+      double Y=(EPST2+C)*EPST+D;
+      if(std::fabs(Y)>K_EM8){
+        bool out=false;
+        EPST=K_ONEP75*EPST;
+        for(int it=0;it<4;it++){
+          EPST2=EPST*EPST; Y=(EPST2+C)*EPST+D;
+          double YP=K_THREE*EPST2+C;
+          EPST=EPST-Y/YP;
+          if(it<3 && EPST<EPSR1DAV){ out=true; break; }
+        }
+        if(out) continue;
+      }
+      EPST=EPST+DAV;
+      EPSTT[i]=EPST;
+      FAIL[i]=std::max(K_EM20,std::min(K_ONE,(m.epsr2-EPST)/(m.epsr2-m.epsr1)));
+    }
+  }
   auto VT=[&](int i,int k)->int&{ return vartmp[(size_t)(k-1)*nel+i]; };
   if(nrate==1){                                                            /* :398-414 */
     const int f=m.ifunc[0];
@@ -318,7 +351,7 @@ static void sigeps36(const Oracle& o,const orgpu_law36& m,int nel,int ipla,
       orc_vinter(o.TF,o.NPF[f],o.NPF[f+1]-o.NPF[f],ipos,pla[i],dydx,y1);
       VT(i,3)=ipos;
       double YFAC=m.yfac[0]*K_ONE;                  /* FACYLDI = 1 (no L_FAC_YLD) */
-      double FACT=K_ONE*K_ONE*YFAC;
+      double FACT=FAIL[i]*K_ONE*YFAC;
       H[i]=dydx*FACT;
       yld[i]=y1*FACT;                               /* FISOKIN == 0 */
     }
@@ -343,7 +376,7 @@ static void sigeps36(const Oracle& o,const orgpu_law36& m,int nel,int ipla,
       orc_vinter(o.TF,o.NPF[f2],o.NPF[f2+1]-o.NPF[f2],ipos2,pla[i],dydx2,y2);
       VT(i,J1+2)=ipos1; VT(i,J2+2)=ipos2;
       y1=y1*YFAC1; y2=y2*YFAC2;
-      double FAC=RFAC, CC=K_ONE*K_ONE;
+      double FAC=RFAC, CC=FAIL[i]*K_ONE;
       yld[i]=(y1+FAC*(y2-y1))*CC;
       dydx1=dydx1*YFAC1; dydx2=dydx2*YFAC2;
       H[i]=(dydx1+FAC*(dydx2-dydx1))*CC;
@@ -380,6 +413,9 @@ static void sigeps36(const Oracle& o,const orgpu_law36& m,int nel,int ipla,
   }
   if(m.ifail==1){                                                            /* :1546-1555 (IFAIL=1, no non-local) */
     for(int i=0;i<nel;i++) if(pla[i]>m.epsmax && off[i]==K_ONE) off[i]=K_FOUR_OVER_5;
+  }
+  else if(m.ifail==2){                                                       /* :1524-1533 */
+    for(int i=0;i<nel;i++) if((pla[i]>m.epsmax || EPSTT[i]>m.epsf) && off[i]==K_ONE) off[i]=K_FOUR_OVER_5;
   }
 }
 
@@ -437,7 +473,7 @@ static void mulaw36(const Oracle& o,OrcSolidGroup& g,int nel,const int* ngl,
   if(israte>0) asrate=std::min(K_ONE,m.asrate*DT1);
   mstrain_rate(nel,israte,asrate,epsd,1,ep1,ep2,ep3,ep4,ep5,ep6);
   sigeps36(o,m,nel,g.prop.ipla,de1,de2,de3,de4,de5,de6,so1,so2,so3,so4,so5,so6,s1,s2,s3,s4,s5,s6,
-           ssp,viscmax,off,epsd,sigy,defp,dpla,amu,g.vartmp.data());
+           ssp,viscmax,off,epsd,sigy,defp,dpla,amu,g.vartmp.data(),g.stra.data());
   /* plastic work (L_PLA>0, no L_SEQ) */
   for(int i=0;i<nel;i++){
     dpla[i]=defp[i]-defp0[i];

@@ -279,6 +279,39 @@ def test_law36_epsmax_failure_erodes_the_same_bricks():
     assert np.isfinite(g.download_fsky()).all()
 
 
+@pytest.mark.parametrize("scale", [1.0, 0.05])
+def test_law36_tensile_strain_failure_erodes_the_same_bricks(scale):
+    """LAW36 IFAIL = 2 on solids: largest principal total strain by the reference's 4 Newton steps (or, for strains so small
+    that the cubic's residual is under the absolute 1e-8, its starting bound), damage factor on the yield stress,
+    deletion beyond EPS_f (sigeps36.F:331-395, 1524-1533)"""
+    mat, npf, tf = meshgen.steel_law36(eps_t=(2.0e-3 * scale, 1.2e-2 * scale, 6.0e-3 * scale))
+    m = meshgen.hex_block(6, 6, 8, 12.0, 12.0, 16.0, law=36, mat=mat, v0=(0, 0, -40.0 * scale), fix_bottom_z=True, vrand=10.0 * scale,
+                          prop=meshgen.default_prop_solid(istrain=1))
+    m.npf, m.tf = npf, tf
+    g, o = pair(m)
+    g.run_cycles(5); o.run_cycles(5)
+    check_state36(g, o, tol=1e-10, fields=("sig", "eint", "rho", "pla", "epsd", "off", "stra"))
+    g.run_cycles(10); o.run_cycles(10)
+    dead = []
+    for c in range(5):
+        og, oo = g.solid_state("off"), o.solid_state("off")
+        assert np.array_equal(og, oo), c
+        dead.append(int((oo == 0).sum()))
+        ng, no = g.download_nodes(("X", "V")), o.download_nodes(("X", "V"))
+        assert rel_err(ng["X"], no["X"]) <= 1e-9 and rel_err(ng["V"], no["V"]) <= 1e-8, c
+        g.run_cycles(15); o.run_cycles(15)
+    assert 0 < dead[-1] < m.numels and dead[-1] >= dead[0]
+    assert np.isfinite(g.download_fsky()).all()
+
+
+def test_law36_tensile_strain_failure_needs_istrain_on_solids():
+    mat, npf, tf = meshgen.steel_law36(eps_t=(2.0e-3, 1.2e-2, 6.0e-3))
+    m = meshgen.hex_block(2, 2, 2, 4.0, 4.0, 4.0, law=36, mat=mat)
+    m.npf, m.tf = npf, tf
+    with pytest.raises(RuntimeError, match="Istrain"):
+        Engine(m)
+
+
 def test_law36_and_law2_groups_in_one_model():
     """Two brick super-groups with different laws in one model (material change breaks the fusion)."""
     m = meshgen.hex_block(6, 6, 8, 12.0, 12.0, 16.0, v0=(0, 0, -80.0), fix_bottom_z=True, vrand=10.0)

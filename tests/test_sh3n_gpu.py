@@ -159,6 +159,26 @@ def test_c3_nodal_time_step():
     assert rel_err(g.download_nodes(("D",))["D"], o.download_nodes(("D",))["D"]) <= DISP_TOL
 
 
+def test_c3_law36_tensile_strain_failure_deletes_the_same_triangles():
+    """LAW36 IFAIL = 2 through C3FORC3 -> CMAIN3 -> MULAWC -> SIGEPS36C (sigeps36c.F:256-264, 940-950)"""
+    mat, npf, tf = meshgen.steel_law36(eps_t=(1.5e-3, 8.0e-3, 4.0e-3))
+    m = meshgen.tri_plate(10, 9, 100.0, 90.0, mat=mat, pressure=60.0, vrand=8.0)
+    m.npf, m.tf = npf, tf
+    g, o = pair(m)
+    g.run_cycles(5); o.run_cycles(5)
+    check_state(g, o, m, tol=1e-10)
+    g.run_cycles(5); o.run_cycles(5)
+    dead = []
+    for c in range(4):
+        assert np.array_equal(g.sh3n_state("off"), o.sh3n_state("off")), c
+        dead.append(int((o.sh3n_state("off") == 0).sum()))
+        ng, no = g.download_nodes(("X", "V", "VR")), o.download_nodes(("X", "V", "VR"))
+        for k in ("X", "V", "VR"):
+            assert rel_err(ng[k], no[k]) <= 1e-9, (k, c)
+        g.run_cycles(10); o.run_cycles(10)
+    assert 0 < dead[-1] < m.numeltg and dead[-1] > dead[0]
+
+
 def test_c3_large_plate_properties():
     """500 k triangles: size-independent properties (self-equilibrated elements, finite state, reproducible checksum)"""
     import zlib

@@ -229,6 +229,41 @@ def test_law36_epsmax_failure_deletes_the_same_shells(ihbe):
     assert np.all(f[g.shell_state("off")[0] == 0][:, :, :6] == 0.0)   # deleted elements leave zero rows
 
 
+@pytest.mark.parametrize("ihbe", [24, 1])
+def test_law36_tensile_strain_failure_deletes_the_same_shells(ihbe):
+    """LAW36 IFAIL = 2 (EPS_t1, EPS_t2, EPS_f): the yield of every integration point is scaled by the damage factor on its
+    largest in-plane principal total strain, and the element is deleted once that strain passes EPS_f
+    (sigeps36c.F:256-264, 940-950; mulawc.F90:856-862): same state after 5 cycles, same elements dead in the same cycles"""
+    mat, npf, tf = meshgen.steel_law36(eps_t=(1.5e-3, 8.0e-3, 4.0e-3))
+    m = meshgen.shell_plate(10, 9, 100.0, 90.0, mat=mat, prop=meshgen.default_prop_shell(ihbe=ihbe, npt=5), pressure=60.0, vrand=8.0)
+    m.npf, m.tf = npf, tf
+    g, o = pair(m)
+    g.run_cycles(5); o.run_cycles(5)
+    check_state(g, o, tol=1e-10)
+    assert o.shell_state("pla").max() > 0.0
+    g.run_cycles(5); o.run_cycles(5)
+    dead = []
+    for c in range(5):
+        og, oo = g.shell_state("off"), o.shell_state("off")
+        assert np.array_equal(og, oo), c
+        dead.append(int((oo == 0).sum()))
+        ng, no = g.download_nodes(("X", "V", "VR")), o.download_nodes(("X", "V", "VR"))
+        for k in ("X", "V", "VR"):
+            assert rel_err(ng[k], no[k]) <= 1e-9, (k, c)
+        g.run_cycles(10); o.run_cycles(10)
+    assert 0 < dead[-1] < m.numelc and dead[-1] > dead[0]
+    assert np.isfinite(g.download_fsky()).all()
+
+
+def test_law36_tensile_strain_failure_needs_istrain():
+    mat, npf, tf = meshgen.steel_law36(eps_t=(1.5e-3, 8.0e-3, 4.0e-3))
+    prop = meshgen.default_prop_shell(); prop.istrain = 0
+    m = meshgen.shell_plate(3, 3, 30.0, 30.0, mat=mat, prop=prop)
+    m.npf, m.tf = npf, tf
+    with pytest.raises(RuntimeError, match="Istrain"):
+        Engine(m)
+
+
 def test_many_super_groups_one_model():
     """a model whose consecutive groups never fuse (alternating properties): 100 super-groups, one launch each; the
     table of super-groups lives in device memory (limit ORGPU_MAX_SG = 4096)"""
