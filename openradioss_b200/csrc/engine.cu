@@ -981,3 +981,5 @@ int orgpu_get_profile(orgpu_engine* e, int cls, double* ms, long long* launches)
 }
 
 } // extern "C"
+
+#include "shell_gpu_compat.cuh"   // the reference's own shell_gpu_* ABI on top of the entries above

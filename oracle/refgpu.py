@@ -27,11 +27,14 @@ def _p(a):
 class RefShellGPU:
     """One super-unit (all shell groups of the model: one BT property, one LAW2 material)."""
 
-    def __init__(self, m, compute_sti=2):
+    def __init__(self, m, compute_sti=2, lib=None, asrate=1.0):
+        """lib: another library exporting the same ABI (liborgpu.so exports it: include/shell_gpu_abi.h), default the
+        reference's own; asrate: what goes into the ASRATE slot (the reference's kernels use it as the filter coefficient,
+        its Fortran caller passes PM(9) = 2 pi Fcut, which is what liborgpu expects)"""
         assert m.numels == 0 and m.shell_groups and all(g.law == 2 for g in m.shell_groups)
-        L = self.lib = C.CDLL(LIB)
-        L.shell_gpu_global_create.restype = C.c_void_p
-        L.shell_gpu_data_create.restype = C.c_void_p
+        L = self.lib = C.CDLL(lib or LIB)
+        for f in ("shell_gpu_global_create", "shell_gpu_data_create"):
+            getattr(L, f).restype = C.c_void_p
         g0 = m.shell_groups[0]
         mat, prop = g0.mat, g0.prop
         self.n, self.ne, self.npt = m.numnod, m.numelc, prop.npt
@@ -41,7 +44,7 @@ class RefShellGPU:
         L.shell_gpu_set_global(self.g, self.gh)
         m_exp = mat.z3 if mat.iform == 0 else 1.0
         args = [mat.young, mat.nu, mat.shear, mat.a11, mat.a12, mat.ca, mat.cb, mat.cn, mat.cc, mat.epdr, mat.epmx, mat.sigmx, m_exp,
-                mat.fisokin, mat.rhocp, mat.tref, mat.tmelt, 1.0, mat.rho0, mat.ssp, prop.shf]   # ASRATE: the filter COEFFICIENT itself (1 = unfiltered)
+                mat.fisokin, mat.rhocp, mat.tref, mat.tmelt, asrate, mat.rho0, mat.ssp, prop.shf]   # ASRATE: for the reference's kernels the filter COEFFICIENT itself (1 = unfiltered)
         L.shell_gpu_set_mat_params(self.g, *[R(float(a)) for a in args], C.c_int(prop.ipla), C.c_int(mat.vp), C.c_int(mat.iform), C.c_int(mat.icc),
                                    R(float(mat.z3)), R(float(mat.z4)))
         L.shell_gpu_set_hg_params(self.g, *[R(float(a)) for a in (prop.h1, prop.h2, prop.h3, prop.srh1, prop.srh2, prop.srh3, 0.5, 0.5, 0.0)])     # HVISC, HELAS, HVLIN: radioss2.F:641-643
@@ -87,3 +90,22 @@ class RefShellGPU:
         self.lib.shell_gpu_min_dt(self.g, R(float(dtfac)), _p(out))
         self.lib.shell_gpu_synchronize(self.g)
         return float(out[0])
+
+    def energy(self):
+        out = np.zeros(2 * self.ne)
+        self.lib.shell_gpu_download_energy(self.g, _p(out))
+        return out.reshape(2, self.ne)
+
+    def state(self):
+        """shell_gpu_download_state: dict of OFF, THK, GSTR (8, ne), EPSD, SIG (npt, 5, ne), PLA (npt, ne), EPSD_ip, TEMP"""
+        ne, nip = self.ne, self.npt * self.ne
+        a = {k: np.zeros(n) for k, n in (("off", ne), ("thk", ne), ("gstr", 8 * ne), ("epsd", ne), ("sxx", nip), ("syy", nip), ("sxy", nip),
+                                         ("syz", nip), ("szx", nip), ("pla", nip), ("epsd_ip", nip), ("bxx", nip), ("byy", nip), ("bxy", nip), ("temp", nip))}
+        self.lib.shell_gpu_download_state(self.g, *[_p(v) for v in a.values()])
+        sig = np.stack([a[k].reshape(self.npt, ne) for k in ("sxx", "syy", "sxy", "syz", "szx")], 1)
+        return {"off": a["off"], "thk": a["thk"], "gstr": a["gstr"].reshape(8, ne), "epsd": a["epsd"], "sig": sig,
+                "pla": a["pla"].reshape(self.npt, ne), "epsd_ip": a["epsd_ip"].reshape(self.npt, ne), "temp": a["temp"].reshape(self.npt, ne)}
+
+    def close(self):
+        L = self.lib
+        L.shell_gpu_deallocate(self.g); L.shell_gpu_data_destroy(self.g); L.shell_gpu_global_destroy(self.gh)
