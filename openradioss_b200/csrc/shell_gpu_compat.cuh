@@ -47,7 +47,7 @@ static void sg_die(const char* what)
   fprintf(stderr, "liborgpu shell_gpu ABI: %s%s%s\n", what, orgpu_last_error()[0] ? ": " : "", orgpu_last_error());
   exit(EXIT_FAILURE);
 }
-#define SG_OK(call) do { if ((call) != 0) sg_die(#call); } while (0)
+#define SG_OK(call) do { if ((call) < 0) sg_die(#call); } while (0)   /* orgpu_add_*_group return the group index */
 #define SG_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { fprintf(stderr, "liborgpu shell_gpu ABI: %s: %s\n", #call, cudaGetErrorString(_e)); exit(EXIT_FAILURE); } } while (0)
 
 __global__ void sg_pack_soa_kernel(const double* __restrict__ A, const double* __restrict__ AR, const double* __restrict__ STIFN,

@@ -73,6 +73,16 @@ class RefShellGPU:
         L.shell_gpu_synchronize(self.g)
         return self.out.reshape(8, self.n).T.copy()
 
+    def step_raw(self, dt1, X, V, VR):
+        """the same calls without any numpy work around them (timing): result stays in self.out (SoA)"""
+        L = self.lib
+        L.shell_gpu_global_upload_nodes(self.gh, _p(X), _p(V), _p(VR))
+        L.shell_gpu_global_wait_upload(self.gh, self.g)
+        L.shell_gpu_run_kernels(self.g, R(float(dt1)))
+        L.shell_gpu_global_wait_su(self.gh, self.g)
+        L.shell_gpu_global_download_forces(self.gh, _p(self.out))
+        L.shell_gpu_global_synchronize(self.gh)
+
     def pin(self, X, V, VR):
         """shell_gpu_global_pin_host: page-lock the caller's nodal arrays and the force buffer (what FORINTC_PREPARE_GPU does)"""
         self._pinned = [np.ascontiguousarray(a, np.float64) for a in (X, V, VR)]
