@@ -108,7 +108,7 @@ static void sg_build(ShellGPUGlobal* gh)
     while (i < g->NUMELC) {                    // IPARG groups: <= 128 elements; ITHK = 0 keeps the initial thickness per group
       int j = i + 1;
       while (j < g->NUMELC && j - i < 128 && (g->ITHK > 0 || g->thk0[j] == g->thk0[i])) j++;
-      orgpu_prop_shell p = g->prop; p.thick = g->thk0[i];
+      orgpu_prop_shell p = g->prop; p.thick = g->ITHK > 0 ? g->thk0[0] : g->thk0[i];   // ITHK > 0: GBUF%THK is state (uploaded below), one property so the groups fuse
       SG_OK(orgpu_add_shell_group(gh->e, j - i, g->nft + i, 2, &g->mat, &p));
       i = j;
     }

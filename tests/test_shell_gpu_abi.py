@@ -109,6 +109,54 @@ def test_same_driver_two_libraries(ipla, npt, rate, shear):
 
 
 @gpu
+@pytest.mark.parametrize("ihbe,compute_sti", [(4, 2), (1, 1), (3, 0)])
+def test_thickness_state_ishell_and_sti_modes(ihbe, compute_sti):
+    """ITHK = 1 with a per-element initial thickness (shell_gpu_upload_constant h_THK0 -> GBUF%THK), Ishell 3 / 4,
+    compute_sti 1 (nodal stiffnesses of the NODADT /= 0 branch, shell_internal_forces.F90:637-648) and 0 (none)"""
+    m = plate(1, 3, True, True)
+    for sg in m.shell_groups:
+        sg.prop.ithk = 1; sg.prop.ihbe = ihbe
+        if ihbe == 3:
+            sg.prop.h1 = sg.prop.h2 = 0.1; sg.prop.srh1 = sg.prop.srh2 = float(np.sqrt(0.1))
+    m.control.nodadt = 1 if compute_sti == 1 else 0
+    thk = 1.2 + 0.3 * np.random.default_rng(3).uniform(size=m.numelc)
+    g = Engine(m)
+    g.upload_shell_state("thk", thk[None, :])
+    mat, prop = m.shell_groups[0].mat, m.shell_groups[0].prop
+
+    d = drop_in(m, compute_sti=compute_sti)
+    # the driver uploaded a uniform thickness: give the handle the per-element one before the first cycle
+    import ctypes as C
+    ne = m.numelc
+    conn = [np.ascontiguousarray(m.ixc[:, 1 + k] - 1, np.int32) for k in range(4)]
+    ones = lambda v: np.full(ne, float(v))
+    arrs = [thk.copy(), ones(1.0), ones(mat.ssp), ones(mat.rho0), ones(mat.young), ones(mat.nu), ones(mat.a11), ones(mat.shear), ones(prop.shf)]
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    d.lib.shell_gpu_upload_constant(d.g, *[p(c) for c in conn], *[p(a) for a in arrs])
+    dt1 = 0.0
+    for c in range(6):
+        nd = g.download_nodes(("X", "V", "VR"))
+        f = d.step(dt1, nd["X"], nd["V"], nd["VR"])
+        g.forces_phase(dt1); g.assemble()
+        a = g.download_nodes(("A", "AR", "STIFN", "STIFR"))
+        assert np.array_equal(f[:, :3], a["A"]) and np.array_equal(f[:, 3:6], a["AR"]), c
+        if compute_sti == 0:
+            assert np.all(f[:, 6:] == 0.0)
+        else:
+            assert np.array_equal(f[:, 6], a["STIFN"]) and np.array_equal(f[:, 7], a["STIFR"]) and a["STIFN"].max() > 0.0, c
+        dt2 = g.time()["dt2t"]
+        if compute_sti == 2:
+            assert d.min_dt(m.control.dtfac_shell) == pytest.approx(dt2, rel=1e-15)
+        else:
+            assert d.min_dt(m.control.dtfac_shell) == 1e30
+        dt2 = min(dt2, 2.0e-4)
+        g.advance(0.5 * (dt1 + dt2), dt2); dt1 = dt2
+    assert np.abs(a["A"]).max() > 0.0 and not np.array_equal(d.state()["thk"], thk)      # ITHK = 1: the thickness evolves
+    assert np.array_equal(d.state()["thk"], g.shell_state("thk")[0])
+    d.close()
+
+
+@gpu
 def test_two_super_units_on_one_global_handle():
     """two ShellGPUData (different thickness) attached to one ShellGPUGlobal, launched one after the other as
     gpu_shell_launch_async does: the sum of both lands in the one force buffer, equal to the single-engine model"""
