@@ -53,6 +53,11 @@ int  orgpu_set_itab(orgpu_engine* e, const int* itab);
  * record k = IBFV(1,k) node (1-based), IBFV(2,k) direction 1..3 in the global frame, IBFV(3,k) curve (0-based),
  * VEL(1,k) FAC, VEL(2,k) start time, VEL(3,k) stop time, VEL(5,k) FACX.  Before orgpu_finalize. */
 int  orgpu_set_fixvel(orgpu_engine* e, int nfxvel, const int* ibfv /*(3,n)*/, const double* vel /*(4,n)*/);
+/* gravity loads (GRAVIT, engine/source/loads/general/grav/gravit.F:84-160; resol.F:7123, after ACCELE and before BCS10):
+ * A(N2,node) += FCY * FINTER(IFUNC, TT*FCX).  Load l = IGRV(1,l) node count, IGRV(2,l) direction 1..3 (global frame: ISK <= 1),
+ * IGRV(3,l) curve (0-based, -1 = constant); AGRV(1,l) FCY, AGRV(2,l) FCX; ib = the node lists IB one after the other
+ * (1-based, sign ignored: it only selects the nodes counted in the external work).  No sensor.  Before orgpu_finalize. */
+int  orgpu_set_gravity(orgpu_engine* e, int ngrav, const int* igrv /*(3,n)*/, const double* agrv /*(2,n)*/, const int* ib, int lib);
 int  orgpu_set_solids(orgpu_engine* e, int numels, const int* ixs, const int* iads);
 int  orgpu_set_shells(orgpu_engine* e, int numelc, const int* ixc, const int* iadc);
 /* 3-node shells (ITY=7, C3FORC3: engine/source/elements/sh3n/coque3n/c3forc3.F:35, called forintc.F:628): IXTG(6,NUMELTG)

@@ -74,6 +74,8 @@ class Binding:
             self._call("set_load_function", self.h, C.c_int(int(m.load_func[0])), C.c_double(float(m.load_func[1])))
         if m.ibfv is not None and len(m.ibfv):
             self._call("set_fixvel", self.h, C.c_int(len(m.ibfv)), _opt(m.ibfv, np.int32), _opt(m.vel, np.float64))
+        if m.igrv is not None and len(m.igrv):
+            self._call("set_gravity", self.h, C.c_int(len(m.igrv)), _opt(m.igrv, np.int32), _opt(m.agrv, np.float64), _opt(m.ibgrv, np.int32), C.c_int(len(m.ibgrv)))
         for g in m.shell_groups:
             r = self._call_group("add_shell_group", self.h, C.c_int(g.nel), C.c_int(g.nft), C.c_int(g.law),
                                  C.byref(g.mat), C.byref(g.prop))

@@ -53,6 +53,8 @@ struct orgpu_engine {
   std::vector<HostShellGroup> tgroups;
   std::vector<int> npf; std::vector<double> tf;
   int lf_func = -1; double lf_fcx = 1.0;            // time function of the nodal loads
+  int ngrav = 0; int gdir[ORGPU_MAXGRAV] = {}, gfunc[ORGPU_MAXGRAV] = {}; double gfcy[ORGPU_MAXGRAV] = {}, gfcx[ORGPU_MAXGRAV] = {};   // /GRAV loads
+  std::vector<unsigned char> gmask; unsigned char* d_gmask = nullptr;
   std::vector<int> fv_idx; std::vector<FixVelNode> fv;   // imposed velocities, per node
   double* d_btf = nullptr; int* d_bnpf = nullptr;   // LAW36 function table of the brick super-groups
   double* d_ftf = nullptr; int* d_fnpf = nullptr; int* d_fv_idx = nullptr; FixVelNode* d_fv = nullptr;
@@ -147,7 +149,7 @@ int orgpu_destroy(orgpu_engine* e)
   for (auto& s : e->csg) for (void* p : s.owned) cudaFree(p);
   void* ptrs[] = {e->nd.pos, e->nd.vel, e->nd.rot, e->nd.D, e->nd.A, e->nd.AR, e->nd.STIFN, e->nd.STIFR, e->nd.MS, e->nd.IN,
                   e->d_stage3a, e->d_stage3b, e->d_fext, e->d_mext, e->d_icodt, e->d_icodr, e->d_adsky, e->d_fsky, e->d_cs,
-                  e->db.dt, e->db.order, e->d_sgr, e->d_btf, e->d_bnpf, e->d_ftf, e->d_fnpf, e->d_fv_idx, e->d_fv, e->d_itab, e->d_nd_dt, e->d_nd_node};
+                  e->db.dt, e->db.order, e->d_sgr, e->d_btf, e->d_bnpf, e->d_ftf, e->d_fnpf, e->d_fv_idx, e->d_fv, e->d_itab, e->d_nd_dt, e->d_nd_node, e->d_gmask};
   for (void* p : ptrs) if (p) cudaFree(p);
   { Exchange& x = e->xc;
     void* xp[] = {x.d_send_slots, x.d_recv_slots, x.d_sendbuf, x.d_recvbuf, x.d_cand_send, x.d_cand_recv, x.d_slots_tmp, x.d_rows_tmp};
@@ -248,6 +250,28 @@ int orgpu_set_load_function(orgpu_engine* e, int ifunc, double fcx)
   NEED(e && !e->finalized, -1, "orgpu_set_load_function: bad handle / already finalized");
   NEED(ifunc >= -1, -1, "orgpu_set_load_function: bad function index %d", ifunc);
   e->lf_func = ifunc; e->lf_fcx = fcx;
+  return 0;
+}
+
+int orgpu_set_gravity(orgpu_engine* e, int ngrav, const int* igrv /*(3,n): NN, direction 1..3, function*/, const double* agrv /*(2,n): FCY, FCX*/,
+                      const int* ib, int lib)
+{
+  NEED(e && !e->finalized && ngrav >= 0 && (ngrav == 0 || (igrv && agrv && ib)), -1, "orgpu_set_gravity: bad arguments / already finalized");
+  NEED(ngrav <= ORGPU_MAXGRAV, -5, "%d gravity loads: more than the %d carried", ngrav, ORGPU_MAXGRAV);
+  e->ngrav = ngrav; e->gmask.assign(ngrav ? e->numnod : 0, 0);
+  int iad = 0;
+  for (int l = 0; l < ngrav; l++) {
+    const int nn = igrv[3 * l], dir = igrv[3 * l + 1], f = igrv[3 * l + 2];
+    NEED(dir >= 1 && dir <= 3, -5, "gravity load %d: direction %d (a skew / moving frame, IGRV(2) >= 10) is outside the built path", l, dir);
+    NEED(nn >= 0 && iad + nn <= lib && f >= -1, -4, "gravity load %d: bad node count / function", l);
+    e->gdir[l] = dir - 1; e->gfunc[l] = f; e->gfcy[l] = agrv[2 * l]; e->gfcx[l] = agrv[2 * l + 1];
+    for (int j = 0; j < nn; j++) {
+      const int node = abs(ib[iad + j]);              // the sign of IB only selects the nodes counted in the external work
+      NEED(node >= 1 && node <= e->numnod, -4, "gravity load %d: node %d out of range", l, node);
+      e->gmask[node - 1] |= (unsigned char)(1u << l);
+    }
+    iad += nn;
+  }
   return 0;
 }
 
@@ -411,13 +435,22 @@ int orgpu_finalize(orgpu_engine* e)
     if (!e->itab.empty()) { if (dev_alloc(&e->d_itab, e->itab.size())) return -100;
       CUDA_OK(cudaMemcpy(e->d_itab, e->itab.data(), 4 * e->itab.size(), cudaMemcpyHostToDevice)); e->nd.itab = e->d_itab; }
   }
+  // /GRAV loads: per-node mask, per-load scalars for the finalize kernel
+  e->fa.ngrav = e->ngrav; e->nd.gmask = nullptr;
+  for (int l = 0; l < ORGPU_MAXGRAV; l++) { e->fa.gfunc[l] = e->gfunc[l]; e->fa.gfcy[l] = e->gfcy[l]; e->fa.gfcx[l] = e->gfcx[l]; e->nd.gdir[l] = e->gdir[l]; }
+  if (e->ngrav > 0) {
+    if (dev_alloc(&e->d_gmask, e->gmask.size())) return -100;
+    CUDA_OK(cudaMemcpy(e->d_gmask, e->gmask.data(), e->gmask.size(), cudaMemcpyHostToDevice)); e->nd.gmask = e->d_gmask;
+  }
   // time functions used at node level (loads, imposed velocities)
   e->fa.lf_func = -1; e->fa.lf_fcx = 1.0; e->fa.ft = FuncTable{nullptr, nullptr};
-  if (e->lf_func >= 0 || !e->fv.empty()) {
+  bool gfun = false; for (int l = 0; l < e->ngrav; l++) gfun = gfun || e->gfunc[l] >= 0;
+  if (e->lf_func >= 0 || !e->fv.empty() || gfun) {
     NEED(!e->npf.empty(), -4, "a load / imposed-velocity time function needs orgpu_set_functions");
     const int nf = (int)e->npf.size() - 1;
     auto check = [&](int f, int maxpts) { return f >= 0 && f < nf && e->npf[f + 1] - e->npf[f] >= 1 && e->npf[f + 1] - e->npf[f] <= maxpts; };
     if (e->lf_func >= 0) NEED(check(e->lf_func, 20), -5, "load function %d missing or longer than 20 points (FINTER dichotomy branch is outside the built path)", e->lf_func);
+    for (int l = 0; l < e->ngrav; l++) if (e->gfunc[l] >= 0) NEED(check(e->gfunc[l], 20), -5, "gravity function %d missing or longer than 20 points (FINTER dichotomy branch is outside the built path)", e->gfunc[l]);
     for (auto& r : e->fv) for (int j = 0; j < 3; j++) if (r.func[j] >= 0) NEED(check(r.func[j], 1 << 30) && e->npf[r.func[j] + 1] - e->npf[r.func[j]] >= 2, -4, "imposed-velocity function %d missing or shorter than 2 points", r.func[j]);
     if (dev_alloc(&e->d_ftf, e->tf.size()) || dev_alloc(&e->d_fnpf, e->npf.size())) return -100;
     CUDA_OK(cudaMemcpy(e->d_ftf, e->tf.data(), 8 * e->tf.size(), cudaMemcpyHostToDevice));

@@ -79,7 +79,7 @@ __device__ __forceinline__ NodeIn node_load(const DevNodes& nd, int n, int irodd
   return q;
 }
 
-__device__ __forceinline__ void node_update(const DevNodes& nd, int n, const NodeIn& q, NodeAcc& r, double dt12, double dt2, double tt0, int iroddl)
+__device__ __forceinline__ void node_update(const DevNodes& nd, int n, const NodeIn& q, NodeAcc& r, double dt12, double dt2, double tt0, int iroddl, const double* gv)
 {
   // ACCELE
   const double ms = q.ms;
@@ -89,6 +89,16 @@ __device__ __forceinline__ void node_update(const DevNodes& nd, int n, const Nod
     const double in = q.in;
     if (in > K_ZERO) { const double rt = or_div(K_ONE, in); r.ar[0] = r.ar[0] * rt; r.ar[1] = r.ar[1] * rt; r.ar[2] = r.ar[2] * rt; }
     else { r.ar[0] = K_ZERO; r.ar[1] = K_ZERO; r.ar[2] = K_ZERO; }
+  }
+  // GRAVIT (loads/general/grav/gravit.F:84-160, global frame, no sensor; resol.F:7123, between ACCELE and BCS10):
+  // A(N2,N1) += FCY * FINTER(IFUNC, TT*FCX) for the nodes of each load, loads in their order
+  if (nd.gmask) {
+    unsigned m = nd.gmask[n];
+    while (m) {
+      const int l = __ffs(m) - 1; m &= m - 1;
+      const int d = nd.gdir[l]; const double g = gv[l];
+      if (d == 0) r.a[0] = r.a[0] + g; else if (d == 1) r.a[1] = r.a[1] + g; else r.a[2] = r.a[2] + g;
+    }
   }
   // BCS
   if (nd.icodt) {
@@ -214,7 +224,7 @@ node_advance_kernel(const __grid_constant__ DevNodes nd, const CycleState* __res
   r.a[0] = nd.A[3 * n]; r.a[1] = nd.A[3 * n + 1]; r.a[2] = nd.A[3 * n + 2];
   r.ar[0] = nd.AR[3 * n]; r.ar[1] = nd.AR[3 * n + 1]; r.ar[2] = nd.AR[3 * n + 2];
   const NodeIn q = node_load(nd, n, iroddl);
-  node_update(nd, n, q, r, cs->dt12, cs->dt2, cs->tt0, iroddl);
+  node_update(nd, n, q, r, cs->dt12, cs->dt2, cs->tt0, iroddl, cs->gv);
   nd.A[3 * n] = K_ZERO; nd.A[3 * n + 1] = K_ZERO; nd.A[3 * n + 2] = K_ZERO;        // velocity.F:62-64
   nd.AR[3 * n] = K_ZERO; nd.AR[3 * n + 1] = K_ZERO; nd.AR[3 * n + 2] = K_ZERO;
 }
@@ -229,7 +239,7 @@ node_fused_kernel(const __grid_constant__ DevNodes nd, const double* __restrict_
   if (n >= nd.n) return;
   const NodeIn q = node_load(nd, n, iroddl);
   NodeAcc r = node_gather<ROWW>(nd, fsky, n, iroddl, cs->fscale);
-  node_update(nd, n, q, r, cs->dt12, cs->dt2, cs->tt0, iroddl);
+  node_update(nd, n, q, r, cs->dt12, cs->dt2, cs->tt0, iroddl, cs->gv);
 }
 
 __global__ void set_dt_kernel(CycleState* cs, double dt1, double dt12, double dt2, int which)

@@ -129,6 +129,13 @@ def decompose(m: Model, dom_s: Optional[np.ndarray], dom_c: Optional[np.ndarray]
     lm = Model(X=sub(m.X), V=sub(m.V), VR=sub(m.VR), MS=sub(m.MS), IN=sub(m.IN), control=m.control, ixs=ixs, ixc=ixc, ixtg=ixtg,
                vol0=m.vol0[solid_gid] if len(m.vol0) else m.vol0, icodt=sub(m.icodt), icodr=sub(m.icodr),
                fext=sub(m.fext), mext=sub(m.mext), itab=sub(m.itab), npf=m.npf, tf=m.tf, load_func=m.load_func)
+    if m.igrv is not None and len(m.igrv):                       # gravity: every domain keeps the loads, with its own nodes of each list
+        lm.igrv = m.igrv.copy(); lm.agrv = m.agrv.copy(); parts = []; iad = 0
+        for l in range(len(m.igrv)):
+            ib = np.abs(m.ibgrv[iad:iad + m.igrv[l, 0]]); iad += m.igrv[l, 0]
+            loc = (g2l[ib[mine[ib - 1]] - 1] + 1).astype(np.int32)
+            lm.igrv[l, 0] = len(loc); parts.append(loc)
+        lm.ibgrv = np.concatenate(parts) if parts else np.zeros(0, np.int32)
     if m.ibfv is not None and len(m.ibfv):
         keep = mine[m.ibfv[:, 0] - 1]
         lm.ibfv = m.ibfv[keep].copy(); lm.vel = m.vel[keep].copy()

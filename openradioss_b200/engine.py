@@ -17,7 +17,7 @@ EXPORTS = """create destroy last_error upload_nodes set_loads set_bcs set_solids
 set_functions add_solid_group add_solid_group_law add_shell_group set_sh3n add_sh3n_group download_sh3n_state upload_sh3n_state finalize forces_phase assemble advance run_cycles
 synchronize get_time download_nodes download_fsky download_solid_state download_shell_state
 step_host launch_count last_run_ms set_profile get_profile pack_rows unpack_rows comm_unique_id comm_init
-set_exchange exchange get_energies p2p_export p2p_connect set_load_function set_fixvel upload_solid_state upload_shell_state set_time set_itab""".split()
+set_exchange exchange get_energies p2p_export p2p_connect set_load_function set_fixvel set_gravity upload_solid_state upload_shell_state set_time set_itab""".split()
 
 
 def load_library() -> C.CDLL:

@@ -393,6 +393,18 @@ def add_function(m: Model, x, y) -> int:
     return len(m.npf) - 2
 
 
+def add_gravity(m: Model, direction: int, fcy: float, nodes=None, curve=None, fcx: float = 1.0) -> None:
+    """One /GRAV load (gravit.F): acceleration fcy * f(TT * fcx) along `direction` (1..3) on `nodes` (0-based; all when None);
+    curve = (x, y) time function or None for a constant."""
+    nodes = np.arange(m.numnod) if nodes is None else np.asarray(nodes)
+    f = -1 if curve is None else add_function(m, *curve)
+    row = np.array([[len(nodes), direction, f]], np.int32); a = np.array([[fcy, fcx]], float)
+    m.igrv = row if m.igrv is None else np.concatenate([m.igrv, row])
+    m.agrv = a if m.agrv is None else np.concatenate([m.agrv, a])
+    ib = (nodes + 1).astype(np.int32)
+    m.ibgrv = ib if m.ibgrv is None else np.concatenate([m.ibgrv, ib])
+
+
 def plate_c2(scale: int = 1) -> Model:
     """C2: 1000 x 1000 QEPH shells, LAW36, NPT=5, clamped, pressure pulse (1 MPa step)."""
     n = max(4, 1000 // scale)

@@ -104,6 +104,9 @@ class Model:
     load_func: Optional[tuple] = None   # (curve index, FCX): time function shared by the nodal loads fext / mext
     ibfv: Optional[np.ndarray] = None   # imposed velocities (n,3) int32: node (1-based), direction 1..3, curve index
     vel: Optional[np.ndarray] = None    # (n,4): FAC, STARTT, STOPT, FACX
+    igrv: Optional[np.ndarray] = None   # gravity loads (n,3) int32: node count, direction 1..3, curve index (-1: constant)   (gravit.F)
+    agrv: Optional[np.ndarray] = None   # (n,2): FCY, FCX
+    ibgrv: Optional[np.ndarray] = None  # node lists of the loads, one after the other (1-based)
 
     @property
     def numnod(self): return int(self.X.shape[0])

@@ -59,6 +59,9 @@ void orc_set_load_function(void* h,int ifunc,double fcx){ Oracle* o=(Oracle*)h; 
 void orc_set_fixvel(void* h,int nfxvel,const int* ibfv /*(3,n)*/,const double* vel /*(4,n)*/){
   Oracle* o=(Oracle*)h; o->IBFV.assign(ibfv,ibfv+(size_t)3*nfxvel); o->VEL.assign(vel,vel+(size_t)4*nfxvel);
 }
+void orc_set_gravity(void* h,int ngrav,const int* igrv /*(3,n)*/,const double* agrv /*(2,n)*/,const int* ib,int lib){
+  Oracle* o=(Oracle*)h; o->IGRV.assign(igrv,igrv+(size_t)3*ngrav); o->AGRV.assign(agrv,agrv+(size_t)2*ngrav); o->IBGRV.assign(ib,ib+lib);
+}
 /* connectivity + /PARITH/ON tables (all 1-based, Fortran layout) */
 void orc_set_solids(void* h,int numels,const int* ixs /*(11,numels)*/,const int* iads /*(8,numels)*/){
   Oracle* o=(Oracle*)h; o->numels=numels;
@@ -151,7 +154,7 @@ void orc_assemble(void* h){ Oracle* o=(Oracle*)h; orc_asspar4(*o); if(o->ctl.nod
 void orc_set_itab(void* h,const int* itab){ Oracle* o=(Oracle*)h; o->ITAB.assign(itab,itab+o->numnod); }
 void orc_advance(void* h,double dt12,double dt2){
   Oracle* o=(Oracle*)h; o->DT12=dt12; o->DT2=dt2;
-  orc_accele(*o); orc_bcs(*o); orc_fixvel(*o); orc_velocity(*o); orc_depla(*o); o->TT+=dt2; o->NCYCLE++;
+  orc_accele(*o); orc_gravit(*o); orc_bcs(*o); orc_fixvel(*o); orc_velocity(*o); orc_depla(*o); o->TT+=dt2; o->NCYCLE++;
 }
 void orc_run_cycles(void* h,int ncycles){ Oracle* o=(Oracle*)h; for(int c=0;c<ncycles;c++) orc_cycle(*o); }
 

@@ -50,6 +50,25 @@ void orc_accele(Oracle& o)
   }
 }
 
+static double orc_finter(const Oracle& o,int f,double XX);
+/* GRAVIT  engine/source/loads/general/grav/gravit.F:84-160 (ISK<=1 global frame, N2D=0, no sensor: TS=TT, ISMOOTH=0):
+ * A0/GAMA :103-119, A(N2,N1)=A(N2,N1)+AA :149-153.  Called after ACCELE and before BCS10 (resol.F:6921, 7123, 7322), so AA is an
+ * acceleration.  The external work WFEXT (:152) is energy bookkeeping outside the path. */
+void orc_gravit(Oracle& o)
+{
+  const int ngrav=(int)(o.IGRV.size()/3);
+  int IAD=0;
+  for(int NL=0;NL<ngrav;NL++){
+    const double FCY=o.AGRV[2*NL], FCX=o.AGRV[2*NL+1];
+    const int NN=o.IGRV[3*NL], N2=o.IGRV[3*NL+1], IFUNC=o.IGRV[3*NL+2];
+    const double TS=o.TT;
+    const double GAMA = IFUNC>=0 ? FCY*orc_finter(o,IFUNC,TS*FCX) : FCY;
+    const double AA=GAMA;
+    for(int J=IAD;J<IAD+NN;J++){ const int N1=std::abs(o.IBGRV[J]); o.A[3*(N1-1)+(N2-1)]=o.A[3*(N1-1)+(N2-1)]+AA; }
+    IAD+=NN;
+  }
+}
+
 /* BCS10 (global-frame codes only): zero the acceleration of fixed dofs.
  * code bits as in ICODT/ICODR: 4 -> x, 2 -> y, 1 -> z   (bcs10.F, skew 0 branch) */
 void orc_bcs(Oracle& o)
@@ -216,6 +235,7 @@ void orc_cycle(Oracle& o)
   o.DT2OLD=o.DT2;                 /* resol.F:6494 */
   o.DT12=K_HALF*(o.DT1+o.DT2);    /* resol.F:6496 */
   orc_accele(o);
+  orc_gravit(o);                  /* resol.F:7123 */
   orc_bcs(o);
   orc_fixvel(o);
   orc_velocity(o);

@@ -57,6 +57,8 @@ struct Oracle {
   int LF_FUNC=-1; double LF_FCX=1.0;  /* time function of the concentrated loads (force.F90:195-196, 235) */
   std::vector<int> IBFV;              /* imposed velocities (3,n): node, direction, curve (fixvel.F) */
   std::vector<double> VEL;            /* (4,n): FAC, STARTT, STOPT, FACX */
+  std::vector<int> IGRV, IBGRV;       /* gravity loads (3,n): node count, direction, curve; node lists (gravit.F) */
+  std::vector<double> AGRV;           /* (2,n): FCY, FCX */
   /* connectivity */
   std::vector<int> IXS;   /* (11,NUMELS) 1-based nodes in 2..9, user id in 11 */
   std::vector<int> IXC;   /* (7,NUMELC)  1-based nodes in 2..5, user id in 7  */
@@ -91,6 +93,7 @@ void orc_c3forc3(Oracle& o, OrcShellGroup& g, double& dt2t, int& neltst, int& it
 /* assembly.cpp */
 void orc_asspar4(Oracle& o);
 void orc_accele(Oracle& o);
+void orc_gravit(Oracle& o);
 void orc_bcs(Oracle& o);
 void orc_fixvel(Oracle& o);
 void orc_dtnoda(Oracle& o);

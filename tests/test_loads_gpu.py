@@ -62,6 +62,33 @@ def test_plate_pressure_pulse_matches_oracle():
     assert rel_err(g.download_nodes(("D",))["D"], o.download_nodes(("D",))["D"]) <= 1e-8
 
 
+def test_gravity_loads_match_oracle():
+    """GRAVIT on the device (node kernel, between ACCELE and BCS): constant g on all nodes + a ramped lateral load on a
+    node subset, on a plate under pressure and on a block; phased 1e-12, then 300 cycles of the device loop"""
+    m = meshgen.shell_plate(10, 9, 100.0, 90.0, pulse_tau=5.0e-3, vrand=2.0)
+    meshgen.add_gravity(m, 3, -9.81e-3)
+    meshgen.add_gravity(m, 1, 5.0e-2, nodes=np.nonzero(m.X[:, 0] > 50.0)[0], curve=([0.0, 1.0e-3, 1.0], [0.0, 1.0, 1.0]), fcx=1.5)
+    phased(m, 6)
+    g, o = Engine(m), Oracle(m, threads=0)
+    g.run_cycles(300); g.synchronize(); o.run_cycles(300)
+    assert rel_err(g.download_nodes(("D",))["D"], o.download_nodes(("D",))["D"]) <= 1e-8
+    # free fall of an unloaded block: the same bits as the oracle (no libm on the path)
+    m = meshgen.hex_block(3, 3, 3, 6.0, 6.0, 6.0)
+    meshgen.add_gravity(m, 3, -9.81e-3)
+    g, o = Engine(m), Oracle(m, threads=0)
+    g.run_cycles(40); g.synchronize(); o.run_cycles(40)
+    vg, vo = g.download_nodes(("V",))["V"], o.download_nodes(("V",))["V"]
+    assert np.array_equal(vg[:, 2], vo[:, 2]) and vo[:, 2].max() < 0.0
+
+
+def test_gravity_rejects_what_is_not_built():
+    m = meshgen.hex_block(2, 2, 2, 2.0, 2.0, 2.0)
+    meshgen.add_gravity(m, 3, -1.0)
+    m.igrv[0, 1] = 13                                   # IGRV(2) = 10*ISK + N2: a skew frame
+    with pytest.raises(RuntimeError, match="skew"):
+        Engine(m)
+
+
 @pytest.mark.parametrize("nproc", [2, 3])
 def test_tube_domains_bitwise(nproc):
     """z-slab decomposition of the mixed tube (host-staged exchange): same bits as one domain, with the

@@ -56,3 +56,62 @@ def test_add_function_appends_a_curve():
     n0 = len(m.npf) - 1
     k = meshgen.add_function(m, [0.0, 1.0, 2.0], [0.0, 5.0, 5.0])
     assert k == n0 and m.npf[-1] - m.npf[-2] == 3 and list(m.tf[-6:]) == [0.0, 0.0, 1.0, 5.0, 2.0, 5.0]
+
+
+def test_gravity_is_a_free_fall_for_an_unloaded_block():
+    """GRAVIT (gravit.F:84-160): every node gets A(3) += FCY after ACCELE, so a block without other loads falls rigidly:
+    V = sum of DT12 * g, no strain, no internal force; a second load with a time function adds FCY2 * f(TT * FCX)."""
+    import pytest
+    m = meshgen.hex_block(3, 3, 3, 6.0, 6.0, 6.0)
+    meshgen.add_gravity(m, 3, -9.81e-3)
+    meshgen.add_gravity(m, 1, 2.0e-3, curve=([0.0, 1.0e-3, 1.0], [0.0, 1.0, 1.0]), fcx=2.0)
+    o = Oracle(m)
+    vz = vx = 0.0
+    for c in range(30):
+        t0 = o.time()["tt"]
+        o.run_cycles(1)
+        t = o.time()
+        vz += t["dt12"] * -9.81e-3
+        vx += t["dt12"] * 2.0e-3 * min(t0 * 2.0 / 1.0e-3, 1.0)
+        v = o.download_nodes(("V",))["V"]
+        tol = 1e-13 if c == 0 else 1e-5        # later cycles: K * (rounding of rho / rho0 - 1) is a real, 1e-11 N force on these tiny velocities
+        assert np.allclose(v[:, 2], vz, rtol=tol, atol=0.0) and np.allclose(v[:, 0], vx, rtol=tol, atol=1e-300), c
+        assert np.abs(v[:, 1]).max() <= 1e-5 * abs(vz)          # unloaded direction: the same rounding-level forces only
+    assert o.time()["tt"] * 2.0 > 1.0e-3                               # the flat part of the curve was reached
+    assert np.abs(o.solid_state("sig")).max() < 1e-8                   # rigid motion: no stress beyond rounding
+    assert vx > 0.0
+
+
+def test_gravity_acts_before_the_boundary_conditions_and_only_on_its_nodes():
+    """resol.F order ACCELE (:6921) -> GRAVIT (:7123) -> BCS10 (:7322): fixed dofs stay fixed; nodes outside IB feel it only
+    through the elements"""
+    m = meshgen.hex_block(2, 2, 4, 4.0, 4.0, 8.0, fix_bottom_z=True)
+    top = np.nonzero(m.X[:, 2] > 7.0)[0]
+    meshgen.add_gravity(m, 3, -5.0, nodes=top)
+    o = Oracle(m)
+    o.run_cycles(1)
+    v = o.download_nodes(("V",))["V"]
+    dt12 = o.time()["dt12"]
+    rest = np.setdiff1d(np.arange(m.numnod), top)
+    assert np.allclose(v[top, 2], -5.0 * dt12, rtol=1e-13) and np.abs(v[rest]).max() == 0.0
+    o.run_cycles(60)
+    v = o.download_nodes(("V",))["V"]
+    assert np.abs(v[m.icodt == 1, 2]).max() == 0.0 and np.abs(v[rest, 2]).max() > 0.0
+
+
+def test_gravity_follows_its_nodes_into_the_domains():
+    from openradioss_b200 import domdec, spmd
+    m = meshgen.hex_block(4, 3, 6, 8.0, 6.0, 12.0, fix_bottom_z=True, vrand=1.0)
+    meshgen.add_gravity(m, 3, -9.81e-3)
+    meshgen.add_gravity(m, 2, 4.0e-3, nodes=np.nonzero(m.X[:, 2] > 7.0)[0], curve=([0.0, 1.0e-4, 1.0], [0.0, 1.0, 1.0]))
+    ref = Oracle(m)
+    ref.run_cycles(25)
+    doms = [domdec.decompose_strips(m, 3, r, axis=2) for r in range(3)]
+    assert sum(int(d.model.igrv[1, 0]) for d in doms) >= int(m.igrv[1, 0]) and all(len(d.model.igrv) == 2 for d in doms)
+    backs = [Oracle(d.model) for d in doms]
+    spmd.run_local(backs, doms, 25)
+    xr = ref.download_nodes(("X", "V"))
+    for b, d in zip(backs, doms):
+        x = b.download_nodes(("X", "V"))
+        assert np.array_equal(x["X"], xr["X"][d.node_gid]) and np.array_equal(x["V"], xr["V"][d.node_gid])
+
