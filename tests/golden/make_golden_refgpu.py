@@ -2,16 +2,16 @@
 """Generates tests/golden/refgpu_bt_law2_*.npz ON A GPU BOX (gpurun): nodal forces computed by the reference's own CUDA
 shell path (oracle/_ref/libshellgpu_ref.so, built unmodified from /root/reference by `make -C oracle refgpu`) for seeded
 flat-plate cases, together with the nodal arrays it was fed.  The CPU suite (tests/test_golden_refgpu.py) replays the same
-cases through the oracle.  Usage: gpurun -- 'python scripts/make_golden_refgpu.py'  then copy gpurun_out/golden/* to tests/golden/."""
+cases through the oracle.  Usage: gpurun -- 'python tests/golden/make_golden_refgpu.py'  then copy gpurun_out/golden/* to tests/golden/."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle.orc import Oracle
 from oracle import refgpu
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 from refgpu_cases import plate          # the seeded cases of the GPU pin test
 
-out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "golden")
+out = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "gpurun_out", "golden")
 os.makedirs(out, exist_ok=True)
 for ipla, npt, rate, shear in [(0, 3, True, False), (1, 5, True, True), (2, 3, False, True), (1, 3, False, False)]:
     m = plate(ipla, npt, rate, shear)

@@ -2,7 +2,7 @@
 
 tests/golden/refgpu_bt_law2_*.npz hold, per cycle of a seeded flat-plate case, the nodal arrays fed to -- and the nodal
 forces / moments and time step returned by -- the reference's CUDA shell path (Belytschko-Tsay + LAW2), compiled unmodified
-from /root/reference and run on a B200 (scripts/make_golden_refgpu.py; the cases are tests/test_ref_gpu_pin.py::plate).
+from /root/reference and run on a B200 (tests/golden/make_golden_refgpu.py; the cases are tests/test_ref_gpu_pin.py::plate).
 The oracle replays the same cycles from the same initial model and must reproduce those forces to rounding (the reference
 kernels contract fma and sum with atomics: 1e-12 of the largest nodal force)."""
 import glob

@@ -1,9 +1,9 @@
 #!/usr/bin/env python3
 """Head to head on one B200: the reference's own CUDA shell path (oracle/_ref/libshellgpu_ref.so, built unmodified from
 /root/reference: three kernels per cycle, atomics, nodal arrays re-uploaded and forces downloaded every cycle) against
-liborgpu on the same Belytschko-Tsay / LAW2 / NPT=5 plate.  Usage (gpurun): python scripts/ref_gpu_headtohead.py [nx ny]"""
+liborgpu on the same Belytschko-Tsay / LAW2 / NPT=5 plate.  Usage (gpurun): python tests/tools/ref_gpu_headtohead.py [nx ny]"""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from openradioss_b200 import meshgen
 from openradioss_b200.engine import Engine
@@ -51,7 +51,7 @@ for _ in range(100):
 r.synchronize()
 res["ref_kernels_ms_per_cycle"] = (time.perf_counter() - t0) / 100 * 1e3    # the three kernels only (forces + atomics; no nodal update)
 # the SAME ABI and the SAME driver calls, two libraries: liborgpu.so exports the reference's shell_gpu_* entry points too
-ORGPU = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "openradioss_b200", "csrc", "liborgpu.so")
+ORGPU = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "openradioss_b200", "csrc", "liborgpu.so")
 d = refgpu.RefShellGPU(m, lib=ORGPU, asrate=m.shell_groups[0].mat.asrate)
 dX, dV, dVR = d.pin(nd["X"], nd["V"], nd["VR"])
 for name, lib, arrs in (("ref", r, (pX, pV, pVR)), ("orgpu", d, (dX, dV, dVR))):
