@@ -42,6 +42,34 @@ def test_header_is_the_reference_header_name_for_name():
     assert bound <= set(ours), sorted(bound - set(ours))
 
 
+def test_without_a_gpu_the_drop_in_fails_loudly():
+    """no CPU fallback behind the reference's ABI either: handles and parameters are recorded without a device, the first
+    per-cycle call prints the reason and exits with status 1 (the reference's own error convention, shell_gpu_driver.cu:47-55)"""
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import subprocess, sys, textwrap
+    code = textwrap.dedent(f"""
+        import ctypes as C, numpy as np
+        L = C.CDLL({ORGPU!r}); R = C.c_double
+        L.shell_gpu_global_create.restype = C.c_void_p; L.shell_gpu_data_create.restype = C.c_void_p
+        gh = C.c_void_p(L.shell_gpu_global_create(C.c_int(4))); g = C.c_void_p(L.shell_gpu_data_create())
+        L.shell_gpu_allocate(g, C.c_int(1), C.c_int(4), C.c_int(3), C.c_int(2), C.c_int(0)); L.shell_gpu_set_global(g, gh)
+        L.shell_gpu_set_mat_params(g, *[R(v) for v in (210e3, .3, 80e3, 230e3, 69e3, 250., 400., .4, 0., 1e-3, 1e30, 1e30, 1., 0., 0., 300., 1e30, 0., 7.85e-3, 5400., 5 / 6)],
+                                   C.c_int(1), C.c_int(2), C.c_int(0), C.c_int(1), R(0.), R(0.))
+        L.shell_gpu_set_hg_params(g, *[R(v) for v in (.01, .01, .01, .1, .1, .1, .5, .5, 0.)])
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        n = [np.array([k], np.int32) for k in range(4)]; one = lambda v: np.array([float(v)])
+        arrs = [one(1.2), one(1.), one(5400.), one(7.85e-3), one(210e3), one(.3), one(230e3), one(80e3), one(5 / 6)]
+        L.shell_gpu_upload_constant(g, *[p(a) for a in n], *[p(a) for a in arrs])
+        print("recorded", flush=True)
+        X = np.zeros((4, 3)); L.shell_gpu_global_upload_nodes(gh, p(X), p(X), p(X))
+        print("not reached", flush=True)
+    """)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "recorded" in r.stdout and "not reached" not in r.stdout
+    assert "liborgpu shell_gpu ABI" in r.stderr
+
+
 gpu = pytest.mark.gpu
 if torch.cuda.is_available():
     from openradioss_b200.engine import Engine
