@@ -14,6 +14,10 @@ def models():
     yield "brick", meshgen.hex_block(5, 4, 6, 1.0, 0.8, 1.2, v0=(0, 0, -100.0), vrand=5.0, fix_bottom_z=True, user_id_perm=True)
     yield "sh3n_mixed", meshgen.tri_plate(9, 7, 90.0, 70.0, quads="checker", pressure=20.0, vrand=5.0, user_id_perm=True)
     yield "brick_law36", meshgen.hex_block(5, 4, 6, 10.0, 8.0, 12.0, law=36, v0=(0, 0, -60.0), vrand=20.0, fix_bottom_z=True)
+    m = meshgen.shell_plate(9, 7, 90.0, 70.0, pressure=20.0, vrand=5.0)      # gravity on all nodes + a ramped load on a node subset
+    meshgen.add_gravity(m, 3, -9.81e-3)
+    meshgen.add_gravity(m, 1, 0.05, nodes=np.nonzero(m.X[:, 0] > 40.0)[0], curve=([0.0, 1.0e-3, 1.0], [0.0, 1.0, 1.0]))
+    yield "shell_gravity", m
 
 
 @pytest.mark.parametrize("nproc", [2, 3, 4])
@@ -72,11 +76,17 @@ def test_domains_reproduce_single_domain_bitwise(nproc):
             assert np.array_equal(x["X"], xr["X"][d.node_gid]) and np.array_equal(x["V"], xr["V"][d.node_gid])
 
 
+def _gloo_model():
+    m = meshgen.shell_plate(8, 6, 80.0, 60.0, pressure=20.0, vrand=5.0)
+    meshgen.add_gravity(m, 3, -9.81e-3)                                      # loads follow their nodes into the ranks
+    return m
+
+
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    m = meshgen.shell_plate(8, 6, 80.0, 60.0, pressure=20.0, vrand=5.0)
+    m = _gloo_model()
     d = domdec.decompose_strips(m, world, rank)
     b = Oracle(d.model)
     comm = spmd.TorchComm(dist)
@@ -100,7 +110,7 @@ def test_two_gloo_processes_match_single_domain():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    m = meshgen.shell_plate(8, 6, 80.0, 60.0, pressure=20.0, vrand=5.0)
+    m = _gloo_model()
     ref = Oracle(m); ref.run_cycles(20)
     xr = ref.download_nodes(("X",))["X"]
     for rank, gid, x, tt in res:
