@@ -35,6 +35,11 @@ B_ALG = {
 }
 
 
+# C2 / C3 start from a smooth velocity field (amplitude mm/ms, wavelength mm) that drives the plate into yield within the first
+# cycles: the timed cycles then run the plastic return of SIGEPS36C (sigeps36c.F:503-593) at most integration points instead of
+# timing an idle elastic plate; `config.plastic_fraction` reports the share of integration points that yielded in the last cycle
+VWAVE = (60.0, 100.0)
+
 STRONG = ("c3_plate_qeph_4m", "c4_tube", "c4_tube_small", "c1_taylor_bar")    # total model fixed, cut into `world` domains
 
 
@@ -44,7 +49,7 @@ def workload(name, world=1):
     `world` strips / slabs.  Returns (model, family of the dominant kernel, decomposition axis)."""
     from openradioss_b200 import meshgen
     if name == "c3_plate_qeph_4m":          # C3: 2000 x 2000 QEPH shells, LAW36, x strips
-        return meshgen.shell_plate(2000, 2000, 2000.0, 2000.0, pulse_tau=0.05), "shell", 0
+        return meshgen.shell_plate(2000, 2000, 2000.0, 2000.0, pulse_tau=0.05, vwave=VWAVE), "shell", 0
     if name == "c4_tube":                   # C4: 2.0 M QEPH shells (LAW36) + 501 k bricks (LAW2), imposed-velocity crush, z slabs
         return meshgen.crush_tube(708, 706, 1), "mixed", 2
     if name == "c4_tube_small":
@@ -56,6 +61,8 @@ def workload(name, world=1):
     if name == "brick_small":
         return meshgen.hex_block(40, 40, 40 * world, 40.0, 40.0, 40.0 * world, vrand=1.0), "brick", 2
     if name == "c2_plate_qeph_1m":          # C2 / C3: 1000 x 1000 QEPH shells per GPU (x strips), LAW36, NPT=5
+        return meshgen.shell_plate(1000 * world, 1000, 1000.0 * world, 1000.0, pulse_tau=0.05, vwave=VWAVE), "shell", 0
+    if name == "c2_plate_qeph_1m_elastic":  # the same plate starting from rest: the pressure pulse leaves it elastic over the timed cycles
         return meshgen.shell_plate(1000 * world, 1000, 1000.0 * world, 1000.0, pulse_tau=0.05), "shell", 0
     if name == "tri_plate_1m":              # extra: 707 x 707 cells x 2 = 999 698 3-node shells per GPU, LAW36, NPT=5
         return meshgen.tri_plate(707 * world, 707, 1000.0 * world, 1000.0), "sh3n", 0
@@ -94,6 +101,16 @@ class ClockSampler:
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
+
+
+def csrc_sha():
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "openradioss_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:12]
 
 
 def peaks():
@@ -211,13 +228,24 @@ def main():
                             "avg_launch_ms": nms / nn if nn else None, "bytes_per_node": b["node"]},
             "whole_cycle": {"achieved": b["total"] * ne * world / (ms * 1e-3 / args.steps) / 1e9 / world,
                             "frac": b["total"] * ne / (ms * 1e-3 / args.steps) / 1e9 / peak, "bytes_per_element": b["total"]}}
+    # DRAM bytes per launch from the committed `ncu --set full` capture of this workload -- only while the kernel sources are
+    # the ones that were captured (sha of csrc/*.cu*), otherwise null: a stale constant would be worse than none
     tr = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr) and fam != "sh3n":                     # DRAM bytes per launch from the committed ncu capture (per element x elements of this launch)
+    if os.path.exists(tr):
         try:
-            per = json.load(open(tr)).get(dom + "_per_element")
-            roof["traffic"] = per * ne_dom if per else None
+            rec = json.load(open(tr)).get(args.workload, {})
+            if rec.get("src_sha") == csrc_sha() and rec.get("kernel") == dom:
+                roof["traffic"] = rec["dram_bytes_per_element"] * ne_dom
+                roof["traffic_source"] = rec.get("capture")
         except Exception:
             pass
+
+    # ---- how plastic the timed cycles were: integration points whose plastic strain grew during one more cycle
+    plastic = None
+    if world == 1 and (m.numelc or m.numeltg):
+        st = g.shell_state if m.numelc else g.sh3n_state
+        p0 = st("pla"); g.run_cycles(1); g.synchronize(); p1 = st("pla")
+        plastic = {"last_cycle": float((p1 > p0).mean()), "ever": float((p1 > 0).mean()), "pla_max": float(p1.max())}
 
     # ---- end to end through the host-buffer C-ABI call (pinned host arrays, copies inside the timed region)
     n = m.numnod
@@ -257,6 +285,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong" if args.workload in STRONG else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": args.workload, "family": fam, "elements_per_gpu": ne, "nodes_per_gpu": n,
+                           "plastic_fraction": plastic,
                            "l2": "inputs larger than L2 (element state >> 126 MB)" if ne >= 500000 else "working set may fit L2",
                            "parallelism": f"domains={world}" + ("" if world == 1 else " (strips / slabs; peer-memory corner-row exchange + dt fold per cycle, one CUDA graph)")},
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,

@@ -111,6 +111,28 @@ int  orgpu_set_time(orgpu_engine* e, double tt, double dt2, double dt2old, long 
  *    -> ECRIT output/ecrit.F:259-373): out = internal energy of solids, of shells, nodal kinetic
  *    energy of translations, of rotations.  Deterministic (fixed-order) reduction. */
 int  orgpu_get_energies(orgpu_engine* e, double out[4]);
+/* -- the same balances as the Engine books them on a print cycle (IPRI = 1), per part and for the global line of the
+ *    listing.  orgpu_set_parts (before orgpu_finalize): part (0-based) of every element = IPARTC / IPARTS / IPARTTG, and
+ *    GBUF%VOL of the shells (initial area x thickness, Starter output), the mass CBILAN uses.  orgpu_set_print(1): every
+ *    following cycle also runs
+ *      CBILAN  (engine/source/elements/shell/coque/cbilan.F:183-275, called czforc3.F:639 / cforc3.F:648),
+ *      C3BILAN (sh3n/coque3n/c3bilan.F:150-167, 282-300; c3forc3.F:616), SBILAN (solid/solide/sbilan.F:110-157; sforc3.F:1436)
+ *        -> PARTSAV(1:6, part): internal energy, kinetic energy from the nodal velocities the force routine sees, momenta, mass;
+ *      ECRIT   (engine/source/output/ecrit.F:178-240, 322-352): ENCIN / ENROT from V(n-1/2) + DT1/2 A with A after every
+ *        kinematic condition, ENINT = sum of PARTSAV(1,:), momenta, mass;
+ *      the work of the imposed velocities as FIXVEL books it (constraints/general/impvel/fixvel.F:342-344, 391-394, 834-837).
+ *    Scratch rows + a fixed-order two-level reduction (no atomics, nothing allocated per cycle); one domain only.
+ *    orgpu_get_balance: out = ENCIN, ENROT, ENINT, WFEXT, XMOMT, YMOMT, ZMOMT, XMASS of the last cycle, partsav (6,npart)
+ *    or NULL; orgpu_get_balance_history: the rows of the last n cycles, oldest first (n <= 8192). */
+int  orgpu_set_parts(orgpu_engine* e, int npart, const int* ipartc, const int* iparts, const int* iparttg,
+                     const double* gvolc, const double* gvoltg);
+int  orgpu_set_print(orgpu_engine* e, int ipri);
+int  orgpu_get_balance(orgpu_engine* e, double out[8], double* partsav);
+int  orgpu_get_balance_history(orgpu_engine* e, int n, double* out /*[n][8]*/);
+/* -- through-thickness integration rule of the NPT-point /PROP/SHELL: positions Z0, force weights WF, moment weights WM
+ *    (engine/source/elements/shell/coqini.F:46-122 by default; layini.F:246-254, mulawc.F90:769-777).  Replaces the row of the
+ *    device tables (shared by the engines of a process) until the next orgpu_finalize.  After orgpu_finalize. */
+int  orgpu_set_quadrature(orgpu_engine* e, int npt, const double* z0, const double* wf, const double* wm);
 
 /* -- domain decomposition (one process / MPI rank per GPU).
  *    Host-staged: corner rows of the given 0-based local FSKY slots out of / into the device

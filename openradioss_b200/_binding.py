@@ -90,8 +90,59 @@ class Binding:
             else:
                 self._call_group("add_solid_group_law", self.h, C.c_int(g.nel), C.c_int(g.nft), C.c_int(g.law),
                                  C.byref(g.mat), C.byref(g.prop), v0.ctypes.data_as(C.c_void_p))
+        self._set_parts(m)
         self._call("finalize", self.h)
         return self
+
+    def _set_parts(self, m: Model):
+        """Part of every element (IPARTC / IPARTS / IPARTTG, 0-based here) and GBUF%VOL of the shells (initial area x
+        thickness, what the Starter stores): the inputs of the print-cycle balances (CBILAN / SBILAN / ECRIT)."""
+        from . import meshgen
+        def parts(groups, n, given):
+            if given is not None:
+                return np.ascontiguousarray(given, np.int32)
+            out = np.zeros(n, np.int32)
+            for g in groups:
+                out[g.nft:g.nft + g.nel] = getattr(g, "part", 0)
+            return out
+        ipc = parts(m.shell_groups, m.numelc, m.ipartc); ips = parts(m.solid_groups, m.numels, m.iparts)
+        ipt = parts(m.sh3n_groups, m.numeltg, m.iparttg)
+        npart = int(max([0] + [a.max() + 1 for a in (ipc, ips, ipt) if a.size]))
+        gvc = np.zeros(m.numelc); gvt = np.zeros(m.numeltg)
+        if m.numelc:
+            area = meshgen.shell_areas(m.X, m.ixc)
+            for g in m.shell_groups:
+                gvc[g.nft:g.nft + g.nel] = area[g.nft:g.nft + g.nel] * g.prop.thick
+        if m.numeltg:
+            P = m.X[m.ixtg[:, 1:4] - 1]
+            area = 0.5 * np.linalg.norm(np.cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0]), axis=1)
+            for g in m.sh3n_groups:
+                gvt[g.nft:g.nft + g.nel] = area[g.nft:g.nft + g.nel] * g.prop.thick
+        self.npart = max(npart, 1)
+        self._call("set_parts", self.h, C.c_int(self.npart), _opt(ipc, np.int32), _opt(ips, np.int32), _opt(ipt, np.int32),
+                   _opt(gvc, np.float64), _opt(gvt, np.float64))
+
+    def set_quadrature(self, npt, z0, wf, wm):
+        """Through-thickness rule of the NPT-point shells (positions, force weights, moment weights); process-wide."""
+        a = [np.ascontiguousarray(x, np.float64) for x in (z0, wf, wm)]
+        self._call("set_quadrature", self.h, C.c_int(npt), *[x.ctypes.data_as(C.c_void_p) for x in a])
+
+    def balance_history(self, n):
+        out = np.zeros((n, 8))
+        self._call("get_balance_history", self.h, C.c_int(n), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def set_print(self, on: bool = True):
+        """IPRI = 1: every following cycle also books the balances of the reference's print cycles."""
+        self._call("set_print", self.h, C.c_int(1 if on else 0))
+
+    def balance(self):
+        """The global line ECRIT prints for the last cycle (ecrit.F:178-352) and PARTSAV(1:6, part)."""
+        out = np.zeros(8); ps = np.zeros((self.npart, 6))
+        self._call("get_balance", self.h, out.ctypes.data_as(C.c_void_p), ps.ctypes.data_as(C.c_void_p))
+        d = dict(zip(("encin", "enrot", "enint", "wfext", "xmomt", "ymomt", "zmomt", "xmass"), out))
+        d["partsav"] = ps
+        return d
 
     def _call_group(self, name, *args):
         fn = self._f(name); fn.restype = C.c_int
@@ -158,6 +209,25 @@ class Binding:
         out = np.zeros((nc * npt, self.model.numeltg))
         self._call("download_sh3n_state", self.h, C.c_int(fid), out.ctypes.data_as(C.c_void_p))
         return out
+
+    # -- restart / state hand-over ------------------------------------------------------------------
+    def upload_solid_state(self, name, arr):
+        fid, nc = self.SOLID_FIELDS[name]
+        a = np.ascontiguousarray(arr, np.float64); assert a.shape == (nc, self.model.numels)
+        self._call("upload_solid_state", self.h, C.c_int(fid), a.ctypes.data_as(C.c_void_p))
+
+    def upload_shell_state(self, name, arr):
+        fid, _ = self.SHELL_FIELDS[name]
+        a = np.ascontiguousarray(arr, np.float64); assert a.shape[1] == self.model.numelc
+        self._call("upload_shell_state", self.h, C.c_int(fid), a.ctypes.data_as(C.c_void_p))
+
+    def upload_sh3n_state(self, name, arr):
+        fid, _ = self.SHELL_FIELDS[name]
+        a = np.ascontiguousarray(arr, np.float64); assert a.shape[1] == self.model.numeltg
+        self._call("upload_sh3n_state", self.h, C.c_int(fid), a.ctypes.data_as(C.c_void_p))
+
+    def set_time(self, tt, dt2, dt2old, ncycle):
+        self._call("set_time", self.h, C.c_double(tt), C.c_double(dt2), C.c_double(dt2old), C.c_longlong(ncycle))
 
     # -- corner rows of the skyline (domain exchange) ------------------------------------
     def pack_rows(self, slots):

@@ -155,6 +155,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     for (int k = 0; k < 8; k++) prefetch_l1(P.nd.vel + nc[k]);
     if (STAGED) mbar_wait(&s_bar, 0);                     // the state tile has landed (issued before the gather)
     double OFFG = T.ld(BW_OFF);
+    const bool dying_in = OFFG < K_ZERO;                  // SCOOR3 zeroes the velocities of such an element (also what SBILAN sees)
     double OFF;
     if (ISMSTR <= 4 && fabs(OFFG) > K_ONE) {
       #pragma unroll
@@ -624,6 +625,27 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       else OFFG = OFF;
     }
     T.st(BW_OFF, OFFG);
+    // ---- SBILAN (sbilan.F:110-157, sforc3.F:1436) on a print cycle: EI = EINT*VOL, mean of the squared nodal velocities
+    if (g.bal && P.cs->ipri) {
+      double bx[8], by[8], bz[8];
+      #pragma unroll
+      for (int k = 0; k < 8; k++) { const double4 v = ldg4(P.nd.vel + nc[k]); bx[k] = v.x; by[k] = v.y; bz[k] = v.z; }
+      if (dying_in) {
+        #pragma unroll
+        for (int k = 0; k < 8; k++) { bx[k] = K_ZERO; by[k] = K_ZERO; bz[k] = K_ZERO; }
+      }
+      double vxa = bx[0] + bx[1] + bx[2] + bx[3] + bx[4] + bx[5] + bx[6] + bx[7];
+      double vya = by[0] + by[1] + by[2] + by[3] + by[4] + by[5] + by[6] + by[7];
+      double vza = bz[0] + bz[1] + bz[2] + bz[3] + bz[4] + bz[5] + bz[6] + bz[7];
+      double va2 = bx[0] * bx[0] + bx[1] * bx[1] + bx[2] * bx[2] + bx[3] * bx[3] + bx[4] * bx[4] + bx[5] * bx[5] + bx[6] * bx[6] + bx[7] * bx[7]
+                 + by[0] * by[0] + by[1] * by[1] + by[2] * by[2] + by[3] * by[3] + by[4] * by[4] + by[5] * by[5] + by[6] * by[6] + by[7] * by[7]
+                 + bz[0] * bz[0] + bz[1] * bz[1] + bz[2] * bz[2] + bz[3] * bz[3] + bz[4] * bz[4] + bz[5] * bz[5] + bz[6] * bz[6] + bz[7] * bz[7];
+      vxa = vxa * K_ONE_OVER_8; vya = vya * K_ONE_OVER_8; vza = vza * K_ONE_OVER_8; va2 = va2 * K_ONE_OVER_8;
+      const double xmas = RHON * VOLN;
+      double* b = g.bal + e; const size_t ld = g.bal_ld;
+      b[0] = EINT * VOLO; b[ld] = xmas * va2 * K_HALF; b[2 * ld] = xmas * vxa; b[3 * ld] = xmas * vya; b[4 * ld] = xmas * vza;
+      b[5 * ld] = (OFFG >= K_ONE) ? xmas : K_ZERO;
+    }
     // ---- SHVIS3
     double F1[8], F2[8], F3[8];
     {

@@ -224,6 +224,7 @@ bt_forces_kernel(const __grid_constant__ ShellParams P)
     io.area = AREA; io.thk0 = THK0; io.gs = G * SHF; io.rho = RHO; io.off = OFF; io.sigy = K_EP30;
     shell_material_loop<LAW, false, STAGED>(g, T, DT1, io);
     OFF = io.off;
+    if (g.bal && P.cs->ipri) shell_bilan<4, STAGED>(P, T, e, RHO, OFF);        // CBILAN (cforc3.F:648; CHVIS3 leaves EINT alone)
     const double SSP = io.ssp;
     const double VISCMX = or_sqrt(K_ONE + io.viscmx * io.viscmx) - io.viscmx;
     // ---- CHVIS3

@@ -187,6 +187,7 @@ c3_forces_kernel(const __grid_constant__ ShellParams P)
     io.area = AREA; io.thk0 = THK0; io.gs = G * SHF; io.rho = RHO; io.off = OFF; io.sigy = K_EP30;
     shell_material_loop<LAW, false, STAGED>(g, T, DT1, io);
     OFF = io.off;
+    if (g.bal && P.cs->ipri) shell_bilan<3, STAGED>(P, T, e, RHO, OFF);        // C3BILAN (c3forc3.F:616)
     const double SSP = io.ssp;
     // ---- C3DT3 (IGTYP=1, ZOFFSET=0, IDTMIN(7)=0)
     double STI, STIR;

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstdarg>
 #include <cstring>
+#include <cstddef>
 #include <vector>
 #include <string>
 #include "../../include/orgpu.h"
@@ -33,9 +34,9 @@ template <class T> static int dev_alloc(T** p, size_t n) {
   return 0;
 }
 
-struct HostSolidGroup { int nel, nft, law; orgpu_law2 mat; orgpu_law36 m36; orgpu_prop_solid prop; std::vector<double> vol0; };
+struct HostSolidGroup { int nel, nft, law; orgpu_law2 mat; orgpu_law36 m36; orgpu_prop_solid prop; std::vector<double> vol0; int part = 0; };
 
-struct BrickSGHost { BrickSG d; int first_elem; std::vector<void*> owned; };
+struct BrickSGHost { BrickSG d; int first_elem; int part = 0; std::vector<void*> owned; };
 
 struct orgpu_engine {
   int device = 0, numnod = 0;
@@ -76,6 +77,11 @@ struct orgpu_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> evpool;
   Exchange xc;                        // domain exchange (one process per GPU)
+  // print-cycle balances (CBILAN / SBILAN / ECRIT): parts, GBUF%VOL of the shells, scratch rows and their fixed-order reduction
+  int npart = 1; bool have_parts = false; std::vector<int> ipartc, iparts, iparttg; std::vector<double> gvolc, gvoltg;
+  int ipri = 0; int bal_ld = 0, nbal_ld = 0, nchunk = 0, nnchunk = 0;
+  double *d_bal = nullptr, *d_nbal = nullptr, *d_epart = nullptr, *d_npartial = nullptr, *d_partsav = nullptr, *d_hist = nullptr;
+  BalChunk* d_chunks = nullptr; BalState* d_bs = nullptr;
 };
 
 // ---- small layout kernels ---------------------------------------------------------------
@@ -149,7 +155,8 @@ int orgpu_destroy(orgpu_engine* e)
   for (auto& s : e->csg) for (void* p : s.owned) cudaFree(p);
   void* ptrs[] = {e->nd.pos, e->nd.vel, e->nd.rot, e->nd.D, e->nd.A, e->nd.AR, e->nd.STIFN, e->nd.STIFR, e->nd.MS, e->nd.IN,
                   e->d_stage3a, e->d_stage3b, e->d_fext, e->d_mext, e->d_icodt, e->d_icodr, e->d_adsky, e->d_fsky, e->d_cs,
-                  e->db.dt, e->db.order, e->d_sgr, e->d_btf, e->d_bnpf, e->d_ftf, e->d_fnpf, e->d_fv_idx, e->d_fv, e->d_itab, e->d_nd_dt, e->d_nd_node, e->d_gmask};
+                  e->db.dt, e->db.order, e->d_sgr, e->d_btf, e->d_bnpf, e->d_ftf, e->d_fnpf, e->d_fv_idx, e->d_fv, e->d_itab, e->d_nd_dt, e->d_nd_node, e->d_gmask,
+                  e->d_bal, e->d_nbal, e->d_epart, e->d_npartial, e->d_partsav, e->d_hist, e->d_chunks, e->d_bs};
   for (void* p : ptrs) if (p) cudaFree(p);
   { Exchange& x = e->xc;
     void* xp[] = {x.d_send_slots, x.d_recv_slots, x.d_sendbuf, x.d_recvbuf, x.d_cand_send, x.d_cand_recv, x.d_slots_tmp, x.d_rows_tmp};
@@ -242,6 +249,18 @@ int orgpu_set_itab(orgpu_engine* e, const int* itab)
 {
   NEED(e && itab && !e->finalized, -1, "orgpu_set_itab: bad arguments / already finalized");
   e->itab.assign(itab, itab + e->numnod);
+  return 0;
+}
+
+int orgpu_set_parts(orgpu_engine* e, int npart, const int* ipartc, const int* iparts, const int* iparttg, const double* gvolc, const double* gvoltg)
+{
+  NEED(e && !e->finalized && npart >= 1, -1, "orgpu_set_parts: bad arguments / already finalized (call it after set_solids / set_shells / set_sh3n)");
+  NEED((e->numelc == 0 || (ipartc && gvolc)) && (e->numels == 0 || iparts) && (e->numeltg == 0 || (iparttg && gvoltg)), -1, "orgpu_set_parts: a table is missing");
+  auto chk = [&](const int* p, int n) { for (int i = 0; i < n; i++) if (p[i] < 0 || p[i] >= npart) return false; return true; };
+  NEED(chk(ipartc, e->numelc) && chk(iparts, e->numels) && chk(iparttg, e->numeltg), -4, "orgpu_set_parts: part index out of range");
+  e->npart = npart; e->have_parts = true;
+  e->ipartc.assign(ipartc, ipartc + e->numelc); e->iparts.assign(iparts, iparts + e->numels); e->iparttg.assign(iparttg, iparttg + e->numeltg);
+  e->gvolc.assign(gvolc, gvolc + e->numelc); e->gvoltg.assign(gvoltg, gvoltg + e->numeltg);
   return 0;
 }
 
@@ -354,6 +373,13 @@ int orgpu_finalize(orgpu_engine* e)
   { std::vector<int> a0(e->adsky.size()); for (size_t i = 0; i < a0.size(); i++) a0[i] = e->adsky[i] - 1;
     if (dev_alloc(&e->d_adsky, a0.size())) return -100;
     CUDA_OK(cudaMemcpy(e->d_adsky, a0.data(), 4 * a0.size(), cudaMemcpyHostToDevice)); e->nd.adsky = e->d_adsky; }
+  // part of a group = part of its elements (one part per group, as in the Engine's group building)
+  { auto gpart = [&](const std::vector<int>& ip, int nft, int nel, int& part) {
+      part = 0; if (ip.empty()) return true; part = ip[nft];
+      for (int i = 1; i < nel; i++) if (ip[nft + i] != part) return false; return true; };
+    for (auto& g : e->cgroups) NEED(gpart(e->ipartc, g.nft, g.nel, g.part), -4, "a shell group spans several parts");
+    for (auto& g : e->tgroups) NEED(gpart(e->iparttg, g.nft, g.nel, g.part), -4, "a 3-node shell group spans several parts");
+    for (auto& g : e->sgroups) NEED(gpart(e->iparts, g.nft, g.nel, g.part), -4, "a solid group spans several parts"); }
   int order = 0, blk = 0; e->fa.nsg = 0; e->sgr.clear();
   // shells are processed first (FORINTC resol.F:4138), solids after (FORINT resol.F:4225)
   { int rc = shell_build_supergroups(e->cgroups, e->csg, e->ixc, e->iadc, 4, e->npf, e->tf, e->ctl, e->numnod, e->lsky, order, blk, e->sgr); if (rc) return rc; }
@@ -367,12 +393,12 @@ int orgpu_finalize(orgpu_engine* e)
     while (gj < e->sgroups.size() && e->sgroups[gj].nft == e->sgroups[gj - 1].nft + e->sgroups[gj - 1].nel &&
            e->sgroups[gj].law == e->sgroups[gi].law &&
            !memcmp(&e->sgroups[gj].mat, &e->sgroups[gi].mat, sizeof(orgpu_law2)) && !memcmp(&e->sgroups[gj].m36, &e->sgroups[gi].m36, sizeof(orgpu_law36)) &&
-           !memcmp(&e->sgroups[gj].prop, &e->sgroups[gi].prop, sizeof(orgpu_prop_solid))) gj++;
+           !memcmp(&e->sgroups[gj].prop, &e->sgroups[gi].prop, sizeof(orgpu_prop_solid)) && e->sgroups[gj].part == e->sgroups[gi].part) gj++;
     int ne = 0; for (size_t k = gi; k < gj; k++) ne += e->sgroups[k].nel;
     const int nft = e->sgroups[gi].nft;
     const int np = ((ne + ORGPU_BLOCK - 1) / ORGPU_BLOCK) * ORGPU_BLOCK;
-    e->bsg.emplace_back(); BrickSGHost& S = e->bsg.back(); S.first_elem = nft;
-    BrickSG& d = S.d; d.ne = ne; d.ne_pad = np; d.order0 = order; d.blk0 = blk;
+    e->bsg.emplace_back(); BrickSGHost& S = e->bsg.back(); S.first_elem = nft; S.part = e->sgroups[gi].part;
+    BrickSG& d = S.d; d.bal = nullptr; d.bal_ld = 0; d.ne = ne; d.ne_pad = np; d.order0 = order; d.blk0 = blk;
     d.mat = e->sgroups[gi].mat; d.prop = e->sgroups[gi].prop; d.dtfac = e->ctl.dtfac_brick; d.nodadt = e->ctl.nodadt;
     std::vector<int> conn((size_t)8 * np, 0), ngl(np, 0), conn_t;
     // state slab: read/write words first (SIG 6, EINT, RHO, QVIS, PLA, EPSD, OFF[, TEMP]), then VOL and the slot rows
@@ -422,6 +448,14 @@ int orgpu_finalize(orgpu_engine* e)
     order += ne; blk += nblk; gi = gj;
   }
   NEED(blk > 0, -4, "orgpu_finalize: no element groups");
+  // GBUF%VOL of the shells (mass of CBILAN / C3BILAN), element order of each super-group
+  for (auto& S : e->csg) {
+    S.d.bal = nullptr; S.d.bal_ld = 0; S.d.gvol = nullptr;
+    const std::vector<double>& gv = S.sh3n ? e->gvoltg : e->gvolc;
+    if (gv.empty()) continue;
+    std::vector<double> h(gv.begin() + S.first_elem, gv.begin() + S.first_elem + S.d.ne); h.resize(S.d.ne_pad, 0.0);
+    double* dg; if (upload_vec(S.owned, &dg, h)) return -100; S.d.gvol = dg;
+  }
   if (dev_alloc(&e->d_sgr, e->sgr.size())) return -100;
   CUDA_OK(cudaMemcpy(e->d_sgr, e->sgr.data(), sizeof(SGRange) * e->sgr.size(), cudaMemcpyHostToDevice));
   e->fa.nsg = (int)e->sgr.size(); e->fa.sg = e->d_sgr;
@@ -505,6 +539,16 @@ static void launch_element_phase(orgpu_engine* e, int fused, size_t* evi)
   element_finalize_kernel<<<1, ORGPU_FINALIZE_BLOCK, 0, e->st>>>(e->d_cs, e->db, e->fa); e->launches++;
 }
 
+// print cycle: fold the element / node scratch rows in a fixed order (three small launches)
+static void launch_balance(orgpu_engine* e)
+{
+  if (!e->ipri) return;
+  balance_chunk_kernel<6><<<e->nchunk, 256, 0, e->st>>>(e->d_bal, e->bal_ld, e->bal_ld, e->d_chunks, e->d_epart);
+  balance_chunk_kernel<8><<<e->nnchunk, 256, 0, e->st>>>(e->d_nbal, e->nbal_ld, e->numnod, nullptr, e->d_npartial);
+  balance_finalize_kernel<<<1, 256, 0, e->st>>>(e->d_chunks, e->nchunk, e->d_epart, e->npart, e->d_npartial, e->nnchunk, e->d_partsav, e->d_bs, e->d_hist, e->d_cs);
+  e->launches += 3;
+}
+
 // gather + update: one fused kernel, or with /DT/NODA assemble (+ nodal dt candidates) -> fold + clock -> advance
 static void launch_node_phase(orgpu_engine* e)
 {
@@ -514,6 +558,7 @@ static void launch_node_phase(orgpu_engine* e)
     launch_node_advance(e->nd, e->d_cs, e->ctl.iroddl, e->st);
     e->launches += 3;
   } else { launch_node_fused(e->nd, e->d_fsky, e->roww, e->d_cs, e->ctl.iroddl, e->st); e->launches++; }
+  launch_balance(e);
 }
 
 int orgpu_forces_phase(orgpu_engine* e, double dt1)
@@ -537,6 +582,7 @@ int orgpu_advance(orgpu_engine* e, double dt12, double dt2)
   NEED(e && e->finalized, -1, "orgpu_advance: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
   launch_set_dt(e->d_cs, 0, dt12, dt2, 1, e->st); e->launches++;
   launch_node_advance(e->nd, e->d_cs, e->ctl.iroddl, e->st); e->launches++;
+  launch_balance(e);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -608,7 +654,8 @@ static void p2p_node_phase(orgpu_engine* e)
 int orgpu_run_cycles(orgpu_engine* e, int ncycles)
 {
   NEED(e && e->finalized && ncycles >= 0, -1, "orgpu_run_cycles: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
-  const int per_cycle = (int)(e->csg.size() + e->bsg.size()) + (e->ctl.nodadt ? 4 : 2);   // force kernels + dt finalize + node kernel(s)
+  const int per_cycle = (int)(e->csg.size() + e->bsg.size()) + (e->ctl.nodadt ? 4 : 2) + (e->ipri ? 3 : 0);   // force kernels + dt finalize + node kernel(s) [+ balances]
+  NEED(!(e->ipri && e->xc.nranks > 1), -5, "print-cycle balances across domains (frontier-node weights) are outside the built path");
   NEED(!(e->ctl.nodadt && e->xc.nranks > 1 && (!e->xc.p2p || e->profile)), -5, "/DT/NODA across domains needs the peer-memory exchange (orgpu_p2p_connect), unprofiled");
   if (e->xc.nranks > 1 && e->xc.p2p && !e->profile) {
     // one process per GPU, peer-memory exchange: the whole cycle (forces, dt fold, push, wait+unpack, gather+update)
@@ -1002,6 +1049,75 @@ int orgpu_get_energies(orgpu_engine* e, double out[4])
   for (auto& S : e->csg) if (energy_sum(e, S.d.slab + SW_EINT * ORGPU_TILE, S.d.slab + (SW_EINT + 1) * ORGPU_TILE, S.d.slab + SW_OFF * ORGPU_TILE, S.d.nw, S.d.ne, 1, &out[1])) return -100;
   if (energy_sum(e, e->nd.MS, (const double*)e->nd.vel, nullptr, 0, e->numnod, 2, &out[2])) return -100;
   if (e->nd.rot && energy_sum(e, e->nd.IN, (const double*)e->nd.rot, nullptr, 0, e->numnod, 2, &out[3])) return -100;
+  return 0;
+}
+
+// IPRI: the following cycles also book the balances of the reference's print cycles.  The scratch rows, chunk table and
+// result buffers are allocated once, here (nothing is allocated per cycle or per query).
+int orgpu_set_print(orgpu_engine* e, int ipri)
+{
+  NEED(e && e->finalized, -1, "orgpu_set_print: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  ipri = ipri ? 1 : 0;
+  if (ipri && !e->d_bal) {
+    NEED(e->have_parts, -4, "orgpu_set_print: parts and shell volumes missing (orgpu_set_parts before orgpu_finalize)");
+    std::vector<BalChunk> ch; int ofs = 0;
+    auto add = [&](int ne, int ne_pad, int part) {
+      for (int s0 = 0; s0 < ne; s0 += ORGPU_BAL_CHUNK) ch.push_back(BalChunk{ofs + s0, (ne - s0 < ORGPU_BAL_CHUNK) ? ne - s0 : ORGPU_BAL_CHUNK, part});
+      const int o = ofs; ofs += ne_pad; return o; };
+    std::vector<int> so, bo;
+    for (auto& S : e->csg) so.push_back(add(S.d.ne, S.d.ne_pad, S.part));
+    for (auto& S : e->bsg) bo.push_back(add(S.d.ne, S.d.ne_pad, S.part));
+    e->bal_ld = ofs; e->nchunk = (int)ch.size(); e->nbal_ld = e->numnod; e->nnchunk = (e->numnod + ORGPU_BAL_CHUNK - 1) / ORGPU_BAL_CHUNK;
+    if (dev_alloc(&e->d_bal, (size_t)6 * e->bal_ld) || dev_alloc(&e->d_nbal, (size_t)8 * e->nbal_ld) || dev_alloc(&e->d_epart, (size_t)6 * e->nchunk) ||
+        dev_alloc(&e->d_npartial, (size_t)8 * e->nnchunk) || dev_alloc(&e->d_partsav, (size_t)6 * e->npart) || dev_alloc(&e->d_hist, (size_t)8 * ORGPU_BAL_HIST) ||
+        dev_alloc(&e->d_chunks, ch.size()) || dev_alloc(&e->d_bs, 1)) return -100;
+    CUDA_OK(cudaMemcpy(e->d_chunks, ch.data(), sizeof(BalChunk) * ch.size(), cudaMemcpyHostToDevice));
+    for (size_t k = 0; k < e->csg.size(); k++) { e->csg[k].d.bal = e->d_bal + so[k]; e->csg[k].d.bal_ld = e->bal_ld; }
+    for (size_t k = 0; k < e->bsg.size(); k++) { e->bsg[k].d.bal = e->d_bal + bo[k]; e->bsg[k].d.bal_ld = e->bal_ld; }
+    e->nd.nbal = e->d_nbal; e->nd.nbal_ld = e->nbal_ld;
+  }
+  if (ipri != e->ipri && e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }   // the cycle graph gains / loses the three balance launches
+  e->ipri = ipri;
+  CUDA_OK(cudaMemcpy(reinterpret_cast<char*>(e->d_cs) + offsetof(CycleState, ipri), &ipri, sizeof(int), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// out: ENCIN, ENROT, ENINT, WFEXT, XMOMT, YMOMT, ZMOMT, XMASS of the last print cycle (ecrit.F:322-352); partsav (6, npart) or null
+int orgpu_get_balance(orgpu_engine* e, double out[8], double* partsav)
+{
+  NEED(e && e->finalized && out && e->d_bs, -1, "orgpu_get_balance: no print cycle was run (orgpu_set_print)"); CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  BalState bs; CUDA_OK(cudaMemcpy(&bs, e->d_bs, sizeof bs, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 8; k++) out[k] = bs.glob[k];
+  if (partsav) CUDA_OK(cudaMemcpy(partsav, e->d_partsav, sizeof(double) * 6 * e->npart, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// rows of the last n print cycles (oldest first), n <= ORGPU_BAL_HIST: what the listing shows cycle by cycle
+int orgpu_get_balance_history(orgpu_engine* e, int n, double* out /*[n][8]*/)
+{
+  NEED(e && e->finalized && out && e->d_bs && n >= 0 && n <= ORGPU_BAL_HIST, -1, "orgpu_get_balance_history: bad arguments / no print cycle was run"); CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  CycleState cs; CUDA_OK(cudaMemcpy(&cs, e->d_cs, sizeof cs, cudaMemcpyDeviceToHost));
+  NEED(cs.ncycle >= n, -4, "orgpu_get_balance_history: only %lld cycles were run", cs.ncycle);
+  std::vector<double> h((size_t)8 * ORGPU_BAL_HIST);
+  CUDA_OK(cudaMemcpy(h.data(), e->d_hist, 8 * h.size(), cudaMemcpyDeviceToHost));
+  for (int j = 0; j < n; j++) { const long long row = (cs.ncycle - n + j) % ORGPU_BAL_HIST; memcpy(out + 8 * (size_t)j, &h[8 * (size_t)row], 64); }
+  return 0;
+}
+
+// Through-thickness rule of the NPT-point /PROP/SHELL (positions Z0, force weights WF, moment weights WM, coqini.F tables by
+// default): replaces the row of the device tables shared by every engine of the process until the next orgpu_finalize.  The
+// reference's own CUDA kernels integrate with the mid-point rule (shell_strain_material_kernel.cu:696-701); with that rule
+// loaded here the bending response is pinned against them (tests/test_ref_gpu_pin.py).
+int orgpu_set_quadrature(orgpu_engine* e, int npt, const double* z0, const double* wf, const double* wm)
+{
+  NEED(e && e->finalized && npt >= 1 && npt <= 10 && z0 && wf && wm, -1, "orgpu_set_quadrature: bad arguments / engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  const size_t off = sizeof(double) * 11 * (npt - 1);
+  CUDA_OK(cudaMemcpyToSymbol(c_Z0, z0, sizeof(double) * npt, off)); CUDA_OK(cudaMemcpyToSymbol(c_WF, wf, sizeof(double) * npt, off));
+  CUDA_OK(cudaMemcpyToSymbol(c_WM, wm, sizeof(double) * npt, off));
   return 0;
 }
 

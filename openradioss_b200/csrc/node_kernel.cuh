@@ -79,8 +79,10 @@ __device__ __forceinline__ NodeIn node_load(const DevNodes& nd, int n, int irodd
   return q;
 }
 
-__device__ __forceinline__ void node_update(const DevNodes& nd, int n, const NodeIn& q, NodeAcc& r, double dt12, double dt2, double tt0, int iroddl, const double* gv)
+__device__ __forceinline__ void node_update(const DevNodes& nd, int n, const NodeIn& q, NodeAcc& r, double dt12, double dt2, double tt0, int iroddl, const double* gv,
+                                            int ipri = 0, double dt1 = 0.0)
 {
+  double dw = K_ZERO;                                // print cycles: work rate of the imposed velocities on this node
   // ACCELE
   const double ms = q.ms;
   if (ms > K_ZERO) { const double rt = or_div(K_ONE, ms); r.a[0] = r.a[0] * rt; r.a[1] = r.a[1] * rt; r.a[2] = r.a[2] * rt; }
@@ -120,10 +122,25 @@ __device__ __forceinline__ void node_update(const DevNodes& nd, int n, const Nod
           const int i0 = nd.ft.npf[f.func[j]];
           double yc = or_vinterdp(nd.ft.tf, i0, nd.ft.npf[f.func[j] + 1] - i0, tsc);
           yc = yc * f.fac[j];
+          const double aold = r.a[j];
           r.a[j] = or_div(yc - vj[j], dt12);
+          // DW = 1/4 MS (A DT12 + 2 V)(A - AOLD)   (fixvel.F:391-394)
+          if (ipri) dw = dw + K_FOURTH * ms * (r.a[j] * dt12 + K_TWO * vj[j]) * (r.a[j] - aold);
         }
       }
     }
+  }
+  // ECRIT on a print cycle (ecrit.F:196-240, 322-336): the node's terms of ENCIN, ENROT, the momenta and the mass with
+  // V(n) = V(n-1/2) + DT1/2 A, A after every kinematic condition; and the two halves of the imposed-velocity work
+  if (ipri && nd.nbal) {
+    const double dt05 = K_HALF * dt1;
+    const double vx = q.v.x + dt05 * r.a[0], vy = q.v.y + dt05 * r.a[1], vz = q.v.z + dt05 * r.a[2];
+    double* b = nd.nbal + n; const size_t ld = nd.nbal_ld;
+    b[0] = (vx * vx + vy * vy + vz * vz) * K_HALF * ms;
+    double er = K_ZERO;
+    if (iroddl) { const double wx = q.w.x + dt05 * r.ar[0], wy = q.w.y + dt05 * r.ar[1], wz = q.w.z + dt05 * r.ar[2]; er = (wx * wx + wy * wy + wz * wz) * K_HALF * q.in; }
+    b[ld] = er; b[2 * ld] = vx * ms; b[3 * ld] = vy * ms; b[4 * ld] = vz * ms; b[5 * ld] = ms;
+    b[6 * ld] = dt1 * dw; b[7 * ld] = dt2 * dw;
   }
   // VELOCITY
   double4 v = q.v;
@@ -224,7 +241,7 @@ node_advance_kernel(const __grid_constant__ DevNodes nd, const CycleState* __res
   r.a[0] = nd.A[3 * n]; r.a[1] = nd.A[3 * n + 1]; r.a[2] = nd.A[3 * n + 2];
   r.ar[0] = nd.AR[3 * n]; r.ar[1] = nd.AR[3 * n + 1]; r.ar[2] = nd.AR[3 * n + 2];
   const NodeIn q = node_load(nd, n, iroddl);
-  node_update(nd, n, q, r, cs->dt12, cs->dt2, cs->tt0, iroddl, cs->gv);
+  node_update(nd, n, q, r, cs->dt12, cs->dt2, cs->tt0, iroddl, cs->gv, cs->ipri, cs->dt1);
   nd.A[3 * n] = K_ZERO; nd.A[3 * n + 1] = K_ZERO; nd.A[3 * n + 2] = K_ZERO;        // velocity.F:62-64
   nd.AR[3 * n] = K_ZERO; nd.AR[3 * n + 1] = K_ZERO; nd.AR[3 * n + 2] = K_ZERO;
 }
@@ -239,7 +256,7 @@ node_fused_kernel(const __grid_constant__ DevNodes nd, const double* __restrict_
   if (n >= nd.n) return;
   const NodeIn q = node_load(nd, n, iroddl);
   NodeAcc r = node_gather<ROWW>(nd, fsky, n, iroddl, cs->fscale);
-  node_update(nd, n, q, r, cs->dt12, cs->dt2, cs->tt0, iroddl, cs->gv);
+  node_update(nd, n, q, r, cs->dt12, cs->dt2, cs->tt0, iroddl, cs->gv, cs->ipri, cs->dt1);
 }
 
 __global__ void set_dt_kernel(CycleState* cs, double dt1, double dt12, double dt2, int which)
@@ -298,4 +315,57 @@ energy_partial_kernel(const double* __restrict__ a, const double* __restrict__ b
   s[threadIdx.x] = v; __syncthreads();
   for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) s[threadIdx.x] = s[threadIdx.x] + s[threadIdx.x + k]; __syncthreads(); }
   if (threadIdx.x == 0) partial[blockIdx.x] = s[0];
+}
+
+// ---- print-cycle balances: fixed-order reduction (CBILAN / SBILAN -> PARTSAV, ECRIT) ----------------------------------
+// Level 1: CTA c folds elements [start, start+n) of each of NCOMP scratch rows (<= ORGPU_BAL_CHUNK of them): every thread a
+// strided left fold, then a fixed shared-memory tree.  chunks == null: node rows, chunk c = nodes [c*CHUNK, (c+1)*CHUNK).
+template <int NCOMP>
+__global__ void __launch_bounds__(256)
+balance_chunk_kernel(const double* __restrict__ rows, int ld, int ntot, const BalChunk* __restrict__ chunks, double* __restrict__ partial)
+{
+  __shared__ double s[256];
+  int start, n;
+  if (chunks) { start = chunks[blockIdx.x].start; n = chunks[blockIdx.x].n; }
+  else { start = blockIdx.x * ORGPU_BAL_CHUNK; n = min(ORGPU_BAL_CHUNK, ntot - start); }
+  for (int k = 0; k < NCOMP; k++) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) v = v + rows[(size_t)k * ld + start + i];
+    s[threadIdx.x] = v; __syncthreads();
+    for (int h = 128; h > 0; h >>= 1) { if (threadIdx.x < h) s[threadIdx.x] = s[threadIdx.x] + s[threadIdx.x + h]; __syncthreads(); }
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * NCOMP + k] = s[0];
+    __syncthreads();
+  }
+}
+// Level 2 (one CTA): PARTSAV(k, part) = left fold of the chunk sums of that part in chunk order; ENINT = sum of PARTSAV(1,:);
+// the node sums; the imposed-velocity work with its one-cycle-late half; one row of the history ring
+__global__ void __launch_bounds__(256)
+balance_finalize_kernel(const BalChunk* __restrict__ chunks, int nchunk, const double* __restrict__ epart, int npart,
+                        const double* __restrict__ npartial, int nnchunk, double* __restrict__ partsav, BalState* __restrict__ bs,
+                        double* __restrict__ hist, const CycleState* __restrict__ cs)
+{
+  __shared__ double s_node[8];
+  for (int t = threadIdx.x; t < 6 * npart; t += 256) {
+    const int part = t / 6, k = t % 6;
+    double v = 0.0;
+    for (int c = 0; c < nchunk; c++) if (chunks[c].part == part) v = v + epart[(size_t)c * 6 + k];
+    partsav[t] = v;
+  }
+  if (threadIdx.x < 8) {
+    double v = 0.0;
+    for (int c = 0; c < nnchunk; c++) v = v + npartial[(size_t)c * 8 + threadIdx.x];
+    s_node[threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double enint = 0.0;
+    for (int m = 0; m < npart; m++) enint = enint + partsav[6 * m];
+    bs->wfext = bs->wfext + bs->pending + s_node[6];
+    bs->pending = s_node[7];
+    bs->glob[0] = s_node[0]; bs->glob[1] = s_node[1]; bs->glob[2] = enint; bs->glob[3] = bs->wfext;
+    bs->glob[4] = s_node[2]; bs->glob[5] = s_node[3]; bs->glob[6] = s_node[4]; bs->glob[7] = s_node[5];
+    // the cycle this row belongs to: ncycle was already advanced by the time-step bookkeeping
+    const long long row = (cs->ncycle - 1) % ORGPU_BAL_HIST;
+    if (row >= 0) for (int k = 0; k < 8; k++) hist[8 * row + k] = bs->glob[k];
+  }
 }

@@ -387,6 +387,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
 #endif
     shell_material_loop<LAW, true, STAGED>(g, T, DT1, io);
     OFF = io.off;
+    if (g.bal && P.cs->ipri) shell_bilan<4, STAGED>(P, T, e, io.rho, OFF);     // CBILAN (czforc3.F:639)
     // ---- re-derive the geometry needed by the force assembly (same expressions as before the loop)
     QephGeo q1; qeph_geo(XL2, YL2, XL3, YL3, XL4, YL4, q1);
     const double* CX = q1.CX; const double* CY = q1.CY;

@@ -34,6 +34,8 @@ struct ShellSG {
   orgpu_law2 m2; orgpu_law36 m36; orgpu_prop_shell prop;
   double dtfac;               // DTFAC1(3)
   int nodadt;                 // /DT/NODA: nodal stiffnesses of cndt3.F:194-221, no element time step
+  double* bal; int bal_ld;    // print cycles: the elements' PARTSAV(1:6) terms, bal[k * bal_ld + e] (null until orgpu_set_print)
+  const double* gvol;         // GBUF%VOL of the group's elements (initial area x thickness): the mass of CBILAN
 };
 
 enum { SW_FOR = 0, SW_MOM = 5, SW_EINT = 8, SW_THK = 10, SW_OFF = 11, SW_STRA = 12, SW_EPSD = 20, SW_HOURG = 21 };
@@ -84,6 +86,35 @@ __device__ __forceinline__ void ip_store(const ShellSG& g, const TileAcc<STAGED>
 }
 
 #define ORGPU_SHELL_CTA ORGPU_TILE   // one CTA = one state tile
+
+// CBILAN (cbilan.F:183-275, NN = 4) / C3BILAN (c3bilan.F:150-167, NN = 3) on a print cycle: the element's terms of
+// PARTSAV(1:6, part) -- internal energy EINT(1)+EINT(2), kinetic energy from the nodal velocities the force routine
+// sees, momenta, mass -- go to the scratch rows; the nodal velocities are gathered again (print cycles only)
+template <int NN, bool STAGED>
+__device__ __forceinline__ void shell_bilan(const ShellParams& P, const TileAcc<STAGED>& T, int e, double rho, double off)
+{
+  const ShellSG& g = P.sg;
+  const int* cn = g.conn + (size_t)blockIdx.x * NN * ORGPU_TILE + threadIdx.x;
+  double vx[NN], vy[NN], vz[NN];
+  #pragma unroll
+  for (int k = 0; k < NN; k++) { const double4 v = ld256_nc(P.nd.vel + __ldg(cn + k * ORGPU_TILE)); vx[k] = v.x; vy[k] = v.y; vz[k] = v.z; }
+  double vxa = K_ZERO, vya = K_ZERO, vza = K_ZERO, va2 = K_ZERO;
+  #pragma unroll
+  for (int k = 0; k < NN; k++) { vxa = vxa + vx[k]; vya = vya + vy[k]; vza = vza + vz[k]; }
+  #pragma unroll
+  for (int k = 0; k < NN; k++) va2 = va2 + vx[k] * vx[k];
+  #pragma unroll
+  for (int k = 0; k < NN; k++) va2 = va2 + vy[k] * vy[k];
+  #pragma unroll
+  for (int k = 0; k < NN; k++) va2 = va2 + vz[k] * vz[k];
+  const double xmas = rho * __ldg(g.gvol + e);
+  const double ei = T.ld(SW_EINT) + T.ld(SW_EINT + 1);
+  const double ek = (NN == 4) ? xmas * va2 * K_ONE_OVER_8 : xmas * va2 * K_ONE_OVER_6;
+  const double xmas25 = (NN == 4) ? xmas * K_FOURTH : xmas * K_THIRD;
+  double* b = g.bal + e; const size_t ld = g.bal_ld;
+  b[0] = ei; b[ld] = ek; b[2 * ld] = xmas25 * vxa; b[3 * ld] = xmas25 * vya; b[4 * ld] = xmas25 * vza;
+  b[5 * ld] = (off != K_ZERO) ? xmas : K_ZERO;
+}
 
 // ---- SIGEPS36C, VP = 0 -------------------------------------------------------------------
 // FAIL2: IFAIL = 2 (tensile-strain damage / failure), compiled as its own kernel variant (template LAW = 37) so that
@@ -456,7 +487,12 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const Tile
     const double deyy = io.eyy + zt * io.kyy;
     const double dexy = io.exy + zt * io.kxy;
     if (LAW != 2) {
-      law36_ip<STAGED, LAW == 37>(g, T, ipt, g.prop.ipla, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, thklyl, io.gs, io.epsd_pg, zt, off,
+#ifdef ORGPU_FIX_IPLA
+      const int ipla_ = ORGPU_FIX_IPLA;                  // experiment: plasticity algorithm known at compile time
+#else
+      const int ipla_ = g.prop.ipla;
+#endif
+      law36_ip<STAGED, LAW == 37>(g, T, ipt, ipla_, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, thklyl, io.gs, io.epsd_pg, zt, off,
                s, thkn, ssp, etse, sigy);
     } else {
       law2_ip(g, g.prop.ipla, npt, dt1, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, thklyl, io.gs, io.epsd_pg,

@@ -12,8 +12,8 @@
 #include "bt_kernel.cuh"
 #include "c3_kernel.cuh"
 
-struct HostShellGroup { int nel, nft, law, sh3n; orgpu_prop_shell prop; orgpu_law2 m2; orgpu_law36 m36; };
-struct ShellSGHost { ShellSG d; int first_elem = 0; bool sh3n = false; std::vector<void*> owned; };
+struct HostShellGroup { int nel, nft, law, sh3n; orgpu_prop_shell prop; orgpu_law2 m2; orgpu_law36 m36; int part; };
+struct ShellSGHost { ShellSG d; int first_elem = 0; bool sh3n = false; int part = 0; std::vector<void*> owned; };
 
 static inline bool shell_is_qeph(const orgpu_prop_shell& p) { return p.ihbe >= 21 && p.ihbe <= 29; }
 
@@ -73,12 +73,13 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
     size_t gj = gi + 1;
     while (gj < groups.size() && groups[gj].nft == groups[gj - 1].nft + groups[gj - 1].nel && groups[gj].law == groups[gi].law &&
            !memcmp(&groups[gj].prop, &groups[gi].prop, sizeof(orgpu_prop_shell)) &&
-           !memcmp(&groups[gj].m2, &groups[gi].m2, sizeof(orgpu_law2)) && !memcmp(&groups[gj].m36, &groups[gi].m36, sizeof(orgpu_law36))) gj++;
+           !memcmp(&groups[gj].m2, &groups[gi].m2, sizeof(orgpu_law2)) && !memcmp(&groups[gj].m36, &groups[gi].m36, sizeof(orgpu_law36)) &&
+           groups[gj].part == groups[gi].part) gj++;
     int ne = 0; for (size_t k = gi; k < gj; k++) ne += groups[k].nel;
     const HostShellGroup& G = groups[gi];
     const int nft = G.nft;
     const int np = ((ne + ORGPU_BLOCK - 1) / ORGPU_BLOCK) * ORGPU_BLOCK;
-    out.emplace_back(); ShellSGHost& S = out.back(); S.first_elem = nft; S.sh3n = (nnode == 3);
+    out.emplace_back(); ShellSGHost& S = out.back(); S.first_elem = nft; S.sh3n = (nnode == 3); S.part = G.part;
     ShellSG& d = S.d; memset(&d, 0, sizeof d);
     d.ne = ne; d.ne_pad = np; d.order0 = order; d.blk0 = blk; d.law = G.law; d.npt = G.prop.npt;
     d.nvartmp = (G.law == 36) ? 2 + G.m36.nrate : 0;

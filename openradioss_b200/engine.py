@@ -17,7 +17,8 @@ EXPORTS = """create destroy last_error upload_nodes set_loads set_bcs set_solids
 set_functions add_solid_group add_solid_group_law add_shell_group set_sh3n add_sh3n_group download_sh3n_state upload_sh3n_state finalize forces_phase assemble advance run_cycles
 synchronize get_time download_nodes download_fsky download_solid_state download_shell_state
 step_host launch_count last_run_ms set_profile get_profile pack_rows unpack_rows comm_unique_id comm_init
-set_exchange exchange get_energies p2p_export p2p_connect set_load_function set_fixvel set_gravity upload_solid_state upload_shell_state set_time set_itab""".split()
+set_exchange exchange get_energies p2p_export p2p_connect set_load_function set_fixvel set_gravity upload_solid_state upload_shell_state set_time set_itab
+set_parts set_print get_balance get_balance_history set_quadrature""".split()
 
 
 def load_library() -> C.CDLL:
@@ -80,25 +81,6 @@ class Engine(Binding):
             dist.barrier()
 
     def exchange(self): self._call("exchange", self.h)
-
-    # -- restart / state hand-over ------------------------------------------------------------------
-    def upload_solid_state(self, name, arr):
-        fid, nc = self.SOLID_FIELDS[name]
-        a = np.ascontiguousarray(arr, np.float64); assert a.shape == (nc, self.model.numels)
-        self._call("upload_solid_state", self.h, C.c_int(fid), a.ctypes.data_as(C.c_void_p))
-
-    def upload_shell_state(self, name, arr):
-        fid, _ = self.SHELL_FIELDS[name]
-        a = np.ascontiguousarray(arr, np.float64); assert a.shape[1] == self.model.numelc
-        self._call("upload_shell_state", self.h, C.c_int(fid), a.ctypes.data_as(C.c_void_p))
-
-    def upload_sh3n_state(self, name, arr):
-        fid, _ = self.SHELL_FIELDS[name]
-        a = np.ascontiguousarray(arr, np.float64); assert a.shape[1] == self.model.numeltg
-        self._call("upload_sh3n_state", self.h, C.c_int(fid), a.ctypes.data_as(C.c_void_p))
-
-    def set_time(self, tt, dt2, dt2old, ncycle):
-        self._call("set_time", self.h, C.c_double(tt), C.c_double(dt2), C.c_double(dt2old), C.c_longlong(ncycle))
 
     def checkpoint(self):
         """Everything a restart needs: nodal arrays, clock, element state of both families."""

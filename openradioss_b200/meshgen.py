@@ -130,7 +130,9 @@ def default_prop_shell(thick=2.0, ihbe=24, npt=5, ismstr=2, ithk=1, ipla=1) -> P
     p.srh1 = np.sqrt(p.h1); p.srh2 = np.sqrt(p.h2); p.srh3 = np.sqrt(p.h3)
     p.shf = 0.0 if npt == 1 else K["FIVE_OVER_6"]
     p.shfsr = np.sqrt(p.shf)
-    p.dm = 0.0
+    # membrane damping: GEO(16) = 0 in the deck -> the Starter's group default (set_elgroup_param.F:83-108): 1.5 % for QEPH
+    # (internal IHBE 23 = Ishell 24, hm_read_prop01.F:314) with /PROP/SHELL and a law outside its special list, 0 for BT
+    p.dm = K["ZEP015"] if ihbe == 24 else 0.0
     p.npt = npt; p.ismstr = ismstr; p.ithk = ithk; p.ipla = ipla; p.ihbe = ihbe; p.istrain = 1
     return p
 
@@ -231,7 +233,7 @@ def shell_areas(X: np.ndarray, ixc: np.ndarray) -> np.ndarray:
 def shell_plate(nx: int, ny: int, lx: float = 1000.0, ly: float = 1000.0, *, thick: float = 2.0, law: int = 36,
                 mat=None, prop: PropShell = None, jitter: float = 0.05, zjitter: float = 0.05, seed: int = 2024,
                 pressure: float = 1.0, clamp: bool = True, vrand: float = 0.0, vseed: int = 12345,
-                user_id_perm: bool = False, curves=None, rates=None, pulse_tau: float = 0.0) -> Model:
+                user_id_perm: bool = False, curves=None, rates=None, pulse_tau: float = 0.0, vwave=None) -> Model:
     """Square plate of nx*ny 4-node shells in the xy plane (C2: 1000 x 1000 QEPH / LAW36, clamped
     edges, uniform pressure as nodal forces; pulse_tau > 0 ramps them as p0*min(t/tau, 1) through a time
     function, the /CLOAD path of force.F90)."""
@@ -277,6 +279,13 @@ def shell_plate(nx: int, ny: int, lx: float = 1000.0, ly: float = 1000.0, *, thi
     if vrand:
         g = np.random.Generator(np.random.PCG64(vseed))
         V += g.uniform(-vrand, vrand, V.shape); VR += g.uniform(-vrand, vrand, VR.shape) / h
+    if vwave is not None:
+        # smooth initial velocity field (amplitude A, wavelength lam): in-plane stretching / compression plus an out-of-plane
+        # bulge, strong enough that the plate yields within the first cycles (the plastic return of the law is then live)
+        A, lam = vwave
+        kx = 2.0 * np.pi / lam
+        V[:, 0] += A * np.sin(kx * X[:, 0]); V[:, 1] += A * np.sin(kx * X[:, 1])
+        V[:, 2] += 0.5 * A * np.sin(kx * X[:, 0]) * np.sin(kx * X[:, 1])
     fext = None
     if pressure:
         fext = np.zeros((numnod, 3))

@@ -60,6 +60,7 @@ class SolidGroup:
     mat: object              # Law2 | Law36
     prop: PropSolid
     law: int = 2             # 2 (M2LAW) or 36 (MULAW -> SIGEPS36)
+    part: int = 0            # 0-based part of the group's elements
 
 
 @dataclass
@@ -69,6 +70,7 @@ class ShellGroup:
     law: int                 # 2 or 36
     mat: object              # Law2 | Law36
     prop: PropShell
+    part: int = 0            # 0-based part of the group's elements
 
 
 @dataclass
@@ -107,6 +109,9 @@ class Model:
     igrv: Optional[np.ndarray] = None   # gravity loads (n,3) int32: node count, direction 1..3, curve index (-1: constant)   (gravit.F)
     agrv: Optional[np.ndarray] = None   # (n,2): FCY, FCX
     ibgrv: Optional[np.ndarray] = None  # node lists of the loads, one after the other (1-based)
+    ipartc: Optional[np.ndarray] = None  # part (0-based) of every 4-node shell / brick / 3-node shell: IPARTC, IPARTS, IPARTTG
+    iparts: Optional[np.ndarray] = None  #   (default: the `part` attribute of the element's group, else 0)
+    iparttg: Optional[np.ndarray] = None
 
     @property
     def numnod(self): return int(self.X.shape[0])

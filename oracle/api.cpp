@@ -11,6 +11,7 @@ void orc_shell_group_free(OrcShellGroup*);
 OrcShellGroup* orc_shell_group_new(int nel,int nft,int law,const void* mat,const orgpu_prop_shell* prop);
 void orc_shell_group_state(const OrcShellGroup& g,int field,size_t ne,double* out);
 void orc_forces(Oracle& o);
+void orc_shell_group_state_up(OrcShellGroup& g,int field,size_t ne,const double* in);
 
 extern "C" {
 
@@ -187,6 +188,35 @@ void orc_download_solid_state(void* h,int field,double* out){
       case 10: if(!g.stra.empty()) cp(g.stra,6); break; case 11: if(!g.wpla.empty()) cp(g.wpla,1); break;
     }
   }
+}
+
+/* the reverse (restart / initial state hand-over, /INIBRI, /INISHE): same fields, same layout */
+void orc_upload_solid_state(void* h,int field,const double* in){
+  Oracle* o=(Oracle*)h; size_t ne=o->numels;
+  for(auto& g:o->sgroups){
+    auto cp=[&](std::vector<double>& v,int nc){ if(v.empty()) return; for(int k=0;k<nc;k++) for(int i=0;i<g.nel;i++) v[(size_t)k*g.nel+i]=in[k*ne+g.nft+i]; };
+    switch(field){
+      case 0: cp(g.sig,6); break; case 1: cp(g.eint,1); break; case 2: cp(g.rho,1); break;
+      case 3: cp(g.qvis,1); break; case 4: cp(g.pla,1); break; case 5: cp(g.epsd,1); break;
+      case 6: cp(g.vol,1); break; case 7: cp(g.off,1); break; case 8: cp(g.temp,1); break;
+      case 9: cp(g.smstr,21); break; case 10: cp(g.stra,6); break; case 11: cp(g.wpla,1); break;
+    }
+  }
+}
+void orc_upload_shell_state(void* h,int field,const double* in){
+  Oracle* o=(Oracle*)h;
+  for(auto* g:o->cgroups) orc_shell_group_state_up(*g,field,(size_t)o->numelc,in);
+}
+void orc_upload_sh3n_state(void* h,int field,const double* in){
+  Oracle* o=(Oracle*)h;
+  for(auto* g:o->tgroups){
+    if(field==7) continue;
+    if(field==8){ for(int k=0;k<3;k++) for(int i=0;i<g->nel;i++) g->SMSTR[(size_t)k*g->nel+i]=in[(size_t)k*o->numeltg+g->nft+i]; continue; }
+    orc_shell_group_state_up(*g,field,(size_t)o->numeltg,in);
+  }
+}
+void orc_set_time(void* h,double tt,double dt2,double dt2old,long long ncycle){
+  Oracle* o=(Oracle*)h; o->TT=tt; o->DT2=dt2; o->DT2OLD=dt2old; o->NCYCLE=(long)ncycle;
 }
 
 /* corner rows of n FSKY slots (0-based) out of / into the skyline: what SPMD_EXCH2_A_PON packs

@@ -122,6 +122,8 @@ void orc_fixvel(Oracle& o)
     if(o.TT<STARTT) continue;
     if(o.TT>STOPT) continue;
     const int I=o.IBFV[3*N]-1, J=o.IBFV[3*N+1]-1, L=o.IBFV[3*N+2];
+    if(o.FV_DW.size()!=(size_t)nfx) o.FV_DW.assign(nfx,K_ZERO);
+    o.WFEXT=o.WFEXT+o.FV_DW[N]; o.FV_DW[N]=K_ZERO;      /* fixvel.F:342-344 (RW_SMS = 1): the DT2 half booked last cycle */
     const double TSC=(o.TT+K_HALF*o.DT2)*FACX;
     const int IAD=o.NPF[L], NP=o.NPF[L+1]-o.NPF[L];
     const double* TF=o.TF.data();
@@ -132,7 +134,12 @@ void orc_fixvel(Oracle& o)
     double YC=TF2J1+DYDX*(TSC-TF1J1);
     YC=YC*FAC;
     YC=(YC-o.V[3*I+J])/o.DT12;
+    const double AOLD=o.A[3*I+J];
     o.A[3*I+J]=YC;
+    /* work of the imposed velocity (fixvel.F:391-394, 834-837): DW = 1/4 MS (A DT12 + 2 V)(A - AOLD); WFEXT gets DT1*DW now and DT2*DW at the next cycle */
+    const double DW=K_FOURTH*o.MS[I]*(o.A[3*I+J]*o.DT12+K_TWO*o.V[3*I+J])*(o.A[3*I+J]-AOLD);
+    o.WFEXT=o.WFEXT+o.DT1*DW;
+    o.FV_DW[N]=o.FV_DW[N]+o.DT2*DW;                     /* VEL(4,N) = VEL(4,N) + DT2*DW (:837) */
   }
 }
 
@@ -224,6 +231,7 @@ void orc_cycle(Oracle& o)
 {
   o.DT1=o.DT2;                    /* resol.F:2721 */
   o.DT2=K_EP06;                   /* resol.F:2722 */
+  if(o.ipri) std::fill(o.PARTSAV.begin(),o.PARTSAV.end(),K_ZERO);
   orc_forces(o);
   orc_asspar4(o);
   if(o.ctl.nodadt!=0) orc_dtnoda(o);
@@ -238,6 +246,7 @@ void orc_cycle(Oracle& o)
   orc_gravit(o);                  /* resol.F:7123 */
   orc_bcs(o);
   orc_fixvel(o);
+  if(o.ipri) orc_ecrit(o);        /* SORTIE_MAIN -> ECRIT, resol.F:8523 */
   orc_velocity(o);
   orc_depla(o);
   o.TT=o.TT+o.DT2; o.NCYCLE++;    /* resol.F:8599-8608 */

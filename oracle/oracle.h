@@ -57,6 +57,7 @@ struct Oracle {
   int LF_FUNC=-1; double LF_FCX=1.0;  /* time function of the concentrated loads (force.F90:195-196, 235) */
   std::vector<int> IBFV;              /* imposed velocities (3,n): node, direction, curve (fixvel.F) */
   std::vector<double> VEL;            /* (4,n): FAC, STARTT, STOPT, FACX */
+  std::vector<double> FV_DW;          /* VEL(4,N) of the Engine: DT2*DW of the last cycle, booked into WFEXT at the next one */
   std::vector<int> IGRV, IBGRV;       /* gravity loads (3,n): node count, direction, curve; node lists (gravit.F) */
   std::vector<double> AGRV;           /* (2,n): FCY, FCX */
   /* connectivity */
@@ -81,6 +82,12 @@ struct Oracle {
   double DT2T = 0; int NELTST = 0, ITYPTST = 0;
   long NCYCLE = 0;
   int nthreads = 1;
+  /* balances on print cycles (bilan.cpp): IPRI, parts, PARTSAV(1:6,part), the global line of ECRIT */
+  int ipri = 0, npart = 1;
+  std::vector<int> IPARTC, IPARTS, IPARTTG;      /* 0-based part of each element */
+  std::vector<double> GVOLC, GVOLTG;             /* GBUF%VOL of the shells */
+  std::vector<double> PARTSAV;                   /* (6,npart), zeroed at the start of a print cycle */
+  double ENCIN = 0, ENROT = 0, ENINT = 0, WFEXT = 0, XMOMT = 0, YMOMT = 0, ZMOMT = 0, XMASS = 0;
 };
 
 /* solid.cpp */
@@ -90,6 +97,11 @@ void orc_czforc3(Oracle& o, OrcShellGroup& g, double& dt2t, int& neltst, int& it
 void orc_cforc3(Oracle& o, OrcShellGroup& g, double& dt2t, int& neltst, int& ityptst);
 /* shell_c3.cpp */
 void orc_c3forc3(Oracle& o, OrcShellGroup& g, double& dt2t, int& neltst, int& ityptst);
+/* bilan.cpp */
+void orc_bilan_shell(Oracle& o,int elem,int nn,const int* nodes,double eint1,double eint2,double rho,double off);
+void orc_bilan_solid(Oracle& o,int elem,const double vx[8],const double vy[8],const double vz[8],
+                     double eint,double vol,double rho,double vnew,double off);
+void orc_ecrit(Oracle& o);
 /* assembly.cpp */
 void orc_asspar4(Oracle& o);
 void orc_accele(Oracle& o);

@@ -48,3 +48,18 @@ void orc_shell_group_state(const OrcShellGroup& g,int field,size_t ne,double* ou
     case 12: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].temp,1,(int)p); break;
   }
 }
+
+/* same fields the other way (restart / initial state) */
+void orc_shell_group_state_up(OrcShellGroup& g,int field,size_t ne,const double* in)
+{
+  auto cp=[&](std::vector<double>& v,int nc,int k0){ for(int k=0;k<nc;k++) for(int i=0;i<g.nel;i++) v[(size_t)k*g.nel+i]=in[(size_t)(k0+k)*ne+g.nft+i]; };
+  switch(field){
+    case 0: cp(g.FOR,5,0); break; case 1: cp(g.MOM,3,0); break; case 2: cp(g.EINT,2,0); break;
+    case 3: cp(g.THK,1,0); break; case 4: cp(g.OFF,1,0); break; case 5: cp(g.STRA,8,0); break;
+    case 6: cp(g.EPSD,1,0); break; case 7: cp(g.HOURG,g.nhourg,0); break; case 8: cp(g.SMSTR,6,0); break;
+    case 9:  for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].sig,5,5*(int)p); break;
+    case 10: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].pla,1,(int)p); break;
+    case 11: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].epsd,1,(int)p); break;
+    case 12: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].temp,1,(int)p); break;
+  }
+}

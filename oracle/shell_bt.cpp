@@ -298,6 +298,7 @@ void orc_cforc3(Oracle& o, OrcShellGroup& g, double& DT2T, int& NELTST, int& ITY
         }
       }
     }
+    if(o.ipri) orc_bilan_shell(o,g.nft+i,4,nn,g.EINT[i],g.EINT[nel+i],RHO,OFF);   /* CBILAN cforc3.F:648 */
     /* ---- CDT3 (NODADT=0, IDTMIN(3)=2 with DTMIN1(3)=0: no deletion); not called with /DT/NODA (cforc3.F:668) */
     if(o.ctl.nodadt==0){
       ALDT=ALDT*VISCMX/std::sqrt(ALPE);

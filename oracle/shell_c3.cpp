@@ -177,6 +177,7 @@ void orc_c3forc3(Oracle& o, OrcShellGroup& g, double& DT2T, int& NELTST, int& IT
     ShellMatOut mo; mo.sigy=K_EP30;
     orc_cmain3(o,g,i,false,mi,mo);
     OFF=mi.off; SSP=mo.ssp; VOL0=mo.vol0; (void)VOL0;
+    if(o.ipri) orc_bilan_shell(o,g.nft+i,3,nn,g.EINT[i],g.EINT[nel+i],RHO,OFF);   /* C3BILAN c3forc3.F:616 */
     /* ---- C3DT3 (IGTYP=1, ZOFFSET=0, IDTMIN(7)=0) */
     double STI,STIR;
     {

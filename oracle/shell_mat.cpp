@@ -12,6 +12,19 @@
  * non-local, NPG=1.  Expressions keep the Fortran evaluation order (left to right).
  */
 #include "shell.h"
+/* through-thickness tables (coqini.F) with a test-only override of one row: the reference's own CUDA kernels use the
+ * mid-point rule (shell_strain_material_kernel.cu:696-701); loading it here lets them pin the bending path */
+static double g_quad[3][121]; static bool g_quad_init=false;
+const double* orc_quad_tab(int which){
+  if(!g_quad_init){ for(int i=0;i<121;i++){ g_quad[0][i]=OR_Z0[i]; g_quad[1][i]=OR_WF[i]; g_quad[2][i]=OR_WM[i]; } g_quad_init=true; }
+  return g_quad[which];
+}
+extern "C" void orc_set_quadrature(void*,int npt,const double* z0,const double* wf,const double* wm){
+  orc_quad_tab(0);
+  if(!z0){ g_quad_init=false; return; }                       /* NULL: back to the coqini.F tables */
+  for(int i=0;i<npt;i++){ g_quad[0][(npt-1)*11+i]=z0[i]; g_quad[1][(npt-1)*11+i]=wf[i]; g_quad[2][(npt-1)*11+i]=wm[i]; }
+}
+
 
 /* VINTER: monotone forward walk of the persistent cursor, then linear interpolation.
  * Curve points are (x,y) pairs TF[2*p], TF[2*p+1], p in [iad, iad+npts). */
@@ -383,9 +396,9 @@ void orc_cmain3(const Oracle& o, OrcShellGroup& g, int i, bool flag_zcfac, Shell
   double asrate; if(israte>0) asrate=std::min(K_ONE,pm9*dt1); else asrate=K_ONE;
   for(int ipt=1;ipt<=npt;ipt++){
     OrcShellGroup::Lbuf& lb=g.ip[ipt-1];
-    const double thkly=OR_WF[(npt-1)*11+(ipt-1)];          /* layini.F:250 */
-    const double posly=OR_Z0[(npt-1)*11+(ipt-1)]+K_ZERO;   /* layini.F:251 (ZSHIFT=0) */
-    const double wmc=OR_WM[(npt-1)*11+(ipt-1)];            /* mulawc.F90:771-773 */
+    const double thkly=orc_quad_tab(1)[(npt-1)*11+(ipt-1)];          /* WF, layini.F:250 */
+    const double posly=orc_quad_tab(0)[(npt-1)*11+(ipt-1)]+K_ZERO;   /* Z0, layini.F:251 (ZSHIFT=0) */
+    const double wmc=orc_quad_tab(2)[(npt-1)*11+(ipt-1)];            /* WM, mulawc.F90:771-773 */
     IpIO s;
     s.thklyl=thkly*in.thk0;
     const double zt=posly*in.thk0;

@@ -347,6 +347,7 @@ void orc_czforc3(Oracle& o, OrcShellGroup& g, double& DT2T, int& NELTST, int& IT
     OFF=mi.off; SSP=mo.ssp; SIGY=mo.sigy; VOL0=mo.vol0;
     double VISCMX=mo.viscmx;
     const double ZCFAC[2]={mo.zcfac1,mo.zcfac2};
+    if(o.ipri){ const int nd[4]={n1,n2,n3,n4}; orc_bilan_shell(o,g.nft+i,4,nd,g.EINT[i],g.EINT[nel+i],RHO,OFF); }   /* CBILAN czforc3.F:639 */
     /* ---- CNDT3 */
     double STI,STIR;
     {

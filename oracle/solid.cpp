@@ -805,6 +805,12 @@ void orc_sforc3(Oracle& o, OrcSolidGroup& g, double& dt2t, int& neltst, int& ity
       else OFFG[i]=OFF[i];
     }
   }
+  if(o.ipri){                                          /* SBILAN sforc3.F:1436-1458 */
+    for(int i=0;i<nel;i++){
+      double vx[8],vy[8],vz[8]; for(int k=0;k<8;k++){ vx[k]=VX[k][i]; vy[k]=VY[k][i]; vz[k]=VZ[k][i]; }
+      orc_bilan_solid(o,nft+i,vx,vy,vz,g.eint[i],g.vol[i],g.rho[i],VOLN[i],OFFG[i]);
+    }
+  }
   /* ---- SHVIS3  shvis3.F:164-412 (INVSTR>=35, FLUID=0) */
   double F1[8][MVSIZ],F2[8][MVSIZ],F3[8][MVSIZ];   /* F1[k]=F1(k+1): x-force on node k+1 */
   {

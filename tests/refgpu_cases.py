@@ -18,3 +18,23 @@ def plate(ipla, npt, rate, shear, seed=5, vs=1.0):
         else:
             g.mat.cc = 0.0
     return m
+
+
+def midpoint_rule(npt):
+    """The through-thickness rule of the reference's CUDA kernels (shell_strain_material_kernel.cu:696-701, 812-819): points at the
+    layer centres zeta = -1/2 + (i + 1/2)/NPT, force weight 1/NPT, moment weight zeta/NPT."""
+    z = np.array([-0.5 + (i + 0.5) / npt for i in range(npt)])
+    return z, np.full(npt, 1.0 / npt), z / npt
+
+
+def bent_plate(ipla, npt, seed=7, vs=1.0, warp=0.0):
+    """Free BT / LAW2 plate with random translational AND rotational velocities: curvature, moments, rotational hourglass."""
+    prop = meshgen.default_prop_shell(thick=1.2, ihbe=1, npt=npt, ipla=ipla, ismstr=2, ithk=0)
+    m = meshgen.shell_plate(9, 7, 90.0, 70.0, law=2, prop=prop, pressure=0.0, clamp=False, zjitter=warp, vrand=0.0)
+    rng = np.random.default_rng(seed)
+    m.V[:, :2] = rng.uniform(-30.0, 30.0, (m.numnod, 2)) * vs
+    m.V[:, 2] = rng.uniform(-20.0, 20.0, m.numnod) * vs
+    m.VR[:] = rng.uniform(-4.0, 4.0, (m.numnod, 3)) * vs
+    for g in m.shell_groups:
+        g.mat.cc = 0.0
+    return m

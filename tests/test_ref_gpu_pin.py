@@ -74,3 +74,41 @@ def test_elastic_regime_and_time_step_match_the_reference_gpu_path():
         assert dtr == pytest.approx(dt2, rel=1e-12), (c, dtr, dt2)
         o.advance(0.5 * (dt1 + dt2), dt2); dt1 = dt2
     assert o.shell_state("pla").max() == 0.0
+
+
+@needs_ref
+@pytest.mark.parametrize("warp", [0.0, 0.05], ids=["flat", "warped"])
+@pytest.mark.parametrize("ipla,npt", [(1, 5), (0, 3), (2, 3)])
+def test_bending_matches_the_reference_gpu_path_under_its_own_thickness_rule(ipla, npt, warp):
+    """Curvature, moments and the rotational hourglass part: with the reference CUDA kernels' mid-point rule loaded into the
+    oracle and into the CUDA path (orc_set_quadrature / orgpu_set_quadrature) the three must agree in bending too.  Pins CCURV3,
+    the z-dependence of the strains, MOM, the moment part of CFINT3 and HOUR(4:5) of CHVIS3 on reference code that executes."""
+    from refgpu_cases import bent_plate, midpoint_rule
+    m = bent_plate(ipla, npt, warp=warp)
+    g, o, r = Engine(m), Oracle(m), refgpu.RefShellGPU(m)
+    z, wf, wm = midpoint_rule(npt)
+    g.set_quadrature(npt, z, wf, wm); o.set_quadrature(npt, z, wf, wm)
+    try:
+        dt1, worst = 0.0, 0.0
+        for c in range(10):
+            nd = o.download_nodes(("X", "V", "VR"))
+            fr = r.step(dt1, nd["X"], nd["V"], nd["VR"])
+            for b in (g, o):
+                b.forces_phase(dt1); b.assemble()
+            fo, fg = o.download_nodes(("A", "AR")), g.download_nodes(("A", "AR"))
+            if c > 0:
+                sf, sm = np.abs(fo["A"]).max(), np.abs(fo["AR"]).max()
+                assert sf > 0.0 and sm > 0.0
+                errs = [np.abs(fr[:, :3] - fo["A"]).max() / sf, np.abs(fr[:, :3] - fg["A"]).max() / sf,
+                        np.abs(fr[:, 3:6] - fo["AR"]).max() / sm, np.abs(fr[:, 3:6] - fg["AR"]).max() / sm]
+                worst = max(worst, *errs)
+                print(f"cycle {c}: force oracle/cuda {errs[0]:.2e} {errs[1]:.2e}  moment oracle/cuda {errs[2]:.2e} {errs[3]:.2e}")
+                assert max(errs) <= TOL, (c, errs)
+            dt2 = o.time()["dt2t"]
+            for b in (g, o):
+                b.advance(0.5 * (dt1 + dt2), dt2)
+            dt1 = dt2
+        assert np.abs(o.shell_state("mom")).max() > 0.0 and o.shell_state("pla").max() > 1e-4
+        print(f"bending ipla={ipla} npt={npt} warp={warp}: worst difference to the reference GPU path {worst:.2e}")
+    finally:
+        o.set_quadrature(npt, *[None] * 3) if False else o.lib.orc_set_quadrature(o.h, 0, None, None, None)
