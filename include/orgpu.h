@@ -129,6 +129,16 @@ int  orgpu_set_parts(orgpu_engine* e, int npart, const int* ipartc, const int* i
 int  orgpu_set_print(orgpu_engine* e, int ipri);
 int  orgpu_get_balance(orgpu_engine* e, double out[8], double* partsav);
 int  orgpu_get_balance_history(orgpu_engine* e, int n, double* out /*[n][8]*/);
+/* -- tie-break keys of the time-step arg-min across domains: index of every local element in the processing order of the
+ *    undecomposed model (4-node shells, 3-node shells, solids) and global index of every local node.  SPMD_GLOB_MIN5
+ *    (engine/source/mpi/generic/spmd_glob_min5.F:122) keeps the first minimum in reduction order; with these keys N domains
+ *    elect, on an exact tie, the element one domain elects (NELTST identical on any GPU count).  NULL = local order.
+ *    Before orgpu_finalize. */
+int  orgpu_set_global_order(orgpu_engine* e, const int* gshell, const int* gsh3n, const int* gsolid, const int* gnode);
+/* -- how long a rank waits for its neighbours inside the peer-memory exchange before the handle is declared dead (default
+ *    30 s, or ORGPU_P2P_TIMEOUT_S).  A timeout is sticky: every later kernel of the handle is a no-op, the device state stays at
+ *    the last completed cycle, and orgpu_synchronize / get_time / download_* / step_host return -8. */
+int  orgpu_set_exchange_timeout(orgpu_engine* e, double seconds);
 /* -- through-thickness integration rule of the NPT-point /PROP/SHELL: positions Z0, force weights WF, moment weights WM
  *    (engine/source/elements/shell/coqini.F:46-122 by default; layini.F:246-254, mulawc.F90:769-777).  Replaces the row of the
  *    device tables (shared by the engines of a process) until the next orgpu_finalize.  After orgpu_finalize. */

@@ -91,6 +91,10 @@ class Binding:
                 self._call_group("add_solid_group_law", self.h, C.c_int(g.nel), C.c_int(g.nft), C.c_int(g.law),
                                  C.byref(g.mat), C.byref(g.prop), v0.ctypes.data_as(C.c_void_p))
         self._set_parts(m)
+        if self.status and getattr(m, "gorder", None) is not None:      # a domain of a decomposed model: tie-break keys of the dt arg-min
+            go = m.gorder
+            self._call("set_global_order", self.h, _opt(go.get("shell"), np.int32), _opt(go.get("sh3n"), np.int32),
+                       _opt(go.get("solid"), np.int32), _opt(go.get("node"), np.int32))
         self._call("finalize", self.h)
         return self
 
@@ -168,7 +172,7 @@ class Binding:
     def upload_nodes(self, X=None, V=None, VR=None, D=None, MS=None, IN=None):
         self._call("upload_nodes", self.h, *[_opt(a, np.float64) for a in (X, V, VR, D, MS, IN)])
 
-    def download_nodes(self, names=("X", "V", "D", "A")):
+    def download_nodes(self, names=("X", "V", "D")):
         n = self.model.numnod
         order = ("X", "V", "VR", "D", "A", "AR", "STIFN", "STIFR")
         out = {k: (np.zeros((n, 3)) if k not in ("STIFN", "STIFR") else np.zeros(n)) for k in names}

@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(ORGPU_BLOCK, ORGPU_BRICK_MINB * ORGPU_PER128)
 brick_forces_kernel(const __grid_constant__ BrickParams P)
 {
   const BrickSG& g = P.sg;
+  if (P.cs->abort) return;                               // sticky: a peer-memory wait timed out (exchange.cuh)
   const int e = blockIdx.x * ORGPU_TILE + threadIdx.x;
   __shared__ __align__(8) unsigned long long s_bar;
   double* const g_tile = g.slab + (size_t)blockIdx.x * g.nw * ORGPU_TILE;

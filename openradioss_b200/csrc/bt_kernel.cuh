@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(ORGPU_SHELL_CTA, 3 * ORGPU_PER128)
 bt_forces_kernel(const __grid_constant__ ShellParams P)
 {
   const ShellSG& g = P.sg;
+  if (P.cs->abort) return;                               // sticky: a peer-memory wait timed out (exchange.cuh)
   const int e = blockIdx.x * ORGPU_TILE + threadIdx.x;
   __shared__ __align__(8) unsigned long long s_bar;
   double* const g_tile = g.slab + (size_t)blockIdx.x * g.nw * ORGPU_TILE;

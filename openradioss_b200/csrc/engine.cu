@@ -77,6 +77,7 @@ struct orgpu_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> evpool;
   Exchange xc;                        // domain exchange (one process per GPU)
+  std::vector<int> gord_c, gord_t, gord_s, gnode; int* d_gnode = nullptr;   // global processing order / node index of a domain's elements / nodes
   // print-cycle balances (CBILAN / SBILAN / ECRIT): parts, GBUF%VOL of the shells, scratch rows and their fixed-order reduction
   int npart = 1; bool have_parts = false; std::vector<int> ipartc, iparts, iparttg; std::vector<double> gvolc, gvoltg;
   int ipri = 0; int bal_ld = 0, nbal_ld = 0, nchunk = 0, nnchunk = 0;
@@ -117,6 +118,7 @@ template <class T> static int upload_vec(std::vector<void*>& owned, T** p, const
 }
 
 extern "C" {
+static int create_body(orgpu_engine* e, int numnod, const orgpu_control* ctl);
 
 int orgpu_create(orgpu_engine** out, int device, int numnod, const orgpu_control* ctl)
 {
@@ -127,6 +129,14 @@ int orgpu_create(orgpu_engine** out, int device, int numnod, const orgpu_control
   CUDA_OK(cudaSetDevice(device));
   orgpu_engine* e = new orgpu_engine();
   e->device = device; e->numnod = numnod; e->ctl = *ctl;
+  const int rc = create_body(e, numnod, ctl);
+  if (rc) { orgpu_destroy(e); return rc; }          // nothing of a half-built engine is leaked
+  *out = e;
+  return 0;
+}
+
+static int create_body(orgpu_engine* e, int numnod, const orgpu_control* ctl)
+{
   CUDA_OK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
   for (int k = 0; k < ORGPU_NSIDE; k++) { CUDA_OK(cudaStreamCreateWithFlags(&e->side[k], cudaStreamNonBlocking)); CUDA_OK(cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming)); }
   CUDA_OK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
@@ -141,7 +151,6 @@ int orgpu_create(orgpu_engine** out, int device, int numnod, const orgpu_control
   cs.tt0 = ctl->tt_init; cs.fscale = 1.0;
   CUDA_OK(cudaMemcpy(e->d_cs, &cs, sizeof cs, cudaMemcpyHostToDevice));
   CUDA_OK(cudaEventCreate(&e->ev0)); CUDA_OK(cudaEventCreate(&e->ev1));
-  *out = e;
   return 0;
 }
 
@@ -156,7 +165,7 @@ int orgpu_destroy(orgpu_engine* e)
   void* ptrs[] = {e->nd.pos, e->nd.vel, e->nd.rot, e->nd.D, e->nd.A, e->nd.AR, e->nd.STIFN, e->nd.STIFR, e->nd.MS, e->nd.IN,
                   e->d_stage3a, e->d_stage3b, e->d_fext, e->d_mext, e->d_icodt, e->d_icodr, e->d_adsky, e->d_fsky, e->d_cs,
                   e->db.dt, e->db.order, e->d_sgr, e->d_btf, e->d_bnpf, e->d_ftf, e->d_fnpf, e->d_fv_idx, e->d_fv, e->d_itab, e->d_nd_dt, e->d_nd_node, e->d_gmask,
-                  e->d_bal, e->d_nbal, e->d_epart, e->d_npartial, e->d_partsav, e->d_hist, e->d_chunks, e->d_bs};
+                  e->d_gnode, e->d_bal, e->d_nbal, e->d_epart, e->d_npartial, e->d_partsav, e->d_hist, e->d_chunks, e->d_bs};
   for (void* p : ptrs) if (p) cudaFree(p);
   { Exchange& x = e->xc;
     void* xp[] = {x.d_send_slots, x.d_recv_slots, x.d_sendbuf, x.d_recvbuf, x.d_cand_send, x.d_cand_recv, x.d_slots_tmp, x.d_rows_tmp};
@@ -169,7 +178,7 @@ int orgpu_destroy(orgpu_engine* e)
   if (e->ev0) cudaEventDestroy(e->ev0); if (e->ev1) cudaEventDestroy(e->ev1);
   for (int k = 0; k < ORGPU_NSIDE; k++) { if (e->side[k]) cudaStreamDestroy(e->side[k]); if (e->ev_join[k]) cudaEventDestroy(e->ev_join[k]); }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
-  cudaStreamDestroy(e->st);
+  if (e->st) cudaStreamDestroy(e->st);
   delete e;
   return 0;
 }
@@ -234,8 +243,9 @@ int orgpu_set_sh3n(orgpu_engine* e, int numeltg, const int* ixtg, const int* iad
 int orgpu_set_pon(orgpu_engine* e, const int* adsky, int lsky)
 {
   NEED(e && adsky && lsky >= 0 && !e->finalized, -1, "orgpu_set_pon: bad arguments / already finalized");
+  NEED(adsky[0] == 1 && adsky[e->numnod] == lsky + 1, -4, "orgpu_set_pon: ADSKY does not span 1..LSKY+1");
+  for (int n = 0; n < e->numnod; n++) NEED(adsky[n + 1] >= adsky[n], -4, "orgpu_set_pon: ADSKY decreases at node %d", n + 1);
   e->adsky.assign(adsky, adsky + e->numnod + 1); e->lsky = lsky;
-  NEED(e->adsky[0] == 1 && e->adsky[e->numnod] == lsky + 1, -4, "orgpu_set_pon: ADSKY does not span 1..LSKY+1");
   return 0;
 }
 int orgpu_set_functions(orgpu_engine* e, int nfunc, const int* npf, const double* tf)
@@ -249,6 +259,37 @@ int orgpu_set_itab(orgpu_engine* e, const int* itab)
 {
   NEED(e && itab && !e->finalized, -1, "orgpu_set_itab: bad arguments / already finalized");
   e->itab.assign(itab, itab + e->numnod);
+  return 0;
+}
+
+// a peer-memory wait that timed out is fatal for the handle (exchange.cuh: the device state stopped advancing)
+static int check_abort(orgpu_engine* e)
+{
+  if (!e->xc.p2p || !e->xc.d_err) return 0;
+  int err = 0; CUDA_OK(cudaMemcpy(&err, e->xc.d_err, 4, cudaMemcpyDeviceToHost));
+  NEED(err == 0, -8, "orgpu: peer-memory exchange timed out waiting for a neighbour (a rank stopped stepping); the device state of this handle is frozen at the last completed cycle");
+  return 0;
+}
+
+// Tie-break keys for the time-step arg-min across domains: the index of every local element in the processing order of the
+// undecomposed model (4-node shells, then 3-node shells, then solids: what one domain would use), and the global index of
+// every local node (nodal time step).  With them N domains elect, on an exact tie, the element a single domain elects.
+// Any pointer may be NULL (local order).  Before orgpu_finalize.
+int orgpu_set_global_order(orgpu_engine* e, const int* gshell, const int* gsh3n, const int* gsolid, const int* gnode)
+{
+  NEED(e && !e->finalized, -1, "orgpu_set_global_order: bad handle / already finalized");
+  if (gshell) e->gord_c.assign(gshell, gshell + e->numelc);
+  if (gsh3n) e->gord_t.assign(gsh3n, gsh3n + e->numeltg);
+  if (gsolid) e->gord_s.assign(gsolid, gsolid + e->numels);
+  if (gnode) e->gnode.assign(gnode, gnode + e->numnod);
+  return 0;
+}
+
+int orgpu_set_exchange_timeout(orgpu_engine* e, double seconds)
+{
+  NEED(e && seconds > 0.0, -1, "orgpu_set_exchange_timeout: bad arguments");
+  e->xc.timeout_ns = (unsigned long long)(seconds * 1.0e9);
+  if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
   return 0;
 }
 
@@ -444,7 +485,7 @@ int orgpu_finalize(orgpu_engine* e)
     if (push_dev(S.owned, &d.smstr, (size_t)21 * np)) return -100;
     const int nblk = np / ORGPU_TILE;                    // dt candidate slots: one per CTA
     NEED((int)e->sgr.size() < ORGPU_MAX_SG, -6, "too many super-groups (%d)", ORGPU_MAX_SG);
-    e->sgr.push_back(SGRange{blk, nblk, ORGPU_FAM_BRICK, d.order0, d.ngl});
+    e->sgr.push_back(SGRange{blk, nblk, ORGPU_FAM_BRICK, d.order0, d.ngl, nullptr});
     order += ne; blk += nblk; gi = gj;
   }
   NEED(blk > 0, -4, "orgpu_finalize: no element groups");
@@ -456,6 +497,16 @@ int orgpu_finalize(orgpu_engine* e)
     std::vector<double> h(gv.begin() + S.first_elem, gv.begin() + S.first_elem + S.d.ne); h.resize(S.d.ne_pad, 0.0);
     double* dg; if (upload_vec(S.owned, &dg, h)) return -100; S.d.gvol = dg;
   }
+  { // global processing order of every super-group's elements (tie-break across domains); sgr follows csg then bsg
+    size_t k = 0;
+    auto up = [&](std::vector<void*>& owned, const std::vector<int>& g, int first, int ne, SGRange& r) -> int {
+      r.gord = nullptr; if (g.empty()) return 0;
+      std::vector<int> h(g.begin() + first, g.begin() + first + ne); int* d; if (upload_vec(owned, &d, h)) return -100; r.gord = d; return 0; };
+    for (auto& S : e->csg) { if (up(S.owned, S.sh3n ? e->gord_t : e->gord_c, S.first_elem, S.d.ne, e->sgr[k])) return -100; k++; }
+    for (auto& S : e->bsg) { if (up(S.owned, e->gord_s, S.first_elem, S.d.ne, e->sgr[k])) return -100; k++; }
+    e->nd.gnode = nullptr;
+    if (!e->gnode.empty()) { if (dev_alloc(&e->d_gnode, e->gnode.size())) return -100;
+      CUDA_OK(cudaMemcpy(e->d_gnode, e->gnode.data(), 4 * e->gnode.size(), cudaMemcpyHostToDevice)); e->nd.gnode = e->d_gnode; } }
   if (dev_alloc(&e->d_sgr, e->sgr.size())) return -100;
   CUDA_OK(cudaMemcpy(e->d_sgr, e->sgr.data(), sizeof(SGRange) * e->sgr.size(), cudaMemcpyHostToDevice));
   e->fa.nsg = (int)e->sgr.size(); e->fa.sg = e->d_sgr;
@@ -634,8 +685,8 @@ static void p2p_exchange_on_stream(orgpu_engine* e)
     e->launches++; }
   { const int nthr = x.nrecv * V > 1 ? x.nrecv * V : 1; const int nb = (nthr + 255) / 256;
     const int adv = e->ctl.nodadt ? 0 : 1;                 // /DT/NODA: the clock advances after the nodal dt exchange
-    if (e->roww == 8) p2p_wait_unpack_kernel<8><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_recv_slots, x.nrecv, x.win, e->d_cs, x.nranks, x.d_xcycle, x.d_err, adv);
-    else              p2p_wait_unpack_kernel<4><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_recv_slots, x.nrecv, x.win, e->d_cs, x.nranks, x.d_xcycle, x.d_err, adv);
+    if (e->roww == 8) p2p_wait_unpack_kernel<8><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_recv_slots, x.nrecv, x.win, e->d_cs, x.nranks, x.d_xcycle, x.d_err, adv, x.timeout_ns);
+    else              p2p_wait_unpack_kernel<4><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_recv_slots, x.nrecv, x.win, e->d_cs, x.nranks, x.d_xcycle, x.d_err, adv, x.timeout_ns);
     e->launches++; }
 }
 // node phase of a multi-domain cycle over peer memory
@@ -646,7 +697,7 @@ static void p2p_node_phase(orgpu_engine* e)
   launch_node_assemble(e->nd, e->d_fsky, e->roww, e->d_cs, e->ctl.iroddl, e->st);
   launch_dtnoda_finalize(e->nd, e->d_cs, 0, e->st);                       // local nodal DT2T
   p2p_dt_push_kernel<<<1, 32, 0, e->st>>>(e->d_cs, x.d_peer_win, x.nranks, x.rank, x.d_xcycle);
-  p2p_dt_wait_kernel<<<1, 32, 0, e->st>>>(e->d_cs, x.win, x.nranks, x.d_xcycle, x.d_err);
+  p2p_dt_wait_kernel<<<1, 32, 0, e->st>>>(e->d_cs, x.win, x.nranks, x.d_xcycle, x.d_err, x.timeout_ns);
   launch_node_advance(e->nd, e->d_cs, e->ctl.iroddl, e->st);
   e->launches += 5;
 }
@@ -764,8 +815,7 @@ int orgpu_synchronize(orgpu_engine* e)
 {
   NEED(e, -1, "null handle"); CUDA_OK(cudaSetDevice(e->device));
   CUDA_OK(cudaStreamSynchronize(e->st));
-  if (e->xc.p2p) { int err = 0; CUDA_OK(cudaMemcpy(&err, e->xc.d_err, 4, cudaMemcpyDeviceToHost));
-                   NEED(err == 0, -8, "orgpu: peer-memory exchange timed out waiting for a neighbour's rows (a rank stopped stepping)"); }
+  { int rc = check_abort(e); if (rc) return rc; }
   if (!e->profile) { float ms = 0; if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_run_ms = ms; else cudaGetLastError(); }
   return 0;
 }
@@ -774,6 +824,7 @@ int orgpu_get_time(orgpu_engine* e, double out[5], int iout[3])
 {
   NEED(e, -1, "null handle"); CUDA_OK(cudaSetDevice(e->device));
   CUDA_OK(cudaStreamSynchronize(e->st));
+  { int rc = check_abort(e); if (rc) return rc; }
   CycleState cs; CUDA_OK(cudaMemcpy(&cs, e->d_cs, sizeof cs, cudaMemcpyDeviceToHost));
   out[0] = cs.tt; out[1] = cs.dt1; out[2] = cs.dt2; out[3] = cs.dt12; out[4] = cs.dt2t;
   iout[0] = cs.neltst; iout[1] = cs.ityptst; iout[2] = (int)cs.ncycle;
@@ -785,6 +836,7 @@ int orgpu_download_nodes(orgpu_engine* e, double* X, double* V, double* VR, doub
 {
   NEED(e, -1, "null handle"); CUDA_OK(cudaSetDevice(e->device));
   CUDA_OK(cudaStreamSynchronize(e->st));
+  { int rc = check_abort(e); if (rc) return rc; }
   const size_t n = e->numnod;
   if (X) { if (download4to3(e, e->nd.pos, X)) return -100; }
   if (V) { if (download4to3(e, e->nd.vel, V)) return -100; }
@@ -813,6 +865,7 @@ static int solid_state_xfer(orgpu_engine* e, int field, double* buf, bool up)
 {
   NEED(e && e->finalized && buf, -1, "engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
   CUDA_OK(cudaStreamSynchronize(e->st));
+  { int rc = check_abort(e); if (rc) return rc; }
   const size_t NE = e->numels;
   for (auto& S : e->bsg) {
     const BrickSG& d = S.d; int w0 = 0, nc = 1; double* base = d.slab; int nw = d.nw;
@@ -834,6 +887,7 @@ int orgpu_download_shell_state(orgpu_engine* e, int field, double* out)
 {
   NEED(e && e->finalized && out, -1, "engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
   CUDA_OK(cudaStreamSynchronize(e->st));
+  { int rc = check_abort(e); if (rc) return rc; }
   return shell_state_xfer(e->csg, e->numelc, field, out, false);
 }
 int orgpu_upload_shell_state(orgpu_engine* e, int field, const double* in)
@@ -854,7 +908,8 @@ int orgpu_upload_sh3n_state(orgpu_engine* e, int field, const double* in)
   CUDA_OK(cudaStreamSynchronize(e->st));
   return shell_state_xfer(e->csg, e->numeltg, field, const_cast<double*>(in), true, true);
 }
-/* LAW36 table cursors (VARTMP) are integer state: per integration point the live cursor(s) */
+/* (the LAW36 VARTMP cursors are not part of a hand-over: they are forward-only walks on the monotone plastic strain and re-find
+ * their segment from zero in the first cycle after an upload) */
 int orgpu_set_time(orgpu_engine* e, double tt, double dt2, double dt2old, long long ncycle)
 {
   NEED(e, -1, "null handle"); CUDA_OK(cudaSetDevice(e->device));
@@ -877,7 +932,7 @@ int orgpu_step_host(orgpu_engine* e, const double* X, const double* V, const dou
   if (Xout) { unpack4to3_kernel<<<nb, 256, 0, e->st>>>(e->nd.pos, e->d_stage3a, n); e->launches++; CUDA_OK(cudaMemcpyAsync(Xout, e->d_stage3a, 24 * (size_t)n, cudaMemcpyDeviceToHost, e->st)); }
   if (Vout) { unpack4to3_kernel<<<nb, 256, 0, e->st>>>(e->nd.vel, e->d_stage3b, n); e->launches++; CUDA_OK(cudaMemcpyAsync(Vout, e->d_stage3b, 24 * (size_t)n, cudaMemcpyDeviceToHost, e->st)); }
   CUDA_OK(cudaStreamSynchronize(e->st));
-  return 0;
+  return check_abort(e);
 }
 
 // ---- domain exchange ------------------------------------------------------------------------------
@@ -942,6 +997,7 @@ int orgpu_set_exchange(orgpu_engine* e, int nneigh, const int* ranks, const int*
 {
   NEED(e && e->finalized && nneigh >= 0, -1, "orgpu_set_exchange: engine not finalized / bad arguments"); CUDA_OK(cudaSetDevice(e->device));
   Exchange& x = e->xc;
+  NEED(x.nranks <= 32, -7, "orgpu_set_exchange: more than 32 ranks on one node");
   x.nb_rank.assign(ranks, ranks + nneigh); x.send_ptr.assign(send_ptr, send_ptr + nneigh + 1); x.recv_ptr.assign(recv_ptr, recv_ptr + nneigh + 1);
   x.nsend = nneigh ? send_ptr[nneigh] : 0; x.nrecv = nneigh ? recv_ptr[nneigh] : 0;
   for (int j = 0; j < x.nsend; j++) NEED(send_slots[j] >= 0 && send_slots[j] < e->lsky, -4, "orgpu_set_exchange: send slot out of range");
@@ -958,7 +1014,7 @@ int orgpu_p2p_export(orgpu_engine* e, unsigned char handle[64])
 {
   NEED(e && e->finalized && handle, -1, "orgpu_p2p_export: engine not finalized / bad arguments"); CUDA_OK(cudaSetDevice(e->device));
   Exchange& x = e->xc;
-  NEED(x.nranks > 1 && !x.nb_rank.empty(), -7, "orgpu_p2p_export: call orgpu_comm_init and orgpu_set_exchange first");
+  NEED(x.nranks > 1 && x.d_send_slots, -7, "orgpu_p2p_export: call orgpu_comm_init and orgpu_set_exchange first");   // a rank without neighbours still needs its window: dt candidates and flags
   NEED(x.nranks <= 32, -7, "orgpu_p2p_export: more than 32 ranks on one node");
   NEED(!x.win, -7, "orgpu_p2p_export: window already exported");
   x.win_bytes = win_rows_off(x.nranks) + (size_t)2 * (x.nrecv + 1) * e->roww * 8;

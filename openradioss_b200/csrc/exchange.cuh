@@ -62,6 +62,7 @@ struct Exchange {
   double** d_peer_cand = nullptr;                        // [nranks] candidate area of every window
   unsigned long long** d_peer_flag = nullptr;            // [nranks] &flags[rank] inside every window
   unsigned long long* d_xcycle = nullptr; unsigned int* d_done = nullptr; int* d_err = nullptr;
+  unsigned long long timeout_ns = 30000000000ull;        // peer wait budget (orgpu_set_exchange_timeout / ORGPU_P2P_TIMEOUT_S)
   unsigned char** d_peer_win = nullptr;                  // [nranks] window bases (for the /DT/NODA candidate exchange)
 };
 
@@ -93,6 +94,57 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
 
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// (dt, key) candidates of the ranks fold with the total order the single-domain fold uses (common.cuh cand_better): smaller dt;
+// on a tie a solid replaces a shell ("<=" after "<"), among shells the earlier, among solids the later element of the
+// undecomposed model's processing order.  key = order + 2^32 for a solid.
+#define ORGPU_KEY_SOLID 4294967296.0
+__device__ __forceinline__ bool xcand_better(double da, double ka, double db, double kb) {
+  if (da < db) return true;
+  if (da > db) return false;
+  const bool sa = ka >= ORGPU_KEY_SOLID, sb = kb >= ORGPU_KEY_SOLID;
+  if (sa != sb) return sa;
+  return sa ? (ka > kb) : (ka < kb);
+}
+__device__ __forceinline__ double cand_key(const CycleState* cs) { return (double)cs->gkey + (cs->wsolid ? ORGPU_KEY_SOLID : 0.0); }
+// fold of the ranks' candidates in rank order + the RESOL bookkeeping (resol.F:2721-2722, 6124-6128, 6327, 6352, 6494-6497, 8599-8608)
+__device__ __forceinline__ void fold_candidates_and_advance(CycleState* cs, const double* cand, int nranks, bool cg)
+{
+  double cur = K_EP06, key = 1.0e300; int typ = 0, ngl = 0;
+  for (int r = 0; r < nranks; r++) {
+    const double d = cg ? __ldcg(cand + 4 * r) : cand[4 * r], k = cg ? __ldcg(cand + 4 * r + 3) : cand[4 * r + 3];
+    if (xcand_better(d, k, cur, key) && d < K_EP06) {
+      cur = d; key = k;
+      const double t1 = cg ? __ldcg(cand + 4 * r + 1) : cand[4 * r + 1], t2 = cg ? __ldcg(cand + 4 * r + 2) : cand[4 * r + 2];
+      typ = (int)t1; ngl = (int)t2;
+    }
+  }
+  cs->dt2t = cur; cs->ityptst = typ; cs->neltst = ngl;
+  const double dt1 = cs->dt2;
+  double dt2 = K_EP06;
+  if (cur < dt2) dt2 = cur;
+  const double c11 = (double)1.1f;
+  dt2 = fmin(dt2, fmin(c11 * cs->dt2old, cs->dtmx));
+  cs->dt2old = dt2;
+  cs->dt12 = K_HALF * (dt1 + dt2);
+  cs->dt1 = dt1; cs->dt2 = dt2;
+  cs->tt = cs->tt + dt2; cs->ncycle += 1;
+}
+// bounded wait for every rank's flag to reach cycle c; a timeout is FATAL for the handle: *err and cs->abort are sticky, every
+// later force / node / exchange kernel returns at once, and the host sees -8 at its next query
+__device__ __forceinline__ bool wait_flags(const unsigned long long* flags, int nranks, unsigned long long c, unsigned long long budget_ns,
+                                           int* err, CycleState* cs)
+{
+  const unsigned long long t0 = global_ns();
+  for (int q = 0; q < nranks; q++) {
+    while (ld_acquire_sys(flags + q) < c) {
+      if (global_ns() - t0 > budget_ns) { *err = 1; cs->abort = 1; __threadfence(); return false; }
+      __nanosleep(100);
+    }
+  }
+  return true;
+}
+
 template <int ROWW>
 __global__ void __launch_bounds__(256)
 p2p_push_kernel(const double* __restrict__ fsky, const int* __restrict__ send_slots, const int* __restrict__ send_nb,
@@ -100,6 +152,7 @@ p2p_push_kernel(const double* __restrict__ fsky, const int* __restrict__ send_sl
                 const CycleState* cs, double* const* __restrict__ peer_cand, unsigned long long* const* __restrict__ peer_flag,
                 int nranks, int rank, unsigned long long* xcycle, unsigned int* done)
 {
+  if (cs->abort) return;
   const unsigned long long c = *reinterpret_cast<volatile unsigned long long*>(xcycle) + 1ull;   // the exchange being pushed
   const int par = (int)(c & 1ull);
   constexpr int V = ROWW / 4;
@@ -115,10 +168,10 @@ p2p_push_kernel(const double* __restrict__ fsky, const int* __restrict__ send_sl
     const unsigned prev = atomicAdd(done, 1u);
     if (prev == gridDim.x - 1) {                      // last CTA: every row of this rank is on its way
       *done = 0u;
-      const double d0 = cs->dt2t, d1 = (double)cs->ityptst, d2 = (double)cs->neltst;
+      const double d0 = cs->dt2t, d1 = (double)cs->ityptst, d2 = (double)cs->neltst, d3 = cand_key(cs);
       for (int q = 0; q < nranks; q++) {
         double* cd = peer_cand[q] + ((size_t)par * nranks + rank) * 4;
-        cd[0] = d0; cd[1] = d1; cd[2] = d2; cd[3] = 0.0;
+        cd[0] = d0; cd[1] = d1; cd[2] = d2; cd[3] = d3;
       }
       __threadfence_system();
       for (int q = 0; q < nranks; q++) st_release_sys(peer_flag[q], c);
@@ -130,21 +183,15 @@ p2p_push_kernel(const double* __restrict__ fsky, const int* __restrict__ send_sl
 template <int ROWW>
 __global__ void __launch_bounds__(256)
 p2p_wait_unpack_kernel(double* __restrict__ fsky, const int* __restrict__ recv_slots, int nrecv, const unsigned char* win,
-                       CycleState* cs, int nranks, const unsigned long long* xcycle, int* err, int advance)
+                       CycleState* cs, int nranks, const unsigned long long* xcycle, int* err, int advance, unsigned long long budget_ns)
 {
+  if (cs->abort) return;
   const unsigned long long c = *reinterpret_cast<const volatile unsigned long long*>(xcycle);
   const int par = (int)(c & 1ull);
-  if (threadIdx.x == 0) {
-    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(win + ORGPU_WIN_FLAGS);
-    const long long t0 = clock64();
-    for (int q = 0; q < nranks; q++) {
-      while (ld_acquire_sys(flags + q) < c) {
-        if (clock64() - t0 > 8000000000ll) { *err = 1; break; }      // ~4 s: a peer died; never hang the GPU
-        __nanosleep(100);
-      }
-    }
-  }
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) s_ok = wait_flags(reinterpret_cast<const unsigned long long*>(win + ORGPU_WIN_FLAGS), nranks, c, budget_ns, err, cs) ? 1 : 0;
   __syncthreads();
+  if (!s_ok) return;                                  // a peer died: nothing is scattered, the clock does not advance
   constexpr int V = ROWW / 4;
   const double* rows = reinterpret_cast<const double*>(win + win_rows_off_dev(nranks)) + (size_t)par * nrecv * ROWW;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -153,24 +200,8 @@ p2p_wait_unpack_kernel(double* __restrict__ fsky, const int* __restrict__ recv_s
     const double4 v = ld256_cg(reinterpret_cast<const double4*>(rows + (size_t)j * ROWW + 4 * cc));
     st256(reinterpret_cast<double4*>(fsky + (size_t)recv_slots[j] * ROWW + 4 * cc), v);
   }
-  if (i == 0 && advance) {                            // GLOB_MIN over the ranks + RESOL bookkeeping (as rows_unpack_kernel)
-    const double* cand = reinterpret_cast<const double*>(win + ORGPU_WIN_CAND) + (size_t)par * nranks * 4;
-    double cur = K_EP06; int typ = 0, ngl = 0;
-    for (int r = 0; r < nranks; r++) {
-      const double d = __ldcg(cand + 4 * r);
-      if (d < cur) { cur = d; typ = (int)__ldcg(cand + 4 * r + 1); ngl = (int)__ldcg(cand + 4 * r + 2); }
-    }
-    cs->dt2t = cur; cs->ityptst = typ; cs->neltst = ngl;
-    const double dt1 = cs->dt2;
-    double dt2 = K_EP06;
-    if (cur < dt2) dt2 = cur;
-    const double c11 = (double)1.1f;
-    dt2 = fmin(dt2, fmin(c11 * cs->dt2old, cs->dtmx));
-    cs->dt2old = dt2;
-    cs->dt12 = K_HALF * (dt1 + dt2);
-    cs->dt1 = dt1; cs->dt2 = dt2;
-    cs->tt = cs->tt + dt2; cs->ncycle += 1;
-  }
+  if (i == 0 && advance)                              // GLOB_MIN over the ranks + RESOL bookkeeping
+    fold_candidates_and_advance(cs, reinterpret_cast<const double*>(win + ORGPU_WIN_CAND) + (size_t)par * nranks * 4, nranks, true);
 }
 
 // rows out of the skyline into a contiguous buffer; ROWW doubles per row on both sides
@@ -184,7 +215,7 @@ __global__ void rows_pack_kernel(const double* __restrict__ fsky, const int* __r
     const int j = i / V, c = i - j * V;
     reinterpret_cast<double2*>(buf)[(size_t)j * V + c] = reinterpret_cast<const double2*>(fsky)[(size_t)slots[j] * V + c];
   }
-  if (cand && i == 0) { cand[0] = cs->dt2t; cand[1] = (double)cs->ityptst; cand[2] = (double)cs->neltst; cand[3] = 0.0; }
+  if (cand && i == 0) { cand[0] = cs->dt2t; cand[1] = (double)cs->ityptst; cand[2] = (double)cs->neltst; cand[3] = cand_key(cs); }
 }
 
 // received rows into their reserved slots; thread 0 of block 0 folds the dt candidates of all ranks in
@@ -200,23 +231,7 @@ __global__ void rows_unpack_kernel(double* __restrict__ fsky, const int* __restr
     const int j = i / V, c = i - j * V;
     reinterpret_cast<double2*>(fsky)[(size_t)slots[j] * V + c] = reinterpret_cast<const double2*>(buf)[(size_t)j * V + c];
   }
-  if (cand && i == 0) {
-    double cur = K_EP06; int typ = 0, ngl = 0;
-    for (int r = 0; r < nranks; r++) {
-      const double d = cand[4 * r];
-      if (d < cur) { cur = d; typ = (int)cand[4 * r + 1]; ngl = (int)cand[4 * r + 2]; }
-    }
-    cs->dt2t = cur; cs->ityptst = typ; cs->neltst = ngl;
-    const double dt1 = cs->dt2;
-    double dt2 = K_EP06;
-    if (cur < dt2) dt2 = cur;
-    const double c11 = (double)1.1f;
-    dt2 = fmin(dt2, fmin(c11 * cs->dt2old, cs->dtmx));
-    cs->dt2old = dt2;
-    cs->dt12 = K_HALF * (dt1 + dt2);
-    cs->dt1 = dt1; cs->dt2 = dt2;
-    cs->tt = cs->tt + dt2; cs->ncycle += 1;
-  }
+  if (cand && i == 0) fold_candidates_and_advance(cs, cand, nranks, false);
 }
 
 // host-staged variants always speak 8-double rows (the reference FSKY(8,LSKY)); ROWW=4 device rows
@@ -245,37 +260,21 @@ __global__ void p2p_dt_push_kernel(const CycleState* cs, unsigned char* const* _
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const unsigned long long c = *reinterpret_cast<const volatile unsigned long long*>(xcycle);
   const int par = (int)(c & 1ull);
-  const double d0 = cs->dt2t, d1 = (double)cs->ityptst, d2 = (double)cs->neltst;
+  if (cs->abort) return;
+  const double d0 = cs->dt2t, d1 = (double)cs->ityptst, d2 = (double)cs->neltst, d3 = cand_key(cs);
   for (int q = 0; q < nranks; q++) {
     double* cd = reinterpret_cast<double*>(peer_win[q] + ORGPU_WIN_CAND + (size_t)2 * nranks * 32) + ((size_t)par * nranks + rank) * 4;
-    cd[0] = d0; cd[1] = d1; cd[2] = d2; cd[3] = 0.0;
+    cd[0] = d0; cd[1] = d1; cd[2] = d2; cd[3] = d3;
   }
   __threadfence_system();
   for (int q = 0; q < nranks; q++) st_release_sys(reinterpret_cast<unsigned long long*>(peer_win[q] + ORGPU_WIN_FLAGS2) + rank, c);
 }
-__global__ void p2p_dt_wait_kernel(CycleState* cs, const unsigned char* win, int nranks, const unsigned long long* xcycle, int* err)
+__global__ void p2p_dt_wait_kernel(CycleState* cs, const unsigned char* win, int nranks, const unsigned long long* xcycle, int* err,
+                                   unsigned long long budget_ns)
 {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (threadIdx.x != 0 || blockIdx.x != 0 || cs->abort) return;
   const unsigned long long c = *reinterpret_cast<const volatile unsigned long long*>(xcycle);
   const int par = (int)(c & 1ull);
-  const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(win + ORGPU_WIN_FLAGS2);
-  const long long t0 = clock64();
-  for (int q = 0; q < nranks; q++)
-    while (ld_acquire_sys(flags + q) < c) { if (clock64() - t0 > 8000000000ll) { *err = 1; break; } __nanosleep(100); }
-  const double* cand = reinterpret_cast<const double*>(win + ORGPU_WIN_CAND + (size_t)2 * nranks * 32) + (size_t)par * nranks * 4;
-  double cur = K_EP06; int typ = 0, ngl = 0;
-  for (int r = 0; r < nranks; r++) {
-    const double d = __ldcg(cand + 4 * r);
-    if (d < cur) { cur = d; typ = (int)__ldcg(cand + 4 * r + 1); ngl = (int)__ldcg(cand + 4 * r + 2); }
-  }
-  cs->dt2t = cur; cs->ityptst = typ; cs->neltst = ngl;
-  const double dt1 = cs->dt2;
-  double dt2 = K_EP06;
-  if (cur < dt2) dt2 = cur;
-  const double c11 = (double)1.1f;
-  dt2 = fmin(dt2, fmin(c11 * cs->dt2old, cs->dtmx));
-  cs->dt2old = dt2;
-  cs->dt12 = K_HALF * (dt1 + dt2);
-  cs->dt1 = dt1; cs->dt2 = dt2;
-  cs->tt = cs->tt + dt2; cs->ncycle += 1;
+  if (!wait_flags(reinterpret_cast<const unsigned long long*>(win + ORGPU_WIN_FLAGS2), nranks, c, budget_ns, err, cs)) return;
+  fold_candidates_and_advance(cs, reinterpret_cast<const double*>(win + ORGPU_WIN_CAND + (size_t)2 * nranks * 32) + (size_t)par * nranks * 4, nranks, true);
 }

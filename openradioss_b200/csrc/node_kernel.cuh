@@ -164,6 +164,7 @@ template <int ROWW>
 __global__ void __launch_bounds__(ORGPU_NODE_BLOCK)
 node_assemble_kernel(const __grid_constant__ DevNodes nd, const double* __restrict__ fsky, const CycleState* __restrict__ cs, int iroddl)
 {
+  if (cs->abort) return;
   const int n = blockIdx.x * ORGPU_NODE_BLOCK + threadIdx.x;
   double dtt = K_EP30, dtr = K_EP30;
   if (n < nd.n) {
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(1024)
 dtnoda_finalize_kernel(CycleState* cs, const __grid_constant__ DevNodes nd, int ncta, int fused)
 {
   __shared__ double s_dt[32]; __shared__ int s_ord[32];
+  if (cs->abort) return;
   double cur = cs->dt2t; int curn = -1;
   for (int f = 0; f < 2; f++) {
     double dt = K_EP30; int ord = 0x7fffffff;
@@ -216,7 +218,8 @@ dtnoda_finalize_kernel(CycleState* cs, const __grid_constant__ DevNodes nd, int 
     if (threadIdx.x == 0 && dt < cur) { cur = dt; curn = ord; }
   }
   if (threadIdx.x == 0) {
-    if (curn >= 0) { cs->dt2t = cur; cs->neltst = nd.itab ? nd.itab[curn] : curn + 1; cs->ityptst = 11; }
+    if (curn >= 0) { cs->dt2t = cur; cs->neltst = nd.itab ? nd.itab[curn] : curn + 1; cs->ityptst = 11;
+                     cs->gkey = nd.gnode ? nd.gnode[curn] : curn; cs->wsolid = 0; }
     if (fused) {
       const double dt1 = cs->dt2;
       double dt2 = K_EP06;
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(ORGPU_NODE_BLOCK)
 node_advance_kernel(const __grid_constant__ DevNodes nd, const CycleState* __restrict__ cs, int iroddl)
 {
   const int n = blockIdx.x * ORGPU_NODE_BLOCK + threadIdx.x;
-  if (n >= nd.n) return;
+  if (n >= nd.n || cs->abort) return;
   NodeAcc r;
   r.a[0] = nd.A[3 * n]; r.a[1] = nd.A[3 * n + 1]; r.a[2] = nd.A[3 * n + 2];
   r.ar[0] = nd.AR[3 * n]; r.ar[1] = nd.AR[3 * n + 1]; r.ar[2] = nd.AR[3 * n + 2];
@@ -253,7 +256,7 @@ node_fused_kernel(const __grid_constant__ DevNodes nd, const double* __restrict_
                   const CycleState* __restrict__ cs, int iroddl)
 {
   const int n = blockIdx.x * ORGPU_NODE_BLOCK + threadIdx.x;
-  if (n >= nd.n) return;
+  if (n >= nd.n || cs->abort) return;
   const NodeIn q = node_load(nd, n, iroddl);
   NodeAcc r = node_gather<ROWW>(nd, fsky, n, iroddl, cs->fscale);
   node_update(nd, n, q, r, cs->dt12, cs->dt2, cs->tt0, iroddl, cs->gv, cs->ipri, cs->dt1);

@@ -99,10 +99,11 @@ __device__ __forceinline__ void qeph_warp_proj(const QephGeo& q, double Z1, doub
 #define ORGPU_SHELL_MINB 3
 #endif
 
-template <int LAW, bool STAGED>
+template <int LAW, bool STAGED, int FAST = 0>
 __global__ void __launch_bounds__(ORGPU_SHELL_CTA, ORGPU_SHELL_MINB * ORGPU_PER128)
 qeph_forces_kernel(const __grid_constant__ ShellParams P)
 {
+  if (P.cs->abort) return;                               // sticky: a peer-memory wait timed out (exchange.cuh)
   const ShellSG& g = P.sg;
   const int e = blockIdx.x * ORGPU_TILE + threadIdx.x;
   __shared__ __align__(8) unsigned long long s_bar;
@@ -382,10 +383,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     ORGPU_OPAQUE(XL2); ORGPU_OPAQUE(YL2); ORGPU_OPAQUE(XL3); ORGPU_OPAQUE(YL3); ORGPU_OPAQUE(XL4); ORGPU_OPAQUE(YL4);
     ORGPU_OPAQUE(Z1); ORGPU_OPAQUE(AREA);
     // ---- CMAIN3
-#ifdef ORGPU_UNROLL_NPT5
-    if (NPT == 5) shell_material_loop<LAW, true, STAGED, 5>(g, T, DT1, io); else
-#endif
-    shell_material_loop<LAW, true, STAGED>(g, T, DT1, io);
+    shell_material_loop<LAW, true, STAGED, 0, FAST>(g, T, DT1, io);
     OFF = io.off;
     if (g.bal && P.cs->ipri) shell_bilan<4, STAGED>(P, T, e, io.rho, OFF);     // CBILAN (czforc3.F:639)
     // ---- re-derive the geometry needed by the force assembly (same expressions as before the loop)

@@ -118,17 +118,20 @@ __device__ __forceinline__ void shell_bilan(const ShellParams& P, const TileAcc<
 
 // ---- SIGEPS36C, VP = 0 -------------------------------------------------------------------
 // FAIL2: IFAIL = 2 (tensile-strain damage / failure), compiled as its own kernel variant (template LAW = 37) so that
-// the common LAW36 kernels carry none of it
-template <bool STAGED, bool FAIL2>
-__device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>& T, int ipt, int ipla, double asrate,
-                                         double dexx, double deyy, double dexy, double deyz, double dezx, double dtinv,
-                                         double thklyl, double gs, double epsd_pg, double zt, double& off,
-                                         IpState& s, double& thk, double& ssp, double& etse, double& yld_out)
+// the common LAW36 kernels carry none of it.
+// The law is written in three stages so that two integration points can be advanced side by side (law36_pair_ip1):
+//   law36_trial : elastic predictor :277-281, strain rate :288-296, yield stress and hardening modulus from the curves :317-461
+//   the return  : Iplas 0 :472-501, 1 :503-593 (three Newton steps), 2 :595-661
+//   the tail    : failure :928-950
+template <bool STAGED, bool FAIL2, int FAST = 0>
+__device__ __forceinline__ void law36_trial(const ShellSG& g, const TileAcc<STAGED>& T, int ipt, double asrate,
+                                            double dexx, double deyy, double dexy, double deyz, double dezx, double dtinv,
+                                            double gs, double epsd_pg, double zt, IpState& s, double& YLD, double& H, double& EPST)
 {
   const orgpu_law36& m = g.m36;
   // IFAIL = 2: damage factor on the largest in-plane principal total strain at the point (mulawc.F90:856-862,
   // sigeps36c.F:256-264); GBUF%STRA was accumulated by the strain routine earlier in this cycle
-  double FAIL = K_ONE, EPST = K_ZERO;
+  double FAIL = K_ONE; EPST = K_ZERO;
   if (FAIL2) {
     const double epsxx = T.ld(SW_STRA) + zt * T.ld(SW_STRA + 5);
     const double epsyy = T.ld(SW_STRA + 1) + zt * T.ld(SW_STRA + 6);
@@ -136,9 +139,8 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
     EPST = K_HALF * (epsxx + epsyy + or_sqrt((epsxx - epsyy) * (epsxx - epsyy) + epsxy * epsxy));
     FAIL = fmax(K_EM20, fmin(K_ONE, or_div(m.epsr2 - EPST, m.epsr2 - m.epsr1)));
   }
-  const double E = m.young, A1 = m.a1u, A2 = m.a2u, G = m.shear, G3 = m.g3;
-  ssp = m.soundsp; etse = K_ONE;
-  double pla = s.pla;
+  const double A1 = m.a1u, A2 = m.a2u, G = m.shear;
+  const double pla = s.pla;
   // elastic predictor
   const double sox = s.sxx, soy = s.syy, soxy = s.sxy;
   s.sxx = sox + A1 * dexx + A2 * deyy;
@@ -156,12 +158,11 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
   }
   s.epsd = epsd;
   // yield stress and hardening modulus from the tabulated curves
-  double YLD, H;
-  if (m.nrate == 1) {
+  if (FAST == 1 || m.nrate == 1) {
     int ipos = s.ipos;
     const int f = m.ifunc[0];
     double dydx, y1;
-    if (g.ct.n > 0) vinter1c(g.ct, 0, ipos, pla, dydx, y1);
+    if (FAST == 1 || g.ct.n > 0) vinter1c(g.ct, 0, ipos, pla, dydx, y1);
     else { const int i0 = __ldg(g.npf + f), i1 = __ldg(g.npf + f + 1); vinter1(g.tf, i0, i1 - i0, ipos, pla, dydx, y1); }
     s.ipos = ipos;
     const double FACT = FAIL * K_ONE * (m.yfac[0] * K_ONE);
@@ -197,6 +198,37 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
     T.sti(g.w_vt, ipt * g.nvt + 1 + JJ, ipos1); T.sti(g.w_vt, ipt * g.nvt + 2 + JJ, ipos2);
   }
   if (m.yldcheck == 1) YLD = fmax(YLD, K_EM20);
+}
+
+// one Newton step of the Iplas = 1 return (sigeps36c.F:534-560): DPLA_J -> (DPLA_I, DR, PP, QQ, next DPLA_J)
+struct L36Newton { double AA, BB, YLD, HI, NU11, NU21, DPLA_I, DPLA_J, DR, PP, QQ; };
+__device__ __forceinline__ void law36_newton_step(double E, L36Newton& n, bool last)
+{
+  n.DPLA_I = n.DPLA_J;
+  const double YLD_I = n.YLD + n.HI * n.DPLA_I;
+  n.DR = or_div(K_HALF * E * n.DPLA_I, YLD_I);
+  n.PP = or_div(K_ONE, (K_ONE + n.DR * n.NU11));
+  n.QQ = or_div(K_ONE, (K_ONE + n.DR * n.NU21));
+  if (last) return;                                   // the third step's residual is never used
+  const double P2 = n.PP * n.PP, Q2 = n.QQ * n.QQ;
+  const double F = n.AA * P2 + n.BB * Q2 - YLD_I * YLD_I;
+  double DF = -or_div((n.AA * n.NU11 * P2 * n.PP + n.BB * n.NU21 * Q2 * n.QQ) * (E - K_TWO * n.DR * n.HI), YLD_I) - K_TWO * n.HI * YLD_I;
+  DF = copysign(fmax(fabs(DF), K_EM20), DF);
+  n.DPLA_J = (n.DPLA_I > K_ZERO) ? fmax(K_ZERO, n.DPLA_I - or_div(F, DF)) : K_ZERO;
+}
+
+template <bool STAGED, bool FAIL2, int FAST = 0>
+__device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>& T, int ipt, int ipla, double asrate,
+                                         double dexx, double deyy, double dexy, double deyz, double dezx, double dtinv,
+                                         double thklyl, double gs, double epsd_pg, double zt, double& off,
+                                         IpState& s, double& thk, double& ssp, double& etse, double& yld_out)
+{
+  const orgpu_law36& m = g.m36;
+  const double E = m.young, G3 = m.g3;
+  ssp = m.soundsp; etse = K_ONE;
+  double pla = s.pla;
+  double YLD, H, EPST;
+  law36_trial<STAGED, FAIL2, FAST>(g, T, ipt, asrate, dexx, deyy, dexy, deyz, dezx, dtinv, gs, epsd_pg, zt, s, YLD, H, EPST);
   // projection on the yield surface
   if (ipla == 0) {
     const double NU3 = K_ONE - m.nu_mnu;
@@ -221,35 +253,23 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
     { const double DEZZ = -(dexx + deyy) * m.nu_mnu; thk = thk + DEZZ * thklyl * off; }
     if (SVM2 > YLD * YLD && off == K_ONE) {
       const double SVM = or_sqrt(SVM2);
-      double DPLA_J = or_div((SVM - YLD), (G3 + H));
       etse = or_div(H, (H + E));
-      const double HI = H * (K_ONE - m.fisokin);
       const double HK = K_TWO_THIRD * H * m.fisokin;
       const double NU3 = K_ONE - m.nu_mnu;
       const double AAA = or_div(K_THREE * HK, E);
-      const double NU11 = m.u_mnu + AAA, NU21 = m.t_pnu + AAA;
-      double DPLA_I = K_ZERO, DR = K_ZERO, PP = K_ONE, QQ = K_ONE;
-      #pragma unroll
-      for (int N = 0; N < 3; N++) {                       // NITER = 3 (sigeps36c.F:167)
-        DPLA_I = DPLA_J;
-        const double YLD_I = YLD + HI * DPLA_I;
-        DR = or_div(K_HALF * E * DPLA_I, YLD_I);
-        PP = or_div(K_ONE, (K_ONE + DR * NU11));
-        QQ = or_div(K_ONE, (K_ONE + DR * NU21));
-        const double P2 = PP * PP, Q2 = QQ * QQ;
-        const double F = AA * P2 + BB * Q2 - YLD_I * YLD_I;
-        double DF = -or_div((AA * NU11 * P2 * PP + BB * NU21 * Q2 * QQ) * (E - K_TWO * DR * HI), YLD_I) - K_TWO * HI * YLD_I;
-        DF = copysign(fmax(fabs(DF), K_EM20), DF);
-        DPLA_J = (DPLA_I > K_ZERO) ? fmax(K_ZERO, DPLA_I - or_div(F, DF)) : K_ZERO;
-      }
-      pla = pla + DPLA_I;
-      S1 = (s.sxx + s.syy) * PP;
-      S2 = (s.sxx - s.syy) * QQ;
+      L36Newton n;
+      n.AA = AA; n.BB = BB; n.YLD = YLD; n.HI = H * (K_ONE - m.fisokin); n.NU11 = m.u_mnu + AAA; n.NU21 = m.t_pnu + AAA;
+      n.DPLA_J = or_div((SVM - YLD), (G3 + H));
+      n.DPLA_I = K_ZERO; n.DR = K_ZERO; n.PP = K_ONE; n.QQ = K_ONE;
+      law36_newton_step(E, n, false); law36_newton_step(E, n, false); law36_newton_step(E, n, true);   // NITER = 3 (sigeps36c.F:167)
+      pla = pla + n.DPLA_I;
+      S1 = (s.sxx + s.syy) * n.PP;
+      S2 = (s.sxx - s.syy) * n.QQ;
       s.sxx = K_HALF * (S1 + S2);
       s.syy = K_HALF * (S1 - S2);
-      s.sxy = s.sxy * QQ;
-      { const double DEZZ = -or_div(NU3 * DR * S1, E); thk = thk + DEZZ * thklyl * off; }
-      YLD = YLD + HI * DPLA_I;
+      s.sxy = s.sxy * n.QQ;
+      { const double DEZZ = -or_div(NU3 * n.DR * S1, E); thk = thk + DEZZ * thklyl * off; }
+      YLD = YLD + n.HI * n.DPLA_I;
     }
   } else {
     H = fmax(K_ZERO, H);
@@ -277,7 +297,8 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
     }
   }
   // IFAIL = 1: failure on the maximum plastic strain (sigeps36c.F:928-938); MULAWC completes the deletion in the same cycle
-  if (!FAIL2 && m.ifail == 1) { if (off == K_ONE && pla > m.epsmax) off = K_FOUR_OVER_5; }
+  if (FAST == 1) {}
+  else if (!FAIL2 && m.ifail == 1) { if (off == K_ONE && pla > m.epsmax) off = K_FOUR_OVER_5; }
   else if (FAIL2) { if (off == K_ONE && (pla > m.epsmax || EPST > m.epsf)) off = K_FOUR_OVER_5; }   // :940-950
   s.pla = pla;
   yld_out = YLD;
@@ -437,7 +458,13 @@ __device__ __forceinline__ void law2_ip(const ShellSG& g, int ipla, int npttot, 
 // FLAG_ZCFAC: QEPH (JHBE 21..29) keeps SIGY / ZCFAC for the hourglass plasticity (mulawc.F90:521-522).
 // NPTC > 0: compile-time point count (loop fully unrolled so independent points overlap in the
 // fp64 pipe); NPTC = 0: run-time count.
-template <int LAW, bool FLAG_ZCFAC, bool STAGED, int NPTC = 0>
+// FAST = 1: LAW36 with Iplas = 1, IFAIL = 0, one static curve held in the kernel parameters -- all known at compile time (the
+// default /PROP/SHELL + /MAT/PLAS_TAB combination): the other return algorithms, the rate interpolation and the global-memory
+// curve walk are not compiled in.  The kernels are instruction-fetch sensitive (a 90 KB body walked by 12 warps in different
+// phases against a 32 KB L1.5 instruction cache), so less code is measurably faster: -10 % on the plastic C2 plate.
+// (Advancing two integration points side by side through the Newton steps was measured too: the extra live state spills,
+// 0.589 vs 0.447 ms at 3 CTAs / SM, 0.533 with 248 registers at 2 -- not kept.)
+template <int LAW, bool FLAG_ZCFAC, bool STAGED, int NPTC = 0, int FAST = 0>
 __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const TileAcc<STAGED>& T, double dt1, MatIO& io)
 {
   const int npt = NPTC > 0 ? NPTC : g.prop.npt;
@@ -466,14 +493,15 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const Tile
   const double pm9 = (LAW != 2) ? g.m36.asrate : g.m2.asrate;
   const double asrate = (israte > 0) ? fmin(K_ONE, pm9 * dt1) : K_ONE;
   const int qrow = (npt - 1) * 11;
+  const int ipt0 = 0;
   IpState nxt;
-  if (!STAGED) nxt = ip_load<LAW>(g, T, 0);
+  if (!STAGED) nxt = ip_load<LAW>(g, T, ipt0);
 #ifdef ORGPU_IP_UNROLL1
   #pragma unroll 1
 #else
   #pragma unroll
 #endif
-  for (int ipt = 0; ipt < npt; ipt++) {
+  for (int ipt = ipt0; ipt < npt; ipt++) {
     IpState s;
     if (STAGED) s = ip_load<LAW>(g, T, ipt);                     // shared memory: no latency to hide
     else { s = nxt; if (ipt + 1 < npt) nxt = ip_load<LAW>(g, T, ipt + 1); }   // software pipeline: next point's state in flight
@@ -487,12 +515,8 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const Tile
     const double deyy = io.eyy + zt * io.kyy;
     const double dexy = io.exy + zt * io.kxy;
     if (LAW != 2) {
-#ifdef ORGPU_FIX_IPLA
-      const int ipla_ = ORGPU_FIX_IPLA;                  // experiment: plasticity algorithm known at compile time
-#else
-      const int ipla_ = g.prop.ipla;
-#endif
-      law36_ip<STAGED, LAW == 37>(g, T, ipt, ipla_, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, thklyl, io.gs, io.epsd_pg, zt, off,
+      const int ipla_ = (FAST == 1) ? 1 : g.prop.ipla;
+      law36_ip<STAGED, LAW == 37, FAST>(g, T, ipt, ipla_, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, thklyl, io.gs, io.epsd_pg, zt, off,
                s, thkn, ssp, etse, sigy);
     } else {
       law2_ip(g, g.prop.ipla, npt, dt1, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, thklyl, io.gs, io.epsd_pg,

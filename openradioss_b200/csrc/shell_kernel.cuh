@@ -6,6 +6,7 @@
 #pragma once
 #include <vector>
 #include <cstring>
+#include <cstdlib>
 #include "common.cuh"
 #include "shell_common.cuh"
 #include "qeph_kernel.cuh"
@@ -154,6 +155,13 @@ static void shell_launch_one(K kern_staged, K kern_direct, const ShellParams& P,
   kern_direct<<<nblk, ORGPU_SHELL_CTA, 0, st>>>(P);
 }
 
+// the compile-time specialisation of the LAW36 kernels: Iplas = 1, no failure inside the law, one static curve small enough for
+// the kernel parameters (ORGPU_NO_FAST=1: generic path)
+static inline bool shell_fast(const ShellSG& d) {
+  static const bool off = getenv("ORGPU_NO_FAST") != nullptr;
+  return !off && d.law == 36 && d.prop.ipla == 1 && d.m36.ifail == 0 && d.m36.nrate == 1 && d.ct.n > 0;
+}
+
 static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky, int roww, CycleState* cs,
                                 const DtBlocks& db, const FinalizeArgs& fa, cudaStream_t st)
 {
@@ -166,6 +174,7 @@ static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky
     else               shell_launch_one(c3_forces_kernel<2, true>, c3_forces_kernel<2, false>, P, nblk, st);
   } else if (shell_is_qeph(S.d.prop)) {
     if (S.d.law == 36 && S.d.m36.ifail == 2) shell_launch_one(qeph_forces_kernel<37, true>, qeph_forces_kernel<37, false>, P, nblk, st);
+    else if (S.d.law == 36 && shell_fast(S.d)) shell_launch_one(qeph_forces_kernel<36, true, 1>, qeph_forces_kernel<36, false, 1>, P, nblk, st);
     else if (S.d.law == 36) shell_launch_one(qeph_forces_kernel<36, true>, qeph_forces_kernel<36, false>, P, nblk, st);
     else               shell_launch_one(qeph_forces_kernel<2, true>, qeph_forces_kernel<2, false>, P, nblk, st);
   } else {

@@ -140,6 +140,14 @@ def decompose(m: Model, dom_s: Optional[np.ndarray], dom_c: Optional[np.ndarray]
         keep = mine[m.ibfv[:, 0] - 1]
         lm.ibfv = m.ibfv[keep].copy(); lm.vel = m.vel[keep].copy()
         lm.ibfv[:, 0] = (g2l[lm.ibfv[:, 0] - 1] + 1).astype(np.int32)
+    # tie-break keys of the time-step arg-min: where each local element sits in the undecomposed model's processing order
+    # (4-node shells, then 3-node shells, then solids), and the global node index
+    lm.gorder = dict(shell=shell_gid.astype(np.int32), sh3n=(m.numelc + sh3n_gid).astype(np.int32),
+                     solid=(m.numelc + m.numeltg + solid_gid).astype(np.int32), node=node_gid.astype(np.int32))
+    # parts follow their elements
+    if m.ipartc is not None: lm.ipartc = m.ipartc[shell_gid]
+    if m.iparts is not None: lm.iparts = m.iparts[solid_gid]
+    if m.iparttg is not None: lm.iparttg = m.iparttg[sh3n_gid]
     lm.adsky = (ladsky0 + 1).astype(np.int32); lm.iads = iads; lm.iadc = iadc; lm.iadtg = iadtg; lm.lsky = lsky
     # groups
     if m.solid_groups:

@@ -18,7 +18,7 @@ set_functions add_solid_group add_solid_group_law add_shell_group set_sh3n add_s
 synchronize get_time download_nodes download_fsky download_solid_state download_shell_state
 step_host launch_count last_run_ms set_profile get_profile pack_rows unpack_rows comm_unique_id comm_init
 set_exchange exchange get_energies p2p_export p2p_connect set_load_function set_fixvel set_gravity upload_solid_state upload_shell_state set_time set_itab
-set_parts set_print get_balance get_balance_history set_quadrature""".split()
+set_parts set_print get_balance get_balance_history set_quadrature set_global_order set_exchange_timeout""".split()
 
 
 def load_library() -> C.CDLL:
@@ -61,6 +61,8 @@ class Engine(Binding):
         dist.broadcast(t, 0)
         uid = (C.c_ubyte * 128)(*t.cpu().tolist())
         self._call("comm_init", self.h, C.c_int(world), C.c_int(rank), uid)
+        if os.environ.get("ORGPU_P2P_TIMEOUT_S"):
+            self._call("set_exchange_timeout", self.h, C.c_double(float(os.environ["ORGPU_P2P_TIMEOUT_S"])))
         nbs = domain.neighbors
         ranks = np.array([nb.rank for nb in nbs], np.int32)
         sp = np.zeros(len(nbs) + 1, np.int32); rp = np.zeros(len(nbs) + 1, np.int32)
@@ -88,10 +90,15 @@ class Engine(Binding):
         ck = dict(nodes=self.download_nodes(("X", "V", "VR", "D")), time=self.time())
         if self.model.numels:
             ck["solid"] = {f: self.solid_state(f) for f in ("sig", "eint", "rho", "qvis", "pla", "epsd", "off", "temp", "smstr")}
+        therm = lambda groups: any(g.law == 2 and getattr(g.mat, "has_temp", 0) for g in groups)
         if self.model.numelc:
             ck["shell"] = {f: self.shell_state(f) for f in ("forc", "mom", "eint", "thk", "off", "stra", "epsd", "hourg", "smstr", "sig", "pla", "epsd_ip")}
+            if therm(self.model.shell_groups):
+                ck["shell"]["temp"] = self.shell_state("temp")          # per-point temperature of thermal Johnson-Cook shells
         if self.model.numeltg:
             ck["sh3n"] = {f: self.sh3n_state(f) for f in ("forc", "mom", "eint", "thk", "off", "stra", "epsd", "smstr", "sig", "pla", "epsd_ip")}
+            if therm(self.model.sh3n_groups):
+                ck["sh3n"]["temp"] = self.sh3n_state("temp")
         if self.model.numels and any(getattr(g, "law", 2) == 36 for g in self.model.solid_groups):
             ck["solid"].update({f: self.solid_state(f) for f in ("wpla", "stra")})
         return ck

@@ -112,6 +112,7 @@ class Model:
     ipartc: Optional[np.ndarray] = None  # part (0-based) of every 4-node shell / brick / 3-node shell: IPARTC, IPARTS, IPARTTG
     iparts: Optional[np.ndarray] = None  #   (default: the `part` attribute of the element's group, else 0)
     iparttg: Optional[np.ndarray] = None
+    gorder: Optional[dict] = None       # a domain of a decomposed model: global processing order of its elements / global node index (domdec)
 
     @property
     def numnod(self): return int(self.X.shape[0])

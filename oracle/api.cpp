@@ -149,13 +149,17 @@ void orc_finalize(void*){}
 
 /* phases (same split as the device library) */
 void orc_forces_phase(void* h,double dt1){
-  Oracle* o=(Oracle*)h; o->DT1=dt1; o->DT2=K_EP06; orc_forces(*o);
+  Oracle* o=(Oracle*)h; o->DT1=dt1; o->DT2=K_EP06;
+  if(o->ipri) std::fill(o->PARTSAV.begin(),o->PARTSAV.end(),K_ZERO);
+  orc_forces(*o);
 }
 void orc_assemble(void* h){ Oracle* o=(Oracle*)h; orc_asspar4(*o); if(o->ctl.nodadt!=0) orc_dtnoda(*o); }
 void orc_set_itab(void* h,const int* itab){ Oracle* o=(Oracle*)h; o->ITAB.assign(itab,itab+o->numnod); }
 void orc_advance(void* h,double dt12,double dt2){
   Oracle* o=(Oracle*)h; o->DT12=dt12; o->DT2=dt2;
-  orc_accele(*o); orc_gravit(*o); orc_bcs(*o); orc_fixvel(*o); orc_velocity(*o); orc_depla(*o); o->TT+=dt2; o->NCYCLE++;
+  orc_accele(*o); orc_gravit(*o); orc_bcs(*o); orc_fixvel(*o);
+  if(o->ipri) orc_ecrit(*o);
+  orc_velocity(*o); orc_depla(*o); o->TT+=dt2; o->NCYCLE++;
 }
 void orc_run_cycles(void* h,int ncycles){ Oracle* o=(Oracle*)h; for(int c=0;c<ncycles;c++) orc_cycle(*o); }
 

@@ -24,6 +24,10 @@ def models():
     yield "sh3n_mixed", meshgen.tri_plate(12, 9, 120.0, 90.0, quads="checker", pressure=20.0, vrand=5.0, user_id_perm=True)
     yield "brick_law36", meshgen.hex_block(6, 5, 7, 12.0, 10.0, 14.0, law=36, v0=(0, 0, -60.0), vrand=20.0, fix_bottom_z=True, user_id_perm=True)
     yield "tube_dtnoda", t                                     # /DT/NODA: the nodal dt crosses the domains after the assembly
+    # perfectly regular meshes at rest: every element has the same time step, so the arg-min is decided by the tie rules alone
+    # (shells: first in processing order; solids: last) -- N domains must elect the element one domain elects
+    yield "shell_tie", meshgen.shell_plate(12, 9, 120.0, 90.0, pressure=20.0, jitter=0.0, zjitter=0.0)
+    yield "brick_tie", meshgen.hex_block(6, 5, 7, 1.2, 1.0, 1.4, jitter=0.0, v0=(0, 0, -1.0))
 
 
 @pytest.mark.parametrize("nproc", [2, 3])
@@ -75,7 +79,8 @@ def _nccl_worker(rank, world, port, q, kind, p2p=True):
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 @pytest.mark.parametrize("kind,p2p", [("shell", True), ("shell", False), ("brick", True), ("brick", False), ("tube", True), ("tube", False),
-                                      ("tube_dtnoda", True), ("sh3n_mixed", True), ("brick_law36", True)])
+                                      ("tube_dtnoda", True), ("sh3n_mixed", True), ("brick_law36", True),
+                                      ("shell_tie", True), ("shell_tie", False), ("brick_tie", True), ("brick_tie", False)])
 def test_multi_gpu_domains_match_single_gpu_bitwise(kind, p2p):
     import torch.multiprocessing as mp
     world = min(4, torch.cuda.device_count())
@@ -95,3 +100,4 @@ def test_multi_gpu_domains_match_single_gpu_bitwise(kind, p2p):
     for rank, gid, x, v, t in res:
         assert np.array_equal(x, xr["X"][gid]) and np.array_equal(v, xr["V"][gid]), (kind, rank)
         assert t["tt"] == tr["tt"] and t["ncycle"] == tr["ncycle"] and t["dt2"] == tr["dt2"]
+        assert t["neltst"] == tr["neltst"] and t["ityptst"] == tr["ityptst"], (kind, rank, t, tr)     # also on exact ties
