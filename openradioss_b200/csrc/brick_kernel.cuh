@@ -121,22 +121,22 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
 {
   const BrickSG& g = P.sg;
   if (P.cs->abort) return;                               // sticky: a peer-memory wait timed out (exchange.cuh)
-  const int e = blockIdx.x * ORGPU_TILE + threadIdx.x;
+  const int tile = cta_tile(g.tile_map, blockIdx.x);
+  const int e = tile * ORGPU_TILE + threadIdx.x;
   __shared__ __align__(8) unsigned long long s_bar;
-  double* const g_tile = g.slab + (size_t)blockIdx.x * g.nw * ORGPU_TILE;
-  if (STAGED) tile_load_begin(s_tile_dyn, &s_bar, g_tile, (unsigned)g.nw * ORGPU_TILE * 8u);
+  double* const g_tile = g.slab + (size_t)tile * g.nw * ORGPU_TILE;
+  const int tile_pf = ORGPU_PREFETCH_TILE > 0 ? cta_tile_ahead(g.tile_map, ORGPU_PREFETCH_TILE) : -1;
+  if (STAGED) tile_load_begin(s_tile_dyn, &s_bar, g_tile, (unsigned)g.nw * ORGPU_TILE * 8u, tile_pf >= 0 ? g.slab + (size_t)tile_pf * g.nw * ORGPU_TILE : nullptr);
   const TileAcc<STAGED> T{(STAGED ? s_tile_dyn : g_tile) + threadIdx.x};
-#if ORGPU_PREFETCH_TILE > 0
-  if (!STAGED && threadIdx.x == 0 && blockIdx.x + ORGPU_PREFETCH_TILE < gridDim.x)      // in-place tiles: same wave-ahead L2 prefetch
-    bulk_prefetch_l2(g_tile + (size_t)ORGPU_PREFETCH_TILE * g.nw * ORGPU_TILE, (unsigned)g.nw * ORGPU_TILE * 8u);
-#endif
+  if (!STAGED && threadIdx.x == 0 && tile_pf >= 0)      // in-place tiles: same wave-ahead L2 prefetch
+    bulk_prefetch_l2(g.slab + (size_t)tile_pf * g.nw * ORGPU_TILE, (unsigned)g.nw * ORGPU_TILE * 8u);
   // SMSTR (21 words, rewritten every cycle by S8SAV3 / SMALLA3) goes straight to HBM with streaming stores:
   // collecting it in shared memory for a bulk store was measured slower (0.472 vs 0.450 ms on C5)
-  double* const sm = g.smstr + (size_t)blockIdx.x * 21 * ORGPU_TILE + threadIdx.x;     // SMSTR word k at sm[k*TILE]
+  double* const sm = g.smstr + (size_t)tile * 21 * ORGPU_TILE + threadIdx.x;     // SMSTR word k at sm[k*TILE]
 #if ORGPU_PREFETCH_NEXT > 0
   // a CTA about one wave ahead: start its connectivity toward L2 (its first load is then an L2 hit: -3 % kernel time)
-  { const unsigned nb = blockIdx.x + ORGPU_PREFETCH_NEXT;
-    if (nb < gridDim.x && threadIdx.x < (8 * ORGPU_TILE * 4) / 128) prefetch_l2(reinterpret_cast<const char*>(g.conn + (size_t)nb * 8 * ORGPU_TILE) + 128 * threadIdx.x); }
+  { const int nb = cta_tile_ahead(g.tile_map, ORGPU_PREFETCH_NEXT);
+    if (nb >= 0 && threadIdx.x < (8 * ORGPU_TILE * 4) / 128) prefetch_l2(reinterpret_cast<const char*>(g.conn + (size_t)nb * 8 * ORGPU_TILE) + 128 * threadIdx.x); }
 #endif
   double dt_cand = K_EP30; int order = -1;
   if (e < g.ne) {
@@ -144,7 +144,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     const double TT = P.cs->tt;
     const orgpu_law2& m = g.mat;
     int nc[8];
-    { const int* cn = g.conn + (size_t)blockIdx.x * 8 * ORGPU_TILE + threadIdx.x;
+    { const int* cn = g.conn + (size_t)tile * 8 * ORGPU_TILE + threadIdx.x;
       #pragma unroll
       for (int k = 0; k < 8; k++) nc[k] = __ldg(cn + k * ORGPU_TILE); }
     order = g.order0 + e;
@@ -718,7 +718,8 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     if (P.roww == 4) {
       #pragma unroll
       for (int k = 0; k < 8; k++) {
-        st256(reinterpret_cast<double4*>(P.fsky + (size_t)4 * sl[k]), make_double4(F1[k], F2[k], F3[k], STI));
+        const double4 r0 = make_double4(F1[k], F2[k], F3[k], STI);
+        st256(reinterpret_cast<double4*>(P.fsky + (size_t)4 * sl[k]), r0);
       }
     } else {
       #pragma unroll
@@ -726,12 +727,15 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
         // mixed models (8-wide rows): write the whole row -- two full 32-byte sectors instead of four partial stores that
         // the L2 would have to merge; the moment / rotational-stiffness words of a brick corner are zero anyway
         double4* row = reinterpret_cast<double4*>(P.fsky + (size_t)8 * sl[k]);
-        st256(row, make_double4(F1[k], F2[k], F3[k], K_ZERO));
-        st256(row + 1, make_double4(K_ZERO, K_ZERO, STI, K_ZERO));
+        const double4 r0 = make_double4(F1[k], F2[k], F3[k], K_ZERO), r1 = make_double4(K_ZERO, K_ZERO, STI, K_ZERO);
+        st256(row, r0); st256(row + 1, r1);
       }
     }
+    if (g.xs_ftile && g.xs_ftile[tile]) {                 // frontier tile: rows to the neighbours' windows
+      if (P.roww == 4) xsend_rows<4, STAGED>(P.nd.xs, T, g.w_slot, 8, P.fsky); else xsend_rows<8, STAGED>(P.nd.xs, T, g.w_slot, 8, P.fsky);
+    }
   }
-  cta_epilogue<true, STAGED>(dt_cand, order, P.db, g.blk0 + blockIdx.x, g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
+  cta_epilogue<true, STAGED>(dt_cand, order, P.db, g.blk0 + tile, g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
 }
 
 template <int JHBE, int ISMSTR, int LAW>

@@ -18,26 +18,26 @@ c3_forces_kernel(const __grid_constant__ ShellParams P)
 {
   const ShellSG& g = P.sg;
   if (P.cs->abort) return;                               // sticky: a peer-memory wait timed out (exchange.cuh)
-  const int e = blockIdx.x * ORGPU_TILE + threadIdx.x;
+  const int tile = cta_tile(g.tile_map, blockIdx.x);
+  const int e = tile * ORGPU_TILE + threadIdx.x;
   __shared__ __align__(8) unsigned long long s_bar;
-  double* const g_tile = g.slab + (size_t)blockIdx.x * g.nw * ORGPU_TILE;
-  if (STAGED) tile_load_begin(s_tile_dyn, &s_bar, g_tile, (unsigned)g.nw * ORGPU_TILE * 8u);
+  double* const g_tile = g.slab + (size_t)tile * g.nw * ORGPU_TILE;
+  const int tile_pf = ORGPU_PREFETCH_TILE > 0 ? cta_tile_ahead(g.tile_map, ORGPU_PREFETCH_TILE) : -1;
+  if (STAGED) tile_load_begin(s_tile_dyn, &s_bar, g_tile, (unsigned)g.nw * ORGPU_TILE * 8u, tile_pf >= 0 ? g.slab + (size_t)tile_pf * g.nw * ORGPU_TILE : nullptr);
   const TileAcc<STAGED> T{(STAGED ? s_tile_dyn : g_tile) + threadIdx.x};
-#if ORGPU_PREFETCH_TILE > 0
-  if (!STAGED && threadIdx.x == 0 && blockIdx.x + ORGPU_PREFETCH_TILE < gridDim.x)
-    bulk_prefetch_l2(g_tile + (size_t)ORGPU_PREFETCH_TILE * g.nw * ORGPU_TILE, (unsigned)g.nw * ORGPU_TILE * 8u);
-#endif
-  double* const sm = g.smstr + (size_t)blockIdx.x * 3 * ORGPU_TILE + threadIdx.x;      // SMSTR word k at sm[k*128]
+  if (!STAGED && threadIdx.x == 0 && tile_pf >= 0)      // in-place tiles: same wave-ahead L2 prefetch
+    bulk_prefetch_l2(g.slab + (size_t)tile_pf * g.nw * ORGPU_TILE, (unsigned)g.nw * ORGPU_TILE * 8u);
+  double* const sm = g.smstr + (size_t)tile * 3 * ORGPU_TILE + threadIdx.x;      // SMSTR word k at sm[k*128]
 #if ORGPU_PREFETCH_NEXT > 0
-  { const unsigned nb = blockIdx.x + ORGPU_PREFETCH_NEXT;
-    if (nb < gridDim.x && threadIdx.x < (3 * ORGPU_TILE * 4) / 128) prefetch_l2(reinterpret_cast<const char*>(g.conn + (size_t)nb * 3 * ORGPU_TILE) + 128 * threadIdx.x); }
+  { const int nb = cta_tile_ahead(g.tile_map, ORGPU_PREFETCH_NEXT);
+    if (nb >= 0 && threadIdx.x < (3 * ORGPU_TILE * 4) / 128) prefetch_l2(reinterpret_cast<const char*>(g.conn + (size_t)nb * 3 * ORGPU_TILE) + 128 * threadIdx.x); }
 #endif
   double dt_cand = K_EP30; int order = 0x7fffffff;
   if (e < g.ne) {
     const double DT1 = P.cs->dt2;
     const int ISMSTR = g.prop.ismstr, NPT = g.prop.npt, ISH3N = g.prop.ihbe;
     int nc[3];
-    { const int* cn = g.conn + (size_t)blockIdx.x * 3 * ORGPU_TILE + threadIdx.x;
+    { const int* cn = g.conn + (size_t)tile * 3 * ORGPU_TILE + threadIdx.x;
       #pragma unroll
       for (int k = 0; k < 3; k++) nc[k] = __ldg(cn + k * ORGPU_TILE); }
     order = g.order0 + e;
@@ -188,7 +188,7 @@ c3_forces_kernel(const __grid_constant__ ShellParams P)
     io.area = AREA; io.thk0 = THK0; io.gs = G * SHF; io.rho = RHO; io.off = OFF; io.sigy = K_EP30;
     shell_material_loop<LAW, false, STAGED>(g, T, DT1, io);
     OFF = io.off;
-    if (g.bal && P.cs->ipri) shell_bilan<3, STAGED>(P, T, e, RHO, OFF);        // C3BILAN (c3forc3.F:616)
+    if (g.bal && P.cs->ipri) shell_bilan<3, STAGED>(P, T, tile, e, RHO, OFF);        // C3BILAN (c3forc3.F:616)
     const double SSP = io.ssp;
     // ---- C3DT3 (IGTYP=1, ZOFFSET=0, IDTMIN(7)=0)
     double STI, STIR;
@@ -266,9 +266,10 @@ c3_forces_kernel(const __grid_constant__ ShellParams P)
       }
       if (dead) { f[0] = f[1] = f[2] = K_ZERO; mm[0] = mm[1] = mm[2] = K_ZERO; }
       double4* row = reinterpret_cast<double4*>(P.fsky + (size_t)8 * sl[J]);
-      st256(row, make_double4(-f[0], -f[1], -f[2], -mm[0]));
-      st256(row + 1, make_double4(-mm[1], -mm[2], STI, STIR));
+      const double4 r0 = make_double4(-f[0], -f[1], -f[2], -mm[0]), r1 = make_double4(-mm[1], -mm[2], STI, STIR);
+      st256(row, r0); st256(row + 1, r1);
     }
+    if (g.xs_ftile && g.xs_ftile[tile]) xsend_rows<8, STAGED>(P.nd.xs, T, g.w_slot, 3, P.fsky);   // frontier tile: rows to the neighbours' windows
   }
-  cta_epilogue<false, STAGED>(dt_cand, order, P.db, g.blk0 + blockIdx.x, g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
+  cta_epilogue<false, STAGED>(dt_cand, order, P.db, g.blk0 + tile, g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
 }

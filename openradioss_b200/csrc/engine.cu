@@ -45,6 +45,7 @@ struct orgpu_engine {
 #define ORGPU_NSIDE 15
   cudaStream_t side[ORGPU_NSIDE] = {};     // side streams: super-groups are independent, their kernels may overlap
   cudaEvent_t ev_fork = nullptr, ev_join[ORGPU_NSIDE] = {};
+  bool split = false;                                    // corner rows leave from inside the force kernels (XSend; set by orgpu_p2p_connect)
   DevNodes nd{};                      // device pointers
   double *d_stage3a = nullptr, *d_stage3b = nullptr;   // (3,N) staging for pack/unpack
   double *d_fext = nullptr, *d_mext = nullptr; int *d_icodt = nullptr, *d_icodr = nullptr, *d_adsky = nullptr;
@@ -171,7 +172,7 @@ int orgpu_destroy(orgpu_engine* e)
     void* xp[] = {x.d_send_slots, x.d_recv_slots, x.d_sendbuf, x.d_recvbuf, x.d_cand_send, x.d_cand_recv, x.d_slots_tmp, x.d_rows_tmp};
     for (void* p : xp) if (p) cudaFree(p);
     for (size_t q = 0; q < x.peer.size(); q++) if (x.peer[q] && (int)q != x.rank) cudaIpcCloseMemHandle(x.peer[q]);
-    void* pp[] = {x.win, x.d_send_nb, x.d_nb_sendptr, x.d_nb_rows, x.d_peer_cand, x.d_peer_flag, x.d_xcycle, x.d_done, x.d_err, x.d_peer_win};
+    void* pp[] = {x.win, x.d_send_nb, x.d_nb_sendptr, x.d_nb_rows, x.d_peer_cand, x.d_peer_flag, x.d_xcycle, x.d_done, x.d_err, x.d_peer_win, x.d_xsend};
     for (void* p : pp) if (p) cudaFree(p);
     if (x.comm && nccl_api()) nccl_api()->CommDestroy(x.comm); }
   for (auto ev : e->evpool) cudaEventDestroy(ev);
@@ -439,7 +440,7 @@ int orgpu_finalize(orgpu_engine* e)
     const int nft = e->sgroups[gi].nft;
     const int np = ((ne + ORGPU_BLOCK - 1) / ORGPU_BLOCK) * ORGPU_BLOCK;
     e->bsg.emplace_back(); BrickSGHost& S = e->bsg.back(); S.first_elem = nft; S.part = e->sgroups[gi].part;
-    BrickSG& d = S.d; d.bal = nullptr; d.bal_ld = 0; d.ne = ne; d.ne_pad = np; d.order0 = order; d.blk0 = blk;
+    BrickSG& d = S.d; d.bal = nullptr; d.bal_ld = 0; d.tile_map = nullptr; d.xs_ftile = nullptr; d.ne = ne; d.ne_pad = np; d.order0 = order; d.blk0 = blk;
     d.mat = e->sgroups[gi].mat; d.prop = e->sgroups[gi].prop; d.dtfac = e->ctl.dtfac_brick; d.nodadt = e->ctl.nodadt;
     std::vector<int> conn((size_t)8 * np, 0), ngl(np, 0), conn_t;
     // state slab: read/write words first (SIG 6, EINT, RHO, QVIS, PLA, EPSD, OFF[, TEMP]), then VOL and the slot rows
@@ -561,6 +562,11 @@ static cudaEvent_t get_event(orgpu_engine* e, size_t i) {
   return e->evpool[i];
 }
 
+static void launch_sg_shell(orgpu_engine* e, ShellSGHost& S, cudaStream_t st)
+{ launch_shell_forces(S, e->nd, e->d_fsky, e->roww, e->d_cs, e->db, e->fa, st); e->launches++; }
+static void launch_sg_brick(orgpu_engine* e, BrickSGHost& S, cudaStream_t st)
+{ launch_brick_forces(S.d, e->nd, e->d_fsky, e->roww, e->d_cs, e->db, e->fa, st); e->launches++; }
+
 static void launch_element_phase(orgpu_engine* e, int fused, size_t* evi)
 {
   e->fa.fused = fused;
@@ -578,12 +584,12 @@ static void launch_element_phase(orgpu_engine* e, int fused, size_t* evi)
   if (fork) { cudaEventRecord(e->ev_fork, e->st); for (int j = 0; j < nside; j++) cudaStreamWaitEvent(e->side[j], e->ev_fork, 0); }
   for (auto& S : e->csg) {
     if (evi) cudaEventRecord(get_event(e, (*evi)++), e->st);
-    launch_shell_forces(S, e->nd, e->d_fsky, e->roww, e->d_cs, e->db, e->fa, pick()); e->launches++;
+    launch_sg_shell(e, S, pick());
     if (evi) cudaEventRecord(get_event(e, (*evi)++), e->st);
   }
   for (auto& S : e->bsg) {
     if (evi) cudaEventRecord(get_event(e, (*evi)++), e->st);
-    launch_brick_forces(S.d, e->nd, e->d_fsky, e->roww, e->d_cs, e->db, e->fa, pick()); e->launches++;
+    launch_sg_brick(e, S, pick());
     if (evi) cudaEventRecord(get_event(e, (*evi)++), e->st);
   }
   for (int j = 0; j < nside; j++) { cudaEventRecord(e->ev_join[j], e->side[j]); cudaStreamWaitEvent(e->st, e->ev_join[j], 0); }
@@ -679,6 +685,9 @@ static void p2p_exchange_on_stream(orgpu_engine* e)
 {
   Exchange& x = e->xc;
   const int V = e->roww / 4;
+  if (e->split) {                                          // the rows left from inside the force kernels (XSend): candidate + flags only
+    p2p_publish_kernel<<<1, 32, 0, e->st>>>(e->d_cs, x.d_peer_cand, x.d_peer_flag, x.nranks, x.rank, x.d_xcycle); e->launches++;
+  } else
   { const int nthr = x.nsend * V > 1 ? x.nsend * V : 1; const int nb = (nthr + 255) / 256;
     if (e->roww == 8) p2p_push_kernel<8><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_send_slots, x.d_send_nb, x.d_nb_sendptr, x.d_nb_rows, x.nsend, e->d_cs, x.d_peer_cand, x.d_peer_flag, x.nranks, x.rank, x.d_xcycle, x.d_done);
     else              p2p_push_kernel<4><<<nb, 256, 0, e->st>>>(e->d_fsky, x.d_send_slots, x.d_send_nb, x.d_nb_sendptr, x.d_nb_rows, x.nsend, e->d_cs, x.d_peer_cand, x.d_peer_flag, x.nranks, x.rank, x.d_xcycle, x.d_done);
@@ -1072,6 +1081,46 @@ int orgpu_p2p_connect(orgpu_engine* e, const unsigned char* handles /*[nranks][6
   CUDA_OK(cudaDeviceSynchronize());
   if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
   x.p2p = true;
+  // inline sends: every send slot with exactly one destination leaves from the force kernel that computes it (XSend, common.cuh);
+  // a decomposition where some slot has several (a node shared by 3+ domains) keeps the push kernel.  ORGPU_NO_OVERLAP=1: push kernel.
+  e->split = false; e->nd.xs = XSend{nullptr, nullptr, nullptr};
+  if (!getenv("ORGPU_NO_OVERLAP") && !e->ctl.nodadt) {
+    std::vector<int> ss(x.nsend > 0 ? x.nsend : 1);
+    if (x.nsend) CUDA_OK(cudaMemcpy(ss.data(), x.d_send_slots, 4 * (size_t)x.nsend, cudaMemcpyDeviceToHost));
+    std::vector<int2> ref(e->lsky > 0 ? e->lsky : 1, make_int2(-1, -1));
+    bool single = true;
+    for (int j = 0; j < x.nsend && single; j++) {
+      const int k = send_nb[j];
+      if (ref[ss[j]].x >= 0) single = false; else ref[ss[j]] = make_int2(k, j - sendptr[k]);
+    }
+    if (single) {
+      // frontier tiles of every super-group
+      auto ftiles = [&](std::vector<void*>& owned, const std::vector<int>& iad, int nn, int first, int ne, int ne_pad, const unsigned char** out) -> int {
+        std::vector<unsigned char> f(ne_pad / ORGPU_TILE, 0);
+        for (int i = 0; i < ne; i++) for (int k = 0; k < nn; k++) if (ref[iad[(size_t)nn * (first + i) + k] - 1].x >= 0) { f[i / ORGPU_TILE] = 1; break; }
+        unsigned char* d; if (upload_vec(owned, &d, f)) return -100; *out = d; return 0; };
+      for (auto& S : e->csg) if (ftiles(S.owned, S.sh3n ? e->iadtg : e->iadc, S.sh3n ? 3 : 4, S.first_elem, S.d.ne, S.d.ne_pad, &S.d.xs_ftile)) return -100;
+      for (auto& S : e->bsg) if (ftiles(S.owned, e->iads, 8, S.first_elem, S.d.ne, S.d.ne_pad, &S.d.xs_ftile)) return -100;
+      // worth it only when few tiles are frontier tiles (slabs of a block numbered layer by layer: 4 % on C5, -4 us per cycle);
+      // strips across an x-fastest numbering put two frontier elements in every mesh row, i.e. in a quarter of the tiles (C2),
+      // and the read-back loops then cost more than the push kernel (+18 us): those keep the push kernel
+      size_t nt = 0, nf = 0;
+      { std::vector<unsigned char> h;
+        auto cnt = [&](const unsigned char* d, int n) { h.resize(n); cudaMemcpy(h.data(), d, n, cudaMemcpyDeviceToHost); nt += n; for (int i = 0; i < n; i++) nf += h[i]; };
+        for (auto& S : e->csg) cnt(S.d.xs_ftile, S.d.ne_pad / ORGPU_TILE);
+        for (auto& S : e->bsg) cnt(S.d.xs_ftile, S.d.ne_pad / ORGPU_TILE); }
+      const char* fr = getenv("ORGPU_XSEND_MAX_FRAC"); const double maxfrac = fr ? atof(fr) : 0.10;
+      if ((double)nf <= maxfrac * (double)nt) {
+        if (dev_alloc(&x.d_xsend, ref.size())) return -100;
+        CUDA_OK(cudaMemcpy(x.d_xsend, ref.data(), sizeof(int2) * ref.size(), cudaMemcpyHostToDevice));
+        e->nd.xs = XSend{x.d_xsend, x.d_nb_rows, x.d_xcycle};
+        e->split = true;
+      } else {
+        for (auto& S : e->csg) S.d.xs_ftile = nullptr;
+        for (auto& S : e->bsg) S.d.xs_ftile = nullptr;
+      }
+    }
+  }
   return 0;
 }
 

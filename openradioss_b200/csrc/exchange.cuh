@@ -64,6 +64,7 @@ struct Exchange {
   unsigned long long* d_xcycle = nullptr; unsigned int* d_done = nullptr; int* d_err = nullptr;
   unsigned long long timeout_ns = 30000000000ull;        // peer wait budget (orgpu_set_exchange_timeout / ORGPU_P2P_TIMEOUT_S)
   unsigned char** d_peer_win = nullptr;                  // [nranks] window bases (for the /DT/NODA candidate exchange)
+  int2* d_xsend = nullptr;                               // [lsky] inline-send table of the force kernels (common.cuh XSend)
 };
 
 // ---- peer-memory exchange --------------------------------------------------------------------------
@@ -132,17 +133,20 @@ __device__ __forceinline__ void fold_candidates_and_advance(CycleState* cs, cons
 }
 // bounded wait for every rank's flag to reach cycle c; a timeout is FATAL for the handle: *err and cs->abort are sticky, every
 // later force / node / exchange kernel returns at once, and the host sees -8 at its next query
+// (called by the first warp of a CTA: lane q polls rank q's flag, so the ranks are awaited side by side; <= 32 ranks)
 __device__ __forceinline__ bool wait_flags(const unsigned long long* flags, int nranks, unsigned long long c, unsigned long long budget_ns,
                                            int* err, CycleState* cs)
 {
-  const unsigned long long t0 = global_ns();
-  for (int q = 0; q < nranks; q++) {
+  const int q = threadIdx.x & 31;
+  bool ok = true;
+  if (q < nranks) {
+    const unsigned long long t0 = global_ns();
     while (ld_acquire_sys(flags + q) < c) {
-      if (global_ns() - t0 > budget_ns) { *err = 1; cs->abort = 1; __threadfence(); return false; }
-      __nanosleep(100);
+      if (global_ns() - t0 > budget_ns) { *err = 1; cs->abort = 1; __threadfence(); ok = false; break; }
+      __nanosleep(64);
     }
   }
-  return true;
+  return __all_sync(0xffffffffu, ok);
 }
 
 template <int ROWW>
@@ -180,6 +184,48 @@ p2p_push_kernel(const double* __restrict__ fsky, const int* __restrict__ send_sl
   }
 }
 
+// Fused variant (default): the rows leave from inside the force kernels (XSend, common.cuh) -- each CTA stores the corner rows
+// a neighbour needs into that neighbour's window right next to the local store, so the transfer overlaps the element loop and
+// no pack / push kernel is left on the cycle's critical path; p2p_publish_kernel hands over the dt candidate and releases the
+// flags once the local arg-min is known.  Same window layout, same waiting side.  (Measured alternatives, 2 x B200, C2 / C5:
+// serial push kernel 0.5295 / 0.5591 ms per cycle; frontier tiles in a first launch + push on a side stream while the
+// interior tiles run 0.5415 / 0.5751 -- two waves' tails and scattered tiles cost more than the push kernel they hide.)
+// p2p_push_rows_kernel is the stand-alone row push for decompositions with several destinations per slot.
+template <int ROWW>
+__global__ void __launch_bounds__(256)
+p2p_push_rows_kernel(const double* __restrict__ fsky, const int* __restrict__ send_slots, const int* __restrict__ send_nb,
+                     const int* __restrict__ nb_sendptr, double* const* __restrict__ nb_rows, int nsend,
+                     const CycleState* cs, const unsigned long long* xcycle)
+{
+  if (cs->abort) return;
+  const unsigned long long c = *reinterpret_cast<const volatile unsigned long long*>(xcycle) + 1ull;
+  const int par = (int)(c & 1ull);
+  constexpr int V = ROWW / 4;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nsend * V) {
+    const int j = i / V, cc = i - j * V, nb = send_nb[j];
+    double* dst = nb_rows[2 * nb + par] + (size_t)(j - nb_sendptr[nb]) * ROWW + 4 * cc;
+    st256(reinterpret_cast<double4*>(dst), ld256(reinterpret_cast<const double4*>(fsky + (size_t)send_slots[j] * ROWW + 4 * cc)));
+  }
+  __threadfence_system();
+}
+// one warp: lane q hands rank q this rank's (dt, type, id, key) and releases its flag
+__global__ void p2p_publish_kernel(const CycleState* cs, double* const* __restrict__ peer_cand, unsigned long long* const* __restrict__ peer_flag,
+                                   int nranks, int rank, unsigned long long* xcycle)
+{
+  if (cs->abort) return;
+  const unsigned long long c = *reinterpret_cast<volatile unsigned long long*>(xcycle) + 1ull;
+  const int par = (int)(c & 1ull), q = threadIdx.x;
+  if (q < nranks) {
+    double* cd = peer_cand[q] + ((size_t)par * nranks + rank) * 4;
+    cd[0] = cs->dt2t; cd[1] = (double)cs->ityptst; cd[2] = (double)cs->neltst; cd[3] = cand_key(cs);
+    __threadfence_system();
+    st_release_sys(peer_flag[q], c);
+  }
+  __syncwarp();
+  if (q == 0) *reinterpret_cast<volatile unsigned long long*>(xcycle) = c;
+}
+
 template <int ROWW>
 __global__ void __launch_bounds__(256)
 p2p_wait_unpack_kernel(double* __restrict__ fsky, const int* __restrict__ recv_slots, int nrecv, const unsigned char* win,
@@ -189,7 +235,8 @@ p2p_wait_unpack_kernel(double* __restrict__ fsky, const int* __restrict__ recv_s
   const unsigned long long c = *reinterpret_cast<const volatile unsigned long long*>(xcycle);
   const int par = (int)(c & 1ull);
   __shared__ int s_ok;
-  if (threadIdx.x == 0) s_ok = wait_flags(reinterpret_cast<const unsigned long long*>(win + ORGPU_WIN_FLAGS), nranks, c, budget_ns, err, cs) ? 1 : 0;
+  if (threadIdx.x < 32) { const bool ok = wait_flags(reinterpret_cast<const unsigned long long*>(win + ORGPU_WIN_FLAGS), nranks, c, budget_ns, err, cs);
+                          if (threadIdx.x == 0) s_ok = ok ? 1 : 0; }
   __syncthreads();
   if (!s_ok) return;                                  // a peer died: nothing is scattered, the clock does not advance
   constexpr int V = ROWW / 4;
@@ -272,9 +319,9 @@ __global__ void p2p_dt_push_kernel(const CycleState* cs, unsigned char* const* _
 __global__ void p2p_dt_wait_kernel(CycleState* cs, const unsigned char* win, int nranks, const unsigned long long* xcycle, int* err,
                                    unsigned long long budget_ns)
 {
-  if (threadIdx.x != 0 || blockIdx.x != 0 || cs->abort) return;
+  if (threadIdx.x >= 32 || blockIdx.x != 0 || cs->abort) return;
   const unsigned long long c = *reinterpret_cast<const volatile unsigned long long*>(xcycle);
   const int par = (int)(c & 1ull);
   if (!wait_flags(reinterpret_cast<const unsigned long long*>(win + ORGPU_WIN_FLAGS2), nranks, c, budget_ns, err, cs)) return;
-  fold_candidates_and_advance(cs, reinterpret_cast<const double*>(win + ORGPU_WIN_CAND + (size_t)2 * nranks * 32) + (size_t)par * nranks * 4, nranks, true);
+  if (threadIdx.x == 0) fold_candidates_and_advance(cs, reinterpret_cast<const double*>(win + ORGPU_WIN_CAND + (size_t)2 * nranks * 32) + (size_t)par * nranks * 4, nranks, true);
 }

@@ -105,27 +105,27 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
 {
   if (P.cs->abort) return;                               // sticky: a peer-memory wait timed out (exchange.cuh)
   const ShellSG& g = P.sg;
-  const int e = blockIdx.x * ORGPU_TILE + threadIdx.x;
+  const int tile = cta_tile(g.tile_map, blockIdx.x);
+  const int e = tile * ORGPU_TILE + threadIdx.x;
   __shared__ __align__(8) unsigned long long s_bar;
-  double* const g_tile = g.slab + (size_t)blockIdx.x * g.nw * ORGPU_TILE;
-  if (STAGED) tile_load_begin(s_tile_dyn, &s_bar, g_tile, (unsigned)g.nw * ORGPU_TILE * 8u);
+  double* const g_tile = g.slab + (size_t)tile * g.nw * ORGPU_TILE;
+  const int tile_pf = ORGPU_PREFETCH_TILE > 0 ? cta_tile_ahead(g.tile_map, ORGPU_PREFETCH_TILE) : -1;
+  if (STAGED) tile_load_begin(s_tile_dyn, &s_bar, g_tile, (unsigned)g.nw * ORGPU_TILE * 8u, tile_pf >= 0 ? g.slab + (size_t)tile_pf * g.nw * ORGPU_TILE : nullptr);
   const TileAcc<STAGED> T{(STAGED ? s_tile_dyn : g_tile) + threadIdx.x};
-#if ORGPU_PREFETCH_TILE > 0
-  if (!STAGED && threadIdx.x == 0 && blockIdx.x + ORGPU_PREFETCH_TILE < gridDim.x)      // in-place tiles: same wave-ahead L2 prefetch
-    bulk_prefetch_l2(g_tile + (size_t)ORGPU_PREFETCH_TILE * g.nw * ORGPU_TILE, (unsigned)g.nw * ORGPU_TILE * 8u);
-#endif
-  double* const sm = g.smstr + (size_t)blockIdx.x * 6 * ORGPU_TILE + threadIdx.x;      // SMSTR word k at sm[k*128]
+  if (!STAGED && threadIdx.x == 0 && tile_pf >= 0)      // in-place tiles: same wave-ahead L2 prefetch
+    bulk_prefetch_l2(g.slab + (size_t)tile_pf * g.nw * ORGPU_TILE, (unsigned)g.nw * ORGPU_TILE * 8u);
+  double* const sm = g.smstr + (size_t)tile * 6 * ORGPU_TILE + threadIdx.x;      // SMSTR word k at sm[k*128]
 #if ORGPU_PREFETCH_NEXT > 0
   // a CTA about one wave ahead: start its connectivity toward L2 (its first load is then an L2 hit: -3 % kernel time)
-  { const unsigned nb = blockIdx.x + ORGPU_PREFETCH_NEXT;
-    if (nb < gridDim.x && threadIdx.x < (4 * ORGPU_TILE * 4) / 128) prefetch_l2(reinterpret_cast<const char*>(g.conn + (size_t)nb * 4 * ORGPU_TILE) + 128 * threadIdx.x); }
+  { const int nb = cta_tile_ahead(g.tile_map, ORGPU_PREFETCH_NEXT);
+    if (nb >= 0 && threadIdx.x < (4 * ORGPU_TILE * 4) / 128) prefetch_l2(reinterpret_cast<const char*>(g.conn + (size_t)nb * 4 * ORGPU_TILE) + 128 * threadIdx.x); }
 #endif
   double dt_cand = K_EP30; int order = 0x7fffffff;
   if (e < g.ne) {
     const double DT1 = P.cs->dt2;
     const int ISMSTR = g.prop.ismstr, NPT = g.prop.npt;
     int nc[4];
-    { const int* cn = g.conn + (size_t)blockIdx.x * 4 * ORGPU_TILE + threadIdx.x;
+    { const int* cn = g.conn + (size_t)tile * 4 * ORGPU_TILE + threadIdx.x;
       #pragma unroll
       for (int k = 0; k < 4; k++) nc[k] = __ldg(cn + k * ORGPU_TILE); }
     order = g.order0 + e;
@@ -385,7 +385,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     // ---- CMAIN3
     shell_material_loop<LAW, true, STAGED, 0, FAST>(g, T, DT1, io);
     OFF = io.off;
-    if (g.bal && P.cs->ipri) shell_bilan<4, STAGED>(P, T, e, io.rho, OFF);     // CBILAN (czforc3.F:639)
+    if (g.bal && P.cs->ipri) shell_bilan<4, STAGED>(P, T, tile, e, io.rho, OFF);     // CBILAN (czforc3.F:639)
     // ---- re-derive the geometry needed by the force assembly (same expressions as before the loop)
     QephGeo q1; qeph_geo(XL2, YL2, XL3, YL3, XL4, YL4, q1);
     const double* CX = q1.CX; const double* CY = q1.CY;
@@ -634,9 +634,10 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       }
       const double fac = (J & 1) ? FACN2 : FACN1;
       double4* row = reinterpret_cast<double4*>(P.fsky + (size_t)8 * sl[J]);
-      st256(row, make_double4(-f[0], -f[1], -f[2], -mm[0]));
-      st256(row + 1, make_double4(-mm[1], -mm[2], STI * fac, STIR * fac));
+      const double4 r0 = make_double4(-f[0], -f[1], -f[2], -mm[0]), r1 = make_double4(-mm[1], -mm[2], STI * fac, STIR * fac);
+      st256(row, r0); st256(row + 1, r1);
     }
+    if (g.xs_ftile && g.xs_ftile[tile]) xsend_rows<8, STAGED>(P.nd.xs, T, g.w_slot, 4, P.fsky);   // frontier tile: rows to the neighbours' windows
   }
-  cta_epilogue<false, STAGED>(dt_cand, order, P.db, g.blk0 + blockIdx.x, g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
+  cta_epilogue<false, STAGED>(dt_cand, order, P.db, g.blk0 + tile, g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
 }

@@ -36,6 +36,8 @@ struct ShellSG {
   int nodadt;                 // /DT/NODA: nodal stiffnesses of cndt3.F:194-221, no element time step
   double* bal; int bal_ld;    // print cycles: the elements' PARTSAV(1:6) terms, bal[k * bal_ld + e] (null until orgpu_set_print)
   const double* gvol;         // GBUF%VOL of the group's elements (initial area x thickness): the mass of CBILAN
+  const int* tile_map;        // tiles of this launch (null: all of them, tile = blockIdx.x)
+  const unsigned char* xs_ftile;    // several domains: 1 for the tiles that hold an element with a corner row to send (null: one domain)
 };
 
 enum { SW_FOR = 0, SW_MOM = 5, SW_EINT = 8, SW_THK = 10, SW_OFF = 11, SW_STRA = 12, SW_EPSD = 20, SW_HOURG = 21 };
@@ -91,10 +93,10 @@ __device__ __forceinline__ void ip_store(const ShellSG& g, const TileAcc<STAGED>
 // PARTSAV(1:6, part) -- internal energy EINT(1)+EINT(2), kinetic energy from the nodal velocities the force routine
 // sees, momenta, mass -- go to the scratch rows; the nodal velocities are gathered again (print cycles only)
 template <int NN, bool STAGED>
-__device__ __forceinline__ void shell_bilan(const ShellParams& P, const TileAcc<STAGED>& T, int e, double rho, double off)
+__device__ __forceinline__ void shell_bilan(const ShellParams& P, const TileAcc<STAGED>& T, int tile, int e, double rho, double off)
 {
   const ShellSG& g = P.sg;
-  const int* cn = g.conn + (size_t)blockIdx.x * NN * ORGPU_TILE + threadIdx.x;
+  const int* cn = g.conn + (size_t)tile * NN * ORGPU_TILE + threadIdx.x;
   double vx[NN], vy[NN], vz[NN];
   #pragma unroll
   for (int k = 0; k < NN; k++) { const double4 v = ld256_nc(P.nd.vel + __ldg(cn + k * ORGPU_TILE)); vx[k] = v.x; vy[k] = v.y; vz[k] = v.z; }
