@@ -129,6 +129,17 @@ int  orgpu_set_parts(orgpu_engine* e, int npart, const int* ipartc, const int* i
 int  orgpu_set_print(orgpu_engine* e, int ipri);
 int  orgpu_get_balance(orgpu_engine* e, double out[8], double* partsav);
 int  orgpu_get_balance_history(orgpu_engine* e, int n, double* out /*[n][8]*/);
+/* -- /PARITH/OFF: SPMD_EXCH_A (engine/source/mpi/forces/spmd_exch_a.F:34; pack :153-177, add :517-528).  Every domain assembles
+ *    the corner rows of its own elements only (the reserved remote slots of its skyline stay zero); the partial sums of the
+ *    frontier nodes -- A(1:3), AR(1:3), STIFN, STIFR: 8 doubles per node -- are exchanged and added neighbour by neighbour in
+ *    rank order.  Unlike /PARITH/ON the sum order then depends on the decomposition (results agree to rounding, not bitwise).
+ *    Host-staged (the Engine keeps its MPI): orgpu_forces_phase, orgpu_assemble, orgpu_pack_nodes per neighbour, MPI,
+ *    orgpu_add_nodes per neighbour in rank order, orgpu_advance.  Device-resident: orgpu_comm_init + orgpu_set_exchange_nodes
+ *    (instead of orgpu_set_exchange), then orgpu_run_cycles exchanges over NCCL.  External nodal loads of a frontier node must
+ *    be given to one domain only (the Starter assigns each load record to one domain). */
+int  orgpu_pack_nodes(orgpu_engine* e, int n, const int* nodes /*0-based*/, double* buf /*(8,n)*/);
+int  orgpu_add_nodes(orgpu_engine* e, int n, const int* nodes /*0-based*/, const double* buf /*(8,n)*/);
+int  orgpu_set_exchange_nodes(orgpu_engine* e, int nneigh, const int* ranks /*ascending*/, const int* ptr /*nneigh+1*/, const int* nodes);
 /* -- tie-break keys of the time-step arg-min across domains: index of every local element in the processing order of the
  *    undecomposed model (4-node shells, 3-node shells, solids) and global index of every local node.  SPMD_GLOB_MIN5
  *    (engine/source/mpi/generic/spmd_glob_min5.F:122) keeps the first minimum in reduction order; with these keys N domains

@@ -246,6 +246,19 @@ class Binding:
         if len(slots):
             self._call("unpack_rows", self.h, C.c_int(len(slots)), slots.ctypes.data_as(C.c_void_p), buf.ctypes.data_as(C.c_void_p))
 
+    # -- nodal partial sums of frontier nodes (/PARITH/OFF exchange, SPMD_EXCH_A) -----------------------
+    def pack_nodes(self, nodes):
+        nodes = np.ascontiguousarray(nodes, np.int32)
+        buf = np.zeros((len(nodes), 8))
+        if len(nodes):
+            self._call("pack_nodes", self.h, C.c_int(len(nodes)), nodes.ctypes.data_as(C.c_void_p), buf.ctypes.data_as(C.c_void_p))
+        return buf
+
+    def add_nodes(self, nodes, buf):
+        nodes = np.ascontiguousarray(nodes, np.int32); buf = np.ascontiguousarray(buf, np.float64)
+        if len(nodes):
+            self._call("add_nodes", self.h, C.c_int(len(nodes)), nodes.ctypes.data_as(C.c_void_p), buf.ctypes.data_as(C.c_void_p))
+
     # -- stepping ----------------------------------------------------------------------
     def forces_phase(self, dt1): self._call("forces_phase", self.h, C.c_double(dt1))
     def assemble(self): self._call("assemble", self.h)

@@ -172,7 +172,7 @@ int orgpu_destroy(orgpu_engine* e)
     void* xp[] = {x.d_send_slots, x.d_recv_slots, x.d_sendbuf, x.d_recvbuf, x.d_cand_send, x.d_cand_recv, x.d_slots_tmp, x.d_rows_tmp};
     for (void* p : xp) if (p) cudaFree(p);
     for (size_t q = 0; q < x.peer.size(); q++) if (x.peer[q] && (int)q != x.rank) cudaIpcCloseMemHandle(x.peer[q]);
-    void* pp[] = {x.win, x.d_send_nb, x.d_nb_sendptr, x.d_nb_rows, x.d_peer_cand, x.d_peer_flag, x.d_xcycle, x.d_done, x.d_err, x.d_peer_win, x.d_xsend};
+    void* pp[] = {x.win, x.d_send_nb, x.d_nb_sendptr, x.d_nb_rows, x.d_peer_cand, x.d_peer_flag, x.d_xcycle, x.d_done, x.d_err, x.d_peer_win, x.d_xsend, x.d_xn_nodes, x.d_xn_send, x.d_xn_recv};
     for (void* p : pp) if (p) cudaFree(p);
     if (x.comm && nccl_api()) nccl_api()->CommDestroy(x.comm); }
   for (auto ev : e->evpool) cudaEventDestroy(ev);
@@ -717,6 +717,40 @@ int orgpu_run_cycles(orgpu_engine* e, int ncycles)
   const int per_cycle = (int)(e->csg.size() + e->bsg.size()) + (e->ctl.nodadt ? 4 : 2) + (e->ipri ? 3 : 0);   // force kernels + dt finalize + node kernel(s) [+ balances]
   NEED(!(e->ipri && e->xc.nranks > 1), -5, "print-cycle balances across domains (frontier-node weights) are outside the built path");
   NEED(!(e->ctl.nodadt && e->xc.nranks > 1 && (!e->xc.p2p || e->profile)), -5, "/DT/NODA across domains needs the peer-memory exchange (orgpu_p2p_connect), unprofiled");
+  if (e->xc.nranks > 1 && e->xc.parith_off) {
+    Exchange& x = e->xc; NcclApi* N = nccl_api();
+    NEED(N && x.comm, -7, "orgpu: /PARITH/OFF exchange requested without orgpu_comm_init");
+    CUDA_OK(cudaEventRecord(e->ev0, e->st));
+    const int tot = x.xn_ptr.empty() ? 0 : x.xn_ptr.back();
+    for (int c = 0; c < ncycles; c++) {
+      launch_element_phase(e, 0, nullptr);                                   // forces + the local (dt, type, id)
+      launch_node_assemble(e->nd, e->d_fsky, e->roww, e->d_cs, e->ctl.iroddl, e->st); e->launches++;   // ASSPAR4 of the local rows: partial sums
+      if (tot) { nodes_pack_kernel<<<(tot + 255) / 256, 256, 0, e->st>>>(e->nd, x.d_xn_nodes, tot, x.d_xn_send); e->launches++; }
+      cand_pack_kernel<<<1, 1, 0, e->st>>>(e->d_cs, x.d_cand_send); e->launches++;
+      NCCL_OK(N->GroupStart());
+      for (size_t k = 0; k < x.nb_rank.size(); k++) {
+        const size_t n = x.xn_ptr[k + 1] - x.xn_ptr[k];
+        if (n) { NCCL_OK(N->Send(x.d_xn_send + 8 * (size_t)x.xn_ptr[k], 8 * n, ncclDouble, x.nb_rank[k], x.comm, e->st));
+                 NCCL_OK(N->Recv(x.d_xn_recv + 8 * (size_t)x.xn_ptr[k], 8 * n, ncclDouble, x.nb_rank[k], x.comm, e->st)); }
+      }
+      for (int q = 0; q < x.nranks; q++) {
+        if (q == x.rank) continue;
+        NCCL_OK(N->Send(x.d_cand_send, 4, ncclDouble, q, x.comm, e->st));
+        NCCL_OK(N->Recv(x.d_cand_recv + 4 * q, 4, ncclDouble, q, x.comm, e->st));
+      }
+      NCCL_OK(N->GroupEnd());
+      CUDA_OK(cudaMemcpyAsync(x.d_cand_recv + 4 * x.rank, x.d_cand_send, 32, cudaMemcpyDeviceToDevice, e->st));
+      for (size_t k = 0; k < x.nb_rank.size(); k++) {                        // SPMD_EXCH_A :517-528: neighbour after neighbour, rank order
+        const int n = x.xn_ptr[k + 1] - x.xn_ptr[k];
+        if (n) { nodes_add_kernel<<<(n + 255) / 256, 256, 0, e->st>>>(e->nd, x.d_xn_nodes + x.xn_ptr[k], n, x.d_xn_recv + 8 * (size_t)x.xn_ptr[k]); e->launches++; }
+      }
+      cand_fold_kernel<<<1, 32, 0, e->st>>>(e->d_cs, x.d_cand_recv, x.nranks); e->launches++;
+      launch_node_advance(e->nd, e->d_cs, e->ctl.iroddl, e->st); e->launches++;
+    }
+    CUDA_OK(cudaEventRecord(e->ev1, e->st));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   if (e->xc.nranks > 1 && e->xc.p2p && !e->profile) {
     // one process per GPU, peer-memory exchange: the whole cycle (forces, dt fold, push, wait+unpack, gather+update)
     // is one CUDA graph, replayed ncycles times with no host involvement and no library call
@@ -979,6 +1013,53 @@ int orgpu_unpack_rows(orgpu_engine* e, int n, const int* slots, const double* bu
   CUDA_OK(cudaMemcpyAsync(e->xc.d_rows_tmp, buf, 64 * (size_t)n, cudaMemcpyHostToDevice, e->st));
   rows_scatter8_kernel<<<(n + 255) / 256, 256, 0, e->st>>>(e->d_fsky, e->roww, e->xc.d_slots_tmp, n, e->xc.d_rows_tmp); e->launches++;
   CUDA_OK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+// host-staged /PARITH/OFF exchange (the Engine keeps its MPI): partial sums of n frontier nodes (0-based) out of / added into
+// A, AR, STIFN, STIFR as orgpu_assemble left them; buf is (8, n)
+int orgpu_pack_nodes(orgpu_engine* e, int n, const int* nodes, double* buf)
+{
+  NEED(e && e->finalized && n >= 0 && (n == 0 || (nodes && buf)), -1, "orgpu_pack_nodes: bad arguments"); CUDA_OK(cudaSetDevice(e->device));
+  if (n == 0) return 0;
+  for (int j = 0; j < n; j++) NEED(nodes[j] >= 0 && nodes[j] < e->numnod, -4, "orgpu_pack_nodes: node %d out of range", nodes[j]);
+  if (rows_tmp(e, n)) return -100;
+  CUDA_OK(cudaMemcpyAsync(e->xc.d_slots_tmp, nodes, 4 * (size_t)n, cudaMemcpyHostToDevice, e->st));
+  nodes_pack_kernel<<<(n + 255) / 256, 256, 0, e->st>>>(e->nd, e->xc.d_slots_tmp, n, e->xc.d_rows_tmp); e->launches++;
+  CUDA_OK(cudaMemcpyAsync(buf, e->xc.d_rows_tmp, 64 * (size_t)n, cudaMemcpyDeviceToHost, e->st));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+int orgpu_add_nodes(orgpu_engine* e, int n, const int* nodes, const double* buf)
+{
+  NEED(e && e->finalized && n >= 0 && (n == 0 || (nodes && buf)), -1, "orgpu_add_nodes: bad arguments"); CUDA_OK(cudaSetDevice(e->device));
+  if (n == 0) return 0;
+  for (int j = 0; j < n; j++) NEED(nodes[j] >= 0 && nodes[j] < e->numnod, -4, "orgpu_add_nodes: node %d out of range", nodes[j]);
+  if (rows_tmp(e, n)) return -100;
+  CUDA_OK(cudaMemcpyAsync(e->xc.d_slots_tmp, nodes, 4 * (size_t)n, cudaMemcpyHostToDevice, e->st));
+  CUDA_OK(cudaMemcpyAsync(e->xc.d_rows_tmp, buf, 64 * (size_t)n, cudaMemcpyHostToDevice, e->st));
+  nodes_add_kernel<<<(n + 255) / 256, 256, 0, e->st>>>(e->nd, e->xc.d_slots_tmp, n, e->xc.d_rows_tmp); e->launches++;
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+// device-resident /PARITH/OFF loop: after orgpu_comm_init, instead of orgpu_set_exchange.  Neighbour k shares the nodes
+// nodes[ptr[k] .. ptr[k+1]) with this rank (0-based local nodes, the same order on both sides: ascending global id).
+// orgpu_run_cycles then runs, per cycle: forces -> local dt arg-min -> ASSPAR4 of the local rows -> pack the frontier sums ->
+// one NCCL group (sums to / from every neighbour + the ranks' dt candidates) -> add, neighbours in rank order -> nodal update.
+int orgpu_set_exchange_nodes(orgpu_engine* e, int nneigh, const int* ranks, const int* ptr, const int* nodes)
+{
+  NEED(e && e->finalized && nneigh >= 0 && e->xc.comm, -1, "orgpu_set_exchange_nodes: engine not finalized / orgpu_comm_init missing"); CUDA_OK(cudaSetDevice(e->device));
+  NEED(!e->ctl.nodadt, -5, "/PARITH/OFF with /DT/NODA is outside the built path");
+  Exchange& x = e->xc;
+  for (int k = 0; k < nneigh; k++) { NEED(ranks[k] >= 0 && ranks[k] < x.nranks && ranks[k] != x.rank, -4, "orgpu_set_exchange_nodes: neighbour rank %d invalid", ranks[k]);
+                                     NEED(k == 0 || ranks[k] > ranks[k - 1], -4, "orgpu_set_exchange_nodes: neighbours must come in ascending rank order (the order of the additions)"); }
+  const int tot = nneigh ? ptr[nneigh] : 0;
+  for (int j = 0; j < tot; j++) NEED(nodes[j] >= 0 && nodes[j] < e->numnod, -4, "orgpu_set_exchange_nodes: node out of range");
+  x.nb_rank.assign(ranks, ranks + nneigh); x.xn_ptr.assign(ptr, ptr + nneigh + 1);
+  if (dev_alloc(&x.d_xn_nodes, (size_t)tot + 1) || dev_alloc(&x.d_xn_send, 8 * ((size_t)tot + 1)) || dev_alloc(&x.d_xn_recv, 8 * ((size_t)tot + 1))) return -100;
+  if (tot) CUDA_OK(cudaMemcpy(x.d_xn_nodes, nodes, 4 * (size_t)tot, cudaMemcpyHostToDevice));
+  x.parith_off = true;
   return 0;
 }
 

@@ -65,6 +65,8 @@ struct Exchange {
   unsigned long long timeout_ns = 30000000000ull;        // peer wait budget (orgpu_set_exchange_timeout / ORGPU_P2P_TIMEOUT_S)
   unsigned char** d_peer_win = nullptr;                  // [nranks] window bases (for the /DT/NODA candidate exchange)
   int2* d_xsend = nullptr;                               // [lsky] inline-send table of the force kernels (common.cuh XSend)
+  // /PARITH/OFF (SPMD_EXCH_A): frontier nodes shared with each neighbour (same order on both sides), 8 doubles per node
+  bool parith_off = false; std::vector<int> xn_ptr; int* d_xn_nodes = nullptr; double* d_xn_send = nullptr; double* d_xn_recv = nullptr;
 };
 
 // ---- peer-memory exchange --------------------------------------------------------------------------
@@ -297,6 +299,31 @@ __global__ void rows_scatter8_kernel(double* __restrict__ fsky, int roww, const 
   if (roww == 8) { for (int c = 0; c < 8; c++) r[c] = o[c]; }
   else { r[0] = o[0]; r[1] = o[1]; r[2] = o[2]; r[3] = o[6]; }
 }
+
+// ---- /PARITH/OFF: SPMD_EXCH_A (engine/source/mpi/forces/spmd_exch_a.F) -- every domain assembles the corner rows of its own
+// elements only, then the PARTIAL SUMS of the frontier nodes are exchanged: pack :153-166 (A(1:3), AR(1:3), STIFN, STIFR of the
+// nodes FR_ELEM shared with one neighbour), add :517-528 (neighbours in rank order, nodes in list order).  8 doubles per node.
+__global__ void nodes_pack_kernel(const DevNodes nd, const int* __restrict__ nodes, int n, double* __restrict__ buf)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x; if (j >= n) return;
+  const int N = nodes[j]; double* b = buf + 8 * (size_t)j;
+  b[0] = nd.A[3 * N]; b[1] = nd.A[3 * N + 1]; b[2] = nd.A[3 * N + 2];
+  b[3] = nd.AR[3 * N]; b[4] = nd.AR[3 * N + 1]; b[5] = nd.AR[3 * N + 2];
+  b[6] = nd.STIFN[N]; b[7] = nd.STIFR[N];
+}
+__global__ void nodes_add_kernel(const DevNodes nd, const int* __restrict__ nodes, int n, const double* __restrict__ buf)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x; if (j >= n) return;
+  const int N = nodes[j]; const double* b = buf + 8 * (size_t)j;
+  nd.A[3 * N] = nd.A[3 * N] + b[0]; nd.A[3 * N + 1] = nd.A[3 * N + 1] + b[1]; nd.A[3 * N + 2] = nd.A[3 * N + 2] + b[2];
+  nd.AR[3 * N] = nd.AR[3 * N] + b[3]; nd.AR[3 * N + 1] = nd.AR[3 * N + 1] + b[4]; nd.AR[3 * N + 2] = nd.AR[3 * N + 2] + b[5];
+  nd.STIFN[N] = nd.STIFN[N] + b[6]; nd.STIFR[N] = nd.STIFR[N] + b[7];
+}
+// the ranks' dt candidates alone (the rows of /PARITH/ON travel with them; here the node sums do)
+__global__ void cand_pack_kernel(const CycleState* cs, double* cand)
+{ cand[0] = cs->dt2t; cand[1] = (double)cs->ityptst; cand[2] = (double)cs->neltst; cand[3] = cand_key(cs); }
+__global__ void cand_fold_kernel(CycleState* cs, const double* __restrict__ cand, int nranks)
+{ if (threadIdx.x == 0 && blockIdx.x == 0) fold_candidates_and_advance(cs, cand, nranks, false); }
 
 // /DT/NODA across domains: the nodal time step is known only after the assembly, so it travels in a second, tiny
 // exchange: one thread publishes this rank's (DT2T, ITYPTST, NELTST) to every window and releases flags2[rank];

@@ -25,6 +25,8 @@ class Neighbor:
     rank: int
     send: np.ndarray          # local 0-based FSKY slots whose rows go to `rank`   (ISENDP)
     recv: np.ndarray          # local 0-based FSKY slots filled by rows from `rank` (IRECVP)
+    nodes: np.ndarray = None  # local 0-based nodes shared with `rank`, ascending global id on both sides (FR_ELEM / IAD_ELEM of
+                              # SPMD_EXCH_A: the /PARITH/OFF exchange of nodal partial sums)
 
 
 @dataclass
@@ -177,8 +179,21 @@ def decompose(m: Model, dom_s: Optional[np.ndarray], dom_c: Optional[np.ndarray]
         recv = np.nonzero(ldom == q)[0]                         # rows rank q computes for my nodes
         theirs = np.nonzero((slot_dom == rank) & masks[q][slot_node])[0]   # my rows at nodes q also holds
         send = gs2l[theirs]
-        if len(recv) or len(send):
-            d.neighbors.append(Neighbor(rank=q, send=send.astype(np.int32), recv=recv.astype(np.int32)))
+        shared = g2l[np.nonzero(mine & masks[q])[0]]            # ascending global node id
+        if len(recv) or len(send) or len(shared):
+            d.neighbors.append(Neighbor(rank=q, send=send.astype(np.int32), recv=recv.astype(np.int32), nodes=shared.astype(np.int32)))
+    return d
+
+
+def parith_off(d: Domain) -> Domain:
+    """The same domain prepared for the /PARITH/OFF exchange (SPMD_EXCH_A: every domain assembles its own elements, the
+    partial sums of the frontier nodes are exchanged and added): an external nodal load must then sit on ONE replica of a
+    frontier node -- the Starter gives each load record to one domain -- here the lowest rank holding the node."""
+    m = d.model
+    for name in ("fext", "mext"):
+        a = getattr(m, name)
+        if a is not None:
+            a = a.copy(); a[~d.owner] = 0.0; setattr(m, name, a)
     return d
 
 

@@ -18,7 +18,7 @@ set_functions add_solid_group add_solid_group_law add_shell_group set_sh3n add_s
 synchronize get_time download_nodes download_fsky download_solid_state download_shell_state
 step_host launch_count last_run_ms set_profile get_profile pack_rows unpack_rows comm_unique_id comm_init
 set_exchange exchange get_energies p2p_export p2p_connect set_load_function set_fixvel set_gravity upload_solid_state upload_shell_state set_time set_itab
-set_parts set_print get_balance get_balance_history set_quadrature set_global_order set_exchange_timeout""".split()
+set_parts set_print get_balance get_balance_history set_quadrature set_global_order set_exchange_timeout pack_nodes add_nodes set_exchange_nodes""".split()
 
 
 def load_library() -> C.CDLL:
@@ -46,7 +46,7 @@ class Engine(Binding):
                    C.c_int(ncycles), Xout.ctypes.data_as(C.c_void_p), Vout.ctypes.data_as(C.c_void_p))
 
     # -- one process per GPU: NCCL exchange inside run_cycles ------------------------------------
-    def comm_init(self, dist, domain, p2p=True):
+    def comm_init(self, dist, domain, p2p=True, parith_off=False):
         """Create the NCCL communicator (id from rank 0, broadcast through torch.distributed) and
         register the neighbour send / receive slot lists of this rank's Domain.  With p2p (default, ranks of
         one NVLink node) the receive windows are then exchanged through CUDA IPC and run_cycles uses the
@@ -63,6 +63,16 @@ class Engine(Binding):
         self._call("comm_init", self.h, C.c_int(world), C.c_int(rank), uid)
         if os.environ.get("ORGPU_P2P_TIMEOUT_S"):
             self._call("set_exchange_timeout", self.h, C.c_double(float(os.environ["ORGPU_P2P_TIMEOUT_S"])))
+        if parith_off:
+            # /PARITH/OFF (SPMD_EXCH_A): partial sums of the frontier nodes over NCCL, neighbours in ascending rank order
+            nbs = sorted([nb for nb in domain.neighbors if nb.nodes is not None and len(nb.nodes)], key=lambda n: n.rank)
+            ranks = np.array([nb.rank for nb in nbs], np.int32)
+            ptr = np.zeros(len(nbs) + 1, np.int32)
+            for k, nb in enumerate(nbs):
+                ptr[k + 1] = ptr[k] + len(nb.nodes)
+            nodes = np.concatenate([nb.nodes for nb in nbs]).astype(np.int32) if nbs else np.zeros(0, np.int32)
+            self._call("set_exchange_nodes", self.h, C.c_int(len(nbs)), _opt(ranks, np.int32), _opt(ptr, np.int32), _opt(nodes, np.int32))
+            return
         nbs = domain.neighbors
         ranks = np.array([nb.rank for nb in nbs], np.int32)
         sp = np.zeros(len(nbs) + 1, np.int32); rp = np.zeros(len(nbs) + 1, np.int32)

@@ -99,3 +99,44 @@ def run_local(backends, doms, ncycles, on_cycle=None):
             b.advance(dt12, dt2)
             s["dt2old"] = dt2; s["dt2"] = dt2
     return states
+
+
+def run_local_off(backends, doms, ncycles, on_cycle=None):
+    """/PARITH/OFF in lock-step: every domain assembles the corner rows of its OWN elements (the reserved remote slots of its
+    skyline stay zero), then the partial sums of the frontier nodes travel -- SPMD_EXCH_A (spmd_exch_a.F:153-166 pack,
+    :517-528 add): 8 values per node, added neighbour by neighbour in rank order.  `doms` must come from domdec.parith_off."""
+    states = [initial_state(d.model.control) for d in doms]
+    for c in range(ncycles):
+        dt1 = states[0]["dt2"]
+        for b in backends:
+            b.forces_phase(dt1); b.assemble()
+        packed = {(d.rank, nb.rank): b.pack_nodes(nb.nodes) for b, d in zip(backends, doms) for nb in d.neighbors}
+        for b, d in zip(backends, doms):
+            for nb in sorted(d.neighbors, key=lambda n: n.rank):
+                b.add_nodes(nb.nodes, packed[(nb.rank, d.rank)])
+        if on_cycle:
+            on_cycle(c)
+        dt2 = min([EP06] + [b.time()["dt2t"] for b in backends])
+        dt2 = min(dt2, float(np.float32(1.1)) * states[0]["dt2old"], states[0]["dtmx"])
+        dt12 = 0.5 * (dt1 + dt2)
+        for b, s in zip(backends, states):
+            b.advance(dt12, dt2)
+            s["dt2old"] = dt2; s["dt2"] = dt2
+    return states
+
+
+def cycle_off(backend, dom, comm, state):
+    """One /PARITH/OFF cycle of one domain in its own process (SPMD_EXCH_A + SPMD_GLOB_MIN5 over `comm`)."""
+    dt1 = state["dt2"]
+    backend.forces_phase(dt1); backend.assemble()
+    sends = {nb.rank: (backend.pack_nodes(nb.nodes), len(nb.nodes)) for nb in dom.neighbors}
+    got = comm.exchange(sends)
+    for nb in sorted(dom.neighbors, key=lambda n: n.rank):
+        backend.add_nodes(nb.nodes, got[nb.rank])
+    t = backend.time()
+    dt2 = comm.min_dt(min(EP06, t["dt2t"]), t["ityptst"], t["neltst"])
+    dt2 = min(dt2, float(np.float32(1.1)) * state["dt2old"], state["dtmx"])
+    state["dt2old"] = dt2
+    backend.advance(0.5 * (dt1 + dt2), dt2)
+    state["dt2"] = dt2; state["tt"] = state.get("tt", 0.0) + dt2
+    return state

@@ -234,6 +234,22 @@ void orc_unpack_rows(void* h,int n,const int* slots,const double* buf){
   for(int j=0;j<n;j++) memcpy(&o->FSKY[8*(size_t)slots[j]],buf+8*(size_t)j,64);
 }
 
+/* /PARITH/OFF exchange of nodal partial sums, SPMD_EXCH_A (engine/source/mpi/forces/spmd_exch_a.F): pack :153-166 (IRODDL/=0:
+ * A(1:3), AR(1:3), STIFN, STIFR of the frontier nodes FR_ELEM shared with one neighbour), add :517-528 (neighbours in rank
+ * order, nodes in list order).  nodes are 0-based; buf is (8,n). */
+void orc_pack_nodes(void* h,int n,const int* nodes,double* buf){
+  Oracle* o=(Oracle*)h;
+  for(int j=0;j<n;j++){ const int N=nodes[j]; double* b=buf+8*(size_t)j;
+    b[0]=o->A[3*N]; b[1]=o->A[3*N+1]; b[2]=o->A[3*N+2]; b[3]=o->AR[3*N]; b[4]=o->AR[3*N+1]; b[5]=o->AR[3*N+2]; b[6]=o->STIFN[N]; b[7]=o->STIFR[N]; }
+}
+void orc_add_nodes(void* h,int n,const int* nodes,const double* buf){
+  Oracle* o=(Oracle*)h;
+  for(int j=0;j<n;j++){ const int N=nodes[j]; const double* b=buf+8*(size_t)j;
+    o->A[3*N]=o->A[3*N]+b[0]; o->A[3*N+1]=o->A[3*N+1]+b[1]; o->A[3*N+2]=o->A[3*N+2]+b[2];
+    o->AR[3*N]=o->AR[3*N]+b[3]; o->AR[3*N+1]=o->AR[3*N+1]+b[4]; o->AR[3*N+2]=o->AR[3*N+2]+b[5];
+    o->STIFN[N]=o->STIFN[N]+b[6]; o->STIFR[N]=o->STIFR[N]+b[7]; }
+}
+
 void orc_download_shell_state(void* h,int field,double* out){
   Oracle* o=(Oracle*)h;
   for(auto* g:o->cgroups) orc_shell_group_state(*g,field,(size_t)o->numelc,out);

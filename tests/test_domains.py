@@ -116,3 +116,94 @@ def test_two_gloo_processes_match_single_domain():
     for rank, gid, x, tt in res:
         assert np.array_equal(x, xr[gid])
         assert tt == ref.time()["tt"]
+
+
+# ---- /PARITH/OFF: SPMD_EXCH_A, partial sums of the frontier nodes -------------------------------------------------------------
+@pytest.mark.parametrize("nproc", [2, 3])
+def test_parith_off_exchange_reproduces_the_single_domain_run_to_rounding(nproc):
+    """Every domain assembles its own elements, the frontier sums travel and are added in rank order (spmd_exch_a.F:153-166,
+    517-528): the nodal forces equal the single-domain ones up to the order of the additions -- 1e-12, not bitwise."""
+    some_differ = False
+    for name, m in models():
+        ref = Oracle(m)
+        doms = [domdec.parith_off(domdec.decompose_strips(m, nproc, r)) for r in range(nproc)]
+        backs = [Oracle(d.model) for d in doms]
+        st = spmd.initial_state(m.control)
+        ref_acc = []
+        for c in range(15):
+            dt1 = st["dt2"]
+            ref.forces_phase(dt1); ref.assemble()
+            ref_acc.append(ref.download_nodes(("A", "AR", "STIFN")))
+            dt2 = min(spmd.EP06, ref.time()["dt2t"], float(np.float32(1.1)) * st["dt2old"], st["dtmx"])
+            ref.advance(0.5 * (dt1 + dt2), dt2); st["dt2"] = dt2; st["dt2old"] = dt2
+
+        def check(c):
+            nonlocal some_differ
+            for b, d in zip(backs, doms):
+                a = b.download_nodes(("A", "AR", "STIFN"))
+                for k in ("A", "AR", "STIFN"):
+                    want = ref_acc[c][k][d.node_gid]
+                    scale = max(np.abs(ref_acc[c][k]).max(), 1e-300)
+                    assert np.abs(a[k] - want).max() <= 1e-11 * scale, (name, c, k, d.rank)
+                    some_differ = some_differ or not np.array_equal(a[k], want)
+        spmd.run_local_off(backs, doms, 15, on_cycle=check)
+        xr = ref.download_nodes(("X",))["X"]
+        for b, d in zip(backs, doms):
+            x = b.download_nodes(("X",))["X"]
+            assert np.abs(x - xr[d.node_gid]).max() <= 1e-11 * np.abs(xr).max(), (name, d.rank)
+    assert some_differ          # the sum order really is another one: this is not the /PARITH/ON path under another name
+
+
+def test_parith_off_partial_sums_add_up_at_a_frontier_node():
+    m = meshgen.shell_plate(6, 4, 60.0, 40.0, pressure=10.0, vrand=5.0)
+    doms = [domdec.parith_off(domdec.decompose_strips(m, 2, r)) for r in range(2)]
+    backs = [Oracle(d.model) for d in doms]
+    for b in backs:
+        b.forces_phase(0.0); b.assemble()
+    part = [b.download_nodes(("A",))["A"] for b in backs]
+    nb0 = doms[0].neighbors[0]; nb1 = doms[1].neighbors[0]
+    assert np.array_equal(doms[0].node_gid[nb0.nodes], doms[1].node_gid[nb1.nodes])      # same nodes, same order on both sides
+    buf01 = backs[0].pack_nodes(nb0.nodes); buf10 = backs[1].pack_nodes(nb1.nodes)
+    backs[0].add_nodes(nb0.nodes, buf10); backs[1].add_nodes(nb1.nodes, buf01)
+    a0 = backs[0].download_nodes(("A",))["A"]; a1 = backs[1].download_nodes(("A",))["A"]
+    assert np.array_equal(a0[nb0.nodes], part[0][nb0.nodes] + part[1][nb1.nodes])
+    assert np.array_equal(a1[nb1.nodes], part[1][nb1.nodes] + part[0][nb0.nodes])
+    # the external load of a frontier node sits on one replica only
+    f0, f1 = doms[0].model.fext[nb0.nodes], doms[1].model.fext[nb1.nodes]
+    assert np.abs(f0).max() > 0.0 and np.abs(f1).max() == 0.0
+
+
+def _gloo_worker_off(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m = _gloo_model()
+    d = domdec.parith_off(domdec.decompose_strips(m, world, rank))
+    b = Oracle(d.model)
+    comm = spmd.TorchComm(dist)
+    st = spmd.initial_state(m.control)
+    for _ in range(20):
+        st = spmd.cycle_off(b, d, comm, st)
+    q.put((rank, d.node_gid, b.download_nodes(("X",))["X"], st["tt"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gloo_processes_parith_off():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker_off, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    m = _gloo_model()
+    ref = Oracle(m); ref.run_cycles(20)
+    xr = ref.download_nodes(("X",))["X"]
+    for rank, gid, x, tt in res:
+        assert np.abs(x - xr[gid]).max() <= 1e-11 * np.abs(xr).max()
+        assert abs(tt - ref.time()["tt"]) <= 1e-12 * ref.time()["tt"]

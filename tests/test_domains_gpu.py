@@ -101,3 +101,73 @@ def test_multi_gpu_domains_match_single_gpu_bitwise(kind, p2p):
         assert np.array_equal(x, xr["X"][gid]) and np.array_equal(v, xr["V"][gid]), (kind, rank)
         assert t["tt"] == tr["tt"] and t["ncycle"] == tr["ncycle"] and t["dt2"] == tr["dt2"]
         assert t["neltst"] == tr["neltst"] and t["ityptst"] == tr["ityptst"], (kind, rank, t, tr)     # also on exact ties
+
+
+# ---- /PARITH/OFF (SPMD_EXCH_A) ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nproc", [2, 3])
+def test_host_staged_parith_off_matches_the_oracle(nproc):
+    """Two / three Engine handles on one GPU play the domains; the partial sums of the frontier nodes go through
+    orgpu_pack_nodes / orgpu_add_nodes.  Against the oracle stepping the same domains the same way: 1e-12 on the assembled
+    forces every cycle; against the single-domain run: rounding of another sum order."""
+    from oracle.orc import Oracle
+    for name, m in models():
+        if m.control.nodadt:
+            continue
+        doms = [domdec.parith_off(domdec.decompose_strips(m, nproc, r)) for r in range(nproc)]
+        gb = [Engine(d.model) for d in doms]; ob = [Oracle(d.model) for d in doms]
+        acc = []
+        so = spmd.run_local_off(ob, doms, 12, on_cycle=lambda c: acc.append([o.download_nodes(("A", "AR", "STIFN")) for o in ob]))
+
+        def check(c):
+            for g, ao in zip(gb, acc[c]):
+                ag = g.download_nodes(("A", "AR", "STIFN"))
+                for k in ("A", "AR", "STIFN"):
+                    assert np.abs(ag[k] - ao[k]).max() <= 1e-12 * max(np.abs(ao[k]).max(), 1e-300), (name, c, k)
+        sg = spmd.run_local_off(gb, doms, 12, on_cycle=check)
+        ref = Engine(m); ref.run_cycles(12)
+        xr = ref.download_nodes(("X",))["X"]
+        for g, o, d in zip(gb, ob, doms):
+            xg, xo = g.download_nodes(("X",))["X"], o.download_nodes(("X",))["X"]
+            assert np.abs(xg - xo).max() <= 1e-12 * np.abs(xo).max(), (name, d.rank)
+            assert np.abs(xg - xr[d.node_gid]).max() <= 1e-11 * np.abs(xr).max(), (name, d.rank)
+        assert sg[0]["dt2"] == pytest.approx(so[0]["dt2"], rel=1e-12)
+
+
+def _nccl_worker_off(rank, world, port, q, kind):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    m = dict(models())[kind]
+    d = domdec.parith_off(domdec.decompose_strips(m, world, rank))
+    g = Engine(d.model, device=rank)
+    g.comm_init(dist, d, parith_off=True)
+    g.run_cycles(25); g.synchronize(); g.run_cycles(15); g.synchronize()
+    out = g.download_nodes(("X", "V"))
+    q.put((rank, d.node_gid, out["X"], out["V"], g.time()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("kind", ["shell", "brick", "tube"])
+def test_multi_gpu_parith_off_over_nccl(kind):
+    import torch.multiprocessing as mp
+    world = min(4, torch.cuda.device_count())
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31700 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_nccl_worker_off, args=(r, world, port, q, kind)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    m = dict(models())[kind]
+    ref = Engine(m); ref.run_cycles(40); ref.synchronize()
+    xr = ref.download_nodes(("X", "V")); tr = ref.time()
+    for rank, gid, x, v, t in res:
+        assert np.abs(x - xr["X"][gid]).max() <= 1e-10 * np.abs(xr["X"]).max(), (kind, rank)
+        assert np.abs(v - xr["V"][gid]).max() <= 1e-9 * np.abs(xr["V"]).max(), (kind, rank)
+        assert t["ncycle"] == tr["ncycle"] and t["tt"] == pytest.approx(tr["tt"], rel=1e-11)
