@@ -268,6 +268,22 @@ def main():
         except Exception:
             pass
 
+    # ---- the same plate from rest (the pressure pulse leaves it elastic over the window): the dominant kernel without the
+    # plastic return, for comparison with the yielding headline above (same mesh, same kernel, fresh state)
+    elastic = None
+    if world == 1 and args.workload == "c2_plate_qeph_1m":
+        import copy
+        m0 = copy.copy(m); m0.V = np.zeros_like(m.V); m0.VR = np.zeros_like(m.VR)
+        g0 = Engine(m0, device=local)
+        g0.run_cycles(args.warmup); g0.synchronize()
+        g0.set_profile(True); g0.run_cycles(min(args.steps, 64)); g0.synchronize()
+        ems, en = g0.profile(1); g0.set_profile(False)
+        if en:
+            ea = (b["forces"] * ne_dom) / (ems / en * 1e-3) / 1e9
+            elastic = {"avg_launch_ms": ems / en, "achieved": ea, "frac": ea / peak, "note": "same plate starting from rest: no integration point yields"}
+        del g0
+    roof["elastic_state"] = elastic
+
     # ---- how plastic the timed cycles were: integration points whose plastic strain grew during one more cycle
     plastic = None
     if world == 1 and (m.numelc or m.numeltg):
@@ -275,26 +291,40 @@ def main():
         p0 = st("pla"); g.run_cycles(1); g.synchronize(); p1 = st("pla")
         plastic = {"last_cycle": float((p1 > p0).mean()), "ever": float((p1 > 0).mean()), "pla_max": float(p1.max())}
 
-    # ---- end to end through the host-buffer C-ABI call (pinned host arrays, copies inside the timed region)
+    # ---- end to end through the host-buffer C-ABI call (pinned host arrays, copies inside the timed region): the host owns the
+    # nodal arrays and hands ALL of them over every step -- X, V and, for models with rotational dofs, VR -- and takes them back
     n = m.numnod
-    hX = torch.empty((n, 3), dtype=torch.float64).pin_memory(); hV = torch.empty((n, 3), dtype=torch.float64).pin_memory()
-    oX = torch.empty((n, 3), dtype=torch.float64).pin_memory(); oV = torch.empty((n, 3), dtype=torch.float64).pin_memory()
-    nd = g.download_nodes(("X", "V"))
-    hX.numpy()[:] = nd["X"]; hV.numpy()[:] = nd["V"]
+    rot = bool(m.control.iroddl)
+    narr = 3 if rot else 2
+    pin = lambda: torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    hin = [pin() for _ in range(narr)]; hout = [pin() for _ in range(narr)]
+    nd = g.download_nodes(("X", "V", "VR"))
+    for t_, k in zip(hin, ("X", "V", "VR")):
+        t_.numpy()[:] = nd[k]
+
+    def e2e_step():
+        a = [t_.numpy() for t_ in hin]; b = [t_.numpy() for t_ in hout]
+        g.step_host(a[0], a[1], a[2] if rot else None, 1, b[0], b[1], b[2] if rot else None)
     e2e_steps = max(3, min(args.steps, 50))
     for _ in range(3):
-        g.step_host(hX.numpy(), hV.numpy(), None, 1, oX.numpy(), oV.numpy()); hX.copy_(oX); hV.copy_(oV)
+        e2e_step(); hin, hout = hout, hin
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        g.step_host(hX.numpy(), hV.numpy(), None, 1, oX.numpy(), oV.numpy())
-        hX, oX = oX, hX; hV, oV = oV, hV
+        e2e_step(); hin, hout = hout, hin
     barrier()
     e2e_dt = time.perf_counter() - t0
     t = torch.tensor([e2e_dt], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = ne_total * e2e_steps / float(t.item())
+    # the link itself: one pinned 24 n-byte array each way, timed alone (what bounds the call above)
+    dbuf = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    dbuf.copy_(hin[0], non_blocking=True); torch.cuda.synchronize()
+    ev[0].record(); dbuf.copy_(hin[0], non_blocking=True); ev[1].record(); hout[0].copy_(dbuf, non_blocking=True); ev[2].record(); torch.cuda.synchronize()
+    h2d_gbs = 24e-9 * n / (ev[0].elapsed_time(ev[1]) * 1e-3); d2h_gbs = 24e-9 * n / (ev[1].elapsed_time(ev[2]) * 1e-3)
+    link_ms = 1e3 * (24e-9 * n * narr / h2d_gbs + 24e-9 * n * narr / d2h_gbs)
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
@@ -317,8 +347,11 @@ def main():
                            "l2": "inputs larger than L2 (element state >> 126 MB)" if ne >= 500000 else "working set may fit L2",
                            "parallelism": f"domains={world}" + ("" if world == 1 else " (strips / slabs; peer-memory corner-row exchange + dt fold per cycle, one CUDA graph)")},
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "pon_check": pon_check,
-                "e2e": {"value": e2e_val, "unit": "element-cycles/s", "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 48 * n,
-                        "steps": e2e_steps, "call": "orgpu_step_host (X,V pinned host -> 1 cycle -> X,V host)"},
+                "e2e": {"value": e2e_val, "unit": "element-cycles/s", "h2d_bytes_per_step": 24 * narr * n, "d2h_bytes_per_step": 24 * narr * n,
+                        "steps": e2e_steps, "ms_per_step": 1e3 * float(t.item()) / e2e_steps,
+                        "call": "orgpu_step_host_rot (X,V,VR pinned host -> 1 cycle -> X,V,VR host)" if rot else "orgpu_step_host (X,V pinned host -> 1 cycle -> X,V host)",
+                        "pcie": {"h2d_gbs": h2d_gbs, "d2h_gbs": d2h_gbs, "transfer_ms_per_step": link_ms,
+                                 "note": "the copies alone at the measured link rate; they cannot overlap the cycle (it needs every node first, the host needs the result next)"}},
                 "gpu_launches": launches,
                 "kernel_ms": {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()}}
         print(json.dumps(line), flush=True)

@@ -182,9 +182,13 @@ int  orgpu_exchange(orgpu_engine* e);   /* phased mode: pack -> NCCL -> unpack o
 int  orgpu_p2p_export(orgpu_engine* e, unsigned char handle[64]);
 int  orgpu_p2p_connect(orgpu_engine* e, const unsigned char* handles /*[nranks][64] in rank order*/);
 
-/* -- host-buffer convenience used for end-to-end timing: upload X,V(,VR), run, download X,V,A */
+/* -- host-owned nodal arrays, one call per step (the usage pattern of the reference's own -gpu path, which re-uploads X, V, VR
+ *    every cycle: shell_internal_forces.F90:106): X, V, VR in (NULL: keep the device copy), ncycles on the device, X, V(, VR) out.
+ *    Pinned host memory; PCIe-bound (24 bytes per node, array and direction). */
 int  orgpu_step_host(orgpu_engine* e, const double* X, const double* V, const double* VR,
                      int ncycles, double* Xout, double* Vout);
+int  orgpu_step_host_rot(orgpu_engine* e, const double* X, const double* V, const double* VR,
+                         int ncycles, double* Xout, double* Vout, double* VRout);
 
 /* -- instrumentation: number of kernels launched by this handle so far; device ms of the last
  *    orgpu_run_cycles measured with CUDA events on the library's stream */

@@ -42,12 +42,14 @@ struct orgpu_engine {
   int device = 0, numnod = 0;
   orgpu_control ctl{};
   cudaStream_t st = nullptr;
-#define ORGPU_NSIDE 15
+#ifndef ORGPU_NSIDE
+#define ORGPU_NSIDE 111     // with the main stream 112 concurrent launches (the device runs up to 128 kernels side by side); 15 / 47 / 111 measured
+#endif
   cudaStream_t side[ORGPU_NSIDE] = {};     // side streams: super-groups are independent, their kernels may overlap
   cudaEvent_t ev_fork = nullptr, ev_join[ORGPU_NSIDE] = {};
   bool split = false;                                    // corner rows leave from inside the force kernels (XSend; set by orgpu_p2p_connect)
   DevNodes nd{};                      // device pointers
-  double *d_stage3a = nullptr, *d_stage3b = nullptr;   // (3,N) staging for pack/unpack
+  double *d_stage3a = nullptr, *d_stage3b = nullptr, *d_stage3c = nullptr;   // (3,N) staging for pack/unpack
   double *d_fext = nullptr, *d_mext = nullptr; int *d_icodt = nullptr, *d_icodr = nullptr, *d_adsky = nullptr;
   // connectivity as given by the caller
   std::vector<int> ixs, iads, ixc, iadc, adsky; int numels = 0, numelc = 0, lsky = 0;
@@ -164,7 +166,7 @@ int orgpu_destroy(orgpu_engine* e)
   for (auto& s : e->bsg) for (void* p : s.owned) cudaFree(p);
   for (auto& s : e->csg) for (void* p : s.owned) cudaFree(p);
   void* ptrs[] = {e->nd.pos, e->nd.vel, e->nd.rot, e->nd.D, e->nd.A, e->nd.AR, e->nd.STIFN, e->nd.STIFR, e->nd.MS, e->nd.IN,
-                  e->d_stage3a, e->d_stage3b, e->d_fext, e->d_mext, e->d_icodt, e->d_icodr, e->d_adsky, e->d_fsky, e->d_cs,
+                  e->d_stage3a, e->d_stage3b, e->d_stage3c, e->d_fext, e->d_mext, e->d_icodt, e->d_icodr, e->d_adsky, e->d_fsky, e->d_cs,
                   e->db.dt, e->db.order, e->d_sgr, e->d_btf, e->d_bnpf, e->d_ftf, e->d_fnpf, e->d_fv_idx, e->d_fv, e->d_itab, e->d_nd_dt, e->d_nd_node, e->d_gmask,
                   e->d_gnode, e->d_bal, e->d_nbal, e->d_epart, e->d_npartial, e->d_partsav, e->d_hist, e->d_chunks, e->d_bs};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -571,7 +573,7 @@ static void launch_element_phase(orgpu_engine* e, int fused, size_t* evi)
 {
   e->fa.fused = fused;
   // Super-groups write disjoint FSKY rows, state tiles and dt slots: with more than one of them (models with many parts)
-  // their kernels are spread over the main stream and up to 15 side streams (fork / join by events, also inside the graph
+  // their kernels are spread over the main stream and up to ORGPU_NSIDE side streams (fork / join by events, also inside the graph
   // capture of run_cycles) so that small launches overlap; the profiled run keeps them in sequence to time each one.
   const size_t nsg = e->csg.size() + e->bsg.size();
   const bool fork = (evi == nullptr) && nsg > 1;
@@ -963,20 +965,36 @@ int orgpu_set_time(orgpu_engine* e, double tt, double dt2, double dt2old, long l
   return 0;
 }
 
-int orgpu_step_host(orgpu_engine* e, const double* X, const double* V, const double* VR,
-                    int ncycles, double* Xout, double* Vout)
+// Host-owned nodal arrays, one call per step: X, V, VR in (pinned host memory), ncycles on the device, X, V, VR out.  The three
+// uploads are queued back to back on the stream (one staging buffer each: no host synchronisation between them), each followed by
+// its 24 -> 32-byte record kernel; the downloads likewise.  The call is bound by the PCIe link: 24 bytes per node and array each
+// way (bench.py reports the measured link rate beside it) -- the cycle needs every node before it starts and the host needs
+// the result before its next call, so nothing of the transfer can hide behind the compute.
+static int step_host_impl(orgpu_engine* e, const double* X, const double* V, const double* VR, int ncycles, double* Xout, double* Vout, double* VRout)
 {
   NEED(e && e->finalized, -1, "engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
   const int n = e->numnod; const int nb = (n + 255) / 256;
-  if (X) { CUDA_OK(cudaMemcpyAsync(e->d_stage3a, X, 24 * (size_t)n, cudaMemcpyHostToDevice, e->st)); pack3to4_kernel<<<nb, 256, 0, e->st>>>(e->d_stage3a, e->nd.pos, n); e->launches++; }
-  if (V) { CUDA_OK(cudaMemcpyAsync(e->d_stage3b, V, 24 * (size_t)n, cudaMemcpyHostToDevice, e->st)); pack3to4_kernel<<<nb, 256, 0, e->st>>>(e->d_stage3b, e->nd.vel, n); e->launches++; }
-  if (VR && e->nd.rot) { CUDA_OK(cudaStreamSynchronize(e->st)); CUDA_OK(cudaMemcpyAsync(e->d_stage3a, VR, 24 * (size_t)n, cudaMemcpyHostToDevice, e->st)); pack3to4_kernel<<<nb, 256, 0, e->st>>>(e->d_stage3a, e->nd.rot, n); e->launches++; }
+  if (e->nd.rot && (VR || VRout) && !e->d_stage3c) { if (dev_alloc(&e->d_stage3c, 3 * (size_t)n)) return -100; }
+  if (X) CUDA_OK(cudaMemcpyAsync(e->d_stage3a, X, 24 * (size_t)n, cudaMemcpyHostToDevice, e->st));
+  if (V) CUDA_OK(cudaMemcpyAsync(e->d_stage3b, V, 24 * (size_t)n, cudaMemcpyHostToDevice, e->st));
+  if (VR && e->nd.rot) CUDA_OK(cudaMemcpyAsync(e->d_stage3c, VR, 24 * (size_t)n, cudaMemcpyHostToDevice, e->st));
+  if (X) { pack3to4_kernel<<<nb, 256, 0, e->st>>>(e->d_stage3a, e->nd.pos, n); e->launches++; }
+  if (V) { pack3to4_kernel<<<nb, 256, 0, e->st>>>(e->d_stage3b, e->nd.vel, n); e->launches++; }
+  if (VR && e->nd.rot) { pack3to4_kernel<<<nb, 256, 0, e->st>>>(e->d_stage3c, e->nd.rot, n); e->launches++; }
   { int rc = orgpu_run_cycles(e, ncycles); if (rc) return rc; }
-  if (Xout) { unpack4to3_kernel<<<nb, 256, 0, e->st>>>(e->nd.pos, e->d_stage3a, n); e->launches++; CUDA_OK(cudaMemcpyAsync(Xout, e->d_stage3a, 24 * (size_t)n, cudaMemcpyDeviceToHost, e->st)); }
-  if (Vout) { unpack4to3_kernel<<<nb, 256, 0, e->st>>>(e->nd.vel, e->d_stage3b, n); e->launches++; CUDA_OK(cudaMemcpyAsync(Vout, e->d_stage3b, 24 * (size_t)n, cudaMemcpyDeviceToHost, e->st)); }
+  if (Xout) { unpack4to3_kernel<<<nb, 256, 0, e->st>>>(e->nd.pos, e->d_stage3a, n); e->launches++; }
+  if (Vout) { unpack4to3_kernel<<<nb, 256, 0, e->st>>>(e->nd.vel, e->d_stage3b, n); e->launches++; }
+  if (VRout && e->nd.rot) { unpack4to3_kernel<<<nb, 256, 0, e->st>>>(e->nd.rot, e->d_stage3c, n); e->launches++; }
+  if (Xout) CUDA_OK(cudaMemcpyAsync(Xout, e->d_stage3a, 24 * (size_t)n, cudaMemcpyDeviceToHost, e->st));
+  if (Vout) CUDA_OK(cudaMemcpyAsync(Vout, e->d_stage3b, 24 * (size_t)n, cudaMemcpyDeviceToHost, e->st));
+  if (VRout && e->nd.rot) CUDA_OK(cudaMemcpyAsync(VRout, e->d_stage3c, 24 * (size_t)n, cudaMemcpyDeviceToHost, e->st));
   CUDA_OK(cudaStreamSynchronize(e->st));
   return check_abort(e);
 }
+int orgpu_step_host(orgpu_engine* e, const double* X, const double* V, const double* VR, int ncycles, double* Xout, double* Vout)
+{ return step_host_impl(e, X, V, VR, ncycles, Xout, Vout, nullptr); }
+int orgpu_step_host_rot(orgpu_engine* e, const double* X, const double* V, const double* VR, int ncycles, double* Xout, double* Vout, double* VRout)
+{ return step_host_impl(e, X, V, VR, ncycles, Xout, Vout, VRout); }
 
 // ---- domain exchange ------------------------------------------------------------------------------
 

@@ -103,7 +103,9 @@ template <int LAW, bool STAGED, int FAST = 0>
 __global__ void __launch_bounds__(ORGPU_SHELL_CTA, ORGPU_SHELL_MINB * ORGPU_PER128)
 qeph_forces_kernel(const __grid_constant__ ShellParams P)
 {
+#ifndef ORGPU_NO_ABORT
   if (P.cs->abort) return;                               // sticky: a peer-memory wait timed out (exchange.cuh)
+#endif
   const ShellSG& g = P.sg;
   const int tile = cta_tile(g.tile_map, blockIdx.x);
   const int e = tile * ORGPU_TILE + threadIdx.x;
@@ -385,7 +387,9 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     // ---- CMAIN3
     shell_material_loop<LAW, true, STAGED, 0, FAST>(g, T, DT1, io);
     OFF = io.off;
+#ifndef ORGPU_NO_BILAN
     if (g.bal && P.cs->ipri) shell_bilan<4, STAGED>(P, T, tile, e, io.rho, OFF);     // CBILAN (czforc3.F:639)
+#endif
     // ---- re-derive the geometry needed by the force assembly (same expressions as before the loop)
     QephGeo q1; qeph_geo(XL2, YL2, XL3, YL3, XL4, YL4, q1);
     const double* CX = q1.CX; const double* CY = q1.CY;
@@ -637,7 +641,9 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       const double4 r0 = make_double4(-f[0], -f[1], -f[2], -mm[0]), r1 = make_double4(-mm[1], -mm[2], STI * fac, STIR * fac);
       st256(row, r0); st256(row + 1, r1);
     }
+#ifndef ORGPU_NO_XSEND
     if (g.xs_ftile && g.xs_ftile[tile]) xsend_rows<8, STAGED>(P.nd.xs, T, g.w_slot, 4, P.fsky);   // frontier tile: rows to the neighbours' windows
+#endif
   }
   cta_epilogue<false, STAGED>(dt_cand, order, P.db, g.blk0 + tile, g_tile, s_tile_dyn, (unsigned)g.nw_rw * ORGPU_TILE * 8u);
 }

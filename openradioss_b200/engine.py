@@ -18,7 +18,7 @@ set_functions add_solid_group add_solid_group_law add_shell_group set_sh3n add_s
 synchronize get_time download_nodes download_fsky download_solid_state download_shell_state
 step_host launch_count last_run_ms set_profile get_profile pack_rows unpack_rows comm_unique_id comm_init
 set_exchange exchange get_energies p2p_export p2p_connect set_load_function set_fixvel set_gravity upload_solid_state upload_shell_state set_time set_itab
-set_parts set_print get_balance get_balance_history set_quadrature set_global_order set_exchange_timeout pack_nodes add_nodes set_exchange_nodes""".split()
+set_parts set_print get_balance get_balance_history set_quadrature set_global_order set_exchange_timeout pack_nodes add_nodes set_exchange_nodes step_host_rot""".split()
 
 
 def load_library() -> C.CDLL:
@@ -40,10 +40,14 @@ class Engine(Binding):
         if model is not None:
             self.load(model, device)
 
-    def step_host(self, X, V, VR, ncycles, Xout, Vout):
+    def step_host(self, X, V, VR, ncycles, Xout, Vout, VRout=None):
         """End-to-end entry: host nodal arrays in, ncycles on the device, host arrays out."""
-        self._call("step_host", self.h, _opt(X, np.float64), _opt(V, np.float64), _opt(VR, np.float64),
-                   C.c_int(ncycles), Xout.ctypes.data_as(C.c_void_p), Vout.ctypes.data_as(C.c_void_p))
+        if VRout is None:
+            self._call("step_host", self.h, _opt(X, np.float64), _opt(V, np.float64), _opt(VR, np.float64),
+                       C.c_int(ncycles), Xout.ctypes.data_as(C.c_void_p), Vout.ctypes.data_as(C.c_void_p))
+        else:
+            self._call("step_host_rot", self.h, _opt(X, np.float64), _opt(V, np.float64), _opt(VR, np.float64),
+                       C.c_int(ncycles), Xout.ctypes.data_as(C.c_void_p), Vout.ctypes.data_as(C.c_void_p), VRout.ctypes.data_as(C.c_void_p))
 
     # -- one process per GPU: NCCL exchange inside run_cycles ------------------------------------
     def comm_init(self, dist, domain, p2p=True, parith_off=False):

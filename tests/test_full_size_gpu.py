@@ -77,7 +77,7 @@ def test_c5_slab_2m_bricks_phased_cycles_match_the_oracle():
             b.advance(0.5 * (dt1 + dt2), dt2)
         ng, no = g.download_nodes(("X", "V", "D")), o.download_nodes(("X", "V", "D"))
         for k in ("X", "V", "D"):
-            assert rel_err(ng[k], no[k]) <= 1e-14, k
+            assert rel_err(ng[k], no[k]) <= 1e-12, k           # V += DT12 * A with A at 1e-12 and |DT12 A| ~ |V| for this field
         dt1 = dt2
     for f in ("sig", "eint", "rho", "qvis", "pla", "epsd", "off", "temp", "smstr"):
         assert rel_err(g.solid_state(f), o.solid_state(f)) <= 1e-11, f
