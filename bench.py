@@ -120,6 +120,50 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measure_extra(name, world, rank, local, dist, steps, warmup):
+    """Device-resident throughput of one more BASELINE configuration inside the same run (short: `steps` timed cycles): returns
+    the entry for the line's `other_configs`.  Same engine, same timing rules as the headline (CUDA events on the library's
+    stream, max over ranks)."""
+    import torch
+    from openradioss_b200.engine import Engine
+    from openradioss_b200 import domdec
+    gm, fam, axis = workload(name, world)
+    if world > 1:
+        dom = domdec.decompose_strips(gm, world, rank, axis=axis); m = dom.model
+    else:
+        m = gm
+    ne = m.numels + m.numelc + m.numeltg
+    g = Engine(m, device=local)
+    if world > 1:
+        g.comm_init(dist, dom)
+    net = torch.tensor([ne], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(net)
+    g.run_cycles(warmup); g.synchronize()
+    if world > 1:
+        dist.barrier()
+    g.run_cycles(steps); g.synchronize()
+    t = torch.tensor([g.last_run_ms()], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    out = {"elements": int(net.item()), "family": fam, "n_gpus": world, "steps": steps, "ms_per_step": ms / steps,
+           "value": int(net.item()) * steps / (ms * 1e-3), "unit": "element-cycles/s",
+           "scaling": "strong" if name in STRONG else "weak"}
+    if world == 1:
+        g.set_profile(True); g.run_cycles(min(steps, 32)); g.synchronize()
+        prof = {k: g.profile(i) for i, k in enumerate(("brick_forces", "shell_forces", "node"))}
+        out["kernel_ms"] = {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()}
+        peak, _ = peaks()
+        if fam in ("brick", "shell"):
+            k = "brick_forces" if fam == "brick" else "shell_forces"
+            nel = m.numels if fam == "brick" else m.numelc
+            if prof[k][1]:
+                out["roofline_frac"] = B_ALG[fam]["forces"] * nel / (prof[k][0] / prof[k][1] * 1e-3) / 1e9 / peak
+    del g
+    return out
+
+
 def run_reference(args, rank):
     """CPU arm: the oracle restatement on all host cores, same workload / metric."""
     if rank != 0:
@@ -151,6 +195,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("ORGPU_WORKLOAD", "c2_plate_qeph_1m"))
     ap.add_argument("--cpu-cycles", type=int, default=20, help="cycles of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other BASELINE configurations (other_configs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -338,6 +383,21 @@ def main():
                "sample": f"{args.workload}: {ne} elements x {args.cpu_cycles} cycles (oracle restatement, OpenMP over groups of 128)"}
         o.close()
 
+    # ---- the other BASELINE configurations, briefly, in the same run: C1 (Taylor bar), C5 (brick slab, 2 M per GPU), C4 (crush tube:
+    # shells + bricks) on one GPU; C3 (4 M shells, strong scaling) and C5 / C4 across the domains of a multi-GPU run
+    extras = None
+    if not args.no_extras and os.environ.get("ORGPU_BENCH_EXTRAS", "1") != "0" and args.workload == "c2_plate_qeph_1m":
+        extras = {}
+        del g
+        torch.cuda.empty_cache()
+        names = ("c1_taylor_bar", "c5_brick_slab_2m", "c4_tube") if world == 1 else ("c3_plate_qeph_4m", "c5_brick_slab_2m", "c4_tube")
+        for nm in names:
+            try:
+                extras[nm] = measure_extra(nm, world, rank, local, dist if world > 1 else None, 100, 10)
+            except Exception as ex:                                  # an extra must never cost the headline
+                extras[nm] = {"error": str(ex)[:200]}
+            torch.cuda.empty_cache()
+
     if rank == 0:
         line = {"metric": "element-cycles/sec", "value": value, "unit": "element-cycles/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -346,7 +406,7 @@ def main():
                            "plastic_fraction": plastic,
                            "l2": "inputs larger than L2 (element state >> 126 MB)" if ne >= 500000 else "working set may fit L2",
                            "parallelism": f"domains={world}" + ("" if world == 1 else " (strips / slabs; peer-memory corner-row exchange + dt fold per cycle, one CUDA graph)")},
-                "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "pon_check": pon_check,
+                "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "pon_check": pon_check, "other_configs": extras,
                 "e2e": {"value": e2e_val, "unit": "element-cycles/s", "h2d_bytes_per_step": 24 * narr * n, "d2h_bytes_per_step": 24 * narr * n,
                         "steps": e2e_steps, "ms_per_step": 1e3 * float(t.item()) / e2e_steps,
                         "call": "orgpu_step_host_rot (X,V,VR pinned host -> 1 cycle -> X,V,VR host)" if rot else "orgpu_step_host (X,V pinned host -> 1 cycle -> X,V host)",

@@ -26,6 +26,7 @@ struct ShellSG {
   double* slab;               // [tile][nw][128]
   int nw, nw_rw;              // words per tile / written back
   int w_ip0, nwip;            // first word of integration point 0, words per point
+  int iw_sigb;                // LBUF%SIGB (3 words: kinematic hardening, FISOKIN > 0) inside a point's words, -1: none
   int w_vt, nvt;              // first word of the VARTMP int rows, int rows per point (1 when NRATE=1: only cursor 3 is live)
   int w_thke, w_slot;         // initial-thickness word (-1 when ITHK>0), first word of the 4 slot int rows
   double* smstr;              // tile-major [tile][6][128]
@@ -60,10 +61,10 @@ struct MatIO {
   double fo[5], mo[3];                             // out: new GBUF%FOR / GBUF%MOM
 };
 
-struct IpState { double sxx, syy, sxy, syz, szx, pla, epsd, temp; int ipos; };
+struct IpState { double sxx, syy, sxy, syz, szx, pla, epsd, temp; int ipos; double sbx, sby, sbxy; };   // sb*: back stress (FISOKIN > 0)
 
 // state of one integration point out of / into the CTA's tile
-template <int LAW, bool STAGED>
+template <int LAW, bool STAGED, int FAST = 0>
 __device__ __forceinline__ IpState ip_load(const ShellSG& g, const TileAcc<STAGED>& T, int ipt)
 {
   const int w = g.w_ip0 + ipt * g.nwip;
@@ -71,18 +72,20 @@ __device__ __forceinline__ IpState ip_load(const ShellSG& g, const TileAcc<STAGE
   s.sxx = T.ld(w + IW_SIG); s.syy = T.ld(w + IW_SIG + 1); s.sxy = T.ld(w + IW_SIG + 2); s.syz = T.ld(w + IW_SIG + 3); s.szx = T.ld(w + IW_SIG + 4);
   s.pla = T.ld(w + IW_PLA);
   s.epsd = T.ld(w + IW_EPSD);
-  s.temp = K_ZERO; s.ipos = 0;
+  s.temp = K_ZERO; s.ipos = 0; s.sbx = K_ZERO; s.sby = K_ZERO; s.sbxy = K_ZERO;
+  if (FAST != 1 && g.iw_sigb >= 0) { s.sbx = T.ld(w + g.iw_sigb); s.sby = T.ld(w + g.iw_sigb + 1); s.sbxy = T.ld(w + g.iw_sigb + 2); }
   if (LAW == 2) { if (g.m2.has_temp) s.temp = T.ld(w + IW_TEMP); }
   else if (g.m36.nrate == 1) s.ipos = T.ldi(g.w_vt, ipt);
   return s;
 }
-template <int LAW, bool STAGED>
+template <int LAW, bool STAGED, int FAST = 0>
 __device__ __forceinline__ void ip_store(const ShellSG& g, const TileAcc<STAGED>& T, int ipt, const IpState& s, int ipos_old, double temp_old)
 {
   const int w = g.w_ip0 + ipt * g.nwip;
   T.st(w + IW_SIG, s.sxx); T.st(w + IW_SIG + 1, s.syy); T.st(w + IW_SIG + 2, s.sxy); T.st(w + IW_SIG + 3, s.syz); T.st(w + IW_SIG + 4, s.szx);
   T.st(w + IW_PLA, s.pla);
   T.st(w + IW_EPSD, s.epsd);
+  if (FAST != 1 && g.iw_sigb >= 0) { T.st(w + g.iw_sigb, s.sbx); T.st(w + g.iw_sigb + 1, s.sby); T.st(w + g.iw_sigb + 2, s.sbxy); }
   if (LAW == 2) { if (g.m2.has_temp && s.temp != temp_old) T.st(w + IW_TEMP, s.temp); }
   else if (g.m36.nrate == 1 && s.ipos != ipos_old) T.sti(g.w_vt, ipt, s.ipos);
 }
@@ -143,8 +146,10 @@ __device__ __forceinline__ void law36_trial(const ShellSG& g, const TileAcc<STAG
   }
   const double A1 = m.a1u, A2 = m.a2u, G = m.shear;
   const double pla = s.pla;
-  // elastic predictor
-  const double sox = s.sxx, soy = s.syy, soxy = s.sxy;
+  // elastic predictor, from the stress shifted by the back stress when the hardening has a kinematic part (sigeps36c.F:272-274)
+  const double FISOKIN = (FAST == 1) ? K_ZERO : m.fisokin;
+  double sox = s.sxx, soy = s.syy, soxy = s.sxy;
+  if (FISOKIN > K_ZERO) { sox = sox - s.sbx; soy = soy - s.sby; soxy = soxy - s.sbxy; }
   s.sxx = sox + A1 * dexx + A2 * deyy;
   s.syy = soy + A2 * dexx + A1 * deyy;
   s.sxy = soxy + G * dexy;
@@ -169,7 +174,11 @@ __device__ __forceinline__ void law36_trial(const ShellSG& g, const TileAcc<STAG
     s.ipos = ipos;
     const double FACT = FAIL * K_ONE * (m.yfac[0] * K_ONE);
     H = dydx * FACT;
-    YLD = y1 * FACT;
+    if (FISOKIN == K_ZERO) YLD = y1 * FACT;                            // :329-337
+    else {
+      const double YLD0 = (g.ct.n > 0) ? g.ct.tf[2 * g.ct.i0[0] + 1] : __ldg(g.tf + 2 * (size_t)__ldg(g.npf + f) + 1);   // first point of the curve
+      YLD = (FISOKIN == K_ONE) ? YLD0 * FACT : ((K_ONE - FISOKIN) * y1 + FISOKIN * YLD0) * FACT;
+    }
   } else {
     int JJ = 1;
     for (int J = 2; J <= m.nrate - 1; J++) if (epsd >= m.rate[J - 1]) JJ = J;
@@ -190,13 +199,38 @@ __device__ __forceinline__ void law36_trial(const ShellSG& g, const TileAcc<STAG
       { const int i0 = __ldg(g.npf + f1), i1 = __ldg(g.npf + f1 + 1); vinter1(g.tf, i0, i1 - i0, ipos1, pla, dydx1, y1); }
       { const int i0 = __ldg(g.npf + f2), i1 = __ldg(g.npf + f2 + 1); vinter1(g.tf, i0, i1 - i0, ipos2, pla, dydx2, y2); }
     }
-    y1 = y1 * YFAC1; y2 = y2 * YFAC2;
-    YLD = FAIL * (y1 + RFAC * (y2 - y1));
-    YLD = fmax(YLD, K_EM20);
-    dydx1 = dydx1 * YFAC1; dydx2 = dydx2 * YFAC2;
-    H = FAIL * (dydx1 + RFAC * (dydx2 - dydx1));
-    YLD = YLD * fmax(K_ZERO, K_ONE);
-    H = H * fmax(K_ZERO, K_ONE);
+    if (FISOKIN == K_ZERO) {                                            // :383-404
+      y1 = y1 * YFAC1; y2 = y2 * YFAC2;
+      YLD = FAIL * (y1 + RFAC * (y2 - y1));
+      YLD = fmax(YLD, K_EM20);
+      dydx1 = dydx1 * YFAC1; dydx2 = dydx2 * YFAC2;
+      H = FAIL * (dydx1 + RFAC * (dydx2 - dydx1));
+      YLD = YLD * fmax(K_ZERO, K_ONE);
+      H = H * fmax(K_ZERO, K_ONE);
+    } else {
+      // first points of the two curves: the yield stress of the kinematic part (:405-460)
+      double y01, y02;
+      if (g.ct.n > 0) { y01 = g.ct.tf[2 * g.ct.i0[JJ - 1] + 1]; y02 = g.ct.tf[2 * g.ct.i0[JJ] + 1]; }
+      else { y01 = __ldg(g.tf + 2 * (size_t)__ldg(g.npf + f1) + 1); y02 = __ldg(g.tf + 2 * (size_t)__ldg(g.npf + f2) + 1); }
+      if (FISOKIN == K_ONE) {
+        dydx1 = dydx1 * YFAC1; dydx2 = dydx2 * YFAC2;
+        H = FAIL * (dydx1 + RFAC * (dydx2 - dydx1));
+        y1 = y01 * YFAC1; y2 = y02 * YFAC2;
+        YLD = FAIL * (y1 + RFAC * (y2 - y1));
+        YLD = YLD * fmax(K_ZERO, K_ONE);
+        H = H * fmax(K_ZERO, K_ONE);
+      } else {
+        y1 = y1 * YFAC1; y2 = y2 * YFAC2;
+        YLD = FAIL * (y1 + RFAC * (y2 - y1));
+        YLD = fmax(YLD, K_EM20);
+        dydx1 = dydx1 * YFAC1; dydx2 = dydx2 * YFAC2;
+        H = FAIL * (dydx1 + RFAC * (dydx2 - dydx1));
+        y1 = y01 * YFAC1; y2 = y02 * YFAC2;
+        YLD = (K_ONE - FISOKIN) * YLD + FISOKIN * (FAIL * (y1 + RFAC * (y2 - y1)));
+        YLD = YLD * fmax(K_ZERO, K_ONE);
+        H = H * fmax(K_ZERO, K_ONE);
+      }
+    }
     T.sti(g.w_vt, ipt * g.nvt + 1 + JJ, ipos1); T.sti(g.w_vt, ipt * g.nvt + 2 + JJ, ipos2);
   }
   if (m.yldcheck == 1) YLD = fmax(YLD, K_EM20);
@@ -231,6 +265,7 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
   double pla = s.pla;
   double YLD, H, EPST;
   law36_trial<STAGED, FAIL2, FAST>(g, T, ipt, asrate, dexx, deyy, dexy, deyz, dezx, dtinv, gs, epsd_pg, zt, s, YLD, H, EPST);
+  double DPLA_I = K_ZERO;                              // plastic strain increment of the point (drives the back stress)
   // projection on the yield surface
   if (ipla == 0) {
     const double NU3 = K_ONE - m.nu_mnu;
@@ -240,6 +275,7 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
       const double R = or_div(YLD, SVM);
       s.sxx = s.sxx * R; s.syy = s.syy * R; s.sxy = s.sxy * R;
       const double DPLA = or_div(off * SVM * (K_ONE - R), (G3 + H));
+      DPLA_I = DPLA;
       pla = pla + DPLA;
       double DEZZ = (YLD != 0) ? or_div(DPLA * K_HALF * (s.sxx + s.syy), YLD) : K_ZERO;
       DEZZ = -(dexx + deyy) * m.nu_mnu - NU3 * DEZZ;
@@ -264,7 +300,7 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
       n.DPLA_J = or_div((SVM - YLD), (G3 + H));
       n.DPLA_I = K_ZERO; n.DR = K_ZERO; n.PP = K_ONE; n.QQ = K_ONE;
       law36_newton_step(E, n, false); law36_newton_step(E, n, false); law36_newton_step(E, n, true);   // NITER = 3 (sigeps36c.F:167)
-      pla = pla + n.DPLA_I;
+      pla = pla + n.DPLA_I; DPLA_I = n.DPLA_I;
       S1 = (s.sxx + s.syy) * n.PP;
       S2 = (s.sxx - s.syy) * n.QQ;
       s.sxx = K_HALF * (S1 + S2);
@@ -287,6 +323,7 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
       s.sxx = S1; s.syy = S2; s.sxy = S3;
       double SVM = or_sqrt(SVM2);
       const double DPLA = or_div(off * (SVM - YLD), (G3 + H));
+      DPLA_I = DPLA;
       YLD = YLD + H * (K_ONE - m.fisokin) * DPLA;
       SVM = or_sqrt(s.sxx * s.sxx + s.syy * s.syy - s.sxx * s.syy + K_THREE * s.sxy * s.sxy);
       const double R = fmin(K_ONE, or_div(YLD, fmax(K_EM20, SVM)));
@@ -297,6 +334,12 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
       thk = thk + DEZZ * thklyl * off;
       etse = or_div(H, (H + E));
     }
+  }
+  // kinematic part of the hardening (sigeps36c.F:986-1002): the back stress grows along the new stress, which gets it back
+  if (FAST != 1 && m.fisokin > K_ZERO) {
+    const double ALPHA = or_div(m.fisokin * H * DPLA_I, YLD);
+    s.sbx = s.sbx + ALPHA * s.sxx; s.sby = s.sby + ALPHA * s.syy; s.sbxy = s.sbxy + ALPHA * s.sxy;
+    s.sxx = s.sxx + s.sbx; s.syy = s.syy + s.sby; s.sxy = s.sxy + s.sbxy;
   }
   // IFAIL = 1: failure on the maximum plastic strain (sigeps36c.F:928-938); MULAWC completes the deletion in the same cycle
   if (FAST == 1) {}
@@ -497,7 +540,7 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const Tile
   const int qrow = (npt - 1) * 11;
   const int ipt0 = 0;
   IpState nxt;
-  if (!STAGED) nxt = ip_load<LAW>(g, T, ipt0);
+  if (!STAGED) nxt = ip_load<LAW, STAGED, FAST>(g, T, ipt0);
 #ifdef ORGPU_IP_UNROLL1
   #pragma unroll 1
 #else
@@ -505,8 +548,8 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const Tile
 #endif
   for (int ipt = ipt0; ipt < npt; ipt++) {
     IpState s;
-    if (STAGED) s = ip_load<LAW>(g, T, ipt);                     // shared memory: no latency to hide
-    else { s = nxt; if (ipt + 1 < npt) nxt = ip_load<LAW>(g, T, ipt + 1); }   // software pipeline: next point's state in flight
+    if (STAGED) s = ip_load<LAW, STAGED, FAST>(g, T, ipt);        // shared memory: no latency to hide
+    else { s = nxt; if (ipt + 1 < npt) nxt = ip_load<LAW, STAGED, FAST>(g, T, ipt + 1); }   // software pipeline: next point's state in flight
     const int ipos_old = s.ipos; const double temp_old = s.temp;
     const double thkly = c_WF[qrow + ipt];
     const double posly = c_Z0[qrow + ipt] + K_ZERO;
@@ -525,7 +568,7 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const Tile
               off, off_old, ioff_duct, epchk, s, thkn, etse, sigy);
     }
     viscmx = fmax(DM, viscmx);
-    ip_store<LAW>(g, T, ipt, s, ipos_old, temp_old);
+    ip_store<LAW, STAGED, FAST>(g, T, ipt, s, ipos_old, temp_old);
     fo[0] = fo[0] + thkly * s.sxx; fo[1] = fo[1] + thkly * s.syy; fo[2] = fo[2] + thkly * s.sxy;
     fo[3] = fo[3] + thkly * s.syz; fo[4] = fo[4] + thkly * s.szx;
     mo[0] = mo[0] + wmc * s.sxx; mo[1] = mo[1] + wmc * s.syy; mo[2] = mo[2] + wmc * s.sxy;

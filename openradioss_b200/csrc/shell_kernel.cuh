@@ -36,7 +36,7 @@ static int shell_add_group(std::vector<HostShellGroup>& groups, int nel, int nft
   g.nel = nel; g.nft = nft; g.law = law; g.sh3n = sh3n ? 1 : 0; g.prop = *prop;
   if (law == 36) {
     g.m36 = *(const orgpu_law36*)mat;
-    if (g.m36.fisokin != 0.0 || g.m36.vp != 0 || g.m36.ifail < 0 || g.m36.ifail > 2) { orgpu_set_error("LAW36 kinematic hardening / VP=1 are outside the built path"); return -5; }
+    if (g.m36.fisokin < 0.0 || g.m36.fisokin > 1.0 || g.m36.vp != 0 || g.m36.ifail < 0 || g.m36.ifail > 2) { orgpu_set_error("LAW36 VP=1 / FISOKIN outside [0,1] are outside the built path"); return -5; }
     if (g.m36.ifail == 2 && prop->istrain == 0) { orgpu_set_error("LAW36 tensile-strain failure (IFAIL=2) needs the total strains (Istrain=1)"); return -5; }
     if (g.m36.nrate < 1 || g.m36.nrate > ORGPU_MAXFUNC36) { orgpu_set_error("LAW36 NRATE=%d out of range", g.m36.nrate); return -5; }
   } else {
@@ -103,6 +103,8 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
     // ---- slab word map (shell_common.cuh)
     const bool has_temp = (G.law == 2) && G.m2.has_temp;
     d.w_ip0 = SW_HOURG + d.nhourg; d.nwip = has_temp ? 8 : 7;
+    d.iw_sigb = -1;
+    if (G.law == 36 && G.m36.fisokin > 0.0) { d.iw_sigb = d.nwip; d.nwip += 3; }      // LBUF%SIGB: back stress of the kinematic hardening
     d.w_vt = d.w_ip0 + d.npt * d.nwip;
     d.nvt = (G.law == 36) ? (G.m36.nrate == 1 ? 1 : d.nvartmp) : 0;
     d.nw_rw = d.w_vt + (d.npt * d.nvt + 1) / 2;
@@ -159,7 +161,7 @@ static void shell_launch_one(K kern_staged, K kern_direct, const ShellParams& P,
 // the kernel parameters (ORGPU_NO_FAST=1: generic path)
 static inline bool shell_fast(const ShellSG& d) {
   static const bool off = getenv("ORGPU_NO_FAST") != nullptr;
-  return !off && d.law == 36 && d.prop.ipla == 1 && d.m36.ifail == 0 && d.m36.nrate == 1 && d.ct.n > 0;
+  return !off && d.law == 36 && d.prop.ipla == 1 && d.m36.ifail == 0 && d.m36.nrate == 1 && d.ct.n > 0 && d.m36.fisokin == 0.0;
 }
 
 static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky, int roww, CycleState* cs,
@@ -185,7 +187,7 @@ static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky
 }
 
 // fields: 0 for(5) 1 mom(3) 2 eint(2) 3 thk 4 off 5 stra(8) 6 epsd 7 hourg(nhourg) 8 smstr(6)
-//         9 sig(5*npt) 10 pla(npt) 11 epsd_ip(npt) 12 temp(npt) ; out[k*numelc + e]
+//         9 sig(5*npt) 10 pla(npt) 11 epsd_ip(npt) 12 temp(npt) 13 sigb(3*npt) ; out[k*numelc + e]
 static int shell_state_xfer(std::vector<ShellSGHost>& sgs, int numelc, int field, double* out, bool up, bool sh3n = false)
 {
   const size_t NE = numelc;
@@ -197,12 +199,14 @@ static int shell_state_xfer(std::vector<ShellSGHost>& sgs, int numelc, int field
       case 3: w0 = SW_THK; break; case 4: w0 = SW_OFF; break; case 5: w0 = SW_STRA; nc = 8; break; case 6: w0 = SW_EPSD; break;
       case 7: w0 = SW_HOURG; nc = d.nhourg; if (nc == 0) continue; break; case 8: base = d.smstr; nw = S.sh3n ? 3 : 6; w0 = 0; nc = nw; break;
       case 9: ipw = IW_SIG; nc = 5 * d.npt; break; case 10: ipw = IW_PLA; nc = d.npt; break; case 11: ipw = IW_EPSD; nc = d.npt; break;
-      case 12: if (d.nwip <= IW_TEMP) continue; ipw = IW_TEMP; nc = d.npt; break;
+      case 12: if (d.law != 2 || !d.m2.has_temp) continue; ipw = IW_TEMP; nc = d.npt; break;
+      case 13: if (d.iw_sigb < 0) continue; nc = 3 * d.npt; break;
       default: orgpu_set_error("unknown shell field %d", field); return -1;
     }
     for (int k = 0; k < nc; k++) {
       int w = w0 + k;
       if (ipw >= 0) w = (field == 9) ? d.w_ip0 + (k / 5) * d.nwip + IW_SIG + (k % 5) : d.w_ip0 + k * d.nwip + ipw;
+      if (field == 13) w = d.w_ip0 + (k / 3) * d.nwip + d.iw_sigb + (k % 3);
       if ((up ? slab_upload_word(base, nw, w, d.ne, out + k * NE + S.first_elem)
               : slab_download_word(base, nw, w, d.ne, out + k * NE + S.first_elem)) != cudaSuccess) {
         orgpu_set_error("shell state transfer failed"); return -100; }

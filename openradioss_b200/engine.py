@@ -109,10 +109,14 @@ class Engine(Binding):
             ck["shell"] = {f: self.shell_state(f) for f in ("forc", "mom", "eint", "thk", "off", "stra", "epsd", "hourg", "smstr", "sig", "pla", "epsd_ip")}
             if therm(self.model.shell_groups):
                 ck["shell"]["temp"] = self.shell_state("temp")          # per-point temperature of thermal Johnson-Cook shells
+            if any(getattr(g.mat, "fisokin", 0.0) > 0.0 for g in self.model.shell_groups):
+                ck["shell"]["sigb"] = self.shell_state("sigb")          # back stress of the kinematic hardening
         if self.model.numeltg:
             ck["sh3n"] = {f: self.sh3n_state(f) for f in ("forc", "mom", "eint", "thk", "off", "stra", "epsd", "smstr", "sig", "pla", "epsd_ip")}
             if therm(self.model.sh3n_groups):
                 ck["sh3n"]["temp"] = self.sh3n_state("temp")
+            if any(getattr(g.mat, "fisokin", 0.0) > 0.0 for g in self.model.sh3n_groups):
+                ck["sh3n"]["sigb"] = self.sh3n_state("sigb")
         if self.model.numels and any(getattr(g, "law", 2) == 36 for g in self.model.solid_groups):
             ck["solid"].update({f: self.solid_state(f) for f in ("wpla", "stra")})
         return ck

@@ -46,6 +46,7 @@ void orc_shell_group_state(const OrcShellGroup& g,int field,size_t ne,double* ou
     case 10: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].pla,1,(int)p); break;
     case 11: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].epsd,1,(int)p); break;
     case 12: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].temp,1,(int)p); break;
+    case 13: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].sigb,3,3*(int)p); break;   /* LBUF%SIGB (kinematic hardening) */
   }
 }
 
@@ -61,5 +62,6 @@ void orc_shell_group_state_up(OrcShellGroup& g,int field,size_t ne,const double*
     case 10: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].pla,1,(int)p); break;
     case 11: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].epsd,1,(int)p); break;
     case 12: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].temp,1,(int)p); break;
+    case 13: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].sigb,3,3*(int)p); break;
   }
 }

@@ -54,7 +54,7 @@ struct IpIO {             /* one integration point, one element */
 /* ---- SIGEPS36C, VP=0 branch, one element ------------------------------------------------ */
 void sigeps36c(const Oracle& o, const orgpu_law36& m, int ipla, double asrate, const ShellMatIn& in, IpIO& s,
                double& pla, double& epsd, int* vartmp, double& off, double& thk, double& ssp, double& viscmax,
-               double& etse, double& yld_out)
+               double& etse, double& yld_out, double* sigb /*SIGBXX, SIGBYY, SIGBXY of the point*/)
 {
   const int NITER=3;
   const int nrate=m.nrate;
@@ -69,8 +69,9 @@ void sigeps36c(const Oracle& o, const orgpu_law36& m, int ipla, double asrate, c
     EPST=K_HALF*(s.epsxx+s.epsyy+std::sqrt((s.epsxx-s.epsyy)*(s.epsxx-s.epsyy)+s.epsxy*s.epsxy));
     FAIL=std::max(K_EM20,std::min(K_ONE,(m.epsr2-EPST)/(m.epsr2-m.epsr1)));
   }
-  /* elastic predictor (sigeps36c.F:272-284); back stress is zero (FISOKIN=0) */
-  s.sigoxx=s.sigoxx-K_ZERO; s.sigoyy=s.sigoyy-K_ZERO; s.sigoxy=s.sigoxy-K_ZERO;
+  /* elastic predictor (sigeps36c.F:272-284) from the stress shifted by the back stress (zero unless FISOKIN > 0) */
+  s.sigoxx=s.sigoxx-sigb[0]; s.sigoyy=s.sigoyy-sigb[1]; s.sigoxy=s.sigoxy-sigb[2];
+  double DPLA_I=K_ZERO;                                   /* plastic strain increment of the point: drives the back stress */
   s.signxx=s.sigoxx+A1*s.depsxx+A2*s.depsyy;
   s.signyy=s.sigoyy+A2*s.depsxx+A1*s.depsyy;
   s.signxy=s.sigoxy+G*s.depsxy;
@@ -94,7 +95,9 @@ void sigeps36c(const Oracle& o, const orgpu_law36& m, int ipla, double asrate, c
     vartmp[2]=ipos;
     const double FACT=FAIL*PFAC*YFAC1;
     H=dydx1*FACT;
-    YLD=y1*FACT;
+    if(FISOKIN==K_ZERO) YLD=y1*FACT;                                   /* :329-337 */
+    else if(FISOKIN==K_ONE){ const double YLD0=o.TF[2*(size_t)o.NPF[f]+1]; YLD=YLD0*FACT; }
+    else { const double YLD0=o.TF[2*(size_t)o.NPF[f]+1]; YLD=((K_ONE-FISOKIN)*y1+FISOKIN*YLD0)*FACT; }
   } else {
     int JJ=1;
     for(int J=2;J<=nrate-1;J++) if(epsd>=m.rate[J-1]) JJ=J;
@@ -113,14 +116,35 @@ void sigeps36c(const Oracle& o, const orgpu_law36& m, int ipla, double asrate, c
     double dydx1,y1,dydx2,y2;
     orc_vinter(o.TF,o.NPF[f1],o.NPF[f1+1]-o.NPF[f1],ipos1,pla,dydx1,y1);
     orc_vinter(o.TF,o.NPF[f2],o.NPF[f2+1]-o.NPF[f2],ipos2,pla,dydx2,y2);
-    y1=y1*YFAC1; y2=y2*YFAC2;
     const double FAC=RFAC;
-    YLD=FAIL*(y1+FAC*(y2-y1));
-    YLD=std::max(YLD,K_EM20);
-    dydx1=dydx1*YFAC1; dydx2=dydx2*YFAC2;
-    H=FAIL*(dydx1+FAC*(dydx2-dydx1));
-    YLD=YLD*std::max(K_ZERO,PFAC);
-    H=H*std::max(K_ZERO,PFAC);
+    if(FISOKIN==K_ZERO){                                               /* :383-404 */
+      y1=y1*YFAC1; y2=y2*YFAC2;
+      YLD=FAIL*(y1+FAC*(y2-y1));
+      YLD=std::max(YLD,K_EM20);
+      dydx1=dydx1*YFAC1; dydx2=dydx2*YFAC2;
+      H=FAIL*(dydx1+FAC*(dydx2-dydx1));
+      YLD=YLD*std::max(K_ZERO,PFAC);
+      H=H*std::max(K_ZERO,PFAC);
+    } else if(FISOKIN==K_ONE){                                         /* :405-429: the yield stress stays the curves' first point */
+      dydx1=dydx1*YFAC1; dydx2=dydx2*YFAC2;
+      H=FAIL*(dydx1+FAC*(dydx2-dydx1));
+      y1=o.TF[2*(size_t)o.NPF[f1]+1]; y2=o.TF[2*(size_t)o.NPF[f2]+1];
+      y1=y1*YFAC1; y2=y2*YFAC2;
+      YLD=FAIL*(y1+FAC*(y2-y1));
+      YLD=YLD*std::max(K_ZERO,PFAC);
+      H=H*std::max(K_ZERO,PFAC);
+    } else {                                                           /* :430-460 mixed hardening */
+      y1=y1*YFAC1; y2=y2*YFAC2;
+      YLD=FAIL*(y1+FAC*(y2-y1));
+      YLD=std::max(YLD,K_EM20);
+      dydx1=dydx1*YFAC1; dydx2=dydx2*YFAC2;
+      H=FAIL*(dydx1+FAC*(dydx2-dydx1));
+      y1=o.TF[2*(size_t)o.NPF[f1]+1]; y2=o.TF[2*(size_t)o.NPF[f2]+1];
+      y1=y1*YFAC1; y2=y2*YFAC2;
+      YLD=(K_ONE-FISOKIN)*YLD+FISOKIN*(FAIL*(y1+FAC*(y2-y1)));
+      YLD=YLD*std::max(K_ZERO,PFAC);
+      H=H*std::max(K_ZERO,PFAC);
+    }
     vartmp[1+J1]=ipos1; vartmp[1+J2]=ipos2;
   }
   if(m.yldcheck==1) YLD=std::max(YLD,K_EM20);
@@ -133,6 +157,7 @@ void sigeps36c(const Oracle& o, const orgpu_law36& m, int ipla, double asrate, c
       double R=YLD/SVM;
       s.signxx=s.signxx*R; s.signyy=s.signyy*R; s.signxy=s.signxy*R;
       double DPLA=off*SVM*(K_ONE-R)/(G3+H);
+      DPLA_I=DPLA;
       pla=pla+DPLA;
       double DEZZ;
       if(YLD!=0) DEZZ=DPLA*K_HALF*(s.signxx+s.signyy)/YLD; else DEZZ=K_ZERO;
@@ -154,7 +179,7 @@ void sigeps36c(const Oracle& o, const orgpu_law36& m, int ipla, double asrate, c
       const double HI=H*(K_ONE-FISOKIN);
       const double HK=K_TWO_THIRD*H*FISOKIN;
       const double NU3=K_ONE-NU_MNU;
-      double DPLA_I=K_ZERO,DR=K_ZERO,PP=K_ONE,QQ=K_ONE;
+      double DR=K_ZERO,PP=K_ONE,QQ=K_ONE;
       for(int N=1;N<=NITER;N++){
         DPLA_I=DPLA_J;
         double YLD_I=YLD+HI*DPLA_I;
@@ -192,6 +217,7 @@ void sigeps36c(const Oracle& o, const orgpu_law36& m, int ipla, double asrate, c
       s.signxx=S1; s.signyy=S2; s.signxy=S3;
       double SVM=std::sqrt(SVM2);
       double DPLA=off*(SVM-YLD)/(G3+H);
+      DPLA_I=DPLA;
       double HK=H*(K_ONE-FISOKIN);
       YLD=YLD+HK*DPLA;
       SVM=std::sqrt(s.signxx*s.signxx+s.signyy*s.signyy-s.signxx*s.signyy+K_THREE*s.signxy*s.signxy);
@@ -203,6 +229,14 @@ void sigeps36c(const Oracle& o, const orgpu_law36& m, int ipla, double asrate, c
       thk=thk+DEZZ*s.thklyl*off;
       etse=H/(H+E);
     }
+  }
+  /* kinematic part of the hardening (sigeps36c.F:986-1002): the back stress grows along the new stress, which gets it back */
+  if(FISOKIN>K_ZERO){
+    const double HKIN=FISOKIN*H;
+    const double ALPHA=HKIN*DPLA_I/YLD;
+    const double SIGPXX=ALPHA*s.signxx, SIGPYY=ALPHA*s.signyy, SIGPXY=ALPHA*s.signxy;
+    sigb[0]=sigb[0]+SIGPXX; sigb[1]=sigb[1]+SIGPYY; sigb[2]=sigb[2]+SIGPXY;
+    s.signxx=s.signxx+sigb[0]; s.signyy=s.signyy+sigb[1]; s.signxy=s.signxy+sigb[2];
   }
   /* IFAIL = 1: failure on the maximum plastic strain (sigeps36c.F:928-938, no non-local): the element starts its
    * deletion; MULAWC completes it in the same cycle (mulawc.F90:2937-2941) */
@@ -410,7 +444,9 @@ void orc_cmain3(const Oracle& o, OrcShellGroup& g, int i, bool flag_zcfac, Shell
     { const double* GS_=g.STRA.data(); s.epsxx=GS_[i]+zt*GS_[5*nel+i]; s.epsyy=GS_[nel+i]+zt*GS_[6*nel+i]; s.epsxy=GS_[2*nel+i]+zt*GS_[7*nel+i]; }
     s.sigoxx=lb.sig[i]; s.sigoyy=lb.sig[nel+i]; s.sigoxy=lb.sig[2*nel+i]; s.sigoyz=lb.sig[3*nel+i]; s.sigozx=lb.sig[4*nel+i];
     if(g.law==36){
-      sigeps36c(o,g.m36,g.prop.ipla,asrate,in,s,lb.pla[i],lb.epsd[i],&lb.vartmp[(size_t)g.nvartmp*i],off,thkn,ssp,viscmx,etse,sigy);
+      double sb[3]={lb.sigb[i],lb.sigb[nel+i],lb.sigb[2*nel+i]};
+      sigeps36c(o,g.m36,g.prop.ipla,asrate,in,s,lb.pla[i],lb.epsd[i],&lb.vartmp[(size_t)g.nvartmp*i],off,thkn,ssp,viscmx,etse,sigy,sb);
+      lb.sigb[i]=sb[0]; lb.sigb[nel+i]=sb[1]; lb.sigb[2*nel+i]=sb[2];
     } else {
       sigeps02c(g.m2,g.prop.ipla,npt,dt1,asrate,in,s,lb.pla[i],lb.epsd[i],lb.temp[i],g.m2.has_temp!=0,off,off_old,ioff_duct,
                 epchk,thkn,etse,sigy);

@@ -162,3 +162,43 @@ def test_vinter_cursor_matches_numpy_interp():
         # radial return (Iplas=0): stress sits on the yield value evaluated at the plastic strain of the step start
         assert svm <= np.interp(pla, x, y) * (1 + 1e-12) + 1e-9
     assert pla > 0.3
+
+
+# ---- kinematic / mixed hardening of LAW36 (FISOKIN > 0, sigeps36c.F:272-274, 329-337, 986-1002) ---------------------------------
+def _stretch_run(fisokin, ncyc=400, reverse_at=None):
+    """One flat QEPH element strip stretched in x by prescribed nodal velocities (optionally reversed): returns the history of
+    (sigma_xx, back stress xx, plastic strain) of the mid-surface point of element 0."""
+    m = meshgen.shell_plate(2, 1, 20.0, 10.0, pressure=0.0, clamp=False, jitter=0.0, zjitter=0.0)
+    for g in m.shell_groups:
+        g.mat.fisokin = fisokin; g.prop.dm = 0.0
+    o = Oracle(m)
+    rate = 2.0                                   # 1/ms
+    hist = []
+    for c in range(ncyc):
+        sgn = -1.0 if (reverse_at is not None and c >= reverse_at) else 1.0
+        V = np.zeros_like(m.X); V[:, 0] = sgn * rate * m.X[:, 0]; V[:, 1] = -0.5 * sgn * rate * m.X[:, 1] * 0.0
+        o.upload_nodes(X=m.X, V=V, VR=np.zeros_like(V))
+        o.forces_phase(1.0e-5)
+        sig = o.shell_state("sig").reshape(5, 5, -1); sb = o.shell_state("sigb").reshape(5, 3, -1)
+        hist.append((sig[2, 0, 0], sig[2, 1, 0], sb[2, 0, 0], o.shell_state("pla")[2, 0]))
+    return np.array(hist)
+
+
+def test_kinematic_hardening_matches_isotropic_under_monotonic_proportional_loading():
+    """Radial monotonic loading cannot tell the two apart: |sigma - back stress| stays on the initial yield surface while the
+    back stress carries H*eps_p, so the total stress follows the same curve."""
+    iso, kin, mix = _stretch_run(0.0), _stretch_run(1.0), _stretch_run(0.5)
+    assert iso[-1, 3] > 0.005 and np.all(iso[:, 2] == 0.0) and kin[-1, 2] > 0.0
+    for h in (kin, mix):
+        assert np.allclose(h[-1, :2], iso[-1, :2], rtol=1e-2)
+        assert np.isclose(h[-1, 3], iso[-1, 3], rtol=5e-3)
+
+
+def test_kinematic_hardening_shows_the_bauschinger_effect():
+    """Reverse the stretch after hardening: with isotropic hardening reverse yield waits for -sigma_max; with kinematic
+    hardening it comes 2*sigma_y0 below the forward stress, i.e. much earlier -- more plastic strain for the same reversal."""
+    iso = _stretch_run(0.0, ncyc=700, reverse_at=400); kin = _stretch_run(1.0, ncyc=700, reverse_at=400)
+    assert np.isclose(iso[399, 3], kin[399, 3], rtol=5e-3)            # same state when the load turns
+    d_iso, d_kin = iso[-1, 3] - iso[399, 3], kin[-1, 3] - kin[399, 3]
+    assert d_kin > d_iso + 2e-4            # ~ (sigma_max - sigma_y0) * 2 / E' of extra reverse flow
+    assert kin[-1, 2] < kin[399, 2]                                    # the back stress follows the reversed flow

@@ -320,3 +320,39 @@ def test_large_plate_properties():
     assert abs(ie + ke - wext) <= 0.02 * wext
     w = d["D"][:, 2].reshape(201, 201)          # node (i,j) -> i + 201*j : axis 0 is j
     assert rel_err(w, w[::-1, :]) <= 1e-9 and rel_err(w, w[:, ::-1]) <= 1e-9
+
+
+@pytest.mark.parametrize("family", ["qeph", "bt", "sh3n"])
+@pytest.mark.parametrize("ipla", [0, 1, 2])
+@pytest.mark.parametrize("fisokin", [0.5, 1.0])
+def test_law36_kinematic_hardening_matches_oracle(fisokin, ipla, family):
+    """FISOKIN > 0 (sigeps36c.F:272-274, 329-337, 986-1002): back stress LBUF%SIGB per integration point, mixed and purely
+    kinematic, the three return algorithms, all three shell families (the tile grows by 3 words per point)."""
+    if family == "sh3n":
+        prop = meshgen.default_prop_shell(thick=1.5, ihbe=2, npt=3, ipla=ipla)
+        m = meshgen.tri_plate(6, 5, 60.0, 50.0, prop=prop, pressure=40.0, vrand=40.0)
+        groups, state = m.sh3n_groups, "sh3n_state"
+    else:
+        prop = meshgen.default_prop_shell(thick=1.5, ihbe=24 if family == "qeph" else 1, npt=3, ipla=ipla)
+        m = meshgen.shell_plate(7, 6, 70.0, 60.0, prop=prop, pressure=50.0, vrand=40.0)
+        groups, state = m.shell_groups, "shell_state"
+    for g_ in groups:
+        g_.mat.fisokin = fisokin
+    g, o = pair(m)
+    dt1 = 0.0
+    for c in range(5):
+        for b in (g, o):
+            b.forces_phase(dt1)
+        fg, fo = g.download_fsky(), o.download_fsky()
+        assert rel_err(fg[:, :3], fo[:, :3]) <= FORCE_TOL and rel_err(fg[:, 3:6], fo[:, 3:6]) <= FORCE_TOL, (c,)
+        for b in (g, o):
+            b.assemble()
+        dt2 = o.time()["dt2t"]
+        assert g.time()["dt2t"] == pytest.approx(dt2, rel=1e-13)
+        for b in (g, o):
+            b.advance(0.5 * (dt1 + dt2), dt2)
+        dt1 = dt2
+    for f in ("sig", "pla", "sigb", "thk", "eint"):
+        a, b = getattr(g, state)(f), getattr(o, state)(f)
+        assert rel_err(a, b) <= 1e-11, (f, rel_err(a, b))
+    assert np.abs(getattr(o, state)("sigb")).max() > 1.0              # the back stress is live
