@@ -384,6 +384,8 @@ __device__ __forceinline__ void law2_ip(const ShellSG& g, int ipla, int npttot, 
   // M2CPLR
   double CA = m.ca, CB = m.cb, YMAX = m.sigmx, H = K_ZERO, DPLA = K_ZERO, YLD;
   etse = K_ONE;
+  const double FISOKIN = m.fisokin;
+  if (FISOKIN > K_ZERO) { s.sxx = s.sxx - s.sbx; s.syy = s.syy - s.sby; s.sxy = s.sxy - s.sbxy; }   // m2cplr.F:115-121
   s.sxx = s.sxx + a11 * dexx + a12 * deyy;
   { const double t = s.syy + a12 * dexx + a11 * deyy; s.syy = t; }
   s.sxy = s.sxy + gg * dexy;
@@ -437,7 +439,14 @@ __device__ __forceinline__ void law2_ip(const ShellSG& g, int ipla, int npttot, 
       H = (YLD >= YMAX) ? K_ZERO : cn * CB * exp((cn - K_ONE) * log(pla + SMALL));
       double DPLA_J = or_div((SVM - YLD), (K_THREE * gg + H));
       etse = or_div(H, (H + young));
-      const double ANU1 = A * NU1, BNU2 = K_THREE * B * NU2, H2 = K_TWO * H;
+      // FISOKIN = 0: m2cplr.F:289-318; kinematic / mixed hardening :319-363 (HI, HK, modified Poisson terms, isotropic share of CB)
+      const bool kin = FISOKIN > K_ZERO;
+      const double BETAH = H * FISOKIN;
+      const double HI = kin ? H - BETAH : H;
+      const double AAA = kin ? or_div(K_THREE * (K_TWO_THIRD * BETAH), young) : K_ZERO;
+      const double NU11 = NU1 + AAA, NU21 = K_THREE * NU2 + AAA;
+      const double ANU1 = kin ? A * NU11 : A * NU1, BNU2 = kin ? B * NU21 : K_THREE * B * NU2, H2 = K_TWO * HI;
+      const double CBI = kin ? (K_ONE - FISOKIN) * CB : CB;
       double DPLA_I = K_ZERO, DR = K_ZERO, P = K_ONE, Qq = K_ONE;
       #pragma unroll 1
       for (int N = 0; N < 3; N++) {                       // NMAX = 3 (m2cplr.F:104)
@@ -446,10 +455,10 @@ __device__ __forceinline__ void law2_ip(const ShellSG& g, int ipla, int npttot, 
         DPLA = DPLA_J;
         double YLD_I;
         if (PLA_I == K_ZERO) YLD_I = fmin(YMAX, CA);
-        else YLD_I = fmin(YMAX, CA + CB * exp(cn * log(PLA_I)));
+        else YLD_I = fmin(YMAX, CA + CBI * exp(cn * log(PLA_I)));
         DR = or_div(K_HALF * young * DPLA_I, YLD_I);
-        P = or_div(K_ONE, (K_ONE + DR * NU1));
-        Qq = or_div(K_ONE, (K_ONE + K_THREE * DR * NU2));
+        P = or_div(K_ONE, (K_ONE + DR * (kin ? NU11 : NU1)));
+        Qq = or_div(K_ONE, (K_ONE + (kin ? DR * NU21 : K_THREE * DR * NU2)));
         const double P2 = P * P, Q2 = Qq * Qq;
         const double F = A * P2 + B * Q2 - YLD_I * YLD_I;
         const double DF = -or_div((ANU1 * P2 * P + BNU2 * Q2 * Qq) * (young - DR * H2), YLD_I) - H2 * YLD_I;
@@ -463,6 +472,7 @@ __device__ __forceinline__ void law2_ip(const ShellSG& g, int ipla, int npttot, 
       s.syy = K_HALF * (S1 - S2);
       s.sxy = s.sxy * Qq;
       EZZ = or_div(DR * S1, young);
+      if (kin) YLD = (pla == K_ZERO) ? CA : fmin(YMAX, CA + (K_ONE - FISOKIN) * CB * exp(cn * log(pla)));   // :474-487
     }
   } else {
     const double SVM2 = s.sxx * s.sxx + s.syy * s.syy - s.sxx * s.syy + K_THREE * s.sxy * s.sxy;
@@ -484,6 +494,11 @@ __device__ __forceinline__ void law2_ip(const ShellSG& g, int ipla, int npttot, 
       s.sxx = s.sxx * R; s.syy = s.syy * R; s.sxy = s.sxy * R;
       EZZ = or_div(DPLA * K_HALF * (s.sxx + s.syy), YLD);
     }
+  }
+  if (FISOKIN > K_ZERO) {                                  // m2cplr.F:488-499: back stress along the new shifted stress
+    const double ALPHA = or_div(FISOKIN * H * DPLA, YLD);
+    s.sbx = s.sbx + ALPHA * s.sxx; s.sby = s.sby + ALPHA * s.syy; s.sbxy = s.sbxy + ALPHA * s.sxy;
+    s.sxx = s.sxx + s.sbx; s.syy = s.syy + s.sby; s.sxy = s.sxy + s.sbxy;
   }
   if (m.vp == 1) { epsdot = or_div(DPLA, fmax(K_EM20, dt1)); epsd = asrate * epsdot + (K_ONE - asrate) * epsd; }
   sigy = sigy + or_div(YLD, npttot);

@@ -41,7 +41,7 @@ static int shell_add_group(std::vector<HostShellGroup>& groups, int nel, int nft
     if (g.m36.nrate < 1 || g.m36.nrate > ORGPU_MAXFUNC36) { orgpu_set_error("LAW36 NRATE=%d out of range", g.m36.nrate); return -5; }
   } else {
     g.m2 = *(const orgpu_law2*)mat;
-    if (g.m2.fisokin != 0.0) { orgpu_set_error("LAW2 kinematic hardening (FISOKIN>0) is outside the built path"); return -5; }
+    if (g.m2.fisokin < 0.0 || g.m2.fisokin > 1.0) { orgpu_set_error("LAW2 FISOKIN outside [0,1]"); return -5; }
   }
   groups.push_back(g);
   return (int)groups.size() - 1;
@@ -104,7 +104,7 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
     const bool has_temp = (G.law == 2) && G.m2.has_temp;
     d.w_ip0 = SW_HOURG + d.nhourg; d.nwip = has_temp ? 8 : 7;
     d.iw_sigb = -1;
-    if (G.law == 36 && G.m36.fisokin > 0.0) { d.iw_sigb = d.nwip; d.nwip += 3; }      // LBUF%SIGB: back stress of the kinematic hardening
+    if ((G.law == 36 && G.m36.fisokin > 0.0) || (G.law == 2 && G.m2.fisokin > 0.0)) { d.iw_sigb = d.nwip; d.nwip += 3; }      // LBUF%SIGB: back stress of the kinematic hardening
     d.w_vt = d.w_ip0 + d.npt * d.nwip;
     d.nvt = (G.law == 36) ? (G.m36.nrate == 1 ? 1 : d.nvartmp) : 0;
     d.nw_rw = d.w_vt + (d.npt * d.nvt + 1) / 2;

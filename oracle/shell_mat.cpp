@@ -248,8 +248,9 @@ void sigeps36c(const Oracle& o, const orgpu_law36& m, int ipla, double asrate, c
 /* ---- SIGEPS02C + M2CPLR, one element (FISOKIN=0) ------------------------------------------ */
 void sigeps02c(const orgpu_law2& m, int ipla, int npttot, double dt1, double asrate, const ShellMatIn& in, IpIO& s,
                double& pla, double& epsd, double& temp, bool has_temp, double& off, double off_old, int& ioff_duct,
-               double& epchk, double& thk, double& etse, double& sigy)
+               double& epchk, double& thk, double& etse, double& sigy, double* sigb /*SIGBAKXX, SIGBAKYY, SIGBAKXY*/)
 {
+  const double FISOKIN=m.fisokin;
   const int NMAX=3;
   const double SMALL=K_EM7;
   const int iform=m.iform, icc=m.icc, vp=m.vp, israte=m.israte;
@@ -279,6 +280,7 @@ void sigeps02c(const orgpu_law2& m, int ipla, int npttot, double dt1, double asr
   double CA=ca, CB=cb, YMAX=ymax, H=K_ZERO, DPLA=K_ZERO, YLD;
   etse=K_ONE;
   s.signxx=s.sigoxx; s.signyy=s.sigoyy; s.signxy=s.sigoxy; s.signyz=s.sigoyz; s.signzx=s.sigozx;
+  if(FISOKIN>K_ZERO){ s.signxx=s.signxx-sigb[0]; s.signyy=s.signyy-sigb[1]; s.signxy=s.signxy-sigb[2]; }   /* m2cplr.F:115-121 */
   s.signxx=s.signxx+a11*s.depsxx+a12*s.depsyy;
   s.signyy=s.signyy+a12*s.depsxx+a11*s.depsyy;
   s.signxy=s.signxy+g*s.depsxy;
@@ -338,22 +340,46 @@ void sigeps02c(const orgpu_law2& m, int ipla, int npttot, double dt1, double asr
       if(YLD>=YMAX) H=K_ZERO; else H=cn*CB*std::exp((cn-K_ONE)*std::log(pla+SMALL));
       double DPLA_J=(SVM-YLD)/(K_THREE*g+H);
       etse=H/(H+young);
-      const double ANU1=A*NU1, BNU2=K_THREE*B*NU2, H2=K_TWO*H;
       double DPLA_I=K_ZERO,DR=K_ZERO,P=K_ONE,Qq=K_ONE;
-      for(int N=1;N<=NMAX;N++){
-        DPLA_I=DPLA_J;
-        double PLA_I=pla+DPLA_I;
-        DPLA=DPLA_J;
-        double YLD_I;
-        if(PLA_I==K_ZERO) YLD_I=std::min(YMAX,CA);
-        else YLD_I=std::min(YMAX,CA+CB*std::exp(cn*std::log(PLA_I)));
-        DR=K_HALF*young*DPLA_I/YLD_I;
-        P=K_ONE/(K_ONE+DR*NU1);
-        Qq=K_ONE/(K_ONE+K_THREE*DR*NU2);
-        double P2=P*P, Q2=Qq*Qq;
-        double F=A*P2+B*Q2-YLD_I*YLD_I;
-        double DF=-(ANU1*P2*P+BNU2*Q2*Qq)*(young-DR*H2)/YLD_I-H2*YLD_I;
-        if(DPLA_I>K_ZERO) DPLA_J=std::max(K_ZERO,DPLA_I-F/DF); else DPLA_J=K_ZERO;
+      if(FISOKIN==K_ZERO){                                 /* m2cplr.F:289-318 */
+        const double ANU1=A*NU1, BNU2=K_THREE*B*NU2, H2=K_TWO*H;
+        for(int N=1;N<=NMAX;N++){
+          DPLA_I=DPLA_J;
+          double PLA_I=pla+DPLA_I;
+          DPLA=DPLA_J;
+          double YLD_I;
+          if(PLA_I==K_ZERO) YLD_I=std::min(YMAX,CA);
+          else YLD_I=std::min(YMAX,CA+CB*std::exp(cn*std::log(PLA_I)));
+          DR=K_HALF*young*DPLA_I/YLD_I;
+          P=K_ONE/(K_ONE+DR*NU1);
+          Qq=K_ONE/(K_ONE+K_THREE*DR*NU2);
+          double P2=P*P, Q2=Qq*Qq;
+          double F=A*P2+B*Q2-YLD_I*YLD_I;
+          double DF=-(ANU1*P2*P+BNU2*Q2*Qq)*(young-DR*H2)/YLD_I-H2*YLD_I;
+          if(DPLA_I>K_ZERO) DPLA_J=std::max(K_ZERO,DPLA_I-F/DF); else DPLA_J=K_ZERO;
+        }
+      } else {                                             /* :319-363 kinematic / mixed hardening */
+        double BETA=H*FISOKIN;
+        const double HI=H-BETA, HK=K_TWO_THIRD*BETA;
+        const double AAA=K_THREE*HK/young;
+        const double NU11=NU1+AAA, NU21=K_THREE*NU2+AAA;
+        const double ANU1=A*NU11, BNU2=B*NU21, H2=K_TWO*HI;
+        for(int N=1;N<=NMAX;N++){
+          DPLA_I=DPLA_J;
+          double PLA_I=pla+DPLA_I;
+          DPLA=DPLA_J;
+          BETA=K_ONE-FISOKIN;
+          double YLD_I;
+          if(PLA_I==K_ZERO) YLD_I=std::min(YMAX,CA);
+          else YLD_I=std::min(YMAX,CA+BETA*CB*std::exp(cn*std::log(PLA_I)));
+          DR=K_HALF*young*DPLA_I/YLD_I;
+          P=K_ONE/(K_ONE+DR*NU11);
+          Qq=K_ONE/(K_ONE+DR*NU21);
+          double P2=P*P, Q2=Qq*Qq;
+          double F=A*P2+B*Q2-YLD_I*YLD_I;
+          double DF=-(ANU1*P2*P+BNU2*Q2*Qq)*(young-DR*H2)/YLD_I-H2*YLD_I;
+          if(DPLA_I>K_ZERO) DPLA_J=std::max(K_ZERO,DPLA_I-F/DF); else DPLA_J=K_ZERO;
+        }
       }
       pla=pla+DPLA_I;
       epchk=std::max(pla,epchk);
@@ -363,6 +389,10 @@ void sigeps02c(const orgpu_law2& m, int ipla, int npttot, double dt1, double asr
       s.signyy=K_HALF*(S1-S2);
       s.signxy=s.signxy*Qq;
       EZZ=DR*S1/young;
+      if(FISOKIN>K_ZERO){                                  /* :474-487: the yield stress at the new plastic strain, isotropic part only */
+        const double BETA=K_ONE-FISOKIN;
+        if(pla==K_ZERO) YLD=CA; else YLD=std::min(YMAX,CA+BETA*CB*std::exp(cn*std::log(pla)));
+      }
     }
   } else {
     double SVM2=s.signxx*s.signxx+s.signyy*s.signyy-s.signxx*s.signyy+K_THREE*s.signxy*s.signxy;
@@ -384,6 +414,13 @@ void sigeps02c(const orgpu_law2& m, int ipla, int npttot, double dt1, double asr
       s.signxx=s.signxx*R; s.signyy=s.signyy*R; s.signxy=s.signxy*R;
       EZZ=DPLA*K_HALF*(s.signxx+s.signyy)/YLD;
     }
+  }
+  /* kinematic part (m2cplr.F:488-499): the back stress grows along the new shifted stress, which then gets it back */
+  if(FISOKIN>K_ZERO){
+    const double HKIN=FISOKIN*H;
+    const double ALPHA=HKIN*DPLA/YLD;
+    sigb[0]=sigb[0]+ALPHA*s.signxx; sigb[1]=sigb[1]+ALPHA*s.signyy; sigb[2]=sigb[2]+ALPHA*s.signxy;
+    s.signxx=s.signxx+sigb[0]; s.signyy=s.signyy+sigb[1]; s.signxy=s.signxy+sigb[2];
   }
   /* ---- back in SIGEPS02C (:172-230) */
   if(vp==1){ epsdot=DPLA/std::max(K_EM20,dt1); epsd=asrate*epsdot+(K_ONE-asrate)*epsd; }
@@ -448,8 +485,10 @@ void orc_cmain3(const Oracle& o, OrcShellGroup& g, int i, bool flag_zcfac, Shell
       sigeps36c(o,g.m36,g.prop.ipla,asrate,in,s,lb.pla[i],lb.epsd[i],&lb.vartmp[(size_t)g.nvartmp*i],off,thkn,ssp,viscmx,etse,sigy,sb);
       lb.sigb[i]=sb[0]; lb.sigb[nel+i]=sb[1]; lb.sigb[2*nel+i]=sb[2];
     } else {
+      double sb[3]={lb.sigb[i],lb.sigb[nel+i],lb.sigb[2*nel+i]};
       sigeps02c(g.m2,g.prop.ipla,npt,dt1,asrate,in,s,lb.pla[i],lb.epsd[i],lb.temp[i],g.m2.has_temp!=0,off,off_old,ioff_duct,
-                epchk,thkn,etse,sigy);
+                epchk,thkn,etse,sigy,sb);
+      lb.sigb[i]=sb[0]; lb.sigb[nel+i]=sb[1]; lb.sigb[2*nel+i]=sb[2];
     }
     viscmx=std::max(DM,viscmx);
     lb.sig[i]=s.signxx*K_ONE; lb.sig[nel+i]=s.signyy*K_ONE; lb.sig[2*nel+i]=s.signxy*K_ONE;

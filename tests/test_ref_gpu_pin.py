@@ -112,3 +112,45 @@ def test_bending_matches_the_reference_gpu_path_under_its_own_thickness_rule(ipl
         print(f"bending ipla={ipla} npt={npt} warp={warp}: worst difference to the reference GPU path {worst:.2e}")
     finally:
         o.set_quadrature(npt, *[None] * 3) if False else o.lib.orc_set_quadrature(o.h, 0, None, None, None)
+
+
+@needs_ref
+@pytest.mark.parametrize("bend", [False, True], ids=["membrane", "bending"])
+@pytest.mark.parametrize("ipla", [0, 1, 2])
+@pytest.mark.parametrize("fisokin", [0.5, 1.0])
+def test_kinematic_hardening_matches_the_reference_gpu_path(fisokin, ipla, bend):
+    """FISOKIN > 0 through the reference's own m2cplr_device (shell_strain_material_kernel.cu:118-123, 238-262, 330-340): the back
+    stress, the modified Newton return and the mixed yield stress of M2CPLR, pinned on reference code that executes."""
+    from refgpu_cases import bent_plate, midpoint_rule
+    npt = 3
+    m = bent_plate(ipla, npt) if bend else plate(ipla, npt, False, False)
+    for g_ in m.shell_groups:
+        g_.mat.fisokin = fisokin
+    g, o, r = Engine(m), Oracle(m), refgpu.RefShellGPU(m)
+    if bend:
+        z, wf, wm = midpoint_rule(npt)
+        g.set_quadrature(npt, z, wf, wm); o.set_quadrature(npt, z, wf, wm)
+    try:
+        dt1, worst = 0.0, 0.0
+        for c in range(10):
+            nd = o.download_nodes(("X", "V", "VR"))
+            fr = r.step(dt1, nd["X"], nd["V"], nd["VR"])
+            for b in (g, o):
+                b.forces_phase(dt1); b.assemble()
+            fo, fg = o.download_nodes(("A", "AR")), g.download_nodes(("A", "AR"))
+            if c > 0:
+                sf = np.abs(fo["A"]).max()
+                errs = [np.abs(fr[:, :3] - fo["A"]).max() / sf, np.abs(fr[:, :3] - fg["A"]).max() / sf]
+                if bend:
+                    sm = np.abs(fo["AR"]).max()
+                    errs += [np.abs(fr[:, 3:6] - fo["AR"]).max() / sm, np.abs(fr[:, 3:6] - fg["AR"]).max() / sm]
+                worst = max(worst, *errs)
+                assert max(errs) <= TOL, (c, errs)
+            dt2 = o.time()["dt2t"]
+            for b in (g, o):
+                b.advance(0.5 * (dt1 + dt2), dt2)
+            dt1 = dt2
+        assert o.shell_state("pla").max() > 1e-3 and np.abs(o.shell_state("sigb")).max() > 0.0
+        print(f"kinematic fisokin={fisokin} ipla={ipla} bend={bend}: worst difference to the reference GPU path {worst:.2e}")
+    finally:
+        o.lib.orc_set_quadrature(o.h, 0, None, None, None)
