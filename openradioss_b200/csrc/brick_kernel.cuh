@@ -19,6 +19,7 @@
 
 struct BrickParams {            // scalar copies so the kernel reads them from the constant bank
   BrickSG sg; DevNodes nd; double* fsky; int roww; CycleState* cs; DtBlocks db;
+  const BrickSG* sgtab; const int2* cta_map;      // batched launch over several super-groups (common.cuh cta_work); null otherwise
 };
 
 // SLEN (slen.F:68-88)
@@ -115,28 +116,28 @@ __device__ __forceinline__ void brick_mqviscb(const BrickSG& g, double DXX, doub
 #define ORGPU_BRICK_MINB 3
 #endif
 
-template <int JHBE, int ISMSTR, int LAW, bool STAGED>
+template <int JHBE, int ISMSTR, int LAW, bool STAGED, bool TAB = false>
 __global__ void __launch_bounds__(ORGPU_BLOCK, ORGPU_BRICK_MINB * ORGPU_PER128)
 brick_forces_kernel(const __grid_constant__ BrickParams P)
 {
-  const BrickSG& g = P.sg;
   if (P.cs->abort) return;                               // sticky: a peer-memory wait timed out (exchange.cuh)
-  const int tile = cta_tile(g.tile_map, blockIdx.x);
+  const CtaWork<BrickSG> W = cta_work<BrickSG, TAB>(P.sg, P.sgtab, P.cta_map);
+  const BrickSG& g = *W.g;
+  const int tile = W.tile;
   const int e = tile * ORGPU_TILE + threadIdx.x;
   __shared__ __align__(8) unsigned long long s_bar;
   double* const g_tile = g.slab + (size_t)tile * g.nw * ORGPU_TILE;
-  const int tile_pf = ORGPU_PREFETCH_TILE > 0 ? cta_tile_ahead(g.tile_map, ORGPU_PREFETCH_TILE) : -1;
-  if (STAGED) tile_load_begin(s_tile_dyn, &s_bar, g_tile, (unsigned)g.nw * ORGPU_TILE * 8u, tile_pf >= 0 ? g.slab + (size_t)tile_pf * g.nw * ORGPU_TILE : nullptr);
+  const double* const g_pf = W.tile_pf >= 0 ? W.g_pf->slab + (size_t)W.tile_pf * W.g_pf->nw * ORGPU_TILE : nullptr;   // tile of the CTA one wave ahead
+  if (STAGED) tile_load_begin(s_tile_dyn, &s_bar, g_tile, (unsigned)g.nw * ORGPU_TILE * 8u, g_pf);
   const TileAcc<STAGED> T{(STAGED ? s_tile_dyn : g_tile) + threadIdx.x};
-  if (!STAGED && threadIdx.x == 0 && tile_pf >= 0)      // in-place tiles: same wave-ahead L2 prefetch
-    bulk_prefetch_l2(g.slab + (size_t)tile_pf * g.nw * ORGPU_TILE, (unsigned)g.nw * ORGPU_TILE * 8u);
+  if (!STAGED && threadIdx.x == 0 && g_pf)              // in-place tiles: same wave-ahead L2 prefetch
+    bulk_prefetch_l2(g_pf, (unsigned)g.nw * ORGPU_TILE * 8u);
   // SMSTR (21 words, rewritten every cycle by S8SAV3 / SMALLA3) goes straight to HBM with streaming stores:
   // collecting it in shared memory for a bulk store was measured slower (0.472 vs 0.450 ms on C5)
   double* const sm = g.smstr + (size_t)tile * 21 * ORGPU_TILE + threadIdx.x;     // SMSTR word k at sm[k*TILE]
 #if ORGPU_PREFETCH_NEXT > 0
   // a CTA about one wave ahead: start its connectivity toward L2 (its first load is then an L2 hit: -3 % kernel time)
-  { const int nb = cta_tile_ahead(g.tile_map, ORGPU_PREFETCH_NEXT);
-    if (nb >= 0 && threadIdx.x < (8 * ORGPU_TILE * 4) / 128) prefetch_l2(reinterpret_cast<const char*>(g.conn + (size_t)nb * 8 * ORGPU_TILE) + 128 * threadIdx.x); }
+  if (W.tile_nx >= 0 && threadIdx.x < (8 * ORGPU_TILE * 4) / 128) prefetch_l2(reinterpret_cast<const char*>(W.g_nx->conn + (size_t)W.tile_nx * 8 * ORGPU_TILE) + 128 * threadIdx.x);
 #endif
   double dt_cand = K_EP30; int order = -1;
   if (e < g.ne) {
@@ -775,9 +776,27 @@ static void launch_brick_jhbe(const BrickParams& P, int nblk, cudaStream_t st)
 void launch_brick_forces(const BrickSG& sg, const DevNodes& nd, double* fsky, int roww,
                          CycleState* cs, const DtBlocks& db, const FinalizeArgs& fa, cudaStream_t st)
 {
-  BrickParams P{sg, nd, fsky, roww, cs, db};
+  BrickParams P{sg, nd, fsky, roww, cs, db, nullptr, nullptr};
   const int nblk = sg.ne_pad / ORGPU_TILE;
   if (sg.law == 36 && sg.m36.ifail == 2) launch_brick_jhbe<37>(P, nblk, st);
   else if (sg.law == 36) launch_brick_jhbe<36>(P, nblk, st);
   else              launch_brick_jhbe<2>(P, nblk, st);
+}
+
+// batched launch (see shell_kernel.cuh): the two common brick variants (Isolid 1, Ismstr 4, staged tile; LAW2 / LAW36)
+enum { BRV_LAW2 = 0, BRV_LAW36, BRV_COUNT };
+static inline int brick_tab_variant(const BrickSG& d)
+{
+  if (d.prop.jhbe != 1 || d.prop.ismstr != 4 || (size_t)d.nw * ORGPU_TILE * 8 > ORGPU_STAGE_MAX_BYTES) return -1;
+  if (d.law == 36) return d.m36.ifail == 2 ? -1 : BRV_LAW36;
+  return BRV_LAW2;
+}
+void launch_brick_forces_tab(int variant, const BrickSG* d_tab, const int2* d_map, int nblk, size_t bytes, const DevNodes& nd,
+                             double* fsky, int roww, CycleState* cs, const DtBlocks& db, cudaStream_t st)
+{
+  BrickParams P; memset(&P.sg, 0, sizeof P.sg); P.nd = nd; P.fsky = fsky; P.roww = roww; P.cs = cs; P.db = db; P.sgtab = d_tab; P.cta_map = d_map;
+  if (variant == BRV_LAW36) { stage_attr((const void*)brick_forces_kernel<1, 4, 36, true, true>, bytes, ORGPU_BRICK_MINB);
+                              brick_forces_kernel<1, 4, 36, true, true><<<nblk, ORGPU_BLOCK, bytes, st>>>(P); }
+  else { stage_attr((const void*)brick_forces_kernel<1, 4, 2, true, true>, bytes, ORGPU_BRICK_MINB);
+         brick_forces_kernel<1, 4, 2, true, true><<<nblk, ORGPU_BLOCK, bytes, st>>>(P); }
 }

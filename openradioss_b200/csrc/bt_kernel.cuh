@@ -11,26 +11,26 @@
 #pragma once
 #include "shell_common.cuh"
 
-template <int LAW, bool STAGED>
+template <int LAW, bool STAGED, bool TAB = false>
 __global__ void __launch_bounds__(ORGPU_SHELL_CTA, 3 * ORGPU_PER128)
 bt_forces_kernel(const __grid_constant__ ShellParams P)
 {
-  const ShellSG& g = P.sg;
   if (P.cs->abort) return;                               // sticky: a peer-memory wait timed out (exchange.cuh)
-  const int tile = cta_tile(g.tile_map, blockIdx.x);
+  const CtaWork<ShellSG> W = cta_work<ShellSG, TAB>(P.sg, P.sgtab, P.cta_map);
+  const ShellSG& g = *W.g;
+  const int tile = W.tile;
   const int e = tile * ORGPU_TILE + threadIdx.x;
   __shared__ __align__(8) unsigned long long s_bar;
   double* const g_tile = g.slab + (size_t)tile * g.nw * ORGPU_TILE;
-  const int tile_pf = ORGPU_PREFETCH_TILE > 0 ? cta_tile_ahead(g.tile_map, ORGPU_PREFETCH_TILE) : -1;
-  if (STAGED) tile_load_begin(s_tile_dyn, &s_bar, g_tile, (unsigned)g.nw * ORGPU_TILE * 8u, tile_pf >= 0 ? g.slab + (size_t)tile_pf * g.nw * ORGPU_TILE : nullptr);
+  const double* const g_pf = W.tile_pf >= 0 ? W.g_pf->slab + (size_t)W.tile_pf * W.g_pf->nw * ORGPU_TILE : nullptr;   // tile of the CTA one wave ahead
+  if (STAGED) tile_load_begin(s_tile_dyn, &s_bar, g_tile, (unsigned)g.nw * ORGPU_TILE * 8u, g_pf);
   const TileAcc<STAGED> T{(STAGED ? s_tile_dyn : g_tile) + threadIdx.x};
-  if (!STAGED && threadIdx.x == 0 && tile_pf >= 0)      // in-place tiles: same wave-ahead L2 prefetch
-    bulk_prefetch_l2(g.slab + (size_t)tile_pf * g.nw * ORGPU_TILE, (unsigned)g.nw * ORGPU_TILE * 8u);
+  if (!STAGED && threadIdx.x == 0 && g_pf)              // in-place tiles: same wave-ahead L2 prefetch
+    bulk_prefetch_l2(g_pf, (unsigned)g.nw * ORGPU_TILE * 8u);
   double* const sm = g.smstr + (size_t)tile * 6 * ORGPU_TILE + threadIdx.x;      // SMSTR word k at sm[k*128]
 #if ORGPU_PREFETCH_NEXT > 0
   // a CTA about one wave ahead: start its connectivity toward L2 (its first load is then an L2 hit: -3 % kernel time)
-  { const int nb = cta_tile_ahead(g.tile_map, ORGPU_PREFETCH_NEXT);
-    if (nb >= 0 && threadIdx.x < (4 * ORGPU_TILE * 4) / 128) prefetch_l2(reinterpret_cast<const char*>(g.conn + (size_t)nb * 4 * ORGPU_TILE) + 128 * threadIdx.x); }
+  if (W.tile_nx >= 0 && threadIdx.x < (4 * ORGPU_TILE * 4) / 128) prefetch_l2(reinterpret_cast<const char*>(W.g_nx->conn + (size_t)W.tile_nx * 4 * ORGPU_TILE) + 128 * threadIdx.x);
 #endif
   double dt_cand = K_EP30; int order = 0x7fffffff;
   if (e < g.ne) {

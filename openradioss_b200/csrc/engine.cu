@@ -13,6 +13,7 @@
 #include <cstddef>
 #include <vector>
 #include <string>
+#include <algorithm>
 #include "../../include/orgpu.h"
 #include "common.cuh"
 #include "brick_kernel.cuh"
@@ -81,6 +82,9 @@ struct orgpu_engine {
   std::vector<cudaEvent_t> evpool;
   Exchange xc;                        // domain exchange (one process per GPU)
   std::vector<int> gord_c, gord_t, gord_s, gnode; int* d_gnode = nullptr;   // global processing order / node index of a domain's elements / nodes
+  // batched launches (decks with many parts): super-groups of one kernel variant share a launch when there are enough of them
+  struct Batch { bool brick; int variant; std::vector<int> sgs; int ntile = 0; size_t bytes = 0; void* d_tab = nullptr; int2* d_map = nullptr; };
+  std::vector<Batch> batches; std::vector<char> sh_batched, br_batched; bool tabs_dirty = true;
   // print-cycle balances (CBILAN / SBILAN / ECRIT): parts, GBUF%VOL of the shells, scratch rows and their fixed-order reduction
   int npart = 1; bool have_parts = false; std::vector<int> ipartc, iparts, iparttg; std::vector<double> gvolc, gvoltg;
   int ipri = 0; int bal_ld = 0, nbal_ld = 0, nchunk = 0, nnchunk = 0;
@@ -177,6 +181,7 @@ int orgpu_destroy(orgpu_engine* e)
     void* pp[] = {x.win, x.d_send_nb, x.d_nb_sendptr, x.d_nb_rows, x.d_peer_cand, x.d_peer_flag, x.d_xcycle, x.d_done, x.d_err, x.d_peer_win, x.d_xsend, x.d_xn_nodes, x.d_xn_send, x.d_xn_recv};
     for (void* p : pp) if (p) cudaFree(p);
     if (x.comm && nccl_api()) nccl_api()->CommDestroy(x.comm); }
+  for (auto& b : e->batches) { if (b.d_tab) cudaFree(b.d_tab); if (b.d_map) cudaFree(b.d_map); }
   for (auto ev : e->evpool) cudaEventDestroy(ev);
   if (e->ev0) cudaEventDestroy(e->ev0); if (e->ev1) cudaEventDestroy(e->ev1);
   for (int k = 0; k < ORGPU_NSIDE; k++) { if (e->side[k]) cudaStreamDestroy(e->side[k]); if (e->ev_join[k]) cudaEventDestroy(e->ev_join[k]); }
@@ -442,7 +447,7 @@ int orgpu_finalize(orgpu_engine* e)
     const int nft = e->sgroups[gi].nft;
     const int np = ((ne + ORGPU_BLOCK - 1) / ORGPU_BLOCK) * ORGPU_BLOCK;
     e->bsg.emplace_back(); BrickSGHost& S = e->bsg.back(); S.first_elem = nft; S.part = e->sgroups[gi].part;
-    BrickSG& d = S.d; d.bal = nullptr; d.bal_ld = 0; d.tile_map = nullptr; d.xs_ftile = nullptr; d.ne = ne; d.ne_pad = np; d.order0 = order; d.blk0 = blk;
+    BrickSG& d = S.d; d.bal = nullptr; d.bal_ld = 0; d.xs_ftile = nullptr; d.ne = ne; d.ne_pad = np; d.order0 = order; d.blk0 = blk;
     d.mat = e->sgroups[gi].mat; d.prop = e->sgroups[gi].prop; d.dtfac = e->ctl.dtfac_brick; d.nodadt = e->ctl.nodadt;
     std::vector<int> conn((size_t)8 * np, 0), ngl(np, 0), conn_t;
     // state slab: read/write words first (SIG 6, EINT, RHO, QVIS, PLA, EPSD, OFF[, TEMP]), then VOL and the slot rows
@@ -564,6 +569,42 @@ static cudaEvent_t get_event(orgpu_engine* e, size_t i) {
   return e->evpool[i];
 }
 
+// (Re)build the device tables of the batched launches: descriptors change when the balances or the inline sends are switched on,
+// so this runs before the first launch and whenever a descriptor changed -- never inside a graph capture.
+static int refresh_batches(orgpu_engine* e)
+{
+  if (!e->tabs_dirty) return 0;
+  for (auto& b : e->batches) { if (b.d_tab) cudaFree(b.d_tab); if (b.d_map) cudaFree(b.d_map); }
+  e->batches.clear(); e->sh_batched.assign(e->csg.size(), 0); e->br_batched.assign(e->bsg.size(), 0);
+  const char* mn = getenv("ORGPU_TAB_MIN"); const size_t tab_min = mn ? (size_t)atoi(mn) : 8;      // fewer super-groups of a variant: one launch each
+  for (int brick = 0; brick < 2; brick++) {
+    const int nv = brick ? BRV_COUNT : SHV_COUNT;
+    for (int v = 0; v < nv; v++) {
+      orgpu_engine::Batch b; b.brick = brick != 0; b.variant = v;
+      if (brick) { for (size_t k = 0; k < e->bsg.size(); k++) if (brick_tab_variant(e->bsg[k].d) == v) b.sgs.push_back((int)k); }
+      else       { for (size_t k = 0; k < e->csg.size(); k++) if (shell_tab_variant(e->csg[k]) == v) b.sgs.push_back((int)k); }
+      if (b.sgs.size() < tab_min) continue;
+      std::vector<int2> map;
+      if (brick) {
+        std::vector<BrickSG> tab;
+        for (size_t j = 0; j < b.sgs.size(); j++) { const BrickSG& d = e->bsg[b.sgs[j]].d; tab.push_back(d);
+          b.bytes = std::max(b.bytes, (size_t)d.nw * ORGPU_TILE * 8); for (int t = 0; t < d.ne_pad / ORGPU_TILE; t++) map.push_back(make_int2((int)j, t)); e->br_batched[b.sgs[j]] = 1; }
+        CUDA_OK(cudaMalloc(&b.d_tab, sizeof(BrickSG) * tab.size())); CUDA_OK(cudaMemcpy(b.d_tab, tab.data(), sizeof(BrickSG) * tab.size(), cudaMemcpyHostToDevice));
+      } else {
+        std::vector<ShellSG> tab;
+        for (size_t j = 0; j < b.sgs.size(); j++) { const ShellSG& d = e->csg[b.sgs[j]].d; tab.push_back(d);
+          b.bytes = std::max(b.bytes, (size_t)d.nw * ORGPU_TILE * 8); for (int t = 0; t < d.ne_pad / ORGPU_TILE; t++) map.push_back(make_int2((int)j, t)); e->sh_batched[b.sgs[j]] = 1; }
+        CUDA_OK(cudaMalloc(&b.d_tab, sizeof(ShellSG) * tab.size())); CUDA_OK(cudaMemcpy(b.d_tab, tab.data(), sizeof(ShellSG) * tab.size(), cudaMemcpyHostToDevice));
+      }
+      b.ntile = (int)map.size();
+      CUDA_OK(cudaMalloc((void**)&b.d_map, sizeof(int2) * map.size())); CUDA_OK(cudaMemcpy(b.d_map, map.data(), sizeof(int2) * map.size(), cudaMemcpyHostToDevice));
+      e->batches.push_back(std::move(b));
+    }
+  }
+  e->tabs_dirty = false;
+  return 0;
+}
+
 static void launch_sg_shell(orgpu_engine* e, ShellSGHost& S, cudaStream_t st)
 { launch_shell_forces(S, e->nd, e->d_fsky, e->roww, e->d_cs, e->db, e->fa, st); e->launches++; }
 static void launch_sg_brick(orgpu_engine* e, BrickSGHost& S, cudaStream_t st)
@@ -584,14 +625,22 @@ static void launch_element_phase(orgpu_engine* e, int fused, size_t* evi)
     return (j == 0) ? e->st : e->side[j - 1];
   };
   if (fork) { cudaEventRecord(e->ev_fork, e->st); for (int j = 0; j < nside; j++) cudaStreamWaitEvent(e->side[j], e->ev_fork, 0); }
-  for (auto& S : e->csg) {
+  const bool tab = !evi && !e->tabs_dirty;                 // the profiled run times every super-group on its own
+  if (tab) for (auto& b : e->batches) {
+    if (b.brick) launch_brick_forces_tab(b.variant, (const BrickSG*)b.d_tab, b.d_map, b.ntile, b.bytes, e->nd, e->d_fsky, e->roww, e->d_cs, e->db, pick());
+    else         launch_shell_forces_tab(b.variant, (const ShellSG*)b.d_tab, b.d_map, b.ntile, b.bytes, e->nd, e->d_fsky, e->d_cs, e->db, pick());
+    e->launches++;
+  }
+  for (size_t k = 0; k < e->csg.size(); k++) {
+    if (tab && e->sh_batched[k]) continue;
     if (evi) cudaEventRecord(get_event(e, (*evi)++), e->st);
-    launch_sg_shell(e, S, pick());
+    launch_sg_shell(e, e->csg[k], pick());
     if (evi) cudaEventRecord(get_event(e, (*evi)++), e->st);
   }
-  for (auto& S : e->bsg) {
+  for (size_t k = 0; k < e->bsg.size(); k++) {
+    if (tab && e->br_batched[k]) continue;
     if (evi) cudaEventRecord(get_event(e, (*evi)++), e->st);
-    launch_sg_brick(e, S, pick());
+    launch_sg_brick(e, e->bsg[k], pick());
     if (evi) cudaEventRecord(get_event(e, (*evi)++), e->st);
   }
   for (int j = 0; j < nside; j++) { cudaEventRecord(e->ev_join[j], e->side[j]); cudaStreamWaitEvent(e->st, e->ev_join[j], 0); }
@@ -623,6 +672,7 @@ static void launch_node_phase(orgpu_engine* e)
 int orgpu_forces_phase(orgpu_engine* e, double dt1)
 {
   NEED(e && e->finalized, -1, "orgpu_forces_phase: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
+  { int rc = refresh_batches(e); if (rc) return rc; }
   launch_set_dt(e->d_cs, dt1, 0, 0, 0, e->st); e->launches++;
   launch_element_phase(e, 0, nullptr);
   CUDA_OK(cudaGetLastError());
@@ -716,6 +766,7 @@ static void p2p_node_phase(orgpu_engine* e)
 int orgpu_run_cycles(orgpu_engine* e, int ncycles)
 {
   NEED(e && e->finalized && ncycles >= 0, -1, "orgpu_run_cycles: engine not finalized"); CUDA_OK(cudaSetDevice(e->device));
+  { int rc = refresh_batches(e); if (rc) return rc; }
   const int per_cycle = (int)(e->csg.size() + e->bsg.size()) + (e->ctl.nodadt ? 4 : 2) + (e->ipri ? 3 : 0);   // force kernels + dt finalize + node kernel(s) [+ balances]
   NEED(!(e->ipri && e->xc.nranks > 1), -5, "print-cycle balances across domains (frontier-node weights) are outside the built path");
   NEED(!(e->ctl.nodadt && e->xc.nranks > 1 && (!e->xc.p2p || e->profile)), -5, "/DT/NODA across domains needs the peer-memory exchange (orgpu_p2p_connect), unprofiled");
@@ -1179,6 +1230,7 @@ int orgpu_p2p_connect(orgpu_engine* e, const unsigned char* handles /*[nranks][6
   CUDA_OK(cudaMemcpy(x.d_peer_win, x.peer.data(), 8 * (size_t)R, cudaMemcpyHostToDevice));
   CUDA_OK(cudaDeviceSynchronize());
   if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
+  e->tabs_dirty = true;
   x.p2p = true;
   // inline sends: every send slot with exactly one destination leaves from the force kernel that computes it (XSend, common.cuh);
   // a decomposition where some slot has several (a node shared by 3+ domains) keeps the push kernel.  ORGPU_NO_OVERLAP=1: push kernel.
@@ -1280,6 +1332,7 @@ int orgpu_set_print(orgpu_engine* e, int ipri)
     for (size_t k = 0; k < e->csg.size(); k++) { e->csg[k].d.bal = e->d_bal + so[k]; e->csg[k].d.bal_ld = e->bal_ld; }
     for (size_t k = 0; k < e->bsg.size(); k++) { e->bsg[k].d.bal = e->d_bal + bo[k]; e->bsg[k].d.bal_ld = e->bal_ld; }
     e->nd.nbal = e->d_nbal; e->nd.nbal_ld = e->nbal_ld;
+    e->tabs_dirty = true;
   }
   if (ipri != e->ipri && e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }   // the cycle graph gains / loses the three balance launches
   e->ipri = ipri;

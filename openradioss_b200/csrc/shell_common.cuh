@@ -37,7 +37,6 @@ struct ShellSG {
   int nodadt;                 // /DT/NODA: nodal stiffnesses of cndt3.F:194-221, no element time step
   double* bal; int bal_ld;    // print cycles: the elements' PARTSAV(1:6) terms, bal[k * bal_ld + e] (null until orgpu_set_print)
   const double* gvol;         // GBUF%VOL of the group's elements (initial area x thickness): the mass of CBILAN
-  const int* tile_map;        // tiles of this launch (null: all of them, tile = blockIdx.x)
   const unsigned char* xs_ftile;    // several domains: 1 for the tiles that hold an element with a corner row to send (null: one domain)
 };
 
@@ -46,6 +45,7 @@ enum { IW_SIG = 0, IW_PLA = 5, IW_EPSD = 6, IW_TEMP = 7 };
 
 struct ShellParams {
   ShellSG sg; DevNodes nd; double* fsky; CycleState* cs; DtBlocks db;
+  const ShellSG* sgtab; const int2* cta_map;     // batched launch over several super-groups (common.cuh cta_work); null otherwise
 };
 
 __constant__ double c_Z0[121];

@@ -168,7 +168,7 @@ static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky
                                 const DtBlocks& db, const FinalizeArgs& fa, cudaStream_t st)
 {
   (void)roww; (void)fa;                        // shell models always use 8-wide rows
-  ShellParams P{S.d, nd, fsky, cs, db};
+  ShellParams P{S.d, nd, fsky, cs, db, nullptr, nullptr};
   const int nblk = S.d.ne_pad / ORGPU_TILE;
   if (S.sh3n) {
     if (S.d.law == 36 && S.d.m36.ifail == 2) shell_launch_one(c3_forces_kernel<37, true>, c3_forces_kernel<37, false>, P, nblk, st);
@@ -213,4 +213,31 @@ static int shell_state_xfer(std::vector<ShellSGHost>& sgs, int numelc, int field
     }
   }
   return 0;
+}
+
+// ---- batched launches: all super-groups of one kernel variant in ONE launch (table-driven CTA -> (super-group, tile)) --------
+// variant of a shell super-group whose table-driven kernel is compiled (-1: launched on its own)
+enum { SHV_QEPH36F = 0, SHV_QEPH36, SHV_QEPH2, SHV_BT36, SHV_BT2, SHV_COUNT };
+static inline int shell_tab_variant(const ShellSGHost& S)
+{
+  const ShellSG& d = S.d;
+  if (S.sh3n || (size_t)d.nw * ORGPU_TILE * 8 > ORGPU_STAGE_MAX_BYTES) return -1;
+  if (d.law == 36 && d.m36.ifail == 2) return -1;
+  if (shell_is_qeph(d.prop)) return d.law == 36 ? (shell_fast(d) ? SHV_QEPH36F : SHV_QEPH36) : SHV_QEPH2;
+  return d.law == 36 ? SHV_BT36 : SHV_BT2;
+}
+template <class K>
+static void shell_launch_tab_k(K kern, const ShellParams& P, int nblk, size_t bytes, cudaStream_t st)
+{ stage_attr((const void*)kern, bytes, ORGPU_SHELL_MINB); kern<<<nblk, ORGPU_SHELL_CTA, bytes, st>>>(P); }
+static void launch_shell_forces_tab(int variant, const ShellSG* d_tab, const int2* d_map, int nblk, size_t bytes, const DevNodes& nd,
+                                    double* fsky, CycleState* cs, const DtBlocks& db, cudaStream_t st)
+{
+  ShellParams P; memset(&P.sg, 0, sizeof P.sg); P.nd = nd; P.fsky = fsky; P.cs = cs; P.db = db; P.sgtab = d_tab; P.cta_map = d_map;
+  switch (variant) {
+    case SHV_QEPH36F: shell_launch_tab_k(qeph_forces_kernel<36, true, 1, true>, P, nblk, bytes, st); break;
+    case SHV_QEPH36:  shell_launch_tab_k(qeph_forces_kernel<36, true, 0, true>, P, nblk, bytes, st); break;
+    case SHV_QEPH2:   shell_launch_tab_k(qeph_forces_kernel<2, true, 0, true>, P, nblk, bytes, st); break;
+    case SHV_BT36:    shell_launch_tab_k(bt_forces_kernel<36, true, true>, P, nblk, bytes, st); break;
+    default:          shell_launch_tab_k(bt_forces_kernel<2, true, true>, P, nblk, bytes, st); break;
+  }
 }

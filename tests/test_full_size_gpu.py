@@ -65,13 +65,14 @@ def test_c5_slab_2m_bricks_phased_cycles_match_the_oracle():
         assert rel_err(fg, fo) <= 1e-12
         if c > 0:
             assert rel_err_rows(fg[:, :3], fo[:, :3]) <= 1e-9
+        fscale = np.abs(fo[:, :3]).max()                       # size of the terms ASSPAR4 adds up (the net nodal force of this random field is ~20x smaller)
         del fg, fo
         tg, to = g.time(), o.time()
         assert tg["dt2t"] == pytest.approx(to["dt2t"], rel=1e-14) and tg["neltst"] == to["neltst"] and tg["ityptst"] == 1
         for b in (g, o):
             b.assemble()
         ng, no = g.download_nodes(("A", "STIFN")), o.download_nodes(("A", "STIFN"))
-        assert rel_err(ng["A"], no["A"]) <= 1e-12 and rel_err(ng["STIFN"], no["STIFN"]) <= 1e-12
+        assert np.abs(ng["A"] - no["A"]).max() <= 1e-12 * fscale and rel_err(ng["STIFN"], no["STIFN"]) <= 1e-12
         dt2 = to["dt2t"]
         for b in (g, o):
             b.advance(0.5 * (dt1 + dt2), dt2)

