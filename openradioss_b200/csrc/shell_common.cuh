@@ -614,3 +614,153 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const Tile
   for (int k = 0; k < 3; k++) T.st(SW_MOM + k, mo[k]);
   io.off = off; io.ssp = ssp; io.viscmx = viscmx; io.sigy = sigy; io.zcfac1 = zcfac1; io.zcfac2 = zcfac2; io.vol0 = vol0;
 }
+
+// ---- the through-thickness loop of the FAST = 1 kernels, in three passes ---------------------------------------------------
+// The Newton return of Iplas = 1 (sigeps36c.F:503-593: three steps, 13 divisions in series) costs a warp its full length for
+// every point at which ANY of its lanes yields.  In a deck that yields locally -- the usual state of a crash model, and of the
+// C2 plate after its first 200 cycles -- 10-30 % of the points yield in a cycle, spread so that a warp pays 2-5 returns per
+// element for what fills one or two.  So:
+//   pass 1, every lane, point by point: elastic predictor, strain rate, yield stress, the yield test; the trial state goes
+//           back into the staged tile and (lane, point) of every yielding point is appended to a byte list of the warp;
+//   pass 2, the warp walks that list DENSELY, one yielding point per lane whoever owns it: re-reads the trial stress of
+//           (lane, point) from the tile, redoes the curve lookup (same cursor, same arithmetic) and the Newton return, writes
+//           the returned stress and plastic strain back and leaves the thickness-strain term for the owner;
+//   pass 3, every lane again, point by point: thickness, force and moment sums in the reference's order.
+// Every value is produced by the same operations on the same operands as in law36_ip, so the results are bit-identical; the
+// list and the hand-back slots are the tile words of GBUF%FOR / GBUF%MOM, which are dead between the loop's first read and its
+// last store.  Needs the staged tile (cross-lane reads) and NPT <= 5 (slots): shell_fast() on the host.
+// Measured on C2 (B200, kernel ms; profiles/r02_qeph_forces_ncu.md): 10-30 % of the points yielding 0.437 -> 0.392, no point
+// yielding 0.321 -> 0.323, 60-90 % yielding (the plate's first 150 cycles) 0.394 -> 0.418.  Variants that did not pay: two /
+// three / four listed points per lane side by side (spills: 0.427 / 0.444 / 0.494 in the 10-30 % state), rows most of whose
+// lanes yield returning on the spot (a second copy of the return in the code: +3 % even where no point yields -- the kernel is
+// instruction-fetch sensitive), the same with one copy of the return in a merged loop of turns (0.405, and 0.331 elastic).
+template <bool FLAG_ZCFAC>
+__device__ __forceinline__ void shell_material_loop_compact(const ShellSG& g, const TileAcc<true>& T, double dt1, MatIO& io, unsigned wmask)
+{
+  const orgpu_law36& m = g.m36;
+  const int npt = g.prop.npt;
+  const double DM = g.prop.dm, E = m.young, G3 = m.g3, NU3 = K_ONE - m.nu_mnu;
+  double* fo = io.fo; double* mo = io.mo;
+  #pragma unroll
+  for (int k = 0; k < 5; k++) fo[k] = T.ld(SW_FOR + k);
+  #pragma unroll
+  for (int k = 0; k < 3; k++) mo[k] = T.ld(SW_MOM + k);
+  double degmb = fo[0] * io.exx + fo[1] * io.eyy + fo[2] * io.exy + fo[3] * io.eyz + fo[4] * io.exz;
+  double degfx = mo[0] * io.kxx + mo[1] * io.kyy + mo[2] * io.kxy;
+  const double vol0 = io.area * io.thk0;
+  double sigy = io.sigy;
+  if (!FLAG_ZCFAC) sigy = K_ZERO;
+  double zcfac1 = K_ZERO, zcfac2 = FLAG_ZCFAC ? K_ONE : K_ZERO;
+  double off = io.off; const double off_old = off;
+  double viscmx = K_ZERO;
+  const double dtinv = or_div(dt1, fmax(dt1 * dt1, K_EM20));
+  const double asrate = (m.israte > 0) ? fmin(K_ONE, m.asrate * dt1) : K_ONE;
+  const int qrow = (npt - 1) * 11;
+  const int lane = threadIdx.x & 31;
+  const int nact = __popc(wmask);                         // the lanes with an element are the low ones
+  double* const wbase = T.t - lane;                       // lane 0 of this warp
+  unsigned char* const list = reinterpret_cast<unsigned char*>(wbase + SW_FOR * ORGPU_TILE);   // 256 bytes: word FOR(1) of the 32 lanes
+  __syncwarp(wmask);                                      // every lane has read its FOR / MOM words
+  // ---- pass 1
+  unsigned pmask = 0; int cnt = 0;                  // points of this lane that yield; entries of the warp's list
+  #pragma unroll 1
+  for (int ipt = 0; ipt < npt; ipt++) {
+    IpState s = ip_load<36, true, 1>(g, T, ipt);
+    const int ipos_old = s.ipos;
+    const double thkly = c_WF[qrow + ipt];
+    const double zt = (c_Z0[qrow + ipt] + K_ZERO) * io.thk0;
+    const double dexx = io.exx + zt * io.kxx, deyy = io.eyy + zt * io.kyy, dexy = io.exy + zt * io.kxy;
+    double YLD, H, EPST;
+    law36_trial<true, false, 1>(g, T, ipt, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, io.gs, io.epsd_pg, zt, s, YLD, H, EPST);
+    H = fmax(K_ZERO, H);
+    const double S1 = s.sxx + s.syy, S2 = s.sxx - s.syy, S3 = s.sxy;
+    const double SVM2 = K_FOURTH * S1 * S1 + (K_THREE_OVER_4 * S2 * S2 + K_THREE * S3 * S3);
+    const bool pl = SVM2 > YLD * YLD && off == K_ONE;
+    double etse = K_ONE;
+    if (pl) etse = or_div(H, (H + E));
+    if (FLAG_ZCFAC) { zcfac1 = zcfac1 + etse * thkly; zcfac2 = fmin(etse, zcfac2); }
+    viscmx = fmax(DM, viscmx);
+    ip_store<36, true, 1>(g, T, ipt, s, ipos_old, K_ZERO);         // trial state (PLA unchanged)
+    const unsigned b = __ballot_sync(wmask, pl);
+    if (pl) { list[cnt + __popc(b & ((1u << lane) - 1u))] = (unsigned char)(lane | (ipt << 5)); pmask |= 1u << ipt; }
+    cnt += __popc(b);
+    sigy = YLD;
+  }
+  __syncwarp(wmask);
+  // ---- pass 2: one listed point per lane and turn (sigeps36c.F:503-593; FISOKIN = 0: HK = 0, AAA = 0 exactly, :520-527)
+  #pragma unroll 1
+  for (int k = lane; k < cnt; k += nact) {
+    const int it = list[k], l = it & 31, ip = it >> 5;
+    double* const own = wbase + l;                                   // word 0 of the point's owner
+    double* const q = own + (size_t)(g.w_ip0 + ip * g.nwip) * ORGPU_TILE;
+    const double sxx = q[IW_SIG * ORGPU_TILE], syy = q[(IW_SIG + 1) * ORGPU_TILE], sxy = q[(IW_SIG + 2) * ORGPU_TILE], pla = q[IW_PLA * ORGPU_TILE];
+    int ipos = T.ldi_lane(g.w_vt, ip, threadIdx.x - lane + l);
+    double dydx, y1;
+    vinter1c(g.ct, 0, ipos, pla, dydx, y1);                          // the cursor already stands on the segment: same slope, same value
+    const double FACT = K_ONE * K_ONE * (m.yfac[0] * K_ONE);
+    double H = dydx * FACT, YLD = y1 * FACT;
+    if (m.yldcheck == 1) YLD = fmax(YLD, K_EM20);
+    H = fmax(K_ZERO, H);
+    double S1 = sxx + syy, S2 = sxx - syy;
+    L36Newton n;
+    n.AA = K_FOURTH * S1 * S1;
+    n.BB = K_THREE_OVER_4 * S2 * S2 + K_THREE * sxy * sxy;
+    const double SVM = or_sqrt(n.AA + n.BB);
+    n.YLD = YLD; n.HI = H; n.NU11 = m.u_mnu; n.NU21 = m.t_pnu;
+    n.DPLA_J = or_div((SVM - YLD), (G3 + H));
+    n.DPLA_I = K_ZERO; n.DR = K_ZERO; n.PP = K_ONE; n.QQ = K_ONE;
+    law36_newton_step(E, n, false); law36_newton_step(E, n, false); law36_newton_step(E, n, true);
+    S1 = S1 * n.PP;
+    S2 = S2 * n.QQ;
+    q[IW_SIG * ORGPU_TILE] = K_HALF * (S1 + S2);
+    q[(IW_SIG + 1) * ORGPU_TILE] = K_HALF * (S1 - S2);
+    q[(IW_SIG + 2) * ORGPU_TILE] = sxy * n.QQ;
+    q[IW_PLA * ORGPU_TILE] = pla + n.DPLA_I;
+    own[(SW_FOR + 1 + ip) * ORGPU_TILE] = -or_div(NU3 * n.DR * S1, E);             // DEZZ of the return, for the owner
+    if (ip == npt - 1) own[(SW_MOM + 2) * ORGPU_TILE] = YLD + n.HI * n.DPLA_I;
+  }
+  __syncwarp(wmask);
+  // ---- pass 3
+  double thkn = T.ld(SW_THK);
+  if ((pmask >> (npt - 1)) & 1u) sigy = T.ld(SW_MOM + 2);
+  #pragma unroll
+  for (int k = 0; k < 5; k++) fo[k] = K_ZERO;
+  #pragma unroll
+  for (int k = 0; k < 3; k++) mo[k] = K_ZERO;
+  #pragma unroll 1
+  for (int ipt = 0; ipt < npt; ipt++) {
+    const int w = g.w_ip0 + ipt * g.nwip;
+    const double thkly = c_WF[qrow + ipt], wmc = c_WM[qrow + ipt];
+    const double thklyl = thkly * io.thk0;
+    const double zt = (c_Z0[qrow + ipt] + K_ZERO) * io.thk0;
+    const double dexx = io.exx + zt * io.kxx, deyy = io.eyy + zt * io.kyy;
+    { const double DEZZ = -(dexx + deyy) * m.nu_mnu; thkn = thkn + DEZZ * thklyl * off; }
+    if ((pmask >> ipt) & 1u) thkn = thkn + T.ld(SW_FOR + 1 + ipt) * thklyl * off;
+    const double sxx = T.ld(w + IW_SIG), syy = T.ld(w + IW_SIG + 1), sxy = T.ld(w + IW_SIG + 2), syz = T.ld(w + IW_SIG + 3), szx = T.ld(w + IW_SIG + 4);
+    fo[0] = fo[0] + thkly * sxx; fo[1] = fo[1] + thkly * syy; fo[2] = fo[2] + thkly * sxy;
+    fo[3] = fo[3] + thkly * syz; fo[4] = fo[4] + thkly * szx;
+    mo[0] = mo[0] + wmc * sxx; mo[1] = mo[1] + wmc * syy; mo[2] = mo[2] + wmc * sxy;
+  }
+  if (off == K_FOUR_OVER_5 || (off > K_ZERO && off_old < K_EM01)) off = K_ZERO;
+  T.st(SW_THK, fmax(thkn, K_EM30));
+  const double fact = K_ONEP414 * DM;
+  const double visc = fact * m.soundsp * or_sqrt(io.area) * dtinv * io.rho;
+  fo[0] = fo[0] + visc * (io.exx + K_HALF * io.eyy);
+  fo[1] = fo[1] + visc * (io.eyy + K_HALF * io.exx);
+  fo[2] = fo[2] + visc * io.exy * K_THIRD;
+  #pragma unroll
+  for (int k = 0; k < 5; k++) fo[k] = fo[k] * off;
+  #pragma unroll
+  for (int k = 0; k < 3; k++) mo[k] = mo[k] * off;
+  degmb = degmb + fo[0] * io.exx + fo[1] * io.eyy + fo[2] * io.exy + fo[3] * io.eyz + fo[4] * io.exz;
+  degfx = degfx + mo[0] * io.kxx + mo[1] * io.kyy + mo[2] * io.kxy;
+  const double vol2 = K_HALF * vol0;
+  T.st(SW_EINT, T.ld(SW_EINT) + degmb * vol2);
+  T.st(SW_EINT + 1, T.ld(SW_EINT + 1) + degfx * io.thk0 * vol2);
+  __syncwarp(wmask);                                      // the list and the slots have been read by everyone: FOR / MOM get their values
+  #pragma unroll
+  for (int k = 0; k < 5; k++) T.st(SW_FOR + k, fo[k]);
+  #pragma unroll
+  for (int k = 0; k < 3; k++) T.st(SW_MOM + k, mo[k]);
+  io.off = off; io.ssp = m.soundsp; io.viscmx = viscmx; io.sigy = sigy; io.zcfac1 = zcfac1; io.zcfac2 = zcfac2; io.vol0 = vol0;
+}

@@ -161,7 +161,8 @@ static void shell_launch_one(K kern_staged, K kern_direct, const ShellParams& P,
 // the kernel parameters (ORGPU_NO_FAST=1: generic path)
 static inline bool shell_fast(const ShellSG& d) {
   static const bool off = getenv("ORGPU_NO_FAST") != nullptr;
-  return !off && d.law == 36 && d.prop.ipla == 1 && d.m36.ifail == 0 && d.m36.nrate == 1 && d.ct.n > 0 && d.m36.fisokin == 0.0;
+  return !off && d.law == 36 && d.prop.ipla == 1 && d.m36.ifail == 0 && d.m36.nrate == 1 && d.ct.n > 0 && d.m36.fisokin == 0.0
+         && d.prop.npt <= 5 && (size_t)d.nw * ORGPU_TILE * 8 <= ORGPU_STAGE_MAX_BYTES;     // the three-pass loop: staged tile, NPT <= 5 (shell_common.cuh)
 }
 
 static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky, int roww, CycleState* cs,
@@ -176,7 +177,7 @@ static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky
     else               shell_launch_one(c3_forces_kernel<2, true>, c3_forces_kernel<2, false>, P, nblk, st);
   } else if (shell_is_qeph(S.d.prop)) {
     if (S.d.law == 36 && S.d.m36.ifail == 2) shell_launch_one(qeph_forces_kernel<37, true>, qeph_forces_kernel<37, false>, P, nblk, st);
-    else if (S.d.law == 36 && shell_fast(S.d)) shell_launch_one(qeph_forces_kernel<36, true, 1>, qeph_forces_kernel<36, false, 1>, P, nblk, st);
+    else if (S.d.law == 36 && shell_fast(S.d)) shell_launch_one(qeph_forces_kernel<36, true, 1>, qeph_forces_kernel<36, false>, P, nblk, st);
     else if (S.d.law == 36) shell_launch_one(qeph_forces_kernel<36, true>, qeph_forces_kernel<36, false>, P, nblk, st);
     else               shell_launch_one(qeph_forces_kernel<2, true>, qeph_forces_kernel<2, false>, P, nblk, st);
   } else {
