@@ -353,40 +353,66 @@ def main():
         p0 = st("pla"); g.run_cycles(1); g.synchronize(); p1 = st("pla")
         plastic = {"last_cycle": float((p1 > p0).mean()), "ever": float((p1 > 0).mean()), "pla_max": float(p1.max())}
 
-    # ---- end to end through the host-buffer C-ABI call (pinned host arrays, copies inside the timed region): the host owns the
-    # nodal arrays and hands ALL of them over every step -- X, V and, for models with rotational dofs, VR -- and takes them back
+    # ---- end to end through the host-buffer C-ABI calls (pinned host arrays, copies inside the timed region).  Headline:
+    # orgpu_forces_host, the cycle of the reference's own -gpu ABI in one call -- the host owns the nodal arrays, hands X, V (and VR
+    # for models with rotational dofs) over every step and takes the assembled internal forces (8 doubles per node) and the time
+    # step back; uploads, kernels and downloads pipelined over chunks of the node range.  Beside it: orgpu_step_host_rot (X, V, VR
+    # in, the whole cycle incl. the nodal update on the device, X, V, VR out), which cannot overlap anything.
     n = m.numnod
     rot = bool(m.control.iroddl)
     narr = 3 if rot else 2
-    pin = lambda: torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    pin = lambda w=3: torch.empty((n, w), dtype=torch.float64).pin_memory()
     hin = [pin() for _ in range(narr)]; hout = [pin() for _ in range(narr)]
     nd = g.download_nodes(("X", "V", "VR"))
     for t_, k in zip(hin, ("X", "V", "VR")):
         t_.numpy()[:] = nd[k]
+    e2e_steps = max(3, min(args.steps, 50))
 
-    def e2e_step():
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_host_step():
+        nonlocal hin, hout
         a = [t_.numpy() for t_ in hin]; b = [t_.numpy() for t_ in hout]
         g.step_host(a[0], a[1], a[2] if rot else None, 1, b[0], b[1], b[2] if rot else None)
-    e2e_steps = max(3, min(args.steps, 50))
-    for _ in range(3):
-        e2e_step(); hin, hout = hout, hin
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step(); hin, hout = hout, hin
-    barrier()
-    e2e_dt = time.perf_counter() - t0
-    t = torch.tensor([e2e_dt], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = ne_total * e2e_steps / float(t.item())
-    # the link itself: one pinned 24 n-byte array each way, timed alone (what bounds the call above)
+        hin, hout = hout, hin
+    sh_dt = timed(step_host_step)
+    e2e_alt = {"value": ne_total * e2e_steps / sh_dt, "ms_per_step": 1e3 * sh_dt / e2e_steps, "h2d_bytes_per_step": 24 * narr * n, "d2h_bytes_per_step": 24 * narr * n,
+               "call": "orgpu_step_host_rot (X,V,VR pinned host -> 1 cycle incl. nodal update -> X,V,VR host)" if rot else "orgpu_step_host (X,V pinned host -> 1 cycle -> X,V host)"}
+    fh_ok = world == 1 and not m.control.nodadt
+    if fh_ok:
+        F8 = pin(8)
+        dt1 = g.time()["dt2"]
+        a = [t_.numpy() for t_ in hin]
+
+        def forces_host_step():
+            g.forces_host(a[0], a[1], a[2] if rot else None, dt1, F8.numpy())
+        fh_dt = timed(forces_host_step)
+        e2e = {"value": ne_total * e2e_steps / fh_dt, "unit": "element-cycles/s", "h2d_bytes_per_step": 24 * narr * n, "d2h_bytes_per_step": 64 * n + 64,
+               "steps": e2e_steps, "ms_per_step": 1e3 * fh_dt / e2e_steps,
+               "call": "orgpu_forces_host (X,V,VR pinned host -> internal forces of one cycle -> F(8,NUMNOD) + dt host; pipelined over node chunks)",
+               "step_host": e2e_alt}
+    else:
+        e2e = dict(e2e_alt, unit="element-cycles/s", steps=e2e_steps)
+    # the link itself: one pinned 24 n-byte array each way, timed alone (what bounds the calls above)
     dbuf = torch.empty((n, 3), dtype=torch.float64, device="cuda")
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     dbuf.copy_(hin[0], non_blocking=True); torch.cuda.synchronize()
     ev[0].record(); dbuf.copy_(hin[0], non_blocking=True); ev[1].record(); hout[0].copy_(dbuf, non_blocking=True); ev[2].record(); torch.cuda.synchronize()
     h2d_gbs = 24e-9 * n / (ev[0].elapsed_time(ev[1]) * 1e-3); d2h_gbs = 24e-9 * n / (ev[1].elapsed_time(ev[2]) * 1e-3)
-    link_ms = 1e3 * (24e-9 * n * narr / h2d_gbs + 24e-9 * n * narr / d2h_gbs)
+    e2e["pcie"] = {"h2d_gbs": h2d_gbs, "d2h_gbs": d2h_gbs,
+                   "floor_ms_per_step": 1e3 * max(e2e["h2d_bytes_per_step"] / h2d_gbs, e2e["d2h_bytes_per_step"] / d2h_gbs) * 1e-9,
+                   "note": "single copies alone at the measured link rate; floor = the longer direction, both at once"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
@@ -424,11 +450,7 @@ def main():
                            "l2": "inputs larger than L2 (element state >> 126 MB)" if ne >= 500000 else "working set may fit L2",
                            "parallelism": f"domains={world}" + ("" if world == 1 else " (strips / slabs; peer-memory corner-row exchange + dt fold per cycle, one CUDA graph)")},
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "pon_check": pon_check, "other_configs": extras,
-                "e2e": {"value": e2e_val, "unit": "element-cycles/s", "h2d_bytes_per_step": 24 * narr * n, "d2h_bytes_per_step": 24 * narr * n,
-                        "steps": e2e_steps, "ms_per_step": 1e3 * float(t.item()) / e2e_steps,
-                        "call": "orgpu_step_host_rot (X,V,VR pinned host -> 1 cycle -> X,V,VR host)" if rot else "orgpu_step_host (X,V pinned host -> 1 cycle -> X,V host)",
-                        "pcie": {"h2d_gbs": h2d_gbs, "d2h_gbs": d2h_gbs, "transfer_ms_per_step": link_ms,
-                                 "note": "the copies alone at the measured link rate; they cannot overlap the cycle (it needs every node first, the host needs the result next)"}},
+                "e2e": e2e,
                 "gpu_launches": launches,
                 "kernel_ms": {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()}}
         print(json.dumps(line), flush=True)

@@ -189,6 +189,15 @@ int  orgpu_step_host(orgpu_engine* e, const double* X, const double* V, const do
                      int ncycles, double* Xout, double* Vout);
 int  orgpu_step_host_rot(orgpu_engine* e, const double* X, const double* V, const double* VR,
                          int ncycles, double* Xout, double* Vout, double* VRout);
+/* -- the cycle of the reference's -gpu path in ONE call (shell_internal_forces.F90:106-190 + shell_gpu_driver.cu:150-190: upload
+ *    X, V, VR, run the force kernels, download the assembled nodal forces; the host integrates): X, V, VR(3,NUMNOD) in, the
+ *    internal forces F8(8,NUMNOD) = Fx,Fy,Fz,Mx,My,Mz,STIFN,STIFR per node out (what ASSPAR4 leaves in A, AR, STIFN, STIFR, without
+ *    the external loads: those are the caller's), and the element time step DT2T with its element (NELTST, ITYPTST).  Element
+ *    state advances by one cycle exactly as in orgpu_forces_phase(dt1).  Uploads, kernels and downloads are pipelined over
+ *    chunks of the node range (both directions of the link at once, kernels hidden behind them); host arrays must be pinned
+ *    (cudaHostRegister / cudaMallocHost) for that.  Single domain, element time step (no /DT/NODA), not on a print cycle. */
+int  orgpu_forces_host(orgpu_engine* e, const double* X, const double* V, const double* VR, double dt1,
+                       double* F8, double* dt2t, int* neltst, int* ityptst);
 
 /* -- instrumentation: number of kernels launched by this handle so far; device ms of the last
  *    orgpu_run_cycles measured with CUDA events on the library's stream */

@@ -14,6 +14,7 @@
 #include <vector>
 #include <string>
 #include <algorithm>
+#include <ctime>
 #include "../../include/orgpu.h"
 #include "common.cuh"
 #include "brick_kernel.cuh"
@@ -85,6 +86,18 @@ struct orgpu_engine {
   // batched launches (decks with many parts): super-groups of one kernel variant share a launch when there are enough of them
   struct Batch { bool brick; int variant; std::vector<int> sgs; int ntile = 0; size_t bytes = 0; void* d_tab = nullptr; int2* d_map = nullptr; };
   std::vector<Batch> batches; std::vector<char> sh_batched, br_batched; bool tabs_dirty = true;
+  // orgpu_forces_host: the cycle of the reference's -gpu ABI as a pipeline over node chunks (built at the first call)
+  struct PipeLaunch { bool brick; int variant; const void* d_tab; int2* d_map; int ntile; size_t bytes; };
+  struct HostPipe {
+    int K = 0, desc_gen = -1; std::vector<int> nb;               // chunk k = nodes [nb[k], nb[k+1])
+    std::vector<std::vector<PipeLaunch>> grp;                    // batched launches that become ready with upload chunk j
+    std::vector<std::vector<int>> solo_c, solo_b;                // super-groups launched on their own, by the chunk that completes them
+    std::vector<std::vector<int>> done;                          // node chunks complete after element group j
+    std::vector<void*> owned;
+    cudaStream_t up = nullptr, down = nullptr, asmb = nullptr; std::vector<cudaEvent_t> ev_up, ev_el, ev_as, ev_dn; cudaEvent_t ev_start = nullptr, ev_down = nullptr;
+    double* d_f8 = nullptr; CycleState* h_cs = nullptr;
+  } hp;
+  int desc_gen = 0;                   // bumped whenever a super-group descriptor changes (device tables must follow)
   // print-cycle balances (CBILAN / SBILAN / ECRIT): parts, GBUF%VOL of the shells, scratch rows and their fixed-order reduction
   int npart = 1; bool have_parts = false; std::vector<int> ipartc, iparts, iparttg; std::vector<double> gvolc, gvoltg;
   int ipri = 0; int bal_ld = 0, nbal_ld = 0, nchunk = 0, nnchunk = 0;
@@ -96,6 +109,14 @@ struct orgpu_engine {
 __global__ void pack3to4_kernel(const double* __restrict__ a3, double4* __restrict__ a4, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
   a4[i] = make_double4(a3[3 * i], a3[3 * i + 1], a3[3 * i + 2], 0.0);
+}
+// up to three (3,n) arrays -> 32-byte records in one launch (orgpu_forces_host: one per upload chunk)
+__global__ void pack3to4x3_kernel(const double* __restrict__ a, double4* __restrict__ a4, const double* __restrict__ b, double4* __restrict__ b4,
+                                  const double* __restrict__ c, double4* __restrict__ c4, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  a4[i] = make_double4(a[3 * i], a[3 * i + 1], a[3 * i + 2], 0.0);
+  b4[i] = make_double4(b[3 * i], b[3 * i + 1], b[3 * i + 2], 0.0);
+  if (c) c4[i] = make_double4(c[3 * i], c[3 * i + 1], c[3 * i + 2], 0.0);
 }
 __global__ void unpack4to3_kernel(const double4* __restrict__ a4, double* __restrict__ a3, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
@@ -161,6 +182,7 @@ static int create_body(orgpu_engine* e, int numnod, const orgpu_control* ctl)
   return 0;
 }
 
+static void pipe_free(orgpu_engine* e);
 int orgpu_destroy(orgpu_engine* e)
 {
   if (!e) return 0;
@@ -182,6 +204,7 @@ int orgpu_destroy(orgpu_engine* e)
     for (void* p : pp) if (p) cudaFree(p);
     if (x.comm && nccl_api()) nccl_api()->CommDestroy(x.comm); }
   for (auto& b : e->batches) { if (b.d_tab) cudaFree(b.d_tab); if (b.d_map) cudaFree(b.d_map); }
+  pipe_free(e);
   for (auto ev : e->evpool) cudaEventDestroy(ev);
   if (e->ev0) cudaEventDestroy(e->ev0); if (e->ev1) cudaEventDestroy(e->ev1);
   for (int k = 0; k < ORGPU_NSIDE; k++) { if (e->side[k]) cudaStreamDestroy(e->side[k]); if (e->ev_join[k]) cudaEventDestroy(e->ev_join[k]); }
@@ -1047,6 +1070,183 @@ int orgpu_step_host(orgpu_engine* e, const double* X, const double* V, const dou
 int orgpu_step_host_rot(orgpu_engine* e, const double* X, const double* V, const double* VR, int ncycles, double* Xout, double* Vout, double* VRout)
 { return step_host_impl(e, X, V, VR, ncycles, Xout, Vout, VRout); }
 
+// ---- orgpu_forces_host ------------------------------------------------------------------------------------------------
+// The cycle of the reference's own -gpu ABI (shell_internal_forces.F90:106-190: X, V, VR up, internal forces, the assembled
+// nodal forces down; the host integrates) moves 24 x 3 bytes per node up and 64 down and is bound by the PCIe link when the
+// three steps run one after the other.  Here they are a pipeline over K chunks of the node range:
+//   stream `up`  : chunk j of X, V, VR host -> staging, 24 -> 32-byte records                                  (H2D engine)
+//   main stream  : after upload j, the state tiles all of whose nodes have arrived (batched launches over a per-chunk
+//                  CTA map: common.cuh cta_work), then the dt fold
+//   stream `down`: after element group j, ASSPAR4 of the node chunks no later tile touches, 8 doubles per node, -> host
+//                                                                                                               (D2H engine)
+// so the link runs in both directions at once and the kernels hide behind it (C2 on a B200, PCIe 5 x16: 3.02 -> 2.27 ms per
+// cycle; what is left is the copy engines' own cost of chunked copies in both directions at once -- 24 + 8 pieces of 72 MB move
+// at 35.7 GB/s each way against 49.8 for two single copies -- and the one-chunk lag of the assembly behind the uploads).  Any node / element numbering is handled
+// (a tile waits for its highest node, a node chunk for the last tile that touches its range); a mesh numbered with locality --
+// what mesh generators and the Starter's domain decomposition produce -- overlaps almost completely, a random numbering
+// degrades to upload, compute, download in sequence.  Results are bit-identical to orgpu_forces_phase + orgpu_assemble.
+static void pipe_free(orgpu_engine* e)
+{
+  auto& hp = e->hp;
+  for (void* p : hp.owned) cudaFree(p);
+  hp.owned.clear(); hp.grp.clear(); hp.solo_c.clear(); hp.solo_b.clear(); hp.done.clear();
+  for (auto ev : hp.ev_up) cudaEventDestroy(ev); for (auto ev : hp.ev_el) cudaEventDestroy(ev); for (auto ev : hp.ev_as) cudaEventDestroy(ev); for (auto ev : hp.ev_dn) cudaEventDestroy(ev);
+  hp.ev_up.clear(); hp.ev_el.clear(); hp.ev_as.clear(); hp.ev_dn.clear();
+  if (hp.ev_start) { cudaEventDestroy(hp.ev_start); hp.ev_start = nullptr; } if (hp.ev_down) { cudaEventDestroy(hp.ev_down); hp.ev_down = nullptr; }
+  if (hp.up) { cudaStreamDestroy(hp.up); hp.up = nullptr; } if (hp.down) { cudaStreamDestroy(hp.down); hp.down = nullptr; }
+  if (hp.asmb) { cudaStreamDestroy(hp.asmb); hp.asmb = nullptr; }
+  if (hp.d_f8) { cudaFree(hp.d_f8); hp.d_f8 = nullptr; } if (hp.h_cs) { cudaFreeHost(hp.h_cs); hp.h_cs = nullptr; }
+  hp.K = 0; hp.desc_gen = -1;
+}
+
+static int pipe_build(orgpu_engine* e)
+{
+  auto& hp = e->hp;
+  if (hp.K > 0 && hp.desc_gen == e->desc_gen) return 0;
+  pipe_free(e);
+  const int n = e->numnod;
+  const char* kc = getenv("ORGPU_PIPE_CHUNKS"); int K = kc ? atoi(kc) : 8;     // 4 / 8 / 16 / 32 measured on C2: 2.36 / 2.27 / 2.37 / 2.54 ms (one after the other: 3.02)
+  if (K < 1) K = 1; if (K > 64) K = 64; if (K > (n + 255) / 256) K = (n + 255) / 256; if (K < 1) K = 1;
+  hp.nb.assign(K + 1, 0);
+  for (int k = 0; k <= K; k++) { long long b = (long long)n * k / K; b = (b + 127) / 128 * 128; if (b > n || k == K) b = n; hp.nb[k] = (int)b; }
+  auto chunk_of = [&](int node) { int c = (int)(std::upper_bound(hp.nb.begin(), hp.nb.end(), node) - hp.nb.begin()) - 1; return c < 0 ? 0 : (c >= K ? K - 1 : c); };
+  hp.grp.assign(K, {}); hp.solo_c.assign(K, {}); hp.solo_b.assign(K, {}); hp.done.assign(K, {});
+  std::vector<int> cout(K); for (int k = 0; k < K; k++) cout[k] = k;
+  auto touch = [&](int cmin, int cmax) { for (int k = cmin; k <= cmax; k++) if (cout[k] < cmax) cout[k] = cmax; };
+  // chunk range of every state tile
+  struct TileC { int cmin, cmax; };
+  auto tile_chunks = [&](const std::vector<int>& ix, int stride, int nn, int first, int ne, std::vector<TileC>& out) {
+    const int nt = (ne + ORGPU_TILE - 1) / ORGPU_TILE; out.assign(nt, TileC{K - 1, 0});
+    for (int i = 0; i < ne; i++) {
+      const int* r = &ix[(size_t)stride * (first + i)]; TileC& t = out[i / ORGPU_TILE];
+      for (int c = 1; c <= nn; c++) { const int ch = chunk_of(r[c] - 1); if (ch < t.cmin) t.cmin = ch; if (ch > t.cmax) t.cmax = ch; }
+    }
+  };
+  std::vector<std::vector<TileC>> tc_c(e->csg.size()), tc_b(e->bsg.size());
+  for (size_t k = 0; k < e->csg.size(); k++) {
+    const ShellSGHost& S = e->csg[k];
+    if (S.sh3n) tile_chunks(e->ixtg, 6, 3, S.first_elem, S.d.ne, tc_c[k]); else tile_chunks(e->ixc, 7, 4, S.first_elem, S.d.ne, tc_c[k]);
+  }
+  for (size_t k = 0; k < e->bsg.size(); k++) tile_chunks(e->ixs, 11, 8, e->bsg[k].first_elem, e->bsg[k].d.ne, tc_b[k]);
+  // batched launches: one device table of descriptors per kernel variant, one CTA map per (variant, chunk)
+  for (int brick = 0; brick < 2; brick++) {
+    const int nv = brick ? BRV_COUNT : SHV_COUNT; const size_t nsg = brick ? e->bsg.size() : e->csg.size();
+    std::vector<char> batched(nsg, 0);
+    for (int v = 0; v < nv; v++) {
+      std::vector<int> sgs;
+      for (size_t k = 0; k < nsg; k++) if ((brick ? brick_tab_variant(e->bsg[k].d) : shell_tab_variant(e->csg[k])) == v) sgs.push_back((int)k);
+      if (sgs.empty()) continue;
+      void* d_tab = nullptr; size_t bytes = 0;
+      if (brick) { std::vector<BrickSG> tab; for (int k : sgs) { tab.push_back(e->bsg[k].d); bytes = std::max(bytes, (size_t)e->bsg[k].d.nw * ORGPU_TILE * 8); }
+                   CUDA_OK(cudaMalloc(&d_tab, sizeof(BrickSG) * tab.size())); hp.owned.push_back(d_tab);
+                   CUDA_OK(cudaMemcpy(d_tab, tab.data(), sizeof(BrickSG) * tab.size(), cudaMemcpyHostToDevice)); }
+      else       { std::vector<ShellSG> tab; for (int k : sgs) { tab.push_back(e->csg[k].d); bytes = std::max(bytes, (size_t)e->csg[k].d.nw * ORGPU_TILE * 8); }
+                   CUDA_OK(cudaMalloc(&d_tab, sizeof(ShellSG) * tab.size())); hp.owned.push_back(d_tab);
+                   CUDA_OK(cudaMemcpy(d_tab, tab.data(), sizeof(ShellSG) * tab.size(), cudaMemcpyHostToDevice)); }
+      std::vector<std::vector<int2>> maps(K);
+      for (size_t j = 0; j < sgs.size(); j++) {
+        const auto& tc = brick ? tc_b[sgs[j]] : tc_c[sgs[j]]; batched[sgs[j]] = 1;
+        for (size_t t = 0; t < tc.size(); t++) { maps[tc[t].cmax].push_back(make_int2((int)j, (int)t)); touch(tc[t].cmin, tc[t].cmax); }
+      }
+      for (int c = 0; c < K; c++) if (!maps[c].empty()) {
+        int2* d_map = nullptr; CUDA_OK(cudaMalloc((void**)&d_map, sizeof(int2) * maps[c].size())); hp.owned.push_back(d_map);
+        CUDA_OK(cudaMemcpy(d_map, maps[c].data(), sizeof(int2) * maps[c].size(), cudaMemcpyHostToDevice));
+        hp.grp[c].push_back(orgpu_engine::PipeLaunch{brick != 0, v, d_tab, d_map, (int)maps[c].size(), bytes});
+      }
+    }
+    for (size_t k = 0; k < nsg; k++) if (!batched[k]) {       // no table-driven variant of this kernel: the whole super-group when its last node is there
+      const auto& tc = brick ? tc_b[k] : tc_c[k]; int cmin = K - 1, cmax = 0;
+      for (auto& t : tc) { cmin = std::min(cmin, t.cmin); cmax = std::max(cmax, t.cmax); }
+      if (tc.empty()) continue;
+      touch(cmin, cmax); (brick ? hp.solo_b : hp.solo_c)[cmax].push_back((int)k);
+    }
+  }
+  for (int k = 0; k < K; k++) hp.done[cout[k]].push_back(k);
+  { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);      // the transfer-side kernels go first when an SM slot frees up
+    CUDA_OK(cudaStreamCreateWithPriority(&hp.up, cudaStreamNonBlocking, hi)); CUDA_OK(cudaStreamCreateWithPriority(&hp.down, cudaStreamNonBlocking, hi));
+    CUDA_OK(cudaStreamCreateWithPriority(&hp.asmb, cudaStreamNonBlocking, hi)); }
+  hp.ev_up.resize(K); hp.ev_el.resize(K); hp.ev_as.resize(K);
+  const unsigned evf = getenv("ORGPU_PIPE_DEBUG") ? cudaEventDefault : cudaEventDisableTiming;
+  hp.ev_dn.resize(K);
+  for (int k = 0; k < K; k++) { CUDA_OK(cudaEventCreateWithFlags(&hp.ev_up[k], evf)); CUDA_OK(cudaEventCreateWithFlags(&hp.ev_el[k], evf));
+                                CUDA_OK(cudaEventCreateWithFlags(&hp.ev_as[k], evf)); CUDA_OK(cudaEventCreateWithFlags(&hp.ev_dn[k], evf)); }
+  CUDA_OK(cudaEventCreateWithFlags(&hp.ev_start, evf)); CUDA_OK(cudaEventCreateWithFlags(&hp.ev_down, evf));
+  CUDA_OK(cudaMalloc((void**)&hp.d_f8, 64 * (size_t)(n + 1))); CUDA_OK(cudaMallocHost((void**)&hp.h_cs, sizeof(CycleState)));
+  if (e->nd.rot && !e->d_stage3c) { if (dev_alloc(&e->d_stage3c, 3 * (size_t)n)) return -100; }
+  hp.K = K; hp.desc_gen = e->desc_gen;
+  return 0;
+}
+
+int orgpu_forces_host(orgpu_engine* e, const double* X, const double* V, const double* VR, double dt1, double* F8, double* dt2t, int* neltst, int* ityptst)
+{
+  NEED(e && e->finalized && X && V && F8, -1, "orgpu_forces_host: engine not finalized / null array"); CUDA_OK(cudaSetDevice(e->device));
+  NEED(e->xc.nranks <= 1 && !e->ctl.nodadt && !e->ipri, -5, "orgpu_forces_host: single domain, element time step, no print cycle (use the phased calls otherwise)");
+  NEED(!e->nd.rot || VR, -1, "orgpu_forces_host: the model has rotational dofs, VR is required");
+  { int rc = pipe_build(e); if (rc) return rc; }
+  auto& hp = e->hp; const int K = hp.K; const bool rot = e->nd.rot != nullptr;
+  static const bool dbg = getenv("ORGPU_PIPE_DEBUG") != nullptr;
+  timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
+  DevNodes ndi = e->nd; ndi.FEXT = nullptr; ndi.MEXT = nullptr;          // internal forces: the caller owns the loads
+  CUDA_OK(cudaEventRecord(hp.ev_start, e->st));                         // behind whatever the handle still has in flight
+  CUDA_OK(cudaStreamWaitEvent(hp.up, hp.ev_start, 0)); CUDA_OK(cudaStreamWaitEvent(hp.down, hp.ev_start, 0)); CUDA_OK(cudaStreamWaitEvent(hp.asmb, hp.ev_start, 0));
+  launch_set_dt(e->d_cs, dt1, 0, 0, 0, e->st); e->launches++;
+  e->fa.fused = 0;
+  // (Letting the kernels themselves read X, V, VR from / store the rows into mapped host memory instead of using the copy
+  // engines was measured: 3.6 ms (stores only) and 4.1 ms (both) per cycle on C2 against 2.3 ms with the engines.)
+  // `up` and `down` carry copies only (back to back on their copy engines: a kernel between two copies of one stream costs the
+  // engine a dependency round trip each way); the record kernels run on the main stream, the assembly on a stream of its own
+  for (int j = 0; j < K; j++) {
+    const int n0 = hp.nb[j], cnt = hp.nb[j + 1] - n0;
+    if (cnt > 0) {
+      CUDA_OK(cudaMemcpyAsync(e->d_stage3a + 3 * (size_t)n0, X + 3 * (size_t)n0, 24 * (size_t)cnt, cudaMemcpyHostToDevice, hp.up));
+      CUDA_OK(cudaMemcpyAsync(e->d_stage3b + 3 * (size_t)n0, V + 3 * (size_t)n0, 24 * (size_t)cnt, cudaMemcpyHostToDevice, hp.up));
+      if (rot) CUDA_OK(cudaMemcpyAsync(e->d_stage3c + 3 * (size_t)n0, VR + 3 * (size_t)n0, 24 * (size_t)cnt, cudaMemcpyHostToDevice, hp.up));
+    }
+    CUDA_OK(cudaEventRecord(hp.ev_up[j], hp.up));
+  }
+  for (int j = 0; j < K; j++) {
+    CUDA_OK(cudaStreamWaitEvent(e->st, hp.ev_up[j], 0));
+    { const int n0 = hp.nb[j], cnt = hp.nb[j + 1] - n0;
+      if (cnt > 0) { pack3to4x3_kernel<<<(cnt + 255) / 256, 256, 0, e->st>>>(e->d_stage3a + 3 * (size_t)n0, e->nd.pos + n0, e->d_stage3b + 3 * (size_t)n0, e->nd.vel + n0,
+                                                                           rot ? e->d_stage3c + 3 * (size_t)n0 : nullptr, rot ? e->nd.rot + n0 : nullptr, cnt); e->launches++; } }
+    for (const auto& L : hp.grp[j]) {
+      if (L.brick) launch_brick_forces_tab(L.variant, (const BrickSG*)L.d_tab, L.d_map, L.ntile, L.bytes, e->nd, e->d_fsky, e->roww, e->d_cs, e->db, e->st);
+      else         launch_shell_forces_tab(L.variant, (const ShellSG*)L.d_tab, L.d_map, L.ntile, L.bytes, e->nd, e->d_fsky, e->d_cs, e->db, e->st);
+      e->launches++;
+    }
+    for (int k : hp.solo_c[j]) launch_sg_shell(e, e->csg[k], e->st);
+    for (int k : hp.solo_b[j]) launch_sg_brick(e, e->bsg[k], e->st);
+    if (hp.done[j].empty()) continue;
+    CUDA_OK(cudaEventRecord(hp.ev_el[j], e->st));
+    CUDA_OK(cudaStreamWaitEvent(hp.asmb, hp.ev_el[j], 0));
+    for (int k : hp.done[j]) {
+      const int n0 = hp.nb[k], n1 = hp.nb[k + 1]; if (n1 <= n0) continue;
+      const int nblk = (n1 - n0 + ORGPU_NODE_BLOCK - 1) / ORGPU_NODE_BLOCK;
+      if (e->roww == 4) node_forces8_kernel<4><<<nblk, ORGPU_NODE_BLOCK, 0, hp.asmb>>>(ndi, e->d_fsky, e->d_cs, e->ctl.iroddl, n0, n1, hp.d_f8);
+      else              node_forces8_kernel<8><<<nblk, ORGPU_NODE_BLOCK, 0, hp.asmb>>>(ndi, e->d_fsky, e->d_cs, e->ctl.iroddl, n0, n1, hp.d_f8);
+      e->launches++;
+      CUDA_OK(cudaEventRecord(hp.ev_as[k], hp.asmb));
+      CUDA_OK(cudaStreamWaitEvent(hp.down, hp.ev_as[k], 0));
+      CUDA_OK(cudaMemcpyAsync(F8 + 8 * (size_t)n0, hp.d_f8 + 8 * (size_t)n0, 64 * (size_t)(n1 - n0), cudaMemcpyDeviceToHost, hp.down));
+      if (dbg) cudaEventRecord(hp.ev_dn[k], hp.down);
+    }
+  }
+  element_finalize_kernel<<<1, ORGPU_FINALIZE_BLOCK, 0, e->st>>>(e->d_cs, e->db, e->fa); e->launches++;
+  CUDA_OK(cudaMemcpyAsync(hp.h_cs, e->d_cs, sizeof(CycleState), cudaMemcpyDeviceToHost, e->st));
+  CUDA_OK(cudaEventRecord(hp.ev_down, hp.down)); CUDA_OK(cudaStreamWaitEvent(e->st, hp.ev_down, 0));    // the handle's stream is the one callers synchronise
+  timespec ts1; if (dbg) clock_gettime(CLOCK_MONOTONIC, &ts1);
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  if (dbg) { timespec ts2; clock_gettime(CLOCK_MONOTONIC, &ts2);
+    fprintf(stderr, "forces_host: submit %.3f ms, wait %.3f ms\n", (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6, (ts2.tv_sec - ts1.tv_sec) * 1e3 + (ts2.tv_nsec - ts1.tv_nsec) * 1e-6);
+    for (int k = 0; k < K; k++) { float a = -1, b = -1, c = -1, d = -1; cudaEventElapsedTime(&a, hp.ev_start, hp.ev_up[k]); cudaEventElapsedTime(&b, hp.ev_start, hp.ev_el[k]);
+      cudaEventElapsedTime(&c, hp.ev_start, hp.ev_as[k]); cudaEventElapsedTime(&d, hp.ev_start, hp.ev_dn[k]);
+      fprintf(stderr, "  chunk %2d: uploaded %.3f  elements %.3f  assembled %.3f  downloaded %.3f ms\n", k, a, b, c, d); }
+    cudaGetLastError(); }
+  CUDA_OK(cudaGetLastError());
+  if (dt2t) *dt2t = hp.h_cs->dt2t; if (neltst) *neltst = hp.h_cs->neltst; if (ityptst) *ityptst = hp.h_cs->ityptst;
+  return check_abort(e);
+}
+
 // ---- domain exchange ------------------------------------------------------------------------------
 
 static int rows_tmp(orgpu_engine* e, size_t n)
@@ -1230,7 +1430,7 @@ int orgpu_p2p_connect(orgpu_engine* e, const unsigned char* handles /*[nranks][6
   CUDA_OK(cudaMemcpy(x.d_peer_win, x.peer.data(), 8 * (size_t)R, cudaMemcpyHostToDevice));
   CUDA_OK(cudaDeviceSynchronize());
   if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
-  e->tabs_dirty = true;
+  e->tabs_dirty = true; e->desc_gen++;
   x.p2p = true;
   // inline sends: every send slot with exactly one destination leaves from the force kernel that computes it (XSend, common.cuh);
   // a decomposition where some slot has several (a node shared by 3+ domains) keeps the push kernel.  ORGPU_NO_OVERLAP=1: push kernel.
@@ -1332,7 +1532,7 @@ int orgpu_set_print(orgpu_engine* e, int ipri)
     for (size_t k = 0; k < e->csg.size(); k++) { e->csg[k].d.bal = e->d_bal + so[k]; e->csg[k].d.bal_ld = e->bal_ld; }
     for (size_t k = 0; k < e->bsg.size(); k++) { e->bsg[k].d.bal = e->d_bal + bo[k]; e->bsg[k].d.bal_ld = e->bal_ld; }
     e->nd.nbal = e->d_nbal; e->nd.nbal_ld = e->nbal_ld;
-    e->tabs_dirty = true;
+    e->tabs_dirty = true; e->desc_gen++;
   }
   if (ipri != e->ipri && e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }   // the cycle graph gains / loses the three balance launches
   e->ipri = ipri;

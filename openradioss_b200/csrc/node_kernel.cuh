@@ -159,6 +159,19 @@ __device__ __forceinline__ void node_update(const DevNodes& nd, int n, const Nod
   st256(nd.pos + n, p);
 }
 
+// ASSPAR4 of the nodes [n0, n1) as (8, n) rows Fx,Fy,Fz,Mx,My,Mz,STIFN,STIFR for the host (orgpu_forces_host, engine.cu)
+template <int ROWW>
+__global__ void __launch_bounds__(ORGPU_NODE_BLOCK)
+node_forces8_kernel(const __grid_constant__ DevNodes nd, const double* __restrict__ fsky, const CycleState* __restrict__ cs, int iroddl, int n0, int n1, double* __restrict__ f8)
+{
+  if (cs->abort) return;
+  const int n = n0 + blockIdx.x * ORGPU_NODE_BLOCK + threadIdx.x;
+  if (n >= n1) return;
+  const NodeAcc r = node_gather<ROWW>(nd, fsky, n, iroddl, K_ZERO);
+  double4* o = reinterpret_cast<double4*>(f8 + (size_t)8 * n);
+  st256(o, make_double4(r.a[0], r.a[1], r.a[2], r.ar[0])); st256(o + 1, make_double4(r.ar[1], r.ar[2], r.stifn, r.stifr));
+}
+
 // phased mode, step 2: ASSPAR4 only (A, AR, STIFN, STIFR stored for the caller)
 template <int ROWW>
 __global__ void __launch_bounds__(ORGPU_NODE_BLOCK)

@@ -18,7 +18,7 @@ set_functions add_solid_group add_solid_group_law add_shell_group set_sh3n add_s
 synchronize get_time download_nodes download_fsky download_solid_state download_shell_state
 step_host launch_count last_run_ms set_profile get_profile pack_rows unpack_rows comm_unique_id comm_init
 set_exchange exchange get_energies p2p_export p2p_connect set_load_function set_fixvel set_gravity upload_solid_state upload_shell_state set_time set_itab
-set_parts set_print get_balance get_balance_history set_quadrature set_global_order set_exchange_timeout pack_nodes add_nodes set_exchange_nodes step_host_rot""".split()
+set_parts set_print get_balance get_balance_history set_quadrature set_global_order set_exchange_timeout pack_nodes add_nodes set_exchange_nodes step_host_rot forces_host""".split()
 
 
 def load_library() -> C.CDLL:
@@ -48,6 +48,14 @@ class Engine(Binding):
         else:
             self._call("step_host_rot", self.h, _opt(X, np.float64), _opt(V, np.float64), _opt(VR, np.float64),
                        C.c_int(ncycles), Xout.ctypes.data_as(C.c_void_p), Vout.ctypes.data_as(C.c_void_p), VRout.ctypes.data_as(C.c_void_p))
+
+    def forces_host(self, X, V, VR, dt1, F8):
+        """The reference -gpu path's cycle in one pipelined call: host X, V, VR (n,3) in, internal nodal forces F8 (n,8) =
+        Fx,Fy,Fz,Mx,My,Mz,STIFN,STIFR out; returns (dt2t, neltst, ityptst).  Pinned host arrays overlap the two directions."""
+        dt2t = C.c_double(0.0); nel = C.c_int(0); ityp = C.c_int(0)
+        self._call("forces_host", self.h, _opt(X, np.float64), _opt(V, np.float64), _opt(VR, np.float64), C.c_double(dt1),
+                   F8.ctypes.data_as(C.c_void_p), C.byref(dt2t), C.byref(nel), C.byref(ityp))
+        return dt2t.value, nel.value, ityp.value
 
     # -- one process per GPU: NCCL exchange inside run_cycles ------------------------------------
     def comm_init(self, dist, domain, p2p=True, parith_off=False):
