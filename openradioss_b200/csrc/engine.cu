@@ -565,8 +565,8 @@ int orgpu_finalize(orgpu_engine* e)
     NEED(!e->npf.empty(), -4, "a load / imposed-velocity time function needs orgpu_set_functions");
     const int nf = (int)e->npf.size() - 1;
     auto check = [&](int f, int maxpts) { return f >= 0 && f < nf && e->npf[f + 1] - e->npf[f] >= 1 && e->npf[f + 1] - e->npf[f] <= maxpts; };
-    if (e->lf_func >= 0) NEED(check(e->lf_func, 20), -5, "load function %d missing or longer than 20 points (FINTER dichotomy branch is outside the built path)", e->lf_func);
-    for (int l = 0; l < e->ngrav; l++) if (e->gfunc[l] >= 0) NEED(check(e->gfunc[l], 20), -5, "gravity function %d missing or longer than 20 points (FINTER dichotomy branch is outside the built path)", e->gfunc[l]);
+    if (e->lf_func >= 0) NEED(check(e->lf_func, 1 << 30), -4, "load function %d missing", e->lf_func);
+    for (int l = 0; l < e->ngrav; l++) if (e->gfunc[l] >= 0) NEED(check(e->gfunc[l], 1 << 30), -4, "gravity function %d missing", e->gfunc[l]);
     for (auto& r : e->fv) for (int j = 0; j < 3; j++) if (r.func[j] >= 0) NEED(check(r.func[j], 1 << 30) && e->npf[r.func[j] + 1] - e->npf[r.func[j]] >= 2, -4, "imposed-velocity function %d missing or shorter than 2 points", r.func[j]);
     if (dev_alloc(&e->d_ftf, e->tf.size()) || dev_alloc(&e->d_fnpf, e->npf.size())) return -100;
     CUDA_OK(cudaMemcpy(e->d_ftf, e->tf.data(), 8 * e->tf.size(), cudaMemcpyHostToDevice));

@@ -86,25 +86,53 @@ void orc_bcs(Oracle& o)
   }
 }
 
-/* FINTER, classical branch (engine/source/tools/curve/finter.F:165-246; fewer than 20 segments).
- * TF holds (x,y) pairs; curve f = points NPF[f] .. NPF[f+1]-1 (0-based) */
+/* FINTER (engine/source/tools/curve/finter.F:165-356): fewer than 20 segments -> the classical walk (:210-229); otherwise the
+ * two end segments first (:236-289), a dichotomy down to fewer than 20 segments (:294-330), then the walk over what is left
+ * (:343-356).  TF holds (x,y) pairs; curve f = points NPF[f] .. NPF[f+1]-1 (0-based) */
+static double orc_finter_seg(const double* TF,int i0,int I,double DX1,double DX2)
+{
+  double DIV0=TF[2*(i0+I)]-TF[2*(i0+I-1)];
+  double DIV=std::max(std::fabs(DIV0),K_EM16);
+  DIV=std::copysign(DIV,DIV0);
+  double DERI=(TF[2*(i0+I)+1]-TF[2*(i0+I-1)+1])/DIV;
+  if(DX1<=DX2) return TF[2*(i0+I-1)+1]+DX1*DERI;
+  return TF[2*(i0+I)+1]-DX2*DERI;
+}
 static double orc_finter(const Oracle& o,int f,double XX)
 {
   const int i0=o.NPF[f], n=o.NPF[f+1]-o.NPF[f];
   const double* TF=o.TF.data();
   if(n==1) return TF[2*i0+1];
+  const int POINT_NBR=n-1, MIN_GAP=20;
   double DX2=TF[2*i0]-XX;
-  for(int I=1;I<n;I++){
-    double DX1=-DX2;
-    DX2=TF[2*(i0+I)]-XX;
-    if(DX2>=K_ZERO || I==n-1){
-      double DIV0=TF[2*(i0+I)]-TF[2*(i0+I-1)];
-      double DIV=std::max(std::fabs(DIV0),K_EM16);
-      DIV=std::copysign(DIV,DIV0);
-      double DERI=(TF[2*(i0+I)+1]-TF[2*(i0+I-1)+1])/DIV;
-      if(DX1<=DX2) return TF[2*(i0+I-1)+1]+DX1*DERI;
-      return TF[2*(i0+I)+1]-DX2*DERI;
+  if(POINT_NBR<MIN_GAP){
+    for(int I=1;I<n;I++){
+      double DX1=-DX2;
+      DX2=TF[2*(i0+I)]-XX;
+      if(DX2>=K_ZERO || I==n-1) return orc_finter_seg(TF,i0,I,DX1,DX2);
     }
+    return K_ZERO;
+  }
+  { double DX1=-DX2; DX2=TF[2*(i0+1)]-XX;                               /* first shot (a): the first segment */
+    if(DX2>=K_ZERO) return orc_finter_seg(TF,i0,1,DX1,DX2); }
+  { DX2=TF[2*(i0+n-1)]-XX; double DX1=-DX2;                              /* first shot (b): beyond the last point */
+    if(DX2<=K_ZERO){ if(DX1==K_ZERO && DX2==K_ZERO) return TF[2*(i0+n-1)+1]; return orc_finter_seg(TF,i0,n-1,DX1,DX2); } }
+  int FIRST=1, LAST=POINT_NBR, COUNTER=0; bool BOOL=true;
+  while(BOOL){
+    const int MIDDLE=(LAST-FIRST)/2+FIRST;
+    const double DX2_FIRST=TF[2*(i0+FIRST)]-XX, DX2_LAST=TF[2*(i0+LAST)]-XX, DX2_MIDDLE=TF[2*(i0+MIDDLE)]-XX;
+    const double PRODUCT_FM=DX2_FIRST*DX2_MIDDLE, PRODUCT_ML=DX2_MIDDLE*DX2_LAST;
+    if(PRODUCT_FM<0) LAST=MIDDLE; else if(PRODUCT_ML<0) FIRST=MIDDLE; else BOOL=false;
+    if(LAST-FIRST<MIN_GAP) BOOL=false;
+    COUNTER=COUNTER+1;
+    if(COUNTER>POINT_NBR){ COUNTER=-1; BOOL=false; }
+  }
+  if(COUNTER==-1){ FIRST=1; LAST=POINT_NBR; }
+  DX2=TF[2*(i0+FIRST-1)]-XX;
+  for(int J=FIRST;J<=LAST;J++){
+    double DX1=-DX2;
+    DX2=TF[2*(i0+J)]-XX;
+    if(DX2>=K_ZERO || J==LAST) return orc_finter_seg(TF,i0,J,DX1,DX2);
   }
   return K_ZERO;
 }

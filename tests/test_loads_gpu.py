@@ -81,6 +81,20 @@ def test_gravity_loads_match_oracle():
     assert np.array_equal(vg[:, 2], vo[:, 2]) and vo[:, 2].max() < 0.0
 
 
+def test_long_time_function_on_the_device_is_bitwise_the_oracle():
+    """64-point load curve: the dichotomy branch of FINTER (finter.F:231-356) in element_finalize_kernel, same bits as the oracle"""
+    x = np.concatenate([[0.0], np.cumsum(np.linspace(0.5e-4, 2.0e-4, 63))])
+    y = np.sin(400.0 * x) + 2.0 * x
+    m = meshgen.hex_block(3, 3, 3, 6.0, 6.0, 6.0)
+    meshgen.add_gravity(m, 3, 1.0e-3, curve=(x, y), fcx=3.0)
+    g, o = Engine(m), Oracle(m, threads=0)
+    for n in (5, 60, 200):
+        g.run_cycles(n); g.synchronize(); o.run_cycles(n)
+        vg, vo = g.download_nodes(("V",))["V"], o.download_nodes(("V",))["V"]
+        assert np.array_equal(vg[:, 2], vo[:, 2])
+    assert o.time()["tt"] * 3.0 > x[-1]                      # the run went past the end of the curve
+
+
 def test_gravity_rejects_what_is_not_built():
     m = meshgen.hex_block(2, 2, 2, 2.0, 2.0, 2.0)
     meshgen.add_gravity(m, 3, -1.0)

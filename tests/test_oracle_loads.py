@@ -115,3 +115,28 @@ def test_gravity_follows_its_nodes_into_the_domains():
         x = b.download_nodes(("X", "V"))
         assert np.array_equal(x["X"], xr["X"][d.node_gid]) and np.array_equal(x["V"], xr["V"][d.node_gid])
 
+
+
+def test_long_time_function_takes_the_dichotomy_branch_of_finter():
+    """FINTER with 20 segments or more (finter.F:231-356: end segments first, dichotomy, walk over the reduced interval) must
+    give what the classical walk gives: the linear interpolant, taken from the nearer end point, end segments extrapolating.
+    A free-falling block under a load with a 64-point curve sees exactly FCY * f(TT * FCX) as its acceleration."""
+    x = np.concatenate([[0.0], np.cumsum(np.linspace(0.5e-4, 2.0e-4, 63))])          # uneven spacing, last point ~ 8e-3
+    y = np.sin(400.0 * x) + 2.0 * x
+    m = meshgen.hex_block(2, 2, 2, 4.0, 4.0, 4.0)
+    meshgen.add_gravity(m, 3, 10.0, curve=(x, y), fcx=3.0)            # large enough that rounding-level internal forces do not show
+    o = Oracle(m)
+    seen_mid = seen_end = False
+    for c in range(400):
+        t0 = o.time()["tt"]
+        v0 = o.download_nodes(("V",))["V"][0, 2]
+        o.run_cycles(1)
+        t = o.time()
+        xx = t0 * 3.0
+        if xx <= x[-1]:
+            f = np.interp(xx, x, y); seen_mid = True
+        else:                                                    # beyond the last point: the last segment extrapolates
+            f = y[-1] + (xx - x[-1]) * (y[-1] - y[-2]) / (x[-1] - x[-2]); seen_end = True
+        dv = o.download_nodes(("V",))["V"][0, 2] - v0
+        assert dv == __import__("pytest").approx(t["dt12"] * 10.0 * f, rel=1e-7, abs=1e-12), (c, xx)      # rounding-level internal forces act too (see the free-fall test)
+    assert seen_mid and seen_end
