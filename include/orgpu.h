@@ -95,7 +95,7 @@ int  orgpu_get_time(orgpu_engine* e, double out[5] /*tt,dt1,dt2,dt12,dt2t*/, int
 int  orgpu_download_nodes(orgpu_engine* e, double* X, double* V, double* VR, double* D,
                           double* A, double* AR, double* STIFN, double* STIFR);
 int  orgpu_download_fsky(orgpu_engine* e, double* fsky /*(8,LSKY)*/);
-/* fields: 0 sig(6) 1 eint 2 rho 3 qvis 4 pla 5 epsd 6 vol 7 off 8 temp 9 smstr(21) 10 stra(6) 11 wpla (LAW36); out[k*numels+e] */
+/* fields: 0 sig(6) 1 eint 2 rho 3 qvis 4 pla 5 epsd 6 vol 7 off 8 temp 9 smstr(21) 10 stra(6) 11 wpla (LAW36) 12 sigb(6) (LAW2 with FISOKIN > 0: LBUF%SIGB); out[k*numels+e] */
 int  orgpu_download_solid_state(orgpu_engine* e, int field, double* out);
 int  orgpu_download_shell_state(orgpu_engine* e, int field, double* out);
 int  orgpu_download_sh3n_state(orgpu_engine* e, int field, double* out);   /* shell fields; smstr has 3 words, no hourg */

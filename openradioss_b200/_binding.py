@@ -21,7 +21,7 @@ def _opt(a, dtype):
 class Binding:
     """Thin object wrapper over one handle of either library."""
     SOLID_FIELDS = dict(sig=(0, 6), eint=(1, 1), rho=(2, 1), qvis=(3, 1), pla=(4, 1), epsd=(5, 1),
-                        vol=(6, 1), off=(7, 1), temp=(8, 1), smstr=(9, 21), stra=(10, 6), wpla=(11, 1))
+                        vol=(6, 1), off=(7, 1), temp=(8, 1), smstr=(9, 21), stra=(10, 6), wpla=(11, 1), sigb=(12, 6))
     SHELL_FIELDS = dict(forc=(0, 5), mom=(1, 3), eint=(2, 2), thk=(3, 1), off=(4, 1), stra=(5, 8),
                         epsd=(6, 1), hourg=(7, 12), smstr=(8, 6), sig=(9, 5), pla=(10, 1),
                         epsd_ip=(11, 1), temp=(12, 1), sigb=(13, 3))

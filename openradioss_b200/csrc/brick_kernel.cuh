@@ -366,6 +366,9 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       const double rhocpi = (m.rhocp > K_ZERO) ? or_div(K_ONE, m.rhocp) : K_ZERO;
       const double G = m.shear * OFF;
       double CA = m.ca, SIGMX = m.sigmx;
+      const bool KIN = g.w_sigb >= 0;                         // kinematic / mixed hardening (m2law.F:181-190, 300-337, 364-390)
+      if (KIN) { SG1 = SG1 - T.ld(g.w_sigb); SG2 = SG2 - T.ld(g.w_sigb + 1); SG3 = SG3 - T.ld(g.w_sigb + 2);
+                 SG4 = SG4 - T.ld(g.w_sigb + 3); SG5 = SG5 - T.ld(g.w_sigb + 4); SG6 = SG6 - T.ld(g.w_sigb + 5); }
       double Pm = -K_THIRD * (SG1 + SG2 + SG3);
       double DAV = -K_THIRD * (DXX + DYY + DZZ);
       double G1 = DT1 * G, G2 = K_TWO * G1;
@@ -413,26 +416,37 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
         EPD = K_ONE - ((TSTAR > K_ZERO) ? pow(TSTAR, MT) : K_ZERO);
         if (m.icc == 1) SIGMX = m.sigmx * EPD;
       }
-      double AK, QH;
-      if (m.cn == K_ONE) { AK = CA + m.cb * EPXE; QH = m.cb * EPD; }
+      double AK, QH, SIGY;
+      const double BETA = K_ONE - m.fisokin;                  // isotropic share of the hardening (1 without a kinematic part)
+      if (m.cn == K_ONE) { SIGY = CA + m.cb * EPXE; AK = KIN ? CA + BETA * m.cb * EPXE : SIGY; QH = m.cb * EPD; }
       else if (EPXE > K_ZERO) {
         // one pow instead of two: EPXE**(CN-1) = EPXE**CN / EPXE (m2law.F:230-238; a pow is ~180 instructions, the
         // quotient differs from the library value by <= 2 ulp, far inside the 1e-12 force tolerance)
         const double PN = pow(EPXE, m.cn);
-        AK = CA + m.cb * PN;
+        SIGY = CA + m.cb * PN; AK = KIN ? CA + BETA * m.cb * PN : SIGY;
         if (m.cn > K_ONE) QH = (m.cb * m.cn * or_div(PN, EPXE)) * EPD;
         else              QH = (or_div(m.cb * m.cn, or_div(EPXE, PN))) * EPD;
-      } else { AK = CA; QH = K_ZERO; }
+      } else { AK = CA; SIGY = CA; QH = K_ZERO; }
       AK = AK * EPD;
+      if (KIN) SIGY = SIGY * EPD;
       if (SIGMX < AK) { AK = SIGMX; QH = K_ZERO; }
-      double SIGY = AK;
+      SIGY = KIN ? fmin(SIGY, SIGMX) : AK;
       if (EPXE > m.epmx) { AK = K_ZERO; QH = K_ZERO; }
+      const double SE1 = SG1, SE2 = SG2, SE3 = SG3, SE4 = SG4, SE5 = SG5, SE6 = SG6;     // elastic predictors (:213-222)
       double SCALE = fmin(K_ONE, or_div(AK, fmax(AJ2, K_EM15)));
       const double DPLA = or_div((K_ONE - SCALE) * AJ2, fmax(K_THREE * G + QH, K_EM15));
       AK = AK + (K_ONE - m.fisokin) * DPLA * QH;
       SCALE = fmin(K_ONE, or_div(AK, fmax(AJ2, K_EM15)));
       SG1 = SCALE * SG1; SG2 = SCALE * SG2; SG3 = SCALE * SG3; SG4 = SCALE * SG4; SG5 = SCALE * SG5; SG6 = SCALE * SG6;
       EPXE = EPXE + DPLA;
+      if (KIN) {                                              // back stress along the plastic corrector, stress gets it back
+        const double HKIN = K_TWO_THIRD * m.fisokin * QH;
+        const double ALPHA = or_div(HKIN, fmax(K_TWO * G + HKIN, K_EM15));
+        const double B1 = T.ld(g.w_sigb) + ALPHA * (SE1 - SG1), B2 = T.ld(g.w_sigb + 1) + ALPHA * (SE2 - SG2), B3 = T.ld(g.w_sigb + 2) + ALPHA * (SE3 - SG3);
+        const double B4 = T.ld(g.w_sigb + 3) + ALPHA * (SE4 - SG4), B5 = T.ld(g.w_sigb + 4) + ALPHA * (SE5 - SG5), B6 = T.ld(g.w_sigb + 5) + ALPHA * (SE6 - SG6);
+        T.st(g.w_sigb, B1); T.st(g.w_sigb + 1, B2); T.st(g.w_sigb + 2, B3); T.st(g.w_sigb + 3, B4); T.st(g.w_sigb + 4, B5); T.st(g.w_sigb + 5, B6);
+        SG1 = SG1 + B1; SG2 = SG2 + B2; SG3 = SG3 + B3; SG4 = SG4 + B4; SG5 = SG5 + B5; SG6 = SG6 + B6;
+      }
       // ---- MQVISCB (IMPL=0, N2D=0, NPG=1, JTHE=0, IDTMINS/=2, NODADT=0)
       brick_mqviscb<ISMSTR>(g, DXX, DYY, DZZ, SSP, OFF, OFFG, VOLN, VOLO, RHON, RHOREF, CBV, DELTAX, QNEW, SSP_EQ, STI, dt_cand);
       // ---- pressure + internal energy (m2law.F:433-453)

@@ -390,7 +390,7 @@ int orgpu_add_solid_group(orgpu_engine* e, int nel, int nft, const orgpu_law2* m
 {
   NEED(e && mat && prop && vol0 && nel > 0 && !e->finalized, -1, "orgpu_add_solid_group: bad arguments / already finalized");
   NEED(nft >= 0 && nft + nel <= e->numels, -4, "orgpu_add_solid_group: elements [%d,%d) outside IXS (%d)", nft, nft + nel, e->numels);
-  NEED(mat->fisokin == 0.0, -5, "LAW2 kinematic hardening (FISOKIN>0) is outside the built path");
+  NEED(mat->fisokin >= 0.0 && mat->fisokin <= 1.0, -4, "LAW2 FISOKIN = %g outside [0, 1]", mat->fisokin);
   NEED(prop->jhbe == 0 || prop->jhbe == 1 || prop->jhbe == 2, -5, "Isolid=%d is outside the built path (0,1,2)", prop->jhbe);
   NEED(prop->ismstr == 1 || prop->ismstr == 2 || prop->ismstr == 4, -5, "Ismstr=%d is outside the built path (1,2,4)", prop->ismstr);
   HostSolidGroup g; g.nel = nel; g.nft = nft; g.law = 2; g.mat = *mat; memset(&g.m36, 0, sizeof g.m36); g.prop = *prop; g.vol0.assign(vol0, vol0 + nel);
@@ -478,6 +478,8 @@ int orgpu_finalize(orgpu_engine* e)
     d.w_temp = d.mat.has_temp ? BW_NFIX : -1;
     d.nw_rw = BW_NFIX + (d.mat.has_temp ? 1 : 0);
     d.w_stra = d.w_wpla = d.w_vt = -1; d.nvt = 0; d.tf = nullptr; d.npf = nullptr; memset(&d.ct, 0, sizeof d.ct);
+    d.w_sigb = -1;
+    if (d.law == 2 && d.mat.fisokin > 0.0) { d.w_sigb = d.nw_rw; d.nw_rw += 6; }     // LBUF%SIGB (m2law.F:181-190, 364-390)
     if (d.law == 36) {                                   // LBUF%WPLA, LBUF%STRA (ISTRAIN>0), VARTMP cursors
       d.w_wpla = d.nw_rw++;
       if (d.prop.istrain > 0) { d.w_stra = d.nw_rw; d.nw_rw += 6; }
@@ -991,7 +993,8 @@ static int solid_state_xfer(orgpu_engine* e, int field, double* buf, bool up)
     switch (field) { case 0: w0 = BW_SIG; nc = 6; break; case 1: w0 = BW_EINT; break; case 2: w0 = BW_RHO; break; case 3: w0 = BW_QVIS; break;
                      case 4: w0 = BW_PLA; break; case 5: w0 = BW_EPSD; break; case 6: w0 = d.w_vol; break; case 7: w0 = BW_OFF; break;
                      case 8: w0 = d.w_temp; break; case 9: base = d.smstr; nw = 21; w0 = 0; nc = 21; break;
-                     case 10: w0 = d.w_stra; nc = 6; if (w0 < 0) continue; break; case 11: w0 = d.w_wpla; if (w0 < 0) continue; break; default: FAIL(-1, "unknown solid field %d", field); }
+                     case 10: w0 = d.w_stra; nc = 6; if (w0 < 0) continue; break; case 11: w0 = d.w_wpla; if (w0 < 0) continue; break;
+                     case 12: w0 = d.w_sigb; nc = 6; if (w0 < 0) continue; break; default: FAIL(-1, "unknown solid field %d", field); }
     if (w0 < 0) { if (!up) for (int i = 0; i < d.ne; i++) buf[S.first_elem + i] = d.mat.tini; continue; }   // no temperature buffer
     for (int k = 0; k < nc; k++)
       CUDA_OK(up ? slab_upload_word(base, nw, w0 + k, d.ne, buf + k * NE + S.first_elem)

@@ -125,6 +125,8 @@ class Engine(Binding):
                 ck["sh3n"]["temp"] = self.sh3n_state("temp")
             if any(getattr(g.mat, "fisokin", 0.0) > 0.0 for g in self.model.sh3n_groups):
                 ck["sh3n"]["sigb"] = self.sh3n_state("sigb")
+        if self.model.numels and any(getattr(g, "law", 2) == 2 and getattr(g.mat, "fisokin", 0.0) > 0.0 for g in self.model.solid_groups):
+            ck["solid"]["sigb"] = self.solid_state("sigb")             # back stress of the kinematic hardening (LBUF%SIGB)
         if self.model.numels and any(getattr(g, "law", 2) == 36 for g in self.model.solid_groups):
             ck["solid"].update({f: self.solid_state(f) for f in ("wpla", "stra")})
         return ck

@@ -90,8 +90,8 @@ int orc_add_solid_group(void* h,int nel,int nft,const orgpu_law2* mat,const orgp
 {
   Oracle* o=(Oracle*)h;
   if(nel>MVSIZ-1) return -1;
-  if(mat->fisokin!=0.0) return -2;
   OrcSolidGroup g; g.nel=nel; g.nft=nft; g.mat=*mat; g.prop=*prop;
+  if(mat->fisokin>0.0) g.sigb.assign(6*nel,0);             /* LBUF%SIGB (m2law.F:181-190, 364-390) */
   g.sig.assign(6*nel,0); g.eint.assign(nel,0); g.rho.assign(nel,mat->rho0); g.qvis.assign(nel,0);
   g.pla.assign(nel,0); g.epsd.assign(nel,0); g.vol.assign(vol0,vol0+nel); g.off.assign(nel,1.0);
   g.temp.assign(nel,mat->tini); g.dmg.assign(nel,0); g.smstr.assign(21*nel,0);
@@ -179,7 +179,7 @@ void orc_download_nodes(void* h,double* X,double* V,double* VR,double* D,double*
 void orc_download_fsky(void* h,double* fsky){ Oracle* o=(Oracle*)h; memcpy(fsky,o->FSKY.data(),64*(size_t)o->lsky); }
 
 /* solid state of all groups concatenated in element order, component-major over NUMELS:
- * sig[k*numels+e] ; fields: 0 sig(6) 1 eint 2 rho 3 qvis 4 pla 5 epsd 6 vol 7 off 8 temp 9 smstr(21) 10 stra(6) 11 wpla */
+ * sig[k*numels+e] ; fields: 0 sig(6) 1 eint 2 rho 3 qvis 4 pla 5 epsd 6 vol 7 off 8 temp 9 smstr(21) 10 stra(6) 11 wpla 12 sigb(6) */
 void orc_download_solid_state(void* h,int field,double* out){
   Oracle* o=(Oracle*)h; size_t ne=o->numels;
   for(auto& g:o->sgroups){
@@ -190,6 +190,7 @@ void orc_download_solid_state(void* h,int field,double* out){
       case 6: cp(g.vol,1); break; case 7: cp(g.off,1); break; case 8: cp(g.temp,1); break;
       case 9: cp(g.smstr,21); break;
       case 10: if(!g.stra.empty()) cp(g.stra,6); break; case 11: if(!g.wpla.empty()) cp(g.wpla,1); break;
+      case 12: if(!g.sigb.empty()) cp(g.sigb,6); break;
     }
   }
 }
@@ -203,7 +204,7 @@ void orc_upload_solid_state(void* h,int field,const double* in){
       case 0: cp(g.sig,6); break; case 1: cp(g.eint,1); break; case 2: cp(g.rho,1); break;
       case 3: cp(g.qvis,1); break; case 4: cp(g.pla,1); break; case 5: cp(g.epsd,1); break;
       case 6: cp(g.vol,1); break; case 7: cp(g.off,1); break; case 8: cp(g.temp,1); break;
-      case 9: cp(g.smstr,21); break; case 10: cp(g.stra,6); break; case 11: cp(g.wpla,1); break;
+      case 9: cp(g.smstr,21); break; case 10: cp(g.stra,6); break; case 11: cp(g.wpla,1); break; case 12: cp(g.sigb,6); break;
     }
   }
 }

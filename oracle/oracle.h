@@ -41,6 +41,7 @@ struct OrcSolidGroup {          /* one element group, ITY=1 (forint.F -> SFORC3)
   std::vector<double> eint, rho, qvis, pla, epsd, vol, off, temp, dmg;
   std::vector<double> smstr;    /* SAV(nel,21) */
   std::vector<double> stra, wpla; /* MLW=36: LBUF%STRA(6*nel) when ISTRAIN>0, LBUF%WPLA */
+  std::vector<double> sigb;     /* MLW=2, FISOKIN>0: LBUF%SIGB(6*nel), the back stress of the kinematic hardening */
   std::vector<int> vartmp;      /* MLW=36: VARTMP(nel,2+NRATE) table cursors */
 };
 

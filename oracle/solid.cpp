@@ -161,7 +161,7 @@ static void m2law(const Oracle& o,OrcSolidGroup& g,int nel,const int* ngl,
                   double* qnew,double* ssp_eq,
                   const double* sold1,const double* sold2,const double* sold3,
                   const double* sold4,const double* sold5,const double* sold6,
-                  const double* tstar,double* tempel,double* dmg,const double* rhoref)
+                  const double* tstar,double* tempel,double* dmg,const double* rhoref,double* sigbak_of_call /*6*nel comp-major, or null*/)
 {
   const orgpu_law2& m=g.mat;
   const double facq0=K_ONE;
@@ -178,7 +178,13 @@ static void m2law(const Oracle& o,OrcSolidGroup& g,int nel,const int* ngl,
   auto S=[&](int i,int k)->double&{ return sig[k*nel+i]; };
   const double DT1=o.DT1;
   for(int i=0;i<nel;i++){ G[i]=g0*off[i]; CA[i]=ca0; SIGMX[i]=sigm0; }   /* :171-176 */
-  /* FISOKIN>0 (kinematic hardening, SIGBAK) is not built: assert in api */
+  double* SIGBAK = nullptr;                                                /* LBUF%SIGB of the elements of this call */
+  auto B=[&](int i,int k)->double&{ return SIGBAK[k*nel+i]; };
+  std::vector<double> SIGE;
+  if(fisokin>K_ZERO){                                                      /* :181-190 kinematic hardening: stress shifted by the back stress */
+    SIGBAK = sigbak_of_call;
+    for(int i=0;i<nel;i++) for(int k=0;k<6;k++) S(i,k)=S(i,k)-B(i,k);
+  }
   for(int i=0;i<nel;i++){                                                  /* :192-210 */
     double P=-K_THIRD*(S(i,0)+S(i,1)+S(i,2));
     DAV[i]=-K_THIRD*(d1[i]+d2[i]+d3[i]);
@@ -195,6 +201,7 @@ static void m2law(const Oracle& o,OrcSolidGroup& g,int nel,const int* ngl,
           + S(i,3)*S(i,3)+S(i,4)*S(i,4)+S(i,5)*S(i,5);
     AJ2[i]=std::sqrt(K_THREE*AJ2[i]);
   }
+  if(fisokin>K_ZERO){ SIGE.resize((size_t)6*nel); for(int i=0;i<nel;i++) for(int k=0;k<6;k++) SIGE[k*nel+i]=S(i,k); }   /* :213-222 */
   const int idev=vp-2;                                                     /* :226-228 */
   mstrain_rate(nel,israte,asrate,epsd,idev,d1,d2,d3,d4,d5,d6);
   for(int i=0;i<nel;i++) EPD[i]=K_ONE;                                     /* :231 */
@@ -220,6 +227,7 @@ static void m2law(const Oracle& o,OrcSolidGroup& g,int nel,const int* ngl,
     double MT=std::max(K_EM15,z3);
     for(int i=0;i<nel;i++){ EPD[i]=K_ONE-std::pow(tstar[i],MT); if(icc==1) SIGMX[i]=sigm0*EPD[i]; }
   }
+  if(fisokin==K_ZERO){
   /* isotropic hardening :269-299 */
   if(cn==K_ONE){
     for(int i=0;i<nel;i++){ AK[i]=CA[i]+cb*epxe[i]; QH[i]=cb*EPD[i]; }
@@ -238,6 +246,29 @@ static void m2law(const Oracle& o,OrcSolidGroup& g,int nel,const int* ngl,
     SIGY[i]=AK[i];
     if(epxe[i]>epmx){ AK[i]=K_ZERO; QH[i]=K_ZERO; }
   }
+  } else {
+  /* kinematic / mixed hardening :300-337: the isotropic share BETA of the hardening stays in the yield stress */
+  for(int i=0;i<nel;i++){
+    const double BETA=K_ONE-fisokin;
+    if(cn==K_ONE){
+      SIGY[i]=CA[i]+cb*epxe[i];
+      AK[i]=CA[i]+BETA*cb*epxe[i];
+      QH[i]=cb*EPD[i];
+    } else {
+      if(epxe[i]>K_ZERO){
+        SIGY[i]=CA[i]+cb*std::pow(epxe[i],cn);
+        AK[i]=CA[i]+BETA*cb*std::pow(epxe[i],cn);
+        if(cn>K_ONE) QH[i]=(cb*cn*std::pow(epxe[i],(cn-K_ONE)))*EPD[i];
+        else         QH[i]=(cb*cn/std::pow(epxe[i],(K_ONE-cn)))*EPD[i];
+      } else { AK[i]=CA[i]; SIGY[i]=CA[i]; QH[i]=K_ZERO; }
+    }
+    AK[i]=AK[i]*EPD[i];
+    SIGY[i]=SIGY[i]*EPD[i];
+    if(SIGMX[i]<AK[i]){ AK[i]=SIGMX[i]; QH[i]=K_ZERO; }
+    SIGY[i]=std::min(SIGY[i],SIGMX[i]);
+    if(epxe[i]>epmx){ AK[i]=K_ZERO; QH[i]=K_ZERO; }
+  }
+  }
   /* radial return :339-354 */
   for(int i=0;i<nel;i++){
     double SCALE=std::min(K_ONE,AK[i]/std::max(AJ2[i],K_EM15));
@@ -247,6 +278,15 @@ static void m2law(const Oracle& o,OrcSolidGroup& g,int nel,const int* ngl,
     S(i,0)=SCALE*S(i,0); S(i,1)=SCALE*S(i,1); S(i,2)=SCALE*S(i,2);
     S(i,3)=SCALE*S(i,3); S(i,4)=SCALE*S(i,4); S(i,5)=SCALE*S(i,5);
     epxe[i]=epxe[i]+DPLA[i];
+  }
+  if(fisokin>K_ZERO){                                                      /* :364-390 back stress along the plastic corrector */
+    for(int i=0;i<nel;i++){
+      double DS[6]; for(int k=0;k<6;k++) DS[k]=SIGE[k*nel+i]-S(i,k);
+      const double HKIN=K_TWO_THIRD*fisokin*QH[i];
+      const double ALPHA=HKIN/std::max(K_TWO*G[i]+HKIN,K_EM15);
+      for(int k=0;k<6;k++) B(i,k)=B(i,k)+ALPHA*DS[k];
+      for(int k=0;k<6;k++) S(i,k)=S(i,k)+B(i,k);
+    }
   }
   /* :393-407 MQVISCB */
   double bid[MVSIZ]; for(int i=0;i<MVSIZ;i++) bid[i]=K_ZERO; (void)bid;
@@ -780,7 +820,8 @@ void orc_sforc3(Oracle& o, OrcSolidGroup& g, double& dt2t, int& neltst, int& ity
     } else
     m2law(o,g,nel,NGL,OFF,SIG,EINT,RHON,g.qvis.data(),g.pla.data(),g.epsd.data(),g.vol.data(),STI,
           dt2t,neltst,ityptst,OFFG,AMU,VOL_AVG,CXX,DVOL,VOLN,VD2,DELTAX,VIS,
-          DXX,DYY,DZZ,D4,D5,D6,QVIS,SSP_EQ,S1,S2,S3,S4,S5,S6,TSTAR,el_temp,g.dmg.data(),RHOREF);
+          DXX,DYY,DZZ,D4,D5,D6,QVIS,SSP_EQ,S1,S2,S3,S4,S5,S6,TSTAR,el_temp,g.dmg.data(),RHOREF,
+          g.mat.fisokin>K_ZERO ? g.sigb.data() : nullptr);
     /* m2law stored QNEW into QVIS and then QOLD(=lbuf%qvis) = QNEW */
     /* mmain.F90 tail: l_temp>0 entropy heating of the artificial viscosity */
     if(g.mat.has_temp){

@@ -246,3 +246,40 @@ def test_law36_epsmax_failure_relaxes_the_brick_off():
     assert np.allclose(seq[k:k + 10], 0.8 * 0.8 ** np.arange(10), rtol=1e-14)   # 0.8^11 = 0.0859 < 0.1 -> zero next
     assert seq[k + 11] == 0.0 and seq[-1] == 0.0
     assert np.abs(o.solid_state("sig")).max() == 0.0
+
+
+@pytest.mark.parametrize("fisokin", [0.5, 1.0])
+def test_law2_kinematic_hardening_shifts_the_yield_surface(fisokin):
+    """M2LAW with FISOKIN > 0 (m2law.F:181-190, 300-337, 364-390): after a plastic step the stress SHIFTED by the back stress
+    sits on a yield surface that has grown by the isotropic share (1 - FISOKIN) of the hardening only, the back stress has
+    grown along the plastic corrector by ALPHA = HKIN / (2G + HKIN), HKIN = 2/3 FISOKIN QH, and reversing the load yields
+    earlier than the isotropic law does (Bauschinger)."""
+    def run(fk, reverse):
+        m = block(2, jitter=0.0)
+        mat = m.solid_groups[0].mat
+        mat.cc = 0.0; mat.has_temp = 0; mat.rhocp = 0.0; mat.cn = 1.0; mat.fisokin = fk          # linear hardening: QH = CB
+        gam = 2.0 * mat.ca / (np.sqrt(3.0) * mat.shear * 1e-3)                                     # trial von Mises = 2 CA in one step
+        m.V = np.zeros_like(m.X); m.V[:, 0] = gam * m.X[:, 1]
+        o = Oracle(m)
+        o.forces_phase(1e-3)
+        out = [(o.solid_state("sig")[:, 0].copy(), o.solid_state("sigb")[:, 0].copy() if fk > 0 else np.zeros(6), o.solid_state("pla").ravel()[0])]
+        if reverse:
+            o.upload_nodes(V=-1.5 * m.V)
+            o.forces_phase(1e-3)
+            out.append((o.solid_state("sig")[:, 0].copy(), o.solid_state("sigb")[:, 0].copy() if fk > 0 else np.zeros(6), o.solid_state("pla").ravel()[0]))
+        return m.solid_groups[0].mat, out
+    vm = lambda s: np.sqrt(0.5 * ((s[0] - s[1]) ** 2 + (s[1] - s[2]) ** 2 + (s[2] - s[0]) ** 2) + 3 * (s[3] ** 2 + s[4] ** 2 + s[5] ** 2))
+    mat, [(sig, sb, pla)] = run(fisokin, False)
+    trial = 2.0 * mat.ca
+    dp = (trial - mat.ca) / (3.0 * mat.shear + mat.cb)
+    assert pla == pytest.approx(dp, rel=1e-12)
+    ak = mat.ca + (1.0 - fisokin) * mat.cb * dp
+    assert vm(sig - sb) == pytest.approx(ak, rel=1e-12)                  # shifted stress on the (partly) grown surface
+    hkin = 2.0 / 3.0 * fisokin * mat.cb
+    alpha = hkin / (2.0 * mat.shear + hkin)
+    assert vm(sb) == pytest.approx(alpha * (trial - ak), rel=1e-10)       # back stress = ALPHA * (predictor - returned), same direction
+    assert sb[3] > 0.0 and abs(sb[0]) + abs(sb[1]) + abs(sb[2]) < 1e-9 * sb[3]
+    # Bauschinger: the same reversed increment produces more plastic strain with a kinematic part than without
+    _, out_k = run(fisokin, True)
+    _, out_i = run(0.0, True)
+    assert out_k[1][2] - out_k[0][2] > (out_i[1][2] - out_i[0][2]) * (1.0 + 1e-6)
