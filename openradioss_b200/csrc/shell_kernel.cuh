@@ -173,6 +173,7 @@ static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky
   const int nblk = S.d.ne_pad / ORGPU_TILE;
   if (S.sh3n) {
     if (S.d.law == 36 && S.d.m36.ifail == 2) shell_launch_one(c3_forces_kernel<37, true>, c3_forces_kernel<37, false>, P, nblk, st);
+    else if (S.d.law == 36 && shell_fast(S.d)) shell_launch_one(c3_forces_kernel<36, true, 1>, c3_forces_kernel<36, false>, P, nblk, st);
     else if (S.d.law == 36) shell_launch_one(c3_forces_kernel<36, true>, c3_forces_kernel<36, false>, P, nblk, st);
     else               shell_launch_one(c3_forces_kernel<2, true>, c3_forces_kernel<2, false>, P, nblk, st);
   } else if (shell_is_qeph(S.d.prop)) {
@@ -182,6 +183,7 @@ static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky
     else               shell_launch_one(qeph_forces_kernel<2, true>, qeph_forces_kernel<2, false>, P, nblk, st);
   } else {
     if (S.d.law == 36 && S.d.m36.ifail == 2) shell_launch_one(bt_forces_kernel<37, true>, bt_forces_kernel<37, false>, P, nblk, st);
+    else if (S.d.law == 36 && shell_fast(S.d)) shell_launch_one(bt_forces_kernel<36, true, 1>, bt_forces_kernel<36, false>, P, nblk, st);
     else if (S.d.law == 36) shell_launch_one(bt_forces_kernel<36, true>, bt_forces_kernel<36, false>, P, nblk, st);
     else               shell_launch_one(bt_forces_kernel<2, true>, bt_forces_kernel<2, false>, P, nblk, st);
   }
@@ -218,14 +220,14 @@ static int shell_state_xfer(std::vector<ShellSGHost>& sgs, int numelc, int field
 
 // ---- batched launches: all super-groups of one kernel variant in ONE launch (table-driven CTA -> (super-group, tile)) --------
 // variant of a shell super-group whose table-driven kernel is compiled (-1: launched on its own)
-enum { SHV_QEPH36F = 0, SHV_QEPH36, SHV_QEPH2, SHV_BT36, SHV_BT2, SHV_COUNT };
+enum { SHV_QEPH36F = 0, SHV_QEPH36, SHV_QEPH2, SHV_BT36F, SHV_BT36, SHV_BT2, SHV_COUNT };
 static inline int shell_tab_variant(const ShellSGHost& S)
 {
   const ShellSG& d = S.d;
   if (S.sh3n || (size_t)d.nw * ORGPU_TILE * 8 > ORGPU_STAGE_MAX_BYTES) return -1;
   if (d.law == 36 && d.m36.ifail == 2) return -1;
   if (shell_is_qeph(d.prop)) return d.law == 36 ? (shell_fast(d) ? SHV_QEPH36F : SHV_QEPH36) : SHV_QEPH2;
-  return d.law == 36 ? SHV_BT36 : SHV_BT2;
+  return d.law == 36 ? (shell_fast(d) ? SHV_BT36F : SHV_BT36) : SHV_BT2;
 }
 template <class K>
 static void shell_launch_tab_k(K kern, const ShellParams& P, int nblk, size_t bytes, cudaStream_t st)
@@ -238,7 +240,8 @@ static void launch_shell_forces_tab(int variant, const ShellSG* d_tab, const int
     case SHV_QEPH36F: shell_launch_tab_k(qeph_forces_kernel<36, true, 1, true>, P, nblk, bytes, st); break;
     case SHV_QEPH36:  shell_launch_tab_k(qeph_forces_kernel<36, true, 0, true>, P, nblk, bytes, st); break;
     case SHV_QEPH2:   shell_launch_tab_k(qeph_forces_kernel<2, true, 0, true>, P, nblk, bytes, st); break;
-    case SHV_BT36:    shell_launch_tab_k(bt_forces_kernel<36, true, true>, P, nblk, bytes, st); break;
-    default:          shell_launch_tab_k(bt_forces_kernel<2, true, true>, P, nblk, bytes, st); break;
+    case SHV_BT36F:   shell_launch_tab_k(bt_forces_kernel<36, true, 1, true>, P, nblk, bytes, st); break;
+    case SHV_BT36:    shell_launch_tab_k(bt_forces_kernel<36, true, 0, true>, P, nblk, bytes, st); break;
+    default:          shell_launch_tab_k(bt_forces_kernel<2, true, 0, true>, P, nblk, bytes, st); break;
   }
 }

@@ -308,7 +308,7 @@ def shell_plate(nx: int, ny: int, lx: float = 1000.0, ly: float = 1000.0, *, thi
 def tri_plate(nx: int, ny: int, lx: float = 1000.0, ly: float = 1000.0, *, thick: float = 2.0, law: int = 36, mat=None,
               prop: PropShell = None, quads: str = "none", jitter: float = 0.05, zjitter: float = 0.05, seed: int = 2024,
               pressure: float = 1.0, clamp: bool = True, vrand: float = 0.0, vseed: int = 12345, user_id_perm: bool = False,
-              curves=None, rates=None, quad_prop: PropShell = None) -> Model:
+              curves=None, rates=None, quad_prop: PropShell = None, vwave=None) -> Model:
     """Plate of 3-node shells (C3FORC3, Ish3n = prop.ihbe in {1, 2}): every cell of an nx*ny grid split into two triangles;
     quads="checker" keeps every other cell as a 4-node shell (quad_prop, default QEPH) so that both families share nodes.
     Nodal masses / inertias of the triangles as the Starter distributes them (c3inmas.F:598, 1113, 1126-1140: by the
@@ -378,6 +378,11 @@ def tri_plate(nx: int, ny: int, lx: float = 1000.0, ly: float = 1000.0, *, thick
     if vrand:
         g = np.random.Generator(np.random.PCG64(vseed))
         V += g.uniform(-vrand, vrand, V.shape); VR += g.uniform(-vrand, vrand, VR.shape) / h
+    if vwave is not None:                                   # the smooth yielding field of shell_plate
+        A, lam = vwave
+        kx = 2.0 * np.pi / lam
+        V[:, 0] += A * np.sin(kx * X[:, 0]); V[:, 1] += A * np.sin(kx * X[:, 1])
+        V[:, 2] += 0.5 * A * np.sin(kx * X[:, 0]) * np.sin(kx * X[:, 1])
     icodt = icodr = None
     if clamp:
         icodt = np.zeros(numnod, np.int32); icodr = np.zeros(numnod, np.int32)
