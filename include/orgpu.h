@@ -77,6 +77,12 @@ int  orgpu_add_shell_group(orgpu_engine* e, int nel, int nft, int law, const voi
 /* one 3-node shell group: elements [nft, nft+nel) of IXTG; prop->ihbe carries Ish3n = IPARG(23) (1 or 2) */
 int  orgpu_add_sh3n_group(orgpu_engine* e, int nel, int nft, int law, const void* mat,
                           const orgpu_prop_shell* prop);
+/* /FAIL/JOHNSON for one shell group (sh3n = 0: the index orgpu_add_shell_group returned, 1: orgpu_add_sh3n_group): damage
+ * DFMAX += DPLA / eps_f per integration point after the law (mulawc.F90:2118-2127 -> fail_johnson_c.F), a failed point keeps
+ * contributing this cycle's stress but restarts from zero stress every cycle (:2608-2637), the element is deleted when the
+ * broken share of its thickness / of its points reaches P_thickfail (fail_setoff_c.F:123-186).  Two more words per point
+ * (damage, point flag): shell state fields 14 dfmax(npt), 15 foff(npt).  Before orgpu_finalize. */
+int  orgpu_set_shell_group_fail(orgpu_engine* e, int sh3n, int group, const orgpu_fail* f);
 /* FORINTC_PREPARE_GPU analogue: fuse consecutive compatible groups into super-groups, re-lay
  * ELBUF out as device SoA, upload tables.  Must be called once before stepping. */
 int  orgpu_finalize(orgpu_engine* e);

@@ -114,6 +114,19 @@ typedef struct orgpu_prop_shell {
 } orgpu_prop_shell;
 
 /* Engine-wide scalars (COMMON blocks / engine deck) the path reads */
+/* /FAIL/JOHNSON on shells: FAIL_JOHNSON_C (engine/source/materials/fail/johnson_cook/fail_johnson_c.F:111-130, called from
+ * mulawc.F90:2118-2127 after the law, per integration point) and the element deletion rule of FAIL_SETOFF_C for one layer
+ * (fail/fail_setoff_c.F:123-186).  IXFEM = 0, local (no /NONLOCAL), D5 = 0 (no temperature term). */
+typedef struct orgpu_fail {
+  int irupt;            /* 0: none, 1: /FAIL/JOHNSON (mat_param%fail(ifl)%irupt)                              */
+  int pad;
+  double d1, d2, d3, d4, d5;   /* UPARAM(1:5): eps_f = (D1 + D2 exp(D3 sigma*)) (1 + D4 ln(max(1, epsp / EPSP0)))   */
+  double epsp0;         /* UPARAM(6)  reference strain rate                                                       */
+  double epsf_min;      /* UPARAM(12) lower bound of the failure strain                                           */
+  double pthk;          /* fail%pthk: > 0 broken fraction of the thickness, < 0 ratio of broken points, 0: the property's */
+  double pthickg;       /* GEO(42,PID): P_thickfail of the property                                               */
+} orgpu_fail;
+
 typedef struct orgpu_control {
   double dtfac_brick;   /* DTFAC1(1)  /DT/BRICK scale                 */
   double dtfac_shell;   /* DTFAC1(3)  /DT/SHELL scale                 */

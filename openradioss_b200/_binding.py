@@ -24,7 +24,7 @@ class Binding:
                         vol=(6, 1), off=(7, 1), temp=(8, 1), smstr=(9, 21), stra=(10, 6), wpla=(11, 1), sigb=(12, 6))
     SHELL_FIELDS = dict(forc=(0, 5), mom=(1, 3), eint=(2, 2), thk=(3, 1), off=(4, 1), stra=(5, 8),
                         epsd=(6, 1), hourg=(7, 12), smstr=(8, 6), sig=(9, 5), pla=(10, 1),
-                        epsd_ip=(11, 1), temp=(12, 1), sigb=(13, 3))
+                        epsd_ip=(11, 1), temp=(12, 1), sigb=(13, 3), dfmax=(14, 1), foff=(15, 1))
 
     def __init__(self, lib: C.CDLL, prefix: str, returns_status: bool):
         self.lib, self.p, self.status = lib, prefix, returns_status
@@ -79,9 +79,13 @@ class Binding:
         for g in m.shell_groups:
             r = self._call_group("add_shell_group", self.h, C.c_int(g.nel), C.c_int(g.nft), C.c_int(g.law),
                                  C.byref(g.mat), C.byref(g.prop))
+            if getattr(g, "fail", None) is not None:
+                self._call_group("set_shell_group_fail", self.h, C.c_int(0), C.c_int(r), C.byref(g.fail))
         for g in m.sh3n_groups:
-            self._call_group("add_sh3n_group", self.h, C.c_int(g.nel), C.c_int(g.nft), C.c_int(g.law),
-                             C.byref(g.mat), C.byref(g.prop))
+            r = self._call_group("add_sh3n_group", self.h, C.c_int(g.nel), C.c_int(g.nft), C.c_int(g.law),
+                                 C.byref(g.mat), C.byref(g.prop))
+            if getattr(g, "fail", None) is not None:
+                self._call_group("set_shell_group_fail", self.h, C.c_int(1), C.c_int(r), C.byref(g.fail))
         for g in m.solid_groups:
             v0 = np.ascontiguousarray(m.vol0[g.nft:g.nft + g.nel])
             if getattr(g, "law", 2) == 2:
@@ -194,7 +198,7 @@ class Binding:
     def shell_state(self, name):
         fid, nc = self.SHELL_FIELDS[name]
         npt = 1
-        if name in ("sig", "pla", "epsd_ip", "temp", "sigb"):
+        if name in ("sig", "pla", "epsd_ip", "temp", "sigb", "dfmax", "foff"):
             npt = max(g.prop.npt for g in self.model.shell_groups)
         if name == "hourg" and not all(21 <= g.prop.ihbe <= 29 for g in self.model.shell_groups):
             nc = 12 if any(21 <= g.prop.ihbe <= 29 for g in self.model.shell_groups) else 5
@@ -206,7 +210,7 @@ class Binding:
         """State of the 3-node shells, same field names as shell_state (no hourglass words; smstr has 3 components)."""
         fid, nc = self.SHELL_FIELDS[name]
         npt = 1
-        if name in ("sig", "pla", "epsd_ip", "temp", "sigb"):
+        if name in ("sig", "pla", "epsd_ip", "temp", "sigb", "dfmax", "foff"):
             npt = max(g.prop.npt for g in self.model.sh3n_groups)
         if name == "smstr":
             nc = 3

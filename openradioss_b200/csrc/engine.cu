@@ -434,6 +434,18 @@ int orgpu_add_sh3n_group(orgpu_engine* e, int nel, int nft, int law, const void*
 
 // ---- FORINTC_PREPARE_GPU analogue -----------------------------------------------------------
 
+int orgpu_set_shell_group_fail(orgpu_engine* e, int sh3n, int group, const orgpu_fail* f)
+{
+  NEED(e && f && !e->finalized, -1, "orgpu_set_shell_group_fail: bad arguments / already finalized");
+  std::vector<HostShellGroup>& gs = sh3n ? e->tgroups : e->cgroups;
+  NEED(group >= 0 && group < (int)gs.size(), -4, "orgpu_set_shell_group_fail: group %d does not exist", group);
+  NEED(f->irupt == 0 || f->irupt == 1, -5, "failure model %d is outside the built path (1: /FAIL/JOHNSON)", f->irupt);
+  NEED(f->irupt == 0 || f->d5 == 0.0, -5, "/FAIL/JOHNSON with D5 (temperature term) is outside the built path");
+  NEED(f->irupt == 0 || f->d4 == 0.0 || f->epsp0 > 0.0, -4, "/FAIL/JOHNSON: D4 needs a positive reference strain rate");
+  gs[group].fail = *f; gs[group].fail.pad = 0;
+  return 0;
+}
+
 int orgpu_finalize(orgpu_engine* e)
 {
   NEED(e && !e->finalized, -1, "orgpu_finalize: bad handle / already finalized");

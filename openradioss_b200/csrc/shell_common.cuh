@@ -38,6 +38,9 @@ struct ShellSG {
   double* bal; int bal_ld;    // print cycles: the elements' PARTSAV(1:6) terms, bal[k * bal_ld + e] (null until orgpu_set_print)
   const double* gvol;         // GBUF%VOL of the group's elements (initial area x thickness): the mass of CBILAN
   const unsigned char* xs_ftile;    // several domains: 1 for the tiles that hold an element with a corner row to send (null: one domain)
+  orgpu_fail fail;            // /FAIL/JOHNSON (irupt = 1) or none
+  int iw_dfmax, iw_foff;      // damage / point flag inside a point's words (-1: no failure model)
+  double fail_pthkf;          // P_thickfail as fail_setoff_c.F:139-151 resolves it (card value against the property's)
 };
 
 enum { SW_FOR = 0, SW_MOM = 5, SW_EINT = 8, SW_THK = 10, SW_OFF = 11, SW_STRA = 12, SW_EPSD = 20, SW_HOURG = 21 };
@@ -566,6 +569,7 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const Tile
     if (STAGED) s = ip_load<LAW, STAGED, FAST>(g, T, ipt);        // shared memory: no latency to hide
     else { s = nxt; if (ipt + 1 < npt) nxt = ip_load<LAW, STAGED, FAST>(g, T, ipt + 1); }   // software pipeline: next point's state in flight
     const int ipos_old = s.ipos; const double temp_old = s.temp;
+    const double pla_old = s.pla;
     const double thkly = c_WF[qrow + ipt];
     const double posly = c_Z0[qrow + ipt] + K_ZERO;
     const double wmc = c_WM[qrow + ipt];
@@ -583,6 +587,28 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const Tile
               off, off_old, ioff_duct, epchk, s, thkn, etse, sigy);
     }
     viscmx = fmax(DM, viscmx);
+    if (FAST != 1 && g.fail.irupt == 1) {
+      // /FAIL/JOHNSON after the law (mulawc.F90:2064-2069 DPLA = PLA - PLA0, EPSD = LBUF%EPSD; :2118-2127 -> fail_johnson_c.F:111-130;
+      // :2608-2616, 2633-2637: the stress kept in LBUF is scaled by SIGOFF, the sums below take this cycle's stress)
+      const int w = g.w_ip0 + ipt * g.nwip;
+      double dfmax = T.ld(w + g.iw_dfmax), foff = T.ld(w + g.iw_foff);
+      const double dpla = s.pla - pla_old;
+      if (off == K_ONE && foff == K_ONE && dpla > K_ZERO) {
+        const double PR = K_THIRD * (s.sxx + s.syy);
+        const double SVM = or_sqrt(s.sxx * s.sxx + s.syy * s.syy - s.sxx * s.syy + K_THREE * s.sxy * s.sxy);
+        double EPSF = or_div(g.fail.d3 * PR, fmax(K_EM20, SVM));
+        EPSF = (g.fail.d1 + g.fail.d2 * exp(EPSF));
+        if (g.fail.d4 != K_ZERO) EPSF = EPSF * (K_ONE + g.fail.d4 * log(fmax(K_ONE, or_div(s.epsd, g.fail.epsp0))));
+        EPSF = fmax(EPSF, g.fail.epsf_min);
+        if (EPSF > K_ZERO) dfmax = dfmax + or_div(dpla, EPSF);
+        if (dfmax >= K_ONE) foff = K_ZERO;
+      }
+      dfmax = fmin(K_ONE, dfmax);
+      T.st(w + g.iw_dfmax, dfmax); T.st(w + g.iw_foff, foff);
+      if (foff == K_ZERO) { IpState z = s; z.sxx = s.sxx * K_ZERO; z.syy = s.syy * K_ZERO; z.sxy = s.sxy * K_ZERO; z.syz = s.syz * K_ZERO; z.szx = s.szx * K_ZERO;
+                            ip_store<LAW, STAGED, FAST>(g, T, ipt, z, ipos_old, temp_old); }
+      else ip_store<LAW, STAGED, FAST>(g, T, ipt, s, ipos_old, temp_old);
+    } else
     ip_store<LAW, STAGED, FAST>(g, T, ipt, s, ipos_old, temp_old);
     fo[0] = fo[0] + thkly * s.sxx; fo[1] = fo[1] + thkly * s.syy; fo[2] = fo[2] + thkly * s.sxy;
     fo[3] = fo[3] + thkly * s.syz; fo[4] = fo[4] + thkly * s.szx;
@@ -591,6 +617,14 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const Tile
       if (LAW != 2) zcfac1 = zcfac1 + etse * thkly; else zcfac1 = zcfac1 + or_div(etse, npt);
       zcfac2 = fmin(etse, zcfac2);
     }
+  }
+  if (FAST != 1 && g.fail.irupt == 1 && off == K_ONE) {
+    // FAIL_SETOFF_C, one layer (fail_setoff_c.F:155-186): broken share of the thickness / of the points against P_thickfail
+    double thfact = K_ZERO, npfail = K_ZERO;
+    for (int ipt = 0; ipt < npt; ipt++)
+      if (T.ld(g.w_ip0 + ipt * g.nwip + g.iw_foff) < K_ONE) { thfact = thfact + c_WF[qrow + ipt]; npfail = npfail + or_div(K_ONE, npt); }
+    const double pthkf = g.fail_pthkf;
+    if ((thfact >= pthkf && pthkf > K_ZERO) || (npfail >= fabs(pthkf) && pthkf < K_ZERO)) off = K_FOUR_OVER_5;
   }
   if ((off == K_FOUR_OVER_5 && ioff_duct == 0) || (off > K_ZERO && off_old < K_EM01)) off = K_ZERO;
   T.st(SW_THK, fmax(thkn, K_EM30));

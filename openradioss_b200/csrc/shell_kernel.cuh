@@ -13,7 +13,7 @@
 #include "bt_kernel.cuh"
 #include "c3_kernel.cuh"
 
-struct HostShellGroup { int nel, nft, law, sh3n; orgpu_prop_shell prop; orgpu_law2 m2; orgpu_law36 m36; int part; };
+struct HostShellGroup { int nel, nft, law, sh3n; orgpu_prop_shell prop; orgpu_law2 m2; orgpu_law36 m36; int part; orgpu_fail fail; };
 struct ShellSGHost { ShellSG d; int first_elem = 0; bool sh3n = false; int part = 0; std::vector<void*> owned; };
 
 static inline bool shell_is_qeph(const orgpu_prop_shell& p) { return p.ihbe >= 21 && p.ihbe <= 29; }
@@ -75,7 +75,7 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
     while (gj < groups.size() && groups[gj].nft == groups[gj - 1].nft + groups[gj - 1].nel && groups[gj].law == groups[gi].law &&
            !memcmp(&groups[gj].prop, &groups[gi].prop, sizeof(orgpu_prop_shell)) &&
            !memcmp(&groups[gj].m2, &groups[gi].m2, sizeof(orgpu_law2)) && !memcmp(&groups[gj].m36, &groups[gi].m36, sizeof(orgpu_law36)) &&
-           groups[gj].part == groups[gi].part) gj++;
+           !memcmp(&groups[gj].fail, &groups[gi].fail, sizeof(orgpu_fail)) && groups[gj].part == groups[gi].part) gj++;
     int ne = 0; for (size_t k = gi; k < gj; k++) ne += groups[k].nel;
     const HostShellGroup& G = groups[gi];
     const int nft = G.nft;
@@ -105,6 +105,15 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
     d.w_ip0 = SW_HOURG + d.nhourg; d.nwip = has_temp ? 8 : 7;
     d.iw_sigb = -1;
     if ((G.law == 36 && G.m36.fisokin > 0.0) || (G.law == 2 && G.m2.fisokin > 0.0)) { d.iw_sigb = d.nwip; d.nwip += 3; }      // LBUF%SIGB: back stress of the kinematic hardening
+    d.fail = G.fail; d.iw_dfmax = d.iw_foff = -1; d.fail_pthkf = 0.0;
+    if (G.fail.irupt == 1) {                                    // /FAIL/JOHNSON: damage and point flag of every integration point
+      d.iw_dfmax = d.nwip++; d.iw_foff = d.nwip++;
+      double p = G.fail.pthk; const double pg = G.fail.pthickg;  // fail_setoff_c.F:139-151
+      if (p > 0.0)      { p = std::min(p, std::fabs(pg)); p = std::max(std::min(p, 1.0 - 1e-6), 1e-6); }
+      else if (p < 0.0) { p = std::max(p, -std::fabs(pg)); p = std::min(std::max(p, -1.0 + 1e-6), -1e-6); }
+      else p = pg;
+      d.fail_pthkf = p;
+    }
     d.w_vt = d.w_ip0 + d.npt * d.nwip;
     d.nvt = (G.law == 36) ? (G.m36.nrate == 1 ? 1 : d.nvartmp) : 0;
     d.nw_rw = d.w_vt + (d.npt * d.nvt + 1) / 2;
@@ -118,6 +127,7 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
     for (int i = 0; i < np; i++) {
       H.at(SW_THK, i) = G.prop.thick; if (d.w_thke >= 0) H.at(d.w_thke, i) = G.prop.thick;
       if (has_temp) for (int ip = 0; ip < d.npt; ip++) H.at(d.w_ip0 + ip * d.nwip + IW_TEMP, i) = G.m2.tini;
+      if (d.iw_foff >= 0) for (int ip = 0; ip < d.npt; ip++) H.at(d.w_ip0 + ip * d.nwip + d.iw_foff, i) = 1.0;      // FOFF = 1: point alive
     }
     for (int i = 0; i < ne; i++) {
       const int* ix = &ixc[(size_t)ixs_ * (nft + i)];
@@ -161,7 +171,7 @@ static void shell_launch_one(K kern_staged, K kern_direct, const ShellParams& P,
 // the kernel parameters (ORGPU_NO_FAST=1: generic path)
 static inline bool shell_fast(const ShellSG& d) {
   static const bool off = getenv("ORGPU_NO_FAST") != nullptr;
-  return !off && d.law == 36 && d.prop.ipla == 1 && d.m36.ifail == 0 && d.m36.nrate == 1 && d.ct.n > 0 && d.m36.fisokin == 0.0
+  return !off && d.law == 36 && d.prop.ipla == 1 && d.m36.ifail == 0 && d.m36.nrate == 1 && d.ct.n > 0 && d.m36.fisokin == 0.0 && d.fail.irupt == 0
          && d.prop.npt <= 5 && (size_t)d.nw * ORGPU_TILE * 8 <= ORGPU_STAGE_MAX_BYTES;     // the three-pass loop: staged tile, NPT <= 5 (shell_common.cuh)
 }
 
@@ -204,6 +214,7 @@ static int shell_state_xfer(std::vector<ShellSGHost>& sgs, int numelc, int field
       case 9: ipw = IW_SIG; nc = 5 * d.npt; break; case 10: ipw = IW_PLA; nc = d.npt; break; case 11: ipw = IW_EPSD; nc = d.npt; break;
       case 12: if (d.law != 2 || !d.m2.has_temp) continue; ipw = IW_TEMP; nc = d.npt; break;
       case 13: if (d.iw_sigb < 0) continue; nc = 3 * d.npt; break;
+      case 14: if (d.iw_dfmax < 0) continue; ipw = d.iw_dfmax; nc = d.npt; break; case 15: if (d.iw_foff < 0) continue; ipw = d.iw_foff; nc = d.npt; break;
       default: orgpu_set_error("unknown shell field %d", field); return -1;
     }
     for (int k = 0; k < nc; k++) {

@@ -72,7 +72,7 @@ def _regroup(groups, gid_of_local, cls):
             if cls is SolidGroup:
                 out.append(SolidGroup(nft=start, nel=i - start, mat=g.mat, prop=g.prop, law=getattr(g, "law", 2)))
             else:
-                out.append(ShellGroup(nft=start, nel=i - start, law=g.law, mat=g.mat, prop=g.prop))
+                out.append(ShellGroup(nft=start, nel=i - start, law=g.law, mat=g.mat, prop=g.prop, fail=getattr(g, "fail", None)))
             start = i
     return out
 

@@ -18,7 +18,7 @@ set_functions add_solid_group add_solid_group_law add_shell_group set_sh3n add_s
 synchronize get_time download_nodes download_fsky download_solid_state download_shell_state
 step_host launch_count last_run_ms set_profile get_profile pack_rows unpack_rows comm_unique_id comm_init
 set_exchange exchange get_energies p2p_export p2p_connect set_load_function set_fixvel set_gravity upload_solid_state upload_shell_state set_time set_itab
-set_parts set_print get_balance get_balance_history set_quadrature set_global_order set_exchange_timeout pack_nodes add_nodes set_exchange_nodes step_host_rot forces_host""".split()
+set_parts set_print get_balance get_balance_history set_quadrature set_global_order set_exchange_timeout pack_nodes add_nodes set_exchange_nodes step_host_rot forces_host set_shell_group_fail""".split()
 
 
 def load_library() -> C.CDLL:
@@ -119,12 +119,16 @@ class Engine(Binding):
                 ck["shell"]["temp"] = self.shell_state("temp")          # per-point temperature of thermal Johnson-Cook shells
             if any(getattr(g.mat, "fisokin", 0.0) > 0.0 for g in self.model.shell_groups):
                 ck["shell"]["sigb"] = self.shell_state("sigb")          # back stress of the kinematic hardening
+            if any(getattr(g, "fail", None) is not None for g in self.model.shell_groups):
+                ck["shell"].update(dfmax=self.shell_state("dfmax"), foff=self.shell_state("foff"))     # /FAIL/JOHNSON damage and point flags
         if self.model.numeltg:
             ck["sh3n"] = {f: self.sh3n_state(f) for f in ("forc", "mom", "eint", "thk", "off", "stra", "epsd", "smstr", "sig", "pla", "epsd_ip")}
             if therm(self.model.sh3n_groups):
                 ck["sh3n"]["temp"] = self.sh3n_state("temp")
             if any(getattr(g.mat, "fisokin", 0.0) > 0.0 for g in self.model.sh3n_groups):
                 ck["sh3n"]["sigb"] = self.sh3n_state("sigb")
+            if any(getattr(g, "fail", None) is not None for g in self.model.sh3n_groups):
+                ck["sh3n"].update(dfmax=self.sh3n_state("dfmax"), foff=self.sh3n_state("foff"))
         if self.model.numels and any(getattr(g, "law", 2) == 2 and getattr(g.mat, "fisokin", 0.0) > 0.0 for g in self.model.solid_groups):
             ck["solid"]["sigb"] = self.solid_state("sigb")             # back stress of the kinematic hardening (LBUF%SIGB)
         if self.model.numels and any(getattr(g, "law", 2) == 36 for g in self.model.solid_groups):

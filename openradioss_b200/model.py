@@ -39,6 +39,11 @@ class PropShell(C.Structure):
                [(n, i) for n in "npt ismstr ithk ipla ihbe istrain".split()]
 
 
+class Fail(C.Structure):
+    """orgpu_fail: /FAIL/JOHNSON of a shell group's material (irupt = 1) + P_thickfail (fail%pthk, GEO(42))."""
+    _fields_ = [("irupt", i), ("pad", i)] + [(n, d) for n in "d1 d2 d3 d4 d5 epsp0 epsf_min pthk pthickg".split()]
+
+
 class Control(C.Structure):
     _fields_ = [(n, d) for n in "dtfac_brick dtfac_shell dtmx dt_init dt2old_init tt_init".split()] + \
                [("iroddl", i), ("nodadt", i), ("dtfac_node", d), ("dtfac_sh3n", d)]
@@ -71,6 +76,7 @@ class ShellGroup:
     mat: object              # Law2 | Law36
     prop: PropShell
     part: int = 0            # 0-based part of the group's elements
+    fail: Optional[Fail] = None   # /FAIL/JOHNSON of the group's material
 
 
 @dataclass

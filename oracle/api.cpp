@@ -145,6 +145,17 @@ int orc_add_sh3n_group(void* h,int nel,int nft,int law,const void* mat,const org
   return (int)o->tgroups.size()-1;
 }
 
+/* /FAIL/JOHNSON for one shell group (mirror of orgpu_set_shell_group_fail) */
+int orc_set_shell_group_fail(void* h,int sh3n,int group,const orgpu_fail* f)
+{
+  Oracle* o=(Oracle*)h;
+  auto& gs = sh3n? o->tgroups : o->cgroups;
+  if(group<0 || group>=(int)gs.size()) return -1;
+  if(f->irupt!=0 && (f->irupt!=1 || f->d5!=0.0)) return -2;
+  gs[group]->fail=*f;
+  return 0;
+}
+
 void orc_finalize(void*){}
 
 /* phases (same split as the device library) */

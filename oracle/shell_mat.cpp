@@ -471,6 +471,7 @@ void orc_cmain3(const Oracle& o, OrcShellGroup& g, int i, bool flag_zcfac, Shell
     const double posly=orc_quad_tab(0)[(npt-1)*11+(ipt-1)]+K_ZERO;   /* Z0, layini.F:251 (ZSHIFT=0) */
     const double wmc=orc_quad_tab(2)[(npt-1)*11+(ipt-1)];            /* WM, mulawc.F90:771-773 */
     IpIO s;
+    const double pla0=lb.pla[i];                                   /* mulawc.F90: PLA0 kept for the failure models */
     s.thklyl=thkly*in.thk0;
     const double zt=posly*in.thk0;
     s.depsxx=in.exx+zt*in.kxx;
@@ -491,8 +492,26 @@ void orc_cmain3(const Oracle& o, OrcShellGroup& g, int i, bool flag_zcfac, Shell
       lb.sigb[i]=sb[0]; lb.sigb[nel+i]=sb[1]; lb.sigb[2*nel+i]=sb[2];
     }
     viscmx=std::max(DM,viscmx);
-    lb.sig[i]=s.signxx*K_ONE; lb.sig[nel+i]=s.signyy*K_ONE; lb.sig[2*nel+i]=s.signxy*K_ONE;
-    lb.sig[3*nel+i]=s.signyz*K_ONE; lb.sig[4*nel+i]=s.signzx*K_ONE;
+    double sigoff=K_ONE;                                           /* mulawc.F90:2037 */
+    if(g.fail.irupt==1){
+      /* mulawc.F90:2064-2069: DPLA = LBUF%PLA - PLA0, EPSD = LBUF%EPSD; :2118-2127 FAIL_JOHNSON_C (fail_johnson_c.F:111-130) */
+      const double DPLA=lb.pla[i]-pla0, EPSP=lb.epsd[i];
+      const orgpu_fail& f=g.fail;
+      if(off==K_ONE && lb.foff[i]==K_ONE && DPLA>K_ZERO){
+        const double P=K_THIRD*(s.signxx+s.signyy);
+        const double SVM=std::sqrt(s.signxx*s.signxx+s.signyy*s.signyy-s.signxx*s.signyy+K_THREE*s.signxy*s.signxy);
+        double EPSF=f.d3*P/std::max(K_EM20,SVM);
+        EPSF=(f.d1+f.d2*std::exp(EPSF));
+        if(f.d4!=K_ZERO) EPSF=EPSF*(K_ONE+f.d4*std::log(std::max(K_ONE,EPSP/f.epsp0)));
+        EPSF=std::max(EPSF,f.epsf_min);
+        if(EPSF>K_ZERO) lb.dfmax[i]=lb.dfmax[i]+DPLA/EPSF;
+        if(lb.dfmax[i]>=K_ONE) lb.foff[i]=K_ZERO;
+      }
+      lb.dfmax[i]=std::min(K_ONE,lb.dfmax[i]);                     /* :143-145 */
+      if(lb.foff[i]==K_ZERO){ lb.off[i]=K_ZERO; sigoff=K_ZERO; }   /* mulawc.F90:2608-2616 */
+    }
+    lb.sig[i]=s.signxx*sigoff; lb.sig[nel+i]=s.signyy*sigoff; lb.sig[2*nel+i]=s.signxy*sigoff;   /* :2633-2637 */
+    lb.sig[3*nel+i]=s.signyz*sigoff; lb.sig[4*nel+i]=s.signzx*sigoff;
     F_(1)=F_(1)+thkly*s.signxx; F_(2)=F_(2)+thkly*s.signyy; F_(3)=F_(3)+thkly*s.signxy;
     F_(4)=F_(4)+thkly*s.signyz; F_(5)=F_(5)+thkly*s.signzx;
     M_(1)=M_(1)+wmc*s.signxx; M_(2)=M_(2)+wmc*s.signyy; M_(3)=M_(3)+wmc*s.signxy;
@@ -502,6 +521,25 @@ void orc_cmain3(const Oracle& o, OrcShellGroup& g, int i, bool flag_zcfac, Shell
       if(flag_zcfac){ zcfac1=zcfac1+etse/npt; zcfac2=std::min(etse,zcfac2); }
     }
     ssp_eq=ssp_eq+ssp*thkly;
+  }
+  /* FAIL_SETOFF_C, NLAY = 1 (mulawc.F90:2912-2920 -> fail_setoff_c.F:123-186) */
+  if(g.fail.irupt==1){
+    double PTHKF=g.fail.pthk; const double P_THICKG=g.fail.pthickg;
+    if(PTHKF>K_ZERO){ PTHKF=std::min(PTHKF,std::fabs(P_THICKG)); PTHKF=std::max(std::min(PTHKF,K_ONE-K_EM06),K_EM06); }
+    else if(PTHKF<K_ZERO){ PTHKF=std::max(PTHKF,-std::fabs(P_THICKG)); PTHKF=std::min(std::max(PTHKF,-K_ONE+K_EM06),-K_EM06); }
+    else PTHKF=P_THICKG;
+    double THFACT=K_ZERO, NPFAIL=K_ZERO;
+    for(int ipt=1;ipt<=npt;ipt++){
+      if(off==K_ONE){
+        if(g.ip[ipt-1].foff[i]<K_ONE){
+          THFACT=THFACT+orc_quad_tab(1)[(npt-1)*11+(ipt-1)];
+          NPFAIL=NPFAIL+K_ONE/npt;
+        }
+      }
+    }
+    if(off==K_ONE){
+      if(((THFACT>=PTHKF)&&(PTHKF>K_ZERO)) || ((NPFAIL>=std::fabs(PTHKF))&&(PTHKF<K_ZERO))) off=K_FOUR_OVER_5;
+    }
   }
   /* tail (mulawc.F90:2934-3091) */
   if((off==K_FOUR_OVER_5 && ioff_duct==0) || (off>K_ZERO && off_old<K_EM01)) off=K_ZERO;
