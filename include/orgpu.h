@@ -77,6 +77,12 @@ int  orgpu_add_shell_group(orgpu_engine* e, int nel, int nft, int law, const voi
 /* one 3-node shell group: elements [nft, nft+nel) of IXTG; prop->ihbe carries Ish3n = IPARG(23) (1 or 2) */
 int  orgpu_add_sh3n_group(orgpu_engine* e, int nel, int nft, int law, const void* mat,
                           const orgpu_prop_shell* prop);
+/* Concentrated loads record by record, as the Engine holds them (FORCE, engine/source/loads/general/force.F90:188-312; IB / FAC of
+ * /CLOAD): record l loads node ib[3l] (1-based) in direction ib[3l+1] (1..3 forces, 4..6 moments, global frame) with
+ * FCY * f(TT * FCX), f = time function ib[3l+2] (0-based index into orgpu_set_functions, -1: constant), FCY = fac[2l], FCX = fac[2l+1].
+ * Any number of functions; records of one node are added in record order.  Instead of orgpu_set_loads / orgpu_set_load_function
+ * (one curve for all loads).  Sensors, skew frames and displacement- / velocity-dependent abscissae are outside the built path. */
+int  orgpu_set_cloads(orgpu_engine* e, int nload, const int* ib /*(3,nload)*/, const double* fac /*(2,nload)*/);
 /* /FAIL/JOHNSON for one shell group (sh3n = 0: the index orgpu_add_shell_group returned, 1: orgpu_add_sh3n_group): damage
  * DFMAX += DPLA / eps_f per integration point after the law (mulawc.F90:2118-2127 -> fail_johnson_c.F), a failed point keeps
  * contributing this cycle's stress but restarts from zero stress every cycle (:2608-2637), the element is deleted when the

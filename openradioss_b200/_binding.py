@@ -70,6 +70,8 @@ class Binding:
             self._call("set_functions", self.h, C.c_int(len(m.npf) - 1), _opt(m.npf, np.int32), _opt(m.tf, np.float64))
         if m.itab is not None:
             self._call("set_itab", self.h, _opt(m.itab, np.int32))
+        if m.cload_ib is not None and len(m.cload_ib):
+            self._call("set_cloads", self.h, C.c_int(len(m.cload_ib)), _opt(m.cload_ib, np.int32), _opt(m.cload_fac, np.float64))
         if m.load_func is not None:
             self._call("set_load_function", self.h, C.c_int(int(m.load_func[0])), C.c_double(float(m.load_func[1])))
         if m.ibfv is not None and len(m.ibfv):

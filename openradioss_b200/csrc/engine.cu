@@ -59,6 +59,9 @@ struct orgpu_engine {
   std::vector<HostShellGroup> tgroups;
   std::vector<int> npf; std::vector<double> tf;
   int lf_func = -1; double lf_fcx = 1.0;            // time function of the nodal loads
+  // concentrated loads record by record (force.F90:188-312: every record its node, direction, time function, FCY, FCX)
+  std::vector<int> cl_ib; std::vector<double> cl_fac; int n_cl_nodes = 0;
+  int *d_cl_ptr = nullptr, *d_cl_nodes = nullptr; int2* d_cl_rec = nullptr; double2* d_cl_fac = nullptr;
   int ngrav = 0; int gdir[ORGPU_MAXGRAV] = {}, gfunc[ORGPU_MAXGRAV] = {}; double gfcy[ORGPU_MAXGRAV] = {}, gfcx[ORGPU_MAXGRAV] = {};   // /GRAV loads
   std::vector<unsigned char> gmask; unsigned char* d_gmask = nullptr;
   std::vector<int> fv_idx; std::vector<FixVelNode> fv;   // imposed velocities, per node
@@ -205,6 +208,7 @@ int orgpu_destroy(orgpu_engine* e)
     if (x.comm && nccl_api()) nccl_api()->CommDestroy(x.comm); }
   for (auto& b : e->batches) { if (b.d_tab) cudaFree(b.d_tab); if (b.d_map) cudaFree(b.d_map); }
   pipe_free(e);
+  { void* pp[] = {e->d_cl_ptr, e->d_cl_nodes, e->d_cl_rec, e->d_cl_fac}; for (void* p : pp) if (p) cudaFree(p); }
   for (auto ev : e->evpool) cudaEventDestroy(ev);
   if (e->ev0) cudaEventDestroy(e->ev0); if (e->ev1) cudaEventDestroy(e->ev1);
   for (int k = 0; k < ORGPU_NSIDE; k++) { if (e->side[k]) cudaStreamDestroy(e->side[k]); if (e->ev_join[k]) cudaEventDestroy(e->ev_join[k]); }
@@ -341,6 +345,39 @@ int orgpu_set_load_function(orgpu_engine* e, int ifunc, double fcx)
   NEED(e && !e->finalized, -1, "orgpu_set_load_function: bad handle / already finalized");
   NEED(ifunc >= -1, -1, "orgpu_set_load_function: bad function index %d", ifunc);
   e->lf_func = ifunc; e->lf_fcx = fcx;
+  return 0;
+}
+
+// FORCE, concentrated loads with a time-dependent abscissa (force.F90:223-245, 301-312): AA = FCY * FINTER(N3, TT * FCX), added to
+// A(N2, N1) / AR(N2 - 3, N1) record after record.  One thread per loaded node sums its records in record order (from zero:
+// 0 + AA is AA) into the FEXT / MEXT arrays the node kernels start their fold from; runs once per cycle after the dt fold
+// (TT of the cycle is cs->tt0).
+__global__ void cload_eval_kernel(const CycleState* __restrict__ cs, const FuncTable ft, int nn, const int* __restrict__ ptr, const int* __restrict__ nodes,
+                                  const int2* __restrict__ rec, const double2* __restrict__ fac, double* __restrict__ fext, double* __restrict__ mext)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= nn || cs->abort) return;
+  const int n = nodes[i]; const double tt = cs->tt0;
+  double a[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int r = ptr[i]; r < ptr[i + 1]; r++) {
+    const int2 q = rec[r]; const double2 f = fac[r];
+    double v = f.x;
+    if (q.y >= 0) { const int i0 = ft.npf[q.y]; v = f.x * or_finter(ft.tf, i0, ft.npf[q.y + 1] - i0, tt * f.y); }
+    a[q.x] = a[q.x] + v;
+  }
+  fext[3 * n] = a[0]; fext[3 * n + 1] = a[1]; fext[3 * n + 2] = a[2];
+  if (mext) { mext[3 * n] = a[3]; mext[3 * n + 1] = a[4]; mext[3 * n + 2] = a[5]; }
+}
+
+int orgpu_set_cloads(orgpu_engine* e, int nload, const int* ib /*(3,nload): node (1-based), direction 1..6, function (0-based, -1: constant)*/,
+                     const double* fac /*(2,nload): FCY, FCX*/)
+{
+  NEED(e && !e->finalized && nload >= 0 && (nload == 0 || (ib && fac)), -1, "orgpu_set_cloads: bad arguments / already finalized");
+  for (int l = 0; l < nload; l++) {
+    NEED(ib[3 * l] >= 1 && ib[3 * l] <= e->numnod, -4, "orgpu_set_cloads: record %d: node %d out of range", l + 1, ib[3 * l]);
+    NEED(ib[3 * l + 1] >= 1 && ib[3 * l + 1] <= 6, -5, "orgpu_set_cloads: record %d: direction %d (skew frames are outside the built path)", l + 1, ib[3 * l + 1]);
+    NEED(ib[3 * l + 1] <= 3 || e->ctl.iroddl, -4, "orgpu_set_cloads: record %d loads a rotation of a model without rotational dofs", l + 1);
+  }
+  e->cl_ib.assign(ib, ib + (size_t)3 * nload); e->cl_fac.assign(fac, fac + (size_t)2 * nload);
   return 0;
 }
 
@@ -575,6 +612,9 @@ int orgpu_finalize(orgpu_engine* e)
   // time functions used at node level (loads, imposed velocities)
   e->fa.lf_func = -1; e->fa.lf_fcx = 1.0; e->fa.ft = FuncTable{nullptr, nullptr};
   bool gfun = false; for (int l = 0; l < e->ngrav; l++) gfun = gfun || e->gfunc[l] >= 0;
+  const int ncl = (int)e->cl_ib.size() / 3;
+  for (int l = 0; l < ncl; l++) gfun = gfun || e->cl_ib[3 * l + 2] >= 0;
+  NEED(!(ncl && (e->lf_func >= 0 || e->nd.FEXT || e->nd.MEXT)), -4, "concentrated loads come either as records (orgpu_set_cloads) or as nodal arrays (orgpu_set_loads / orgpu_set_load_function), not both");
   if (e->lf_func >= 0 || !e->fv.empty() || gfun) {
     NEED(!e->npf.empty(), -4, "a load / imposed-velocity time function needs orgpu_set_functions");
     const int nf = (int)e->npf.size() - 1;
@@ -587,12 +627,34 @@ int orgpu_finalize(orgpu_engine* e)
     CUDA_OK(cudaMemcpy(e->d_fnpf, e->npf.data(), 4 * e->npf.size(), cudaMemcpyHostToDevice));
     e->fa.ft = FuncTable{e->d_ftf, e->d_fnpf}; e->nd.ft = e->fa.ft;
     e->fa.lf_func = e->lf_func; e->fa.lf_fcx = e->lf_fcx;
+    for (int l = 0; l < ncl; l++) if (e->cl_ib[3 * l + 2] >= 0) NEED(check(e->cl_ib[3 * l + 2], 1 << 30), -4, "load function %d of record %d missing", e->cl_ib[3 * l + 2], l + 1);
     if (!e->fv.empty()) {
       if (dev_alloc(&e->d_fv_idx, e->fv_idx.size()) || dev_alloc(&e->d_fv, e->fv.size())) return -100;
       CUDA_OK(cudaMemcpy(e->d_fv_idx, e->fv_idx.data(), 4 * e->fv_idx.size(), cudaMemcpyHostToDevice));
       CUDA_OK(cudaMemcpy(e->d_fv, e->fv.data(), sizeof(FixVelNode) * e->fv.size(), cudaMemcpyHostToDevice));
       e->nd.fv_idx = e->d_fv_idx; e->nd.fv = e->d_fv;
     }
+  }
+  if (ncl) {
+    // records grouped by node, record order kept inside a node (the order of the additions)
+    std::vector<int> idx(ncl); for (int l = 0; l < ncl; l++) idx[l] = l;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return e->cl_ib[3 * a] < e->cl_ib[3 * b]; });
+    std::vector<int> ptr, nodes; std::vector<int2> rec(ncl); std::vector<double2> fac(ncl);
+    bool anyrot = false;
+    for (int k = 0; k < ncl; k++) {
+      const int l = idx[k], n = e->cl_ib[3 * l] - 1;
+      if (nodes.empty() || nodes.back() != n) { nodes.push_back(n); ptr.push_back(k); }
+      rec[k] = make_int2(e->cl_ib[3 * l + 1] - 1, e->cl_ib[3 * l + 2]); fac[k] = make_double2(e->cl_fac[2 * l], e->cl_fac[2 * l + 1]);
+      anyrot = anyrot || e->cl_ib[3 * l + 1] > 3;
+    }
+    ptr.push_back(ncl); e->n_cl_nodes = (int)nodes.size();
+    if (dev_alloc(&e->d_cl_ptr, ptr.size()) || dev_alloc(&e->d_cl_nodes, nodes.size()) || dev_alloc(&e->d_cl_rec, rec.size()) || dev_alloc(&e->d_cl_fac, fac.size())) return -100;
+    CUDA_OK(cudaMemcpy(e->d_cl_ptr, ptr.data(), 4 * ptr.size(), cudaMemcpyHostToDevice)); CUDA_OK(cudaMemcpy(e->d_cl_nodes, nodes.data(), 4 * nodes.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(e->d_cl_rec, rec.data(), sizeof(int2) * rec.size(), cudaMemcpyHostToDevice)); CUDA_OK(cudaMemcpy(e->d_cl_fac, fac.data(), sizeof(double2) * fac.size(), cudaMemcpyHostToDevice));
+    const size_t n = e->numnod;
+    if (!e->d_fext && dev_alloc(&e->d_fext, 3 * n)) return -100;          // dev_alloc zero-fills: nodes without a record stay unloaded
+    e->nd.FEXT = e->d_fext;
+    if (anyrot) { if (!e->d_mext && dev_alloc(&e->d_mext, 3 * n)) return -100; e->nd.MEXT = e->d_mext; }
   }
   e->db.nblocks_total = blk;
   if (dev_alloc(&e->db.dt, blk) || dev_alloc(&e->db.order, blk)) return -100;
@@ -682,6 +744,10 @@ static void launch_element_phase(orgpu_engine* e, int fused, size_t* evi)
   }
   for (int j = 0; j < nside; j++) { cudaEventRecord(e->ev_join[j], e->side[j]); cudaStreamWaitEvent(e->st, e->ev_join[j], 0); }
   element_finalize_kernel<<<1, ORGPU_FINALIZE_BLOCK, 0, e->st>>>(e->d_cs, e->db, e->fa); e->launches++;
+  if (e->n_cl_nodes) {            // concentrated loads of this cycle (TT = cs->tt0), before any node kernel reads FEXT / MEXT
+    cload_eval_kernel<<<(e->n_cl_nodes + 127) / 128, 128, 0, e->st>>>(e->d_cs, e->fa.ft, e->n_cl_nodes, e->d_cl_ptr, e->d_cl_nodes, e->d_cl_rec, e->d_cl_fac,
+                                                                    e->d_fext, e->nd.MEXT ? e->d_mext : nullptr); e->launches++;
+  }
 }
 
 // print cycle: fold the element / node scratch rows in a fixed order (three small launches)

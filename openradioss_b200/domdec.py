@@ -131,6 +131,10 @@ def decompose(m: Model, dom_s: Optional[np.ndarray], dom_c: Optional[np.ndarray]
     lm = Model(X=sub(m.X), V=sub(m.V), VR=sub(m.VR), MS=sub(m.MS), IN=sub(m.IN), control=m.control, ixs=ixs, ixc=ixc, ixtg=ixtg,
                vol0=m.vol0[solid_gid] if len(m.vol0) else m.vol0, icodt=sub(m.icodt), icodr=sub(m.icodr),
                fext=sub(m.fext), mext=sub(m.mext), itab=sub(m.itab), npf=m.npf, tf=m.tf, load_func=m.load_func)
+    if m.cload_ib is not None and len(m.cload_ib):               # load records follow their node into every domain that holds it (record order kept)
+        keep = mine[m.cload_ib[:, 0] - 1]
+        lm.cload_ib = m.cload_ib[keep].copy(); lm.cload_fac = m.cload_fac[keep].copy()
+        lm.cload_ib[:, 0] = (g2l[lm.cload_ib[:, 0] - 1] + 1).astype(np.int32)
     if m.igrv is not None and len(m.igrv):                       # gravity: every domain keeps the loads, with its own nodes of each list
         lm.igrv = m.igrv.copy(); lm.agrv = m.agrv.copy(); parts = []; iad = 0
         for l in range(len(m.igrv)):
@@ -194,6 +198,9 @@ def parith_off(d: Domain) -> Domain:
         a = getattr(m, name)
         if a is not None:
             a = a.copy(); a[~d.owner] = 0.0; setattr(m, name, a)
+    if m.cload_ib is not None and len(m.cload_ib):
+        keep = d.owner[m.cload_ib[:, 0] - 1]
+        m.cload_ib = m.cload_ib[keep].copy(); m.cload_fac = m.cload_fac[keep].copy()
     return d
 
 

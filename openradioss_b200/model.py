@@ -110,6 +110,8 @@ class Model:
     npf: Optional[np.ndarray] = None
     tf: Optional[np.ndarray] = None
     load_func: Optional[tuple] = None   # (curve index, FCX): time function shared by the nodal loads fext / mext
+    cload_ib: Optional[np.ndarray] = None    # concentrated loads record by record (n,3) int32: node (1-based), direction 1..6, curve (0-based, -1 constant)
+    cload_fac: Optional[np.ndarray] = None   # (n,2): FCY, FCX   (instead of fext / mext / load_func)
     ibfv: Optional[np.ndarray] = None   # imposed velocities (n,3) int32: node (1-based), direction 1..3, curve index
     vel: Optional[np.ndarray] = None    # (n,4): FAC, STARTT, STOPT, FACX
     igrv: Optional[np.ndarray] = None   # gravity loads (n,3) int32: node count, direction 1..3, curve index (-1: constant)   (gravit.F)

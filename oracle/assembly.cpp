@@ -204,6 +204,14 @@ void orc_forces(Oracle& o)
    * STIFN/STIFR restart from zero each cycle */
   const double fs=orc_load_scale(o);   /* force.F90:235, 301-312: AA = FCY*FINTER(IFUN,TT*FCX) */
   for(int i=0;i<3*n;i++){ o.A[i]= o.FEXT.empty()? K_ZERO : o.FEXT[i]*fs; o.AR[i]= o.MEXT.empty()? K_ZERO : o.MEXT[i]*fs; }
+  /* FORCE record by record (force.F90:188-312, IFUN = 1, no sensor, global frame): AA = FCY*FINTER(N3,TS*FCX); A(N2,N1) += AA */
+  for(size_t NL=0; NL<o.CL_IB.size()/3; NL++){
+    const int N1=o.CL_IB[3*NL]-1, N2=o.CL_IB[3*NL+1], N3=o.CL_IB[3*NL+2];
+    const double FCY=o.CL_FAC[2*NL], FCX=o.CL_FAC[2*NL+1];
+    const double AA = N3>=0 ? FCY*orc_finter(o,N3,o.TT*FCX) : FCY;
+    if(N2<=3) o.A[3*N1+N2-1]=o.A[3*N1+N2-1]+AA;
+    else      o.AR[3*N1+N2-4]=o.AR[3*N1+N2-4]+AA;
+  }
   /* with /DT/NODA the nodal stiffnesses restart from EM20 (dtnoda.F:336-338, rotational part alike) */
   const double st0 = o.ctl.nodadt!=0 ? K_EM20 : K_ZERO;
   for(int i=0;i<n;i++){ o.STIFN[i]=st0; o.STIFR[i]=st0; }

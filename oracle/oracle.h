@@ -56,6 +56,7 @@ struct Oracle {
   std::vector<int>    ICODT, ICODR;   /* BCS codes (bit 4=x,2=y,1=z fixed), bcs10.F */
   std::vector<int> ITAB;              /* user node ids (NELTST of a nodal time step) */
   int LF_FUNC=-1; double LF_FCX=1.0;  /* time function of the concentrated loads (force.F90:195-196, 235) */
+  std::vector<int> CL_IB; std::vector<double> CL_FAC;   /* ... or the load records themselves: (node, direction, function), (FCY, FCX) */
   std::vector<int> IBFV;              /* imposed velocities (3,n): node, direction, curve (fixvel.F) */
   std::vector<double> VEL;            /* (4,n): FAC, STARTT, STOPT, FACX */
   std::vector<double> FV_DW;          /* VEL(4,N) of the Engine: DT2*DW of the last cycle, booked into WFEXT at the next one */

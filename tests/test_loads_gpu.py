@@ -95,6 +95,35 @@ def test_long_time_function_on_the_device_is_bitwise_the_oracle():
     assert o.time()["tt"] * 3.0 > x[-1]                      # the run went past the end of the curve
 
 
+def test_load_records_match_oracle_and_follow_their_nodes():
+    """orgpu_set_cloads: /CLOAD records with several time functions (force.F90:188-312) -- phased 1e-12 and 200 cycles of the
+    device loop against the oracle; with one curve bitwise the nodal-array path; two domains bitwise the single domain."""
+    from test_oracle_loads import _plate_with_records
+    m, nodes, fz, ib, fac, _ = _plate_with_records(False)
+    m.fext = None; m.mext = None; m.load_func = None; m.cload_ib = ib; m.cload_fac = fac
+    phased(m, 6)
+    g, o = Engine(m), Oracle(m, threads=0)
+    g.run_cycles(200); g.synchronize(); o.run_cycles(200)
+    assert rel_err(g.download_nodes(("D",))["D"], o.download_nodes(("D",))["D"]) <= 1e-8
+    ma, _, _, ib1, fac1, _ = _plate_with_records(True)
+    mb, _, _, _, _, _ = _plate_with_records(True)
+    mb.fext = None; mb.mext = None; mb.load_func = None; mb.cload_ib = ib1; mb.cload_fac = fac1
+    a, b = Engine(ma), Engine(mb)
+    a.run_cycles(60); b.run_cycles(60); a.synchronize(); b.synchronize()
+    assert np.array_equal(a.download_nodes(("X",))["X"], b.download_nodes(("X",))["X"])
+    ref = Engine(m); ref.run_cycles(40); ref.synchronize()
+    doms = [domdec.decompose_strips(m, 2, r) for r in range(2)]
+    backs = [Engine(d.model) for d in doms]
+    spmd.run_local(backs, doms, 40)
+    xr = ref.download_nodes(("X",))["X"]
+    for bk, d in zip(backs, doms):
+        assert np.array_equal(bk.download_nodes(("X",))["X"], xr[d.node_gid])
+    mc, _, _, ib2, fac2, _ = _plate_with_records(True)
+    mc.cload_ib = ib2; mc.cload_fac = fac2                       # records AND nodal arrays: rejected
+    with pytest.raises(RuntimeError, match="not both"):
+        Engine(mc)
+
+
 def test_gravity_rejects_what_is_not_built():
     m = meshgen.hex_block(2, 2, 2, 2.0, 2.0, 2.0)
     meshgen.add_gravity(m, 3, -1.0)

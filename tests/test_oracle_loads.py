@@ -140,3 +140,54 @@ def test_long_time_function_takes_the_dichotomy_branch_of_finter():
         dv = o.download_nodes(("V",))["V"][0, 2] - v0
         assert dv == __import__("pytest").approx(t["dt12"] * 10.0 * f, rel=1e-7, abs=1e-12), (c, xx)      # rounding-level internal forces act too (see the free-fall test)
     assert seen_mid and seen_end
+
+
+def _plate_with_records(single_curve):
+    """6 x 6 plate; its pressure load rewritten as /CLOAD records (one per node and direction)."""
+    m = meshgen.shell_plate(6, 6, 60.0, 60.0, pulse_tau=0.05, vrand=0.0, jitter=0.0, zjitter=0.0)
+    fz = m.fext[:, 2].copy()
+    nodes = np.nonzero(fz)[0]
+    k0 = int(m.load_func[0])
+    k1 = meshgen.add_function(m, [0.0, 0.01, 0.2, 1.0], [0.0, 0.3, 1.0, 1.0])
+    ib, fac = [], []
+    for n in nodes:
+        ib.append((n + 1, 3, k0)); fac.append((fz[n], float(m.load_func[1])))
+    if not single_curve:                                   # a second record on every other node, another curve, a lateral direction too
+        for n in nodes[::2]:
+            ib.append((n + 1, 3, k1)); fac.append((0.5 * fz[n], 2.0))
+            ib.append((n + 1, 1, k1)); fac.append((0.25 * fz[n], 1.0))
+            ib.append((n + 1, 5, -1)); fac.append((1.0e-3 * fz[n], 1.0))          # a constant moment about y
+    return m, nodes, fz, np.array(ib, np.int32), np.array(fac, np.float64), (k0, k1)
+
+
+def test_load_records_with_one_curve_equal_the_nodal_array_path_bitwise():
+    m, nodes, fz, ib, fac, _ = _plate_with_records(True)
+    a = Oracle(m); a.run_cycles(40)
+    m2, _, _, ib, fac, _ = _plate_with_records(True)
+    m2.fext = None; m2.mext = None; m2.load_func = None; m2.cload_ib = ib; m2.cload_fac = fac
+    b = Oracle(m2); b.run_cycles(40)
+    for k in ("X", "V", "VR"):
+        assert np.array_equal(a.download_nodes((k,))[k], b.download_nodes((k,))[k])
+
+
+def test_load_records_with_several_curves_add_up_in_record_order():
+    """A(dir, N) starts from the sum of the node's records, each FCY * f(TT * FCX) with its own curve (force.F90:301-312)."""
+    m, nodes, fz, ib, fac, (k0, k1) = _plate_with_records(False)
+    fcx0 = float(m.load_func[1])
+    m.fext = None; m.mext = None; m.load_func = None; m.cload_ib = ib; m.cload_fac = fac
+    o = Oracle(m); o.run_cycles(7)
+    tt = o.time()["tt"]
+    o.forces_phase(o.time()["dt2"]); o.assemble()
+    acc = o.download_nodes(("A", "AR"))
+    fs = o.download_fsky()
+    internal = np.zeros((m.numnod, 6))
+    for n in range(m.numnod):
+        internal[n] = fs[m.adsky[n] - 1:m.adsky[n + 1] - 1, :6].sum(0)
+    curve = lambda k, x: np.interp(x, m.tf[2 * m.npf[k]:2 * m.npf[k + 1]:2], m.tf[2 * m.npf[k] + 1:2 * m.npf[k + 1]:2])
+    want = np.zeros((m.numnod, 6))
+    for (n, d, k), (fcy, fcx) in zip(ib, fac):
+        want[n - 1, d - 1] += fcy * (curve(k, tt * fcx) if k >= 0 else 1.0)
+    got = np.hstack([acc["A"], acc["AR"]]) - internal
+    scale = max(np.abs(want).max(), np.abs(internal).max())
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-12 * scale)
+    assert np.abs(want[:, 0]).max() > 0 and np.abs(want[:, 4]).max() > 0 and 0.0 < curve(k1, tt * 2.0) < 1.0
