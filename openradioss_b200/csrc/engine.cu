@@ -63,7 +63,7 @@ struct orgpu_engine {
   std::vector<int> cl_ib; std::vector<double> cl_fac; int n_cl_nodes = 0;
   int *d_cl_ptr = nullptr, *d_cl_nodes = nullptr; int2* d_cl_rec = nullptr; double2* d_cl_fac = nullptr;
   int ngrav = 0; int gdir[ORGPU_MAXGRAV] = {}, gfunc[ORGPU_MAXGRAV] = {}; double gfcy[ORGPU_MAXGRAV] = {}, gfcx[ORGPU_MAXGRAV] = {};   // /GRAV loads
-  std::vector<unsigned char> gmask; unsigned char* d_gmask = nullptr;
+  std::vector<unsigned int> gmask; unsigned int* d_gmask = nullptr;
   std::vector<int> fv_idx; std::vector<FixVelNode> fv;   // imposed velocities, per node
   double* d_btf = nullptr; int* d_bnpf = nullptr;   // LAW36 function table of the brick super-groups
   double* d_ftf = nullptr; int* d_fnpf = nullptr; int* d_fv_idx = nullptr; FixVelNode* d_fv = nullptr;
@@ -396,7 +396,7 @@ int orgpu_set_gravity(orgpu_engine* e, int ngrav, const int* igrv /*(3,n): NN, d
     for (int j = 0; j < nn; j++) {
       const int node = abs(ib[iad + j]);              // the sign of IB only selects the nodes counted in the external work
       NEED(node >= 1 && node <= e->numnod, -4, "gravity load %d: node %d out of range", l, node);
-      e->gmask[node - 1] |= (unsigned char)(1u << l);
+      e->gmask[node - 1] |= (1u << l);
     }
     iad += nn;
   }
@@ -607,7 +607,7 @@ int orgpu_finalize(orgpu_engine* e)
   for (int l = 0; l < ORGPU_MAXGRAV; l++) { e->fa.gfunc[l] = e->gfunc[l]; e->fa.gfcy[l] = e->gfcy[l]; e->fa.gfcx[l] = e->gfcx[l]; e->nd.gdir[l] = e->gdir[l]; }
   if (e->ngrav > 0) {
     if (dev_alloc(&e->d_gmask, e->gmask.size())) return -100;
-    CUDA_OK(cudaMemcpy(e->d_gmask, e->gmask.data(), e->gmask.size(), cudaMemcpyHostToDevice)); e->nd.gmask = e->d_gmask;
+    CUDA_OK(cudaMemcpy(e->d_gmask, e->gmask.data(), 4 * e->gmask.size(), cudaMemcpyHostToDevice)); e->nd.gmask = e->d_gmask;
   }
   // time functions used at node level (loads, imposed velocities)
   e->fa.lf_func = -1; e->fa.lf_fcx = 1.0; e->fa.ft = FuncTable{nullptr, nullptr};
