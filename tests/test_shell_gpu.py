@@ -266,7 +266,7 @@ def test_law36_tensile_strain_failure_needs_istrain():
 
 def test_many_super_groups_one_model():
     """a model whose consecutive groups never fuse (alternating properties): 100 super-groups, one launch each; the
-    table of super-groups lives in device memory (limit ORGPU_MAX_SG = 4096)"""
+    table of super-groups lives in device memory (limit ORGPU_MAX_SG = 65536)"""
     m = meshgen.shell_plate(128, 100, 1280.0, 1000.0, pressure=20.0, vrand=5.0)
     pa, pb = meshgen.default_prop_shell(thick=2.0), meshgen.default_prop_shell(thick=2.0)
     pb.h1 = pa.h1 * 1.25
