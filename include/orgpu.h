@@ -89,6 +89,10 @@ int  orgpu_set_cloads(orgpu_engine* e, int nload, const int* ib /*(3,nload)*/, c
  * broken share of its thickness / of its points reaches P_thickfail (fail_setoff_c.F:123-186).  Two more words per point
  * (damage, point flag): shell state fields 14 dfmax(npt), 15 foff(npt).  Before orgpu_finalize. */
 int  orgpu_set_shell_group_fail(orgpu_engine* e, int sh3n, int group, const orgpu_fail* f);
+/* ... and for one LAW2 solid group (the index orgpu_add_solid_group returned): FAIL_JOHNSON behind MMAIN's own failure section
+ * (mmain.F90:2250-2416 -> fail/johnson_cook/fail_johnson.F:95-141, Ifail_so = 1): elements whose damage reaches 1 get OFF = 4/5
+ * and relax by 0.8 per cycle until they are deleted.  One more state word (solid state field 13 dfmax); pthk / pthickg unused. */
+int  orgpu_set_solid_group_fail(orgpu_engine* e, int group, const orgpu_fail* f);
 /* FORINTC_PREPARE_GPU analogue: fuse consecutive compatible groups into super-groups, re-lay
  * ELBUF out as device SoA, upload tables.  Must be called once before stepping. */
 int  orgpu_finalize(orgpu_engine* e);
@@ -107,7 +111,7 @@ int  orgpu_get_time(orgpu_engine* e, double out[5] /*tt,dt1,dt2,dt12,dt2t*/, int
 int  orgpu_download_nodes(orgpu_engine* e, double* X, double* V, double* VR, double* D,
                           double* A, double* AR, double* STIFN, double* STIFR);
 int  orgpu_download_fsky(orgpu_engine* e, double* fsky /*(8,LSKY)*/);
-/* fields: 0 sig(6) 1 eint 2 rho 3 qvis 4 pla 5 epsd 6 vol 7 off 8 temp 9 smstr(21) 10 stra(6) 11 wpla (LAW36) 12 sigb(6) (LAW2 with FISOKIN > 0: LBUF%SIGB); out[k*numels+e] */
+/* fields: 0 sig(6) 1 eint 2 rho 3 qvis 4 pla 5 epsd 6 vol 7 off 8 temp 9 smstr(21) 10 stra(6) 11 wpla (LAW36) 12 sigb(6) (LAW2 with FISOKIN > 0: LBUF%SIGB) 13 dfmax (/FAIL/JOHNSON); out[k*numels+e] */
 int  orgpu_download_solid_state(orgpu_engine* e, int field, double* out);
 int  orgpu_download_shell_state(orgpu_engine* e, int field, double* out);
 int  orgpu_download_sh3n_state(orgpu_engine* e, int field, double* out);   /* shell fields; smstr has 3 words, no hourg */

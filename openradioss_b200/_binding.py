@@ -21,7 +21,7 @@ def _opt(a, dtype):
 class Binding:
     """Thin object wrapper over one handle of either library."""
     SOLID_FIELDS = dict(sig=(0, 6), eint=(1, 1), rho=(2, 1), qvis=(3, 1), pla=(4, 1), epsd=(5, 1),
-                        vol=(6, 1), off=(7, 1), temp=(8, 1), smstr=(9, 21), stra=(10, 6), wpla=(11, 1), sigb=(12, 6))
+                        vol=(6, 1), off=(7, 1), temp=(8, 1), smstr=(9, 21), stra=(10, 6), wpla=(11, 1), sigb=(12, 6), dfmax=(13, 1))
     SHELL_FIELDS = dict(forc=(0, 5), mom=(1, 3), eint=(2, 2), thk=(3, 1), off=(4, 1), stra=(5, 8),
                         epsd=(6, 1), hourg=(7, 12), smstr=(8, 6), sig=(9, 5), pla=(10, 1),
                         epsd_ip=(11, 1), temp=(12, 1), sigb=(13, 3), dfmax=(14, 1), foff=(15, 1))
@@ -91,11 +91,13 @@ class Binding:
         for g in m.solid_groups:
             v0 = np.ascontiguousarray(m.vol0[g.nft:g.nft + g.nel])
             if getattr(g, "law", 2) == 2:
-                self._call_group("add_solid_group", self.h, C.c_int(g.nel), C.c_int(g.nft), C.byref(g.mat),
-                                 C.byref(g.prop), v0.ctypes.data_as(C.c_void_p))
+                r = self._call_group("add_solid_group", self.h, C.c_int(g.nel), C.c_int(g.nft), C.byref(g.mat),
+                                     C.byref(g.prop), v0.ctypes.data_as(C.c_void_p))
             else:
-                self._call_group("add_solid_group_law", self.h, C.c_int(g.nel), C.c_int(g.nft), C.c_int(g.law),
-                                 C.byref(g.mat), C.byref(g.prop), v0.ctypes.data_as(C.c_void_p))
+                r = self._call_group("add_solid_group_law", self.h, C.c_int(g.nel), C.c_int(g.nft), C.c_int(g.law),
+                                     C.byref(g.mat), C.byref(g.prop), v0.ctypes.data_as(C.c_void_p))
+            if getattr(g, "fail", None) is not None:
+                self._call_group("set_solid_group_fail", self.h, C.c_int(r), C.byref(g.fail))
         self._set_parts(m)
         if self.status and getattr(m, "gorder", None) is not None:      # a domain of a decomposed model: tie-break keys of the dt arg-min
             go = m.gorder

@@ -361,6 +361,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     // ---- M2LAW
     double EPXE = T.ld(BW_PLA), EPSD = T.ld(BW_EPSD);
     double SSP, QNEW, STI, SSP_EQ;
+    double DPLA_F = K_ZERO, EPSP_F = K_ZERO;
     if (LAW == 2) {
       const double asrate = fmin(K_ONE, m.asrate * DT1);
       const double rhocpi = (m.rhocp > K_ZERO) ? or_div(K_ONE, m.rhocp) : K_ZERO;
@@ -458,6 +459,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       double E4 = D4 * (S4 + SG4), E5 = D5 * (S5 + SG5), E6 = D6 * (S6 + SG6);
       double EINC = VOL_AVG * (E1 + E2 + E3 + E4 + E5 + E6) * DTA - K_HALF * DVOL * (QOLD + QNEW);
       EINT = or_div((EINT + EINC * OFF), fmax(K_EM15, VOLO));
+      DPLA_F = DPLA; EPSP_F = EPSD;                        // what M2LAW hands the failure models (DPLA; EPSP = EPSD of m2law.F:229)
       if (m.vp == 1) { double PLAP = or_div(DPLA, fmax(K_EM20, DT1)); EPSD = asrate * PLAP + (K_ONE - asrate) * EPSD; }
       if (m.rhocp > K_ZERO) { SIGY = fmax(SIGY, AK); TEMP = TEMP + SIGY * DPLA * rhocpi; }
     } else {
@@ -629,6 +631,31 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
         TEMP = fmax(K_ZERO, TEMP);
       }
       T.st(g.w_temp, TEMP);
+    }
+    if (LAW == 2 && g.w_dfmax >= 0) {
+      // /FAIL/JOHNSON behind MMAIN (mmain.F90:2250-2262, 2288-2300, 2410-2416 -> fail_johnson.F:95-141, Ifail_so = 1; EPSP is the
+      // strain rate M2LAW hands back, m2law.F:229): elements on their way out relax first, then the damage of the living ones
+      // grows by DPLA / eps_f; the energy takes the (zero) stress correction of :2788-2802 -- a multiply and a divide by the volume
+      if (OFF < (double)0.1f) OFF = K_ZERO;                 // 0.1 and 0.8 are REAL*4 literals (fail_johnson.F:103-104)
+      if (OFF < K_ONE) OFF = OFF * (double)0.8f;
+      double DFMAX = T.ld(g.w_dfmax);
+      if (OFF == K_ONE) {
+        if (DPLA_F != K_ZERO) {
+          const double PR = K_THIRD * (SG1 + SG2 + SG3);
+          const double SXX = SG1 - PR, SYY = SG2 - PR, SZZ = SG3 - PR;
+          double SVM = K_HALF * (SXX * SXX + SYY * SYY + SZZ * SZZ) + SG4 * SG4 + SG6 * SG6 + SG5 * SG5;
+          SVM = or_sqrt(K_THREE * SVM);
+          double EPSF = or_div(g.fail.d3 * PR, fmax(K_EM20, SVM));
+          EPSF = g.fail.d1 + g.fail.d2 * exp(EPSF);
+          if (g.fail.d4 != K_ZERO) EPSF = EPSF * (K_ONE + g.fail.d4 * log(fmax(K_ONE, or_div(EPSP_F, g.fail.epsp0))));
+          EPSF = fmax(EPSF, g.fail.epsf_min);
+          if (EPSF > K_ZERO) DFMAX = DFMAX + or_div(DPLA_F, EPSF);
+          DFMAX = fmin(K_ONE, DFMAX);
+        }
+        if (DFMAX >= K_ONE && OFF == K_ONE) OFF = K_FOUR_OVER_5;
+      }
+      T.st(g.w_dfmax, DFMAX);
+      EINT = or_div(EINT * VOLO, fmax(VOLO, K_EM20));
     }
     // ---- state write-back
     T.st(BW_SIG, SG1); T.st(BW_SIG + 1, SG2); T.st(BW_SIG + 2, SG3); T.st(BW_SIG + 3, SG4); T.st(BW_SIG + 4, SG5); T.st(BW_SIG + 5, SG6);

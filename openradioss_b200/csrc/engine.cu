@@ -36,7 +36,7 @@ template <class T> static int dev_alloc(T** p, size_t n) {
   return 0;
 }
 
-struct HostSolidGroup { int nel, nft, law; orgpu_law2 mat; orgpu_law36 m36; orgpu_prop_solid prop; std::vector<double> vol0; int part = 0; };
+struct HostSolidGroup { int nel, nft, law; orgpu_law2 mat; orgpu_law36 m36; orgpu_prop_solid prop; std::vector<double> vol0; int part = 0; orgpu_fail fail{}; };
 
 struct BrickSGHost { BrickSG d; int first_elem; int part = 0; std::vector<void*> owned; };
 
@@ -483,6 +483,18 @@ int orgpu_set_shell_group_fail(orgpu_engine* e, int sh3n, int group, const orgpu
   return 0;
 }
 
+int orgpu_set_solid_group_fail(orgpu_engine* e, int group, const orgpu_fail* f)
+{
+  NEED(e && f && !e->finalized, -1, "orgpu_set_solid_group_fail: bad arguments / already finalized");
+  NEED(group >= 0 && group < (int)e->sgroups.size(), -4, "orgpu_set_solid_group_fail: group %d does not exist", group);
+  NEED(f->irupt == 0 || f->irupt == 1, -5, "failure model %d is outside the built path (1: /FAIL/JOHNSON)", f->irupt);
+  NEED(f->irupt == 0 || e->sgroups[group].law == 2, -5, "/FAIL/JOHNSON on solids is built behind MMAIN's own failure section (LAW2), not behind MULAW (LAW36)");
+  NEED(f->irupt == 0 || f->d5 == 0.0, -5, "/FAIL/JOHNSON with D5 (temperature term) is outside the built path");
+  NEED(f->irupt == 0 || f->d4 == 0.0 || f->epsp0 > 0.0, -4, "/FAIL/JOHNSON: D4 needs a positive reference strain rate");
+  e->sgroups[group].fail = *f; e->sgroups[group].fail.pad = 0;
+  return 0;
+}
+
 int orgpu_finalize(orgpu_engine* e)
 {
   NEED(e && !e->finalized, -1, "orgpu_finalize: bad handle / already finalized");
@@ -514,7 +526,8 @@ int orgpu_finalize(orgpu_engine* e)
     while (gj < e->sgroups.size() && e->sgroups[gj].nft == e->sgroups[gj - 1].nft + e->sgroups[gj - 1].nel &&
            e->sgroups[gj].law == e->sgroups[gi].law &&
            !memcmp(&e->sgroups[gj].mat, &e->sgroups[gi].mat, sizeof(orgpu_law2)) && !memcmp(&e->sgroups[gj].m36, &e->sgroups[gi].m36, sizeof(orgpu_law36)) &&
-           !memcmp(&e->sgroups[gj].prop, &e->sgroups[gi].prop, sizeof(orgpu_prop_solid)) && e->sgroups[gj].part == e->sgroups[gi].part) gj++;
+           !memcmp(&e->sgroups[gj].prop, &e->sgroups[gi].prop, sizeof(orgpu_prop_solid)) && e->sgroups[gj].part == e->sgroups[gi].part &&
+           !memcmp(&e->sgroups[gj].fail, &e->sgroups[gi].fail, sizeof(orgpu_fail))) gj++;
     int ne = 0; for (size_t k = gi; k < gj; k++) ne += e->sgroups[k].nel;
     const int nft = e->sgroups[gi].nft;
     const int np = ((ne + ORGPU_BLOCK - 1) / ORGPU_BLOCK) * ORGPU_BLOCK;
@@ -529,6 +542,8 @@ int orgpu_finalize(orgpu_engine* e)
     d.w_stra = d.w_wpla = d.w_vt = -1; d.nvt = 0; d.tf = nullptr; d.npf = nullptr; memset(&d.ct, 0, sizeof d.ct);
     d.w_sigb = -1;
     if (d.law == 2 && d.mat.fisokin > 0.0) { d.w_sigb = d.nw_rw; d.nw_rw += 6; }     // LBUF%SIGB (m2law.F:181-190, 364-390)
+    d.fail = e->sgroups[gi].fail; d.w_dfmax = -1;
+    if (d.fail.irupt == 1) d.w_dfmax = d.nw_rw++;                                     // /FAIL/JOHNSON: FBUF%FLOC%DAMMX of the element
     if (d.law == 36) {                                   // LBUF%WPLA, LBUF%STRA (ISTRAIN>0), VARTMP cursors
       d.w_wpla = d.nw_rw++;
       if (d.prop.istrain > 0) { d.w_stra = d.nw_rw; d.nw_rw += 6; }
@@ -1072,7 +1087,7 @@ static int solid_state_xfer(orgpu_engine* e, int field, double* buf, bool up)
                      case 4: w0 = BW_PLA; break; case 5: w0 = BW_EPSD; break; case 6: w0 = d.w_vol; break; case 7: w0 = BW_OFF; break;
                      case 8: w0 = d.w_temp; break; case 9: base = d.smstr; nw = 21; w0 = 0; nc = 21; break;
                      case 10: w0 = d.w_stra; nc = 6; if (w0 < 0) continue; break; case 11: w0 = d.w_wpla; if (w0 < 0) continue; break;
-                     case 12: w0 = d.w_sigb; nc = 6; if (w0 < 0) continue; break; default: FAIL(-1, "unknown solid field %d", field); }
+                     case 12: w0 = d.w_sigb; nc = 6; if (w0 < 0) continue; break; case 13: w0 = d.w_dfmax; if (w0 < 0) continue; break; default: FAIL(-1, "unknown solid field %d", field); }
     if (w0 < 0) { if (!up) for (int i = 0; i < d.ne; i++) buf[S.first_elem + i] = d.mat.tini; continue; }   // no temperature buffer
     for (int k = 0; k < nc; k++)
       CUDA_OK(up ? slab_upload_word(base, nw, w0 + k, d.ne, buf + k * NE + S.first_elem)

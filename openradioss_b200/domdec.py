@@ -70,7 +70,7 @@ def _regroup(groups, gid_of_local, cls):
         if i == len(gid_of_local) or gid_of_local[i] != gid_of_local[start] or i - start == NVSIZ:
             g = groups[gid_of_local[start]]
             if cls is SolidGroup:
-                out.append(SolidGroup(nft=start, nel=i - start, mat=g.mat, prop=g.prop, law=getattr(g, "law", 2)))
+                out.append(SolidGroup(nft=start, nel=i - start, mat=g.mat, prop=g.prop, law=getattr(g, "law", 2), fail=getattr(g, "fail", None)))
             else:
                 out.append(ShellGroup(nft=start, nel=i - start, law=g.law, mat=g.mat, prop=g.prop, fail=getattr(g, "fail", None)))
             start = i

@@ -18,7 +18,7 @@ set_functions add_solid_group add_solid_group_law add_shell_group set_sh3n add_s
 synchronize get_time download_nodes download_fsky download_solid_state download_shell_state
 step_host launch_count last_run_ms set_profile get_profile pack_rows unpack_rows comm_unique_id comm_init
 set_exchange exchange get_energies p2p_export p2p_connect set_load_function set_fixvel set_gravity upload_solid_state upload_shell_state set_time set_itab
-set_parts set_print get_balance get_balance_history set_quadrature set_global_order set_exchange_timeout pack_nodes add_nodes set_exchange_nodes step_host_rot forces_host set_shell_group_fail set_cloads""".split()
+set_parts set_print get_balance get_balance_history set_quadrature set_global_order set_exchange_timeout pack_nodes add_nodes set_exchange_nodes step_host_rot forces_host set_shell_group_fail set_cloads set_solid_group_fail""".split()
 
 
 def load_library() -> C.CDLL:
@@ -131,6 +131,8 @@ class Engine(Binding):
                 ck["sh3n"].update(dfmax=self.sh3n_state("dfmax"), foff=self.sh3n_state("foff"))
         if self.model.numels and any(getattr(g, "law", 2) == 2 and getattr(g.mat, "fisokin", 0.0) > 0.0 for g in self.model.solid_groups):
             ck["solid"]["sigb"] = self.solid_state("sigb")             # back stress of the kinematic hardening (LBUF%SIGB)
+        if self.model.numels and any(getattr(g, "fail", None) is not None for g in self.model.solid_groups):
+            ck["solid"]["dfmax"] = self.solid_state("dfmax")           # /FAIL/JOHNSON damage
         if self.model.numels and any(getattr(g, "law", 2) == 36 for g in self.model.solid_groups):
             ck["solid"].update({f: self.solid_state(f) for f in ("wpla", "stra")})
         return ck

@@ -66,6 +66,7 @@ class SolidGroup:
     prop: PropSolid
     law: int = 2             # 2 (M2LAW) or 36 (MULAW -> SIGEPS36)
     part: int = 0            # 0-based part of the group's elements
+    fail: Optional["Fail"] = None   # /FAIL/JOHNSON of the group's material (LAW2)
 
 
 @dataclass

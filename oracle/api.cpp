@@ -148,6 +148,16 @@ int orc_add_sh3n_group(void* h,int nel,int nft,int law,const void* mat,const org
   return (int)o->tgroups.size()-1;
 }
 
+/* /FAIL/JOHNSON for one LAW2 solid group (mirror of orgpu_set_solid_group_fail) */
+int orc_set_solid_group_fail(void* h,int group,const orgpu_fail* f)
+{
+  Oracle* o=(Oracle*)h;
+  if(group<0 || group>=(int)o->sgroups.size()) return -1;
+  if(f->irupt!=0 && (f->irupt!=1 || f->d5!=0.0 || o->sgroups[group].law!=2)) return -2;
+  o->sgroups[group].fail=*f; o->sgroups[group].dfmax.assign(o->sgroups[group].nel,0.0);
+  return 0;
+}
+
 /* /FAIL/JOHNSON for one shell group (mirror of orgpu_set_shell_group_fail) */
 int orc_set_shell_group_fail(void* h,int sh3n,int group,const orgpu_fail* f)
 {
@@ -193,7 +203,7 @@ void orc_download_nodes(void* h,double* X,double* V,double* VR,double* D,double*
 void orc_download_fsky(void* h,double* fsky){ Oracle* o=(Oracle*)h; memcpy(fsky,o->FSKY.data(),64*(size_t)o->lsky); }
 
 /* solid state of all groups concatenated in element order, component-major over NUMELS:
- * sig[k*numels+e] ; fields: 0 sig(6) 1 eint 2 rho 3 qvis 4 pla 5 epsd 6 vol 7 off 8 temp 9 smstr(21) 10 stra(6) 11 wpla 12 sigb(6) */
+ * sig[k*numels+e] ; fields: 0 sig(6) 1 eint 2 rho 3 qvis 4 pla 5 epsd 6 vol 7 off 8 temp 9 smstr(21) 10 stra(6) 11 wpla 12 sigb(6) 13 dfmax */
 void orc_download_solid_state(void* h,int field,double* out){
   Oracle* o=(Oracle*)h; size_t ne=o->numels;
   for(auto& g:o->sgroups){
@@ -205,6 +215,7 @@ void orc_download_solid_state(void* h,int field,double* out){
       case 9: cp(g.smstr,21); break;
       case 10: if(!g.stra.empty()) cp(g.stra,6); break; case 11: if(!g.wpla.empty()) cp(g.wpla,1); break;
       case 12: if(!g.sigb.empty()) cp(g.sigb,6); break;
+      case 13: if(!g.dfmax.empty()) cp(g.dfmax,1); break;
     }
   }
 }
@@ -218,7 +229,7 @@ void orc_upload_solid_state(void* h,int field,const double* in){
       case 0: cp(g.sig,6); break; case 1: cp(g.eint,1); break; case 2: cp(g.rho,1); break;
       case 3: cp(g.qvis,1); break; case 4: cp(g.pla,1); break; case 5: cp(g.epsd,1); break;
       case 6: cp(g.vol,1); break; case 7: cp(g.off,1); break; case 8: cp(g.temp,1); break;
-      case 9: cp(g.smstr,21); break; case 10: cp(g.stra,6); break; case 11: cp(g.wpla,1); break; case 12: cp(g.sigb,6); break;
+      case 9: cp(g.smstr,21); break; case 10: cp(g.stra,6); break; case 11: cp(g.wpla,1); break; case 12: cp(g.sigb,6); break; case 13: cp(g.dfmax,1); break;
     }
   }
 }

@@ -42,6 +42,8 @@ struct OrcSolidGroup {          /* one element group, ITY=1 (forint.F -> SFORC3)
   std::vector<double> smstr;    /* SAV(nel,21) */
   std::vector<double> stra, wpla; /* MLW=36: LBUF%STRA(6*nel) when ISTRAIN>0, LBUF%WPLA */
   std::vector<double> sigb;     /* MLW=2, FISOKIN>0: LBUF%SIGB(6*nel), the back stress of the kinematic hardening */
+  orgpu_fail fail{};            /* /FAIL/JOHNSON of the group's material (MLW=2; irupt = 0: none) */
+  std::vector<double> dfmax;    /* FBUF%FLOC%DAMMX */
   std::vector<int> vartmp;      /* MLW=36: VARTMP(nel,2+NRATE) table cursors */
 };
 

@@ -161,7 +161,8 @@ static void m2law(const Oracle& o,OrcSolidGroup& g,int nel,const int* ngl,
                   double* qnew,double* ssp_eq,
                   const double* sold1,const double* sold2,const double* sold3,
                   const double* sold4,const double* sold5,const double* sold6,
-                  const double* tstar,double* tempel,double* dmg,const double* rhoref,double* sigbak_of_call /*6*nel comp-major, or null*/)
+                  const double* tstar,double* tempel,double* dmg,const double* rhoref,double* sigbak_of_call /*6*nel comp-major, or null*/,
+                  double* dpla_out,double* epsp_out /* what MMAIN hands the failure models, or null */)
 {
   const orgpu_law2& m=g.mat;
   const double facq0=K_ONE;
@@ -204,6 +205,7 @@ static void m2law(const Oracle& o,OrcSolidGroup& g,int nel,const int* ngl,
   if(fisokin>K_ZERO){ SIGE.resize((size_t)6*nel); for(int i=0;i<nel;i++) for(int k=0;k<6;k++) SIGE[k*nel+i]=S(i,k); }   /* :213-222 */
   const int idev=vp-2;                                                     /* :226-228 */
   mstrain_rate(nel,israte,asrate,epsd,idev,d1,d2,d3,d4,d5,d6);
+  if(epsp_out) for(int i=0;i<nel;i++) epsp_out[i]=epsd[i];                 /* :229 EPSP = EPSD */
   for(int i=0;i<nel;i++) EPD[i]=K_ONE;                                     /* :231 */
   if(cc!=K_ZERO){                                                          /* :233-260 */
     if(vp==1){ for(int i=0;i<nel;i++){ EPD[i]=std::max(epsd[i],epdr); EPD[i]=std::log(EPD[i]/epdr);} }
@@ -314,6 +316,7 @@ static void m2law(const Oracle& o,OrcSolidGroup& g,int nel,const int* ngl,
     eint[i]=(eint[i]+EINC*off[i])/std::max(K_EM15,vol[i]);
   }
   for(int i=0;i<nel;i++){ qold[i]=qnew[i]; }                               /* :477-481 (DEFP,SIGY outputs unused) */
+  if(dpla_out) for(int i=0;i<nel;i++) dpla_out[i]=DPLA[i];
   if(vp==1){                                                               /* :539-544 */
     for(int i=0;i<nel;i++){
       double plap=DPLA[i]/std::max(K_EM20,DT1);
@@ -807,6 +810,7 @@ void orc_sforc3(Oracle& o, OrcSolidGroup& g, double& dt2t, int& neltst, int& ity
       for(int i=0;i<nel;i++) TSTAR[i]=std::max(K_ZERO,(g.temp[i]-g.mat.tref)/std::max((g.mat.tmelt-g.mat.tref),K_EM20));
     } else { for(int i=0;i<nel;i++) TSTAR[i]=K_ZERO; }
     double vecnul[MVSIZ]; for(int i=0;i<nel;i++) vecnul[i]=K_ZERO;
+    double DPLA_F[MVSIZ],EPSP_F[MVSIZ]; for(int i=0;i<nel;i++){ DPLA_F[i]=K_ZERO; EPSP_F[i]=K_ZERO; }
     double* el_temp = g.mat.has_temp ? g.temp.data() : vecnul;
     if(g.law==36){
       /* mmain.F90:1899-1960 MULAW, then :1996-2004 energy -> energy density */
@@ -821,7 +825,7 @@ void orc_sforc3(Oracle& o, OrcSolidGroup& g, double& dt2t, int& neltst, int& ity
     m2law(o,g,nel,NGL,OFF,SIG,EINT,RHON,g.qvis.data(),g.pla.data(),g.epsd.data(),g.vol.data(),STI,
           dt2t,neltst,ityptst,OFFG,AMU,VOL_AVG,CXX,DVOL,VOLN,VD2,DELTAX,VIS,
           DXX,DYY,DZZ,D4,D5,D6,QVIS,SSP_EQ,S1,S2,S3,S4,S5,S6,TSTAR,el_temp,g.dmg.data(),RHOREF,
-          g.mat.fisokin>K_ZERO ? g.sigb.data() : nullptr);
+          g.mat.fisokin>K_ZERO ? g.sigb.data() : nullptr, DPLA_F, EPSP_F);
     /* m2law stored QNEW into QVIS and then QOLD(=lbuf%qvis) = QNEW */
     /* mmain.F90 tail: l_temp>0 entropy heating of the artificial viscosity */
     if(g.mat.has_temp){
@@ -835,6 +839,35 @@ void orc_sforc3(Oracle& o, OrcSolidGroup& g, double& dt2t, int& neltst, int& ity
           g.temp[i]=std::max(K_ZERO,g.temp[i]);
         }
       }
+    }
+    /* failure models of MMAIN (mmain.F90:2250-2262 NFAIL>0, MTN<28; :2288-2300; :2410-2416 FAIL_JOHNSON, fail_johnson.F:95-141 with
+     * Ifail_so = 1; the stress is left alone, so the energy correction of :2788-2802 is a multiply and a divide by the volume) */
+    if(g.law==2 && g.fail.irupt==1){
+      const orgpu_fail& f=g.fail;
+      for(int i=0;i<nel;i++){
+        if(OFF[i]<(double)0.1f) OFF[i]=K_ZERO;                  /* REAL*4 literals 0.1, 0.8 */
+        if(OFF[i]<K_ONE) OFF[i]=OFF[i]*(double)0.8f;
+      }
+      for(int i=0;i<nel;i++){
+        if(OFF[i]==K_ONE){
+          if(DPLA_F[i]!=K_ZERO){
+            const double* S_=SIG;
+            const double sxx_=S_[i], syy_=S_[nel+i], szz_=S_[2*nel+i], sxy_=S_[3*nel+i], syz_=S_[4*nel+i], szx_=S_[5*nel+i];
+            const double P=K_THIRD*(sxx_+syy_+szz_);
+            const double SXX=sxx_-P, SYY=syy_-P, SZZ=szz_-P;
+            double SVM=K_HALF*(SXX*SXX+SYY*SYY+SZZ*SZZ)+sxy_*sxy_+szx_*szx_+syz_*syz_;
+            SVM=std::sqrt(K_THREE*SVM);
+            double EPSF=f.d3*P/std::max(K_EM20,SVM);
+            EPSF=f.d1+f.d2*std::exp(EPSF);
+            if(f.d4!=K_ZERO) EPSF=EPSF*(K_ONE+f.d4*std::log(std::max(K_ONE,EPSP_F[i]/f.epsp0)));
+            EPSF=std::max(EPSF,f.epsf_min);
+            if(EPSF>K_ZERO) g.dfmax[i]=g.dfmax[i]+DPLA_F[i]/EPSF;
+            g.dfmax[i]=std::min(K_ONE,g.dfmax[i]);
+          }
+          if(g.dfmax[i]>=K_ONE && OFF[i]==K_ONE) OFF[i]=K_FOUR_OVER_5;
+        }
+      }
+      for(int i=0;i<nel;i++){ const double e=EINT[i]*g.vol[i]; EINT[i]=e/std::max(g.vol[i],K_EM20); }
     }
   }
   /* ---- SMALLB3  smallb3.F:65-81 */

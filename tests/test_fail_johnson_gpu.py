@@ -115,6 +115,34 @@ def test_two_domains_delete_the_same_elements():
     assert (ref.shell_state("off") == 0).any()
 
 
+def test_law2_bricks_fail_and_relax_in_the_same_cycles():
+    """FAIL_JOHNSON behind MMAIN on LAW2 bricks: an impacting bar whose front elements fail, relax by 0.8 per cycle and are
+    deleted -- OFF bit-identical to the oracle in every block of cycles, damage 1e-9, restart bitwise."""
+    m = meshgen.hex_block(5, 5, 12, 1.0, 1.0, 3.96, v0=(0, 0, -227.0), fix_bottom_z=True, vrand=5.0, user_id_perm=True)
+    f = fail(d1=0.04, d2=0.05, d3=-1.0, d4=0.01, epsp0=1.0e-2)
+    for grp in m.solid_groups:
+        grp.fail = f
+    g, o = Engine(m), Oracle(m, threads=0)
+    dead = []
+    for c in range(8):
+        g.run_cycles(40); g.synchronize(); o.run_cycles(40)
+        assert np.array_equal(g.solid_state("off"), o.solid_state("off")), c
+        assert rel_err(g.solid_state("dfmax"), o.solid_state("dfmax")) <= 1e-9, c
+        assert rel_err(g.download_nodes(("X",))["X"], o.download_nodes(("X",))["X"]) <= 1e-9, c
+        dead.append(int((o.solid_state("off") == 0).sum()))
+    assert 0 < dead[-1] < m.numels
+    off = o.solid_state("off")[0]
+    a = Engine(m); a.run_cycles(100); a.synchronize()
+    ck = a.checkpoint(); assert "dfmax" in ck["solid"]
+    b = Engine(m); b.restore(ck)
+    a.run_cycles(60); b.run_cycles(60); a.synchronize(); b.synchronize()
+    assert np.array_equal(a.download_nodes(("X",))["X"], b.download_nodes(("X",))["X"]) and np.array_equal(a.solid_state("off"), b.solid_state("off"))
+    m36 = meshgen.hex_block(2, 2, 2, 1.0, 1.0, 1.0, law=36)
+    m36.solid_groups[0].fail = f
+    with pytest.raises(RuntimeError):
+        Engine(m36)
+
+
 def test_rejected_outside_its_envelope():
     m = meshgen.shell_plate(4, 4, 40.0, 40.0)
     f = fail(); f.d5 = 0.3

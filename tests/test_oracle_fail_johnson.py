@@ -97,3 +97,51 @@ def test_no_failure_model_leaves_the_law_alone():
     for o in (a, b):
         o.run_cycles(30)
     assert np.array_equal(a.download_nodes(("X",))["X"], b.download_nodes(("X",))["X"])
+
+
+# ---- solids: FAIL_JOHNSON behind MMAIN (mmain.F90:2250-2416 -> fail_johnson.F:95-141, Ifail_so = 1), LAW2 bricks
+
+def sheared_block(f, gam=60.0):
+    m = meshgen.hex_block(2, 2, 2, 2.0, 2.0, 2.0, jitter=0.0)
+    for g in m.solid_groups:
+        g.mat.cc = 0.0; g.mat.has_temp = 0; g.mat.rhocp = 0.0; g.fail = f
+    m.V = np.zeros_like(m.X); m.V[:, 0] = gam * m.X[:, 1]
+    return m
+
+
+def test_solid_damage_grows_by_dpla_over_the_failure_strain_and_the_element_relaxes_away():
+    """Pure shear, D2 = D4 = 0: DFMAX = PLA / D1 while the element lives; in the cycle DFMAX reaches 1 OFF becomes 4/5, then it
+    shrinks by the REAL*4 factor 0.8 per cycle until it drops below 0.1 and the element is gone."""
+    f = fail(d1=0.015)
+    m = sheared_block(f)
+    o = Oracle(m)
+    dt1 = 2e-4
+    offs = []
+    for c in range(40):
+        o.forces_phase(dt1)
+        pla, dmg, off = o.solid_state("pla")[0], o.solid_state("dfmax")[0], o.solid_state("off")[0]
+        offs.append(off[0])
+        if off[0] == 1.0:
+            assert np.allclose(dmg, np.minimum(1.0, pla / 0.015), rtol=1e-12)
+        o.assemble(); o.advance(dt1, dt1)
+        if off[0] == 0.0:
+            break
+    offs = np.array(offs)
+    k = int(np.argmax(offs < 1.0))
+    assert k > 0 and offs[k] == 0.8 and offs[-1] == 0.0
+    r = float(np.float32(0.8))
+    assert np.allclose(offs[k + 1:k + 4], 0.8 * r ** np.arange(1, 4), rtol=1e-15)          # 0.8 is a single-precision literal there
+    assert np.all(o.solid_state("dfmax")[0] == 1.0)
+
+
+def test_solid_triaxiality_term():
+    f = fail(d1=0.02, d2=0.3, d3=-1.5)
+    m = sheared_block(f, gam=30.0)
+    m.V[:, 1] += 8.0 * m.X[:, 1]                     # some hydrostatic part
+    o = Oracle(m)
+    o.forces_phase(2e-4)
+    s, pla, dmg = o.solid_state("sig"), o.solid_state("pla")[0], o.solid_state("dfmax")[0]
+    p = (s[0] + s[1] + s[2]) / 3.0
+    svm = np.sqrt(3.0 * (0.5 * ((s[0] - p) ** 2 + (s[1] - p) ** 2 + (s[2] - p) ** 2) + s[3] ** 2 + s[4] ** 2 + s[5] ** 2))
+    assert pla.min() > 0.0
+    assert np.allclose(dmg, pla / (0.02 + 0.3 * np.exp(-1.5 * p / svm)), rtol=1e-12)
