@@ -94,6 +94,8 @@ typedef struct orgpu_prop_solid {
   int    ismstr;        /* IPARG(9): 1,2,4                             */
   int    ipla;          /* IPARG(29) = IPLAST (default 1, starter sgrtails.F:510): radial-return variant of SIGEPS36 */
   int    istrain;       /* IPARG(44): MULAW accumulates LBUF%STRA (mulaw.F90:886-892)   */
+  int    jcvt;          /* IPARG(37) = Iframe - 1: 0 global frame (Jaumann rate, SROTA3), 1 Belytschko co-rotational frame (SRCOOR3 / SRROTA3) */
+  int    pad;
 } orgpu_prop_solid;
 
 /* /PROP/SHELL (IGTYP 1) slots read on the path (starter hm_read_prop01.F:156-262) */

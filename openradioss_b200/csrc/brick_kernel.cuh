@@ -116,10 +116,12 @@ __device__ __forceinline__ void brick_mqviscb(const BrickSG& g, double DXX, doub
 #define ORGPU_BRICK_MINB 3
 #endif
 
-template <int JHBE, int ISMSTR, int LAW, bool STAGED, bool TAB = false>
+// JHBE_CVT = JHBE + 10 * JCVT: values 10, 11, 12 are Isolid 0, 1, 2 in Belytschko's co-rotational frame (SRCOOR3 instead of SCOOR3)
+template <int JHBE_CVT, int ISMSTR, int LAW, bool STAGED, bool TAB = false>
 __global__ void __launch_bounds__(ORGPU_BLOCK, ORGPU_BRICK_MINB * ORGPU_PER128)
 brick_forces_kernel(const __grid_constant__ BrickParams P)
 {
+  constexpr int JHBE = JHBE_CVT % 10; constexpr bool CVT = JHBE_CVT >= 10;
   if (P.cs->abort) return;                               // sticky: a peer-memory wait timed out (exchange.cuh)
   const CtaWork<BrickSG> W = cta_work<BrickSG, TAB>(P.sg, P.sgtab, P.cta_map);
   const BrickSG& g = *W.g;
@@ -159,12 +161,57 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     double OFFG = T.ld(BW_OFF);
     const bool dying_in = OFFG < K_ZERO;                  // SCOOR3 zeroes the velocities of such an element (also what SBILAN sees)
     double OFF;
+    double R11 = K_ONE, R12 = K_ZERO, R13 = K_ZERO, R21 = K_ZERO, R22 = K_ONE, R23 = K_ZERO, R31 = K_ZERO, R32 = K_ZERO, R33 = K_ONE;
+    if (CVT) {
+      // SRCOOR3 (srcoor3.F:265-303): frame of the iso-parametric axes of the current coordinates (SREPISO3 srepiso3.F:80-111),
+      // made orthonormal by SORTHO3 (sortho3.F:75-150: three sweeps, then e1, e3 = e1 x v, e2 = e3 x e1); columns of R
+      const double X17 = x[6] - x[0], X28 = x[7] - x[1], X35 = x[4] - x[2], X46 = x[5] - x[3];
+      const double Y17 = y[6] - y[0], Y28 = y[7] - y[1], Y35 = y[4] - y[2], Y46 = y[5] - y[3];
+      const double Z17 = z[6] - z[0], Z28 = z[7] - z[1], Z35 = z[4] - z[2], Z46 = z[5] - z[3];
+      const double A17 = X17 + X46, A28 = X28 + X35, B17 = Y17 + Y46, B28 = Y28 + Y35, C17 = Z17 + Z46, C28 = Z28 + Z35;
+      const double RX = X17 + X28 - X35 - X46, RY = Y17 + Y28 - Y35 - Y46, RZ = Z17 + Z28 - Z35 - Z46;
+      const double SX = A17 + A28, SY = B17 + B28, SZ = C17 + C28;
+      const double TX = A17 - A28, TY = B17 - B28, TZ = C17 - C28;
+      double aa = or_sqrt(RX * RX + RY * RY + RZ * RZ); if (aa != K_ZERO) aa = or_div(K_ONE, aa);
+      double Ux = RX * aa, Uy = RY * aa, Uz = RZ * aa;
+      aa = or_sqrt(SX * SX + SY * SY + SZ * SZ); if (aa != K_ZERO) aa = or_div(K_ONE, aa);
+      double Vx = SX * aa, Vy = SY * aa, Vz = SZ * aa;
+      aa = or_sqrt(TX * TX + TY * TY + TZ * TZ); if (aa != K_ZERO) aa = or_div(K_ONE, aa);
+      double Wx = TX * aa, Wy = TY * aa, Wz = TZ * aa;
+      #pragma unroll 1
+      for (int N = 0; N < 3; N++) {
+        const double e1x = Vy * Wz - Vz * Wy + Ux, e1y = Vz * Wx - Vx * Wz + Uy, e1z = Vx * Wy - Vy * Wx + Uz;
+        const double e2x = Wy * Uz - Wz * Uy + Vx, e2y = Wz * Ux - Wx * Uz + Vy, e2z = Wx * Uy - Wy * Ux + Vz;
+        const double e3x = Uy * Vz - Uz * Vy + Wx, e3y = Uz * Vx - Ux * Vz + Wy, e3z = Ux * Vy - Uy * Vx + Wz;
+        double bb = or_sqrt(e1x * e1x + e1y * e1y + e1z * e1z); if (bb != K_ZERO) bb = or_div(K_ONE, bb);
+        Ux = e1x * bb; Uy = e1y * bb; Uz = e1z * bb;
+        bb = or_sqrt(e2x * e2x + e2y * e2y + e2z * e2z); if (bb != K_ZERO) bb = or_div(K_ONE, bb);
+        Vx = e2x * bb; Vy = e2y * bb; Vz = e2z * bb;
+        bb = or_sqrt(e3x * e3x + e3y * e3y + e3z * e3z); if (bb != K_ZERO) bb = or_div(K_ONE, bb);
+        Wx = e3x * bb; Wy = e3y * bb; Wz = e3z * bb;
+      }
+      double e3x = Uy * Vz - Uz * Vy, e3y = Uz * Vx - Ux * Vz, e3z = Ux * Vy - Uy * Vx;
+      aa = or_sqrt(e3x * e3x + e3y * e3y + e3z * e3z); if (aa != K_ZERO) aa = or_div(K_ONE, aa);
+      e3x = e3x * aa; e3y = e3y * aa; e3z = e3z * aa;
+      R11 = Ux; R21 = Uy; R31 = Uz;
+      R13 = e3x; R23 = e3y; R33 = e3z;
+      R12 = e3y * Uz - e3z * Uy; R22 = e3z * Ux - e3x * Uz; R32 = e3x * Uy - e3y * Ux;
+    }
     if (ISMSTR <= 4 && fabs(OFFG) > K_ONE) {
       #pragma unroll
       for (int k = 0; k < 7; k++) { x[k] = sm[(3 * k) * ORGPU_TILE]; y[k] = sm[(3 * k + 1) * ORGPU_TILE]; z[k] = sm[(3 * k + 2) * ORGPU_TILE]; }
       x[7] = K_ZERO; y[7] = K_ZERO; z[7] = K_ZERO;
       OFF = fabs(OFFG) - K_ONE;
-    } else OFF = fabs(OFFG);
+    } else {
+      OFF = fabs(OFFG);
+      if (CVT) {                                          // X' = t(R) X (srcoor3.F:364-418); the saved reference above already lives in the frame
+        #pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const double XDL = R11 * x[k] + R21 * y[k] + R31 * z[k], YDL = R12 * x[k] + R22 * y[k] + R32 * z[k], ZDL = R13 * x[k] + R23 * y[k] + R33 * z[k];
+          x[k] = XDL; y[k] = YDL; z[k] = ZDL;
+        }
+      }
+    }
     // SDLEN3 works on the X1..Z8 copies taken here (before a possible negative-volume switch)
     double areamax = K_EM20;
     areamax = fmax(slen_face(x, y, z, 0, 1, 2, 3), areamax);
@@ -237,6 +284,13 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     double vx[8], vy[8], vz[8];
     #pragma unroll
     for (int k = 0; k < 8; k++) { double4 p = ldg4(P.nd.vel + nc[k]); vx[k] = p.x; vy[k] = p.y; vz[k] = p.z; }
+    if (CVT) {                                            // V' = t(R) V (srcoor3.F:672-681)
+      #pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const double X = R11 * vx[k] + R21 * vy[k] + R31 * vz[k], Y = R12 * vx[k] + R22 * vy[k] + R32 * vz[k], Z = R13 * vx[k] + R23 * vy[k] + R33 * vz[k];
+        vx[k] = X; vy[k] = Y; vz[k] = Z;
+      }
+    }
     if (OFFG < K_ZERO) {
       #pragma unroll
       for (int k = 0; k < 8; k++) { vx[k] = K_ZERO; vy[k] = K_ZERO; vz[k] = K_ZERO; }
@@ -280,7 +334,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       }
     }
     const double DT1D2 = K_HALF * DT1;
-    if (JHBE >= 2) {
+    if (CVT || JHBE >= 2) {                               // sdefo3.F:158-220 (co-rotational: no spin) / :222-256
       double EXX = DXX, EYY = DYY, EZZ = DZZ, EXY = DXY, EYX = DYX, EXZ = DXZ, EZX = DZX, EYZ = DYZ, EZY = DZY;
       DXX = DXX - DT1D2 * (EXX * EXX + EYX * EYX + EZX * EZX);
       DYY = DYY - DT1D2 * (EYY * EYY + EZY * EZY + EXY * EXY);
@@ -291,12 +345,15 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       DYZ = DYZ - AAA; DZY = DZY - AAA; D5 = DYZ + DZY;
       AAA = DT1D2 * (EZZ * EZX + EXZ * EXX + EYZ * EYX);
       DXZ = DXZ - AAA; DZX = DZX - AAA; D6 = DXZ + DZX;
+      if (CVT) { WXX = K_ZERO; WYY = K_ZERO; WZZ = K_ZERO; }
+      else {
       double PXX2 = PX[0] * PX[0] + PX[1] * PX[1] + PX[2] * PX[2] + PX[3] * PX[3];
       double PYY2 = PY[0] * PY[0] + PY[1] * PY[1] + PY[2] * PY[2] + PY[3] * PY[3];
       double PZZ2 = PZ[0] * PZ[0] + PZ[1] * PZ[1] + PZ[2] * PZ[2] + PZ[3] * PZ[3];
       WZZ = or_div(DT1 * (PYY2 * DYX - PXX2 * DXY), (PXX2 + PYY2));
       WXX = or_div(DT1 * (PZZ2 * DZY - PYY2 * DYZ), (PYY2 + PZZ2));
       WYY = or_div(DT1 * (PXX2 * DXZ - PZZ2 * DZX), (PZZ2 + PXX2));
+      }
     } else {
       D4 = DXY + DYX; D5 = DYZ + DZY; D6 = DXZ + DZX;
       WZZ = DT1D2 * (DYX - DXY);
@@ -329,7 +386,8 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
     // ---- SROTA3
     double S1 = T.ld(BW_SIG), S2 = T.ld(BW_SIG + 1), S3 = T.ld(BW_SIG + 2), S4 = T.ld(BW_SIG + 3), S5 = T.ld(BW_SIG + 4), S6 = T.ld(BW_SIG + 5);
     double SG1, SG2, SG3, SG4, SG5, SG6;
-    {
+    if (CVT) { SG1 = S1; SG2 = S2; SG3 = S3; SG4 = S4; SG5 = S5; SG6 = S6; }     // SRMALLA3: the stress lives in the co-rotating frame
+    else {
       double Q1 = K_TWO * S4 * WZZ, Q2 = K_TWO * S6 * WYY, Q3 = K_TWO * S5 * WXX;
       SG1 = S1 - Q1 + Q2;
       SG2 = S2 + Q1 - Q3;
@@ -339,7 +397,7 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
       SG6 = S6 + WYY * (S3 - S1) + WXX * S4 - WZZ * S5;
     }
     // ---- SMALLA3 (rotate the frozen reference) then S8SAV3 (refresh it)
-    if (ISMSTR <= 4 && OFFG > K_ONE) {
+    if (!CVT && ISMSTR <= 4 && OFFG > K_ONE) {
       #pragma unroll
       for (int k = 0; k < 7; k++) {
         double X = sm[(3 * k) * ORGPU_TILE], Y = sm[(3 * k + 1) * ORGPU_TILE], Z = sm[(3 * k + 2) * ORGPU_TILE];
@@ -746,6 +804,13 @@ brick_forces_kernel(const __grid_constant__ BrickParams P)
         F3[a[k]] = F3[a[k]] - FINT; F3[b[k]] = F3[b[k]] + FINT;
       }
     }
+    if (CVT) {                                            // F = R F' (sforc3.F:1634-1645)
+      #pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const double X = R11 * F1[k] + R12 * F2[k] + R13 * F3[k], Y = R21 * F1[k] + R22 * F2[k] + R23 * F3[k], Z = R31 * F1[k] + R32 * F2[k] + R33 * F3[k];
+        F1[k] = X; F2[k] = Y; F3[k] = Z;
+      }
+    }
     // ---- SCUMU3P
     if (OFFG < K_ZERO) {
       #pragma unroll
@@ -807,6 +872,10 @@ static void launch_brick_ismstr(const BrickParams& P, int ismstr, int nblk, cuda
 template <int LAW>
 static void launch_brick_jhbe(const BrickParams& P, int nblk, cudaStream_t st)
 {
+  if (LAW != 37 && P.sg.prop.jcvt != 0) {                  // Belytschko's co-rotational frame (Iframe = 2): compiled for Isolid 1
+    launch_brick_ismstr<11, LAW>(P, P.sg.prop.ismstr, nblk, st);
+    return;
+  }
   switch (P.sg.prop.jhbe) {
     case 0: launch_brick_ismstr<0, LAW>(P, P.sg.prop.ismstr, nblk, st); break;
     case 2: launch_brick_ismstr<2, LAW>(P, P.sg.prop.ismstr, nblk, st); break;
@@ -828,7 +897,7 @@ void launch_brick_forces(const BrickSG& sg, const DevNodes& nd, double* fsky, in
 enum { BRV_LAW2 = 0, BRV_LAW36, BRV_COUNT };
 static inline int brick_tab_variant(const BrickSG& d)
 {
-  if (d.prop.jhbe != 1 || d.prop.ismstr != 4 || (size_t)d.nw * ORGPU_TILE * 8 > ORGPU_STAGE_MAX_BYTES) return -1;
+  if (d.prop.jhbe != 1 || d.prop.ismstr != 4 || d.prop.jcvt != 0 || (size_t)d.nw * ORGPU_TILE * 8 > ORGPU_STAGE_MAX_BYTES) return -1;
   if (d.law == 36) return d.m36.ifail == 2 ? -1 : BRV_LAW36;
   return BRV_LAW2;
 }

@@ -137,14 +137,14 @@ def default_prop_shell(thick=2.0, ihbe=24, npt=5, ismstr=2, ithk=1, ipla=1) -> P
     return p
 
 
-def default_prop_solid(jhbe=1, ismstr=4, ipla=1, istrain=0) -> PropSolid:
+def default_prop_solid(jhbe=1, ismstr=4, ipla=1, istrain=0, jcvt=0) -> PropSolid:
     p = PropSolid()
     p.qa, p.qb = 1.1, 0.05
     p.cns1 = p.cns2 = 0.0
     p.hcoef = 0.1
     p.dtmin = 0.0
     p.jhbe = jhbe; p.ismstr = ismstr
-    p.ipla = ipla; p.istrain = istrain
+    p.ipla = ipla; p.istrain = istrain; p.jcvt = jcvt; p.pad = 0
     return p
 
 

@@ -31,7 +31,7 @@ class Law36(C.Structure):
 
 
 class PropSolid(C.Structure):
-    _fields_ = [(n, d) for n in "qa qb cns1 cns2 hcoef dtmin".split()] + [("jhbe", i), ("ismstr", i), ("ipla", i), ("istrain", i)]
+    _fields_ = [(n, d) for n in "qa qb cns1 cns2 hcoef dtmin".split()] + [("jhbe", i), ("ismstr", i), ("ipla", i), ("istrain", i), ("jcvt", i), ("pad", i)]
 
 
 class PropShell(C.Structure):

@@ -551,7 +551,7 @@ static void mulaw36(const Oracle& o,OrcSolidGroup& g,int nel,const int* ngl,
 void orc_sforc3(Oracle& o, OrcSolidGroup& g, double& dt2t, int& neltst, int& ityptst)
 {
   const int nel=g.nel, nft=g.nft;
-  const int ismstr=g.prop.ismstr, jhbe=g.prop.jhbe;
+  const int ismstr=g.prop.ismstr, jhbe=g.prop.jhbe, jcvt=g.prop.jcvt;
   const double DT1=o.DT1;
   static thread_local Vec X1,X2,X3,X4,X5,X6,X7,X8,Y1,Y2,Y3,Y4,Y5,Y6,Y7,Y8,Z1,Z2,Z3,Z4,Z5,Z6,Z7,Z8;
   static thread_local Vec XD[8],YD[8],ZD[8],VX[8],VY[8],VZ[8];
@@ -572,6 +572,64 @@ void orc_sforc3(Oracle& o, OrcSolidGroup& g, double& dt2t, int& neltst, int& ity
     int n=NC[k][i]-1;
     XD[k][i]=o.X[3*n]; YD[k][i]=o.X[3*n+1]; ZD[k][i]=o.X[3*n+2];
   }
+  /* ---- SRCOOR3 (srcoor3.F:143-723, JCVT /= 0: Belytschko's co-rotational frame; ISORTH=0, IRESP=0): the frame from the
+   * iso-parametric axes of the CURRENT coordinates (SREPISO3 srepiso3.F:80-111, SORTHO3 sortho3.F:75-150), then coordinates --
+   * or the saved small-strain reference, which already lives in that frame -- and velocities in it */
+  static thread_local Vec R11,R12,R13,R21,R22,R23,R31,R32,R33;
+  if(jcvt!=0){
+    for(int i=0;i<nel;i++){
+      const double X17=XD[6][i]-XD[0][i], X28=XD[7][i]-XD[1][i], X35=XD[4][i]-XD[2][i], X46=XD[5][i]-XD[3][i];
+      const double Y17=YD[6][i]-YD[0][i], Y28=YD[7][i]-YD[1][i], Y35=YD[4][i]-YD[2][i], Y46=YD[5][i]-YD[3][i];
+      const double Z17=ZD[6][i]-ZD[0][i], Z28=ZD[7][i]-ZD[1][i], Z35=ZD[4][i]-ZD[2][i], Z46=ZD[5][i]-ZD[3][i];
+      const double A17=X17+X46, A28=X28+X35, B17=Y17+Y46, B28=Y28+Y35, C17=Z17+Z46, C28=Z28+Z35;
+      const double RX=X17+X28-X35-X46, RY=Y17+Y28-Y35-Y46, RZ=Z17+Z28-Z35-Z46;
+      const double SX=A17+A28, SY=B17+B28, SZ=C17+C28;
+      const double TX=A17-A28, TY=B17-B28, TZ=C17-C28;
+      double aa=std::sqrt(RX*RX+RY*RY+RZ*RZ); if(aa!=K_ZERO) aa=K_ONE/aa;
+      double Ux=RX*aa, Uy=RY*aa, Uz=RZ*aa;
+      aa=std::sqrt(SX*SX+SY*SY+SZ*SZ); if(aa!=K_ZERO) aa=K_ONE/aa;
+      double Vx=SX*aa, Vy=SY*aa, Vz=SZ*aa;
+      aa=std::sqrt(TX*TX+TY*TY+TZ*TZ); if(aa!=K_ZERO) aa=K_ONE/aa;
+      double Wx=TX*aa, Wy=TY*aa, Wz=TZ*aa;
+      for(int N=0;N<3;N++){                                      /* NITER = 3 */
+        const double e1x=Vy*Wz-Vz*Wy+Ux, e1y=Vz*Wx-Vx*Wz+Uy, e1z=Vx*Wy-Vy*Wx+Uz;
+        const double e2x=Wy*Uz-Wz*Uy+Vx, e2y=Wz*Ux-Wx*Uz+Vy, e2z=Wx*Uy-Wy*Ux+Vz;
+        const double e3x=Uy*Vz-Uz*Vy+Wx, e3y=Uz*Vx-Ux*Vz+Wy, e3z=Ux*Vy-Uy*Vx+Wz;
+        double bb=std::sqrt(e1x*e1x+e1y*e1y+e1z*e1z); if(bb!=K_ZERO) bb=K_ONE/bb;
+        Ux=e1x*bb; Uy=e1y*bb; Uz=e1z*bb;
+        bb=std::sqrt(e2x*e2x+e2y*e2y+e2z*e2z); if(bb!=K_ZERO) bb=K_ONE/bb;
+        Vx=e2x*bb; Vy=e2y*bb; Vz=e2z*bb;
+        bb=std::sqrt(e3x*e3x+e3y*e3y+e3z*e3z); if(bb!=K_ZERO) bb=K_ONE/bb;
+        Wx=e3x*bb; Wy=e3y*bb; Wz=e3z*bb;
+      }
+      const double e1x=Ux, e1y=Uy, e1z=Uz;
+      double e3x=e1y*Vz-e1z*Vy, e3y=e1z*Vx-e1x*Vz, e3z=e1x*Vy-e1y*Vx;
+      aa=std::sqrt(e3x*e3x+e3y*e3y+e3z*e3z); if(aa!=K_ZERO) aa=K_ONE/aa;
+      e3x=e3x*aa; e3y=e3y*aa; e3z=e3z*aa;
+      const double e2x=e3y*e1z-e3z*e1y, e2y=e3z*e1x-e3x*e1z, e2z=e3x*e1y-e3y*e1x;
+      /* SORTHO3(..., E1X=R11, E1Y=R12(!), ...) as SRCOOR3 passes them: R11,R12,R13 receive e1x,e2x,e3x; R21.. e1y,e2y,e3y; R31.. e1z,e2z,e3z */
+      R11[i]=e1x; R12[i]=e2x; R13[i]=e3x; R21[i]=e1y; R22[i]=e2y; R23[i]=e3y; R31[i]=e1z; R32[i]=e2z; R33[i]=e3z;
+    }
+  }
+  if(jcvt!=0 && ismstr<=4){                           /* srcoor3.F:328-420 */
+    for(int i=0;i<nel;i++){
+      if(std::fabs(OFFG[i])>K_ONE){
+        for(int k=0;k<7;k++){ XD[k][i]=sav(i,3*k+1); YD[k][i]=sav(i,3*k+2); ZD[k][i]=sav(i,3*k+3); }
+        XD[7][i]=K_ZERO; YD[7][i]=K_ZERO; ZD[7][i]=K_ZERO;
+        OFF[i]=std::fabs(OFFG[i])-K_ONE;
+        OFF_L=std::min(OFF_L,OFFG[i]);
+      } else {
+        for(int k=0;k<8;k++){
+          const double XDL=R11[i]*XD[k][i]+R21[i]*YD[k][i]+R31[i]*ZD[k][i];
+          const double YDL=R12[i]*XD[k][i]+R22[i]*YD[k][i]+R32[i]*ZD[k][i];
+          const double ZDL=R13[i]*XD[k][i]+R23[i]*YD[k][i]+R33[i]*ZD[k][i];
+          XD[k][i]=XDL; YD[k][i]=YDL; ZD[k][i]=ZDL;
+        }
+        OFF[i]=std::fabs(OFFG[i]);
+        OFF_L=std::min(OFF_L,OFFG[i]);
+      }
+    }
+  } else
   if(ismstr<=4){                                      /* :218-253 (JLAG>0) */
     for(int i=0;i<nel;i++){
       if(std::fabs(OFFG[i])>K_ONE){
@@ -594,6 +652,19 @@ void orc_sforc3(Oracle& o, OrcSolidGroup& g, double& dt2t, int& neltst, int& ity
   for(int i=0;i<nel;i++) for(int k=0;k<8;k++){
     int n=NC[k][i]-1;
     VX[k][i]=o.V[3*n]; VY[k][i]=o.V[3*n+1]; VZ[k][i]=o.V[3*n+2];
+  }
+  static thread_local Vec VGX[8],VGY[8],VGZ[8];          /* velocities in the global frame: what SRBILAN books (srcoor3.F:231-244) */
+  if(jcvt!=0 && o.ipri) for(int i=0;i<nel;i++) for(int k=0;k<8;k++){ VGX[k][i]=VX[k][i]; VGY[k][i]=VY[k][i]; VGZ[k][i]=VZ[k][i]; }
+  if(jcvt!=0){
+    /* srcoor3.F:672-681: CALL SRROTA3(R11,R12,R13,R21,R22,R23,R31,R32,R33, VX.., VY.., VZ..) -- SRROTA3's dummies are
+     * (R11,R21,R31,R12,R22,R32,R13,R23,R33), so its X = R11*VX + R21*VY + R31*VZ reads R11*VX + R12*VY + R13*VZ here... with
+     * the actual arguments in that order the velocity gets  V_loc = t(R) V:  x' = R11 vx + R21 vy + R31 vz */
+    for(int i=0;i<nel;i++) for(int k=0;k<8;k++){
+      const double X=R11[i]*VX[k][i]+R21[i]*VY[k][i]+R31[i]*VZ[k][i];
+      const double Y=R12[i]*VX[k][i]+R22[i]*VY[k][i]+R32[i]*VZ[k][i];
+      const double Z=R13[i]*VX[k][i]+R23[i]*VY[k][i]+R33[i]*VZ[k][i];
+      VX[k][i]=X; VY[k][i]=Y; VZ[k][i]=Z;
+    }
   }
   if(OFF_L<K_ZERO){
     for(int i=0;i<nel;i++) if(OFFG[i]<K_ZERO) for(int k=0;k<8;k++){ VX[k][i]=K_ZERO; VY[k][i]=K_ZERO; VZ[k][i]=K_ZERO; }
@@ -704,6 +775,21 @@ void orc_sforc3(Oracle& o, OrcSolidGroup& g, double& dt2t, int& neltst, int& ity
     DZY[i]=PY1[i]*VZ17+PY2[i]*VZ28+PY3[i]*VZ35+PY4[i]*VZ46;
   }
   const double DT1D2=K_HALF*DT1;
+  if(jcvt!=0){                                       /* sdefo3.F:158-220 (ISMSTR /= 11, IMPL_S = 0): no spin in the co-rotating frame, second-order strain rate */
+    for(int i=0;i<nel;i++){
+      WXX[i]=K_ZERO; WYY[i]=K_ZERO; WZZ[i]=K_ZERO;
+      double EXX=DXX[i],EYY=DYY[i],EZZ=DZZ[i],EXY=DXY[i],EYX=DYX[i],EXZ=DXZ[i],EZX=DZX[i],EYZ=DYZ[i],EZY=DZY[i];
+      DXX[i]=DXX[i]-DT1D2*(EXX*EXX+EYX*EYX+EZX*EZX);
+      DYY[i]=DYY[i]-DT1D2*(EYY*EYY+EZY*EZY+EXY*EXY);
+      DZZ[i]=DZZ[i]-DT1D2*(EZZ*EZZ+EXZ*EXZ+EYZ*EYZ);
+      double AAA=DT1D2*(EXX*EXY+EYX*EYY+EZX*EZY);
+      DXY[i]=DXY[i]-AAA; DYX[i]=DYX[i]-AAA; D4[i]=DXY[i]+DYX[i];
+      AAA=DT1D2*(EYY*EYZ+EZY*EZZ+EXY*EXZ);
+      DYZ[i]=DYZ[i]-AAA; DZY[i]=DZY[i]-AAA; D5[i]=DYZ[i]+DZY[i];
+      AAA=DT1D2*(EZZ*EZX+EXZ*EXX+EYZ*EYX);
+      DXZ[i]=DXZ[i]-AAA; DZX[i]=DZX[i]-AAA; D6[i]=DXZ[i]+DZX[i];
+    }
+  } else
   if(jhbe>=2){                                       /* :222-256 */
     for(int i=0;i<nel;i++){
       double EXX=DXX[i],EYY=DYY[i],EZZ=DZZ[i],EXY=DXY[i],EYX=DYX[i],EXZ=DXZ[i],EZX=DZX[i],EYZ=DYZ[i],EZY=DZY[i];
@@ -758,6 +844,7 @@ void orc_sforc3(Oracle& o, OrcSolidGroup& g, double& dt2t, int& neltst, int& ity
   double S1[MVSIZ],S2[MVSIZ],S3[MVSIZ],S4[MVSIZ],S5[MVSIZ],S6[MVSIZ];
   double* SIG=g.sig.data(); auto SG=[&](int i,int k)->double&{ return SIG[k*nel+i]; };
   for(int i=0;i<nel;i++){ S1[i]=SG(i,0);S2[i]=SG(i,1);S3[i]=SG(i,2);S4[i]=SG(i,3);S5[i]=SG(i,4);S6[i]=SG(i,5); }
+  if(jcvt==0)                                        /* JCVT /= 0: SRMALLA3 (srmall3.F) only copies the old stress, it lives in the co-rotating frame */
   for(int i=0;i<nel;i++){
     double Q1=K_TWO*S4[i]*WZZ[i], Q2=K_TWO*S6[i]*WYY[i], Q3=K_TWO*S5[i]*WXX[i];
     SG(i,0)=S1[i]-Q1+Q2;
@@ -767,8 +854,8 @@ void orc_sforc3(Oracle& o, OrcSolidGroup& g, double& dt2t, int& neltst, int& ity
     SG(i,4)=S5[i]+WXX[i]*(S2[i]-S3[i])+WZZ[i]*S6[i]-WYY[i]*S4[i];
     SG(i,5)=S6[i]+WYY[i]*(S3[i]-S1[i])+WXX[i]*S4[i]-WZZ[i]*S5[i];
   }
-  /* ---- SMALLA3  smalla3.F:118-173 (ISMSTR<=4, JLAG>0) */
-  if(ismstr<=4){
+  /* ---- SMALLA3  smalla3.F:118-173 (ISMSTR<=4, JLAG>0; not called for JCVT /= 0, sforc3.F:807-822) */
+  if(ismstr<=4 && jcvt==0){
     for(int i=0;i<nel;i++) if(OFFG[i]>K_ONE){
       for(int k=0;k<7;k++){
         double X=sav(i,3*k+1),Y=sav(i,3*k+2),Z=sav(i,3*k+3);
@@ -882,6 +969,7 @@ void orc_sforc3(Oracle& o, OrcSolidGroup& g, double& dt2t, int& neltst, int& ity
   if(o.ipri){                                          /* SBILAN sforc3.F:1436-1458 */
     for(int i=0;i<nel;i++){
       double vx[8],vy[8],vz[8]; for(int k=0;k<8;k++){ vx[k]=VX[k][i]; vy[k]=VY[k][i]; vz[k]=VZ[k][i]; }
+      if(jcvt!=0) for(int k=0;k<8;k++){ vx[k]=VGX[k][i]; vy[k]=VGY[k][i]; vz[k]=VGZ[k][i]; }   /* SRBILAN (sforc3.F:1459-1470): the same sums, from the global velocities */
       orc_bilan_solid(o,nft+i,vx,vy,vz,g.eint[i],g.vol[i],g.rho[i],VOLN[i],OFFG[i]);
     }
   }
@@ -984,6 +1072,14 @@ void orc_sforc3(Oracle& o, OrcSolidGroup& g, double& dt2t, int& neltst, int& ity
       F2[a[k]][i]=F2[a[k]][i]-FINT; F2[b[k]][i]=F2[b[k]][i]+FINT;
       FINT=s3*PZ[k][i]+s6*PX[k][i]+s5*PY[k][i];
       F3[a[k]][i]=F3[a[k]][i]-FINT; F3[b[k]][i]=F3[b[k]][i]+FINT;
+    }
+  }
+  if(jcvt!=0){                                        /* sforc3.F:1634-1645 SRROTA3(R11,R21,R31,R12,...): F_global = R F_local */
+    for(int i=0;i<nel;i++) for(int k=0;k<8;k++){
+      const double X=R11[i]*F1[k][i]+R12[i]*F2[k][i]+R13[i]*F3[k][i];
+      const double Y=R21[i]*F1[k][i]+R22[i]*F2[k][i]+R23[i]*F3[k][i];
+      const double Z=R31[i]*F1[k][i]+R32[i]*F2[k][i]+R33[i]*F3[k][i];
+      F1[k][i]=X; F2[k][i]=Y; F3[k][i]=Z;
     }
   }
   /* ---- SCUMU3P  scumu3p.F:104-309 (IPARTSPH=0, JTHE>=0, IVECTOR=0) */

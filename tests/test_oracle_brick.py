@@ -283,3 +283,60 @@ def test_law2_kinematic_hardening_shifts_the_yield_surface(fisokin):
     _, out_k = run(fisokin, True)
     _, out_i = run(0.0, True)
     assert out_k[1][2] - out_k[0][2] > (out_i[1][2] - out_i[0][2]) * (1.0 + 1e-6)
+
+
+def _rot(axis, ang):
+    axis = np.asarray(axis, float) / np.linalg.norm(axis)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * (K @ K)
+
+
+def _impact_block(jcvt, Q=None):
+    m = meshgen.hex_block(3, 3, 5, 1.0, 1.0, 1.66, jitter=0.05, v0=(0, 0, -180.0), vrand=8.0,
+                          prop=meshgen.default_prop_solid(jcvt=jcvt))
+    m.V[m.X[:, 2] < 0.3] *= 0.0                     # the lower layers at rest: the block compresses and yields
+    if Q is not None:
+        m.X = m.X @ Q.T; m.V = m.V @ Q.T
+    return m
+
+
+def test_corotational_frame_is_objective():
+    """JCVT = 1 (SRCOOR3: Belytschko's co-rotational frame): everything is computed in a frame that turns with the element,
+    so a model and the same model turned by an arbitrary rotation Q give corner forces, and after 150 yielding cycles positions,
+    related by Q to rounding -- also with plastic strain and hourglass forces in play.  (The Jaumann path of JCVT = 0 is
+    objective to the accuracy of the time integration only.)"""
+    Q = _rot([0.3, -0.5, 0.8], 1.1)
+    a, b = Oracle(_impact_block(1)), Oracle(_impact_block(1, Q))
+    for o in (a, b):
+        o.forces_phase(0.0)
+    fa, fb = a.download_fsky()[:, :3], b.download_fsky()[:, :3]
+    assert np.abs(fb - fa @ Q.T).max() <= 1e-12 * np.abs(fa).max()
+    ma = _impact_block(1)
+    a, b = Oracle(ma), Oracle(_impact_block(1, Q))
+    a.run_cycles(150); b.run_cycles(150)
+    xa, xb = a.download_nodes(("X",))["X"], b.download_nodes(("X",))["X"]
+    assert np.abs(xb - xa @ Q.T).max() <= 1e-9 * np.abs(xa).max()
+    assert a.solid_state("pla").max() > 0.01
+    assert np.allclose(a.solid_state("sig"), b.solid_state("sig"), rtol=0, atol=1e-8 * np.abs(a.solid_state("sig")).max())   # the stress lives in the element's frame
+    # and the two formulations describe the same physics: displacements within a fraction of a per cent of each other
+    c = Oracle(_impact_block(0)); c.run_cycles(150)
+    xc = c.download_nodes(("X",))["X"]
+    assert np.abs(xc - xa).max() <= 5e-3 * np.abs(xa - ma.X).max()
+
+
+def test_corotational_axis_aligned_cube_without_spin_is_the_global_frame_to_second_order():
+    """A cube aligned with the axes under pure stretching has R = 1: the only difference to JCVT = 0 (JHBE = 1) is the
+    second-order strain-rate term (sdefo3.F:171-199), -dt/2 (L^T L) -- checked in closed form on the first elastic step."""
+    L = 1e-3 * np.diag([1.0, -0.4, 0.7])
+    out = []
+    for jcvt in (0, 1):
+        m = meshgen.hex_block(2, 2, 2, 2.0, 2.0, 2.0, jitter=0.0, prop=meshgen.default_prop_solid(jcvt=jcvt))
+        m.V = m.X @ L.T
+        o = Oracle(m); o.forces_phase(1e-3)
+        out.append((o.solid_state("sig")[:, 0].copy(), m.solid_groups[0].mat.shear))
+    (s0, G), (s1, _) = out
+    dt = 1e-3
+    D0 = np.diag(L); D1 = D0 - 0.5 * dt * D0 ** 2
+    dev = lambda D: 2 * G * dt * (D - D.sum() / 3)
+    assert np.allclose(s0[:3], dev(D0), rtol=1e-10)
+    assert np.allclose(np.sort(s1[:3]), np.sort(dev(D1)), rtol=1e-10)      # in the element's own axes: a permutation of x, y, z here
