@@ -48,7 +48,36 @@ def parse_listing(path):
                 ienergy=a[:, 5], kenergy_t=a[:, 6], kenergy_r=a[:, 7], extwork=a[:, 8], mass=a[:, 9], eltype=np.array(typ))
 
 
+def export_loi13_deck():
+    """Nodes, bricks (with their part) and node groups of qa-tests/miniqa/LOIS/LOI13/solide/data/MODELE_0000.rad: what
+    tests/qa_decks.loi13_solide() builds its model from (732 nodes, 464 + 48 bricks)."""
+    p = os.path.join(REF, "LOIS/LOI13/solide/data/MODELE_0000.rad")
+    if not os.path.exists(p):
+        print("missing", p); return
+    lines = [l.rstrip("\n") for l in open(p, errors="ignore")]
+
+    def block(key):
+        out, on = [], False
+        for l in lines:
+            if l.startswith("/"):
+                on = (l.strip() == key); continue
+            if on and not l.startswith("#") and l.strip():
+                out.append(l)
+        return out
+    nodes = [(int(l[:10]), float(l[10:30]), float(l[30:50]), float(l[50:70])) for l in block("/NODE")]
+    bricks, part = [], []
+    for k in (1, 2, 4, 5):
+        for l in block(f"/BRICK/{k}"):
+            bricks.append([int(l[i * 10:(i + 1) * 10]) for i in range(9)]); part.append(k)
+    grnod = lambda k: np.array([int(x) for l in block(f"/GRNOD/NODE/{k}")[1:] for x in l.split()], np.int32)
+    np.savez_compressed(os.path.join(HERE, "qa_loi13_deck.npz"), node_id=np.array([n[0] for n in nodes], np.int32),
+                        X=np.array([n[1:] for n in nodes]), brick=np.array(bricks, np.int32), part=np.array(part, np.int32),
+                        grnod2=grnod(2), grnod3=grnod(3))
+    print(f"loi13 deck: {len(nodes)} nodes, {len(bricks)} bricks")
+
+
 if __name__ == "__main__":
+    export_loi13_deck()
     for name, rel in DECKS.items():
         p = os.path.join(REF, rel)
         if not os.path.exists(p):

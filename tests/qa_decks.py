@@ -196,3 +196,46 @@ def inibri_stress() -> Model:
     m.adsky, m.iads, m.iadc, m.lsky = build_pon(8, m.ixs, m.ixc)
     m.initial_solid_sig = np.array([[900.0], [0.0], [0.0], [0.0], [0.0], [0.0]])
     return m
+
+
+def loi13_solide() -> Model:
+    """qa-tests/miniqa/LOIS/LOI13/solide (MODELE): a 30 mm cube of 464 8-node bricks (Isolid 1, Ismstr default -> 4, Iframe 2 =
+    Belytschko's co-rotational frame, qa 1.1, qb 0.05, h 0.1) of /MAT/PLAS_JOHNS (rho 0.78, E 210000, nu 0.3, a 206, b 450,
+    n 0.5, no rate term) crushed along z: the top face (/GRNOD 2) clamped, the bottom face (/GRNOD 3) held in x, y and driven in z
+    by /IMPVEL with the ramp v = 0.05 t.  48 more bricks of /MAT/RIGID (LAW13) sit inside: the Engine's force loop skips LAW13
+    groups (forint.F:355) -- but the Starter turns every LAW13 part into a rigid body of its own (lectur.F:8670-8690 RIGID_MAT; the
+    deck's nodes 730-732 are their masters), and rigid bodies are outside the built path.  Here the 48 bricks only add their mass
+    to the nodes they share, i.e. the inclusions are voids instead of rigid: the model is softer than the reference's, so only
+    what does not depend on them is comparable -- the time step of cycle 0 (test_qa_decks.py); from there the energies of the
+    listing run 16-19 % higher.  Units Mg, mm, s; /DT 0.9.  Geometry from tests/golden/qa_loi13_deck.npz
+    (make_golden_qa.export_loi13_deck)."""
+    import os
+    from openradioss_b200.model import SolidGroup
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "qa_loi13_deck.npz"))
+    nid, X = d["node_id"], d["X"].astype(float)
+    loc = {int(n): i + 1 for i, n in enumerate(nid)}                # user id -> 1-based index
+    br, part = d["brick"], d["part"]
+    conn = np.vectorize(loc.get)(br[:, 1:9]).astype(np.int32)
+    ixs_all = np.zeros((len(br), 11), np.int32); ixs_all[:, 0] = 1; ixs_all[:, 1:9] = conn; ixs_all[:, 9] = 1; ixs_all[:, 10] = br[:, 0]
+    vol_all = meshgen.brick_volumes(X, ixs_all)
+    rho = 0.78
+    MS = np.zeros(len(nid)); np.add.at(MS, (conn - 1).reshape(-1), np.repeat(rho * vol_all / 8.0, 8))     # LAW13 bricks included: same density
+    keep = part == 1
+    ixs = np.ascontiguousarray(ixs_all[keep]); vol0 = vol_all[keep]
+    mat = law2(rho, 210000.0, 0.3, 206.0, 450.0, 0.5)
+    prop = meshgen.default_prop_solid(jhbe=1, ismstr=4, jcvt=1)
+    n = len(nid)
+    icodt = np.zeros(n, np.int32)
+    icodt[[loc[int(k)] - 1 for k in d["grnod2"]]] = 7               # /BCS 111
+    g3 = np.array([loc[int(k)] for k in d["grnod3"]], np.int32)
+    icodt[g3 - 1] = 6                                               # /BCS 110: x, y
+    ctl = meshgen.default_control(0); ctl.dtfac_brick = 0.9
+    m = Model(X=X, V=np.zeros_like(X), VR=np.zeros_like(X), MS=MS, IN=np.zeros(n), control=ctl, ixs=ixs, vol0=vol0,
+              icodt=icodt, itab=nid.astype(np.int32))
+    ne = len(ixs)
+    m.solid_groups = [SolidGroup(nft=s0, nel=min(128, ne - s0), mat=mat, prop=prop, law=2) for s0 in range(0, ne, 128)]
+    m.adsky, m.iads, m.iadc, m.lsky = build_pon(n, m.ixs, m.ixc)
+    f1 = meshgen.add_function(m, [0.0, 100.0], [0.0, 5.0])
+    m.ibfv = np.stack([g3, np.full(len(g3), 3, np.int32), np.full(len(g3), f1, np.int32)], 1).astype(np.int32)
+    m.vel = np.tile(np.array([1.0, 0.0, 1.0e30, 1.0]), (len(g3), 1))
+    return m

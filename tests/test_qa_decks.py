@@ -93,6 +93,20 @@ def test_inibri_stress_oracle_reproduces_the_reference_listing():
     check_inibri(Oracle(qa_decks.inibri_stress()))
 
 
+def test_loi13_solide_first_time_step_matches_the_reference_listing():
+    """464 LAW2 bricks in the co-rotational frame (Iframe = 2): the element time step of cycle 0 -- SDLEN3's characteristic length,
+    the sound speed of M2LAW, DTFAC -- to the listing's four digits.  The later cycles are not comparable: the deck's LAW13
+    inclusions are rigid bodies in the reference (qa_decks.loi13_solide), and the listing's energies show it: they run 16-19 %
+    above a model with voids in their place, growing with the compression."""
+    g = listing("loi13_solide")
+    o = Oracle(qa_decks.loi13_solide())
+    r = run_listing(o, 101)
+    assert close(r[0:1, 1], g["dt"][0:1], 0.0).all() and r[0, 2] == 0.0
+    k = int(np.nonzero(g["cycle"] == 100)[0][0])
+    assert 0.75 * g["ienergy"][k] < r[100, 2] < g["ienergy"][k]            # softer than the reference, same order
+    assert abs(r[100, 0] - g["time"][k]) <= 1e-3 * g["time"][k]
+
+
 def test_membrane_damping_default_is_the_starters():
     """Without the Starter's 1.5 % membrane damping for QEPH (set_elgroup_param.F:83-108) the internal energy of ELEM_SAMP is
     4 % short at cycle 1 and 0.1 % short throughout: the listing discriminates that term."""
