@@ -43,7 +43,7 @@ VWAVE = (60.0, 100.0)
 # cycles 60-90 % of the plate's integration points yield at once, a state no crash deck stays in; from cycle 200 on it yields
 # locally (10-30 % of the points per cycle, every point has yielded before) -- the state the metric is quoted on.  The per-regime
 # kernel times are in profiles/r02_qeph_forces_ncu.md.
-PREROLL = {"c2_plate_qeph_1m": 200, "c3_plate_qeph_4m": 200, "tri_plate_1m_yielding": 200, "bt_plate_1m_yielding": 200}
+PREROLL = {"c2_plate_qeph_1m": 200, "c2_plate_qeph_1m_rates": 200, "c3_plate_qeph_4m": 200, "tri_plate_1m_yielding": 200, "bt_plate_1m_yielding": 200}
 
 STRONG = ("c3_plate_qeph_4m", "c4_tube", "c4_tube_small", "c1_taylor_bar")    # total model fixed, cut into `world` domains
 
@@ -71,6 +71,10 @@ def workload(name, world=1):
         return meshgen.shell_plate(1000 * world, 1000, 1000.0 * world, 1000.0, pulse_tau=0.05), "shell", 0
     if name == "tri_plate_1m":              # extra: 707 x 707 cells x 2 = 999 698 3-node shells per GPU, LAW36, NPT=5
         return meshgen.tri_plate(707 * world, 707, 1000.0 * world, 1000.0), "sh3n", 0
+    if name == "c2_plate_qeph_1m_rates":    # C2 with a rate-dependent /MAT/PLAS_TAB: three yield curves (strain rates 0, 0.1, 10 /ms: +0 / +8 / +20 %), strain-rate filter
+        x = np.array([0.0, 0.01, 0.02, 0.05, 0.10, 0.15, 0.20, 0.30]); y = np.array([250.0, 290.0, 315.0, 355.0, 395.0, 420.0, 435.0, 450.0])
+        return meshgen.shell_plate(1000 * world, 1000, 1000.0 * world, 1000.0, pulse_tau=0.05, vwave=VWAVE,
+                                   curves=[(x, y), (x, 1.08 * y), (x, 1.2 * y)], rates=[0.0, 0.1, 10.0]), "shell", 0
     if name == "tri_plate_1m_yielding":     # the same plate driven into yield like C2
         return meshgen.tri_plate(707 * world, 707, 1000.0 * world, 1000.0, vwave=VWAVE), "sh3n", 0
     if name == "bt_plate_1m_yielding":      # 1 M Belytschko-Tsay shells (Ishell 1), LAW36, NPT=5, yielding like C2 (the family the reference's own GPU path covers)

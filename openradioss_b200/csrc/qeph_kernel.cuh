@@ -124,7 +124,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
   if (W.tile_nx >= 0 && threadIdx.x < (4 * ORGPU_TILE * 4) / 128) prefetch_l2(reinterpret_cast<const char*>(W.g_nx->conn + (size_t)W.tile_nx * 4 * ORGPU_TILE) + 128 * threadIdx.x);
 #endif
   double dt_cand = K_EP30; int order = 0x7fffffff;
-  const unsigned wmask = (FAST == 1) ? __ballot_sync(0xffffffffu, e < g.ne) : 0u;     // the warp's lanes that own an element
+  const unsigned wmask = (FAST >= 1) ? __ballot_sync(0xffffffffu, e < g.ne) : 0u;     // the warp's lanes that own an element
   if (e < g.ne) {
     const double DT1 = P.cs->dt2;
     const int ISMSTR = g.prop.ismstr, NPT = g.prop.npt;
@@ -388,7 +388,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     ORGPU_OPAQUE(Z1); ORGPU_OPAQUE(AREA);
     // ---- CMAIN3
 #ifndef ORGPU_NO_COMPACT
-    if constexpr (FAST == 1 && STAGED) shell_material_loop_compact<true>(g, T, DT1, io, wmask);
+    if constexpr (FAST >= 1 && STAGED) shell_material_loop_compact<true, FAST>(g, T, DT1, io, wmask);
     else
 #endif
     shell_material_loop<LAW, true, STAGED, 0, FAST>(g, T, DT1, io);

@@ -20,14 +20,15 @@
 
 struct ShellSG {
   int ne, ne_pad, order0, blk0;
-  int law, npt, nvartmp, nhourg;
+  int law, npt, nvartmp, nhourg, vt_bytes;
   const int* conn;            // tile-major [tile][4][128], 0-based node
   const int* ngl;             // user ids [ne_pad]
   double* slab;               // [tile][nw][128]
   int nw, nw_rw;              // words per tile / written back
   int w_ip0, nwip;            // first word of integration point 0, words per point
   int iw_sigb;                // LBUF%SIGB (3 words: kinematic hardening, FISOKIN > 0) inside a point's words, -1: none
-  int w_vt, nvt;              // first word of the VARTMP int rows, int rows per point (1 when NRATE=1: only cursor 3 is live)
+  int w_vt, nvt;              // first word of the VARTMP int rows, int rows per point (1 when NRATE=1: only cursor 3 is live);
+                              // FAST = 2 with NRATE > 1: BYTE rows, NRATE per point (the cursors are search hints, not state)
   int w_thke, w_slot;         // initial-thickness word (-1 when ITHK>0), first word of the 4 slot int rows
   double* smstr;              // tile-major [tile][6][128]
   const double* tf; const int* npf;    // LAW36 function table (pairs), 0-based curve starts
@@ -195,7 +196,9 @@ __device__ __forceinline__ void law36_trial(const ShellSG& g, const TileAcc<STAG
     }
     const double YFAC1 = m.yfac[JJ - 1] * K_ONE, YFAC2 = m.yfac[JJ] * K_ONE;
     const int f1 = m.ifunc[JJ - 1], f2 = m.ifunc[JJ];
-    int ipos1 = T.ldi(g.w_vt, ipt * g.nvt + 1 + JJ), ipos2 = T.ldi(g.w_vt, ipt * g.nvt + 2 + JJ);
+    int ipos1, ipos2;
+    if constexpr (FAST == 2) { ipos1 = T.ldb_lane(g.w_vt, ipt * g.nvt + JJ - 1, threadIdx.x); ipos2 = T.ldb_lane(g.w_vt, ipt * g.nvt + JJ, threadIdx.x); }   // byte rows, one per rate curve
+    else { ipos1 = T.ldi(g.w_vt, ipt * g.nvt + 1 + JJ); ipos2 = T.ldi(g.w_vt, ipt * g.nvt + 2 + JJ); }
     double dydx1, y1, dydx2, y2;
     if (g.ct.n > 0) { vinter1c(g.ct, JJ - 1, ipos1, pla, dydx1, y1); vinter1c(g.ct, JJ, ipos2, pla, dydx2, y2); }
     else {
@@ -234,7 +237,8 @@ __device__ __forceinline__ void law36_trial(const ShellSG& g, const TileAcc<STAG
         H = H * fmax(K_ZERO, K_ONE);
       }
     }
-    T.sti(g.w_vt, ipt * g.nvt + 1 + JJ, ipos1); T.sti(g.w_vt, ipt * g.nvt + 2 + JJ, ipos2);
+    if constexpr (FAST == 2) { T.stb(g.w_vt, ipt * g.nvt + JJ - 1, ipos1); T.stb(g.w_vt, ipt * g.nvt + JJ, ipos2); }
+    else { T.sti(g.w_vt, ipt * g.nvt + 1 + JJ, ipos1); T.sti(g.w_vt, ipt * g.nvt + 2 + JJ, ipos2); }
   }
   if (m.yldcheck == 1) YLD = fmax(YLD, K_EM20);
 }
@@ -649,6 +653,53 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const Tile
   io.off = off; io.ssp = ssp; io.viscmx = viscmx; io.sigy = sigy; io.zcfac1 = zcfac1; io.zcfac2 = zcfac2; io.vol0 = vol0;
 }
 
+// Yield stress and slope of a LISTED point once more (pass 2 of the three-pass loop), any NRATE, FISOKIN = 0, no damage factor:
+// the same statements as law36_trial (sigeps36c.F:317-404) on the point's stored strain rate and plastic strain; the table
+// cursors of the point -- another lane's -- were advanced by pass 1 and are only read here (the walks are idempotent).
+__device__ __forceinline__ void law36_yield_again(const ShellSG& g, const TileAcc<true>& T, int ip, int tid, double epsd, double pla, double& YLD, double& H)
+{
+  const orgpu_law36& m = g.m36;
+  if (m.nrate == 1) {
+    int ipos = T.ldi_lane(g.w_vt, ip, tid);
+    const int f = m.ifunc[0];
+    double dydx, y1;
+    if (g.ct.n > 0) vinter1c(g.ct, 0, ipos, pla, dydx, y1);
+    else { const int i0 = __ldg(g.npf + f), i1 = __ldg(g.npf + f + 1); vinter1(g.tf, i0, i1 - i0, ipos, pla, dydx, y1); }
+    const double FACT = K_ONE * K_ONE * (m.yfac[0] * K_ONE);
+    H = dydx * FACT; YLD = y1 * FACT;
+  } else {
+    int JJ = 1;
+    for (int J = 2; J <= m.nrate - 1; J++) if (epsd >= m.rate[J - 1]) JJ = J;
+    double RFAC;
+    if (m.ismooth == 2) {
+      const double EPSP1 = fmax(m.rate[JJ - 1], K_EM20), EPSP2 = m.rate[JJ];
+      RFAC = or_div(log(or_div(fmax(epsd, K_EM20), EPSP1)), log(or_div(EPSP2, EPSP1)));
+    } else {
+      const double EPSP1 = m.rate[JJ - 1], EPSP2 = m.rate[JJ];
+      RFAC = or_div((epsd - EPSP1), (EPSP2 - EPSP1));
+    }
+    const double YFAC1 = m.yfac[JJ - 1] * K_ONE, YFAC2 = m.yfac[JJ] * K_ONE;
+    const int f1 = m.ifunc[JJ - 1], f2 = m.ifunc[JJ];
+    int ipos1 = T.ldb_lane(g.w_vt, ip * g.nvt + JJ - 1, tid), ipos2 = T.ldb_lane(g.w_vt, ip * g.nvt + JJ, tid);
+    double dydx1, y1, dydx2, y2;
+    if (g.ct.n > 0) { vinter1c(g.ct, JJ - 1, ipos1, pla, dydx1, y1); vinter1c(g.ct, JJ, ipos2, pla, dydx2, y2); }
+    else {
+      { const int i0 = __ldg(g.npf + f1), i1 = __ldg(g.npf + f1 + 1); vinter1(g.tf, i0, i1 - i0, ipos1, pla, dydx1, y1); }
+      { const int i0 = __ldg(g.npf + f2), i1 = __ldg(g.npf + f2 + 1); vinter1(g.tf, i0, i1 - i0, ipos2, pla, dydx2, y2); }
+    }
+    y1 = y1 * YFAC1; y2 = y2 * YFAC2;
+    YLD = K_ONE * (y1 + RFAC * (y2 - y1));
+    YLD = fmax(YLD, K_EM20);
+    dydx1 = dydx1 * YFAC1; dydx2 = dydx2 * YFAC2;
+    H = K_ONE * (dydx1 + RFAC * (dydx2 - dydx1));
+    YLD = YLD * fmax(K_ZERO, K_ONE);
+    H = H * fmax(K_ZERO, K_ONE);
+  }
+  if (m.yldcheck == 1) YLD = fmax(YLD, K_EM20);
+  H = fmax(K_ZERO, H);
+}
+
+
 // ---- the through-thickness loop of the FAST = 1 kernels, in three passes ---------------------------------------------------
 // The Newton return of Iplas = 1 (sigeps36c.F:503-593: three steps, 13 divisions in series) costs a warp its full length for
 // every point at which ANY of its lanes yields.  In a deck that yields locally -- the usual state of a crash model, and of the
@@ -668,7 +719,9 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const Tile
 // three / four listed points per lane side by side (spills: 0.427 / 0.444 / 0.494 in the 10-30 % state), rows most of whose
 // lanes yield returning on the spot (a second copy of the return in the code: +3 % even where no point yields -- the kernel is
 // instruction-fetch sensitive), the same with one copy of the return in a merged loop of turns (0.405, and 0.331 elastic).
-template <bool FLAG_ZCFAC>
+// FAST = 1: one static curve in the kernel parameters (everything about the law known at compile time); FAST = 2: any number of rate
+// curves, in the parameters or in global memory, strain-rate filter -- what /MAT/PLAS_TAB decks with rate dependence use.
+template <bool FLAG_ZCFAC, int FAST = 1>
 __device__ __forceinline__ void shell_material_loop_compact(const ShellSG& g, const TileAcc<true>& T, double dt1, MatIO& io, unsigned wmask)
 {
   const orgpu_law36& m = g.m36;
@@ -699,13 +752,13 @@ __device__ __forceinline__ void shell_material_loop_compact(const ShellSG& g, co
   unsigned pmask = 0; int cnt = 0;                  // points of this lane that yield; entries of the warp's list
   #pragma unroll 1
   for (int ipt = 0; ipt < npt; ipt++) {
-    IpState s = ip_load<36, true, 1>(g, T, ipt);
+    IpState s = ip_load<36, true, FAST>(g, T, ipt);
     const int ipos_old = s.ipos;
     const double thkly = c_WF[qrow + ipt];
     const double zt = (c_Z0[qrow + ipt] + K_ZERO) * io.thk0;
     const double dexx = io.exx + zt * io.kxx, deyy = io.eyy + zt * io.kyy, dexy = io.exy + zt * io.kxy;
     double YLD, H, EPST;
-    law36_trial<true, false, 1>(g, T, ipt, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, io.gs, io.epsd_pg, zt, s, YLD, H, EPST);
+    law36_trial<true, false, FAST>(g, T, ipt, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, io.gs, io.epsd_pg, zt, s, YLD, H, EPST);
     H = fmax(K_ZERO, H);
     const double S1 = s.sxx + s.syy, S2 = s.sxx - s.syy, S3 = s.sxy;
     const double SVM2 = K_FOURTH * S1 * S1 + (K_THREE_OVER_4 * S2 * S2 + K_THREE * S3 * S3);
@@ -714,7 +767,7 @@ __device__ __forceinline__ void shell_material_loop_compact(const ShellSG& g, co
     if (pl) etse = or_div(H, (H + E));
     if (FLAG_ZCFAC) { zcfac1 = zcfac1 + etse * thkly; zcfac2 = fmin(etse, zcfac2); }
     viscmx = fmax(DM, viscmx);
-    ip_store<36, true, 1>(g, T, ipt, s, ipos_old, K_ZERO);         // trial state (PLA unchanged)
+    ip_store<36, true, FAST>(g, T, ipt, s, ipos_old, K_ZERO);         // trial state (PLA unchanged)
     const unsigned b = __ballot_sync(wmask, pl);
     if (pl) { list[cnt + __popc(b & ((1u << lane) - 1u))] = (unsigned char)(lane | (ipt << 5)); pmask |= 1u << ipt; }
     cnt += __popc(b);
@@ -728,13 +781,16 @@ __device__ __forceinline__ void shell_material_loop_compact(const ShellSG& g, co
     double* const own = wbase + l;                                   // word 0 of the point's owner
     double* const q = own + (size_t)(g.w_ip0 + ip * g.nwip) * ORGPU_TILE;
     const double sxx = q[IW_SIG * ORGPU_TILE], syy = q[(IW_SIG + 1) * ORGPU_TILE], sxy = q[(IW_SIG + 2) * ORGPU_TILE], pla = q[IW_PLA * ORGPU_TILE];
-    int ipos = T.ldi_lane(g.w_vt, ip, threadIdx.x - lane + l);
-    double dydx, y1;
-    vinter1c(g.ct, 0, ipos, pla, dydx, y1);                          // the cursor already stands on the segment: same slope, same value
-    const double FACT = K_ONE * K_ONE * (m.yfac[0] * K_ONE);
-    double H = dydx * FACT, YLD = y1 * FACT;
-    if (m.yldcheck == 1) YLD = fmax(YLD, K_EM20);
-    H = fmax(K_ZERO, H);
+    double H, YLD;
+    if (FAST == 1) {
+      int ipos = T.ldi_lane(g.w_vt, ip, threadIdx.x - lane + l);
+      double dydx, y1;
+      vinter1c(g.ct, 0, ipos, pla, dydx, y1);                        // the cursor already stands on the segment: same slope, same value
+      const double FACT = K_ONE * K_ONE * (m.yfac[0] * K_ONE);
+      H = dydx * FACT; YLD = y1 * FACT;
+      if (m.yldcheck == 1) YLD = fmax(YLD, K_EM20);
+      H = fmax(K_ZERO, H);
+    } else law36_yield_again(g, T, ip, threadIdx.x - lane + l, q[IW_EPSD * ORGPU_TILE], pla, YLD, H);
     double S1 = sxx + syy, S2 = sxx - syy;
     L36Newton n;
     n.AA = K_FOURTH * S1 * S1;

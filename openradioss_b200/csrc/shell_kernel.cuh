@@ -115,12 +115,23 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
       d.fail_pthkf = p;
     }
     d.w_vt = d.w_ip0 + d.npt * d.nwip;
-    d.nvt = (G.law == 36) ? (G.m36.nrate == 1 ? 1 : d.nvartmp) : 0;
-    d.nw_rw = d.w_vt + (d.npt * d.nvt + 1) / 2;
-    int w = d.nw_rw;
-    d.w_thke = (G.prop.ithk > 0) ? -1 : w; if (d.w_thke >= 0) w++;
-    d.w_slot = w; w += 2;
-    d.nw = w;
+    // The VARTMP cursors of a rate-dependent LAW36 (2 + NRATE ints per point) would push the NPT = 5 tile past what stages
+    // three-per-SM; they are search hints (the segment found does not depend on where the search starts), so the groups the
+    // FAST = 2 kernel takes keep one BYTE per rate curve and point when every curve has at most 255 points.
+    bool vt_bytes = !getenv("ORGPU_NO_FAST") && G.law == 36 && G.m36.nrate > 1 && G.prop.ipla == 1 && G.m36.ifail == 0 && G.m36.fisokin == 0.0 &&
+                    G.fail.irupt == 0 && G.prop.npt <= 5 && nnode == 4 && shell_is_qeph(G.prop);
+    if (vt_bytes) for (int j = 0; j < G.m36.nrate; j++) if (npf[G.m36.ifunc[j] + 1] - npf[G.m36.ifunc[j]] > 255) vt_bytes = false;
+    for (;;) {
+      d.vt_bytes = vt_bytes;
+      d.nvt = (G.law == 36) ? (G.m36.nrate == 1 ? 1 : vt_bytes ? G.m36.nrate : d.nvartmp) : 0;
+      d.nw_rw = d.w_vt + (vt_bytes ? (d.npt * d.nvt + 7) / 8 : (d.npt * d.nvt + 1) / 2);
+      int w = d.nw_rw;
+      d.w_thke = (G.prop.ithk > 0) ? -1 : w; if (d.w_thke >= 0) w++;
+      d.w_slot = w; w += 2;
+      d.nw = w;
+      if (!vt_bytes || (size_t)d.nw * ORGPU_TILE * 8 <= ORGPU_STAGE_MAX_BYTES) break;
+      vt_bytes = false;                                          // does not stage either way: the generic kernel and its int rows
+    }
     HostSlab H; H.init(d.nw, np);
     const int ixs_ = (nnode == 3) ? 6 : 7, iuid = (nnode == 3) ? 5 : 6;      // row length of IXTG / IXC, column of the user id
     std::vector<int> conn((size_t)nnode * np, 0), ngl(np, 0), conn_t;
@@ -175,6 +186,14 @@ static inline bool shell_fast(const ShellSG& d) {
          && d.prop.npt <= 5 && (size_t)d.nw * ORGPU_TILE * 8 <= ORGPU_STAGE_MAX_BYTES;     // the three-pass loop: staged tile, NPT <= 5 (shell_common.cuh)
 }
 
+// ... and its wider sibling (FAST = 2): LAW36, Iplas = 1, no failure, isotropic hardening with ANY number of rate curves (in the
+// kernel parameters or in global memory) -- rate-dependent /MAT/PLAS_TAB, the usual crash material -- through the three-pass loop
+static inline bool shell_fast2(const ShellSG& d) {
+  static const bool off = getenv("ORGPU_NO_FAST") != nullptr;
+  return !off && !shell_fast(d) && d.law == 36 && d.prop.ipla == 1 && d.m36.ifail == 0 && d.m36.fisokin == 0.0 && d.fail.irupt == 0
+         && d.prop.npt <= 5 && (d.m36.nrate == 1 || d.vt_bytes) && (size_t)d.nw * ORGPU_TILE * 8 <= ORGPU_STAGE_MAX_BYTES;
+}
+
 static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky, int roww, CycleState* cs,
                                 const DtBlocks& db, const FinalizeArgs& fa, cudaStream_t st)
 {
@@ -189,6 +208,7 @@ static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky
   } else if (shell_is_qeph(S.d.prop)) {
     if (S.d.law == 36 && S.d.m36.ifail == 2) shell_launch_one(qeph_forces_kernel<37, true>, qeph_forces_kernel<37, false>, P, nblk, st);
     else if (S.d.law == 36 && shell_fast(S.d)) shell_launch_one(qeph_forces_kernel<36, true, 1>, qeph_forces_kernel<36, false>, P, nblk, st);
+    else if (S.d.law == 36 && shell_fast2(S.d)) shell_launch_one(qeph_forces_kernel<36, true, 2>, qeph_forces_kernel<36, false>, P, nblk, st);
     else if (S.d.law == 36) shell_launch_one(qeph_forces_kernel<36, true>, qeph_forces_kernel<36, false>, P, nblk, st);
     else               shell_launch_one(qeph_forces_kernel<2, true>, qeph_forces_kernel<2, false>, P, nblk, st);
   } else {
@@ -237,6 +257,7 @@ static inline int shell_tab_variant(const ShellSGHost& S)
   const ShellSG& d = S.d;
   if (S.sh3n || (size_t)d.nw * ORGPU_TILE * 8 > ORGPU_STAGE_MAX_BYTES) return -1;
   if (d.law == 36 && d.m36.ifail == 2) return -1;
+  if (shell_is_qeph(d.prop) && shell_fast2(d)) return -1;                       // no table-driven copy of the FAST = 2 kernel
   if (shell_is_qeph(d.prop)) return d.law == 36 ? (shell_fast(d) ? SHV_QEPH36F : SHV_QEPH36) : SHV_QEPH2;
   return d.law == 36 ? (shell_fast(d) ? SHV_BT36F : SHV_BT36) : SHV_BT2;
 }

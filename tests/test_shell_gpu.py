@@ -96,6 +96,27 @@ def test_qeph_law36_rate_dependent_curves():
     assert o.shell_state("pla").max() > 0.0
 
 
+@pytest.mark.parametrize("npt", [1, 3, 5])
+@pytest.mark.parametrize("ismooth", [1, 2])
+def test_qeph_law36_rate_dependent_three_pass(npt, ismooth):
+    """Rate-dependent LAW36 through the three-pass loop (FAST = 2): byte cursors, one per rate curve and point; linear and
+    logarithmic interpolation between the rate curves; enough cycles for the cursors to move along the curves."""
+    curves, rates = three_curves()
+    prop = meshgen.default_prop_shell(thick=1.5, npt=npt)
+    m = meshgen.shell_plate(9, 7, 90.0, 70.0, prop=prop, pressure=40.0, vrand=40.0, curves=curves, rates=rates)
+    for grp in m.shell_groups: grp.mat.ismooth = ismooth
+    g, o = cycle_check(m, ncheck=8)
+    assert o.shell_state("pla").max() > 0.01
+
+
+def test_qeph_law36_rate_dependent_long_curves_keep_int_cursors():
+    """Curves of more than 255 points do not fit the byte cursors: generic kernel, int rows, same results."""
+    x = np.concatenate([[0.0], np.geomspace(1e-4, 0.6, 299)]); y = 250.0 + 330.0 * x ** 0.3
+    m = meshgen.shell_plate(7, 6, 70.0, 60.0, pressure=40.0, vrand=40.0, curves=[(x, y), (x, 1.2 * y), (x, 1.5 * y)], rates=[0.0, 0.5, 50.0])
+    g, o = cycle_check(m, ncheck=5)
+    assert o.shell_state("pla").max() > 0.01
+
+
 def test_qeph_law2_johnson_cook():
     m = meshgen.shell_plate(7, 7, 70.0, 70.0, law=2, pressure=30.0, vrand=30.0)
     g, o = cycle_check(m, ncheck=4, state_tol=1e-10)      # exp/log in the JC hardening: libm vs CUDA
