@@ -33,7 +33,7 @@ c3_forces_kernel(const __grid_constant__ ShellParams P)
   if (W.tile_nx >= 0 && threadIdx.x < (3 * ORGPU_TILE * 4) / 128) prefetch_l2(reinterpret_cast<const char*>(g.conn + (size_t)W.tile_nx * 3 * ORGPU_TILE) + 128 * threadIdx.x);
 #endif
   double dt_cand = K_EP30; int order = 0x7fffffff;
-  const unsigned wmask = (FAST == 1) ? __ballot_sync(0xffffffffu, e < g.ne) : 0u;     // the warp's lanes that own an element
+  const unsigned wmask = (FAST >= 1) ? __ballot_sync(0xffffffffu, e < g.ne) : 0u;     // the warp's lanes that own an element
   if (e < g.ne) {
     const double DT1 = P.cs->dt2;
     const int ISMSTR = g.prop.ismstr, NPT = g.prop.npt, ISH3N = g.prop.ihbe;
@@ -187,7 +187,7 @@ c3_forces_kernel(const __grid_constant__ ShellParams P)
     }
     // ---- CMAIN3
     io.area = AREA; io.thk0 = THK0; io.gs = G * SHF; io.rho = RHO; io.off = OFF; io.sigy = K_EP30;
-    if constexpr (FAST == 1 && STAGED) shell_material_loop_compact<false>(g, T, DT1, io, wmask);     // three-pass loop (shell_common.cuh)
+    if constexpr (FAST >= 1 && STAGED) shell_material_loop_compact<false, FAST>(g, T, DT1, io, wmask);     // three-pass loop (shell_common.cuh)
     else shell_material_loop<LAW, false, STAGED, 0, FAST>(g, T, DT1, io);
     OFF = io.off;
     if (g.bal && P.cs->ipri) shell_bilan<3, STAGED>(P, T, tile, e, RHO, OFF);        // C3BILAN (c3forc3.F:616)

@@ -119,7 +119,7 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
     // three-per-SM; they are search hints (the segment found does not depend on where the search starts), so the groups the
     // FAST = 2 kernel takes keep one BYTE per rate curve and point when every curve has at most 255 points.
     bool vt_bytes = !getenv("ORGPU_NO_FAST") && G.law == 36 && G.m36.nrate > 1 && G.prop.ipla == 1 && G.m36.ifail == 0 && G.m36.fisokin == 0.0 &&
-                    G.fail.irupt == 0 && G.prop.npt <= 5 && nnode == 4 && shell_is_qeph(G.prop);
+                    G.fail.irupt == 0 && G.prop.npt <= 5;
     if (vt_bytes) for (int j = 0; j < G.m36.nrate; j++) if (npf[G.m36.ifunc[j] + 1] - npf[G.m36.ifunc[j]] > 255) vt_bytes = false;
     for (;;) {
       d.vt_bytes = vt_bytes;
@@ -203,6 +203,7 @@ static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky
   if (S.sh3n) {
     if (S.d.law == 36 && S.d.m36.ifail == 2) shell_launch_one(c3_forces_kernel<37, true>, c3_forces_kernel<37, false>, P, nblk, st);
     else if (S.d.law == 36 && shell_fast(S.d)) shell_launch_one(c3_forces_kernel<36, true, 1>, c3_forces_kernel<36, false>, P, nblk, st);
+    else if (S.d.law == 36 && shell_fast2(S.d)) shell_launch_one(c3_forces_kernel<36, true, 2>, c3_forces_kernel<36, false>, P, nblk, st);
     else if (S.d.law == 36) shell_launch_one(c3_forces_kernel<36, true>, c3_forces_kernel<36, false>, P, nblk, st);
     else               shell_launch_one(c3_forces_kernel<2, true>, c3_forces_kernel<2, false>, P, nblk, st);
   } else if (shell_is_qeph(S.d.prop)) {
@@ -214,6 +215,7 @@ static void launch_shell_forces(ShellSGHost& S, const DevNodes& nd, double* fsky
   } else {
     if (S.d.law == 36 && S.d.m36.ifail == 2) shell_launch_one(bt_forces_kernel<37, true>, bt_forces_kernel<37, false>, P, nblk, st);
     else if (S.d.law == 36 && shell_fast(S.d)) shell_launch_one(bt_forces_kernel<36, true, 1>, bt_forces_kernel<36, false>, P, nblk, st);
+    else if (S.d.law == 36 && shell_fast2(S.d)) shell_launch_one(bt_forces_kernel<36, true, 2>, bt_forces_kernel<36, false>, P, nblk, st);
     else if (S.d.law == 36) shell_launch_one(bt_forces_kernel<36, true>, bt_forces_kernel<36, false>, P, nblk, st);
     else               shell_launch_one(bt_forces_kernel<2, true>, bt_forces_kernel<2, false>, P, nblk, st);
   }
@@ -251,15 +253,14 @@ static int shell_state_xfer(std::vector<ShellSGHost>& sgs, int numelc, int field
 
 // ---- batched launches: all super-groups of one kernel variant in ONE launch (table-driven CTA -> (super-group, tile)) --------
 // variant of a shell super-group whose table-driven kernel is compiled (-1: launched on its own)
-enum { SHV_QEPH36F = 0, SHV_QEPH36, SHV_QEPH2, SHV_BT36F, SHV_BT36, SHV_BT2, SHV_COUNT };
+enum { SHV_QEPH36F = 0, SHV_QEPH36R, SHV_QEPH36, SHV_QEPH2, SHV_BT36F, SHV_BT36R, SHV_BT36, SHV_BT2, SHV_COUNT };   // F / R: three-pass loop, one static curve / rate curves
 static inline int shell_tab_variant(const ShellSGHost& S)
 {
   const ShellSG& d = S.d;
   if (S.sh3n || (size_t)d.nw * ORGPU_TILE * 8 > ORGPU_STAGE_MAX_BYTES) return -1;
   if (d.law == 36 && d.m36.ifail == 2) return -1;
-  if (shell_is_qeph(d.prop) && shell_fast2(d)) return -1;                       // no table-driven copy of the FAST = 2 kernel
-  if (shell_is_qeph(d.prop)) return d.law == 36 ? (shell_fast(d) ? SHV_QEPH36F : SHV_QEPH36) : SHV_QEPH2;
-  return d.law == 36 ? (shell_fast(d) ? SHV_BT36F : SHV_BT36) : SHV_BT2;
+  if (shell_is_qeph(d.prop)) return d.law == 36 ? (shell_fast(d) ? SHV_QEPH36F : shell_fast2(d) ? SHV_QEPH36R : SHV_QEPH36) : SHV_QEPH2;
+  return d.law == 36 ? (shell_fast(d) ? SHV_BT36F : shell_fast2(d) ? SHV_BT36R : SHV_BT36) : SHV_BT2;
 }
 template <class K>
 static void shell_launch_tab_k(K kern, const ShellParams& P, int nblk, size_t bytes, cudaStream_t st)
@@ -270,9 +271,11 @@ static void launch_shell_forces_tab(int variant, const ShellSG* d_tab, const int
   ShellParams P; memset(&P.sg, 0, sizeof P.sg); P.nd = nd; P.fsky = fsky; P.cs = cs; P.db = db; P.sgtab = d_tab; P.cta_map = d_map;
   switch (variant) {
     case SHV_QEPH36F: shell_launch_tab_k(qeph_forces_kernel<36, true, 1, true>, P, nblk, bytes, st); break;
+    case SHV_QEPH36R: shell_launch_tab_k(qeph_forces_kernel<36, true, 2, true>, P, nblk, bytes, st); break;
     case SHV_QEPH36:  shell_launch_tab_k(qeph_forces_kernel<36, true, 0, true>, P, nblk, bytes, st); break;
     case SHV_QEPH2:   shell_launch_tab_k(qeph_forces_kernel<2, true, 0, true>, P, nblk, bytes, st); break;
     case SHV_BT36F:   shell_launch_tab_k(bt_forces_kernel<36, true, 1, true>, P, nblk, bytes, st); break;
+    case SHV_BT36R:   shell_launch_tab_k(bt_forces_kernel<36, true, 2, true>, P, nblk, bytes, st); break;
     case SHV_BT36:    shell_launch_tab_k(bt_forces_kernel<36, true, 0, true>, P, nblk, bytes, st); break;
     default:          shell_launch_tab_k(bt_forces_kernel<2, true, 0, true>, P, nblk, bytes, st); break;
   }

@@ -303,6 +303,35 @@ def test_many_super_groups_one_model():
     assert tg["neltst"] == to["neltst"] and tg["dt2"] == pytest.approx(to["dt2"], rel=1e-12)
 
 
+@pytest.mark.parametrize("ihbe", [24, 1])
+def test_many_super_groups_rate_dependent(ihbe):
+    """the same with a rate-dependent LAW36: the table-driven copies of the FAST = 2 kernels (QEPH and BT)"""
+    curves, rates = three_curves()
+    pa, pb = meshgen.default_prop_shell(thick=2.0, ihbe=ihbe), meshgen.default_prop_shell(thick=2.0, ihbe=ihbe)
+    pb.h1 = pa.h1 * 1.25
+    m = meshgen.shell_plate(128, 20, 1280.0, 200.0, prop=pa, pressure=40.0, vrand=40.0, curves=curves, rates=rates)
+    for k, sg in enumerate(m.shell_groups):
+        sg.prop = pa if k % 2 == 0 else pb
+    assert len(m.shell_groups) == 20
+    g, o = pair(m)
+    g.run_cycles(20); o.run_cycles(20)
+    ng, no = g.download_nodes(("X", "V", "VR")), o.download_nodes(("X", "V", "VR"))
+    for k in ("X", "V", "VR"):
+        assert rel_err(ng[k], no[k]) <= 1e-10, k
+    assert o.shell_state("pla").max() > 0.01
+    assert rel_err(g.shell_state("pla"), o.shell_state("pla")) <= 1e-10
+
+
+@pytest.mark.parametrize("ihbe", [1, 3])
+@pytest.mark.parametrize("npt", [3, 5])
+def test_bt_law36_rate_dependent_three_pass(ihbe, npt):
+    curves, rates = three_curves()
+    prop = meshgen.default_prop_shell(thick=1.5, npt=npt, ihbe=ihbe)
+    m = meshgen.shell_plate(9, 7, 90.0, 70.0, prop=prop, pressure=40.0, vrand=40.0, curves=curves, rates=rates)
+    g, o = cycle_check(m, ncheck=8)
+    assert o.shell_state("pla").max() > 0.01
+
+
 def energies(b, m):
     d = b.download_nodes(("V", "VR"))
     ke = 0.5 * (m.MS[:, None] * d["V"] ** 2).sum() + 0.5 * (m.IN[:, None] * d["VR"] ** 2).sum()
