@@ -125,12 +125,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
 #endif
   double dt_cand = K_EP30; int order = 0x7fffffff;
   const unsigned wmask = (FAST >= 1) ? __ballot_sync(0xffffffffu, e < g.ne) : 0u;     // the warp's lanes that own an element
-#ifdef ORGPU_PHASE_SYNC
-  const bool full_tile = (tile + 1) * ORGPU_TILE <= g.ne;    // experiment: keep the CTA's four warps in the same code region
-#define PHASE_SYNC() do { if (full_tile) __syncthreads(); } while (0)
-#else
-#define PHASE_SYNC() do {} while (0)
-#endif
+  const bool full_tile = (tile + 1) * ORGPU_TILE <= g.ne;    // all 128 threads own an element: the phase barriers are safe (common.cuh)
   if (e < g.ne) {
     const double DT1 = P.cs->dt2;
     const int ISMSTR = g.prop.ismstr, NPT = g.prop.npt;
@@ -393,14 +388,14 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     ORGPU_OPAQUE(XL2); ORGPU_OPAQUE(YL2); ORGPU_OPAQUE(XL3); ORGPU_OPAQUE(YL3); ORGPU_OPAQUE(XL4); ORGPU_OPAQUE(YL4);
     ORGPU_OPAQUE(Z1); ORGPU_OPAQUE(AREA);
     // ---- CMAIN3
-    PHASE_SYNC();
+    PHASE_SYNC(0);
 #ifndef ORGPU_NO_COMPACT
-    if constexpr (FAST >= 1 && STAGED) shell_material_loop_compact<true, FAST>(g, T, DT1, io, wmask);
+    if constexpr (FAST >= 1 && STAGED) shell_material_loop_compact<true, FAST>(g, T, DT1, io, wmask, full_tile);
     else
 #endif
     shell_material_loop<LAW, true, STAGED, 0, FAST>(g, T, DT1, io);
     OFF = io.off;
-    PHASE_SYNC();
+    PHASE_SYNC(1);
 #ifndef ORGPU_NO_BILAN
     if (g.bal && P.cs->ipri) shell_bilan<4, STAGED>(P, T, tile, e, io.rho, OFF);     // CBILAN (czforc3.F:639)
 #endif
@@ -418,6 +413,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
     const double SHF = (NPT == 1) ? K_ZERO : g.prop.shf, SHFSR = (NPT == 1) ? K_ZERO : g.prop.shfsr;
     const double AMU = (g.prop.h1 == K_ZERO) ? K_ZEP01 + K_FIVEEM3 : g.prop.h1;
     // ---- CNDT3
+    PHASE_SYNC(4);
     double STI, STIR = K_ZERO;
     {
       double VISCMX = fmax(io.viscmx, AMU);
@@ -462,7 +458,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       VF[1][1] = VF[1][1] - C2 * (Y24 * MO[1] + X24S8);
     }
     // ---- CZFINTN1 : elasto-plastic hourglass stresses + linear damping
-    PHASE_SYNC();
+    PHASE_SYNC(2);
     {
       const double FAC1 = g.prop.cvis;
       const double C7 = K_FOUR_OVER_3;
@@ -590,6 +586,7 @@ qeph_forces_kernel(const __grid_constant__ ShellParams P)
       T.st(SW_EINT, ein1); T.st(SW_EINT + 1, ein2);
     }
     // ---- CZPROJN (IFINI=0) + CUPDTN3P
+    PHASE_SYNC(3);
     if (OFF < K_ONE) OFFG = OFF;
     T.st(SW_OFF, OFFG);
     const bool dead = OFFG < K_ZERO;

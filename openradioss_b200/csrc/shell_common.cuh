@@ -722,7 +722,7 @@ __device__ __forceinline__ void law36_yield_again(const ShellSG& g, const TileAc
 // FAST = 1: one static curve in the kernel parameters (everything about the law known at compile time); FAST = 2: any number of rate
 // curves, in the parameters or in global memory, strain-rate filter -- what /MAT/PLAS_TAB decks with rate dependence use.
 template <bool FLAG_ZCFAC, int FAST = 1>
-__device__ __forceinline__ void shell_material_loop_compact(const ShellSG& g, const TileAcc<true>& T, double dt1, MatIO& io, unsigned wmask)
+__device__ __forceinline__ void shell_material_loop_compact(const ShellSG& g, const TileAcc<true>& T, double dt1, MatIO& io, unsigned wmask, bool full_tile = false)
 {
   const orgpu_law36& m = g.m36;
   const int npt = g.prop.npt;
@@ -774,6 +774,7 @@ __device__ __forceinline__ void shell_material_loop_compact(const ShellSG& g, co
     sigy = YLD;
   }
   __syncwarp(wmask);
+  PHASE_SYNC(7);
   // ---- pass 2: one listed point per lane and turn (sigeps36c.F:503-593; FISOKIN = 0: HK = 0, AAA = 0 exactly, :520-527)
   #pragma unroll 1
   for (int k = lane; k < cnt; k += nact) {
@@ -810,6 +811,7 @@ __device__ __forceinline__ void shell_material_loop_compact(const ShellSG& g, co
     if (ip == npt - 1) own[(SW_MOM + 2) * ORGPU_TILE] = YLD + n.HI * n.DPLA_I;
   }
   __syncwarp(wmask);
+  PHASE_SYNC(7);
   // ---- pass 3
   double thkn = T.ld(SW_THK);
   if ((pmask >> (npt - 1)) & 1u) sigy = T.ld(SW_MOM + 2);
