@@ -113,6 +113,9 @@ int  orgpu_download_nodes(orgpu_engine* e, double* X, double* V, double* VR, dou
 int  orgpu_download_fsky(orgpu_engine* e, double* fsky /*(8,LSKY)*/);
 /* fields: 0 sig(6) 1 eint 2 rho 3 qvis 4 pla 5 epsd 6 vol 7 off 8 temp 9 smstr(21) 10 stra(6) 11 wpla (LAW36) 12 sigb(6) (LAW2 with FISOKIN > 0: LBUF%SIGB) 13 dfmax (/FAIL/JOHNSON); out[k*numels+e] */
 int  orgpu_download_solid_state(orgpu_engine* e, int field, double* out);
+/* shell fields: 0 for(5) 1 mom(3) 2 eint(2) 3 thk 4 off 5 stra(8) 6 epsd 7 hourg(12 | 5) 8 smstr(6) 9 sig(5*npt) 10 pla(npt) 11 epsd_ip(npt)
+ * 12 temp(npt) 13 sigb(3*npt) 14 dfmax(npt) 15 foff(npt) 16 plap(npt) (LAW36 VP = 1: UVAR(2), the filtered plastic strain rate,
+ * sigeps36c.F:705, 976-982); out[k*numelc+e] */
 int  orgpu_download_shell_state(orgpu_engine* e, int field, double* out);
 int  orgpu_download_sh3n_state(orgpu_engine* e, int field, double* out);   /* shell fields; smstr has 3 words, no hourg */
 /* -- state hand-over in the other direction (restart / a run that starts from an initial state: the role of

@@ -78,7 +78,8 @@ typedef struct orgpu_law36 {
   int    ifunc[ORGPU_MAXFUNC36];  /* 0-based curve ids into the function table         */
   int    nrate;             /* UPARAM(1)                                               */
   int    israte;            /* IPM(3)                                                  */
-  int    vp, ifail, yldcheck, ismooth; /* UPARAM(2*nrate+26..29)                       */
+  int    vp, ifail, yldcheck, ismooth; /* UPARAM(2*nrate+26..29); vp = 1 (curves on the plastic strain rate): shells only,
+                                           needs nrate > 1 as the Starter enforces (hm_read_mat36.F:199) */
 } orgpu_law36;
 
 /* Function table TF/NPF for LAW36 curves: curve c occupies points

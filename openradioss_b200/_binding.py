@@ -24,7 +24,7 @@ class Binding:
                         vol=(6, 1), off=(7, 1), temp=(8, 1), smstr=(9, 21), stra=(10, 6), wpla=(11, 1), sigb=(12, 6), dfmax=(13, 1))
     SHELL_FIELDS = dict(forc=(0, 5), mom=(1, 3), eint=(2, 2), thk=(3, 1), off=(4, 1), stra=(5, 8),
                         epsd=(6, 1), hourg=(7, 12), smstr=(8, 6), sig=(9, 5), pla=(10, 1),
-                        epsd_ip=(11, 1), temp=(12, 1), sigb=(13, 3), dfmax=(14, 1), foff=(15, 1))
+                        epsd_ip=(11, 1), temp=(12, 1), sigb=(13, 3), dfmax=(14, 1), foff=(15, 1), plap=(16, 1))
 
     def __init__(self, lib: C.CDLL, prefix: str, returns_status: bool):
         self.lib, self.p, self.status = lib, prefix, returns_status
@@ -202,7 +202,7 @@ class Binding:
     def shell_state(self, name):
         fid, nc = self.SHELL_FIELDS[name]
         npt = 1
-        if name in ("sig", "pla", "epsd_ip", "temp", "sigb", "dfmax", "foff"):
+        if name in ("sig", "pla", "epsd_ip", "temp", "sigb", "dfmax", "foff", "plap"):
             npt = max(g.prop.npt for g in self.model.shell_groups)
         if name == "hourg" and not all(21 <= g.prop.ihbe <= 29 for g in self.model.shell_groups):
             nc = 12 if any(21 <= g.prop.ihbe <= 29 for g in self.model.shell_groups) else 5
@@ -214,7 +214,7 @@ class Binding:
         """State of the 3-node shells, same field names as shell_state (no hourglass words; smstr has 3 components)."""
         fid, nc = self.SHELL_FIELDS[name]
         npt = 1
-        if name in ("sig", "pla", "epsd_ip", "temp", "sigb", "dfmax", "foff"):
+        if name in ("sig", "pla", "epsd_ip", "temp", "sigb", "dfmax", "foff", "plap"):
             npt = max(g.prop.npt for g in self.model.sh3n_groups)
         if name == "smstr":
             nc = 3

@@ -27,6 +27,7 @@ struct ShellSG {
   int nw, nw_rw;              // words per tile / written back
   int w_ip0, nwip;            // first word of integration point 0, words per point
   int iw_sigb;                // LBUF%SIGB (3 words: kinematic hardening, FISOKIN > 0) inside a point's words, -1: none
+  int iw_plap;                // UVAR(2) of LAW36 with VP = 1 (filtered plastic strain rate of the point), -1: none
   int w_vt, nvt;              // first word of the VARTMP int rows, int rows per point (1 when NRATE=1: only cursor 3 is live);
                               // FAST = 2 with NRATE > 1: BYTE rows, NRATE per point (the cursors are search hints, not state)
   int w_thke, w_slot;         // initial-thickness word (-1 when ITHK>0), first word of the 4 slot int rows
@@ -65,7 +66,7 @@ struct MatIO {
   double fo[5], mo[3];                             // out: new GBUF%FOR / GBUF%MOM
 };
 
-struct IpState { double sxx, syy, sxy, syz, szx, pla, epsd, temp; int ipos; double sbx, sby, sbxy; };   // sb*: back stress (FISOKIN > 0)
+struct IpState { double sxx, syy, sxy, syz, szx, pla, epsd, temp; int ipos; double sbx, sby, sbxy, plap; };   // sb*: back stress (FISOKIN > 0); plap: UVAR(2) (LAW36 VP = 1)
 
 // state of one integration point out of / into the CTA's tile
 template <int LAW, bool STAGED, int FAST = 0>
@@ -76,7 +77,8 @@ __device__ __forceinline__ IpState ip_load(const ShellSG& g, const TileAcc<STAGE
   s.sxx = T.ld(w + IW_SIG); s.syy = T.ld(w + IW_SIG + 1); s.sxy = T.ld(w + IW_SIG + 2); s.syz = T.ld(w + IW_SIG + 3); s.szx = T.ld(w + IW_SIG + 4);
   s.pla = T.ld(w + IW_PLA);
   s.epsd = T.ld(w + IW_EPSD);
-  s.temp = K_ZERO; s.ipos = 0; s.sbx = K_ZERO; s.sby = K_ZERO; s.sbxy = K_ZERO;
+  s.temp = K_ZERO; s.ipos = 0; s.sbx = K_ZERO; s.sby = K_ZERO; s.sbxy = K_ZERO; s.plap = K_ZERO;
+  if (FAST == 0 && LAW != 2 && g.iw_plap >= 0) s.plap = T.ld(w + g.iw_plap);
   if (FAST != 1 && g.iw_sigb >= 0) { s.sbx = T.ld(w + g.iw_sigb); s.sby = T.ld(w + g.iw_sigb + 1); s.sbxy = T.ld(w + g.iw_sigb + 2); }
   if (LAW == 2) { if (g.m2.has_temp) s.temp = T.ld(w + IW_TEMP); }
   else if (g.m36.nrate == 1) s.ipos = T.ldi(g.w_vt, ipt);
@@ -90,6 +92,7 @@ __device__ __forceinline__ void ip_store(const ShellSG& g, const TileAcc<STAGED>
   T.st(w + IW_PLA, s.pla);
   T.st(w + IW_EPSD, s.epsd);
   if (FAST != 1 && g.iw_sigb >= 0) { T.st(w + g.iw_sigb, s.sbx); T.st(w + g.iw_sigb + 1, s.sby); T.st(w + g.iw_sigb + 2, s.sbxy); }
+  if (FAST == 0 && LAW != 2 && g.iw_plap >= 0) T.st(w + g.iw_plap, s.plap);
   if (LAW == 2) { if (g.m2.has_temp && s.temp != temp_old) T.st(w + IW_TEMP, s.temp); }
   else if (g.m36.nrate == 1 && s.ipos != ipos_old) T.sti(g.w_vt, ipt, s.ipos);
 }
@@ -160,14 +163,20 @@ __device__ __forceinline__ void law36_trial(const ShellSG& g, const TileAcc<STAG
   s.syz = s.syz + gs * deyz;
   s.szx = s.szx + gs * dezx;
   // strain rate
+  // VP = 1 (sigeps36c.F:665-923): the curves are interpolated on the point's filtered PLASTIC strain rate UVAR(2); LBUF%EPSD is
+  // left alone (the Starter keeps VP = 0 for a single curve, hm_read_mat36.F:199)
+  const bool vp1 = (FAST == 0) && m.vp == 1;
   double epsd;
-  if (m.israte == 0) {
-    const double exx = dexx * dtinv, eyy = deyy * dtinv, exy = dexy * dtinv;
-    epsd = K_HALF * (fabs(exx + eyy) + or_sqrt((exx - eyy) * (exx - eyy) + exy * exy));
-  } else {
-    epsd = asrate * epsd_pg + (K_ONE - asrate) * s.epsd;
+  if (vp1) epsd = s.plap;
+  else {
+    if (m.israte == 0) {
+      const double exx = dexx * dtinv, eyy = deyy * dtinv, exy = dexy * dtinv;
+      epsd = K_HALF * (fabs(exx + eyy) + or_sqrt((exx - eyy) * (exx - eyy) + exy * exy));
+    } else {
+      epsd = asrate * epsd_pg + (K_ONE - asrate) * s.epsd;
+    }
+    s.epsd = epsd;
   }
-  s.epsd = epsd;
   // yield stress and hardening modulus from the tabulated curves
   if (FAST == 1 || m.nrate == 1) {
     int ipos = s.ipos;
@@ -264,10 +273,12 @@ template <bool STAGED, bool FAIL2, int FAST = 0>
 __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>& T, int ipt, int ipla, double asrate,
                                          double dexx, double deyy, double dexy, double deyz, double dezx, double dtinv,
                                          double thklyl, double gs, double epsd_pg, double zt, double& off,
-                                         IpState& s, double& thk, double& ssp, double& etse, double& yld_out)
+                                         IpState& s, double& thk, double& ssp, double& etse, double& yld_out, double dt1)
 {
   const orgpu_law36& m = g.m36;
   const double E = m.young, G3 = m.g3;
+  const bool vp1 = (FAST == 0) && m.vp == 1;
+  if (vp1) ipla = 1;                                   // VP = 1: always the three Newton steps (sigeps36c.F:832-921)
   ssp = m.soundsp; etse = K_ONE;
   double pla = s.pla;
   double YLD, H, EPST;
@@ -342,6 +353,8 @@ __device__ __forceinline__ void law36_ip(const ShellSG& g, const TileAcc<STAGED>
       etse = or_div(H, (H + E));
     }
   }
+  // VP = 1: filter of the plastic strain rate (sigeps36c.F:976-982)
+  if (vp1) { const double DTINV = or_div(K_ONE, fmax(dt1, K_EM20)); s.plap = asrate * DPLA_I * DTINV + (K_ONE - asrate) * s.plap; }
   // kinematic part of the hardening (sigeps36c.F:986-1002): the back stress grows along the new stress, which gets it back
   if (FAST != 1 && m.fisokin > K_ZERO) {
     const double ALPHA = or_div(m.fisokin * H * DPLA_I, YLD);
@@ -585,7 +598,7 @@ __device__ __forceinline__ void shell_material_loop(const ShellSG& g, const Tile
     if (LAW != 2) {
       const int ipla_ = (FAST == 1) ? 1 : g.prop.ipla;
       law36_ip<STAGED, LAW == 37, FAST>(g, T, ipt, ipla_, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, thklyl, io.gs, io.epsd_pg, zt, off,
-               s, thkn, ssp, etse, sigy);
+               s, thkn, ssp, etse, sigy, dt1);
     } else {
       law2_ip(g, g.prop.ipla, npt, dt1, asrate, dexx, deyy, dexy, io.eyz, io.exz, dtinv, thklyl, io.gs, io.epsd_pg,
               off, off_old, ioff_duct, epchk, s, thkn, etse, sigy);

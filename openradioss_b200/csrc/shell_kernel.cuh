@@ -36,7 +36,8 @@ static int shell_add_group(std::vector<HostShellGroup>& groups, int nel, int nft
   g.nel = nel; g.nft = nft; g.law = law; g.sh3n = sh3n ? 1 : 0; g.prop = *prop;
   if (law == 36) {
     g.m36 = *(const orgpu_law36*)mat;
-    if (g.m36.fisokin < 0.0 || g.m36.fisokin > 1.0 || g.m36.vp != 0 || g.m36.ifail < 0 || g.m36.ifail > 2) { orgpu_set_error("LAW36 VP=1 / FISOKIN outside [0,1] are outside the built path"); return -5; }
+    if (g.m36.fisokin < 0.0 || g.m36.fisokin > 1.0 || g.m36.vp < 0 || g.m36.vp > 1 || g.m36.ifail < 0 || g.m36.ifail > 2) { orgpu_set_error("LAW36 VP outside {0,1} / FISOKIN outside [0,1] are outside the built path"); return -5; }
+    if (g.m36.vp == 1 && g.m36.nrate < 2) { orgpu_set_error("LAW36 VP=1 needs more than one curve (the Starter resets VP to 0 for a single curve, hm_read_mat36.F:199)"); return -5; }
     if (g.m36.ifail == 2 && prop->istrain == 0) { orgpu_set_error("LAW36 tensile-strain failure (IFAIL=2) needs the total strains (Istrain=1)"); return -5; }
     if (g.m36.nrate < 1 || g.m36.nrate > ORGPU_MAXFUNC36) { orgpu_set_error("LAW36 NRATE=%d out of range", g.m36.nrate); return -5; }
   } else {
@@ -105,6 +106,8 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
     d.w_ip0 = SW_HOURG + d.nhourg; d.nwip = has_temp ? 8 : 7;
     d.iw_sigb = -1;
     if ((G.law == 36 && G.m36.fisokin > 0.0) || (G.law == 2 && G.m2.fisokin > 0.0)) { d.iw_sigb = d.nwip; d.nwip += 3; }      // LBUF%SIGB: back stress of the kinematic hardening
+    d.iw_plap = -1;
+    if (G.law == 36 && G.m36.vp == 1) d.iw_plap = d.nwip++;     // UVAR(2): filtered plastic strain rate of the point
     d.fail = G.fail; d.iw_dfmax = d.iw_foff = -1; d.fail_pthkf = 0.0;
     if (G.fail.irupt == 1) {                                    // /FAIL/JOHNSON: damage and point flag of every integration point
       d.iw_dfmax = d.nwip++; d.iw_foff = d.nwip++;
@@ -118,7 +121,7 @@ static int shell_build_supergroups(std::vector<HostShellGroup>& groups, std::vec
     // The VARTMP cursors of a rate-dependent LAW36 (2 + NRATE ints per point) would push the NPT = 5 tile past what stages
     // three-per-SM; they are search hints (the segment found does not depend on where the search starts), so the groups the
     // FAST = 2 kernel takes keep one BYTE per rate curve and point when every curve has at most 255 points.
-    bool vt_bytes = !getenv("ORGPU_NO_FAST") && G.law == 36 && G.m36.nrate > 1 && G.prop.ipla == 1 && G.m36.ifail == 0 && G.m36.fisokin == 0.0 &&
+    bool vt_bytes = !getenv("ORGPU_NO_FAST") && G.law == 36 && G.m36.nrate > 1 && G.prop.ipla == 1 && G.m36.ifail == 0 && G.m36.fisokin == 0.0 && G.m36.vp == 0 &&
                     G.fail.irupt == 0 && G.prop.npt <= 5;
     if (vt_bytes) for (int j = 0; j < G.m36.nrate; j++) if (npf[G.m36.ifunc[j] + 1] - npf[G.m36.ifunc[j]] > 255) vt_bytes = false;
     for (;;) {
@@ -190,7 +193,7 @@ static inline bool shell_fast(const ShellSG& d) {
 // kernel parameters or in global memory) -- rate-dependent /MAT/PLAS_TAB, the usual crash material -- through the three-pass loop
 static inline bool shell_fast2(const ShellSG& d) {
   static const bool off = getenv("ORGPU_NO_FAST") != nullptr;
-  return !off && !shell_fast(d) && d.law == 36 && d.prop.ipla == 1 && d.m36.ifail == 0 && d.m36.fisokin == 0.0 && d.fail.irupt == 0
+  return !off && !shell_fast(d) && d.law == 36 && d.prop.ipla == 1 && d.m36.ifail == 0 && d.m36.fisokin == 0.0 && d.m36.vp == 0 && d.fail.irupt == 0
          && d.prop.npt <= 5 && (d.m36.nrate == 1 || d.vt_bytes) && (size_t)d.nw * ORGPU_TILE * 8 <= ORGPU_STAGE_MAX_BYTES;
 }
 
@@ -237,6 +240,7 @@ static int shell_state_xfer(std::vector<ShellSGHost>& sgs, int numelc, int field
       case 12: if (d.law != 2 || !d.m2.has_temp) continue; ipw = IW_TEMP; nc = d.npt; break;
       case 13: if (d.iw_sigb < 0) continue; nc = 3 * d.npt; break;
       case 14: if (d.iw_dfmax < 0) continue; ipw = d.iw_dfmax; nc = d.npt; break; case 15: if (d.iw_foff < 0) continue; ipw = d.iw_foff; nc = d.npt; break;
+      case 16: if (d.iw_plap < 0) continue; ipw = d.iw_plap; nc = d.npt; break;
       default: orgpu_set_error("unknown shell field %d", field); return -1;
     }
     for (int k = 0; k < nc; k++) {

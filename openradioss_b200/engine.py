@@ -119,6 +119,8 @@ class Engine(Binding):
                 ck["shell"]["temp"] = self.shell_state("temp")          # per-point temperature of thermal Johnson-Cook shells
             if any(getattr(g.mat, "fisokin", 0.0) > 0.0 for g in self.model.shell_groups):
                 ck["shell"]["sigb"] = self.shell_state("sigb")          # back stress of the kinematic hardening
+            if any(g.law == 36 and getattr(g.mat, "vp", 0) == 1 for g in self.model.shell_groups):
+                ck["shell"]["plap"] = self.shell_state("plap")          # LAW36 VP = 1: filtered plastic strain rate of the points (UVAR(2))
             if any(getattr(g, "fail", None) is not None for g in self.model.shell_groups):
                 ck["shell"].update(dfmax=self.shell_state("dfmax"), foff=self.shell_state("foff"))     # /FAIL/JOHNSON damage and point flags
         if self.model.numeltg:
@@ -127,6 +129,8 @@ class Engine(Binding):
                 ck["sh3n"]["temp"] = self.sh3n_state("temp")
             if any(getattr(g.mat, "fisokin", 0.0) > 0.0 for g in self.model.sh3n_groups):
                 ck["sh3n"]["sigb"] = self.sh3n_state("sigb")
+            if any(g.law == 36 and getattr(g.mat, "vp", 0) == 1 for g in self.model.sh3n_groups):
+                ck["sh3n"]["plap"] = self.sh3n_state("plap")
             if any(getattr(g, "fail", None) is not None for g in self.model.sh3n_groups):
                 ck["sh3n"].update(dfmax=self.sh3n_state("dfmax"), foff=self.sh3n_state("foff"))
         if self.model.numels and any(getattr(g, "law", 2) == 2 and getattr(g.mat, "fisokin", 0.0) > 0.0 for g in self.model.solid_groups):

@@ -130,6 +130,7 @@ int orc_add_shell_group(void* h,int nel,int nft,int law,const void* mat,const or
   if(nel>MVSIZ-1) return -1;
   if(law!=2 && law!=36) return -2;
   if(prop->npt<1 || prop->npt>10) return -3;
+  if(law==36){ const orgpu_law36* m=(const orgpu_law36*)mat; if(m->vp<0 || m->vp>1 || (m->vp==1 && m->nrate<2)) return -5; }   /* hm_read_mat36.F:199 */
   o->cgroups.push_back(orc_shell_group_new(nel,nft,law,mat,prop));
   return (int)o->cgroups.size()-1;
 }
@@ -142,6 +143,7 @@ int orc_add_sh3n_group(void* h,int nel,int nft,int law,const void* mat,const org
   if(law!=2 && law!=36) return -2;
   if(prop->npt<1 || prop->npt>10) return -3;
   if(prop->ihbe!=1 && prop->ihbe!=2) return -4;
+  if(law==36){ const orgpu_law36* m=(const orgpu_law36*)mat; if(m->vp<0 || m->vp>1 || (m->vp==1 && m->nrate<2)) return -5; }
   OrcShellGroup* g=orc_shell_group_new(nel,nft,law,mat,prop);
   g->nhourg=0; g->HOURG.clear(); g->SMSTR.assign(3*nel,0);
   o->tgroups.push_back(g);

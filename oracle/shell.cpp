@@ -28,7 +28,7 @@ OrcShellGroup* orc_shell_group_new(int nel,int nft,int law,const void* mat,const
   for(auto& lb:g->ip){
     lb.sig.assign(5*nel,0); lb.pla.assign(nel,0); lb.epsd.assign(nel,0);
     lb.temp.assign(nel, law==2? g->m2.tini : 0.0); lb.sigb.assign(3*nel,0); lb.off.assign(nel,1.0);
-    lb.dfmax.assign(nel,0.0); lb.foff.assign(nel,1.0);
+    lb.dfmax.assign(nel,0.0); lb.foff.assign(nel,1.0); lb.plap.assign(nel,0.0);
     lb.vartmp.assign((size_t)(g->nvartmp>0?g->nvartmp:1)*nel,0);
   }
   return g;
@@ -50,6 +50,7 @@ void orc_shell_group_state(const OrcShellGroup& g,int field,size_t ne,double* ou
     case 13: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].sigb,3,3*(int)p); break;   /* LBUF%SIGB (kinematic hardening) */
     case 14: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].dfmax,1,(int)p); break;     /* /FAIL/JOHNSON damage */
     case 15: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].foff,1,(int)p); break;      /* ... and point flag */
+    case 16: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].plap,1,(int)p); break;      /* LAW36 VP = 1: UVAR(2), filtered plastic strain rate */
   }
 }
 
@@ -68,5 +69,6 @@ void orc_shell_group_state_up(OrcShellGroup& g,int field,size_t ne,const double*
     case 13: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].sigb,3,3*(int)p); break;
     case 14: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].dfmax,1,(int)p); break;
     case 15: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].foff,1,(int)p); break;
+    case 16: for(size_t p=0;p<g.ip.size();p++) cp(g.ip[p].plap,1,(int)p); break;
   }
 }

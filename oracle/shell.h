@@ -16,7 +16,7 @@ struct OrcShellGroup {
   /* GBUF */
   std::vector<double> FOR, MOM, EINT, THK, OFF, STRA, EPSD, HOURG, SMSTR, THKE;
   /* LBUF per integration point */
-  struct Lbuf { std::vector<double> sig, pla, epsd, temp, sigb, off; std::vector<int> vartmp;
+  struct Lbuf { std::vector<double> sig, pla, epsd, temp, sigb, off, plap; std::vector<int> vartmp;
                 std::vector<double> dfmax, foff; };    /* /FAIL/JOHNSON: FBUF%FLOC%DAMMX, FBUF%FLOC%OFF of the point */
   orgpu_fail fail{};               /* failure model of the group's material (irupt = 0: none) */
   std::vector<Lbuf> ip;

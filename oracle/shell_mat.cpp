@@ -54,9 +54,15 @@ struct IpIO {             /* one integration point, one element */
 /* ---- SIGEPS36C, VP=0 branch, one element ------------------------------------------------ */
 void sigeps36c(const Oracle& o, const orgpu_law36& m, int ipla, double asrate, const ShellMatIn& in, IpIO& s,
                double& pla, double& epsd, int* vartmp, double& off, double& thk, double& ssp, double& viscmax,
-               double& etse, double& yld_out, double* sigb /*SIGBXX, SIGBYY, SIGBXY of the point*/)
+               double& etse, double& yld_out, double* sigb /*SIGBXX, SIGBYY, SIGBXY of the point*/,
+               double& plap /*UVAR(2): filtered plastic strain rate of the point (VP = 1)*/, double dt1)
 {
   const int NITER=3;
+  /* VP = 1 (sigeps36c.F:665-923, 976-982): the curves are interpolated on the PLASTIC strain rate UVAR(2) instead of the total
+   * one, the return is always the three Newton steps of Iplas = 1, LBUF%EPSD is left alone; the Starter keeps VP = 0 for a
+   * single curve (hm_read_mat36.F:199) */
+  const bool vp1=(m.vp==1);
+  if(vp1) ipla=1;
   const int nrate=m.nrate;
   const double E=m.young, A1=m.a1u, A2=m.a2u, G=m.shear, G3=m.g3;
   const double NU_MNU=m.nu_mnu, T_PNU=m.t_pnu, U_MNU=m.u_mnu, FISOKIN=m.fisokin;
@@ -78,7 +84,8 @@ void sigeps36c(const Oracle& o, const orgpu_law36& m, int ipla, double asrate, c
   s.signyz=s.sigoyz+GS*s.depsyz;
   s.signzx=s.sigozx+GS*s.depszx;
   /* strain rate (:288-296) */
-  if(m.israte==0){
+  if(vp1){ /* :665-: no total strain rate */ }
+  else if(m.israte==0){
     epsd=K_HALF*( std::fabs(s.epspxx+s.epspyy)
          + std::sqrt( (s.epspxx-s.epspyy)*(s.epspxx-s.epspyy) + s.epspxy*s.epspxy ) );
   } else {
@@ -99,15 +106,16 @@ void sigeps36c(const Oracle& o, const orgpu_law36& m, int ipla, double asrate, c
     else if(FISOKIN==K_ONE){ const double YLD0=o.TF[2*(size_t)o.NPF[f]+1]; YLD=YLD0*FACT; }
     else { const double YLD0=o.TF[2*(size_t)o.NPF[f]+1]; YLD=((K_ONE-FISOKIN)*y1+FISOKIN*YLD0)*FACT; }
   } else {
+    const double rate_x = vp1 ? plap : epsd;                            /* :705 PLAP = UVAR(2) */
     int JJ=1;
-    for(int J=2;J<=nrate-1;J++) if(epsd>=m.rate[J-1]) JJ=J;
+    for(int J=2;J<=nrate-1;J++) if(rate_x>=m.rate[J-1]) JJ=J;
     double RFAC,YFAC1,YFAC2;
     if(m.ismooth==2){
       double EPSP1=std::max(m.rate[JJ-1],K_EM20), EPSP2=m.rate[JJ];
-      RFAC=std::log(std::max(epsd,K_EM20)/EPSP1)/std::log(EPSP2/EPSP1);
+      RFAC=std::log(std::max(rate_x,K_EM20)/EPSP1)/std::log(EPSP2/EPSP1);
     } else {
       double EPSP1=m.rate[JJ-1], EPSP2=m.rate[JJ];
-      RFAC=(epsd-EPSP1)/(EPSP2-EPSP1);
+      RFAC=(rate_x-EPSP1)/(EPSP2-EPSP1);
     }
     YFAC1=m.yfac[JJ-1]*FACYLDI; YFAC2=m.yfac[JJ]*FACYLDI;
     const int J1=JJ,J2=JJ+1;
@@ -230,6 +238,8 @@ void sigeps36c(const Oracle& o, const orgpu_law36& m, int ipla, double asrate, c
       etse=H/(H+E);
     }
   }
+  /* plastic strain rate filter (sigeps36c.F:976-982) */
+  if(vp1){ const double DTINV=K_ONE/std::max(dt1,K_EM20); plap=asrate*DPLA_I*DTINV+(K_ONE-asrate)*plap; }
   /* kinematic part of the hardening (sigeps36c.F:986-1002): the back stress grows along the new stress, which gets it back */
   if(FISOKIN>K_ZERO){
     const double HKIN=FISOKIN*H;
@@ -483,7 +493,7 @@ void orc_cmain3(const Oracle& o, OrcShellGroup& g, int i, bool flag_zcfac, Shell
     s.sigoxx=lb.sig[i]; s.sigoyy=lb.sig[nel+i]; s.sigoxy=lb.sig[2*nel+i]; s.sigoyz=lb.sig[3*nel+i]; s.sigozx=lb.sig[4*nel+i];
     if(g.law==36){
       double sb[3]={lb.sigb[i],lb.sigb[nel+i],lb.sigb[2*nel+i]};
-      sigeps36c(o,g.m36,g.prop.ipla,asrate,in,s,lb.pla[i],lb.epsd[i],&lb.vartmp[(size_t)g.nvartmp*i],off,thkn,ssp,viscmx,etse,sigy,sb);
+      sigeps36c(o,g.m36,g.prop.ipla,asrate,in,s,lb.pla[i],lb.epsd[i],&lb.vartmp[(size_t)g.nvartmp*i],off,thkn,ssp,viscmx,etse,sigy,sb,lb.plap[i],dt1);
       lb.sigb[i]=sb[0]; lb.sigb[nel+i]=sb[1]; lb.sigb[2*nel+i]=sb[2];
     } else {
       double sb[3]={lb.sigb[i],lb.sigb[nel+i],lb.sigb[2*nel+i]};

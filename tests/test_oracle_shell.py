@@ -202,3 +202,53 @@ def test_kinematic_hardening_shows_the_bauschinger_effect():
     d_iso, d_kin = iso[-1, 3] - iso[399, 3], kin[-1, 3] - kin[399, 3]
     assert d_kin > d_iso + 2e-4            # ~ (sigma_max - sigma_y0) * 2 / E' of extra reverse flow
     assert kin[-1, 2] < kin[399, 2]                                    # the back stress follows the reversed flow
+
+
+# ---- LAW36 with VP = 1: curves interpolated on the filtered PLASTIC strain rate (sigeps36c.F:665-923, 976-982) ---------------------
+def _vp1_run(vp, ncyc=500, rate=2.0, dt=1.0e-5):
+    x = np.array([0.0, 0.01, 0.03, 0.08, 0.2, 0.5]); y = np.array([250.0, 300.0, 340.0, 390.0, 440.0, 480.0])
+    m = meshgen.shell_plate(2, 1, 20.0, 10.0, pressure=0.0, clamp=False, jitter=0.0, zjitter=0.0,
+                            curves=[(x, y), (x, 1.15 * y), (x, 1.4 * y)], rates=[0.0, 0.5, 50.0])
+    for g in m.shell_groups:
+        g.mat.vp = vp; g.prop.dm = 0.0
+    o = Oracle(m)
+    hist = []
+    for c in range(ncyc):
+        V = np.zeros_like(m.X); V[:, 0] = rate * m.X[:, 0]
+        o.upload_nodes(X=m.X, V=V, VR=np.zeros_like(V))
+        o.forces_phase(dt)
+        sig = o.shell_state("sig").reshape(5, 5, -1)
+        hist.append((sig[2, 0, 0], sig[2, 1, 0], o.shell_state("pla")[2, 0], o.shell_state("plap")[2, 0], o.shell_state("epsd_ip")[2, 0]))
+    return np.array(hist), m.shell_groups[0].mat, (x, y), dt
+
+
+def test_law36_vp1_filters_the_plastic_strain_rate_and_leaves_the_total_one_alone():
+    h, mat, _, dt = _vp1_run(1)
+    a = min(1.0, mat.asrate * dt)
+    assert h[-1, 2] > 0.003 and np.all(h[:, 4] == 0.0)               # plastic; LBUF%EPSD untouched
+    dpla = np.diff(np.concatenate([[0.0], h[:, 2]]))
+    plap = 0.0
+    for c in range(len(h)):                                            # UVAR(2) <- a * DPLA / dt + (1 - a) * UVAR(2)
+        plap = a * dpla[c] / dt + (1.0 - a) * plap
+        assert np.isclose(h[c, 3], plap, rtol=1e-9, atol=1e-12), c
+    assert 1.5 < h[-1, 3] < 2.0 * 2.0 / np.sqrt(3.0)                   # steady flow with eps_yy = 0: just below 2/sqrt(3) times the stretch rate of 2 / ms
+
+
+def test_law36_vp1_stress_sits_on_the_curve_interpolated_at_the_plastic_rate():
+    h, mat, (x, y), dt = _vp1_run(1)
+    sxx, syy, pla, plap = h[-1, 0], h[-1, 1], h[-1, 2], h[-2, 3]       # the yield stress of the last cycle used the rate of the one before
+    svm = np.sqrt(sxx * sxx + syy * syy - sxx * syy)
+    rfac = (plap - 0.5) / (50.0 - 0.5)
+    y0 = np.interp(pla, x, y)
+    assert np.isclose(svm, y0 * (1.15 + rfac * (1.4 - 1.15)), rtol=2e-4)
+    # the total-rate form (VP = 0) reads a higher rate during the elastic rise and the same one in steady flow
+    h0, *_ = _vp1_run(0)
+    assert np.isclose(h0[-1, 0], h[-1, 0], rtol=5e-3) and h0[-1, 3] == 0.0 and h0[-1, 4] > 0.0
+
+
+def test_law36_vp1_needs_rate_curves():
+    m = meshgen.shell_plate(2, 1, 20.0, 10.0)
+    for g in m.shell_groups:
+        g.mat.vp = 1
+    with pytest.raises(Exception):
+        Oracle(m)

@@ -102,6 +102,16 @@ def test_c3_rate_dependent_curves_long_table_in_global_memory():
     assert o.sh3n_state("pla").max() > 0.0
 
 
+def test_c3_law36_vp1_plastic_strain_rate():
+    x = np.array([0.0, 0.01, 0.03, 0.08, 0.2, 0.5]); y = np.array([250.0, 300.0, 340.0, 390.0, 440.0, 480.0])
+    prop = meshgen.default_prop_shell(thick=1.5, ihbe=2, npt=5)
+    m = meshgen.tri_plate(8, 7, 80.0, 70.0, prop=prop, pressure=40.0, vrand=40.0, curves=[(x, y), (x, 1.15 * y), (x, 1.4 * y)], rates=[0.0, 0.5, 50.0])
+    for grp in m.sh3n_groups: grp.mat.vp = 1
+    g, o = cycle_check(m, ncheck=8)
+    assert o.sh3n_state("pla").max() > 0.01 and o.sh3n_state("plap").max() > 0.0
+    assert rel_err(g.sh3n_state("plap"), o.sh3n_state("plap")) <= 1e-11
+
+
 @pytest.mark.parametrize("npt", [1, 5])
 def test_c3_rate_dependent_three_pass(npt):
     """three short curves (kernel parameters), byte cursors, the three-pass loop of the triangle kernel"""

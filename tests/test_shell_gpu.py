@@ -117,6 +117,31 @@ def test_qeph_law36_rate_dependent_long_curves_keep_int_cursors():
     assert o.shell_state("pla").max() > 0.01
 
 
+@pytest.mark.parametrize("ihbe,npt,ismooth", [(24, 5, 1), (24, 3, 2), (1, 5, 1), (3, 3, 1)])
+def test_law36_vp1_plastic_strain_rate(ihbe, npt, ismooth):
+    """LAW36 with VP = 1: curves on the filtered plastic strain rate (UVAR(2): one more word per point), always the Newton
+    return; QEPH and BT; the rate state itself is compared too."""
+    curves, rates = three_curves()
+    prop = meshgen.default_prop_shell(thick=1.5, npt=npt, ihbe=ihbe, ipla=0)          # Iplas is overridden by VP = 1
+    m = meshgen.shell_plate(9, 7, 90.0, 70.0, prop=prop, pressure=40.0, vrand=40.0, curves=curves, rates=rates)
+    for grp in m.shell_groups: grp.mat.vp = 1; grp.mat.ismooth = ismooth
+    g, o = cycle_check(m, ncheck=8, fields=STATE + ("plap",))
+    assert o.shell_state("pla").max() > 0.01 and o.shell_state("plap").max() > 0.0
+    assert np.all(o.shell_state("epsd_ip") == 0.0)
+
+
+def test_law36_vp1_with_mixed_hardening_and_restart():
+    curves, rates = three_curves()
+    m = meshgen.shell_plate(8, 6, 80.0, 60.0, pressure=40.0, vrand=40.0, curves=curves, rates=rates)
+    for grp in m.shell_groups: grp.mat.vp = 1; grp.mat.fisokin = 0.4
+    g, o = cycle_check(m, ncheck=6, fields=STATE + ("plap", "sigb"))
+    ck = g.checkpoint(); assert "plap" in ck["shell"]
+    g2 = Engine(m); g2.restore(ck)
+    g.run_cycles(5); g2.run_cycles(5)
+    assert np.array_equal(g.download_nodes(("X",))["X"], g2.download_nodes(("X",))["X"])
+    assert np.array_equal(g.shell_state("plap"), g2.shell_state("plap"))
+
+
 def test_qeph_law2_johnson_cook():
     m = meshgen.shell_plate(7, 7, 70.0, 70.0, law=2, pressure=30.0, vrand=30.0)
     g, o = cycle_check(m, ncheck=4, state_tol=1e-10)      # exp/log in the JC hardening: libm vs CUDA
