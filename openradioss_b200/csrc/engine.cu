@@ -428,10 +428,11 @@ int orgpu_add_solid_group(orgpu_engine* e, int nel, int nft, const orgpu_law2* m
   NEED(e && mat && prop && vol0 && nel > 0 && !e->finalized, -1, "orgpu_add_solid_group: bad arguments / already finalized");
   NEED(nft >= 0 && nft + nel <= e->numels, -4, "orgpu_add_solid_group: elements [%d,%d) outside IXS (%d)", nft, nft + nel, e->numels);
   NEED(mat->fisokin >= 0.0 && mat->fisokin <= 1.0, -4, "LAW2 FISOKIN = %g outside [0, 1]", mat->fisokin);
-  NEED(prop->jhbe == 0 || prop->jhbe == 1 || prop->jhbe == 2, -5, "Isolid=%d is outside the built path (0,1,2)", prop->jhbe);
+  NEED(prop->jhbe == 0 || prop->jhbe == 1 || prop->jhbe == 2 || prop->jhbe == 101 || prop->jhbe == 102, -5, "Isolid=%d is outside the built path (0,1,2,101,102)", prop->jhbe);
   NEED(prop->ismstr == 1 || prop->ismstr == 2 || prop->ismstr == 4, -5, "Ismstr=%d is outside the built path (1,2,4)", prop->ismstr);
   NEED(prop->jcvt == 0 || (prop->jcvt == 1 && prop->jhbe == 1), -5, "solid Iframe: JCVT=%d with Isolid=%d is outside the built path (0 global; 1 co-rotational with Isolid 1)", prop->jcvt, prop->jhbe);
   HostSolidGroup g; g.nel = nel; g.nft = nft; g.law = 2; g.mat = *mat; memset(&g.m36, 0, sizeof g.m36); g.prop = *prop; g.vol0.assign(vol0, vol0 + nel);
+  if (g.prop.jhbe > 100) g.prop.jhbe = 2;   // Isolid 101 / 102 (forint.F:1159): the Engine only tests JHBE /= 0 (sderi3.F:303), >= 1 (shvis3.F:318), >= 2 (sdefo3.F:222)
   e->sgroups.push_back(std::move(g));
   return (int)e->sgroups.size() - 1;
 }
@@ -447,12 +448,13 @@ int orgpu_add_solid_group_law(orgpu_engine* e, int nel, int nft, int law, const 
   NEED(m->fisokin == 0.0 && m->vp == 0 && m->ifail >= 0 && m->ifail <= 2, -5, "LAW36 kinematic hardening / VP=1 are outside the built path");
   NEED(m->ifail != 2 || prop->istrain > 0, -5, "LAW36 tensile-strain failure (IFAIL=2) needs the total strains (Istrain=1)");
   NEED(m->nrate >= 1 && m->nrate <= ORGPU_MAXFUNC36, -5, "LAW36 NRATE=%d out of range", m->nrate);
-  NEED(prop->jhbe == 0 || prop->jhbe == 1 || prop->jhbe == 2, -5, "Isolid=%d is outside the built path (0,1,2)", prop->jhbe);
+  NEED(prop->jhbe == 0 || prop->jhbe == 1 || prop->jhbe == 2 || prop->jhbe == 101 || prop->jhbe == 102, -5, "Isolid=%d is outside the built path (0,1,2,101,102)", prop->jhbe);
   NEED(prop->ismstr == 1 || prop->ismstr == 2 || prop->ismstr == 4, -5, "Ismstr=%d is outside the built path (1,2,4)", prop->ismstr);
   NEED(prop->ipla >= 0 && prop->ipla <= 2, -5, "solid Iplas=%d is outside the built path (0,1,2)", prop->ipla);
   NEED(prop->jcvt == 0 || (prop->jcvt == 1 && prop->jhbe == 1 && m->ifail != 2), -5, "solid Iframe: JCVT=%d with Isolid=%d / IFAIL=%d is outside the built path", prop->jcvt, prop->jhbe, m->ifail);
   HostSolidGroup g; g.nel = nel; g.nft = nft; g.law = 36; memset(&g.mat, 0, sizeof g.mat); g.mat.rho0 = m->rho0;
   g.m36 = *m; g.prop = *prop; g.vol0.assign(vol0, vol0 + nel);
+  if (g.prop.jhbe > 100) g.prop.jhbe = 2;   // Isolid 101 / 102 (forint.F:1159): the Engine only tests JHBE /= 0 (sderi3.F:303), >= 1 (shvis3.F:318), >= 2 (sdefo3.F:222)
   e->sgroups.push_back(std::move(g));
   return (int)e->sgroups.size() - 1;
 }

@@ -84,7 +84,7 @@ def test_elastic_cycle_is_bit_exact():
             assert np.array_equal(a, b_), f
 
 
-@pytest.mark.parametrize("jhbe,ismstr", [(1, 4), (2, 4), (0, 4), (1, 1), (1, 2), (2, 2)])
+@pytest.mark.parametrize("jhbe,ismstr", [(1, 4), (2, 4), (0, 4), (1, 1), (1, 2), (2, 2), (101, 4), (102, 2)])
 def test_formulation_variants_match_oracle(jhbe, ismstr):
     m = meshgen.hex_block(6, 6, 10, 1.2, 1.2, 3.3, v0=(0, 0, -150.0), fix_bottom_z=True, vrand=2.0,
                           prop=meshgen.default_prop_solid(jhbe=jhbe, ismstr=ismstr))
@@ -220,7 +220,7 @@ def test_law36_elastic_and_return_are_bit_exact():
     assert rel_err(g.solid_state("eint"), o.solid_state("eint")) <= 1e-14
 
 
-@pytest.mark.parametrize("jhbe,ismstr", [(1, 4), (2, 4), (0, 4), (1, 1), (1, 2), (2, 2)])
+@pytest.mark.parametrize("jhbe,ismstr", [(1, 4), (2, 4), (0, 4), (1, 1), (1, 2), (2, 2), (102, 4)])
 def test_law36_formulation_variants_match_oracle(jhbe, ismstr):
     m = meshgen.hex_block(6, 6, 10, 12.0, 12.0, 33.0, law=36, v0=(0, 0, -40.0), fix_bottom_z=True, vrand=10.0,
                           prop=meshgen.default_prop_solid(jhbe=jhbe, ismstr=ismstr))

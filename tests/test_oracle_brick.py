@@ -340,3 +340,16 @@ def test_corotational_axis_aligned_cube_without_spin_is_the_global_frame_to_seco
     dev = lambda D: 2 * G * dt * (D - D.sum() / 3)
     assert np.allclose(s0[:3], dev(D0), rtol=1e-10)
     assert np.allclose(np.sort(s1[:3]), np.sort(dev(D1)), rtol=1e-10)      # in the element's own axes: a permutation of x, y, z here
+
+
+def test_isolid_101_and_102_run_the_second_order_strain_rate_of_isolid_2():
+    """The Engine only compares JHBE with 0, >= 1 and >= 2 on this path (sderi3.F:303, shvis3.F:240/318, sdefo3.F:222; forint.F:1159
+    sends 1, 2, 101 and 102 to SFORC3): the old-format values 101 / 102 are Isolid 2 to it."""
+    runs = {}
+    for jhbe in (2, 101, 102, 1):
+        m = meshgen.hex_block(3, 3, 4, 1.0, 1.0, 1.5, v0=(0, 0, -120.0), fix_bottom_z=True, vrand=3.0, prop=meshgen.default_prop_solid(jhbe=jhbe))
+        o = Oracle(m); o.run_cycles(30)
+        runs[jhbe] = (o.download_nodes(("X",))["X"], o.solid_state("sig"))
+    for jhbe in (101, 102):
+        assert np.array_equal(runs[jhbe][0], runs[2][0]) and np.array_equal(runs[jhbe][1], runs[2][1])
+    assert not np.array_equal(runs[1][1], runs[2][1])
