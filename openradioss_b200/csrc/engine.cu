@@ -430,7 +430,7 @@ int orgpu_add_solid_group(orgpu_engine* e, int nel, int nft, const orgpu_law2* m
   NEED(mat->fisokin >= 0.0 && mat->fisokin <= 1.0, -4, "LAW2 FISOKIN = %g outside [0, 1]", mat->fisokin);
   NEED(prop->jhbe == 0 || prop->jhbe == 1 || prop->jhbe == 2 || prop->jhbe == 101 || prop->jhbe == 102, -5, "Isolid=%d is outside the built path (0,1,2,101,102)", prop->jhbe);
   NEED(prop->ismstr == 1 || prop->ismstr == 2 || prop->ismstr == 4, -5, "Ismstr=%d is outside the built path (1,2,4)", prop->ismstr);
-  NEED(prop->jcvt == 0 || (prop->jcvt == 1 && prop->jhbe == 1), -5, "solid Iframe: JCVT=%d with Isolid=%d is outside the built path (0 global; 1 co-rotational with Isolid 1)", prop->jcvt, prop->jhbe);
+  NEED(prop->jcvt == 0 || (prop->jcvt == 1 && prop->jhbe != 0), -5, "solid Iframe: JCVT=%d with Isolid=%d is outside the built path (0 global; 1 co-rotational with Isolid 1 / 2: SDEFO3 tests JCVT before JHBE, sdefo3.F:158, 222)", prop->jcvt, prop->jhbe);
   HostSolidGroup g; g.nel = nel; g.nft = nft; g.law = 2; g.mat = *mat; memset(&g.m36, 0, sizeof g.m36); g.prop = *prop; g.vol0.assign(vol0, vol0 + nel);
   if (g.prop.jhbe > 100) g.prop.jhbe = 2;   // Isolid 101 / 102 (forint.F:1159): the Engine only tests JHBE /= 0 (sderi3.F:303), >= 1 (shvis3.F:318), >= 2 (sdefo3.F:222)
   e->sgroups.push_back(std::move(g));
@@ -451,7 +451,7 @@ int orgpu_add_solid_group_law(orgpu_engine* e, int nel, int nft, int law, const 
   NEED(prop->jhbe == 0 || prop->jhbe == 1 || prop->jhbe == 2 || prop->jhbe == 101 || prop->jhbe == 102, -5, "Isolid=%d is outside the built path (0,1,2,101,102)", prop->jhbe);
   NEED(prop->ismstr == 1 || prop->ismstr == 2 || prop->ismstr == 4, -5, "Ismstr=%d is outside the built path (1,2,4)", prop->ismstr);
   NEED(prop->ipla >= 0 && prop->ipla <= 2, -5, "solid Iplas=%d is outside the built path (0,1,2)", prop->ipla);
-  NEED(prop->jcvt == 0 || (prop->jcvt == 1 && prop->jhbe == 1 && m->ifail != 2), -5, "solid Iframe: JCVT=%d with Isolid=%d / IFAIL=%d is outside the built path", prop->jcvt, prop->jhbe, m->ifail);
+  NEED(prop->jcvt == 0 || (prop->jcvt == 1 && prop->jhbe != 0 && m->ifail != 2), -5, "solid Iframe: JCVT=%d with Isolid=%d / IFAIL=%d is outside the built path", prop->jcvt, prop->jhbe, m->ifail);
   HostSolidGroup g; g.nel = nel; g.nft = nft; g.law = 36; memset(&g.mat, 0, sizeof g.mat); g.mat.rho0 = m->rho0;
   g.m36 = *m; g.prop = *prop; g.vol0.assign(vol0, vol0 + nel);
   if (g.prop.jhbe > 100) g.prop.jhbe = 2;   // Isolid 101 / 102 (forint.F:1159): the Engine only tests JHBE /= 0 (sderi3.F:303), >= 1 (shvis3.F:318), >= 2 (sdefo3.F:222)

@@ -408,6 +408,19 @@ def test_corotational_frame_matches_oracle(law, ismstr):
     assert o.solid_state("pla").max() > 0.01
 
 
+@pytest.mark.parametrize("jhbe", [2, 102])
+def test_corotational_frame_with_isolid_2_is_the_isolid_1_path(jhbe):
+    """SDEFO3 tests JCVT before JHBE (sdefo3.F:158, 222): in the co-rotational frame Isolid 2 / 102 run the statements of Isolid 1"""
+    def run(j):
+        m = meshgen.hex_block(4, 4, 8, 1.0, 1.0, 2.4, v0=(0, 0, -200.0), fix_bottom_z=True, vrand=5.0, prop=meshgen.default_prop_solid(jhbe=j, jcvt=1))
+        g, o = pair(m)
+        g.run_cycles(80); o.run_cycles(80)
+        dg, do = g.download_nodes(("D",))["D"], o.download_nodes(("D",))["D"]
+        assert rel_err(dg, do) <= DISP_TOL and o.solid_state("pla").max() > 0.01
+        return dg
+    assert np.array_equal(run(jhbe), run(1))
+
+
 def test_corotational_frame_is_objective_on_the_device():
     """a model and the same model turned by a rotation Q: positions related by Q after 150 yielding cycles (1e-9)"""
     from test_oracle_brick import _impact_block, _rot
