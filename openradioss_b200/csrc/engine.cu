@@ -82,7 +82,7 @@ struct orgpu_engine {
   // instrumentation
   long long launches = 0; double last_run_ms = 0; int profile = 0;
   double prof_ms[3] = {0, 0, 0}; long long prof_n[3] = {0, 0, 0};
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_recorded = false;     // ev0 / ev1 bracket the last orgpu_run_cycles
   std::vector<cudaEvent_t> evpool;
   Exchange xc;                        // domain exchange (one process per GPU)
   std::vector<int> gord_c, gord_t, gord_s, gnode; int* d_gnode = nullptr;   // global processing order / node index of a domain's elements / nodes
@@ -696,7 +696,7 @@ static int refresh_batches(orgpu_engine* e)
   e->batches.clear(); e->sh_batched.assign(e->csg.size(), 0); e->br_batched.assign(e->bsg.size(), 0);
   const char* mn = getenv("ORGPU_TAB_MIN"); const size_t tab_min = mn ? (size_t)atoi(mn) : 8;      // fewer super-groups of a variant: one launch each
   for (int brick = 0; brick < 2; brick++) {
-    const int nv = brick ? BRV_COUNT : SHV_COUNT;
+    const int nv = brick ? (int)BRV_COUNT : (int)SHV_COUNT;
     for (int v = 0; v < nv; v++) {
       orgpu_engine::Batch b; b.brick = brick != 0; b.variant = v;
       if (brick) { for (size_t k = 0; k < e->bsg.size(); k++) if (brick_tab_variant(e->bsg[k].d) == v) b.sgs.push_back((int)k); }
@@ -922,7 +922,7 @@ int orgpu_run_cycles(orgpu_engine* e, int ncycles)
       cand_fold_kernel<<<1, 32, 0, e->st>>>(e->d_cs, x.d_cand_recv, x.nranks); e->launches++;
       launch_node_advance(e->nd, e->d_cs, e->ctl.iroddl, e->st); e->launches++;
     }
-    CUDA_OK(cudaEventRecord(e->ev1, e->st));
+    CUDA_OK(cudaEventRecord(e->ev1, e->st)); e->ev_recorded = true;
     CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -944,7 +944,7 @@ int orgpu_run_cycles(orgpu_engine* e, int ncycles)
     }
     CUDA_OK(cudaEventRecord(e->ev0, e->st));
     for (int c = 0; c < ncycles; c++) CUDA_OK(cudaGraphLaunch(e->gexec, e->st));
-    CUDA_OK(cudaEventRecord(e->ev1, e->st));
+    CUDA_OK(cudaEventRecord(e->ev1, e->st)); e->ev_recorded = true;
     e->launches += (long long)per * ncycles;
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -977,7 +977,7 @@ int orgpu_run_cycles(orgpu_engine* e, int ncycles)
         }
       }
     }
-    CUDA_OK(cudaEventRecord(e->ev1, e->st));
+    CUDA_OK(cudaEventRecord(e->ev1, e->st)); e->ev_recorded = true;
     if (prof) { CUDA_OK(cudaStreamSynchronize(e->st)); float ms; CUDA_OK(cudaEventElapsedTime(&ms, e->ev0, e->ev1)); e->last_run_ms = ms; }
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -1004,7 +1004,7 @@ int orgpu_run_cycles(orgpu_engine* e, int ncycles)
         { float ms; cudaEventElapsedTime(&ms, e->evpool[k], e->evpool[k + 1]); e->prof_ms[2] += ms; e->prof_n[2]++; k += 2; }
       }
     }
-    CUDA_OK(cudaEventRecord(e->ev1, e->st));
+    CUDA_OK(cudaEventRecord(e->ev1, e->st)); e->ev_recorded = true;
     CUDA_OK(cudaStreamSynchronize(e->st));
     float ms; CUDA_OK(cudaEventElapsedTime(&ms, e->ev0, e->ev1)); e->last_run_ms = ms;
     CUDA_OK(cudaGetLastError());
@@ -1023,7 +1023,7 @@ int orgpu_run_cycles(orgpu_engine* e, int ncycles)
   }
   CUDA_OK(cudaEventRecord(e->ev0, e->st));
   for (int c = 0; c < ncycles; c++) CUDA_OK(cudaGraphLaunch(e->gexec, e->st));
-  CUDA_OK(cudaEventRecord(e->ev1, e->st));
+  CUDA_OK(cudaEventRecord(e->ev1, e->st)); e->ev_recorded = true;
   e->launches += (long long)per_cycle * ncycles;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -1034,7 +1034,7 @@ int orgpu_synchronize(orgpu_engine* e)
   NEED(e, -1, "null handle"); CUDA_OK(cudaSetDevice(e->device));
   CUDA_OK(cudaStreamSynchronize(e->st));
   { int rc = check_abort(e); if (rc) return rc; }
-  if (!e->profile) { float ms = 0; if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_run_ms = ms; else cudaGetLastError(); }
+  if (!e->profile && e->ev_recorded) { float ms = 0; if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_run_ms = ms; else cudaGetLastError(); }
   return 0;
 }
 
@@ -1230,7 +1230,7 @@ static int pipe_build(orgpu_engine* e)
   for (size_t k = 0; k < e->bsg.size(); k++) tile_chunks(e->ixs, 11, 8, e->bsg[k].first_elem, e->bsg[k].d.ne, tc_b[k]);
   // batched launches: one device table of descriptors per kernel variant, one CTA map per (variant, chunk)
   for (int brick = 0; brick < 2; brick++) {
-    const int nv = brick ? BRV_COUNT : SHV_COUNT; const size_t nsg = brick ? e->bsg.size() : e->csg.size();
+    const int nv = brick ? (int)BRV_COUNT : (int)SHV_COUNT; const size_t nsg = brick ? e->bsg.size() : e->csg.size();
     std::vector<char> batched(nsg, 0);
     for (int v = 0; v < nv; v++) {
       std::vector<int> sgs;
