@@ -77,6 +77,11 @@ int  orgpu_add_shell_group(orgpu_engine* e, int nel, int nft, int law, const voi
 /* one 3-node shell group: elements [nft, nft+nel) of IXTG; prop->ihbe carries Ish3n = IPARG(23) (1 or 2) */
 int  orgpu_add_sh3n_group(orgpu_engine* e, int nel, int nft, int law, const void* mat,
                           const orgpu_prop_shell* prop);
+/* IPARIT of the Engine (default 1 = /PARITH/ON): with /PARITH/ON FORCE leaves each load record in an FSKY row of its own, which the
+ * Starter places BEHIND the node's element rows (force.F90:714-1034, starter/source/spmd/domdec2.F:2363-2388), so ASSPAR4 adds a node's
+ * load after its element forces; with /PARITH/OFF (iparit = 0) FORCE adds to A before the element loop (force.F90:182-312) and the
+ * nodal sum starts from the load.  orgpu_set_exchange_nodes (the device-resident /PARITH/OFF exchange) implies 0. */
+int  orgpu_set_parith(orgpu_engine* e, int iparit);
 /* Concentrated loads record by record, as the Engine holds them (FORCE, engine/source/loads/general/force.F90:188-312; IB / FAC of
  * /CLOAD): record l loads node ib[3l] (1-based) in direction ib[3l+1] (1..3 forces, 4..6 moments, global frame) with
  * FCY * f(TT * FCX), f = time function ib[3l+2] (0-based index into orgpu_set_functions, -1: constant), FCY = fac[2l], FCX = fac[2l+1].

@@ -255,6 +255,11 @@ class Binding:
             self._call("unpack_rows", self.h, C.c_int(len(slots)), slots.ctypes.data_as(C.c_void_p), buf.ctypes.data_as(C.c_void_p))
 
     # -- nodal partial sums of frontier nodes (/PARITH/OFF exchange, SPMD_EXCH_A) -----------------------
+    def set_parith(self, iparit):
+        """IPARIT: 1 (default) the load of a node is added behind its element rows (FORCE's own FSKY rows, /PARITH/ON), 0 the nodal
+        sum starts from it (/PARITH/OFF: FORCE adds to A before the element loop)."""
+        self._call("set_parith", self.h, C.c_int(iparit))
+
     def pack_nodes(self, nodes):
         nodes = np.ascontiguousarray(nodes, np.int32)
         buf = np.zeros((len(nodes), 8))

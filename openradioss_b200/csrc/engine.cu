@@ -1428,7 +1428,16 @@ int orgpu_set_exchange_nodes(orgpu_engine* e, int nneigh, const int* ranks, cons
   x.nb_rank.assign(ranks, ranks + nneigh); x.xn_ptr.assign(ptr, ptr + nneigh + 1);
   if (dev_alloc(&x.d_xn_nodes, (size_t)tot + 1) || dev_alloc(&x.d_xn_send, 8 * ((size_t)tot + 1)) || dev_alloc(&x.d_xn_recv, 8 * ((size_t)tot + 1))) return -100;
   if (tot) CUDA_OK(cudaMemcpy(x.d_xn_nodes, nodes, 4 * (size_t)tot, cudaMemcpyHostToDevice));
-  x.parith_off = true;
+  x.parith_off = true; e->nd.load_first = 1;            // /PARITH/OFF: FORCE adds to A before the element loop
+  return 0;
+}
+
+// IPARIT of the Engine: where FORCE's load records enter a node's sum (DevNodes::load_first).  Before the first cycle.
+int orgpu_set_parith(orgpu_engine* e, int iparit)
+{
+  NEED(e && (iparit == 0 || iparit == 1), -1, "orgpu_set_parith: bad arguments");
+  if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }     // the captured cycle carries the flag in its kernel arguments
+  e->nd.load_first = iparit ? 0 : 1;
   return 0;
 }
 

@@ -33,11 +33,14 @@ __device__ __forceinline__ NodeAcc node_gather(const DevNodes& nd, const double*
       for (int c = 0; c < NV; c++) buf[j][c] = ld256_cs(base + (size_t)NV * (k0 + j) + c);
     }
   }
-  // A starts from the external nodal loads (FORCE, force.F90:301-312: A += FCY * FINTER(IFUN, TT*FCX))
-  if (nd.FEXT) { r.a[0] = nd.FEXT[3 * n] * fscale; r.a[1] = nd.FEXT[3 * n + 1] * fscale; r.a[2] = nd.FEXT[3 * n + 2] * fscale; }
-  else { r.a[0] = K_ZERO; r.a[1] = K_ZERO; r.a[2] = K_ZERO; }
-  if (nd.MEXT) { r.ar[0] = nd.MEXT[3 * n] * fscale; r.ar[1] = nd.MEXT[3 * n + 1] * fscale; r.ar[2] = nd.MEXT[3 * n + 2] * fscale; }
-  else { r.ar[0] = K_ZERO; r.ar[1] = K_ZERO; r.ar[2] = K_ZERO; }
+  // the node's external load (FORCE: FCY * FINTER(IFUN, TT*FCX)): with /PARITH/OFF A starts from it (force.F90:182-312: A += AA before
+  // the element loop); with /PARITH/ON it is added behind the element rows, where ASSPAR4 finds FORCE's own rows (force.F90:714-1034)
+  double la[3] = {K_ZERO, K_ZERO, K_ZERO}, lar[3] = {K_ZERO, K_ZERO, K_ZERO};
+  if (nd.FEXT) { la[0] = nd.FEXT[3 * n] * fscale; la[1] = nd.FEXT[3 * n + 1] * fscale; la[2] = nd.FEXT[3 * n + 2] * fscale; }
+  if (nd.MEXT) { lar[0] = nd.MEXT[3 * n] * fscale; lar[1] = nd.MEXT[3 * n + 1] * fscale; lar[2] = nd.MEXT[3 * n + 2] * fscale; }
+  const bool lf = nd.load_first != 0;
+  #pragma unroll
+  for (int c = 0; c < 3; c++) { r.a[c] = lf ? la[c] : K_ZERO; r.ar[c] = lf ? lar[c] : K_ZERO; }
   r.stifn = nd.nodadt ? K_EM20 : K_ZERO; r.stifr = r.stifn;
   for (int kb = k0; kb < k1; kb += NB) {
     if (kb != k0) {                                  // irregular node with more than NB corners
@@ -60,6 +63,10 @@ __device__ __forceinline__ NodeAcc node_gather(const DevNodes& nd, const double*
         }
       }
     }
+  }
+  if (!lf) {
+    if (nd.FEXT) { r.a[0] = r.a[0] + la[0]; r.a[1] = r.a[1] + la[1]; r.a[2] = r.a[2] + la[2]; }
+    if (nd.MEXT) { r.ar[0] = r.ar[0] + lar[0]; r.ar[1] = r.ar[1] + lar[1]; r.ar[2] = r.ar[2] + lar[2]; }
   }
   (void)iroddl;
   return r;

@@ -18,7 +18,7 @@ set_functions add_solid_group add_solid_group_law add_shell_group set_sh3n add_s
 synchronize get_time download_nodes download_fsky download_solid_state download_shell_state
 step_host launch_count last_run_ms set_profile get_profile pack_rows unpack_rows comm_unique_id comm_init
 set_exchange exchange get_energies p2p_export p2p_connect set_load_function set_fixvel set_gravity upload_solid_state upload_shell_state set_time set_itab
-set_parts set_print get_balance get_balance_history set_quadrature set_global_order set_exchange_timeout pack_nodes add_nodes set_exchange_nodes step_host_rot forces_host set_shell_group_fail set_cloads set_solid_group_fail""".split()
+set_parts set_print get_balance get_balance_history set_quadrature set_global_order set_exchange_timeout pack_nodes add_nodes set_exchange_nodes step_host_rot forces_host set_shell_group_fail set_cloads set_solid_group_fail set_parith""".split()
 
 
 def load_library() -> C.CDLL:

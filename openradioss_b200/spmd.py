@@ -106,6 +106,8 @@ def run_local_off(backends, doms, ncycles, on_cycle=None):
     skyline stay zero), then the partial sums of the frontier nodes travel -- SPMD_EXCH_A (spmd_exch_a.F:153-166 pack,
     :517-528 add): 8 values per node, added neighbour by neighbour in rank order.  `doms` must come from domdec.parith_off."""
     states = [initial_state(d.model.control) for d in doms]
+    for b in backends:
+        b.set_parith(0)                       # /PARITH/OFF: FORCE adds to A before the element loop (force.F90:182-312)
     for c in range(ncycles):
         dt1 = states[0]["dt2"]
         for b in backends:
@@ -128,6 +130,8 @@ def run_local_off(backends, doms, ncycles, on_cycle=None):
 def cycle_off(backend, dom, comm, state):
     """One /PARITH/OFF cycle of one domain in its own process (SPMD_EXCH_A + SPMD_GLOB_MIN5 over `comm`)."""
     dt1 = state["dt2"]
+    if not state.get("iparit0"):
+        backend.set_parith(0); state["iparit0"] = True      # /PARITH/OFF: the nodal sum starts from the load
     backend.forces_phase(dt1); backend.assemble()
     sends = {nb.rank: (backend.pack_nodes(nb.nodes), len(nb.nodes)) for nb in dom.neighbors}
     got = comm.exchange(sends)

@@ -59,6 +59,7 @@ void orc_set_bcs(void* h,const int* icodt,const int* icodr){
 void orc_set_cloads(void* h,int nload,const int* ib,const double* fac){
   Oracle* o=(Oracle*)h; o->CL_IB.assign(ib,ib+(size_t)3*nload); o->CL_FAC.assign(fac,fac+(size_t)2*nload);
 }
+void orc_set_parith(void* h,int iparit){ ((Oracle*)h)->iparit=iparit; }   /* IPARIT: where FORCE's records enter the nodal sum (oracle.h) */
 void orc_set_load_function(void* h,int ifunc,double fcx){ Oracle* o=(Oracle*)h; o->LF_FUNC=ifunc; o->LF_FCX=fcx; }
 void orc_set_fixvel(void* h,int nfxvel,const int* ibfv /*(3,n)*/,const double* vel /*(4,n)*/){
   Oracle* o=(Oracle*)h; o->IBFV.assign(ibfv,ibfv+(size_t)3*nfxvel); o->VEL.assign(vel,vel+(size_t)4*nfxvel);

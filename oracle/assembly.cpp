@@ -28,6 +28,11 @@ void orc_asspar4(Oracle& o)
       o.STIFN[N]=o.STIFN[N]+f[6];
       o.STIFR[N]=o.STIFR[N]+f[7];
     }
+    /* /PARITH/ON: the load records are the LAST rows of a node's skyline (pseudo-elements appended after all elements,
+     * starter/source/spmd/domdec2.F:2363-2388; FORCE fills them, force.F90:714-1034) */
+    if(o.iparit!=0 && !o.LA.empty()){
+      for(int c=0;c<3;c++){ o.A[3*N+c]=o.A[3*N+c]+o.LA[3*N+c]; o.AR[3*N+c]=o.AR[3*N+c]+o.LAR[3*N+c]; }
+    }
   }
 }
 
@@ -196,22 +201,28 @@ void orc_depla(Oracle& o)
   }
 }
 
-/* element force phase: external loads pre-loaded into A/AR, then all groups write FSKY */
+/* element force phase: this cycle's nodal loads (into A / AR at once with /PARITH/OFF, kept for ASSPAR4 with /PARITH/ON), then all groups write FSKY */
 void orc_forces(Oracle& o)
 {
   const int n=o.numnod;
   /* resol.F: A/AR hold external nodal loads when the element loop starts (FORCE, resol.F:2929);
    * STIFN/STIFR restart from zero each cycle */
   const double fs=orc_load_scale(o);   /* force.F90:235, 301-312: AA = FCY*FINTER(IFUN,TT*FCX) */
-  for(int i=0;i<3*n;i++){ o.A[i]= o.FEXT.empty()? K_ZERO : o.FEXT[i]*fs; o.AR[i]= o.MEXT.empty()? K_ZERO : o.MEXT[i]*fs; }
-  /* FORCE record by record (force.F90:188-312, IFUN = 1, no sensor, global frame): AA = FCY*FINTER(N3,TS*FCX); A(N2,N1) += AA */
+  const bool loaded = !o.FEXT.empty() || !o.MEXT.empty() || !o.CL_IB.empty();
+  if(loaded){ o.LA.assign((size_t)3*n,K_ZERO); o.LAR.assign((size_t)3*n,K_ZERO); } else { o.LA.clear(); o.LAR.clear(); }
+  if(loaded) for(int i=0;i<3*n;i++){ o.LA[i]= o.FEXT.empty()? K_ZERO : o.FEXT[i]*fs; o.LAR[i]= o.MEXT.empty()? K_ZERO : o.MEXT[i]*fs; }
+  /* FORCE record by record (force.F90:188-312, IFUN = 1, no sensor, global frame): AA = FCY*FINTER(N3,TS*FCX); the records
+   * of one node and direction are summed in record order */
   for(size_t NL=0; NL<o.CL_IB.size()/3; NL++){
     const int N1=o.CL_IB[3*NL]-1, N2=o.CL_IB[3*NL+1], N3=o.CL_IB[3*NL+2];
     const double FCY=o.CL_FAC[2*NL], FCX=o.CL_FAC[2*NL+1];
     const double AA = N3>=0 ? FCY*orc_finter(o,N3,o.TT*FCX) : FCY;
-    if(N2<=3) o.A[3*N1+N2-1]=o.A[3*N1+N2-1]+AA;
-    else      o.AR[3*N1+N2-4]=o.AR[3*N1+N2-4]+AA;
+    if(N2<=3) o.LA[3*N1+N2-1]=o.LA[3*N1+N2-1]+AA;
+    else      o.LAR[3*N1+N2-4]=o.LAR[3*N1+N2-4]+AA;
   }
+  /* /PARITH/OFF: A += AA before the element loop (force.F90:182-312); /PARITH/ON: the records wait in their FSKY rows, which
+   * ASSPAR4 reaches after the element rows (orc_asspar4) */
+  for(int i=0;i<3*n;i++){ o.A[i]= (loaded && o.iparit==0)? o.LA[i] : K_ZERO; o.AR[i]= (loaded && o.iparit==0)? o.LAR[i] : K_ZERO; }
   /* with /DT/NODA the nodal stiffnesses restart from EM20 (dtnoda.F:336-338, rotational part alike) */
   const double st0 = o.ctl.nodadt!=0 ? K_EM20 : K_ZERO;
   for(int i=0;i<n;i++){ o.STIFN[i]=st0; o.STIFR[i]=st0; }

@@ -54,7 +54,11 @@ struct Oracle {
   orgpu_control ctl{};
   /* nodal arrays, Fortran (3,NUMNOD) column-major -> [3*n+c]  (nodal_arrays.F90:125-176) */
   std::vector<double> X, V, VR, D, DR, A, AR, MS, IN, STIFN, STIFR;
-  std::vector<double> FEXT, MEXT;     /* constant external nodal loads (3,N) pre-loaded into A/AR */
+  std::vector<double> FEXT, MEXT;     /* constant external nodal loads (3,N) */
+  std::vector<double> LA, LAR;        /* this cycle's nodal load sums (3,N): FEXT * f + the load records in record order */
+  int iparit = 1;                     /* IPARIT: 1 /PARITH/ON -- FORCE leaves its records in FSKY rows BEHIND the element rows of a node
+                                         (force.F90:714-1034, Starter order domdec2.F:2363-2388), ASSPAR4 adds them last;
+                                         0 /PARITH/OFF -- FORCE adds to A before the element loop (force.F90:182-312) */
   std::vector<int>    ICODT, ICODR;   /* BCS codes (bit 4=x,2=y,1=z fixed), bcs10.F */
   std::vector<int> ITAB;              /* user node ids (NELTST of a nodal time step) */
   int LF_FUNC=-1; double LF_FCX=1.0;  /* time function of the concentrated loads (force.F90:195-196, 235) */

@@ -62,6 +62,31 @@ def test_plate_pressure_pulse_matches_oracle():
     assert rel_err(g.download_nodes(("D",))["D"], o.download_nodes(("D",))["D"]) <= 1e-8
 
 
+@pytest.mark.parametrize("iparit", [1, 0])
+def test_load_enters_the_nodal_sum_where_the_reference_adds_it(iparit):
+    """/PARITH/ON (default): behind the element rows, where ASSPAR4 finds FORCE's own FSKY rows; /PARITH/OFF: before them.  The
+    device fold is restated in numpy from the device's own rows and must match bit for bit, in both modes."""
+    m = meshgen.shell_plate(12, 9, 120.0, 90.0, pressure=30.0, vrand=5.0)
+    g = Engine(m); g.set_parith(iparit)
+    g.forces_phase(0.0)
+    fsky = g.download_fsky()
+    g.assemble()
+    A = g.download_nodes(("A",))["A"]
+    ref = np.zeros_like(A)
+    for n in range(m.numnod):
+        acc = m.fext[n].copy() if iparit == 0 else np.zeros(3)
+        for k in range(m.adsky[n] - 1, m.adsky[n + 1] - 1):
+            acc = acc + fsky[k, :3]
+        ref[n] = acc + m.fext[n] if iparit == 1 else acc
+    assert np.array_equal(A, ref)
+    o = Oracle(m, threads=0); o.set_parith(iparit); o.forces_phase(0.0); o.assemble()
+    assert rel_err(A, o.download_nodes(("A",))["A"]) <= 1e-12
+    # the fused device loop (same gather) against the oracle's loop in the same mode
+    g2 = Engine(m); g2.set_parith(iparit); g2.run_cycles(30); g2.synchronize()
+    o2 = Oracle(m, threads=0); o2.set_parith(iparit); o2.run_cycles(30)
+    assert rel_err(g2.download_nodes(("V",))["V"], o2.download_nodes(("V",))["V"]) <= 1e-10
+
+
 def test_gravity_loads_match_oracle():
     """GRAVIT on the device (node kernel, between ACCELE and BCS): constant g on all nodes + a ramped lateral load on a
     node subset, on a plate under pressure and on a block; phased 1e-12, then 300 cycles of the device loop"""

@@ -191,3 +191,28 @@ def test_load_records_with_several_curves_add_up_in_record_order():
     scale = max(np.abs(want).max(), np.abs(internal).max())
     assert np.allclose(got, want, rtol=1e-9, atol=1e-12 * scale)
     assert np.abs(want[:, 0]).max() > 0 and np.abs(want[:, 4]).max() > 0 and 0.0 < curve(k1, tt * 2.0) < 1.0
+
+
+# ---- where FORCE's records enter the nodal sum: /PARITH/ON behind the element rows, /PARITH/OFF before them ---------------------
+def test_parith_on_adds_the_load_behind_the_rows_and_parith_off_before_them():
+    """/PARITH/ON: FORCE leaves each record in an FSKY row of its own (force.F90:714-1034) and the Starter appends those
+    pseudo-elements after all elements of a node (starter/source/spmd/domdec2.F:2363-2388): ASSPAR4 adds the load LAST.
+    /PARITH/OFF: A += AA before the element loop (force.F90:182-312).  Both folds are restated here in numpy and must match bit for bit."""
+    m = meshgen.shell_plate(6, 5, 60.0, 50.0, pressure=30.0, vrand=5.0)
+    res = {}
+    for iparit in (1, 0):
+        o = Oracle(m); o.set_parith(iparit)
+        o.forces_phase(0.0)
+        fsky = o.download_fsky()
+        o.assemble()
+        A = o.download_nodes(("A",))["A"]
+        ref = np.zeros_like(A)
+        for n in range(m.numnod):
+            acc = m.fext[n].copy() if iparit == 0 else np.zeros(3)
+            for k in range(m.adsky[n] - 1, m.adsky[n + 1] - 1):
+                acc = acc + fsky[k, :3]
+            ref[n] = acc + m.fext[n] if iparit == 1 else acc
+        assert np.array_equal(A, ref), iparit
+        res[iparit] = A
+    assert not np.array_equal(res[0], res[1])                      # the order shows in the last bits of some loaded nodes
+    assert np.abs(res[0] - res[1]).max() <= 4e-16 * np.abs(res[1]).max()
